@@ -1,0 +1,221 @@
+/*
+ * ugaitnet_b200 -- C ABI of the B200 (sm_100a) hot path of UGaitNet.
+ *
+ * The reference (avagait/ugaitnet) is pure Python/Keras and has NO FFI / operator
+ * boundary of its own; every entry point below therefore replaces a Keras layer call or
+ * Lambda body of the reference graph, cited as  file:line  relative to the reference
+ * root.  The reference-side binding (ctypes) a maintainer would add is shown in
+ * INTEGRATION.md; the in-tree binding is ugaitnet_b200/_ffi.py.
+ *
+ * Conventions
+ *  - extern "C", plain structs/pointers only.  Tensors cross as `ugn_tensor`, which is
+ *    layout-identical to DLPack's `DLTensor` (dlpack.h, v0.8/v1.0): Python passes
+ *    `&DLManagedTensor.dl_tensor` of a `tensor.__dlpack__()` capsule.  The library never
+ *    takes ownership and never calls the DLPack deleter; the caller keeps the capsule
+ *    alive until the stream has been synchronised.
+ *  - All tensors must live on the ctx's CUDA device (device_type == kDLCUDA == 2), be
+ *    dense row-major (strides NULL or compact) and have byte_offset folded by the caller
+ *    or left in the struct (both honoured).
+ *  - Every call returns 0 on success or a negative ugn_status; `ugn_last_error()` gives
+ *    the thread-local message.  Nothing throws across the boundary.
+ *  - Every call is asynchronous on `stream` (a cudaStream_t passed as void*).
+ *  - There is NO CPU fallback: a call on a non-CUDA tensor fails with UGN_ERR_DEVICE.
+ *
+ * Storage modes (selected by the dtype of the activation / weight operands):
+ *  - f32 : "fp32 validation mode" -- SIMT FFMA kernels, NHWC f32 activations.
+ *  - bf16: tensor-core mode -- tcgen05.mma (kind::f16, BF16 in / FP32 accumulate in
+ *          TMEM) fed by TMA.  A bf16 operand carries a leading plane dimension P:
+ *          P == 1 plain bf16;  P == 2 "split" (plane 0 = hi = bf16(x), plane 1 = lo =
+ *          bf16(x - hi)); with split operands the kernels issue hi*hi + hi*lo + lo*hi,
+ *          i.e. ~fp32-accurate products on the BF16 tensor cores at 3x the MMA work.
+ *
+ * Layouts
+ *  - activations: NHWC, channel count padded to a multiple of 32 (64-byte rows) in bf16
+ *    mode ("Cp"); f32 mode uses the same padded shapes so one host plan serves both.
+ *  - conv weights: OHWI  [Cout][kh][kw][Cp_in]  (master copy f32 unpadded
+ *    [Cout][kh][kw][Cin]); dense weights [out][in].
+ */
+#ifndef UGAITNET_B200_H_
+#define UGAITNET_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define UGN_ABI_VERSION 1
+
+typedef enum {
+  UGN_OK = 0,
+  UGN_ERR_INVALID = -1,      /* bad shape / dtype / argument */
+  UGN_ERR_CUDA = -2,         /* CUDA runtime or driver error */
+  UGN_ERR_UNSUPPORTED = -3,  /* valid request this build does not implement */
+  UGN_ERR_DEVICE = -4        /* tensor is not on the ctx device (no CPU fallback) */
+} ugn_status;
+
+/* DLPack-compatible view (== DLTensor). */
+typedef struct {
+  void* data;
+  int32_t device_type; /* kDLCUDA = 2 */
+  int32_t device_id;
+  int32_t ndim;
+  uint8_t dtype_code; /* kDLInt=0, kDLUInt=1, kDLFloat=2, kDLBfloat=4 */
+  uint8_t dtype_bits;
+  uint16_t dtype_lanes;
+  int64_t* shape;
+  int64_t* strides; /* NULL = compact row-major */
+  uint64_t byte_offset;
+} ugn_tensor;
+
+typedef struct ugn_ctx ugn_ctx;
+
+enum { UGN_ACT_LINEAR = 0, UGN_ACT_RELU = 1, UGN_ACT_LEAKY = 2 };
+enum { UGN_MERGE_MAX = 0, UGN_MERGE_AVG = 1, UGN_MERGE_SIGNMAX = 2 };
+
+int ugn_abi_version(void);
+const char* ugn_last_error(void);
+int ugn_ctx_create(int device, ugn_ctx** out);
+int ugn_ctx_destroy(ugn_ctx* ctx);
+/* 1 if the device is compute capability 10.x (tcgen05/TMEM/TMA path usable). */
+int ugn_ctx_has_tcgen05(ugn_ctx* ctx);
+
+/* ---- a0: step input contract (data/mj_dataGeneratorMMUWYHsingle.py:664-823) ----------
+ * x_nchw f32 [B,C,H,W] (what the Keras Input layers receive, nets/mj_uwyhNets_ba.py:1069-1074)
+ * -> NHWC with C padded to Cp: f32 [B,H,W,Cp] or bf16 [P,B,H,W,Cp]; pad channels = 0. */
+int ugn_pack_input(ugn_ctx*, const ugn_tensor* x_nchw, ugn_tensor* x_nhwc, void* stream);
+
+/* master f32 conv kernel [Cout][kh][kw][Cin] -> compute copy f32 [Cout][kh][kw][Cp] or
+ * bf16 [P][Cout][kh][kw][Cp]; also used for dense weights with w viewed as [out][1][1][in]. */
+int ugn_pack_weight(ugn_ctx*, const ugn_tensor* w_master, ugn_tensor* w_packed, void* stream);
+
+/* ---- a1: Conv2D(valid, stride 1)+bias+act [+MaxPooling2D 2x2] -------------------------
+ * replaces Conv2D/LeakyReLU/MaxPooling2D of UWYHNet.buildBranch{,LReLU}
+ * (nets/mj_uwyhNets_ba.py:82-92, :125-137).
+ * x [.,B,H,W,Cp_in]; w packed; bias f32 [Cout]; y [.,B,Hp,Wp,Cout] (pooled if pool!=0,
+ * floor); pool_idx u8 [B,Hp,Wp,Cout] = argmax position 0..3 inside the 2x2 window
+ * (ties -> first in (dy,dx) scan order), required iff pool != 0. */
+int ugn_conv2d_fwd(ugn_ctx*, const ugn_tensor* x, const ugn_tensor* w, const ugn_tensor* bias,
+                   ugn_tensor* y, ugn_tensor* pool_idx, int act, float alpha, int pool,
+                   void* stream);
+
+/* backward through pool+act: dy f32 [B,Hp,Wp,C] (grad wrt layer output), y = layer output,
+ * -> dz (grad wrt conv pre-activation) [.,B,Ho,Wo,C] in the storage mode of `dz`. */
+int ugn_conv2d_bwd_act(ugn_ctx*, const ugn_tensor* dy, const ugn_tensor* y,
+                       const ugn_tensor* pool_idx, ugn_tensor* dz, int act, float alpha,
+                       int pool, void* stream);
+
+/* dx f32 [B,H,W,Cp_in] = full correlation of dz with w (Keras Conv2D input gradient). */
+int ugn_conv2d_dgrad(ugn_ctx*, const ugn_tensor* dz, const ugn_tensor* w, ugn_tensor* dx,
+                     void* stream);
+
+/* dw f32 [Cout][kh][kw][Cin] (master layout, OVERWRITTEN), db f32 [Cout]. */
+int ugn_conv2d_wgrad(ugn_ctx*, const ugn_tensor* x, const ugn_tensor* dz, ugn_tensor* dw,
+                     ugn_tensor* db, void* stream);
+
+/* Flatten() in the reference is over (C,H,W) (channels_first, :94): convert the last conv
+ * output NHWC [.,B,H,W,C] <-> flat [.,B,C*H*W] (forward) and the f32 gradient back. */
+int ugn_flatten_chw(ugn_ctx*, const ugn_tensor* y_nhwc, ugn_tensor* flat, void* stream);
+int ugn_unflatten_chw(ugn_ctx*, const ugn_tensor* dflat_f32, ugn_tensor* dy_nhwc_f32, void* stream);
+
+/* ---- a1/a5/a6: Dense (nets/mj_uwyhNets_ba.py:97-105, :1194-1214) ----------------------
+ * y f32 [B,N] = act((x [.,B,K] . w[.,N,K]^T + bias)) * drop_mask (f32 [B,N], nullable,
+ * already scaled by 1/(1-p): Keras inverted dropout).  y16 (nullable) receives the bf16
+ * copy [P,B,N] for the next tensor-core consumer. */
+int ugn_linear_fwd(ugn_ctx*, const ugn_tensor* x, const ugn_tensor* w, const ugn_tensor* bias,
+                   const ugn_tensor* drop_mask, ugn_tensor* y, ugn_tensor* y16, int act,
+                   float alpha, void* stream);
+/* Backward through dropout mask and activation of a Dense layer:
+ * dz = dy * drop_mask * act'(y)  (y = the layer output; nullable for linear layers).
+ * dz f32 (nullable) and/or dz16 bf16 [P,...] (nullable) receive the result. */
+int ugn_act_mask_bwd(ugn_ctx*, const ugn_tensor* dy, const ugn_tensor* y, const ugn_tensor* drop_mask,
+                     ugn_tensor* dz, ugn_tensor* dz16, int act, float alpha, void* stream);
+/* dz [.,B,N] is the gradient wrt the pre-activation output (storage mode of x / w).
+ * Outputs (each nullable): dx f32 [B,K], dw f32 [N,K] (overwritten), db f32 [N]. */
+int ugn_linear_bwd(ugn_ctx*, const ugn_tensor* x, const ugn_tensor* w, const ugn_tensor* dz,
+                   ugn_tensor* dx, ugn_tensor* dw, ugn_tensor* db, void* stream);
+
+/* ---- a2+a3+a4: gate x use-flag, fusion, l2_normalize ---------------------------------
+ * replaces mj_tensor_times_scalar (:51-54), fMerge(name="fusion") (:1189; sign_max at
+ * mains/mj_trainUWYHGaitNet_DataGen_CasiaB.py:169-178) and tf.math.l2_normalize (:1191).
+ * br[m] f32 [B,d], flags[m] f32 [B,1] (m < nmods <= 4).  Outputs: sig f32 [B,d],
+ * sig16 bf16 [P,B,d] (nullable), winner u8 [B,d] (selected modality; for AVG unused),
+ * inv_norm f32 [B,2] = {1/norm, sum x^2}.  normalize == 0 skips l2_normalize (1-modality graph, :904). */
+int ugn_fuse_fwd(ugn_ctx*, int nmods, const ugn_tensor* const* br, const ugn_tensor* const* flags,
+                 ugn_tensor* sig, ugn_tensor* sig16, ugn_tensor* winner, ugn_tensor* inv_norm,
+                 int merge, int normalize, void* stream);
+/* dsig f32 [B,d] -> dbr[m] f32 [B,d] (gradient wrt each branch output, gate applied). */
+int ugn_fuse_bwd(ugn_ctx*, int nmods, const ugn_tensor* dsig, const ugn_tensor* sig,
+                 const ugn_tensor* winner, const ugn_tensor* inv_norm,
+                 const ugn_tensor* const* flags, ugn_tensor* const* dbr, int merge,
+                 int normalize, void* stream);
+
+/* ---- a6: softmax + categorical cross-entropy (:1214, :1243) ---------------------------
+ * logits f32 [B,C], labels i32 [B].  loss_acc f32 [2] = {mean CE, accuracy};
+ * dlogits f32 [B,C] = scale * (softmax - onehot)/B (nullable). */
+int ugn_softmax_ce(ugn_ctx*, const ugn_tensor* logits, const ugn_tensor* labels,
+                   ugn_tensor* loss_acc, ugn_tensor* dlogits, float scale, void* stream);
+
+/* ---- a7: batch-all triplet loss (nets/triplet_loss_all.py:8-77) -----------------------
+ * emb f32 [n,B,d] (or [B,d] == n = 1), labels i32 [B].  out f32 [2] = {loss, total count of
+ * active triplets}; demb f32 like emb (nullable) = scale * dLoss/dEmb.
+ * workspace: ugn_triplet_workspace_bytes(n,B) bytes, f32-aligned device buffer. */
+int64_t ugn_triplet_workspace_bytes(int n, int B);
+int ugn_triplet_all(ugn_ctx*, const ugn_tensor* emb, const ugn_tensor* labels, float margin,
+                    float scale, ugn_tensor* out, ugn_tensor* demb, ugn_tensor* workspace,
+                    void* stream);
+
+/* ---- a8/a9: regulariser + optimiser --------------------------------------------------
+ * One fused multi-tensor step over a FLAT parameter arena: for segment s covering
+ * [off[s], off[s+1]) elements, g' = g*gscale + 2*l2[s]*w (Keras L2 regulariser gradient),
+ * Keras Adam (mains/mj_trainUWYHGaitNet_DataGen_3mods.py:242): m,v update,
+ * w -= lr_t * m / (sqrt(v)+eps).  seg_off i64 [S+1], seg_l2 f32 [S] device tensors.
+ * reg_out f32 [1] (nullable) accumulates sum_s l2[s]*|w_s|^2 of the PRE-update weights.
+ * lr_dev f32 [1] (nullable): when given, the learning rate is read from device memory
+ * instead of lr_t, so a captured CUDA graph can be replayed with a new rate. */
+int ugn_adam_step(ugn_ctx*, ugn_tensor* w, const ugn_tensor* g, ugn_tensor* m, ugn_tensor* v,
+                  const ugn_tensor* seg_off, const ugn_tensor* seg_l2, float lr_t, float beta1,
+                  float beta2, float eps, float gscale, ugn_tensor* reg_out,
+                  const ugn_tensor* lr_dev, void* stream);
+/* SGD with momentum (optimizers.SGD(lr, momentum), :245): v = mom*v - lr*g'; w += v. */
+int ugn_sgd_step(ugn_ctx*, ugn_tensor* w, const ugn_tensor* g, ugn_tensor* v,
+                 const ugn_tensor* seg_off, const ugn_tensor* seg_l2, float lr, float momentum,
+                 float gscale, ugn_tensor* reg_out, const ugn_tensor* lr_dev, void* stream);
+
+/* ---- a12: brute-force k-NN (mains/mj_testUWYHGaitNet_open_tum.py:331-341) -------------
+ * queries f32 [Q,D], gallery f32 [N,D] (this rank's shard), k <= 32.
+ * Stage 1 (ugn_knn_topk): candidate search, kc >= k candidates per query by approximate
+ *   (fp32 / tensor-core) squared distance, fused top-k (the QxN matrix is never stored),
+ *   then exact fp64 re-rank of the candidates by sum((q-g)^2) with ordering
+ *   (distance, global index).  out_d2 f64 [Q,k], out_idx i64 [Q,k] (+ idx_base),
+ *   out_lab i32 [Q,k] (gallery_labels i32 [N]).
+ * Stage 2 (ugn_knn_merge_vote): merges G shards' [G,Q,k] candidate lists with the same
+ *   ordering and votes (uniform weights, ties -> smallest label). pred i32 [Q]. */
+int64_t ugn_knn_workspace_bytes(int64_t Q, int64_t N, int64_t D, int k);
+/* clf.fit(): per-row squared norms of the gallery shard, g2 f32 [N] (computed once). */
+int ugn_knn_gallery_norms(ugn_ctx*, const ugn_tensor* gallery, ugn_tensor* g2, void* stream);
+int ugn_knn_topk(ugn_ctx*, const ugn_tensor* queries, const ugn_tensor* gallery, const ugn_tensor* g2,
+                 const ugn_tensor* gallery_labels, int k, int64_t idx_base, ugn_tensor* out_d2,
+                 ugn_tensor* out_idx, ugn_tensor* out_lab, ugn_tensor* workspace, void* stream);
+int ugn_knn_merge_vote(ugn_ctx*, const ugn_tensor* d2, const ugn_tensor* idx,
+                       const ugn_tensor* lab, int k, ugn_tensor* out_d2, ugn_tensor* out_idx,
+                       ugn_tensor* out_lab, ugn_tensor* pred, void* stream);
+
+/* ---- generic tensor-core GEMM (building block exposed for tests / k-NN / triplet) ----
+ * C f32 [M,N] (+)= A . B^T with bf16 operands [P,rows,cols]:
+ *   a_mn == 0: A is [P,M,K] (K contiguous);  a_mn == 1: A is [P,K,M] (M contiguous).
+ *   b_mn == 0: B is [P,N,K];                 b_mn == 1: B is [P,K,N].
+ * accumulate != 0 adds into C (split-K partials use red.global.add). */
+int ugn_gemm_bf16(ugn_ctx*, const ugn_tensor* A, int a_mn, const ugn_tensor* B, int b_mn,
+                  ugn_tensor* C, int accumulate, void* stream);
+/* f32 -> bf16 [P,...] split helper (P taken from dst). */
+int ugn_split_bf16(ugn_ctx*, const ugn_tensor* src_f32, ugn_tensor* dst_bf16, void* stream);
+
+/* number of kernels this library has launched on this ctx since creation (bench.py's
+ * gpu_launches claim is read from here). */
+int64_t ugn_launch_count(ugn_ctx*);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* UGAITNET_B200_H_ */

@@ -1,0 +1,276 @@
+"""GPU parity tests, operator by operator, through the C ABI, against the CPU oracle."""
+import os
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from oracle import ugait_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+FP32_TOL = 1e-5   # north_star: <= 1e-5 in the fp32 validation mode
+
+
+def rel(a, b):
+    a, b = a.double().cpu(), b.double().cpu()
+    return float((a - b).norm() / b.norm().clamp_min(1e-30))
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    from ugaitnet_b200 import ops
+    assert torch.cuda.is_available()
+    return ops.get_ctx(0)
+
+
+def nhwc(x):
+    return x.permute(0, 2, 3, 1).contiguous()
+
+
+@pytest.mark.parametrize("B,C,Cp,H,Co,k,pool,act", [
+    (3, 25, 32, 20, 24, 7, True, 1), (2, 50, 64, 15, 40, 5, True, 2), (4, 32, 32, 9, 64, 3, True, 1),
+    (5, 64, 64, 4, 96, 2, False, 1), (1, 3, 3, 12, 5, 3, True, 0), (2, 8, 8, 11, 70, 3, False, 2)])
+def test_conv_layer_fp32(ctx, B, C, Cp, H, Co, k, pool, act):
+    from ugaitnet_b200 import ops
+    g = torch.Generator().manual_seed(B * 100 + C)
+    x = torch.randn(B, C, H, H, generator=g)
+    w = torch.randn(Co, C, k, k, generator=g) * 0.1
+    b = torch.randn(Co, generator=g)
+    xd = torch.zeros(B, H, H, Cp, device="cuda")
+    ops.pack_input(ctx, x.cuda(), xd)
+    assert torch.equal(xd[..., :C].cpu(), nhwc(x)) and (Cp == C or float(xd[..., C:].abs().max()) == 0)
+    wm = w.permute(0, 2, 3, 1).contiguous().cuda()
+    wp = torch.zeros(Co, k, k, Cp, device="cuda")
+    ops.pack_weight(ctx, wm, wp)
+    Ho = H - k + 1
+    Hp = Ho // 2 if pool else Ho
+    y = torch.zeros(B, Hp, Hp, Co, device="cuda")
+    idx = torch.zeros(B, Hp, Hp, Co, dtype=torch.uint8, device="cuda") if pool else None
+    ops.conv2d_fwd(ctx, xd, wp, b.cuda(), y, idx, act=act, alpha=0.3, pool=pool)
+    # oracle (fp64)
+    x64 = x.double().requires_grad_(True)
+    w64 = w.double().requires_grad_(True)
+    b64 = b.double().requires_grad_(True)
+    z = F.conv2d(x64, w64, b64)
+    a = O._act(z, act, 0.3)
+    ref = F.max_pool2d(a, 2) if pool else a
+    assert rel(y.permute(0, 3, 1, 2), ref.detach()) < FP32_TOL
+    # backward
+    dy = torch.randn(ref.shape, generator=g)
+    ref.backward(dy.double())
+    dz = torch.zeros(B, Ho, Ho, Co, device="cuda")
+    ops.conv2d_bwd_act(ctx, nhwc(dy).cuda(), y, idx, dz, act=act, alpha=0.3, pool=pool)
+    dw = torch.zeros(Co, k, k, C, device="cuda")
+    db = torch.zeros(Co, device="cuda")
+    ops.conv2d_wgrad(ctx, xd, dz, dw, db)
+    assert rel(dw.permute(0, 3, 1, 2), w64.grad) < FP32_TOL
+    assert rel(db, b64.grad) < FP32_TOL
+    dx = torch.zeros(B, H, H, Cp, device="cuda")
+    ops.conv2d_dgrad(ctx, dz, wp, dx)
+    assert rel(dx[..., :C].permute(0, 3, 1, 2), x64.grad) < FP32_TOL
+    if Cp > C:
+        assert float(dx[..., C:].abs().max()) == 0.0
+
+
+def test_pool_floor_rows_get_zero_gradient(ctx):
+    from ugaitnet_b200 import ops
+    B, C, Ho, Hp = 2, 8, 9, 4          # 9 -> 4 drops the last row/col (nets/mj_uwyhNets_ba.py:85)
+    y = torch.rand(B, Hp, Hp, C, device="cuda") + 0.1
+    idx = torch.randint(0, 4, (B, Hp, Hp, C), dtype=torch.uint8, device="cuda")
+    dy = torch.randn(B, Hp, Hp, C, device="cuda")
+    dz = torch.full((B, Ho, Ho, C), 7.0, device="cuda")
+    ops.conv2d_bwd_act(ctx, dy, y, idx, dz, act=1, pool=True)
+    assert float(dz[:, 8].abs().max()) == 0 and float(dz[:, :, 8].abs().max()) == 0
+    assert torch.allclose(dz.sum((1, 2)), dy.sum((1, 2)), atol=1e-5)
+
+
+def test_flatten_is_chw_order(ctx):
+    from ugaitnet_b200 import ops
+    y = torch.randn(3, 3, 3, 16, device="cuda")
+    flat = torch.zeros(3, 144, device="cuda")
+    ops.flatten_chw(ctx, y, flat)
+    assert torch.equal(flat, y.permute(0, 3, 1, 2).reshape(3, -1))
+    back = torch.zeros_like(y)
+    ops.unflatten_chw(ctx, flat, back)
+    assert torch.equal(back, y)
+
+
+@pytest.mark.parametrize("B,K,N,act,mask", [(24, 300, 130, 0, False), (7, 64, 150, 1, True), (96, 515, 64, 2, True)])
+def test_linear_fp32(ctx, B, K, N, act, mask):
+    from ugaitnet_b200 import ops
+    g = torch.Generator().manual_seed(K)
+    x, w, b = torch.randn(B, K, generator=g), torch.randn(N, K, generator=g) * 0.1, torch.randn(N, generator=g)
+    m = ((torch.rand(B, N, generator=g) > 0.4).float() / 0.6) if mask else None
+    y = torch.zeros(B, N, device="cuda")
+    ops.linear_fwd(ctx, x.cuda(), w.cuda(), b.cuda(), m.cuda() if mask else None, y, None, act=act, alpha=0.3)
+    x64, w64, b64 = (t.double().requires_grad_(True) for t in (x, w, b))
+    ref = O._act(F.linear(x64, w64, b64), act, 0.3)
+    if mask:
+        ref = ref * m.double()
+    assert rel(y, ref.detach()) < FP32_TOL
+    dy = torch.randn(B, N, generator=g)
+    ref.backward(dy.double())
+    dz = torch.zeros(B, N, device="cuda")
+    ops.act_mask_bwd(ctx, dy.cuda(), y if act else None, m.cuda() if mask else None, dz, None, act=act, alpha=0.3)
+    dx, dw, db = torch.zeros(B, K, device="cuda"), torch.zeros(N, K, device="cuda"), torch.zeros(N, device="cuda")
+    ops.linear_bwd(ctx, x.cuda(), w.cuda(), dz, dx, dw, db)
+    assert rel(dx, x64.grad) < FP32_TOL and rel(dw, w64.grad) < FP32_TOL and rel(db, b64.grad) < FP32_TOL
+
+
+@pytest.mark.parametrize("merge", [0, 1, 2])
+@pytest.mark.parametrize("nmods", [2, 3])
+def test_fusion_fwd_bwd(ctx, merge, nmods):
+    from ugaitnet_b200 import ops
+    B, d = 13, 200
+    g = torch.Generator().manual_seed(merge * 10 + nmods)
+    br = [torch.randn(B, d, generator=g) for _ in range(nmods)]
+    br[1][:, :20] = br[0][:, :20]                 # exact ties between modalities
+    br[1][:, 20:30] = -br[0][:, 20:30]            # |x| ties for sign_max
+    fl = [(torch.rand(B, 1, generator=g) > 0.3).float() for _ in range(nmods)]
+    for f in fl:
+        f[0] = 0.0                                # row 0: every modality missing -> eps path
+    fl[0][1] = 1.0
+    sig = torch.zeros(B, d, device="cuda")
+    win = torch.zeros(B, d, dtype=torch.uint8, device="cuda")
+    inv = torch.zeros(B, 2, device="cuda")
+    ops.fuse_fwd(ctx, [t.cuda() for t in br], [f.cuda() for f in fl], sig, None, win, inv, merge, True)
+    b64 = [t.double().requires_grad_(True) for t in br]
+    ref = O.l2_normalize(O.merge_modalities([t * f.double() for t, f in zip(b64, fl)], merge), 1)
+    assert torch.allclose(sig.cpu().double(), ref.detach(), atol=2e-6, rtol=1e-5)
+    assert float(sig[0].abs().max()) == 0.0
+    dsig = torch.randn(B, d, generator=g)
+    ref.backward(dsig.double())
+    dbr = [torch.zeros(B, d, device="cuda") for _ in range(nmods)]
+    ops.fuse_bwd(ctx, dsig.cuda(), sig, win, inv, [f.cuda() for f in fl], dbr, merge, True)
+    for m in range(nmods):
+        assert rel(dbr[m][1:], b64[m].grad[1:]) < 2e-5, m
+
+
+def test_softmax_ce(ctx):
+    from ugaitnet_b200 import ops
+    B, C = 37, 150
+    g = torch.Generator().manual_seed(0)
+    logits = torch.randn(B, C, generator=g) * 3
+    lab = torch.randint(0, C, (B,), generator=g)
+    out = torch.zeros(2, device="cuda")
+    dl = torch.zeros(B, C, device="cuda")
+    ops.softmax_ce(ctx, logits.cuda(), lab.int().cuda(), out, dl, 0.1)
+    l64 = logits.double().requires_grad_(True)
+    loss, acc = O.softmax_ce(l64, F.one_hot(lab, C).double())
+    (0.1 * loss).backward()
+    assert float(out[0]) == pytest.approx(float(loss), rel=1e-5)
+    assert float(out[1]) == pytest.approx(float(acc), abs=1e-6)
+    assert rel(dl, l64.grad) < FP32_TOL
+
+
+def _run_triplet(ctx, lab, emb, margin, scale=1.0):
+    from ugaitnet_b200 import ops
+    e = torch.tensor(emb, device="cuda")
+    n, B = (e.shape[0], e.shape[1]) if e.dim() == 3 else (1, e.shape[0])
+    out = torch.zeros(2, device="cuda")
+    de = torch.zeros_like(e)
+    ws = torch.zeros(ops.triplet_workspace_bytes(n, B) // 4 + 8, device="cuda")
+    ops.triplet_all(ctx, e, torch.tensor(lab).int().cuda(), margin, scale, out, de, ws)
+    return out.cpu(), de.cpu()
+
+
+def test_triplet_golden_and_gradient(ctx, golden_dir):
+    z = np.load(os.path.join(golden_dir, "triplet.npz"))
+    for i in range(int(z["n"])):
+        lab, emb, margin = z[f"lab{i}"], z[f"emb{i}"], float(z[f"margin{i}"])
+        out, de = _run_triplet(ctx, lab, emb, margin)
+        assert float(out[0]) == pytest.approx(float(z[f"loss{i}"]), rel=1e-3)
+        e64 = torch.tensor(emb, dtype=torch.float64, requires_grad=True)
+        loss, cnt = O.triplet_loss_all(torch.tensor(lab), e64, margin)
+        loss.backward()
+        # active-set counts may differ by a handful of boundary triplets between fp32 and fp64
+        assert abs(float(out[1]) - float(cnt.sum())) <= max(3, 1e-3 * float(cnt.sum()))
+        assert rel(de, e64.grad) < 5e-3
+
+
+def test_triplet_large_balanced_batch(ctx):
+    rng = np.random.default_rng(3)
+    ids, per, d = 48, 2, 128         # cfg2-like: B=96
+    lab = np.repeat(np.arange(ids), per).astype(np.float32)
+    e = rng.normal(size=(ids * per, d))
+    e /= np.linalg.norm(e, axis=1, keepdims=True)
+    out, de = _run_triplet(ctx, lab, e.astype(np.float32), 0.2, scale=0.5)
+    e64 = torch.tensor(e.astype(np.float32), dtype=torch.float64, requires_grad=True)
+    loss, cnt = O.triplet_loss_all(torch.tensor(lab), e64, 0.2)
+    (0.5 * loss).backward()
+    assert float(out[0]) == pytest.approx(float(loss), rel=1e-5)
+    assert float(out[1]) == float(cnt.sum())
+    assert rel(de, e64.grad) < 1e-4
+
+
+def test_triplet_no_active_triplets_is_zero(ctx):
+    lab = np.array([0, 0, 1, 1], dtype=np.float32)
+    e = np.array([[1, 0], [1, 0], [-1, 0], [-1, 0]], dtype=np.float32)
+    out, de = _run_triplet(ctx, lab, e, 0.2)
+    assert float(out[0]) == 0.0 and float(out[1]) == 0.0 and float(de.abs().max()) == 0.0
+
+
+def test_adam_and_sgd_step(ctx):
+    from ugaitnet_b200 import ops
+    n = 64 * 5
+    g = torch.Generator().manual_seed(1)
+    w0, gr = torch.randn(n, generator=g), torch.randn(n, generator=g)
+    off = torch.tensor([0, 128, 192, n], dtype=torch.int64, device="cuda")
+    l2 = torch.tensor([5e-5, 0.0, 1e-3], device="cuda")
+    l2full = torch.cat([torch.full((128,), 5e-5), torch.zeros(64), torch.full((n - 192,), 1e-3)]).double()
+    w, m, v = w0.clone().cuda(), torch.zeros(n, device="cuda"), torch.zeros(n, device="cuda")
+    reg = torch.zeros(1, device="cuda")
+    P = {"w": w0.double().clone()}
+    M, V = {"w": torch.zeros(n, dtype=torch.float64)}, {"w": torch.zeros(n, dtype=torch.float64)}
+    for t in range(1, 4):
+        import math
+        lr_t = 1e-3 * math.sqrt(1 - 0.999 ** t) / (1 - 0.9 ** t)
+        ops.adam_step(ctx, w, gr.cuda(), m, v, off, l2, lr_t, gscale=0.5, reg_out=reg)
+        G = {"w": gr.double() * 0.5 + 2 * l2full * P["w"]}
+        expect_reg = float((l2full * P["w"] ** 2).sum())
+        O.adam_step(P, G, M, V, t, lr=1e-3)
+        assert float(reg) == pytest.approx(expect_reg, rel=1e-5)
+        assert rel(w, P["w"]) < 1e-6
+    w, v = w0.clone().cuda(), torch.zeros(n, device="cuda")
+    ops.sgd_step(ctx, w, gr.cuda(), v, off, l2, 0.01, momentum=0.9)
+    ref = w0.double() - 0.01 * (gr.double() + 2 * l2full * w0.double())
+    assert rel(w, ref) < 1e-6
+
+
+@pytest.mark.parametrize("name", ["knn_small", "knn_dups", "knn_k7"])
+def test_knn_bit_exact_vs_oracle_and_sklearn_golden(ctx, golden_dir, name):
+    from ugaitnet_b200.knn import KNeighborsClassifier
+    z = np.load(os.path.join(golden_dir, name + ".npz"))
+    k = int(z["k"])
+    clf = KNeighborsClassifier(n_neighbors=k).fit(z["G"], z["y"])
+    pred = clf.predict(z["Q"])
+    d2, idx = clf.kneighbors_exact(z["Q"])
+    od2, oidx = O.knn_search(z["G"], z["Q"], k)
+    opred = O.knn_vote(z["y"][oidx])
+    assert np.array_equal(idx, oidx)                    # bit-exact indices (same (dist, idx) rule)
+    assert np.array_equal(pred, opred)                  # bit-exact labels
+    assert np.allclose(d2, od2, rtol=1e-12, atol=1e-15)
+    d2b, _ = O.knn_search(z["G"], z["Q"], k + 1)
+    nb = d2b[:, k - 1] != d2b[:, k]
+    assert np.array_equal(pred[nb], z["pred"][nb])      # == sklearn wherever sklearn is well defined
+
+
+def test_knn_sharded_merge_equals_single(ctx, golden_dir):
+    from ugaitnet_b200.knn import KNeighborsClassifier, knn_sharded_local
+    z = np.load(os.path.join(golden_dir, "knn_dups.npz"))
+    k = int(z["k"])
+    single = KNeighborsClassifier(n_neighbors=k).fit(z["G"], z["y"])
+    _, idx = single.kneighbors_exact(z["Q"])
+    pred, midx = knn_sharded_local(z["G"], z["y"], z["Q"], k, shards=4)
+    assert np.array_equal(midx, idx) and np.array_equal(pred, single.predict(z["Q"]))
+
+
+def test_errors_are_loud(ctx):
+    from ugaitnet_b200 import ops
+    from ugaitnet_b200._ffi import UgnError
+    with pytest.raises(UgnError, match="no CPU fallback|device"):
+        ops.flatten_chw(ctx, torch.zeros(1, 2, 2, 4), torch.zeros(1, 16, device="cuda"))
+    with pytest.raises(UgnError, match="shape"):
+        ops.flatten_chw(ctx, torch.zeros(1, 2, 2, 4, device="cuda"), torch.zeros(1, 15, device="cuda"))

@@ -1,0 +1,144 @@
+"""CPU tests: the oracle against the committed golden vectors (reference-produced where the
+reference can run here) and against itself (literal vs general triplet form)."""
+import ctypes
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import ugait_oracle as O
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _tie_free(dist):
+    d = np.sort(dist, axis=1)
+    return (np.diff(d, axis=1) > 1e-7).all(axis=1)
+
+
+@pytest.mark.parametrize("name", ["knn_small", "knn_dups", "knn_k7"])
+def test_knn_oracle_matches_sklearn_golden(golden_dir, name):
+    z = np.load(os.path.join(golden_dir, name + ".npz"))
+    k = int(z["k"])
+    pred, idx = O.knn_predict(z["G"], z["y"], z["Q"], k)
+    # labels: bit-exact on every query whose k-th / (k+1)-th neighbours are not exactly tied
+    d2, _ = O.knn_search(z["G"], z["Q"], k + 1)
+    boundary_tie = d2[:, k - 1] == d2[:, k]
+    assert (pred[~boundary_tie] == z["pred"][~boundary_tie]).all()
+    # indices: bit-exact on tie-free queries; as sets elsewhere (sklearn's order inside an exact
+    # tie is a heap artefact)
+    tf = _tie_free(z["dist"]) & ~boundary_tie
+    assert tf.sum() > 0
+    assert (idx[tf] == z["idx"][tf]).all()
+    same_set = [set(a) == set(b) for a, b in zip(idx[~boundary_tie], z["idx"][~boundary_tie])]
+    assert all(same_set)
+
+
+def _load_c_oracle():
+    path = os.path.join(ROOT, "oracle", "libknn_oracle.so")
+    if not os.path.exists(path):
+        import subprocess
+        subprocess.run(["make", "-C", os.path.join(ROOT, "oracle")], check=True)
+    return ctypes.CDLL(path)
+
+
+@pytest.mark.parametrize("name", ["knn_small", "knn_dups", "knn_k7"])
+def test_c_knn_oracle_equals_numpy_oracle(golden_dir, name):
+    z = np.load(os.path.join(golden_dir, name + ".npz"))
+    lib = _load_c_oracle()
+    G, Q, y, k = np.ascontiguousarray(z["G"]), np.ascontiguousarray(z["Q"]), np.ascontiguousarray(z["y"]), int(z["k"])
+    idx = np.empty((Q.shape[0], k), dtype=np.int64)
+    d2 = np.empty((Q.shape[0], k), dtype=np.float64)
+    rc = lib.knn_oracle_search(G.ctypes.data_as(ctypes.c_void_p), ctypes.c_int64(G.shape[0]), ctypes.c_int64(G.shape[1]),
+                               Q.ctypes.data_as(ctypes.c_void_p), ctypes.c_int64(Q.shape[0]), ctypes.c_int(k),
+                               idx.ctypes.data_as(ctypes.c_void_p), d2.ctypes.data_as(ctypes.c_void_p))
+    assert rc == 0
+    pred = np.empty(Q.shape[0], dtype=np.int32)
+    lib.knn_oracle_vote(idx.ctypes.data_as(ctypes.c_void_p), ctypes.c_int64(Q.shape[0]), ctypes.c_int(k),
+                        y.ctypes.data_as(ctypes.c_void_p), pred.ctypes.data_as(ctypes.c_void_p))
+    p2, i2 = O.knn_predict(G, y, Q, k)
+    assert (idx == i2).all()
+    assert (pred == p2).all()
+
+
+def test_eer_oracle_matches_reference_golden(golden_dir):
+    z = np.load(os.path.join(golden_dir, "eer.npz"))
+    for i in range(int(z["n"])):
+        eer, thr = O.eer_verif_dist(z[f"y{i}"], z[f"d{i}"])
+        assert eer == pytest.approx(float(z["eer"][i]), abs=1e-12)
+        assert thr == pytest.approx(float(z["thr"][i]), abs=1e-12)
+    # the reference's own demo known-answer (nets/mj_metrics.py:28-35)
+    assert float(z["eer"][0]) == pytest.approx(0.25) and float(z["thr"][0]) == pytest.approx(0.07)
+
+
+def test_triplet_general_form_equals_literal_golden(golden_dir):
+    z = np.load(os.path.join(golden_dir, "triplet.npz"))
+    for i in range(int(z["n"])):
+        lab, emb, margin = z[f"lab{i}"], z[f"emb{i}"], float(z[f"margin{i}"])
+        loss, cnt = O.triplet_loss_all(torch.tensor(lab), torch.tensor(emb, dtype=torch.float64), margin)
+        assert float(loss) == pytest.approx(float(z[f"loss{i}"]), rel=1e-9)
+        assert np.allclose(cnt.numpy(), z[f"cnt{i}"])
+
+
+def test_reference_demo_vectors_give_zero_loss():
+    # nets/triplet_loss_all.py:115-116: trivially separated classes -> 0 for margin <= 1
+    logits = np.array([[1.1, 1.2, 1.4], [1.09, 1.21, 1.41], [0.25, 0.45, 0.75], [0.23, 0.43, 0.7],
+                       [1.5, 2.5, 3.5], [1.55, 2.75, 3.8]], dtype=np.float32)
+    labels = np.array([1, 1, 2, 2, 3, 3], dtype=np.float32)
+    loss, _ = O.triplet_loss_all_literal_np(labels, logits, 0.2)
+    assert loss == 0.0
+
+
+def test_sign_max_and_maximum_tie_rules():
+    a = torch.tensor([[1.0, -2.0, 0.0, 3.0]])
+    b = torch.tensor([[-1.0, 2.0, 0.0, -4.0]])
+    out = O.merge_modalities([a, b], O.MERGE_SIGNMAX)
+    assert out.tolist() == [[1.0, -2.0, 0.0, -4.0]]      # ties -> lowest modality index
+    out = O.merge_modalities([a, b], O.MERGE_MAX)
+    assert out.tolist() == [[1.0, 2.0, 0.0, 3.0]]
+    out = O.merge_modalities([a, b], O.MERGE_AVG)
+    assert out.tolist() == [[0.0, 0.0, 0.0, -0.5]]
+
+
+def test_l2_normalize_eps_path():
+    x = torch.zeros(2, 8)
+    x[1, 0] = 3.0
+    y = O.l2_normalize(x)
+    assert torch.all(y[0] == 0) and y[1, 0] == pytest.approx(1.0)
+
+
+def test_synth_batch_expansion_contract():
+    cfg = O.NetConfig(nd=16, nclasses=150)
+    xs, fl, lab = O.synth_batch(cfg, base_rows=6, expand=4, seed=1)
+    assert xs[0].shape == (24, 50, 60, 60) and xs[1].shape == (24, 25, 60, 60)
+    F = np.concatenate(fl, 1)
+    assert (F[::4] == 1).all()                       # row i*E has every modality
+    assert (F.sum(1) >= 1).all()                     # never all missing
+    for i in range(6):
+        if i % 2 == 1:                               # odd i: exactly one modality enabled
+            assert (F[i * 4 + 1:(i + 1) * 4].sum(1) == 1).all()
+    for m in range(3):
+        off = F[:, m] == 0
+        assert np.all(xs[m][off] == np.float32(1e-9))
+    assert (lab.reshape(6, 4) == lab.reshape(6, 4)[:, :1]).all()
+
+
+def test_oracle_step_gradients_finite_and_adam_decreases_loss():
+    torch.manual_seed(0)
+    cfg = O.NetConfig(in_channels=(4, 3), filters_numbers=(8, 8, 16, 16), nd=16, nclasses=5, merge=O.MERGE_SIGNMAX,
+                      wid=0.1)
+    P = O.init_params(cfg, seed=3, dtype=torch.float64)
+    xs, fl, lab = O.synth_batch(cfg, base_rows=4, expand=2, seed=5, kinds=("of", "gray"))
+    xs = [torch.tensor(x, dtype=torch.float64) for x in xs]
+    fl = [torch.tensor(f, dtype=torch.float64) for f in fl]
+    lab = torch.tensor(lab % 5)
+    M = {k: torch.zeros_like(v) for k, v in P.items()}
+    V = {k: torch.zeros_like(v) for k, v in P.items()}
+    losses = []
+    for t in range(1, 6):
+        res, G = O.loss_and_grads(xs, fl, lab, P, cfg)
+        assert all(torch.isfinite(g).all() for g in G.values())
+        losses.append(float(res["loss"]))
+        O.adam_step(P, G, M, V, t, lr=1e-3)
+    assert losses[-1] < losses[0]

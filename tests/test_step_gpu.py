@@ -1,0 +1,166 @@
+"""GPU parity tests of the whole step (forward, losses, backward, optimiser) against the fp64
+CPU oracle on the same seeded synthetic inputs.  fp32 validation mode: <= 1e-5 (north_star);
+tensor-core modes: descriptor cosine >= 0.999, loss / gradient relative error <= 1e-3."""
+import math
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import ugait_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+def rel(a, b):
+    a, b = a.double().cpu(), b.double().cpu()
+    return float((a - b).norm() / b.norm().clamp_min(1e-30))
+
+
+def make_case(name):
+    if name == "3mod_signmax":       # cfg2-like: missing-modality expansion, sign_max
+        oc = O.NetConfig(in_channels=(6, 4, 4), filters_numbers=(8, 8, 16, 16), nd=32, nclasses=10,
+                         merge=O.MERGE_SIGNMAX, wver=1.0, wid=0.1)
+        return oc, dict(base_rows=6, expand=4, kinds=("of", "gray", "depth")), None
+    if name == "2mod_max_leaky_code":  # FC1 "code" + LeakyReLU + dropout masks
+        oc = O.NetConfig(in_channels=(6, 4), filters_numbers=(8, 8, 16, 16), nd=32, nc=8, nclasses=7,
+                         merge=O.MERGE_MAX, act=O.ACT_LEAKY, wver=1.0, wid=1.0)
+        return oc, dict(base_rows=8, expand=2, kinds=("of", "gray")), 0.3
+    if name == "3mod_avg":
+        oc = O.NetConfig(in_channels=(4, 4, 4), filters_numbers=(8, 8, 16, 16), nd=16, nclasses=6,
+                         merge=O.MERGE_AVG, wver=0.5, wid=0.5)
+        return oc, dict(base_rows=6, expand=3, kinds=("of", "gray", "sil")), None
+    if name == "1mod_gray":          # cfg1: single modality, no fusion / normalisation
+        oc = O.NetConfig(in_channels=(5,), filters_numbers=(8, 8, 16, 16), nd=16, nclasses=9, single=True,
+                         wver=1.0, wid=0.1)
+        return oc, dict(base_rows=12, expand=1, kinds=("gray",)), None
+    if name == "real_shapes":        # reference filter bank [96,192,512,512] on 3 modalities, small nd
+        oc = O.NetConfig(in_channels=(50, 25, 25), nd=64, nclasses=150, merge=O.MERGE_SIGNMAX, wver=1.0, wid=0.1)
+        return oc, dict(base_rows=4, expand=2, kinds=("of", "gray", "depth")), None
+    raise KeyError(name)
+
+
+def to_engine_cfg(oc, dropout=0.0):
+    from ugaitnet_b200.config import NetConfig
+    return NetConfig(in_channels=tuple(oc.in_channels), filters_numbers=tuple(oc.filters_numbers),
+                     filters_size=tuple(oc.filters_size), nd=oc.nd, nc=oc.nc, nclasses=oc.nclasses,
+                     weight_decay=oc.weight_decay, merge=oc.merge, act=oc.act, alpha=oc.alpha, margin=oc.margin,
+                     wver=oc.wver, wid=oc.wid, hw=oc.hw, dropout=dropout, single=oc.single)
+
+
+def setup(name, math_mode="fp32", seed=11):
+    from ugaitnet_b200.net import UGaitEngine
+    oc, sb, drop = make_case(name)
+    xs, fl, lab = O.synth_batch(oc, seed=seed, **sb)
+    lab = lab % oc.nclasses
+    P = O.init_params(oc, seed=seed, dtype=torch.float64)
+    g = torch.Generator().manual_seed(seed)
+    for k in P:                       # non-zero biases so their gradients / paths are exercised
+        if k.endswith("/b"):
+            P[k] = torch.randn(P[k].shape, generator=g, dtype=torch.float64) * 0.05
+    eng = UGaitEngine(to_engine_cfg(oc, drop or 0.0), math_mode=math_mode, lr=1e-3)
+    eng.load_params(P)
+    B = xs[0].shape[0]
+    masks = cmask = None
+    if drop:
+        masks = [((torch.rand(B, 2 * oc.nd, generator=g) >= drop).double() / (1 - drop)) for _ in range(oc.nmods)]
+        cmask = (torch.rand(B, oc.nc, generator=g) >= drop).double() / (1 - drop) if oc.nc else None
+    return oc, eng, P, xs, fl, lab, masks, cmask
+
+
+def oracle_step(oc, P, xs, fl, lab, masks, cmask):
+    x64 = [torch.tensor(x, dtype=torch.float64) for x in xs]
+    f64 = [torch.tensor(f, dtype=torch.float64) for f in fl]
+    return O.loss_and_grads(x64, f64, torch.tensor(lab), P, oc, masks, cmask)
+
+
+def engine_inputs(xs, fl, lab, masks, cmask):
+    cu = lambda a: torch.as_tensor(np.asarray(a), dtype=torch.float32).cuda()
+    return ([cu(x) for x in xs], [cu(f) for f in fl], torch.as_tensor(lab).cuda(),
+            None if masks is None else [m.float().cuda() for m in masks],
+            None if cmask is None else cmask.float().cuda())
+
+
+def reg_grad(oc, name, w):
+    if "/conv" in name and name.endswith("/w"):
+        return 2 * oc.weight_decay * w
+    if name.endswith("ofCode/w"):
+        return 2e-3 * w
+    return torch.zeros_like(w)
+
+
+@pytest.mark.parametrize("name", ["3mod_signmax", "2mod_max_leaky_code", "3mod_avg", "1mod_gray", "real_shapes"])
+def test_step_parity_fp32(name):
+    oc, eng, P, xs, fl, lab, masks, cmask = setup(name)
+    res, G = oracle_step(oc, P, xs, fl, lab, masks, cmask)
+    out = eng.loss_and_grad(*engine_inputs(xs, fl, lab, masks, cmask))
+    torch.cuda.synchronize()
+    tol = 1e-5
+    assert float(out["triplet"]) == pytest.approx(float(res["triplet"]), rel=tol, abs=1e-7)
+    assert float(out["count"]) == float(res["count"].sum())
+    assert float(out["ce"]) == pytest.approx(float(res["ce"]), rel=tol)
+    assert float(out["acc"]) == pytest.approx(float(res["acc"]), abs=1e-6)
+    cos = torch.nn.functional.cosine_similarity(out["signature"].double().cpu(), res["signature"], dim=1)
+    assert float(cos.min()) >= 0.99999
+    assert rel(out["signature"], res["signature"]) < tol
+    grads = eng.export_grads()
+    worst = 0.0
+    for k, g in G.items():
+        ref = g - reg_grad(oc, k, P[k])
+        if float(ref.norm()) < 1e-12:
+            assert float(grads[k].double().norm()) < 1e-9, k
+            continue
+        r = rel(grads[k], ref)
+        worst = max(worst, r)
+        assert r < 2e-5, (k, r)
+    print(f"[{name}] worst gradient rel err {worst:.2e}")
+
+
+def test_train_steps_adam_parity_fp32():
+    oc, eng, P, xs, fl, lab, masks, cmask = setup("3mod_signmax")
+    P = {k: v.clone() for k, v in P.items()}
+    M = {k: torch.zeros_like(v) for k, v in P.items()}
+    V = {k: torch.zeros_like(v) for k, v in P.items()}
+    ins = engine_inputs(xs, fl, lab, masks, cmask)
+    P0 = {k: v.clone() for k, v in P.items()}
+    for t in range(1, 4):
+        res, G = oracle_step(oc, P, xs, fl, lab, masks, cmask)
+        O.adam_step(P, G, M, V, t, lr=1e-3)
+        out = eng.train_step(*ins)
+        total = oc.wver * float(out["triplet"]) + oc.wid * float(out["ce"]) + float(out["reg"])
+        assert total == pytest.approx(float(res["loss"]), rel=1e-4)
+    W = eng.export_params()
+    for k in P:
+        upd_ref = P[k] - P0[k]
+        upd = W[k].double().cpu() - P0[k]
+        if float(upd_ref.norm()) == 0:
+            continue
+        # Adam normalises by sqrt(v): elements whose gradient is at fp32-noise level may flip sign,
+        # so compare update directions rather than element-wise values
+        cosu = float((upd * upd_ref).sum() / (upd.norm() * upd_ref.norm()))
+        assert cosu > 0.999, (k, cosu)
+
+
+def test_cuda_graph_step_equals_eager():
+    from ugaitnet_b200.net import UGaitEngine
+    oc, eng, P, xs, fl, lab, masks, cmask = setup("3mod_signmax")
+    eng_g = UGaitEngine(to_engine_cfg(oc), math_mode="fp32", lr=1e-3, use_graph=True)
+    eng_g.load_params(P)
+    ins = engine_inputs(xs, fl, lab, masks, cmask)
+    for _ in range(3):
+        a = eng.train_step(*ins)
+        b = eng_g.train_step(*ins)
+        assert float(a["triplet"]) == pytest.approx(float(b["triplet"]), rel=1e-5)
+    Wa, Wb = eng.export_params(), eng_g.export_params()
+    for k in Wa:
+        assert rel(Wb[k], Wa[k]) < 1e-5, k
+
+
+def test_predict_matches_oracle_descriptor():
+    oc, eng, P, xs, fl, lab, masks, cmask = setup("3mod_signmax")
+    ins = engine_inputs(xs, fl, lab, None, None)
+    sig = eng.predict(ins[0], ins[1], layer="signature")
+    ref, _ = O.model_forward([torch.tensor(x, dtype=torch.float64) for x in xs],
+                             [torch.tensor(f, dtype=torch.float64) for f in fl], P, oc)
+    cos = torch.nn.functional.cosine_similarity(sig.double().cpu(), ref, dim=1)
+    assert float(cos.min()) >= 0.999

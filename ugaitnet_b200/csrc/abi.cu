@@ -1,0 +1,490 @@
+// C-ABI entry points: validation + dispatch on storage mode (f32 -> SIMT validation kernels,
+// bf16 -> tcgen05/TMA kernels).  No CPU fallback anywhere.
+#include "common.cuh"
+#include "tc.cuh"
+
+static thread_local std::string g_last_error;
+
+void ugn_set_error(const char* fmt, ...) {
+  char buf[1024];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  g_last_error = buf;
+}
+
+int ugn_validate(const ugn_ctx* ctx, const ugn_tensor* t, const char* name, UgnDType dt, int lo,
+                 int hi) {
+  if (!t) UGN_FAIL(UGN_ERR_INVALID, "%s: null tensor", name);
+  if (t->device_type != UGN_DL_CUDA || t->device_id != ctx->device)
+    UGN_FAIL(UGN_ERR_DEVICE, "%s: tensor is on device (%d,%d), expected CUDA device %d (no CPU fallback)",
+             name, t->device_type, t->device_id, ctx->device);
+  if (!t->data && ugn_numel(t) > 0) UGN_FAIL(UGN_ERR_INVALID, "%s: null data pointer", name);
+  if (dt != DT_BAD && ugn_dtype(t) != dt)
+    UGN_FAIL(UGN_ERR_INVALID, "%s: unexpected dtype (code %d, bits %d)", name, t->dtype_code, t->dtype_bits);
+  if (t->ndim < lo || t->ndim > hi)
+    UGN_FAIL(UGN_ERR_INVALID, "%s: rank %d outside [%d,%d]", name, t->ndim, lo, hi);
+  if (t->strides) {
+    int64_t expect = 1;
+    for (int i = t->ndim - 1; i >= 0; --i) {
+      if (t->shape[i] != 1 && t->strides[i] != expect)
+        UGN_FAIL(UGN_ERR_INVALID, "%s: tensor must be dense row-major", name);
+      expect *= t->shape[i];
+    }
+  }
+  return UGN_OK;
+}
+
+extern "C" int ugn_abi_version(void) { return UGN_ABI_VERSION; }
+extern "C" const char* ugn_last_error(void) { return g_last_error.c_str(); }
+
+extern "C" int ugn_ctx_create(int device, ugn_ctx** out) {
+  UGN_CHECK(out, "ugn_ctx_create: null out pointer");
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess || count == 0)
+    UGN_FAIL(UGN_ERR_DEVICE, "no CUDA device available (%s): ugaitnet_b200 has no CPU fallback",
+             e == cudaSuccess ? "count=0" : cudaGetErrorString(e));
+  UGN_CHECK(device >= 0 && device < count, "device %d out of range [0,%d)", device, count);
+  UGN_CUDA(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  UGN_CUDA(cudaGetDeviceProperties(&prop, device));
+  ugn_ctx* c = new ugn_ctx();
+  c->device = device;
+  c->sm_count = prop.multiProcessorCount;
+  c->cc_major = prop.major;
+  c->cc_minor = prop.minor;
+  *out = c;
+  return UGN_OK;
+}
+extern "C" int ugn_ctx_destroy(ugn_ctx* ctx) {
+  delete ctx;
+  return UGN_OK;
+}
+extern "C" int ugn_ctx_has_tcgen05(ugn_ctx* ctx) { return ctx && ctx->cc_major == 10; }
+extern "C" int64_t ugn_launch_count(ugn_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+// ---- implementations living in other translation units --------------------------------
+int ew_pack_input(ugn_ctx*, const float*, void*, int, int, int, int, int, int, cudaStream_t);
+int ew_pack_weight(ugn_ctx*, const float*, void*, int, long long, int, int, cudaStream_t);
+int ew_split(ugn_ctx*, const float*, __nv_bfloat16*, int, long long, cudaStream_t);
+int ew_bwd_act(ugn_ctx*, const float*, const void*, int, const uint8_t*, void*, int, int, int, int, int,
+               int, int, int, float, int, cudaStream_t);
+int ew_flatten(ugn_ctx*, const void*, void*, int, int, int, int, int, int, cudaStream_t);
+int ew_act_mask_bwd(ugn_ctx*, const float*, const float*, const float*, float*, __nv_bfloat16*, int,
+                    long long, int, float, cudaStream_t);
+int ew_fuse_fwd(ugn_ctx*, const FusePtrs&, int, int, int, float*, __nv_bfloat16*, int, uint8_t*, float*,
+                int, int, cudaStream_t);
+int ew_fuse_bwd(ugn_ctx*, const FusePtrs&, int, int, int, const float*, const float*, const uint8_t*,
+                const float*, int, int, cudaStream_t);
+int ew_softmax_ce(ugn_ctx*, const float*, const int*, float*, float*, int, int, float, cudaStream_t);
+int ew_optim(ugn_ctx*, int, float*, const float*, float*, float*, const long long*, const float*, int,
+             long long, float, float, float, float, float, float*, const float*, cudaStream_t);
+int simt_conv_fwd(ugn_ctx*, const ConvGeom&, const float*, const float*, const float*, float*, uint8_t*,
+                  int, float, int, cudaStream_t);
+int simt_conv_dgrad(ugn_ctx*, const ConvGeom&, const float*, const float*, float*, cudaStream_t);
+int simt_conv_wgrad(ugn_ctx*, const ConvGeom&, const float*, const float*, float*, float*, cudaStream_t);
+int simt_linear_fwd(ugn_ctx*, int, int, int, const float*, const float*, const float*, const float*,
+                    float*, int, float, cudaStream_t);
+int simt_linear_bwd(ugn_ctx*, int, int, int, const float*, const float*, const float*, float*, float*,
+                    float*, cudaStream_t);
+
+// mode of an activation/weight operand: 0 = f32, 1 = bf16 P=1, 2 = bf16 P=2, -1 invalid.
+// `rank` is the logical rank (without the plane dimension).
+static int storage_mode(const ugn_tensor* t, int rank) {
+  UgnDType dt = ugn_dtype(t);
+  if (dt == DT_F32 && t->ndim == rank) return 0;
+  if (dt == DT_BF16 && t->ndim == rank + 1 && (t->shape[0] == 1 || t->shape[0] == 2)) return (int)t->shape[0];
+  return -1;
+}
+static inline const int64_t* lshape(const ugn_tensor* t, int rank) { return t->shape + (t->ndim - rank); }
+
+extern "C" int ugn_pack_input(ugn_ctx* ctx, const ugn_tensor* x_nchw, ugn_tensor* x_nhwc, void* stream) {
+  UGN_CHECK(ctx && x_nchw && x_nhwc, "ugn_pack_input: null argument");
+  UGN_TENSOR(x_nchw, DT_F32, 4, 4);
+  UGN_TENSOR(x_nhwc, DT_BAD, 4, 5);
+  int mode = storage_mode(x_nhwc, 4);
+  UGN_CHECK(mode >= 0, "x_nhwc must be f32 [B,H,W,Cp] or bf16 [P,B,H,W,Cp]");
+  const int64_t* s = lshape(x_nhwc, 4);
+  int B = (int)x_nchw->shape[0], C = (int)x_nchw->shape[1], H = (int)x_nchw->shape[2], W = (int)x_nchw->shape[3];
+  UGN_CHECK(s[0] == B && s[1] == H && s[2] == W && s[3] >= C, "pack_input: shape mismatch");
+  UGN_CHECK((size_t)C * (W + 1) * 4 <= 48 * 1024, "pack_input: C*W too large");
+  if (B == 0) return UGN_OK;
+  return ew_pack_input(ctx, ugn_ptr<float>(x_nchw), ugn_ptr<void>(x_nhwc), mode, B, C, H, W, (int)s[3],
+                       (cudaStream_t)stream);
+}
+
+extern "C" int ugn_pack_weight(ugn_ctx* ctx, const ugn_tensor* w_master, ugn_tensor* w_packed, void* stream) {
+  UGN_CHECK(ctx && w_master && w_packed, "ugn_pack_weight: null argument");
+  UGN_TENSOR(w_master, DT_F32, 2, 4);
+  UGN_TENSOR(w_packed, DT_BAD, 2, 5);
+  int rank = w_master->ndim;
+  int mode = storage_mode(w_packed, rank);
+  UGN_CHECK(mode >= 0, "w_packed must be f32 (same rank) or bf16 with a leading plane dimension");
+  const int64_t* s = lshape(w_packed, rank);
+  long long R = 1;
+  for (int i = 0; i < rank - 1; ++i) {
+    UGN_CHECK(s[i] == w_master->shape[i], "pack_weight: leading dims mismatch");
+    R *= s[i];
+  }
+  int Cin = (int)w_master->shape[rank - 1], Cp = (int)s[rank - 1];
+  UGN_CHECK(Cp >= Cin, "pack_weight: padded width smaller than source");
+  return ew_pack_weight(ctx, ugn_ptr<float>(w_master), ugn_ptr<void>(w_packed), mode, R, Cin, Cp,
+                        (cudaStream_t)stream);
+}
+
+extern "C" int ugn_split_bf16(ugn_ctx* ctx, const ugn_tensor* src, ugn_tensor* dst, void* stream) {
+  UGN_CHECK(ctx && src && dst, "ugn_split_bf16: null argument");
+  UGN_TENSOR(src, DT_F32, 1, 8);
+  UGN_TENSOR(dst, DT_BF16, 2, 8);
+  int P = (int)dst->shape[0];
+  UGN_CHECK((P == 1 || P == 2) && ugn_numel(dst) == P * ugn_numel(src), "split_bf16: dst must be [P,...src]");
+  return ew_split(ctx, ugn_ptr<float>(src), ugn_ptr<__nv_bfloat16>(dst), P, ugn_numel(src), (cudaStream_t)stream);
+}
+
+static int conv_geom(const ugn_tensor* x, const ugn_tensor* w, int pool, ConvGeom& g) {
+  const int64_t* xs = lshape(x, 4);
+  const int64_t* ws = lshape(w, 4);
+  g.B = (int)xs[0]; g.H = (int)xs[1]; g.W = (int)xs[2]; g.Cp = (int)xs[3];
+  g.Co = (int)ws[0]; g.KH = (int)ws[1]; g.KW = (int)ws[2];
+  UGN_CHECK(ws[3] == g.Cp, "conv: weight inner dim %lld != activation channels %d", (long long)ws[3], g.Cp);
+  g.Ho = g.H - g.KH + 1; g.Wo = g.W - g.KW + 1;
+  UGN_CHECK(g.Ho > 0 && g.Wo > 0, "conv: kernel larger than input");
+  g.Hp = pool ? g.Ho / 2 : g.Ho;
+  g.Wp = pool ? g.Wo / 2 : g.Wo;
+  g.Cin = g.Cp;
+  return UGN_OK;
+}
+
+extern "C" int ugn_conv2d_fwd(ugn_ctx* ctx, const ugn_tensor* x, const ugn_tensor* w, const ugn_tensor* bias,
+                              ugn_tensor* y, ugn_tensor* pool_idx, int act, float alpha, int pool,
+                              void* stream) {
+  UGN_CHECK(ctx && x && w && y, "ugn_conv2d_fwd: null argument");
+  UGN_TENSOR(x, DT_BAD, 4, 5);
+  UGN_TENSOR(w, DT_BAD, 4, 5);
+  UGN_TENSOR(y, DT_BAD, 4, 5);
+  if (bias) UGN_TENSOR(bias, DT_F32, 1, 1);
+  int mx = storage_mode(x, 4), mw = storage_mode(w, 4), my = storage_mode(y, 4);
+  UGN_CHECK(mx >= 0 && mx == mw && (my == mx), "conv2d_fwd: x/w/y storage modes must match (%d,%d,%d)", mx, mw, my);
+  ConvGeom g;
+  int rc = conv_geom(x, w, pool, g);
+  if (rc != UGN_OK) return rc;
+  const int64_t* ys = lshape(y, 4);
+  UGN_CHECK(ys[0] == g.B && ys[1] == g.Hp && ys[2] == g.Wp && ys[3] == g.Co,
+            "conv2d_fwd: y must be [B=%d,%d,%d,%d]", g.B, g.Hp, g.Wp, g.Co);
+  if (bias) UGN_CHECK(bias->shape[0] == g.Co, "conv2d_fwd: bias must be [Cout]");
+  uint8_t* idx = nullptr;
+  if (pool) {
+    UGN_CHECK(pool_idx, "conv2d_fwd: pool_idx required when pool != 0");
+    UGN_TENSOR(pool_idx, DT_U8, 4, 4);
+    UGN_CHECK(ugn_numel(pool_idx) == (int64_t)g.B * g.Hp * g.Wp * g.Co, "conv2d_fwd: pool_idx shape mismatch");
+    idx = ugn_ptr<uint8_t>(pool_idx);
+  }
+  if (g.B == 0) return UGN_OK;
+  if (mx == 0)
+    return simt_conv_fwd(ctx, g, ugn_ptr<float>(x), ugn_ptr<float>(w), bias ? ugn_ptr<float>(bias) : nullptr,
+                         ugn_ptr<float>(y), idx, act, alpha, pool, (cudaStream_t)stream);
+  return tc_conv_fwd(ctx, g, mx, ugn_ptr<__nv_bfloat16>(x), ugn_ptr<__nv_bfloat16>(w),
+                     bias ? ugn_ptr<float>(bias) : nullptr, ugn_ptr<__nv_bfloat16>(y), idx, act, alpha, pool,
+                     (cudaStream_t)stream);
+}
+
+extern "C" int ugn_conv2d_bwd_act(ugn_ctx* ctx, const ugn_tensor* dy, const ugn_tensor* y,
+                                  const ugn_tensor* pool_idx, ugn_tensor* dz, int act, float alpha, int pool,
+                                  void* stream) {
+  UGN_CHECK(ctx && dy && y && dz, "ugn_conv2d_bwd_act: null argument");
+  UGN_TENSOR(dy, DT_F32, 4, 4);
+  UGN_TENSOR(y, DT_BAD, 4, 5);
+  UGN_TENSOR(dz, DT_BAD, 4, 5);
+  int my = storage_mode(y, 4), mz = storage_mode(dz, 4);
+  UGN_CHECK(my >= 0 && mz >= 0, "bwd_act: bad storage mode");
+  const int64_t* ys = lshape(y, 4);
+  const int64_t* zs = lshape(dz, 4);
+  int B = (int)ys[0], Hp = (int)ys[1], Wp = (int)ys[2], C = (int)ys[3];
+  int Ho = (int)zs[1], Wo = (int)zs[2];
+  UGN_CHECK(zs[0] == B && zs[3] == C && ugn_numel(dy) == (int64_t)B * Hp * Wp * C, "bwd_act: shape mismatch");
+  if (pool) {
+    UGN_CHECK(Hp == Ho / 2 && Wp == Wo / 2 && pool_idx, "bwd_act: pooled shape mismatch");
+    UGN_TENSOR(pool_idx, DT_U8, 4, 4);
+  } else {
+    UGN_CHECK(Hp == Ho && Wp == Wo, "bwd_act: shape mismatch (no pool)");
+  }
+  if (B == 0) return UGN_OK;
+  return ew_bwd_act(ctx, ugn_ptr<float>(dy), ugn_ptr<void>(y), my > 0, pool ? ugn_ptr<uint8_t>(pool_idx) : nullptr,
+                    ugn_ptr<void>(dz), mz, B, Ho, Wo, Hp, Wp, C, act, alpha, pool, (cudaStream_t)stream);
+}
+
+extern "C" int ugn_conv2d_dgrad(ugn_ctx* ctx, const ugn_tensor* dz, const ugn_tensor* w, ugn_tensor* dx,
+                                void* stream) {
+  UGN_CHECK(ctx && dz && w && dx, "ugn_conv2d_dgrad: null argument");
+  UGN_TENSOR(dz, DT_BAD, 4, 5);
+  UGN_TENSOR(w, DT_BAD, 4, 5);
+  UGN_TENSOR(dx, DT_F32, 4, 4);
+  int mz = storage_mode(dz, 4), mw = storage_mode(w, 4);
+  UGN_CHECK(mz >= 0 && mz == mw, "conv2d_dgrad: dz/w storage modes must match");
+  ConvGeom g;
+  int rc = conv_geom(dx, w, 0, g);
+  if (rc != UGN_OK) return rc;
+  const int64_t* zs = lshape(dz, 4);
+  UGN_CHECK(zs[0] == g.B && zs[1] == g.Ho && zs[2] == g.Wo && zs[3] == g.Co, "conv2d_dgrad: dz shape mismatch");
+  if (g.B == 0) return UGN_OK;
+  if (mz == 0)
+    return simt_conv_dgrad(ctx, g, ugn_ptr<float>(dz), ugn_ptr<float>(w), ugn_ptr<float>(dx), (cudaStream_t)stream);
+  return tc_conv_dgrad(ctx, g, mz, ugn_ptr<__nv_bfloat16>(dz), ugn_ptr<__nv_bfloat16>(w), ugn_ptr<float>(dx),
+                       (cudaStream_t)stream);
+}
+
+extern "C" int ugn_conv2d_wgrad(ugn_ctx* ctx, const ugn_tensor* x, const ugn_tensor* dz, ugn_tensor* dw,
+                                ugn_tensor* db, void* stream) {
+  UGN_CHECK(ctx && x && dz && dw, "ugn_conv2d_wgrad: null argument");
+  UGN_TENSOR(x, DT_BAD, 4, 5);
+  UGN_TENSOR(dz, DT_BAD, 4, 5);
+  UGN_TENSOR(dw, DT_F32, 4, 4);
+  if (db) UGN_TENSOR(db, DT_F32, 1, 1);
+  int mx = storage_mode(x, 4), mz = storage_mode(dz, 4);
+  UGN_CHECK(mx >= 0 && mx == mz, "conv2d_wgrad: x/dz storage modes must match");
+  const int64_t* xs = lshape(x, 4);
+  const int64_t* zs = lshape(dz, 4);
+  ConvGeom g;
+  g.B = (int)xs[0]; g.H = (int)xs[1]; g.W = (int)xs[2]; g.Cp = (int)xs[3];
+  g.Co = (int)dw->shape[0]; g.KH = (int)dw->shape[1]; g.KW = (int)dw->shape[2]; g.Cin = (int)dw->shape[3];
+  g.Ho = g.H - g.KH + 1; g.Wo = g.W - g.KW + 1; g.Hp = g.Ho; g.Wp = g.Wo;
+  UGN_CHECK(g.Cin <= g.Cp, "conv2d_wgrad: dw inner dim larger than activation channels");
+  UGN_CHECK(zs[0] == g.B && zs[1] == g.Ho && zs[2] == g.Wo && zs[3] == g.Co, "conv2d_wgrad: dz shape mismatch");
+  if (db) UGN_CHECK(db->shape[0] == g.Co, "conv2d_wgrad: db must be [Cout]");
+  if (mx == 0)
+    return simt_conv_wgrad(ctx, g, ugn_ptr<float>(x), ugn_ptr<float>(dz), ugn_ptr<float>(dw),
+                           db ? ugn_ptr<float>(db) : nullptr, (cudaStream_t)stream);
+  return tc_conv_wgrad(ctx, g, mx, ugn_ptr<__nv_bfloat16>(x), ugn_ptr<__nv_bfloat16>(dz), ugn_ptr<float>(dw),
+                       db ? ugn_ptr<float>(db) : nullptr, (cudaStream_t)stream);
+}
+
+extern "C" int ugn_flatten_chw(ugn_ctx* ctx, const ugn_tensor* y, ugn_tensor* flat, void* stream) {
+  UGN_CHECK(ctx && y && flat, "ugn_flatten_chw: null argument");
+  UGN_TENSOR(y, DT_BAD, 4, 5);
+  UGN_TENSOR(flat, DT_BAD, 2, 3);
+  int my = storage_mode(y, 4), mf = storage_mode(flat, 2);
+  UGN_CHECK(my >= 0 && my == mf, "flatten: storage modes must match");
+  const int64_t* ys = lshape(y, 4);
+  UGN_CHECK(lshape(flat, 2)[0] == ys[0] && lshape(flat, 2)[1] == ys[1] * ys[2] * ys[3], "flatten: shape mismatch");
+  if (ys[0] == 0) return UGN_OK;
+  return ew_flatten(ctx, ugn_ptr<void>(y), ugn_ptr<void>(flat), my > 0, my > 0 ? my : 1, (int)ys[0],
+                    (int)(ys[1] * ys[2]), (int)ys[3], 1, (cudaStream_t)stream);
+}
+extern "C" int ugn_unflatten_chw(ugn_ctx* ctx, const ugn_tensor* dflat, ugn_tensor* dy, void* stream) {
+  UGN_CHECK(ctx && dflat && dy, "ugn_unflatten_chw: null argument");
+  UGN_TENSOR(dflat, DT_F32, 2, 2);
+  UGN_TENSOR(dy, DT_F32, 4, 4);
+  UGN_CHECK(dflat->shape[0] == dy->shape[0] && dflat->shape[1] == dy->shape[1] * dy->shape[2] * dy->shape[3],
+            "unflatten: shape mismatch");
+  if (dy->shape[0] == 0) return UGN_OK;
+  return ew_flatten(ctx, ugn_ptr<void>(dflat), ugn_ptr<void>(dy), 0, 1, (int)dy->shape[0],
+                    (int)(dy->shape[1] * dy->shape[2]), (int)dy->shape[3], 0, (cudaStream_t)stream);
+}
+
+extern "C" int ugn_linear_fwd(ugn_ctx* ctx, const ugn_tensor* x, const ugn_tensor* w, const ugn_tensor* bias,
+                              const ugn_tensor* drop_mask, ugn_tensor* y, ugn_tensor* y16, int act, float alpha,
+                              void* stream) {
+  UGN_CHECK(ctx && x && w && y, "ugn_linear_fwd: null argument");
+  UGN_TENSOR(x, DT_BAD, 2, 3);
+  UGN_TENSOR(w, DT_BAD, 2, 3);
+  UGN_TENSOR(y, DT_F32, 2, 2);
+  int mx = storage_mode(x, 2), mw = storage_mode(w, 2);
+  UGN_CHECK(mx >= 0 && mx == mw, "linear_fwd: x/w storage modes must match");
+  const int64_t* xs = lshape(x, 2);
+  const int64_t* ws = lshape(w, 2);
+  int B = (int)xs[0], K = (int)xs[1], N = (int)ws[0];
+  UGN_CHECK(ws[1] == K && y->shape[0] == B && y->shape[1] == N, "linear_fwd: shape mismatch");
+  if (bias) { UGN_TENSOR(bias, DT_F32, 1, 1); UGN_CHECK(bias->shape[0] == N, "linear_fwd: bias must be [N]"); }
+  if (drop_mask) { UGN_TENSOR(drop_mask, DT_F32, 2, 2); UGN_CHECK(ugn_numel(drop_mask) == (int64_t)B * N, "linear_fwd: mask must be [B,N]"); }
+  int P16 = 0;
+  if (y16) {
+    UGN_TENSOR(y16, DT_BF16, 3, 3);
+    P16 = (int)y16->shape[0];
+    UGN_CHECK((P16 == 1 || P16 == 2) && y16->shape[1] == B && y16->shape[2] == N, "linear_fwd: y16 must be [P,B,N]");
+  }
+  if (B == 0) return UGN_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  int rc;
+  if (mx == 0) {
+    rc = simt_linear_fwd(ctx, B, N, K, ugn_ptr<float>(x), ugn_ptr<float>(w), bias ? ugn_ptr<float>(bias) : nullptr,
+                         drop_mask ? ugn_ptr<float>(drop_mask) : nullptr, ugn_ptr<float>(y), act, alpha, st);
+  } else {
+    rc = tc_linear_fwd(ctx, mx, B, N, K, ugn_ptr<__nv_bfloat16>(x), ugn_ptr<__nv_bfloat16>(w),
+                       bias ? ugn_ptr<float>(bias) : nullptr, drop_mask ? ugn_ptr<float>(drop_mask) : nullptr,
+                       ugn_ptr<float>(y), act, alpha, st);
+  }
+  if (rc != UGN_OK) return rc;
+  if (y16) return ew_split(ctx, ugn_ptr<float>(y), ugn_ptr<__nv_bfloat16>(y16), P16, (long long)B * N, st);
+  return UGN_OK;
+}
+
+extern "C" int ugn_act_mask_bwd(ugn_ctx* ctx, const ugn_tensor* dy, const ugn_tensor* y, const ugn_tensor* drop_mask,
+                                ugn_tensor* dz, ugn_tensor* dz16, int act, float alpha, void* stream) {
+  UGN_CHECK(ctx && dy && (dz || dz16), "ugn_act_mask_bwd: null argument");
+  UGN_TENSOR(dy, DT_F32, 1, 4);
+  long long n = ugn_numel(dy);
+  if (y) { UGN_TENSOR(y, DT_F32, 1, 4); UGN_CHECK(ugn_numel(y) == n, "act_mask_bwd: y shape mismatch"); }
+  if (drop_mask) { UGN_TENSOR(drop_mask, DT_F32, 1, 4); UGN_CHECK(ugn_numel(drop_mask) == n, "act_mask_bwd: mask shape mismatch"); }
+  if (dz) { UGN_TENSOR(dz, DT_F32, 1, 4); UGN_CHECK(ugn_numel(dz) == n, "act_mask_bwd: dz shape mismatch"); }
+  int P = 0;
+  if (dz16) {
+    UGN_TENSOR(dz16, DT_BF16, 2, 5);
+    P = (int)dz16->shape[0];
+    UGN_CHECK((P == 1 || P == 2) && ugn_numel(dz16) == P * n, "act_mask_bwd: dz16 must be [P,...]");
+  }
+  if (n == 0) return UGN_OK;
+  return ew_act_mask_bwd(ctx, ugn_ptr<float>(dy), y ? ugn_ptr<float>(y) : nullptr,
+                         drop_mask ? ugn_ptr<float>(drop_mask) : nullptr, dz ? ugn_ptr<float>(dz) : nullptr,
+                         dz16 ? ugn_ptr<__nv_bfloat16>(dz16) : nullptr, P, n, act, alpha, (cudaStream_t)stream);
+}
+
+extern "C" int ugn_linear_bwd(ugn_ctx* ctx, const ugn_tensor* x, const ugn_tensor* w, const ugn_tensor* dz,
+                              ugn_tensor* dx, ugn_tensor* dw, ugn_tensor* db, void* stream) {
+  UGN_CHECK(ctx && x && w && dz, "ugn_linear_bwd: null argument");
+  UGN_TENSOR(x, DT_BAD, 2, 3);
+  UGN_TENSOR(w, DT_BAD, 2, 3);
+  UGN_TENSOR(dz, DT_BAD, 2, 3);
+  int mx = storage_mode(x, 2), mw = storage_mode(w, 2), mz = storage_mode(dz, 2);
+  UGN_CHECK(mx >= 0 && mx == mw && mx == mz, "linear_bwd: x/w/dz storage modes must match");
+  const int64_t* xs = lshape(x, 2);
+  const int64_t* ws = lshape(w, 2);
+  const int64_t* zs = lshape(dz, 2);
+  int B = (int)xs[0], K = (int)xs[1], N = (int)ws[0];
+  UGN_CHECK(ws[1] == K && zs[0] == B && zs[1] == N, "linear_bwd: shape mismatch");
+  if (dx) { UGN_TENSOR(dx, DT_F32, 2, 2); UGN_CHECK(dx->shape[0] == B && dx->shape[1] == K, "linear_bwd: dx must be [B,K]"); }
+  if (dw) { UGN_TENSOR(dw, DT_F32, 2, 2); UGN_CHECK(dw->shape[0] == N && dw->shape[1] <= K, "linear_bwd: dw must be [N,<=K]"); }
+  if (db) { UGN_TENSOR(db, DT_F32, 1, 1); UGN_CHECK(db->shape[0] == N, "linear_bwd: db must be [N]"); }
+  if (dw) UGN_CHECK(dw->shape[1] == K, "linear_bwd: dw inner dim must equal K (dense weights are never padded)");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (mx == 0)
+    return simt_linear_bwd(ctx, B, N, K, ugn_ptr<float>(x), ugn_ptr<float>(w), ugn_ptr<float>(dz),
+                           dx ? ugn_ptr<float>(dx) : nullptr, dw ? ugn_ptr<float>(dw) : nullptr,
+                           db ? ugn_ptr<float>(db) : nullptr, st);
+  return tc_linear_bwd(ctx, mx, B, N, K, ugn_ptr<__nv_bfloat16>(x), ugn_ptr<__nv_bfloat16>(w),
+                       ugn_ptr<__nv_bfloat16>(dz), dx ? ugn_ptr<float>(dx) : nullptr,
+                       dw ? ugn_ptr<float>(dw) : nullptr, db ? ugn_ptr<float>(db) : nullptr, st);
+}
+
+static int fuse_common(ugn_ctx* ctx, int nmods, const ugn_tensor* const* br, const ugn_tensor* const* flags,
+                       int& B, int& d) {
+  UGN_CHECK(nmods >= 1 && nmods <= 4, "fuse: 1..4 modalities supported");
+  for (int m = 0; m < nmods; ++m) {
+    UGN_TENSOR(br[m], DT_F32, 2, 2);
+    UGN_TENSOR(flags[m], DT_F32, 1, 2);
+    if (m == 0) { B = (int)br[0]->shape[0]; d = (int)br[0]->shape[1]; }
+    UGN_CHECK(br[m]->shape[0] == B && br[m]->shape[1] == d && ugn_numel(flags[m]) == B, "fuse: shape mismatch at modality %d", m);
+  }
+  UGN_CHECK((size_t)d * 4 <= 48 * 1024, "fuse: signature dimension too large");
+  return UGN_OK;
+}
+
+extern "C" int ugn_fuse_fwd(ugn_ctx* ctx, int nmods, const ugn_tensor* const* br, const ugn_tensor* const* flags,
+                            ugn_tensor* sig, ugn_tensor* sig16, ugn_tensor* winner, ugn_tensor* inv_norm, int merge,
+                            int normalize, void* stream) {
+  UGN_CHECK(ctx && br && flags && sig, "ugn_fuse_fwd: null argument");
+  int B = 0, d = 0;
+  int rc = fuse_common(ctx, nmods, br, flags, B, d);
+  if (rc != UGN_OK) return rc;
+  UGN_TENSOR(sig, DT_F32, 2, 2);
+  UGN_CHECK(sig->shape[0] == B && sig->shape[1] == d, "fuse_fwd: sig must be [B,d]");
+  int P = 0;
+  if (sig16) {
+    UGN_TENSOR(sig16, DT_BF16, 3, 3);
+    P = (int)sig16->shape[0];
+    UGN_CHECK((P == 1 || P == 2) && sig16->shape[1] == B && sig16->shape[2] == d, "fuse_fwd: sig16 must be [P,B,d]");
+  }
+  if (winner) { UGN_TENSOR(winner, DT_U8, 2, 2); UGN_CHECK(ugn_numel(winner) == (int64_t)B * d, "fuse_fwd: winner must be [B,d]"); }
+  if (inv_norm) { UGN_TENSOR(inv_norm, DT_F32, 2, 2); UGN_CHECK(inv_norm->shape[0] == B && inv_norm->shape[1] == 2, "fuse_fwd: inv_norm must be [B,2]"); }
+  UGN_CHECK(merge >= 0 && merge <= 2, "fuse_fwd: unknown merge mode %d", merge);
+  if (B == 0) return UGN_OK;
+  FusePtrs p{};
+  for (int m = 0; m < nmods; ++m) { p.br[m] = ugn_ptr<float>(br[m]); p.flag[m] = ugn_ptr<float>(flags[m]); }
+  return ew_fuse_fwd(ctx, p, nmods, B, d, ugn_ptr<float>(sig), sig16 ? ugn_ptr<__nv_bfloat16>(sig16) : nullptr, P,
+                     winner ? ugn_ptr<uint8_t>(winner) : nullptr, inv_norm ? ugn_ptr<float>(inv_norm) : nullptr,
+                     merge, normalize, (cudaStream_t)stream);
+}
+
+extern "C" int ugn_fuse_bwd(ugn_ctx* ctx, int nmods, const ugn_tensor* dsig, const ugn_tensor* sig,
+                            const ugn_tensor* winner, const ugn_tensor* inv_norm, const ugn_tensor* const* flags,
+                            ugn_tensor* const* dbr, int merge, int normalize, void* stream) {
+  UGN_CHECK(ctx && dsig && sig && flags && dbr, "ugn_fuse_bwd: null argument");
+  int B = 0, d = 0;
+  int rc = fuse_common(ctx, nmods, (const ugn_tensor* const*)dbr, flags, B, d);
+  if (rc != UGN_OK) return rc;
+  UGN_TENSOR(dsig, DT_F32, 2, 2);
+  UGN_TENSOR(sig, DT_F32, 2, 2);
+  UGN_CHECK(ugn_numel(dsig) == (int64_t)B * d && ugn_numel(sig) == (int64_t)B * d, "fuse_bwd: shape mismatch");
+  if (merge != UGN_MERGE_AVG) { UGN_CHECK(winner, "fuse_bwd: winner required"); UGN_TENSOR(winner, DT_U8, 2, 2); }
+  if (normalize) { UGN_CHECK(inv_norm, "fuse_bwd: inv_norm required"); UGN_TENSOR(inv_norm, DT_F32, 2, 2); }
+  if (B == 0) return UGN_OK;
+  FusePtrs p{};
+  for (int m = 0; m < nmods; ++m) { p.dbr[m] = ugn_ptr<float>(dbr[m]); p.flag[m] = ugn_ptr<float>(flags[m]); }
+  return ew_fuse_bwd(ctx, p, nmods, B, d, ugn_ptr<float>(dsig), ugn_ptr<float>(sig),
+                     winner ? ugn_ptr<uint8_t>(winner) : nullptr, inv_norm ? ugn_ptr<float>(inv_norm) : nullptr, merge,
+                     normalize, (cudaStream_t)stream);
+}
+
+extern "C" int ugn_softmax_ce(ugn_ctx* ctx, const ugn_tensor* logits, const ugn_tensor* labels, ugn_tensor* loss_acc,
+                              ugn_tensor* dlogits, float scale, void* stream) {
+  UGN_CHECK(ctx && logits && labels && loss_acc, "ugn_softmax_ce: null argument");
+  UGN_TENSOR(logits, DT_F32, 2, 2);
+  UGN_TENSOR(labels, DT_I32, 1, 2);
+  UGN_TENSOR(loss_acc, DT_F32, 1, 1);
+  int B = (int)logits->shape[0], C = (int)logits->shape[1];
+  UGN_CHECK(ugn_numel(labels) == B && loss_acc->shape[0] >= 2, "softmax_ce: shape mismatch");
+  if (dlogits) { UGN_TENSOR(dlogits, DT_F32, 2, 2); UGN_CHECK(ugn_numel(dlogits) == (int64_t)B * C, "softmax_ce: dlogits shape mismatch"); }
+  if (B == 0) return UGN_OK;
+  return ew_softmax_ce(ctx, ugn_ptr<float>(logits), ugn_ptr<int>(labels), ugn_ptr<float>(loss_acc),
+                       dlogits ? ugn_ptr<float>(dlogits) : nullptr, B, C, scale, (cudaStream_t)stream);
+}
+
+static int optim_common(ugn_ctx* ctx, int opt, ugn_tensor* w, const ugn_tensor* g, ugn_tensor* m, ugn_tensor* v,
+                        const ugn_tensor* seg_off, const ugn_tensor* seg_l2, float lr, float b1, float b2, float eps,
+                        float gscale, ugn_tensor* reg_out, const ugn_tensor* lr_dev, void* stream) {
+  UGN_CHECK(ctx && w && g && v && seg_off && seg_l2, "optimizer: null argument");
+  if (lr_dev) UGN_TENSOR(lr_dev, DT_F32, 1, 1);
+  UGN_TENSOR(w, DT_F32, 1, 1);
+  UGN_TENSOR(g, DT_F32, 1, 1);
+  UGN_TENSOR(v, DT_F32, 1, 1);
+  if (opt == 0) { UGN_CHECK(m, "adam: m required"); UGN_TENSOR(m, DT_F32, 1, 1); }
+  UGN_TENSOR(seg_off, DT_I64, 1, 1);
+  UGN_TENSOR(seg_l2, DT_F32, 1, 1);
+  long long n = w->shape[0];
+  int S = (int)seg_l2->shape[0];
+  UGN_CHECK(g->shape[0] == n && v->shape[0] == n && (!m || m->shape[0] == n), "optimizer: arena length mismatch");
+  UGN_CHECK(seg_off->shape[0] == S + 1 && S >= 1, "optimizer: seg_off must be i64[S+1]");
+  if (reg_out) UGN_TENSOR(reg_out, DT_F32, 1, 1);
+  if (n == 0) return UGN_OK;
+  return ew_optim(ctx, opt, ugn_ptr<float>(w), ugn_ptr<float>(g), m ? ugn_ptr<float>(m) : nullptr, ugn_ptr<float>(v),
+                  ugn_ptr<long long>(seg_off), ugn_ptr<float>(seg_l2), S, n, lr, b1, b2, eps, gscale,
+                  reg_out ? ugn_ptr<float>(reg_out) : nullptr, lr_dev ? ugn_ptr<float>(lr_dev) : nullptr,
+                  (cudaStream_t)stream);
+}
+
+extern "C" int ugn_adam_step(ugn_ctx* ctx, ugn_tensor* w, const ugn_tensor* g, ugn_tensor* m, ugn_tensor* v,
+                             const ugn_tensor* seg_off, const ugn_tensor* seg_l2, float lr_t, float beta1, float beta2,
+                             float eps, float gscale, ugn_tensor* reg_out, const ugn_tensor* lr_dev, void* stream) {
+  return optim_common(ctx, 0, w, g, m, v, seg_off, seg_l2, lr_t, beta1, beta2, eps, gscale, reg_out, lr_dev, stream);
+}
+extern "C" int ugn_sgd_step(ugn_ctx* ctx, ugn_tensor* w, const ugn_tensor* g, ugn_tensor* v, const ugn_tensor* seg_off,
+                            const ugn_tensor* seg_l2, float lr, float momentum, float gscale, ugn_tensor* reg_out,
+                            const ugn_tensor* lr_dev, void* stream) {
+  return optim_common(ctx, 1, w, g, nullptr, v, seg_off, seg_l2, lr, momentum, 0.f, 0.f, gscale, reg_out, lr_dev, stream);
+}
+
+extern "C" int ugn_gemm_bf16(ugn_ctx* ctx, const ugn_tensor* A, int a_mn, const ugn_tensor* B, int b_mn, ugn_tensor* C,
+                             int accumulate, void* stream) {
+  UGN_CHECK(ctx && A && B && C, "ugn_gemm_bf16: null argument");
+  UGN_TENSOR(A, DT_BF16, 3, 3);
+  UGN_TENSOR(B, DT_BF16, 3, 3);
+  UGN_TENSOR(C, DT_F32, 2, 2);
+  int P = (int)A->shape[0];
+  UGN_CHECK((P == 1 || P == 2) && B->shape[0] == P, "gemm_bf16: plane counts must match (1 or 2)");
+  int M = (int)(a_mn ? A->shape[2] : A->shape[1]), K = (int)(a_mn ? A->shape[1] : A->shape[2]);
+  int N = (int)(b_mn ? B->shape[2] : B->shape[1]), Kb = (int)(b_mn ? B->shape[1] : B->shape[2]);
+  UGN_CHECK(K == Kb && C->shape[0] == M && C->shape[1] == N, "gemm_bf16: shape mismatch (M=%d N=%d K=%d/%d)", M, N, K, Kb);
+  return tc_gemm(ctx, P, M, N, K, ugn_ptr<__nv_bfloat16>(A), a_mn, ugn_ptr<__nv_bfloat16>(B), b_mn, ugn_ptr<float>(C),
+                 accumulate, (cudaStream_t)stream);
+}

@@ -1,0 +1,490 @@
+// HBM-bound kernels of the step: layout packing, pool/activation backward, flatten,
+// gated fusion + l2_normalize, softmax-CE, optimiser.  All are coalesced, vectorised where
+// the layout allows, and sized from the SM count.
+#include "common.cuh"
+
+static inline int grid_for(ugn_ctx* ctx, long long work_items, int block) {
+  long long g = (work_items + block - 1) / block;
+  long long cap = (long long)ctx->sm_count * 16;
+  return (int)std::max<long long>(1, std::min(g, cap));
+}
+
+// ---------------------------------------------------------------------------------------
+// a0: NCHW f32 -> NHWC (f32 | bf16 P planes), channel padding zero-filled.
+// One block per (b, y): coalesced row reads, smem transpose, coalesced channel-run writes.
+// ---------------------------------------------------------------------------------------
+template <int MODE>  // 0 f32, 1 bf16 P=1, 2 bf16 P=2
+__global__ void pack_input_kernel(const float* __restrict__ x, void* __restrict__ out, int B, int C,
+                                  int H, int W, int Cp, long long plane) {
+  extern __shared__ float sm[];  // [C][W+1]
+  int by = blockIdx.x;
+  int b = by / H, y = by % H;
+  for (int e = threadIdx.x; e < C * W; e += blockDim.x) {
+    int c = e / W, xx = e % W;
+    sm[c * (W + 1) + xx] = x[(((long long)b * C + c) * H + y) * W + xx];
+  }
+  __syncthreads();
+  long long obase = ((long long)b * H + y) * W * Cp;
+  for (int e = threadIdx.x; e < W * Cp; e += blockDim.x) {
+    int xx = e / Cp, c = e % Cp;
+    float v = c < C ? sm[c * (W + 1) + xx] : 0.f;
+    if (MODE == 0) {
+      reinterpret_cast<float*>(out)[obase + e] = v;
+    } else {
+      __nv_bfloat16 hi, lo;
+      ugn_split(v, hi, lo);
+      __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(out);
+      o[obase + e] = hi;
+      if (MODE == 2) o[plane + obase + e] = lo;
+    }
+  }
+}
+
+int ew_pack_input(ugn_ctx* ctx, const float* x, void* out, int mode, int B, int C, int H, int W,
+                  int Cp, cudaStream_t st) {
+  size_t smem = sizeof(float) * C * (W + 1);
+  long long plane = (long long)B * H * W * Cp;
+  if (mode == 0) pack_input_kernel<0><<<B * H, 256, smem, st>>>(x, out, B, C, H, W, Cp, plane);
+  else if (mode == 1) pack_input_kernel<1><<<B * H, 256, smem, st>>>(x, out, B, C, H, W, Cp, plane);
+  else pack_input_kernel<2><<<B * H, 256, smem, st>>>(x, out, B, C, H, W, Cp, plane);
+  UGN_LAUNCHED(ctx);
+  return UGN_OK;
+}
+
+// master [R][Cin] -> packed [P][R][Cp]   (R = Cout*kh*kw, or out-features for dense)
+template <int MODE>
+__global__ void pack_weight_kernel(const float* __restrict__ w, void* __restrict__ out, long long R,
+                                   int Cin, int Cp) {
+  long long total = R * Cp;
+  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total;
+       e += (long long)gridDim.x * blockDim.x) {
+    long long r = e / Cp;
+    int c = (int)(e % Cp);
+    float v = c < Cin ? w[r * Cin + c] : 0.f;
+    if (MODE == 0) reinterpret_cast<float*>(out)[e] = v;
+    else {
+      __nv_bfloat16 hi, lo;
+      ugn_split(v, hi, lo);
+      __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(out);
+      o[e] = hi;
+      if (MODE == 2) o[total + e] = lo;
+    }
+  }
+}
+
+int ew_pack_weight(ugn_ctx* ctx, const float* w, void* out, int mode, long long R, int Cin, int Cp,
+                   cudaStream_t st) {
+  int g = grid_for(ctx, R * Cp, 256);
+  if (mode == 0) pack_weight_kernel<0><<<g, 256, 0, st>>>(w, out, R, Cin, Cp);
+  else if (mode == 1) pack_weight_kernel<1><<<g, 256, 0, st>>>(w, out, R, Cin, Cp);
+  else pack_weight_kernel<2><<<g, 256, 0, st>>>(w, out, R, Cin, Cp);
+  UGN_LAUNCHED(ctx);
+  return UGN_OK;
+}
+
+// generic f32 -> bf16 planes
+template <int P>
+__global__ void split_kernel(const float* __restrict__ s, __nv_bfloat16* __restrict__ d, long long n) {
+  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < n;
+       e += (long long)gridDim.x * blockDim.x) {
+    __nv_bfloat16 hi, lo;
+    ugn_split(s[e], hi, lo);
+    d[e] = hi;
+    if (P == 2) d[n + e] = lo;
+  }
+}
+int ew_split(ugn_ctx* ctx, const float* s, __nv_bfloat16* d, int P, long long n, cudaStream_t st) {
+  int g = grid_for(ctx, n, 256);
+  if (P == 1) split_kernel<1><<<g, 256, 0, st>>>(s, d, n);
+  else split_kernel<2><<<g, 256, 0, st>>>(s, d, n);
+  UGN_LAUNCHED(ctx);
+  return UGN_OK;
+}
+
+// ---------------------------------------------------------------------------------------
+// backward through MaxPooling2D(2x2, floor) + activation:
+// dz[b,yo,xo,c] = (pos(yo,xo) == idx[b,yo/2,xo/2,c]) ? dy * act'(y) : 0 ; rows/cols beyond the
+// floor region get 0 (nets/mj_uwyhNets_ba.py:85,92 -- 23->11 and 9->4 drop the last row/col).
+// ---------------------------------------------------------------------------------------
+template <int MODE, typename YT>
+__global__ void bwd_act_kernel(const float* __restrict__ dy, const YT* __restrict__ y,
+                               const uint8_t* __restrict__ idx, void* __restrict__ dz, int B, int Ho,
+                               int Wo, int Hp, int Wp, int C, int act, float alpha, int pool) {
+  long long total = (long long)B * Ho * Wo * C;
+  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total;
+       e += (long long)gridDim.x * blockDim.x) {
+    int c = (int)(e % C);
+    long long pix = e / C;
+    int xo = (int)(pix % Wo);
+    int yo = (int)((pix / Wo) % Ho);
+    int b = (int)(pix / ((long long)Wo * Ho));
+    float v = 0.f;
+    if (pool) {
+      int yp = yo >> 1, xp = xo >> 1;
+      if (yp < Hp && xp < Wp) {
+        long long o = (((long long)b * Hp + yp) * Wp + xp) * C + c;
+        int pos = ((yo & 1) << 1) | (xo & 1);
+        if (idx[o] == pos) v = dy[o] * ugn_act_bwd((float)y[o], act, alpha);
+      }
+    } else {
+      v = dy[e] * ugn_act_bwd((float)y[e], act, alpha);
+    }
+    if (MODE == 0) reinterpret_cast<float*>(dz)[e] = v;
+    else {
+      __nv_bfloat16 hi, lo;
+      ugn_split(v, hi, lo);
+      __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(dz);
+      o[e] = hi;
+      if (MODE == 2) o[total + e] = lo;
+    }
+  }
+}
+
+int ew_bwd_act(ugn_ctx* ctx, const float* dy, const void* y, int y_bf16, const uint8_t* idx,
+               void* dz, int mode, int B, int Ho, int Wo, int Hp, int Wp, int C, int act,
+               float alpha, int pool, cudaStream_t st) {
+  int g = grid_for(ctx, (long long)B * Ho * Wo * C, 256);
+#define LAUNCH(M, YT) \
+  bwd_act_kernel<M, YT><<<g, 256, 0, st>>>(dy, (const YT*)y, idx, dz, B, Ho, Wo, Hp, Wp, C, act, alpha, pool)
+  if (y_bf16) {
+    if (mode == 0) LAUNCH(0, __nv_bfloat16);
+    else if (mode == 1) LAUNCH(1, __nv_bfloat16);
+    else LAUNCH(2, __nv_bfloat16);
+  } else {
+    if (mode == 0) LAUNCH(0, float);
+    else if (mode == 1) LAUNCH(1, float);
+    else LAUNCH(2, float);
+  }
+#undef LAUNCH
+  UGN_LAUNCHED(ctx);
+  return UGN_OK;
+}
+
+// ---------------------------------------------------------------------------------------
+// Flatten over (C,H,W) (channels_first): NHWC [B,H,W,C] -> [B, C*H*W] and back.
+// ---------------------------------------------------------------------------------------
+template <typename T>
+__global__ void flatten_kernel(const T* __restrict__ src, T* __restrict__ dst, long long planes_stride,
+                               int P, int B, int HW, int C, int to_chw) {
+  long long total = (long long)B * HW * C;
+  for (int pl = 0; pl < P; ++pl) {
+    const T* s = src + pl * planes_stride;
+    T* d = dst + pl * planes_stride;
+    for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total;
+         e += (long long)gridDim.x * blockDim.x) {
+      int b = (int)(e / ((long long)HW * C));
+      int r = (int)(e % ((long long)HW * C));
+      if (to_chw) {  // e indexes dst [b][c][hw]
+        int c = r / HW, hw = r % HW;
+        d[e] = s[((long long)b * HW + hw) * C + c];
+      } else {       // e indexes dst [b][hw][c]
+        int hw = r / C, c = r % C;
+        d[e] = s[((long long)b * C + c) * HW + hw];
+      }
+    }
+  }
+}
+
+int ew_flatten(ugn_ctx* ctx, const void* src, void* dst, int bf16, int P, int B, int HW, int C,
+               int to_chw, cudaStream_t st) {
+  long long n = (long long)B * HW * C;
+  int g = grid_for(ctx, n, 256);
+  if (bf16)
+    flatten_kernel<__nv_bfloat16><<<g, 256, 0, st>>>((const __nv_bfloat16*)src, (__nv_bfloat16*)dst, n, P, B, HW, C, to_chw);
+  else
+    flatten_kernel<float><<<g, 256, 0, st>>>((const float*)src, (float*)dst, n, P, B, HW, C, to_chw);
+  UGN_LAUNCHED(ctx);
+  return UGN_OK;
+}
+
+// ---------------------------------------------------------------------------------------
+// dense backward helper: dz = dy * mask * act'(y)   (+ optional bf16 copy)
+// ---------------------------------------------------------------------------------------
+template <int P>
+__global__ void act_mask_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ y,
+                                    const float* __restrict__ mask, float* __restrict__ dz,
+                                    __nv_bfloat16* __restrict__ dz16, long long n, int act, float alpha) {
+  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < n;
+       e += (long long)gridDim.x * blockDim.x) {
+    float v = dy[e];
+    if (mask) v *= mask[e];
+    if (y) v *= ugn_act_bwd(y[e], act, alpha);
+    if (dz) dz[e] = v;
+    if (P > 0) {
+      __nv_bfloat16 hi, lo;
+      ugn_split(v, hi, lo);
+      dz16[e] = hi;
+      if (P == 2) dz16[n + e] = lo;
+    }
+  }
+}
+int ew_act_mask_bwd(ugn_ctx* ctx, const float* dy, const float* y, const float* mask, float* dz,
+                    __nv_bfloat16* dz16, int P, long long n, int act, float alpha, cudaStream_t st) {
+  int g = grid_for(ctx, n, 256);
+  if (P == 0) act_mask_bwd_kernel<0><<<g, 256, 0, st>>>(dy, y, mask, dz, dz16, n, act, alpha);
+  else if (P == 1) act_mask_bwd_kernel<1><<<g, 256, 0, st>>>(dy, y, mask, dz, dz16, n, act, alpha);
+  else act_mask_bwd_kernel<2><<<g, 256, 0, st>>>(dy, y, mask, dz, dz16, n, act, alpha);
+  UGN_LAUNCHED(ctx);
+  return UGN_OK;
+}
+
+// ---------------------------------------------------------------------------------------
+// a2+a3+a4: gate x flag -> merge (max | avg | sign_max) -> l2_normalize.  One CTA per row;
+// float4 loads of every modality's signature, warp-shuffle + smem reduction of sum(x^2).
+// ---------------------------------------------------------------------------------------
+template <int P>
+__global__ void __launch_bounds__(256) fuse_fwd_kernel(FusePtrs ptrs, int nmods, int d,
+                                                       float* __restrict__ sig,
+                                                       __nv_bfloat16* __restrict__ sig16,
+                                                       uint8_t* __restrict__ winner,
+                                                       float* __restrict__ inv_norm, int merge,
+                                                       int normalize, long long plane) {
+  extern __shared__ float row[];  // [d] fused values
+  __shared__ float red[8];
+  const int b = blockIdx.x;
+  float fl[4];
+  for (int m = 0; m < nmods; ++m) fl[m] = ptrs.flag[m][b];
+  float ss = 0.f;
+  for (int j = threadIdx.x; j < d; j += blockDim.x) {
+    float best = ptrs.br[0][(long long)b * d + j] * fl[0];
+    int win = 0;
+    if (merge == UGN_MERGE_AVG) {
+      for (int m = 1; m < nmods; ++m) best += ptrs.br[m][(long long)b * d + j] * fl[m];
+      best = best / (float)nmods;
+    } else {
+      float key = merge == UGN_MERGE_SIGNMAX ? fabsf(best) : best;
+      for (int m = 1; m < nmods; ++m) {
+        float v = ptrs.br[m][(long long)b * d + j] * fl[m];
+        float kv = merge == UGN_MERGE_SIGNMAX ? fabsf(v) : v;
+        if (kv > key) { key = kv; best = v; win = m; }   // strict: ties -> earlier modality
+      }
+    }
+    row[j] = best;
+    if (winner) winner[(long long)b * d + j] = (uint8_t)win;
+    ss += best * best;
+  }
+  ss = warp_sum(ss);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = ss;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    float v = threadIdx.x < (blockDim.x >> 5) ? red[threadIdx.x] : 0.f;
+    v = warp_sum(v);
+    if (threadIdx.x == 0) red[0] = v;
+  }
+  __syncthreads();
+  ss = red[0];
+  float inv = normalize ? rsqrtf(fmaxf(ss, 1e-12f)) : 1.f;
+  if (threadIdx.x == 0 && inv_norm) {
+    inv_norm[2 * b] = inv;
+    inv_norm[2 * b + 1] = ss;
+  }
+  for (int j = threadIdx.x; j < d; j += blockDim.x) {
+    float v = row[j] * inv;
+    sig[(long long)b * d + j] = v;
+    if (P > 0) {
+      __nv_bfloat16 hi, lo;
+      ugn_split(v, hi, lo);
+      sig16[(long long)b * d + j] = hi;
+      if (P == 2) sig16[plane + (long long)b * d + j] = lo;
+    }
+  }
+}
+
+int ew_fuse_fwd(ugn_ctx* ctx, const FusePtrs& ptrs, int nmods, int B, int d, float* sig,
+                __nv_bfloat16* sig16, int P, uint8_t* winner, float* inv_norm, int merge,
+                int normalize, cudaStream_t st) {
+  size_t smem = sizeof(float) * d;
+  long long plane = (long long)B * d;
+  if (P == 0) fuse_fwd_kernel<0><<<B, 256, smem, st>>>(ptrs, nmods, d, sig, sig16, winner, inv_norm, merge, normalize, plane);
+  else if (P == 1) fuse_fwd_kernel<1><<<B, 256, smem, st>>>(ptrs, nmods, d, sig, sig16, winner, inv_norm, merge, normalize, plane);
+  else fuse_fwd_kernel<2><<<B, 256, smem, st>>>(ptrs, nmods, d, sig, sig16, winner, inv_norm, merge, normalize, plane);
+  UGN_LAUNCHED(ctx);
+  return UGN_OK;
+}
+
+// backward: y = x*inv, inv = rsqrt(max(ss,eps)).  ss > eps: dx = inv*(dy - y*sum(dy*y));
+// clamped (ss <= eps): inv is a constant, dx = dy*inv.  Then route dx to the winning modality
+// (max / sign_max) or spread it (avg), times the gate flag.
+__global__ void __launch_bounds__(256) fuse_bwd_kernel(FusePtrs ptrs, int nmods, int d,
+                                                       const float* __restrict__ dsig,
+                                                       const float* __restrict__ sig,
+                                                       const uint8_t* __restrict__ winner,
+                                                       const float* __restrict__ inv_norm, int merge,
+                                                       int normalize) {
+  __shared__ float red[8];
+  const int b = blockIdx.x;
+  float inv = 1.f, dot = 0.f;
+  bool clamped = true;
+  if (normalize) {
+    inv = inv_norm[2 * b];
+    clamped = !(inv_norm[2 * b + 1] > 1e-12f);
+    if (!clamped) {
+      for (int j = threadIdx.x; j < d; j += blockDim.x)
+        dot += dsig[(long long)b * d + j] * sig[(long long)b * d + j];
+      dot = warp_sum(dot);
+      if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = dot;
+      __syncthreads();
+      if (threadIdx.x < 32) {
+        float v = threadIdx.x < (blockDim.x >> 5) ? red[threadIdx.x] : 0.f;
+        v = warp_sum(v);
+        if (threadIdx.x == 0) red[0] = v;
+      }
+      __syncthreads();
+      dot = red[0];
+    }
+  }
+  float fl[4];
+  for (int m = 0; m < nmods; ++m) fl[m] = ptrs.flag[m][b];
+  for (int j = threadIdx.x; j < d; j += blockDim.x) {
+    long long o = (long long)b * d + j;
+    float g = dsig[o];
+    if (normalize) g = clamped ? g * inv : inv * (g - sig[o] * dot);
+    if (merge == UGN_MERGE_AVG) {
+      for (int m = 0; m < nmods; ++m) ptrs.dbr[m][o] = g * fl[m] / (float)nmods;
+    } else {
+      int w = winner[o];
+      for (int m = 0; m < nmods; ++m) ptrs.dbr[m][o] = (m == w) ? g * fl[m] : 0.f;
+    }
+  }
+}
+
+int ew_fuse_bwd(ugn_ctx* ctx, const FusePtrs& ptrs, int nmods, int B, int d, const float* dsig,
+                const float* sig, const uint8_t* winner, const float* inv_norm, int merge,
+                int normalize, cudaStream_t st) {
+  fuse_bwd_kernel<<<B, 256, 0, st>>>(ptrs, nmods, d, dsig, sig, winner, inv_norm, merge, normalize);
+  UGN_LAUNCHED(ctx);
+  return UGN_OK;
+}
+
+// ---------------------------------------------------------------------------------------
+// softmax + categorical CE (fused log-softmax), one warp per row, C <= 32*32.
+// ---------------------------------------------------------------------------------------
+__global__ void softmax_ce_kernel(const float* __restrict__ logits, const int* __restrict__ labels,
+                                  float* __restrict__ loss_acc, float* __restrict__ dlogits, int B, int C,
+                                  float scale) {
+  int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (warp >= B) return;
+  const float* row = logits + (long long)warp * C;
+  float mx = -INFINITY;
+  int amax = 0;
+  for (int j = lane; j < C; j += 32) {
+    float v = row[j];
+    if (v > mx) { mx = v; amax = j; }
+  }
+  // warp argmax with lowest-index tie rule
+  for (int o = 16; o > 0; o >>= 1) {
+    float om = __shfl_xor_sync(0xffffffffu, mx, o);
+    int oa = __shfl_xor_sync(0xffffffffu, amax, o);
+    if (om > mx || (om == mx && oa < amax)) { mx = om; amax = oa; }
+  }
+  float se = 0.f;
+  for (int j = lane; j < C; j += 32) se += expf(row[j] - mx);
+  se = warp_sum(se);
+  float lse = mx + logf(se);
+  int lab = labels[warp];
+  if (lane == 0) {
+    atomicAdd(loss_acc, (lse - row[lab]) / (float)B);
+    atomicAdd(loss_acc + 1, (amax == lab ? 1.f : 0.f) / (float)B);
+  }
+  if (dlogits) {
+    float s = scale / (float)B;
+    for (int j = lane; j < C; j += 32) {
+      float p = expf(row[j] - lse);
+      dlogits[(long long)warp * C + j] = s * (p - (j == lab ? 1.f : 0.f));
+    }
+  }
+}
+
+int ew_softmax_ce(ugn_ctx* ctx, const float* logits, const int* labels, float* loss_acc,
+                  float* dlogits, int B, int C, float scale, cudaStream_t st) {
+  UGN_CUDA(cudaMemsetAsync(loss_acc, 0, 2 * sizeof(float), st));
+  int threads = 128, blocks = ugn_cdiv((long long)B * 32, threads);
+  softmax_ce_kernel<<<blocks, threads, 0, st>>>(logits, labels, loss_acc, dlogits, B, C, scale);
+  UGN_LAUNCHED(ctx);
+  return UGN_OK;
+}
+
+// ---------------------------------------------------------------------------------------
+// a8/a9: fused regulariser + optimiser over a flat arena (segments padded to 4 elements).
+// 7 arena-sized streams for Adam (read w,g,m,v; write w,m,v) = 28 B/param -> HBM-bound.
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ int seg_find(const long long* __restrict__ off, int S, long long e) {
+  int lo = 0, hi = S;  // off[lo] <= e < off[hi]
+  while (hi - lo > 1) {
+    int mid = (lo + hi) >> 1;
+    if (off[mid] <= e) lo = mid; else hi = mid;
+  }
+  return lo;
+}
+
+template <int OPT>  // 0 adam, 1 sgd-momentum
+__global__ void __launch_bounds__(256) optim_kernel(float* __restrict__ w, const float* __restrict__ g,
+                                                    float* __restrict__ m, float* __restrict__ v,
+                                                    const long long* __restrict__ off,
+                                                    const float* __restrict__ l2, int S, long long n4,
+                                                    float lr, float b1, float b2, float eps, float gscale,
+                                                    float* __restrict__ reg_out,
+                                                    const float* __restrict__ lr_dev) {
+  float reg = 0.f;
+  if (lr_dev) lr = *lr_dev;  // CUDA-graph friendly: the step-dependent rate lives in device memory
+  for (long long q = blockIdx.x * (long long)blockDim.x + threadIdx.x; q < n4;
+       q += (long long)gridDim.x * blockDim.x) {
+    int s = seg_find(off, S, q * 4);
+    float c = l2[s];
+    float4 wv = reinterpret_cast<float4*>(w)[q];
+    float4 gv = reinterpret_cast<const float4*>(g)[q];
+    float ww[4] = {wv.x, wv.y, wv.z, wv.w}, gg[4] = {gv.x, gv.y, gv.z, gv.w};
+    if (OPT == 0) {
+      float4 mv = reinterpret_cast<float4*>(m)[q];
+      float4 vv = reinterpret_cast<float4*>(v)[q];
+      float mm[4] = {mv.x, mv.y, mv.z, mv.w}, v2[4] = {vv.x, vv.y, vv.z, vv.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        reg += c * ww[i] * ww[i];
+        float gr = gg[i] * gscale + 2.f * c * ww[i];
+        mm[i] = b1 * mm[i] + (1.f - b1) * gr;
+        v2[i] = b2 * v2[i] + (1.f - b2) * gr * gr;
+        ww[i] -= lr * mm[i] / (sqrtf(v2[i]) + eps);
+      }
+      reinterpret_cast<float4*>(m)[q] = make_float4(mm[0], mm[1], mm[2], mm[3]);
+      reinterpret_cast<float4*>(v)[q] = make_float4(v2[0], v2[1], v2[2], v2[3]);
+    } else {
+      float4 vv = reinterpret_cast<float4*>(v)[q];
+      float v2[4] = {vv.x, vv.y, vv.z, vv.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        reg += c * ww[i] * ww[i];
+        float gr = gg[i] * gscale + 2.f * c * ww[i];
+        v2[i] = b1 * v2[i] - lr * gr;
+        ww[i] += v2[i];
+      }
+      reinterpret_cast<float4*>(v)[q] = make_float4(v2[0], v2[1], v2[2], v2[3]);
+    }
+    reinterpret_cast<float4*>(w)[q] = make_float4(ww[0], ww[1], ww[2], ww[3]);
+  }
+  if (reg_out) {
+    __shared__ float red[8];
+    reg = warp_sum(reg);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = reg;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+      float r = threadIdx.x < 8 ? red[threadIdx.x] : 0.f;
+      r = warp_sum(r);
+      if (threadIdx.x == 0) atomicAdd(reg_out, r);
+    }
+  }
+}
+
+int ew_optim(ugn_ctx* ctx, int opt, float* w, const float* g, float* m, float* v,
+             const long long* off, const float* l2, int S, long long n, float lr, float b1,
+             float b2, float eps, float gscale, float* reg_out, const float* lr_dev, cudaStream_t st) {
+  UGN_CHECK(n % 4 == 0, "optimizer arena length must be a multiple of 4 (got %lld)", n);
+  if (reg_out) UGN_CUDA(cudaMemsetAsync(reg_out, 0, sizeof(float), st));
+  long long n4 = n / 4;
+  int grid = (int)std::min<long long>((n4 + 255) / 256, (long long)ctx->sm_count * 8);
+  grid = std::max(grid, 1);
+  if (opt == 0) optim_kernel<0><<<grid, 256, 0, st>>>(w, g, m, v, off, l2, S, n4, lr, b1, b2, eps, gscale, reg_out, lr_dev);
+  else optim_kernel<1><<<grid, 256, 0, st>>>(w, g, m, v, off, l2, S, n4, lr, b1, b2, eps, gscale, reg_out, lr_dev);
+  UGN_LAUNCHED(ctx);
+  return UGN_OK;
+}

@@ -1,0 +1,372 @@
+// Open-world k-NN (mains/mj_testUWYHGaitNet_open_tum.py:331-341):
+//   KNeighborsClassifier(n_neighbors=k).fit(gallery, labels).predict(probe)
+// brute-force Euclidean, uniform vote, vote ties -> smallest label.
+//
+// Stage 1  scan   : approximate score s(q,g) = |g|^2 - 2 q.g (|q|^2 is rank-irrelevant) tile by
+//                   tile with a FUSED top-KC filter -- the Q x N matrix is never materialised.
+//                   Every CTA keeps, per query row, a sorted (score, idx) list in shared memory
+//                   and a threshold; tile scores that beat the threshold are appended with a
+//                   shared-memory atomic and merged between tiles (the append rate decays as KC/n).
+// Stage 2  rerank : the CTAs' candidate lists are merged per query, the surviving KC candidates
+//                   are re-ranked with EXACT fp64 sum((q-g)^2) and ordered (distance, index) --
+//                   the same rule as oracle/knn_oracle.c, so indices/labels are bit-exact.
+// Stage 3  vote   : merge of G shards' results + uniform vote (multi-GPU gallery sharding).
+#include "common.cuh"
+#include <float.h>
+
+#define KNN_TQ 64     // queries per CTA
+#define KNN_TG 64     // gallery rows per tile
+#define KNN_TK 16
+#define KNN_MAXKC 32
+#define KNN_CB 64     // append buffer entries per row (>= KNN_TG so one tile can never overflow)
+
+struct Cand {
+  float s;
+  int i;
+};
+__device__ __forceinline__ bool cand_less(float s0, int i0, float s1, int i1) {
+  return s0 < s1 || (s0 == s1 && i0 < i1);
+}
+
+// sorted insert of (s,i) into list[0..kc) (ascending by (s,i)); list is full-length with
+// +inf sentinels.  Called by ONE thread per row.
+__device__ __forceinline__ void list_insert(Cand* list, int kc, float s, int i) {
+  if (!cand_less(s, i, list[kc - 1].s, list[kc - 1].i)) return;
+  int p = kc - 1;
+  while (p > 0 && cand_less(s, i, list[p - 1].s, list[p - 1].i)) {
+    list[p] = list[p - 1];
+    --p;
+  }
+  list[p].s = s;
+  list[p].i = i;
+}
+
+__global__ void knn_norms_kernel(const float* __restrict__ G, long long N, int D, float* __restrict__ g2) {
+  long long row = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
+  int lane = threadIdx.x & 31;
+  if (row >= N) return;
+  const float* g = G + row * D;
+  float s = 0.f;
+  for (int j = lane; j < D; j += 32) s = fmaf(g[j], g[j], s);
+  s = warp_sum(s);
+  if (lane == 0) g2[row] = s;
+}
+
+// dynamic smem layout (bytes): top[TQ][kc] Cand | buf[TQ][CB] Cand | As | Bs | cnt[TQ] | thr[TQ]
+__global__ void __launch_bounds__(256) knn_scan_kernel(const float* __restrict__ Qm,
+                                                       const float* __restrict__ Gm,
+                                                       const float* __restrict__ g2, int Q, long long N,
+                                                       int D, int kc, long long rows_per_chunk,
+                                                       Cand* __restrict__ out) {
+  extern __shared__ __align__(16) unsigned char smraw[];
+  Cand* top = reinterpret_cast<Cand*>(smraw);
+  Cand* buf = top + KNN_TQ * kc;
+  float* As = reinterpret_cast<float*>(buf + KNN_TQ * KNN_CB);       // [TK][TQ+4]
+  float* Bs = As + KNN_TK * (KNN_TQ + 4);                            // [TK][TG+4]
+  int* cnt = reinterpret_cast<int*>(Bs + KNN_TK * (KNN_TG + 4));
+  float* thr = reinterpret_cast<float*>(cnt + KNN_TQ);
+
+  const int t = threadIdx.x;
+  const int q0 = blockIdx.x * KNN_TQ;
+  const long long c0 = (long long)blockIdx.y * rows_per_chunk;
+  const long long c1 = min(N, c0 + rows_per_chunk);
+  for (int e = t; e < KNN_TQ * kc; e += 256) { top[e].s = FLT_MAX; top[e].i = 0x7fffffff; }
+  if (t < KNN_TQ) { cnt[t] = 0; thr[t] = FLT_MAX; }
+  __syncthreads();
+
+  const int kk = t & 15, r = t >> 4, ty = t >> 4, tx = t & 15;
+  for (long long gt = c0; gt < c1; gt += KNN_TG) {
+    float acc[4][4];
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+      for (int b = 0; b < 4; ++b) acc[a][b] = 0.f;
+    for (int k0 = 0; k0 < D; k0 += KNN_TK) {
+      int k = k0 + kk;
+#pragma unroll
+      for (int jj = 0; jj < 4; ++jj) {
+        int row = r + 16 * jj;
+        int qi = q0 + row;
+        long long gi = gt + row;
+        As[kk * (KNN_TQ + 4) + row] = (k < D && qi < Q) ? __ldg(Qm + (long long)qi * D + k) : 0.f;
+        Bs[kk * (KNN_TG + 4) + row] = (k < D && gi < c1) ? __ldg(Gm + gi * D + k) : 0.f;
+      }
+      __syncthreads();
+#pragma unroll
+      for (int q = 0; q < KNN_TK; ++q) {
+        float4 av = *reinterpret_cast<const float4*>(&As[q * (KNN_TQ + 4) + ty * 4]);
+        float4 bv = *reinterpret_cast<const float4*>(&Bs[q * (KNN_TG + 4) + tx * 4]);
+        float a4[4] = {av.x, av.y, av.z, av.w}, b4[4] = {bv.x, bv.y, bv.z, bv.w};
+#pragma unroll
+        for (int a = 0; a < 4; ++a)
+#pragma unroll
+          for (int b = 0; b < 4; ++b) acc[a][b] = fmaf(a4[a], b4[b], acc[a][b]);
+      }
+      __syncthreads();
+    }
+    // fused top-k filter
+#pragma unroll
+    for (int b = 0; b < 4; ++b) {
+      long long gi = gt + tx * 4 + b;
+      if (gi >= c1) continue;
+      float n2 = g2[gi];
+#pragma unroll
+      for (int a = 0; a < 4; ++a) {
+        int row = ty * 4 + a;
+        float s = n2 - 2.f * acc[a][b];
+        if (s <= thr[row]) {
+          int pos = atomicAdd(&cnt[row], 1);
+          buf[row * KNN_CB + pos].s = s;
+          buf[row * KNN_CB + pos].i = (int)gi;
+        }
+      }
+    }
+    __syncthreads();
+    if (t < KNN_TQ) {
+      int c = cnt[t];
+      if (c) {
+        Cand* lst = top + t * kc;
+        for (int e = 0; e < c; ++e) list_insert(lst, kc, buf[t * KNN_CB + e].s, buf[t * KNN_CB + e].i);
+        thr[t] = lst[kc - 1].s;
+        cnt[t] = 0;
+      }
+    }
+    __syncthreads();
+  }
+  // write this CTA's lists: out[q][chunk][kc]
+  for (int e = t; e < KNN_TQ * kc; e += 256) {
+    int row = e / kc, j = e % kc;
+    int qi = q0 + row;
+    if (qi < Q) out[((long long)qi * gridDim.y + blockIdx.y) * kc + j] = top[e];
+  }
+}
+
+// one CTA per query: select the KC best approximate candidates over all chunks, re-rank them
+// exactly in fp64 and emit the k nearest as (d2, global idx, label).
+__global__ void __launch_bounds__(256) knn_rerank_kernel(const float* __restrict__ Qm,
+                                                         const float* __restrict__ Gm,
+                                                         const int* __restrict__ labels,
+                                                         const Cand* __restrict__ cands, int ncand, int kc,
+                                                         int k, int D, long long idx_base,
+                                                         double* __restrict__ out_d2,
+                                                         long long* __restrict__ out_idx,
+                                                         int* __restrict__ out_lab) {
+  __shared__ Cand sel[KNN_MAXKC];
+  __shared__ double ex[KNN_MAXKC];
+  __shared__ float rs[8];
+  __shared__ int ri[8], rp[8];
+  const int q = blockIdx.x, t = threadIdx.x;
+  const Cand* cq = cands + (long long)q * ncand;
+  // KC rounds of block-wide lexicographic argmin over entries greater than the previous pick
+  float ps = -FLT_MAX;
+  int pi = -1;
+  for (int round = 0; round < kc; ++round) {
+    float bs = FLT_MAX;
+    int bi = 0x7fffffff;
+    for (int e = t; e < ncand; e += 256) {
+      float s = cq[e].s;
+      int i = cq[e].i;
+      if (cand_less(ps, pi, s, i) && cand_less(s, i, bs, bi)) { bs = s; bi = i; }
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+      float os = __shfl_xor_sync(0xffffffffu, bs, o);
+      int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+      if (cand_less(os, oi, bs, bi)) { bs = os; bi = oi; }
+    }
+    if ((t & 31) == 0) { rs[t >> 5] = bs; ri[t >> 5] = bi; }
+    __syncthreads();
+    if (t == 0) {
+      for (int w = 1; w < 8; ++w)
+        if (cand_less(rs[w], ri[w], bs, bi)) { bs = rs[w]; bi = ri[w]; }
+      sel[round].s = bs;
+      sel[round].i = bi;
+    }
+    __syncthreads();
+    ps = sel[round].s;
+    pi = sel[round].i;
+  }
+  // exact fp64 distances, one warp per candidate
+  const float* qv = Qm + (long long)q * D;
+  for (int c = t >> 5; c < kc; c += 8) {
+    int gi = sel[c].i;
+    double s = 0.0;
+    if (gi != 0x7fffffff) {
+      const float* gv = Gm + (long long)gi * D;
+      for (int j = t & 31; j < D; j += 32) {
+        double df = (double)qv[j] - (double)gv[j];
+        s = fma(df, df, s);
+      }
+      s = warp_sum_d(s);
+    } else {
+      s = DBL_MAX;
+    }
+    if ((t & 31) == 0) ex[c] = s;
+  }
+  __syncthreads();
+  if (t == 0) {
+    // selection sort of <= 32 entries by (d2, idx)
+    (void)rp;
+    for (int j = 0; j < k; ++j) {
+      int best = -1;
+      for (int c = 0; c < kc; ++c) {
+        if (sel[c].i == -2) continue;
+        if (best < 0 || ex[c] < ex[best] || (ex[c] == ex[best] && sel[c].i < sel[best].i)) best = c;
+      }
+      int gi = sel[best].i;
+      out_d2[(long long)q * k + j] = ex[best];
+      out_idx[(long long)q * k + j] = (gi == 0x7fffffff) ? -1 : idx_base + gi;
+      out_lab[(long long)q * k + j] = (gi == 0x7fffffff) ? -1 : labels[gi];
+      sel[best].i = -2;
+    }
+  }
+}
+
+// merge G shards' [G,Q,k] lists by (d2, idx), emit the k best and the uniform vote.
+__global__ void knn_merge_vote_kernel(const double* __restrict__ d2, const long long* __restrict__ idx,
+                                      const int* __restrict__ lab, int G, int Q, int k,
+                                      double* __restrict__ od2, long long* __restrict__ oidx,
+                                      int* __restrict__ olab, int* __restrict__ pred) {
+  int q = blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= Q) return;
+  int head[16];
+  for (int g = 0; g < G; ++g) head[g] = 0;
+  int labs[KNN_MAXKC];
+  for (int j = 0; j < k; ++j) {
+    int bg = -1;
+    double bd = 0.0;
+    long long bi = 0;
+    for (int g = 0; g < G; ++g) {
+      if (head[g] >= k) continue;
+      long long o = ((long long)g * Q + q) * k + head[g];
+      long long ii = idx[o];
+      if (ii < 0) continue;
+      double dd = d2[o];
+      if (bg < 0 || dd < bd || (dd == bd && ii < bi)) { bg = g; bd = dd; bi = ii; }
+    }
+    int lb = -1;
+    if (bg >= 0) {
+      lb = lab[((long long)bg * Q + q) * k + head[bg]];
+      head[bg]++;
+    } else {
+      bd = DBL_MAX; bi = -1;
+    }
+    labs[j] = lb;
+    if (od2) od2[(long long)q * k + j] = bd;
+    if (oidx) oidx[(long long)q * k + j] = bi;
+    if (olab) olab[(long long)q * k + j] = lb;
+  }
+  // uniform vote, ties -> smallest label
+  int best = 0x7fffffff, bestc = -1;
+  for (int a = 0; a < k; ++a) {
+    if (labs[a] < 0) continue;
+    int c = 0;
+    for (int b = 0; b < k; ++b) c += labs[b] == labs[a];
+    if (c > bestc || (c == bestc && labs[a] < best)) { bestc = c; best = labs[a]; }
+  }
+  pred[q] = bestc < 0 ? -1 : best;
+}
+
+static int knn_kc(int k) { return k <= 4 ? 8 : (k <= 8 ? 16 : 32); }
+static int knn_chunks(ugn_ctx* ctx, long long Q, long long N) {
+  long long qt = (Q + KNN_TQ - 1) / KNN_TQ;
+  long long want = std::max<long long>(1, (2LL * ctx->sm_count + qt - 1) / qt);
+  long long maxc = std::max<long long>(1, N / (4 * KNN_TG));
+  return (int)std::min<long long>(std::min(want, maxc), 1024);
+}
+
+extern "C" int64_t ugn_knn_workspace_bytes(int64_t Q, int64_t N, int64_t D, int k) {
+  (void)D;
+  // worst case chunk count (sm_count unknown here): 1024
+  return Q * 1024 * (int64_t)knn_kc(k) * (int64_t)sizeof(Cand);
+}
+
+extern "C" int ugn_knn_gallery_norms(ugn_ctx* ctx, const ugn_tensor* gallery, ugn_tensor* g2,
+                                     void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  UGN_CHECK(ctx && gallery && g2, "ugn_knn_gallery_norms: null argument");
+  UGN_TENSOR(gallery, DT_F32, 2, 2);
+  UGN_TENSOR(g2, DT_F32, 1, 1);
+  long long N = gallery->shape[0];
+  int D = (int)gallery->shape[1];
+  UGN_CHECK(g2->shape[0] == N, "g2 must be f32[N]");
+  if (N == 0) return UGN_OK;
+  knn_norms_kernel<<<ugn_cdiv(N * 32, 256), 256, 0, st>>>(ugn_ptr<float>(gallery), N, D, ugn_ptr<float>(g2));
+  UGN_LAUNCHED(ctx);
+  return UGN_OK;
+}
+
+extern "C" int ugn_knn_topk(ugn_ctx* ctx, const ugn_tensor* queries, const ugn_tensor* gallery,
+                            const ugn_tensor* g2, const ugn_tensor* gallery_labels, int k,
+                            int64_t idx_base, ugn_tensor* out_d2, ugn_tensor* out_idx,
+                            ugn_tensor* out_lab, ugn_tensor* workspace, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  UGN_CHECK(ctx && queries && gallery && g2 && gallery_labels && out_d2 && out_idx && out_lab && workspace,
+            "ugn_knn_topk: null argument");
+  UGN_TENSOR(queries, DT_F32, 2, 2);
+  UGN_TENSOR(gallery, DT_F32, 2, 2);
+  UGN_TENSOR(g2, DT_F32, 1, 1);
+  UGN_TENSOR(gallery_labels, DT_I32, 1, 1);
+  UGN_TENSOR(out_d2, DT_F64, 2, 2);
+  UGN_TENSOR(out_idx, DT_I64, 2, 2);
+  UGN_TENSOR(out_lab, DT_I32, 2, 2);
+  UGN_TENSOR(workspace, DT_BAD, 1, 8);
+  long long Q = queries->shape[0], N = gallery->shape[0];
+  int D = (int)queries->shape[1];
+  UGN_CHECK(gallery->shape[1] == D, "gallery/query dimension mismatch (%lld vs %d)", (long long)gallery->shape[1], D);
+  UGN_CHECK(k >= 1 && k <= KNN_MAXKC, "k must be in [1,%d]", KNN_MAXKC);
+  UGN_CHECK(N >= k, "gallery shard has fewer rows (%lld) than k=%d", N, k);
+  UGN_CHECK(N < 0x7fffffffLL, "gallery shard too large for 32-bit local indices");
+  UGN_CHECK(g2->shape[0] == N && gallery_labels->shape[0] == N, "g2/labels must have N entries");
+  UGN_CHECK(out_d2->shape[0] == Q && out_d2->shape[1] == k && out_idx->shape[0] == Q && out_idx->shape[1] == k &&
+                out_lab->shape[0] == Q && out_lab->shape[1] == k, "outputs must be [Q,k]");
+  if (Q == 0) return UGN_OK;
+  int kc = knn_kc(k);
+  int chunks = knn_chunks(ctx, Q, N);
+  long long rows = (N + chunks - 1) / chunks;
+  rows = (rows + KNN_TG - 1) / KNN_TG * KNN_TG;
+  chunks = (int)((N + rows - 1) / rows);
+  long long need = Q * chunks * (long long)kc * (long long)sizeof(Cand);
+  long long have = ugn_numel(workspace) * (workspace->dtype_bits / 8);
+  UGN_CHECK(have >= need, "knn workspace too small: %lld < %lld", have, need);
+  Cand* cands = ugn_ptr<Cand>(workspace);
+  size_t smem = sizeof(Cand) * KNN_TQ * (kc + KNN_CB) + sizeof(float) * KNN_TK * (KNN_TQ + 4 + KNN_TG + 4) +
+                sizeof(int) * KNN_TQ + sizeof(float) * KNN_TQ;
+  UGN_CUDA(cudaFuncSetAttribute(knn_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  dim3 grid(ugn_cdiv(Q, KNN_TQ), chunks);
+  knn_scan_kernel<<<grid, 256, smem, st>>>(ugn_ptr<float>(queries), ugn_ptr<float>(gallery), ugn_ptr<float>(g2),
+                                           (int)Q, N, D, kc, rows, cands);
+  UGN_LAUNCHED(ctx);
+  knn_rerank_kernel<<<(int)Q, 256, 0, st>>>(ugn_ptr<float>(queries), ugn_ptr<float>(gallery),
+                                            ugn_ptr<int>(gallery_labels), cands, chunks * kc, kc, k, D,
+                                            idx_base, ugn_ptr<double>(out_d2), ugn_ptr<long long>(out_idx),
+                                            ugn_ptr<int>(out_lab));
+  UGN_LAUNCHED(ctx);
+  return UGN_OK;
+}
+
+extern "C" int ugn_knn_merge_vote(ugn_ctx* ctx, const ugn_tensor* d2, const ugn_tensor* idx,
+                                  const ugn_tensor* lab, int k, ugn_tensor* out_d2, ugn_tensor* out_idx,
+                                  ugn_tensor* out_lab, ugn_tensor* pred, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  UGN_CHECK(ctx && d2 && idx && lab && pred, "ugn_knn_merge_vote: null argument");
+  UGN_TENSOR(d2, DT_F64, 3, 3);
+  UGN_TENSOR(idx, DT_I64, 3, 3);
+  UGN_TENSOR(lab, DT_I32, 3, 3);
+  UGN_TENSOR(pred, DT_I32, 1, 1);
+  int G = (int)d2->shape[0];
+  long long Q = d2->shape[1];
+  UGN_CHECK(G >= 1 && G <= 16, "1..16 shards supported");
+  UGN_CHECK(d2->shape[2] == k && k <= KNN_MAXKC, "lists must be [G,Q,k]");
+  UGN_CHECK(ugn_numel(idx) == ugn_numel(d2) && ugn_numel(lab) == ugn_numel(d2) && pred->shape[0] == Q,
+            "merge_vote shape mismatch");
+  if (out_d2) UGN_TENSOR(out_d2, DT_F64, 2, 2);
+  if (out_idx) UGN_TENSOR(out_idx, DT_I64, 2, 2);
+  if (out_lab) UGN_TENSOR(out_lab, DT_I32, 2, 2);
+  if (Q == 0) return UGN_OK;
+  knn_merge_vote_kernel<<<ugn_cdiv(Q, 128), 128, 0, st>>>(
+      ugn_ptr<double>(d2), ugn_ptr<long long>(idx), ugn_ptr<int>(lab), G, (int)Q, k,
+      out_d2 ? ugn_ptr<double>(out_d2) : nullptr, out_idx ? ugn_ptr<long long>(out_idx) : nullptr,
+      out_lab ? ugn_ptr<int>(out_lab) : nullptr, ugn_ptr<int>(pred));
+  UGN_LAUNCHED(ctx);
+  return UGN_OK;
+}

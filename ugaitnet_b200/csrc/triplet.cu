@@ -1,0 +1,197 @@
+// Batch-all triplet loss, forward + analytic backward.
+// Replaces triplet_loss(margin)/batch_dist of the reference (nets/triplet_loss_all.py:8-77).
+//
+//   dist[n,a,b] = sqrt(max(|x_a|^2 + |x_b|^2 - 2 x_a.x_b, 0)), entries <= 0 forced to 0 with
+//                 zero gradient (:72-76)
+//   L_n = sum_{a, p: lab_p==lab_a (p==a included), q: lab_q!=lab_a} max(margin + (d_ap - d_aq), 0)
+//         / #{terms > 0}          (0 when no term is active, :55-59);   loss = mean_n L_n (:61)
+//
+// Mask semantics are implemented directly (any label multiset); on the balanced P x K batches the
+// reference's boolean_mask+reshape requires, both agree.
+// Backward (the active count is a constant under autodiff):
+//   dL/dd_ab = (+#{q active} if same(a,b) else -#{p active}) / (n_parts * c_n)
+//   dd_ab/dx_a = (x_a - x_b)/d_ab,  dd_ab/dx_b = -(x_a - x_b)/d_ab, both 0 where d_ab == 0.
+#include "simt.cuh"
+
+struct TripAcc {
+  double sum;
+  unsigned long long cnt;
+};
+
+__global__ void trip_diag_kernel(const float* __restrict__ G, float* __restrict__ x2, int B) {
+  int n = blockIdx.y;
+  int a = blockIdx.x * blockDim.x + threadIdx.x;
+  if (a < B) x2[(long long)n * B + a] = G[((long long)n * B + a) * B + a];
+}
+
+__global__ void trip_dist_kernel(float* __restrict__ G, const float* __restrict__ x2, int B) {
+  int n = blockIdx.z, a = blockIdx.y;
+  int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  long long o = ((long long)n * B + a) * B + b;
+  float d2 = x2[(long long)n * B + a] + x2[(long long)n * B + b] - 2.0f * G[o];
+  d2 = fmaxf(d2, 0.f);
+  G[o] = d2 > 0.f ? sqrtf(d2) : 0.f;
+}
+
+__global__ void __launch_bounds__(128) trip_hinge_kernel(const float* __restrict__ D,
+                                                         const int* __restrict__ labels,
+                                                         float* __restrict__ Wc, TripAcc* __restrict__ acc,
+                                                         int B, float margin) {
+  extern __shared__ float sm[];  // drow[B] | lab[B]
+  float* drow = sm;
+  int* lab = reinterpret_cast<int*>(sm + B);
+  const int a = blockIdx.x, n = blockIdx.y;
+  const float* Da = D + ((long long)n * B + a) * B;
+  for (int b = threadIdx.x; b < B; b += blockDim.x) {
+    drow[b] = Da[b];
+    lab[b] = labels[b];
+  }
+  __syncthreads();
+  const int la = lab[a];
+  double sum = 0.0;
+  unsigned long long cnt = 0;
+  for (int b = threadIdx.x; b < B; b += blockDim.x) {
+    const float db = drow[b];
+    int c_act = 0;
+    if (lab[b] == la) {
+      float s = 0.f;
+      for (int q = 0; q < B; ++q) {
+        if (lab[q] != la) {
+          float t = margin + (db - drow[q]);
+          if (t > 0.f) { s += t; ++c_act; }
+        }
+      }
+      sum += (double)s;
+      cnt += (unsigned long long)c_act;
+      Wc[((long long)n * B + a) * B + b] = (float)c_act;
+    } else {
+      for (int p = 0; p < B; ++p) {
+        if (lab[p] == la) {
+          float t = margin + (drow[p] - db);
+          if (t > 0.f) ++c_act;
+        }
+      }
+      Wc[((long long)n * B + a) * B + b] = -(float)c_act;
+    }
+  }
+  // block reduction (4 warps)
+  __shared__ double rs[4];
+  __shared__ unsigned long long rc[4];
+  sum = warp_sum_d(sum);
+  unsigned int lo = (unsigned int)cnt;  // per-thread counts fit 32 bits (<= B*B/128)
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) lo += __shfl_xor_sync(0xffffffffu, lo, o);
+  if ((threadIdx.x & 31) == 0) { rs[threadIdx.x >> 5] = sum; rc[threadIdx.x >> 5] = lo; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double s = rs[0] + rs[1] + rs[2] + rs[3];
+    unsigned long long c = rc[0] + rc[1] + rc[2] + rc[3];
+    if (c) {
+      atomicAdd(&acc[n].sum, s);
+      atomicAdd(&acc[n].cnt, c);
+    }
+  }
+}
+
+__global__ void trip_finalize_kernel(const TripAcc* __restrict__ acc, int nparts, float* __restrict__ out) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    double loss = 0.0, total = 0.0;
+    for (int n = 0; n < nparts; ++n) {
+      if (acc[n].cnt) loss += (double)((float)acc[n].sum / (float)acc[n].cnt);
+      total += (double)acc[n].cnt;
+    }
+    out[0] = (float)(loss / nparts);
+    out[1] = (float)total;
+  }
+}
+
+__global__ void __launch_bounds__(256) trip_bwd_kernel(const float* __restrict__ emb,
+                                                       const float* __restrict__ D,
+                                                       const float* __restrict__ Wc,
+                                                       const TripAcc* __restrict__ acc,
+                                                       float* __restrict__ demb, int nparts, int B, int d,
+                                                       float scale) {
+  extern __shared__ float coef[];  // [B]
+  const int a = blockIdx.x, n = blockIdx.y;
+  const long long base = (long long)n * B * B;
+  unsigned long long c = acc[n].cnt;
+  float s = c ? scale / ((float)nparts * (float)c) : 0.f;
+  for (int b = threadIdx.x; b < B; b += blockDim.x) {
+    float dab = D[base + (long long)a * B + b], dba = D[base + (long long)b * B + a];
+    float v = 0.f;
+    if (dab > 0.f) v += Wc[base + (long long)a * B + b] / dab;
+    if (dba > 0.f) v += Wc[base + (long long)b * B + a] / dba;
+    coef[b] = v;
+  }
+  __syncthreads();
+  const float* X = emb + (long long)n * B * d;
+  for (int j = threadIdx.x; j < d; j += blockDim.x) {
+    float xa = X[(long long)a * d + j], g = 0.f;
+    for (int b = 0; b < B; ++b) {
+      float cb = coef[b];
+      if (cb != 0.f) g = fmaf(cb, xa - X[(long long)b * d + j], g);
+    }
+    demb[((long long)n * B + a) * d + j] = s * g;
+  }
+}
+
+extern "C" int64_t ugn_triplet_workspace_bytes(int n, int B) {
+  int64_t accb = ((int64_t)n * sizeof(TripAcc) + 255) / 256 * 256;
+  int64_t x2b = ((int64_t)n * B * 4 + 255) / 256 * 256;
+  return accb + x2b + 2 * (int64_t)n * B * B * 4;
+}
+
+extern "C" int ugn_triplet_all(ugn_ctx* ctx, const ugn_tensor* emb, const ugn_tensor* labels,
+                               float margin, float scale, ugn_tensor* out, ugn_tensor* demb,
+                               ugn_tensor* workspace, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  UGN_CHECK(ctx && emb && labels && out && workspace, "ugn_triplet_all: null argument");
+  UGN_TENSOR(emb, DT_F32, 2, 3);
+  UGN_TENSOR(labels, DT_I32, 1, 2);
+  UGN_TENSOR(out, DT_F32, 1, 1);
+  UGN_TENSOR(workspace, DT_BAD, 1, 8);
+  int n = emb->ndim == 3 ? (int)emb->shape[0] : 1;
+  int B = (int)emb->shape[emb->ndim - 2], d = (int)emb->shape[emb->ndim - 1];
+  UGN_CHECK(ugn_numel(labels) == B, "labels must have B=%d entries", B);
+  UGN_CHECK(out->shape[0] >= 2, "out must be f32[2]");
+  UGN_CHECK(B <= 8192, "triplet batch too large");
+  int64_t need = ugn_triplet_workspace_bytes(n, B);
+  int64_t have = ugn_numel(workspace) * (workspace->dtype_bits / 8);
+  UGN_CHECK(have >= need, "triplet workspace too small: %lld < %lld", (long long)have, (long long)need);
+  if (demb) {
+    UGN_TENSOR(demb, DT_F32, 2, 3);
+    UGN_CHECK(ugn_numel(demb) == ugn_numel(emb), "demb shape mismatch");
+  }
+  char* ws = ugn_ptr<char>(workspace);
+  int64_t accb = ((int64_t)n * sizeof(TripAcc) + 255) / 256 * 256;
+  int64_t x2b = ((int64_t)n * B * 4 + 255) / 256 * 256;
+  TripAcc* acc = reinterpret_cast<TripAcc*>(ws);
+  float* x2 = reinterpret_cast<float*>(ws + accb);
+  float* D = reinterpret_cast<float*>(ws + accb + x2b);
+  float* Wc = D + (int64_t)n * B * B;
+  const float* X = ugn_ptr<float>(emb);
+  UGN_CUDA(cudaMemsetAsync(acc, 0, n * sizeof(TripAcc), st));
+
+  SGemm p;  // Gram: G[n] = X[n] X[n]^T  (fp32 FFMA; fp32-accurate Gram is required)
+  p.A = X; p.B = X; p.C = D;
+  p.M = B; p.N = B; p.K = d;
+  p.ar = radix1(d); p.ak = radix1(1); p.br = radix1(d); p.bk = radix1(1);
+  p.ldc = B;
+  p.batches = n; p.batch_a = (long long)B * d; p.batch_b = (long long)B * d; p.batch_c = (long long)B * B;
+  int rc = simt_gemm_launch(ctx, p, st);
+  if (rc != UGN_OK) return rc;
+  trip_diag_kernel<<<dim3(ugn_cdiv(B, 128), n), 128, 0, st>>>(D, x2, B);
+  UGN_LAUNCHED(ctx);
+  trip_dist_kernel<<<dim3(ugn_cdiv(B, 128), B, n), 128, 0, st>>>(D, x2, B);
+  UGN_LAUNCHED(ctx);
+  trip_hinge_kernel<<<dim3(B, n), 128, 2 * B * sizeof(float), st>>>(D, ugn_ptr<int>(labels), Wc, acc, B, margin);
+  UGN_LAUNCHED(ctx);
+  trip_finalize_kernel<<<1, 32, 0, st>>>(acc, n, ugn_ptr<float>(out));
+  UGN_LAUNCHED(ctx);
+  if (demb) {
+    trip_bwd_kernel<<<dim3(B, n), 256, B * sizeof(float), st>>>(X, D, Wc, acc, ugn_ptr<float>(demb), n, B, d, scale);
+    UGN_LAUNCHED(ctx);
+  }
+  return UGN_OK;
+}

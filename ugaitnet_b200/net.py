@@ -1,0 +1,501 @@
+"""UGaitNet step engine: host-side orchestration of the C-ABI kernels.
+
+One :class:`UGaitEngine` owns, for one GPU:
+  * a flat f32 parameter arena (+ gradient, Adam m/v arenas of the same layout) whose
+    segments are the trainable tensors of the reference graph
+    (/root/reference/nets/mj_uwyhNets_ba.py:67-107, :1163-1214),
+  * per-batch-size activation plans (all buffers preallocated, exported once via DLPack),
+  * the forward / backward / optimiser schedule of one training step, optionally captured
+    in a CUDA graph.
+
+PyTorch is used for memory, streams, RNG (dropout masks) and NCCL only; every arithmetic op
+of the step is a kernel of libugaitnet_b200.so.
+"""
+from __future__ import annotations
+
+import math
+from typing import Dict, List, Optional, Sequence
+
+import torch
+
+from . import ops
+from ._ffi import TRef, check, lib, ptr_array, stream_ptr
+from .config import ACT_LINEAR, BRANCH_NAMES, MERGE_AVG, NetConfig, round_up
+
+MATH_MODES = ("fp32", "bf16", "bf16x3")
+
+
+class _Seg:
+    __slots__ = ("name", "shape", "off", "n", "l2")
+
+    def __init__(self, name, shape, off, n, l2):
+        self.name, self.shape, self.off, self.n, self.l2 = name, shape, off, n, l2
+
+
+class UGaitEngine:
+    def __init__(self, cfg: NetConfig, device: Optional[int] = None, math_mode: str = "fp32",
+                 seed: int = 232323, optimizer: str = "adam", lr: float = 1e-4, momentum: float = 0.9,
+                 beta1: float = 0.9, beta2: float = 0.999, eps: float = 1e-7, process_group=None,
+                 use_graph: bool = False):
+        if not torch.cuda.is_available():
+            raise RuntimeError("ugaitnet_b200 needs a CUDA device (no CPU fallback)")
+        assert math_mode in MATH_MODES
+        self.cfg = cfg
+        self.dev = torch.device("cuda", torch.cuda.current_device() if device is None else device)
+        self.ctx = ops.get_ctx(self.dev.index)
+        self.math_mode = math_mode
+        self.P = {"fp32": 0, "bf16": 1, "bf16x3": 2}[math_mode]
+        self.pad = 32 if self.P else 1
+        self.optimizer, self.lr, self.momentum = optimizer.lower(), float(lr), momentum
+        self.beta1, self.beta2, self.eps = beta1, beta2, eps
+        self.pg = process_group
+        self.world = torch.distributed.get_world_size(process_group) if process_group is not None else 1
+        self.use_graph = use_graph
+        self.t = 0
+        self._plans: Dict[tuple, "_Plan"] = {}
+        self._graphs = {}
+        self._build_arena()
+        self.init_weights(seed)
+
+    # ------------------------------------------------------------------ parameters
+    def _build_arena(self):
+        cfg = self.cfg
+        segs: List[_Seg] = []
+        off = 0
+
+        def add(name, shape, l2=0.0):
+            nonlocal off
+            n = 1
+            for s in shape:
+                n *= s
+            segs.append(_Seg(name, tuple(shape), off, n, l2))
+            off += round_up(n, 64)
+
+        for m in range(cfg.nmods):
+            bn = BRANCH_NAMES[m]
+            for li, L in enumerate(cfg.layers(m, 1)):
+                add(f"{bn}/conv{li}/w", (L["co"], L["k"], L["k"], L["cin"]), cfg.weight_decay)
+                add(f"{bn}/conv{li}/b", (L["co"],))
+            add(f"{bn}/dense/w", (2 * cfg.nd, cfg.flat))
+            add(f"{bn}/dense/b", (2 * cfg.nd,))
+            add(f"{bn}/ofCode/w", (cfg.nd, 2 * cfg.nd), 1e-3)
+            add(f"{bn}/ofCode/b", (cfg.nd,))
+        feat = cfg.nd
+        if cfg.nc > 0:
+            add("code/w", (cfg.nc, cfg.nd))
+            add("code/b", (cfg.nc,))
+            feat = cfg.nc
+        if cfg.nclasses > 0:
+            add("classprob/w", (cfg.nclasses, feat))
+            add("classprob/b", (cfg.nclasses,))
+        self.segs = {s.name: s for s in segs}
+        self.seg_list = segs
+        self.n_arena = off
+        d = self.dev
+        self.w = torch.zeros(off, device=d)
+        self.g = torch.zeros(off, device=d)
+        self.m = torch.zeros(off, device=d)
+        self.v = torch.zeros(off, device=d)
+        self.seg_off = torch.tensor([s.off for s in segs] + [off], dtype=torch.int64, device=d)
+        self.seg_l2 = torch.tensor([s.l2 for s in segs], dtype=torch.float32, device=d)
+        self.reg_out = torch.zeros(1, device=d)
+        self.lr_dev = torch.zeros(1, device=d)
+        self._lr_host = torch.zeros(1).pin_memory()
+        self.R = {k: TRef(t) for k, t in dict(w=self.w, g=self.g, m=self.m, v=self.v, seg_off=self.seg_off,
+                                               seg_l2=self.seg_l2, reg_out=self.reg_out, lr_dev=self.lr_dev).items()}
+        self.pw: Dict[str, torch.Tensor] = {}   # master views
+        self.pg_: Dict[str, torch.Tensor] = {}  # gradient views
+        self.Rw: Dict[str, TRef] = {}
+        self.Rg: Dict[str, TRef] = {}
+        for s in segs:
+            self.pw[s.name] = self.w[s.off:s.off + s.n].view(s.shape)
+            self.pg_[s.name] = self.g[s.off:s.off + s.n].view(s.shape)
+            self.Rw[s.name] = TRef(self.pw[s.name])
+            self.Rg[s.name] = TRef(self.pg_[s.name])
+        # compute copies: conv / big dense weights, padded (+ bf16 planes in tensor-core mode)
+        self.cw: Dict[str, torch.Tensor] = {}
+        self.Rcw: Dict[str, TRef] = {}
+        for m in range(cfg.nmods):
+            bn = BRANCH_NAMES[m]
+            for li, L in enumerate(cfg.layers(m, self.pad)):
+                name = f"{bn}/conv{li}/w"
+                shape = (L["co"], L["k"], L["k"], L["cp"])
+                if self.P:
+                    self.cw[name] = torch.zeros((self.P,) + shape, dtype=torch.bfloat16, device=d)
+                elif L["cp"] != L["cin"]:
+                    self.cw[name] = torch.zeros(shape, device=d)
+                else:
+                    self.cw[name] = self.pw[name]
+            for nm in ("dense", "ofCode"):
+                name = f"{bn}/{nm}/w"
+                if self.P:
+                    self.cw[name] = torch.zeros((self.P,) + self.segs[name].shape, dtype=torch.bfloat16, device=d)
+                else:
+                    self.cw[name] = self.pw[name]
+        for k, t in self.cw.items():
+            self.Rcw[k] = TRef(t)
+
+    def repack_weights(self):
+        """master f32 -> padded / bf16 compute copies (after every optimiser step)."""
+        for name, t in self.cw.items():
+            if t.data_ptr() != self.pw[name].data_ptr():
+                check(lib.ugn_pack_weight(self.ctx.h, self.Rw[name].ptr, self.Rcw[name].ptr, stream_ptr()))
+
+    def init_weights(self, seed: int):
+        """Keras defaults: glorot_uniform kernels, zero biases, he_uniform for ofCode
+        (nets/mj_uwyhNets_ba.py:82-105)."""
+        g = torch.Generator(device="cpu").manual_seed(seed)
+        for s in self.seg_list:
+            if s.name.endswith("/b"):
+                self.pw[s.name].zero_()
+                continue
+            if len(s.shape) == 4:
+                co, kh, kw, cin = s.shape
+                fan_in, fan_out = cin * kh * kw, co * kh * kw
+            else:
+                fan_out, fan_in = s.shape
+            limit = math.sqrt(6.0 / fan_in) if s.name.endswith("ofCode/w") else math.sqrt(6.0 / (fan_in + fan_out))
+            vals = (torch.rand(s.shape, generator=g, dtype=torch.float32) * 2 - 1) * limit
+            self.pw[s.name].copy_(vals)
+        self.repack_weights()
+
+    def load_params(self, params: Dict[str, torch.Tensor]):
+        """params in the oracle / PyTorch layout: conv [Cout,Cin,kh,kw], dense [out,in]."""
+        for name, val in params.items():
+            s = self.segs[name]
+            v = val.detach().to(torch.float32)
+            if len(s.shape) == 4:
+                v = v.permute(0, 2, 3, 1)
+            self.pw[name].copy_(v.contiguous().to(self.dev))
+        self.repack_weights()
+
+    def _export(self, views) -> Dict[str, torch.Tensor]:
+        out = {}
+        for s in self.seg_list:
+            v = views[s.name].detach().clone()
+            if len(s.shape) == 4:
+                v = v.permute(0, 3, 1, 2).contiguous()
+            out[s.name] = v
+        return out
+
+    def export_params(self):
+        return self._export(self.pw)
+
+    def export_grads(self):
+        return self._export(self.pg_)
+
+    # ------------------------------------------------------------------ plans
+    def plan(self, B: int, train: bool) -> "_Plan":
+        key = (B, train)
+        p = self._plans.get(key)
+        if p is None:
+            p = self._plans[key] = _Plan(self, B, train)
+        return p
+
+    # ------------------------------------------------------------------ forward
+    def _forward(self, p: "_Plan", train: bool):
+        cfg, h, st = self.cfg, self.ctx.h, stream_ptr()
+        for m in range(cfg.nmods):
+            bn = BRANCH_NAMES[m]
+            b = p.br[m]
+            check(lib.ugn_pack_input(h, b.R["x_in"].ptr, b.R["a0"].ptr, st))
+            for li, L in enumerate(b.layers):
+                check(lib.ugn_conv2d_fwd(h, b.R[f"a{li}"].ptr, self.Rcw[f"{bn}/conv{li}/w"].ptr,
+                                         self.Rw[f"{bn}/conv{li}/b"].ptr, b.R[f"a{li + 1}"].ptr,
+                                         b.R[f"idx{li}"].ptr if L["pool"] else None, cfg.act, cfg.alpha,
+                                         int(L["pool"]), st))
+            nl = len(b.layers)
+            check(lib.ugn_flatten_chw(h, b.R[f"a{nl}"].ptr, b.R["flat"].ptr, st))
+            mask = b.R["mask"].ptr if (train and cfg.dropout > 0.001) else None
+            check(lib.ugn_linear_fwd(h, b.R["flat"].ptr, self.Rcw[f"{bn}/dense/w"].ptr, self.Rw[f"{bn}/dense/b"].ptr,
+                                     mask, b.R["h1"].ptr, b.R["h1_16"].ptr if self.P else None, ACT_LINEAR, 0.0, st))
+            check(lib.ugn_linear_fwd(h, (b.R["h1_16"] if self.P else b.R["h1"]).ptr, self.Rcw[f"{bn}/ofCode/w"].ptr,
+                                     self.Rw[f"{bn}/ofCode/b"].ptr, None, b.R["out"].ptr, None, ACT_LINEAR, 0.0, st))
+        if cfg.single:
+            sig = p.br[0].R["out"]
+        else:
+            check(lib.ugn_fuse_fwd(h, cfg.nmods, p.br_ptrs, p.flag_ptrs, p.R["sig"].ptr, None, p.R["winner"].ptr,
+                                   p.R["inv_norm"].ptr, cfg.merge, 1, st))
+            sig = p.R["sig"]
+        feat = sig
+        if cfg.nc > 0:
+            cmask = p.R["cmask"].ptr if (train and cfg.dropout > 0.001) else None
+            check(lib.ugn_linear_fwd(h, sig.ptr, self.Rw["code/w"].ptr, self.Rw["code/b"].ptr, None, p.R["code"].ptr,
+                                     None, cfg.act, cfg.alpha, st))
+            if cmask is not None:
+                torch.mul(p.code, p.cmask, out=p.dropcode)
+                feat = p.R["dropcode"]
+            else:
+                feat = p.R["code"]
+        if cfg.nclasses > 0:
+            check(lib.ugn_linear_fwd(h, feat.ptr, self.Rw["classprob/w"].ptr, self.Rw["classprob/b"].ptr, None,
+                                     p.R["logits"].ptr, None, ACT_LINEAR, 0.0, st))
+        return sig, feat
+
+    def _set_inputs(self, p, inputs, flags, labels=None, drop_masks=None, code_drop_mask=None):
+        cfg = self.cfg
+        for m in range(cfg.nmods):
+            p.br[m].x_in.copy_(inputs[m], non_blocking=True)
+            if not cfg.single:
+                p.flags[m].copy_(flags[m].reshape(-1, 1), non_blocking=True)
+            if p.train and cfg.dropout > 0.001:
+                if drop_masks is not None:
+                    p.br[m].mask.copy_(drop_masks[m])
+                else:
+                    keep = 1.0 - cfg.dropout
+                    p.br[m].mask.bernoulli_(keep).div_(keep)
+        if p.train and cfg.dropout > 0.001 and cfg.nc > 0:
+            if code_drop_mask is not None:
+                p.cmask.copy_(code_drop_mask)
+            else:
+                keep = 1.0 - cfg.dropout
+                p.cmask.bernoulli_(keep).div_(keep)
+        if labels is not None:
+            p.labels.copy_(labels.reshape(-1).to(torch.int32), non_blocking=True)
+
+    @torch.no_grad()
+    def predict(self, inputs: Sequence[torch.Tensor], flags: Optional[Sequence[torch.Tensor]] = None,
+                layer: str = "signature") -> torch.Tensor:
+        """model_code.predict of the reference test scripts
+        (mains/mj_testUWYHGaitNet_open_tum.py:139-148,192-198).  layer in
+        {signature, code, classprob(logits), flatten}."""
+        B = int(inputs[0].shape[0])
+        p = self.plan(B, False)
+        self._set_inputs(p, inputs, flags)
+        self._forward(p, False)
+        if layer == "signature":
+            return (p.br[0].out if self.cfg.single else p.sig).clone()
+        if layer == "code":
+            return p.code.clone()
+        if layer in ("classprob", "logits"):
+            return p.logits.clone()
+        raise KeyError(layer)
+
+    # ------------------------------------------------------------------ backward
+    def _losses_and_backward(self, p: "_Plan", sig: TRef, feat: TRef):
+        cfg, h, st = self.cfg, self.ctx.h, stream_ptr()
+        B = p.B
+        # triplet: demb = wver * dL/dsig
+        check(lib.ugn_triplet_all(h, sig.ptr, p.R["labels"].ptr, cfg.margin, cfg.wver, p.R["trip_out"].ptr,
+                                  p.R["dsig"].ptr, p.R["trip_ws"].ptr, st))
+        if cfg.nclasses > 0:
+            check(lib.ugn_softmax_ce(h, p.R["logits"].ptr, p.R["labels"].ptr, p.R["ce_out"].ptr, p.R["dlogits"].ptr,
+                                     cfg.wid, st))
+            check(lib.ugn_linear_bwd(h, feat.ptr, self.Rw["classprob/w"].ptr, p.R["dlogits"].ptr, p.R["dfeat"].ptr,
+                                     self.Rg["classprob/w"].ptr, self.Rg["classprob/b"].ptr, st))
+            dfeat = p.R["dfeat"]
+            if cfg.nc > 0:
+                # activity regulariser l2(1e-3) on "code": + 1e-3*sum(code^2)/B  (:1196)
+                use_mask = cfg.dropout > 0.001
+                check(lib.ugn_act_mask_bwd(h, dfeat.ptr, None, p.R["cmask"].ptr if use_mask else None,
+                                           p.R["dcode"].ptr, None, ACT_LINEAR, 0.0, st))
+                p.dcode.add_(p.code, alpha=2e-3 / B)
+                check(lib.ugn_act_mask_bwd(h, p.R["dcode"].ptr, p.R["code"].ptr, None, p.R["dcode_z"].ptr, None,
+                                           cfg.act, cfg.alpha, st))
+                check(lib.ugn_linear_bwd(h, sig.ptr, self.Rw["code/w"].ptr, p.R["dcode_z"].ptr, p.R["dsig2"].ptr,
+                                         self.Rg["code/w"].ptr, self.Rg["code/b"].ptr, st))
+                p.dsig.add_(p.dsig2)
+            else:
+                p.dsig.add_(p.dfeat)
+        if cfg.single:
+            p.br[0].dout.copy_(p.dsig)
+        else:
+            check(lib.ugn_fuse_bwd(h, cfg.nmods, p.R["dsig"].ptr, p.R["sig"].ptr, p.R["winner"].ptr,
+                                   p.R["inv_norm"].ptr, p.flag_ptrs, p.dbr_ptrs, cfg.merge, 1, st))
+        for m in range(cfg.nmods):
+            bn = BRANCH_NAMES[m]
+            b = p.br[m]
+            R = b.R
+            use_mask = cfg.dropout > 0.001
+            # ofCode
+            if self.P:
+                check(lib.ugn_act_mask_bwd(h, R["dout"].ptr, None, None, None, R["dout16"].ptr, ACT_LINEAR, 0.0, st))
+            check(lib.ugn_linear_bwd(h, (R["h1_16"] if self.P else R["h1"]).ptr, self.Rcw[f"{bn}/ofCode/w"].ptr,
+                                     (R["dout16"] if self.P else R["dout"]).ptr, R["dh1"].ptr,
+                                     self.Rg[f"{bn}/ofCode/w"].ptr, self.Rg[f"{bn}/ofCode/b"].ptr, st))
+            # dense (+dropout)
+            check(lib.ugn_act_mask_bwd(h, R["dh1"].ptr, None, R["mask"].ptr if use_mask else None,
+                                       None if self.P else R["dz1"].ptr, R["dz1_16"].ptr if self.P else None,
+                                       ACT_LINEAR, 0.0, st))
+            check(lib.ugn_linear_bwd(h, R["flat"].ptr, self.Rcw[f"{bn}/dense/w"].ptr,
+                                     (R["dz1_16"] if self.P else R["dz1"]).ptr, R["dflat"].ptr,
+                                     self.Rg[f"{bn}/dense/w"].ptr, self.Rg[f"{bn}/dense/b"].ptr, st))
+            nl = len(b.layers)
+            check(lib.ugn_unflatten_chw(h, R["dflat"].ptr, R[f"da{nl}"].ptr, st))
+            for li in range(nl - 1, -1, -1):
+                L = b.layers[li]
+                check(lib.ugn_conv2d_bwd_act(h, R[f"da{li + 1}"].ptr, R[f"a{li + 1}"].ptr,
+                                             R[f"idx{li}"].ptr if L["pool"] else None, R[f"dz{li}c"].ptr, cfg.act,
+                                             cfg.alpha, int(L["pool"]), st))
+                check(lib.ugn_conv2d_wgrad(h, R[f"a{li}"].ptr, R[f"dz{li}c"].ptr, self.Rg[f"{bn}/conv{li}/w"].ptr,
+                                           self.Rg[f"{bn}/conv{li}/b"].ptr, st))
+                if li > 0:
+                    check(lib.ugn_conv2d_dgrad(h, R[f"dz{li}c"].ptr, self.Rcw[f"{bn}/conv{li}/w"].ptr, R[f"da{li}"].ptr, st))
+
+    def _optim(self, gscale: float):
+        h, st, R = self.ctx.h, stream_ptr(), self.R
+        if self.optimizer == "adam":
+            check(lib.ugn_adam_step(h, R["w"].ptr, R["g"].ptr, R["m"].ptr, R["v"].ptr, R["seg_off"].ptr,
+                                    R["seg_l2"].ptr, 0.0, self.beta1, self.beta2, self.eps, gscale,
+                                    R["reg_out"].ptr, R["lr_dev"].ptr, st))
+        elif self.optimizer == "sgd":
+            check(lib.ugn_sgd_step(h, R["w"].ptr, R["g"].ptr, R["v"].ptr, R["seg_off"].ptr, R["seg_l2"].ptr, 0.0,
+                                   self.momentum, gscale, R["reg_out"].ptr, R["lr_dev"].ptr, st))
+        else:
+            raise ValueError(f"unknown optimizer {self.optimizer}")
+        self.repack_weights()
+
+    def _step_body(self, p: "_Plan", do_optim: bool):
+        sig, feat = self._forward(p, True)
+        self._losses_and_backward(p, sig, feat)
+        if do_optim:
+            if self.world > 1:
+                torch.distributed.all_reduce(self.g, group=self.pg)
+            self._optim(1.0 / self.world)
+
+    def _next_lr(self):
+        self.t += 1
+        if self.optimizer == "adam":
+            lr_t = self.lr * math.sqrt(1.0 - self.beta2 ** self.t) / (1.0 - self.beta1 ** self.t)
+        else:
+            lr_t = self.lr
+        self._lr_host[0] = lr_t
+        self.lr_dev.copy_(self._lr_host, non_blocking=True)
+
+    @torch.no_grad()
+    def loss_and_grad(self, inputs, flags, labels, drop_masks=None, code_drop_mask=None) -> Dict[str, torch.Tensor]:
+        """Forward + losses + full backward into the gradient arena, no optimiser step.
+        Gradients exclude the L2-regulariser terms (those are applied inside the optimiser
+        kernel, ugn_adam_step)."""
+        B = int(inputs[0].shape[0])
+        p = self.plan(B, True)
+        self._set_inputs(p, inputs, flags, labels, drop_masks, code_drop_mask)
+        self._step_body(p, False)
+        return self._report(p)
+
+    @torch.no_grad()
+    def train_step(self, inputs, flags, labels, drop_masks=None, code_drop_mask=None) -> Dict[str, torch.Tensor]:
+        """One Keras train_function step: fwd -> losses -> bwd -> (all-reduce) -> optimiser."""
+        B = int(inputs[0].shape[0])
+        p = self.plan(B, True)
+        self._set_inputs(p, inputs, flags, labels, drop_masks, code_drop_mask)
+        self._next_lr()
+        if self.use_graph and self.world == 1:
+            gkey = B
+            gr = self._graphs.get(gkey)
+            if gr is None:
+                # warm-up on a side stream (first-use allocations / attribute sets), then capture
+                s = torch.cuda.Stream()
+                s.wait_stream(torch.cuda.current_stream())
+                saved = (self.w.clone(), self.m.clone(), self.v.clone())
+                with torch.cuda.stream(s):
+                    self._step_body(p, True)
+                torch.cuda.current_stream().wait_stream(s)
+                torch.cuda.synchronize()
+                self.w.copy_(saved[0]); self.m.copy_(saved[1]); self.v.copy_(saved[2])
+                self.repack_weights()
+                gr = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(gr):
+                    self._step_body(p, True)
+                self._graphs[gkey] = gr
+                # the capture itself did not execute: fall through to replay
+            gr.replay()
+        else:
+            self._step_body(p, True)
+        return self._report(p, with_reg=True)
+
+    def _report(self, p: "_Plan", with_reg: bool = False) -> Dict[str, torch.Tensor]:
+        out = {"triplet": p.trip_out[0], "count": p.trip_out[1], "signature": p.br[0].out if self.cfg.single else p.sig}
+        if self.cfg.nclasses > 0:
+            out["ce"], out["acc"], out["logits"] = p.ce_out[0], p.ce_out[1], p.logits
+        if with_reg:
+            out["reg"] = self.reg_out[0]
+        return out
+
+    def launches_per_step(self) -> int:
+        return self.ctx.launches
+
+
+class _Branch:
+    pass
+
+
+class _Plan:
+    """All activation / gradient buffers of one batch size, exported once through DLPack."""
+
+    def __init__(self, eng: UGaitEngine, B: int, train: bool):
+        cfg, d, P = eng.cfg, eng.dev, eng.P
+        self.B, self.train = B, train
+        f32 = dict(device=d, dtype=torch.float32)
+
+        def act(shape):
+            if P:
+                return torch.zeros((P,) + tuple(shape), device=d, dtype=torch.bfloat16)
+            return torch.zeros(tuple(shape), **f32)
+
+        self.br: List[_Branch] = []
+        self.flags = [torch.ones(B, 1, **f32) for _ in range(cfg.nmods)]
+        for m in range(cfg.nmods):
+            b = _Branch()
+            b.layers = cfg.layers(m, eng.pad)
+            T = {}
+            L0 = b.layers[0]
+            b.x_in = T["x_in"] = torch.zeros(B, L0["cin"], cfg.hw, cfg.hw, **f32)
+            T["a0"] = act((B, L0["h"], L0["h"], L0["cp"]))
+            for li, L in enumerate(b.layers):
+                T[f"a{li + 1}"] = act((B, L["hp"], L["hp"], L["co"]))
+                if L["pool"]:
+                    T[f"idx{li}"] = torch.zeros(B, L["hp"], L["hp"], L["co"], device=d, dtype=torch.uint8)
+                if train:
+                    T[f"dz{li}c"] = act((B, L["ho"], L["ho"], L["co"]))
+                    T[f"da{li + 1}"] = torch.zeros(B, L["hp"], L["hp"], L["co"], **f32)
+            T["flat"] = act((B, cfg.flat))
+            b.h1 = T["h1"] = torch.zeros(B, 2 * cfg.nd, **f32)
+            if P:
+                T["h1_16"] = torch.zeros(P, B, 2 * cfg.nd, device=d, dtype=torch.bfloat16)
+            b.out = T["out"] = torch.zeros(B, cfg.nd, **f32)
+            if train:
+                b.mask = T["mask"] = torch.ones(B, 2 * cfg.nd, **f32)
+                b.dout = T["dout"] = torch.zeros(B, cfg.nd, **f32)
+                T["dh1"] = torch.zeros(B, 2 * cfg.nd, **f32)
+                T["dflat"] = torch.zeros(B, cfg.flat, **f32)
+                if P:
+                    T["dout16"] = torch.zeros(P, B, cfg.nd, device=d, dtype=torch.bfloat16)
+                    T["dz1_16"] = torch.zeros(P, B, 2 * cfg.nd, device=d, dtype=torch.bfloat16)
+                else:
+                    T["dz1"] = torch.zeros(B, 2 * cfg.nd, **f32)
+            b.T = T
+            b.R = {k: TRef(v) for k, v in T.items()}
+            self.br.append(b)
+        T = {}
+        self.sig = T["sig"] = torch.zeros(B, cfg.nd, **f32)
+        T["winner"] = torch.zeros(B, cfg.nd, device=d, dtype=torch.uint8)
+        T["inv_norm"] = torch.zeros(B, 2, **f32)
+        feat = cfg.nd
+        if cfg.nc > 0:
+            self.code = T["code"] = torch.zeros(B, cfg.nc, **f32)
+            self.dropcode = T["dropcode"] = torch.zeros(B, cfg.nc, **f32)
+            self.cmask = T["cmask"] = torch.ones(B, cfg.nc, **f32)
+            feat = cfg.nc
+        if cfg.nclasses > 0:
+            self.logits = T["logits"] = torch.zeros(B, cfg.nclasses, **f32)
+        if train:
+            self.labels = T["labels"] = torch.zeros(B, device=d, dtype=torch.int32)
+            self.trip_out = T["trip_out"] = torch.zeros(2, **f32)
+            self.dsig = T["dsig"] = torch.zeros(B, cfg.nd, **f32)
+            T["trip_ws"] = torch.zeros(ops.triplet_workspace_bytes(1, B) // 4 + 16, **f32)
+            if cfg.nclasses > 0:
+                self.ce_out = T["ce_out"] = torch.zeros(2, **f32)
+                T["dlogits"] = torch.zeros(B, cfg.nclasses, **f32)
+                self.dfeat = T["dfeat"] = torch.zeros(B, feat, **f32)
+            if cfg.nc > 0:
+                self.dcode = T["dcode"] = torch.zeros(B, cfg.nc, **f32)
+                T["dcode_z"] = torch.zeros(B, cfg.nc, **f32)
+                self.dsig2 = T["dsig2"] = torch.zeros(B, cfg.nd, **f32)
+        self.T = T
+        self.R = {k: TRef(v) for k, v in T.items()}
+        self.R_flags = [TRef(f) for f in self.flags]
+        self.br_ptrs = ptr_array([b.R["out"] for b in self.br])
+        self.flag_ptrs = ptr_array(self.R_flags)
+        if train:
+            self.dbr_ptrs = ptr_array([b.R["dout"] for b in self.br])
