@@ -1,0 +1,379 @@
+#!/usr/bin/env python
+"""Benchmark of the UGaitNet hot path (BASELINE.json metric / configs[1]).
+
+    python bench.py --gpus N --steps K --warmup W [--impl reference] [--mode bf16|bf16x3|fp32]
+
+A "step" is one Keras train_function step of the 3-modality (OF+gray+depth) TUM-GAID-shaped model
+(nd=2048, 150 classes, sign_max fusion, dropout 0.4, Adam) on one batch of bs=24 literal sequences
+expanded x4 by the reference's missing-modality generator = 96 rows per GPU (weak scaling, batch
+data-parallel, gradient all-reduce over NCCL).  One JSON line is printed by rank 0.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import math
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+BS_LITERAL, EXPAND = 24, 4
+ND, NCLASSES = 2048, 150
+FLOP_FWD_ROW = {"of": 2.0214e9 + 0.0545e9, "c25": 1.3356e9 + 0.0545e9}
+TRAIN_FLOP_ROW = 11.83e9                                                  # 3-mod fwd+dgrad+wgrad
+
+
+def peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            p = json.load(f)
+        return dict(hbm=p["hbm_gbs"], tf_burst=p["bf16_tflops"], tf_sust=p["bf16_tflops_sustained"], src="measured")
+    except Exception:
+        return dict(hbm=6650.0, tf_burst=1590.0, tf_sust=1400.0, src="fallback")
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.stop_flag, self.rows = index, False, []
+
+    def run(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-i",
+                                      str(self.index)], capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([c.strip() for c in out.split(",")])
+            except Exception:
+                pass
+            time.sleep(0.2)
+
+    def summary(self):
+        if not self.rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unsampled"]}
+        sm = sorted(int(r[0]) for r in self.rows if r[0].isdigit())
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(len(r) > 2 + i and r[2 + i].lower().startswith("active") for r in self.rows)]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None,
+                "sm_max_mhz": int(self.rows[0][1]) if self.rows[0][1].isdigit() else None, "reasons": reasons}
+
+
+def make_batch(seed):
+    """Synthetic cfg2 batch: host numpy arrays in the reference generator's layout."""
+    from oracle.ugait_oracle import NetConfig as OC, synth_batch
+    oc = OC(in_channels=(50, 25, 25), nd=ND, nclasses=NCLASSES)
+    xs, fl, lab = synth_batch(oc, base_rows=BS_LITERAL, expand=EXPAND, seed=seed)
+    return xs, fl, lab
+
+
+def engine_cfg():
+    from ugaitnet_b200.config import MERGE_SIGNMAX, NetConfig
+    return NetConfig(in_channels=(50, 25, 25), nd=ND, nc=0, nclasses=NCLASSES, weight_decay=5e-5,
+                     merge=MERGE_SIGNMAX, margin=0.2, wver=1.0, wid=0.1, dropout=0.4)
+
+
+# ------------------------------------------------------------------------------------------
+def run_reference(args, rank, world):
+    """Reference arm: the reference's CPU implementation of the path on the host cores.  TensorFlow is
+    not installable (no network), so this is the oracle port (PyTorch-CPU fp32 restatement of the same
+    graph, oneDNN, all host threads) -- the one other place bench.py may execute oracle/."""
+    if rank != 0:
+        return
+    from oracle import ugait_oracle as O
+    torch.set_num_threads(os.cpu_count() or 1)
+    oc = O.NetConfig(in_channels=(50, 25, 25), nd=ND, nclasses=NCLASSES, merge=O.MERGE_SIGNMAX, wver=1.0, wid=0.1)
+    rows = 24          # bounded sample: 24 of the 96 rows of one step (6 sequences x 4 variants)
+    xs, fl, lab = O.synth_batch(oc, base_rows=rows // EXPAND, expand=EXPAND, seed=232323)
+    xs = [torch.tensor(x) for x in xs]
+    fl = [torch.tensor(f) for f in fl]
+    lab = torch.tensor(lab)
+    P = O.init_params(oc, seed=1)
+    M = {k: torch.zeros_like(v) for k, v in P.items()}
+    V = {k: torch.zeros_like(v) for k, v in P.items()}
+    keep = 0.6
+    g = torch.Generator().manual_seed(0)
+
+    def step(t):
+        masks = [(torch.rand(rows, 2 * ND, generator=g) < keep).float() / keep for _ in range(3)]
+        _, G = O.loss_and_grads(xs, fl, lab, P, oc, masks, None)
+        O.adam_step(P, G, M, V, t, lr=1e-4)
+
+    for t in range(1, args.warmup + 1):
+        step(t)
+    t0 = time.perf_counter()
+    for t in range(args.steps):
+        step(args.warmup + t + 1)
+    dt = (time.perf_counter() - t0) / args.steps
+    val = rows / dt
+    line = {"metric": "train rows/s (3-mod fwd+bwd+triplet+CE+Adam)", "value": val, "unit": "rows/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "impl": "reference",
+            "config": workload_config(world),
+            "cpu_baseline": {"value": val, "unit": "rows/s", "cores": torch.get_num_threads(), "kind": "port",
+                             "sample": f"{rows} of the 96 rows of one cfg2 step per CPU step, {args.steps} steps"},
+            "e2e": {"value": val, "unit": "rows/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(world):
+    return {"workload": "cfg2: UGaitNet 3-modality (gray+OF+depth) TUM-GAID shape, missing-modality masking, "
+                        "mergefun=sign_max, nd=2048, nclasses=150, bs=24 literal x expand 4 = 96 rows per GPU",
+            "rows_per_gpu": BS_LITERAL * EXPAND, "literal_bs_per_gpu": BS_LITERAL, "parallelism": f"dp{world}",
+            "l2": "working set (358 MB weights + 1.4 GB Adam state + activations) exceeds the 126 MB L2"}
+
+
+# ------------------------------------------------------------------------------------------
+def cpu_baseline_leg():
+    """Oracle port (PyTorch-CPU fp32) timed on the host cores on a bounded sample of the same step."""
+    from oracle import ugait_oracle as O
+    torch.set_num_threads(os.cpu_count() or 1)
+    oc = O.NetConfig(in_channels=(50, 25, 25), nd=ND, nclasses=NCLASSES, merge=O.MERGE_SIGNMAX, wver=1.0, wid=0.1)
+    rows = 24
+    xs, fl, lab = O.synth_batch(oc, base_rows=rows // EXPAND, expand=EXPAND, seed=232323)
+    xs = [torch.tensor(x) for x in xs]
+    fl = [torch.tensor(f) for f in fl]
+    lab = torch.tensor(lab)
+    P = O.init_params(oc, seed=1)
+    M = {k: torch.zeros_like(v) for k, v in P.items()}
+    V = {k: torch.zeros_like(v) for k, v in P.items()}
+    times = []
+    for t in range(1, 4):
+        t0 = time.perf_counter()
+        _, G = O.loss_and_grads(xs, fl, lab, P, oc)
+        O.adam_step(P, G, M, V, t, lr=1e-4)
+        times.append(time.perf_counter() - t0)
+    dt = min(times[1:])
+    return {"value": rows / dt, "unit": "rows/s", "cores": torch.get_num_threads(), "kind": "port",
+            "sample": f"PyTorch-CPU fp32 restatement (TensorFlow unavailable), {rows} of 96 rows/step, best of 2 after 1 warm-up"}
+
+
+class OpTimer:
+    """CUDA-event timing of every C-ABI call of a profiling pass (same stream as the launches)."""
+
+    def __init__(self):
+        self.records = []
+
+    def install(self):
+        from ugaitnet_b200 import _ffi
+        self._orig = {}
+        for name in _ffi.EXPORTED_SYMBOLS:
+            fn = getattr(_ffi.lib, name)
+            if fn.restype is not ctypes_int() or name in ("ugn_abi_version", "ugn_ctx_create", "ugn_ctx_destroy",
+                                                          "ugn_ctx_check", "ugn_ctx_has_tcgen05"):
+                continue
+            self._orig[name] = fn
+            setattr(_ffi.lib, name, self._wrap(name, fn))
+
+    def _wrap(self, name, fn):
+        def call(*a):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            rc = fn(*a)
+            e1.record()
+            self.records.append((name, a, e0, e1))
+            return rc
+        return call
+
+    def uninstall(self):
+        from ugaitnet_b200 import _ffi
+        for name, fn in self._orig.items():
+            setattr(_ffi.lib, name, fn)
+
+
+def ctypes_int():
+    import ctypes
+    return ctypes.c_int
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours")
+    ap.add_argument("--mode", default=os.environ.get("UGN_BENCH_MODE", "bf16x3"))
+    ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--no-knn", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    torch.cuda.set_device(local)
+    pg = None
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        torch.distributed.init_process_group("nccl", device_id=torch.device("cuda", local))
+        pg = torch.distributed.group.WORLD
+
+    from ugaitnet_b200.net import UGaitEngine
+    eng = UGaitEngine(engine_cfg(), device=local, math_mode=args.mode, lr=1e-4, process_group=pg,
+                      use_graph=(not args.no_graph and world == 1))
+    xs, fl, lab = make_batch(232323 + rank)
+    B = xs[0].shape[0]
+    # host copies in pinned memory (e2e leg) and device-resident copies (value leg)
+    hx = [torch.from_numpy(np.ascontiguousarray(x)).pin_memory() for x in xs]
+    hf = [torch.from_numpy(np.ascontiguousarray(f)).pin_memory() for f in fl]
+    hl = torch.from_numpy(np.ascontiguousarray(lab.reshape(-1).astype(np.int32))).pin_memory()
+    dx = [t.cuda(non_blocking=True) for t in hx]
+    df = [t.cuda(non_blocking=True) for t in hf]
+    dl = hl.cuda(non_blocking=True)
+    h2d = sum(t.numel() * t.element_size() for t in hx + hf) + hl.numel() * 4
+
+    def barrier():
+        if world > 1:
+            torch.distributed.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], device="cuda")
+            torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+            ms = float(t)
+        return ms / steps
+
+    step_dev = lambda: eng.train_step(dx, df, dl)
+    loss_host = torch.zeros(3).pin_memory()
+
+    def step_e2e():
+        out = eng.train_step(hx, hf, hl)          # H2D copies of this step's inputs happen inside
+        loss_host[0].copy_(out["triplet"], non_blocking=True)
+        loss_host[1].copy_(out["ce"], non_blocking=True)
+        loss_host[2].copy_(out["reg"], non_blocking=True)
+        torch.cuda.current_stream().synchronize()  # the user reads the loss every step
+
+    for _ in range(args.warmup):
+        step_dev()
+    l0 = eng.ctx.launches
+    sampler = ClockSampler(local)
+    sampler.start()
+    ms = timed(step_dev, args.steps)
+    sampler.stop_flag = True
+    launches = eng.ctx.launches - l0
+    if eng.use_graph:
+        launches = eng.graph_launches * args.steps
+    for _ in range(2):
+        step_e2e()
+    ms_e2e = timed(step_e2e, args.steps)
+    eng.ctx.check()
+    rows_total = B * world
+    value = rows_total / (ms * 1e-3)
+    e2e = rows_total / (ms_e2e * 1e-3)
+
+    line = {"metric": "train rows/s (3-mod fwd+bwd+triplet+CE+Adam)", "value": value, "unit": "rows/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": {"fp32": "f32", "bf16": "bf16", "bf16x3": "bf16 (3-pass hi/lo split, fp32 accumulate)"}[args.mode],
+            "data": "synthetic", "config": workload_config(world),
+            "literal_seq_per_s": value / EXPAND,
+            "e2e": {"value": e2e, "unit": "rows/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 12,
+                    "ms_per_step": ms_e2e},
+            "gpu_launches": int(launches), "clocks": sampler.summary(),
+            "model_tflops": TRAIN_FLOP_ROW * rows_total / (ms * 1e-3) / 1e12}
+
+    if rank == 0:
+        # ---- per-op profile pass (eager, CUDA events on the launch stream) -> dominant kernel roofline
+        pk = peaks()
+        eager = UGaitEngine(engine_cfg(), device=local, math_mode=args.mode, lr=1e-4, use_graph=False) if eng.use_graph else eng
+        if eager is not eng:
+            eager.w.copy_(eng.w)
+            eager.repack_weights()
+        for _ in range(2):
+            eager.train_step(dx, df, dl) if world == 1 else None
+        if world == 1:
+            tm = OpTimer()
+            tm.install()
+            nprof = 3
+            for _ in range(nprof):
+                eager.train_step(dx, df, dl)
+            torch.cuda.synchronize()
+            tm.uninstall()
+            agg = {}
+            for name, a, e0, e1 in tm.records:
+                agg.setdefault(name, []).append(e0.elapsed_time(e1))
+            per_step = {k: sum(v) / nprof for k, v in agg.items()}
+            total = sum(per_step.values())
+            line["op_ms_per_step"] = {k: round(v, 4) for k, v in sorted(per_step.items(), key=lambda kv: -kv[1])}
+            conv_ops = ("ugn_conv2d_fwd", "ugn_conv2d_dgrad", "ugn_conv2d_wgrad")
+            conv_ms = sum(per_step.get(k, 0.0) for k in conv_ops)
+            # algorithmic conv FLOPs of one step: fwd + wgrad over all layers, dgrad without conv1
+            conv_fwd_row = 2.0214e9 + 2 * 1.3356e9
+            conv_flops = (3 * conv_fwd_row - (1.3717e9 + 2 * 0.6858e9)) * B
+            passes = {"fp32": 1, "bf16": 1, "bf16x3": 3}[args.mode]
+            ach = conv_flops / (conv_ms * 1e-3) / 1e12
+            line["roofline"] = {"bound": "tensor", "kernel": "tc_kernel<MODE_CONV|MODE_WGRAD> (conv fwd+dgrad+wgrad)",
+                                "achieved": ach, "peak": pk["tf_sust"], "unit": "TFLOP/s", "frac": ach / pk["tf_sust"],
+                                "traffic": None, "share_of_step": conv_ms / total if total else None,
+                                "mma_passes": passes, "issued_frac": ach * passes / pk["tf_sust"],
+                                "peak_source": pk["src"] + " bf16 sustained"}
+            line["cpu_baseline"] = cpu_baseline_leg()
+            if not args.no_knn:
+                line["knn"] = knn_leg(pk)
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        torch.distributed.destroy_process_group()
+
+
+def knn_leg(pk):
+    """k=3 queries/s over a synthetic gallery (cfg5 shape scaled to one GPU)."""
+    from ugaitnet_b200.knn import KNeighborsClassifier
+    rng = np.random.default_rng(5)
+    N, D, Q, k = 200_000, 256, 256, 3
+    cent = rng.normal(size=(155, D)).astype(np.float32)
+    lab = rng.integers(0, 155, N).astype(np.int32)
+    G = cent[lab] + 0.35 * rng.normal(size=(N, D)).astype(np.float32)
+    G /= np.linalg.norm(G, axis=1, keepdims=True)
+    Qm = G[rng.integers(0, N, Q)] + 0.05 * rng.normal(size=(Q, D)).astype(np.float32)
+    clf = KNeighborsClassifier(n_neighbors=k).fit(G, lab)
+    qd = torch.from_numpy(Qm).cuda()
+    clf.predict_device(qd)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(5):
+        pred = clf.predict_device(qd)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / 5
+    out = {"queries_per_s": Q / (ms * 1e-3), "ms": ms, "N": N, "D": D, "Q": Q, "k": k}
+    try:
+        from sklearn.neighbors import KNeighborsClassifier as SK
+        sk = SK(n_neighbors=k).fit(G, lab)
+        t0 = time.perf_counter()
+        sp = sk.predict(Qm)
+        dt = time.perf_counter() - t0
+        out["cpu_sklearn_queries_per_s"] = Q / dt
+        out["labels_equal_sklearn"] = bool((sp == pred.cpu().numpy()).all())
+    except Exception as e:  # pragma: no cover
+        out["cpu_sklearn_error"] = str(e)
+    return out
+
+
+if __name__ == "__main__":
+    main()

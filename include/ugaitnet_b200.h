@@ -77,6 +77,8 @@ int ugn_abi_version(void);
 const char* ugn_last_error(void);
 int ugn_ctx_create(int device, ugn_ctx** out);
 int ugn_ctx_destroy(ugn_ctx* ctx);
+/* cudaDeviceSynchronize + report of asynchronous kernel-side failures (tests / debugging). */
+int ugn_ctx_check(ugn_ctx* ctx);
 /* 1 if the device is compute capability 10.x (tcgen05/TMEM/TMA path usable). */
 int ugn_ctx_has_tcgen05(ugn_ctx* ctx);
 

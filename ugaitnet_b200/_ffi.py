@@ -41,6 +41,7 @@ _PROTOS = {
     "ugn_last_error": (c_char_p, []),
     "ugn_ctx_create": (c_int, [c_int, POINTER(c_void_p)]),
     "ugn_ctx_destroy": (c_int, [c_void_p]),
+    "ugn_ctx_check": (c_int, [c_void_p]),
     "ugn_ctx_has_tcgen05": (c_int, [c_void_p]),
     "ugn_launch_count": (c_int64, [c_void_p]),
     "ugn_pack_input": (c_int, [c_void_p, _T, _T, c_void_p]),
@@ -140,6 +141,10 @@ class Ctx:
                 self.h = None
         except Exception:
             pass
+
+    def check(self):
+        """Synchronise and raise if any kernel reported an asynchronous failure."""
+        check(lib.ugn_ctx_check(self.h))
 
     @property
     def launches(self) -> int:

@@ -59,7 +59,22 @@ extern "C" int ugn_ctx_create(int device, ugn_ctx** out) {
   return UGN_OK;
 }
 extern "C" int ugn_ctx_destroy(ugn_ctx* ctx) {
+  if (ctx && ctx->err_flag) cudaFree(ctx->err_flag);
   delete ctx;
+  return UGN_OK;
+}
+// Synchronises the device and reports asynchronous kernel-side failures.
+extern "C" int ugn_ctx_check(ugn_ctx* ctx) {
+  UGN_CHECK(ctx, "ugn_ctx_check: null ctx");
+  UGN_CUDA(cudaDeviceSynchronize());
+  if (ctx->err_flag) {
+    int flag = 0;
+    UGN_CUDA(cudaMemcpy(&flag, ctx->err_flag, sizeof(int), cudaMemcpyDeviceToHost));
+    if (flag) {
+      UGN_CUDA(cudaMemset(ctx->err_flag, 0, sizeof(int)));
+      UGN_FAIL(UGN_ERR_CUDA, "tensor-core kernel pipeline timeout (role %d: 1=TMA producer, 2=MMA issuer, 3=epilogue)", flag);
+    }
+  }
   return UGN_OK;
 }
 extern "C" int ugn_ctx_has_tcgen05(ugn_ctx* ctx) { return ctx && ctx->cc_major == 10; }

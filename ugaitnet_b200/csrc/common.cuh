@@ -22,6 +22,8 @@ struct ugn_ctx {
   long long launches = 0;
   // driver entry point for TMA descriptor encoding (resolved lazily; no libcuda link)
   void* encode_tiled = nullptr;
+  // device flag set by a tensor-core kernel whose mbarrier wait timed out (protocol bug guard)
+  int* err_flag = nullptr;
 };
 
 void ugn_set_error(const char* fmt, ...);

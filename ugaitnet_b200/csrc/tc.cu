@@ -1,8 +1,577 @@
+// Tensor-core path: ONE warp-specialised tcgen05 kernel (TMA producer warp -> smem ring ->
+// single-thread tcgen05.mma issue into TMEM -> 4 epilogue warps via tcgen05.ld) specialised by
+// MODE for
+//   MODE_GEMM  : C[M,N] (+)= A.B^T, operands K-major or MN-major (dense layers, Gram/distance GEMMs)
+//   MODE_CONV  : implicit-GEMM convolution over NHWC activations; the A tile of every filter tap is a
+//                shifted TMA box of the activation tensor (no im2col buffer).  sgn=+1 forward
+//                (bias+act[+2x2 max-pool+argmax] epilogue), sgn=-1 input gradient.
+//   MODE_WGRAD : kernel gradient; K = output pixels, both operands MN-major straight from NHWC,
+//                split-K over pixel boxes with fp32 red.add.
+// Operands are bf16 with P planes (P=2: hi/lo split -> hi*hi + hi*lo + lo*hi, ~fp32 products).
+// Replaces the Conv2D / Dense layers of UWYHNet.buildBranch (nets/mj_uwyhNets_ba.py:82-105).
 #include "tc.cuh"
-#define TC_TODO(name) UGN_FAIL(UGN_ERR_UNSUPPORTED, name ": tensor-core path not built yet")
-int tc_gemm(ugn_ctx*, int, int, int, int, const __nv_bfloat16*, int, const __nv_bfloat16*, int, float*, int, cudaStream_t) { TC_TODO("tc_gemm"); }
-int tc_conv_fwd(ugn_ctx*, const ConvGeom&, int, const __nv_bfloat16*, const __nv_bfloat16*, const float*, __nv_bfloat16*, uint8_t*, int, float, int, cudaStream_t) { TC_TODO("tc_conv_fwd"); }
-int tc_conv_dgrad(ugn_ctx*, const ConvGeom&, int, const __nv_bfloat16*, const __nv_bfloat16*, float*, cudaStream_t) { TC_TODO("tc_conv_dgrad"); }
-int tc_conv_wgrad(ugn_ctx*, const ConvGeom&, int, const __nv_bfloat16*, const __nv_bfloat16*, float*, float*, cudaStream_t) { TC_TODO("tc_conv_wgrad"); }
-int tc_linear_fwd(ugn_ctx*, int, int, int, int, const __nv_bfloat16*, const __nv_bfloat16*, const float*, const float*, float*, int, float, cudaStream_t) { TC_TODO("tc_linear_fwd"); }
-int tc_linear_bwd(ugn_ctx*, int, int, int, int, const __nv_bfloat16*, const __nv_bfloat16*, const __nv_bfloat16*, float*, float*, float*, cudaStream_t) { TC_TODO("tc_linear_bwd"); }
+#include "tc_ptx.cuh"
+#include <algorithm>
+
+using namespace tc;
+
+enum { MODE_GEMM = 0, MODE_CONV = 1, MODE_WGRAD = 2 };
+enum { EPI_F32 = 0, EPI_F32_ATOMIC = 1, EPI_BF16_ACT = 2, EPI_BF16_POOL = 3 };
+
+struct alignas(64) TcOp {
+  CUtensorMap map;
+  int major;        // 0 K-major, 1 MN-major
+  int rowbytes;     // swizzle span == inner box bytes: 128 | 64
+  int nbox;         // TMA boxes per plane per stage
+  int box_bytes;
+  int plane_bytes;  // 1024-aligned
+  int lbo, sbo, kadv;
+};
+
+struct TcParams {
+  TcOp a, b;
+  int mode, epi;
+  int M, N, block_n;
+  int ksteps_total, ksplit, kslices, planes, stages;
+  // conv
+  int bw, bh, bn, ntx, nty, KW, ncc, sgn, Wout, Hout, Bn, Cout;
+  int Hp, Wp;
+  // wgrad
+  int nbx, nby, nch, cw, ntaps, Cin, Co;
+  // epilogue
+  float* out_f32;
+  __nv_bfloat16* out_bf16;
+  long long out_plane;  // elements between bf16 planes
+  uint8_t* pool_idx;
+  const float* bias;
+  const float* mask;
+  int ldc, act;
+  float alpha;
+  int* err;
+};
+
+static constexpr int kThreads = 192;
+static constexpr int kTmemCols = 256;
+
+__device__ __forceinline__ void epi_barrier() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+
+template <int MODE>
+__global__ void __launch_bounds__(kThreads, 1) tc_kernel(const __grid_constant__ TcParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  // carve: [stages x (A planes | B planes)] | barriers | tmem ptr
+  const uint32_t a_stage = p.planes * p.a.plane_bytes, b_stage = p.planes * p.b.plane_bytes;
+  const uint32_t stage_bytes = a_stage + b_stage;
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + (size_t)p.stages * stage_bytes);
+  uint64_t* empty = full + p.stages;
+  uint64_t* tmem_full = empty + p.stages;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_full + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int tile_m = blockIdx.x, tile_n = blockIdx.y;
+
+  // K range of this CTA
+  int per = (p.ksteps_total + p.ksplit - 1) / p.ksplit;
+  int ks_beg = blockIdx.z * per, ks_end = min(p.ksteps_total, ks_beg + per);
+  int nsteps = ks_end - ks_beg;
+  if (nsteps <= 0) return;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < p.stages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    mbar_init(tmem_full, 1);
+    fence_mbar_init();
+    prefetch_tmap(&p.a.map);
+    prefetch_tmap(&p.b.map);
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_ptr, kTmemCols);
+    tmem_relinquish();
+  }
+  fence_before_sync();
+  __syncthreads();
+  fence_after_sync();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  // tile origin
+  int m0 = tile_m * 128, n0 = tile_n * p.block_n;
+  int x0 = 0, y0 = 0, nn0 = 0;
+  if (MODE == MODE_CONV) {
+    int tx = tile_m % p.ntx, ty = (tile_m / p.ntx) % p.nty, tn = tile_m / (p.ntx * p.nty);
+    x0 = tx * p.bw; y0 = ty * p.bh; nn0 = tn * p.bn;
+  }
+  const int BK = p.kslices * 16;
+  const int cwA = p.a.rowbytes >> 1, cwB = p.b.rowbytes >> 1;
+
+  if (warp == 0 && lane == 0) {
+    // ===================== TMA producer =====================
+    int nb_b = p.b.nbox;
+    if (MODE == MODE_WGRAD) {
+      int remain = p.nch * p.ntaps - tile_n * p.b.nbox;
+      nb_b = min(nb_b, remain);
+    }
+    const uint32_t tx_bytes = p.planes * (p.a.nbox * p.a.box_bytes + nb_b * p.b.box_bytes);
+    for (int it = 0; it < nsteps; ++it) {
+      const int s = it % p.stages, ph = (it / p.stages) & 1;
+      if (!mbar_wait(&empty[s], ph ^ 1, p.err, 1)) break;
+      mbar_expect_tx(&full[s], tx_bytes);
+      const int ks = ks_beg + it;
+      uint8_t* sa = smem + (size_t)s * stage_bytes;
+      uint8_t* sb = sa + a_stage;
+      for (int pl = 0; pl < p.planes; ++pl) {
+        if (MODE == MODE_GEMM) {
+          for (int j = 0; j < p.a.nbox; ++j) {
+            if (p.a.major == 0) tma_load_5d(&p.a.map, &full[s], sa + pl * p.a.plane_bytes, ks * BK, m0, pl, 0, 0);
+            else tma_load_5d(&p.a.map, &full[s], sa + pl * p.a.plane_bytes + j * p.a.box_bytes, m0 + j * cwA, ks * BK, pl, 0, 0);
+          }
+          for (int j = 0; j < p.b.nbox; ++j) {
+            if (p.b.major == 0) tma_load_5d(&p.b.map, &full[s], sb + pl * p.b.plane_bytes, ks * BK, n0, pl, 0, 0);
+            else tma_load_5d(&p.b.map, &full[s], sb + pl * p.b.plane_bytes + j * p.b.box_bytes, n0 + j * cwB, ks * BK, pl, 0, 0);
+          }
+        } else if (MODE == MODE_CONV) {
+          const int cc = ks % p.ncc, tap = ks / p.ncc, kw = tap % p.KW, kh = tap / p.KW;
+          tma_load_5d(&p.a.map, &full[s], sa + pl * p.a.plane_bytes, cc * BK, x0 + p.sgn * kw, y0 + p.sgn * kh, nn0, pl);
+          for (int j = 0; j < p.b.nbox; ++j) {
+            if (p.b.major == 0) tma_load_5d(&p.b.map, &full[s], sb + pl * p.b.plane_bytes, cc * BK, tap, n0, pl, 0);
+            else tma_load_5d(&p.b.map, &full[s], sb + pl * p.b.plane_bytes + j * p.b.box_bytes, n0 + j * cwB, tap, cc * BK, pl, 0);
+          }
+        } else {
+          const int bx = ks % p.nbx, by = (ks / p.nbx) % p.nby, bb = ks / (p.nbx * p.nby);
+          const int px = bx * p.bw, py = by * p.bh, pn = bb * p.bn;
+          for (int j = 0; j < p.a.nbox; ++j)
+            tma_load_5d(&p.a.map, &full[s], sa + pl * p.a.plane_bytes + j * p.a.box_bytes, m0 + j * cwA, px, py, pn, pl);
+          for (int j = 0; j < nb_b; ++j) {
+            const int gb = tile_n * p.b.nbox + j, chunk = gb % p.nch, tap = gb / p.nch;
+            tma_load_5d(&p.b.map, &full[s], sb + pl * p.b.plane_bytes + j * p.b.box_bytes, chunk * p.cw,
+                        px + tap % p.KW, py + tap / p.KW, pn, pl);
+          }
+        }
+      }
+    }
+  } else if (warp == 1 && lane == 0) {
+    // ===================== MMA issuer (one thread) =====================
+    const uint32_t idesc = make_idesc_bf16(128, p.block_n, p.a.major, p.b.major);
+    const uint32_t la = p.a.rowbytes == 128 ? 2u : 4u, lb = p.b.rowbytes == 128 ? 2u : 4u;
+    uint32_t accum = 0;
+    for (int it = 0; it < nsteps; ++it) {
+      const int s = it % p.stages, ph = (it / p.stages) & 1;
+      if (!mbar_wait(&full[s], ph, p.err, 2)) break;
+      fence_after_sync();
+      const uint32_t sa = smem_u32(smem + (size_t)s * stage_bytes);
+      const uint32_t sb = sa + a_stage;
+      for (int k = 0; k < p.kslices; ++k) {
+        const uint64_t a_hi = make_smem_desc(sa + k * p.a.kadv, p.a.lbo, p.a.sbo, la);
+        const uint64_t b_hi = make_smem_desc(sb + k * p.b.kadv, p.b.lbo, p.b.sbo, lb);
+        umma_f16(tmem_base, a_hi, b_hi, idesc, accum);
+        accum = 1;
+        if (p.planes == 2) {
+          const uint64_t a_lo = make_smem_desc(sa + p.a.plane_bytes + k * p.a.kadv, p.a.lbo, p.a.sbo, la);
+          const uint64_t b_lo = make_smem_desc(sb + p.b.plane_bytes + k * p.b.kadv, p.b.lbo, p.b.sbo, lb);
+          umma_f16(tmem_base, a_hi, b_lo, idesc, 1);
+          umma_f16(tmem_base, a_lo, b_hi, idesc, 1);
+        }
+      }
+      umma_commit(&empty[s]);  // frees the smem slot once these MMAs have read it
+    }
+    umma_commit(tmem_full);    // accumulator complete
+  } else if (warp >= 2) {
+    // ===================== epilogue (4 warps, one TMEM lane quadrant each) =====================
+    const int q = warp & 3;
+    const int r = q * 32 + lane;  // accumulator row owned by this thread
+    bool ok = mbar_wait(tmem_full, 0, p.err, 3);
+    fence_after_sync();
+    const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16);
+    float v[16];
+
+    if (MODE == MODE_GEMM) {
+      const int m = m0 + r;
+      for (int c0 = 0; c0 < p.block_n; c0 += 16) {
+        tmem_ld16(trow + c0, v);
+        if (!ok || m >= p.M) continue;
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          const int n = n0 + c0 + i;
+          if (n >= p.N) continue;
+          const long long o = (long long)m * p.ldc + n;
+          if (p.epi == EPI_F32_ATOMIC) {
+            atomicAdd(p.out_f32 + o, v[i]);
+          } else {
+            float z = v[i] + (p.bias ? p.bias[n] : 0.f);
+            z = ugn_act_fwd(z, p.act, p.alpha);
+            if (p.mask) z *= p.mask[o];
+            p.out_f32[o] = z;
+          }
+        }
+      }
+    } else if (MODE == MODE_CONV) {
+      const int xl = r % p.bw, yl = (r / p.bw) % p.bh, nl = r / (p.bw * p.bh);
+      const int x = x0 + xl, y = y0 + yl, n = nn0 + nl;
+      const bool rv = ok && nl < p.bn && x < p.Wout && y < p.Hout && n < p.Bn;
+      if (p.epi != EPI_BF16_POOL) {
+        const long long obase = (((long long)n * p.Hout + y) * p.Wout + x) * p.Cout;
+        for (int c0 = 0; c0 < p.block_n; c0 += 16) {
+          tmem_ld16(trow + c0, v);
+          if (!rv) continue;
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const int c = n0 + c0 + i;
+            if (c >= p.Cout) continue;
+            if (p.epi == EPI_F32) {
+              p.out_f32[obase + c] = v[i];
+            } else {
+              float z = ugn_act_fwd(v[i] + (p.bias ? p.bias[c] : 0.f), p.act, p.alpha);
+              __nv_bfloat16 hi, lo;
+              ugn_split(z, hi, lo);
+              p.out_bf16[obase + c] = hi;
+              if (p.planes == 2) p.out_bf16[p.out_plane + obase + c] = lo;
+            }
+          }
+        }
+      } else {
+        // fused 2x2 max-pool: stage act(z+b) through the (now idle) stage-0 smem, 32 columns at a time
+        float* stg = reinterpret_cast<float*>(smem);  // [128][33]
+        const int t = threadIdx.x - 64;
+        const int pw = p.bw >> 1, ph2 = p.bh >> 1, npool = pw * ph2 * p.bn;
+        for (int c0 = 0; c0 < p.block_n; c0 += 32) {
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            tmem_ld16(trow + c0 + 16 * h, v);
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              const int c = n0 + c0 + 16 * h + i;
+              float z = v[i] + ((p.bias && c < p.Cout) ? p.bias[c] : 0.f);
+              stg[r * 33 + 16 * h + i] = ugn_act_fwd(z, p.act, p.alpha);
+            }
+          }
+          epi_barrier();
+          const int col = t & 31, c = n0 + c0 + col;
+          for (int pp = t >> 5; pp < npool; pp += 4) {
+            const int pxl = pp % pw, pyl = (pp / pw) % ph2, pnl = pp / (pw * ph2);
+            const int r00 = (pnl * p.bh + 2 * pyl) * p.bw + 2 * pxl;
+            float best = stg[r00 * 33 + col];
+            int pos = 0;
+            float o1 = stg[(r00 + 1) * 33 + col], o2 = stg[(r00 + p.bw) * 33 + col], o3 = stg[(r00 + p.bw + 1) * 33 + col];
+            if (o1 > best) { best = o1; pos = 1; }
+            if (o2 > best) { best = o2; pos = 2; }
+            if (o3 > best) { best = o3; pos = 3; }
+            const int xp = (x0 >> 1) + pxl, yp = (y0 >> 1) + pyl, nn = nn0 + pnl;
+            if (ok && c < p.Cout && xp < p.Wp && yp < p.Hp && nn < p.Bn) {
+              const long long o = (((long long)nn * p.Hp + yp) * p.Wp + xp) * p.Cout + c;
+              __nv_bfloat16 hi, lo;
+              ugn_split(best, hi, lo);
+              p.out_bf16[o] = hi;
+              if (p.planes == 2) p.out_bf16[p.out_plane + o] = lo;
+              p.pool_idx[o] = (uint8_t)pos;
+            }
+          }
+          epi_barrier();
+        }
+      }
+    } else {  // MODE_WGRAD: rows = co, columns = (box j -> tap, ci chunk)
+      const int co = m0 + r;
+      for (int c0 = 0; c0 < p.block_n; c0 += 16) {
+        tmem_ld16(trow + c0, v);
+        if (!ok || co >= p.Co) continue;
+        const int j = c0 / p.cw, gb = tile_n * p.b.nbox + j;
+        if (gb >= p.nch * p.ntaps) continue;
+        const int chunk = gb % p.nch, tap = gb / p.nch;
+        const int cib = chunk * p.cw + (c0 % p.cw);
+        float* dst = p.out_f32 + ((long long)co * p.ntaps + tap) * p.Cin;
+#pragma unroll
+        for (int i = 0; i < 16; ++i)
+          if (cib + i < p.Cin) atomicAdd(dst + cib + i, v[i]);
+      }
+    }
+    fence_before_sync();
+  }
+  __syncthreads();
+  if (warp == 1) {
+    __syncwarp();
+    fence_after_sync();
+    tmem_dealloc(tmem_base, kTmemCols);
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static int get_encoder(ugn_ctx* ctx, EncodeTiledFn* fn) {
+  if (!ctx->encode_tiled) {
+    void* f = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    UGN_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &qres));
+    if (!f || qres != cudaDriverEntryPointSuccess) UGN_FAIL(UGN_ERR_CUDA, "cuTensorMapEncodeTiled not available");
+    ctx->encode_tiled = f;
+  }
+  *fn = (EncodeTiledFn)ctx->encode_tiled;
+  return UGN_OK;
+}
+
+// 5-D bf16 tensor map; dims innermost first; strides[i] = byte stride of dim i+1.
+static int make_map(ugn_ctx* ctx, CUtensorMap* map, const void* base, const uint64_t dims[5],
+                    const uint64_t strides_bytes[4], const uint32_t box[5], int rowbytes) {
+  EncodeTiledFn enc;
+  int rc = get_encoder(ctx, &enc);
+  if (rc != UGN_OK) return rc;
+  cuuint64_t gd[5], gs[4];
+  cuuint32_t bx[5], es[5] = {1, 1, 1, 1, 1};
+  for (int i = 0; i < 5; ++i) { gd[i] = dims[i]; bx[i] = box[i]; }
+  for (int i = 0; i < 4; ++i) gs[i] = strides_bytes[i];
+  UGN_CHECK(((uintptr_t)base & 15) == 0, "tensor-core operand must be 16-byte aligned");
+  for (int i = 0; i < 4; ++i) UGN_CHECK(gs[i] % 16 == 0, "tensor-core operand stride %d (=%llu B) not a multiple of 16", i, (unsigned long long)gs[i]);
+  for (int i = 0; i < 5; ++i) UGN_CHECK(bx[i] >= 1 && bx[i] <= 256, "TMA box dim %d = %u out of range", i, bx[i]);
+  UGN_CHECK((int)(bx[0] * 2) == rowbytes, "inner box must span the swizzle width");
+  CUtensorMapSwizzle sw = rowbytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(base), gd, gs, bx, es,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) UGN_FAIL(UGN_ERR_CUDA, "cuTensorMapEncodeTiled failed with %d", (int)r);
+  return UGN_OK;
+}
+
+static void finish_op(TcOp& op, int major, int rowbytes, int nbox, int box_rows, int plane_rows_reserved) {
+  op.major = major;
+  op.rowbytes = rowbytes;
+  op.nbox = nbox;
+  op.box_bytes = box_rows * rowbytes;
+  int reserved = std::max(nbox * op.box_bytes, plane_rows_reserved * rowbytes);
+  op.plane_bytes = (reserved + 1023) / 1024 * 1024;
+  op.sbo = 8 * rowbytes;
+  if (major == 0) { op.lbo = 0; op.kadv = 32; }
+  else { op.lbo = op.box_bytes; op.kadv = 16 * rowbytes; }
+}
+
+template <int MODE>
+static int launch(ugn_ctx* ctx, TcParams& p, dim3 grid, cudaStream_t st) {
+  UGN_CHECK(ctx->cc_major == 10, "tensor-core path needs an sm_100 device (found sm_%d%d)", ctx->cc_major, ctx->cc_minor);
+  UGN_CHECK(p.block_n % 16 == 0 && p.block_n >= 16 && p.block_n <= 256, "block_n=%d invalid", p.block_n);
+  size_t stage = (size_t)p.planes * (p.a.plane_bytes + p.b.plane_bytes);
+  int stages = (int)std::min<size_t>(8, (200 * 1024) / stage);
+  UGN_CHECK(stages >= 2, "tensor-core tile does not fit shared memory (stage=%zu B)", stage);
+  stages = std::min(stages, std::max(2, (p.ksteps_total + p.ksplit - 1) / p.ksplit));
+  p.stages = stages;
+  size_t smem = stages * stage + 1024 /*align*/ + (2 * stages + 1) * 8 + 16;
+  smem = std::max(smem, (size_t)(128 * 33 * 4 + 2048));
+  if (!ctx->err_flag) {
+    UGN_CUDA(cudaMalloc(&ctx->err_flag, sizeof(int)));
+    UGN_CUDA(cudaMemset(ctx->err_flag, 0, sizeof(int)));
+  }
+  p.err = ctx->err_flag;
+  UGN_CUDA(cudaFuncSetAttribute(tc_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  tc_kernel<MODE><<<grid, kThreads, smem, st>>>(p);
+  UGN_LAUNCHED(ctx);
+  return UGN_OK;
+}
+
+// ---- plain GEMM -------------------------------------------------------------------------
+static int gemm_operand(ugn_ctx* ctx, TcOp& op, const __nv_bfloat16* base, int P, int rows, int K, int mn_major,
+                        int tile_rows, int BK) {
+  uint64_t dims[5];
+  uint64_t str[4];
+  uint32_t box[5] = {1, 1, 1, 1, 1};
+  if (!mn_major) {  // [P][rows][K]
+    UGN_CHECK(K % 8 == 0, "K-major operand needs K %% 8 == 0 (K=%d)", K);
+    dims[0] = K; dims[1] = rows; dims[2] = P; dims[3] = 1; dims[4] = 1;
+    str[0] = (uint64_t)K * 2; str[1] = (uint64_t)rows * K * 2; str[2] = str[1] * P; str[3] = str[2];
+    box[0] = 64; box[1] = tile_rows;
+    finish_op(op, 0, 128, 1, tile_rows, tile_rows);
+  } else {          // [P][K][rows]
+    UGN_CHECK(rows % 8 == 0, "MN-major operand needs its contiguous extent %% 8 == 0 (got %d)", rows);
+    dims[0] = rows; dims[1] = K; dims[2] = P; dims[3] = 1; dims[4] = 1;
+    str[0] = (uint64_t)rows * 2; str[1] = (uint64_t)rows * K * 2; str[2] = str[1] * P; str[3] = str[2];
+    box[0] = 64; box[1] = BK;
+    finish_op(op, 1, 128, tile_rows / 64, BK, 0);
+  }
+  return make_map(ctx, &op.map, base, dims, str, box, 128);
+}
+
+int tc_gemm_ex(ugn_ctx* ctx, int P, int M, int N, int K, const __nv_bfloat16* A, int a_mn, const __nv_bfloat16* B,
+               int b_mn, float* C, int ldc, int accumulate, const float* bias, const float* mask, int act,
+               float alpha, cudaStream_t st) {
+  TcParams p{};
+  p.mode = MODE_GEMM;
+  p.M = M; p.N = N; p.planes = P;
+  p.block_n = N > 128 ? 256 : (N > 64 ? 128 : 64);
+  if (P == 2 && p.block_n > 128) p.block_n = 128;
+  p.kslices = 4;
+  const int BK = 64;
+  int rc;
+  if ((rc = gemm_operand(ctx, p.a, A, P, M, K, a_mn, 128, BK)) != UGN_OK) return rc;
+  if ((rc = gemm_operand(ctx, p.b, B, P, N, K, b_mn, p.block_n, BK)) != UGN_OK) return rc;
+  p.ksteps_total = (K + BK - 1) / BK;
+  int tiles = ugn_cdiv(M, 128) * ugn_cdiv(N, p.block_n);
+  int split = 1;
+  if (!bias && !mask && act == UGN_ACT_LINEAR) {
+    split = std::max(1, std::min(ctx->sm_count / std::max(tiles, 1), p.ksteps_total / 4));
+    split = std::min(split, 32);
+  }
+  p.ksplit = split;
+  p.epi = (split > 1 || accumulate) ? EPI_F32_ATOMIC : EPI_F32;
+  p.out_f32 = C; p.ldc = ldc; p.bias = bias; p.mask = mask; p.act = act; p.alpha = alpha;
+  if (split > 1 && !accumulate) UGN_CUDA(cudaMemsetAsync(C, 0, sizeof(float) * (size_t)M * ldc, st));
+  dim3 grid(ugn_cdiv(M, 128), ugn_cdiv(N, p.block_n), split);
+  return launch<MODE_GEMM>(ctx, p, grid, st);
+}
+
+int tc_gemm(ugn_ctx* ctx, int P, int M, int N, int K, const __nv_bfloat16* A, int a_mn, const __nv_bfloat16* B,
+            int b_mn, float* C, int accumulate, cudaStream_t st) {
+  return tc_gemm_ex(ctx, P, M, N, K, A, a_mn, B, b_mn, C, N, accumulate, nullptr, nullptr, UGN_ACT_LINEAR, 0.f, st);
+}
+
+// ---- convolution ------------------------------------------------------------------------
+// activation tensor [P][B][H][W][C] as a 5-D map (C, W, H, B, P)
+static int act_map(ugn_ctx* ctx, TcOp& op, const __nv_bfloat16* base, int P, int B, int H, int W, int C, int cbox,
+                   int bw, int bh, int bn, int major, int nbox, int rows_reserved) {
+  uint64_t dims[5] = {(uint64_t)C, (uint64_t)W, (uint64_t)H, (uint64_t)B, (uint64_t)P};
+  uint64_t str[4] = {(uint64_t)C * 2, (uint64_t)W * C * 2, (uint64_t)H * W * C * 2, (uint64_t)B * H * W * C * 2};
+  uint32_t box[5] = {(uint32_t)cbox, (uint32_t)bw, (uint32_t)bh, (uint32_t)bn, 1};
+  finish_op(op, major, cbox * 2, nbox, bw * bh * bn, rows_reserved);
+  return make_map(ctx, &op.map, base, dims, str, box, cbox * 2);
+}
+
+static void conv_box(int Wn, int Hn, int Bn, int pool, int& bw, int& bh, int& bn) {
+  // spatial box of <= 128 output pixels covering the needed region Wn x Hn
+  bw = Wn;
+  if (pool && (bw & 1)) bw -= 1;
+  bw = std::min(bw, 128);
+  int rows = std::max(1, 128 / bw);
+  bh = std::min(Hn, rows);
+  if (pool) bh = std::max(2, bh & ~1);
+  if (bh >= Hn) {
+    bh = pool ? (Hn & ~1) : Hn;
+    bn = std::max(1, std::min(Bn, 128 / (bw * bh)));
+  } else {
+    bn = 1;
+  }
+}
+
+int tc_conv_fwd(ugn_ctx* ctx, const ConvGeom& g, int P, const __nv_bfloat16* x, const __nv_bfloat16* w,
+                const float* bias, __nv_bfloat16* y, uint8_t* idx, int act, float alpha, int pool,
+                cudaStream_t st) {
+  UGN_CHECK(g.Cp % 32 == 0 && g.Co % 16 == 0, "tensor-core conv needs Cin %% 32 == 0 and Cout %% 16 == 0");
+  TcParams p{};
+  p.mode = MODE_CONV; p.planes = P; p.sgn = 1;
+  const int cbox = (g.Cp % 64 == 0) ? 64 : 32;
+  p.kslices = cbox / 16;
+  p.ncc = g.Cp / cbox; p.KW = g.KW;
+  p.ksteps_total = g.KH * g.KW * p.ncc; p.ksplit = 1;
+  const int Wn = pool ? g.Wp * 2 : g.Wo, Hn = pool ? g.Hp * 2 : g.Ho;
+  conv_box(Wn, Hn, g.B, pool, p.bw, p.bh, p.bn);
+  p.ntx = ugn_cdiv(Wn, p.bw); p.nty = ugn_cdiv(Hn, p.bh);
+  p.Wout = pool ? Wn : g.Wo; p.Hout = pool ? Hn : g.Ho; p.Bn = g.B; p.Cout = g.Co;
+  p.Hp = g.Hp; p.Wp = g.Wp;
+  p.block_n = g.Co > 128 ? ((g.Co % 256 == 0 || g.Co > 192) ? 256 : (g.Co + 15) / 16 * 16) : (g.Co + 15) / 16 * 16;
+  if (p.block_n > 256) p.block_n = 256;
+  if (P == 2 && p.block_n > 128) p.block_n = (g.Co % 128 == 0) ? 128 : ((g.Co % 96 == 0) ? 96 : 64);
+  int rc = act_map(ctx, p.a, x, P, g.B, g.H, g.W, g.Cp, cbox, p.bw, p.bh, p.bn, 0, 1, 128);
+  if (rc != UGN_OK) return rc;
+  {  // weights [P][Co][taps][Cp] K-major: dims (Cp, taps, Co, P, 1)
+    const int taps = g.KH * g.KW;
+    uint64_t dims[5] = {(uint64_t)g.Cp, (uint64_t)taps, (uint64_t)g.Co, (uint64_t)P, 1};
+    uint64_t str[4] = {(uint64_t)g.Cp * 2, (uint64_t)taps * g.Cp * 2, (uint64_t)g.Co * taps * g.Cp * 2,
+                       (uint64_t)P * g.Co * taps * g.Cp * 2};
+    uint32_t box[5] = {(uint32_t)cbox, 1, (uint32_t)p.block_n, 1, 1};
+    finish_op(p.b, 0, cbox * 2, 1, p.block_n, p.block_n);
+    if ((rc = make_map(ctx, &p.b.map, w, dims, str, box, cbox * 2)) != UGN_OK) return rc;
+  }
+  p.epi = pool ? EPI_BF16_POOL : EPI_BF16_ACT;
+  p.out_bf16 = y; p.out_plane = (long long)g.B * g.Hp * g.Wp * g.Co;
+  p.pool_idx = idx; p.bias = bias; p.act = act; p.alpha = alpha;
+  dim3 grid(p.ntx * p.nty * ugn_cdiv(g.B, p.bn), ugn_cdiv(g.Co, p.block_n), 1);
+  return launch<MODE_CONV>(ctx, p, grid, st);
+}
+
+int tc_conv_dgrad(ugn_ctx* ctx, const ConvGeom& g, int P, const __nv_bfloat16* dz, const __nv_bfloat16* w,
+                  float* dx, cudaStream_t st) {
+  UGN_CHECK(g.Co % 64 == 0 && g.Cp % 32 == 0, "tensor-core dgrad needs Cout %% 64 == 0 and Cin %% 32 == 0");
+  TcParams p{};
+  p.mode = MODE_CONV; p.planes = P; p.sgn = -1;
+  p.kslices = 4;                       // K stage = 64 output channels
+  p.ncc = g.Co / 64; p.KW = g.KW;
+  p.ksteps_total = g.KH * g.KW * p.ncc; p.ksplit = 1;
+  conv_box(g.W, g.H, g.B, 0, p.bw, p.bh, p.bn);
+  p.ntx = ugn_cdiv(g.W, p.bw); p.nty = ugn_cdiv(g.H, p.bh);
+  p.Wout = g.W; p.Hout = g.H; p.Bn = g.B; p.Cout = g.Cp;
+  const int cw = (g.Cp % 64 == 0) ? 64 : 32;
+  int bn_cols = std::min(g.Cp, P == 2 ? 128 : 256);
+  bn_cols = bn_cols / cw * cw;
+  p.block_n = bn_cols;
+  int rc = act_map(ctx, p.a, dz, P, g.B, g.Ho, g.Wo, g.Co, 64, p.bw, p.bh, p.bn, 0, 1, 128);
+  if (rc != UGN_OK) return rc;
+  {  // weights as MN-major B: N = ci (contiguous), K = co: dims (Cp, taps, Co, P, 1), box (cw, 1, 64, 1, 1)
+    const int taps = g.KH * g.KW;
+    uint64_t dims[5] = {(uint64_t)g.Cp, (uint64_t)taps, (uint64_t)g.Co, (uint64_t)P, 1};
+    uint64_t str[4] = {(uint64_t)g.Cp * 2, (uint64_t)taps * g.Cp * 2, (uint64_t)g.Co * taps * g.Cp * 2,
+                       (uint64_t)P * g.Co * taps * g.Cp * 2};
+    uint32_t box[5] = {(uint32_t)cw, 1, 64, 1, 1};
+    finish_op(p.b, 1, cw * 2, p.block_n / cw, 64, 0);
+    if ((rc = make_map(ctx, &p.b.map, w, dims, str, box, cw * 2)) != UGN_OK) return rc;
+  }
+  p.epi = EPI_F32; p.out_f32 = dx;
+  dim3 grid(p.ntx * p.nty * ugn_cdiv(g.B, p.bn), ugn_cdiv(g.Cp, p.block_n), 1);
+  return launch<MODE_CONV>(ctx, p, grid, st);
+}
+
+int simt_colsum_bf16(ugn_ctx* ctx, const __nv_bfloat16* X, int P, long long rows, int cols, float* out,
+                     cudaStream_t st);
+
+int tc_conv_wgrad(ugn_ctx* ctx, const ConvGeom& g, int P, const __nv_bfloat16* x, const __nv_bfloat16* dz,
+                  float* dw, float* db, cudaStream_t st) {
+  UGN_CHECK(g.Cp % 32 == 0 && g.Co % 8 == 0, "tensor-core wgrad needs Cin %% 32 == 0");
+  TcParams p{};
+  p.mode = MODE_WGRAD; p.planes = P;
+  // K stage = a box of output pixels (rows zero-filled by TMA beyond the dz extent)
+  int bw = 1;
+  while (bw < g.Wo && bw < 64) bw <<= 1;
+  int bh = std::max(1, 64 / bw);
+  bh = std::min(bh, 1 << (31 - __builtin_clz(std::max(1, g.Ho))));
+  if (bh < 1) bh = 1;
+  int bn = std::max(1, 64 / (bw * bh));
+  while (bw * bh * bn > 64) bn >>= 1;
+  if (bn < 1) bn = 1;
+  while ((bw * bh * bn) % 16 != 0) bn *= 2;
+  p.bw = bw; p.bh = bh; p.bn = bn;
+  p.kslices = bw * bh * bn / 16;
+  p.nbx = ugn_cdiv(g.Wo, bw); p.nby = ugn_cdiv(g.Ho, bh);
+  p.ksteps_total = p.nbx * p.nby * ugn_cdiv(g.B, bn);
+  p.KW = g.KW; p.ntaps = g.KH * g.KW; p.Cin = g.Cin; p.Co = g.Co;
+  p.cw = (g.Cp % 64 == 0) ? 64 : 32;
+  p.nch = g.Cp / p.cw;
+  const int maxcols = P == 2 ? 128 : 256;
+  int nboxB = std::max(1, std::min(maxcols / p.cw, p.nch * p.ntaps));
+  p.block_n = nboxB * p.cw;
+  int rc = act_map(ctx, p.a, dz, P, g.B, g.Ho, g.Wo, g.Co, 64, bw, bh, bn, 1, 2, 0);
+  if (rc != UGN_OK) return rc;
+  if ((rc = act_map(ctx, p.b, x, P, g.B, g.H, g.W, g.Cp, p.cw, bw, bh, bn, 1, nboxB, 0)) != UGN_OK) return rc;
+  int ntile_n = ugn_cdiv(p.nch * p.ntaps, nboxB), ntile_m = ugn_cdiv(g.Co, 128);
+  int split = std::max(1, std::min((2 * ctx->sm_count) / std::max(1, ntile_n * ntile_m), p.ksteps_total / 2));
+  split = std::min(split, 65535);
+  p.ksplit = split;
+  p.epi = EPI_F32_ATOMIC; p.out_f32 = dw;
+  UGN_CUDA(cudaMemsetAsync(dw, 0, sizeof(float) * (size_t)g.Co * p.ntaps * g.Cin, st));
+  dim3 grid(ntile_m, ntile_n, split);
+  rc = launch<MODE_WGRAD>(ctx, p, grid, st);
+  if (rc != UGN_OK) return rc;
+  if (db) return simt_colsum_bf16(ctx, dz, P, (long long)g.B * g.Ho * g.Wo, g.Co, db, st);
+  return UGN_OK;
+}
+
+// ---- dense ------------------------------------------------------------------------------
+int tc_linear_fwd(ugn_ctx* ctx, int P, int B, int N, int K, const __nv_bfloat16* x, const __nv_bfloat16* w,
+                  const float* bias, const float* mask, float* y, int act, float alpha, cudaStream_t st) {
+  return tc_gemm_ex(ctx, P, B, N, K, x, 0, w, 0, y, N, 0, bias, mask, act, alpha, st);
+}
+
+int tc_linear_bwd(ugn_ctx* ctx, int P, int B, int N, int K, const __nv_bfloat16* x, const __nv_bfloat16* w,
+                  const __nv_bfloat16* dz, float* dx, float* dw, float* db, cudaStream_t st) {
+  int rc;
+  // dx[B,K] = dz[B,N] . w[N,K]      : A = dz K-major (K'=N), B = w as MN-major [K'=N rows][K contiguous]
+  if (dx && (rc = tc_gemm_ex(ctx, P, B, K, N, dz, 0, w, 1, dx, K, 0, nullptr, nullptr, 0, 0.f, st)) != UGN_OK) return rc;
+  // dw[N,K] = dz^T . x             : A = dz MN-major [K'=B rows][N contiguous], B = x MN-major [B rows][K contiguous]
+  if (dw && (rc = tc_gemm_ex(ctx, P, N, K, B, dz, 1, x, 1, dw, K, 0, nullptr, nullptr, 0, 0.f, st)) != UGN_OK) return rc;
+  if (db) return simt_colsum_bf16(ctx, dz, P, B, N, db, st);
+  return UGN_OK;
+}

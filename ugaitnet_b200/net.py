@@ -52,6 +52,7 @@ class UGaitEngine:
         self.world = torch.distributed.get_world_size(process_group) if process_group is not None else 1
         self.use_graph = use_graph
         self.t = 0
+        self.graph_launches = 0
         self._plans: Dict[tuple, "_Plan"] = {}
         self._graphs = {}
         self._build_arena()
@@ -395,8 +396,10 @@ class UGaitEngine:
                 self.w.copy_(saved[0]); self.m.copy_(saved[1]); self.v.copy_(saved[2])
                 self.repack_weights()
                 gr = torch.cuda.CUDAGraph()
+                l0 = self.ctx.launches
                 with torch.cuda.graph(gr):
                     self._step_body(p, True)
+                self.graph_launches = self.ctx.launches - l0   # kernels of ours inside one replay
                 self._graphs[gkey] = gr
                 # the capture itself did not execute: fall through to replay
             gr.replay()
