@@ -207,6 +207,7 @@ def main():
     ap.add_argument("--mode", default=os.environ.get("UGN_BENCH_MODE", "bf16x3"))
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-knn", action="store_true")
+    ap.add_argument("--lite", action="store_true", help="timed steps only (for runs under ncu)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
 
@@ -278,6 +279,11 @@ def main():
     launches = eng.ctx.launches - l0
     if eng.use_graph:
         launches = eng.graph_launches * args.steps
+    if args.lite:
+        if rank == 0:
+            print(json.dumps({"lite": True, "ms_per_step": ms, "rows_per_s": B * world / (ms * 1e-3),
+                              "gpu_launches": int(launches)}), flush=True)
+        return
     for _ in range(2):
         step_e2e()
     ms_e2e = timed(step_e2e, args.steps)

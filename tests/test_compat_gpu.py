@@ -1,0 +1,112 @@
+"""The Keras-shaped drop-in surface (reference builder signatures, fit/predict/encode protocol)."""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import ugait_oracle as O
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+class FakeGen:
+    """Stands in for DataGeneratorGaitMMUWYH: len(), [i] -> (X_list, y_list), on_epoch_end()."""
+
+    def __init__(self, oc, n=3, base_rows=4, expand=4, seed=0):
+        self.items = []
+        for i in range(n):
+            xs, fl, lab = O.synth_batch(oc, base_rows=base_rows, expand=expand, seed=seed + i)
+            lab = lab % oc.nclasses
+            X = []
+            for x, f in zip(xs, fl):
+                X += [x.astype(np.float64), f.astype(np.float64)]       # the reference feeds float64
+            onehot = np.eye(oc.nclasses)[lab.reshape(-1).astype(int)]
+            self.items.append((X, [lab, onehot]))
+        self.epochs_ended = 0
+
+    def __len__(self):
+        return len(self.items)
+
+    def __getitem__(self, i):
+        return self.items[i]
+
+    def on_epoch_end(self):
+        self.epochs_ended += 1
+
+
+@pytest.fixture()
+def compat_path(monkeypatch):
+    monkeypatch.setenv("UGN_MATH_MODE", "fp32")
+    monkeypatch.syspath_prepend(os.path.join(ROOT, "ugaitnet_b200", "compat"))
+    for m in [k for k in sys.modules if k == "nets" or k.startswith("nets.")]:
+        del sys.modules[m]
+    yield
+    for m in [k for k in sys.modules if k == "nets" or k.startswith("nets.")]:
+        del sys.modules[m]
+
+
+def test_reference_import_paths_and_training_protocol(compat_path, tmp_path):
+    # exactly the imports / calls of mains/mj_trainUWYHGaitNet_DataGen_3mods.py:339-343,559-572
+    from nets.mj_uwyhNets_ba import UWYHSemiNet, UWYHSemiNet3Mods
+    from nets.mj_metrics import mj_eerVerifDist
+    from ugaitnet_b200.compat import optimizers, sign_max
+    import nets.mj_uwyhNets_ba as mod
+    mod.MATH_MODE = "fp32"
+    input_shape = [(6, 60, 60), (4, 60, 60), (4, 60, 60)]
+    model = UWYHSemiNet3Mods.build_or_load(input_shape, 4, [(7, 7), (5, 5), (3, 3), (2, 2)], [8, 8, 16, 16],
+                                           32, 0.00005, 0.0, optimizer=optimizers.Adam(lr=1e-3), margin=0.2,
+                                           nclasses=10, loss_weights=[1.0, 0.1], initnet="", fMerge=sign_max)
+    model.summary()
+    oc = O.NetConfig(in_channels=(6, 4, 4), filters_numbers=(8, 8, 16, 16), nd=32, nclasses=10)
+    gen, val = FakeGen(oc, n=3), FakeGen(oc, n=1, seed=50)
+    model, hist = UWYHSemiNet.fit_generator(model, 4, [], gen, val, 0, len(gen), len(val))
+    assert hist.epoch == [0, 1, 2, 3] and gen.epochs_ended == 4
+    for key in ("loss", "classprob_acc", "val_classprob_acc", "lr", "val_loss"):
+        assert key in hist.history and len(hist.history[key]) == 4
+    assert hist.history["loss"][-1] < hist.history["loss"][0]
+    assert model.get_layer("classprob").units == 10 and model.dtype == "float32"
+    # predict protocol + sub-model on a named layer (mains/mj_testUWYHGaitNet_open_tum.py:139-148)
+    from ugaitnet_b200.compat import Model
+    X, _ = gen[0]
+    sig, prob = model.predict(X)
+    assert sig.shape == (16, 32) and prob.shape == (16, 10)
+    assert np.allclose(prob.sum(1), 1.0, atol=1e-5) and np.allclose(np.linalg.norm(sig, axis=1), 1.0, atol=1e-5)
+    sub = Model(model.input, model.get_layer("signature").output)
+    assert np.array_equal(sub.predict(X), sig)
+    # encode(): first two modalities, always Maximum (nets/mj_uwyhNets_ba.py:971-999)
+    codes = UWYHSemiNet.encode(model, [X[0], X[2]], [X[1], X[3]])
+    P = {k: v.double().cpu() for k, v in model.engine.export_params().items()}
+    b0 = O.branch_forward(torch.tensor(X[0]), P, "ofBranch", oc) * torch.tensor(X[1])
+    b1 = O.branch_forward(torch.tensor(X[2]), P, "grayBranch", oc) * torch.tensor(X[3])
+    ref = O.l2_normalize(torch.maximum(b0, b1), 1)
+    assert np.allclose(codes, ref.numpy(), atol=2e-5)
+    # weights round trip by layer name
+    path = str(tmp_path / "model-state-0004_weights.hdf5")
+    model.save_weights(path)
+    m2 = UWYHSemiNet3Mods.build(input_shape, 4, [(7, 7), (5, 5), (3, 3), (2, 2)], [8, 8, 16, 16], 32, 0.00005, 0.0,
+                                optimizer=optimizers.Adam(lr=1e-3), nclasses=10, loss_weights=[1.0, 0.1], fMerge=sign_max)
+    m2.load_weights(path, by_name=True, skip_mismatch=True)
+    assert np.array_equal(m2.predict(X)[0], sig)
+    w = model.get_layer("classprob").get_weights()
+    assert sorted(a.shape for a in w) == [(10,), (32, 10)]          # Keras (in,out) kernel + bias
+    eer, thr = mj_eerVerifDist(np.array([1, 1, 1, 1, 1, 0, 0, 0, 0]),
+                               np.array([0.01, 0.02, 0.015, 0.08, 0.05, 0.07, 0.2, 0.15, 0.18]))
+    assert eer == pytest.approx(0.25) and thr == pytest.approx(0.07)   # the reference demo's known answer
+
+
+def test_triplet_loss_closure_and_unsupported_options(compat_path):
+    from nets.triplet_loss_all import triplet_loss
+    from nets.mj_uwyhNets_ba import UWYHSemiNet3Mods
+    loss = triplet_loss(0.2)
+    loss.margin = np.float32(0.2)
+    rng = np.random.default_rng(0)
+    e = rng.normal(size=(3, 12, 16)).astype(np.float32)
+    lab = np.repeat(np.arange(4), 3).reshape(-1, 1).astype(np.float32)
+    got = float(loss(lab, e))
+    ref, _ = O.triplet_loss_all_literal_np(lab, e, 0.2)
+    assert got == pytest.approx(ref, rel=1e-5)
+    with pytest.raises(NotImplementedError, match="gaitset"):
+        UWYHSemiNet3Mods.build([(50, 60, 60)] * 3, 4, [7, 5, 3, 2], [96, 192, 512, 512], gaitset=True)

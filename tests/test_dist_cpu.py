@@ -1,0 +1,56 @@
+"""world_size-2 gloo tests (CPU) of the host-side multi-GPU logic: gallery sharding + top-k list merge,
+and the data-parallel gradient averaging contract (sum all-reduce, 1/G scale inside the optimiser)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from oracle import ugait_oracle as O
+
+
+def _worker(rank, world, port, tmp):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from ugaitnet_b200.dist import allgather_topk, merge_topk_host, shard_bounds, allreduce_mean_
+    rng = np.random.default_rng(0)                 # same data on every rank
+    N, D, Q, k = 1001, 16, 37, 3
+    G = rng.normal(size=(N, D)).astype(np.float32)
+    G[500:510] = G[0:10]
+    y = rng.integers(0, 9, N).astype(np.int32)
+    Qm = rng.normal(size=(Q, D)).astype(np.float32)
+    lo, hi = shard_bounds(N, rank, world)
+    d2, idx = O.knn_search(G[lo:hi], Qm, k)        # the local search (GPU kernel on the box; oracle here)
+    d2t, idxt = torch.from_numpy(d2), torch.from_numpy(idx + lo)
+    labt = torch.from_numpy(y[lo:hi][idx])
+    D2, IX, LB = allgather_topk(d2t, idxt, labt)
+    md2, midx, mlab, pred = merge_topk_host(D2.numpy(), IX.numpy(), LB.numpy(), k)
+    rd2, ridx = O.knn_search(G, Qm, k)
+    ok_knn = np.array_equal(midx, ridx) and np.array_equal(pred, O.knn_vote(y[ridx]))
+    # DP contract: every rank holds a different gradient; after the collective all hold the mean
+    g = torch.full((130,), float(rank + 1))
+    allreduce_mean_(g)
+    ok_dp = torch.allclose(g, torch.full((130,), (world + 1) / 2.0))
+    with open(os.path.join(tmp, f"r{rank}"), "w") as f:
+        f.write(f"{int(ok_knn)} {int(ok_dp)}")
+    dist.destroy_process_group()
+
+
+def test_sharded_knn_merge_and_dp_mean_gloo(tmp_path):
+    port = 29500 + os.getpid() % 2000
+    mp.spawn(_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    for r in range(2):
+        assert open(tmp_path / f"r{r}").read() == "1 1"
+
+
+def test_shard_bounds_cover_everything():
+    from ugaitnet_b200.dist import shard_bounds
+    for n in (0, 1, 7, 1000, 1_000_003):
+        for w in (1, 2, 3, 8):
+            b = [shard_bounds(n, r, w) for r in range(w)]
+            assert b[0][0] == 0 and b[-1][1] == n
+            assert all(b[i][1] == b[i + 1][0] for i in range(w - 1))
+            assert max(h - l for l, h in b) - min(h - l for l, h in b) <= 1

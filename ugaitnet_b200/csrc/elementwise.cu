@@ -140,9 +140,63 @@ __global__ void bwd_act_kernel(const float* __restrict__ dy, const YT* __restric
   }
 }
 
+// tensor-core storage variant: 8 channels per thread, 32-bit index math, 16-byte loads / stores
+template <int P>
+__global__ void __launch_bounds__(256) bwd_act_vec8_kernel(const float* __restrict__ dy,
+                                                           const __nv_bfloat16* __restrict__ y,
+                                                           const uint8_t* __restrict__ idx,
+                                                           __nv_bfloat16* __restrict__ dz, int B, int Ho, int Wo,
+                                                           int Hp, int Wp, int C8, int act, float alpha, int pool) {
+  const unsigned total = (unsigned)B * Ho * Wo * C8;
+  const long long plane = (long long)total * 8;
+  for (unsigned e = blockIdx.x * blockDim.x + threadIdx.x; e < total; e += gridDim.x * blockDim.x) {
+    const unsigned c8 = e % C8, pix = e / C8;
+    const unsigned xo = pix % Wo, t2 = pix / Wo, yo = t2 % Ho, b = t2 / Ho;
+    float v[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = 0.f;
+    bool live = true;
+    long long o = (long long)e * 8;
+    int pos = 0;
+    if (pool) {
+      const unsigned yp = yo >> 1, xp = xo >> 1;
+      live = yp < (unsigned)Hp && xp < (unsigned)Wp;
+      o = ((((long long)b * Hp + yp) * Wp + xp) * C8 + c8) * 8;
+      pos = ((yo & 1) << 1) | (xo & 1);
+    }
+    if (live) {
+      const float4 d0 = *reinterpret_cast<const float4*>(dy + o), d1 = *reinterpret_cast<const float4*>(dy + o + 4);
+      const uint4 yr = *reinterpret_cast<const uint4*>(y + o);
+      const __nv_bfloat16* yh = reinterpret_cast<const __nv_bfloat16*>(&yr);
+      const float dd[8] = {d0.x, d0.y, d0.z, d0.w, d1.x, d1.y, d1.z, d1.w};
+      unsigned long long ib = 0;
+      if (pool) ib = *reinterpret_cast<const unsigned long long*>(idx + o);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const bool sel = !pool || (int)((ib >> (8 * i)) & 0xff) == pos;
+        if (sel) v[i] = dd[i] * ugn_act_bwd(__bfloat162float(yh[i]), act, alpha);
+      }
+    }
+    __align__(16) __nv_bfloat16 hi[8], lo[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) ugn_split(v[i], hi[i], lo[i]);
+    *reinterpret_cast<uint4*>(dz + (long long)e * 8) = *reinterpret_cast<const uint4*>(hi);
+    if (P == 2) *reinterpret_cast<uint4*>(dz + plane + (long long)e * 8) = *reinterpret_cast<const uint4*>(lo);
+  }
+}
+
 int ew_bwd_act(ugn_ctx* ctx, const float* dy, const void* y, int y_bf16, const uint8_t* idx,
                void* dz, int mode, int B, int Ho, int Wo, int Hp, int Wp, int C, int act,
                float alpha, int pool, cudaStream_t st) {
+  if (y_bf16 && mode > 0 && C % 8 == 0 && (long long)B * Ho * Wo * (C / 8) < 0x7fffffffLL) {
+    int g8 = grid_for(ctx, (long long)B * Ho * Wo * (C / 8), 256);
+    if (mode == 1)
+      bwd_act_vec8_kernel<1><<<g8, 256, 0, st>>>(dy, (const __nv_bfloat16*)y, idx, (__nv_bfloat16*)dz, B, Ho, Wo, Hp, Wp, C / 8, act, alpha, pool);
+    else
+      bwd_act_vec8_kernel<2><<<g8, 256, 0, st>>>(dy, (const __nv_bfloat16*)y, idx, (__nv_bfloat16*)dz, B, Ho, Wo, Hp, Wp, C / 8, act, alpha, pool);
+    UGN_LAUNCHED(ctx);
+    return UGN_OK;
+  }
   int g = grid_for(ctx, (long long)B * Ho * Wo * C, 256);
 #define LAUNCH(M, YT) \
   bwd_act_kernel<M, YT><<<g, 256, 0, st>>>(dy, (const YT*)y, idx, dz, B, Ho, Wo, Hp, Wp, C, act, alpha, pool)

@@ -48,6 +48,7 @@ struct TcParams {
   int ldc, act;
   float alpha;
   int* err;
+  int dbg_shift, dbg_bo;   // experiment: row-shifted A view (UGN_DBG_SHIFT / UGN_DBG_BASEOFF)
 };
 
 static constexpr int kThreads = 192;
@@ -102,77 +103,94 @@ __global__ void __launch_bounds__(kThreads, 1) tc_kernel(const __grid_constant__
   const int BK = p.kslices * 16;
   const int cwA = p.a.rowbytes >> 1, cwB = p.b.rowbytes >> 1;
 
-  if (warp == 0 && lane == 0) {
-    // ===================== TMA producer =====================
+  if (warp == 0) {
+    // ===================== TMA producer (whole warp, one elected lane issues) =====================
     int nb_b = p.b.nbox;
     if (MODE == MODE_WGRAD) {
       int remain = p.nch * p.ntaps - tile_n * p.b.nbox;
       nb_b = min(nb_b, remain);
     }
     const uint32_t tx_bytes = p.planes * (p.a.nbox * p.a.box_bytes + nb_b * p.b.box_bytes);
+    // incremental K-step decode (no div/mod in the loop)
+    int d0 = 0, d1 = 0, d2 = 0;   // CONV: cc, kw, kh ; WGRAD: bx, by, bb
+    if (MODE == MODE_CONV) { d0 = ks_beg % p.ncc; int tap = ks_beg / p.ncc; d1 = tap % p.KW; d2 = tap / p.KW; }
+    if (MODE == MODE_WGRAD) { d0 = ks_beg % p.nbx; d1 = (ks_beg / p.nbx) % p.nby; d2 = ks_beg / (p.nbx * p.nby); }
+    int s = 0, ph = 0;
     for (int it = 0; it < nsteps; ++it) {
-      const int s = it % p.stages, ph = (it / p.stages) & 1;
       if (!mbar_wait(&empty[s], ph ^ 1, p.err, 1)) break;
-      mbar_expect_tx(&full[s], tx_bytes);
+      mbar_expect_tx_elect(&full[s], tx_bytes);
       const int ks = ks_beg + it;
       uint8_t* sa = smem + (size_t)s * stage_bytes;
       uint8_t* sb = sa + a_stage;
       for (int pl = 0; pl < p.planes; ++pl) {
         if (MODE == MODE_GEMM) {
           for (int j = 0; j < p.a.nbox; ++j) {
-            if (p.a.major == 0) tma_load_5d(&p.a.map, &full[s], sa + pl * p.a.plane_bytes, ks * BK, m0, pl, 0, 0);
-            else tma_load_5d(&p.a.map, &full[s], sa + pl * p.a.plane_bytes + j * p.a.box_bytes, m0 + j * cwA, ks * BK, pl, 0, 0);
+            if (p.a.major == 0) tma_load_5d_elect(&p.a.map, &full[s], sa + pl * p.a.plane_bytes, ks * BK, m0, pl, 0, 0);
+            else tma_load_5d_elect(&p.a.map, &full[s], sa + pl * p.a.plane_bytes + j * p.a.box_bytes, m0 + j * cwA, ks * BK, pl, 0, 0);
           }
           for (int j = 0; j < p.b.nbox; ++j) {
-            if (p.b.major == 0) tma_load_5d(&p.b.map, &full[s], sb + pl * p.b.plane_bytes, ks * BK, n0, pl, 0, 0);
-            else tma_load_5d(&p.b.map, &full[s], sb + pl * p.b.plane_bytes + j * p.b.box_bytes, n0 + j * cwB, ks * BK, pl, 0, 0);
+            if (p.b.major == 0) tma_load_5d_elect(&p.b.map, &full[s], sb + pl * p.b.plane_bytes, ks * BK, n0, pl, 0, 0);
+            else tma_load_5d_elect(&p.b.map, &full[s], sb + pl * p.b.plane_bytes + j * p.b.box_bytes, n0 + j * cwB, ks * BK, pl, 0, 0);
           }
         } else if (MODE == MODE_CONV) {
-          const int cc = ks % p.ncc, tap = ks / p.ncc, kw = tap % p.KW, kh = tap / p.KW;
-          tma_load_5d(&p.a.map, &full[s], sa + pl * p.a.plane_bytes, cc * BK, x0 + p.sgn * kw, y0 + p.sgn * kh, nn0, pl);
+          const int cc = d0, kw = d1, kh = d2, tap = kh * p.KW + kw;
+          tma_load_5d_elect(&p.a.map, &full[s], sa + pl * p.a.plane_bytes, cc * BK, x0 + p.sgn * kw, y0 + p.sgn * kh, nn0, pl);
           for (int j = 0; j < p.b.nbox; ++j) {
-            if (p.b.major == 0) tma_load_5d(&p.b.map, &full[s], sb + pl * p.b.plane_bytes, cc * BK, tap, n0, pl, 0);
-            else tma_load_5d(&p.b.map, &full[s], sb + pl * p.b.plane_bytes + j * p.b.box_bytes, n0 + j * cwB, tap, cc * BK, pl, 0);
+            if (p.b.major == 0) tma_load_5d_elect(&p.b.map, &full[s], sb + pl * p.b.plane_bytes, cc * BK, tap, n0, pl, 0);
+            else tma_load_5d_elect(&p.b.map, &full[s], sb + pl * p.b.plane_bytes + j * p.b.box_bytes, n0 + j * cwB, tap, cc * BK, pl, 0);
           }
         } else {
-          const int bx = ks % p.nbx, by = (ks / p.nbx) % p.nby, bb = ks / (p.nbx * p.nby);
-          const int px = bx * p.bw, py = by * p.bh, pn = bb * p.bn;
+          const int px = d0 * p.bw, py = d1 * p.bh, pn = d2 * p.bn;
           for (int j = 0; j < p.a.nbox; ++j)
-            tma_load_5d(&p.a.map, &full[s], sa + pl * p.a.plane_bytes + j * p.a.box_bytes, m0 + j * cwA, px, py, pn, pl);
+            tma_load_5d_elect(&p.a.map, &full[s], sa + pl * p.a.plane_bytes + j * p.a.box_bytes, m0 + j * cwA, px, py, pn, pl);
+          int chunk = (tile_n * p.b.nbox) % p.nch, tap = (tile_n * p.b.nbox) / p.nch;
+          int tkw = tap % p.KW, tkh = tap / p.KW;
           for (int j = 0; j < nb_b; ++j) {
-            const int gb = tile_n * p.b.nbox + j, chunk = gb % p.nch, tap = gb / p.nch;
-            tma_load_5d(&p.b.map, &full[s], sb + pl * p.b.plane_bytes + j * p.b.box_bytes, chunk * p.cw,
-                        px + tap % p.KW, py + tap / p.KW, pn, pl);
+            tma_load_5d_elect(&p.b.map, &full[s], sb + pl * p.b.plane_bytes + j * p.b.box_bytes, chunk * p.cw,
+                              px + tkw, py + tkh, pn, pl);
+            if (++chunk == p.nch) { chunk = 0; if (++tkw == p.KW) { tkw = 0; ++tkh; } }
           }
         }
       }
+      if (MODE == MODE_CONV) { if (++d0 == p.ncc) { d0 = 0; if (++d1 == p.KW) { d1 = 0; ++d2; } } }
+      if (MODE == MODE_WGRAD) { if (++d0 == p.nbx) { d0 = 0; if (++d1 == p.nby) { d1 = 0; ++d2; } } }
+      if (++s == p.stages) { s = 0; ph ^= 1; }
     }
-  } else if (warp == 1 && lane == 0) {
-    // ===================== MMA issuer (one thread) =====================
+  } else if (warp == 1) {
+    // ===================== MMA issuer (whole warp converged, one elected lane issues) =====================
     const uint32_t idesc = make_idesc_bf16(128, p.block_n, p.a.major, p.b.major);
     const uint32_t la = p.a.rowbytes == 128 ? 2u : 4u, lb = p.b.rowbytes == 128 ? 2u : 4u;
+    const uint32_t smem0 = smem_u32(smem);
+    // descriptors of stage 0 / plane 0 / slice 0; everything else is a 16-byte-unit add on the low word
+    const uint64_t a0 = make_smem_desc(smem0, p.a.lbo, p.a.sbo, la);
+    const uint64_t b0 = make_smem_desc(smem0 + a_stage, p.b.lbo, p.b.sbo, lb);
+    const uint32_t st16 = stage_bytes >> 4, ka16 = p.a.kadv >> 4, kb16 = p.b.kadv >> 4;
+    const uint32_t pa16 = p.a.plane_bytes >> 4, pb16 = p.b.plane_bytes >> 4;
     uint32_t accum = 0;
+    int s = 0, ph = 0;
     for (int it = 0; it < nsteps; ++it) {
-      const int s = it % p.stages, ph = (it / p.stages) & 1;
       if (!mbar_wait(&full[s], ph, p.err, 2)) break;
       fence_after_sync();
-      const uint32_t sa = smem_u32(smem + (size_t)s * stage_bytes);
-      const uint32_t sb = sa + a_stage;
+      uint64_t a_hi = a0 + (uint64_t)(s * st16), b_hi = b0 + (uint64_t)(s * st16);
+      if (p.dbg_shift) {
+        const uint32_t sh = smem0 + s * stage_bytes + p.dbg_shift * p.a.rowbytes;
+        const uint32_t bo = p.dbg_bo == 1 ? ((sh >> 7) & 7) : (p.dbg_bo == 2 ? (p.dbg_shift & 7) : 0);
+        a_hi = make_smem_desc(sh, p.a.lbo, p.a.sbo, la, bo);
+      }
       for (int k = 0; k < p.kslices; ++k) {
-        const uint64_t a_hi = make_smem_desc(sa + k * p.a.kadv, p.a.lbo, p.a.sbo, la);
-        const uint64_t b_hi = make_smem_desc(sb + k * p.b.kadv, p.b.lbo, p.b.sbo, lb);
-        umma_f16(tmem_base, a_hi, b_hi, idesc, accum);
+        umma_f16_elect(tmem_base, a_hi, b_hi, idesc, accum);
         accum = 1;
         if (p.planes == 2) {
-          const uint64_t a_lo = make_smem_desc(sa + p.a.plane_bytes + k * p.a.kadv, p.a.lbo, p.a.sbo, la);
-          const uint64_t b_lo = make_smem_desc(sb + p.b.plane_bytes + k * p.b.kadv, p.b.lbo, p.b.sbo, lb);
-          umma_f16(tmem_base, a_hi, b_lo, idesc, 1);
-          umma_f16(tmem_base, a_lo, b_hi, idesc, 1);
+          umma_f16_elect(tmem_base, a_hi, b_hi + pb16, idesc, 1);
+          umma_f16_elect(tmem_base, a_hi + pa16, b_hi, idesc, 1);
         }
+        a_hi += ka16;
+        b_hi += kb16;
       }
-      umma_commit(&empty[s]);  // frees the smem slot once these MMAs have read it
+      umma_commit_elect(&empty[s]);  // frees the smem slot once these MMAs have read it
+      if (++s == p.stages) { s = 0; ph ^= 1; }
     }
-    umma_commit(tmem_full);    // accumulator complete
+    umma_commit_elect(tmem_full);    // accumulator complete
   } else if (warp >= 2) {
     // ===================== epilogue (4 warps, one TMEM lane quadrant each) =====================
     const int q = warp & 3;
@@ -411,6 +429,8 @@ int tc_gemm_ex(ugn_ctx* ctx, int P, int M, int N, int K, const __nv_bfloat16* A,
   p.ksplit = split;
   p.epi = (split > 1 || accumulate) ? EPI_F32_ATOMIC : EPI_F32;
   p.out_f32 = C; p.ldc = ldc; p.bias = bias; p.mask = mask; p.act = act; p.alpha = alpha;
+  if (const char* e = getenv("UGN_DBG_SHIFT")) p.dbg_shift = atoi(e);
+  if (const char* e = getenv("UGN_DBG_BASEOFF")) p.dbg_bo = atoi(e);
   if (split > 1 && !accumulate) UGN_CUDA(cudaMemsetAsync(C, 0, sizeof(float) * (size_t)M * ldc, st));
   dim3 grid(ugn_cdiv(M, 128), ugn_cdiv(N, p.block_n), split);
   return launch<MODE_GEMM>(ctx, p, grid, st);

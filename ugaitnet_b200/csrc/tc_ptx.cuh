@@ -122,13 +122,56 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
   for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+// ---- single-issuer variants: executed by a whole (converged) warp, one elected lane issues.
+// Keeping the control flow warp-uniform lets ptxas hold descriptors / coordinates in uniform
+// registers instead of wrapping every UTCHMMA / UTMALDG in an ELECT + R2UR.BROADCAST waterfall loop.
+__device__ __forceinline__ void mbar_expect_tx_elect(uint64_t* bar, uint32_t bytes) {
+  asm volatile(
+      "{\n\t.reg .pred P;\n\t"
+      "elect.sync _|P, 0xffffffff;\n\t"
+      "@P mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n\t}\n" ::"r"(smem_u32(bar)), "r"(bytes)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_5d_elect(const CUtensorMap* m, uint64_t* bar, void* dst, int c0, int c1,
+                                                  int c2, int c3, int c4) {
+  asm volatile(
+      "{\n\t.reg .pred P;\n\t"
+      "elect.sync _|P, 0xffffffff;\n\t"
+      "@P cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, "
+      "%6, %7}], [%2];\n\t}\n"
+      :
+      : "r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2),
+        "r"(c3), "r"(c4)
+      : "memory");
+}
+__device__ __forceinline__ void umma_f16_elect(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                               uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred P, Q;\n\t"
+      "elect.sync _|P, 0xffffffff;\n\t"
+      "setp.ne.b32 Q, %4, 0;\n\t"
+      "@P tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, Q;\n\t}\n"
+      :
+      : "r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_elect(uint64_t* bar) {
+  asm volatile(
+      "{\n\t.reg .pred P;\n\t"
+      "elect.sync _|P, 0xffffffff;\n\t"
+      "@P tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}\n" ::"r"(smem_u32(bar))
+      : "memory");
+}
+
 // ---- UMMA descriptors -----------------------------------------------------------------
 // Shared-memory matrix descriptor (cute::UMMA::SmemDescriptor bit layout):
 //   [0,14) start address >> 4 | [16,30) leading byte offset >> 4 | [32,46) stride byte offset >> 4
 //   [46,48) version = 1 (Blackwell) | [49,52) base offset = 0 | [61,64) layout type
 //   layout type: 0 none, 2 SWIZZLE_128B, 4 SWIZZLE_64B, 6 SWIZZLE_32B
-__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo, uint32_t sbo, uint32_t layout) {
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo, uint32_t sbo, uint32_t layout,
+                                                   uint32_t base_offset = 0) {
   uint64_t d = 0;
+  d |= (uint64_t)(base_offset & 7) << 49;
   d |= (uint64_t)((saddr >> 4) & 0x3fff);
   d |= (uint64_t)((lbo >> 4) & 0x3fff) << 16;
   d |= (uint64_t)((sbo >> 4) & 0x3fff) << 32;

@@ -407,6 +407,21 @@ class UGaitEngine:
             self._step_body(p, True)
         return self._report(p, with_reg=True)
 
+    @torch.no_grad()
+    def eval_losses(self, inputs, flags, labels) -> Dict[str, torch.Tensor]:
+        """Forward in inference mode + the two losses (Keras test_function / validation pass)."""
+        cfg, h = self.cfg, self.ctx.h
+        B = int(inputs[0].shape[0])
+        p = self.plan(B, True)
+        self._set_inputs(p, inputs, flags, labels)
+        sig, _ = self._forward(p, False)
+        st = stream_ptr()
+        check(lib.ugn_triplet_all(h, sig.ptr, p.R["labels"].ptr, cfg.margin, 1.0, p.R["trip_out"].ptr, None,
+                                  p.R["trip_ws"].ptr, st))
+        if cfg.nclasses > 0:
+            check(lib.ugn_softmax_ce(h, p.R["logits"].ptr, p.R["labels"].ptr, p.R["ce_out"].ptr, None, 1.0, st))
+        return self._report(p)
+
     def _report(self, p: "_Plan", with_reg: bool = False) -> Dict[str, torch.Tensor]:
         out = {"triplet": p.trip_out[0], "count": p.trip_out[1], "signature": p.br[0].out if self.cfg.single else p.sig}
         if self.cfg.nclasses > 0:
