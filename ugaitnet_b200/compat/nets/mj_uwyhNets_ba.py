@@ -19,11 +19,11 @@ from typing import Dict, List, Optional
 import numpy as np
 import torch
 
-from ... import ops
-from ...config import ACT_LEAKY, ACT_RELU, BRANCH_NAMES, MERGE_MAX, NetConfig
-from ...net import UGaitEngine
-from ..keras_shim import Average, History, Maximum, _Tag, merge_id_of, optimizers  # noqa: F401
-from .triplet_loss_all import triplet_loss
+from ugaitnet_b200 import ops
+from ugaitnet_b200.config import ACT_LEAKY, ACT_RELU, BRANCH_NAMES, MERGE_MAX, NetConfig
+from ugaitnet_b200.net import UGaitEngine
+from ugaitnet_b200.compat.keras_shim import Average, History, Maximum, _Tag, merge_id_of, optimizers  # noqa: F401
+from ugaitnet_b200.compat.nets.triplet_loss_all import triplet_loss
 
 MATH_MODE = os.environ.get("UGN_MATH_MODE", "bf16x3")
 

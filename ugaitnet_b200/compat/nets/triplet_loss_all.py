@@ -8,7 +8,7 @@ from __future__ import annotations
 import numpy as np
 import torch
 
-from ... import ops
+from ugaitnet_b200 import ops
 
 
 class _TripletLoss:

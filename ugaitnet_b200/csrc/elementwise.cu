@@ -542,3 +542,21 @@ int ew_optim(ugn_ctx* ctx, int opt, float* w, const float* g, float* m, float* v
   UGN_LAUNCHED(ctx);
   return UGN_OK;
 }
+
+// y = act(y + bias[col]) * mask   (post pass of the split-K dense forward)
+__global__ void bias_act_mask_kernel(float* __restrict__ y, const float* __restrict__ bias,
+                                     const float* __restrict__ mask, long long n, int cols, int act, float alpha) {
+  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < n; e += (long long)gridDim.x * blockDim.x) {
+    float v = y[e] + (bias ? bias[e % cols] : 0.f);
+    v = ugn_act_fwd(v, act, alpha);
+    if (mask) v *= mask[e];
+    y[e] = v;
+  }
+}
+int ew_bias_act_mask(ugn_ctx* ctx, float* y, const float* bias, const float* mask, long long rows, int cols,
+                     int act, float alpha, cudaStream_t st) {
+  long long n = rows * cols;
+  bias_act_mask_kernel<<<grid_for(ctx, n, 256), 256, 0, st>>>(y, bias, mask, n, cols, act, alpha);
+  UGN_LAUNCHED(ctx);
+  return UGN_OK;
+}

@@ -49,12 +49,92 @@ struct TcParams {
   float alpha;
   int* err;
   int dbg_shift, dbg_bo;   // experiment: row-shifted A view (UGN_DBG_SHIFT / UGN_DBG_BASEOFF)
+  // patch-resident conv (tc_convp_kernel)
+  int T, SW, RH, PR, KH, xorg, yorg, tiles_y, tmem_cols;
+  int patch_chunk_bytes, patch_plane_bytes;
 };
 
 static constexpr int kThreads = 192;
 static constexpr int kTmemCols = 256;
 
 __device__ __forceinline__ void epi_barrier() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+
+// Epilogue of one 128-row conv accumulator tile whose rows are the (bn x bh x bw) pixel box at
+// (nn0, y0, x0): bias + activation, then bf16 hi/lo store, f32 store (dgrad) or fused 2x2 max-pool.
+__device__ __forceinline__ void conv_tile_epilogue(const TcParams& p, uint8_t* smem, uint32_t trow, int r, bool ok,
+                                                   int x0, int y0, int nn0, int n0) {
+  float v[16];
+  const int xl = r % p.bw, yl = (r / p.bw) % p.bh, nl = r / (p.bw * p.bh);
+    const int x = x0 + xl, y = y0 + yl, n = nn0 + nl;
+    const bool rv = ok && nl < p.bn && x < p.Wout && y < p.Hout && n < p.Bn;
+    if (p.epi != EPI_BF16_POOL) {
+      const long long obase = (((long long)n * p.Hout + y) * p.Wout + x) * p.Cout;
+      for (int c0 = 0; c0 < p.block_n; c0 += 16) {
+        tmem_ld16(trow + c0, v);
+        if (!rv) continue;
+        if (p.epi == EPI_F32 && (p.Cout & 3) == 0 && n0 + c0 + 16 <= p.Cout) {
+          float* dst = p.out_f32 + obase + n0 + c0;
+#pragma unroll
+          for (int i = 0; i < 16; i += 4)
+            *reinterpret_cast<float4*>(dst + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+          continue;
+        }
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          const int c = n0 + c0 + i;
+          if (c >= p.Cout) continue;
+          if (p.epi == EPI_F32) {
+            p.out_f32[obase + c] = v[i];
+          } else {
+            float z = ugn_act_fwd(v[i] + (p.bias ? p.bias[c] : 0.f), p.act, p.alpha);
+            __nv_bfloat16 hi, lo;
+            ugn_split(z, hi, lo);
+            p.out_bf16[obase + c] = hi;
+            if (p.planes == 2) p.out_bf16[p.out_plane + obase + c] = lo;
+          }
+        }
+      }
+    } else {
+      // fused 2x2 max-pool: stage act(z+b) through the (now idle) stage-0 smem, 32 columns at a time
+      float* stg = reinterpret_cast<float*>(smem);  // [128][33]
+      const int t = threadIdx.x - 64;
+      const int pw = p.bw >> 1, ph2 = p.bh >> 1, npool = pw * ph2 * p.bn;
+      for (int c0 = 0; c0 < p.block_n; c0 += 32) {
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          tmem_ld16(trow + c0 + 16 * h, v);
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const int c = n0 + c0 + 16 * h + i;
+            float z = v[i] + ((p.bias && c < p.Cout) ? p.bias[c] : 0.f);
+            stg[r * 33 + 16 * h + i] = ugn_act_fwd(z, p.act, p.alpha);
+          }
+        }
+        epi_barrier();
+        const int col = t & 31, c = n0 + c0 + col;
+        for (int pp = t >> 5; pp < npool; pp += 4) {
+          const int pxl = pp % pw, pyl = (pp / pw) % ph2, pnl = pp / (pw * ph2);
+          const int r00 = (pnl * p.bh + 2 * pyl) * p.bw + 2 * pxl;
+          float best = stg[r00 * 33 + col];
+          int pos = 0;
+          float o1 = stg[(r00 + 1) * 33 + col], o2 = stg[(r00 + p.bw) * 33 + col], o3 = stg[(r00 + p.bw + 1) * 33 + col];
+          if (o1 > best) { best = o1; pos = 1; }
+          if (o2 > best) { best = o2; pos = 2; }
+          if (o3 > best) { best = o3; pos = 3; }
+          const int xp = (x0 >> 1) + pxl, yp = (y0 >> 1) + pyl, nn = nn0 + pnl;
+          if (ok && c < p.Cout && xp < p.Wp && yp < p.Hp && nn < p.Bn) {
+            const long long o = (((long long)nn * p.Hp + yp) * p.Wp + xp) * p.Cout + c;
+            __nv_bfloat16 hi, lo;
+            ugn_split(best, hi, lo);
+            p.out_bf16[o] = hi;
+            if (p.planes == 2) p.out_bf16[p.out_plane + o] = lo;
+            p.pool_idx[o] = (uint8_t)pos;
+          }
+        }
+        epi_barrier();
+      }
+    }
+}
 
 template <int MODE>
 __global__ void __launch_bounds__(kThreads, 1) tc_kernel(const __grid_constant__ TcParams p) {
@@ -104,7 +184,9 @@ __global__ void __launch_bounds__(kThreads, 1) tc_kernel(const __grid_constant__
   const int cwA = p.a.rowbytes >> 1, cwB = p.b.rowbytes >> 1;
 
   if (warp == 0) {
-    // ===================== TMA producer (whole warp, one elected lane issues) =====================
+   if (elect_one()) {
+    // ===================== TMA producer (one elected lane; `if (elect.sync)` lets ptxas treat the
+    // region as single-threaded: descriptors / coordinates live in uniform registers) =====================
     int nb_b = p.b.nbox;
     if (MODE == MODE_WGRAD) {
       int remain = p.nch * p.ntaps - tile_n * p.b.nbox;
@@ -118,35 +200,35 @@ __global__ void __launch_bounds__(kThreads, 1) tc_kernel(const __grid_constant__
     int s = 0, ph = 0;
     for (int it = 0; it < nsteps; ++it) {
       if (!mbar_wait(&empty[s], ph ^ 1, p.err, 1)) break;
-      mbar_expect_tx_elect(&full[s], tx_bytes);
+      mbar_expect_tx(&full[s], tx_bytes);
       const int ks = ks_beg + it;
       uint8_t* sa = smem + (size_t)s * stage_bytes;
       uint8_t* sb = sa + a_stage;
       for (int pl = 0; pl < p.planes; ++pl) {
         if (MODE == MODE_GEMM) {
           for (int j = 0; j < p.a.nbox; ++j) {
-            if (p.a.major == 0) tma_load_5d_elect(&p.a.map, &full[s], sa + pl * p.a.plane_bytes, ks * BK, m0, pl, 0, 0);
-            else tma_load_5d_elect(&p.a.map, &full[s], sa + pl * p.a.plane_bytes + j * p.a.box_bytes, m0 + j * cwA, ks * BK, pl, 0, 0);
+            if (p.a.major == 0) tma_load_5d(&p.a.map, &full[s], sa + pl * p.a.plane_bytes, ks * BK, m0, pl, 0, 0);
+            else tma_load_5d(&p.a.map, &full[s], sa + pl * p.a.plane_bytes + j * p.a.box_bytes, m0 + j * cwA, ks * BK, pl, 0, 0);
           }
           for (int j = 0; j < p.b.nbox; ++j) {
-            if (p.b.major == 0) tma_load_5d_elect(&p.b.map, &full[s], sb + pl * p.b.plane_bytes, ks * BK, n0, pl, 0, 0);
-            else tma_load_5d_elect(&p.b.map, &full[s], sb + pl * p.b.plane_bytes + j * p.b.box_bytes, n0 + j * cwB, ks * BK, pl, 0, 0);
+            if (p.b.major == 0) tma_load_5d(&p.b.map, &full[s], sb + pl * p.b.plane_bytes, ks * BK, n0, pl, 0, 0);
+            else tma_load_5d(&p.b.map, &full[s], sb + pl * p.b.plane_bytes + j * p.b.box_bytes, n0 + j * cwB, ks * BK, pl, 0, 0);
           }
         } else if (MODE == MODE_CONV) {
           const int cc = d0, kw = d1, kh = d2, tap = kh * p.KW + kw;
-          tma_load_5d_elect(&p.a.map, &full[s], sa + pl * p.a.plane_bytes, cc * BK, x0 + p.sgn * kw, y0 + p.sgn * kh, nn0, pl);
+          tma_load_5d(&p.a.map, &full[s], sa + pl * p.a.plane_bytes, cc * BK, x0 + p.sgn * kw, y0 + p.sgn * kh, nn0, pl);
           for (int j = 0; j < p.b.nbox; ++j) {
-            if (p.b.major == 0) tma_load_5d_elect(&p.b.map, &full[s], sb + pl * p.b.plane_bytes, cc * BK, tap, n0, pl, 0);
-            else tma_load_5d_elect(&p.b.map, &full[s], sb + pl * p.b.plane_bytes + j * p.b.box_bytes, n0 + j * cwB, tap, cc * BK, pl, 0);
+            if (p.b.major == 0) tma_load_5d(&p.b.map, &full[s], sb + pl * p.b.plane_bytes, cc * BK, tap, n0, pl, 0);
+            else tma_load_5d(&p.b.map, &full[s], sb + pl * p.b.plane_bytes + j * p.b.box_bytes, n0 + j * cwB, tap, cc * BK, pl, 0);
           }
         } else {
           const int px = d0 * p.bw, py = d1 * p.bh, pn = d2 * p.bn;
           for (int j = 0; j < p.a.nbox; ++j)
-            tma_load_5d_elect(&p.a.map, &full[s], sa + pl * p.a.plane_bytes + j * p.a.box_bytes, m0 + j * cwA, px, py, pn, pl);
+            tma_load_5d(&p.a.map, &full[s], sa + pl * p.a.plane_bytes + j * p.a.box_bytes, m0 + j * cwA, px, py, pn, pl);
           int chunk = (tile_n * p.b.nbox) % p.nch, tap = (tile_n * p.b.nbox) / p.nch;
           int tkw = tap % p.KW, tkh = tap / p.KW;
           for (int j = 0; j < nb_b; ++j) {
-            tma_load_5d_elect(&p.b.map, &full[s], sb + pl * p.b.plane_bytes + j * p.b.box_bytes, chunk * p.cw,
+            tma_load_5d(&p.b.map, &full[s], sb + pl * p.b.plane_bytes + j * p.b.box_bytes, chunk * p.cw,
                               px + tkw, py + tkh, pn, pl);
             if (++chunk == p.nch) { chunk = 0; if (++tkw == p.KW) { tkw = 0; ++tkh; } }
           }
@@ -156,8 +238,10 @@ __global__ void __launch_bounds__(kThreads, 1) tc_kernel(const __grid_constant__
       if (MODE == MODE_WGRAD) { if (++d0 == p.nbx) { d0 = 0; if (++d1 == p.nby) { d1 = 0; ++d2; } } }
       if (++s == p.stages) { s = 0; ph ^= 1; }
     }
+   }
   } else if (warp == 1) {
-    // ===================== MMA issuer (whole warp converged, one elected lane issues) =====================
+   if (elect_one()) {
+    // ===================== MMA issuer (one elected lane) =====================
     const uint32_t idesc = make_idesc_bf16(128, p.block_n, p.a.major, p.b.major);
     const uint32_t la = p.a.rowbytes == 128 ? 2u : 4u, lb = p.b.rowbytes == 128 ? 2u : 4u;
     const uint32_t smem0 = smem_u32(smem);
@@ -178,19 +262,20 @@ __global__ void __launch_bounds__(kThreads, 1) tc_kernel(const __grid_constant__
         a_hi = make_smem_desc(sh, p.a.lbo, p.a.sbo, la, bo);
       }
       for (int k = 0; k < p.kslices; ++k) {
-        umma_f16_elect(tmem_base, a_hi, b_hi, idesc, accum);
+        umma_f16(tmem_base, a_hi, b_hi, idesc, accum);
         accum = 1;
         if (p.planes == 2) {
-          umma_f16_elect(tmem_base, a_hi, b_hi + pb16, idesc, 1);
-          umma_f16_elect(tmem_base, a_hi + pa16, b_hi, idesc, 1);
+          umma_f16(tmem_base, a_hi, b_hi + pb16, idesc, 1);
+          umma_f16(tmem_base, a_hi + pa16, b_hi, idesc, 1);
         }
         a_hi += ka16;
         b_hi += kb16;
       }
-      umma_commit_elect(&empty[s]);  // frees the smem slot once these MMAs have read it
+      umma_commit(&empty[s]);  // frees the smem slot once these MMAs have read it
       if (++s == p.stages) { s = 0; ph ^= 1; }
     }
-    umma_commit_elect(tmem_full);    // accumulator complete
+    umma_commit(tmem_full);    // accumulator complete
+   }
   } else if (warp >= 2) {
     // ===================== epilogue (4 warps, one TMEM lane quadrant each) =====================
     const int q = warp & 3;
@@ -202,9 +287,23 @@ __global__ void __launch_bounds__(kThreads, 1) tc_kernel(const __grid_constant__
 
     if (MODE == MODE_GEMM) {
       const int m = m0 + r;
+      const bool vec = (p.ldc & 3) == 0 && p.epi == EPI_F32 && !p.mask;
       for (int c0 = 0; c0 < p.block_n; c0 += 16) {
         tmem_ld16(trow + c0, v);
         if (!ok || m >= p.M) continue;
+        if (vec && n0 + c0 + 16 <= p.N) {
+          float* dst = p.out_f32 + (long long)m * p.ldc + n0 + c0;
+#pragma unroll
+          for (int i = 0; i < 16; i += 4) {
+            float4 o4;
+            o4.x = ugn_act_fwd(v[i] + (p.bias ? p.bias[n0 + c0 + i] : 0.f), p.act, p.alpha);
+            o4.y = ugn_act_fwd(v[i + 1] + (p.bias ? p.bias[n0 + c0 + i + 1] : 0.f), p.act, p.alpha);
+            o4.z = ugn_act_fwd(v[i + 2] + (p.bias ? p.bias[n0 + c0 + i + 2] : 0.f), p.act, p.alpha);
+            o4.w = ugn_act_fwd(v[i + 3] + (p.bias ? p.bias[n0 + c0 + i + 3] : 0.f), p.act, p.alpha);
+            *reinterpret_cast<float4*>(dst + i) = o4;
+          }
+          continue;
+        }
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
           const int n = n0 + c0 + i;
@@ -221,69 +320,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_kernel(const __grid_constant__
         }
       }
     } else if (MODE == MODE_CONV) {
-      const int xl = r % p.bw, yl = (r / p.bw) % p.bh, nl = r / (p.bw * p.bh);
-      const int x = x0 + xl, y = y0 + yl, n = nn0 + nl;
-      const bool rv = ok && nl < p.bn && x < p.Wout && y < p.Hout && n < p.Bn;
-      if (p.epi != EPI_BF16_POOL) {
-        const long long obase = (((long long)n * p.Hout + y) * p.Wout + x) * p.Cout;
-        for (int c0 = 0; c0 < p.block_n; c0 += 16) {
-          tmem_ld16(trow + c0, v);
-          if (!rv) continue;
-#pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            const int c = n0 + c0 + i;
-            if (c >= p.Cout) continue;
-            if (p.epi == EPI_F32) {
-              p.out_f32[obase + c] = v[i];
-            } else {
-              float z = ugn_act_fwd(v[i] + (p.bias ? p.bias[c] : 0.f), p.act, p.alpha);
-              __nv_bfloat16 hi, lo;
-              ugn_split(z, hi, lo);
-              p.out_bf16[obase + c] = hi;
-              if (p.planes == 2) p.out_bf16[p.out_plane + obase + c] = lo;
-            }
-          }
-        }
-      } else {
-        // fused 2x2 max-pool: stage act(z+b) through the (now idle) stage-0 smem, 32 columns at a time
-        float* stg = reinterpret_cast<float*>(smem);  // [128][33]
-        const int t = threadIdx.x - 64;
-        const int pw = p.bw >> 1, ph2 = p.bh >> 1, npool = pw * ph2 * p.bn;
-        for (int c0 = 0; c0 < p.block_n; c0 += 32) {
-#pragma unroll
-          for (int h = 0; h < 2; ++h) {
-            tmem_ld16(trow + c0 + 16 * h, v);
-#pragma unroll
-            for (int i = 0; i < 16; ++i) {
-              const int c = n0 + c0 + 16 * h + i;
-              float z = v[i] + ((p.bias && c < p.Cout) ? p.bias[c] : 0.f);
-              stg[r * 33 + 16 * h + i] = ugn_act_fwd(z, p.act, p.alpha);
-            }
-          }
-          epi_barrier();
-          const int col = t & 31, c = n0 + c0 + col;
-          for (int pp = t >> 5; pp < npool; pp += 4) {
-            const int pxl = pp % pw, pyl = (pp / pw) % ph2, pnl = pp / (pw * ph2);
-            const int r00 = (pnl * p.bh + 2 * pyl) * p.bw + 2 * pxl;
-            float best = stg[r00 * 33 + col];
-            int pos = 0;
-            float o1 = stg[(r00 + 1) * 33 + col], o2 = stg[(r00 + p.bw) * 33 + col], o3 = stg[(r00 + p.bw + 1) * 33 + col];
-            if (o1 > best) { best = o1; pos = 1; }
-            if (o2 > best) { best = o2; pos = 2; }
-            if (o3 > best) { best = o3; pos = 3; }
-            const int xp = (x0 >> 1) + pxl, yp = (y0 >> 1) + pyl, nn = nn0 + pnl;
-            if (ok && c < p.Cout && xp < p.Wp && yp < p.Hp && nn < p.Bn) {
-              const long long o = (((long long)nn * p.Hp + yp) * p.Wp + xp) * p.Cout + c;
-              __nv_bfloat16 hi, lo;
-              ugn_split(best, hi, lo);
-              p.out_bf16[o] = hi;
-              if (p.planes == 2) p.out_bf16[p.out_plane + o] = lo;
-              p.pool_idx[o] = (uint8_t)pos;
-            }
-          }
-          epi_barrier();
-        }
-      }
+      conv_tile_epilogue(p, smem, trow, r, ok, x0, y0, nn0, n0);
     } else {  // MODE_WGRAD: rows = co, columns = (box j -> tap, ci chunk)
       const int co = m0 + r;
       for (int c0 = 0; c0 < p.block_n; c0 += 16) {
@@ -306,6 +343,164 @@ __global__ void __launch_bounds__(kThreads, 1) tc_kernel(const __grid_constant__
     __syncwarp();
     fence_after_sync();
     tmem_dealloc(tmem_base, kTmemCols);
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// Patch-resident implicit-GEMM convolution.
+// One CTA owns T M-tiles = T*RH consecutive output rows of one image.  The activation patch
+// (PR = T*RH+KH-1 image rows x SW pixel slots, every channel chunk, every plane) is loaded ONCE by TMA
+// into 128B/64B-swizzled smem; the A operand of filter tap (kh,kw) for tile t is the SAME patch viewed
+// through a UMMA descriptor whose start address is advanced by ((t*RH+kh)*SW+kw) rows (the swizzle is a
+// function of the absolute smem address, so row-shifted views are exact -- scripts/shift_check.py).
+// Only the weight tile of each (tap, channel chunk) streams through the mbarrier ring, and it is shared by
+// the T accumulators in TMEM.  sgn=-1 (input gradient) flips the taps and shifts the patch origin.
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kThreads, 1) tc_convp_kernel(const __grid_constant__ TcParams p) {
+  // PERSISTENT: each CTA walks tiles blockIdx.x, +gridDim.x, ...; two TMEM accumulator sets so that the
+  // epilogue of tile i (CUDA cores) overlaps the mainloop of tile i+1 (tensor pipe).
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const uint32_t patch_bytes = p.planes * p.patch_plane_bytes;
+  const uint32_t b_stage = p.planes * p.b.plane_bytes;
+  uint8_t* stg = smem + patch_bytes;                 // epilogue staging, 128 x 33 floats (17 KB region)
+  uint8_t* ring = stg + 17 * 1024;
+  uint64_t* full = reinterpret_cast<uint64_t*>(ring + (size_t)p.stages * b_stage);
+  uint64_t* empty = full + p.stages;
+  uint64_t* patch_full = empty + p.stages;
+  uint64_t* patch_empty = patch_full + 1;
+  uint64_t* tmem_full = patch_empty + 1;   // [2]
+  uint64_t* tmem_empty = tmem_full + 2;    // [2]
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nsteps = p.ksteps_total;
+  const int ntiles = p.M;          // total tiles = n_tiles_n * images * tiles_y
+  const int tiles_mn = p.N;        // images * tiles_y
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < p.stages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    mbar_init(patch_full, 1);
+    mbar_init(patch_empty, 1);
+    for (int b = 0; b < 2; ++b) { mbar_init(&tmem_full[b], 1); mbar_init(&tmem_empty[b], 128); }
+    fence_mbar_init();
+    prefetch_tmap(&p.a.map);
+    prefetch_tmap(&p.b.map);
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_ptr, 512);
+    tmem_relinquish();
+  }
+  fence_before_sync();
+  __syncthreads();
+  fence_after_sync();
+  const uint32_t tmem_base = *tmem_ptr;
+  const int BK = p.kslices * 16;
+  const int cwB = p.b.rowbytes >> 1;
+  const uint32_t acc_cols = (uint32_t)(p.T * p.block_n);
+
+  if (warp == 0) {
+   if (elect_one()) {
+    // ---- producer ----
+    const uint32_t tx_bytes = p.planes * p.b.nbox * p.b.box_bytes;
+    int s = 0, ph = 0, li = 0;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++li) {
+      const int tile_n = tile / tiles_mn, rem = tile % tiles_mn;
+      const int img = rem / p.tiles_y, ty = rem % p.tiles_y;
+      const int y0 = ty * p.T * p.RH, n0 = tile_n * p.block_n;
+      mbar_wait(patch_empty, (li & 1) ^ 1, p.err, 5);
+      mbar_expect_tx(patch_full, patch_bytes);
+      for (int pl = 0; pl < p.planes; ++pl)
+        for (int cc = 0; cc < p.ncc; ++cc)
+          tma_load_5d(&p.a.map, patch_full, smem + pl * p.patch_plane_bytes + cc * p.patch_chunk_bytes,
+                      cc * (p.a.rowbytes >> 1), p.xorg, y0 + p.yorg, img, pl);
+      int cc = 0, tap = 0;
+      for (int it = 0; it < nsteps; ++it) {
+        mbar_wait(&empty[s], ph ^ 1, p.err, 1);
+        mbar_expect_tx(&full[s], tx_bytes);
+        uint8_t* sb = ring + (size_t)s * b_stage;
+        for (int pl = 0; pl < p.planes; ++pl)
+          for (int j = 0; j < p.b.nbox; ++j) {
+            if (p.b.major == 0) tma_load_5d(&p.b.map, &full[s], sb + pl * p.b.plane_bytes, cc * BK, tap, n0, pl, 0);
+            else tma_load_5d(&p.b.map, &full[s], sb + pl * p.b.plane_bytes + j * p.b.box_bytes, n0 + j * cwB, tap, cc * BK, pl, 0);
+          }
+        if (++cc == p.ncc) { cc = 0; ++tap; }
+        if (++s == p.stages) { s = 0; ph ^= 1; }
+      }
+    }
+   }
+  } else if (warp == 1) {
+   if (elect_one()) {
+    // ---- MMA issuer ----
+    const uint32_t idesc = make_idesc_bf16(128, p.block_n, 0, p.b.major);
+    const uint32_t la = p.a.rowbytes == 128 ? 2u : 4u, lb = p.b.rowbytes == 128 ? 2u : 4u;
+    const uint32_t smem0 = smem_u32(smem);
+    const uint64_t a0 = make_smem_desc(smem0, 0, 8 * p.a.rowbytes, la);
+    const uint64_t b0 = make_smem_desc(smem_u32(ring), p.b.lbo, p.b.sbo, lb);
+    const uint32_t st16 = b_stage >> 4, kb16 = p.b.kadv >> 4, pb16 = p.b.plane_bytes >> 4;
+    const uint32_t pa16 = p.patch_plane_bytes >> 4, ch16 = p.patch_chunk_bytes >> 4, row16 = p.a.rowbytes >> 4;
+    const uint32_t tile16 = (uint32_t)(p.RH * p.SW) * row16;
+    int s = 0, ph = 0, li = 0;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++li) {
+      const int buf = li & 1;
+      mbar_wait(&tmem_empty[buf], ((li >> 1) & 1) ^ 1, p.err, 6);
+      mbar_wait(patch_full, li & 1, p.err, 4);
+      fence_after_sync();
+      const uint32_t tacc = tmem_base + buf * acc_cols;
+      int cc = 0, kw = 0, kh = 0;
+      for (int it = 0; it < nsteps; ++it) {
+        mbar_wait(&full[s], ph, p.err, 2);
+        fence_after_sync();
+        const int ay = p.sgn > 0 ? kh : (p.KH - 1 - kh), ax = p.sgn > 0 ? kw : (p.KW - 1 - kw);
+        const uint64_t a_tap = a0 + (uint64_t)(cc * ch16 + (uint32_t)(ay * p.SW + ax) * row16);
+        const uint64_t b_st = b0 + (uint64_t)(s * st16);
+        const uint32_t acc0 = it > 0 ? 1u : 0u;
+        for (int t = 0; t < p.T; ++t) {
+          uint64_t a_hi = a_tap + (uint64_t)(t * tile16), b_hi = b_st;
+          const uint32_t td = tacc + t * p.block_n;
+          for (int k = 0; k < p.kslices; ++k) {
+            umma_f16(td, a_hi, b_hi, idesc, (k > 0) ? 1u : acc0);
+            if (p.planes == 2) {
+              umma_f16(td, a_hi, b_hi + pb16, idesc, 1);
+              umma_f16(td, a_hi + pa16, b_hi, idesc, 1);
+            }
+            a_hi += 2;      // 32 bytes = one UMMA_K slice inside the swizzled row
+            b_hi += kb16;
+          }
+        }
+        umma_commit(&empty[s]);
+        if (++cc == p.ncc) { cc = 0; if (++kw == p.KW) { kw = 0; ++kh; } }
+        if (++s == p.stages) { s = 0; ph ^= 1; }
+      }
+      umma_commit(patch_empty);        // patch may be overwritten once these MMAs have read it
+      umma_commit(&tmem_full[buf]);    // accumulators of this tile complete
+    }
+   }
+  } else {
+    // ---- epilogue: T accumulator tiles per work item, each an (RH x SW) pixel box ----
+    const int q = warp & 3;
+    const int r = q * 32 + lane;
+    int li = 0;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++li) {
+      const int tile_n = tile / tiles_mn, rem = tile % tiles_mn;
+      const int img = rem / p.tiles_y, ty = rem % p.tiles_y;
+      const int y0 = ty * p.T * p.RH, n0 = tile_n * p.block_n;
+      const int buf = li & 1;
+      bool ok = mbar_wait(&tmem_full[buf], (li >> 1) & 1, p.err, 3);
+      fence_after_sync();
+      for (int t = 0; t < p.T; ++t) {
+        const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + buf * acc_cols + t * p.block_n;
+        conv_tile_epilogue(p, stg, trow, r, ok, 0, y0 + t * p.RH, img, n0);
+      }
+      fence_before_sync();
+      mbar_arrive(&tmem_empty[buf]);
+    }
+  }
+  __syncthreads();
+  if (warp == 1) {
+    __syncwarp();
+    fence_after_sync();
+    tmem_dealloc(tmem_base, 512);
   }
 }
 
@@ -468,6 +663,65 @@ static void conv_box(int Wn, int Hn, int Bn, int pool, int& bw, int& bh, int& bn
   }
 }
 
+// patch-resident launch (forward with sgn=+1, input gradient with sgn=-1); returns UGN_ERR_UNSUPPORTED when
+// the geometry does not fit so that the caller falls back to the per-tap-box kernel.
+static int convp_launch(ugn_ctx* ctx, TcParams& p, const __nv_bfloat16* act, int P, int B, int H, int W, int C,
+                        int KH, int KW, int Wneed, int Hneed, int pool, int sgn, cudaStream_t st) {
+  const int cbox = (C % 64 == 0) ? 64 : 32;
+  const int rowbytes = cbox * 2;
+  int SW = 16;
+  while (SW < (sgn > 0 ? W : Wneed + KW - 1)) SW <<= 1;
+  if (SW > 64) return UGN_ERR_UNSUPPORTED;
+  const int RH = 128 / SW;
+  if (pool && (RH & 1)) return UGN_ERR_UNSUPPORTED;
+  p.ncc = C / cbox; p.KW = KW; p.KH = KH; p.sgn = sgn;
+  p.kslices = cbox / 16;
+  p.ksteps_total = KH * KW * p.ncc; p.ksplit = 1;
+  const size_t b_stage = (size_t)P * p.b.plane_bytes;
+  const size_t budget = 222 * 1024, fixed = 17 * 1024 + 2048;
+  int T = 0;
+  for (int cand : {2, 1}) {
+    if (cand * p.block_n > 256) continue;                 // two accumulator sets must fit 512 TMEM columns
+    if (cand > 1 && (cand - 1) * RH >= Hneed) continue;
+    size_t patch = (size_t)P * p.ncc * (size_t)(cand * RH + KH - 1) * SW * rowbytes;
+    if (patch + fixed + 2 * b_stage <= budget) { T = cand; break; }
+  }
+  if (!T) return UGN_ERR_UNSUPPORTED;
+  p.T = T; p.SW = SW; p.RH = RH; p.PR = T * RH + KH - 1;
+  p.bw = SW; p.bh = RH; p.bn = 1;
+  p.patch_chunk_bytes = p.PR * SW * rowbytes;
+  p.patch_plane_bytes = p.ncc * p.patch_chunk_bytes;
+  p.xorg = sgn > 0 ? 0 : -(KW - 1);
+  p.yorg = sgn > 0 ? 0 : -(KH - 1);
+  p.tiles_y = ugn_cdiv(Hneed, T * RH);
+  {
+    uint64_t dims[5] = {(uint64_t)C, (uint64_t)W, (uint64_t)H, (uint64_t)B, (uint64_t)P};
+    uint64_t str[4] = {(uint64_t)C * 2, (uint64_t)W * C * 2, (uint64_t)H * W * C * 2, (uint64_t)B * H * W * C * 2};
+    uint32_t box[5] = {(uint32_t)cbox, (uint32_t)SW, (uint32_t)p.PR, 1, 1};
+    p.a.major = 0; p.a.rowbytes = rowbytes; p.a.nbox = 1; p.a.box_bytes = p.patch_chunk_bytes;
+    int rc = make_map(ctx, &p.a.map, act, dims, str, box, rowbytes);
+    if (rc != UGN_OK) return rc;
+  }
+  size_t patch = (size_t)P * p.patch_plane_bytes;
+  int stages = (int)std::min<size_t>(8, (budget - fixed - patch) / b_stage);
+  stages = std::max(2, stages);
+  p.stages = stages;
+  size_t smem = patch + 17 * 1024 + stages * b_stage + 1024 + (2 * stages + 6) * 8 + 16;
+  if (!ctx->err_flag) {
+    UGN_CUDA(cudaMalloc(&ctx->err_flag, sizeof(int)));
+    UGN_CUDA(cudaMemset(ctx->err_flag, 0, sizeof(int)));
+  }
+  p.err = ctx->err_flag;
+  const int tiles_mn = p.tiles_y * B, tiles_n = ugn_cdiv(p.Cout, p.block_n);
+  p.N = tiles_mn;
+  p.M = tiles_mn * tiles_n;
+  UGN_CUDA(cudaFuncSetAttribute(tc_convp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  dim3 grid(std::min(p.M, ctx->sm_count), 1, 1);
+  tc_convp_kernel<<<grid, kThreads, smem, st>>>(p);
+  UGN_LAUNCHED(ctx);
+  return UGN_OK;
+}
+
 int tc_conv_fwd(ugn_ctx* ctx, const ConvGeom& g, int P, const __nv_bfloat16* x, const __nv_bfloat16* w,
                 const float* bias, __nv_bfloat16* y, uint8_t* idx, int act, float alpha, int pool,
                 cudaStream_t st) {
@@ -479,15 +733,12 @@ int tc_conv_fwd(ugn_ctx* ctx, const ConvGeom& g, int P, const __nv_bfloat16* x, 
   p.ncc = g.Cp / cbox; p.KW = g.KW;
   p.ksteps_total = g.KH * g.KW * p.ncc; p.ksplit = 1;
   const int Wn = pool ? g.Wp * 2 : g.Wo, Hn = pool ? g.Hp * 2 : g.Ho;
-  conv_box(Wn, Hn, g.B, pool, p.bw, p.bh, p.bn);
-  p.ntx = ugn_cdiv(Wn, p.bw); p.nty = ugn_cdiv(Hn, p.bh);
   p.Wout = pool ? Wn : g.Wo; p.Hout = pool ? Hn : g.Ho; p.Bn = g.B; p.Cout = g.Co;
   p.Hp = g.Hp; p.Wp = g.Wp;
   p.block_n = g.Co > 128 ? ((g.Co % 256 == 0 || g.Co > 192) ? 256 : (g.Co + 15) / 16 * 16) : (g.Co + 15) / 16 * 16;
   if (p.block_n > 256) p.block_n = 256;
   if (P == 2 && p.block_n > 128) p.block_n = (g.Co % 128 == 0) ? 128 : ((g.Co % 96 == 0) ? 96 : 64);
-  int rc = act_map(ctx, p.a, x, P, g.B, g.H, g.W, g.Cp, cbox, p.bw, p.bh, p.bn, 0, 1, 128);
-  if (rc != UGN_OK) return rc;
+  int rc;
   {  // weights [P][Co][taps][Cp] K-major: dims (Cp, taps, Co, P, 1)
     const int taps = g.KH * g.KW;
     uint64_t dims[5] = {(uint64_t)g.Cp, (uint64_t)taps, (uint64_t)g.Co, (uint64_t)P, 1};
@@ -500,6 +751,13 @@ int tc_conv_fwd(ugn_ctx* ctx, const ConvGeom& g, int P, const __nv_bfloat16* x, 
   p.epi = pool ? EPI_BF16_POOL : EPI_BF16_ACT;
   p.out_bf16 = y; p.out_plane = (long long)g.B * g.Hp * g.Wp * g.Co;
   p.pool_idx = idx; p.bias = bias; p.act = act; p.alpha = alpha;
+  if (!getenv("UGN_NO_CONVP")) {
+    rc = convp_launch(ctx, p, x, P, g.B, g.H, g.W, g.Cp, g.KH, g.KW, Wn, Hn, pool, +1, st);
+    if (rc != UGN_ERR_UNSUPPORTED) return rc;
+  }
+  conv_box(Wn, Hn, g.B, pool, p.bw, p.bh, p.bn);
+  p.ntx = ugn_cdiv(Wn, p.bw); p.nty = ugn_cdiv(Hn, p.bh);
+  if ((rc = act_map(ctx, p.a, x, P, g.B, g.H, g.W, g.Cp, cbox, p.bw, p.bh, p.bn, 0, 1, 128)) != UGN_OK) return rc;
   dim3 grid(p.ntx * p.nty * ugn_cdiv(g.B, p.bn), ugn_cdiv(g.Co, p.block_n), 1);
   return launch<MODE_CONV>(ctx, p, grid, st);
 }
@@ -580,8 +838,20 @@ int tc_conv_wgrad(ugn_ctx* ctx, const ConvGeom& g, int P, const __nv_bfloat16* x
 }
 
 // ---- dense ------------------------------------------------------------------------------
+int ew_bias_act_mask(ugn_ctx* ctx, float* y, const float* bias, const float* mask, long long rows, int cols,
+                     int act, float alpha, cudaStream_t st);
+
 int tc_linear_fwd(ugn_ctx* ctx, int P, int B, int N, int K, const __nv_bfloat16* x, const __nv_bfloat16* w,
                   const float* bias, const float* mask, float* y, int act, float alpha, cudaStream_t st) {
+  // Small batch: the layer is a weight-streaming (HBM-bound) GEMM with a single M tile, so spread K over
+  // the SMs (split-K, red.add into zeroed y) and apply bias / activation / dropout mask in a tiny post pass.
+  int tiles = ugn_cdiv(B, 128) * ugn_cdiv(N, P == 2 ? 128 : 256);
+  if (tiles * 2 <= ctx->sm_count && K >= 512) {
+    int rc = tc_gemm_ex(ctx, P, B, N, K, x, 0, w, 0, y, N, 0, nullptr, nullptr, UGN_ACT_LINEAR, 0.f, st);
+    if (rc != UGN_OK) return rc;
+    if (bias || mask || act != UGN_ACT_LINEAR) return ew_bias_act_mask(ctx, y, bias, mask, B, N, act, alpha, st);
+    return UGN_OK;
+  }
   return tc_gemm_ex(ctx, P, B, N, K, x, 0, w, 0, y, N, 0, bias, mask, act, alpha, st);
 }
 
