@@ -505,6 +505,172 @@ __global__ void __launch_bounds__(kThreads, 1) tc_convp_kernel(const __grid_cons
 }
 
 // ---------------------------------------------------------------------------------------
+// Kernel-gradient v2 ("row-resident" wgrad).
+//   dw[co][kh][kw][ci] = sum_pix dz[pix][co] * x[pix + (kh,kw)][ci]
+// K-step = one box of 64 output-pixel slots (PW pixel slots x bh rows x bn images, PW >= Wo+KW-1 so that
+// the A rows which would pair with wrapped B rows are TMA zero-filled).  Per (kh, ci-chunk) ONE activation
+// box is loaded; the KW taps of that filter row are NOT separate loads: they are the same box viewed
+// through an MN-major UMMA descriptor whose N-blocks overlap -- leading-byte-offset = one pixel row -- so a
+// single tcgen05.mma of N = nkw*cw columns produces the gradients of nkw taps at once.
+// A (dz, MN-major) is shared by every segment of the CTA; accumulators of up to 512 TMEM columns.
+// ---------------------------------------------------------------------------------------
+struct WgSeg { int box, kh, chunk, kw0, nkw, col0; };
+struct alignas(64) WgParams {
+  CUtensorMap amap, bmap;
+  int planes, stages, ksteps_total, ksplit;
+  int PW, bh, bn, nby;                 // K-step box; steps decode: by = ks % nby, bb = ks / nby
+  int cw, rowbytes_b, KW, ntaps, Cin, Co;
+  int a_box_bytes, a_plane_bytes, b_box_bytes, b_plane_bytes;   // b_box_bytes includes the zero tail
+  int ntiles_n;
+  int tile_seg0[33];                   // segments of N-tile j: [tile_seg0[j], tile_seg0[j+1])
+  int tile_box0[33];                   // activation boxes of N-tile j
+  WgSeg seg[40];
+  int box_kh[40], box_chunk[40];
+  float* dw;
+  int* err;
+};
+
+__global__ void __launch_bounds__(kThreads, 1) tc_wgradv_kernel(const __grid_constant__ WgParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int tile_m = blockIdx.x, tile_n = blockIdx.y;
+  const int seg0 = p.tile_seg0[tile_n], seg1 = p.tile_seg0[tile_n + 1];
+  const int box0 = p.tile_box0[tile_n], nboxes = p.tile_box0[tile_n + 1] - box0;
+  const uint32_t a_stage = p.planes * p.a_plane_bytes, b_stage = p.planes * p.b_plane_bytes;
+  const uint32_t stage_bytes = a_stage + b_stage;
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + (size_t)p.stages * stage_bytes);
+  uint64_t* empty = full + p.stages;
+  uint64_t* tmem_full = empty + p.stages;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_full + 1);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  int per = (p.ksteps_total + p.ksplit - 1) / p.ksplit;
+  const int ks_beg = blockIdx.z * per, ks_end = min(p.ksteps_total, ks_beg + per);
+  const int nsteps = ks_end - ks_beg;
+  if (nsteps <= 0) return;
+
+  // zero the tail rows of every activation box slot (TMA never writes them; shifted views read them)
+  {
+    const int tail = p.b_box_bytes - 64 * p.rowbytes_b;
+    const int slots = p.stages * p.planes * 4;
+    for (int e = threadIdx.x; e < slots * (tail / 16); e += blockDim.x) {
+      int slot = e / (tail / 16), off = e % (tail / 16);
+      int st = slot / (p.planes * 4), rem = slot % (p.planes * 4), pl = rem / 4, bx = rem % 4;
+      uint8_t* base = smem + (size_t)st * stage_bytes + a_stage + pl * p.b_plane_bytes + bx * p.b_box_bytes +
+                      64 * p.rowbytes_b;
+      if (bx * p.b_box_bytes + p.b_box_bytes <= p.b_plane_bytes)
+        reinterpret_cast<uint4*>(base)[off] = make_uint4(0, 0, 0, 0);
+    }
+  }
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < p.stages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    mbar_init(tmem_full, 1);
+    fence_mbar_init();
+    prefetch_tmap(&p.amap);
+    prefetch_tmap(&p.bmap);
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_ptr, 512);
+    tmem_relinquish();
+  }
+  // make the generic-proxy zero fill visible to the async proxy (UMMA reads)
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  fence_before_sync();
+  __syncthreads();
+  fence_after_sync();
+  const uint32_t tmem_base = *tmem_ptr;
+  const int m0 = tile_m * 128;
+
+  if (warp == 0) {
+   if (elect_one()) {
+    const uint32_t tx_bytes = p.planes * (2 * p.a_box_bytes + nboxes * 64 * p.rowbytes_b);
+    int by = ks_beg % p.nby, bb = ks_beg / p.nby, s = 0, ph = 0;
+    for (int it = 0; it < nsteps; ++it) {
+      mbar_wait(&empty[s], ph ^ 1, p.err, 1);
+      mbar_expect_tx(&full[s], tx_bytes);
+      uint8_t* sa = smem + (size_t)s * stage_bytes;
+      uint8_t* sb = sa + a_stage;
+      const int py = by * p.bh, pn = bb * p.bn;
+      for (int pl = 0; pl < p.planes; ++pl) {
+        tma_load_5d(&p.amap, &full[s], sa + pl * p.a_plane_bytes, m0, 0, py, pn, pl);
+        tma_load_5d(&p.amap, &full[s], sa + pl * p.a_plane_bytes + p.a_box_bytes, m0 + 64, 0, py, pn, pl);
+        for (int j = 0; j < nboxes; ++j)
+          tma_load_5d(&p.bmap, &full[s], sb + pl * p.b_plane_bytes + j * p.b_box_bytes,
+                      p.box_chunk[box0 + j] * p.cw, 0, py + p.box_kh[box0 + j], pn, pl);
+      }
+      if (++by == p.nby) { by = 0; ++bb; }
+      if (++s == p.stages) { s = 0; ph ^= 1; }
+    }
+   }
+  } else if (warp == 1) {
+   if (elect_one()) {
+    const uint32_t lb = p.rowbytes_b == 128 ? 2u : 4u;
+    const uint32_t smem0 = smem_u32(smem);
+    // A: dz box, MN-major SW128: N-blocks (64 co) are a_box_bytes apart, 8 K-rows = 1024 B
+    const uint64_t a0 = make_smem_desc(smem0, p.a_box_bytes, 1024, 2u);
+    // B: activation box, MN-major; overlapping N-blocks: LBO = one pixel row
+    const uint64_t b0 = make_smem_desc(smem0 + a_stage, p.rowbytes_b, 8 * p.rowbytes_b, lb);
+    const uint32_t st16 = stage_bytes >> 4, pa16 = p.a_plane_bytes >> 4, pb16 = p.b_plane_bytes >> 4;
+    const uint32_t ka16 = (16 * 128) >> 4, kb16 = (16 * p.rowbytes_b) >> 4, row16 = p.rowbytes_b >> 4;
+    int s = 0, ph = 0;
+    for (int it = 0; it < nsteps; ++it) {
+      mbar_wait(&full[s], ph, p.err, 2);
+      fence_after_sync();
+      const uint64_t a_st = a0 + (uint64_t)(s * st16), b_st = b0 + (uint64_t)(s * st16);
+      for (int g = seg0; g < seg1; ++g) {
+        const WgSeg sg = p.seg[g];
+        const uint32_t idesc = make_idesc_bf16(128, sg.nkw * p.cw, 1, 1);
+        const uint32_t td = tmem_base + sg.col0;
+        uint64_t a_hi = a_st;
+        uint64_t b_hi = b_st + (uint64_t)((sg.box - box0) * (p.b_box_bytes >> 4) + sg.kw0 * row16);
+        for (int k = 0; k < 4; ++k) {
+          umma_f16(td, a_hi, b_hi, idesc, (it > 0 || k > 0) ? 1u : 0u);
+          if (p.planes == 2) {
+            umma_f16(td, a_hi, b_hi + pb16, idesc, 1);
+            umma_f16(td, a_hi + pa16, b_hi, idesc, 1);
+          }
+          a_hi += ka16;
+          b_hi += kb16;
+        }
+      }
+      umma_commit(&empty[s]);
+      if (++s == p.stages) { s = 0; ph ^= 1; }
+    }
+    umma_commit(tmem_full);
+   }
+  } else {
+    const int q = warp & 3;
+    const int r = q * 32 + lane;
+    const int co = m0 + r;
+    bool ok = mbar_wait(tmem_full, 0, p.err, 3);
+    fence_after_sync();
+    const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16);
+    float v[16];
+    for (int g = seg0; g < seg1; ++g) {
+      const WgSeg sg = p.seg[g];
+      const int ncols = sg.nkw * p.cw;
+      for (int c0 = 0; c0 < ncols; c0 += 16) {
+        tmem_ld16(trow + sg.col0 + c0, v);
+        if (!ok || co >= p.Co) continue;
+        const int tap = sg.kh * p.KW + sg.kw0 + c0 / p.cw;
+        const int cib = sg.chunk * p.cw + (c0 % p.cw);
+        float* dst = p.dw + ((long long)co * p.ntaps + tap) * p.Cin;
+#pragma unroll
+        for (int i = 0; i < 16; ++i)
+          if (cib + i < p.Cin) atomicAdd(dst + cib + i, v[i]);
+      }
+    }
+    fence_before_sync();
+  }
+  __syncthreads();
+  if (warp == 1) {
+    __syncwarp();
+    fence_after_sync();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+// ---------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -796,9 +962,104 @@ int tc_conv_dgrad(ugn_ctx* ctx, const ConvGeom& g, int P, const __nv_bfloat16* d
 int simt_colsum_bf16(ugn_ctx* ctx, const __nv_bfloat16* X, int P, long long rows, int cols, float* out,
                      cudaStream_t st);
 
+static int wgradv_launch(ugn_ctx* ctx, const ConvGeom& g, int P, const __nv_bfloat16* x, const __nv_bfloat16* dz,
+                         float* dw, cudaStream_t st) {
+  WgParams p{};
+  p.planes = P;
+  p.cw = (g.Cp % 64 == 0) ? 64 : 32;
+  p.rowbytes_b = p.cw * 2;
+  const int nch = g.Cp / p.cw;
+  int PW = 8;
+  while (PW < g.Wo + g.KW - 1) PW <<= 1;
+  if (PW > 64 || g.Ho * g.Wo <= 16) return UGN_ERR_UNSUPPORTED;   // tiny maps: the per-tap-box kernel is faster
+  int bh = 64 / PW, bn = 1;
+  int hcap = 1;
+  while (hcap * 2 <= g.Ho) hcap <<= 1;
+  if (bh > hcap) { bn = bh / hcap; bh = hcap; }
+  p.PW = PW; p.bh = bh; p.bn = bn;
+  p.nby = ugn_cdiv(g.Ho, bh);
+  p.ksteps_total = p.nby * ugn_cdiv(g.B, bn);
+  p.KW = g.KW; p.ntaps = g.KH * g.KW; p.Cin = g.Cin; p.Co = g.Co;
+  p.a_box_bytes = 64 * 128;
+  p.a_plane_bytes = 2 * p.a_box_bytes;
+  p.b_box_bytes = (64 + 8) * p.rowbytes_b;
+  // segments
+  const int max_nkw = std::max(1, 256 / p.cw);
+  int nseg = 0, nbox = 0, ntile = 0;
+  int cols = 0, boxes_in_tile = 0;
+  p.tile_seg0[0] = 0; p.tile_box0[0] = 0;
+  for (int kh = 0; kh < g.KH; ++kh)
+    for (int ch = 0; ch < nch; ++ch) {
+      int need = g.KW * p.cw;
+      if (cols + need > 512 || boxes_in_tile == 4) {   // close the current N-tile
+        if (ntile >= 32) return UGN_ERR_UNSUPPORTED;
+        ++ntile; p.tile_seg0[ntile] = nseg; p.tile_box0[ntile] = nbox; cols = 0; boxes_in_tile = 0;
+      }
+      if (nbox >= 40) return UGN_ERR_UNSUPPORTED;
+      p.box_kh[nbox] = kh; p.box_chunk[nbox] = ch;
+      for (int kw0 = 0; kw0 < g.KW; kw0 += max_nkw) {
+        if (nseg >= 40) return UGN_ERR_UNSUPPORTED;
+        int nkw = std::min(max_nkw, g.KW - kw0);
+        if ((nkw * p.cw) % 16 != 0) return UGN_ERR_UNSUPPORTED;
+        p.seg[nseg] = WgSeg{nbox, kh, ch, kw0, nkw, cols};
+        cols += nkw * p.cw;
+        ++nseg;
+      }
+      ++nbox; ++boxes_in_tile;
+    }
+  ++ntile; p.tile_seg0[ntile] = nseg; p.tile_box0[ntile] = nbox;
+  p.ntiles_n = ntile;
+  int max_boxes = 0;
+  for (int j = 0; j < ntile; ++j) max_boxes = std::max(max_boxes, p.tile_box0[j + 1] - p.tile_box0[j]);
+  p.b_plane_bytes = (4 * p.b_box_bytes + 1023) / 1024 * 1024;   // 4 box slots (zero-tail loop assumes 4)
+  if (max_boxes > 4) return UGN_ERR_UNSUPPORTED;
+  size_t stage = (size_t)P * (p.a_plane_bytes + p.b_plane_bytes);
+  int stages = (int)std::min<size_t>(6, (220 * 1024) / stage);
+  if (stages < 2) return UGN_ERR_UNSUPPORTED;
+  p.stages = stages;
+  int rc;
+  EncodeTiledFn enc;
+  if ((rc = get_encoder(ctx, &enc)) != UGN_OK) return rc;
+  {
+    uint64_t dims[5] = {(uint64_t)g.Co, (uint64_t)g.Wo, (uint64_t)g.Ho, (uint64_t)g.B, (uint64_t)P};
+    uint64_t str[4] = {(uint64_t)g.Co * 2, (uint64_t)g.Wo * g.Co * 2, (uint64_t)g.Ho * g.Wo * g.Co * 2,
+                       (uint64_t)g.B * g.Ho * g.Wo * g.Co * 2};
+    uint32_t box[5] = {64, (uint32_t)PW, (uint32_t)bh, (uint32_t)bn, 1};
+    if ((rc = make_map(ctx, &p.amap, dz, dims, str, box, 128)) != UGN_OK) return rc;
+  }
+  {
+    uint64_t dims[5] = {(uint64_t)g.Cp, (uint64_t)g.W, (uint64_t)g.H, (uint64_t)g.B, (uint64_t)P};
+    uint64_t str[4] = {(uint64_t)g.Cp * 2, (uint64_t)g.W * g.Cp * 2, (uint64_t)g.H * g.W * g.Cp * 2,
+                       (uint64_t)g.B * g.H * g.W * g.Cp * 2};
+    uint32_t box[5] = {(uint32_t)p.cw, (uint32_t)PW, (uint32_t)bh, (uint32_t)bn, 1};
+    if ((rc = make_map(ctx, &p.bmap, x, dims, str, box, p.rowbytes_b)) != UGN_OK) return rc;
+  }
+  const int ntile_m = ugn_cdiv(g.Co, 128);
+  int split = std::max(1, std::min(ctx->sm_count / std::max(1, ntile * ntile_m), p.ksteps_total / 2));
+  p.ksplit = std::min(split, 65535);
+  p.dw = dw;
+  if (!ctx->err_flag) {
+    UGN_CUDA(cudaMalloc(&ctx->err_flag, sizeof(int)));
+    UGN_CUDA(cudaMemset(ctx->err_flag, 0, sizeof(int)));
+  }
+  p.err = ctx->err_flag;
+  size_t smem = stages * stage + 1024 + (2 * stages + 1) * 8 + 16;
+  UGN_CUDA(cudaFuncSetAttribute(tc_wgradv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  UGN_CUDA(cudaMemsetAsync(dw, 0, sizeof(float) * (size_t)g.Co * p.ntaps * g.Cin, st));
+  dim3 grid(ntile_m, ntile, p.ksplit);
+  tc_wgradv_kernel<<<grid, kThreads, smem, st>>>(p);
+  UGN_LAUNCHED(ctx);
+  return UGN_OK;
+}
+
 int tc_conv_wgrad(ugn_ctx* ctx, const ConvGeom& g, int P, const __nv_bfloat16* x, const __nv_bfloat16* dz,
                   float* dw, float* db, cudaStream_t st) {
   UGN_CHECK(g.Cp % 32 == 0 && g.Co % 8 == 0, "tensor-core wgrad needs Cin %% 32 == 0");
+  if (!getenv("UGN_NO_WGRADV")) {
+    int rcv = wgradv_launch(ctx, g, P, x, dz, dw, st);
+    if (rcv == UGN_OK) return db ? simt_colsum_bf16(ctx, dz, P, (long long)g.B * g.Ho * g.Wo, g.Co, db, st) : UGN_OK;
+    if (rcv != UGN_ERR_UNSUPPORTED) return rcv;
+  }
   TcParams p{};
   p.mode = MODE_WGRAD; p.planes = P;
   // K stage = a box of output pixels (rows zero-filled by TMA beyond the dz extent)
