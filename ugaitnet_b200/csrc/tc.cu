@@ -52,6 +52,7 @@ struct TcParams {
   // patch-resident conv (tc_convp_kernel)
   int T, SW, RH, PR, KH, xorg, yorg, tiles_y, tmem_cols;
   int patch_chunk_bytes, patch_plane_bytes;
+  int cps, nslots, ngroups;   // channel chunks per patch slot, patch slots (1 | 2), groups per tile = ncc / cps
 };
 
 static constexpr int kThreads = 192;
@@ -361,15 +362,16 @@ __global__ void __launch_bounds__(kThreads, 1) tc_convp_kernel(const __grid_cons
   // epilogue of tile i (CUDA cores) overlaps the mainloop of tile i+1 (tensor pipe).
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  const uint32_t patch_bytes = p.planes * p.patch_plane_bytes;
+  // patch slot = cps channel chunks x planes; nslots == 2 streams the chunks through a 2-deep ring
+  const uint32_t slot_bytes = p.planes * p.patch_plane_bytes;
   const uint32_t b_stage = p.planes * p.b.plane_bytes;
-  uint8_t* stg = smem + patch_bytes;                 // epilogue staging, 128 x 33 floats (17 KB region)
+  uint8_t* stg = smem + p.nslots * slot_bytes;                 // epilogue staging, 128 x 33 floats (17 KB region)
   uint8_t* ring = stg + 17 * 1024;
   uint64_t* full = reinterpret_cast<uint64_t*>(ring + (size_t)p.stages * b_stage);
   uint64_t* empty = full + p.stages;
-  uint64_t* patch_full = empty + p.stages;
-  uint64_t* patch_empty = patch_full + 1;
-  uint64_t* tmem_full = patch_empty + 1;   // [2]
+  uint64_t* patch_full = empty + p.stages;     // [2]
+  uint64_t* patch_empty = patch_full + 2;      // [2]
+  uint64_t* tmem_full = patch_empty + 2;       // [2]
   uint64_t* tmem_empty = tmem_full + 2;    // [2]
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty + 2);
 
@@ -380,9 +382,10 @@ __global__ void __launch_bounds__(kThreads, 1) tc_convp_kernel(const __grid_cons
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < p.stages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
-    mbar_init(patch_full, 1);
-    mbar_init(patch_empty, 1);
-    for (int b = 0; b < 2; ++b) { mbar_init(&tmem_full[b], 1); mbar_init(&tmem_empty[b], 128); }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(&patch_full[b], 1); mbar_init(&patch_empty[b], 1);
+      mbar_init(&tmem_full[b], 1); mbar_init(&tmem_empty[b], 128);
+    }
     fence_mbar_init();
     prefetch_tmap(&p.a.map);
     prefetch_tmap(&p.b.map);
@@ -408,24 +411,29 @@ __global__ void __launch_bounds__(kThreads, 1) tc_convp_kernel(const __grid_cons
       const int tile_n = tile / tiles_mn, rem = tile % tiles_mn;
       const int img = rem / p.tiles_y, ty = rem % p.tiles_y;
       const int y0 = ty * p.T * p.RH, n0 = tile_n * p.block_n;
-      mbar_wait(patch_empty, (li & 1) ^ 1, p.err, 5);
-      mbar_expect_tx(patch_full, patch_bytes);
-      for (int pl = 0; pl < p.planes; ++pl)
-        for (int cc = 0; cc < p.ncc; ++cc)
-          tma_load_5d(&p.a.map, patch_full, smem + pl * p.patch_plane_bytes + cc * p.patch_chunk_bytes,
-                      cc * (p.a.rowbytes >> 1), p.xorg, y0 + p.yorg, img, pl);
-      int cc = 0, tap = 0;
-      for (int it = 0; it < nsteps; ++it) {
-        mbar_wait(&empty[s], ph ^ 1, p.err, 1);
-        mbar_expect_tx(&full[s], tx_bytes);
-        uint8_t* sb = ring + (size_t)s * b_stage;
+      for (int g = 0; g < p.ngroups; ++g) {
+        const int u = li * p.ngroups + g, slot = u % p.nslots, sph = (u / p.nslots) & 1;
+        uint8_t* pslot = smem + slot * slot_bytes;
+        mbar_wait(&patch_empty[slot], sph ^ 1, p.err, 5);
+        mbar_expect_tx(&patch_full[slot], slot_bytes);
         for (int pl = 0; pl < p.planes; ++pl)
-          for (int j = 0; j < p.b.nbox; ++j) {
-            if (p.b.major == 0) tma_load_5d(&p.b.map, &full[s], sb + pl * p.b.plane_bytes, cc * BK, tap, n0, pl, 0);
-            else tma_load_5d(&p.b.map, &full[s], sb + pl * p.b.plane_bytes + j * p.b.box_bytes, n0 + j * cwB, tap, cc * BK, pl, 0);
-          }
-        if (++cc == p.ncc) { cc = 0; ++tap; }
-        if (++s == p.stages) { s = 0; ph ^= 1; }
+          for (int c = 0; c < p.cps; ++c)
+            tma_load_5d(&p.a.map, &patch_full[slot], pslot + pl * p.patch_plane_bytes + c * p.patch_chunk_bytes,
+                        (g * p.cps + c) * (p.a.rowbytes >> 1), p.xorg, y0 + p.yorg, img, pl);
+        int c = 0, tap = 0;
+        for (int it = 0; it < nsteps / p.ngroups; ++it) {
+          const int cc = g * p.cps + c;
+          mbar_wait(&empty[s], ph ^ 1, p.err, 1);
+          mbar_expect_tx(&full[s], tx_bytes);
+          uint8_t* sb = ring + (size_t)s * b_stage;
+          for (int pl = 0; pl < p.planes; ++pl)
+            for (int j = 0; j < p.b.nbox; ++j) {
+              if (p.b.major == 0) tma_load_5d(&p.b.map, &full[s], sb + pl * p.b.plane_bytes, cc * BK, tap, n0, pl, 0);
+              else tma_load_5d(&p.b.map, &full[s], sb + pl * p.b.plane_bytes + j * p.b.box_bytes, n0 + j * cwB, tap, cc * BK, pl, 0);
+            }
+          if (++c == p.cps) { c = 0; ++tap; }
+          if (++s == p.stages) { s = 0; ph ^= 1; }
+        }
       }
     }
    }
@@ -444,17 +452,20 @@ __global__ void __launch_bounds__(kThreads, 1) tc_convp_kernel(const __grid_cons
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++li) {
       const int buf = li & 1;
       mbar_wait(&tmem_empty[buf], ((li >> 1) & 1) ^ 1, p.err, 6);
-      mbar_wait(patch_full, li & 1, p.err, 4);
-      fence_after_sync();
       const uint32_t tacc = tmem_base + buf * acc_cols;
+      for (int g = 0; g < p.ngroups; ++g) {
+      const int u = li * p.ngroups + g, slot = u % p.nslots, sph = (u / p.nslots) & 1;
+      mbar_wait(&patch_full[slot], sph, p.err, 4);
+      fence_after_sync();
+      const uint64_t a_slot = a0 + (uint64_t)(slot * (slot_bytes >> 4));
       int cc = 0, kw = 0, kh = 0;
-      for (int it = 0; it < nsteps; ++it) {
+      for (int it = 0; it < nsteps / p.ngroups; ++it) {
         mbar_wait(&full[s], ph, p.err, 2);
         fence_after_sync();
         const int ay = p.sgn > 0 ? kh : (p.KH - 1 - kh), ax = p.sgn > 0 ? kw : (p.KW - 1 - kw);
-        const uint64_t a_tap = a0 + (uint64_t)(cc * ch16 + (uint32_t)(ay * p.SW + ax) * row16);
+        const uint64_t a_tap = a_slot + (uint64_t)(cc * ch16 + (uint32_t)(ay * p.SW + ax) * row16);
         const uint64_t b_st = b0 + (uint64_t)(s * st16);
-        const uint32_t acc0 = it > 0 ? 1u : 0u;
+        const uint32_t acc0 = (g > 0 || it > 0) ? 1u : 0u;
         for (int t = 0; t < p.T; ++t) {
           uint64_t a_hi = a_tap + (uint64_t)(t * tile16), b_hi = b_st;
           const uint32_t td = tacc + t * p.block_n;
@@ -469,10 +480,11 @@ __global__ void __launch_bounds__(kThreads, 1) tc_convp_kernel(const __grid_cons
           }
         }
         umma_commit(&empty[s]);
-        if (++cc == p.ncc) { cc = 0; if (++kw == p.KW) { kw = 0; ++kh; } }
+        if (++cc == p.cps) { cc = 0; if (++kw == p.KW) { kw = 0; ++kh; } }
         if (++s == p.stages) { s = 0; ph ^= 1; }
       }
-      umma_commit(patch_empty);        // patch may be overwritten once these MMAs have read it
+      umma_commit(&patch_empty[slot]);   // slot may be overwritten once these MMAs have read it
+      }
       umma_commit(&tmem_full[buf]);    // accumulators of this tile complete
     }
    }
@@ -846,17 +858,23 @@ static int convp_launch(ugn_ctx* ctx, TcParams& p, const __nv_bfloat16* act, int
   const size_t b_stage = (size_t)P * p.b.plane_bytes;
   const size_t budget = 222 * 1024, fixed = 17 * 1024 + 2048;
   int T = 0;
-  for (int cand : {2, 1}) {
-    if (cand * p.block_n > 256) continue;                 // two accumulator sets must fit 512 TMEM columns
-    if (cand > 1 && (cand - 1) * RH >= Hneed) continue;
-    size_t patch = (size_t)P * p.ncc * (size_t)(cand * RH + KH - 1) * SW * rowbytes;
-    if (patch + fixed + 2 * b_stage <= budget) { T = cand; break; }
+  p.cps = p.ncc; p.nslots = 1;
+  for (int ring = 0; ring < 2 && !T; ++ring) {           // ring: stream one channel chunk at a time (2 slots)
+    if (ring && p.ncc == 1) break;
+    for (int cand : {2, 1}) {
+      if (cand * p.block_n > 256) continue;               // two accumulator sets must fit 512 TMEM columns
+      if (cand > 1 && (cand - 1) * RH >= Hneed) continue;
+      size_t chunk = (size_t)P * (size_t)(cand * RH + KH - 1) * SW * rowbytes;
+      size_t patch = ring ? 2 * chunk : p.ncc * chunk;
+      if (patch + fixed + 2 * b_stage <= budget) { T = cand; p.cps = ring ? 1 : p.ncc; p.nslots = ring ? 2 : 1; break; }
+    }
   }
   if (!T) return UGN_ERR_UNSUPPORTED;
+  p.ngroups = p.ncc / p.cps;
   p.T = T; p.SW = SW; p.RH = RH; p.PR = T * RH + KH - 1;
   p.bw = SW; p.bh = RH; p.bn = 1;
   p.patch_chunk_bytes = p.PR * SW * rowbytes;
-  p.patch_plane_bytes = p.ncc * p.patch_chunk_bytes;
+  p.patch_plane_bytes = p.cps * p.patch_chunk_bytes;
   p.xorg = sgn > 0 ? 0 : -(KW - 1);
   p.yorg = sgn > 0 ? 0 : -(KH - 1);
   p.tiles_y = ugn_cdiv(Hneed, T * RH);
@@ -868,11 +886,11 @@ static int convp_launch(ugn_ctx* ctx, TcParams& p, const __nv_bfloat16* act, int
     int rc = make_map(ctx, &p.a.map, act, dims, str, box, rowbytes);
     if (rc != UGN_OK) return rc;
   }
-  size_t patch = (size_t)P * p.patch_plane_bytes;
+  size_t patch = (size_t)p.nslots * P * p.patch_plane_bytes;
   int stages = (int)std::min<size_t>(8, (budget - fixed - patch) / b_stage);
   stages = std::max(2, stages);
   p.stages = stages;
-  size_t smem = patch + 17 * 1024 + stages * b_stage + 1024 + (2 * stages + 6) * 8 + 16;
+  size_t smem = patch + 17 * 1024 + stages * b_stage + 1024 + (2 * stages + 8) * 8 + 16;
   if (!ctx->err_flag) {
     UGN_CUDA(cudaMalloc(&ctx->err_flag, sizeof(int)));
     UGN_CUDA(cudaMemset(ctx->err_flag, 0, sizeof(int)));
@@ -917,7 +935,7 @@ int tc_conv_fwd(ugn_ctx* ctx, const ConvGeom& g, int P, const __nv_bfloat16* x, 
   p.epi = pool ? EPI_BF16_POOL : EPI_BF16_ACT;
   p.out_bf16 = y; p.out_plane = (long long)g.B * g.Hp * g.Wp * g.Co;
   p.pool_idx = idx; p.bias = bias; p.act = act; p.alpha = alpha;
-  if (!getenv("UGN_NO_CONVP")) {
+  if (!getenv("UGN_NO_CONVP") && g.H * g.W > 16) {
     rc = convp_launch(ctx, p, x, P, g.B, g.H, g.W, g.Cp, g.KH, g.KW, Wn, Hn, pool, +1, st);
     if (rc != UGN_ERR_UNSUPPORTED) return rc;
   }
@@ -936,15 +954,12 @@ int tc_conv_dgrad(ugn_ctx* ctx, const ConvGeom& g, int P, const __nv_bfloat16* d
   p.kslices = 4;                       // K stage = 64 output channels
   p.ncc = g.Co / 64; p.KW = g.KW;
   p.ksteps_total = g.KH * g.KW * p.ncc; p.ksplit = 1;
-  conv_box(g.W, g.H, g.B, 0, p.bw, p.bh, p.bn);
-  p.ntx = ugn_cdiv(g.W, p.bw); p.nty = ugn_cdiv(g.H, p.bh);
   p.Wout = g.W; p.Hout = g.H; p.Bn = g.B; p.Cout = g.Cp;
   const int cw = (g.Cp % 64 == 0) ? 64 : 32;
   int bn_cols = std::min(g.Cp, P == 2 ? 128 : 256);
   bn_cols = bn_cols / cw * cw;
   p.block_n = bn_cols;
-  int rc = act_map(ctx, p.a, dz, P, g.B, g.Ho, g.Wo, g.Co, 64, p.bw, p.bh, p.bn, 0, 1, 128);
-  if (rc != UGN_OK) return rc;
+  int rc;
   {  // weights as MN-major B: N = ci (contiguous), K = co: dims (Cp, taps, Co, P, 1), box (cw, 1, 64, 1, 1)
     const int taps = g.KH * g.KW;
     uint64_t dims[5] = {(uint64_t)g.Cp, (uint64_t)taps, (uint64_t)g.Co, (uint64_t)P, 1};
@@ -955,6 +970,14 @@ int tc_conv_dgrad(ugn_ctx* ctx, const ConvGeom& g, int P, const __nv_bfloat16* d
     if ((rc = make_map(ctx, &p.b.map, w, dims, str, box, cw * 2)) != UGN_OK) return rc;
   }
   p.epi = EPI_F32; p.out_f32 = dx;
+  if (!getenv("UGN_NO_CONVP") && g.H * g.W >= 400) {   // small maps: the per-tap-box kernel is faster
+    rc = convp_launch(ctx, p, dz, P, g.B, g.Ho, g.Wo, g.Co, g.KH, g.KW, g.W, g.H, 0, -1, st);
+    if (rc != UGN_ERR_UNSUPPORTED) return rc;
+    p.ncc = g.Co / 64; p.kslices = 4; p.ksteps_total = g.KH * g.KW * p.ncc;
+  }
+  conv_box(g.W, g.H, g.B, 0, p.bw, p.bh, p.bn);
+  p.ntx = ugn_cdiv(g.W, p.bw); p.nty = ugn_cdiv(g.H, p.bh);
+  if ((rc = act_map(ctx, p.a, dz, P, g.B, g.Ho, g.Wo, g.Co, 64, p.bw, p.bh, p.bn, 0, 1, 128)) != UGN_OK) return rc;
   dim3 grid(p.ntx * p.nty * ugn_cdiv(g.B, p.bn), ugn_cdiv(g.Cp, p.block_n), 1);
   return launch<MODE_CONV>(ctx, p, grid, st);
 }

@@ -179,6 +179,13 @@ extern "C" int ugn_triplet_all(ugn_ctx* ctx, const ugn_tensor* emb, const ugn_te
   p.ar = radix1(d); p.ak = radix1(1); p.br = radix1(d); p.bk = radix1(1);
   p.ldc = B;
   p.batches = n; p.batch_a = (long long)B * d; p.batch_b = (long long)B * d; p.batch_c = (long long)B * B;
+  if (n == 1 && B <= 256 && d >= 512) {
+    // small batch: only (B/64)^2 output tiles -> spread the feature dimension over the SMs (split-K + red.add)
+    p.batches = 1;
+    p.ksplit = std::min(32, d / 64);
+    p.epi = EPI_ATOMIC;
+    UGN_CUDA(cudaMemsetAsync(D, 0, sizeof(float) * (size_t)B * B, st));
+  }
   int rc = simt_gemm_launch(ctx, p, st);
   if (rc != UGN_OK) return rc;
   trip_diag_kernel<<<dim3(ugn_cdiv(B, 128), n), 128, 0, st>>>(D, x2, B);
