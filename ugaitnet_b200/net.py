@@ -52,6 +52,8 @@ class UGaitEngine:
         self.world = torch.distributed.get_world_size(process_group) if process_group is not None else 1
         self.use_graph = use_graph
         self.t = 0
+        self._dp_async = True      # bucketed, overlapped all-reduce (False: one blocking all-reduce)
+        self._works = []
         self.graph_launches = 0
         self._plans: Dict[tuple, "_Plan"] = {}
         self._graphs = {}
@@ -92,6 +94,13 @@ class UGaitEngine:
         self.segs = {s.name: s for s in segs}
         self.seg_list = segs
         self.n_arena = off
+        # all-reduce buckets: one per branch (its backward finishes as a unit) + the heads
+        self.buckets = {}
+        for m in range(cfg.nmods):
+            mine = [s for s in segs if s.name.startswith(BRANCH_NAMES[m] + "/")]
+            self.buckets[m] = (mine[0].off, round_up(mine[-1].off + mine[-1].n, 64))
+        heads = [s for s in segs if "/" in s.name and s.name.split("/")[0] in ("code", "classprob")]
+        self.buckets["heads"] = (heads[0].off, off) if heads else None
         d = self.dev
         self.w = torch.zeros(off, device=d)
         self.g = torch.zeros(off, device=d)
@@ -273,9 +282,17 @@ class UGaitEngine:
         raise KeyError(layer)
 
     # ------------------------------------------------------------------ backward
+    def _reduce_bucket(self, key):
+        """Data-parallel gradient exchange, bucketed so that the all-reduce of a finished branch overlaps
+        the backward pass of the next one (NCCL runs on its own stream)."""
+        if self.world > 1 and self._dp_async and self.buckets.get(key) is not None:
+            lo, hi = self.buckets[key]
+            self._works.append(torch.distributed.all_reduce(self.g[lo:hi], group=self.pg, async_op=True))
+
     def _losses_and_backward(self, p: "_Plan", sig: TRef, feat: TRef):
         cfg, h, st = self.cfg, self.ctx.h, stream_ptr()
         B = p.B
+        self._works = []
         # triplet: demb = wver * dL/dsig
         check(lib.ugn_triplet_all(h, sig.ptr, p.R["labels"].ptr, cfg.margin, cfg.wver, p.R["trip_out"].ptr,
                                   p.R["dsig"].ptr, p.R["trip_ws"].ptr, st))
@@ -298,6 +315,7 @@ class UGaitEngine:
                 p.dsig.add_(p.dsig2)
             else:
                 p.dsig.add_(p.dfeat)
+        self._reduce_bucket("heads")
         if cfg.single:
             p.br[0].dout.copy_(p.dsig)
         else:
@@ -332,6 +350,7 @@ class UGaitEngine:
                                            self.Rg[f"{bn}/conv{li}/b"].ptr, st))
                 if li > 0:
                     check(lib.ugn_conv2d_dgrad(h, R[f"dz{li}c"].ptr, self.Rcw[f"{bn}/conv{li}/w"].ptr, R[f"da{li}"].ptr, st))
+            self._reduce_bucket(m)
 
     def _optim(self, gscale: float):
         h, st, R = self.ctx.h, stream_ptr(), self.R
@@ -351,7 +370,11 @@ class UGaitEngine:
         self._losses_and_backward(p, sig, feat)
         if do_optim:
             if self.world > 1:
-                torch.distributed.all_reduce(self.g, group=self.pg)
+                if self._dp_async:
+                    for w in self._works:
+                        w.wait()
+                else:
+                    torch.distributed.all_reduce(self.g, group=self.pg)
             self._optim(1.0 / self.world)
 
     def _next_lr(self):
@@ -421,6 +444,44 @@ class UGaitEngine:
         if cfg.nclasses > 0:
             check(lib.ugn_softmax_ce(h, p.R["logits"].ptr, p.R["labels"].ptr, p.R["ce_out"].ptr, None, 1.0, st))
         return self._report(p)
+
+    # ------------------------------------------------------------------ host -> device pipelining
+    def prefetch(self, inputs, flags, labels):
+        """Enqueue the H2D copy of the NEXT step's (pinned) host batch on a side stream into the alternate
+        staging set, so it overlaps the step that is running; consume it with train_step_staged()."""
+        if not hasattr(self, "_copy_stream"):
+            self._copy_stream = torch.cuda.Stream(device=self.dev)
+            self._staging = [None, None]
+            self._stage_evt = [torch.cuda.Event(), torch.cuda.Event()]
+            self._stage_free = [torch.cuda.Event(), torch.cuda.Event()]
+            self._stage_k = 0
+        k = self._stage_k ^ 1
+        B = int(inputs[0].shape[0])
+        st = self._staging[k]
+        if st is None or st[0][0].shape[0] != B:
+            st = ([torch.empty(tuple(x.shape), device=self.dev) for x in inputs],
+                  None if flags is None else [torch.empty(B, 1, device=self.dev) for _ in flags],
+                  torch.empty(B, dtype=torch.int32, device=self.dev))
+            self._staging[k] = st
+        with torch.cuda.stream(self._copy_stream):
+            self._copy_stream.wait_event(self._stage_free[k])      # previous consumer of this set is done
+            for d, h in zip(st[0], inputs):
+                d.copy_(h, non_blocking=True)
+            if flags is not None:
+                for d, h in zip(st[1], flags):
+                    d.copy_(h.reshape(-1, 1), non_blocking=True)
+            st[2].copy_(labels.reshape(-1).to(torch.int32), non_blocking=True)
+            self._stage_evt[k].record(self._copy_stream)
+        self._stage_k = k
+
+    def train_step_staged(self):
+        """train_step on the batch most recently passed to prefetch()."""
+        k = self._stage_k
+        torch.cuda.current_stream().wait_event(self._stage_evt[k])
+        st = self._staging[k]
+        out = self.train_step(st[0], st[1], st[2])
+        self._stage_free[k].record(torch.cuda.current_stream())
+        return out
 
     def _report(self, p: "_Plan", with_reg: bool = False) -> Dict[str, torch.Tensor]:
         out = {"triplet": p.trip_out[0], "count": p.trip_out[1], "signature": p.br[0].out if self.cfg.single else p.sig}
