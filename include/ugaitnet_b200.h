@@ -23,11 +23,19 @@
  *
  * Storage modes (selected by the dtype of the activation / weight operands):
  *  - f32 : "fp32 validation mode" -- SIMT FFMA kernels, NHWC f32 activations.
- *  - bf16: tensor-core mode -- tcgen05.mma (kind::f16, BF16 in / FP32 accumulate in
- *          TMEM) fed by TMA.  A bf16 operand carries a leading plane dimension P:
- *          P == 1 plain bf16;  P == 2 "split" (plane 0 = hi = bf16(x), plane 1 = lo =
- *          bf16(x - hi)); with split operands the kernels issue hi*hi + hi*lo + lo*hi,
- *          i.e. ~fp32-accurate products on the BF16 tensor cores at 3x the MMA work.
+ *  - bf16 | f16: tensor-core mode -- tcgen05.mma (kind::f16, 16-bit in / FP32 accumulate
+ *          in TMEM) fed by TMA.  A 16-bit operand carries a leading plane dimension P:
+ *          P == 1 plain;  P == 2 "split" (plane 0 = hi = rn16(x), plane 1 = lo =
+ *          rn16(x - hi)); with split operands the kernels issue hi*hi + hi*lo + lo*hi,
+ *          i.e. ~fp32-accurate products on the 16-bit tensor cores at 3x the MMA work.
+ *          All 16-bit operands of one call share one dtype: bf16 (kDLBfloat) or IEEE fp16
+ *          (kDLFloat, 16 bits; 11-bit significand per plane).  Backward calls (dgrad, wgrad,
+ *          linear_bwd) use min(P) over their operands, so a P == 1 gradient operand against
+ *          P == 2 activations / weights runs ONE pass on the hi planes.
+ *          16-bit GRADIENT operands (the dz written by ugn_conv2d_bwd_act / ugn_act_mask_bwd)
+ *          are stored multiplied by the ctx's gradient scale s and every consumer multiplies
+ *          its f32 result by 1/s (ugn_grad_scale_*; s == 1 unless set) -- fp16 range
+ *          management; conversions to fp16 saturate at +-65504.
  *
  * Layouts
  *  - activations: NHWC, channel count padded to a multiple of 32 (64-byte rows) in bf16
@@ -60,7 +68,7 @@ typedef struct {
   int32_t device_type; /* kDLCUDA = 2 */
   int32_t device_id;
   int32_t ndim;
-  uint8_t dtype_code; /* kDLInt=0, kDLUInt=1, kDLFloat=2, kDLBfloat=4 */
+  uint8_t dtype_code; /* kDLInt=0, kDLUInt=1, kDLFloat=2 (32 | 16 | 64 bits), kDLBfloat=4 */
   uint8_t dtype_bits;
   uint16_t dtype_lanes;
   int64_t* shape;
@@ -204,14 +212,21 @@ int ugn_knn_merge_vote(ugn_ctx*, const ugn_tensor* d2, const ugn_tensor* idx,
                        ugn_tensor* out_lab, ugn_tensor* pred, void* stream);
 
 /* ---- generic tensor-core GEMM (building block exposed for tests / k-NN / triplet) ----
- * C f32 [M,N] (+)= A . B^T with bf16 operands [P,rows,cols]:
+ * C f32 [M,N] (+)= A . B^T with bf16 (or f16) operands [P,rows,cols]:
  *   a_mn == 0: A is [P,M,K] (K contiguous);  a_mn == 1: A is [P,K,M] (M contiguous).
  *   b_mn == 0: B is [P,N,K];                 b_mn == 1: B is [P,K,N].
  * accumulate != 0 adds into C (split-K partials use red.global.add). */
 int ugn_gemm_bf16(ugn_ctx*, const ugn_tensor* A, int a_mn, const ugn_tensor* B, int b_mn,
                   ugn_tensor* C, int accumulate, void* stream);
-/* f32 -> bf16 [P,...] split helper (P taken from dst). */
+/* f32 -> 16-bit [P,...] split helper (P and bf16 | f16 taken from dst). */
 int ugn_split_bf16(ugn_ctx*, const ugn_tensor* src_f32, ugn_tensor* dst_bf16, void* stream);
+
+/* ---- gradient scale of the ctx (16-bit gradient operands, see "Storage modes") ---------
+ * update: s = 2^floor(log2(target / max|ref|)) computed ON DEVICE from a reference gradient of
+ * the step (f32, any shape; the engine passes dL/dsignature), so it is CUDA-graph capturable.
+ * set: fixed value (1 = off).  Both are stream-ordered. */
+int ugn_grad_scale_update(ugn_ctx*, const ugn_tensor* ref, float target, void* stream);
+int ugn_grad_scale_set(ugn_ctx*, float scale, void* stream);
 
 /* number of kernels this library has launched on this ctx since creation (bench.py's
  * gpu_launches claim is read from here). */

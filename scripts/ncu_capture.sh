@@ -1,18 +1,33 @@
 #!/bin/bash
-# Runs on the GPU box (via gpurun): plain run, launch list, then two small --set full captures.
+# Runs on the GPU box (via gpurun): GPU tests, bench line, ncu launch list of one eager step, then
+# `--set full` captures of the dominant kernels.  Everything lands in gpurun_out/ (scratch); the
+# summaries that are to be judged are condensed into profiles/ by scripts/summarise_profiles.py.
+#   usage: scripts/ncu_capture.sh [tag] [notests]
+TAG=${1:-r01}
+OUT=gpurun_out/$TAG
+mkdir -p $OUT
 set -x
-mkdir -p gpurun_out
+if [ "$2" != "notests" ]; then
+  timeout 1500 python -m pytest tests -m gpu -x -q > $OUT/pytest_gpu.log 2>&1
+  tail -n 5 $OUT/pytest_gpu.log
+fi
+timeout 600 python bench.py > $OUT/bench_n1.json 2> $OUT/bench_n1.err || tail -n 20 $OUT/bench_n1.err
+tail -c 3000 $OUT/bench_n1.json
 CMD="python bench.py --steps 2 --warmup 3 --no-graph --lite"
-$CMD > gpurun_out/plain.log 2>&1 || { tail -5 gpurun_out/plain.log; exit 1; }
-ncu --metrics gpu__time_duration.sum --clock-control none -s 480 -c 320 --csv --log-file gpurun_out/launches.csv $CMD > gpurun_out/ncu1.log 2>&1
-ncu --set full --clock-control none --import-source on -k regex:tc_kernel -s 153 -c 10 -o gpurun_out/prof_fwd $CMD > gpurun_out/ncu2.log 2>&1
-ncu --set full --clock-control none --import-source on -k regex:tc_kernel -s 175 -c 7 -o gpurun_out/prof_bwd $CMD > gpurun_out/ncu3.log 2>&1
-for f in prof_fwd prof_bwd; do
-  ncu -i gpurun_out/$f.ncu-rep --page raw --csv > gpurun_out/${f}_raw.csv 2>/dev/null
+$CMD > $OUT/plain.log 2>&1 || { tail -5 $OUT/plain.log; exit 1; }
+# launch list: skip the 3 warm-up steps (per-step launch count is printed by the plain run)
+NL=$(python -c "import json,sys; print(json.loads(open('$OUT/plain.log').read().strip().splitlines()[-1])['gpu_launches']//2)")
+timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -s $((NL*3)) -c $NL --csv \
+    --log-file $OUT/launches.csv $CMD > $OUT/ncu_list.log 2>&1
+for KS in tc_convp_kernel:40:14 tc_wgradv_kernel:30:10 tc_kernel:80:20 optim_kernel:3:1; do
+  K=${KS%%:*}; R=${KS#*:}; S=${R%%:*}; C=${R#*:}
+  timeout 900 ncu --set full --clock-control none --import-source on -k regex:^$K\$ -s $S -c $C -o $OUT/prof_$K $CMD > $OUT/ncu_$K.log 2>&1
+  ncu -i $OUT/prof_$K.ncu-rep --page raw --csv > $OUT/prof_${K}_raw.csv 2>/dev/null
 done
-ls -la gpurun_out
-du -sm gpurun_out
+ncu -i $OUT/prof_tc_convp_kernel.ncu-rep --page source --csv > $OUT/prof_tc_convp_kernel_src.csv 2>/dev/null
+du -sm $OUT
 # keep the payload under the 64 MiB copy-back limit
-if [ $(du -sm gpurun_out | cut -f1) -gt 55 ]; then rm -f gpurun_out/prof_bwd.ncu-rep; fi
-if [ $(du -sm gpurun_out | cut -f1) -gt 55 ]; then rm -f gpurun_out/prof_fwd.ncu-rep; fi
-tail -n 3 gpurun_out/plain.log
+for K in optim_kernel tc_kernel tc_wgradv_kernel tc_convp_kernel; do
+  if [ $(du -sm gpurun_out | cut -f1) -gt 50 ]; then rm -f $OUT/prof_$K.ncu-rep; fi
+done
+ls -la $OUT

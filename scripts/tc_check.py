@@ -9,13 +9,23 @@ from ugaitnet_b200 import ops
 
 ctx = ops.get_ctx(0)
 torch.manual_seed(0)
+# UGN_CHECK_DT=f16 -> fp16 planes; UGN_CHECK_MIXED=1 -> backward operands dz with ONE plane against
+# two-plane activations / weights (single-pass backward); UGN_CHECK_GS=<s> -> gradient scale s (dz planes
+# hold s*dz, outputs must come back unscaled); UGN_CHECK_MAG=<m> -> operand magnitude (subnormal-lo test)
+DT = torch.float16 if os.environ.get("UGN_CHECK_DT") == "f16" else torch.bfloat16
+MIXED = bool(int(os.environ.get("UGN_CHECK_MIXED", "0")))
+GS = float(os.environ.get("UGN_CHECK_GS", "1"))
+MAG = float(os.environ.get("UGN_CHECK_MAG", "1"))
+if GS != 1:
+    ops.grad_scale_set(ctx, GS)
+print(f"dtype {DT} mixed {MIXED} grad-scale {GS} magnitude {MAG}")
 
 
 def planes(x, P):
-    hi = x.to(torch.bfloat16)
+    hi = x.to(DT)
     if P == 1:
         return hi.unsqueeze(0).contiguous(), hi.double()
-    lo = (x - hi.float()).to(torch.bfloat16)
+    lo = (x - hi.float()).to(DT)
     return torch.stack([hi, lo]).contiguous(), hi.double() + lo.double()
 
 
@@ -24,8 +34,8 @@ def rel(a, b):
 
 
 def gemm_case(M, N, K, a_mn, b_mn, P):
-    A = torch.randn(M, K, device="cuda")
-    B = torch.randn(N, K, device="cuda")
+    A = torch.randn(M, K, device="cuda") * MAG
+    B = torch.randn(N, K, device="cuda") * MAG
     Ap, Ae = planes(A.t().contiguous() if a_mn else A, P)
     Bp, Be = planes(B.t().contiguous() if b_mn else B, P)
     C = torch.full((M, N), float("nan"), device="cuda")
@@ -38,7 +48,8 @@ def gemm_case(M, N, K, a_mn, b_mn, P):
         ref = Ar @ Br.t()
         if P == 2:   # the kernel drops the lo*lo term
             pass
-        print(f"{tag}: rel {rel(C, ref):.3e} nan {int(torch.isnan(C).sum())}")
+        exact = (A.double() @ B.double().t())
+        print(f"{tag}: rel {rel(C, ref):.3e} vs-fp64-inputs {rel(C, exact):.3e} nan {int(torch.isnan(C).sum())}")
     except Exception as e:
         print(f"{tag}: ERROR {e}")
 
@@ -50,15 +61,15 @@ def conv_case(B, C, H, Co, k, pool, P, act=1):
         w = torch.randn(Co, C, k, k, device="cuda") * 0.1
         b = torch.randn(Co, device="cuda") * 0.1
         Cp = (C + 31) // 32 * 32
-        xd = torch.zeros(P, B, H, H, Cp, dtype=torch.bfloat16, device="cuda")
+        xd = torch.zeros(P, B, H, H, Cp, dtype=DT, device="cuda")
         ops.pack_input(ctx, x, xd)
-        wp = torch.zeros(P, Co, k, k, Cp, dtype=torch.bfloat16, device="cuda")
+        wp = torch.zeros(P, Co, k, k, Cp, dtype=DT, device="cuda")
         ops.pack_weight(ctx, w.permute(0, 2, 3, 1).contiguous(), wp)
         xe = xd.double().sum(0)[..., :C].permute(0, 3, 1, 2)
         we = wp.double().sum(0)[..., :C].permute(0, 3, 1, 2)
         Ho = H - k + 1
         Hp = Ho // 2 if pool else Ho
-        y = torch.zeros(P, B, Hp, Hp, Co, dtype=torch.bfloat16, device="cuda")
+        y = torch.zeros(P, B, Hp, Hp, Co, dtype=DT, device="cuda")
         idx = torch.zeros(B, Hp, Hp, Co, dtype=torch.uint8, device="cuda") if pool else None
         ops.conv2d_fwd(ctx, xd, wp, b, y, idx, act=act, alpha=0.3, pool=pool)
         ctx.check()
@@ -70,7 +81,13 @@ def conv_case(B, C, H, Co, k, pool, P, act=1):
         print(f"{tag}: fwd rel {rel(got, ref.detach()):.3e}")
         # backward pieces with a random dz (bf16 planes)
         dzf = torch.randn(B, Ho, Ho, Co, device="cuda") * (torch.rand(B, Ho, Ho, Co, device="cuda") < 0.3)
-        dzp, dze = planes(dzf, P)
+        PB = 1 if MIXED else P
+        dzp, dze = planes(dzf * GS, PB)
+        dze = dze / GS
+        if MIXED:   # single pass on the hi planes: the reference operands are the hi planes too
+            xe = xd[0].double()[..., :C].permute(0, 3, 1, 2).requires_grad_(True)
+            we = wp[0].double()[..., :C].permute(0, 3, 1, 2).requires_grad_(True)
+            z = F.conv2d(xe, we, b.double())
         z.backward(dze.permute(0, 3, 1, 2))
         dw = torch.zeros(Co, k, k, C, device="cuda"); db = torch.zeros(Co, device="cuda")
         ops.conv2d_wgrad(ctx, xd, dzp, dw, db)

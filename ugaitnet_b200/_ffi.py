@@ -71,6 +71,8 @@ _PROTOS = {
     "ugn_knn_topk": (c_int, [c_void_p, _T, _T, _T, _T, c_int, c_int64, _T, _T, _T, _T, c_void_p]),
     "ugn_knn_merge_vote": (c_int, [c_void_p, _T, _T, _T, c_int, _T, _T, _T, _T, c_void_p]),
     "ugn_gemm_bf16": (c_int, [c_void_p, _T, c_int, _T, c_int, _T, c_int, c_void_p]),
+    "ugn_grad_scale_update": (c_int, [c_void_p, _T, c_float, c_void_p]),
+    "ugn_grad_scale_set": (c_int, [c_void_p, c_float, c_void_p]),
 }
 
 EXPORTED_SYMBOLS = tuple(_PROTOS)

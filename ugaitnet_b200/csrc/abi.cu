@@ -55,11 +55,18 @@ extern "C" int ugn_ctx_create(int device, ugn_ctx** out) {
   c->sm_count = prop.multiProcessorCount;
   c->cc_major = prop.major;
   c->cc_minor = prop.minor;
+  const float gs0[4] = {1.f, 1.f, 0.f, 0.f};
+  if (cudaMalloc(&c->gscale, sizeof(gs0)) != cudaSuccess ||
+      cudaMemcpy(c->gscale, gs0, sizeof(gs0), cudaMemcpyHostToDevice) != cudaSuccess) {
+    delete c;
+    UGN_FAIL(UGN_ERR_CUDA, "ugn_ctx_create: cannot allocate the gradient-scale buffer");
+  }
   *out = c;
   return UGN_OK;
 }
 extern "C" int ugn_ctx_destroy(ugn_ctx* ctx) {
   if (ctx && ctx->err_flag) cudaFree(ctx->err_flag);
+  if (ctx && ctx->gscale) cudaFree(ctx->gscale);
   delete ctx;
   return UGN_OK;
 }
@@ -81,16 +88,17 @@ extern "C" int ugn_ctx_has_tcgen05(ugn_ctx* ctx) { return ctx && ctx->cc_major =
 extern "C" int64_t ugn_launch_count(ugn_ctx* ctx) { return ctx ? ctx->launches : 0; }
 
 // ---- implementations living in other translation units --------------------------------
-int ew_pack_input(ugn_ctx*, const float*, void*, int, int, int, int, int, int, cudaStream_t);
-int ew_pack_weight(ugn_ctx*, const float*, void*, int, long long, int, int, cudaStream_t);
-int ew_split(ugn_ctx*, const float*, __nv_bfloat16*, int, long long, cudaStream_t);
-int ew_bwd_act(ugn_ctx*, const float*, const void*, int, const uint8_t*, void*, int, int, int, int, int,
+int ew_pack_input(ugn_ctx*, const float*, void*, int, int, int, int, int, int, int, cudaStream_t);
+int ew_pack_weight(ugn_ctx*, const float*, void*, int, int, long long, int, int, cudaStream_t);
+int ew_split(ugn_ctx*, const float*, __nv_bfloat16*, int, int, long long, cudaStream_t);
+int ew_bwd_act(ugn_ctx*, const float*, const void*, int, const uint8_t*, void*, int, int, int, int, int, int,
                int, int, int, float, int, cudaStream_t);
 int ew_flatten(ugn_ctx*, const void*, void*, int, int, int, int, int, int, cudaStream_t);
-int ew_act_mask_bwd(ugn_ctx*, const float*, const float*, const float*, float*, __nv_bfloat16*, int,
+int ew_act_mask_bwd(ugn_ctx*, const float*, const float*, const float*, float*, __nv_bfloat16*, int, int,
                     long long, int, float, cudaStream_t);
-int ew_fuse_fwd(ugn_ctx*, const FusePtrs&, int, int, int, float*, __nv_bfloat16*, int, uint8_t*, float*,
+int ew_fuse_fwd(ugn_ctx*, const FusePtrs&, int, int, int, float*, __nv_bfloat16*, int, int, uint8_t*, float*,
                 int, int, cudaStream_t);
+int ew_gscale_update(ugn_ctx*, const float*, long long, float, float, cudaStream_t);
 int ew_fuse_bwd(ugn_ctx*, const FusePtrs&, int, int, int, const float*, const float*, const uint8_t*,
                 const float*, int, int, cudaStream_t);
 int ew_softmax_ce(ugn_ctx*, const float*, const int*, float*, float*, int, int, float, cudaStream_t);
@@ -105,14 +113,20 @@ int simt_linear_fwd(ugn_ctx*, int, int, int, const float*, const float*, const f
 int simt_linear_bwd(ugn_ctx*, int, int, int, const float*, const float*, const float*, float*, float*,
                     float*, cudaStream_t);
 
-// mode of an activation/weight operand: 0 = f32, 1 = bf16 P=1, 2 = bf16 P=2, -1 invalid.
-// `rank` is the logical rank (without the plane dimension).
+// mode of an activation/weight operand: 0 = f32, 1 = 16-bit P=1, 2 = 16-bit P=2, -1 invalid.
+// `rank` is the logical rank (without the plane dimension).  16-bit storage is bf16 or fp16 (is_f16).
 static int storage_mode(const ugn_tensor* t, int rank) {
   UgnDType dt = ugn_dtype(t);
   if (dt == DT_F32 && t->ndim == rank) return 0;
-  if (dt == DT_BF16 && t->ndim == rank + 1 && (t->shape[0] == 1 || t->shape[0] == 2)) return (int)t->shape[0];
+  if ((dt == DT_BF16 || dt == DT_F16) && t->ndim == rank + 1 && (t->shape[0] == 1 || t->shape[0] == 2))
+    return (int)t->shape[0];
   return -1;
 }
+static inline int is_f16(const ugn_tensor* t) { return ugn_dtype(t) == DT_F16; }
+static inline bool is_16(const ugn_tensor* t) { UgnDType d = ugn_dtype(t); return d == DT_BF16 || d == DT_F16; }
+// operands of one tensor-core call: all f32, or all 16-bit of the same format
+#define UGN_SAME_FMT(a, b, what) \
+  UGN_CHECK(ugn_dtype(a) == ugn_dtype(b), what ": operands must share one storage dtype (f32 | bf16 | f16)")
 static inline const int64_t* lshape(const ugn_tensor* t, int rank) { return t->shape + (t->ndim - rank); }
 
 extern "C" int ugn_pack_input(ugn_ctx* ctx, const ugn_tensor* x_nchw, ugn_tensor* x_nhwc, void* stream) {
@@ -126,7 +140,7 @@ extern "C" int ugn_pack_input(ugn_ctx* ctx, const ugn_tensor* x_nchw, ugn_tensor
   UGN_CHECK(s[0] == B && s[1] == H && s[2] == W && s[3] >= C, "pack_input: shape mismatch");
   UGN_CHECK((size_t)C * (W + 1) * 4 <= 48 * 1024, "pack_input: C*W too large");
   if (B == 0) return UGN_OK;
-  return ew_pack_input(ctx, ugn_ptr<float>(x_nchw), ugn_ptr<void>(x_nhwc), mode, B, C, H, W, (int)s[3],
+  return ew_pack_input(ctx, ugn_ptr<float>(x_nchw), ugn_ptr<void>(x_nhwc), mode, is_f16(x_nhwc), B, C, H, W, (int)s[3],
                        (cudaStream_t)stream);
 }
 
@@ -145,17 +159,18 @@ extern "C" int ugn_pack_weight(ugn_ctx* ctx, const ugn_tensor* w_master, ugn_ten
   }
   int Cin = (int)w_master->shape[rank - 1], Cp = (int)s[rank - 1];
   UGN_CHECK(Cp >= Cin, "pack_weight: padded width smaller than source");
-  return ew_pack_weight(ctx, ugn_ptr<float>(w_master), ugn_ptr<void>(w_packed), mode, R, Cin, Cp,
+  return ew_pack_weight(ctx, ugn_ptr<float>(w_master), ugn_ptr<void>(w_packed), mode, is_f16(w_packed), R, Cin, Cp,
                         (cudaStream_t)stream);
 }
 
 extern "C" int ugn_split_bf16(ugn_ctx* ctx, const ugn_tensor* src, ugn_tensor* dst, void* stream) {
   UGN_CHECK(ctx && src && dst, "ugn_split_bf16: null argument");
   UGN_TENSOR(src, DT_F32, 1, 8);
-  UGN_TENSOR(dst, DT_BF16, 2, 8);
+  UGN_TENSOR(dst, DT_BAD, 2, 8);
+  UGN_CHECK(is_16(dst), "split_bf16: dst must be bf16 or f16");
   int P = (int)dst->shape[0];
   UGN_CHECK((P == 1 || P == 2) && ugn_numel(dst) == P * ugn_numel(src), "split_bf16: dst must be [P,...src]");
-  return ew_split(ctx, ugn_ptr<float>(src), ugn_ptr<__nv_bfloat16>(dst), P, ugn_numel(src), (cudaStream_t)stream);
+  return ew_split(ctx, ugn_ptr<float>(src), ugn_ptr<__nv_bfloat16>(dst), P, is_f16(dst), ugn_numel(src), (cudaStream_t)stream);
 }
 
 static int conv_geom(const ugn_tensor* x, const ugn_tensor* w, int pool, ConvGeom& g) {
@@ -182,6 +197,8 @@ extern "C" int ugn_conv2d_fwd(ugn_ctx* ctx, const ugn_tensor* x, const ugn_tenso
   if (bias) UGN_TENSOR(bias, DT_F32, 1, 1);
   int mx = storage_mode(x, 4), mw = storage_mode(w, 4), my = storage_mode(y, 4);
   UGN_CHECK(mx >= 0 && mx == mw && (my == mx), "conv2d_fwd: x/w/y storage modes must match (%d,%d,%d)", mx, mw, my);
+  UGN_SAME_FMT(x, w, "conv2d_fwd");
+  UGN_SAME_FMT(x, y, "conv2d_fwd");
   ConvGeom g;
   int rc = conv_geom(x, w, pool, g);
   if (rc != UGN_OK) return rc;
@@ -200,7 +217,7 @@ extern "C" int ugn_conv2d_fwd(ugn_ctx* ctx, const ugn_tensor* x, const ugn_tenso
   if (mx == 0)
     return simt_conv_fwd(ctx, g, ugn_ptr<float>(x), ugn_ptr<float>(w), bias ? ugn_ptr<float>(bias) : nullptr,
                          ugn_ptr<float>(y), idx, act, alpha, pool, (cudaStream_t)stream);
-  return tc_conv_fwd(ctx, g, mx, ugn_ptr<__nv_bfloat16>(x), ugn_ptr<__nv_bfloat16>(w),
+  return tc_conv_fwd(ctx, g, mx, is_f16(x), ugn_ptr<__nv_bfloat16>(x), ugn_ptr<__nv_bfloat16>(w),
                      bias ? ugn_ptr<float>(bias) : nullptr, ugn_ptr<__nv_bfloat16>(y), idx, act, alpha, pool,
                      (cudaStream_t)stream);
 }
@@ -226,8 +243,10 @@ extern "C" int ugn_conv2d_bwd_act(ugn_ctx* ctx, const ugn_tensor* dy, const ugn_
     UGN_CHECK(Hp == Ho && Wp == Wo, "bwd_act: shape mismatch (no pool)");
   }
   if (B == 0) return UGN_OK;
+  if (my > 0 && mz > 0) UGN_SAME_FMT(y, dz, "bwd_act");
   return ew_bwd_act(ctx, ugn_ptr<float>(dy), ugn_ptr<void>(y), my > 0, pool ? ugn_ptr<uint8_t>(pool_idx) : nullptr,
-                    ugn_ptr<void>(dz), mz, B, Ho, Wo, Hp, Wp, C, act, alpha, pool, (cudaStream_t)stream);
+                    ugn_ptr<void>(dz), mz, mz > 0 ? is_f16(dz) : is_f16(y), B, Ho, Wo, Hp, Wp, C, act, alpha, pool,
+                    (cudaStream_t)stream);
 }
 
 extern "C" int ugn_conv2d_dgrad(ugn_ctx* ctx, const ugn_tensor* dz, const ugn_tensor* w, ugn_tensor* dx,
@@ -237,7 +256,9 @@ extern "C" int ugn_conv2d_dgrad(ugn_ctx* ctx, const ugn_tensor* dz, const ugn_te
   UGN_TENSOR(w, DT_BAD, 4, 5);
   UGN_TENSOR(dx, DT_F32, 4, 4);
   int mz = storage_mode(dz, 4), mw = storage_mode(w, 4);
-  UGN_CHECK(mz >= 0 && mz == mw, "conv2d_dgrad: dz/w storage modes must match");
+  // 16-bit: the MMA uses min(planes(dz), planes(w)) planes of each operand (1 = single pass on the hi planes)
+  UGN_CHECK(mz >= 0 && mw >= 0 && (mz == 0) == (mw == 0), "conv2d_dgrad: dz/w storage modes must match");
+  UGN_SAME_FMT(dz, w, "conv2d_dgrad");
   ConvGeom g;
   int rc = conv_geom(dx, w, 0, g);
   if (rc != UGN_OK) return rc;
@@ -246,7 +267,7 @@ extern "C" int ugn_conv2d_dgrad(ugn_ctx* ctx, const ugn_tensor* dz, const ugn_te
   if (g.B == 0) return UGN_OK;
   if (mz == 0)
     return simt_conv_dgrad(ctx, g, ugn_ptr<float>(dz), ugn_ptr<float>(w), ugn_ptr<float>(dx), (cudaStream_t)stream);
-  return tc_conv_dgrad(ctx, g, mz, ugn_ptr<__nv_bfloat16>(dz), ugn_ptr<__nv_bfloat16>(w), ugn_ptr<float>(dx),
+  return tc_conv_dgrad(ctx, g, mz < mw ? mz : mw, is_f16(dz), ugn_ptr<__nv_bfloat16>(dz), ugn_ptr<__nv_bfloat16>(w), ugn_ptr<float>(dx),
                        (cudaStream_t)stream);
 }
 
@@ -258,7 +279,8 @@ extern "C" int ugn_conv2d_wgrad(ugn_ctx* ctx, const ugn_tensor* x, const ugn_ten
   UGN_TENSOR(dw, DT_F32, 4, 4);
   if (db) UGN_TENSOR(db, DT_F32, 1, 1);
   int mx = storage_mode(x, 4), mz = storage_mode(dz, 4);
-  UGN_CHECK(mx >= 0 && mx == mz, "conv2d_wgrad: x/dz storage modes must match");
+  UGN_CHECK(mx >= 0 && mz >= 0 && (mx == 0) == (mz == 0), "conv2d_wgrad: x/dz storage modes must match");
+  UGN_SAME_FMT(x, dz, "conv2d_wgrad");
   const int64_t* xs = lshape(x, 4);
   const int64_t* zs = lshape(dz, 4);
   ConvGeom g;
@@ -271,7 +293,7 @@ extern "C" int ugn_conv2d_wgrad(ugn_ctx* ctx, const ugn_tensor* x, const ugn_ten
   if (mx == 0)
     return simt_conv_wgrad(ctx, g, ugn_ptr<float>(x), ugn_ptr<float>(dz), ugn_ptr<float>(dw),
                            db ? ugn_ptr<float>(db) : nullptr, (cudaStream_t)stream);
-  return tc_conv_wgrad(ctx, g, mx, ugn_ptr<__nv_bfloat16>(x), ugn_ptr<__nv_bfloat16>(dz), ugn_ptr<float>(dw),
+  return tc_conv_wgrad(ctx, g, mx < mz ? mx : mz, is_f16(x), ugn_ptr<__nv_bfloat16>(x), ugn_ptr<__nv_bfloat16>(dz), ugn_ptr<float>(dw),
                        db ? ugn_ptr<float>(db) : nullptr, (cudaStream_t)stream);
 }
 
@@ -281,6 +303,7 @@ extern "C" int ugn_flatten_chw(ugn_ctx* ctx, const ugn_tensor* y, ugn_tensor* fl
   UGN_TENSOR(flat, DT_BAD, 2, 3);
   int my = storage_mode(y, 4), mf = storage_mode(flat, 2);
   UGN_CHECK(my >= 0 && my == mf, "flatten: storage modes must match");
+  UGN_SAME_FMT(y, flat, "flatten");
   const int64_t* ys = lshape(y, 4);
   UGN_CHECK(lshape(flat, 2)[0] == ys[0] && lshape(flat, 2)[1] == ys[1] * ys[2] * ys[3], "flatten: shape mismatch");
   if (ys[0] == 0) return UGN_OK;
@@ -307,6 +330,7 @@ extern "C" int ugn_linear_fwd(ugn_ctx* ctx, const ugn_tensor* x, const ugn_tenso
   UGN_TENSOR(y, DT_F32, 2, 2);
   int mx = storage_mode(x, 2), mw = storage_mode(w, 2);
   UGN_CHECK(mx >= 0 && mx == mw, "linear_fwd: x/w storage modes must match");
+  UGN_SAME_FMT(x, w, "linear_fwd");
   const int64_t* xs = lshape(x, 2);
   const int64_t* ws = lshape(w, 2);
   int B = (int)xs[0], K = (int)xs[1], N = (int)ws[0];
@@ -315,7 +339,8 @@ extern "C" int ugn_linear_fwd(ugn_ctx* ctx, const ugn_tensor* x, const ugn_tenso
   if (drop_mask) { UGN_TENSOR(drop_mask, DT_F32, 2, 2); UGN_CHECK(ugn_numel(drop_mask) == (int64_t)B * N, "linear_fwd: mask must be [B,N]"); }
   int P16 = 0;
   if (y16) {
-    UGN_TENSOR(y16, DT_BF16, 3, 3);
+    UGN_TENSOR(y16, DT_BAD, 3, 3);
+    UGN_CHECK(is_16(y16), "linear_fwd: y16 must be bf16 or f16");
     P16 = (int)y16->shape[0];
     UGN_CHECK((P16 == 1 || P16 == 2) && y16->shape[1] == B && y16->shape[2] == N, "linear_fwd: y16 must be [P,B,N]");
   }
@@ -326,12 +351,12 @@ extern "C" int ugn_linear_fwd(ugn_ctx* ctx, const ugn_tensor* x, const ugn_tenso
     rc = simt_linear_fwd(ctx, B, N, K, ugn_ptr<float>(x), ugn_ptr<float>(w), bias ? ugn_ptr<float>(bias) : nullptr,
                          drop_mask ? ugn_ptr<float>(drop_mask) : nullptr, ugn_ptr<float>(y), act, alpha, st);
   } else {
-    rc = tc_linear_fwd(ctx, mx, B, N, K, ugn_ptr<__nv_bfloat16>(x), ugn_ptr<__nv_bfloat16>(w),
+    rc = tc_linear_fwd(ctx, mx, is_f16(x), B, N, K, ugn_ptr<__nv_bfloat16>(x), ugn_ptr<__nv_bfloat16>(w),
                        bias ? ugn_ptr<float>(bias) : nullptr, drop_mask ? ugn_ptr<float>(drop_mask) : nullptr,
                        ugn_ptr<float>(y), act, alpha, st);
   }
   if (rc != UGN_OK) return rc;
-  if (y16) return ew_split(ctx, ugn_ptr<float>(y), ugn_ptr<__nv_bfloat16>(y16), P16, (long long)B * N, st);
+  if (y16) return ew_split(ctx, ugn_ptr<float>(y), ugn_ptr<__nv_bfloat16>(y16), P16, is_f16(y16), (long long)B * N, st);
   return UGN_OK;
 }
 
@@ -345,14 +370,16 @@ extern "C" int ugn_act_mask_bwd(ugn_ctx* ctx, const ugn_tensor* dy, const ugn_te
   if (dz) { UGN_TENSOR(dz, DT_F32, 1, 4); UGN_CHECK(ugn_numel(dz) == n, "act_mask_bwd: dz shape mismatch"); }
   int P = 0;
   if (dz16) {
-    UGN_TENSOR(dz16, DT_BF16, 2, 5);
+    UGN_TENSOR(dz16, DT_BAD, 2, 5);
+    UGN_CHECK(is_16(dz16), "act_mask_bwd: dz16 must be bf16 or f16");
     P = (int)dz16->shape[0];
     UGN_CHECK((P == 1 || P == 2) && ugn_numel(dz16) == P * n, "act_mask_bwd: dz16 must be [P,...]");
   }
   if (n == 0) return UGN_OK;
   return ew_act_mask_bwd(ctx, ugn_ptr<float>(dy), y ? ugn_ptr<float>(y) : nullptr,
                          drop_mask ? ugn_ptr<float>(drop_mask) : nullptr, dz ? ugn_ptr<float>(dz) : nullptr,
-                         dz16 ? ugn_ptr<__nv_bfloat16>(dz16) : nullptr, P, n, act, alpha, (cudaStream_t)stream);
+                         dz16 ? ugn_ptr<__nv_bfloat16>(dz16) : nullptr, P, dz16 ? is_f16(dz16) : 0, n, act, alpha,
+                         (cudaStream_t)stream);
 }
 
 extern "C" int ugn_linear_bwd(ugn_ctx* ctx, const ugn_tensor* x, const ugn_tensor* w, const ugn_tensor* dz,
@@ -362,7 +389,11 @@ extern "C" int ugn_linear_bwd(ugn_ctx* ctx, const ugn_tensor* x, const ugn_tenso
   UGN_TENSOR(w, DT_BAD, 2, 3);
   UGN_TENSOR(dz, DT_BAD, 2, 3);
   int mx = storage_mode(x, 2), mw = storage_mode(w, 2), mz = storage_mode(dz, 2);
-  UGN_CHECK(mx >= 0 && mx == mw && mx == mz, "linear_bwd: x/w/dz storage modes must match");
+  UGN_CHECK(mx >= 0 && mw >= 0 && mz >= 0 && (mx == 0) == (mw == 0) && (mx == 0) == (mz == 0),
+            "linear_bwd: x/w/dz storage modes must match");
+  UGN_SAME_FMT(x, w, "linear_bwd");
+  UGN_SAME_FMT(x, dz, "linear_bwd");
+  const int mp = mx < mz ? (mx < mw ? mx : mw) : (mz < mw ? mz : mw);   // planes used by the MMAs
   const int64_t* xs = lshape(x, 2);
   const int64_t* ws = lshape(w, 2);
   const int64_t* zs = lshape(dz, 2);
@@ -377,7 +408,7 @@ extern "C" int ugn_linear_bwd(ugn_ctx* ctx, const ugn_tensor* x, const ugn_tenso
     return simt_linear_bwd(ctx, B, N, K, ugn_ptr<float>(x), ugn_ptr<float>(w), ugn_ptr<float>(dz),
                            dx ? ugn_ptr<float>(dx) : nullptr, dw ? ugn_ptr<float>(dw) : nullptr,
                            db ? ugn_ptr<float>(db) : nullptr, st);
-  return tc_linear_bwd(ctx, mx, B, N, K, ugn_ptr<__nv_bfloat16>(x), ugn_ptr<__nv_bfloat16>(w),
+  return tc_linear_bwd(ctx, mp, is_f16(x), B, N, K, ugn_ptr<__nv_bfloat16>(x), ugn_ptr<__nv_bfloat16>(w),
                        ugn_ptr<__nv_bfloat16>(dz), dx ? ugn_ptr<float>(dx) : nullptr,
                        dw ? ugn_ptr<float>(dw) : nullptr, db ? ugn_ptr<float>(db) : nullptr, st);
 }
@@ -406,7 +437,8 @@ extern "C" int ugn_fuse_fwd(ugn_ctx* ctx, int nmods, const ugn_tensor* const* br
   UGN_CHECK(sig->shape[0] == B && sig->shape[1] == d, "fuse_fwd: sig must be [B,d]");
   int P = 0;
   if (sig16) {
-    UGN_TENSOR(sig16, DT_BF16, 3, 3);
+    UGN_TENSOR(sig16, DT_BAD, 3, 3);
+    UGN_CHECK(is_16(sig16), "fuse_fwd: sig16 must be bf16 or f16");
     P = (int)sig16->shape[0];
     UGN_CHECK((P == 1 || P == 2) && sig16->shape[1] == B && sig16->shape[2] == d, "fuse_fwd: sig16 must be [P,B,d]");
   }
@@ -417,6 +449,7 @@ extern "C" int ugn_fuse_fwd(ugn_ctx* ctx, int nmods, const ugn_tensor* const* br
   FusePtrs p{};
   for (int m = 0; m < nmods; ++m) { p.br[m] = ugn_ptr<float>(br[m]); p.flag[m] = ugn_ptr<float>(flags[m]); }
   return ew_fuse_fwd(ctx, p, nmods, B, d, ugn_ptr<float>(sig), sig16 ? ugn_ptr<__nv_bfloat16>(sig16) : nullptr, P,
+                     sig16 ? is_f16(sig16) : 0,
                      winner ? ugn_ptr<uint8_t>(winner) : nullptr, inv_norm ? ugn_ptr<float>(inv_norm) : nullptr,
                      merge, normalize, (cudaStream_t)stream);
 }
@@ -492,14 +525,28 @@ extern "C" int ugn_sgd_step(ugn_ctx* ctx, ugn_tensor* w, const ugn_tensor* g, ug
 extern "C" int ugn_gemm_bf16(ugn_ctx* ctx, const ugn_tensor* A, int a_mn, const ugn_tensor* B, int b_mn, ugn_tensor* C,
                              int accumulate, void* stream) {
   UGN_CHECK(ctx && A && B && C, "ugn_gemm_bf16: null argument");
-  UGN_TENSOR(A, DT_BF16, 3, 3);
-  UGN_TENSOR(B, DT_BF16, 3, 3);
+  UGN_TENSOR(A, DT_BAD, 3, 3);
+  UGN_TENSOR(B, DT_BAD, 3, 3);
+  UGN_CHECK(is_16(A), "gemm_bf16: operands must be bf16 or f16");
+  UGN_SAME_FMT(A, B, "gemm_bf16");
   UGN_TENSOR(C, DT_F32, 2, 2);
   int P = (int)A->shape[0];
   UGN_CHECK((P == 1 || P == 2) && B->shape[0] == P, "gemm_bf16: plane counts must match (1 or 2)");
   int M = (int)(a_mn ? A->shape[2] : A->shape[1]), K = (int)(a_mn ? A->shape[1] : A->shape[2]);
   int N = (int)(b_mn ? B->shape[2] : B->shape[1]), Kb = (int)(b_mn ? B->shape[1] : B->shape[2]);
   UGN_CHECK(K == Kb && C->shape[0] == M && C->shape[1] == N, "gemm_bf16: shape mismatch (M=%d N=%d K=%d/%d)", M, N, K, Kb);
-  return tc_gemm(ctx, P, M, N, K, ugn_ptr<__nv_bfloat16>(A), a_mn, ugn_ptr<__nv_bfloat16>(B), b_mn, ugn_ptr<float>(C),
+  return tc_gemm(ctx, P, is_f16(A), M, N, K, ugn_ptr<__nv_bfloat16>(A), a_mn, ugn_ptr<__nv_bfloat16>(B), b_mn, ugn_ptr<float>(C),
                  accumulate, (cudaStream_t)stream);
+}
+
+// ---- gradient scale for 16-bit gradient operands ---------------------------------------------
+extern "C" int ugn_grad_scale_update(ugn_ctx* ctx, const ugn_tensor* ref, float target, void* stream) {
+  UGN_CHECK(ctx && ref, "ugn_grad_scale_update: null argument");
+  UGN_TENSOR(ref, DT_F32, 1, 4);
+  UGN_CHECK(target > 0.f, "ugn_grad_scale_update: target must be positive");
+  return ew_gscale_update(ctx, ugn_ptr<float>(ref), ugn_numel(ref), target, 0.f, (cudaStream_t)stream);
+}
+extern "C" int ugn_grad_scale_set(ugn_ctx* ctx, float scale, void* stream) {
+  UGN_CHECK(ctx && scale > 0.f, "ugn_grad_scale_set: scale must be positive");
+  return ew_gscale_update(ctx, nullptr, 0, 1.f, scale, (cudaStream_t)stream);
 }

@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cuda.h>
 #include <stdint.h>
 #include <stdio.h>
@@ -24,6 +25,10 @@ struct ugn_ctx {
   void* encode_tiled = nullptr;
   // device flag set by a tensor-core kernel whose mbarrier wait timed out (protocol bug guard)
   int* err_flag = nullptr;
+  // device-resident gradient scale {s, 1/s}: 16-bit gradient operands (dz) are stored multiplied by s
+  // and every kernel that consumes them multiplies its f32 output by 1/s (fp16 range management;
+  // lives in device memory so that a captured CUDA graph picks up each step's value)
+  float* gscale = nullptr;
 };
 
 void ugn_set_error(const char* fmt, ...);
@@ -59,13 +64,14 @@ void ugn_set_error(const char* fmt, ...);
     (ctx)->launches++;                                                             \
   } while (0)
 
-enum UgnDType { DT_F32, DT_BF16, DT_I32, DT_I64, DT_U8, DT_F64, DT_BAD };
+enum UgnDType { DT_F32, DT_BF16, DT_I32, DT_I64, DT_U8, DT_F64, DT_F16, DT_BAD };
 
 static inline UgnDType ugn_dtype(const ugn_tensor* t) {
   if (t->dtype_lanes != 1) return DT_BAD;
   if (t->dtype_code == UGN_DL_FLOAT && t->dtype_bits == 32) return DT_F32;
   if (t->dtype_code == UGN_DL_FLOAT && t->dtype_bits == 64) return DT_F64;
   if (t->dtype_code == UGN_DL_BFLOAT && t->dtype_bits == 16) return DT_BF16;
+  if (t->dtype_code == UGN_DL_FLOAT && t->dtype_bits == 16) return DT_F16;
   if (t->dtype_code == UGN_DL_INT && t->dtype_bits == 32) return DT_I32;
   if (t->dtype_code == UGN_DL_INT && t->dtype_bits == 64) return DT_I64;
   if (t->dtype_code == UGN_DL_UINT && t->dtype_bits == 8) return DT_U8;
@@ -128,6 +134,24 @@ __device__ __forceinline__ float warp_max(float v) {
 __device__ __forceinline__ void ugn_split(float x, __nv_bfloat16& hi, __nv_bfloat16& lo) {
   hi = __float2bfloat16_rn(x);
   lo = __float2bfloat16_rn(x - __bfloat162float(hi));
+}
+// 16-bit storage is either bf16 (f16 == 0) or IEEE fp16 (f16 == 1); `u16` is the raw container.
+// fp16 conversions saturate at +-65504 instead of producing inf (range guard for scaled gradients).
+typedef __nv_bfloat16 u16;
+__device__ __forceinline__ u16 ugn_cvt16(float x, int f16) {
+  if (f16) {
+    x = fminf(fmaxf(x, -65504.f), 65504.f);
+    return __ushort_as_bfloat16(__half_as_ushort(__float2half_rn(x)));
+  }
+  return __float2bfloat16_rn(x);
+}
+__device__ __forceinline__ float ugn_f16to32(u16 v, int f16) {
+  if (f16) return __half2float(__ushort_as_half(__bfloat16_as_ushort(v)));
+  return __bfloat162float(v);
+}
+__device__ __forceinline__ void ugn_split16(float x, int f16, u16& hi, u16& lo) {
+  hi = ugn_cvt16(x, f16);
+  lo = ugn_cvt16(x - ugn_f16to32(hi, f16), f16);
 }
 
 // forward declarations of the per-file implementations (dispatch lives in abi.cu)

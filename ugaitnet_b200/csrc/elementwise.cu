@@ -15,7 +15,7 @@ static inline int grid_for(ugn_ctx* ctx, long long work_items, int block) {
 // ---------------------------------------------------------------------------------------
 template <int MODE>  // 0 f32, 1 bf16 P=1, 2 bf16 P=2
 __global__ void pack_input_kernel(const float* __restrict__ x, void* __restrict__ out, int B, int C,
-                                  int H, int W, int Cp, long long plane) {
+                                  int H, int W, int Cp, long long plane, int f16) {
   extern __shared__ float sm[];  // [C][W+1]
   int by = blockIdx.x;
   int b = by / H, y = by % H;
@@ -31,22 +31,22 @@ __global__ void pack_input_kernel(const float* __restrict__ x, void* __restrict_
     if (MODE == 0) {
       reinterpret_cast<float*>(out)[obase + e] = v;
     } else {
-      __nv_bfloat16 hi, lo;
-      ugn_split(v, hi, lo);
-      __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(out);
+      u16 hi, lo;
+      ugn_split16(v, f16, hi, lo);
+      u16* o = reinterpret_cast<u16*>(out);
       o[obase + e] = hi;
       if (MODE == 2) o[plane + obase + e] = lo;
     }
   }
 }
 
-int ew_pack_input(ugn_ctx* ctx, const float* x, void* out, int mode, int B, int C, int H, int W,
+int ew_pack_input(ugn_ctx* ctx, const float* x, void* out, int mode, int f16, int B, int C, int H, int W,
                   int Cp, cudaStream_t st) {
   size_t smem = sizeof(float) * C * (W + 1);
   long long plane = (long long)B * H * W * Cp;
-  if (mode == 0) pack_input_kernel<0><<<B * H, 256, smem, st>>>(x, out, B, C, H, W, Cp, plane);
-  else if (mode == 1) pack_input_kernel<1><<<B * H, 256, smem, st>>>(x, out, B, C, H, W, Cp, plane);
-  else pack_input_kernel<2><<<B * H, 256, smem, st>>>(x, out, B, C, H, W, Cp, plane);
+  if (mode == 0) pack_input_kernel<0><<<B * H, 256, smem, st>>>(x, out, B, C, H, W, Cp, plane, f16);
+  else if (mode == 1) pack_input_kernel<1><<<B * H, 256, smem, st>>>(x, out, B, C, H, W, Cp, plane, f16);
+  else pack_input_kernel<2><<<B * H, 256, smem, st>>>(x, out, B, C, H, W, Cp, plane, f16);
   UGN_LAUNCHED(ctx);
   return UGN_OK;
 }
@@ -54,7 +54,7 @@ int ew_pack_input(ugn_ctx* ctx, const float* x, void* out, int mode, int B, int 
 // master [R][Cin] -> packed [P][R][Cp]   (R = Cout*kh*kw, or out-features for dense)
 template <int MODE>
 __global__ void pack_weight_kernel(const float* __restrict__ w, void* __restrict__ out, long long R,
-                                   int Cin, int Cp) {
+                                   int Cin, int Cp, int f16) {
   long long total = R * Cp;
   for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total;
        e += (long long)gridDim.x * blockDim.x) {
@@ -63,9 +63,9 @@ __global__ void pack_weight_kernel(const float* __restrict__ w, void* __restrict
     float v = c < Cin ? w[r * Cin + c] : 0.f;
     if (MODE == 0) reinterpret_cast<float*>(out)[e] = v;
     else {
-      __nv_bfloat16 hi, lo;
-      ugn_split(v, hi, lo);
-      __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(out);
+      u16 hi, lo;
+      ugn_split16(v, f16, hi, lo);
+      u16* o = reinterpret_cast<u16*>(out);
       o[e] = hi;
       if (MODE == 2) o[total + e] = lo;
     }
@@ -75,59 +75,59 @@ __global__ void pack_weight_kernel(const float* __restrict__ w, void* __restrict
 // unpadded fast path: flat f32 -> bf16 planes, 4 elements per thread (dense weights are 92 % of the bytes)
 template <int P>
 __global__ void __launch_bounds__(256) split4_kernel(const float4* __restrict__ s, uint2* __restrict__ d,
-                                                     long long n4) {
+                                                     long long n4, int f16) {
   for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < n4; e += (long long)gridDim.x * blockDim.x) {
     const float4 v = s[e];
-    __align__(8) __nv_bfloat16 hi[4], lo[4];
-    ugn_split(v.x, hi[0], lo[0]);
-    ugn_split(v.y, hi[1], lo[1]);
-    ugn_split(v.z, hi[2], lo[2]);
-    ugn_split(v.w, hi[3], lo[3]);
+    __align__(8) u16 hi[4], lo[4];
+    ugn_split16(v.x, f16, hi[0], lo[0]);
+    ugn_split16(v.y, f16, hi[1], lo[1]);
+    ugn_split16(v.z, f16, hi[2], lo[2]);
+    ugn_split16(v.w, f16, hi[3], lo[3]);
     d[e] = *reinterpret_cast<const uint2*>(hi);
     if (P == 2) d[n4 + e] = *reinterpret_cast<const uint2*>(lo);
   }
 }
 
-int ew_pack_weight(ugn_ctx* ctx, const float* w, void* out, int mode, long long R, int Cin, int Cp,
+int ew_pack_weight(ugn_ctx* ctx, const float* w, void* out, int mode, int f16, long long R, int Cin, int Cp,
                    cudaStream_t st) {
   const long long n = R * Cp;
   if (mode > 0 && Cin == Cp && (n & 3) == 0 && ((uintptr_t)w & 15) == 0 && ((uintptr_t)out & 7) == 0) {
     int g4 = grid_for(ctx, n / 4, 256);
-    if (mode == 1) split4_kernel<1><<<g4, 256, 0, st>>>((const float4*)w, (uint2*)out, n / 4);
-    else split4_kernel<2><<<g4, 256, 0, st>>>((const float4*)w, (uint2*)out, n / 4);
+    if (mode == 1) split4_kernel<1><<<g4, 256, 0, st>>>((const float4*)w, (uint2*)out, n / 4, f16);
+    else split4_kernel<2><<<g4, 256, 0, st>>>((const float4*)w, (uint2*)out, n / 4, f16);
     UGN_LAUNCHED(ctx);
     return UGN_OK;
   }
   int g = grid_for(ctx, R * Cp, 256);
-  if (mode == 0) pack_weight_kernel<0><<<g, 256, 0, st>>>(w, out, R, Cin, Cp);
-  else if (mode == 1) pack_weight_kernel<1><<<g, 256, 0, st>>>(w, out, R, Cin, Cp);
-  else pack_weight_kernel<2><<<g, 256, 0, st>>>(w, out, R, Cin, Cp);
+  if (mode == 0) pack_weight_kernel<0><<<g, 256, 0, st>>>(w, out, R, Cin, Cp, f16);
+  else if (mode == 1) pack_weight_kernel<1><<<g, 256, 0, st>>>(w, out, R, Cin, Cp, f16);
+  else pack_weight_kernel<2><<<g, 256, 0, st>>>(w, out, R, Cin, Cp, f16);
   UGN_LAUNCHED(ctx);
   return UGN_OK;
 }
 
 // generic f32 -> bf16 planes
 template <int P>
-__global__ void split_kernel(const float* __restrict__ s, __nv_bfloat16* __restrict__ d, long long n) {
+__global__ void split_kernel(const float* __restrict__ s, __nv_bfloat16* __restrict__ d, long long n, int f16) {
   for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < n;
        e += (long long)gridDim.x * blockDim.x) {
-    __nv_bfloat16 hi, lo;
-    ugn_split(s[e], hi, lo);
+    u16 hi, lo;
+    ugn_split16(s[e], f16, hi, lo);
     d[e] = hi;
     if (P == 2) d[n + e] = lo;
   }
 }
-int ew_split(ugn_ctx* ctx, const float* s, __nv_bfloat16* d, int P, long long n, cudaStream_t st) {
+int ew_split(ugn_ctx* ctx, const float* s, __nv_bfloat16* d, int P, int f16, long long n, cudaStream_t st) {
   if ((n & 3) == 0 && ((uintptr_t)s & 15) == 0 && ((uintptr_t)d & 7) == 0) {
     int g4 = grid_for(ctx, n / 4, 256);
-    if (P == 1) split4_kernel<1><<<g4, 256, 0, st>>>((const float4*)s, (uint2*)d, n / 4);
-    else split4_kernel<2><<<g4, 256, 0, st>>>((const float4*)s, (uint2*)d, n / 4);
+    if (P == 1) split4_kernel<1><<<g4, 256, 0, st>>>((const float4*)s, (uint2*)d, n / 4, f16);
+    else split4_kernel<2><<<g4, 256, 0, st>>>((const float4*)s, (uint2*)d, n / 4, f16);
     UGN_LAUNCHED(ctx);
     return UGN_OK;
   }
   int g = grid_for(ctx, n, 256);
-  if (P == 1) split_kernel<1><<<g, 256, 0, st>>>(s, d, n);
-  else split_kernel<2><<<g, 256, 0, st>>>(s, d, n);
+  if (P == 1) split_kernel<1><<<g, 256, 0, st>>>(s, d, n, f16);
+  else split_kernel<2><<<g, 256, 0, st>>>(s, d, n, f16);
   UGN_LAUNCHED(ctx);
   return UGN_OK;
 }
@@ -137,11 +137,16 @@ int ew_split(ugn_ctx* ctx, const float* s, __nv_bfloat16* d, int P, long long n,
 // dz[b,yo,xo,c] = (pos(yo,xo) == idx[b,yo/2,xo/2,c]) ? dy * act'(y) : 0 ; rows/cols beyond the
 // floor region get 0 (nets/mj_uwyhNets_ba.py:85,92 -- 23->11 and 9->4 drop the last row/col).
 // ---------------------------------------------------------------------------------------
+__device__ __forceinline__ float yval(float v, int) { return v; }
+__device__ __forceinline__ float yval(u16 v, int f16) { return ugn_f16to32(v, f16); }
+
 template <int MODE, typename YT>
 __global__ void bwd_act_kernel(const float* __restrict__ dy, const YT* __restrict__ y,
                                const uint8_t* __restrict__ idx, void* __restrict__ dz, int B, int Ho,
-                               int Wo, int Hp, int Wp, int C, int act, float alpha, int pool) {
+                               int Wo, int Hp, int Wp, int C, int act, float alpha, int pool, int f16,
+                               const float* __restrict__ gs) {
   long long total = (long long)B * Ho * Wo * C;
+  const float scale = (MODE > 0 && gs) ? gs[0] : 1.f;
   for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total;
        e += (long long)gridDim.x * blockDim.x) {
     int c = (int)(e % C);
@@ -155,16 +160,16 @@ __global__ void bwd_act_kernel(const float* __restrict__ dy, const YT* __restric
       if (yp < Hp && xp < Wp) {
         long long o = (((long long)b * Hp + yp) * Wp + xp) * C + c;
         int pos = ((yo & 1) << 1) | (xo & 1);
-        if (idx[o] == pos) v = dy[o] * ugn_act_bwd((float)y[o], act, alpha);
+        if (idx[o] == pos) v = dy[o] * ugn_act_bwd(yval(y[o], f16), act, alpha);
       }
     } else {
-      v = dy[e] * ugn_act_bwd((float)y[e], act, alpha);
+      v = dy[e] * ugn_act_bwd(yval(y[e], f16), act, alpha);
     }
     if (MODE == 0) reinterpret_cast<float*>(dz)[e] = v;
     else {
-      __nv_bfloat16 hi, lo;
-      ugn_split(v, hi, lo);
-      __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(dz);
+      u16 hi, lo;
+      ugn_split16(v * scale, f16, hi, lo);
+      u16* o = reinterpret_cast<u16*>(dz);
       o[e] = hi;
       if (MODE == 2) o[total + e] = lo;
     }
@@ -177,7 +182,9 @@ __global__ void __launch_bounds__(256) bwd_act_vec8_kernel(const float* __restri
                                                            const __nv_bfloat16* __restrict__ y,
                                                            const uint8_t* __restrict__ idx,
                                                            __nv_bfloat16* __restrict__ dz, int B, int Ho, int Wo,
-                                                           int Hp, int Wp, int C8, int act, float alpha, int pool) {
+                                                           int Hp, int Wp, int C8, int act, float alpha, int pool,
+                                                           int f16, const float* __restrict__ gs) {
+  const float scale = gs ? gs[0] : 1.f;
   const unsigned total = (unsigned)B * Ho * Wo * C8;
   const long long plane = (long long)total * 8;
   for (unsigned e = blockIdx.x * blockDim.x + threadIdx.x; e < total; e += gridDim.x * blockDim.x) {
@@ -205,32 +212,33 @@ __global__ void __launch_bounds__(256) bwd_act_vec8_kernel(const float* __restri
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
         const bool sel = !pool || (int)((ib >> (8 * i)) & 0xff) == pos;
-        if (sel) v[i] = dd[i] * ugn_act_bwd(__bfloat162float(yh[i]), act, alpha);
+        if (sel) v[i] = dd[i] * scale * ugn_act_bwd(ugn_f16to32(yh[i], f16), act, alpha);
       }
     }
-    __align__(16) __nv_bfloat16 hi[8], lo[8];
+    __align__(16) u16 hi[8], lo[8];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) ugn_split(v[i], hi[i], lo[i]);
+    for (int i = 0; i < 8; ++i) ugn_split16(v[i], f16, hi[i], lo[i]);
     *reinterpret_cast<uint4*>(dz + (long long)e * 8) = *reinterpret_cast<const uint4*>(hi);
     if (P == 2) *reinterpret_cast<uint4*>(dz + plane + (long long)e * 8) = *reinterpret_cast<const uint4*>(lo);
   }
 }
 
 int ew_bwd_act(ugn_ctx* ctx, const float* dy, const void* y, int y_bf16, const uint8_t* idx,
-               void* dz, int mode, int B, int Ho, int Wo, int Hp, int Wp, int C, int act,
+               void* dz, int mode, int f16, int B, int Ho, int Wo, int Hp, int Wp, int C, int act,
                float alpha, int pool, cudaStream_t st) {
+  const float* gs = ctx->gscale;
   if (y_bf16 && mode > 0 && C % 8 == 0 && (long long)B * Ho * Wo * (C / 8) < 0x7fffffffLL) {
     int g8 = grid_for(ctx, (long long)B * Ho * Wo * (C / 8), 256);
     if (mode == 1)
-      bwd_act_vec8_kernel<1><<<g8, 256, 0, st>>>(dy, (const __nv_bfloat16*)y, idx, (__nv_bfloat16*)dz, B, Ho, Wo, Hp, Wp, C / 8, act, alpha, pool);
+      bwd_act_vec8_kernel<1><<<g8, 256, 0, st>>>(dy, (const __nv_bfloat16*)y, idx, (__nv_bfloat16*)dz, B, Ho, Wo, Hp, Wp, C / 8, act, alpha, pool, f16, gs);
     else
-      bwd_act_vec8_kernel<2><<<g8, 256, 0, st>>>(dy, (const __nv_bfloat16*)y, idx, (__nv_bfloat16*)dz, B, Ho, Wo, Hp, Wp, C / 8, act, alpha, pool);
+      bwd_act_vec8_kernel<2><<<g8, 256, 0, st>>>(dy, (const __nv_bfloat16*)y, idx, (__nv_bfloat16*)dz, B, Ho, Wo, Hp, Wp, C / 8, act, alpha, pool, f16, gs);
     UGN_LAUNCHED(ctx);
     return UGN_OK;
   }
   int g = grid_for(ctx, (long long)B * Ho * Wo * C, 256);
 #define LAUNCH(M, YT) \
-  bwd_act_kernel<M, YT><<<g, 256, 0, st>>>(dy, (const YT*)y, idx, dz, B, Ho, Wo, Hp, Wp, C, act, alpha, pool)
+  bwd_act_kernel<M, YT><<<g, 256, 0, st>>>(dy, (const YT*)y, idx, dz, B, Ho, Wo, Hp, Wp, C, act, alpha, pool, f16, gs)
   if (y_bf16) {
     if (mode == 0) LAUNCH(0, __nv_bfloat16);
     else if (mode == 1) LAUNCH(1, __nv_bfloat16);
@@ -288,7 +296,9 @@ int ew_flatten(ugn_ctx* ctx, const void* src, void* dst, int bf16, int P, int B,
 template <int P>
 __global__ void act_mask_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ y,
                                     const float* __restrict__ mask, float* __restrict__ dz,
-                                    __nv_bfloat16* __restrict__ dz16, long long n, int act, float alpha) {
+                                    __nv_bfloat16* __restrict__ dz16, long long n, int act, float alpha,
+                                    int f16, const float* __restrict__ gs) {
+  const float scale = (P > 0 && gs) ? gs[0] : 1.f;
   for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < n;
        e += (long long)gridDim.x * blockDim.x) {
     float v = dy[e];
@@ -296,19 +306,20 @@ __global__ void act_mask_bwd_kernel(const float* __restrict__ dy, const float* _
     if (y) v *= ugn_act_bwd(y[e], act, alpha);
     if (dz) dz[e] = v;
     if (P > 0) {
-      __nv_bfloat16 hi, lo;
-      ugn_split(v, hi, lo);
+      u16 hi, lo;
+      ugn_split16(v * scale, f16, hi, lo);
       dz16[e] = hi;
       if (P == 2) dz16[n + e] = lo;
     }
   }
 }
 int ew_act_mask_bwd(ugn_ctx* ctx, const float* dy, const float* y, const float* mask, float* dz,
-                    __nv_bfloat16* dz16, int P, long long n, int act, float alpha, cudaStream_t st) {
+                    __nv_bfloat16* dz16, int P, int f16, long long n, int act, float alpha, cudaStream_t st) {
   int g = grid_for(ctx, n, 256);
-  if (P == 0) act_mask_bwd_kernel<0><<<g, 256, 0, st>>>(dy, y, mask, dz, dz16, n, act, alpha);
-  else if (P == 1) act_mask_bwd_kernel<1><<<g, 256, 0, st>>>(dy, y, mask, dz, dz16, n, act, alpha);
-  else act_mask_bwd_kernel<2><<<g, 256, 0, st>>>(dy, y, mask, dz, dz16, n, act, alpha);
+  const float* gs = ctx->gscale;
+  if (P == 0) act_mask_bwd_kernel<0><<<g, 256, 0, st>>>(dy, y, mask, dz, dz16, n, act, alpha, f16, gs);
+  else if (P == 1) act_mask_bwd_kernel<1><<<g, 256, 0, st>>>(dy, y, mask, dz, dz16, n, act, alpha, f16, gs);
+  else act_mask_bwd_kernel<2><<<g, 256, 0, st>>>(dy, y, mask, dz, dz16, n, act, alpha, f16, gs);
   UGN_LAUNCHED(ctx);
   return UGN_OK;
 }
@@ -323,7 +334,7 @@ __global__ void __launch_bounds__(256) fuse_fwd_kernel(FusePtrs ptrs, int nmods,
                                                        __nv_bfloat16* __restrict__ sig16,
                                                        uint8_t* __restrict__ winner,
                                                        float* __restrict__ inv_norm, int merge,
-                                                       int normalize, long long plane) {
+                                                       int normalize, long long plane, int f16) {
   extern __shared__ float row[];  // [d] fused values
   __shared__ float red[8];
   const int b = blockIdx.x;
@@ -367,8 +378,8 @@ __global__ void __launch_bounds__(256) fuse_fwd_kernel(FusePtrs ptrs, int nmods,
     float v = row[j] * inv;
     sig[(long long)b * d + j] = v;
     if (P > 0) {
-      __nv_bfloat16 hi, lo;
-      ugn_split(v, hi, lo);
+      u16 hi, lo;
+      ugn_split16(v, f16, hi, lo);
       sig16[(long long)b * d + j] = hi;
       if (P == 2) sig16[plane + (long long)b * d + j] = lo;
     }
@@ -376,13 +387,13 @@ __global__ void __launch_bounds__(256) fuse_fwd_kernel(FusePtrs ptrs, int nmods,
 }
 
 int ew_fuse_fwd(ugn_ctx* ctx, const FusePtrs& ptrs, int nmods, int B, int d, float* sig,
-                __nv_bfloat16* sig16, int P, uint8_t* winner, float* inv_norm, int merge,
+                __nv_bfloat16* sig16, int P, int f16, uint8_t* winner, float* inv_norm, int merge,
                 int normalize, cudaStream_t st) {
   size_t smem = sizeof(float) * d;
   long long plane = (long long)B * d;
-  if (P == 0) fuse_fwd_kernel<0><<<B, 256, smem, st>>>(ptrs, nmods, d, sig, sig16, winner, inv_norm, merge, normalize, plane);
-  else if (P == 1) fuse_fwd_kernel<1><<<B, 256, smem, st>>>(ptrs, nmods, d, sig, sig16, winner, inv_norm, merge, normalize, plane);
-  else fuse_fwd_kernel<2><<<B, 256, smem, st>>>(ptrs, nmods, d, sig, sig16, winner, inv_norm, merge, normalize, plane);
+  if (P == 0) fuse_fwd_kernel<0><<<B, 256, smem, st>>>(ptrs, nmods, d, sig, sig16, winner, inv_norm, merge, normalize, plane, f16);
+  else if (P == 1) fuse_fwd_kernel<1><<<B, 256, smem, st>>>(ptrs, nmods, d, sig, sig16, winner, inv_norm, merge, normalize, plane, f16);
+  else fuse_fwd_kernel<2><<<B, 256, smem, st>>>(ptrs, nmods, d, sig, sig16, winner, inv_norm, merge, normalize, plane, f16);
   UGN_LAUNCHED(ctx);
   return UGN_OK;
 }
@@ -588,6 +599,44 @@ int ew_bias_act_mask(ugn_ctx* ctx, float* y, const float* bias, const float* mas
                      int act, float alpha, cudaStream_t st) {
   long long n = rows * cols;
   bias_act_mask_kernel<<<grid_for(ctx, n, 256), 256, 0, st>>>(y, bias, mask, n, cols, act, alpha);
+  UGN_LAUNCHED(ctx);
+  return UGN_OK;
+}
+
+// ---------------------------------------------------------------------------------------
+// Gradient scale for 16-bit (fp16) gradient operands.  ctx->gscale = {s, 1/s, amax bits, -}.
+// ugn_grad_scale_update: s = 2^floor(log2(target / max|ref|)) from a reference gradient of the step
+// (the signature gradient), so every dz = s * true gradient sits in fp16's normal range; consumers
+// (dgrad, wgrad, dense backward, bias sums) multiply their f32 results by 1/s.  Power-of-two scales
+// are exact in floating point, so the only effect is on range.
+// ---------------------------------------------------------------------------------------
+__global__ void amax_kernel(const float* __restrict__ x, long long n, unsigned* __restrict__ amax_bits) {
+  float m = 0.f;
+  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < n; e += (long long)gridDim.x * blockDim.x) {
+    float a = fabsf(x[e]);
+    if (a < INFINITY) m = fmaxf(m, a);   // NaN / inf never drive the scale
+  }
+  m = warp_max(m);
+  if ((threadIdx.x & 31) == 0 && m > 0.f) atomicMax(amax_bits, __float_as_uint(m));
+}
+__global__ void gscale_set_kernel(float* __restrict__ gs, float target, float fixed) {
+  float s = fixed;
+  if (!(fixed > 0.f)) {
+    float a = __uint_as_float(reinterpret_cast<unsigned*>(gs)[2]);
+    s = a > 0.f ? exp2f(floorf(log2f(target / a))) : 1.f;
+    s = fminf(fmaxf(s, 1.f / 1024.f), 16777216.f);
+  }
+  gs[0] = s;
+  gs[1] = 1.f / s;
+  reinterpret_cast<unsigned*>(gs)[2] = 0u;
+}
+int ew_gscale_update(ugn_ctx* ctx, const float* ref, long long n, float target, float fixed, cudaStream_t st) {
+  UGN_CHECK(ctx->gscale, "gradient scale buffer missing");
+  if (!(fixed > 0.f)) {
+    amax_kernel<<<grid_for(ctx, n, 256), 256, 0, st>>>(ref, n, reinterpret_cast<unsigned*>(ctx->gscale) + 2);
+    UGN_LAUNCHED(ctx);
+  }
+  gscale_set_kernel<<<1, 1, 0, st>>>(ctx->gscale, target, fixed);
   UGN_LAUNCHED(ctx);
   return UGN_OK;
 }

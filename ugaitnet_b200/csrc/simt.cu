@@ -288,7 +288,7 @@ int simt_linear_bwd(ugn_ctx* ctx, int B, int N, int K, const float* x, const flo
 
 // column sums of a bf16 [P][rows][cols] tensor (hi + lo planes): bias gradients in tensor-core mode
 __global__ void colsum_bf16_kernel(const __nv_bfloat16* __restrict__ X, int P, long long rows, int cols,
-                                   float* __restrict__ out) {
+                                   float* __restrict__ out, int f16, const float* __restrict__ gs) {
   __shared__ float sm[8][33];
   int j = blockIdx.x * 32 + threadIdx.x;
   long long per = (rows + gridDim.y - 1) / gridDim.y;
@@ -296,23 +296,24 @@ __global__ void colsum_bf16_kernel(const __nv_bfloat16* __restrict__ X, int P, l
   float s = 0.f;
   if (j < cols)
     for (int pl = 0; pl < P; ++pl)
-      for (long long i = r0 + threadIdx.y; i < r1; i += 8) s += __bfloat162float(X[((long long)pl * rows + i) * cols + j]);
+      for (long long i = r0 + threadIdx.y; i < r1; i += 8) s += ugn_f16to32(X[((long long)pl * rows + i) * cols + j], f16);
   sm[threadIdx.y][threadIdx.x] = s;
   __syncthreads();
   if (threadIdx.y == 0 && j < cols) {
     float tsum = 0.f;
 #pragma unroll
     for (int q = 0; q < 8; ++q) tsum += sm[q][threadIdx.x];
-    atomicAdd(out + j, tsum);
+    atomicAdd(out + j, tsum * (gs ? gs[1] : 1.f));
   }
 }
 
-int simt_colsum_bf16(ugn_ctx* ctx, const __nv_bfloat16* X, int P, long long rows, int cols, float* out,
+// X is a (scaled) 16-bit gradient operand: the sum is multiplied by 1/s (ctx->gscale)
+int simt_colsum_bf16(ugn_ctx* ctx, const __nv_bfloat16* X, int P, int f16, long long rows, int cols, float* out,
                      cudaStream_t st) {
   UGN_CUDA(cudaMemsetAsync(out, 0, sizeof(float) * cols, st));
   int gy = (int)std::min<long long>(std::max<long long>(rows / 256, 1), 256);
   dim3 grid(ugn_cdiv(cols, 32), gy), block(32, 8);
-  colsum_bf16_kernel<<<grid, block, 0, st>>>(X, P, rows, cols, out);
+  colsum_bf16_kernel<<<grid, block, 0, st>>>(X, P, rows, cols, out, f16, ctx->gscale);
   UGN_LAUNCHED(ctx);
   return UGN_OK;
 }

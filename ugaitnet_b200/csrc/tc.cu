@@ -48,6 +48,8 @@ struct TcParams {
   int ldc, act;
   float alpha;
   int* err;
+  int f16;                 // 16-bit operand format: 0 bf16, 1 fp16
+  const float* oscale;     // device scalar multiplied into f32 outputs (1/grad-scale for backward ops), nullable
   int dbg_shift, dbg_bo;   // experiment: row-shifted A view (UGN_DBG_SHIFT / UGN_DBG_BASEOFF)
   // patch-resident conv (tc_convp_kernel)
   int T, SW, RH, PR, KH, xorg, yorg, tiles_y, tmem_cols;
@@ -65,6 +67,7 @@ __device__ __forceinline__ void epi_barrier() { asm volatile("bar.sync 1, 128;" 
 __device__ __forceinline__ void conv_tile_epilogue(const TcParams& p, uint8_t* smem, uint32_t trow, int r, bool ok,
                                                    int x0, int y0, int nn0, int n0) {
   float v[16];
+  const float os = p.oscale ? *p.oscale : 1.f;
   const int xl = r % p.bw, yl = (r / p.bw) % p.bh, nl = r / (p.bw * p.bh);
     const int x = x0 + xl, y = y0 + yl, n = nn0 + nl;
     const bool rv = ok && nl < p.bn && x < p.Wout && y < p.Hout && n < p.Bn;
@@ -77,7 +80,7 @@ __device__ __forceinline__ void conv_tile_epilogue(const TcParams& p, uint8_t* s
           float* dst = p.out_f32 + obase + n0 + c0;
 #pragma unroll
           for (int i = 0; i < 16; i += 4)
-            *reinterpret_cast<float4*>(dst + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+            *reinterpret_cast<float4*>(dst + i) = make_float4(v[i] * os, v[i + 1] * os, v[i + 2] * os, v[i + 3] * os);
           continue;
         }
 #pragma unroll
@@ -85,11 +88,11 @@ __device__ __forceinline__ void conv_tile_epilogue(const TcParams& p, uint8_t* s
           const int c = n0 + c0 + i;
           if (c >= p.Cout) continue;
           if (p.epi == EPI_F32) {
-            p.out_f32[obase + c] = v[i];
+            p.out_f32[obase + c] = v[i] * os;
           } else {
             float z = ugn_act_fwd(v[i] + (p.bias ? p.bias[c] : 0.f), p.act, p.alpha);
-            __nv_bfloat16 hi, lo;
-            ugn_split(z, hi, lo);
+            u16 hi, lo;
+            ugn_split16(z, p.f16, hi, lo);
             p.out_bf16[obase + c] = hi;
             if (p.planes == 2) p.out_bf16[p.out_plane + obase + c] = lo;
           }
@@ -125,8 +128,8 @@ __device__ __forceinline__ void conv_tile_epilogue(const TcParams& p, uint8_t* s
           const int xp = (x0 >> 1) + pxl, yp = (y0 >> 1) + pyl, nn = nn0 + pnl;
           if (ok && c < p.Cout && xp < p.Wp && yp < p.Hp && nn < p.Bn) {
             const long long o = (((long long)nn * p.Hp + yp) * p.Wp + xp) * p.Cout + c;
-            __nv_bfloat16 hi, lo;
-            ugn_split(best, hi, lo);
+            u16 hi, lo;
+            ugn_split16(best, p.f16, hi, lo);
             p.out_bf16[o] = hi;
             if (p.planes == 2) p.out_bf16[p.out_plane + o] = lo;
             p.pool_idx[o] = (uint8_t)pos;
@@ -243,7 +246,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_kernel(const __grid_constant__
   } else if (warp == 1) {
    if (elect_one()) {
     // ===================== MMA issuer (one elected lane) =====================
-    const uint32_t idesc = make_idesc_bf16(128, p.block_n, p.a.major, p.b.major);
+    const uint32_t idesc = make_idesc16(128, p.block_n, p.a.major, p.b.major, p.f16);
     const uint32_t la = p.a.rowbytes == 128 ? 2u : 4u, lb = p.b.rowbytes == 128 ? 2u : 4u;
     const uint32_t smem0 = smem_u32(smem);
     // descriptors of stage 0 / plane 0 / slice 0; everything else is a 16-byte-unit add on the low word
@@ -286,6 +289,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_kernel(const __grid_constant__
     const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16);
     float v[16];
 
+    const float os = p.oscale ? *p.oscale : 1.f;
     if (MODE == MODE_GEMM) {
       const int m = m0 + r;
       const bool vec = (p.ldc & 3) == 0 && p.epi == EPI_F32 && !p.mask;
@@ -297,10 +301,10 @@ __global__ void __launch_bounds__(kThreads, 1) tc_kernel(const __grid_constant__
 #pragma unroll
           for (int i = 0; i < 16; i += 4) {
             float4 o4;
-            o4.x = ugn_act_fwd(v[i] + (p.bias ? p.bias[n0 + c0 + i] : 0.f), p.act, p.alpha);
-            o4.y = ugn_act_fwd(v[i + 1] + (p.bias ? p.bias[n0 + c0 + i + 1] : 0.f), p.act, p.alpha);
-            o4.z = ugn_act_fwd(v[i + 2] + (p.bias ? p.bias[n0 + c0 + i + 2] : 0.f), p.act, p.alpha);
-            o4.w = ugn_act_fwd(v[i + 3] + (p.bias ? p.bias[n0 + c0 + i + 3] : 0.f), p.act, p.alpha);
+            o4.x = ugn_act_fwd(v[i] * os + (p.bias ? p.bias[n0 + c0 + i] : 0.f), p.act, p.alpha);
+            o4.y = ugn_act_fwd(v[i + 1] * os + (p.bias ? p.bias[n0 + c0 + i + 1] : 0.f), p.act, p.alpha);
+            o4.z = ugn_act_fwd(v[i + 2] * os + (p.bias ? p.bias[n0 + c0 + i + 2] : 0.f), p.act, p.alpha);
+            o4.w = ugn_act_fwd(v[i + 3] * os + (p.bias ? p.bias[n0 + c0 + i + 3] : 0.f), p.act, p.alpha);
             *reinterpret_cast<float4*>(dst + i) = o4;
           }
           continue;
@@ -311,9 +315,9 @@ __global__ void __launch_bounds__(kThreads, 1) tc_kernel(const __grid_constant__
           if (n >= p.N) continue;
           const long long o = (long long)m * p.ldc + n;
           if (p.epi == EPI_F32_ATOMIC) {
-            atomicAdd(p.out_f32 + o, v[i]);
+            atomicAdd(p.out_f32 + o, v[i] * os);
           } else {
-            float z = v[i] + (p.bias ? p.bias[n] : 0.f);
+            float z = v[i] * os + (p.bias ? p.bias[n] : 0.f);
             z = ugn_act_fwd(z, p.act, p.alpha);
             if (p.mask) z *= p.mask[o];
             p.out_f32[o] = z;
@@ -334,7 +338,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_kernel(const __grid_constant__
         float* dst = p.out_f32 + ((long long)co * p.ntaps + tap) * p.Cin;
 #pragma unroll
         for (int i = 0; i < 16; ++i)
-          if (cib + i < p.Cin) atomicAdd(dst + cib + i, v[i]);
+          if (cib + i < p.Cin) atomicAdd(dst + cib + i, v[i] * os);
       }
     }
     fence_before_sync();
@@ -440,7 +444,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_convp_kernel(const __grid_cons
   } else if (warp == 1) {
    if (elect_one()) {
     // ---- MMA issuer ----
-    const uint32_t idesc = make_idesc_bf16(128, p.block_n, 0, p.b.major);
+    const uint32_t idesc = make_idesc16(128, p.block_n, 0, p.b.major, p.f16);
     const uint32_t la = p.a.rowbytes == 128 ? 2u : 4u, lb = p.b.rowbytes == 128 ? 2u : 4u;
     const uint32_t smem0 = smem_u32(smem);
     const uint64_t a0 = make_smem_desc(smem0, 0, 8 * p.a.rowbytes, la);
@@ -540,6 +544,8 @@ struct alignas(64) WgParams {
   int box_kh[40], box_chunk[40];
   float* dw;
   int* err;
+  int f16;
+  const float* oscale;
 };
 
 __global__ void __launch_bounds__(kThreads, 1) tc_wgradv_kernel(const __grid_constant__ WgParams p) {
@@ -631,7 +637,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_wgradv_kernel(const __grid_con
       const uint64_t a_st = a0 + (uint64_t)(s * st16), b_st = b0 + (uint64_t)(s * st16);
       for (int g = seg0; g < seg1; ++g) {
         const WgSeg sg = p.seg[g];
-        const uint32_t idesc = make_idesc_bf16(128, sg.nkw * p.cw, 1, 1);
+        const uint32_t idesc = make_idesc16(128, sg.nkw * p.cw, 1, 1, p.f16);
         const uint32_t td = tmem_base + sg.col0;
         uint64_t a_hi = a_st;
         uint64_t b_hi = b_st + (uint64_t)((sg.box - box0) * (p.b_box_bytes >> 4) + sg.kw0 * row16);
@@ -657,6 +663,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_wgradv_kernel(const __grid_con
     bool ok = mbar_wait(tmem_full, 0, p.err, 3);
     fence_after_sync();
     const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16);
+    const float os = p.oscale ? *p.oscale : 1.f;
     float v[16];
     for (int g = seg0; g < seg1; ++g) {
       const WgSeg sg = p.seg[g];
@@ -669,7 +676,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_wgradv_kernel(const __grid_con
         float* dst = p.dw + ((long long)co * p.ntaps + tap) * p.Cin;
 #pragma unroll
         for (int i = 0; i < 16; ++i)
-          if (cib + i < p.Cin) atomicAdd(dst + cib + i, v[i]);
+          if (cib + i < p.Cin) atomicAdd(dst + cib + i, v[i] * os);
       }
     }
     fence_before_sync();
@@ -779,11 +786,11 @@ static int gemm_operand(ugn_ctx* ctx, TcOp& op, const __nv_bfloat16* base, int P
   return make_map(ctx, &op.map, base, dims, str, box, 128);
 }
 
-int tc_gemm_ex(ugn_ctx* ctx, int P, int M, int N, int K, const __nv_bfloat16* A, int a_mn, const __nv_bfloat16* B,
-               int b_mn, float* C, int ldc, int accumulate, const float* bias, const float* mask, int act,
-               float alpha, cudaStream_t st) {
+int tc_gemm_ex(ugn_ctx* ctx, int P, int f16, int M, int N, int K, const __nv_bfloat16* A, int a_mn,
+               const __nv_bfloat16* B, int b_mn, float* C, int ldc, int accumulate, const float* bias,
+               const float* mask, int act, float alpha, const float* oscale, cudaStream_t st) {
   TcParams p{};
-  p.mode = MODE_GEMM;
+  p.mode = MODE_GEMM; p.f16 = f16; p.oscale = oscale;
   p.M = M; p.N = N; p.planes = P;
   p.block_n = N > 128 ? 256 : (N > 64 ? 128 : 64);
   if (P == 2 && p.block_n > 128) p.block_n = 128;
@@ -809,9 +816,10 @@ int tc_gemm_ex(ugn_ctx* ctx, int P, int M, int N, int K, const __nv_bfloat16* A,
   return launch<MODE_GEMM>(ctx, p, grid, st);
 }
 
-int tc_gemm(ugn_ctx* ctx, int P, int M, int N, int K, const __nv_bfloat16* A, int a_mn, const __nv_bfloat16* B,
-            int b_mn, float* C, int accumulate, cudaStream_t st) {
-  return tc_gemm_ex(ctx, P, M, N, K, A, a_mn, B, b_mn, C, N, accumulate, nullptr, nullptr, UGN_ACT_LINEAR, 0.f, st);
+int tc_gemm(ugn_ctx* ctx, int P, int f16, int M, int N, int K, const __nv_bfloat16* A, int a_mn,
+            const __nv_bfloat16* B, int b_mn, float* C, int accumulate, cudaStream_t st) {
+  return tc_gemm_ex(ctx, P, f16, M, N, K, A, a_mn, B, b_mn, C, N, accumulate, nullptr, nullptr, UGN_ACT_LINEAR, 0.f,
+                    nullptr, st);
 }
 
 // ---- convolution ------------------------------------------------------------------------
@@ -906,12 +914,12 @@ static int convp_launch(ugn_ctx* ctx, TcParams& p, const __nv_bfloat16* act, int
   return UGN_OK;
 }
 
-int tc_conv_fwd(ugn_ctx* ctx, const ConvGeom& g, int P, const __nv_bfloat16* x, const __nv_bfloat16* w,
+int tc_conv_fwd(ugn_ctx* ctx, const ConvGeom& g, int P, int f16, const __nv_bfloat16* x, const __nv_bfloat16* w,
                 const float* bias, __nv_bfloat16* y, uint8_t* idx, int act, float alpha, int pool,
                 cudaStream_t st) {
   UGN_CHECK(g.Cp % 32 == 0 && g.Co % 16 == 0, "tensor-core conv needs Cin %% 32 == 0 and Cout %% 16 == 0");
   TcParams p{};
-  p.mode = MODE_CONV; p.planes = P; p.sgn = 1;
+  p.mode = MODE_CONV; p.planes = P; p.sgn = 1; p.f16 = f16;
   const int cbox = (g.Cp % 64 == 0) ? 64 : 32;
   p.kslices = cbox / 16;
   p.ncc = g.Cp / cbox; p.KW = g.KW;
@@ -946,11 +954,11 @@ int tc_conv_fwd(ugn_ctx* ctx, const ConvGeom& g, int P, const __nv_bfloat16* x, 
   return launch<MODE_CONV>(ctx, p, grid, st);
 }
 
-int tc_conv_dgrad(ugn_ctx* ctx, const ConvGeom& g, int P, const __nv_bfloat16* dz, const __nv_bfloat16* w,
+int tc_conv_dgrad(ugn_ctx* ctx, const ConvGeom& g, int P, int f16, const __nv_bfloat16* dz, const __nv_bfloat16* w,
                   float* dx, cudaStream_t st) {
   UGN_CHECK(g.Co % 64 == 0 && g.Cp % 32 == 0, "tensor-core dgrad needs Cout %% 64 == 0 and Cin %% 32 == 0");
   TcParams p{};
-  p.mode = MODE_CONV; p.planes = P; p.sgn = -1;
+  p.mode = MODE_CONV; p.planes = P; p.sgn = -1; p.f16 = f16; p.oscale = ctx->gscale ? ctx->gscale + 1 : nullptr;
   p.kslices = 4;                       // K stage = 64 output channels
   p.ncc = g.Co / 64; p.KW = g.KW;
   p.ksteps_total = g.KH * g.KW * p.ncc; p.ksplit = 1;
@@ -982,13 +990,13 @@ int tc_conv_dgrad(ugn_ctx* ctx, const ConvGeom& g, int P, const __nv_bfloat16* d
   return launch<MODE_CONV>(ctx, p, grid, st);
 }
 
-int simt_colsum_bf16(ugn_ctx* ctx, const __nv_bfloat16* X, int P, long long rows, int cols, float* out,
+int simt_colsum_bf16(ugn_ctx* ctx, const __nv_bfloat16* X, int P, int f16, long long rows, int cols, float* out,
                      cudaStream_t st);
 
-static int wgradv_launch(ugn_ctx* ctx, const ConvGeom& g, int P, const __nv_bfloat16* x, const __nv_bfloat16* dz,
+static int wgradv_launch(ugn_ctx* ctx, const ConvGeom& g, int P, int f16, const __nv_bfloat16* x, const __nv_bfloat16* dz,
                          float* dw, cudaStream_t st) {
   WgParams p{};
-  p.planes = P;
+  p.planes = P; p.f16 = f16; p.oscale = ctx->gscale ? ctx->gscale + 1 : nullptr;
   p.cw = (g.Cp % 64 == 0) ? 64 : 32;
   p.rowbytes_b = p.cw * 2;
   const int nch = g.Cp / p.cw;
@@ -1075,16 +1083,16 @@ static int wgradv_launch(ugn_ctx* ctx, const ConvGeom& g, int P, const __nv_bflo
   return UGN_OK;
 }
 
-int tc_conv_wgrad(ugn_ctx* ctx, const ConvGeom& g, int P, const __nv_bfloat16* x, const __nv_bfloat16* dz,
+int tc_conv_wgrad(ugn_ctx* ctx, const ConvGeom& g, int P, int f16, const __nv_bfloat16* x, const __nv_bfloat16* dz,
                   float* dw, float* db, cudaStream_t st) {
   UGN_CHECK(g.Cp % 32 == 0 && g.Co % 8 == 0, "tensor-core wgrad needs Cin %% 32 == 0");
   if (!getenv("UGN_NO_WGRADV")) {
-    int rcv = wgradv_launch(ctx, g, P, x, dz, dw, st);
-    if (rcv == UGN_OK) return db ? simt_colsum_bf16(ctx, dz, P, (long long)g.B * g.Ho * g.Wo, g.Co, db, st) : UGN_OK;
+    int rcv = wgradv_launch(ctx, g, P, f16, x, dz, dw, st);
+    if (rcv == UGN_OK) return db ? simt_colsum_bf16(ctx, dz, P, f16, (long long)g.B * g.Ho * g.Wo, g.Co, db, st) : UGN_OK;
     if (rcv != UGN_ERR_UNSUPPORTED) return rcv;
   }
   TcParams p{};
-  p.mode = MODE_WGRAD; p.planes = P;
+  p.mode = MODE_WGRAD; p.planes = P; p.f16 = f16; p.oscale = ctx->gscale ? ctx->gscale + 1 : nullptr;
   // K stage = a box of output pixels (rows zero-filled by TMA beyond the dz extent)
   int bw = 1;
   while (bw < g.Wo && bw < 64) bw <<= 1;
@@ -1117,7 +1125,7 @@ int tc_conv_wgrad(ugn_ctx* ctx, const ConvGeom& g, int P, const __nv_bfloat16* x
   dim3 grid(ntile_m, ntile_n, split);
   rc = launch<MODE_WGRAD>(ctx, p, grid, st);
   if (rc != UGN_OK) return rc;
-  if (db) return simt_colsum_bf16(ctx, dz, P, (long long)g.B * g.Ho * g.Wo, g.Co, db, st);
+  if (db) return simt_colsum_bf16(ctx, dz, P, f16, (long long)g.B * g.Ho * g.Wo, g.Co, db, st);
   return UGN_OK;
 }
 
@@ -1125,27 +1133,28 @@ int tc_conv_wgrad(ugn_ctx* ctx, const ConvGeom& g, int P, const __nv_bfloat16* x
 int ew_bias_act_mask(ugn_ctx* ctx, float* y, const float* bias, const float* mask, long long rows, int cols,
                      int act, float alpha, cudaStream_t st);
 
-int tc_linear_fwd(ugn_ctx* ctx, int P, int B, int N, int K, const __nv_bfloat16* x, const __nv_bfloat16* w,
+int tc_linear_fwd(ugn_ctx* ctx, int P, int f16, int B, int N, int K, const __nv_bfloat16* x, const __nv_bfloat16* w,
                   const float* bias, const float* mask, float* y, int act, float alpha, cudaStream_t st) {
   // Small batch: the layer is a weight-streaming (HBM-bound) GEMM with a single M tile, so spread K over
   // the SMs (split-K, red.add into zeroed y) and apply bias / activation / dropout mask in a tiny post pass.
   int tiles = ugn_cdiv(B, 128) * ugn_cdiv(N, P == 2 ? 128 : 256);
   if (tiles * 2 <= ctx->sm_count && K >= 512) {
-    int rc = tc_gemm_ex(ctx, P, B, N, K, x, 0, w, 0, y, N, 0, nullptr, nullptr, UGN_ACT_LINEAR, 0.f, st);
+    int rc = tc_gemm_ex(ctx, P, f16, B, N, K, x, 0, w, 0, y, N, 0, nullptr, nullptr, UGN_ACT_LINEAR, 0.f, nullptr, st);
     if (rc != UGN_OK) return rc;
     if (bias || mask || act != UGN_ACT_LINEAR) return ew_bias_act_mask(ctx, y, bias, mask, B, N, act, alpha, st);
     return UGN_OK;
   }
-  return tc_gemm_ex(ctx, P, B, N, K, x, 0, w, 0, y, N, 0, bias, mask, act, alpha, st);
+  return tc_gemm_ex(ctx, P, f16, B, N, K, x, 0, w, 0, y, N, 0, bias, mask, act, alpha, nullptr, st);
 }
 
-int tc_linear_bwd(ugn_ctx* ctx, int P, int B, int N, int K, const __nv_bfloat16* x, const __nv_bfloat16* w,
+int tc_linear_bwd(ugn_ctx* ctx, int P, int f16, int B, int N, int K, const __nv_bfloat16* x, const __nv_bfloat16* w,
                   const __nv_bfloat16* dz, float* dx, float* dw, float* db, cudaStream_t st) {
   int rc;
+  const float* os = ctx->gscale ? ctx->gscale + 1 : nullptr;   // dz is a scaled gradient operand
   // dx[B,K] = dz[B,N] . w[N,K]      : A = dz K-major (K'=N), B = w as MN-major [K'=N rows][K contiguous]
-  if (dx && (rc = tc_gemm_ex(ctx, P, B, K, N, dz, 0, w, 1, dx, K, 0, nullptr, nullptr, 0, 0.f, st)) != UGN_OK) return rc;
+  if (dx && (rc = tc_gemm_ex(ctx, P, f16, B, K, N, dz, 0, w, 1, dx, K, 0, nullptr, nullptr, 0, 0.f, os, st)) != UGN_OK) return rc;
   // dw[N,K] = dz^T . x             : A = dz MN-major [K'=B rows][N contiguous], B = x MN-major [B rows][K contiguous]
-  if (dw && (rc = tc_gemm_ex(ctx, P, N, K, B, dz, 1, x, 1, dw, K, 0, nullptr, nullptr, 0, 0.f, st)) != UGN_OK) return rc;
-  if (db) return simt_colsum_bf16(ctx, dz, P, B, N, db, st);
+  if (dw && (rc = tc_gemm_ex(ctx, P, f16, N, K, B, dz, 1, x, 1, dw, K, 0, nullptr, nullptr, 0, 0.f, os, st)) != UGN_OK) return rc;
+  if (db) return simt_colsum_bf16(ctx, dz, P, f16, B, N, db, st);
   return UGN_OK;
 }

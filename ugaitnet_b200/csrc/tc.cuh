@@ -2,16 +2,16 @@
 #pragma once
 #include "common.cuh"
 
-int tc_gemm(ugn_ctx* ctx, int P, int M, int N, int K, const __nv_bfloat16* A, int a_mn,
+int tc_gemm(ugn_ctx* ctx, int P, int f16, int M, int N, int K, const __nv_bfloat16* A, int a_mn,
             const __nv_bfloat16* B, int b_mn, float* C, int accumulate, cudaStream_t st);
-int tc_conv_fwd(ugn_ctx* ctx, const ConvGeom& g, int P, const __nv_bfloat16* x, const __nv_bfloat16* w,
+int tc_conv_fwd(ugn_ctx* ctx, const ConvGeom& g, int P, int f16, const __nv_bfloat16* x, const __nv_bfloat16* w,
                 const float* bias, __nv_bfloat16* y, uint8_t* idx, int act, float alpha, int pool,
                 cudaStream_t st);
-int tc_conv_dgrad(ugn_ctx* ctx, const ConvGeom& g, int P, const __nv_bfloat16* dz, const __nv_bfloat16* w,
+int tc_conv_dgrad(ugn_ctx* ctx, const ConvGeom& g, int P, int f16, const __nv_bfloat16* dz, const __nv_bfloat16* w,
                   float* dx, cudaStream_t st);
-int tc_conv_wgrad(ugn_ctx* ctx, const ConvGeom& g, int P, const __nv_bfloat16* x, const __nv_bfloat16* dz,
+int tc_conv_wgrad(ugn_ctx* ctx, const ConvGeom& g, int P, int f16, const __nv_bfloat16* x, const __nv_bfloat16* dz,
                   float* dw, float* db, cudaStream_t st);
-int tc_linear_fwd(ugn_ctx* ctx, int P, int B, int N, int K, const __nv_bfloat16* x, const __nv_bfloat16* w,
+int tc_linear_fwd(ugn_ctx* ctx, int P, int f16, int B, int N, int K, const __nv_bfloat16* x, const __nv_bfloat16* w,
                   const float* bias, const float* mask, float* y, int act, float alpha, cudaStream_t st);
-int tc_linear_bwd(ugn_ctx* ctx, int P, int B, int N, int K, const __nv_bfloat16* x, const __nv_bfloat16* w,
+int tc_linear_bwd(ugn_ctx* ctx, int P, int f16, int B, int N, int K, const __nv_bfloat16* x, const __nv_bfloat16* w,
                   const __nv_bfloat16* dz, float* dx, float* dw, float* db, cudaStream_t st);

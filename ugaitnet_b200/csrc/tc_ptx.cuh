@@ -194,5 +194,11 @@ __host__ __device__ inline uint32_t make_idesc_bf16(int M, int N, int a_mn, int 
   d |= (uint32_t)(M >> 4) << 24;
   return d;
 }
+// same with a selectable 16-bit operand format: f16 != 0 -> IEEE fp16 (format 0), else bf16 (format 1)
+__host__ __device__ inline uint32_t make_idesc16(int M, int N, int a_mn, int b_mn, int f16) {
+  uint32_t d = make_idesc_bf16(M, N, a_mn, b_mn);
+  if (f16) d &= ~((7u << 7) | (7u << 10));
+  return d;
+}
 
 }  // namespace tc

@@ -22,7 +22,17 @@ from . import ops
 from ._ffi import TRef, check, lib, ptr_array, stream_ptr
 from .config import ACT_LINEAR, BRANCH_NAMES, MERGE_AVG, NetConfig, round_up
 
-MATH_MODES = ("fp32", "bf16", "bf16x3")
+# math mode -> (forward planes, backward/gradient planes, 16-bit dtype)
+#   fp32    SIMT FFMA validation path
+#   bf16    single-pass bf16 (fast, NOT parity-passing)
+#   bf16x3  bf16 hi/lo split, 3 MMA passes forward and backward
+#   f16x3   fp16 hi/lo split, 3 passes forward and backward (22-bit operands)
+#   f16mix  fp16 hi/lo split 3-pass FORWARD (every discrete decision -- ReLU, max-pool argmax, sign_max
+#           winner -- is taken at ~fp32 accuracy), single-pass fp16 BACKWARD on the hi planes with a
+#           device-side power-of-two gradient scale (linear maps of the gradient need 11 bits, not 22)
+MATH_MODES = {"fp32": (0, 0, None), "bf16": (1, 1, torch.bfloat16), "bf16x3": (2, 2, torch.bfloat16),
+              "f16x3": (2, 2, torch.float16), "f16mix": (2, 1, torch.float16)}
+GRAD_SCALE_TARGET = 1024.0      # max|dL/dsignature| * s lands in [512, 1024]: 6 binades of headroom below 65504
 
 
 class _Seg:
@@ -44,7 +54,8 @@ class UGaitEngine:
         self.dev = torch.device("cuda", torch.cuda.current_device() if device is None else device)
         self.ctx = ops.get_ctx(self.dev.index)
         self.math_mode = math_mode
-        self.P = {"fp32": 0, "bf16": 1, "bf16x3": 2}[math_mode]
+        self.P, self.PB, self.dt16 = MATH_MODES[math_mode]
+        self.scaled = self.dt16 is torch.float16
         self.pad = 32 if self.P else 1
         self.optimizer, self.lr, self.momentum = optimizer.lower(), float(lr), momentum
         self.beta1, self.beta2, self.eps = beta1, beta2, eps
@@ -131,7 +142,7 @@ class UGaitEngine:
                 name = f"{bn}/conv{li}/w"
                 shape = (L["co"], L["k"], L["k"], L["cp"])
                 if self.P:
-                    self.cw[name] = torch.zeros((self.P,) + shape, dtype=torch.bfloat16, device=d)
+                    self.cw[name] = torch.zeros((self.P,) + shape, dtype=self.dt16, device=d)
                 elif L["cp"] != L["cin"]:
                     self.cw[name] = torch.zeros(shape, device=d)
                 else:
@@ -139,7 +150,7 @@ class UGaitEngine:
             for nm in ("dense", "ofCode"):
                 name = f"{bn}/{nm}/w"
                 if self.P:
-                    self.cw[name] = torch.zeros((self.P,) + self.segs[name].shape, dtype=torch.bfloat16, device=d)
+                    self.cw[name] = torch.zeros((self.P,) + self.segs[name].shape, dtype=self.dt16, device=d)
                 else:
                     self.cw[name] = self.pw[name]
         for k, t in self.cw.items():
@@ -316,6 +327,9 @@ class UGaitEngine:
             else:
                 p.dsig.add_(p.dfeat)
         self._reduce_bucket("heads")
+        if self.scaled:
+            # fp16 gradient operands: pick this step's power-of-two scale from the signature gradient
+            check(lib.ugn_grad_scale_update(h, p.R["dsig"].ptr, GRAD_SCALE_TARGET, st))
         if cfg.single:
             p.br[0].dout.copy_(p.dsig)
         else:
@@ -503,13 +517,13 @@ class _Plan:
     """All activation / gradient buffers of one batch size, exported once through DLPack."""
 
     def __init__(self, eng: UGaitEngine, B: int, train: bool):
-        cfg, d, P = eng.cfg, eng.dev, eng.P
+        cfg, d, P, PB, dt16 = eng.cfg, eng.dev, eng.P, eng.PB, eng.dt16
         self.B, self.train = B, train
         f32 = dict(device=d, dtype=torch.float32)
 
-        def act(shape):
-            if P:
-                return torch.zeros((P,) + tuple(shape), device=d, dtype=torch.bfloat16)
+        def act(shape, planes=P):
+            if planes:
+                return torch.zeros((planes,) + tuple(shape), device=d, dtype=dt16)
             return torch.zeros(tuple(shape), **f32)
 
         self.br: List[_Branch] = []
@@ -526,12 +540,12 @@ class _Plan:
                 if L["pool"]:
                     T[f"idx{li}"] = torch.zeros(B, L["hp"], L["hp"], L["co"], device=d, dtype=torch.uint8)
                 if train:
-                    T[f"dz{li}c"] = act((B, L["ho"], L["ho"], L["co"]))
+                    T[f"dz{li}c"] = act((B, L["ho"], L["ho"], L["co"]), PB)
                     T[f"da{li + 1}"] = torch.zeros(B, L["hp"], L["hp"], L["co"], **f32)
             T["flat"] = act((B, cfg.flat))
             b.h1 = T["h1"] = torch.zeros(B, 2 * cfg.nd, **f32)
             if P:
-                T["h1_16"] = torch.zeros(P, B, 2 * cfg.nd, device=d, dtype=torch.bfloat16)
+                T["h1_16"] = torch.zeros(P, B, 2 * cfg.nd, device=d, dtype=dt16)
             b.out = T["out"] = torch.zeros(B, cfg.nd, **f32)
             if train:
                 b.mask = T["mask"] = torch.ones(B, 2 * cfg.nd, **f32)
@@ -539,8 +553,8 @@ class _Plan:
                 T["dh1"] = torch.zeros(B, 2 * cfg.nd, **f32)
                 T["dflat"] = torch.zeros(B, cfg.flat, **f32)
                 if P:
-                    T["dout16"] = torch.zeros(P, B, cfg.nd, device=d, dtype=torch.bfloat16)
-                    T["dz1_16"] = torch.zeros(P, B, 2 * cfg.nd, device=d, dtype=torch.bfloat16)
+                    T["dout16"] = torch.zeros(PB, B, cfg.nd, device=d, dtype=dt16)
+                    T["dz1_16"] = torch.zeros(PB, B, 2 * cfg.nd, device=d, dtype=dt16)
                 else:
                     T["dz1"] = torch.zeros(B, 2 * cfg.nd, **f32)
             b.T = T

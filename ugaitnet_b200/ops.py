@@ -170,3 +170,12 @@ def gemm_bf16(ctx, A, a_mn, B, b_mn, C, accumulate=False):
     rs = [_r(t) for t in (A, B, C)]
     check(lib.ugn_gemm_bf16(ctx.h, rs[0].ptr, int(a_mn), rs[1].ptr, int(b_mn), rs[2].ptr, int(bool(accumulate)),
                             stream_ptr()))
+
+
+def grad_scale_update(ctx, ref, target=1024.0):
+    r = _r(ref)
+    check(lib.ugn_grad_scale_update(ctx.h, r.ptr, float(target), stream_ptr()))
+
+
+def grad_scale_set(ctx, scale: float):
+    check(lib.ugn_grad_scale_set(ctx.h, float(scale), stream_ptr()))
