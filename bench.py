@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Benchmark of the UGaitNet hot path (BASELINE.json metric / configs[1]).
 
-    python bench.py --gpus N --steps K --warmup W [--impl reference] [--mode bf16|bf16x3|fp32]
+    python bench.py --gpus N --steps K --warmup W [--impl reference] [--mode f16mix|f16x3|bf16x3|bf16|fp32]
 
 A "step" is one Keras train_function step of the 3-modality (OF+gray+depth) TUM-GAID-shaped model
 (nd=2048, 150 classes, sign_max fusion, dropout 0.4, Adam) on one batch of bs=24 literal sequences
@@ -29,6 +29,11 @@ BS_LITERAL, EXPAND = 24, 4
 ND, NCLASSES = 2048, 150
 FLOP_FWD_ROW = {"of": 2.0214e9 + 0.0545e9, "c25": 1.3356e9 + 0.0545e9}
 TRAIN_FLOP_ROW = 11.83e9                                                  # 3-mod fwd+dgrad+wgrad
+
+
+DTYPE_NAMES = {"fp32": "f32", "bf16": "bf16", "bf16x3": "bf16 (3-pass hi/lo split, fp32 accumulate)",
+               "f16x3": "f16 (3-pass hi/lo split, fp32 accumulate)",
+               "f16mix": "f16 (forward: 3-pass hi/lo split; backward: 1 pass, scaled fp16 gradients; fp32 accumulate)"}
 
 
 def peaks():
@@ -204,7 +209,7 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours")
-    ap.add_argument("--mode", default=os.environ.get("UGN_BENCH_MODE", "bf16x3"))
+    ap.add_argument("--mode", default=os.environ.get("UGN_BENCH_MODE", "f16mix"))
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-knn", action="store_true")
     ap.add_argument("--lite", action="store_true", help="timed steps only (for runs under ncu)")
@@ -311,7 +316,7 @@ def main():
     line = {"metric": "train rows/s (3-mod fwd+bwd+triplet+CE+Adam)", "value": value, "unit": "rows/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": {"fp32": "f32", "bf16": "bf16", "bf16x3": "bf16 (3-pass hi/lo split, fp32 accumulate)"}[args.mode],
+            "dtype": DTYPE_NAMES[args.mode],
             "data": "synthetic", "config": workload_config(world),
             "literal_seq_per_s": value / EXPAND,
             "e2e": {"value": e2e, "unit": "rows/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 12,
@@ -349,7 +354,10 @@ def main():
             # algorithmic conv FLOPs of one step: fwd + wgrad over all layers, dgrad without conv1
             conv_fwd_row = 2.0214e9 + 2 * 1.3356e9
             conv_flops = (3 * conv_fwd_row - (1.3717e9 + 2 * 0.6858e9)) * B
-            passes = {"fp32": 1, "bf16": 1, "bf16x3": 3}[args.mode]
+            # MMA passes issued per algorithmic product (forward, backward)
+            pf, pb = {"fp32": (1, 1), "bf16": (1, 1), "bf16x3": (3, 3), "f16x3": (3, 3), "f16mix": (3, 1)}[args.mode]
+            fwd_flops = conv_fwd_row * B
+            passes = (pf * fwd_flops + pb * (conv_flops - fwd_flops)) / conv_flops
             ach = conv_flops / (conv_ms * 1e-3) / 1e12
             line["roofline"] = {"bound": "tensor", "kernel": "tc_kernel<MODE_CONV|MODE_WGRAD> (conv fwd+dgrad+wgrad)",
                                 "achieved": ach, "peak": pk["tf_sust"], "unit": "TFLOP/s", "frac": ach / pk["tf_sust"],

@@ -110,10 +110,12 @@ int ugn_conv2d_fwd(ugn_ctx*, const ugn_tensor* x, const ugn_tensor* w, const ugn
                    void* stream);
 
 /* backward through pool+act: dy f32 [B,Hp,Wp,C] (grad wrt layer output), y = layer output,
- * -> dz (grad wrt conv pre-activation) [.,B,Ho,Wo,C] in the storage mode of `dz`. */
+ * -> dz (grad wrt conv pre-activation) [.,B,Ho,Wo,C] in the storage mode of `dz`.
+ * db f32 [C] (nullable, OVERWRITTEN): the Conv2D bias gradient sum_pixels dz, reduced from the f32
+ * values in the same pass (then pass db = NULL to ugn_conv2d_wgrad). */
 int ugn_conv2d_bwd_act(ugn_ctx*, const ugn_tensor* dy, const ugn_tensor* y,
-                       const ugn_tensor* pool_idx, ugn_tensor* dz, int act, float alpha,
-                       int pool, void* stream);
+                       const ugn_tensor* pool_idx, ugn_tensor* dz, ugn_tensor* db, int act,
+                       float alpha, int pool, void* stream);
 
 /* dx f32 [B,H,W,Cp_in] = full correlation of dz with w (Keras Conv2D input gradient). */
 int ugn_conv2d_dgrad(ugn_ctx*, const ugn_tensor* dz, const ugn_tensor* w, ugn_tensor* dx,
@@ -182,15 +184,21 @@ int ugn_triplet_all(ugn_ctx*, const ugn_tensor* emb, const ugn_tensor* labels, f
  * w -= lr_t * m / (sqrt(v)+eps).  seg_off i64 [S+1], seg_l2 f32 [S] device tensors.
  * reg_out f32 [1] (nullable) accumulates sum_s l2[s]*|w_s|^2 of the PRE-update weights.
  * lr_dev f32 [1] (nullable): when given, the learning rate is read from device memory
- * instead of lr_t, so a captured CUDA graph can be replayed with a new rate. */
+ * instead of lr_t, so a captured CUDA graph can be replayed with a new rate.
+ * pack_table i64 [S,2] (nullable, device): {address, numel} of the 16-bit compute copy
+ * [pack_planes][numel] of segment s (address 0 = none): the updated weights are re-split into it
+ * in the same pass (pack_f16: 0 bf16, 1 fp16), replacing a separate ugn_pack_weight for
+ * unpadded (dense) weights. */
 int ugn_adam_step(ugn_ctx*, ugn_tensor* w, const ugn_tensor* g, ugn_tensor* m, ugn_tensor* v,
                   const ugn_tensor* seg_off, const ugn_tensor* seg_l2, float lr_t, float beta1,
                   float beta2, float eps, float gscale, ugn_tensor* reg_out,
-                  const ugn_tensor* lr_dev, void* stream);
+                  const ugn_tensor* lr_dev, const ugn_tensor* pack_table, int pack_planes,
+                  int pack_f16, void* stream);
 /* SGD with momentum (optimizers.SGD(lr, momentum), :245): v = mom*v - lr*g'; w += v. */
 int ugn_sgd_step(ugn_ctx*, ugn_tensor* w, const ugn_tensor* g, ugn_tensor* v,
                  const ugn_tensor* seg_off, const ugn_tensor* seg_l2, float lr, float momentum,
-                 float gscale, ugn_tensor* reg_out, const ugn_tensor* lr_dev, void* stream);
+                 float gscale, ugn_tensor* reg_out, const ugn_tensor* lr_dev,
+                 const ugn_tensor* pack_table, int pack_planes, int pack_f16, void* stream);
 
 /* ---- a12: brute-force k-NN (mains/mj_testUWYHGaitNet_open_tum.py:331-341) -------------
  * queries f32 [Q,D], gallery f32 [N,D] (this rank's shard), k <= 32.

@@ -61,7 +61,9 @@ def test_conv_layer_fp32(ctx, B, C, Cp, H, Co, k, pool, act):
     dy = torch.randn(ref.shape, generator=g)
     ref.backward(dy.double())
     dz = torch.zeros(B, Ho, Ho, Co, device="cuda")
-    ops.conv2d_bwd_act(ctx, nhwc(dy).cuda(), y, idx, dz, act=act, alpha=0.3, pool=pool)
+    db2 = torch.full((Co,), 3.0, device="cuda")
+    ops.conv2d_bwd_act(ctx, nhwc(dy).cuda(), y, idx, dz, act=act, alpha=0.3, pool=pool, db=db2)
+    assert rel(db2, b64.grad) < FP32_TOL       # bias gradient reduced in the same pass
     dw = torch.zeros(Co, k, k, C, device="cuda")
     db = torch.zeros(Co, device="cuda")
     ops.conv2d_wgrad(ctx, xd, dz, dw, db)

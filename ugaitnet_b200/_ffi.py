@@ -48,7 +48,7 @@ _PROTOS = {
     "ugn_pack_weight": (c_int, [c_void_p, _T, _T, c_void_p]),
     "ugn_split_bf16": (c_int, [c_void_p, _T, _T, c_void_p]),
     "ugn_conv2d_fwd": (c_int, [c_void_p, _T, _T, _T, _T, _T, c_int, c_float, c_int, c_void_p]),
-    "ugn_conv2d_bwd_act": (c_int, [c_void_p, _T, _T, _T, _T, c_int, c_float, c_int, c_void_p]),
+    "ugn_conv2d_bwd_act": (c_int, [c_void_p, _T, _T, _T, _T, _T, c_int, c_float, c_int, c_void_p]),
     "ugn_conv2d_dgrad": (c_int, [c_void_p, _T, _T, _T, c_void_p]),
     "ugn_conv2d_wgrad": (c_int, [c_void_p, _T, _T, _T, _T, c_void_p]),
     "ugn_flatten_chw": (c_int, [c_void_p, _T, _T, c_void_p]),
@@ -64,8 +64,9 @@ _PROTOS = {
     "ugn_triplet_workspace_bytes": (c_int64, [c_int, c_int]),
     "ugn_triplet_all": (c_int, [c_void_p, _T, _T, c_float, c_float, _T, _T, _T, c_void_p]),
     "ugn_adam_step": (c_int, [c_void_p, _T, _T, _T, _T, _T, _T, c_float, c_float, c_float, c_float,
-                              c_float, _T, _T, c_void_p]),
-    "ugn_sgd_step": (c_int, [c_void_p, _T, _T, _T, _T, _T, c_float, c_float, c_float, _T, _T, c_void_p]),
+                              c_float, _T, _T, _T, c_int, c_int, c_void_p]),
+    "ugn_sgd_step": (c_int, [c_void_p, _T, _T, _T, _T, _T, c_float, c_float, c_float, _T, _T, _T, c_int, c_int,
+                             c_void_p]),
     "ugn_knn_workspace_bytes": (c_int64, [c_int64, c_int64, c_int64, c_int]),
     "ugn_knn_gallery_norms": (c_int, [c_void_p, _T, _T, c_void_p]),
     "ugn_knn_topk": (c_int, [c_void_p, _T, _T, _T, _T, c_int, c_int64, _T, _T, _T, _T, c_void_p]),

@@ -91,8 +91,10 @@ extern "C" int64_t ugn_launch_count(ugn_ctx* ctx) { return ctx ? ctx->launches :
 int ew_pack_input(ugn_ctx*, const float*, void*, int, int, int, int, int, int, int, cudaStream_t);
 int ew_pack_weight(ugn_ctx*, const float*, void*, int, int, long long, int, int, cudaStream_t);
 int ew_split(ugn_ctx*, const float*, __nv_bfloat16*, int, int, long long, cudaStream_t);
-int ew_bwd_act(ugn_ctx*, const float*, const void*, int, const uint8_t*, void*, int, int, int, int, int, int,
-               int, int, int, float, int, cudaStream_t);
+int ew_bwd_act(ugn_ctx*, const float*, const void*, int, const uint8_t*, void*, float*, int*, int, int, int, int,
+               int, int, int, int, int, float, int, cudaStream_t);
+int simt_colsum(ugn_ctx*, const float*, long long, int, int, float*, cudaStream_t);
+int simt_colsum_bf16(ugn_ctx*, const __nv_bfloat16*, int, int, long long, int, float*, cudaStream_t);
 int ew_flatten(ugn_ctx*, const void*, void*, int, int, int, int, int, int, cudaStream_t);
 int ew_act_mask_bwd(ugn_ctx*, const float*, const float*, const float*, float*, __nv_bfloat16*, int, int,
                     long long, int, float, cudaStream_t);
@@ -103,7 +105,8 @@ int ew_fuse_bwd(ugn_ctx*, const FusePtrs&, int, int, int, const float*, const fl
                 const float*, int, int, cudaStream_t);
 int ew_softmax_ce(ugn_ctx*, const float*, const int*, float*, float*, int, int, float, cudaStream_t);
 int ew_optim(ugn_ctx*, int, float*, const float*, float*, float*, const long long*, const float*, int,
-             long long, float, float, float, float, float, float*, const float*, cudaStream_t);
+             long long, float, float, float, float, float, float*, const float*, const long long*, int, int,
+             cudaStream_t);
 int simt_conv_fwd(ugn_ctx*, const ConvGeom&, const float*, const float*, const float*, float*, uint8_t*,
                   int, float, int, cudaStream_t);
 int simt_conv_dgrad(ugn_ctx*, const ConvGeom&, const float*, const float*, float*, cudaStream_t);
@@ -223,8 +226,8 @@ extern "C" int ugn_conv2d_fwd(ugn_ctx* ctx, const ugn_tensor* x, const ugn_tenso
 }
 
 extern "C" int ugn_conv2d_bwd_act(ugn_ctx* ctx, const ugn_tensor* dy, const ugn_tensor* y,
-                                  const ugn_tensor* pool_idx, ugn_tensor* dz, int act, float alpha, int pool,
-                                  void* stream) {
+                                  const ugn_tensor* pool_idx, ugn_tensor* dz, ugn_tensor* db, int act, float alpha,
+                                  int pool, void* stream) {
   UGN_CHECK(ctx && dy && y && dz, "ugn_conv2d_bwd_act: null argument");
   UGN_TENSOR(dy, DT_F32, 4, 4);
   UGN_TENSOR(y, DT_BAD, 4, 5);
@@ -244,9 +247,16 @@ extern "C" int ugn_conv2d_bwd_act(ugn_ctx* ctx, const ugn_tensor* dy, const ugn_
   }
   if (B == 0) return UGN_OK;
   if (my > 0 && mz > 0) UGN_SAME_FMT(y, dz, "bwd_act");
-  return ew_bwd_act(ctx, ugn_ptr<float>(dy), ugn_ptr<void>(y), my > 0, pool ? ugn_ptr<uint8_t>(pool_idx) : nullptr,
-                    ugn_ptr<void>(dz), mz, mz > 0 ? is_f16(dz) : is_f16(y), B, Ho, Wo, Hp, Wp, C, act, alpha, pool,
-                    (cudaStream_t)stream);
+  if (db) { UGN_TENSOR(db, DT_F32, 1, 1); UGN_CHECK(db->shape[0] == C, "bwd_act: db must be [C]"); }
+  int db_done = 0;
+  int rc = ew_bwd_act(ctx, ugn_ptr<float>(dy), ugn_ptr<void>(y), my > 0, pool ? ugn_ptr<uint8_t>(pool_idx) : nullptr,
+                      ugn_ptr<void>(dz), db ? ugn_ptr<float>(db) : nullptr, &db_done, mz,
+                      mz > 0 ? is_f16(dz) : is_f16(y), B, Ho, Wo, Hp, Wp, C, act, alpha, pool, (cudaStream_t)stream);
+  if (rc != UGN_OK || !db || db_done) return rc;
+  // layouts the fused reduction does not cover: column sums of the dz just written
+  if (mz == 0) return simt_colsum(ctx, ugn_ptr<float>(dz), (long long)B * Ho * Wo, C, C, ugn_ptr<float>(db), (cudaStream_t)stream);
+  return simt_colsum_bf16(ctx, ugn_ptr<__nv_bfloat16>(dz), mz, is_f16(dz), (long long)B * Ho * Wo, C, ugn_ptr<float>(db),
+                          (cudaStream_t)stream);
 }
 
 extern "C" int ugn_conv2d_dgrad(ugn_ctx* ctx, const ugn_tensor* dz, const ugn_tensor* w, ugn_tensor* dx,
@@ -490,7 +500,8 @@ extern "C" int ugn_softmax_ce(ugn_ctx* ctx, const ugn_tensor* logits, const ugn_
 
 static int optim_common(ugn_ctx* ctx, int opt, ugn_tensor* w, const ugn_tensor* g, ugn_tensor* m, ugn_tensor* v,
                         const ugn_tensor* seg_off, const ugn_tensor* seg_l2, float lr, float b1, float b2, float eps,
-                        float gscale, ugn_tensor* reg_out, const ugn_tensor* lr_dev, void* stream) {
+                        float gscale, ugn_tensor* reg_out, const ugn_tensor* lr_dev, const ugn_tensor* pack_table,
+                        int pack_planes, int pack_f16, void* stream) {
   UGN_CHECK(ctx && w && g && v && seg_off && seg_l2, "optimizer: null argument");
   if (lr_dev) UGN_TENSOR(lr_dev, DT_F32, 1, 1);
   UGN_TENSOR(w, DT_F32, 1, 1);
@@ -504,22 +515,31 @@ static int optim_common(ugn_ctx* ctx, int opt, ugn_tensor* w, const ugn_tensor* 
   UGN_CHECK(g->shape[0] == n && v->shape[0] == n && (!m || m->shape[0] == n), "optimizer: arena length mismatch");
   UGN_CHECK(seg_off->shape[0] == S + 1 && S >= 1, "optimizer: seg_off must be i64[S+1]");
   if (reg_out) UGN_TENSOR(reg_out, DT_F32, 1, 1);
+  if (pack_table) {
+    UGN_TENSOR(pack_table, DT_I64, 2, 2);
+    UGN_CHECK(pack_table->shape[0] == S && pack_table->shape[1] == 2, "optimizer: pack_table must be i64 [S,2]");
+    UGN_CHECK(pack_planes == 1 || pack_planes == 2, "optimizer: pack_planes must be 1 or 2");
+  }
   if (n == 0) return UGN_OK;
   return ew_optim(ctx, opt, ugn_ptr<float>(w), ugn_ptr<float>(g), m ? ugn_ptr<float>(m) : nullptr, ugn_ptr<float>(v),
                   ugn_ptr<long long>(seg_off), ugn_ptr<float>(seg_l2), S, n, lr, b1, b2, eps, gscale,
                   reg_out ? ugn_ptr<float>(reg_out) : nullptr, lr_dev ? ugn_ptr<float>(lr_dev) : nullptr,
-                  (cudaStream_t)stream);
+                  pack_table ? ugn_ptr<long long>(pack_table) : nullptr, pack_planes, pack_f16, (cudaStream_t)stream);
 }
 
 extern "C" int ugn_adam_step(ugn_ctx* ctx, ugn_tensor* w, const ugn_tensor* g, ugn_tensor* m, ugn_tensor* v,
                              const ugn_tensor* seg_off, const ugn_tensor* seg_l2, float lr_t, float beta1, float beta2,
-                             float eps, float gscale, ugn_tensor* reg_out, const ugn_tensor* lr_dev, void* stream) {
-  return optim_common(ctx, 0, w, g, m, v, seg_off, seg_l2, lr_t, beta1, beta2, eps, gscale, reg_out, lr_dev, stream);
+                             float eps, float gscale, ugn_tensor* reg_out, const ugn_tensor* lr_dev,
+                             const ugn_tensor* pack_table, int pack_planes, int pack_f16, void* stream) {
+  return optim_common(ctx, 0, w, g, m, v, seg_off, seg_l2, lr_t, beta1, beta2, eps, gscale, reg_out, lr_dev, pack_table,
+                      pack_planes, pack_f16, stream);
 }
 extern "C" int ugn_sgd_step(ugn_ctx* ctx, ugn_tensor* w, const ugn_tensor* g, ugn_tensor* v, const ugn_tensor* seg_off,
                             const ugn_tensor* seg_l2, float lr, float momentum, float gscale, ugn_tensor* reg_out,
-                            const ugn_tensor* lr_dev, void* stream) {
-  return optim_common(ctx, 1, w, g, nullptr, v, seg_off, seg_l2, lr, momentum, 0.f, 0.f, gscale, reg_out, lr_dev, stream);
+                            const ugn_tensor* lr_dev, const ugn_tensor* pack_table, int pack_planes, int pack_f16,
+                            void* stream) {
+  return optim_common(ctx, 1, w, g, nullptr, v, seg_off, seg_l2, lr, momentum, 0.f, 0.f, gscale, reg_out, lr_dev,
+                      pack_table, pack_planes, pack_f16, stream);
 }
 
 extern "C" int ugn_gemm_bf16(ugn_ctx* ctx, const ugn_tensor* A, int a_mn, const ugn_tensor* B, int b_mn, ugn_tensor* C,

@@ -176,63 +176,91 @@ __global__ void bwd_act_kernel(const float* __restrict__ dy, const YT* __restric
   }
 }
 
-// tensor-core storage variant: 8 channels per thread, 32-bit index math, 16-byte loads / stores
+// tensor-core storage variant: 8 channels per thread, 16-byte loads / stores.  A thread keeps ONE channel
+// group (c8 = tid % C8) for its whole pixel loop, so the bias gradient db[c] = sum_pix dz[pix][c] (Keras
+// Conv2D bias, nets/mj_uwyhNets_ba.py:82) is accumulated in registers from the f32 values and reduced
+// through smem + one atomicAdd per channel per block -- no second pass over dz.
 template <int P>
 __global__ void __launch_bounds__(256) bwd_act_vec8_kernel(const float* __restrict__ dy,
                                                            const __nv_bfloat16* __restrict__ y,
                                                            const uint8_t* __restrict__ idx,
-                                                           __nv_bfloat16* __restrict__ dz, int B, int Ho, int Wo,
+                                                           __nv_bfloat16* __restrict__ dz, float* __restrict__ db,
+                                                           int B, int Ho, int Wo,
                                                            int Hp, int Wp, int C8, int act, float alpha, int pool,
                                                            int f16, const float* __restrict__ gs) {
+  __shared__ float red[256 * 8];
   const float scale = gs ? gs[0] : 1.f;
-  const unsigned total = (unsigned)B * Ho * Wo * C8;
-  const long long plane = (long long)total * 8;
-  for (unsigned e = blockIdx.x * blockDim.x + threadIdx.x; e < total; e += gridDim.x * blockDim.x) {
-    const unsigned c8 = e % C8, pix = e / C8;
-    const unsigned xo = pix % Wo, t2 = pix / Wo, yo = t2 % Ho, b = t2 / Ho;
-    float v[8];
+  const unsigned npix = (unsigned)B * Ho * Wo;
+  const long long plane = (long long)npix * C8 * 8;
+  const unsigned lanes = 256u / C8, c8 = threadIdx.x % C8, lane = threadIdx.x / C8;
+  float acc[8];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) v[i] = 0.f;
-    bool live = true;
-    long long o = (long long)e * 8;
-    int pos = 0;
-    if (pool) {
-      const unsigned yp = yo >> 1, xp = xo >> 1;
-      live = yp < (unsigned)Hp && xp < (unsigned)Wp;
-      o = ((((long long)b * Hp + yp) * Wp + xp) * C8 + c8) * 8;
-      pos = ((yo & 1) << 1) | (xo & 1);
-    }
-    if (live) {
-      const float4 d0 = *reinterpret_cast<const float4*>(dy + o), d1 = *reinterpret_cast<const float4*>(dy + o + 4);
-      const uint4 yr = *reinterpret_cast<const uint4*>(y + o);
-      const __nv_bfloat16* yh = reinterpret_cast<const __nv_bfloat16*>(&yr);
-      const float dd[8] = {d0.x, d0.y, d0.z, d0.w, d1.x, d1.y, d1.z, d1.w};
-      unsigned long long ib = 0;
-      if (pool) ib = *reinterpret_cast<const unsigned long long*>(idx + o);
+  for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+  if (lane < lanes) {
+    for (unsigned pix = blockIdx.x * lanes + lane; pix < npix; pix += gridDim.x * lanes) {
+      const unsigned e = pix * C8 + c8;
+      const unsigned xo = pix % Wo, t2 = pix / Wo, yo = t2 % Ho, b = t2 / Ho;
+      float v[8];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const bool sel = !pool || (int)((ib >> (8 * i)) & 0xff) == pos;
-        if (sel) v[i] = dd[i] * scale * ugn_act_bwd(ugn_f16to32(yh[i], f16), act, alpha);
+      for (int i = 0; i < 8; ++i) v[i] = 0.f;
+      bool live = true;
+      long long o = (long long)e * 8;
+      int pos = 0;
+      if (pool) {
+        const unsigned yp = yo >> 1, xp = xo >> 1;
+        live = yp < (unsigned)Hp && xp < (unsigned)Wp;
+        o = ((((long long)b * Hp + yp) * Wp + xp) * C8 + c8) * 8;
+        pos = ((yo & 1) << 1) | (xo & 1);
       }
-    }
-    __align__(16) u16 hi[8], lo[8];
+      if (live) {
+        const float4 d0 = *reinterpret_cast<const float4*>(dy + o), d1 = *reinterpret_cast<const float4*>(dy + o + 4);
+        const uint4 yr = *reinterpret_cast<const uint4*>(y + o);
+        const __nv_bfloat16* yh = reinterpret_cast<const __nv_bfloat16*>(&yr);
+        const float dd[8] = {d0.x, d0.y, d0.z, d0.w, d1.x, d1.y, d1.z, d1.w};
+        unsigned long long ib = 0;
+        if (pool) ib = *reinterpret_cast<const unsigned long long*>(idx + o);
 #pragma unroll
-    for (int i = 0; i < 8; ++i) ugn_split16(v[i], f16, hi[i], lo[i]);
-    *reinterpret_cast<uint4*>(dz + (long long)e * 8) = *reinterpret_cast<const uint4*>(hi);
-    if (P == 2) *reinterpret_cast<uint4*>(dz + plane + (long long)e * 8) = *reinterpret_cast<const uint4*>(lo);
+        for (int i = 0; i < 8; ++i) {
+          const bool sel = !pool || (int)((ib >> (8 * i)) & 0xff) == pos;
+          if (sel) v[i] = dd[i] * ugn_act_bwd(ugn_f16to32(yh[i], f16), act, alpha);
+          acc[i] += v[i];
+        }
+      }
+      __align__(16) u16 hi[8], lo[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) ugn_split16(v[i] * scale, f16, hi[i], lo[i]);
+      *reinterpret_cast<uint4*>(dz + (long long)e * 8) = *reinterpret_cast<const uint4*>(hi);
+      if (P == 2) *reinterpret_cast<uint4*>(dz + plane + (long long)e * 8) = *reinterpret_cast<const uint4*>(lo);
+    }
+  }
+  if (db) {
+    const int C = C8 * 8;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) red[threadIdx.x * 8 + i] = acc[i];   // == red[lane * C + c8 * 8 + i] for live lanes
+    __syncthreads();
+    for (int c = threadIdx.x; c < C; c += 256) {
+      float sacc = 0.f;
+      for (unsigned l = 0; l < lanes; ++l) sacc += red[l * C + c];
+      atomicAdd(db + c, sacc);
+    }
   }
 }
 
 int ew_bwd_act(ugn_ctx* ctx, const float* dy, const void* y, int y_bf16, const uint8_t* idx,
-               void* dz, int mode, int f16, int B, int Ho, int Wo, int Hp, int Wp, int C, int act,
-               float alpha, int pool, cudaStream_t st) {
+               void* dz, float* db, int* db_done, int mode, int f16, int B, int Ho, int Wo, int Hp, int Wp, int C,
+               int act, float alpha, int pool, cudaStream_t st) {
   const float* gs = ctx->gscale;
-  if (y_bf16 && mode > 0 && C % 8 == 0 && (long long)B * Ho * Wo * (C / 8) < 0x7fffffffLL) {
+  *db_done = 0;
+  if (y_bf16 && mode > 0 && C % 8 == 0 && C / 8 <= 256 && (long long)B * Ho * Wo * (C / 8) < 0x7fffffffLL) {
     int g8 = grid_for(ctx, (long long)B * Ho * Wo * (C / 8), 256);
+    if (db) {
+      UGN_CUDA(cudaMemsetAsync(db, 0, sizeof(float) * C, st));
+      *db_done = 1;
+    }
     if (mode == 1)
-      bwd_act_vec8_kernel<1><<<g8, 256, 0, st>>>(dy, (const __nv_bfloat16*)y, idx, (__nv_bfloat16*)dz, B, Ho, Wo, Hp, Wp, C / 8, act, alpha, pool, f16, gs);
+      bwd_act_vec8_kernel<1><<<g8, 256, 0, st>>>(dy, (const __nv_bfloat16*)y, idx, (__nv_bfloat16*)dz, db, B, Ho, Wo, Hp, Wp, C / 8, act, alpha, pool, f16, gs);
     else
-      bwd_act_vec8_kernel<2><<<g8, 256, 0, st>>>(dy, (const __nv_bfloat16*)y, idx, (__nv_bfloat16*)dz, B, Ho, Wo, Hp, Wp, C / 8, act, alpha, pool, f16, gs);
+      bwd_act_vec8_kernel<2><<<g8, 256, 0, st>>>(dy, (const __nv_bfloat16*)y, idx, (__nv_bfloat16*)dz, db, B, Ho, Wo, Hp, Wp, C / 8, act, alpha, pool, f16, gs);
     UGN_LAUNCHED(ctx);
     return UGN_OK;
   }
@@ -520,7 +548,8 @@ __global__ void __launch_bounds__(256) optim_kernel(float* __restrict__ w, const
                                                     const float* __restrict__ l2, int S, long long n4,
                                                     float lr, float b1, float b2, float eps, float gscale,
                                                     float* __restrict__ reg_out,
-                                                    const float* __restrict__ lr_dev) {
+                                                    const float* __restrict__ lr_dev,
+                                                    const long long* __restrict__ pack, int packP, int f16) {
   float reg = 0.f;
   if (lr_dev) lr = *lr_dev;  // CUDA-graph friendly: the step-dependent rate lives in device memory
   for (long long q = blockIdx.x * (long long)blockDim.x + threadIdx.x; q < n4;
@@ -557,6 +586,24 @@ __global__ void __launch_bounds__(256) optim_kernel(float* __restrict__ w, const
       reinterpret_cast<float4*>(v)[q] = make_float4(v2[0], v2[1], v2[2], v2[3]);
     }
     reinterpret_cast<float4*>(w)[q] = make_float4(ww[0], ww[1], ww[2], ww[3]);
+    // fused refresh of the tensor-core compute copy of this segment ([P][numel] 16-bit planes): saves the
+    // separate f32 re-read of ugn_pack_weight for the dense weights (92 % of the parameter bytes)
+    if (pack && pack[2 * s]) {
+      u16* dst = reinterpret_cast<u16*>(pack[2 * s]);
+      const long long numel = pack[2 * s + 1], li = q * 4 - off[s];
+      __align__(8) u16 hi[4], lo[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) ugn_split16(ww[i], f16, hi[i], lo[i]);
+      if (li + 4 <= numel) {
+        *reinterpret_cast<uint2*>(dst + li) = *reinterpret_cast<const uint2*>(hi);
+        if (packP == 2) *reinterpret_cast<uint2*>(dst + numel + li) = *reinterpret_cast<const uint2*>(lo);
+      } else {
+        for (int i = 0; i < 4 && li + i < numel; ++i) {
+          dst[li + i] = hi[i];
+          if (packP == 2) dst[numel + li + i] = lo[i];
+        }
+      }
+    }
   }
   if (reg_out) {
     __shared__ float red[8];
@@ -573,14 +620,15 @@ __global__ void __launch_bounds__(256) optim_kernel(float* __restrict__ w, const
 
 int ew_optim(ugn_ctx* ctx, int opt, float* w, const float* g, float* m, float* v,
              const long long* off, const float* l2, int S, long long n, float lr, float b1,
-             float b2, float eps, float gscale, float* reg_out, const float* lr_dev, cudaStream_t st) {
+             float b2, float eps, float gscale, float* reg_out, const float* lr_dev, const long long* pack,
+             int packP, int f16, cudaStream_t st) {
   UGN_CHECK(n % 4 == 0, "optimizer arena length must be a multiple of 4 (got %lld)", n);
   if (reg_out) UGN_CUDA(cudaMemsetAsync(reg_out, 0, sizeof(float), st));
   long long n4 = n / 4;
   int grid = (int)std::min<long long>((n4 + 255) / 256, (long long)ctx->sm_count * 8);
   grid = std::max(grid, 1);
-  if (opt == 0) optim_kernel<0><<<grid, 256, 0, st>>>(w, g, m, v, off, l2, S, n4, lr, b1, b2, eps, gscale, reg_out, lr_dev);
-  else optim_kernel<1><<<grid, 256, 0, st>>>(w, g, m, v, off, l2, S, n4, lr, b1, b2, eps, gscale, reg_out, lr_dev);
+  if (opt == 0) optim_kernel<0><<<grid, 256, 0, st>>>(w, g, m, v, off, l2, S, n4, lr, b1, b2, eps, gscale, reg_out, lr_dev, pack, packP, f16);
+  else optim_kernel<1><<<grid, 256, 0, st>>>(w, g, m, v, off, l2, S, n4, lr, b1, b2, eps, gscale, reg_out, lr_dev, pack, packP, f16);
   UGN_LAUNCHED(ctx);
   return UGN_OK;
 }

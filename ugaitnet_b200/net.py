@@ -155,10 +155,25 @@ class UGaitEngine:
                     self.cw[name] = self.pw[name]
         for k, t in self.cw.items():
             self.Rcw[k] = TRef(t)
+        # optimiser-fused refresh of the unpadded (dense) compute copies: {address, numel} per segment
+        self.pack_table = None
+        self._fused_pack = set()
+        if self.P:
+            tab = torch.zeros(len(segs), 2, dtype=torch.int64)
+            for i, sg in enumerate(segs):
+                t = self.cw.get(sg.name)
+                if t is not None and t.dtype == self.dt16 and tuple(t.shape[1:]) == sg.shape and sg.n % 4 == 0:
+                    tab[i, 0], tab[i, 1] = t.data_ptr(), sg.n
+                    self._fused_pack.add(sg.name)
+            self.pack_table = tab.to(d)
+            self.R["pack_table"] = TRef(self.pack_table)
 
-    def repack_weights(self):
-        """master f32 -> padded / bf16 compute copies (after every optimiser step)."""
+    def repack_weights(self, after_optim: bool = False):
+        """master f32 -> padded / 16-bit compute copies.  After an optimiser step only the padded (conv)
+        copies are left to do: the dense ones were re-split inside the optimiser kernel."""
         for name, t in self.cw.items():
+            if after_optim and name in self._fused_pack:
+                continue
             if t.data_ptr() != self.pw[name].data_ptr():
                 check(lib.ugn_pack_weight(self.ctx.h, self.Rw[name].ptr, self.Rcw[name].ptr, stream_ptr()))
 
@@ -330,6 +345,11 @@ class UGaitEngine:
         if self.scaled:
             # fp16 gradient operands: pick this step's power-of-two scale from the signature gradient
             check(lib.ugn_grad_scale_update(h, p.R["dsig"].ptr, GRAD_SCALE_TARGET, st))
+            self.ctx.grad_scaled = True
+        elif getattr(self.ctx, "grad_scaled", False):
+            # another engine on this ctx left a scale behind: this mode's gradients are unscaled
+            check(lib.ugn_grad_scale_set(h, 1.0, st))
+            self.ctx.grad_scaled = False
         if cfg.single:
             p.br[0].dout.copy_(p.dsig)
         else:
@@ -358,26 +378,29 @@ class UGaitEngine:
             for li in range(nl - 1, -1, -1):
                 L = b.layers[li]
                 check(lib.ugn_conv2d_bwd_act(h, R[f"da{li + 1}"].ptr, R[f"a{li + 1}"].ptr,
-                                             R[f"idx{li}"].ptr if L["pool"] else None, R[f"dz{li}c"].ptr, cfg.act,
-                                             cfg.alpha, int(L["pool"]), st))
+                                             R[f"idx{li}"].ptr if L["pool"] else None, R[f"dz{li}c"].ptr,
+                                             self.Rg[f"{bn}/conv{li}/b"].ptr, cfg.act, cfg.alpha, int(L["pool"]), st))
                 check(lib.ugn_conv2d_wgrad(h, R[f"a{li}"].ptr, R[f"dz{li}c"].ptr, self.Rg[f"{bn}/conv{li}/w"].ptr,
-                                           self.Rg[f"{bn}/conv{li}/b"].ptr, st))
+                                           None, st))
                 if li > 0:
                     check(lib.ugn_conv2d_dgrad(h, R[f"dz{li}c"].ptr, self.Rcw[f"{bn}/conv{li}/w"].ptr, R[f"da{li}"].ptr, st))
             self._reduce_bucket(m)
 
     def _optim(self, gscale: float):
         h, st, R = self.ctx.h, stream_ptr(), self.R
+        pk = R["pack_table"].ptr if self.pack_table is not None else None
+        f16 = int(self.dt16 is torch.float16)
         if self.optimizer == "adam":
             check(lib.ugn_adam_step(h, R["w"].ptr, R["g"].ptr, R["m"].ptr, R["v"].ptr, R["seg_off"].ptr,
                                     R["seg_l2"].ptr, 0.0, self.beta1, self.beta2, self.eps, gscale,
-                                    R["reg_out"].ptr, R["lr_dev"].ptr, st))
+                                    R["reg_out"].ptr, R["lr_dev"].ptr, pk, max(self.P, 1), f16, st))
         elif self.optimizer == "sgd":
             check(lib.ugn_sgd_step(h, R["w"].ptr, R["g"].ptr, R["v"].ptr, R["seg_off"].ptr, R["seg_l2"].ptr, 0.0,
-                                   self.momentum, gscale, R["reg_out"].ptr, R["lr_dev"].ptr, st))
+                                   self.momentum, gscale, R["reg_out"].ptr, R["lr_dev"].ptr, pk, max(self.P, 1),
+                                   f16, st))
         else:
             raise ValueError(f"unknown optimizer {self.optimizer}")
-        self.repack_weights()
+        self.repack_weights(after_optim=True)
 
     def _step_body(self, p: "_Plan", do_optim: bool):
         sig, feat = self._forward(p, True)

@@ -58,8 +58,8 @@ def conv2d_fwd(ctx, x, w, bias, y, pool_idx, act=ACT_RELU, alpha=0.3, pool=True)
     check(lib.ugn_conv2d_fwd(ctx.h, *[_p(r) for r in rs], int(act), float(alpha), int(bool(pool)), stream_ptr()))
 
 
-def conv2d_bwd_act(ctx, dy, y, pool_idx, dz, act=ACT_RELU, alpha=0.3, pool=True):
-    rs = [_r(t) for t in (dy, y, pool_idx, dz)]
+def conv2d_bwd_act(ctx, dy, y, pool_idx, dz, act=ACT_RELU, alpha=0.3, pool=True, db=None):
+    rs = [_r(t) for t in (dy, y, pool_idx, dz, db)]
     check(lib.ugn_conv2d_bwd_act(ctx.h, *[_p(r) for r in rs], int(act), float(alpha), int(bool(pool)), stream_ptr()))
 
 
@@ -131,18 +131,20 @@ def triplet_all(ctx, emb, labels, margin, scale, out, demb, workspace):
 
 
 def adam_step(ctx, w, g, m, v, seg_off, seg_l2, lr_t, beta1=0.9, beta2=0.999, eps=1e-7, gscale=1.0,
-              reg_out=None, lr_dev=None):
+              reg_out=None, lr_dev=None, pack_table=None, pack_planes=0, pack_f16=0):
     rs = [_r(t) for t in (w, g, m, v, seg_off, seg_l2)]
-    ro = [_r(reg_out), _r(lr_dev)]
+    ro = [_r(reg_out), _r(lr_dev), _r(pack_table)]
     check(lib.ugn_adam_step(ctx.h, *[_p(r) for r in rs], float(lr_t), float(beta1), float(beta2), float(eps),
-                            float(gscale), _p(ro[0]), _p(ro[1]), stream_ptr()))
+                            float(gscale), _p(ro[0]), _p(ro[1]), _p(ro[2]), int(pack_planes), int(pack_f16),
+                            stream_ptr()))
 
 
-def sgd_step(ctx, w, g, v, seg_off, seg_l2, lr, momentum=0.9, gscale=1.0, reg_out=None, lr_dev=None):
+def sgd_step(ctx, w, g, v, seg_off, seg_l2, lr, momentum=0.9, gscale=1.0, reg_out=None, lr_dev=None,
+             pack_table=None, pack_planes=0, pack_f16=0):
     rs = [_r(t) for t in (w, g, v, seg_off, seg_l2)]
-    ro = [_r(reg_out), _r(lr_dev)]
+    ro = [_r(reg_out), _r(lr_dev), _r(pack_table)]
     check(lib.ugn_sgd_step(ctx.h, *[_p(r) for r in rs], float(lr), float(momentum), float(gscale), _p(ro[0]),
-                           _p(ro[1]), stream_ptr()))
+                           _p(ro[1]), _p(ro[2]), int(pack_planes), int(pack_f16), stream_ptr()))
 
 
 def knn_workspace_bytes(Q, N, D, k) -> int:
