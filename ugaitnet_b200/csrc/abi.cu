@@ -36,6 +36,20 @@ int ugn_validate(const ugn_ctx* ctx, const ugn_tensor* t, const char* name, UgnD
   return UGN_OK;
 }
 
+int ugn_scratch(ugn_ctx* ctx, size_t bytes, void** out) {
+  if (bytes > ctx->scratch_bytes) {
+    // a previous (smaller) buffer may still be referenced by in-flight kernels / captured graphs: keep it
+    // alive (leak-once) rather than free it under them
+    void* p = nullptr;
+    size_t want = (bytes + (1u << 20) - 1) & ~(size_t)((1u << 20) - 1);
+    UGN_CUDA(cudaMalloc(&p, want));
+    ctx->scratch = p;
+    ctx->scratch_bytes = want;
+  }
+  *out = ctx->scratch;
+  return UGN_OK;
+}
+
 extern "C" int ugn_abi_version(void) { return UGN_ABI_VERSION; }
 extern "C" const char* ugn_last_error(void) { return g_last_error.c_str(); }
 

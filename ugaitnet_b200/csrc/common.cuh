@@ -29,7 +29,13 @@ struct ugn_ctx {
   // and every kernel that consumes them multiplies its f32 output by 1/s (fp16 range management;
   // lives in device memory so that a captured CUDA graph picks up each step's value)
   float* gscale = nullptr;
+  // grow-only device scratch (split-K partial sums of small convolutions); sized on first use, i.e. in
+  // the warm-up step before any CUDA-graph capture
+  void* scratch = nullptr;
+  size_t scratch_bytes = 0;
 };
+
+int ugn_scratch(ugn_ctx* ctx, size_t bytes, void** out);
 
 void ugn_set_error(const char* fmt, ...);
 

@@ -688,3 +688,23 @@ int ew_gscale_update(ugn_ctx* ctx, const float* ref, long long n, float target, 
   UGN_LAUNCHED(ctx);
   return UGN_OK;
 }
+
+// split-K epilogue of a small convolution: f32 partial sums [rows][cols] -> act(acc + bias) -> 16-bit planes
+__global__ void bias_act_split16_kernel(const float* __restrict__ acc, const float* __restrict__ bias,
+                                        u16* __restrict__ out, long long n, int cols, int P, int f16, int act,
+                                        float alpha) {
+  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < n; e += (long long)gridDim.x * blockDim.x) {
+    float v = ugn_act_fwd(acc[e] + (bias ? bias[e % cols] : 0.f), act, alpha);
+    u16 hi, lo;
+    ugn_split16(v, f16, hi, lo);
+    out[e] = hi;
+    if (P == 2) out[n + e] = lo;
+  }
+}
+int ew_bias_act_split16(ugn_ctx* ctx, const float* acc, const float* bias, __nv_bfloat16* out, long long rows,
+                        int cols, int P, int f16, int act, float alpha, cudaStream_t st) {
+  long long n = rows * cols;
+  bias_act_split16_kernel<<<grid_for(ctx, n, 256), 256, 0, st>>>(acc, bias, out, n, cols, P, f16, act, alpha);
+  UGN_LAUNCHED(ctx);
+  return UGN_OK;
+}

@@ -252,6 +252,9 @@ int simt_conv_wgrad(ugn_ctx* ctx, const ConvGeom& g, const float* x, const float
   return UGN_OK;
 }
 
+int ew_bias_act_mask(ugn_ctx* ctx, float* y, const float* bias, const float* mask, long long rows, int cols,
+                     int act, float alpha, cudaStream_t st);
+
 int simt_linear_fwd(ugn_ctx* ctx, int B, int N, int K, const float* x, const float* w,
                     const float* bias, const float* mask, float* y, int act, float alpha,
                     cudaStream_t st) {
@@ -259,7 +262,19 @@ int simt_linear_fwd(ugn_ctx* ctx, int B, int N, int K, const float* x, const flo
   p.A = x; p.B = w; p.C = y;
   p.M = B; p.N = N; p.K = K;
   p.ar = radix1(K); p.ak = radix1(1); p.br = radix1(K); p.bk = radix1(1);
-  p.bias = bias; p.mask = mask; p.act = act; p.alpha = alpha; p.ldc = N;
+  p.ldc = N;
+  // few output tiles but a long reduction (the "classprob" head: 96 x 150 x 2048): spread K over the SMs
+  // (split-K, red.add into zeroed y) and apply bias / activation / dropout mask in a post pass
+  const int blocks = ugn_cdiv(B, TBM) * ugn_cdiv(N, TBN);
+  if (blocks * 4 <= ctx->sm_count && K >= 512) {
+    p.ksplit = std::max(1, std::min(2 * ctx->sm_count / blocks, K / 64));
+    p.epi = EPI_ATOMIC;
+    UGN_CUDA(cudaMemsetAsync(y, 0, sizeof(float) * (size_t)B * N, st));
+    int rc = simt_gemm_launch(ctx, p, st);
+    if (rc != UGN_OK) return rc;
+    return ew_bias_act_mask(ctx, y, bias, mask, B, N, act, alpha, st);
+  }
+  p.bias = bias; p.mask = mask; p.act = act; p.alpha = alpha;
   return simt_gemm_launch(ctx, p, st);
 }
 

@@ -57,6 +57,22 @@ struct TcParams {
   int cps, nslots, ngroups;   // channel chunks per patch slot, patch slots (1 | 2), groups per tile = ncc / cps
 };
 
+// 16-byte vector reduction (sm_90+): one red.global.add.v4.f32 instead of four scalar atomics
+__device__ __forceinline__ void red_add_v4(float* dst, float a, float b, float c, float d) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+// 16 accumulator columns -> global red.add; vector form when the destination run is 16-byte aligned
+__device__ __forceinline__ void red_add_16(float* dst, const float* v, float os, int nvalid) {
+  if (nvalid >= 16 && (reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
+#pragma unroll
+    for (int i = 0; i < 16; i += 4) red_add_v4(dst + i, v[i] * os, v[i + 1] * os, v[i + 2] * os, v[i + 3] * os);
+  } else {
+#pragma unroll
+    for (int i = 0; i < 16; ++i)
+      if (i < nvalid) atomicAdd(dst + i, v[i] * os);
+  }
+}
+
 static constexpr int kThreads = 192;
 static constexpr int kTmemCols = 256;
 
@@ -76,6 +92,10 @@ __device__ __forceinline__ void conv_tile_epilogue(const TcParams& p, uint8_t* s
       for (int c0 = 0; c0 < p.block_n; c0 += 16) {
         tmem_ld16(trow + c0, v);
         if (!rv) continue;
+        if (p.epi == EPI_F32_ATOMIC) {
+          red_add_16(p.out_f32 + obase + n0 + c0, v, os, p.Cout - (n0 + c0));
+          continue;
+        }
         if (p.epi == EPI_F32 && (p.Cout & 3) == 0 && n0 + c0 + 16 <= p.Cout) {
           float* dst = p.out_f32 + obase + n0 + c0;
 #pragma unroll
@@ -296,6 +316,10 @@ __global__ void __launch_bounds__(kThreads, 1) tc_kernel(const __grid_constant__
       for (int c0 = 0; c0 < p.block_n; c0 += 16) {
         tmem_ld16(trow + c0, v);
         if (!ok || m >= p.M) continue;
+        if (p.epi == EPI_F32_ATOMIC) {
+          red_add_16(p.out_f32 + (long long)m * p.ldc + n0 + c0, v, os, p.N - (n0 + c0));
+          continue;
+        }
         if (vec && n0 + c0 + 16 <= p.N) {
           float* dst = p.out_f32 + (long long)m * p.ldc + n0 + c0;
 #pragma unroll
@@ -336,9 +360,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_kernel(const __grid_constant__
         const int chunk = gb % p.nch, tap = gb / p.nch;
         const int cib = chunk * p.cw + (c0 % p.cw);
         float* dst = p.out_f32 + ((long long)co * p.ntaps + tap) * p.Cin;
-#pragma unroll
-        for (int i = 0; i < 16; ++i)
-          if (cib + i < p.Cin) atomicAdd(dst + cib + i, v[i] * os);
+        red_add_16(dst + cib, v, os, p.Cin - cib);
       }
     }
     fence_before_sync();
@@ -674,9 +696,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_wgradv_kernel(const __grid_con
         const int tap = sg.kh * p.KW + sg.kw0 + c0 / p.cw;
         const int cib = sg.chunk * p.cw + (c0 % p.cw);
         float* dst = p.dw + ((long long)co * p.ntaps + tap) * p.Cin;
-#pragma unroll
-        for (int i = 0; i < 16; ++i)
-          if (cib + i < p.Cin) atomicAdd(dst + cib + i, v[i] * os);
+        red_add_16(dst + cib, v, os, p.Cin - cib);
       }
     }
     fence_before_sync();
@@ -914,6 +934,9 @@ static int convp_launch(ugn_ctx* ctx, TcParams& p, const __nv_bfloat16* act, int
   return UGN_OK;
 }
 
+int ew_bias_act_split16(ugn_ctx* ctx, const float* acc, const float* bias, __nv_bfloat16* out, long long rows,
+                        int cols, int P, int f16, int act, float alpha, cudaStream_t st);
+
 int tc_conv_fwd(ugn_ctx* ctx, const ConvGeom& g, int P, int f16, const __nv_bfloat16* x, const __nv_bfloat16* w,
                 const float* bias, __nv_bfloat16* y, uint8_t* idx, int act, float alpha, int pool,
                 cudaStream_t st) {
@@ -951,6 +974,20 @@ int tc_conv_fwd(ugn_ctx* ctx, const ConvGeom& g, int P, int f16, const __nv_bflo
   p.ntx = ugn_cdiv(Wn, p.bw); p.nty = ugn_cdiv(Hn, p.bh);
   if ((rc = act_map(ctx, p.a, x, P, g.B, g.H, g.W, g.Cp, cbox, p.bw, p.bh, p.bn, 0, 1, 128)) != UGN_OK) return rc;
   dim3 grid(p.ntx * p.nty * ugn_cdiv(g.B, p.bn), ugn_cdiv(g.Co, p.block_n), 1);
+  const int tiles = grid.x * grid.y;
+  if (!pool && tiles * 2 <= ctx->sm_count && p.ksteps_total >= 8 && !getenv("UGN_NO_CONV_SPLITK")) {
+    // few output tiles, long reduction (conv4: 3x3 maps, K = 2048): split the (tap, channel-chunk) steps
+    // over the SMs into f32 partial sums (red.add), then bias + activation + 16-bit split in a post pass
+    const long long rows = (long long)g.B * g.Ho * g.Wo;
+    void* scratch = nullptr;
+    if ((rc = ugn_scratch(ctx, sizeof(float) * rows * g.Co, &scratch)) != UGN_OK) return rc;
+    UGN_CUDA(cudaMemsetAsync(scratch, 0, sizeof(float) * rows * g.Co, st));
+    p.ksplit = std::max(1, std::min(ctx->sm_count / tiles, p.ksteps_total / 4));
+    p.epi = EPI_F32_ATOMIC; p.out_f32 = reinterpret_cast<float*>(scratch);
+    grid.z = p.ksplit;
+    if ((rc = launch<MODE_CONV>(ctx, p, grid, st)) != UGN_OK) return rc;
+    return ew_bias_act_split16(ctx, reinterpret_cast<float*>(scratch), bias, y, rows, g.Co, P, f16, act, alpha, st);
+  }
   return launch<MODE_CONV>(ctx, p, grid, st);
 }
 
@@ -987,6 +1024,13 @@ int tc_conv_dgrad(ugn_ctx* ctx, const ConvGeom& g, int P, int f16, const __nv_bf
   p.ntx = ugn_cdiv(g.W, p.bw); p.nty = ugn_cdiv(g.H, p.bh);
   if ((rc = act_map(ctx, p.a, dz, P, g.B, g.Ho, g.Wo, g.Co, 64, p.bw, p.bh, p.bn, 0, 1, 128)) != UGN_OK) return rc;
   dim3 grid(p.ntx * p.nty * ugn_cdiv(g.B, p.bn), ugn_cdiv(g.Cp, p.block_n), 1);
+  const int tiles = grid.x * grid.y;
+  if (tiles * 2 <= ctx->sm_count && p.ksteps_total >= 8 && !getenv("UGN_NO_CONV_SPLITK")) {
+    p.ksplit = std::max(1, std::min(ctx->sm_count / tiles, p.ksteps_total / 4));
+    p.epi = EPI_F32_ATOMIC;
+    grid.z = p.ksplit;
+    UGN_CUDA(cudaMemsetAsync(dx, 0, sizeof(float) * (size_t)g.B * g.H * g.W * g.Cp, st));
+  }
   return launch<MODE_CONV>(ctx, p, grid, st);
 }
 

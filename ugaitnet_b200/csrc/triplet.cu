@@ -126,14 +126,21 @@ __global__ void __launch_bounds__(256) trip_bwd_kernel(const float* __restrict__
   }
   __syncthreads();
   const float* X = emb + (long long)n * B * d;
-  for (int j = threadIdx.x; j < d; j += blockDim.x) {
-    float xa = X[(long long)a * d + j], g = 0.f;
-    for (int b = 0; b < B; ++b) {
-      float cb = coef[b];
-      if (cb != 0.f) g = fmaf(cb, xa - X[(long long)b * d + j], g);
-    }
-    demb[((long long)n * B + a) * d + j] = s * g;
+  // blockIdx.z slices the feature axis (256 features per block) so that B x d/256 blocks fill the SMs;
+  // four independent accumulators hide the L2 latency of the row sweep
+  const int j = blockIdx.z * blockDim.x + threadIdx.x;
+  if (j >= d) return;
+  const float xa = X[(long long)a * d + j];
+  float g0 = 0.f, g1 = 0.f, g2 = 0.f, g3 = 0.f;
+  int b = 0;
+  for (; b + 4 <= B; b += 4) {
+    g0 = fmaf(coef[b], xa - X[(long long)b * d + j], g0);
+    g1 = fmaf(coef[b + 1], xa - X[(long long)(b + 1) * d + j], g1);
+    g2 = fmaf(coef[b + 2], xa - X[(long long)(b + 2) * d + j], g2);
+    g3 = fmaf(coef[b + 3], xa - X[(long long)(b + 3) * d + j], g3);
   }
+  for (; b < B; ++b) g0 = fmaf(coef[b], xa - X[(long long)b * d + j], g0);
+  demb[((long long)n * B + a) * d + j] = s * ((g0 + g1) + (g2 + g3));
 }
 
 extern "C" int64_t ugn_triplet_workspace_bytes(int n, int B) {
@@ -197,7 +204,7 @@ extern "C" int ugn_triplet_all(ugn_ctx* ctx, const ugn_tensor* emb, const ugn_te
   trip_finalize_kernel<<<1, 32, 0, st>>>(acc, n, ugn_ptr<float>(out));
   UGN_LAUNCHED(ctx);
   if (demb) {
-    trip_bwd_kernel<<<dim3(B, n), 256, B * sizeof(float), st>>>(X, D, Wc, acc, ugn_ptr<float>(demb), n, B, d, scale);
+    trip_bwd_kernel<<<dim3(B, n, ugn_cdiv(d, 256)), 256, B * sizeof(float), st>>>(X, D, Wc, acc, ugn_ptr<float>(demb), n, B, d, scale);
     UGN_LAUNCHED(ctx);
   }
   return UGN_OK;
