@@ -13,7 +13,7 @@ static inline int grid_for(ugn_ctx* ctx, long long work_items, int block) {
 // a0: NCHW f32 -> NHWC (f32 | bf16 P planes), channel padding zero-filled.
 // One block per (b, y): coalesced row reads, smem transpose, coalesced channel-run writes.
 // ---------------------------------------------------------------------------------------
-template <int MODE>  // 0 f32, 1 bf16 P=1, 2 bf16 P=2
+template <int MODE>  // 0 f32, 1 16-bit P=1, 2 16-bit P=2
 __global__ void pack_input_kernel(const float* __restrict__ x, void* __restrict__ out, int B, int C,
                                   int H, int W, int Cp, long long plane, int f16) {
   extern __shared__ float sm[];  // [C][W+1]
@@ -25,6 +25,23 @@ __global__ void pack_input_kernel(const float* __restrict__ x, void* __restrict_
   }
   __syncthreads();
   long long obase = ((long long)b * H + y) * W * Cp;
+  if (MODE != 0 && (Cp & 7) == 0) {
+    // 8 channels per thread: one 16-byte store per plane
+    const int C8 = Cp >> 3;
+    u16* o = reinterpret_cast<u16*>(out);
+    for (int e = threadIdx.x; e < W * C8; e += blockDim.x) {
+      const int xx = e / C8, c0 = (e % C8) * 8;
+      __align__(16) u16 hi[8], lo[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float v = (c0 + i) < C ? sm[(c0 + i) * (W + 1) + xx] : 0.f;
+        ugn_split16(v, f16, hi[i], lo[i]);
+      }
+      *reinterpret_cast<uint4*>(o + obase + (long long)e * 8) = *reinterpret_cast<const uint4*>(hi);
+      if (MODE == 2) *reinterpret_cast<uint4*>(o + plane + obase + (long long)e * 8) = *reinterpret_cast<const uint4*>(lo);
+    }
+    return;
+  }
   for (int e = threadIdx.x; e < W * Cp; e += blockDim.x) {
     int xx = e / Cp, c = e % Cp;
     float v = c < C ? sm[c * (W + 1) + xx] : 0.f;

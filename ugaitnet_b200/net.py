@@ -105,11 +105,15 @@ class UGaitEngine:
         self.segs = {s.name: s for s in segs}
         self.seg_list = segs
         self.n_arena = off
-        # all-reduce buckets: one per branch (its backward finishes as a unit) + the heads
+        # all-reduce buckets: per branch one for the dense layers (92 % of the gradient bytes; complete
+        # right after the two dense backward GEMMs, so their all-reduce overlaps the conv backward of the
+        # same branch) and one for the conv layers (complete when the branch's backward ends); + the heads
         self.buckets = {}
         for m in range(cfg.nmods):
             mine = [s for s in segs if s.name.startswith(BRANCH_NAMES[m] + "/")]
-            self.buckets[m] = (mine[0].off, round_up(mine[-1].off + mine[-1].n, 64))
+            dense0 = self.segs_off(segs, f"{BRANCH_NAMES[m]}/dense/w")
+            self.buckets[m] = (mine[0].off, dense0)
+            self.buckets[(m, "fc")] = (dense0, round_up(mine[-1].off + mine[-1].n, 64))
         heads = [s for s in segs if "/" in s.name and s.name.split("/")[0] in ("code", "classprob")]
         self.buckets["heads"] = (heads[0].off, off) if heads else None
         d = self.dev
@@ -167,6 +171,10 @@ class UGaitEngine:
                     self._fused_pack.add(sg.name)
             self.pack_table = tab.to(d)
             self.R["pack_table"] = TRef(self.pack_table)
+
+    @staticmethod
+    def segs_off(segs, name):
+        return next(s.off for s in segs if s.name == name)
 
     def repack_weights(self, after_optim: bool = False):
         """master f32 -> padded / 16-bit compute copies.  After an optimiser step only the padded (conv)
@@ -373,6 +381,7 @@ class UGaitEngine:
             check(lib.ugn_linear_bwd(h, R["flat"].ptr, self.Rcw[f"{bn}/dense/w"].ptr,
                                      (R["dz1_16"] if self.P else R["dz1"]).ptr, R["dflat"].ptr,
                                      self.Rg[f"{bn}/dense/w"].ptr, self.Rg[f"{bn}/dense/b"].ptr, st))
+            self._reduce_bucket((m, "fc"))
             nl = len(b.layers)
             check(lib.ugn_unflatten_chw(h, R["dflat"].ptr, R[f"da{nl}"].ptr, st))
             for li in range(nl - 1, -1, -1):
