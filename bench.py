@@ -213,6 +213,7 @@ def main():
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-knn", action="store_true")
     ap.add_argument("--lite", action="store_true", help="timed steps only (for runs under ncu)")
+    ap.add_argument("--knn-only", action="store_true", help="only the open-world k-NN leg (development aid)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
 
@@ -229,6 +230,14 @@ def main():
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         torch.distributed.init_process_group("nccl", device_id=torch.device("cuda", local))
         pg = torch.distributed.group.WORLD
+
+    if args.knn_only:
+        kn = knn_leg(peaks(), rank, world, pg)
+        if rank == 0:
+            print(json.dumps({"knn": kn}), flush=True)
+        if world > 1:
+            torch.distributed.destroy_process_group()
+        return
 
     from ugaitnet_b200.net import UGaitEngine
     eng = UGaitEngine(engine_cfg(), device=local, math_mode=args.mode, lr=1e-4, process_group=pg,
@@ -365,45 +374,95 @@ def main():
                                 "mma_passes": passes, "issued_frac": ach * passes / pk["tf_sust"],
                                 "peak_source": pk["src"] + " bf16 sustained"}
             line["cpu_baseline"] = cpu_baseline_leg()
-            if not args.no_knn:
-                line["knn"] = knn_leg(pk)
+        if not args.no_knn and world == 1:
+            line["knn"] = knn_leg(pk)
+    if world > 1 and not args.no_knn:
+        kn = knn_leg(peaks(), rank, world, pg)          # collective: every rank searches its gallery shard
+        if rank == 0:
+            line["knn"] = kn
+    if rank == 0:
         print(json.dumps(line), flush=True)
     if world > 1:
         torch.distributed.destroy_process_group()
 
 
-def knn_leg(pk):
-    """k=3 queries/s over a synthetic gallery (cfg5 shape scaled to one GPU)."""
-    from ugaitnet_b200.knn import KNeighborsClassifier
-    rng = np.random.default_rng(5)
-    N, D, Q, k = 200_000, 256, 256, 3
-    cent = rng.normal(size=(155, D)).astype(np.float32)
-    lab = rng.integers(0, 155, N).astype(np.int32)
-    G = cent[lab] + 0.35 * rng.normal(size=(N, D)).astype(np.float32)
-    G /= np.linalg.norm(G, axis=1, keepdims=True)
-    Qm = G[rng.integers(0, N, Q)] + 0.05 * rng.normal(size=(Q, D)).astype(np.float32)
-    clf = KNeighborsClassifier(n_neighbors=k).fit(G, lab)
-    qd = torch.from_numpy(Qm).cuda()
-    clf.predict_device(qd)
-    torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(5):
-        pred = clf.predict_device(qd)
-    e1.record()
-    torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1) / 5
-    out = {"queries_per_s": Q / (ms * 1e-3), "ms": ms, "N": N, "D": D, "Q": Q, "k": k}
-    try:
-        from sklearn.neighbors import KNeighborsClassifier as SK
-        sk = SK(n_neighbors=k).fit(G, lab)
-        t0 = time.perf_counter()
-        sp = sk.predict(Qm)
-        dt = time.perf_counter() - t0
-        out["cpu_sklearn_queries_per_s"] = Q / dt
-        out["labels_equal_sklearn"] = bool((sp == pred.cpu().numpy()).all())
-    except Exception as e:  # pragma: no cover
-        out["cpu_sklearn_error"] = str(e)
+def knn_leg(pk, rank=0, world=1, pg=None):
+    """Open-world test (BASELINE cfg5): k=3 queries/s over a synthetic 1 M x 256 gallery of L2-normalised
+    descriptors clustered around 155 class centroids (0.1 % exact duplicate rows), row-sharded over the
+    ranks; Q = 4096 (tensor-bound) and Q = 64 (gallery-streaming, HBM-bound)."""
+    from ugaitnet_b200.knn import KNeighborsClassifier, shard_bounds
+    N, D, k = 1_000_000, 256, 3
+    lo, hi = shard_bounds(N, rank, world)
+    g = torch.Generator(device="cuda").manual_seed(5)          # same stream on every rank -> same gallery
+    cent = torch.randn(155, D, device="cuda", generator=g)
+    lab_all = torch.randint(0, 155, (N,), device="cuda", generator=g, dtype=torch.int32)
+    G = torch.empty(hi - lo, D, device="cuda")
+    for s in range(0, N, 125_000):                             # generate the full stream, keep this rank's rows
+        blk = cent[lab_all[s:s + 125_000].long()] + 0.35 * torch.randn(125_000, D, device="cuda", generator=g)
+        blk = blk / blk.norm(dim=1, keepdim=True)
+        a, b = max(s, lo), min(s + 125_000, hi)
+        if a < b:
+            G[a - lo:b - lo] = blk[a - s:b - s]
+    dup = torch.arange(0, hi - lo - 1, 1000, device="cuda")
+    G[dup + 1] = G[dup]                                        # exact duplicates (distance ties)
+    lab = lab_all[lo:hi].contiguous()
+    Qall = torch.randn(4096, D, device="cuda", generator=g) * 0.05
+    Qall += cent[torch.randint(0, 155, (4096,), device="cuda", generator=g)] + 0.3 * torch.randn(4096, D, device="cuda", generator=g)
+    Qall = Qall / Qall.norm(dim=1, keepdim=True)
+    clf = KNeighborsClassifier(n_neighbors=k, process_group=pg).fit(G, lab, idx_base=lo, sharded=True)
+    out = {"N": N, "D": D, "k": k, "gallery_rows_per_gpu": hi - lo, "scan": "tcgen05 fp16 hi/lo 3-pass + fused top-k"
+           if clf.use_tc else "simt fp32"}
+
+    def timed(fn, reps):
+        fn()
+        if world > 1:
+            torch.distributed.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            r = fn()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / reps
+        if world > 1:
+            t = torch.tensor([ms], device="cuda")
+            torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+            ms = float(t)
+        return ms, r
+
+    for Q in (4096, 64):
+        qd = Qall[:Q].contiguous()
+        ms, pred = timed(lambda: clf.predict_device(qd), 5)
+        flops = 2.0 * Q * N * D
+        gal_bytes = (hi - lo) * clf.dp * 4 if clf.use_tc else (hi - lo) * D * 4
+        out[f"Q{Q}"] = {"queries_per_s": Q / (ms * 1e-3), "ms": ms, "flagged_exact_recompute": clf.flagged_queries(),
+                        "algorithmic_tflops": flops / (ms * 1e-3) / 1e12,
+                        "tensor_frac_of_peak": flops / (ms * 1e-3) / 1e12 / pk["tf_sust"],
+                        "gallery_GBps_per_gpu": gal_bytes / (ms * 1e-3) / 1e9, "hbm_frac_of_peak": gal_bytes / (ms * 1e-3) / 1e9 / pk["hbm"]}
+    # end to end: pinned host queries -> labels on the host
+    hq = Qall.cpu().pin_memory()
+    hp = torch.empty(4096, dtype=torch.int32).pin_memory()
+
+    def e2e():
+        hp.copy_(clf.predict_device(hq.cuda(non_blocking=True)), non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+    ms, _ = timed(e2e, 3)
+    out["e2e_Q4096"] = {"queries_per_s": 4096 / (ms * 1e-3), "ms": ms, "h2d_bytes": 4096 * D * 4, "d2h_bytes": 4096 * 4}
+    out["queries_per_s"] = out["Q4096"]["queries_per_s"]
+    if rank == 0 and world == 1:
+        try:   # the reference's exact call on the host cores, bounded sample of the same queries
+            from sklearn.neighbors import KNeighborsClassifier as SK
+            Gh, yh, Qh = G.cpu().numpy(), lab.cpu().numpy(), Qall[:128].cpu().numpy()
+            sk = SK(n_neighbors=k).fit(Gh, yh)
+            t0 = time.perf_counter()
+            sp = sk.predict(Qh)
+            dt = time.perf_counter() - t0
+            pred128 = clf.predict(Qall[:128])
+            out["cpu_sklearn"] = {"queries_per_s": 128 / dt, "cores": os.cpu_count(), "sample": "128 of the 4096 queries, full 1 M x 256 gallery",
+                                  "labels_equal": bool((sp == pred128).all())}
+        except Exception as e:  # pragma: no cover
+            out["cpu_sklearn_error"] = str(e)
     return out
 
 

@@ -210,11 +210,26 @@ int ugn_sgd_step(ugn_ctx*, ugn_tensor* w, const ugn_tensor* g, ugn_tensor* v,
  * Stage 2 (ugn_knn_merge_vote): merges G shards' [G,Q,k] candidate lists with the same
  *   ordering and votes (uniform weights, ties -> smallest label). pred i32 [Q]. */
 int64_t ugn_knn_workspace_bytes(int64_t Q, int64_t N, int64_t D, int k);
-/* clf.fit(): per-row squared norms of the gallery shard, g2 f32 [N] (computed once). */
-int ugn_knn_gallery_norms(ugn_ctx*, const ugn_tensor* gallery, ugn_tensor* g2, void* stream);
+/* clf.fit(): per-row squared norms of the gallery shard.  g2 f32 [Npad >= N]: rows >= N are set to
+ * +inf (padding for the tensor-core scan, which wants Npad = roundup(N,256)); gmax2 f32 [1]
+ * (nullable) receives max_row |g|^2. */
+int ugn_knn_gallery_norms(ugn_ctx*, const ugn_tensor* gallery, ugn_tensor* g2, ugn_tensor* gmax2,
+                          void* stream);
+/* SIMT (fp32 FFMA) candidate scan + exact re-rank. */
 int ugn_knn_topk(ugn_ctx*, const ugn_tensor* queries, const ugn_tensor* gallery, const ugn_tensor* g2,
                  const ugn_tensor* gallery_labels, int k, int64_t idx_base, ugn_tensor* out_d2,
                  ugn_tensor* out_idx, ugn_tensor* out_lab, ugn_tensor* workspace, void* stream);
+/* Tensor-core candidate scan: the distance GEMM Q.G^T on tcgen05 (fp16 hi/lo planes q16 [2,Q,Dp],
+ * g16 [2,N,Dp] made with ugn_pack_weight; Dp % 8 == 0) with the top-KC filter fused into the GEMM
+ * epilogue, then the same exact fp64 re-rank.  The re-rank PROVES per query that the true top-k lie
+ * inside the candidate set (error bound of the split-fp16 GEMM vs the KC-th candidate score); queries
+ * that fail the proof are flagged (flags i32 [Q], output) and recomputed by brute force in fp64, so
+ * indices / labels are bit-exact in every case. */
+int ugn_knn_topk_tc(ugn_ctx*, const ugn_tensor* queries, const ugn_tensor* q16,
+                    const ugn_tensor* gallery, const ugn_tensor* g16, const ugn_tensor* g2,
+                    const ugn_tensor* gmax2, const ugn_tensor* gallery_labels, int k, int64_t idx_base,
+                    ugn_tensor* out_d2, ugn_tensor* out_idx, ugn_tensor* out_lab, ugn_tensor* flags,
+                    ugn_tensor* workspace, void* stream);
 int ugn_knn_merge_vote(ugn_ctx*, const ugn_tensor* d2, const ugn_tensor* idx,
                        const ugn_tensor* lab, int k, ugn_tensor* out_d2, ugn_tensor* out_idx,
                        ugn_tensor* out_lab, ugn_tensor* pred, void* stream);

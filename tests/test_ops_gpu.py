@@ -259,6 +259,66 @@ def test_knn_bit_exact_vs_oracle_and_sklearn_golden(ctx, golden_dir, name):
     assert np.array_equal(pred[nb], z["pred"][nb])      # == sklearn wherever sklearn is well defined
 
 
+@pytest.mark.parametrize("N,D,Q,k", [(5000, 100, 37, 3), (20000, 256, 300, 7), (3000, 64, 130, 20), (70000, 32, 64, 3),
+                                     (6000, 328, 150, 3)])   # D > 256: streaming-query variant
+def test_knn_tensor_core_scan_bit_exact(ctx, N, D, Q, k):
+    """tcgen05 distance GEMM + fused top-k (ugn_knn_topk_tc) against the C oracle: clustered unit-norm
+    descriptors with exact duplicates (distance ties), ragged N / D / Q (not multiples of the tiles)."""
+    from ugaitnet_b200.knn import KNeighborsClassifier
+    if not ctx.has_tcgen05:
+        pytest.skip("needs sm_100")
+    rng = np.random.default_rng(N + D)
+    cent = rng.normal(size=(31, D)).astype(np.float32)
+    y = rng.integers(0, 31, N).astype(np.int32)
+    G = cent[y] + 0.3 * rng.normal(size=(N, D)).astype(np.float32)
+    G /= np.linalg.norm(G, axis=1, keepdims=True)
+    dup = rng.integers(0, N, N // 50)
+    G[dup] = G[(dup * 7 + 3) % N]                       # exact duplicate rows -> distance ties
+    Qm = G[rng.integers(0, N, Q)] + 0.05 * rng.normal(size=(Q, D)).astype(np.float32)
+    Qm[: Q // 4] = G[rng.integers(0, N, Q // 4)]        # queries that ARE gallery rows (distance 0)
+    clf = KNeighborsClassifier(n_neighbors=k).fit(G, y)
+    assert clf.use_tc
+    pred = clf.predict(Qm)
+    d2, idx = clf.kneighbors_exact(Qm)
+    od2, oidx = O.knn_search(G, Qm, k)
+    assert np.array_equal(idx, oidx)
+    assert np.array_equal(pred, O.knn_vote(y[oidx]))
+    assert np.allclose(d2, od2, rtol=1e-12, atol=1e-15)
+    ctx.check()
+    print(f"[knn-tc N={N} D={D} Q={Q} k={k}] flagged (recomputed exactly): {clf.flagged_queries()} of {Q}")
+    assert clf.flagged_queries() <= Q // 4 + Q // 10    # the proof may fail on zero-distance / duplicate queries only
+
+
+def test_knn_exact_fallback_path(ctx):
+    """Gallery made of near-identical rows: the containment proof cannot separate k-th from KC-th
+    neighbour, every query is flagged and the fp64 brute-force kernel must still be bit-exact."""
+    from ugaitnet_b200.knn import KNeighborsClassifier
+    if not ctx.has_tcgen05:
+        pytest.skip("needs sm_100")
+    rng = np.random.default_rng(9)
+    base = rng.normal(size=(1, 48)).astype(np.float32)
+    G = (base + 1e-6 * rng.normal(size=(4000, 48))).astype(np.float32)
+    y = rng.integers(0, 5, 4000).astype(np.int32)
+    Qm = (base + 1e-6 * rng.normal(size=(20, 48))).astype(np.float32)
+    clf = KNeighborsClassifier(n_neighbors=3).fit(G, y)
+    d2, idx = clf.kneighbors_exact(Qm)
+    od2, oidx = O.knn_search(G, Qm, 3)
+    assert clf.flagged_queries() > 0
+    assert np.array_equal(idx, oidx) and np.allclose(d2, od2, rtol=1e-12, atol=1e-18)
+
+
+def test_knn_simt_scan_still_bit_exact(ctx, golden_dir, monkeypatch):
+    from ugaitnet_b200.knn import KNeighborsClassifier
+    monkeypatch.setenv("UGN_KNN_SIMT", "1")
+    z = np.load(os.path.join(golden_dir, "knn_dups.npz"))
+    k = int(z["k"])
+    clf = KNeighborsClassifier(n_neighbors=k).fit(z["G"], z["y"])
+    assert not clf.use_tc
+    _, idx = clf.kneighbors_exact(z["Q"])
+    _, oidx = O.knn_search(z["G"], z["Q"], k)
+    assert np.array_equal(idx, oidx)
+
+
 def test_knn_sharded_merge_equals_single(ctx, golden_dir):
     from ugaitnet_b200.knn import KNeighborsClassifier, knn_sharded_local
     z = np.load(os.path.join(golden_dir, "knn_dups.npz"))

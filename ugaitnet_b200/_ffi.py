@@ -68,7 +68,8 @@ _PROTOS = {
     "ugn_sgd_step": (c_int, [c_void_p, _T, _T, _T, _T, _T, c_float, c_float, c_float, _T, _T, _T, c_int, c_int,
                              c_void_p]),
     "ugn_knn_workspace_bytes": (c_int64, [c_int64, c_int64, c_int64, c_int]),
-    "ugn_knn_gallery_norms": (c_int, [c_void_p, _T, _T, c_void_p]),
+    "ugn_knn_gallery_norms": (c_int, [c_void_p, _T, _T, _T, c_void_p]),
+    "ugn_knn_topk_tc": (c_int, [c_void_p, _T, _T, _T, _T, _T, _T, _T, c_int, c_int64, _T, _T, _T, _T, _T, c_void_p]),
     "ugn_knn_topk": (c_int, [c_void_p, _T, _T, _T, _T, c_int, c_int64, _T, _T, _T, _T, c_void_p]),
     "ugn_knn_merge_vote": (c_int, [c_void_p, _T, _T, _T, c_int, _T, _T, _T, _T, c_void_p]),
     "ugn_gemm_bf16": (c_int, [c_void_p, _T, c_int, _T, c_int, _T, c_int, c_void_p]),

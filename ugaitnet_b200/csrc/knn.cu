@@ -41,15 +41,25 @@ __device__ __forceinline__ void list_insert(Cand* list, int kc, float s, int i) 
   list[p].i = i;
 }
 
-__global__ void knn_norms_kernel(const float* __restrict__ G, long long N, int D, float* __restrict__ g2) {
+// g2[row] = |g_row|^2 for row < N, +inf for the padding rows N <= row < Npad (the tensor-core scan reads
+// whole 256-row strips; +inf keeps padding rows out of every candidate list); gmax2 = max_row |g|^2.
+__global__ void knn_norms_kernel(const float* __restrict__ G, long long N, long long Npad, int D,
+                                 float* __restrict__ g2, unsigned* __restrict__ gmax2) {
   long long row = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
   int lane = threadIdx.x & 31;
-  if (row >= N) return;
+  if (row >= Npad) return;
+  if (row >= N) {
+    if (lane == 0) g2[row] = INFINITY;
+    return;
+  }
   const float* g = G + row * D;
   float s = 0.f;
   for (int j = lane; j < D; j += 32) s = fmaf(g[j], g[j], s);
   s = warp_sum(s);
-  if (lane == 0) g2[row] = s;
+  if (lane == 0) {
+    g2[row] = s;
+    if (gmax2 && s > 0.f && s < INFINITY) atomicMax(gmax2, __float_as_uint(s));
+  }
 }
 
 // dynamic smem layout (bytes): top[TQ][kc] Cand | buf[TQ][CB] Cand | As | Bs | cnt[TQ] | thr[TQ]
@@ -150,8 +160,11 @@ __global__ void __launch_bounds__(256) knn_rerank_kernel(const float* __restrict
                                                          int k, int D, long long idx_base,
                                                          double* __restrict__ out_d2,
                                                          long long* __restrict__ out_idx,
-                                                         int* __restrict__ out_lab) {
+                                                         int* __restrict__ out_lab,
+                                                         const float* __restrict__ gmax2, int Dp,
+                                                         int* __restrict__ flags) {
   __shared__ Cand sel[KNN_MAXKC];
+  __shared__ double q2s;
   __shared__ double ex[KNN_MAXKC];
   __shared__ float rs[8];
   __shared__ int ri[8], rp[8];
@@ -185,8 +198,15 @@ __global__ void __launch_bounds__(256) knn_rerank_kernel(const float* __restrict
     ps = sel[round].s;
     pi = sel[round].i;
   }
+  const float ps_last = (pi == 0x7fffffff) ? FLT_MAX : ps;   // KC-th best approximate score (tau)
   // exact fp64 distances, one warp per candidate
   const float* qv = Qm + (long long)q * D;
+  if (flags && t < 32) {
+    double s = 0.0;
+    for (int j = t; j < D; j += 32) s = fma((double)qv[j], (double)qv[j], s);
+    s = warp_sum_d(s);
+    if (t == 0) q2s = s;
+  }
   for (int c = t >> 5; c < kc; c += 8) {
     int gi = sel[c].i;
     double s = 0.0;
@@ -206,6 +226,7 @@ __global__ void __launch_bounds__(256) knn_rerank_kernel(const float* __restrict
   if (t == 0) {
     // selection sort of <= 32 entries by (d2, idx)
     (void)rp;
+    double kth_d2 = 0.0;
     for (int j = 0; j < k; ++j) {
       int best = -1;
       for (int c = 0; c < kc; ++c) {
@@ -214,9 +235,31 @@ __global__ void __launch_bounds__(256) knn_rerank_kernel(const float* __restrict
       }
       int gi = sel[best].i;
       out_d2[(long long)q * k + j] = ex[best];
+      kth_d2 = ex[best];
       out_idx[(long long)q * k + j] = (gi == 0x7fffffff) ? -1 : idx_base + gi;
       out_lab[(long long)q * k + j] = (gi == 0x7fffffff) ? -1 : labels[gi];
       sel[best].i = -2;
+    }
+    if (flags) {
+      // Containment proof for the tensor-core candidate scan.  Every gallery row that is NOT a candidate
+      // has approximate score >= tau (the KC-th best approximate score over all chunks), hence exact
+      // score >= tau - eps.  If the exact k-th best candidate score is below that, no outsider can belong
+      // to the true top-k and the result is exact; otherwise the query is flagged and recomputed by
+      // brute force in fp64 (knn_exact_kernel).
+      //   eps: fp16 hi/lo split drops lo*lo and rounds lo (<= 2^-20 |q||g| in total), fp32 accumulation
+      //   of Dp terms (16-sigma random-walk bound), fp16 subnormal lo planes (2^-24 absolute per element),
+      //   the fp32 row norm (Dp/32+8 roundings) and the final fmaf.
+      const float tau = ps_last;
+      int bad = 0;
+      if (tau < FLT_MAX) {
+        const double qn = sqrt(q2s), gm2 = (double)*gmax2, gn = sqrt(gm2), sq = sqrt((double)Dp);
+        const double u = 5.9604644775390625e-08;  // 2^-24
+        double eps_dot = qn * gn * (16.0 * u + 16.0 * sq * u) + u * sq * (qn + gn);
+        double eps = 2.0 * eps_dot + gm2 * ((double)Dp / 32.0 + 8.0) * 2.0 * u + 4.0 * u * (gm2 + 2.0 * qn * gn);
+        const double sk = kth_d2 - q2s;          // exact score |g|^2 - 2 q.g of the k-th neighbour
+        bad = !(sk + eps < (double)tau);
+      }
+      flags[q] = bad;
     }
   }
 }
@@ -281,16 +324,23 @@ extern "C" int64_t ugn_knn_workspace_bytes(int64_t Q, int64_t N, int64_t D, int 
 }
 
 extern "C" int ugn_knn_gallery_norms(ugn_ctx* ctx, const ugn_tensor* gallery, ugn_tensor* g2,
-                                     void* stream) {
+                                     ugn_tensor* gmax2, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
   UGN_CHECK(ctx && gallery && g2, "ugn_knn_gallery_norms: null argument");
   UGN_TENSOR(gallery, DT_F32, 2, 2);
   UGN_TENSOR(g2, DT_F32, 1, 1);
-  long long N = gallery->shape[0];
+  long long N = gallery->shape[0], Npad = g2->shape[0];
   int D = (int)gallery->shape[1];
-  UGN_CHECK(g2->shape[0] == N, "g2 must be f32[N]");
-  if (N == 0) return UGN_OK;
-  knn_norms_kernel<<<ugn_cdiv(N * 32, 256), 256, 0, st>>>(ugn_ptr<float>(gallery), N, D, ugn_ptr<float>(g2));
+  UGN_CHECK(Npad >= N, "g2 must be f32[>= N]");
+  unsigned* gm = nullptr;
+  if (gmax2) {
+    UGN_TENSOR(gmax2, DT_F32, 1, 1);
+    gm = reinterpret_cast<unsigned*>(ugn_ptr<float>(gmax2));
+    UGN_CUDA(cudaMemsetAsync(gm, 0, sizeof(float), st));
+  }
+  if (Npad == 0) return UGN_OK;
+  knn_norms_kernel<<<ugn_cdiv(Npad * 32, 256), 256, 0, st>>>(ugn_ptr<float>(gallery), N, Npad, D,
+                                                              ugn_ptr<float>(g2), gm);
   UGN_LAUNCHED(ctx);
   return UGN_OK;
 }
@@ -316,7 +366,7 @@ extern "C" int ugn_knn_topk(ugn_ctx* ctx, const ugn_tensor* queries, const ugn_t
   UGN_CHECK(k >= 1 && k <= KNN_MAXKC, "k must be in [1,%d]", KNN_MAXKC);
   UGN_CHECK(N >= k, "gallery shard has fewer rows (%lld) than k=%d", N, k);
   UGN_CHECK(N < 0x7fffffffLL, "gallery shard too large for 32-bit local indices");
-  UGN_CHECK(g2->shape[0] == N && gallery_labels->shape[0] == N, "g2/labels must have N entries");
+  UGN_CHECK(g2->shape[0] >= N && gallery_labels->shape[0] == N, "g2/labels must have N entries");
   UGN_CHECK(out_d2->shape[0] == Q && out_d2->shape[1] == k && out_idx->shape[0] == Q && out_idx->shape[1] == k &&
                 out_lab->shape[0] == Q && out_lab->shape[1] == k, "outputs must be [Q,k]");
   if (Q == 0) return UGN_OK;
@@ -339,7 +389,134 @@ extern "C" int ugn_knn_topk(ugn_ctx* ctx, const ugn_tensor* queries, const ugn_t
   knn_rerank_kernel<<<(int)Q, 256, 0, st>>>(ugn_ptr<float>(queries), ugn_ptr<float>(gallery),
                                             ugn_ptr<int>(gallery_labels), cands, chunks * kc, kc, k, D,
                                             idx_base, ugn_ptr<double>(out_d2), ugn_ptr<long long>(out_idx),
-                                            ugn_ptr<int>(out_lab));
+                                            ugn_ptr<int>(out_lab), nullptr, D, nullptr);
+  UGN_LAUNCHED(ctx);
+  return UGN_OK;
+}
+
+// ---------------------------------------------------------------------------------------
+// Exact recomputation of flagged queries: brute-force fp64 sum((q-g)^2) over the whole shard, one CTA
+// per query (CTAs of unflagged queries exit at once).  Same (distance, index) order as the re-rank.
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) knn_exact_kernel(const float* __restrict__ Qm, const float* __restrict__ Gm,
+                                                        const int* __restrict__ labels,
+                                                        const int* __restrict__ flags, long long N, int D, int k,
+                                                        long long idx_base, double* __restrict__ out_d2,
+                                                        long long* __restrict__ out_idx,
+                                                        int* __restrict__ out_lab) {
+  __shared__ double ld[8][KNN_MAXKC];
+  __shared__ int li[8][KNN_MAXKC];
+  const int q = blockIdx.x, t = threadIdx.x, w = t >> 5, lane = t & 31;
+  if (!flags[q]) return;
+  if (lane == 0)
+    for (int j = 0; j < k; ++j) { ld[w][j] = DBL_MAX; li[w][j] = 0x7fffffff; }
+  __syncwarp();
+  const float* qv = Qm + (long long)q * D;
+  for (long long gi = w; gi < N; gi += 8) {
+    const float* gv = Gm + gi * D;
+    double s = 0.0;
+    for (int j = lane; j < D; j += 32) {
+      double df = (double)qv[j] - (double)gv[j];
+      s = fma(df, df, s);
+    }
+    s = warp_sum_d(s);
+    if (lane == 0) {
+      int ii = (int)gi;
+      if (s < ld[w][k - 1] || (s == ld[w][k - 1] && ii < li[w][k - 1])) {
+        int p = k - 1;
+        while (p > 0 && (s < ld[w][p - 1] || (s == ld[w][p - 1] && ii < li[w][p - 1]))) {
+          ld[w][p] = ld[w][p - 1]; li[w][p] = li[w][p - 1]; --p;
+        }
+        ld[w][p] = s; li[w][p] = ii;
+      }
+    }
+    __syncwarp();
+  }
+  __syncthreads();
+  if (t == 0) {
+    int head[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    for (int j = 0; j < k; ++j) {
+      int bw = -1;
+      for (int x = 0; x < 8; ++x) {
+        if (head[x] >= k) continue;
+        if (bw < 0 || ld[x][head[x]] < ld[bw][head[bw]] ||
+            (ld[x][head[x]] == ld[bw][head[bw]] && li[x][head[x]] < li[bw][head[bw]])) bw = x;
+      }
+      int gi = li[bw][head[bw]];
+      out_d2[(long long)q * k + j] = ld[bw][head[bw]];
+      out_idx[(long long)q * k + j] = (gi == 0x7fffffff) ? -1 : idx_base + gi;
+      out_lab[(long long)q * k + j] = (gi == 0x7fffffff) ? -1 : labels[gi];
+      head[bw]++;
+    }
+  }
+}
+
+int knn_tc_scan(ugn_ctx* ctx, const __nv_bfloat16* q16, const __nv_bfloat16* g16, const float* g2, int Q,
+                long long N, int Dp, int kc, int chunks, long long rows_per_chunk, void* cands, cudaStream_t st);
+
+// Tensor-core variant of ugn_knn_topk: q16 / g16 are the fp16 hi/lo planes [2,rows,Dp] of queries /
+// gallery (ugn_pack_weight), g2 is padded to a multiple of 256 rows (+inf), gmax2 = max |g|^2.
+extern "C" int ugn_knn_topk_tc(ugn_ctx* ctx, const ugn_tensor* queries, const ugn_tensor* q16,
+                               const ugn_tensor* gallery, const ugn_tensor* g16, const ugn_tensor* g2,
+                               const ugn_tensor* gmax2, const ugn_tensor* gallery_labels, int k,
+                               int64_t idx_base, ugn_tensor* out_d2, ugn_tensor* out_idx, ugn_tensor* out_lab,
+                               ugn_tensor* flags, ugn_tensor* workspace, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  UGN_CHECK(ctx && queries && q16 && gallery && g16 && g2 && gmax2 && gallery_labels && out_d2 && out_idx &&
+                out_lab && flags && workspace, "ugn_knn_topk_tc: null argument");
+  UGN_TENSOR(queries, DT_F32, 2, 2);
+  UGN_TENSOR(gallery, DT_F32, 2, 2);
+  UGN_TENSOR(q16, DT_F16, 3, 3);
+  UGN_TENSOR(g16, DT_F16, 3, 3);
+  UGN_TENSOR(g2, DT_F32, 1, 1);
+  UGN_TENSOR(gmax2, DT_F32, 1, 1);
+  UGN_TENSOR(gallery_labels, DT_I32, 1, 1);
+  UGN_TENSOR(out_d2, DT_F64, 2, 2);
+  UGN_TENSOR(out_idx, DT_I64, 2, 2);
+  UGN_TENSOR(out_lab, DT_I32, 2, 2);
+  UGN_TENSOR(flags, DT_I32, 1, 1);
+  UGN_TENSOR(workspace, DT_BAD, 1, 8);
+  long long Q = queries->shape[0], N = gallery->shape[0];
+  int D = (int)queries->shape[1], Dp = (int)q16->shape[2];
+  UGN_CHECK(gallery->shape[1] == D, "gallery/query dimension mismatch");
+  UGN_CHECK(q16->shape[0] == 2 && q16->shape[1] == Q && g16->shape[0] == 2 && g16->shape[1] == N &&
+                g16->shape[2] == Dp && Dp >= D && Dp % 8 == 0, "q16/g16 must be f16 [2,rows,Dp], Dp %% 8 == 0");
+  UGN_CHECK(k >= 1 && k <= KNN_MAXKC && N >= k && N < 0x7fffffffLL, "k-NN: bad k / shard size");
+  UGN_CHECK(g2->shape[0] >= (N + 255) / 256 * 256, "g2 must be padded to a multiple of 256 rows");
+  UGN_CHECK(gallery_labels->shape[0] == N && flags->shape[0] >= Q, "labels [N], flags [Q] expected");
+  UGN_CHECK(out_d2->shape[0] == Q && out_d2->shape[1] == k && out_idx->shape[0] == Q && out_idx->shape[1] == k &&
+                out_lab->shape[0] == Q && out_lab->shape[1] == k, "outputs must be [Q,k]");
+  if (Q == 0) return UGN_OK;
+  int kc = knn_kc(k);
+  // gallery chunks per query tile: one CTA per SM, so pick the chunk count that minimises
+  // (waves of CTAs) x (rows per chunk) -- e.g. 32 query tiles x 37 chunks = 8 full waves of 148
+  long long qt = (Q + 127) / 128;
+  long long maxc = std::max<long long>(1, std::min<long long>(N / 2048, 512));
+  long long best_cost = -1, rows = 0;
+  int chunks = 1;
+  for (long long c = 1; c <= maxc; ++c) {
+    long long r = ((N + c - 1) / c + 255) / 256 * 256;
+    long long cc = (N + r - 1) / r;
+    long long waves = (qt * cc + ctx->sm_count - 1) / ctx->sm_count;
+    long long cost = waves * (r + 2048);          // + fixed per-CTA cost (prologue, list warm-up) in row units
+    if (best_cost < 0 || cost < best_cost) { best_cost = cost; chunks = (int)cc; rows = r; }
+  }
+  long long need = Q * chunks * (long long)kc * (long long)sizeof(Cand);
+  long long have = ugn_numel(workspace) * (workspace->dtype_bits / 8);
+  UGN_CHECK(have >= need, "knn workspace too small: %lld < %lld", have, need);
+  Cand* cands = ugn_ptr<Cand>(workspace);
+  int rc = knn_tc_scan(ctx, ugn_ptr<__nv_bfloat16>(q16), ugn_ptr<__nv_bfloat16>(g16), ugn_ptr<float>(g2), (int)Q, N,
+                       Dp, kc, chunks, rows, cands, st);
+  if (rc != UGN_OK) return rc;
+  knn_rerank_kernel<<<(int)Q, 256, 0, st>>>(ugn_ptr<float>(queries), ugn_ptr<float>(gallery),
+                                            ugn_ptr<int>(gallery_labels), cands, chunks * kc, kc, k, D,
+                                            idx_base, ugn_ptr<double>(out_d2), ugn_ptr<long long>(out_idx),
+                                            ugn_ptr<int>(out_lab), ugn_ptr<float>(gmax2), Dp, ugn_ptr<int>(flags));
+  UGN_LAUNCHED(ctx);
+  knn_exact_kernel<<<(int)Q, 256, 0, st>>>(ugn_ptr<float>(queries), ugn_ptr<float>(gallery),
+                                           ugn_ptr<int>(gallery_labels), ugn_ptr<int>(flags), N, D, k, idx_base,
+                                           ugn_ptr<double>(out_d2), ugn_ptr<long long>(out_idx),
+                                           ugn_ptr<int>(out_lab));
   UGN_LAUNCHED(ctx);
   return UGN_OK;
 }

@@ -750,6 +750,11 @@ static int make_map(ugn_ctx* ctx, CUtensorMap* map, const void* base, const uint
   return UGN_OK;
 }
 
+int tc_make_map(ugn_ctx* ctx, CUtensorMap* map, const void* base, const uint64_t dims[5],
+                const uint64_t strides_bytes[4], const uint32_t box[5], int rowbytes) {
+  return make_map(ctx, map, base, dims, strides_bytes, box, rowbytes);
+}
+
 static void finish_op(TcOp& op, int major, int rowbytes, int nbox, int box_rows, int plane_rows_reserved) {
   op.major = major;
   op.rowbytes = rowbytes;

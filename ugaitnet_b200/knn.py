@@ -10,6 +10,7 @@ rank searches its shard and the per-rank top-k lists are merged after one all-ga
 """
 from __future__ import annotations
 
+import os
 from typing import Optional, Tuple
 
 import numpy as np
@@ -42,6 +43,9 @@ class KNeighborsClassifier:
         self.pg = process_group
         self.query_block = query_block
         self.idx_base = 0
+        # candidate scan on the tensor cores (tcgen05 distance GEMM + fused top-k) unless disabled
+        self.use_tc = self.ctx.has_tcgen05 and not os.environ.get("UGN_KNN_SIMT")
+        self.flagged = 0            # queries whose candidate-containment proof failed (recomputed exactly)
 
     # ---- fit: keep (this rank's shard of) the gallery resident in HBM ------------------------
     def fit(self, X, y, idx_base: int = 0, sharded: bool = False):
@@ -55,8 +59,15 @@ class KNeighborsClassifier:
         self.G = _as_cuda(X, torch.float32, self.dev)
         self.labels = _as_cuda(y, torch.int32, self.dev)
         self.idx_base = int(idx_base)
-        self.g2 = torch.empty(self.G.shape[0], device=self.dev)
-        ops.knn_gallery_norms(self.ctx, self.G, self.g2)
+        n, d = self.G.shape
+        npad = (n + 255) // 256 * 256
+        self.g2 = torch.empty(npad, device=self.dev)
+        self.gmax2 = torch.zeros(1, device=self.dev)
+        ops.knn_gallery_norms(self.ctx, self.G, self.g2, self.gmax2)
+        if self.use_tc:
+            self.dp = (d + 7) // 8 * 8
+            self.G16 = torch.empty(2, n, self.dp, dtype=torch.float16, device=self.dev)
+            ops.pack_weight(self.ctx, self.G, self.G16)     # fp16 hi/lo planes, zero-padded to Dp
         self.classes_ = None
         return self
 
@@ -66,13 +77,25 @@ class KNeighborsClassifier:
         d2 = torch.empty(nq, k, dtype=torch.float64, device=self.dev)
         idx = torch.empty(nq, k, dtype=torch.int64, device=self.dev)
         lab = torch.empty(nq, k, dtype=torch.int32, device=self.dev)
+        flags = torch.zeros(nq, dtype=torch.int32, device=self.dev) if self.use_tc else None
         for s in range(0, nq, self.query_block):
             e = min(nq, s + self.query_block)
             ws = torch.empty(max(ops.knn_workspace_bytes(e - s, self.G.shape[0], self.G.shape[1], k) // 4, 4),
                              dtype=torch.float32, device=self.dev)
-            ops.knn_topk(self.ctx, Q[s:e], self.G, self.g2, self.labels, k, self.idx_base, d2[s:e], idx[s:e],
-                         lab[s:e], ws)
+            if self.use_tc:
+                q16 = torch.empty(2, e - s, self.dp, dtype=torch.float16, device=self.dev)
+                ops.pack_weight(self.ctx, Q[s:e], q16)
+                ops.knn_topk_tc(self.ctx, Q[s:e], q16, self.G, self.G16, self.g2, self.gmax2, self.labels, k,
+                                self.idx_base, d2[s:e], idx[s:e], lab[s:e], flags[s:e], ws)
+            else:
+                ops.knn_topk(self.ctx, Q[s:e], self.G, self.g2, self.labels, k, self.idx_base, d2[s:e], idx[s:e],
+                             lab[s:e], ws)
+        self._flags = flags
         return d2, idx, lab
+
+    def flagged_queries(self) -> int:
+        """How many queries of the last search failed the containment proof and were recomputed exactly."""
+        return 0 if getattr(self, "_flags", None) is None else int(self._flags.sum())
 
     def _search(self, Q):
         Q = _as_cuda(Q, torch.float32, self.dev)

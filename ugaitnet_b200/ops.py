@@ -151,9 +151,17 @@ def knn_workspace_bytes(Q, N, D, k) -> int:
     return int(lib.ugn_knn_workspace_bytes(int(Q), int(N), int(D), int(k)))
 
 
-def knn_gallery_norms(ctx, gallery, g2):
-    a, b = _r(gallery), _r(g2)
-    check(lib.ugn_knn_gallery_norms(ctx.h, a.ptr, b.ptr, stream_ptr()))
+def knn_gallery_norms(ctx, gallery, g2, gmax2=None):
+    a, b, c = _r(gallery), _r(g2), _r(gmax2)
+    check(lib.ugn_knn_gallery_norms(ctx.h, a.ptr, b.ptr, _p(c), stream_ptr()))
+
+
+def knn_topk_tc(ctx, queries, q16, gallery, g16, g2, gmax2, labels, k, idx_base, out_d2, out_idx, out_lab, flags,
+                workspace):
+    rs = [_r(t) for t in (queries, q16, gallery, g16, g2, gmax2, labels)]
+    ro = [_r(t) for t in (out_d2, out_idx, out_lab, flags, workspace)]
+    check(lib.ugn_knn_topk_tc(ctx.h, *[_p(r) for r in rs], int(k), int(idx_base), *[_p(r) for r in ro],
+                              stream_ptr()))
 
 
 def knn_topk(ctx, queries, gallery, g2, labels, k, idx_base, out_d2, out_idx, out_lab, workspace):
