@@ -219,9 +219,11 @@ int ugn_knn_gallery_norms(ugn_ctx*, const ugn_tensor* gallery, ugn_tensor* g2, u
 int ugn_knn_topk(ugn_ctx*, const ugn_tensor* queries, const ugn_tensor* gallery, const ugn_tensor* g2,
                  const ugn_tensor* gallery_labels, int k, int64_t idx_base, ugn_tensor* out_d2,
                  ugn_tensor* out_idx, ugn_tensor* out_lab, ugn_tensor* workspace, void* stream);
-/* Tensor-core candidate scan: the distance GEMM Q.G^T on tcgen05 (fp16 hi/lo planes q16 [2,Q,Dp],
- * g16 [2,N,Dp] made with ugn_pack_weight; Dp % 8 == 0) with the top-KC filter fused into the GEMM
- * epilogue, then the same exact fp64 re-rank.  The re-rank PROVES per query that the true top-k lie
+/* f32 [rows,D] -> operand of the tensor-core scan: fp16 hi/lo planes, K-chunk major
+ * x16 f16 [2, ceil(D/64), rows, 64] (zero padded), so that every TMA box is one contiguous 16 KB run. */
+int ugn_knn_pack(ugn_ctx*, const ugn_tensor* x, ugn_tensor* x16, void* stream);
+/* Tensor-core candidate scan: the distance GEMM Q.G^T on tcgen05 (q16 / g16 from ugn_knn_pack) with
+ * the top-KC filter fused into the GEMM epilogue, then the same exact fp64 re-rank.  The re-rank PROVES per query that the true top-k lie
  * inside the candidate set (error bound of the split-fp16 GEMM vs the KC-th candidate score); queries
  * that fail the proof are flagged (flags i32 [Q], output) and recomputed by brute force in fp64, so
  * indices / labels are bit-exact in every case. */

@@ -69,6 +69,7 @@ _PROTOS = {
                              c_void_p]),
     "ugn_knn_workspace_bytes": (c_int64, [c_int64, c_int64, c_int64, c_int]),
     "ugn_knn_gallery_norms": (c_int, [c_void_p, _T, _T, _T, c_void_p]),
+    "ugn_knn_pack": (c_int, [c_void_p, _T, _T, c_void_p]),
     "ugn_knn_topk_tc": (c_int, [c_void_p, _T, _T, _T, _T, _T, _T, _T, c_int, c_int64, _T, _T, _T, _T, _T, c_void_p]),
     "ugn_knn_topk": (c_int, [c_void_p, _T, _T, _T, _T, c_int, c_int64, _T, _T, _T, _T, c_void_p]),
     "ugn_knn_merge_vote": (c_int, [c_void_p, _T, _T, _T, c_int, _T, _T, _T, _T, c_void_p]),

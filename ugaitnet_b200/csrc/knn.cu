@@ -320,7 +320,7 @@ static int knn_chunks(ugn_ctx* ctx, long long Q, long long N) {
 extern "C" int64_t ugn_knn_workspace_bytes(int64_t Q, int64_t N, int64_t D, int k) {
   (void)D;
   // worst case chunk count (sm_count unknown here): 1024
-  return Q * 1024 * (int64_t)knn_kc(k) * (int64_t)sizeof(Cand);
+  return Q * 1024 * (int64_t)knn_kc(k) * (int64_t)sizeof(Cand) + Q * 4;
 }
 
 extern "C" int ugn_knn_gallery_norms(ugn_ctx* ctx, const ugn_tensor* gallery, ugn_tensor* g2,
@@ -452,10 +452,24 @@ __global__ void __launch_bounds__(256) knn_exact_kernel(const float* __restrict_
 }
 
 int knn_tc_scan(ugn_ctx* ctx, const __nv_bfloat16* q16, const __nv_bfloat16* g16, const float* g2, int Q,
-                long long N, int Dp, int kc, int chunks, long long rows_per_chunk, void* cands, cudaStream_t st);
+                long long N, int KCH, int kc, int chunks, long long rows_per_chunk, void* cands, int* gthr,
+                cudaStream_t st);
+int knn_tc_pack(ugn_ctx* ctx, const float* X, long long rows, int D, __nv_bfloat16* out, cudaStream_t st);
 
-// Tensor-core variant of ugn_knn_topk: q16 / g16 are the fp16 hi/lo planes [2,rows,Dp] of queries /
-// gallery (ugn_pack_weight), g2 is padded to a multiple of 256 rows (+inf), gmax2 = max |g|^2.
+// f32 [rows,D] -> the tensor-core scan's operand: fp16 hi/lo planes, K-chunk major [2, ceil(D/64), rows, 64]
+extern "C" int ugn_knn_pack(ugn_ctx* ctx, const ugn_tensor* x, ugn_tensor* x16, void* stream) {
+  UGN_CHECK(ctx && x && x16, "ugn_knn_pack: null argument");
+  UGN_TENSOR(x, DT_F32, 2, 2);
+  UGN_TENSOR(x16, DT_F16, 4, 4);
+  long long rows = x->shape[0];
+  int D = (int)x->shape[1], KCH = (D + 63) / 64;
+  UGN_CHECK(x16->shape[0] == 2 && x16->shape[1] == KCH && x16->shape[2] == rows && x16->shape[3] == 64,
+            "ugn_knn_pack: x16 must be f16 [2, ceil(D/64)=%d, rows=%lld, 64]", KCH, rows);
+  return knn_tc_pack(ctx, ugn_ptr<float>(x), rows, D, ugn_ptr<__nv_bfloat16>(x16), (cudaStream_t)stream);
+}
+
+// Tensor-core variant of ugn_knn_topk: q16 / g16 are the fp16 hi/lo planes of queries / gallery made by
+// ugn_knn_pack, g2 is padded to a multiple of 256 rows (+inf), gmax2 = max |g|^2.
 extern "C" int ugn_knn_topk_tc(ugn_ctx* ctx, const ugn_tensor* queries, const ugn_tensor* q16,
                                const ugn_tensor* gallery, const ugn_tensor* g16, const ugn_tensor* g2,
                                const ugn_tensor* gmax2, const ugn_tensor* gallery_labels, int k,
@@ -466,8 +480,8 @@ extern "C" int ugn_knn_topk_tc(ugn_ctx* ctx, const ugn_tensor* queries, const ug
                 out_lab && flags && workspace, "ugn_knn_topk_tc: null argument");
   UGN_TENSOR(queries, DT_F32, 2, 2);
   UGN_TENSOR(gallery, DT_F32, 2, 2);
-  UGN_TENSOR(q16, DT_F16, 3, 3);
-  UGN_TENSOR(g16, DT_F16, 3, 3);
+  UGN_TENSOR(q16, DT_F16, 4, 4);
+  UGN_TENSOR(g16, DT_F16, 4, 4);
   UGN_TENSOR(g2, DT_F32, 1, 1);
   UGN_TENSOR(gmax2, DT_F32, 1, 1);
   UGN_TENSOR(gallery_labels, DT_I32, 1, 1);
@@ -477,10 +491,11 @@ extern "C" int ugn_knn_topk_tc(ugn_ctx* ctx, const ugn_tensor* queries, const ug
   UGN_TENSOR(flags, DT_I32, 1, 1);
   UGN_TENSOR(workspace, DT_BAD, 1, 8);
   long long Q = queries->shape[0], N = gallery->shape[0];
-  int D = (int)queries->shape[1], Dp = (int)q16->shape[2];
+  int D = (int)queries->shape[1], KCH = (D + 63) / 64, Dp = KCH * 64;
   UGN_CHECK(gallery->shape[1] == D, "gallery/query dimension mismatch");
-  UGN_CHECK(q16->shape[0] == 2 && q16->shape[1] == Q && g16->shape[0] == 2 && g16->shape[1] == N &&
-                g16->shape[2] == Dp && Dp >= D && Dp % 8 == 0, "q16/g16 must be f16 [2,rows,Dp], Dp %% 8 == 0");
+  UGN_CHECK(q16->shape[0] == 2 && q16->shape[1] == KCH && q16->shape[2] == Q && q16->shape[3] == 64 &&
+                g16->shape[0] == 2 && g16->shape[1] == KCH && g16->shape[2] == N && g16->shape[3] == 64,
+            "q16/g16 must be f16 [2, ceil(D/64), rows, 64] (ugn_knn_pack)");
   UGN_CHECK(k >= 1 && k <= KNN_MAXKC && N >= k && N < 0x7fffffffLL, "k-NN: bad k / shard size");
   UGN_CHECK(g2->shape[0] >= (N + 255) / 256 * 256, "g2 must be padded to a multiple of 256 rows");
   UGN_CHECK(gallery_labels->shape[0] == N && flags->shape[0] >= Q, "labels [N], flags [Q] expected");
@@ -501,15 +516,16 @@ extern "C" int ugn_knn_topk_tc(ugn_ctx* ctx, const ugn_tensor* queries, const ug
     long long cost = waves * (r + 2048);          // + fixed per-CTA cost (prologue, list warm-up) in row units
     if (best_cost < 0 || cost < best_cost) { best_cost = cost; chunks = (int)cc; rows = r; }
   }
-  long long need = Q * chunks * (long long)kc * (long long)sizeof(Cand);
+  long long need = Q * chunks * 2 * (long long)kc * (long long)sizeof(Cand) + Q * 4;   // two column halves per chunk + thresholds
   long long have = ugn_numel(workspace) * (workspace->dtype_bits / 8);
   UGN_CHECK(have >= need, "knn workspace too small: %lld < %lld", have, need);
   Cand* cands = ugn_ptr<Cand>(workspace);
   int rc = knn_tc_scan(ctx, ugn_ptr<__nv_bfloat16>(q16), ugn_ptr<__nv_bfloat16>(g16), ugn_ptr<float>(g2), (int)Q, N,
-                       Dp, kc, chunks, rows, cands, st);
+                       KCH, kc, chunks, rows, cands,
+                       reinterpret_cast<int*>(cands + Q * chunks * 2 * (long long)kc), st);
   if (rc != UGN_OK) return rc;
   knn_rerank_kernel<<<(int)Q, 256, 0, st>>>(ugn_ptr<float>(queries), ugn_ptr<float>(gallery),
-                                            ugn_ptr<int>(gallery_labels), cands, chunks * kc, kc, k, D,
+                                            ugn_ptr<int>(gallery_labels), cands, chunks * 2 * kc, kc, k, D,
                                             idx_base, ugn_ptr<double>(out_d2), ugn_ptr<long long>(out_idx),
                                             ugn_ptr<int>(out_lab), ugn_ptr<float>(gmax2), Dp, ugn_ptr<int>(flags));
   UGN_LAUNCHED(ctx);

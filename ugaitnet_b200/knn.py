@@ -65,9 +65,10 @@ class KNeighborsClassifier:
         self.gmax2 = torch.zeros(1, device=self.dev)
         ops.knn_gallery_norms(self.ctx, self.G, self.g2, self.gmax2)
         if self.use_tc:
-            self.dp = (d + 7) // 8 * 8
-            self.G16 = torch.empty(2, n, self.dp, dtype=torch.float16, device=self.dev)
-            ops.pack_weight(self.ctx, self.G, self.G16)     # fp16 hi/lo planes, zero-padded to Dp
+            self.kch = (d + 63) // 64
+            self.dp = self.kch * 64
+            self.G16 = torch.empty(2, self.kch, n, 64, dtype=torch.float16, device=self.dev)
+            ops.knn_pack(self.ctx, self.G, self.G16)        # fp16 hi/lo planes, K-chunk major, zero padded
         self.classes_ = None
         return self
 
@@ -83,8 +84,8 @@ class KNeighborsClassifier:
             ws = torch.empty(max(ops.knn_workspace_bytes(e - s, self.G.shape[0], self.G.shape[1], k) // 4, 4),
                              dtype=torch.float32, device=self.dev)
             if self.use_tc:
-                q16 = torch.empty(2, e - s, self.dp, dtype=torch.float16, device=self.dev)
-                ops.pack_weight(self.ctx, Q[s:e], q16)
+                q16 = torch.empty(2, self.kch, e - s, 64, dtype=torch.float16, device=self.dev)
+                ops.knn_pack(self.ctx, Q[s:e], q16)
                 ops.knn_topk_tc(self.ctx, Q[s:e], q16, self.G, self.G16, self.g2, self.gmax2, self.labels, k,
                                 self.idx_base, d2[s:e], idx[s:e], lab[s:e], flags[s:e], ws)
             else:

@@ -156,6 +156,11 @@ def knn_gallery_norms(ctx, gallery, g2, gmax2=None):
     check(lib.ugn_knn_gallery_norms(ctx.h, a.ptr, b.ptr, _p(c), stream_ptr()))
 
 
+def knn_pack(ctx, x, x16):
+    a, b = _r(x), _r(x16)
+    check(lib.ugn_knn_pack(ctx.h, a.ptr, b.ptr, stream_ptr()))
+
+
 def knn_topk_tc(ctx, queries, q16, gallery, g16, g2, gmax2, labels, k, idx_base, out_d2, out_idx, out_lab, flags,
                 workspace):
     rs = [_r(t) for t in (queries, q16, gallery, g16, g2, gmax2, labels)]
