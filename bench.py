@@ -241,7 +241,7 @@ def main():
 
     from ugaitnet_b200.net import UGaitEngine
     eng = UGaitEngine(engine_cfg(), device=local, math_mode=args.mode, lr=1e-4, process_group=pg,
-                      use_graph=(not args.no_graph and world == 1))
+                      use_graph=(not args.no_graph and (world == 1 or os.environ.get("UGN_DP_GRAPH") == "1")))
     xs, fl, lab = make_batch(232323 + rank)
     B = xs[0].shape[0]
     # host copies in pinned memory (e2e leg) and device-resident copies (value leg)

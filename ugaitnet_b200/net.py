@@ -14,6 +14,7 @@ of the step is a kernel of libugaitnet_b200.so.
 from __future__ import annotations
 
 import math
+import os
 from typing import Dict, List, Optional, Sequence
 
 import torch
@@ -64,6 +65,10 @@ class UGaitEngine:
         self.use_graph = use_graph
         self.t = 0
         self._dp_async = True      # bucketed, overlapped all-reduce (False: one blocking all-reduce)
+        # EXPERIMENTAL (off): capture the data-parallel step, NCCL all-reduces included, in the CUDA graph.
+        # Hung at N=2 on the first try (capture of async NCCL work handles); the eager path is the
+        # measured one (eager adds ~0.4 ms/step of launch gaps over graph replay at N=1).
+        self.dp_graph = os.environ.get("UGN_DP_GRAPH", "0") == "1"
         self._works = []
         self.graph_launches = 0
         self._plans: Dict[tuple, "_Plan"] = {}
@@ -450,7 +455,7 @@ class UGaitEngine:
         p = self.plan(B, True)
         self._set_inputs(p, inputs, flags, labels, drop_masks, code_drop_mask)
         self._next_lr()
-        if self.use_graph and self.world == 1:
+        if self.use_graph and (self.world == 1 or self.dp_graph):
             gkey = B
             gr = self._graphs.get(gkey)
             if gr is None:
