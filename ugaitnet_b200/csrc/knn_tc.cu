@@ -321,7 +321,9 @@ int knn_tc_scan(ugn_ctx* ctx, const __nv_bfloat16* q16, const __nv_bfloat16* g16
   UGN_CUDA(cudaMemsetAsync(gthr, 0x7f, sizeof(int) * (size_t)Q, st));   // key of 3.4e38: "no threshold yet"
   p.Q = Q; p.kc = kc; p.ksteps = KCH; p.chunks = chunks;
   p.N = N; p.rows_per_chunk = rows_per_chunk;
-  p.skew = getenv("UGN_KNN_NOSKEW") ? 0 : 1;
+  // measured: lock-step sweeps (all query tiles of a chunk read the same gallery lines at the same time)
+  // are FASTER (4.92 vs 6.35 ms on 1 M x 256, Q = 4096): L2 serves the shared lines once; skew is opt-in
+  p.skew = getenv("UGN_KNN_SKEW") ? 1 : 0;
   if (!ctx->err_flag) {
     UGN_CUDA(cudaMalloc(&ctx->err_flag, sizeof(int)));
     UGN_CUDA(cudaMemset(ctx->err_flag, 0, sizeof(int)));
