@@ -7,7 +7,9 @@ from ugaitnet_b200 import ops
 
 ctx = ops.get_ctx(0)
 B = int(os.environ.get("B", "96"))
-P = int(os.environ.get("P", "2"))
+P = int(os.environ.get("P", "2"))          # planes of activations / weights
+PB = int(os.environ.get("PB", "1"))        # planes of the gradient operand dz (1 = single-pass backward)
+DT = torch.bfloat16 if os.environ.get("DT") == "bf16" else torch.float16
 layers = [("conv1-gray", 32, 25, 60, 96, 7, True), ("conv1-of", 64, 50, 60, 96, 7, True),
           ("conv2", 96, 96, 27, 192, 5, True), ("conv3", 192, 192, 11, 512, 3, True),
           ("conv4", 512, 512, 4, 512, 2, False)]
@@ -31,12 +33,12 @@ tot = {k: 0.0 for k in which}
 for name, Cp, C, H, Co, k, pool in layers:
     Ho = H - k + 1
     Hp = Ho // 2 if pool else Ho
-    x = (torch.randn(P, B, H, H, Cp, device="cuda") * 0.5).to(torch.bfloat16)
-    w = (torch.randn(P, Co, k, k, Cp, device="cuda") * 0.05).to(torch.bfloat16)
+    x = (torch.randn(P, B, H, H, Cp, device="cuda") * 0.5).to(DT)
+    w = (torch.randn(P, Co, k, k, Cp, device="cuda") * 0.05).to(DT)
     b = torch.zeros(Co, device="cuda")
-    y = torch.zeros(P, B, Hp, Hp, Co, dtype=torch.bfloat16, device="cuda")
+    y = torch.zeros(P, B, Hp, Hp, Co, dtype=DT, device="cuda")
     idx = torch.zeros(B, Hp, Hp, Co, dtype=torch.uint8, device="cuda") if pool else None
-    dz = (torch.randn(P, B, Ho, Ho, Co, device="cuda") * 0.1).to(torch.bfloat16)
+    dz = (torch.randn(PB, B, Ho, Ho, Co, device="cuda") * 0.1).to(DT)
     dw = torch.zeros(Co, k, k, C, device="cuda")
     db = torch.zeros(Co, device="cuda")
     dx = torch.zeros(B, H, H, Cp, device="cuda")

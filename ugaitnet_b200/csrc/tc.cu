@@ -50,11 +50,16 @@ struct TcParams {
   int* err;
   int f16;                 // 16-bit operand format: 0 bf16, 1 fp16
   const float* oscale;     // device scalar multiplied into f32 outputs (1/grad-scale for backward ops), nullable
-  int dbg_shift, dbg_bo;   // experiment: row-shifted A view (UGN_DBG_SHIFT / UGN_DBG_BASEOFF)
   // patch-resident conv (tc_convp_kernel)
   int T, SW, RH, PR, KH, xorg, yorg, tiles_y, tmem_cols;
   int patch_chunk_bytes, patch_plane_bytes;
   int cps, nslots, ngroups;   // channel chunks per patch slot, patch slots (1 | 2), groups per tile = ncc / cps
+  // accumulator layout of tc_convp_kernel: nbuf TMEM buffers (2 = epilogue overlaps the next tile);
+  // concat = 1: hi*[hi|lo] is issued as ONE N = 2*block_n MMA over the two adjacent weight planes (an
+  // N <= 128 MMA costs 73 clk whatever N is, N = 192 costs 96: profiles/r01_umma_rate.txt), the hi*lo
+  // partial sums live in columns [block_n, 2*block_n) of the tile and are added in the epilogue
+  int nbuf, concat, acc_tile_cols;
+  long long* dbg;   // optional [8] cycle counters (UGN_CONVP_PROF): where each role of tc_convp_kernel waits
 };
 
 // 16-byte vector reduction (sm_90+): one red.global.add.v4.f32 instead of four scalar atomics
@@ -81,7 +86,7 @@ __device__ __forceinline__ void epi_barrier() { asm volatile("bar.sync 1, 128;" 
 // Epilogue of one 128-row conv accumulator tile whose rows are the (bn x bh x bw) pixel box at
 // (nn0, y0, x0): bias + activation, then bf16 hi/lo store, f32 store (dgrad) or fused 2x2 max-pool.
 __device__ __forceinline__ void conv_tile_epilogue(const TcParams& p, uint8_t* smem, uint32_t trow, int r, bool ok,
-                                                   int x0, int y0, int nn0, int n0) {
+                                                   int x0, int y0, int nn0, int n0, int half = 0, int nhalf = 1) {
   float v[16];
   const float os = p.oscale ? *p.oscale : 1.f;
   const int xl = r % p.bw, yl = (r / p.bw) % p.bh, nl = r / (p.bw * p.bh);
@@ -89,8 +94,14 @@ __device__ __forceinline__ void conv_tile_epilogue(const TcParams& p, uint8_t* s
     const bool rv = ok && nl < p.bn && x < p.Wout && y < p.Hout && n < p.Bn;
     if (p.epi != EPI_BF16_POOL) {
       const long long obase = (((long long)n * p.Hout + y) * p.Wout + x) * p.Cout;
-      for (int c0 = 0; c0 < p.block_n; c0 += 16) {
+      for (int c0 = 16 * half; c0 < p.block_n; c0 += 16 * nhalf) {
         tmem_ld16(trow + c0, v);
+        if (p.concat) {
+          float v2[16];
+          tmem_ld16(trow + p.block_n + c0, v2);
+#pragma unroll
+          for (int i = 0; i < 16; ++i) v[i] += v2[i];
+        }
         if (!rv) continue;
         if (p.epi == EPI_F32_ATOMIC) {
           red_add_16(p.out_f32 + obase + n0 + c0, v, os, p.Cout - (n0 + c0));
@@ -127,6 +138,12 @@ __device__ __forceinline__ void conv_tile_epilogue(const TcParams& p, uint8_t* s
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
           tmem_ld16(trow + c0 + 16 * h, v);
+          if (p.concat) {
+            float v2[16];
+            tmem_ld16(trow + p.block_n + c0 + 16 * h, v2);
+#pragma unroll
+            for (int i = 0; i < 16; ++i) v[i] += v2[i];
+          }
 #pragma unroll
           for (int i = 0; i < 16; ++i) {
             const int c = n0 + c0 + 16 * h + i;
@@ -160,7 +177,87 @@ __device__ __forceinline__ void conv_tile_epilogue(const TcParams& p, uint8_t* s
     }
 }
 
-template <int MODE>
+// Fused 2x2 max-pool epilogue of the persistent conv kernel, 8 warps (two per TMEM lane quadrant = two per
+// SM sub-partition, so one hides the other's latencies).  Per pass of 32 channels: thread (row r, half h)
+// pulls its 16 accumulator columns with ONE tcgen05.ld, adds the bias (4 broadcast float4 loads), applies
+// the activation and parks the values in smem [128][33]; after a 256-thread barrier thread (channel,
+// pooled pixel) takes the max of its 2x2 window (ties -> first in (dy,dx) order) and stores the 16-bit
+// planes + arg-max byte, 32 consecutive channels per warp store.  The pooled-pixel geometry of a thread is
+// the same in every pass and is computed once per tile.
+static constexpr int kConvpThreads = 320;
+__device__ __forceinline__ void epi_barrier256() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+
+__device__ __forceinline__ void convp_pool_epilogue(const TcParams& p, float* stg, uint32_t trow, int r, int half,
+                                                    bool ok, int y0, int img, int n0) {
+  const int t = threadIdx.x - 64;                 // 0..255
+  const int pw = p.bw >> 1, ph2 = p.bh >> 1, npool = pw * ph2 * p.bn;
+  const int col = t & 31;
+  // up to 4 pooled pixels per thread and pass (npool <= 32): smem row of the window's top-left pixel and
+  // the output offset (without the channel)
+  int r00[4];
+  long long ob[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int pp = (t >> 5) + 8 * j;
+    r00[j] = -1;
+    ob[j] = 0;
+    if (pp < npool) {
+      const int pxl = pp % pw, pyl = (pp / pw) % ph2, pnl = pp / (pw * ph2);
+      const int xp = pxl, yp = (y0 >> 1) + pyl, nn = img + pnl;
+      if (ok && xp < p.Wp && yp < p.Hp && nn < p.Bn) {
+        r00[j] = (pnl * p.bh + 2 * pyl) * p.bw + 2 * pxl;
+        ob[j] = (((long long)nn * p.Hp + yp) * p.Wp + xp) * p.Cout;
+      }
+    }
+  }
+  float v[16];
+  for (int c0 = 0; c0 < p.block_n; c0 += 32) {
+    tmem_ld16(trow + c0 + 16 * half, v);
+    if (p.concat) {
+      float v2[16];
+      tmem_ld16(trow + p.block_n + c0 + 16 * half, v2);
+#pragma unroll
+      for (int i = 0; i < 16; ++i) v[i] += v2[i];
+    }
+    const int cb = n0 + c0 + 16 * half;
+#pragma unroll
+    for (int i = 0; i < 16; i += 4) {
+      float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (p.bias && cb + i + 4 <= p.Cout) b4 = *reinterpret_cast<const float4*>(p.bias + cb + i);
+      float* d = stg + r * 33 + 16 * half + i;
+      d[0] = ugn_act_fwd(v[i] + b4.x, p.act, p.alpha);
+      d[1] = ugn_act_fwd(v[i + 1] + b4.y, p.act, p.alpha);
+      d[2] = ugn_act_fwd(v[i + 2] + b4.z, p.act, p.alpha);
+      d[3] = ugn_act_fwd(v[i + 3] + b4.w, p.act, p.alpha);
+    }
+    epi_barrier256();
+    const int c = n0 + c0 + col;
+    if (c < p.Cout) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        if (r00[j] < 0) continue;
+        const float* w0 = stg + r00[j] * 33 + col;
+        float best = w0[0];
+        int pos = 0;
+        const float o1 = w0[33], o2 = w0[p.bw * 33], o3 = w0[(p.bw + 1) * 33];
+        if (o1 > best) { best = o1; pos = 1; }
+        if (o2 > best) { best = o2; pos = 2; }
+        if (o3 > best) { best = o3; pos = 3; }
+        u16 hi, lo;
+        ugn_split16(best, p.f16, hi, lo);
+        const long long o = ob[j] + c;
+        p.out_bf16[o] = hi;
+        if (p.planes == 2) p.out_bf16[p.out_plane + o] = lo;
+        p.pool_idx[o] = (uint8_t)pos;
+      }
+    }
+    epi_barrier256();
+  }
+}
+
+// PL2 (split operands) and KSL (K slices per ring stage; 0 = run-time) are compile-time so that the MMA issue
+// sequence of a stage is straight-line code (see tc_convp_kernel).
+template <int MODE, bool PL2, int KSL>
 __global__ void __launch_bounds__(kThreads, 1) tc_kernel(const __grid_constant__ TcParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // carve: [stages x (A planes | B planes)] | barriers | tmem ptr
@@ -280,20 +377,16 @@ __global__ void __launch_bounds__(kThreads, 1) tc_kernel(const __grid_constant__
       if (!mbar_wait(&full[s], ph, p.err, 2)) break;
       fence_after_sync();
       uint64_t a_hi = a0 + (uint64_t)(s * st16), b_hi = b0 + (uint64_t)(s * st16);
-      if (p.dbg_shift) {
-        const uint32_t sh = smem0 + s * stage_bytes + p.dbg_shift * p.a.rowbytes;
-        const uint32_t bo = p.dbg_bo == 1 ? ((sh >> 7) & 7) : (p.dbg_bo == 2 ? (p.dbg_shift & 7) : 0);
-        a_hi = make_smem_desc(sh, p.a.lbo, p.a.sbo, la, bo);
-      }
-      for (int k = 0; k < p.kslices; ++k) {
-        umma_f16(tmem_base, a_hi, b_hi, idesc, accum);
+      const int nk = KSL > 0 ? KSL : p.kslices;
+#pragma unroll
+      for (int k = 0; k < nk; ++k) {
+        const uint64_t ak = a_hi + (uint64_t)(k * ka16), bk = b_hi + (uint64_t)(k * kb16);
+        umma_f16(tmem_base, ak, bk, idesc, accum);
         accum = 1;
-        if (p.planes == 2) {
-          umma_f16(tmem_base, a_hi, b_hi + pb16, idesc, 1);
-          umma_f16(tmem_base, a_hi + pa16, b_hi, idesc, 1);
+        if (PL2) {
+          umma_f16(tmem_base, ak, bk + pb16, idesc, 1);
+          umma_f16(tmem_base, ak + pa16, bk, idesc, 1);
         }
-        a_hi += ka16;
-        b_hi += kb16;
       }
       umma_commit(&empty[s]);  // frees the smem slot once these MMAs have read it
       if (++s == p.stages) { s = 0; ph ^= 1; }
@@ -383,7 +476,13 @@ __global__ void __launch_bounds__(kThreads, 1) tc_kernel(const __grid_constant__
 // Only the weight tile of each (tap, channel chunk) streams through the mbarrier ring, and it is shared by
 // the T accumulators in TMEM.  sgn=-1 (input gradient) flips the taps and shifts the patch origin.
 // ---------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kThreads, 1) tc_convp_kernel(const __grid_constant__ TcParams p) {
+// CONCAT / PROF are compile-time: a run-time branch or the cycle-counter bookkeeping inside the single-thread
+// issue loops costs more than the MMAs they surround when there is only one MMA per K slice (dgrad).
+// TT (tiles per work item), KSL (K slices per ring stage) and PL2 (split operands) are compile-time too, so
+// that the MMA issue sequence of one ring stage is a straight line of UTCHMMAs with immediate descriptor
+// offsets.
+template <bool CONCAT, bool PROF, int TT, int KSL, bool PL2>
+__global__ void __launch_bounds__(kConvpThreads, 1) tc_convp_kernel(const __grid_constant__ TcParams p) {
   // PERSISTENT: each CTA walks tiles blockIdx.x, +gridDim.x, ...; two TMEM accumulator sets so that the
   // epilogue of tile i (CUDA cores) overlaps the mainloop of tile i+1 (tensor pipe).
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -410,7 +509,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_convp_kernel(const __grid_cons
     for (int s = 0; s < p.stages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
     for (int b = 0; b < 2; ++b) {
       mbar_init(&patch_full[b], 1); mbar_init(&patch_empty[b], 1);
-      mbar_init(&tmem_full[b], 1); mbar_init(&tmem_empty[b], 128);
+      mbar_init(&tmem_full[b], 1); mbar_init(&tmem_empty[b], 256);
     }
     fence_mbar_init();
     prefetch_tmap(&p.a.map);
@@ -426,7 +525,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_convp_kernel(const __grid_cons
   const uint32_t tmem_base = *tmem_ptr;
   const int BK = p.kslices * 16;
   const int cwB = p.b.rowbytes >> 1;
-  const uint32_t acc_cols = (uint32_t)(p.T * p.block_n);
+  const uint32_t acc_cols = (uint32_t)(p.T * p.acc_tile_cols);
 
   if (warp == 0) {
    if (elect_one()) {
@@ -440,7 +539,9 @@ __global__ void __launch_bounds__(kThreads, 1) tc_convp_kernel(const __grid_cons
       for (int g = 0; g < p.ngroups; ++g) {
         const int u = li * p.ngroups + g, slot = u % p.nslots, sph = (u / p.nslots) & 1;
         uint8_t* pslot = smem + slot * slot_bytes;
+        long long tw0 = PROF ? clock64() : 0;
         mbar_wait(&patch_empty[slot], sph ^ 1, p.err, 5);
+        if (PROF) atomicAdd((unsigned long long*)p.dbg + 7, (unsigned long long)(clock64() - tw0));
         mbar_expect_tx(&patch_full[slot], slot_bytes);
         for (int pl = 0; pl < p.planes; ++pl)
           for (int c = 0; c < p.cps; ++c)
@@ -449,7 +550,9 @@ __global__ void __launch_bounds__(kThreads, 1) tc_convp_kernel(const __grid_cons
         int c = 0, tap = 0;
         for (int it = 0; it < nsteps / p.ngroups; ++it) {
           const int cc = g * p.cps + c;
+          long long tw1 = PROF ? clock64() : 0;
           mbar_wait(&empty[s], ph ^ 1, p.err, 1);
+          if (PROF) atomicAdd((unsigned long long*)p.dbg + 6, (unsigned long long)(clock64() - tw1));
           mbar_expect_tx(&full[s], tx_bytes);
           uint8_t* sb = ring + (size_t)s * b_stage;
           for (int pl = 0; pl < p.planes; ++pl)
@@ -467,6 +570,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_convp_kernel(const __grid_cons
    if (elect_one()) {
     // ---- MMA issuer ----
     const uint32_t idesc = make_idesc16(128, p.block_n, 0, p.b.major, p.f16);
+    const uint32_t idesc2 = make_idesc16(128, 2 * p.block_n, 0, p.b.major, p.f16);   // concat: both weight planes
     const uint32_t la = p.a.rowbytes == 128 ? 2u : 4u, lb = p.b.rowbytes == 128 ? 2u : 4u;
     const uint32_t smem0 = smem_u32(smem);
     const uint64_t a0 = make_smem_desc(smem0, 0, 8 * p.a.rowbytes, la);
@@ -476,33 +580,46 @@ __global__ void __launch_bounds__(kThreads, 1) tc_convp_kernel(const __grid_cons
     const uint32_t tile16 = (uint32_t)(p.RH * p.SW) * row16;
     int s = 0, ph = 0, li = 0;
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++li) {
-      const int buf = li & 1;
-      mbar_wait(&tmem_empty[buf], ((li >> 1) & 1) ^ 1, p.err, 6);
+      const int buf = li % p.nbuf;
+      long long tm0 = PROF ? clock64() : 0;
+      mbar_wait(&tmem_empty[buf], ((li / p.nbuf) & 1) ^ 1, p.err, 6);
+      if (PROF) atomicAdd((unsigned long long*)p.dbg + 2, (unsigned long long)(clock64() - tm0));
       const uint32_t tacc = tmem_base + buf * acc_cols;
       for (int g = 0; g < p.ngroups; ++g) {
       const int u = li * p.ngroups + g, slot = u % p.nslots, sph = (u / p.nslots) & 1;
+      long long tm1 = PROF ? clock64() : 0;
       mbar_wait(&patch_full[slot], sph, p.err, 4);
+      if (PROF) atomicAdd((unsigned long long*)p.dbg + 0, (unsigned long long)(clock64() - tm1));
       fence_after_sync();
       const uint64_t a_slot = a0 + (uint64_t)(slot * (slot_bytes >> 4));
       int cc = 0, kw = 0, kh = 0;
       for (int it = 0; it < nsteps / p.ngroups; ++it) {
+        long long tm2 = PROF ? clock64() : 0;
         mbar_wait(&full[s], ph, p.err, 2);
+        if (PROF) atomicAdd((unsigned long long*)p.dbg + 1, (unsigned long long)(clock64() - tm2));
         fence_after_sync();
         const int ay = p.sgn > 0 ? kh : (p.KH - 1 - kh), ax = p.sgn > 0 ? kw : (p.KW - 1 - kw);
         const uint64_t a_tap = a_slot + (uint64_t)(cc * ch16 + (uint32_t)(ay * p.SW + ax) * row16);
         const uint64_t b_st = b0 + (uint64_t)(s * st16);
         const uint32_t acc0 = (g > 0 || it > 0) ? 1u : 0u;
-        for (int t = 0; t < p.T; ++t) {
-          uint64_t a_hi = a_tap + (uint64_t)(t * tile16), b_hi = b_st;
-          const uint32_t td = tacc + t * p.block_n;
-          for (int k = 0; k < p.kslices; ++k) {
-            umma_f16(td, a_hi, b_hi, idesc, (k > 0) ? 1u : acc0);
-            if (p.planes == 2) {
-              umma_f16(td, a_hi, b_hi + pb16, idesc, 1);
-              umma_f16(td, a_hi + pa16, b_hi, idesc, 1);
+#pragma unroll
+        for (int t = 0; t < TT; ++t) {
+          const uint64_t a_t = a_tap + (uint64_t)(t * tile16);
+          const uint32_t td = tacc + t * p.acc_tile_cols;
+#pragma unroll
+          for (int k = 0; k < KSL; ++k) {
+            const uint64_t a_hi = a_t + (uint64_t)(2 * k);      // 32 bytes = one UMMA_K slice inside the swizzled row
+            const uint64_t b_hi = b_st + (uint64_t)(k * kb16);
+            if (CONCAT) {
+              umma_f16(td, a_hi, b_hi, idesc2, (k > 0) ? 1u : acc0);   // [hi*hi | hi*lo], N = 2*block_n
+              umma_f16(td, a_hi + pa16, b_hi, idesc, 1);               // lo*hi into the hi*hi columns
+            } else {
+              umma_f16(td, a_hi, b_hi, idesc, (k > 0) ? 1u : acc0);
+              if (PL2) {
+                umma_f16(td, a_hi, b_hi + pb16, idesc, 1);
+                umma_f16(td, a_hi + pa16, b_hi, idesc, 1);
+              }
             }
-            a_hi += 2;      // 32 bytes = one UMMA_K slice inside the swizzled row
-            b_hi += kb16;
           }
         }
         umma_commit(&empty[s]);
@@ -512,26 +629,37 @@ __global__ void __launch_bounds__(kThreads, 1) tc_convp_kernel(const __grid_cons
       umma_commit(&patch_empty[slot]);   // slot may be overwritten once these MMAs have read it
       }
       umma_commit(&tmem_full[buf]);    // accumulators of this tile complete
+      if (PROF) atomicAdd((unsigned long long*)p.dbg + 3, (unsigned long long)(clock64() - tm0));
     }
    }
   } else {
-    // ---- epilogue: T accumulator tiles per work item, each an (RH x SW) pixel box ----
-    const int q = warp & 3;
+    // ---- epilogue: T accumulator tiles per work item, each an (RH x SW) pixel box; 8 warps, warp (q, half)
+    // owns TMEM lanes 32q.. and every second group of 16 columns ----
+    const int q = warp & 3, half = (warp - 2) >> 2;
     const int r = q * 32 + lane;
     int li = 0;
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++li) {
       const int tile_n = tile / tiles_mn, rem = tile % tiles_mn;
       const int img = rem / p.tiles_y, ty = rem % p.tiles_y;
       const int y0 = ty * p.T * p.RH, n0 = tile_n * p.block_n;
-      const int buf = li & 1;
-      bool ok = mbar_wait(&tmem_full[buf], (li >> 1) & 1, p.err, 3);
+      const int buf = li % p.nbuf;
+      long long te0 = (PROF && threadIdx.x == 64) ? clock64() : 0;
+      bool ok = mbar_wait(&tmem_full[buf], (li / p.nbuf) & 1, p.err, 3);
+      long long te1 = (PROF && threadIdx.x == 64) ? clock64() : 0;
       fence_after_sync();
       for (int t = 0; t < p.T; ++t) {
-        const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + buf * acc_cols + t * p.block_n;
-        conv_tile_epilogue(p, stg, trow, r, ok, 0, y0 + t * p.RH, img, n0);
+        const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + buf * acc_cols + t * p.acc_tile_cols;
+        if (p.epi == EPI_BF16_POOL)
+          convp_pool_epilogue(p, reinterpret_cast<float*>(stg), trow, r, half, ok, y0 + t * p.RH, img, n0);
+        else
+          conv_tile_epilogue(p, stg, trow, r, ok, 0, y0 + t * p.RH, img, n0, half, 2);
       }
       fence_before_sync();
       mbar_arrive(&tmem_empty[buf]);
+      if (PROF && threadIdx.x == 64) {
+        atomicAdd((unsigned long long*)p.dbg + 4, (unsigned long long)(te1 - te0));
+        atomicAdd((unsigned long long*)p.dbg + 5, (unsigned long long)(clock64() - te1));
+      }
     }
   }
   __syncthreads();
@@ -570,6 +698,7 @@ struct alignas(64) WgParams {
   const float* oscale;
 };
 
+template <bool PL2>
 __global__ void __launch_bounds__(kThreads, 1) tc_wgradv_kernel(const __grid_constant__ WgParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -652,25 +781,37 @@ __global__ void __launch_bounds__(kThreads, 1) tc_wgradv_kernel(const __grid_con
     const uint64_t b0 = make_smem_desc(smem0 + a_stage, p.rowbytes_b, 8 * p.rowbytes_b, lb);
     const uint32_t st16 = stage_bytes >> 4, pa16 = p.a_plane_bytes >> 4, pb16 = p.b_plane_bytes >> 4;
     const uint32_t ka16 = (16 * 128) >> 4, kb16 = (16 * p.rowbytes_b) >> 4, row16 = p.rowbytes_b >> 4;
+    // per-segment constants of this N-tile, hoisted out of the K loop (<= 8 segments; the unrolled loops below
+    // keep them in registers): instruction descriptor, accumulator columns, B-descriptor offset
+    constexpr int kMaxSeg = 8;
+    const int nseg = seg1 - seg0;
+    uint32_t s_idesc[kMaxSeg], s_td[kMaxSeg], s_boff[kMaxSeg];
+#pragma unroll
+    for (int gi = 0; gi < kMaxSeg; ++gi) {
+      const WgSeg sg = p.seg[seg0 + (gi < nseg ? gi : 0)];
+      s_idesc[gi] = make_idesc16(128, sg.nkw * p.cw, 1, 1, p.f16);
+      s_td[gi] = tmem_base + sg.col0;
+      s_boff[gi] = (uint32_t)((sg.box - box0) * (p.b_box_bytes >> 4) + sg.kw0 * row16);
+    }
     int s = 0, ph = 0;
     for (int it = 0; it < nsteps; ++it) {
       mbar_wait(&full[s], ph, p.err, 2);
       fence_after_sync();
       const uint64_t a_st = a0 + (uint64_t)(s * st16), b_st = b0 + (uint64_t)(s * st16);
-      for (int g = seg0; g < seg1; ++g) {
-        const WgSeg sg = p.seg[g];
-        const uint32_t idesc = make_idesc16(128, sg.nkw * p.cw, 1, 1, p.f16);
-        const uint32_t td = tmem_base + sg.col0;
-        uint64_t a_hi = a_st;
-        uint64_t b_hi = b_st + (uint64_t)((sg.box - box0) * (p.b_box_bytes >> 4) + sg.kw0 * row16);
-        for (int k = 0; k < 4; ++k) {
-          umma_f16(td, a_hi, b_hi, idesc, (it > 0 || k > 0) ? 1u : 0u);
-          if (p.planes == 2) {
-            umma_f16(td, a_hi, b_hi + pb16, idesc, 1);
-            umma_f16(td, a_hi + pa16, b_hi, idesc, 1);
+      const uint32_t acc = it > 0 ? 1u : 0u;
+#pragma unroll
+      for (int gi = 0; gi < kMaxSeg; ++gi) {
+        if (gi < nseg) {
+          const uint64_t b_sg = b_st + (uint64_t)s_boff[gi];
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const uint64_t a_hi = a_st + (uint64_t)(k * ka16), b_hi = b_sg + (uint64_t)(k * kb16);
+            umma_f16(s_td[gi], a_hi, b_hi, s_idesc[gi], k > 0 ? 1u : acc);
+            if (PL2) {
+              umma_f16(s_td[gi], a_hi, b_hi + pb16, s_idesc[gi], 1);
+              umma_f16(s_td[gi], a_hi + pa16, b_hi, s_idesc[gi], 1);
+            }
           }
-          a_hi += ka16;
-          b_hi += kb16;
         }
       }
       umma_commit(&empty[s]);
@@ -783,8 +924,17 @@ static int launch(ugn_ctx* ctx, TcParams& p, dim3 grid, cudaStream_t st) {
     UGN_CUDA(cudaMemset(ctx->err_flag, 0, sizeof(int)));
   }
   p.err = ctx->err_flag;
-  UGN_CUDA(cudaFuncSetAttribute(tc_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  tc_kernel<MODE><<<grid, kThreads, smem, st>>>(p);
+#define TC_LAUNCH(PL2, KSL)                                                                                     \
+  do {                                                                                                         \
+    UGN_CUDA(cudaFuncSetAttribute(tc_kernel<MODE, PL2, KSL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+    tc_kernel<MODE, PL2, KSL><<<grid, kThreads, smem, st>>>(p);                                                \
+  } while (0)
+  if (p.planes == 2) {
+    if (p.kslices == 4) TC_LAUNCH(true, 4); else if (p.kslices == 2) TC_LAUNCH(true, 2); else TC_LAUNCH(true, 0);
+  } else {
+    if (p.kslices == 4) TC_LAUNCH(false, 4); else if (p.kslices == 2) TC_LAUNCH(false, 2); else TC_LAUNCH(false, 0);
+  }
+#undef TC_LAUNCH
   UGN_LAUNCHED(ctx);
   return UGN_OK;
 }
@@ -834,8 +984,6 @@ int tc_gemm_ex(ugn_ctx* ctx, int P, int f16, int M, int N, int K, const __nv_bfl
   p.ksplit = split;
   p.epi = (split > 1 || accumulate) ? EPI_F32_ATOMIC : EPI_F32;
   p.out_f32 = C; p.ldc = ldc; p.bias = bias; p.mask = mask; p.act = act; p.alpha = alpha;
-  if (const char* e = getenv("UGN_DBG_SHIFT")) p.dbg_shift = atoi(e);
-  if (const char* e = getenv("UGN_DBG_BASEOFF")) p.dbg_bo = atoi(e);
   if (split > 1 && !accumulate) UGN_CUDA(cudaMemsetAsync(C, 0, sizeof(float) * (size_t)M * ldc, st));
   dim3 grid(ugn_cdiv(M, 128), ugn_cdiv(N, p.block_n), split);
   return launch<MODE_GEMM>(ctx, p, grid, st);
@@ -890,12 +1038,17 @@ static int convp_launch(ugn_ctx* ctx, TcParams& p, const __nv_bfloat16* act, int
   p.ksteps_total = KH * KW * p.ncc; p.ksplit = 1;
   const size_t b_stage = (size_t)P * p.b.plane_bytes;
   const size_t budget = 222 * 1024, fixed = 17 * 1024 + 2048;
+  // accumulator columns per tile: block_n, or 2*block_n when hi*[hi|lo] is issued as one MMA (K-major
+  // weight planes that are exactly adjacent in the ring stage)
+  p.concat = (P == 2 && sgn > 0 && p.b.major == 0 && p.block_n <= 128 && p.b.plane_bytes == p.block_n * rowbytes &&
+              !getenv("UGN_NO_CONCAT")) ? 1 : 0;
+  p.acc_tile_cols = p.concat ? 2 * p.block_n : p.block_n;
   int T = 0;
   p.cps = p.ncc; p.nslots = 1;
   for (int ring = 0; ring < 2 && !T; ++ring) {           // ring: stream one channel chunk at a time (2 slots)
     if (ring && p.ncc == 1) break;
     for (int cand : {2, 1}) {
-      if (cand * p.block_n > 256) continue;               // two accumulator sets must fit 512 TMEM columns
+      if (cand * p.acc_tile_cols > 512) continue;         // at least one accumulator set in the 512 TMEM columns
       if (cand > 1 && (cand - 1) * RH >= Hneed) continue;
       size_t chunk = (size_t)P * (size_t)(cand * RH + KH - 1) * SW * rowbytes;
       size_t patch = ring ? 2 * chunk : p.ncc * chunk;
@@ -904,6 +1057,12 @@ static int convp_launch(ugn_ctx* ctx, TcParams& p, const __nv_bfloat16* act, int
   }
   if (!T) return UGN_ERR_UNSUPPORTED;
   p.ngroups = p.ncc / p.cps;
+  // hi*[hi|lo] concatenation doubles the accumulator columns: keep it only while TWO accumulator sets
+  // still fit (measured: conv1-OF / conv3 with T = 1 gain 12-15 %; conv1-gray with T = 2 would fall back
+  // to a single set and lose more to the exposed epilogue than the wider MMA wins)
+  if (p.concat && 2 * T * p.acc_tile_cols > 512) { p.concat = 0; p.acc_tile_cols = p.block_n; }
+  p.nbuf = (2 * T * p.acc_tile_cols <= 512) ? 2 : 1;      // single set (Cout = 192 tiles): the epilogue shares
+                                                          // the tile-boundary bubble with the next patch load
   p.T = T; p.SW = SW; p.RH = RH; p.PR = T * RH + KH - 1;
   p.bw = SW; p.bh = RH; p.bn = 1;
   p.patch_chunk_bytes = p.PR * SW * rowbytes;
@@ -932,10 +1091,49 @@ static int convp_launch(ugn_ctx* ctx, TcParams& p, const __nv_bfloat16* act, int
   const int tiles_mn = p.tiles_y * B, tiles_n = ugn_cdiv(p.Cout, p.block_n);
   p.N = tiles_mn;
   p.M = tiles_mn * tiles_n;
-  UGN_CUDA(cudaFuncSetAttribute(tc_convp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   dim3 grid(std::min(p.M, ctx->sm_count), 1, 1);
-  tc_convp_kernel<<<grid, kThreads, smem, st>>>(p);
+  static long long* dbg_buf = nullptr;
+  const bool prof = getenv("UGN_CONVP_PROF") != nullptr;
+  if (prof) {
+    if (!dbg_buf) UGN_CUDA(cudaMalloc(&dbg_buf, 8 * sizeof(long long)));
+    UGN_CUDA(cudaMemsetAsync(dbg_buf, 0, 8 * sizeof(long long), st));
+    p.dbg = dbg_buf;
+  }
+#define CONVP_LAUNCH(C, PR, TT, KSL, PL2)                                                                      \
+  do {                                                                                                         \
+    UGN_CUDA(cudaFuncSetAttribute(tc_convp_kernel<C, PR, TT, KSL, PL2>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                  (int)smem));                                                                 \
+    tc_convp_kernel<C, PR, TT, KSL, PL2><<<grid, kConvpThreads, smem, st>>>(p);                                \
+  } while (0)
+#define CONVP_T_K(C, PR, PL2)                                                          \
+  do {                                                                                 \
+    if (p.T == 2 && p.kslices == 4) CONVP_LAUNCH(C, PR, 2, 4, PL2);                    \
+    else if (p.T == 2 && p.kslices == 2) CONVP_LAUNCH(C, PR, 2, 2, PL2);               \
+    else if (p.T == 1 && p.kslices == 4) CONVP_LAUNCH(C, PR, 1, 4, PL2);               \
+    else if (p.T == 1 && p.kslices == 2) CONVP_LAUNCH(C, PR, 1, 2, PL2);               \
+    else UGN_FAIL(UGN_ERR_UNSUPPORTED, "convp: unsupported T=%d kslices=%d", p.T, p.kslices); \
+  } while (0)
+  if (prof) {          // profiling build of the two shapes of interest only (code size)
+    if (p.concat) CONVP_T_K(true, true, true);
+    else if (P == 2) CONVP_T_K(false, true, true);
+    else CONVP_T_K(false, true, false);
+  } else if (p.concat) CONVP_T_K(true, false, true);
+  else if (P == 2) CONVP_T_K(false, false, true);
+  else CONVP_T_K(false, false, false);
+#undef CONVP_T_K
+#undef CONVP_LAUNCH
   UGN_LAUNCHED(ctx);
+  if (prof) {   // development aid: synchronous read-back of the per-role wait cycles (averaged per CTA)
+    long long h[8];
+    UGN_CUDA(cudaStreamSynchronize(st));
+    UGN_CUDA(cudaMemcpy(h, dbg_buf, sizeof(h), cudaMemcpyDeviceToHost));
+    const double n = grid.x;
+    fprintf(stderr, "[convp sgn=%d Co=%d bn=%d T=%d nbuf=%d concat=%d stages=%d nslots=%d iters/CTA=%.1f] per CTA kclk: "
+            "mma{wait patch %.0f, wait B %.0f, wait tmem %.0f, total %.0f} epi{wait %.0f, work %.0f} "
+            "prod{wait ring %.0f, wait patch slot %.0f}\n", sgn, p.Cout, p.block_n, p.T, p.nbuf, p.concat, p.stages,
+            p.nslots, p.M / n, h[0] / n / 1e3, h[1] / n / 1e3, h[2] / n / 1e3, h[3] / n / 1e3, h[4] / n / 1e3,
+            h[5] / n / 1e3, h[6] / n / 1e3, h[7] / n / 1e3);
+  }
   return UGN_OK;
 }
 
@@ -957,7 +1155,10 @@ int tc_conv_fwd(ugn_ctx* ctx, const ConvGeom& g, int P, int f16, const __nv_bflo
   p.Hp = g.Hp; p.Wp = g.Wp;
   p.block_n = g.Co > 128 ? ((g.Co % 256 == 0 || g.Co > 192) ? 256 : (g.Co + 15) / 16 * 16) : (g.Co + 15) / 16 * 16;
   if (p.block_n > 256) p.block_n = 256;
-  if (P == 2 && p.block_n > 128) p.block_n = (g.Co % 128 == 0) ? 128 : ((g.Co % 96 == 0) ? 96 : 64);
+  // split operands: N = 192 tiles run at the full tensor rate (96 clk per MMA), N <= 128 tiles cost 73 clk
+  // each and are issued as hi*[hi|lo] pairs instead (convp_launch: concat)
+  if (P == 2 && p.block_n > 128)
+    p.block_n = (g.Co % 192 == 0 && !getenv("UGN_NO_N192")) ? 192 : (g.Co % 128 == 0) ? 128 : ((g.Co % 96 == 0) ? 96 : 64);
   int rc;
   {  // weights [P][Co][taps][Cp] K-major: dims (Cp, taps, Co, P, 1)
     const int taps = g.KH * g.KW;
@@ -1091,10 +1292,13 @@ static int wgradv_launch(ugn_ctx* ctx, const ConvGeom& g, int P, int f16, const 
   p.ntiles_n = ntile;
   int max_boxes = 0;
   for (int j = 0; j < ntile; ++j) max_boxes = std::max(max_boxes, p.tile_box0[j + 1] - p.tile_box0[j]);
-  p.b_plane_bytes = (4 * p.b_box_bytes + 1023) / 1024 * 1024;   // 4 box slots (zero-tail loop assumes 4)
   if (max_boxes > 4) return UGN_ERR_UNSUPPORTED;
+  for (int j = 0; j < ntile; ++j)
+    if (p.tile_seg0[j + 1] - p.tile_seg0[j] > 8) return UGN_ERR_UNSUPPORTED;   // kMaxSeg of the issue loop
+  // ring stage sized by the boxes an N-tile really uses (1-3), not the 4-slot maximum: more stages in flight
+  p.b_plane_bytes = (max_boxes * p.b_box_bytes + 1023) / 1024 * 1024;
   size_t stage = (size_t)P * (p.a_plane_bytes + p.b_plane_bytes);
-  int stages = (int)std::min<size_t>(6, (220 * 1024) / stage);
+  int stages = (int)std::min<size_t>(8, (220 * 1024) / stage);
   if (stages < 2) return UGN_ERR_UNSUPPORTED;
   p.stages = stages;
   int rc;
@@ -1124,10 +1328,15 @@ static int wgradv_launch(ugn_ctx* ctx, const ConvGeom& g, int P, int f16, const 
   }
   p.err = ctx->err_flag;
   size_t smem = stages * stage + 1024 + (2 * stages + 1) * 8 + 16;
-  UGN_CUDA(cudaFuncSetAttribute(tc_wgradv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   UGN_CUDA(cudaMemsetAsync(dw, 0, sizeof(float) * (size_t)g.Co * p.ntaps * g.Cin, st));
   dim3 grid(ntile_m, ntile, p.ksplit);
-  tc_wgradv_kernel<<<grid, kThreads, smem, st>>>(p);
+  if (P == 2) {
+    UGN_CUDA(cudaFuncSetAttribute(tc_wgradv_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    tc_wgradv_kernel<true><<<grid, kThreads, smem, st>>>(p);
+  } else {
+    UGN_CUDA(cudaFuncSetAttribute(tc_wgradv_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    tc_wgradv_kernel<false><<<grid, kThreads, smem, st>>>(p);
+  }
   UGN_LAUNCHED(ctx);
   return UGN_OK;
 }
