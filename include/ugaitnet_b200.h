@@ -94,6 +94,15 @@ int ugn_ctx_has_tcgen05(ugn_ctx* ctx);
  * x_nchw f32 [B,C,H,W] (what the Keras Input layers receive, nets/mj_uwyhNets_ba.py:1069-1074)
  * -> NHWC with C padded to Cp: f32 [B,H,W,Cp] or bf16 [P,B,H,W,Cp]; pad channels = 0. */
 int ugn_pack_input(ugn_ctx*, const ugn_tensor* x_nchw, ugn_tensor* x_nhwc, void* stream);
+/* The same pack with the generator's missing-modality expansion and mirror augmentation done ON THE
+ * DEVICE (data/mj_dataGeneratorMMUWYHsingle.py:780-812, data/mj_augmentation.py:12-32), so only the base
+ * rows cross PCIe: output row b reads x_base row src_row[b] (i32 [B], nullable = identity);
+ * enable f32 [B] (nullable; the modality's use-flag): 0 -> the row's whole volume is the constant
+ * `noise` (the reference's 1e-9); mirror u8 [B] (nullable): != 0 -> every channel flipped left-right
+ * and even channels negated (literally what mj_mirrorsequence does, for every modality). */
+int ugn_pack_input_expand(ugn_ctx*, const ugn_tensor* x_base, const ugn_tensor* src_row,
+                          const ugn_tensor* enable, const ugn_tensor* mirror, float noise,
+                          ugn_tensor* x_nhwc, void* stream);
 
 /* master f32 conv kernel [Cout][kh][kw][Cin] -> compute copy f32 [Cout][kh][kw][Cp] or
  * bf16 [P][Cout][kh][kw][Cp]; also used for dense weights with w viewed as [out][1][1][in]. */
@@ -235,6 +244,19 @@ int ugn_knn_topk_tc(ugn_ctx*, const ugn_tensor* queries, const ugn_tensor* q16,
 int ugn_knn_merge_vote(ugn_ctx*, const ugn_tensor* d2, const ugn_tensor* idx,
                        const ugn_tensor* lab, int k, ugn_tensor* out_d2, ugn_tensor* out_idx,
                        ugn_tensor* out_lab, ugn_tensor* pred, void* stream);
+
+/* ---- a13: video-level summaries of the open-world test -----------------------------------
+ * (mains/mj_testUWYHGaitNet_open_tum.py:355-420).  Rows are grouped by video through a CSR built
+ * on the host the way the reference does (np.unique / np.where): order i32 [N] = row indices sorted
+ * by video (stable), offsets i32 [V+1].
+ * ugn_segment_pool: out f32 [V,D] = per-video mean (use_avg != 0) or max of codes f32 [N,D].
+ * ugn_segment_mode: out i32 [V] = statistics.mode of labels i32 [N] per video: most frequent label,
+ *   ties -> first encountered (Python >= 3.8); legacy_ties != 0 -> on a tie the video's first label
+ *   (the reference's `except:` branch under Python < 3.8, where mode() raised on ties). */
+int ugn_segment_pool(ugn_ctx*, const ugn_tensor* codes, const ugn_tensor* order,
+                     const ugn_tensor* offsets, int use_avg, ugn_tensor* out, void* stream);
+int ugn_segment_mode(ugn_ctx*, const ugn_tensor* labels, const ugn_tensor* order,
+                     const ugn_tensor* offsets, int legacy_ties, ugn_tensor* out, void* stream);
 
 /* ---- generic tensor-core GEMM (building block exposed for tests / k-NN / triplet) ----
  * C f32 [M,N] (+)= A . B^T with bf16 (or f16) operands [P,rows,cols]:

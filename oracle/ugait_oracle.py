@@ -443,3 +443,27 @@ def synth_batch(cfg: NetConfig, base_rows: int, expand: int, seed: int = 232323,
                 else:
                     xs[m][r] = xs[m][i * E]
     return xs, fl, labels
+
+
+def video_level(codes, labels, vids, preds=None, use_avg=True):
+    """mains/mj_testUWYHGaitNet_open_tum.py:355-420 restated loop for loop: per unique video id the
+    descriptors are averaged (or max-pooled), labels / predictions voted with statistics.mode (first
+    encountered mode on ties, Python >= 3.8; first element if mode() raises)."""
+    import statistics
+    codes, labels, vids = np.asarray(codes), np.asarray(labels).reshape(-1), np.asarray(vids).reshape(-1)
+    uvids = np.unique(vids)
+    out_codes, out_labs, out_preds = [], [], []
+    for vix in uvids:
+        idx = np.where(vids == vix)[0]
+        vid_logits = codes[idx, ]
+        out_codes.append(vid_logits.mean(axis=0) if use_avg else vid_logits.max(axis=0))
+        try:
+            out_labs.append(statistics.mode(labels[idx]))
+        except Exception:
+            out_labs.append(labels[idx][0])
+        if preds is not None:
+            try:
+                out_preds.append(statistics.mode(np.asarray(preds)[idx]))
+            except Exception:
+                out_preds.append(np.asarray(preds)[idx][0])
+    return uvids, np.vstack(out_codes), np.asarray(out_labs), (np.asarray(out_preds) if preds is not None else None)

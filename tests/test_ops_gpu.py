@@ -336,3 +336,86 @@ def test_errors_are_loud(ctx):
         ops.flatten_chw(ctx, torch.zeros(1, 2, 2, 4), torch.zeros(1, 16, device="cuda"))
     with pytest.raises(UgnError, match="shape"):
         ops.flatten_chw(ctx, torch.zeros(1, 2, 2, 4, device="cuda"), torch.zeros(1, 15, device="cuda"))
+
+
+@pytest.mark.parametrize("dt", ["f32", "f16"])
+def test_pack_input_expand_and_mirror(ctx, dt):
+    """ugn_pack_input_expand vs the numpy restatement of the generator's expansion (:806-812) and of
+    mj_mirrorsequence (data/mj_augmentation.py:12-32: LR flip + even channels negated)."""
+    from ugaitnet_b200 import ops
+    from ugaitnet_b200.expand import NOISE, expand_on_host, mirror_sequence
+    rng = np.random.default_rng(3)
+    B0, C, H, Cp = 3, 6, 10, 32 if dt == "f16" else 6
+    base = rng.normal(size=(B0, C, H, H)).astype(np.float32)
+    src = np.array([0, 0, 1, 2, 2, 1, 0], dtype=np.int32)
+    en = np.array([1, 0, 1, 1, 0, 1, 1], dtype=np.float32)
+    mir = np.array([0, 0, 1, 0, 1, 1, 0], dtype=np.uint8)
+    ref = expand_on_host(base, src, en)
+    for b in range(len(src)):
+        if mir[b] and en[b]:
+            ref[b] = mirror_sequence(ref[b])
+    if dt == "f32":
+        out = torch.zeros(len(src), H, H, Cp, device="cuda")
+    else:
+        out = torch.zeros(2, len(src), H, H, Cp, dtype=torch.float16, device="cuda")
+    ops.pack_input_expand(ctx, torch.tensor(base).cuda(), torch.tensor(src).cuda(), torch.tensor(en).cuda(),
+                          torch.tensor(mir).cuda(), out, noise=NOISE)
+    got = (out if dt == "f32" else out.float().sum(0))[..., :C].permute(0, 3, 1, 2).cpu().numpy()
+    # fp16 planes: 1e-9 is below the smallest fp16 subnormal and becomes 0 -- immaterial, the row's use-flag
+    # gates the branch output to exactly 0 either way (nets/mj_uwyhNets_ba.py:51-54)
+    assert np.allclose(got, ref, rtol=1e-6 if dt == "f32" else 2e-6, atol=1e-12 if dt == "f32" else 1e-7)   # fp16 lo plane: subnormal below 6e-5
+    if Cp > C:
+        assert float(out.float().abs()[..., C:].max()) == 0.0
+    if dt == "f32":
+        assert np.allclose(got[1], NOISE, rtol=1e-3)   # disabled row == the reference's noise constant
+
+
+@pytest.mark.parametrize("use_avg", [True, False])
+def test_video_level_pool_and_vote(ctx, use_avg):
+    """a13: per-video descriptor pooling + statistics.mode vote vs the oracle's loop-for-loop restatement of
+    mains/mj_testUWYHGaitNet_open_tum.py:355-420 (ragged videos, single-row videos, vote ties)."""
+    from ugaitnet_b200.video import video_groups, pool_per_video, mode_per_video
+    rng = np.random.default_rng(4)
+    N, D = 157, 70
+    vids = rng.integers(0, 23, N)
+    vids[:3] = 99                                   # unsorted ids, a video with 3 rows
+    codes = rng.normal(size=(N, D)).astype(np.float32)
+    labels = rng.integers(0, 4, N).astype(np.int32)     # few classes -> frequent ties
+    preds = rng.integers(0, 4, N).astype(np.int32)
+    uv, oc_, ol, op = O.video_level(codes, labels, vids, preds, use_avg)
+    u, order, offsets = video_groups(vids)
+    assert np.array_equal(u, uv)
+    pc = pool_per_video(ctx, codes, order, offsets, use_avg).cpu().numpy()
+    assert np.allclose(pc, oc_, rtol=1e-6, atol=1e-7)
+    assert np.array_equal(mode_per_video(ctx, labels, order, offsets).cpu().numpy(), ol)      # bit-exact votes
+    assert np.array_equal(mode_per_video(ctx, preds, order, offsets).cpu().numpy(), op)
+
+
+def test_open_world_evaluation_end_to_end(ctx):
+    from ugaitnet_b200.video import evaluate_open_world
+    rng = np.random.default_rng(8)
+    D, ncls = 48, 12
+    cent = rng.normal(size=(ncls, D)).astype(np.float32)
+
+    def make(nv):
+        labs, vids, codes = [], [], []
+        for v in range(nv):
+            c = v % ncls
+            n = int(rng.integers(2, 7))
+            codes.append(cent[c] + 0.4 * rng.normal(size=(n, D)).astype(np.float32))
+            labs += [c] * n
+            vids += [1000 + v] * n
+        return np.vstack(codes), np.array(labs, dtype=np.int32), np.array(vids)
+    cg, lg, vg = make(60)
+    ct, lt, vt = make(40)
+    res = evaluate_open_world(cg, lg, vg, ct, lt, vt, knn=3)
+    pred_o, _ = O.knn_predict(cg, lg, ct, 3)
+    assert np.array_equal(res["pred"].cpu().numpy(), pred_o)
+    uv, cvg, lvg, _ = O.video_level(cg, lg, vg)
+    _, cvt, lvt, pvt = O.video_level(ct, lt, vt, pred_o)
+    assert np.array_equal(res["pred_vid"].cpu().numpy(), pvt) and np.array_equal(res["labs_vid"].cpu().numpy(), lvt)
+    pm, _ = O.knn_predict(cvg, lvg, cvt, 3)
+    # pooled descriptors agree to fp32 rounding; the merged k-NN must give the same labels
+    assert np.array_equal(res["pred_vid_merged"].cpu().numpy(), pm)
+    acc, acc_vid, score = res["summary"]
+    assert acc > 0.9 and acc_vid >= acc - 0.05 and score > 0.9

@@ -142,3 +142,19 @@ def test_oracle_step_gradients_finite_and_adam_decreases_loss():
         losses.append(float(res["loss"]))
         O.adam_step(P, G, M, V, t, lr=1e-3)
     assert losses[-1] < losses[0]
+
+
+def test_expansion_pattern_matches_oracle_generator():
+    """ugaitnet_b200.expand.expansion_pattern (host side of the device-side expansion) draws the same
+    missing-modality pattern as the oracle's restatement of the reference generator (:791-803)."""
+    import random
+    from ugaitnet_b200.expand import expansion_pattern, expand_on_host
+    oc = O.NetConfig(in_channels=(6, 4, 4), filters_numbers=(8, 8, 16, 16), nd=32, nclasses=10)
+    for E in (2, 3, 4):
+        xs, fl, lab = O.synth_batch(oc, base_rows=6, expand=E, seed=11)
+        src, use = expansion_pattern(6, E, 3, random.Random(11))
+        assert np.array_equal(src, np.repeat(np.arange(6), E))
+        for m in range(3):
+            assert np.array_equal(use[:, m], fl[m].reshape(-1))
+            assert np.array_equal(expand_on_host(xs[m][::E], src, use[:, m]), xs[m])
+        assert (use.sum(1) >= 1).all()          # never all modalities missing

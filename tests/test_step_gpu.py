@@ -247,3 +247,35 @@ def test_predict_matches_oracle_descriptor():
                              [torch.tensor(f, dtype=torch.float64) for f in fl], P, oc)
     cos = torch.nn.functional.cosine_similarity(sig.double().cpu(), ref, dim=1)
     assert float(cos.min()) >= 0.999
+
+
+def test_device_side_expansion_equals_host_expanded_batch():
+    """train_step_expanded(base rows + pattern) == train_step(host-expanded batch): the
+    generator's expansion (data/mj_dataGeneratorMMUWYHsingle.py:780-812) done inside the input pack."""
+    import random
+    from ugaitnet_b200.expand import expansion_pattern, expand_on_host
+    from ugaitnet_b200.net import UGaitEngine
+    oc, _, P, xs, fl, lab, _, _ = setup("3mod_signmax")
+    E, B0 = 4, 6
+    base = [x[::E].copy() for x in xs]                      # rows i*E of the synthetic batch are the base rows
+    lab0 = lab[::E].reshape(-1)
+    src, use = expansion_pattern(B0, E, oc.nmods, random.Random(5))
+    full = [expand_on_host(base[m], src, use[:, m]) for m in range(oc.nmods)]
+    flags = [use[:, m:m + 1].copy() for m in range(oc.nmods)]
+    outs = []
+    for expanded in (False, True):
+        eng = UGaitEngine(to_engine_cfg(oc), math_mode="fp32", lr=1e-3)
+        eng.load_params(P)
+        cu = lambda a: torch.as_tensor(np.asarray(a), dtype=torch.float32).cuda()
+        if expanded:
+            o = eng.train_step_expanded([cu(b) for b in base], torch.as_tensor(lab0), src, use)
+        else:
+            o = eng.train_step([cu(f) for f in full], [cu(f) for f in flags], torch.as_tensor(lab0[src]).cuda())
+        eng.ctx.check()
+        outs.append((float(o["triplet"]), float(o["ce"]), eng.export_grads(), o["signature"].clone()))
+    assert outs[0][0] == pytest.approx(outs[1][0], rel=1e-6)
+    assert outs[0][1] == pytest.approx(outs[1][1], rel=1e-6)
+    assert rel(outs[1][3], outs[0][3].double().cpu()) < 1e-6
+    for k in outs[0][2]:
+        if float(outs[0][2][k].norm()) > 0:
+            assert rel(outs[1][2][k], outs[0][2][k].double().cpu()) < 1e-5, k

@@ -45,6 +45,7 @@ _PROTOS = {
     "ugn_ctx_has_tcgen05": (c_int, [c_void_p]),
     "ugn_launch_count": (c_int64, [c_void_p]),
     "ugn_pack_input": (c_int, [c_void_p, _T, _T, c_void_p]),
+    "ugn_pack_input_expand": (c_int, [c_void_p, _T, _T, _T, _T, c_float, _T, c_void_p]),
     "ugn_pack_weight": (c_int, [c_void_p, _T, _T, c_void_p]),
     "ugn_split_bf16": (c_int, [c_void_p, _T, _T, c_void_p]),
     "ugn_conv2d_fwd": (c_int, [c_void_p, _T, _T, _T, _T, _T, c_int, c_float, c_int, c_void_p]),
@@ -73,6 +74,8 @@ _PROTOS = {
     "ugn_knn_topk_tc": (c_int, [c_void_p, _T, _T, _T, _T, _T, _T, _T, c_int, c_int64, _T, _T, _T, _T, _T, c_void_p]),
     "ugn_knn_topk": (c_int, [c_void_p, _T, _T, _T, _T, c_int, c_int64, _T, _T, _T, _T, c_void_p]),
     "ugn_knn_merge_vote": (c_int, [c_void_p, _T, _T, _T, c_int, _T, _T, _T, _T, c_void_p]),
+    "ugn_segment_pool": (c_int, [c_void_p, _T, _T, _T, c_int, _T, c_void_p]),
+    "ugn_segment_mode": (c_int, [c_void_p, _T, _T, _T, c_int, _T, c_void_p]),
     "ugn_gemm_bf16": (c_int, [c_void_p, _T, c_int, _T, c_int, _T, c_int, c_void_p]),
     "ugn_grad_scale_update": (c_int, [c_void_p, _T, c_float, c_void_p]),
     "ugn_grad_scale_set": (c_int, [c_void_p, c_float, c_void_p]),

@@ -102,7 +102,8 @@ extern "C" int ugn_ctx_has_tcgen05(ugn_ctx* ctx) { return ctx && ctx->cc_major =
 extern "C" int64_t ugn_launch_count(ugn_ctx* ctx) { return ctx ? ctx->launches : 0; }
 
 // ---- implementations living in other translation units --------------------------------
-int ew_pack_input(ugn_ctx*, const float*, void*, int, int, int, int, int, int, int, cudaStream_t);
+int ew_pack_input(ugn_ctx*, const float*, void*, int, int, int, int, int, int, int, const int*, const float*,
+                  const uint8_t*, float, cudaStream_t);
 int ew_pack_weight(ugn_ctx*, const float*, void*, int, int, long long, int, int, cudaStream_t);
 int ew_split(ugn_ctx*, const float*, __nv_bfloat16*, int, int, long long, cudaStream_t);
 int ew_bwd_act(ugn_ctx*, const float*, const void*, int, const uint8_t*, void*, float*, int*, int, int, int, int,
@@ -146,19 +147,35 @@ static inline bool is_16(const ugn_tensor* t) { UgnDType d = ugn_dtype(t); retur
   UGN_CHECK(ugn_dtype(a) == ugn_dtype(b), what ": operands must share one storage dtype (f32 | bf16 | f16)")
 static inline const int64_t* lshape(const ugn_tensor* t, int rank) { return t->shape + (t->ndim - rank); }
 
-extern "C" int ugn_pack_input(ugn_ctx* ctx, const ugn_tensor* x_nchw, ugn_tensor* x_nhwc, void* stream) {
+static int pack_input_common(ugn_ctx* ctx, const ugn_tensor* x_nchw, const ugn_tensor* src_row,
+                             const ugn_tensor* enable, const ugn_tensor* mirror, float noise, ugn_tensor* x_nhwc,
+                             void* stream) {
   UGN_CHECK(ctx && x_nchw && x_nhwc, "ugn_pack_input: null argument");
   UGN_TENSOR(x_nchw, DT_F32, 4, 4);
   UGN_TENSOR(x_nhwc, DT_BAD, 4, 5);
   int mode = storage_mode(x_nhwc, 4);
-  UGN_CHECK(mode >= 0, "x_nhwc must be f32 [B,H,W,Cp] or bf16 [P,B,H,W,Cp]");
+  UGN_CHECK(mode >= 0, "x_nhwc must be f32 [B,H,W,Cp] or 16-bit [P,B,H,W,Cp]");
   const int64_t* s = lshape(x_nhwc, 4);
-  int B = (int)x_nchw->shape[0], C = (int)x_nchw->shape[1], H = (int)x_nchw->shape[2], W = (int)x_nchw->shape[3];
-  UGN_CHECK(s[0] == B && s[1] == H && s[2] == W && s[3] >= C, "pack_input: shape mismatch");
+  int B0 = (int)x_nchw->shape[0], C = (int)x_nchw->shape[1], H = (int)x_nchw->shape[2], W = (int)x_nchw->shape[3];
+  int B = (int)s[0];
+  UGN_CHECK(s[1] == H && s[2] == W && s[3] >= C, "pack_input: shape mismatch");
+  UGN_CHECK(src_row || B == B0, "pack_input: output rows %d != input rows %d (no src_row given)", B, B0);
   UGN_CHECK((size_t)C * (W + 1) * 4 <= 48 * 1024, "pack_input: C*W too large");
+  if (src_row) { UGN_TENSOR(src_row, DT_I32, 1, 1); UGN_CHECK(src_row->shape[0] == B, "pack_input: src_row must be i32 [B]"); }
+  if (enable) { UGN_TENSOR(enable, DT_F32, 1, 2); UGN_CHECK(ugn_numel(enable) == B, "pack_input: enable must be f32 [B]"); }
+  if (mirror) { UGN_TENSOR(mirror, DT_U8, 1, 1); UGN_CHECK(mirror->shape[0] == B, "pack_input: mirror must be u8 [B]"); }
   if (B == 0) return UGN_OK;
   return ew_pack_input(ctx, ugn_ptr<float>(x_nchw), ugn_ptr<void>(x_nhwc), mode, is_f16(x_nhwc), B, C, H, W, (int)s[3],
-                       (cudaStream_t)stream);
+                       src_row ? ugn_ptr<int>(src_row) : nullptr, enable ? ugn_ptr<float>(enable) : nullptr,
+                       mirror ? ugn_ptr<uint8_t>(mirror) : nullptr, noise, (cudaStream_t)stream);
+}
+extern "C" int ugn_pack_input(ugn_ctx* ctx, const ugn_tensor* x_nchw, ugn_tensor* x_nhwc, void* stream) {
+  return pack_input_common(ctx, x_nchw, nullptr, nullptr, nullptr, 0.f, x_nhwc, stream);
+}
+extern "C" int ugn_pack_input_expand(ugn_ctx* ctx, const ugn_tensor* x_base, const ugn_tensor* src_row,
+                                     const ugn_tensor* enable, const ugn_tensor* mirror, float noise,
+                                     ugn_tensor* x_nhwc, void* stream) {
+  return pack_input_common(ctx, x_base, src_row, enable, mirror, noise, x_nhwc, stream);
 }
 
 extern "C" int ugn_pack_weight(ugn_ctx* ctx, const ugn_tensor* w_master, ugn_tensor* w_packed, void* stream) {
@@ -583,4 +600,40 @@ extern "C" int ugn_grad_scale_update(ugn_ctx* ctx, const ugn_tensor* ref, float 
 extern "C" int ugn_grad_scale_set(ugn_ctx* ctx, float scale, void* stream) {
   UGN_CHECK(ctx && scale > 0.f, "ugn_grad_scale_set: scale must be positive");
   return ew_gscale_update(ctx, nullptr, 0, 1.f, scale, (cudaStream_t)stream);
+}
+
+// ---- a13: video-level pooling and vote --------------------------------------------------------
+int ew_segment_pool(ugn_ctx*, const float*, const int*, const int*, int, int, int, float*, cudaStream_t);
+int ew_segment_mode(ugn_ctx*, const int*, const int*, const int*, int, int, int*, cudaStream_t);
+
+static int segment_common(ugn_ctx* ctx, const ugn_tensor* order, const ugn_tensor* offsets, long long N, int& V) {
+  UGN_TENSOR(order, DT_I32, 1, 1);
+  UGN_TENSOR(offsets, DT_I32, 1, 1);
+  UGN_CHECK(order->shape[0] == N && offsets->shape[0] >= 1, "segment: order must be i32 [N], offsets i32 [V+1]");
+  V = (int)offsets->shape[0] - 1;
+  return UGN_OK;
+}
+extern "C" int ugn_segment_pool(ugn_ctx* ctx, const ugn_tensor* codes, const ugn_tensor* order,
+                                const ugn_tensor* offsets, int use_avg, ugn_tensor* out, void* stream) {
+  UGN_CHECK(ctx && codes && order && offsets && out, "ugn_segment_pool: null argument");
+  UGN_TENSOR(codes, DT_F32, 2, 2);
+  UGN_TENSOR(out, DT_F32, 2, 2);
+  int V = 0;
+  int rc = segment_common(ctx, order, offsets, codes->shape[0], V);
+  if (rc != UGN_OK) return rc;
+  UGN_CHECK(out->shape[0] == V && out->shape[1] == codes->shape[1], "segment_pool: out must be [V,D]");
+  return ew_segment_pool(ctx, ugn_ptr<float>(codes), ugn_ptr<int>(order), ugn_ptr<int>(offsets), V,
+                         (int)codes->shape[1], use_avg, ugn_ptr<float>(out), (cudaStream_t)stream);
+}
+extern "C" int ugn_segment_mode(ugn_ctx* ctx, const ugn_tensor* labels, const ugn_tensor* order,
+                                const ugn_tensor* offsets, int legacy_ties, ugn_tensor* out, void* stream) {
+  UGN_CHECK(ctx && labels && order && offsets && out, "ugn_segment_mode: null argument");
+  UGN_TENSOR(labels, DT_I32, 1, 1);
+  UGN_TENSOR(out, DT_I32, 1, 1);
+  int V = 0;
+  int rc = segment_common(ctx, order, offsets, labels->shape[0], V);
+  if (rc != UGN_OK) return rc;
+  UGN_CHECK(out->shape[0] == V, "segment_mode: out must be i32 [V]");
+  return ew_segment_mode(ctx, ugn_ptr<int>(labels), ugn_ptr<int>(order), ugn_ptr<int>(offsets), V, legacy_ties,
+                         ugn_ptr<int>(out), (cudaStream_t)stream);
 }

@@ -14,14 +14,29 @@ static inline int grid_for(ugn_ctx* ctx, long long work_items, int block) {
 // One block per (b, y): coalesced row reads, smem transpose, coalesced channel-run writes.
 // ---------------------------------------------------------------------------------------
 template <int MODE>  // 0 f32, 1 16-bit P=1, 2 16-bit P=2
+// Device-side missing-modality expansion / mirror augmentation fused into the pack (the reference builds the
+// E-fold batch on the host, data/mj_dataGeneratorMMUWYHsingle.py:780-812, and mirrors with
+// data/mj_augmentation.py:12-32): output row b reads base row src_row[b]; enable[b] == 0 -> the whole volume
+// is the constant `noise` (1e-9, :102); mirror[b] != 0 -> every channel flipped left-right and, literally as
+// mj_mirrorsequence does for EVERY modality, even channels negated.
 __global__ void pack_input_kernel(const float* __restrict__ x, void* __restrict__ out, int B, int C,
-                                  int H, int W, int Cp, long long plane, int f16) {
+                                  int H, int W, int Cp, long long plane, int f16,
+                                  const int* __restrict__ src_row, const float* __restrict__ enable,
+                                  const uint8_t* __restrict__ mirror, float noise) {
   extern __shared__ float sm[];  // [C][W+1]
   int by = blockIdx.x;
   int b = by / H, y = by % H;
+  const int sb = src_row ? src_row[b] : b;
+  const bool on = !enable || enable[b] != 0.f;
+  const bool mir = mirror && mirror[b];
   for (int e = threadIdx.x; e < C * W; e += blockDim.x) {
     int c = e / W, xx = e % W;
-    sm[c * (W + 1) + xx] = x[(((long long)b * C + c) * H + y) * W + xx];
+    float v = noise;
+    if (on) {
+      v = x[(((long long)sb * C + c) * H + y) * W + (mir ? W - 1 - xx : xx)];
+      if (mir && !(c & 1)) v = -v;
+    }
+    sm[c * (W + 1) + xx] = v;
   }
   __syncthreads();
   long long obase = ((long long)b * H + y) * W * Cp;
@@ -58,12 +73,13 @@ __global__ void pack_input_kernel(const float* __restrict__ x, void* __restrict_
 }
 
 int ew_pack_input(ugn_ctx* ctx, const float* x, void* out, int mode, int f16, int B, int C, int H, int W,
-                  int Cp, cudaStream_t st) {
+                  int Cp, const int* src_row, const float* enable, const uint8_t* mirror, float noise,
+                  cudaStream_t st) {
   size_t smem = sizeof(float) * C * (W + 1);
   long long plane = (long long)B * H * W * Cp;
-  if (mode == 0) pack_input_kernel<0><<<B * H, 256, smem, st>>>(x, out, B, C, H, W, Cp, plane, f16);
-  else if (mode == 1) pack_input_kernel<1><<<B * H, 256, smem, st>>>(x, out, B, C, H, W, Cp, plane, f16);
-  else pack_input_kernel<2><<<B * H, 256, smem, st>>>(x, out, B, C, H, W, Cp, plane, f16);
+  if (mode == 0) pack_input_kernel<0><<<B * H, 256, smem, st>>>(x, out, B, C, H, W, Cp, plane, f16, src_row, enable, mirror, noise);
+  else if (mode == 1) pack_input_kernel<1><<<B * H, 256, smem, st>>>(x, out, B, C, H, W, Cp, plane, f16, src_row, enable, mirror, noise);
+  else pack_input_kernel<2><<<B * H, 256, smem, st>>>(x, out, B, C, H, W, Cp, plane, f16, src_row, enable, mirror, noise);
   UGN_LAUNCHED(ctx);
   return UGN_OK;
 }
@@ -722,6 +738,61 @@ int ew_bias_act_split16(ugn_ctx* ctx, const float* acc, const float* bias, __nv_
                         int cols, int P, int f16, int act, float alpha, cudaStream_t st) {
   long long n = rows * cols;
   bias_act_split16_kernel<<<grid_for(ctx, n, 256), 256, 0, st>>>(acc, bias, out, n, cols, P, f16, act, alpha);
+  UGN_LAUNCHED(ctx);
+  return UGN_OK;
+}
+
+// ---------------------------------------------------------------------------------------
+// a13: video-level summaries of the open-world test (mains/mj_testUWYHGaitNet_open_tum.py:355-420).
+// Rows are grouped by video through a CSR (order i32 [N] = row indices sorted by video, offsets
+// i32 [V+1]); the host builds it with np.unique exactly as the reference does.
+//   segment_pool : out[v] = mean (use_avg) or max over the video's sub-sequence descriptors, summed in
+//                  row order in fp32 like numpy's axis-0 reduction
+//   segment_mode : statistics.mode of the video's labels: most frequent, ties -> first encountered
+//                  (Python >= 3.8); legacy != 0 -> on a tie the first element (the reference's
+//                  `except: ...[idx][0]` branch under Python < 3.8)
+// ---------------------------------------------------------------------------------------
+__global__ void segment_pool_kernel(const float* __restrict__ codes, const int* __restrict__ order,
+                                    const int* __restrict__ offsets, int D, int use_avg, float* __restrict__ out) {
+  const int v = blockIdx.x, j = blockIdx.y * blockDim.x + threadIdx.x;
+  if (j >= D) return;
+  const int a = offsets[v], b = offsets[v + 1];
+  float acc = use_avg ? 0.f : -INFINITY;
+  for (int e = a; e < b; ++e) {
+    const float x = codes[(long long)order[e] * D + j];
+    acc = use_avg ? acc + x : fmaxf(acc, x);
+  }
+  out[(long long)v * D + j] = use_avg ? acc / (float)(b - a) : acc;
+}
+__global__ void segment_mode_kernel(const int* __restrict__ labels, const int* __restrict__ order,
+                                    const int* __restrict__ offsets, int V, int legacy, int* __restrict__ out) {
+  const int v = blockIdx.x * blockDim.x + threadIdx.x;
+  if (v >= V) return;
+  const int a = offsets[v], b = offsets[v + 1];
+  int best = labels[order[a]], bestc = 0, ties = 0;
+  for (int e = a; e < b; ++e) {
+    const int le = labels[order[e]];
+    bool first = true;
+    for (int f = a; f < e; ++f) first = first && labels[order[f]] != le;
+    if (!first) continue;                       // count every distinct label once, in order of appearance
+    int c = 0;
+    for (int f = e; f < b; ++f) c += labels[order[f]] == le;
+    if (c > bestc) { bestc = c; best = le; ties = 0; }
+    else if (c == bestc) ++ties;
+  }
+  out[v] = (legacy && ties) ? labels[order[a]] : best;
+}
+int ew_segment_pool(ugn_ctx* ctx, const float* codes, const int* order, const int* offsets, int V, int D,
+                    int use_avg, float* out, cudaStream_t st) {
+  if (V == 0 || D == 0) return UGN_OK;
+  segment_pool_kernel<<<dim3(V, ugn_cdiv(D, 256)), 256, 0, st>>>(codes, order, offsets, D, use_avg, out);
+  UGN_LAUNCHED(ctx);
+  return UGN_OK;
+}
+int ew_segment_mode(ugn_ctx* ctx, const int* labels, const int* order, const int* offsets, int V, int legacy,
+                    int* out, cudaStream_t st) {
+  if (V == 0) return UGN_OK;
+  segment_mode_kernel<<<ugn_cdiv(V, 128), 128, 0, st>>>(labels, order, offsets, V, legacy, out);
   UGN_LAUNCHED(ctx);
   return UGN_OK;
 }

@@ -1,0 +1,55 @@
+"""Host side of the device-side missing-modality expansion.
+
+The reference's generator builds the E-fold expanded batch on the CPU and ships all of it to the GPU
+(/root/reference/data/mj_dataGeneratorMMUWYHsingle.py:780-812).  Here only the PATTERN is produced on
+the host -- a [B0*E, M] 0/1 table, drawn with Python's `random` exactly as the reference does -- and the
+volumes are expanded by `ugn_pack_input_expand` while they are packed, so only the B0 base rows cross PCIe.
+"""
+from __future__ import annotations
+
+import random as _random
+from typing import Optional, Tuple
+
+import numpy as np
+
+NOISE = 1e-9      # data/mj_dataGeneratorMMUWYHsingle.py:102
+
+
+def expansion_pattern(n_base: int, expand: int, nmods: int, rng: Optional[_random.Random] = None
+                      ) -> Tuple[np.ndarray, np.ndarray]:
+    """Returns (src_row i32 [B], use f32 [B, nmods]) with B = n_base*max(expand,1).
+
+    Row i*E keeps every modality; rows i*E+1+ex follow :791-803 -- even i: min(ex+1, M-1) draws (with
+    replacement, `random.randrange`) of a modality to disable (E == 2: the number of draws itself is
+    drawn from [1, M)); odd i: only modality (i+ex) % 3 enabled."""
+    rng = rng or _random
+    E = max(int(expand), 1)
+    src = np.repeat(np.arange(n_base, dtype=np.int32), E)
+    use = np.ones((n_base * E, nmods), dtype=np.float32)
+    for i in range(n_base):
+        for ex in range(E - 1):
+            if i % 2 == 0:
+                ndis = min(ex + 1, nmods - 1) if E > 2 else rng.randrange(1, nmods, 1)
+                l_dis = [1] * nmods
+                for _ in range(ndis):
+                    l_dis[rng.randrange(0, nmods, 1)] = 0
+            else:
+                l_dis = [0] * nmods
+                l_dis[(i + ex) % 3 % nmods] = 1
+            use[i * E + ex + 1] = l_dis
+    return src, use
+
+
+def expand_on_host(base, src, use_col, noise: float = NOISE):
+    """numpy restatement of what the device pack does for one modality (tests / documentation)."""
+    out = np.asarray(base)[src].copy()
+    out[use_col == 0] = noise
+    return out
+
+
+def mirror_sequence(sample: np.ndarray) -> np.ndarray:
+    """data/mj_augmentation.py:12-32 restated: sample [C,H,W]; every channel flipped left-right, even
+    channels negated (for every modality -- the `isof` argument of the reference is never read)."""
+    out = np.asarray(sample)[..., ::-1].copy()
+    out[0::2] = -out[0::2]
+    return out

@@ -22,6 +22,7 @@ import torch
 from . import ops
 from ._ffi import TRef, check, lib, ptr_array, stream_ptr
 from .config import ACT_LINEAR, BRANCH_NAMES, MERGE_AVG, NetConfig, round_up
+from .expand import NOISE
 
 # math mode -> (forward planes, backward/gradient planes, 16-bit dtype)
 #   fp32    SIMT FFMA validation path
@@ -242,12 +243,20 @@ class UGaitEngine:
         return p
 
     # ------------------------------------------------------------------ forward
-    def _forward(self, p: "_Plan", train: bool):
+    def _forward(self, p: "_Plan", train: bool, expanded: bool = False):
         cfg, h, st = self.cfg, self.ctx.h, stream_ptr()
         for m in range(cfg.nmods):
             bn = BRANCH_NAMES[m]
             b = p.br[m]
-            check(lib.ugn_pack_input(h, b.R["x_in"].ptr, b.R["a0"].ptr, st))
+            if expanded:
+                # device-side missing-modality expansion: row i reads base row src_row[i]; a cleared
+                # use-flag turns the row's volume into the reference's 1e-9 constant
+                check(lib.ugn_pack_input_expand(h, b.R["x_base"].ptr, p.R["src_row"].ptr,
+                                                None if cfg.single else p.R_flags[m].ptr,
+                                                p.R["mirror"].ptr if p.use_mirror else None, NOISE,
+                                                b.R["a0"].ptr, st))
+            else:
+                check(lib.ugn_pack_input(h, b.R["x_in"].ptr, b.R["a0"].ptr, st))
             for li, L in enumerate(b.layers):
                 check(lib.ugn_conv2d_fwd(h, b.R[f"a{li}"].ptr, self.Rcw[f"{bn}/conv{li}/w"].ptr,
                                          self.Rw[f"{bn}/conv{li}/b"].ptr, b.R[f"a{li + 1}"].ptr,
@@ -416,8 +425,8 @@ class UGaitEngine:
             raise ValueError(f"unknown optimizer {self.optimizer}")
         self.repack_weights(after_optim=True)
 
-    def _step_body(self, p: "_Plan", do_optim: bool):
-        sig, feat = self._forward(p, True)
+    def _step_body(self, p: "_Plan", do_optim: bool, expanded: bool = False):
+        sig, feat = self._forward(p, True, expanded)
         self._losses_and_backward(p, sig, feat)
         if do_optim:
             if self.world > 1:
@@ -448,15 +457,65 @@ class UGaitEngine:
         self._step_body(p, False)
         return self._report(p)
 
+    def _set_base_inputs(self, p, base_inputs, src_row, use, labels, mirror=None):
+        """Stage the BASE rows (+ the expansion pattern) of train_step_expanded / predict_expanded."""
+        cfg = self.cfg
+        B0 = int(base_inputs[0].shape[0])
+        p.ensure_base(B0)
+        for m in range(cfg.nmods):
+            p.br[m].x_base.copy_(base_inputs[m], non_blocking=True)
+            if not cfg.single:
+                p.flags[m].copy_(torch.as_tensor(use[:, m]).reshape(-1, 1), non_blocking=True)
+            if p.train and cfg.dropout > 0.001:
+                keep = 1.0 - cfg.dropout
+                p.br[m].mask.bernoulli_(keep).div_(keep)
+        if p.train and cfg.dropout > 0.001 and cfg.nc > 0:
+            keep = 1.0 - cfg.dropout
+            p.cmask.bernoulli_(keep).div_(keep)
+        p.src_row.copy_(torch.as_tensor(src_row, dtype=torch.int32), non_blocking=True)
+        p.use_mirror = mirror is not None
+        if mirror is not None:
+            p.mirror.copy_(torch.as_tensor(mirror, dtype=torch.uint8), non_blocking=True)
+        if labels is not None:
+            lab = torch.as_tensor(labels).reshape(-1).to(torch.int32)
+            if lab.numel() == B0:        # one label per base row: replicate along the expansion
+                lab = lab.to(self.dev)[p.src_row.long()]
+            p.labels.copy_(lab, non_blocking=True)
+
+    @torch.no_grad()
+    def train_step_expanded(self, base_inputs, base_labels, src_row, use, mirror=None) -> Dict[str, torch.Tensor]:
+        """train_step on the reference generator's E-fold batch WITHOUT materialising it: base_inputs are
+        the B0 sequences that have every modality ([B0,C,60,60] per modality), (src_row, use) is the
+        expansion pattern (ugaitnet_b200.expand.expansion_pattern) and the volumes are expanded while
+        they are packed on the device -- only the base rows cross PCIe."""
+        B = int(len(src_row))
+        p = self.plan(B, True)
+        self._set_base_inputs(p, base_inputs, src_row, use, base_labels, mirror)
+        return self._run_train(p, B, expanded=True)
+
+    @torch.no_grad()
+    def predict_expanded(self, base_inputs, src_row, use, mirror=None, layer: str = "signature") -> torch.Tensor:
+        """Descriptor extraction with device-side expansion / mirror augmentation
+        (mains/mj_testUWYHGaitNet_open_tum.py:174-190 stacks the mirrored copies on the host)."""
+        B = int(len(src_row))
+        p = self.plan(B, False)
+        self._set_base_inputs(p, base_inputs, src_row, use, None, mirror)
+        self._forward(p, False, expanded=True)
+        return (p.br[0].out if self.cfg.single else p.sig).clone() if layer == "signature" else \
+            (p.code.clone() if layer == "code" else p.logits.clone())
+
     @torch.no_grad()
     def train_step(self, inputs, flags, labels, drop_masks=None, code_drop_mask=None) -> Dict[str, torch.Tensor]:
         """One Keras train_function step: fwd -> losses -> bwd -> (all-reduce) -> optimiser."""
         B = int(inputs[0].shape[0])
         p = self.plan(B, True)
         self._set_inputs(p, inputs, flags, labels, drop_masks, code_drop_mask)
+        return self._run_train(p, B, expanded=False)
+
+    def _run_train(self, p, B, expanded):
         self._next_lr()
         if self.use_graph and (self.world == 1 or self.dp_graph):
-            gkey = B
+            gkey = (B, expanded, p.use_mirror)
             gr = self._graphs.get(gkey)
             if gr is None:
                 # warm-up on a side stream (first-use allocations / attribute sets), then capture
@@ -464,7 +523,7 @@ class UGaitEngine:
                 s.wait_stream(torch.cuda.current_stream())
                 saved = (self.w.clone(), self.m.clone(), self.v.clone())
                 with torch.cuda.stream(s):
-                    self._step_body(p, True)
+                    self._step_body(p, True, expanded)
                 torch.cuda.current_stream().wait_stream(s)
                 torch.cuda.synchronize()
                 self.w.copy_(saved[0]); self.m.copy_(saved[1]); self.v.copy_(saved[2])
@@ -472,13 +531,13 @@ class UGaitEngine:
                 gr = torch.cuda.CUDAGraph()
                 l0 = self.ctx.launches
                 with torch.cuda.graph(gr):
-                    self._step_body(p, True)
+                    self._step_body(p, True, expanded)
                 self.graph_launches = self.ctx.launches - l0   # kernels of ours inside one replay
                 self._graphs[gkey] = gr
                 # the capture itself did not execute: fall through to replay
             gr.replay()
         else:
-            self._step_body(p, True)
+            self._step_body(p, True, expanded)
         return self._report(p, with_reg=True)
 
     @torch.no_grad()
@@ -563,6 +622,8 @@ class _Plan:
                 return torch.zeros((planes,) + tuple(shape), device=d, dtype=dt16)
             return torch.zeros(tuple(shape), **f32)
 
+        self.eng = eng
+        self.use_mirror = False
         self.br: List[_Branch] = []
         self.flags = [torch.ones(B, 1, **f32) for _ in range(cfg.nmods)]
         for m in range(cfg.nmods):
@@ -629,3 +690,16 @@ class _Plan:
         self.flag_ptrs = ptr_array(self.R_flags)
         if train:
             self.dbr_ptrs = ptr_array([b.R["dout"] for b in self.br])
+
+    def ensure_base(self, B0: int):
+        """Buffers of the device-side expansion: base rows per modality, source-row and mirror tables."""
+        if getattr(self, "_B0", None) == B0:
+            return
+        cfg, d = self.eng.cfg, self.eng.dev
+        for m, b in enumerate(self.br):
+            b.x_base = torch.zeros(B0, b.layers[0]["cin"], cfg.hw, cfg.hw, device=d)
+            b.R["x_base"] = TRef(b.x_base)
+        self.src_row = torch.zeros(self.B, dtype=torch.int32, device=d)
+        self.mirror = torch.zeros(self.B, dtype=torch.uint8, device=d)
+        self.R["src_row"], self.R["mirror"] = TRef(self.src_row), TRef(self.mirror)
+        self._B0 = B0

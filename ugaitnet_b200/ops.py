@@ -43,6 +43,12 @@ def pack_input(ctx, x_nchw, x_nhwc):
     check(lib.ugn_pack_input(ctx.h, a.ptr, b.ptr, stream_ptr()))
 
 
+def pack_input_expand(ctx, x_base, src_row, enable, mirror, x_nhwc, noise=1e-9):
+    rs = [_r(t) for t in (x_base, src_row, enable, mirror)]
+    o = _r(x_nhwc)
+    check(lib.ugn_pack_input_expand(ctx.h, *[_p(r) for r in rs], float(noise), o.ptr, stream_ptr()))
+
+
 def pack_weight(ctx, w_master, w_packed):
     a, b = _r(w_master), _r(w_packed)
     check(lib.ugn_pack_weight(ctx.h, a.ptr, b.ptr, stream_ptr()))
