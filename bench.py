@@ -31,6 +31,9 @@ FLOP_FWD_ROW = {"of": 2.0214e9 + 0.0545e9, "c25": 1.3356e9 + 0.0545e9}   # BASEL
 TRAIN_FLOP_ROW = 11.83e9                                                  # 3-mod fwd+dgrad+wgrad
 
 
+# ncu-derived DRAM traffic of the dominant kernel (profiles/<round>_tc_convp_kernel.md), bytes per step
+NCU_TRAFFIC = {"conv_fwd_bytes_per_step": None}
+
 DTYPE_NAMES = {"fp32": "f32", "bf16": "bf16", "bf16x3": "bf16 (3-pass hi/lo split, fp32 accumulate)",
                "f16x3": "f16 (3-pass hi/lo split, fp32 accumulate)",
                "f16mix": "f16 (forward: 3-pass hi/lo split; backward: 1 pass, scaled fp16 gradients; fp32 accumulate)"}
@@ -241,7 +244,7 @@ def main():
 
     from ugaitnet_b200.net import UGaitEngine
     eng = UGaitEngine(engine_cfg(), device=local, math_mode=args.mode, lr=1e-4, process_group=pg,
-                      use_graph=(not args.no_graph and (world == 1 or os.environ.get("UGN_DP_GRAPH") == "1")))
+                      use_graph=not args.no_graph)
     xs, fl, lab = make_batch(232323 + rank)
     B = xs[0].shape[0]
     # host copies in pinned memory (e2e leg) and device-resident copies (value leg)
@@ -317,6 +320,25 @@ def main():
     for _ in range(2):
         step_e2e_pipelined()
     ms_e2e = timed(step_e2e_pipelined, args.steps)
+
+    # device-side expansion: only the 24 base sequences cross PCIe, the E-fold batch with its
+    # missing-modality pattern is built inside the input pack -- same step, a quarter of the H2D bytes
+    src_row = np.repeat(np.arange(BS_LITERAL, dtype=np.int32), EXPAND)
+    use = np.concatenate([f.reshape(-1, 1) for f in fl], axis=1).astype(np.float32)
+    hbase = [torch.from_numpy(np.ascontiguousarray(x[::EXPAND])).pin_memory() for x in xs]
+    hlab0 = torch.from_numpy(np.ascontiguousarray(lab.reshape(-1)[::EXPAND].astype(np.int32)))
+    h2d_exp = sum(t.numel() * t.element_size() for t in hbase) + use.nbytes + src_row.nbytes + hlab0.numel() * 4
+
+    def step_e2e_expanded():
+        out = eng.train_step_expanded(hbase, hlab0, src_row, use)
+        loss_host[0].copy_(out["triplet"], non_blocking=True)
+        loss_host[1].copy_(out["ce"], non_blocking=True)
+        loss_host[2].copy_(out["reg"], non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+
+    for _ in range(3):
+        step_e2e_expanded()
+    ms_e2e_exp = timed(step_e2e_expanded, args.steps)
     eng.ctx.check()
     rows_total = B * world
     value = rows_total / (ms * 1e-3)
@@ -331,7 +353,10 @@ def main():
             "e2e": {"value": e2e, "unit": "rows/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 12,
                     "ms_per_step": ms_e2e, "api": "UGaitEngine.prefetch + train_step_staged (H2D of step i+1 "
                     "overlaps step i)", "serial_ms_per_step": ms_e2e_serial,
-                    "serial_value": rows_total / (ms_e2e_serial * 1e-3)},
+                    "serial_value": rows_total / (ms_e2e_serial * 1e-3),
+                    "device_expansion": {"value": rows_total / (ms_e2e_exp * 1e-3), "ms_per_step": ms_e2e_exp,
+                                         "h2d_bytes_per_step": int(h2d_exp),
+                                         "api": "UGaitEngine.train_step_expanded (base rows + pattern; serial)"}},
             "gpu_launches": int(launches), "clocks": sampler.summary(),
             "model_tflops": TRAIN_FLOP_ROW * rows_total / (ms * 1e-3) / 1e12}
 
@@ -368,11 +393,23 @@ def main():
             fwd_flops = conv_fwd_row * B
             passes = (pf * fwd_flops + pb * (conv_flops - fwd_flops)) / conv_flops
             ach = conv_flops / (conv_ms * 1e-3) / 1e12
-            line["roofline"] = {"bound": "tensor", "kernel": "tc_kernel<MODE_CONV|MODE_WGRAD> (conv fwd+dgrad+wgrad)",
-                                "achieved": ach, "peak": pk["tf_sust"], "unit": "TFLOP/s", "frac": ach / pk["tf_sust"],
-                                "traffic": None, "share_of_step": conv_ms / total if total else None,
-                                "mma_passes": passes, "issued_frac": ach * passes / pk["tf_sust"],
-                                "peak_source": pk["src"] + " bf16 sustained"}
+            # dominant kernel: tc_convp_kernel = the conv FORWARD launches (ugn_conv2d_fwd, 12 per step): algorithmic
+            # FLOPs of the forward convolutions / their CUDA-event time on the launch stream.  traffic = ncu
+            # dram__bytes_read+write summed over the 12 launches of one step (profiles/, null until captured).
+            fwd_ms = per_step.get("ugn_conv2d_fwd", 0.0)
+            ach_f = fwd_flops / (fwd_ms * 1e-3) / 1e12 if fwd_ms else 0.0
+            line["roofline"] = {"bound": "tensor", "kernel": "tc_convp_kernel (conv forward, 12 launches/step)",
+                                "achieved": ach_f, "peak": pk["tf_sust"], "unit": "TFLOP/s", "frac": ach_f / pk["tf_sust"],
+                                "traffic": NCU_TRAFFIC.get("conv_fwd_bytes_per_step"),
+                                "algorithmic_flop_per_step": fwd_flops, "launch_ms_per_step": fwd_ms,
+                                "share_of_step": fwd_ms / total if total else None,
+                                "mma_passes": pf, "issued_frac": ach_f * pf / pk["tf_sust"],
+                                "note": "N=96 tiles (Cout=96) cost 73 clk per MMA vs 48 ideal (profiles/r01_umma_rate.txt); "
+                                        "channel padding 25->32 / 50->64 and the 64-slot row pitch add x1.5 issued work on conv1",
+                                "peak_source": pk["src"] + " bf16 sustained",
+                                "all_conv": {"kernels": "conv fwd + dgrad + wgrad", "achieved": ach, "frac": ach / pk["tf_sust"],
+                                             "mma_passes": passes, "issued_frac": ach * passes / pk["tf_sust"],
+                                             "share_of_step": conv_ms / total if total else None}}
             line["cpu_baseline"] = cpu_baseline_leg()
         if not args.no_knn and world == 1:
             line["knn"] = knn_leg(pk)

@@ -19,15 +19,16 @@ $CMD > $OUT/plain.log 2>&1 || { tail -5 $OUT/plain.log; exit 1; }
 NL=$(python -c "import json,sys; print(json.loads(open('$OUT/plain.log').read().strip().splitlines()[-1])['gpu_launches']//2)")
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -s $((NL*3)) -c $NL --csv \
     --log-file $OUT/launches.csv $CMD > $OUT/ncu_list.log 2>&1
-for KS in tc_convp_kernel:40:14 tc_wgradv_kernel:30:10 tc_kernel:80:20 optim_kernel:3:1; do
+for KS in tc_convp_kernel:45:15 tc_wgradv_kernel:27:9 tc_kernel:80:20 optim_kernel:3:1 knn_tc_scan_kernel:2:2; do
   K=${KS%%:*}; R=${KS#*:}; S=${R%%:*}; C=${R#*:}
-  timeout 900 ncu --set full --clock-control none --import-source on -k regex:^$K\$ -s $S -c $C -o $OUT/prof_$K $CMD > $OUT/ncu_$K.log 2>&1
+  RUN="$CMD"; if [ $K = knn_tc_scan_kernel ]; then RUN="python bench.py --knn-only"; fi
+  timeout 900 ncu --set full --clock-control none --import-source on -k regex:^$K\$ -s $S -c $C -o $OUT/prof_$K $RUN > $OUT/ncu_$K.log 2>&1
   ncu -i $OUT/prof_$K.ncu-rep --page raw --csv > $OUT/prof_${K}_raw.csv 2>/dev/null
 done
 ncu -i $OUT/prof_tc_convp_kernel.ncu-rep --page source --csv > $OUT/prof_tc_convp_kernel_src.csv 2>/dev/null
 du -sm $OUT
 # keep the payload under the 64 MiB copy-back limit
-for K in optim_kernel tc_kernel tc_wgradv_kernel tc_convp_kernel; do
+for K in optim_kernel knn_tc_scan_kernel tc_kernel tc_wgradv_kernel tc_convp_kernel; do
   if [ $(du -sm gpurun_out | cut -f1) -gt 50 ]; then rm -f $OUT/prof_$K.ncu-rep; fi
 done
 ls -la $OUT

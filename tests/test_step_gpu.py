@@ -279,3 +279,24 @@ def test_device_side_expansion_equals_host_expanded_batch():
     for k in outs[0][2]:
         if float(outs[0][2][k].norm()) > 0:
             assert rel(outs[1][2][k], outs[0][2][k].double().cpu()) < 1e-5, k
+
+
+def test_segmented_graph_capture_equals_eager():
+    """The data-parallel step is replayed as CUDA-graph SEGMENTS cut at the all-reduce points (NCCL stays
+    outside the graphs).  Forced on one GPU here: the segmented replay must reproduce the eager step."""
+    from ugaitnet_b200.net import UGaitEngine
+    oc, eng, P, xs, fl, lab, masks, cmask = setup("3mod_signmax")
+    eng_s = UGaitEngine(to_engine_cfg(oc), math_mode="fp32", lr=1e-3, use_graph=True)
+    eng_s.force_segments = True
+    eng_s.load_params(P)
+    ins = engine_inputs(xs, fl, lab, masks, cmask)
+    for _ in range(3):
+        a = eng.train_step(*ins)
+        b = eng_s.train_step(*ins)
+        assert float(a["triplet"]) == pytest.approx(float(b["triplet"]), rel=1e-5)
+        assert float(a["ce"]) == pytest.approx(float(b["ce"]), rel=1e-5)
+    gr = next(iter(eng_s._graphs.values()))
+    assert isinstance(gr, list) and len(gr) == 1 + 2 * oc.nmods + 1      # heads | (fc, conv) per branch | optim
+    Wa, Wb = eng.export_params(), eng_s.export_params()
+    for k in Wa:
+        assert rel(Wb[k], Wa[k].double().cpu()) < 1e-5, k

@@ -66,11 +66,12 @@ class UGaitEngine:
         self.use_graph = use_graph
         self.t = 0
         self._dp_async = True      # bucketed, overlapped all-reduce (False: one blocking all-reduce)
-        # EXPERIMENTAL (off): capture the data-parallel step, NCCL all-reduces included, in the CUDA graph.
-        # Hung at N=2 on the first try (capture of async NCCL work handles); the eager path is the
-        # measured one (eager adds ~0.4 ms/step of launch gaps over graph replay at N=1).
-        self.dp_graph = os.environ.get("UGN_DP_GRAPH", "0") == "1"
+        # data-parallel CUDA graphs: the step is captured as segments cut at the all-reduce points
+        # (_capture_segments); NCCL itself is never captured (capturing the async work handles hung)
+        self.dp_graph = os.environ.get("UGN_DP_GRAPH", "1") != "0"
+        self.force_segments = False     # tests: use the segmented capture on a single GPU too
         self._works = []
+        self._cap = None           # state of a segmented graph capture (data-parallel CUDA graphs)
         self.graph_launches = 0
         self._plans: Dict[tuple, "_Plan"] = {}
         self._graphs = {}
@@ -333,9 +334,58 @@ class UGaitEngine:
     def _reduce_bucket(self, key):
         """Data-parallel gradient exchange, bucketed so that the all-reduce of a finished branch overlaps
         the backward pass of the next one (NCCL runs on its own stream)."""
-        if self.world > 1 and self._dp_async and self.buckets.get(key) is not None:
+        if (self.world > 1 or self._cap is not None) and self._dp_async and self.buckets.get(key) is not None:
+            if self._cap is not None:          # capturing: close this graph segment, the all-reduce runs between
+                self._cut(key)                 # the replays of two segments
+                return
             lo, hi = self.buckets[key]
             self._works.append(torch.distributed.all_reduce(self.g[lo:hi], group=self.pg, async_op=True))
+
+    # ---- data-parallel CUDA graphs: the step is captured as SEGMENTS cut at the all-reduce points, so the
+    # NCCL calls stay ordinary (un-captured) stream operations between two graph replays
+    def _cut(self, key):
+        cap = self._cap
+        if self.ctx.launches == cap["mark"] and cap["segs"]:
+            cap["segs"][-1][1].append(key)      # nothing launched since the last cut: same boundary
+            return
+        cap["cur"].capture_end()
+        cap["segs"].append((cap["cur"], [key]))
+        g = torch.cuda.CUDAGraph()
+        g.capture_begin(pool=cap["pool"])
+        cap["cur"] = g
+        cap["mark"] = self.ctx.launches
+
+    def _capture_segments(self, p, expanded):
+        cur = torch.cuda.current_stream()
+        side = torch.cuda.Stream()
+        side.wait_stream(cur)
+        torch.cuda.synchronize()
+        l0 = self.ctx.launches
+        with torch.cuda.stream(side):
+            g = torch.cuda.CUDAGraph()
+            self._cap = {"cur": g, "segs": [], "pool": torch.cuda.graph_pool_handle(), "mark": self.ctx.launches}
+            g.capture_begin(pool=self._cap["pool"])
+            try:
+                self._step_body(p, True, expanded)
+                self._cap["cur"].capture_end()
+                self._cap["segs"].append((self._cap["cur"], []))
+            finally:
+                segs, self._cap = self._cap["segs"], None
+        cur.wait_stream(side)
+        self.graph_launches = self.ctx.launches - l0
+        return segs
+
+    def _replay_segments(self, segs):
+        self._works = []
+        for g, keys in segs:
+            g.replay()
+            for key in keys:
+                if key == "wait":
+                    for w in self._works:
+                        w.wait()
+                elif self.world > 1:
+                    lo, hi = self.buckets[key]
+                    self._works.append(torch.distributed.all_reduce(self.g[lo:hi], group=self.pg, async_op=True))
 
     def _losses_and_backward(self, p: "_Plan", sig: TRef, feat: TRef):
         cfg, h, st = self.cfg, self.ctx.h, stream_ptr()
@@ -429,7 +479,9 @@ class UGaitEngine:
         sig, feat = self._forward(p, True, expanded)
         self._losses_and_backward(p, sig, feat)
         if do_optim:
-            if self.world > 1:
+            if self._cap is not None:
+                self._cut("wait")
+            elif self.world > 1:
                 if self._dp_async:
                     for w in self._works:
                         w.wait()
@@ -528,14 +580,20 @@ class UGaitEngine:
                 torch.cuda.synchronize()
                 self.w.copy_(saved[0]); self.m.copy_(saved[1]); self.v.copy_(saved[2])
                 self.repack_weights()
-                gr = torch.cuda.CUDAGraph()
-                l0 = self.ctx.launches
-                with torch.cuda.graph(gr):
-                    self._step_body(p, True, expanded)
-                self.graph_launches = self.ctx.launches - l0   # kernels of ours inside one replay
+                if self.world > 1 or self.force_segments:
+                    gr = self._capture_segments(p, expanded)
+                else:
+                    gr = torch.cuda.CUDAGraph()
+                    l0 = self.ctx.launches
+                    with torch.cuda.graph(gr):
+                        self._step_body(p, True, expanded)
+                    self.graph_launches = self.ctx.launches - l0   # kernels of ours inside one replay
                 self._graphs[gkey] = gr
                 # the capture itself did not execute: fall through to replay
-            gr.replay()
+            if isinstance(gr, list):
+                self._replay_segments(gr)
+            else:
+                gr.replay()
         else:
             self._step_body(p, True, expanded)
         return self._report(p, with_reg=True)
