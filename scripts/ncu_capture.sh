@@ -25,7 +25,6 @@ for KS in tc_convp_kernel:45:15 tc_wgradv_kernel:27:9 tc_kernel:80:20 optim_kern
   timeout 900 ncu --set full --clock-control none --import-source on -k regex:^$K\$ -s $S -c $C -o $OUT/prof_$K $RUN > $OUT/ncu_$K.log 2>&1
   ncu -i $OUT/prof_$K.ncu-rep --page raw --csv > $OUT/prof_${K}_raw.csv 2>/dev/null
 done
-ncu -i $OUT/prof_tc_convp_kernel.ncu-rep --page source --csv > $OUT/prof_tc_convp_kernel_src.csv 2>/dev/null
 du -sm $OUT
 # keep the payload under the 64 MiB copy-back limit
 for K in optim_kernel knn_tc_scan_kernel tc_kernel tc_wgradv_kernel tc_convp_kernel; do
