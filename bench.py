@@ -32,7 +32,9 @@ TRAIN_FLOP_ROW = 11.83e9                                                  # 3-mo
 
 
 # ncu-derived DRAM traffic of the dominant kernel (profiles/<round>_tc_convp_kernel.md), bytes per step
-NCU_TRAFFIC = {"conv_fwd_bytes_per_step": None}
+# r01c: 12 forward launches of one step, sum of dram__bytes_read.sum + dram__bytes_write.sum = 319.6 MB
+# (activation planes in: 177 MB; the pooled outputs mostly stay in the 126 MB L2 until the next layer reads them)
+NCU_TRAFFIC = {"conv_fwd_bytes_per_step": 319.6e6}
 
 DTYPE_NAMES = {"fp32": "f32", "bf16": "bf16", "bf16x3": "bf16 (3-pass hi/lo split, fp32 accumulate)",
                "f16x3": "f16 (3-pass hi/lo split, fp32 accumulate)",

@@ -1060,7 +1060,7 @@ static int convp_launch(ugn_ctx* ctx, TcParams& p, const __nv_bfloat16* act, int
   // hi*[hi|lo] concatenation doubles the accumulator columns: keep it only while TWO accumulator sets
   // still fit (measured: conv1-OF / conv3 with T = 1 gain 12-15 %; conv1-gray with T = 2 would fall back
   // to a single set and lose more to the exposed epilogue than the wider MMA wins)
-  if (p.concat && 2 * T * p.acc_tile_cols > 512) { p.concat = 0; p.acc_tile_cols = p.block_n; }
+  if (p.concat && 2 * T * p.acc_tile_cols > 512 && !getenv("UGN_FORCE_CONCAT")) { p.concat = 0; p.acc_tile_cols = p.block_n; }
   p.nbuf = (2 * T * p.acc_tile_cols <= 512) ? 2 : 1;      // single set (Cout = 192 tiles): the epilogue shares
                                                           // the tile-boundary bubble with the next patch load
   p.T = T; p.SW = SW; p.RH = RH; p.PR = T * RH + KH - 1;
