@@ -37,16 +37,23 @@ int ugn_validate(const ugn_ctx* ctx, const ugn_tensor* t, const char* name, UgnD
 }
 
 int ugn_scratch(ugn_ctx* ctx, size_t bytes, void** out) {
-  if (bytes > ctx->scratch_bytes) {
-    // a previous (smaller) buffer may still be referenced by in-flight kernels / captured graphs: keep it
-    // alive (leak-once) rather than free it under them
-    void* p = nullptr;
+  const int slot = ctx->scratch_next;
+  ctx->scratch_next = (slot + 1) % ugn_ctx::kScratchSlots;
+  if (bytes > ctx->scratch_bytes[slot]) {
+    // grow EVERY slot to the new size at once: this happens in the warm-up step, so the captured step (which
+    // requests the same sizes from other slots of the ring) never allocates inside a CUDA-graph capture.
+    // Previous smaller buffers may still be referenced by in-flight kernels / captured graphs: they are kept
+    // alive (leak-once) rather than freed under them.
     size_t want = (bytes + (1u << 20) - 1) & ~(size_t)((1u << 20) - 1);
-    UGN_CUDA(cudaMalloc(&p, want));
-    ctx->scratch = p;
-    ctx->scratch_bytes = want;
+    for (int i = 0; i < ugn_ctx::kScratchSlots; ++i) {
+      if (ctx->scratch_bytes[i] >= want) continue;
+      void* p = nullptr;
+      UGN_CUDA(cudaMalloc(&p, want));
+      ctx->scratch[i] = p;
+      ctx->scratch_bytes[i] = want;
+    }
   }
-  *out = ctx->scratch;
+  *out = ctx->scratch[slot];
   return UGN_OK;
 }
 
@@ -81,6 +88,9 @@ extern "C" int ugn_ctx_create(int device, ugn_ctx** out) {
 extern "C" int ugn_ctx_destroy(ugn_ctx* ctx) {
   if (ctx && ctx->err_flag) cudaFree(ctx->err_flag);
   if (ctx && ctx->gscale) cudaFree(ctx->gscale);
+  if (ctx)
+    for (int i = 0; i < ugn_ctx::kScratchSlots; ++i)
+      if (ctx->scratch[i]) cudaFree(ctx->scratch[i]);   // (outgrown buffers were leaked on purpose)
   delete ctx;
   return UGN_OK;
 }

@@ -31,8 +31,13 @@ struct ugn_ctx {
   float* gscale = nullptr;
   // grow-only device scratch (split-K partial sums of small convolutions); sized on first use, i.e. in
   // the warm-up step before any CUDA-graph capture
-  void* scratch = nullptr;
-  size_t scratch_bytes = 0;
+  // round-robin pool (the engine runs the modality branches on concurrent streams: consecutive calls
+  // get different buffers; a buffer comes round again only after kScratchSlots further calls, i.e. more
+  // than two steps later, and steps are serialised by the stream joins)
+  static constexpr int kScratchSlots = 8;
+  void* scratch[kScratchSlots] = {};
+  size_t scratch_bytes[kScratchSlots] = {};
+  int scratch_next = 0;
 };
 
 int ugn_scratch(ugn_ctx* ctx, size_t bytes, void** out);

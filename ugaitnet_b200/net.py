@@ -69,6 +69,8 @@ class UGaitEngine:
         # data-parallel CUDA graphs: the step is captured as segments cut at the all-reduce points
         # (_capture_segments); NCCL itself is never captured (capturing the async work handles hung)
         self.dp_graph = os.environ.get("UGN_DP_GRAPH", "1") != "0"
+        self.multistream = os.environ.get("UGN_MULTISTREAM", "1") != "0"   # concurrent modality branches
+        self._bstreams = None
         self.force_segments = False     # tests: use the segmented capture on a single GPU too
         self._works = []
         self._cap = None           # state of a segmented graph capture (data-parallel CUDA graphs)
@@ -244,9 +246,63 @@ class UGaitEngine:
         return p
 
     # ------------------------------------------------------------------ forward
+    # ---- concurrent modality branches: the branches are independent between the input pack and the fusion
+    # (forward) and between the fusion backward and the optimiser (backward), so each runs on its own stream;
+    # the HBM-bound kernels of one branch (packs, pool/act backward, weight-streaming dense GEMMs) then
+    # overlap the tensor-bound conv kernels of another, also inside a captured CUDA graph (fork/join events)
+    def _fork(self):
+        if not self.multistream or self.cfg.nmods == 1:
+            return None
+        if self._bstreams is None:
+            self._bstreams = [torch.cuda.Stream(device=self.dev) for _ in range(self.cfg.nmods - 1)]
+        main = torch.cuda.current_stream()
+        ev = torch.cuda.Event()
+        ev.record(main)
+        for s in self._bstreams:
+            s.wait_event(ev)
+        return [main] + self._bstreams
+
+    def _join(self, streams):
+        if streams is None:
+            return
+        main = streams[0]
+        for s in streams[1:]:
+            ev = torch.cuda.Event()
+            ev.record(s)
+            main.wait_event(ev)
+
     def _forward(self, p: "_Plan", train: bool, expanded: bool = False):
-        cfg, h, st = self.cfg, self.ctx.h, stream_ptr()
+        cfg, h = self.cfg, self.ctx.h
+        streams = self._fork()
         for m in range(cfg.nmods):
+            with torch.cuda.stream(streams[m] if streams else torch.cuda.current_stream()):
+                self._forward_branch(p, m, train, expanded)
+        self._join(streams)
+        st = stream_ptr()
+        if cfg.single:
+            sig = p.br[0].R["out"]
+        else:
+            check(lib.ugn_fuse_fwd(h, cfg.nmods, p.br_ptrs, p.flag_ptrs, p.R["sig"].ptr, None, p.R["winner"].ptr,
+                                   p.R["inv_norm"].ptr, cfg.merge, 1, st))
+            sig = p.R["sig"]
+        feat = sig
+        if cfg.nc > 0:
+            cmask = p.R["cmask"].ptr if (train and cfg.dropout > 0.001) else None
+            check(lib.ugn_linear_fwd(h, sig.ptr, self.Rw["code/w"].ptr, self.Rw["code/b"].ptr, None, p.R["code"].ptr,
+                                     None, cfg.act, cfg.alpha, st))
+            if cmask is not None:
+                torch.mul(p.code, p.cmask, out=p.dropcode)
+                feat = p.R["dropcode"]
+            else:
+                feat = p.R["code"]
+        if cfg.nclasses > 0:
+            check(lib.ugn_linear_fwd(h, feat.ptr, self.Rw["classprob/w"].ptr, self.Rw["classprob/b"].ptr, None,
+                                     p.R["logits"].ptr, None, ACT_LINEAR, 0.0, st))
+        return sig, feat
+
+    def _forward_branch(self, p: "_Plan", m: int, train: bool, expanded: bool):
+        cfg, h, st = self.cfg, self.ctx.h, stream_ptr()
+        if True:   # (kept as a block: body of the former per-branch loop)
             bn = BRANCH_NAMES[m]
             b = p.br[m]
             if expanded:
@@ -270,26 +326,6 @@ class UGaitEngine:
                                      mask, b.R["h1"].ptr, b.R["h1_16"].ptr if self.P else None, ACT_LINEAR, 0.0, st))
             check(lib.ugn_linear_fwd(h, (b.R["h1_16"] if self.P else b.R["h1"]).ptr, self.Rcw[f"{bn}/ofCode/w"].ptr,
                                      self.Rw[f"{bn}/ofCode/b"].ptr, None, b.R["out"].ptr, None, ACT_LINEAR, 0.0, st))
-        if cfg.single:
-            sig = p.br[0].R["out"]
-        else:
-            check(lib.ugn_fuse_fwd(h, cfg.nmods, p.br_ptrs, p.flag_ptrs, p.R["sig"].ptr, None, p.R["winner"].ptr,
-                                   p.R["inv_norm"].ptr, cfg.merge, 1, st))
-            sig = p.R["sig"]
-        feat = sig
-        if cfg.nc > 0:
-            cmask = p.R["cmask"].ptr if (train and cfg.dropout > 0.001) else None
-            check(lib.ugn_linear_fwd(h, sig.ptr, self.Rw["code/w"].ptr, self.Rw["code/b"].ptr, None, p.R["code"].ptr,
-                                     None, cfg.act, cfg.alpha, st))
-            if cmask is not None:
-                torch.mul(p.code, p.cmask, out=p.dropcode)
-                feat = p.R["dropcode"]
-            else:
-                feat = p.R["code"]
-        if cfg.nclasses > 0:
-            check(lib.ugn_linear_fwd(h, feat.ptr, self.Rw["classprob/w"].ptr, self.Rw["classprob/b"].ptr, None,
-                                     p.R["logits"].ptr, None, ACT_LINEAR, 0.0, st))
-        return sig, feat
 
     def _set_inputs(self, p, inputs, flags, labels=None, drop_masks=None, code_drop_mask=None):
         cfg = self.cfg
@@ -427,7 +463,17 @@ class UGaitEngine:
         else:
             check(lib.ugn_fuse_bwd(h, cfg.nmods, p.R["dsig"].ptr, p.R["sig"].ptr, p.R["winner"].ptr,
                                    p.R["inv_norm"].ptr, p.flag_ptrs, p.dbr_ptrs, cfg.merge, 1, st))
+        # per-branch backward on concurrent streams (single GPU; with data parallelism the branches stay in
+        # sequence so that every all-reduce bucket is issued from the one stream NCCL orders against)
+        streams = self._fork() if self.world == 1 and self._cap is None else None
         for m in range(cfg.nmods):
+            with torch.cuda.stream(streams[m] if streams else torch.cuda.current_stream()):
+                self._backward_branch(p, m)
+        self._join(streams)
+
+    def _backward_branch(self, p: "_Plan", m: int):
+        cfg, h, st = self.cfg, self.ctx.h, stream_ptr()
+        if True:   # (body of the former per-branch loop)
             bn = BRANCH_NAMES[m]
             b = p.br[m]
             R = b.R
