@@ -258,6 +258,59 @@ int ugn_segment_pool(ugn_ctx*, const ugn_tensor* codes, const ugn_tensor* order,
 int ugn_segment_mode(ugn_ctx*, const ugn_tensor* labels, const ugn_tensor* order,
                      const ugn_tensor* offsets, int legacy_ties, ugn_tensor* out, void* stream);
 
+/* ---- a16: GaitSet branch type (nets/mj_uwyhNets_ba.py:420-484, MatMul :23-48) --------------
+ * The convolutions of build_gaitset_branch run on ugn_conv2d_* above: padding='same' (:428-466) is
+ * realised with ZERO-BORDERED activation buffers (the caller allocates [.,N,H+2,W+2,C] zero-filled
+ * once, producers fill the interior with ugn_pad_hw, gradients come back through ugn_crop_hw), the
+ * bias argument is NULL (use_bias=False) and act = UGN_ACT_LEAKY, alpha 0.3 (layers.LeakyReLU()).
+ *
+ * ugn_gs_pack_input: x f32 [B,T,H,W,c] (the Keras gaitset input, c = 1 | 2;
+ *   data/mj_dataGeneratorMMUWYHsingle_repetitions.py:426-434) -> im2col of
+ *   TimeDistributed(ZeroPadding2D(2)) + the first 5x5 'same' convolution (:427-428):
+ *   out f32 [B*T,H+4,W+4,Kp] or 16-bit [P,...]; channel j = (ky*5+kx)*c + ci holds
+ *   x[b,t,y+ky-4,x+kx-4,ci] (0 outside the frame and for j >= 25c), so that the first convolution is
+ *   ugn_conv2d_fwd with a 1x1 kernel [32][1][1][Kp] (K = 25c padded to 32 | 64 instead of 25 taps x 32
+ *   padded channels). */
+int ugn_gs_pack_input(ugn_ctx*, const ugn_tensor* x, ugn_tensor* out, void* stream);
+/* interior copy src [.,N,H,W,C] -> dst [.,N,H+2p,W+2p,C] (any storage mode, p from the shapes; the
+ * border of dst is left untouched) and its adjoint on f32 gradients: dst [N,H,W,C] (+)= interior of
+ * src [N,H+2p,W+2p,C]. */
+int ugn_pad_hw(ugn_ctx*, const ugn_tensor* src, ugn_tensor* dst, void* stream);
+int ugn_crop_hw(ugn_ctx*, const ugn_tensor* src, ugn_tensor* dst, int accumulate, void* stream);
+/* Set pooling Lambda(reduce_max(x, axis=1)) over the T frames of a sequence (:435,:454,:465) fused
+ * with the layers.Add() that follows (:455,:466): a [.,B*T,H,W,C] -> m f32 [B,H,W,C] = max_t a
+ * (nullable), y [.,B,H,W,C] = m + addend (nullable; addend [.,B,H,W,C] nullable, any storage mode).
+ * Backward: da f32 [B*T,H,W,C] (+)= dm * [a == m] / #{t: a == m}  (tf reduce_max splits the gradient
+ * evenly among ties). */
+int ugn_setmax_fwd(ugn_ctx*, const ugn_tensor* a, int T, const ugn_tensor* addend, ugn_tensor* m,
+                   ugn_tensor* y, void* stream);
+int ugn_setmax_bwd(ugn_ctx*, const ugn_tensor* dm, const ugn_tensor* a, const ugn_tensor* m, int T,
+                   ugn_tensor* da, int accumulate, void* stream);
+/* Horizontal pyramid pooling (:468-479): x f32 [B,H,W,C] -> rows of feat f32 [62,B,C]; for
+ * nb in {1,2,4,8,16} the H*W positions (row-major) are cut into nb strips, feature = mean + max;
+ * part = 2*(nb-1) + which*nb + strip, which = 0 for the set-level map, 1 for the global map (the
+ * reference's concatenation order, already transposed to [62,B,C], :481-482).
+ * Backward: dx (+)= dfeat/len + dfeat * [x == strip max] / #ties, summed over the 5 levels. */
+int ugn_hpp_fwd(ugn_ctx*, const ugn_tensor* x, int which, ugn_tensor* feat, void* stream);
+int ugn_hpp_bwd(ugn_ctx*, const ugn_tensor* dfeat, const ugn_tensor* x, int which, ugn_tensor* dx,
+                int accumulate, void* stream);
+/* MatMul layer (:41-46) and its gradients: C f32 [n,M,N] = op(A)[n] . op(B)[n]  (fp32 FFMA);
+ * a_t == 0: A [n,M,K], 1: A [n,K,M];  b_t == 0: B [n,K,N], 1: B [n,N,K]. */
+int ugn_bmm_f32(ugn_ctx*, const ugn_tensor* A, int a_t, const ugn_tensor* B, int b_t, ugn_tensor* C,
+                void* stream);
+/* Gate x use-flag (:51-54), fusion (:1189) and tf.math.l2_normalize(axis=1) (:1191) on the GaitSet
+ * layout: br[m] f32 [n,B,d], flags[m] f32 [B,1].  axis 1 of [n,B,d] is the BATCH axis: every
+ * (part, feature) column is normalised over the rows of the batch -- the reference's literal
+ * behaviour.  sig f32 [n,B,d], winner u8 [n,B,d], col_norm f32 [n,d,2] = {1/norm, sum x^2}. */
+int ugn_fuse3_fwd(ugn_ctx*, int nmods, const ugn_tensor* const* br, const ugn_tensor* const* flags,
+                  ugn_tensor* sig, ugn_tensor* winner, ugn_tensor* col_norm, int merge, void* stream);
+int ugn_fuse3_bwd(ugn_ctx*, int nmods, const ugn_tensor* dsig, const ugn_tensor* sig,
+                  const ugn_tensor* winner, const ugn_tensor* col_norm, const ugn_tensor* const* flags,
+                  ugn_tensor* const* dbr, int merge, void* stream);
+/* Lambda(tf.transpose(x, [1,0,2])) in front of Flatten + "classprob" (:1211-1213):
+ * src f32 [A,B,d] -> dst f32 [B,A,d] (or its flattened view [B,A*d]). */
+int ugn_permute102(ugn_ctx*, const ugn_tensor* src, ugn_tensor* dst, void* stream);
+
 /* ---- generic tensor-core GEMM (building block exposed for tests / k-NN / triplet) ----
  * C f32 [M,N] (+)= A . B^T with bf16 (or f16) operands [P,rows,cols]:
  *   a_mn == 0: A is [P,M,K] (K contiguous);  a_mn == 1: A is [P,K,M] (M contiguous).

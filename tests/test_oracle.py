@@ -158,3 +158,42 @@ def test_expansion_pattern_matches_oracle_generator():
             assert np.array_equal(use[:, m], fl[m].reshape(-1))
             assert np.array_equal(expand_on_host(xs[m][::E], src, use[:, m]), xs[m])
         assert (use.sum(1) >= 1).all()          # never all modalities missing
+
+
+# ---- GaitSet oracle (row a16): pin the rank-3 pieces against literal restatements of the reference ops
+def _sign_max_literal_np(xs):
+    """mains/mj_trainUWYHGaitNet_DataGen_CasiaB.py:169-178 op by op (stack, reshape, argmax|.|, gather_nd)."""
+    dims = xs[0].shape
+    cat = np.stack(xs, 0).reshape(len(xs), -1)
+    pos = np.argmax(np.abs(cat), axis=0)                       # first maximum, like tf.math.argmax
+    return cat[pos, np.arange(dims[0] * dims[1] * dims[2])].reshape(dims)
+
+
+def test_gaitset_sign_max_rank3_matches_literal():
+    rng = np.random.default_rng(0)
+    xs = [rng.standard_normal((62, 5, 8)) for _ in range(3)]
+    xs[1][:, :, :2] = -xs[0][:, :, :2]                         # |.| ties -> lowest modality index
+    got = O.merge_modalities([torch.tensor(x) for x in xs], O.MERGE_SIGNMAX).numpy()
+    assert np.array_equal(got, _sign_max_literal_np(xs))
+
+
+def test_gaitset_hpp_layout_and_shapes():
+    from oracle import gaitset_oracle as G
+    cfg = G.GaitSetConfig(in_channels=(1,), frames=2, hw=12, nclasses=0)
+    P = G.init_params(cfg, dtype=torch.float64)
+    x = torch.rand(2, 2, 12, 12, 1, dtype=torch.float64)
+    out, acts = G.gaitset_branch_forward(x, P, "ofBranch", cfg, return_acts=True)
+    assert out.shape == (62, 2, 256) and acts["hpp"].shape == (62, 2, 128)
+    # literal Keras ops on the NHWC map: Reshape((nb,-1,c)) then mean+max over axis 2, a-strips before b-strips
+    a = acts["a_set"].permute(0, 2, 3, 1).numpy()
+    b = acts["b_set"].permute(0, 2, 3, 1).numpy()
+    feats = []
+    for nb in (1, 2, 4, 8, 16):
+        for m in (a, b):
+            r = m.reshape(m.shape[0], nb, -1, m.shape[-1])
+            feats.append(r.mean(2) + r.max(2))
+    lit = np.concatenate(feats, 1).transpose(1, 0, 2)
+    assert np.allclose(acts["hpp"].numpy(), lit, rtol=0, atol=1e-12)
+    # axis=1 of [62,B,d] is the batch axis: every (part, feature) column of the signature has unit norm
+    sig, _ = G.model_forward([x], [torch.ones(2, 1, dtype=torch.float64)], P, cfg)
+    assert torch.allclose((sig ** 2).sum(1), torch.ones(62, 256, dtype=torch.float64))

@@ -76,6 +76,17 @@ _PROTOS = {
     "ugn_knn_merge_vote": (c_int, [c_void_p, _T, _T, _T, c_int, _T, _T, _T, _T, c_void_p]),
     "ugn_segment_pool": (c_int, [c_void_p, _T, _T, _T, c_int, _T, c_void_p]),
     "ugn_segment_mode": (c_int, [c_void_p, _T, _T, _T, c_int, _T, c_void_p]),
+    "ugn_gs_pack_input": (c_int, [c_void_p, _T, _T, c_void_p]),
+    "ugn_pad_hw": (c_int, [c_void_p, _T, _T, c_void_p]),
+    "ugn_crop_hw": (c_int, [c_void_p, _T, _T, c_int, c_void_p]),
+    "ugn_setmax_fwd": (c_int, [c_void_p, _T, c_int, _T, _T, _T, c_void_p]),
+    "ugn_setmax_bwd": (c_int, [c_void_p, _T, _T, _T, c_int, _T, c_int, c_void_p]),
+    "ugn_hpp_fwd": (c_int, [c_void_p, _T, c_int, _T, c_void_p]),
+    "ugn_hpp_bwd": (c_int, [c_void_p, _T, _T, c_int, _T, c_int, c_void_p]),
+    "ugn_bmm_f32": (c_int, [c_void_p, _T, c_int, _T, c_int, _T, c_void_p]),
+    "ugn_fuse3_fwd": (c_int, [c_void_p, c_int, POINTER(c_void_p), POINTER(c_void_p), _T, _T, _T, c_int, c_void_p]),
+    "ugn_fuse3_bwd": (c_int, [c_void_p, c_int, _T, _T, _T, _T, POINTER(c_void_p), POINTER(c_void_p), c_int, c_void_p]),
+    "ugn_permute102": (c_int, [c_void_p, _T, _T, c_void_p]),
     "ugn_gemm_bf16": (c_int, [c_void_p, _T, c_int, _T, c_int, _T, c_int, c_void_p]),
     "ugn_grad_scale_update": (c_int, [c_void_p, _T, c_float, c_void_p]),
     "ugn_grad_scale_set": (c_int, [c_void_p, c_float, c_void_p]),

@@ -15,7 +15,7 @@ CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libugaitnet_b200.so")
 STAMP = os.path.join(HERE, ".build_stamp")
 
-SOURCES = ["abi.cu", "simt.cu", "elementwise.cu", "triplet.cu", "knn.cu", "knn_tc.cu", "tc.cu"]
+SOURCES = ["abi.cu", "simt.cu", "elementwise.cu", "triplet.cu", "knn.cu", "knn_tc.cu", "tc.cu", "gaitset.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-lineinfo", "-O3", "-std=c++17",

@@ -58,3 +58,33 @@ class NetConfig:
     def flat(self) -> int:
         last = self.layers(0, 1)[-1]
         return last["co"] * last["hp"] * last["hp"]
+
+
+# (name, cin, cout, k, input, pooled) of build_gaitset_branch, in graph order
+# (/root/reference/nets/mj_uwyhNets_ba.py:427-466); cin None = the im2col'd per-frame input
+GS_CONVS = (("a1", None, 32, 5), ("a2", 32, 32, 3), ("b1", 32, 64, 3), ("b2", 64, 64, 3), ("a3", 32, 64, 3),
+            ("a4", 64, 64, 3), ("b3", 64, 128, 3), ("b4", 128, 128, 3), ("a5", 64, 128, 3), ("a6", 128, 128, 3))
+GS_PARTS = 62                      # 2 * (1 + 2 + 4 + 8 + 16) HPP strips (:468-479)
+GS_ALPHA = 0.3                     # layers.LeakyReLU() default
+
+
+@dataclass
+class GaitSetConfig:
+    """Arguments of UWYHSemiNet3Mods.build(..., gaitset=True) that shape the graph
+    (/root/reference/nets/mj_uwyhNets_ba.py:1032-1037; branch :420-484)."""
+    in_channels: Sequence[int] = (2, 1, 1)    # per-frame channels: OF (x,y), gray, depth | silhouette
+    frames: int = 25
+    hw: int = 60
+    hidden: int = 256              # MatMul hidden_dim (:24)
+    nc: int = 0                    # ndense_units[1] (FC1 "code"), 0 = absent
+    nclasses: int = 150
+    merge: int = MERGE_MAX
+    alpha: float = 0.3             # LeakyReLU after "code" (gaitset needs fActivation != 'relu', :1101)
+    margin: float = 0.2
+    wver: float = 1.0
+    wid: float = 1.0
+    single: bool = False
+
+    @property
+    def nmods(self) -> int:
+        return len(self.in_channels)

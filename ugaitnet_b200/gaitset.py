@@ -1,0 +1,506 @@
+"""GaitSet branch type of UGaitNet: step engine.
+
+``UWYHSemiNet3Mods.build(..., gaitset=True)`` (/root/reference/nets/mj_uwyhNets_ba.py:1110-1214) around
+``UWYHSemiNet.build_gaitset_branch`` (:420-484): per-frame convolutions (TimeDistributed), set pooling over
+the T frames, the global branch, horizontal pyramid pooling into 62 parts, the per-part ``MatMul`` (:23-48),
+then gate x use-flag, fusion, ``l2_normalize(axis=1)`` on ``[62, B, 256]`` (axis 1 is the batch axis in this
+layout -- kept literally), FC1 "code", transpose + Flatten + FC2 "classprob", batch-all triplet over the
+62 parts.
+
+The engine reuses the conv / dense / loss / optimiser kernels of the stacked-CNN path through the same C
+ABI; ``padding='same'`` is realised with zero-bordered activation buffers (ugn_pad_hw / ugn_crop_hw), the
+first 5x5 convolution over 1 | 2 input channels is an im2col'd 1x1 convolution (ugn_gs_pack_input) so that
+its K is 32 | 64 instead of 25 taps x 32 padded channels.  PyTorch owns memory, streams and NCCL only.
+"""
+from __future__ import annotations
+
+import math
+from typing import Dict, List, Optional, Sequence
+
+import torch
+
+from . import ops
+from ._ffi import TRef, check, lib, ptr_array, stream_ptr
+from .config import ACT_LEAKY, ACT_LINEAR, BRANCH_NAMES, GS_ALPHA, GS_CONVS, GS_PARTS, GaitSetConfig, round_up
+from .net import GRAD_SCALE_TARGET, UGaitEngine, _Seg
+
+# conv name -> (input buffer, output buffer, pooled)
+_GS_WIRING = {"a1": ("col", "a1", 0), "a2": ("a1p", "a2", 1), "b1": ("g0p", "b1", 0), "b2": ("b1p", "b2", 1),
+              "a3": ("a2p", "a3", 0), "a4": ("a3p", "a4", 1), "b3": ("s1p", "b3", 0), "b4": ("b3p", "b4", 0),
+              "a5": ("a4p", "a5", 0), "a6": ("a5p", "a6", 0)}
+
+
+class GaitSetEngine(UGaitEngine):
+    """One training / descriptor-extraction step of the gaitset=True graph on one GPU."""
+
+    def __init__(self, cfg: GaitSetConfig, **kw):
+        super().__init__(cfg, **kw)
+
+    # ------------------------------------------------------------------ parameters
+    def _conv_shapes(self, m: int):
+        """name -> (cout_master, k, cin_master, cin_packed).  In tensor-core mode the 32 output channels of
+        "a2" are padded to 64 (zero rows, zero gradient for ever): its input gradient is a GEMM over the
+        output channels whose K stage is 64."""
+        c = self.cfg.in_channels[m]
+        c2 = 64 if self.P else 32
+        out = {}
+        for name, cin, co, k in GS_CONVS:
+            if name == "a1":
+                out[name] = (co, 1, 25 * c, round_up(25 * c, 32) if self.P else 25 * c, co)
+            else:
+                cm = cin
+                cp = c2 if name in ("b1", "a3") else cin
+                out[name] = (c2 if name == "a2" else co, k, cm, cp, co)
+        return out
+
+    def _build_arena(self):
+        cfg = self.cfg
+        segs: List[_Seg] = []
+        off = 0
+        self.true_co: Dict[str, int] = {}
+
+        def add(name, shape, l2=0.0):
+            nonlocal off
+            n = 1
+            for s in shape:
+                n *= s
+            segs.append(_Seg(name, tuple(shape), off, n, l2))
+            off += round_up(n, 64)
+
+        for m in range(cfg.nmods):
+            bn = BRANCH_NAMES[m]
+            for name, (co, k, cin, cp, true_co) in self._conv_shapes(m).items():
+                add(f"{bn}/{name}/w", (co, k, k, cin))
+                self.true_co[f"{bn}/{name}/w"] = true_co
+            add(f"{bn}/matmul/w", (GS_PARTS, 128, cfg.hidden))
+        feat = cfg.hidden
+        if cfg.nc > 0:
+            add("code/w", (cfg.nc, cfg.hidden))
+            add("code/b", (cfg.nc,))
+            feat = cfg.nc
+        if cfg.nclasses > 0:
+            add("classprob/w", (cfg.nclasses, GS_PARTS * feat))
+            add("classprob/b", (cfg.nclasses,))
+        self.segs = {s.name: s for s in segs}
+        self.seg_list = segs
+        self.n_arena = off
+        self.buckets = {}
+        for m in range(cfg.nmods):
+            mine = [s for s in segs if s.name.startswith(BRANCH_NAMES[m] + "/")]
+            self.buckets[m] = (mine[0].off, round_up(mine[-1].off + mine[-1].n, 64))
+        heads = [s for s in segs if s.name.split("/")[0] in ("code", "classprob")]
+        self.buckets["heads"] = (heads[0].off, off) if heads else None
+        d = self.dev
+        self.w = torch.zeros(off, device=d)
+        self.g = torch.zeros(off, device=d)
+        self.m = torch.zeros(off, device=d)
+        self.v = torch.zeros(off, device=d)
+        self.seg_off = torch.tensor([s.off for s in segs] + [off], dtype=torch.int64, device=d)
+        self.seg_l2 = torch.tensor([s.l2 for s in segs], dtype=torch.float32, device=d)
+        self.reg_out = torch.zeros(1, device=d)
+        self.lr_dev = torch.zeros(1, device=d)
+        self._lr_host = torch.zeros(1).pin_memory()
+        self.R = {k: TRef(t) for k, t in dict(w=self.w, g=self.g, m=self.m, v=self.v, seg_off=self.seg_off,
+                                               seg_l2=self.seg_l2, reg_out=self.reg_out, lr_dev=self.lr_dev).items()}
+        self.pw, self.pg_, self.Rw, self.Rg = {}, {}, {}, {}
+        for s in segs:
+            self.pw[s.name] = self.w[s.off:s.off + s.n].view(s.shape)
+            self.pg_[s.name] = self.g[s.off:s.off + s.n].view(s.shape)
+            self.Rw[s.name] = TRef(self.pw[s.name])
+            self.Rg[s.name] = TRef(self.pg_[s.name])
+        # compute copies of the conv kernels: [P][Cout][k][k][Cp] 16-bit planes, or the f32 master itself
+        self.cw, self.Rcw = {}, {}
+        for m in range(cfg.nmods):
+            bn = BRANCH_NAMES[m]
+            for name, (co, k, cin, cp, _) in self._conv_shapes(m).items():
+                key = f"{bn}/{name}/w"
+                if self.P:
+                    self.cw[key] = torch.zeros((self.P, co, k, k, cp), dtype=self.dt16, device=d)
+                elif cp != cin:
+                    self.cw[key] = torch.zeros((co, k, k, cp), device=d)
+                else:
+                    self.cw[key] = self.pw[key]
+        for k_, t in self.cw.items():
+            self.Rcw[k_] = TRef(t)
+        self.pack_table = None
+        self._fused_pack = set()
+        if self.P:
+            tab = torch.zeros(len(segs), 2, dtype=torch.int64)
+            for i, sg in enumerate(segs):
+                t = self.cw.get(sg.name)
+                if t is not None and tuple(t.shape[1:]) == sg.shape and sg.n % 4 == 0:
+                    tab[i, 0], tab[i, 1] = t.data_ptr(), sg.n
+                    self._fused_pack.add(sg.name)
+            self.pack_table = tab.to(d)
+            self.R["pack_table"] = TRef(self.pack_table)
+
+    def init_weights(self, seed: int):
+        """Keras defaults: glorot_uniform conv kernels without bias (:428-466), GlorotUniform on the rank-3
+        MatMul kernel (:33-34; receptive field 62), glorot Dense + zero bias."""
+        g = torch.Generator(device="cpu").manual_seed(seed)
+        for s in self.seg_list:
+            w = self.pw[s.name]
+            w.zero_()
+            if s.name.endswith("/b"):
+                continue
+            if len(s.shape) == 4:
+                co = self.true_co[s.name]
+                _, kh, kw, cin = s.shape
+                if s.name.endswith("/a1/w"):
+                    fan_in, fan_out = cin, co * 25
+                else:
+                    fan_in, fan_out = cin * kh * kw, co * kh * kw
+                shape = (co, kh, kw, cin)
+            elif len(s.shape) == 3:
+                fan_in, fan_out = GS_PARTS * s.shape[1], GS_PARTS * s.shape[2]
+                shape = s.shape
+            else:
+                fan_out, fan_in = s.shape
+                shape = s.shape
+            limit = math.sqrt(6.0 / (fan_in + fan_out))
+            vals = (torch.rand(shape, generator=g, dtype=torch.float32) * 2 - 1) * limit
+            w[:shape[0]].copy_(vals)
+        self.repack_weights()
+
+    def load_params(self, params: Dict[str, torch.Tensor]):
+        """params in the oracle / PyTorch layout: conv [Cout,Cin,kh,kw] ("a1": [32,c,5,5]), MatMul
+        [62,128,hidden], dense [out,in]."""
+        for name, val in params.items():
+            s = self.segs[name]
+            v = val.detach().to(torch.float32)
+            if len(s.shape) == 4:
+                v = v.permute(0, 2, 3, 1).contiguous()                 # [Cout,kh,kw,Cin]
+                if name.endswith("/a1/w"):
+                    v = v.reshape(v.shape[0], 1, 1, -1)               # tap-major (ky,kx,ci) == the im2col order
+                self.pw[name].zero_()
+                self.pw[name][:v.shape[0]].copy_(v.to(self.dev))
+            else:
+                self.pw[name].copy_(v.contiguous().to(self.dev))
+        self.repack_weights()
+
+    def _export(self, views) -> Dict[str, torch.Tensor]:
+        out = {}
+        for m in range(self.cfg.nmods):
+            pass
+        for s in self.seg_list:
+            v = views[s.name].detach().clone()
+            if len(s.shape) == 4:
+                v = v[:self.true_co[s.name]]
+                if s.name.endswith("/a1/w"):
+                    c = v.shape[-1] // 25
+                    v = v.reshape(v.shape[0], 5, 5, c)
+                v = v.permute(0, 3, 1, 2).contiguous()
+            out[s.name] = v
+        return out
+
+    # ------------------------------------------------------------------ plans
+    def plan(self, B: int, train: bool) -> "_GsPlan":
+        key = (B, train)
+        p = self._plans.get(key)
+        if p is None:
+            p = self._plans[key] = _GsPlan(self, B, train)
+        return p
+
+    def _set_inputs(self, p, inputs, flags, labels=None, drop_masks=None, code_drop_mask=None):
+        for m in range(self.cfg.nmods):
+            p.br[m].x_in.copy_(inputs[m], non_blocking=True)
+            if flags is not None:
+                p.flags[m].copy_(flags[m].reshape(-1, 1), non_blocking=True)
+        if labels is not None:
+            p.labels.copy_(labels.reshape(-1).to(torch.int32), non_blocking=True)
+
+    # ------------------------------------------------------------------ forward
+    def _conv(self, b, bn, name):
+        src, dst, pool = _GS_WIRING[name]
+        check(lib.ugn_conv2d_fwd(self.ctx.h, b.R[src].ptr, self.Rcw[f"{bn}/{name}/w"].ptr, None, b.R[dst].ptr,
+                                 b.R[f"idx_{dst}"].ptr if pool else None, ACT_LEAKY, GS_ALPHA, pool, stream_ptr()))
+
+    def _pad(self, b, src, dst):
+        check(lib.ugn_pad_hw(self.ctx.h, b.R[src].ptr, b.R[dst].ptr, stream_ptr()))
+
+    def _forward_branch(self, p, m: int, train: bool, expanded: bool):
+        h, T = self.ctx.h, self.cfg.frames
+        bn, b = BRANCH_NAMES[m], p.br[m]
+        R = b.R
+        st = stream_ptr()
+        check(lib.ugn_gs_pack_input(h, R["x_in"].ptr, R["col"].ptr, st))
+        self._conv(b, bn, "a1"); self._pad(b, "a1", "a1p")
+        self._conv(b, bn, "a2"); self._pad(b, "a2", "a2p")
+        check(lib.ugn_setmax_fwd(h, R["a2"].ptr, T, None, R["m0"].ptr, R["g0"].ptr, st))
+        self._pad(b, "g0", "g0p")
+        self._conv(b, bn, "b1"); self._pad(b, "b1", "b1p")
+        self._conv(b, bn, "b2")
+        self._conv(b, bn, "a3"); self._pad(b, "a3", "a3p")
+        self._conv(b, bn, "a4"); self._pad(b, "a4", "a4p")
+        check(lib.ugn_setmax_fwd(h, R["a4"].ptr, T, R["b2"].ptr, R["m1"].ptr, R["s1"].ptr, st))
+        self._pad(b, "s1", "s1p")
+        self._conv(b, bn, "b3"); self._pad(b, "b3", "b3p")
+        self._conv(b, bn, "b4")
+        self._conv(b, bn, "a5"); self._pad(b, "a5", "a5p")
+        self._conv(b, bn, "a6")
+        check(lib.ugn_setmax_fwd(h, R["a6"].ptr, T, R["b4"].ptr, R["m2"].ptr, R["s2"].ptr, st))
+        check(lib.ugn_hpp_fwd(h, R["m2"].ptr, 0, R["feat"].ptr, st))
+        check(lib.ugn_hpp_fwd(h, R["s2"].ptr, 1, R["feat"].ptr, st))
+        check(lib.ugn_bmm_f32(h, R["feat"].ptr, 0, self.Rw[f"{bn}/matmul/w"].ptr, 0, R["out"].ptr, st))
+
+    def _forward(self, p, train: bool, expanded: bool = False):
+        cfg, h = self.cfg, self.ctx.h
+        streams = self._fork()
+        for m in range(cfg.nmods):
+            with torch.cuda.stream(streams[m] if streams else torch.cuda.current_stream()):
+                self._forward_branch(p, m, train, expanded)
+        self._join(streams)
+        st = stream_ptr()
+        check(lib.ugn_fuse3_fwd(h, cfg.nmods, p.br_ptrs, p.flag_ptrs, p.R["sig"].ptr, p.R["winner"].ptr,
+                                p.R["col_norm"].ptr, cfg.merge, st))
+        sig = p.R["sig"]
+        feat = p.R["sig2d"]
+        if cfg.nc > 0:
+            check(lib.ugn_linear_fwd(h, p.R["sig2d"].ptr, self.Rw["code/w"].ptr, self.Rw["code/b"].ptr, None,
+                                     p.R["code_lin"].ptr, None, ACT_LINEAR, 0.0, st))
+            # Dense(activation=None) + LeakyReLU(alpha) (:1199-1201): dz = dy * act'(y) with dy = 1 is the
+            # activation itself only for linear maps, so the leaky output comes from the fused bias/act pass
+            check(lib.ugn_linear_fwd(h, p.R["sig2d"].ptr, self.Rw["code/w"].ptr, self.Rw["code/b"].ptr, None,
+                                     p.R["code"].ptr, None, ACT_LEAKY, cfg.alpha, st))
+            feat = p.R["code"]
+        if cfg.nclasses > 0:
+            check(lib.ugn_permute102(h, (p.R["code3d"] if cfg.nc > 0 else p.R["sig"]).ptr, p.R["flat"].ptr, st))
+            check(lib.ugn_linear_fwd(h, p.R["flat"].ptr, self.Rw["classprob/w"].ptr, self.Rw["classprob/b"].ptr, None,
+                                     p.R["logits"].ptr, None, ACT_LINEAR, 0.0, st))
+        return sig, feat
+
+    @torch.no_grad()
+    def predict(self, inputs: Sequence[torch.Tensor], flags: Optional[Sequence[torch.Tensor]] = None,
+                layer: str = "signature") -> torch.Tensor:
+        """model_code.predict (mains/mj_testUWYHGaitNet_open_tum.py:139-148): layer in {signature [62,B,d],
+        flatten [B,62*d] (typecode 3), code, classprob}."""
+        B = int(inputs[0].shape[0])
+        p = self.plan(B, False)
+        self._set_inputs(p, inputs, flags)
+        self._forward(p, False)
+        if layer == "signature":
+            return p.sig.clone()
+        if layer == "flatten":
+            return (p.code3d if self.cfg.nc > 0 else p.sig).permute(1, 0, 2).reshape(B, -1).clone()
+        if layer == "code":
+            return p.code3d.clone()
+        if layer in ("classprob", "logits"):
+            return p.logits.clone()
+        raise KeyError(layer)
+
+    # ------------------------------------------------------------------ backward
+    def _losses_and_backward(self, p, sig: TRef, feat: TRef):
+        cfg, h, st = self.cfg, self.ctx.h, stream_ptr()
+        B = p.B
+        self._works = []
+        check(lib.ugn_triplet_all(h, sig.ptr, p.R["labels"].ptr, cfg.margin, cfg.wver, p.R["trip_out"].ptr,
+                                  p.R["dsig"].ptr, p.R["trip_ws"].ptr, st))
+        if cfg.nclasses > 0:
+            check(lib.ugn_softmax_ce(h, p.R["logits"].ptr, p.R["labels"].ptr, p.R["ce_out"].ptr, p.R["dlogits"].ptr,
+                                     cfg.wid, st))
+            check(lib.ugn_linear_bwd(h, p.R["flat"].ptr, self.Rw["classprob/w"].ptr, p.R["dlogits"].ptr,
+                                     p.R["dflat"].ptr, self.Rg["classprob/w"].ptr, self.Rg["classprob/b"].ptr, st))
+            check(lib.ugn_permute102(h, p.R["dflat3d"].ptr, p.R["dfeat"].ptr, st))        # [B,62,f] -> [62,B,f]
+            if cfg.nc > 0:
+                # through LeakyReLU, then the activity regulariser l2(1e-3) of the LINEAR "code" output,
+                # divided by shape(output)[0] = 62 in this layout (:1199-1200)
+                check(lib.ugn_act_mask_bwd(h, p.R["dfeat2d"].ptr, p.R["code"].ptr, None, p.R["dcode_z"].ptr, None,
+                                           ACT_LEAKY, cfg.alpha, st))
+                p.dcode_z.add_(p.code_lin, alpha=2e-3 / GS_PARTS)
+                check(lib.ugn_linear_bwd(h, p.R["sig2d"].ptr, self.Rw["code/w"].ptr, p.R["dcode_z"].ptr,
+                                         p.R["dsig2"].ptr, self.Rg["code/w"].ptr, self.Rg["code/b"].ptr, st))
+                p.dsig.add_(p.dsig2.view_as(p.dsig))
+            else:
+                p.dsig.add_(p.dfeat)
+        self._reduce_bucket("heads")
+        check(lib.ugn_fuse3_bwd(h, cfg.nmods, p.R["dsig"].ptr, p.R["sig"].ptr, p.R["winner"].ptr, p.R["col_norm"].ptr,
+                                p.flag_ptrs, p.dbr_ptrs, cfg.merge, st))
+        # MatMul + HPP backward stay in f32; the conv stacks below consume 16-bit gradient operands
+        streams = self._fork() if self.world == 1 and self._cap is None else None
+        for m in range(cfg.nmods):
+            with torch.cuda.stream(streams[m] if streams else torch.cuda.current_stream()):
+                self._backward_head(p, m)
+        self._join(streams)
+        if self.scaled:
+            # fp16 gradient operands: this step's power-of-two scale comes from the gradients that ENTER the
+            # conv stacks (d_m2 / d_b4 of every branch, one contiguous buffer).  dL/dsignature, the stacked-CNN
+            # engine's reference, is 64x smaller here: the batch-axis l2_normalize and the 5-level pyramid
+            # amplify the gradient on the way back, and the conv-stack gradients only shrink from there
+            check(lib.ugn_grad_scale_update(h, p.R["dhead"].ptr, GRAD_SCALE_TARGET, st))
+            self.ctx.grad_scaled = True
+        elif getattr(self.ctx, "grad_scaled", False):
+            check(lib.ugn_grad_scale_set(h, 1.0, st))
+            self.ctx.grad_scaled = False
+        streams = self._fork() if self.world == 1 and self._cap is None else None
+        for m in range(cfg.nmods):
+            with torch.cuda.stream(streams[m] if streams else torch.cuda.current_stream()):
+                self._backward_branch(p, m)
+        self._join(streams)
+
+    def _bwd_conv(self, b, bn, name, dgrad: bool = True):
+        """dy (f32, layer output gradient d_<dst>) -> dz; weight gradient; input gradient cropped into d_<src>."""
+        h, st, R = self.ctx.h, stream_ptr(), b.R
+        src, dst, pool = _GS_WIRING[name]
+        check(lib.ugn_conv2d_bwd_act(h, R[f"d_{dst}"].ptr, R[dst].ptr, R[f"idx_{dst}"].ptr if pool else None,
+                                     R[f"dz_{dst}"].ptr, None, ACT_LEAKY, GS_ALPHA, pool, st))
+        check(lib.ugn_conv2d_wgrad(h, R[src].ptr, R[f"dz_{dst}"].ptr, self.Rg[f"{bn}/{name}/w"].ptr, None, st))
+        if dgrad:
+            check(lib.ugn_conv2d_dgrad(h, R[f"dz_{dst}"].ptr, self.Rcw[f"{bn}/{name}/w"].ptr, R[f"dx_{src}"].ptr, st))
+            check(lib.ugn_crop_hw(h, R[f"dx_{src}"].ptr, R[f"d_{src[:-1]}"].ptr, 0, st))
+
+    def _backward_head(self, p, m: int):
+        h, st = self.ctx.h, stream_ptr()
+        bn, b = BRANCH_NAMES[m], p.br[m]
+        R = b.R
+        # MatMul
+        check(lib.ugn_bmm_f32(h, R["dout"].ptr, 0, self.Rw[f"{bn}/matmul/w"].ptr, 1, R["dfeat"].ptr, st))
+        check(lib.ugn_bmm_f32(h, R["feat"].ptr, 1, R["dout"].ptr, 0, self.Rg[f"{bn}/matmul/w"].ptr, st))
+        # HPP: d_b4 = d(s2); d(m2) = d(s2) + set-level strips
+        check(lib.ugn_hpp_bwd(h, R["dfeat"].ptr, R["s2"].ptr, 1, R["d_b4"].ptr, 0, st))
+        b.d_m2.copy_(b.d_b4)
+        check(lib.ugn_hpp_bwd(h, R["dfeat"].ptr, R["m2"].ptr, 0, R["d_m2"].ptr, 1, st))
+
+    def _backward_branch(self, p, m: int):
+        h, st, T = self.ctx.h, stream_ptr(), self.cfg.frames
+        bn, b = BRANCH_NAMES[m], p.br[m]
+        R = b.R
+        # global branch
+        self._bwd_conv(b, bn, "b4")          # -> d_b3
+        self._bwd_conv(b, bn, "b3")          # -> d_s1  (== d_b2 and the gradient of the set pooling of a4)
+        b.d_b2.copy_(b.d_s1)
+        self._bwd_conv(b, bn, "b2")          # -> d_b1
+        self._bwd_conv(b, bn, "b1")          # -> d_g0
+        # set branch
+        check(lib.ugn_setmax_bwd(h, R["d_m2"].ptr, R["a6"].ptr, R["m2"].ptr, T, R["d_a6"].ptr, 0, st))
+        self._bwd_conv(b, bn, "a6")          # -> d_a5
+        self._bwd_conv(b, bn, "a5")          # -> d_a4
+        check(lib.ugn_setmax_bwd(h, R["d_s1"].ptr, R["a4"].ptr, R["m1"].ptr, T, R["d_a4"].ptr, 1, st))
+        self._bwd_conv(b, bn, "a4")          # -> d_a3
+        self._bwd_conv(b, bn, "a3")          # -> d_a2
+        check(lib.ugn_setmax_bwd(h, R["d_g0"].ptr, R["a2"].ptr, R["m0"].ptr, T, R["d_a2"].ptr, 1, st))
+        self._bwd_conv(b, bn, "a2")          # -> d_a1
+        self._bwd_conv(b, bn, "a1", dgrad=False)
+        self._reduce_bucket(m)
+
+    def _report(self, p, with_reg: bool = False) -> Dict[str, torch.Tensor]:
+        out = {"triplet": p.trip_out[0], "count": p.trip_out[1], "signature": p.sig}
+        if self.cfg.nclasses > 0:
+            out["ce"], out["acc"], out["logits"] = p.ce_out[0], p.ce_out[1], p.logits
+        if with_reg:
+            out["reg"] = self.reg_out[0]
+        return out
+
+    def train_step_expanded(self, *a, **k):
+        raise NotImplementedError("device-side expansion is implemented for the stacked-CNN engine only")
+
+    predict_expanded = train_step_expanded
+
+
+class _Branch:
+    pass
+
+
+class _GsPlan:
+    """All activation / gradient buffers of one batch size of the gaitset graph."""
+
+    def __init__(self, eng: GaitSetEngine, B: int, train: bool):
+        cfg, d, P, PB, dt16 = eng.cfg, eng.dev, eng.P, eng.PB, eng.dt16
+        self.B, self.train, self.eng = B, train, eng
+        self.use_mirror = False
+        f32 = dict(device=d, dtype=torch.float32)
+        T = cfg.frames
+        F = B * T
+        Hs = cfg.hw + 4
+        H1, H2 = Hs // 2, Hs // 4
+        assert Hs % 4 == 0 and (H2 * H2) % 16 == 0, "gaitset: (hw+4) must be a multiple of 4 and the last map of 16 positions"
+        c2 = 64 if P else 32
+
+        def act(shape, planes=P):
+            if planes:
+                return torch.zeros((planes,) + tuple(shape), device=d, dtype=dt16)
+            return torch.zeros(tuple(shape), **f32)
+
+        self.br: List[_Branch] = []
+        self.flags = [torch.ones(B, 1, **f32) for _ in range(cfg.nmods)]
+        dhead = torch.zeros(cfg.nmods, 2, B, H2, H2, 128, **f32) if train else None
+        # (name, N, H, C): activations in storage mode; "<name>p" = zero-bordered copy
+        for m in range(cfg.nmods):
+            b = _Branch()
+            c = cfg.in_channels[m]
+            kp = eng._conv_shapes(m)["a1"][3]
+            Tn = {}
+            b.x_in = Tn["x_in"] = torch.zeros(B, T, cfg.hw, cfg.hw, c, **f32)
+            Tn["col"] = act((F, Hs, Hs, kp))
+            geo = {"a1": (F, Hs, 32), "a2": (F, H1, c2), "a3": (F, H1, 64), "a4": (F, H2, 64), "a5": (F, H2, 128),
+                   "a6": (F, H2, 128), "g0": (B, H1, c2), "b1": (B, H1, 64), "b2": (B, H2, 64), "s1": (B, H2, 64),
+                   "b3": (B, H2, 128), "b4": (B, H2, 128)}
+            for name, (n, hh, cc) in geo.items():
+                Tn[name] = act((n, hh, hh, cc))
+                if name not in ("a6", "b4", "b2"):
+                    Tn[name + "p"] = act((n, hh + 2, hh + 2, cc))
+                if name in ("a2", "a4", "b2"):
+                    Tn["idx_" + name] = torch.zeros(n, hh, hh, cc, device=d, dtype=torch.uint8)
+            Tn["m0"] = torch.zeros(B, H1, H1, c2, **f32)
+            Tn["m1"] = torch.zeros(B, H2, H2, 64, **f32)
+            Tn["m2"] = torch.zeros(B, H2, H2, 128, **f32)
+            Tn["s2"] = torch.zeros(B, H2, H2, 128, **f32)
+            Tn["feat"] = torch.zeros(GS_PARTS, B, 128, **f32)
+            b.out = Tn["out"] = torch.zeros(GS_PARTS, B, cfg.hidden, **f32)
+            if train:
+                b.dout = Tn["dout"] = torch.zeros(GS_PARTS, B, cfg.hidden, **f32)
+                Tn["dfeat"] = torch.zeros(GS_PARTS, B, 128, **f32)
+                for name, (n, hh, cc) in geo.items():
+                    Tn["d_" + name] = dhead[m, 1] if name == "b4" else torch.zeros(n, hh, hh, cc, **f32)   # d(layer output)
+                    if name + "p" in Tn:
+                        Tn["dx_" + name + "p"] = torch.zeros(n, hh + 2, hh + 2, cc, **f32)
+                    if name in _DZ_GEO:
+                        Tn["dz_" + name] = act((n, hh * _DZ_GEO[name], hh * _DZ_GEO[name], cc), PB)
+                b.d_m2 = Tn["d_m2"] = dhead[m, 0]
+                b.d_b4, b.d_b2, b.d_s1 = Tn["d_b4"], Tn["d_b2"], Tn["d_s1"]
+            b.T = Tn
+            b.R = {k: TRef(v) for k, v in Tn.items()}
+            self.br.append(b)
+        Tn = {}
+        nd = cfg.hidden
+        self.sig = Tn["sig"] = torch.zeros(GS_PARTS, B, nd, **f32)
+        Tn["sig2d"] = self.sig.view(GS_PARTS * B, nd)
+        Tn["winner"] = torch.zeros(GS_PARTS, B, nd, device=d, dtype=torch.uint8)
+        Tn["col_norm"] = torch.zeros(GS_PARTS, nd, 2, **f32)
+        feat = nd
+        if cfg.nc > 0:
+            self.code_lin = Tn["code_lin"] = torch.zeros(GS_PARTS * B, cfg.nc, **f32)
+            Tn["code"] = torch.zeros(GS_PARTS * B, cfg.nc, **f32)
+            self.code3d = Tn["code3d"] = Tn["code"].view(GS_PARTS, B, cfg.nc)
+            feat = cfg.nc
+        if cfg.nclasses > 0:
+            Tn["flat"] = torch.zeros(B, GS_PARTS * feat, **f32)
+            self.logits = Tn["logits"] = torch.zeros(B, cfg.nclasses, **f32)
+        if train:
+            self.labels = Tn["labels"] = torch.zeros(B, device=d, dtype=torch.int32)
+            self.trip_out = Tn["trip_out"] = torch.zeros(2, **f32)
+            self.dsig = Tn["dsig"] = torch.zeros(GS_PARTS, B, nd, **f32)
+            Tn["trip_ws"] = torch.zeros(ops.triplet_workspace_bytes(GS_PARTS, B) // 4 + 16, **f32)
+            if cfg.nclasses > 0:
+                self.ce_out = Tn["ce_out"] = torch.zeros(2, **f32)
+                Tn["dlogits"] = torch.zeros(B, cfg.nclasses, **f32)
+                Tn["dflat"] = torch.zeros(B, GS_PARTS * feat, **f32)
+                Tn["dflat3d"] = Tn["dflat"].view(B, GS_PARTS, feat)
+                self.dfeat = Tn["dfeat"] = torch.zeros(GS_PARTS, B, feat, **f32)
+                Tn["dfeat2d"] = self.dfeat.view(GS_PARTS * B, feat)
+            if cfg.nc > 0:
+                self.dcode_z = Tn["dcode_z"] = torch.zeros(GS_PARTS * B, cfg.nc, **f32)
+                self.dsig2 = Tn["dsig2"] = torch.zeros(GS_PARTS * B, nd, **f32)
+        if train:
+            Tn["dhead"] = dhead.view(-1)
+        self.T = Tn
+        self.R = {k: TRef(v) for k, v in Tn.items()}
+        self.R_flags = [TRef(f) for f in self.flags]
+        self.br_ptrs = ptr_array([b.R["out"] for b in self.br])
+        self.flag_ptrs = ptr_array(self.R_flags)
+        if train:
+            self.dbr_ptrs = ptr_array([b.R["dout"] for b in self.br])
+
+
+# conv outputs that have a pre-activation gradient buffer: name -> spatial factor (2 = the layer is pooled,
+# dz lives on the pre-pool grid)
+_DZ_GEO = {"a1": 1, "a2": 2, "a3": 1, "a4": 2, "a5": 1, "a6": 1, "b1": 1, "b2": 2, "b3": 1, "b4": 1}
