@@ -264,17 +264,27 @@ int ugn_segment_mode(ugn_ctx*, const ugn_tensor* labels, const ugn_tensor* order
  * once, producers fill the interior with ugn_pad_hw, gradients come back through ugn_crop_hw), the
  * bias argument is NULL (use_bias=False) and act = UGN_ACT_LEAKY, alpha 0.3 (layers.LeakyReLU()).
  *
- * ugn_gs_pack_input: x f32 [B,T,H,W,c] (the Keras gaitset input, c = 1 | 2;
- *   data/mj_dataGeneratorMMUWYHsingle_repetitions.py:426-434) -> im2col of
- *   TimeDistributed(ZeroPadding2D(2)) + the first 5x5 'same' convolution (:427-428):
- *   out f32 [B*T,H+4,W+4,Kp] or 16-bit [P,...]; channel j = (ky*5+kx)*c + ci holds
- *   x[b,t,y+ky-4,x+kx-4,ci] (0 outside the frame and for j >= 25c), so that the first convolution is
- *   ugn_conv2d_fwd with a 1x1 kernel [32][1][1][Kp] (K = 25c padded to 32 | 64 instead of 25 taps x 32
- *   padded channels). */
-int ugn_gs_pack_input(ugn_ctx*, const ugn_tensor* x, ugn_tensor* out, void* stream);
-/* interior copy src [.,N,H,W,C] -> dst [.,N,H+2p,W+2p,C] (any storage mode, p from the shapes; the
- * border of dst is left untouched) and its adjoint on f32 gradients: dst [N,H,W,C] (+)= interior of
- * src [N,H+2p,W+2p,C]. */
+ * Split layout: the tensor-core conv kernels keep an input row in at most 64 pixel slots; a zero-bordered
+ * 66-wide row does not fit, so the 64-wide layers are kept as S = 2 overlapping column halves:
+ * padded input [.,N*S,H+2,W/S+2,C] (half h = padded columns [h*W/S, h*W/S + W/S + 2)), valid-conv output
+ * [.,N*S,H,W/S,C].  ugn_pad_hw / ugn_crop_hw convert between split and plain images (S = ratio of the
+ * leading dimensions).
+ *
+ * ugn_gs_conv1_fwd: TimeDistributed(ZeroPadding2D(2)) + Conv2D(32, 5x5, 'same', no bias) + LeakyReLU
+ *   (:427-429) fused, straight from the Keras input x f32 [B,T,H,W,c] (c = 1 | 2;
+ *   data/mj_dataGeneratorMMUWYHsingle_repetitions.py:426-434) into the interior of the zero-bordered
+ *   (split) input of the next convolution, yp [.,B*T*S,H+6,(W+4)/S+2,32].  w f32 [32,1,1,25c], tap-major
+ *   (ky,kx,ci).  K = 25c is too small for the tensor cores: fp32 FFMA, exact products.
+ * ugn_gs_conv1_wgrad: its kernel gradient with the LeakyReLU derivative and the crop folded in:
+ *   dxp f32 (shape of yp) = gradient wrt the layer output on the padded (split) frame, as written by
+ *   ugn_conv2d_dgrad of the next layer; dw f32 [32,1,1,25c], OVERWRITTEN. */
+int ugn_gs_conv1_fwd(ugn_ctx*, const ugn_tensor* x, const ugn_tensor* w, ugn_tensor* yp, float alpha,
+                     void* stream);
+int ugn_gs_conv1_wgrad(ugn_ctx*, const ugn_tensor* x, const ugn_tensor* dxp, const ugn_tensor* yp,
+                       ugn_tensor* dw, float alpha, void* stream);
+/* interior copy src [.,N*S,H,W,C] -> dst [.,N,H+2p,W*S+2p,C] (any storage mode, p and S from the
+ * shapes; the border of dst is left untouched) and its adjoint on f32 gradients:
+ * dst [N*S,H,W,C] (+)= interior of src [N,H+2p,W*S+2p,C]. */
 int ugn_pad_hw(ugn_ctx*, const ugn_tensor* src, ugn_tensor* dst, void* stream);
 int ugn_crop_hw(ugn_ctx*, const ugn_tensor* src, ugn_tensor* dst, int accumulate, void* stream);
 /* Set pooling Lambda(reduce_max(x, axis=1)) over the T frames of a sequence (:435,:454,:465) fused

@@ -76,7 +76,8 @@ _PROTOS = {
     "ugn_knn_merge_vote": (c_int, [c_void_p, _T, _T, _T, c_int, _T, _T, _T, _T, c_void_p]),
     "ugn_segment_pool": (c_int, [c_void_p, _T, _T, _T, c_int, _T, c_void_p]),
     "ugn_segment_mode": (c_int, [c_void_p, _T, _T, _T, c_int, _T, c_void_p]),
-    "ugn_gs_pack_input": (c_int, [c_void_p, _T, _T, c_void_p]),
+    "ugn_gs_conv1_fwd": (c_int, [c_void_p, _T, _T, _T, c_float, c_void_p]),
+    "ugn_gs_conv1_wgrad": (c_int, [c_void_p, _T, _T, _T, _T, c_float, c_void_p]),
     "ugn_pad_hw": (c_int, [c_void_p, _T, _T, c_void_p]),
     "ugn_crop_hw": (c_int, [c_void_p, _T, _T, c_int, c_void_p]),
     "ugn_setmax_fwd": (c_int, [c_void_p, _T, c_int, _T, _T, _T, c_void_p]),

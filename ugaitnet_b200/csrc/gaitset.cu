@@ -39,44 +39,247 @@ __device__ __forceinline__ void gs_store(void* p, int mode, int f16, long long p
 }
 
 // ---------------------------------------------------------------------------------------------------
-// input pack: x f32 [B,T,H,W,c] (the Keras gaitset input) -> im2col of ZeroPadding2D(2) + the 5x5 'same'
-// convolution: out [.,B*T,H+4,W+4,Kp], channel j = (ky*5 + kx)*c + ci holds x[y+ky-4, x+kx-4, ci]
-// (0 outside the frame and for j >= 25c), so that conv "a1" is a 1x1 convolution with K = Kp.
+// First convolution of the branch, fused: TimeDistributed(ZeroPadding2D(2)) + Conv2D(32, 5x5, 'same',
+// no bias) + LeakyReLU (:427-429) straight from the Keras input x f32 [B,T,H,W,c] (c = 1 | 2) into the
+// ZERO-BORDERED input buffer of the next convolution, y [.,F*S][Hs+2][Hs/S+2][32] (Hs = H+4, S column
+// halves, see ugn_pad_hw below).  K = 25c is far too small for the tensor cores (a 32-channel im2col would cost
+// 2.5 GB of traffic per modality): this is an fp32 FFMA kernel, exact products, HBM-bound on the output.
+// One thread = one output pixel x 32 channels; the 5x5 halo tile of the frame and the kernel live in smem.
 // ---------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) gs_pack_kernel(const float* __restrict__ x, void* __restrict__ out, long long F,
-                                                      int H, int W, int c, int Kp, int mode, int f16) {
-  const int Hs = H + 4, Ws = W + 4;
-  const long long total = F * Hs * Ws * Kp, plane = total;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    int j = (int)(i % Kp);
-    long long pix = i / Kp;
-    int xo = (int)(pix % Ws);
-    int yo = (int)((pix / Ws) % Hs);
-    long long f = pix / ((long long)Ws * Hs);
-    float v = 0.f;
-    if (j < 25 * c) {
-      int ci = j % c, tap = j / c;
-      int yy = yo + tap / 5 - 4, xx = xo + tap % 5 - 4;
-      if (yy >= 0 && yy < H && xx >= 0 && xx < W) v = x[((f * H + yy) * W + xx) * c + ci];
+template <int C>
+__global__ void __launch_bounds__(256) gs_conv1_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                                                           void* __restrict__ y, long long F, int H, int W, int S,
+                                                           int mode, int f16, float alpha) {
+  constexpr int K = 25 * C;
+  extern __shared__ float sm[];
+  const int Ws = W + 4, Hs = H + 4;
+  const int TW = Ws + 4;                       // tile row: output columns 0..Ws-1 need input columns -4..Ws-1
+  float* ws = sm;                              // [K][32]
+  float* xs = sm + K * 32;                     // [8][TW][C]
+  const int rows_per_block = 256 / Ws > 0 ? 256 / Ws : 1;     // output rows per block (Ws <= 256)
+  for (int i = threadIdx.x; i < K * 32; i += 256) ws[i] = w[(i & 31) * K + (i >> 5)];   // w [32][K] -> [K][32]
+  const int tiles_y = (Hs + rows_per_block - 1) / rows_per_block;
+  const long long ntiles = F * tiles_y;
+  const int Wh = Ws / S + 2, Hp = Hs + 2;
+  const long long plane = F * S * (long long)Hp * Wh * 32;
+  for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const long long f = tile / tiles_y;
+    const int y0 = (int)(tile % tiles_y) * rows_per_block;
+    __syncthreads();
+    const int nin = (rows_per_block + 4) * TW * C;
+    for (int i = threadIdx.x; i < nin; i += 256) {
+      int ci = i % C, xx = (i / C) % TW, yy = i / (C * TW);
+      int gy = y0 + yy - 4, gx = xx - 4;
+      xs[i] = (gy >= 0 && gy < H && gx >= 0 && gx < W) ? x[((f * H + gy) * W + gx) * C + ci] : 0.f;
     }
-    gs_store(out, mode, f16, plane, i, v);
+    __syncthreads();
+    const int ly = threadIdx.x / Ws, lx = threadIdx.x - ly * Ws;
+    if (ly >= rows_per_block || y0 + ly >= Hs) continue;
+    float acc[32];
+#pragma unroll
+    for (int o = 0; o < 32; ++o) acc[o] = 0.f;
+    for (int ky = 0; ky < 5; ++ky)
+#pragma unroll
+      for (int kx = 0; kx < 5; ++kx)
+#pragma unroll
+        for (int ci = 0; ci < C; ++ci) {
+          const float xv = xs[((ly + ky) * TW + lx + kx) * C + ci];
+          const float4* wr = reinterpret_cast<const float4*>(ws + ((ky * 5 + kx) * C + ci) * 32);
+#pragma unroll
+          for (int o = 0; o < 8; ++o) {
+            const float4 w4 = wr[o];
+            acc[4 * o] = fmaf(xv, w4.x, acc[4 * o]);
+            acc[4 * o + 1] = fmaf(xv, w4.y, acc[4 * o + 1]);
+            acc[4 * o + 2] = fmaf(xv, w4.z, acc[4 * o + 2]);
+            acc[4 * o + 3] = fmaf(xv, w4.w, acc[4 * o + 3]);
+          }
+        }
+#pragma unroll
+    for (int o = 0; o < 32; ++o) acc[o] = acc[o] > 0.f ? acc[o] : alpha * acc[o];
+    // padded coordinates (y+1, x+1); the pixel belongs to every half whose column window contains it
+    const int yc = y0 + ly + 1, xc = lx + 1, wh = Ws / S;
+    for (int h = 0; h < S; ++h) {
+      const int xl = xc - h * wh;
+      if (xl < 0 || xl >= Wh) continue;
+      const long long o0 = (((f * S + h) * Hp + yc) * Wh + xl) * 32;
+      if (mode == 0) {
+        float4* d = reinterpret_cast<float4*>(reinterpret_cast<float*>(y) + o0);
+#pragma unroll
+        for (int o = 0; o < 8; ++o) d[o] = make_float4(acc[4 * o], acc[4 * o + 1], acc[4 * o + 2], acc[4 * o + 3]);
+      } else {
+        uint32_t hw[16], lw[16];
+#pragma unroll
+        for (int o = 0; o < 32; o += 2) {
+          u16 h0, l0, h1, l1;
+          ugn_split16(acc[o], f16, h0, l0);
+          ugn_split16(acc[o + 1], f16, h1, l1);
+          hw[o >> 1] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
+          lw[o >> 1] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+        }
+        uint4* dh = reinterpret_cast<uint4*>(reinterpret_cast<u16*>(y) + o0);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) dh[q] = make_uint4(hw[4 * q], hw[4 * q + 1], hw[4 * q + 2], hw[4 * q + 3]);
+        if (mode == 2) {
+          uint4* dl = reinterpret_cast<uint4*>(reinterpret_cast<u16*>(y) + plane + o0);
+#pragma unroll
+          for (int q = 0; q < 4; ++q) dl[q] = make_uint4(lw[4 * q], lw[4 * q + 1], lw[4 * q + 2], lw[4 * q + 3]);
+        }
+      }
+    }
   }
 }
 
-extern "C" int ugn_gs_pack_input(ugn_ctx* ctx, const ugn_tensor* x, ugn_tensor* out, void* stream) {
-  UGN_CHECK(ctx && x && out, "ugn_gs_pack_input: null argument");
+static int conv1_geom(ugn_ctx* ctx, const ugn_tensor* x, const ugn_tensor* yp, long long& F, int& H, int& W, int& c, int& S) {
   UGN_TENSOR(x, DT_F32, 5, 5);
-  UGN_TENSOR(out, DT_BAD, 4, 5);
-  int mode = gs_mode(out, 4);
-  UGN_CHECK(mode >= 0, "gs_pack_input: out must be f32 [F,Hs,Ws,Kp] or 16-bit [P,F,Hs,Ws,Kp]");
-  const int64_t* s = gs_shape(out, 4);
-  long long F = x->shape[0] * x->shape[1];
-  int H = (int)x->shape[2], W = (int)x->shape[3], c = (int)x->shape[4];
-  UGN_CHECK(s[0] == F && s[1] == H + 4 && s[2] == W + 4 && s[3] >= 25 * c, "gs_pack_input: out must be [B*T,H+4,W+4,>=25c]");
-  if (F == 0) return UGN_OK;
-  long long total = F * s[1] * s[2] * s[3];
-  gs_pack_kernel<<<gs_grid(ctx, total, 256), 256, 0, (cudaStream_t)stream>>>(ugn_ptr<float>(x), ugn_ptr<void>(out), F, H, W, c,
-                                                                           (int)s[3], mode, gs_f16(out));
+  F = x->shape[0] * x->shape[1];
+  H = (int)x->shape[2]; W = (int)x->shape[3]; c = (int)x->shape[4];
+  UGN_CHECK(c == 1 || c == 2, "gs_conv1: per-frame channels must be 1 or 2");
+  UGN_CHECK(W + 4 <= 256, "gs_conv1: frame too wide");
+  const int64_t* s = gs_shape(yp, 4);
+  UGN_CHECK(F > 0 && s[0] % F == 0, "gs_conv1: padded buffer leading dim must be B*T*S");
+  S = (int)(s[0] / F);
+  UGN_CHECK(S >= 1 && (W + 4) % S == 0 && s[1] == H + 6 && s[2] == (W + 4) / S + 2 && s[3] == 32,
+            "gs_conv1: padded buffer must be [B*T*S, H+6, (W+4)/S+2, 32]");
+  return UGN_OK;
+}
+
+extern "C" int ugn_gs_conv1_fwd(ugn_ctx* ctx, const ugn_tensor* x, const ugn_tensor* w, ugn_tensor* yp, float alpha,
+                                void* stream) {
+  UGN_CHECK(ctx && x && w && yp, "ugn_gs_conv1_fwd: null argument");
+  UGN_TENSOR(yp, DT_BAD, 4, 5);
+  UGN_TENSOR(w, DT_F32, 2, 4);
+  int mode = gs_mode(yp, 4);
+  UGN_CHECK(mode >= 0, "gs_conv1_fwd: bad storage mode of the output");
+  long long F; int H, W, c, S, rc;
+  if ((rc = conv1_geom(ctx, x, yp, F, H, W, c, S)) != UGN_OK) return rc;
+  UGN_CHECK(ugn_numel(w) == 32 * 25 * c, "gs_conv1_fwd: w must be f32 [32,1,1,25c] (tap-major ky,kx,ci)");
+  const int Ws = W + 4, rows = std::max(1, 256 / Ws);
+  const long long ntiles = F * ugn_cdiv(H + 4, rows);
+  size_t smem = sizeof(float) * (25 * c * 32 + (size_t)(rows + 4) * (Ws + 4) * c);
+  int grid = (int)std::min<long long>(ntiles, (long long)ctx->sm_count * 8);
+  if (c == 1)
+    gs_conv1_fwd_kernel<1><<<grid, 256, smem, (cudaStream_t)stream>>>(ugn_ptr<float>(x), ugn_ptr<float>(w), ugn_ptr<void>(yp), F, H, W, S,
+                                                                     mode, gs_f16(yp), alpha);
+  else
+    gs_conv1_fwd_kernel<2><<<grid, 256, smem, (cudaStream_t)stream>>>(ugn_ptr<float>(x), ugn_ptr<float>(w), ugn_ptr<void>(yp), F, H, W, S,
+                                                                     mode, gs_f16(yp), alpha);
+  UGN_LAUNCHED(ctx);
+  return UGN_OK;
+}
+
+// Kernel gradient of that convolution, with the LeakyReLU derivative and the crop of the padded input
+// gradient folded in: dz = dxp * (y > 0 ? 1 : alpha) over the interior of the (split) padded frame, where
+// dxp f32 [F*S][Hs+2][Hs/S+2][32] is what ugn_conv2d_dgrad of the next layer wrote.  A pixel that lives in
+// two halves is simply visited twice (the sum over halves commutes with the reduction over pixels).
+// dw f32 [32][25c] (tap-major), OVERWRITTEN.
+// thread = (4 output channels, 25c/16 taps): per pixel one 16-byte gradient load + one sign load (hi plane
+// only: sign(y) == sign(hi)) + TT broadcast smem reads of the frame tile for 4*TT FMAs; persistent blocks
+// keep their partial sums in registers and issue one round of atomics at the end.
+template <int C, int MODE>
+__global__ void __launch_bounds__(128) gs_conv1_wgrad_kernel(const float* __restrict__ x, const float* __restrict__ dxp,
+                                                             const void* __restrict__ yp, float* __restrict__ dw,
+                                                             long long F, int H, int W, int S, int f16, float alpha) {
+  constexpr int K = 25 * C, TT = (K + 15) / 16, ROWS = 8;
+  extern __shared__ float sm[];
+  const int Ws = W + 4, Hs = H + 4, TW = Ws + 4;
+  float* xs = sm;                              // [ROWS+4][TW][C]
+  const int cg = threadIdx.x & 7, tg = threadIdx.x >> 3;
+  int toff[TT];
+#pragma unroll
+  for (int j = 0; j < TT; ++j) {
+    const int k = tg + 16 * j;
+    const int ci = k % C, tap = (k / C) % 25;
+    toff[j] = ((tap / 5) * TW + tap % 5) * C + ci;
+  }
+  float acc[TT][4];
+#pragma unroll
+  for (int j = 0; j < TT; ++j) acc[j][0] = acc[j][1] = acc[j][2] = acc[j][3] = 0.f;
+  const int tiles_y = (Hs + ROWS - 1) / ROWS;
+  const long long ntiles = F * tiles_y;
+  const int Wh = Ws / S + 2, Hp = Hs + 2, wh = Ws / S;
+  for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const long long f = tile / tiles_y;
+    const int y0 = (int)(tile % tiles_y) * ROWS;
+    __syncthreads();
+    const int nin = (ROWS + 4) * TW * C;
+    for (int i = threadIdx.x; i < nin; i += 128) {
+      int ci = i % C, xx = (i / C) % TW, yy = i / (C * TW);
+      int gy = y0 + yy - 4, gx = xx - 4;
+      xs[i] = (gy >= 0 && gy < H && gx >= 0 && gx < W) ? x[((f * H + gy) * W + gx) * C + ci] : 0.f;
+    }
+    __syncthreads();
+    const int nrow = min(ROWS, Hs - y0);
+    for (int ly = 0; ly < nrow; ++ly) {
+      for (int h = 0; h < S; ++h) {
+        // local columns of half h that are pixels of the layer output: padded column xc = h*wh + xl in [1, Ws]
+        const int xl0 = max(0, 1 - h * wh), xl1 = min(Wh - 1, Ws - h * wh);
+        const long long base = (((f * S + h) * Hp + y0 + ly + 1) * Wh) * 32 + 4 * cg;
+        const float* xrow = xs + (ly * TW + h * wh - 1) * C;
+#pragma unroll 4
+        for (int xl = xl0; xl <= xl1; ++xl) {
+          float4 g = *reinterpret_cast<const float4*>(dxp + base + (long long)xl * 32);
+          bool p0, p1, p2, p3;
+          if (MODE == 0) {
+            const float4 yv = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(yp) + base + (long long)xl * 32);
+            p0 = yv.x > 0.f; p1 = yv.y > 0.f; p2 = yv.z > 0.f; p3 = yv.w > 0.f;
+          } else {
+            const uint2 hv = *reinterpret_cast<const uint2*>(reinterpret_cast<const u16*>(yp) + base + (long long)xl * 32);
+            // 16-bit sign test: positive <=> sign bit clear and magnitude non-zero (bf16 and fp16 alike)
+            p0 = (hv.x & 0x8000u) == 0 && (hv.x & 0x7fffu) != 0;
+            p1 = (hv.x & 0x80000000u) == 0 && (hv.x & 0x7fff0000u) != 0;
+            p2 = (hv.y & 0x8000u) == 0 && (hv.y & 0x7fffu) != 0;
+            p3 = (hv.y & 0x80000000u) == 0 && (hv.y & 0x7fff0000u) != 0;
+          }
+          g.x *= p0 ? 1.f : alpha; g.y *= p1 ? 1.f : alpha; g.z *= p2 ? 1.f : alpha; g.w *= p3 ? 1.f : alpha;
+          const float* xb = xrow + xl * C;
+#pragma unroll
+          for (int j = 0; j < TT; ++j) {
+            const float xv = xb[toff[j]];
+            acc[j][0] = fmaf(g.x, xv, acc[j][0]);
+            acc[j][1] = fmaf(g.y, xv, acc[j][1]);
+            acc[j][2] = fmaf(g.z, xv, acc[j][2]);
+            acc[j][3] = fmaf(g.w, xv, acc[j][3]);
+          }
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < TT; ++j) {
+    const int k = tg + 16 * j;
+    if (k < K) {
+#pragma unroll
+      for (int q = 0; q < 4; ++q) atomicAdd(dw + (4 * cg + q) * K + k, acc[j][q]);
+    }
+  }
+}
+
+extern "C" int ugn_gs_conv1_wgrad(ugn_ctx* ctx, const ugn_tensor* x, const ugn_tensor* dxp, const ugn_tensor* yp,
+                                  ugn_tensor* dw, float alpha, void* stream) {
+  UGN_CHECK(ctx && x && dxp && yp && dw, "ugn_gs_conv1_wgrad: null argument");
+  UGN_TENSOR(yp, DT_BAD, 4, 5);
+  UGN_TENSOR(dxp, DT_F32, 4, 4);
+  UGN_TENSOR(dw, DT_F32, 2, 4);
+  int mode = gs_mode(yp, 4);
+  UGN_CHECK(mode >= 0, "gs_conv1_wgrad: bad storage mode of y");
+  long long F; int H, W, c, S, rc;
+  if ((rc = conv1_geom(ctx, x, yp, F, H, W, c, S)) != UGN_OK) return rc;
+  const int64_t* s = gs_shape(yp, 4);
+  UGN_CHECK(dxp->shape[0] == s[0] && dxp->shape[1] == s[1] && dxp->shape[2] == s[2] && dxp->shape[3] == 32,
+            "gs_conv1_wgrad: dxp must have the (split) padded shape of y");
+  UGN_CHECK(ugn_numel(dw) == 32 * 25 * c, "gs_conv1_wgrad: dw must be f32 [32,1,1,25c]");
+  cudaStream_t st = (cudaStream_t)stream;
+  UGN_CUDA(cudaMemsetAsync(ugn_ptr<float>(dw), 0, sizeof(float) * 32 * 25 * c, st));
+  const int Ws = W + 4;
+  const long long ntiles = F * ugn_cdiv(H + 4, 8);
+  size_t smem = sizeof(float) * ((size_t)12 * (Ws + 4) * c);
+  int grid = (int)std::min<long long>(ntiles, (long long)ctx->sm_count * 8);
+#define GS_WG(C_, M_)                                                                                                  \
+  gs_conv1_wgrad_kernel<C_, M_><<<grid, 128, smem, st>>>(ugn_ptr<float>(x), ugn_ptr<float>(dxp), ugn_ptr<void>(yp),     \
+                                                        ugn_ptr<float>(dw), F, H, W, S, gs_f16(yp), alpha)
+  if (c == 1) { if (mode == 0) GS_WG(1, 0); else GS_WG(1, 1); }
+  else { if (mode == 0) GS_WG(2, 0); else GS_WG(2, 1); }
+#undef GS_WG
   UGN_LAUNCHED(ctx);
   return UGN_OK;
 }
@@ -85,17 +288,24 @@ extern "C" int ugn_gs_pack_input(ugn_ctx* ctx, const ugn_tensor* x, ugn_tensor* 
 // zero-border copies: padding='same' of the 3x3 convolutions.  The destination border is written once
 // (zero) by the owner of the buffer; pad copies only the interior, crop reads only the interior.
 // ---------------------------------------------------------------------------------------------------
+// Split layouts: a tensor-core convolution kernel wants rows of at most 64 pixel slots, so a 66-wide
+// zero-bordered input is kept as S = 2 overlapping column halves, [N*S][H+2][W/S+2][C] (half h = padded
+// columns [h*W/S, h*W/S + W/S + 2)), and its valid-convolution output as [N*S][H][W/S][C].  pad / crop
+// convert between split and plain images: the split factor is the ratio of the leading dimensions.
 __global__ void __launch_bounds__(256) gs_pad_kernel(const uint4* __restrict__ src, uint4* __restrict__ dst, int P,
-                                                     long long N, int H, int W, int rowv, int p) {
-  const int Hd = H + 2 * p, Wd = W + 2 * p;
-  const long long per_plane = N * H * W * rowv, total = per_plane * P;
+                                                     long long Ns, int H, int Ws, int rowv, int p, int S) {
+  // src [P][Ns = N*S][H][Ws][rowv] -> dst [P][N][H+2p][Ws*S+2p][rowv]
+  const int Hd = H + 2 * p, Wd = Ws * S + 2 * p;
+  const long long per_plane = Ns * H * Ws * rowv, total = per_plane * P;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     int v = (int)(i % rowv);
     long long pix = i / rowv;
-    int xx = (int)(pix % W);
-    int yy = (int)((pix / W) % H);
-    long long n = pix / ((long long)W * H);          // plane-major image index (pl*N + n)
-    dst[((n * Hd + yy + p) * Wd + xx + p) * rowv + v] = src[i];
+    int xx = (int)(pix % Ws);
+    int yy = (int)((pix / Ws) % H);
+    long long ns = pix / ((long long)Ws * H);         // plane-major split-image index (pl*Ns + n*S + h)
+    long long n = ns / S;
+    int h = (int)(ns - n * S);
+    dst[((n * Hd + yy + p) * Wd + h * Ws + xx + p) * rowv + v] = src[i];
   }
 }
 
@@ -107,35 +317,41 @@ extern "C" int ugn_pad_hw(ugn_ctx* ctx, const ugn_tensor* src, ugn_tensor* dst, 
   UGN_CHECK(ms >= 0 && ms == md && ugn_dtype(src) == ugn_dtype(dst), "pad_hw: storage modes must match");
   const int64_t* a = gs_shape(src, 4);
   const int64_t* b = gs_shape(dst, 4);
+  UGN_CHECK(b[0] > 0 && a[0] % b[0] == 0, "pad_hw: leading dims must be N*S and N");
+  int S = (int)(a[0] / b[0]);
   int p = (int)(b[1] - a[1]) / 2;
-  UGN_CHECK(a[0] == b[0] && a[3] == b[3] && p >= 0 && b[1] == a[1] + 2 * p && b[2] == a[2] + 2 * p, "pad_hw: dst must be [N,H+2p,W+2p,C]");
+  UGN_CHECK(a[3] == b[3] && p >= 0 && b[1] == a[1] + 2 * p && b[2] == a[2] * S + 2 * p,
+            "pad_hw: dst must be [N,H+2p,W*S+2p,C] for src [N*S,H,W,C]");
   int es = ms == 0 ? 4 : 2;
   UGN_CHECK((a[3] * es) % 16 == 0, "pad_hw: channel row must be a multiple of 16 bytes");
   if (ugn_numel(src) == 0) return UGN_OK;
   int rowv = (int)(a[3] * es / 16), P = ms == 0 ? 1 : ms;
   long long total = (long long)P * a[0] * a[1] * a[2] * rowv;
   gs_pad_kernel<<<gs_grid(ctx, total, 256), 256, 0, (cudaStream_t)stream>>>(ugn_ptr<uint4>(src), ugn_ptr<uint4>(dst), P, a[0],
-                                                                          (int)a[1], (int)a[2], rowv, p);
+                                                                          (int)a[1], (int)a[2], rowv, p, S);
   UGN_LAUNCHED(ctx);
   return UGN_OK;
 }
 
-__global__ void __launch_bounds__(256) gs_crop_kernel(const float4* __restrict__ src, float4* __restrict__ dst, long long N,
-                                                      int H, int W, int rowv, int p, int accumulate) {
-  const int Hs = H + 2 * p, Ws = W + 2 * p;
-  const long long total = N * H * W * rowv;
+__global__ void __launch_bounds__(256) gs_crop_kernel(const float4* __restrict__ src, float4* __restrict__ dst, long long Ns,
+                                                      int H, int Ws, int rowv, int p, int S, int accumulate) {
+  // src [N][H+2p][Ws*S+2p][rowv] -> dst [Ns = N*S][H][Ws][rowv]
+  const int Hs = H + 2 * p, Wsrc = Ws * S + 2 * p;
+  const long long total = Ns * H * Ws * rowv;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     int v = (int)(i % rowv);
     long long pix = i / rowv;
-    int xx = (int)(pix % W);
-    int yy = (int)((pix / W) % H);
-    long long n = pix / ((long long)W * H);
-    float4 s = src[((n * Hs + yy + p) * Ws + xx + p) * rowv + v];
+    int xx = (int)(pix % Ws);
+    int yy = (int)((pix / Ws) % H);
+    long long ns = pix / ((long long)Ws * H);
+    long long n = ns / S;
+    int h = (int)(ns - n * S);
+    float4 s4 = src[((n * Hs + yy + p) * Wsrc + h * Ws + xx + p) * rowv + v];
     if (accumulate) {
       float4 d = dst[i];
-      s.x += d.x; s.y += d.y; s.z += d.z; s.w += d.w;
+      s4.x += d.x; s4.y += d.y; s4.z += d.z; s4.w += d.w;
     }
-    dst[i] = s;
+    dst[i] = s4;
   }
 }
 
@@ -145,14 +361,16 @@ extern "C" int ugn_crop_hw(ugn_ctx* ctx, const ugn_tensor* src, ugn_tensor* dst,
   UGN_TENSOR(dst, DT_F32, 4, 4);
   const int64_t* a = src->shape;
   const int64_t* b = dst->shape;
+  UGN_CHECK(a[0] > 0 && b[0] % a[0] == 0, "crop_hw: leading dims must be N and N*S");
+  int S = (int)(b[0] / a[0]);
   int p = (int)(a[1] - b[1]) / 2;
-  UGN_CHECK(a[0] == b[0] && a[3] == b[3] && p >= 0 && a[1] == b[1] + 2 * p && a[2] == b[2] + 2 * p && b[3] % 4 == 0,
-            "crop_hw: src must be [N,H+2p,W+2p,C]");
+  UGN_CHECK(a[3] == b[3] && p >= 0 && a[1] == b[1] + 2 * p && a[2] == b[2] * S + 2 * p && b[3] % 4 == 0,
+            "crop_hw: src must be [N,H+2p,W*S+2p,C] for dst [N*S,H,W,C]");
   if (ugn_numel(dst) == 0) return UGN_OK;
   int rowv = (int)b[3] / 4;
   long long total = b[0] * b[1] * b[2] * rowv;
   gs_crop_kernel<<<gs_grid(ctx, total, 256), 256, 0, (cudaStream_t)stream>>>(ugn_ptr<float4>(src), ugn_ptr<float4>(dst), b[0],
-                                                                           (int)b[1], (int)b[2], rowv, p, accumulate);
+                                                                           (int)b[1], (int)b[2], rowv, p, S, accumulate);
   UGN_LAUNCHED(ctx);
   return UGN_OK;
 }

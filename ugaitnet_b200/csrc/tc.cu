@@ -114,6 +114,31 @@ __device__ __forceinline__ void conv_tile_epilogue(const TcParams& p, uint8_t* s
             *reinterpret_cast<float4*>(dst + i) = make_float4(v[i] * os, v[i + 1] * os, v[i + 2] * os, v[i + 3] * os);
           continue;
         }
+        if (p.epi == EPI_BF16_ACT && (p.Cout & 7) == 0 && n0 + c0 + 16 <= p.Cout) {
+          // 16 channels of one pixel = 32 contiguous bytes per plane: two 16-byte stores instead of 16
+          // scattered 2-byte stores (the per-frame GaitSet layers are dominated by this epilogue)
+          const int cb = n0 + c0;
+          uint32_t hw[8], lw[8];
+#pragma unroll
+          for (int i = 0; i < 16; i += 2) {
+            const float z0 = ugn_act_fwd(v[i] + (p.bias ? p.bias[cb + i] : 0.f), p.act, p.alpha);
+            const float z1 = ugn_act_fwd(v[i + 1] + (p.bias ? p.bias[cb + i + 1] : 0.f), p.act, p.alpha);
+            u16 h0, l0, h1, l1;
+            ugn_split16(z0, p.f16, h0, l0);
+            ugn_split16(z1, p.f16, h1, l1);
+            hw[i >> 1] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
+            lw[i >> 1] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+          }
+          uint4* dh = reinterpret_cast<uint4*>(p.out_bf16 + obase + cb);
+          dh[0] = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+          dh[1] = make_uint4(hw[4], hw[5], hw[6], hw[7]);
+          if (p.planes == 2) {
+            uint4* dl = reinterpret_cast<uint4*>(p.out_bf16 + p.out_plane + obase + cb);
+            dl[0] = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+            dl[1] = make_uint4(lw[4], lw[5], lw[6], lw[7]);
+          }
+          continue;
+        }
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
           const int c = n0 + c0 + i;
@@ -1199,11 +1224,12 @@ int tc_conv_fwd(ugn_ctx* ctx, const ConvGeom& g, int P, int f16, const __nv_bflo
 
 int tc_conv_dgrad(ugn_ctx* ctx, const ConvGeom& g, int P, int f16, const __nv_bfloat16* dz, const __nv_bfloat16* w,
                   float* dx, cudaStream_t st) {
-  UGN_CHECK(g.Co % 64 == 0 && g.Cp % 32 == 0, "tensor-core dgrad needs Cout %% 64 == 0 and Cin %% 32 == 0");
+  UGN_CHECK(g.Co % 32 == 0 && g.Cp % 32 == 0, "tensor-core dgrad needs Cout %% 32 == 0 and Cin %% 32 == 0");
+  const int kc = (g.Co % 64 == 0) ? 64 : 32;   // K stage = kc output channels
   TcParams p{};
   p.mode = MODE_CONV; p.planes = P; p.sgn = -1; p.f16 = f16; p.oscale = ctx->gscale ? ctx->gscale + 1 : nullptr;
-  p.kslices = 4;                       // K stage = 64 output channels
-  p.ncc = g.Co / 64; p.KW = g.KW;
+  p.kslices = kc / 16;
+  p.ncc = g.Co / kc; p.KW = g.KW;
   p.ksteps_total = g.KH * g.KW * p.ncc; p.ksplit = 1;
   p.Wout = g.W; p.Hout = g.H; p.Bn = g.B; p.Cout = g.Cp;
   const int cw = (g.Cp % 64 == 0) ? 64 : 32;
@@ -1216,19 +1242,19 @@ int tc_conv_dgrad(ugn_ctx* ctx, const ConvGeom& g, int P, int f16, const __nv_bf
     uint64_t dims[5] = {(uint64_t)g.Cp, (uint64_t)taps, (uint64_t)g.Co, (uint64_t)P, 1};
     uint64_t str[4] = {(uint64_t)g.Cp * 2, (uint64_t)taps * g.Cp * 2, (uint64_t)g.Co * taps * g.Cp * 2,
                        (uint64_t)P * g.Co * taps * g.Cp * 2};
-    uint32_t box[5] = {(uint32_t)cw, 1, 64, 1, 1};
-    finish_op(p.b, 1, cw * 2, p.block_n / cw, 64, 0);
+    uint32_t box[5] = {(uint32_t)cw, 1, (uint32_t)kc, 1, 1};
+    finish_op(p.b, 1, cw * 2, p.block_n / cw, kc, 0);
     if ((rc = make_map(ctx, &p.b.map, w, dims, str, box, cw * 2)) != UGN_OK) return rc;
   }
   p.epi = EPI_F32; p.out_f32 = dx;
   if (!getenv("UGN_NO_CONVP") && g.H * g.W >= 400) {   // small maps: the per-tap-box kernel is faster
     rc = convp_launch(ctx, p, dz, P, g.B, g.Ho, g.Wo, g.Co, g.KH, g.KW, g.W, g.H, 0, -1, st);
     if (rc != UGN_ERR_UNSUPPORTED) return rc;
-    p.ncc = g.Co / 64; p.kslices = 4; p.ksteps_total = g.KH * g.KW * p.ncc;
+    p.ncc = g.Co / kc; p.kslices = kc / 16; p.ksteps_total = g.KH * g.KW * p.ncc;
   }
   conv_box(g.W, g.H, g.B, 0, p.bw, p.bh, p.bn);
   p.ntx = ugn_cdiv(g.W, p.bw); p.nty = ugn_cdiv(g.H, p.bh);
-  if ((rc = act_map(ctx, p.a, dz, P, g.B, g.Ho, g.Wo, g.Co, 64, p.bw, p.bh, p.bn, 0, 1, 128)) != UGN_OK) return rc;
+  if ((rc = act_map(ctx, p.a, dz, P, g.B, g.Ho, g.Wo, g.Co, kc, p.bw, p.bh, p.bn, 0, 1, 128)) != UGN_OK) return rc;
   dim3 grid(p.ntx * p.nty * ugn_cdiv(g.B, p.bn), ugn_cdiv(g.Cp, p.block_n), 1);
   const int tiles = grid.x * grid.y;
   if (tiles * 2 <= ctx->sm_count && p.ksteps_total >= 8 && !getenv("UGN_NO_CONV_SPLITK")) {

@@ -25,7 +25,7 @@ from .config import ACT_LEAKY, ACT_LINEAR, BRANCH_NAMES, GS_ALPHA, GS_CONVS, GS_
 from .net import GRAD_SCALE_TARGET, UGaitEngine, _Seg
 
 # conv name -> (input buffer, output buffer, pooled)
-_GS_WIRING = {"a1": ("col", "a1", 0), "a2": ("a1p", "a2", 1), "b1": ("g0p", "b1", 0), "b2": ("b1p", "b2", 1),
+_GS_WIRING = {"a2": ("a1p", "a2", 1), "b1": ("g0p", "b1", 0), "b2": ("b1p", "b2", 1),
               "a3": ("a2p", "a3", 0), "a4": ("a3p", "a4", 1), "b3": ("s1p", "b3", 0), "b4": ("b3p", "b4", 0),
               "a5": ("a4p", "a5", 0), "a6": ("a5p", "a6", 0)}
 
@@ -33,20 +33,19 @@ _GS_WIRING = {"a1": ("col", "a1", 0), "a2": ("a1p", "a2", 1), "b1": ("g0p", "b1"
 class GaitSetEngine(UGaitEngine):
     """One training / descriptor-extraction step of the gaitset=True graph on one GPU."""
 
-    def __init__(self, cfg: GaitSetConfig, **kw):
+    def __init__(self, cfg: GaitSetConfig, force_split: Optional[int] = None, **kw):
+        self.force_split = force_split       # tests: exercise the split layout on small frames / in fp32 mode
         super().__init__(cfg, **kw)
 
     # ------------------------------------------------------------------ parameters
     def _conv_shapes(self, m: int):
-        """name -> (cout_master, k, cin_master, cin_packed).  In tensor-core mode the 32 output channels of
-        "a2" are padded to 64 (zero rows, zero gradient for ever): its input gradient is a GEMM over the
-        output channels whose K stage is 64."""
+        """name -> (cout_master, k, cin_master, cin_packed, cout)."""
         c = self.cfg.in_channels[m]
-        c2 = 64 if self.P else 32
+        c2 = 32
         out = {}
         for name, cin, co, k in GS_CONVS:
             if name == "a1":
-                out[name] = (co, 1, 25 * c, round_up(25 * c, 32) if self.P else 25 * c, co)
+                out[name] = (co, 1, 25 * c, 25 * c, co)        # fused fp32 kernel: reads the f32 master
             else:
                 cm = cin
                 cp = c2 if name in ("b1", "a3") else cin
@@ -114,7 +113,9 @@ class GaitSetEngine(UGaitEngine):
             bn = BRANCH_NAMES[m]
             for name, (co, k, cin, cp, _) in self._conv_shapes(m).items():
                 key = f"{bn}/{name}/w"
-                if self.P:
+                if name == "a1":
+                    self.cw[key] = self.pw[key]
+                elif self.P:
                     self.cw[key] = torch.zeros((self.P, co, k, k, cp), dtype=self.dt16, device=d)
                 elif cp != cin:
                     self.cw[key] = torch.zeros((co, k, k, cp), device=d)
@@ -128,7 +129,7 @@ class GaitSetEngine(UGaitEngine):
             tab = torch.zeros(len(segs), 2, dtype=torch.int64)
             for i, sg in enumerate(segs):
                 t = self.cw.get(sg.name)
-                if t is not None and tuple(t.shape[1:]) == sg.shape and sg.n % 4 == 0:
+                if t is not None and t.dtype == self.dt16 and tuple(t.shape[1:]) == sg.shape and sg.n % 4 == 0:
                     tab[i, 0], tab[i, 1] = t.data_ptr(), sg.n
                     self._fused_pack.add(sg.name)
             self.pack_table = tab.to(d)
@@ -194,6 +195,13 @@ class GaitSetEngine(UGaitEngine):
         return out
 
     # ------------------------------------------------------------------ plans
+    def split_for(self, Hs: int) -> int:
+        """Column halves of the 64-wide layers: the tensor-core conv kernels keep an input row in at most 64
+        pixel slots, a zero-bordered 66-wide row does not fit, two overlapping 34-wide halves do."""
+        if self.force_split is not None:
+            return self.force_split
+        return 2 if (self.P and Hs + 2 > 64 and Hs % 4 == 0) else 1
+
     def plan(self, B: int, train: bool) -> "_GsPlan":
         key = (B, train)
         p = self._plans.get(key)
@@ -223,10 +231,9 @@ class GaitSetEngine(UGaitEngine):
         bn, b = BRANCH_NAMES[m], p.br[m]
         R = b.R
         st = stream_ptr()
-        check(lib.ugn_gs_pack_input(h, R["x_in"].ptr, R["col"].ptr, st))
-        self._conv(b, bn, "a1"); self._pad(b, "a1", "a1p")
+        check(lib.ugn_gs_conv1_fwd(h, R["x_in"].ptr, self.Rw[f"{bn}/a1/w"].ptr, R["a1p"].ptr, GS_ALPHA, st))
         self._conv(b, bn, "a2"); self._pad(b, "a2", "a2p")
-        check(lib.ugn_setmax_fwd(h, R["a2"].ptr, T, None, R["m0"].ptr, R["g0"].ptr, st))
+        check(lib.ugn_setmax_fwd(h, R["a2_set"].ptr, T, None, R["m0"].ptr, R["g0_set"].ptr, st))
         self._pad(b, "g0", "g0p")
         self._conv(b, bn, "b1"); self._pad(b, "b1", "b1p")
         self._conv(b, bn, "b2")
@@ -337,15 +344,15 @@ class GaitSetEngine(UGaitEngine):
                 self._backward_branch(p, m)
         self._join(streams)
 
-    def _bwd_conv(self, b, bn, name, dgrad: bool = True):
+    def _bwd_conv(self, b, bn, name, crop: bool = True):
         """dy (f32, layer output gradient d_<dst>) -> dz; weight gradient; input gradient cropped into d_<src>."""
         h, st, R = self.ctx.h, stream_ptr(), b.R
         src, dst, pool = _GS_WIRING[name]
         check(lib.ugn_conv2d_bwd_act(h, R[f"d_{dst}"].ptr, R[dst].ptr, R[f"idx_{dst}"].ptr if pool else None,
                                      R[f"dz_{dst}"].ptr, None, ACT_LEAKY, GS_ALPHA, pool, st))
         check(lib.ugn_conv2d_wgrad(h, R[src].ptr, R[f"dz_{dst}"].ptr, self.Rg[f"{bn}/{name}/w"].ptr, None, st))
-        if dgrad:
-            check(lib.ugn_conv2d_dgrad(h, R[f"dz_{dst}"].ptr, self.Rcw[f"{bn}/{name}/w"].ptr, R[f"dx_{src}"].ptr, st))
+        check(lib.ugn_conv2d_dgrad(h, R[f"dz_{dst}"].ptr, self.Rcw[f"{bn}/{name}/w"].ptr, R[f"dx_{src}"].ptr, st))
+        if crop:
             check(lib.ugn_crop_hw(h, R[f"dx_{src}"].ptr, R[f"d_{src[:-1]}"].ptr, 0, st))
 
     def _backward_head(self, p, m: int):
@@ -377,9 +384,11 @@ class GaitSetEngine(UGaitEngine):
         check(lib.ugn_setmax_bwd(h, R["d_s1"].ptr, R["a4"].ptr, R["m1"].ptr, T, R["d_a4"].ptr, 1, st))
         self._bwd_conv(b, bn, "a4")          # -> d_a3
         self._bwd_conv(b, bn, "a3")          # -> d_a2
-        check(lib.ugn_setmax_bwd(h, R["d_g0"].ptr, R["a2"].ptr, R["m0"].ptr, T, R["d_a2"].ptr, 1, st))
-        self._bwd_conv(b, bn, "a2")          # -> d_a1
-        self._bwd_conv(b, bn, "a1", dgrad=False)
+        check(lib.ugn_setmax_bwd(h, R["d_g0_set"].ptr, R["a2_set"].ptr, R["m0"].ptr, T, R["d_a2_set"].ptr, 1, st))
+        self._bwd_conv(b, bn, "a2", crop=False)          # -> dx_a1p (gradient wrt a1 on the padded, split frame)
+        # first convolution: LeakyReLU derivative + crop + kernel gradient in one fp32 kernel
+        check(lib.ugn_gs_conv1_wgrad(h, R["x_in"].ptr, R["dx_a1p"].ptr, R["a1p"].ptr, self.Rg[f"{bn}/a1/w"].ptr,
+                                     GS_ALPHA, st))
         self._reduce_bucket(m)
 
     def _report(self, p, with_reg: bool = False) -> Dict[str, torch.Tensor]:
@@ -413,7 +422,8 @@ class _GsPlan:
         Hs = cfg.hw + 4
         H1, H2 = Hs // 2, Hs // 4
         assert Hs % 4 == 0 and (H2 * H2) % 16 == 0, "gaitset: (hw+4) must be a multiple of 4 and the last map of 16 positions"
-        c2 = 64 if P else 32
+        c2 = 32
+        S = eng.split_for(Hs)
 
         def act(shape, planes=P):
             if planes:
@@ -427,20 +437,28 @@ class _GsPlan:
         for m in range(cfg.nmods):
             b = _Branch()
             c = cfg.in_channels[m]
-            kp = eng._conv_shapes(m)["a1"][3]
             Tn = {}
             b.x_in = Tn["x_in"] = torch.zeros(B, T, cfg.hw, cfg.hw, c, **f32)
-            Tn["col"] = act((F, Hs, Hs, kp))
-            geo = {"a1": (F, Hs, 32), "a2": (F, H1, c2), "a3": (F, H1, 64), "a4": (F, H2, 64), "a5": (F, H2, 128),
-                   "a6": (F, H2, 128), "g0": (B, H1, c2), "b1": (B, H1, 64), "b2": (B, H2, 64), "s1": (B, H2, 64),
-                   "b3": (B, H2, 128), "b4": (B, H2, 128)}
-            for name, (n, hh, cc) in geo.items():
-                Tn[name] = act((n, hh, hh, cc))
+            # name -> (N, H, W, C); "a1p" / "a2" / "g0" live in the S-way column-split layout
+            geo = {"a2": (F * S, H1, H1 // S, c2), "a3": (F, H1, H1, 64), "a4": (F, H2, H2, 64), "a5": (F, H2, H2, 128),
+                   "a6": (F, H2, H2, 128), "g0": (B * S, H1, H1 // S, c2), "b1": (B, H1, H1, 64), "b2": (B, H2, H2, 64),
+                   "s1": (B, H2, H2, 64), "b3": (B, H2, H2, 128), "b4": (B, H2, H2, 128)}
+            padded = {"a1p": (F * S, Hs + 2, Hs // S + 2, 32)}
+            for name, (n, hh, ww, cc) in geo.items():
                 if name not in ("a6", "b4", "b2"):
-                    Tn[name + "p"] = act((n, hh + 2, hh + 2, cc))
+                    ns, wfull = (n // S, ww * S) if name in ("a2", "g0") else (n, ww)
+                    padded[name + "p"] = (ns, hh + 2, wfull + 2, cc)
+            for name, (n, hh, ww, cc) in geo.items():
+                Tn[name] = act((n, hh, ww, cc))
                 if name in ("a2", "a4", "b2"):
-                    Tn["idx_" + name] = torch.zeros(n, hh, hh, cc, device=d, dtype=torch.uint8)
-            Tn["m0"] = torch.zeros(B, H1, H1, c2, **f32)
+                    Tn["idx_" + name] = torch.zeros(n, hh, ww, cc, device=d, dtype=torch.uint8)
+            for name, shp in padded.items():
+                Tn[name] = act(shp)
+            # set pooling sees one frame as one contiguous block: [F, S*H1, H1/S, C] views of the split tensors
+            pl = (P,) if P else ()
+            Tn["a2_set"] = Tn["a2"].view(pl + (F, S * H1, H1 // S, c2))
+            Tn["g0_set"] = Tn["g0"].view(pl + (B, S * H1, H1 // S, c2))
+            Tn["m0"] = torch.zeros(B, S * H1, H1 // S, c2, **f32)
             Tn["m1"] = torch.zeros(B, H2, H2, 64, **f32)
             Tn["m2"] = torch.zeros(B, H2, H2, 128, **f32)
             Tn["s2"] = torch.zeros(B, H2, H2, 128, **f32)
@@ -449,12 +467,14 @@ class _GsPlan:
             if train:
                 b.dout = Tn["dout"] = torch.zeros(GS_PARTS, B, cfg.hidden, **f32)
                 Tn["dfeat"] = torch.zeros(GS_PARTS, B, 128, **f32)
-                for name, (n, hh, cc) in geo.items():
-                    Tn["d_" + name] = dhead[m, 1] if name == "b4" else torch.zeros(n, hh, hh, cc, **f32)   # d(layer output)
-                    if name + "p" in Tn:
-                        Tn["dx_" + name + "p"] = torch.zeros(n, hh + 2, hh + 2, cc, **f32)
+                for name, (n, hh, ww, cc) in geo.items():
+                    Tn["d_" + name] = dhead[m, 1] if name == "b4" else torch.zeros(n, hh, ww, cc, **f32)   # d(layer output)
                     if name in _DZ_GEO:
-                        Tn["dz_" + name] = act((n, hh * _DZ_GEO[name], hh * _DZ_GEO[name], cc), PB)
+                        Tn["dz_" + name] = act((n, hh * _DZ_GEO[name], ww * _DZ_GEO[name], cc), PB)
+                for name, shp in padded.items():
+                    Tn["dx_" + name] = torch.zeros(shp, **f32)
+                Tn["d_a2_set"] = Tn["d_a2"].view(F, S * H1, H1 // S, c2)
+                Tn["d_g0_set"] = Tn["d_g0"].view(B, S * H1, H1 // S, c2)
                 b.d_m2 = Tn["d_m2"] = dhead[m, 0]
                 b.d_b4, b.d_b2, b.d_s1 = Tn["d_b4"], Tn["d_b2"], Tn["d_s1"]
             b.T = Tn
@@ -503,4 +523,4 @@ class _GsPlan:
 
 # conv outputs that have a pre-activation gradient buffer: name -> spatial factor (2 = the layer is pooled,
 # dz lives on the pre-pool grid)
-_DZ_GEO = {"a1": 1, "a2": 2, "a3": 1, "a4": 2, "a5": 1, "a6": 1, "b1": 1, "b2": 2, "b3": 1, "b4": 1}
+_DZ_GEO = {"a2": 2, "a3": 1, "a4": 2, "a5": 1, "a6": 1, "b1": 1, "b2": 2, "b3": 1, "b4": 1}
