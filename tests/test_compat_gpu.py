@@ -108,5 +108,60 @@ def test_triplet_loss_closure_and_unsupported_options(compat_path):
     got = float(loss(lab, e))
     ref, _ = O.triplet_loss_all_literal_np(lab, e, 0.2)
     assert got == pytest.approx(ref, rel=1e-5)
-    with pytest.raises(NotImplementedError, match="gaitset"):
-        UWYHSemiNet3Mods.build([(50, 60, 60)] * 3, 4, [7, 5, 3, 2], [96, 192, 512, 512], gaitset=True)
+    with pytest.raises(ValueError, match="gaitset"):        # the reference builds GaitSet branches in its LeakyReLU path only
+        UWYHSemiNet3Mods.build([(25, 60, 60, 1)] * 3, 4, [7, 5, 3, 2], [96, 192, 512, 512], gaitset=True)
+    with pytest.raises(NotImplementedError, match="use3D"):
+        UWYHSemiNet3Mods.build([(50, 60, 60)] * 3, 4, [7, 5, 3, 2], [96, 192, 512, 512], use3D=True)
+
+
+def test_gaitset_builder_protocol(compat_path, tmp_path):
+    """UWYHSemiNet3Mods.build_or_load(..., gaitset=True) (mains/mj_trainUWYHGaitNet_DataGen_CasiaB.py:345-355):
+    training protocol, descriptor layers, encode(gaitset=True) and the weight round trip, against the oracle."""
+    from nets.mj_uwyhNets_ba import UWYHSemiNet, UWYHSemiNet3Mods
+    from ugaitnet_b200.compat import Model, optimizers, sign_max
+    from oracle import gaitset_oracle as G
+    import nets.mj_uwyhNets_ba as mod
+    mod.MATH_MODE = "fp32"
+    shapes = [(3, 12, 12, 2), (3, 12, 12, 1), (3, 12, 12, 1)]
+    model = UWYHSemiNet3Mods.build_or_load(shapes, 4, [(7, 7), (5, 5), (3, 3), (2, 2)], [96, 192, 512, 512], [256, 16],
+                                           0.00005, 0.0, optimizer=optimizers.Adam(lr=1e-3), margin=0.2, nclasses=12,
+                                           loss_weights=[1.0, 0.1], fMerge=sign_max, fActivation='lrelu', gaitset=True)
+    oc = G.GaitSetConfig(in_channels=(2, 1, 1), frames=3, hw=12, nc=16, nclasses=12, merge=O.MERGE_SIGNMAX, wver=1.0, wid=0.1)
+    xs, fl, lab = G.synth_batch(oc, 3, 2, seed=5)
+
+    class Gen:
+        def __len__(self):
+            return 2
+
+        def __getitem__(self, i):
+            X = [xs[0].numpy(), fl[0].numpy(), xs[1].numpy(), fl[1].numpy(), xs[2].numpy(), fl[2].numpy()]
+            return X, [lab.numpy().reshape(-1, 1).astype(np.float32), np.eye(12, dtype=np.float32)[lab.numpy()]]
+
+        def on_epoch_end(self):
+            pass
+
+    gen = Gen()
+    X, _ = gen[0]
+    P = {k: v.double().cpu() for k, v in model.engine.export_params().items()}
+    outs = G.model_forward([x.double() for x in xs], [f.double() for f in fl], P, oc, return_all=True)
+    sig, prob = model.predict(X)
+    assert sig.shape == (62, 6, 256) and np.allclose(sig, outs["signature"].numpy(), atol=2e-5)
+    assert np.allclose(prob, torch.softmax(outs["logits"], 1).numpy(), atol=2e-5)
+    flat = Model(model.input, model.get_layer("flatten").output).predict(X)       # typecode 3 descriptor
+    assert flat.shape == (6, 62 * 16) and np.allclose(flat, outs["code"].permute(1, 0, 2).flatten(1).numpy(), atol=2e-5)
+    codes = UWYHSemiNet.encode(model, [X[0], X[2]], [X[1], X[3]], gaitset=True)
+    g0 = outs["branch0"] * fl[0].double().reshape(1, -1, 1)
+    g1 = outs["branch1"] * fl[1].double().reshape(1, -1, 1)
+    ref = O.l2_normalize(torch.maximum(g0, g1), 1).numpy()
+    # columns whose entries are all tiny are amplified by 1/norm (batch-axis normalisation): compare in norm
+    assert np.linalg.norm(codes - ref) <= 1e-4 * np.linalg.norm(ref) and np.abs(codes - ref).max() < 1e-3
+    model, hist = UWYHSemiNet.fit_generator(model, 3, [], gen, gen, 0, len(gen), 1)
+    assert hist.history["loss"][-1] < hist.history["loss"][0]
+    path = str(tmp_path / "gs_weights.hdf5")
+    model.save_weights(path)
+    m2 = UWYHSemiNet3Mods.build(shapes, 4, [7, 5, 3, 2], [96, 192, 512, 512], [256, 16], nclasses=12,
+                                loss_weights=[1.0, 0.1], fMerge=sign_max, fActivation='lrelu', gaitset=True)
+    m2.load_weights(path, by_name=True)
+    assert np.array_equal(m2.predict(X)[0], model.predict(X)[0])
+    w = model.get_layer("ofBranch").layers[0].get_weights()
+    assert [a.shape for a in w] == [(5, 5, 2, 32)]                               # Keras (kh,kw,cin,cout) kernel

@@ -6,9 +6,13 @@ fit_generator :938-968, encode :971-999); the returned object follows the slice 
 protocol the reference's mains/ scripts use (fit / predict / get_layer / save_weights / ...), and every
 step runs on the B200 engine (ugaitnet_b200.net.UGaitEngine).
 
-Builder arguments that select graphs outside the north-star path raise NotImplementedError:
-use3D, gaitset, aux_losses, smoothlabels, postriplet == 2, init_branches /
-initnet weight surgery from Keras .hdf5 files, tfa TripletHardLoss (compile_hard).
+``gaitset=True`` (with a non-'relu' fActivation, as the reference requires, :1101) builds the GaitSet
+branch type (build_gaitset_branch :420-484) on ugaitnet_b200.gaitset.GaitSetEngine: inputs
+[B,25,60,60,c], signature [62,B,256], descriptor layer "flatten" (typecode 3).
+
+Builder arguments that select graphs outside the hot path raise NotImplementedError:
+use3D, aux_losses, smoothlabels, postriplet == 2, normbfmerge, init_branches / initnet weight surgery
+from Keras .hdf5 files, tfa TripletHardLoss (compile_hard).
 """
 from __future__ import annotations
 
@@ -20,7 +24,8 @@ import numpy as np
 import torch
 
 from ugaitnet_b200 import ops
-from ugaitnet_b200.config import ACT_LEAKY, ACT_RELU, BRANCH_NAMES, MERGE_MAX, NetConfig
+from ugaitnet_b200.config import ACT_LEAKY, ACT_RELU, BRANCH_NAMES, GS_CONVS, MERGE_MAX, GaitSetConfig, NetConfig
+from ugaitnet_b200.gaitset import GaitSetEngine
 from ugaitnet_b200.net import UGaitEngine
 from ugaitnet_b200.compat.keras_shim import Average, History, Maximum, _Tag, merge_id_of, optimizers  # noqa: F401
 from ugaitnet_b200.compat.nets.triplet_loss_all import triplet_loss
@@ -86,7 +91,9 @@ class UGaitModel:
         self.cfg, self.multimodal = cfg, multimodal
         opt = optimizer if optimizer is not None else optimizers.SGD(0.001, 0.9)
         kw = dict(getattr(opt, "kw", {}))
-        self.engine = UGaitEngine(cfg, math_mode=MATH_MODE, optimizer=getattr(opt, "name", "sgd"),
+        self.gaitset = isinstance(cfg, GaitSetConfig)
+        engine_cls = GaitSetEngine if self.gaitset else UGaitEngine
+        self.engine = engine_cls(cfg, math_mode=MATH_MODE, optimizer=getattr(opt, "name", "sgd"),
                                   lr=getattr(opt, "lr", 0.001), momentum=kw.get("momentum", 0.9),
                                   beta1=kw.get("beta1", 0.9), beta2=kw.get("beta2", 0.999), eps=kw.get("eps", 1e-7),
                                   use_graph=os.environ.get("UGN_GRAPH", "1") == "1")
@@ -95,8 +102,12 @@ class UGaitModel:
         self.stop_training = False
         names = []
         for m in range(cfg.nmods):
-            sub = [_LayerProxy(self, f"{BRANCH_NAMES[m]}/{n}") for n in
-                   [f"conv{i}" for i in range(len(cfg.filters_numbers))] + ["ofFlat", "dense", "drop", "ofCode"]]
+            if self.gaitset:
+                sub = [_LayerProxy(self, f"{BRANCH_NAMES[m]}/{n[0]}") for n in GS_CONVS] + \
+                      [_LayerProxy(self, f"{BRANCH_NAMES[m]}/matmul")]
+            else:
+                sub = [_LayerProxy(self, f"{BRANCH_NAMES[m]}/{n}") for n in
+                       [f"conv{i}" for i in range(len(cfg.filters_numbers))] + ["ofFlat", "dense", "drop", "ofCode"]]
             names.append(_LayerProxy(self, BRANCH_NAMES[m], units=cfg.nd, sublayers=sub))
         for n in ("gate_of1", "gate_gray1", "gate_depth1")[:cfg.nmods]:
             names.append(_LayerProxy(self, n))
@@ -104,6 +115,8 @@ class UGaitModel:
         if cfg.nc > 0:
             names += [_LayerProxy(self, "code", units=cfg.nc), _LayerProxy(self, "dropcode")]
         if cfg.nclasses > 0:
+            if self.gaitset:
+                names.append(_LayerProxy(self, "flatten", units=62 * (cfg.nc or cfg.nd)))     # typecode 3 (:1213)
             names.append(_LayerProxy(self, "classprob", units=cfg.nclasses))
         self.layers = names
         self.input = [_Tag(self, n) for n in ("ofinput1", "ofuse1", "grayinput1", "grayuse1", "depthinput1",
@@ -143,6 +156,8 @@ class UGaitModel:
     def _predict_layer(self, x, name, batch_size=None):
         ins, fl = self._split_x(x)
         layer = {"signature": "signature", "code": "code", "classprob": "classprob"}.get(name)
+        if layer is None and self.gaitset and name == "flatten":
+            layer = "flatten"
         if layer is None:
             raise NotImplementedError(f"descriptor layer {name!r} (typecode 3 'flatten' is the GaitSet layout)")
         out = self.engine.predict(ins, fl, layer=layer)
@@ -273,9 +288,7 @@ class UGaitModel:
             if k is None:
                 continue
             v = self._from_keras(z[kn])
-            want = self.engine.export_params()[k].shape if False else None
-            tgt = self.engine.segs[k].shape
-            tshape = (tgt[0], tgt[3], tgt[1], tgt[2]) if len(tgt) == 4 else tgt
+            tshape = self.engine.oracle_shape(k)
             if tuple(v.shape) != tuple(tshape):
                 if skip_mismatch:
                     continue
@@ -309,6 +322,25 @@ def _cfg_from_args(input_shapes, number_convolutional_layers, filters_size, filt
                      hw=int(shapes[0][1]), dropout=float(dropout) if dropout > 0.001 else 0.0, single=single)
 
 
+def _gs_cfg_from_args(input_shapes, ndense_units, dropout, margin, nclasses, loss_weights, fMerge, fActivation, alpha):
+    """gaitset=True: input_shapes [(25,60,60,2), (25,60,60,1), ...] (mains/mj_trainUWYHGaitNet_DataGen_CasiaB.py:212-213)."""
+    if fActivation == 'relu':
+        raise ValueError("gaitset=True needs a non-'relu' fActivation: the reference only builds the GaitSet "
+                         "branches in its LeakyReLU path (nets/mj_uwyhNets_ba.py:1101-1113)")
+    shapes = list(input_shapes)
+    if any(len(s) != 4 for s in shapes):
+        raise ValueError("gaitset=True expects input shapes (frames, H, W, channels)")
+    nc = ndense_units[1] if isinstance(ndense_units, (list, tuple)) and len(ndense_units) > 1 else 0
+    if isinstance(dropout, (list, tuple)):
+        dropout = dropout[-1]
+    lw = list(loss_weights) if isinstance(loss_weights, (list, tuple)) else [loss_weights, loss_weights]
+    return GaitSetConfig(in_channels=tuple(int(s[3]) for s in shapes), frames=int(shapes[0][0]), hw=int(shapes[0][1]),
+                         nc=int(nc), nclasses=int(nclasses), merge=merge_id_of(fMerge), alpha=float(alpha),
+                         margin=float(margin), wver=float(lw[0]) if nclasses > 0 else 1.0,
+                         wid=float(lw[1]) if nclasses > 0 and len(lw) > 1 else 0.0,
+                         dropout=float(dropout) if (dropout > 0.001 and nc) else 0.0)
+
+
 class UWYHNet:
     @staticmethod
     def buildBranch(name, input_shape=(50, 60, 60), number_convolutional_layers=4, filters_size=None,
@@ -338,9 +370,15 @@ class UWYHSemiNet:
               nclasses=0, loss_weights=[1.0, 1.0], use3D=False, smoothlabels=0, postriplet=1, init_branches=None,
               freeze_branches=False, aux_losses=False, fMerge=Maximum, fActivation='relu', alpha=0.3, gaitset=False):
         _unsupported(use3D=use3D, smoothlabels=smoothlabels, postriplet_2=(postriplet == 2), aux_losses=aux_losses,
-                     gaitset=gaitset, freeze_branches=freeze_branches,
+                     freeze_branches=freeze_branches,
                      init_branches=bool(init_branches) and any(init_branches.values()))
         single = not isinstance(input_shapes, list)
+        if gaitset:
+            _unsupported(gaitset_single_modality=single)
+            cfg = _gs_cfg_from_args(input_shapes, ndense_units, dropout, margin, nclasses, loss_weights, fMerge,
+                                    fActivation, alpha)
+            losses = [triplet_loss(margin=margin), 'categorical_crossentropy'] if nclasses > 0 else triplet_loss(margin=margin)
+            return UGaitModel(cfg, optimizer, losses, loss_weights if nclasses > 0 else 1.0, multimodal=True)
         cfg = _cfg_from_args(input_shapes, number_convolutional_layers, filters_size, filters_numbers, ndense_units,
                              weight_decay, dropout, margin, nclasses, loss_weights, fMerge, fActivation, alpha, single)
         losses = [triplet_loss(margin=margin), 'categorical_crossentropy'] if nclasses > 0 else triplet_loss(margin=margin)
@@ -382,9 +420,10 @@ class UWYHSemiNet:
     def encode(model, batch_data, use_data, gaitset=False):
         """:971-999 -- branch codes of the first TWO modalities, gated, ALWAYS Maximum (fMerge is ignored
         there), l2-normalised; returns numpy [B, nd]."""
-        _unsupported(gaitset=gaitset)
         eng = model.engine
         dev = eng.dev
+        if gaitset:
+            return _encode_gaitset(model, batch_data, use_data)
         xs = [torch.as_tensor(np.asarray(b), dtype=torch.float32).to(dev) for b in batch_data[:2]]
         B = xs[0].shape[0]
         p = eng.plan(B, False)
@@ -399,6 +438,30 @@ class UWYHSemiNet:
         return sig.cpu().numpy()
 
 
+def _encode_gaitset(model, batch_data, use_data):
+    """encode(..., gaitset=True) (:973-979,:988-999): the per-branch [62,B,256] codes of the first two
+    modalities (the reference reads them at the 'flatten' / 'flatten_1' layers), gated, Maximum, l2_normalize
+    over axis 1; returns numpy in the layout the fusion kernel works in, [62,B,256]."""
+    from ugaitnet_b200._ffi import TRef, check, lib, ptr_array, stream_ptr
+    eng = model.engine
+    dev = eng.dev
+    xs = [torch.as_tensor(np.asarray(b), dtype=torch.float32).to(dev) for b in batch_data[:2]]
+    B = xs[0].shape[0]
+    p = eng.plan(B, False)
+    fl = [torch.as_tensor(np.asarray(u), dtype=torch.float32).reshape(-1, 1).to(dev).contiguous() for u in use_data[:2]]
+    full_x = xs + [torch.zeros_like(p.br[m].x_in) for m in range(2, eng.cfg.nmods)]
+    eng._set_inputs(p, full_x, fl + [torch.zeros(B, 1, device=dev)] * (eng.cfg.nmods - 2))
+    eng._forward(p, False)
+    n, d = p.sig.shape[0], p.sig.shape[2]
+    sig = torch.zeros(n, B, d, device=dev)
+    win = torch.zeros(n, B, d, dtype=torch.uint8, device=dev)
+    col = torch.zeros(n, d, 2, device=dev)
+    Rb, Rf = [p.br[0].R["out"], p.br[1].R["out"]], [TRef(f) for f in fl]
+    Rs, Rw, Rc = TRef(sig), TRef(win), TRef(col)
+    check(lib.ugn_fuse3_fwd(eng.ctx.h, 2, ptr_array(Rb), ptr_array(Rf), Rs.ptr, Rw.ptr, Rc.ptr, MERGE_MAX, stream_ptr()))
+    return sig.cpu().numpy()
+
+
 class UWYHSemiNet3Mods(UWYHSemiNet):
     def __init__(self):
         super().__init__()
@@ -410,9 +473,14 @@ class UWYHSemiNet3Mods(UWYHSemiNet):
               nclasses=0, loss_weights=[1.0, 1.0], use3D=False, smoothlabels=0,
               postriplet=1, init_branches=None, freeze_branches=False, aux_losses=False, fMerge=Maximum,
               normbfmerge=False, fActivation='relu', alpha=0.3, gaitset=False):
-        _unsupported(use3D=use3D, smoothlabels=smoothlabels, aux_losses=aux_losses, gaitset=gaitset,
+        _unsupported(use3D=use3D, smoothlabels=smoothlabels, aux_losses=aux_losses,
                      normbfmerge=normbfmerge, freeze_branches=freeze_branches,
                      init_branches=bool(init_branches) and any(init_branches.values()))
+        if gaitset:
+            cfg = _gs_cfg_from_args(input_shapes, ndense_units, dropout, margin, nclasses, loss_weights, fMerge,
+                                    fActivation, alpha)
+            losses = [triplet_loss(margin=margin), 'categorical_crossentropy'] if nclasses > 0 else triplet_loss(margin=margin)
+            return UGaitModel(cfg, optimizer, losses, loss_weights if nclasses > 0 else 1.0, multimodal=True)
         cfg = _cfg_from_args(list(input_shapes), number_convolutional_layers, filters_size, filters_numbers,
                              ndense_units, weight_decay, dropout, margin, nclasses, loss_weights, fMerge, fActivation,
                              alpha, single=False)

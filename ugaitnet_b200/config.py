@@ -83,8 +83,13 @@ class GaitSetConfig:
     margin: float = 0.2
     wver: float = 1.0
     wid: float = 1.0
+    dropout: float = 0.0           # Dropout(name="dropcode") after FC1 (:1203); the branches have none
     single: bool = False
 
     @property
     def nmods(self) -> int:
         return len(self.in_channels)
+
+    @property
+    def nd(self) -> int:           # signature width per part (what the stacked-CNN config calls nd)
+        return self.hidden

@@ -181,8 +181,6 @@ class GaitSetEngine(UGaitEngine):
 
     def _export(self, views) -> Dict[str, torch.Tensor]:
         out = {}
-        for m in range(self.cfg.nmods):
-            pass
         for s in self.seg_list:
             v = views[s.name].detach().clone()
             if len(s.shape) == 4:
@@ -214,8 +212,23 @@ class GaitSetEngine(UGaitEngine):
             p.br[m].x_in.copy_(inputs[m], non_blocking=True)
             if flags is not None:
                 p.flags[m].copy_(flags[m].reshape(-1, 1), non_blocking=True)
+        if p.train and self.cfg.dropout > 0.001 and self.cfg.nc > 0:
+            if code_drop_mask is not None:
+                p.cmask.copy_(code_drop_mask.reshape(p.cmask.shape))
+            else:
+                keep = 1.0 - self.cfg.dropout
+                p.cmask.bernoulli_(keep).div_(keep)
         if labels is not None:
             p.labels.copy_(labels.reshape(-1).to(torch.int32), non_blocking=True)
+
+    def oracle_shape(self, name):
+        """Shape of a parameter in the oracle / PyTorch layout (conv [Cout,Cin,kh,kw])."""
+        s = self.segs[name].shape
+        if len(s) == 4:
+            if name.endswith("/a1/w"):
+                return (self.true_co[name], s[3] // 25, 5, 5)
+            return (self.true_co[name], s[3], s[1], s[2])
+        return tuple(s)
 
     # ------------------------------------------------------------------ forward
     def _conv(self, b, bn, name):
@@ -263,11 +276,13 @@ class GaitSetEngine(UGaitEngine):
         sig = p.R["sig"]
         feat = p.R["sig2d"]
         if cfg.nc > 0:
-            check(lib.ugn_linear_fwd(h, p.R["sig2d"].ptr, self.Rw["code/w"].ptr, self.Rw["code/b"].ptr, None,
-                                     p.R["code_lin"].ptr, None, ACT_LINEAR, 0.0, st))
-            # Dense(activation=None) + LeakyReLU(alpha) (:1199-1201): dz = dy * act'(y) with dy = 1 is the
-            # activation itself only for linear maps, so the leaky output comes from the fused bias/act pass
-            check(lib.ugn_linear_fwd(h, p.R["sig2d"].ptr, self.Rw["code/w"].ptr, self.Rw["code/b"].ptr, None,
+            # Dense(activation=None, activity_regularizer) -> LeakyReLU(alpha) -> Dropout (:1199-1203): the linear
+            # output is kept for the regulariser, the activated (and, in training, dropped) one feeds FC2
+            cmask = p.R["cmask"].ptr if (train and cfg.dropout > 0.001) else None
+            if train:
+                check(lib.ugn_linear_fwd(h, p.R["sig2d"].ptr, self.Rw["code/w"].ptr, self.Rw["code/b"].ptr, None,
+                                         p.R["code_lin"].ptr, None, ACT_LINEAR, 0.0, st))
+            check(lib.ugn_linear_fwd(h, p.R["sig2d"].ptr, self.Rw["code/w"].ptr, self.Rw["code/b"].ptr, cmask,
                                      p.R["code"].ptr, None, ACT_LEAKY, cfg.alpha, st))
             feat = p.R["code"]
         if cfg.nclasses > 0:
@@ -311,7 +326,8 @@ class GaitSetEngine(UGaitEngine):
             if cfg.nc > 0:
                 # through LeakyReLU, then the activity regulariser l2(1e-3) of the LINEAR "code" output,
                 # divided by shape(output)[0] = 62 in this layout (:1199-1200)
-                check(lib.ugn_act_mask_bwd(h, p.R["dfeat2d"].ptr, p.R["code"].ptr, None, p.R["dcode_z"].ptr, None,
+                check(lib.ugn_act_mask_bwd(h, p.R["dfeat2d"].ptr, p.R["code"].ptr,
+                                           p.R["cmask"].ptr if cfg.dropout > 0.001 else None, p.R["dcode_z"].ptr, None,
                                            ACT_LEAKY, cfg.alpha, st))
                 p.dcode_z.add_(p.code_lin, alpha=2e-3 / GS_PARTS)
                 check(lib.ugn_linear_bwd(h, p.R["sig2d"].ptr, self.Rw["code/w"].ptr, p.R["dcode_z"].ptr,
@@ -491,6 +507,7 @@ class _GsPlan:
             self.code_lin = Tn["code_lin"] = torch.zeros(GS_PARTS * B, cfg.nc, **f32)
             Tn["code"] = torch.zeros(GS_PARTS * B, cfg.nc, **f32)
             self.code3d = Tn["code3d"] = Tn["code"].view(GS_PARTS, B, cfg.nc)
+            self.cmask = Tn["cmask"] = torch.ones(GS_PARTS * B, cfg.nc, **f32)
             feat = cfg.nc
         if cfg.nclasses > 0:
             Tn["flat"] = torch.zeros(B, GS_PARTS * feat, **f32)

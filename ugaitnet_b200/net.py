@@ -222,6 +222,11 @@ class UGaitEngine:
             self.pw[name].copy_(v.contiguous().to(self.dev))
         self.repack_weights()
 
+    def oracle_shape(self, name):
+        """Shape of a parameter in the oracle / PyTorch layout (conv [Cout,Cin,kh,kw], dense [out,in])."""
+        s = self.segs[name].shape
+        return (s[0], s[3], s[1], s[2]) if len(s) == 4 else tuple(s)
+
     def _export(self, views) -> Dict[str, torch.Tensor]:
         out = {}
         for s in self.seg_list:
