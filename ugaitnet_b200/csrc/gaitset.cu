@@ -172,17 +172,22 @@ extern "C" int ugn_gs_conv1_fwd(ugn_ctx* ctx, const ugn_tensor* x, const ugn_ten
 // dxp f32 [F*S][Hs+2][Hs/S+2][32] is what ugn_conv2d_dgrad of the next layer wrote.  A pixel that lives in
 // two halves is simply visited twice (the sum over halves commutes with the reduction over pixels).
 // dw f32 [32][25c] (tap-major), OVERWRITTEN.
-// thread = (4 output channels, 25c/16 taps): per pixel one 16-byte gradient load + one sign load (hi plane
-// only: sign(y) == sign(hi)) + TT broadcast smem reads of the frame tile for 4*TT FMAs; persistent blocks
-// keep their partial sums in registers and issue one round of atomics at the end.
+// Per tile of 4 output rows: (1) every (position, 4 channels) item is loaded ONCE (16-byte gradient load +
+// sign of the hi plane: sign(y) == sign(hi)), multiplied by the LeakyReLU derivative and parked in smem;
+// (2) thread = (4 output channels, 25c/16 taps) sweeps the parked positions: one LDS.128 + TT broadcast reads
+// of the frame tile for 4*TT FMAs.  Persistent blocks keep their partial sums in registers and issue one
+// round of atomics at the end.
 template <int C, int MODE>
 __global__ void __launch_bounds__(128) gs_conv1_wgrad_kernel(const float* __restrict__ x, const float* __restrict__ dxp,
                                                              const void* __restrict__ yp, float* __restrict__ dw,
                                                              long long F, int H, int W, int S, int f16, float alpha) {
-  constexpr int K = 25 * C, TT = (K + 15) / 16, ROWS = 8;
+  constexpr int K = 25 * C, TT = (K + 15) / 16, ROWS = 4;
   extern __shared__ float sm[];
   const int Ws = W + 4, Hs = H + 4, TW = Ws + 4;
+  const int Wh = Ws / S + 2, Hp = Hs + 2, wh = Ws / S;
   float* xs = sm;                              // [ROWS+4][TW][C]
+  float* dzs = sm + (ROWS + 4) * TW * C;       // [ROWS][npos][32]
+  int* lxs = reinterpret_cast<int*>(dzs + ROWS * (Ws + 2 * S) * 32);   // output column of each position
   const int cg = threadIdx.x & 7, tg = threadIdx.x >> 3;
   int toff[TT];
 #pragma unroll
@@ -194,12 +199,27 @@ __global__ void __launch_bounds__(128) gs_conv1_wgrad_kernel(const float* __rest
   float acc[TT][4];
 #pragma unroll
   for (int j = 0; j < TT; ++j) acc[j][0] = acc[j][1] = acc[j][2] = acc[j][3] = 0.f;
+  // positions of one output row: for every half h the local columns xl whose padded column h*wh + xl lies in
+  // [1, Ws]; a pixel that lives in two halves appears twice (the sum over halves commutes with the reduction)
+  int npos = 0;
+  for (int h = 0; h < S; ++h) npos += min(Wh - 1, Ws - h * wh) - max(0, 1 - h * wh) + 1;
+  if (threadIdx.x < 32)
+    for (int i = threadIdx.x; i < npos; i += 32) {
+      int rem = i, h = 0;
+      for (; h < S; ++h) {
+        const int n = min(Wh - 1, Ws - h * wh) - max(0, 1 - h * wh) + 1;
+        if (rem < n) break;
+        rem -= n;
+      }
+      const int xl = max(0, 1 - h * wh) + rem;
+      lxs[i] = (h << 16) | xl;
+    }
   const int tiles_y = (Hs + ROWS - 1) / ROWS;
   const long long ntiles = F * tiles_y;
-  const int Wh = Ws / S + 2, Hp = Hs + 2, wh = Ws / S;
   for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
     const long long f = tile / tiles_y;
     const int y0 = (int)(tile % tiles_y) * ROWS;
+    const int nrow = min(ROWS, Hs - y0);
     __syncthreads();
     const int nin = (ROWS + 4) * TW * C;
     for (int i = threadIdx.x; i < nin; i += 128) {
@@ -207,39 +227,46 @@ __global__ void __launch_bounds__(128) gs_conv1_wgrad_kernel(const float* __rest
       int gy = y0 + yy - 4, gx = xx - 4;
       xs[i] = (gy >= 0 && gy < H && gx >= 0 && gx < W) ? x[((f * H + gy) * W + gx) * C + ci] : 0.f;
     }
+    // (1) park dz = dxp * act'(y): item = (row, position, channel quad)
+    const int nitem = nrow * npos * 8;
+    for (int i = threadIdx.x; i < nitem; i += 128) {
+      const int q = i & 7, pos = (i >> 3) % npos, ly = (i >> 3) / npos;
+      const int hx = lxs[pos], h = hx >> 16, xl = hx & 0xffff;
+      const long long o = ((((f * S + h) * Hp + y0 + ly + 1) * Wh) + xl) * 32 + 4 * q;
+      float4 g = *reinterpret_cast<const float4*>(dxp + o);
+      bool p0, p1, p2, p3;
+      if (MODE == 0) {
+        const float4 yv = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(yp) + o);
+        p0 = yv.x > 0.f; p1 = yv.y > 0.f; p2 = yv.z > 0.f; p3 = yv.w > 0.f;
+      } else {
+        const uint2 hv = *reinterpret_cast<const uint2*>(reinterpret_cast<const u16*>(yp) + o);
+        // 16-bit sign test: positive <=> sign bit clear and magnitude non-zero (bf16 and fp16 alike)
+        p0 = (hv.x & 0x8000u) == 0 && (hv.x & 0x7fffu) != 0;
+        p1 = (hv.x & 0x80000000u) == 0 && (hv.x & 0x7fff0000u) != 0;
+        p2 = (hv.y & 0x8000u) == 0 && (hv.y & 0x7fffu) != 0;
+        p3 = (hv.y & 0x80000000u) == 0 && (hv.y & 0x7fff0000u) != 0;
+      }
+      g.x *= p0 ? 1.f : alpha; g.y *= p1 ? 1.f : alpha; g.z *= p2 ? 1.f : alpha; g.w *= p3 ? 1.f : alpha;
+      *reinterpret_cast<float4*>(dzs + ((ly * npos + pos) * 32 + 4 * q)) = g;
+    }
     __syncthreads();
-    const int nrow = min(ROWS, Hs - y0);
+    // (2) rank-1 updates
     for (int ly = 0; ly < nrow; ++ly) {
-      for (int h = 0; h < S; ++h) {
-        // local columns of half h that are pixels of the layer output: padded column xc = h*wh + xl in [1, Ws]
-        const int xl0 = max(0, 1 - h * wh), xl1 = min(Wh - 1, Ws - h * wh);
-        const long long base = (((f * S + h) * Hp + y0 + ly + 1) * Wh) * 32 + 4 * cg;
-        const float* xrow = xs + (ly * TW + h * wh - 1) * C;
+      const float* xrow = xs + ly * TW * C;
+      const float* drow = dzs + (ly * npos) * 32 + 4 * cg;
 #pragma unroll 4
-        for (int xl = xl0; xl <= xl1; ++xl) {
-          float4 g = *reinterpret_cast<const float4*>(dxp + base + (long long)xl * 32);
-          bool p0, p1, p2, p3;
-          if (MODE == 0) {
-            const float4 yv = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(yp) + base + (long long)xl * 32);
-            p0 = yv.x > 0.f; p1 = yv.y > 0.f; p2 = yv.z > 0.f; p3 = yv.w > 0.f;
-          } else {
-            const uint2 hv = *reinterpret_cast<const uint2*>(reinterpret_cast<const u16*>(yp) + base + (long long)xl * 32);
-            // 16-bit sign test: positive <=> sign bit clear and magnitude non-zero (bf16 and fp16 alike)
-            p0 = (hv.x & 0x8000u) == 0 && (hv.x & 0x7fffu) != 0;
-            p1 = (hv.x & 0x80000000u) == 0 && (hv.x & 0x7fff0000u) != 0;
-            p2 = (hv.y & 0x8000u) == 0 && (hv.y & 0x7fffu) != 0;
-            p3 = (hv.y & 0x80000000u) == 0 && (hv.y & 0x7fff0000u) != 0;
-          }
-          g.x *= p0 ? 1.f : alpha; g.y *= p1 ? 1.f : alpha; g.z *= p2 ? 1.f : alpha; g.w *= p3 ? 1.f : alpha;
-          const float* xb = xrow + xl * C;
+      for (int pos = 0; pos < npos; ++pos) {
+        const int hx = lxs[pos];
+        const int lx = (hx >> 16) * wh + (hx & 0xffff) - 1;          // output column of this position
+        const float4 g = *reinterpret_cast<const float4*>(drow + pos * 32);
+        const float* xb = xrow + lx * C;
 #pragma unroll
-          for (int j = 0; j < TT; ++j) {
-            const float xv = xb[toff[j]];
-            acc[j][0] = fmaf(g.x, xv, acc[j][0]);
-            acc[j][1] = fmaf(g.y, xv, acc[j][1]);
-            acc[j][2] = fmaf(g.z, xv, acc[j][2]);
-            acc[j][3] = fmaf(g.w, xv, acc[j][3]);
-          }
+        for (int j = 0; j < TT; ++j) {
+          const float xv = xb[toff[j]];
+          acc[j][0] = fmaf(g.x, xv, acc[j][0]);
+          acc[j][1] = fmaf(g.y, xv, acc[j][1]);
+          acc[j][2] = fmaf(g.z, xv, acc[j][2]);
+          acc[j][3] = fmaf(g.w, xv, acc[j][3]);
         }
       }
     }
@@ -271,9 +298,10 @@ extern "C" int ugn_gs_conv1_wgrad(ugn_ctx* ctx, const ugn_tensor* x, const ugn_t
   cudaStream_t st = (cudaStream_t)stream;
   UGN_CUDA(cudaMemsetAsync(ugn_ptr<float>(dw), 0, sizeof(float) * 32 * 25 * c, st));
   const int Ws = W + 4;
-  const long long ntiles = F * ugn_cdiv(H + 4, 8);
-  size_t smem = sizeof(float) * ((size_t)12 * (Ws + 4) * c);
-  int grid = (int)std::min<long long>(ntiles, (long long)ctx->sm_count * 8);
+  const long long ntiles = F * ugn_cdiv(H + 4, 4);
+  size_t smem = sizeof(float) * ((size_t)8 * (Ws + 4) * c + (size_t)4 * (Ws + 2 * S) * 32) + sizeof(int) * (Ws + 2 * S);
+  UGN_CHECK(smem <= 48 * 1024, "gs_conv1_wgrad: frame too wide");
+  int grid = (int)std::min<long long>(ntiles, (long long)ctx->sm_count * 5);
 #define GS_WG(C_, M_)                                                                                                  \
   gs_conv1_wgrad_kernel<C_, M_><<<grid, 128, smem, st>>>(ugn_ptr<float>(x), ugn_ptr<float>(dxp), ugn_ptr<void>(yp),     \
                                                         ugn_ptr<float>(dw), F, H, W, S, gs_f16(yp), alpha)
