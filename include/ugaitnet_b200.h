@@ -176,6 +176,11 @@ int ugn_fuse_bwd(ugn_ctx*, int nmods, const ugn_tensor* dsig, const ugn_tensor* 
  * dlogits f32 [B,C] = scale * (softmax - onehot)/B (nullable). */
 int ugn_softmax_ce(ugn_ctx*, const ugn_tensor* logits, const ugn_tensor* labels,
                    ugn_tensor* loss_acc, ugn_tensor* dlogits, float scale, void* stream);
+/* the same with tf.losses.CategoricalCrossentropy(label_smoothing=e) (`smoothlabels`, :1252-1262):
+ * targets y*(1-e) + e/C; accuracy is still measured against the hard label. */
+int ugn_softmax_ce_ls(ugn_ctx*, const ugn_tensor* logits, const ugn_tensor* labels,
+                      ugn_tensor* loss_acc, ugn_tensor* dlogits, float scale, float label_smoothing,
+                      void* stream);
 
 /* ---- a7: batch-all triplet loss (nets/triplet_loss_all.py:8-77) -----------------------
  * emb f32 [n,B,d] (or [B,d] == n = 1), labels i32 [B].  out f32 [2] = {loss, total count of

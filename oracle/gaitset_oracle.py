@@ -48,6 +48,7 @@ class GaitSetConfig:
     margin: float = 0.2
     wver: float = 1.0
     wid: float = 0.1
+    label_smoothing: float = 0.0                 # smoothlabels (:1252-1262)
 
     @property
     def nmods(self):
@@ -163,6 +164,8 @@ def total_loss(inputs, flags, labels, P, cfg: GaitSetConfig):
     if cfg.nclasses > 0:
         onehot = F.one_hot(labels.reshape(-1).long(), cfg.nclasses).to(trip.dtype)
         ce, acc = softmax_ce(outs["logits"], onehot)
+        if cfg.label_smoothing > 0:
+            ce, _ = softmax_ce(outs["logits"], onehot * (1.0 - cfg.label_smoothing) + cfg.label_smoothing / cfg.nclasses)
         res["ce"], res["acc"] = ce, acc
         loss = loss + cfg.wid * ce
     reg = torch.zeros((), dtype=trip.dtype)

@@ -58,6 +58,8 @@ class NetConfig:
     hw: int = 60
     single: bool = False      # UWYHSemiNet.build with a non-list input_shapes (:900-915): no gate,
     #                           no fusion, NO l2_normalize on the signature.
+    label_smoothing: float = 0.0   # smoothlabels: tf.losses.CategoricalCrossentropy(label_smoothing) (:1252-1262)
+    normbfmerge: bool = False      # per-branch l2_normalize before the gate (:1167-1168)
 
     @property
     def nmods(self):
@@ -261,6 +263,8 @@ def model_forward(inputs, flags, P, cfg: NetConfig, drop_masks=None, code_drop_m
         if cfg.single:
             gated.append(b)
         else:
+            if cfg.normbfmerge:
+                b = l2_normalize(b, 1)                                  # "nrmbfl2*" Lambda (:1167-1168)
             gated.append(b * flags[m])                                  # :51-54
     if cfg.single:
         sig = gated[0]                                                  # :904 (no normalise)
@@ -272,6 +276,9 @@ def model_forward(inputs, flags, P, cfg: NetConfig, drop_masks=None, code_drop_m
     feat = sig
     if cfg.nc > 0:
         code = F.linear(sig, P["code/w"], P["code/b"])
+        # relu: Dense(activation='relu', activity_regularizer) regularises the activated output (:1195-1196);
+        # otherwise Dense(activation=None, activity_regularizer) + a separate LeakyReLU: the LINEAR output (:1198-1201)
+        outs["code_reg"] = F.relu(code) if cfg.act == ACT_RELU else code
         code = _act(code, cfg.act, cfg.alpha)
         outs["code"] = code
         feat = code if code_drop_mask is None else code * code_drop_mask
@@ -292,6 +299,9 @@ def total_loss(inputs, flags, labels, P, cfg: NetConfig, drop_masks=None, code_d
     if cfg.nclasses > 0:
         onehot = F.one_hot(labels.reshape(-1).long(), cfg.nclasses).to(trip.dtype)
         ce, acc = softmax_ce(outs["logits"], onehot)
+        if cfg.label_smoothing > 0:
+            # Keras: y_true * (1 - e) + e / num_classes, then the same categorical cross-entropy
+            ce, _ = softmax_ce(outs["logits"], onehot * (1.0 - cfg.label_smoothing) + cfg.label_smoothing / cfg.nclasses)
         res["ce"], res["acc"] = ce, acc
         loss = loss + cfg.wid * ce
     reg = torch.zeros((), dtype=trip.dtype)
@@ -301,7 +311,7 @@ def total_loss(inputs, flags, labels, P, cfg: NetConfig, drop_masks=None, code_d
             reg = reg + cfg.weight_decay * (P[f"{bn}/conv{li}/w"] ** 2).sum()
         reg = reg + 1e-3 * (P[f"{bn}/ofCode/w"] ** 2).sum()
     if cfg.nc > 0:
-        reg = reg + 1e-3 * (outs["code"] ** 2).sum() / outs["code"].shape[0]
+        reg = reg + 1e-3 * (outs["code_reg"] ** 2).sum() / outs["code_reg"].shape[0]
     res["reg"] = reg
     res["loss"] = loss + reg
     res["signature"] = outs["signature"]

@@ -37,6 +37,14 @@ def run(eng, n):
 
 res = {"B": B, "mode": mode}
 eng = GaitSetEngine(cfg, math_mode=mode, lr=1e-4, use_graph=False)
+import os
+if os.environ.get("GS_LITE"):          # runs under ncu: one warm-up step, one measured step, branches in sequence
+    eng.multistream = False
+    run(eng, 1)
+    l0 = eng.ctx.launches
+    ms, _ = run(eng, 1)
+    print(json.dumps({"lite": True, "B": B, "ms_per_step": ms, "launches_per_step": eng.ctx.launches - l0}), flush=True)
+    sys.exit(0)
 run(eng, 2)
 eng.ctx.check()
 ms, out = run(eng, steps)

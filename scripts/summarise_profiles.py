@@ -53,7 +53,7 @@ def find(row, key):
     return None, None
 
 
-def launches(tag, src, dst):
+def launches(tag, src, dst, what="cfg2, B=96, `bench.py --no-graph --lite`"):
     rows = list(csv.reader(open(src)))
     hdr = None
     agg = collections.OrderedDict()
@@ -73,7 +73,7 @@ def launches(tag, src, dst):
     tot = sum(sum(v) for v in agg.values())
     n = sum(len(v) for v in agg.values())
     with open(dst, "w") as f:
-        f.write(f"# {tag}: launch list of ONE eager training step (cfg2, B=96, `bench.py --no-graph --lite`)\n\n")
+        f.write(f"# {tag}: launch list of ONE eager training step ({what})\n\n")
         f.write("`ncu --metrics gpu__time_duration.sum --clock-control none` -- per-launch times are cold-cache and\n"
                 "serialised, so only each kernel's SHARE of the step is comparable with the live CUDA-event numbers.\n\n")
         f.write(f"{n} launches, {tot / 1e3:.3f} ms summed\n\n| kernel | launches | sum us | max us | share |\n|---|---:|---:|---:|---:|\n")
@@ -103,6 +103,9 @@ def main():
     os.makedirs(dst, exist_ok=True)
     if os.path.exists(os.path.join(src, "launches.csv")):
         launches(tag, os.path.join(src, "launches.csv"), os.path.join(dst, f"{tag}_launches.md"))
+    if os.path.exists(os.path.join(src, "gs_launches.csv")):
+        launches(tag, os.path.join(src, "gs_launches.csv"), os.path.join(dst, f"{tag}_gs_launches.md"),
+                 "GaitSet branches, 3 modalities, 24 rows, `GS_LITE=1 scripts/gs_bench.py 24 f16mix 1`")
     for fn in sorted(os.listdir(src)):
         if fn.startswith("prof_") and fn.endswith("_raw.csv"):
             name = fn[len("prof_"):-len("_raw.csv")]

@@ -222,7 +222,7 @@ def make_case(name):
                                wver=1.0, wid=0.1), dict(ids=3, per_id=2)
     if name == "small_2mod_code":
         return G.GaitSetConfig(in_channels=(2, 1), frames=4, hw=12, nc=16, nclasses=10, merge=O.MERGE_MAX,
-                               wver=1.0, wid=1.0), dict(ids=3, per_id=2)
+                               wver=1.0, wid=1.0, label_smoothing=0.1), dict(ids=3, per_id=2)
     if name == "real_shapes":       # 25 x 60 x 60 clips, the reference's branch at full size, tiny batch
         return G.GaitSetConfig(in_channels=(2, 1), frames=25, hw=60, nc=0, nclasses=20, merge=O.MERGE_SIGNMAX,
                                wver=1.0, wid=0.1), dict(ids=2, per_id=2)
@@ -233,7 +233,7 @@ def to_engine_cfg(oc):
     from ugaitnet_b200.config import GaitSetConfig
     return GaitSetConfig(in_channels=tuple(oc.in_channels), frames=oc.frames, hw=oc.hw, hidden=oc.hidden, nc=oc.nc,
                          nclasses=oc.nclasses, merge=oc.merge, alpha=oc.alpha, margin=oc.margin, wver=oc.wver,
-                         wid=oc.wid)
+                         wid=oc.wid, label_smoothing=oc.label_smoothing)
 
 
 def setup(name, math_mode="fp32", seed=7, dtype=torch.float64, split=None):
@@ -280,6 +280,15 @@ def test_gaitset_predict_layers_fp32():
     assert rel(eng.predict(cu(xs), cu(fl), "code"), outs["code"]) < 1e-5
     assert rel(eng.predict(cu(xs), cu(fl), "flatten"), outs["code"].permute(1, 0, 2).flatten(1)) < 1e-5
     assert rel(eng.predict(cu(xs), cu(fl), "classprob"), outs["logits"]) < 1e-5
+
+
+@pytest.mark.parametrize("B", [1, 5])
+def test_gaitset_predict_any_batch_size(B):
+    oc, eng, P, xs, fl, lab = setup("small_3mod_signmax")
+    xs, fl = [x[:B] for x in xs], [f[:B] for f in fl]
+    ref, _ = G.model_forward(xs, fl, P, oc)
+    got = eng.predict(cu(xs), cu(fl), "signature")
+    assert got.shape == (62, B, 256) and rel(got, ref) < 1e-5
 
 
 @pytest.mark.parametrize("mode,sig_tol,grad_tol", [("fp32", 2e-4, 2e-3), ("f16mix", 1e-3, 1e-2)])

@@ -22,6 +22,10 @@ def make_case(name):
         oc = O.NetConfig(in_channels=(6, 4, 4), filters_numbers=(8, 8, 16, 16), nd=32, nclasses=10,
                          merge=O.MERGE_SIGNMAX, wver=1.0, wid=0.1)
         return oc, dict(base_rows=6, expand=4, kinds=("of", "gray", "depth")), None
+    if name == "3mod_norm_smooth":   # normbfmerge + smoothlabels builder options (a17)
+        oc = O.NetConfig(in_channels=(6, 4, 4), filters_numbers=(8, 8, 16, 16), nd=32, nclasses=10,
+                         merge=O.MERGE_SIGNMAX, wver=1.0, wid=0.5, label_smoothing=0.1, normbfmerge=True)
+        return oc, dict(base_rows=6, expand=4, kinds=("of", "gray", "depth")), None
     if name == "2mod_max_leaky_code":  # FC1 "code" + LeakyReLU + dropout masks
         oc = O.NetConfig(in_channels=(6, 4), filters_numbers=(8, 8, 16, 16), nd=32, nc=8, nclasses=7,
                          merge=O.MERGE_MAX, act=O.ACT_LEAKY, wver=1.0, wid=1.0)
@@ -45,7 +49,8 @@ def to_engine_cfg(oc, dropout=0.0):
     return NetConfig(in_channels=tuple(oc.in_channels), filters_numbers=tuple(oc.filters_numbers),
                      filters_size=tuple(oc.filters_size), nd=oc.nd, nc=oc.nc, nclasses=oc.nclasses,
                      weight_decay=oc.weight_decay, merge=oc.merge, act=oc.act, alpha=oc.alpha, margin=oc.margin,
-                     wver=oc.wver, wid=oc.wid, hw=oc.hw, dropout=dropout, single=oc.single)
+                     wver=oc.wver, wid=oc.wid, hw=oc.hw, dropout=dropout, single=oc.single,
+                     label_smoothing=oc.label_smoothing, normbfmerge=oc.normbfmerge)
 
 
 def setup(name, math_mode="fp32", seed=11):
@@ -89,7 +94,8 @@ def reg_grad(oc, name, w):
     return torch.zeros_like(w)
 
 
-@pytest.mark.parametrize("name", ["3mod_signmax", "2mod_max_leaky_code", "3mod_avg", "1mod_gray", "real_shapes"])
+@pytest.mark.parametrize("name", ["3mod_signmax", "2mod_max_leaky_code", "3mod_avg", "1mod_gray", "real_shapes",
+                                  "3mod_norm_smooth"])
 def test_step_parity_fp32(name):
     oc, eng, P, xs, fl, lab, masks, cmask = setup(name)
     res, G = oracle_step(oc, P, xs, fl, lab, masks, cmask)

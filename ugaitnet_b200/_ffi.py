@@ -62,6 +62,7 @@ _PROTOS = {
     "ugn_fuse_bwd": (c_int, [c_void_p, c_int, _T, _T, _T, _T, POINTER(c_void_p), POINTER(c_void_p),
                              c_int, c_int, c_void_p]),
     "ugn_softmax_ce": (c_int, [c_void_p, _T, _T, _T, _T, c_float, c_void_p]),
+    "ugn_softmax_ce_ls": (c_int, [c_void_p, _T, _T, _T, _T, c_float, c_float, c_void_p]),
     "ugn_triplet_workspace_bytes": (c_int64, [c_int, c_int]),
     "ugn_triplet_all": (c_int, [c_void_p, _T, _T, c_float, c_float, _T, _T, _T, c_void_p]),
     "ugn_adam_step": (c_int, [c_void_p, _T, _T, _T, _T, _T, _T, c_float, c_float, c_float, c_float,

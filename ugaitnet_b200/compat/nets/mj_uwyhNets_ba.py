@@ -10,9 +10,10 @@ step runs on the B200 engine (ugaitnet_b200.net.UGaitEngine).
 branch type (build_gaitset_branch :420-484) on ugaitnet_b200.gaitset.GaitSetEngine: inputs
 [B,25,60,60,c], signature [62,B,256], descriptor layer "flatten" (typecode 3).
 
-Builder arguments that select graphs outside the hot path raise NotImplementedError:
-use3D, aux_losses, smoothlabels, postriplet == 2, normbfmerge, init_branches / initnet weight surgery
-from Keras .hdf5 files, tfa TripletHardLoss (compile_hard).
+``smoothlabels`` (label-smoothed cross-entropy, :1252-1262) and ``normbfmerge`` (per-branch l2_normalize
+before the gate, :1167-1168) are implemented.  Builder arguments that select graphs outside the hot path
+raise NotImplementedError: use3D, aux_losses, postriplet == 2, init_branches / initnet weight surgery from
+Keras .hdf5 files, tfa TripletHardLoss (compile_hard).
 """
 from __future__ import annotations
 
@@ -303,7 +304,8 @@ class UGaitModel:
 
 
 def _cfg_from_args(input_shapes, number_convolutional_layers, filters_size, filters_numbers, ndense_units,
-                   weight_decay, dropout, margin, nclasses, loss_weights, fMerge, fActivation, alpha, single):
+                   weight_decay, dropout, margin, nclasses, loss_weights, fMerge, fActivation, alpha, single,
+                   smoothlabels=0, normbfmerge=False):
     fs = [k[0] if isinstance(k, (tuple, list)) else int(k) for k in filters_size][:number_convolutional_layers]
     fn = list(filters_numbers if filters_numbers is not None else [64, 128, 512, 512])[:number_convolutional_layers]
     if isinstance(ndense_units, (list, tuple)):
@@ -319,10 +321,12 @@ def _cfg_from_args(input_shapes, number_convolutional_layers, filters_size, filt
                      merge=merge_id_of(fMerge) if not single else MERGE_MAX,
                      act=ACT_RELU if fActivation == "relu" else ACT_LEAKY, alpha=float(alpha), margin=float(margin),
                      wver=float(lw[0]) if nclasses > 0 else 1.0, wid=float(lw[1]) if nclasses > 0 and len(lw) > 1 else 0.0,
-                     hw=int(shapes[0][1]), dropout=float(dropout) if dropout > 0.001 else 0.0, single=single)
+                     hw=int(shapes[0][1]), dropout=float(dropout) if dropout > 0.001 else 0.0, single=single,
+                     label_smoothing=float(smoothlabels), normbfmerge=bool(normbfmerge))
 
 
-def _gs_cfg_from_args(input_shapes, ndense_units, dropout, margin, nclasses, loss_weights, fMerge, fActivation, alpha):
+def _gs_cfg_from_args(input_shapes, ndense_units, dropout, margin, nclasses, loss_weights, fMerge, fActivation, alpha,
+                      smoothlabels=0):
     """gaitset=True: input_shapes [(25,60,60,2), (25,60,60,1), ...] (mains/mj_trainUWYHGaitNet_DataGen_CasiaB.py:212-213)."""
     if fActivation == 'relu':
         raise ValueError("gaitset=True needs a non-'relu' fActivation: the reference only builds the GaitSet "
@@ -338,7 +342,7 @@ def _gs_cfg_from_args(input_shapes, ndense_units, dropout, margin, nclasses, los
                          nc=int(nc), nclasses=int(nclasses), merge=merge_id_of(fMerge), alpha=float(alpha),
                          margin=float(margin), wver=float(lw[0]) if nclasses > 0 else 1.0,
                          wid=float(lw[1]) if nclasses > 0 and len(lw) > 1 else 0.0,
-                         dropout=float(dropout) if (dropout > 0.001 and nc) else 0.0)
+                         dropout=float(dropout) if (dropout > 0.001 and nc) else 0.0, label_smoothing=float(smoothlabels))
 
 
 class UWYHNet:
@@ -369,18 +373,19 @@ class UWYHSemiNet:
               ndense_units=512, weight_decay=1e-4, dropout=0.4, optimizer=None, margin=0.2,
               nclasses=0, loss_weights=[1.0, 1.0], use3D=False, smoothlabels=0, postriplet=1, init_branches=None,
               freeze_branches=False, aux_losses=False, fMerge=Maximum, fActivation='relu', alpha=0.3, gaitset=False):
-        _unsupported(use3D=use3D, smoothlabels=smoothlabels, postriplet_2=(postriplet == 2), aux_losses=aux_losses,
+        _unsupported(use3D=use3D, postriplet_2=(postriplet == 2), aux_losses=aux_losses,
                      freeze_branches=freeze_branches,
                      init_branches=bool(init_branches) and any(init_branches.values()))
         single = not isinstance(input_shapes, list)
         if gaitset:
             _unsupported(gaitset_single_modality=single)
             cfg = _gs_cfg_from_args(input_shapes, ndense_units, dropout, margin, nclasses, loss_weights, fMerge,
-                                    fActivation, alpha)
+                                    fActivation, alpha, smoothlabels)
             losses = [triplet_loss(margin=margin), 'categorical_crossentropy'] if nclasses > 0 else triplet_loss(margin=margin)
             return UGaitModel(cfg, optimizer, losses, loss_weights if nclasses > 0 else 1.0, multimodal=True)
         cfg = _cfg_from_args(input_shapes, number_convolutional_layers, filters_size, filters_numbers, ndense_units,
-                             weight_decay, dropout, margin, nclasses, loss_weights, fMerge, fActivation, alpha, single)
+                             weight_decay, dropout, margin, nclasses, loss_weights, fMerge, fActivation, alpha, single,
+                             smoothlabels=smoothlabels)
         losses = [triplet_loss(margin=margin), 'categorical_crossentropy'] if nclasses > 0 else triplet_loss(margin=margin)
         return UGaitModel(cfg, optimizer, losses, loss_weights if nclasses > 0 else 1.0, multimodal=not single)
 
@@ -473,17 +478,16 @@ class UWYHSemiNet3Mods(UWYHSemiNet):
               nclasses=0, loss_weights=[1.0, 1.0], use3D=False, smoothlabels=0,
               postriplet=1, init_branches=None, freeze_branches=False, aux_losses=False, fMerge=Maximum,
               normbfmerge=False, fActivation='relu', alpha=0.3, gaitset=False):
-        _unsupported(use3D=use3D, smoothlabels=smoothlabels, aux_losses=aux_losses,
-                     normbfmerge=normbfmerge, freeze_branches=freeze_branches,
+        _unsupported(use3D=use3D, aux_losses=aux_losses, freeze_branches=freeze_branches,
                      init_branches=bool(init_branches) and any(init_branches.values()))
         if gaitset:
             cfg = _gs_cfg_from_args(input_shapes, ndense_units, dropout, margin, nclasses, loss_weights, fMerge,
-                                    fActivation, alpha)
+                                    fActivation, alpha, smoothlabels)       # (normbfmerge is ignored with gaitset, :1164)
             losses = [triplet_loss(margin=margin), 'categorical_crossentropy'] if nclasses > 0 else triplet_loss(margin=margin)
             return UGaitModel(cfg, optimizer, losses, loss_weights if nclasses > 0 else 1.0, multimodal=True)
         cfg = _cfg_from_args(list(input_shapes), number_convolutional_layers, filters_size, filters_numbers,
                              ndense_units, weight_decay, dropout, margin, nclasses, loss_weights, fMerge, fActivation,
-                             alpha, single=False)
+                             alpha, single=False, smoothlabels=smoothlabels, normbfmerge=normbfmerge)
         losses = [triplet_loss(margin=margin), 'categorical_crossentropy'] if nclasses > 0 else triplet_loss(margin=margin)
         return UGaitModel(cfg, optimizer, losses, loss_weights if nclasses > 0 else 1.0, multimodal=True)
 

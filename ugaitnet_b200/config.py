@@ -34,6 +34,8 @@ class NetConfig:
     hw: int = 60
     dropout: float = 0.0
     single: bool = False           # 1-modality graph: no gate / fusion / l2_normalize (:900-915)
+    label_smoothing: float = 0.0   # smoothlabels -> tf.losses.CategoricalCrossentropy(label_smoothing) (:1252-1262)
+    normbfmerge: bool = False      # l2_normalize every branch output before its gate (:1167-1168)
 
     @property
     def nmods(self) -> int:
@@ -85,6 +87,7 @@ class GaitSetConfig:
     wid: float = 1.0
     dropout: float = 0.0           # Dropout(name="dropcode") after FC1 (:1203); the branches have none
     single: bool = False
+    label_smoothing: float = 0.0   # smoothlabels (:1252-1262)
 
     @property
     def nmods(self) -> int:

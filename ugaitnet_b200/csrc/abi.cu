@@ -128,7 +128,7 @@ int ew_fuse_fwd(ugn_ctx*, const FusePtrs&, int, int, int, float*, __nv_bfloat16*
 int ew_gscale_update(ugn_ctx*, const float*, long long, float, float, cudaStream_t);
 int ew_fuse_bwd(ugn_ctx*, const FusePtrs&, int, int, int, const float*, const float*, const uint8_t*,
                 const float*, int, int, cudaStream_t);
-int ew_softmax_ce(ugn_ctx*, const float*, const int*, float*, float*, int, int, float, cudaStream_t);
+int ew_softmax_ce(ugn_ctx*, const float*, const int*, float*, float*, int, int, float, float, cudaStream_t);
 int ew_optim(ugn_ctx*, int, float*, const float*, float*, float*, const long long*, const float*, int,
              long long, float, float, float, float, float, float*, const float*, const long long*, int, int,
              cudaStream_t);
@@ -525,9 +525,16 @@ extern "C" int ugn_fuse_bwd(ugn_ctx* ctx, int nmods, const ugn_tensor* dsig, con
                      normalize, (cudaStream_t)stream);
 }
 
+extern "C" int ugn_softmax_ce_ls(ugn_ctx* ctx, const ugn_tensor* logits, const ugn_tensor* labels, ugn_tensor* loss_acc,
+                                 ugn_tensor* dlogits, float scale, float label_smoothing, void* stream);
 extern "C" int ugn_softmax_ce(ugn_ctx* ctx, const ugn_tensor* logits, const ugn_tensor* labels, ugn_tensor* loss_acc,
                               ugn_tensor* dlogits, float scale, void* stream) {
+  return ugn_softmax_ce_ls(ctx, logits, labels, loss_acc, dlogits, scale, 0.f, stream);
+}
+extern "C" int ugn_softmax_ce_ls(ugn_ctx* ctx, const ugn_tensor* logits, const ugn_tensor* labels, ugn_tensor* loss_acc,
+                                 ugn_tensor* dlogits, float scale, float label_smoothing, void* stream) {
   UGN_CHECK(ctx && logits && labels && loss_acc, "ugn_softmax_ce: null argument");
+  UGN_CHECK(label_smoothing >= 0.f && label_smoothing < 1.f, "softmax_ce: label_smoothing must be in [0,1)");
   UGN_TENSOR(logits, DT_F32, 2, 2);
   UGN_TENSOR(labels, DT_I32, 1, 2);
   UGN_TENSOR(loss_acc, DT_F32, 1, 1);
@@ -536,7 +543,7 @@ extern "C" int ugn_softmax_ce(ugn_ctx* ctx, const ugn_tensor* logits, const ugn_
   if (dlogits) { UGN_TENSOR(dlogits, DT_F32, 2, 2); UGN_CHECK(ugn_numel(dlogits) == (int64_t)B * C, "softmax_ce: dlogits shape mismatch"); }
   if (B == 0) return UGN_OK;
   return ew_softmax_ce(ctx, ugn_ptr<float>(logits), ugn_ptr<int>(labels), ugn_ptr<float>(loss_acc),
-                       dlogits ? ugn_ptr<float>(dlogits) : nullptr, B, C, scale, (cudaStream_t)stream);
+                       dlogits ? ugn_ptr<float>(dlogits) : nullptr, B, C, scale, label_smoothing, (cudaStream_t)stream);
 }
 
 static int optim_common(ugn_ctx* ctx, int opt, ugn_tensor* w, const ugn_tensor* g, ugn_tensor* m, ugn_tensor* v,

@@ -518,7 +518,7 @@ int ew_fuse_bwd(ugn_ctx* ctx, const FusePtrs& ptrs, int nmods, int B, int d, con
 // ---------------------------------------------------------------------------------------
 __global__ void softmax_ce_kernel(const float* __restrict__ logits, const int* __restrict__ labels,
                                   float* __restrict__ loss_acc, float* __restrict__ dlogits, int B, int C,
-                                  float scale) {
+                                  float scale, float smooth) {
   int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (warp >= B) return;
   const float* row = logits + (long long)warp * C;
@@ -534,29 +534,33 @@ __global__ void softmax_ce_kernel(const float* __restrict__ logits, const int* _
     int oa = __shfl_xor_sync(0xffffffffu, amax, o);
     if (om > mx || (om == mx && oa < amax)) { mx = om; amax = oa; }
   }
-  float se = 0.f;
-  for (int j = lane; j < C; j += 32) se += expf(row[j] - mx);
+  float se = 0.f, sz = 0.f;
+  for (int j = lane; j < C; j += 32) { se += expf(row[j] - mx); sz += row[j]; }
   se = warp_sum(se);
+  sz = warp_sum(sz);
   float lse = mx + logf(se);
   int lab = labels[warp];
+  // label smoothing (tf.losses.CategoricalCrossentropy(label_smoothing=e), nets/mj_uwyhNets_ba.py:1252-1262):
+  // y_s = y*(1-e) + e/C;  loss = -sum_j y_s[j] log p[j] = lse - (1-e) z[lab] - (e/C) sum_j z[j]
+  const float uni = smooth / (float)C;
   if (lane == 0) {
-    atomicAdd(loss_acc, (lse - row[lab]) / (float)B);
+    atomicAdd(loss_acc, (lse - (1.f - smooth) * row[lab] - uni * sz) / (float)B);
     atomicAdd(loss_acc + 1, (amax == lab ? 1.f : 0.f) / (float)B);
   }
   if (dlogits) {
     float s = scale / (float)B;
     for (int j = lane; j < C; j += 32) {
       float p = expf(row[j] - lse);
-      dlogits[(long long)warp * C + j] = s * (p - (j == lab ? 1.f : 0.f));
+      dlogits[(long long)warp * C + j] = s * (p - (j == lab ? 1.f - smooth : 0.f) - uni);
     }
   }
 }
 
 int ew_softmax_ce(ugn_ctx* ctx, const float* logits, const int* labels, float* loss_acc,
-                  float* dlogits, int B, int C, float scale, cudaStream_t st) {
+                  float* dlogits, int B, int C, float scale, float smooth, cudaStream_t st) {
   UGN_CUDA(cudaMemsetAsync(loss_acc, 0, 2 * sizeof(float), st));
   int threads = 128, blocks = ugn_cdiv((long long)B * 32, threads);
-  softmax_ce_kernel<<<blocks, threads, 0, st>>>(logits, labels, loss_acc, dlogits, B, C, scale);
+  softmax_ce_kernel<<<blocks, threads, 0, st>>>(logits, labels, loss_acc, dlogits, B, C, scale, smooth);
   UGN_LAUNCHED(ctx);
   return UGN_OK;
 }

@@ -318,8 +318,8 @@ class GaitSetEngine(UGaitEngine):
         check(lib.ugn_triplet_all(h, sig.ptr, p.R["labels"].ptr, cfg.margin, cfg.wver, p.R["trip_out"].ptr,
                                   p.R["dsig"].ptr, p.R["trip_ws"].ptr, st))
         if cfg.nclasses > 0:
-            check(lib.ugn_softmax_ce(h, p.R["logits"].ptr, p.R["labels"].ptr, p.R["ce_out"].ptr, p.R["dlogits"].ptr,
-                                     cfg.wid, st))
+            check(lib.ugn_softmax_ce_ls(h, p.R["logits"].ptr, p.R["labels"].ptr, p.R["ce_out"].ptr, p.R["dlogits"].ptr,
+                                        cfg.wid, cfg.label_smoothing, st))
             check(lib.ugn_linear_bwd(h, p.R["flat"].ptr, self.Rw["classprob/w"].ptr, p.R["dlogits"].ptr,
                                      p.R["dflat"].ptr, self.Rg["classprob/w"].ptr, self.Rg["classprob/b"].ptr, st))
             check(lib.ugn_permute102(h, p.R["dflat3d"].ptr, p.R["dfeat"].ptr, st))        # [B,62,f] -> [62,B,f]

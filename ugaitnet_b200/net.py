@@ -21,7 +21,7 @@ import torch
 
 from . import ops
 from ._ffi import TRef, check, lib, ptr_array, stream_ptr
-from .config import ACT_LINEAR, BRANCH_NAMES, MERGE_AVG, NetConfig, round_up
+from .config import ACT_LEAKY, ACT_LINEAR, BRANCH_NAMES, MERGE_AVG, NetConfig, round_up
 from .expand import NOISE
 
 # math mode -> (forward planes, backward/gradient planes, 16-bit dtype)
@@ -287,8 +287,15 @@ class UGaitEngine:
         if cfg.single:
             sig = p.br[0].R["out"]
         else:
-            check(lib.ugn_fuse_fwd(h, cfg.nmods, p.br_ptrs, p.flag_ptrs, p.R["sig"].ptr, None, p.R["winner"].ptr,
-                                   p.R["inv_norm"].ptr, cfg.merge, 1, st))
+            if cfg.normbfmerge:
+                # "nrmbfl2*" Lambdas (:1167-1168): l2_normalize of every branch output before its gate = the
+                # fusion kernel on ONE modality with a unit flag (gate x 1 -> max of one -> l2_normalize)
+                for m in range(cfg.nmods):
+                    b = p.br[m]
+                    check(lib.ugn_fuse_fwd(h, 1, b.nrm_in, p.one_ptrs, b.R["outn"].ptr, None, b.R["nwin"].ptr,
+                                           b.R["ninv"].ptr, 0, 1, st))
+            check(lib.ugn_fuse_fwd(h, cfg.nmods, p.brn_ptrs if cfg.normbfmerge else p.br_ptrs, p.flag_ptrs,
+                                   p.R["sig"].ptr, None, p.R["winner"].ptr, p.R["inv_norm"].ptr, cfg.merge, 1, st))
             sig = p.R["sig"]
         feat = sig
         if cfg.nc > 0:
@@ -436,8 +443,8 @@ class UGaitEngine:
         check(lib.ugn_triplet_all(h, sig.ptr, p.R["labels"].ptr, cfg.margin, cfg.wver, p.R["trip_out"].ptr,
                                   p.R["dsig"].ptr, p.R["trip_ws"].ptr, st))
         if cfg.nclasses > 0:
-            check(lib.ugn_softmax_ce(h, p.R["logits"].ptr, p.R["labels"].ptr, p.R["ce_out"].ptr, p.R["dlogits"].ptr,
-                                     cfg.wid, st))
+            check(lib.ugn_softmax_ce_ls(h, p.R["logits"].ptr, p.R["labels"].ptr, p.R["ce_out"].ptr, p.R["dlogits"].ptr,
+                                        cfg.wid, cfg.label_smoothing, st))
             check(lib.ugn_linear_bwd(h, feat.ptr, self.Rw["classprob/w"].ptr, p.R["dlogits"].ptr, p.R["dfeat"].ptr,
                                      self.Rg["classprob/w"].ptr, self.Rg["classprob/b"].ptr, st))
             dfeat = p.R["dfeat"]
@@ -446,9 +453,15 @@ class UGaitEngine:
                 use_mask = cfg.dropout > 0.001
                 check(lib.ugn_act_mask_bwd(h, dfeat.ptr, None, p.R["cmask"].ptr if use_mask else None,
                                            p.R["dcode"].ptr, None, ACT_LINEAR, 0.0, st))
-                p.dcode.add_(p.code, alpha=2e-3 / B)
+                relu = cfg.act != ACT_LEAKY
+                if relu:        # Dense(activation='relu', activity_regularizer): the activated output is regularised
+                    p.dcode.add_(p.code, alpha=2e-3 / B)
                 check(lib.ugn_act_mask_bwd(h, p.R["dcode"].ptr, p.R["code"].ptr, None, p.R["dcode_z"].ptr, None,
                                            cfg.act, cfg.alpha, st))
+                if not relu:    # Dense(activation=None, activity_regularizer) + LeakyReLU (:1198-1201): the LINEAR output,
+                    #             recovered from the activated one (z = y for y > 0, y / alpha otherwise)
+                    torch.where(p.code > 0, p.code, p.code / cfg.alpha, out=p.dsig2_code)
+                    p.dcode_z.add_(p.dsig2_code, alpha=2e-3 / B)
                 check(lib.ugn_linear_bwd(h, sig.ptr, self.Rw["code/w"].ptr, p.R["dcode_z"].ptr, p.R["dsig2"].ptr,
                                          self.Rg["code/w"].ptr, self.Rg["code/b"].ptr, st))
                 p.dsig.add_(p.dsig2)
@@ -467,7 +480,13 @@ class UGaitEngine:
             p.br[0].dout.copy_(p.dsig)
         else:
             check(lib.ugn_fuse_bwd(h, cfg.nmods, p.R["dsig"].ptr, p.R["sig"].ptr, p.R["winner"].ptr,
-                                   p.R["inv_norm"].ptr, p.flag_ptrs, p.dbr_ptrs, cfg.merge, 1, st))
+                                   p.R["inv_norm"].ptr, p.flag_ptrs, p.dbrn_ptrs if cfg.normbfmerge else p.dbr_ptrs,
+                                   cfg.merge, 1, st))
+            if cfg.normbfmerge:
+                for m in range(cfg.nmods):
+                    b = p.br[m]
+                    check(lib.ugn_fuse_bwd(h, 1, b.R["doutn"].ptr, b.R["outn"].ptr, b.R["nwin"].ptr, b.R["ninv"].ptr,
+                                           p.one_ptrs, b.nrm_dout, 0, 1, st))
         # per-branch backward on concurrent streams (single GPU; with data parallelism the branches stay in
         # sequence so that every all-reduce bucket is issued from the one stream NCCL orders against)
         streams = self._fork() if self.world == 1 and self._cap is None else None
@@ -661,7 +680,8 @@ class UGaitEngine:
         check(lib.ugn_triplet_all(h, sig.ptr, p.R["labels"].ptr, cfg.margin, 1.0, p.R["trip_out"].ptr, None,
                                   p.R["trip_ws"].ptr, st))
         if cfg.nclasses > 0:
-            check(lib.ugn_softmax_ce(h, p.R["logits"].ptr, p.R["labels"].ptr, p.R["ce_out"].ptr, None, 1.0, st))
+            check(lib.ugn_softmax_ce_ls(h, p.R["logits"].ptr, p.R["labels"].ptr, p.R["ce_out"].ptr, None, 1.0,
+                                        cfg.label_smoothing, st))
         return self._report(p)
 
     # ------------------------------------------------------------------ host -> device pipelining
@@ -764,8 +784,18 @@ class _Plan:
                     T["dz1_16"] = torch.zeros(PB, B, 2 * cfg.nd, device=d, dtype=dt16)
                 else:
                     T["dz1"] = torch.zeros(B, 2 * cfg.nd, **f32)
+            if cfg.normbfmerge and not cfg.single:
+                T["outn"] = torch.zeros(B, cfg.nd, **f32)
+                T["nwin"] = torch.zeros(B, cfg.nd, device=d, dtype=torch.uint8)
+                T["ninv"] = torch.zeros(B, 2, **f32)
+                if train:
+                    T["doutn"] = torch.zeros(B, cfg.nd, **f32)
             b.T = T
             b.R = {k: TRef(v) for k, v in T.items()}
+            if cfg.normbfmerge and not cfg.single:
+                b.nrm_in = ptr_array([b.R["out"]])
+                if train:
+                    b.nrm_dout = ptr_array([b.R["dout"]])
             self.br.append(b)
         T = {}
         self.sig = T["sig"] = torch.zeros(B, cfg.nd, **f32)
@@ -790,7 +820,8 @@ class _Plan:
                 self.dfeat = T["dfeat"] = torch.zeros(B, feat, **f32)
             if cfg.nc > 0:
                 self.dcode = T["dcode"] = torch.zeros(B, cfg.nc, **f32)
-                T["dcode_z"] = torch.zeros(B, cfg.nc, **f32)
+                self.dcode_z = T["dcode_z"] = torch.zeros(B, cfg.nc, **f32)
+                self.dsig2_code = torch.zeros(B, cfg.nc, **f32)
                 self.dsig2 = T["dsig2"] = torch.zeros(B, cfg.nd, **f32)
         self.T = T
         self.R = {k: TRef(v) for k, v in T.items()}
@@ -799,6 +830,12 @@ class _Plan:
         self.flag_ptrs = ptr_array(self.R_flags)
         if train:
             self.dbr_ptrs = ptr_array([b.R["dout"] for b in self.br])
+        if cfg.normbfmerge and not cfg.single:
+            self._ones = TRef(torch.ones(B, 1, **f32))
+            self.one_ptrs = ptr_array([self._ones])
+            self.brn_ptrs = ptr_array([b.R["outn"] for b in self.br])
+            if train:
+                self.dbrn_ptrs = ptr_array([b.R["doutn"] for b in self.br])
 
     def ensure_base(self, B0: int):
         """Buffers of the device-side expansion: base rows per modality, source-row and mirror tables."""
