@@ -208,7 +208,17 @@ int ugn_adam_step(ugn_ctx*, ugn_tensor* w, const ugn_tensor* g, ugn_tensor* m, u
                   float beta2, float eps, float gscale, ugn_tensor* reg_out,
                   const ugn_tensor* lr_dev, const ugn_tensor* pack_table, int pack_planes,
                   int pack_f16, void* stream);
-/* SGD with momentum (optimizers.SGD(lr, momentum), :245): v = mom*v - lr*g'; w += v. */
+/* The two Adam variants the reference mains select (mains/mj_trainUWYHGaitNet_DataGen_CasiaB.py:232-236):
+ * vhat f32 arena (nullable): optimizers.Adam(amsgrad=True) -- vhat = max(vhat, v), w -= lr_t*m/(sqrt(vhat)+eps);
+ * weight_decay > 0: tfa.optimizers.AdamW -- decoupled decay w -= weight_decay*w (not scaled by the learning
+ * rate) applied together with the Adam update.  All other arguments as ugn_adam_step. */
+int ugn_adam_step_ex(ugn_ctx*, ugn_tensor* w, const ugn_tensor* g, ugn_tensor* m, ugn_tensor* v,
+                     ugn_tensor* vhat, float weight_decay, const ugn_tensor* seg_off,
+                     const ugn_tensor* seg_l2, float lr_t, float beta1, float beta2, float eps, float gscale,
+                     ugn_tensor* reg_out, const ugn_tensor* lr_dev, const ugn_tensor* pack_table,
+                     int pack_planes, int pack_f16, void* stream);
+/* SGD with momentum (optimizers.SGD(lr, momentum, decay), :245): v = mom*v - lr*g'; w += v.  Keras' `decay`
+ * is a learning-rate schedule, lr / (1 + decay*iterations): the caller passes the scheduled rate. */
 int ugn_sgd_step(ugn_ctx*, ugn_tensor* w, const ugn_tensor* g, ugn_tensor* v,
                  const ugn_tensor* seg_off, const ugn_tensor* seg_l2, float lr, float momentum,
                  float gscale, ugn_tensor* reg_out, const ugn_tensor* lr_dev,

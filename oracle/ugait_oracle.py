@@ -327,14 +327,30 @@ def loss_and_grads(inputs, flags, labels, P, cfg, drop_masks=None, code_drop_mas
     return {k: (v.detach() if torch.is_tensor(v) else v) for k, v in res.items()}, grads
 
 
-def adam_step(P, G, M, V, t, lr=1e-4, b1=0.9, b2=0.999, eps=1e-7):
+def adam_step(P, G, M, V, t, lr=1e-4, b1=0.9, b2=0.999, eps=1e-7, Vhat=None, weight_decay=0.0):
     """Keras Adam (mains/mj_trainUWYHGaitNet_DataGen_3mods.py:242): t is the 1-based step.
-    lr_t = lr*sqrt(1-b2^t)/(1-b1^t); w -= lr_t*m/(sqrt(v)+eps)."""
+    lr_t = lr*sqrt(1-b2^t)/(1-b1^t); w -= lr_t*m/(sqrt(v)+eps).
+    Vhat (dict) -> optimizers.Adam(amsgrad=True) (mains/mj_trainUWYHGaitNet_DataGen_CasiaB.py:234): the denominator
+    uses vhat = max(vhat, v).  weight_decay -> tfa.optimizers.AdamW (:236): decoupled var -= weight_decay * var on the
+    pre-update weights, not scaled by the learning rate, then the Adam update."""
     lr_t = lr * math.sqrt(1.0 - b2 ** t) / (1.0 - b1 ** t)
     for k in P:
         M[k].mul_(b1).add_(G[k], alpha=1 - b1)
         V[k].mul_(b2).addcmul_(G[k], G[k], value=1 - b2)
-        P[k].sub_(lr_t * M[k] / (V[k].sqrt() + eps))
+        den = V[k]
+        if Vhat is not None:
+            Vhat[k] = torch.maximum(Vhat[k], V[k])
+            den = Vhat[k]
+        P[k].sub_(weight_decay * P[k] + lr_t * M[k] / (den.sqrt() + eps))
+
+
+def sgd_step(P, G, V, t, lr=1e-3, momentum=0.9, decay=0.0):
+    """Keras SGD(lr, momentum, decay) (mains/mj_trainUWYHGaitNet_DataGen_CasiaB.py:232): t is the 1-based step;
+    lr_t = lr / (1 + decay * (t - 1)); v = momentum*v - lr_t*g; w += v."""
+    lr_t = lr / (1.0 + decay * (t - 1))
+    for k in P:
+        V[k].mul_(momentum).sub_(G[k], alpha=lr_t)
+        P[k].add_(V[k])
 
 
 # --------------------------------------------------------------------------------------

@@ -205,16 +205,28 @@ def test_f16mix_update_matches_f16x3():
         assert float((cw - ref).abs().max()) <= 2e-6 * float(ref.abs().max()), name
 
 
-def test_train_steps_adam_parity_fp32():
+@pytest.mark.parametrize("opt", ["adam", "amsgrad", "adamw", "sgd"])
+def test_train_steps_optimizer_parity_fp32(opt):
+    """Adam and the alternatives the mains select (mains/mj_trainUWYHGaitNet_DataGen_CasiaB.py:228-236):
+    SGD(momentum 0.9, decay 1e-5 -- a larger decay here so that the schedule matters in 3 steps), AMSGrad, tfa AdamW."""
+    from ugaitnet_b200.net import UGaitEngine
     oc, eng, P, xs, fl, lab, masks, cmask = setup("3mod_signmax")
+    if opt != "adam":
+        eng = UGaitEngine(to_engine_cfg(oc), math_mode="fp32", lr=1e-3, optimizer=opt, momentum=0.9, lr_decay=0.5,
+                          decoupled_weight_decay=1e-2)
+        eng.load_params(P)
     P = {k: v.clone() for k, v in P.items()}
     M = {k: torch.zeros_like(v) for k, v in P.items()}
     V = {k: torch.zeros_like(v) for k, v in P.items()}
+    Vh = {k: torch.zeros_like(v) for k, v in P.items()} if opt == "amsgrad" else None
     ins = engine_inputs(xs, fl, lab, masks, cmask)
     P0 = {k: v.clone() for k, v in P.items()}
     for t in range(1, 4):
         res, G = oracle_step(oc, P, xs, fl, lab, masks, cmask)
-        O.adam_step(P, G, M, V, t, lr=1e-3)
+        if opt == "sgd":
+            O.sgd_step(P, G, V, t, lr=1e-3, momentum=0.9, decay=0.5)
+        else:
+            O.adam_step(P, G, M, V, t, lr=1e-3, Vhat=Vh, weight_decay=1e-2 if opt == "adamw" else 0.0)
         out = eng.train_step(*ins)
         total = oc.wver * float(out["triplet"]) + oc.wid * float(out["ce"]) + float(out["reg"])
         assert total == pytest.approx(float(res["loss"]), rel=1e-4)

@@ -67,6 +67,8 @@ _PROTOS = {
     "ugn_triplet_all": (c_int, [c_void_p, _T, _T, c_float, c_float, _T, _T, _T, c_void_p]),
     "ugn_adam_step": (c_int, [c_void_p, _T, _T, _T, _T, _T, _T, c_float, c_float, c_float, c_float,
                               c_float, _T, _T, _T, c_int, c_int, c_void_p]),
+    "ugn_adam_step_ex": (c_int, [c_void_p, _T, _T, _T, _T, _T, c_float, _T, _T, c_float, c_float, c_float, c_float,
+                                 c_float, _T, _T, _T, c_int, c_int, c_void_p]),
     "ugn_sgd_step": (c_int, [c_void_p, _T, _T, _T, _T, _T, c_float, c_float, c_float, _T, _T, _T, c_int, c_int,
                              c_void_p]),
     "ugn_knn_workspace_bytes": (c_int64, [c_int64, c_int64, c_int64, c_int]),

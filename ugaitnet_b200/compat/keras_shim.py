@@ -21,9 +21,14 @@ class optimizers:  # noqa: N801  (mirrors `from tensorflow.keras import optimize
 
     @staticmethod
     def Adam(learning_rate=0.001, beta_1=0.9, beta_2=0.999, epsilon=1e-7, amsgrad=False, lr=None, **kw):
-        if amsgrad:
-            raise NotImplementedError("AMSGrad is outside the B200 hot path (reference default is plain Adam)")
-        return _Optimizer("adam", lr if lr is not None else learning_rate, beta1=beta_1, beta2=beta_2, eps=epsilon)
+        return _Optimizer("amsgrad" if amsgrad else "adam", lr if lr is not None else learning_rate, beta1=beta_1,
+                          beta2=beta_2, eps=epsilon)
+
+    @staticmethod
+    def AdamW(weight_decay=0.0, learning_rate=0.001, beta_1=0.9, beta_2=0.999, epsilon=1e-7, lr=None, **kw):
+        """tfa.optimizers.AdamW(learning_rate=lr, weight_decay=wd) (mains/mj_trainUWYHGaitNet_DataGen_CasiaB.py:236)."""
+        return _Optimizer("adamw", lr if lr is not None else learning_rate, beta1=beta_1, beta2=beta_2, eps=epsilon,
+                          weight_decay=weight_decay)
 
 
 class _Merge:

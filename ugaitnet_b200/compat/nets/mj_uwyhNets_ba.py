@@ -97,6 +97,7 @@ class UGaitModel:
         self.engine = engine_cls(cfg, math_mode=MATH_MODE, optimizer=getattr(opt, "name", "sgd"),
                                   lr=getattr(opt, "lr", 0.001), momentum=kw.get("momentum", 0.9),
                                   beta1=kw.get("beta1", 0.9), beta2=kw.get("beta2", 0.999), eps=kw.get("eps", 1e-7),
+                                  lr_decay=kw.get("decay", 0.0), decoupled_weight_decay=kw.get("weight_decay", 0.0),
                                   use_graph=os.environ.get("UGN_GRAPH", "1") == "1")
         self.loss, self.loss_weights = losses, loss_weights
         self.optimizer = _OptimizerView(self)

@@ -131,7 +131,7 @@ int ew_fuse_bwd(ugn_ctx*, const FusePtrs&, int, int, int, const float*, const fl
 int ew_softmax_ce(ugn_ctx*, const float*, const int*, float*, float*, int, int, float, float, cudaStream_t);
 int ew_optim(ugn_ctx*, int, float*, const float*, float*, float*, const long long*, const float*, int,
              long long, float, float, float, float, float, float*, const float*, const long long*, int, int,
-             cudaStream_t);
+             float*, float, cudaStream_t);
 int simt_conv_fwd(ugn_ctx*, const ConvGeom&, const float*, const float*, const float*, float*, uint8_t*,
                   int, float, int, cudaStream_t);
 int simt_conv_dgrad(ugn_ctx*, const ConvGeom&, const float*, const float*, float*, cudaStream_t);
@@ -549,8 +549,10 @@ extern "C" int ugn_softmax_ce_ls(ugn_ctx* ctx, const ugn_tensor* logits, const u
 static int optim_common(ugn_ctx* ctx, int opt, ugn_tensor* w, const ugn_tensor* g, ugn_tensor* m, ugn_tensor* v,
                         const ugn_tensor* seg_off, const ugn_tensor* seg_l2, float lr, float b1, float b2, float eps,
                         float gscale, ugn_tensor* reg_out, const ugn_tensor* lr_dev, const ugn_tensor* pack_table,
-                        int pack_planes, int pack_f16, void* stream) {
+                        int pack_planes, int pack_f16, void* stream, ugn_tensor* vhat = nullptr, float wd = 0.f) {
   UGN_CHECK(ctx && w && g && v && seg_off && seg_l2, "optimizer: null argument");
+  if (vhat) { UGN_TENSOR(vhat, DT_F32, 1, 1); UGN_CHECK(vhat->shape[0] == w->shape[0], "optimizer: vhat arena length mismatch"); }
+  UGN_CHECK(wd >= 0.f && wd < 1.f, "optimizer: decoupled weight decay must be in [0,1)");
   if (lr_dev) UGN_TENSOR(lr_dev, DT_F32, 1, 1);
   UGN_TENSOR(w, DT_F32, 1, 1);
   UGN_TENSOR(g, DT_F32, 1, 1);
@@ -572,7 +574,8 @@ static int optim_common(ugn_ctx* ctx, int opt, ugn_tensor* w, const ugn_tensor* 
   return ew_optim(ctx, opt, ugn_ptr<float>(w), ugn_ptr<float>(g), m ? ugn_ptr<float>(m) : nullptr, ugn_ptr<float>(v),
                   ugn_ptr<long long>(seg_off), ugn_ptr<float>(seg_l2), S, n, lr, b1, b2, eps, gscale,
                   reg_out ? ugn_ptr<float>(reg_out) : nullptr, lr_dev ? ugn_ptr<float>(lr_dev) : nullptr,
-                  pack_table ? ugn_ptr<long long>(pack_table) : nullptr, pack_planes, pack_f16, (cudaStream_t)stream);
+                  pack_table ? ugn_ptr<long long>(pack_table) : nullptr, pack_planes, pack_f16,
+                  vhat ? ugn_ptr<float>(vhat) : nullptr, wd, (cudaStream_t)stream);
 }
 
 extern "C" int ugn_adam_step(ugn_ctx* ctx, ugn_tensor* w, const ugn_tensor* g, ugn_tensor* m, ugn_tensor* v,
@@ -581,6 +584,14 @@ extern "C" int ugn_adam_step(ugn_ctx* ctx, ugn_tensor* w, const ugn_tensor* g, u
                              const ugn_tensor* pack_table, int pack_planes, int pack_f16, void* stream) {
   return optim_common(ctx, 0, w, g, m, v, seg_off, seg_l2, lr_t, beta1, beta2, eps, gscale, reg_out, lr_dev, pack_table,
                       pack_planes, pack_f16, stream);
+}
+extern "C" int ugn_adam_step_ex(ugn_ctx* ctx, ugn_tensor* w, const ugn_tensor* g, ugn_tensor* m, ugn_tensor* v,
+                                ugn_tensor* vhat, float weight_decay, const ugn_tensor* seg_off, const ugn_tensor* seg_l2,
+                                float lr_t, float beta1, float beta2, float eps, float gscale, ugn_tensor* reg_out,
+                                const ugn_tensor* lr_dev, const ugn_tensor* pack_table, int pack_planes, int pack_f16,
+                                void* stream) {
+  return optim_common(ctx, 0, w, g, m, v, seg_off, seg_l2, lr_t, beta1, beta2, eps, gscale, reg_out, lr_dev, pack_table,
+                      pack_planes, pack_f16, stream, vhat, weight_decay);
 }
 extern "C" int ugn_sgd_step(ugn_ctx* ctx, ugn_tensor* w, const ugn_tensor* g, ugn_tensor* v, const ugn_tensor* seg_off,
                             const ugn_tensor* seg_l2, float lr, float momentum, float gscale, ugn_tensor* reg_out,

@@ -586,7 +586,8 @@ __global__ void __launch_bounds__(256) optim_kernel(float* __restrict__ w, const
                                                     float lr, float b1, float b2, float eps, float gscale,
                                                     float* __restrict__ reg_out,
                                                     const float* __restrict__ lr_dev,
-                                                    const long long* __restrict__ pack, int packP, int f16) {
+                                                    const long long* __restrict__ pack, int packP, int f16,
+                                                    float* __restrict__ vhat, float wd) {
   float reg = 0.f;
   if (lr_dev) lr = *lr_dev;  // CUDA-graph friendly: the step-dependent rate lives in device memory
   for (long long q = blockIdx.x * (long long)blockDim.x + threadIdx.x; q < n4;
@@ -600,16 +601,25 @@ __global__ void __launch_bounds__(256) optim_kernel(float* __restrict__ w, const
       float4 mv = reinterpret_cast<float4*>(m)[q];
       float4 vv = reinterpret_cast<float4*>(v)[q];
       float mm[4] = {mv.x, mv.y, mv.z, mv.w}, v2[4] = {vv.x, vv.y, vv.z, vv.w};
+      float vh[4] = {0.f, 0.f, 0.f, 0.f};
+      if (vhat) {      // AMSGrad (optimizers.Adam(amsgrad=True)): the denominator uses the running maximum of v
+        float4 hv = reinterpret_cast<float4*>(vhat)[q];
+        vh[0] = hv.x; vh[1] = hv.y; vh[2] = hv.z; vh[3] = hv.w;
+      }
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
         reg += c * ww[i] * ww[i];
         float gr = gg[i] * gscale + 2.f * c * ww[i];
         mm[i] = b1 * mm[i] + (1.f - b1) * gr;
         v2[i] = b2 * v2[i] + (1.f - b2) * gr * gr;
-        ww[i] -= lr * mm[i] / (sqrtf(v2[i]) + eps);
+        float den = v2[i];
+        if (vhat) { vh[i] = fmaxf(vh[i], v2[i]); den = vh[i]; }
+        // tfa.optimizers.AdamW: decoupled decay var -= wd * var (not scaled by the learning rate), then Adam
+        ww[i] = ww[i] - wd * ww[i] - lr * mm[i] / (sqrtf(den) + eps);
       }
       reinterpret_cast<float4*>(m)[q] = make_float4(mm[0], mm[1], mm[2], mm[3]);
       reinterpret_cast<float4*>(v)[q] = make_float4(v2[0], v2[1], v2[2], v2[3]);
+      if (vhat) reinterpret_cast<float4*>(vhat)[q] = make_float4(vh[0], vh[1], vh[2], vh[3]);
     } else {
       float4 vv = reinterpret_cast<float4*>(v)[q];
       float v2[4] = {vv.x, vv.y, vv.z, vv.w};
@@ -658,14 +668,14 @@ __global__ void __launch_bounds__(256) optim_kernel(float* __restrict__ w, const
 int ew_optim(ugn_ctx* ctx, int opt, float* w, const float* g, float* m, float* v,
              const long long* off, const float* l2, int S, long long n, float lr, float b1,
              float b2, float eps, float gscale, float* reg_out, const float* lr_dev, const long long* pack,
-             int packP, int f16, cudaStream_t st) {
+             int packP, int f16, float* vhat, float wd, cudaStream_t st) {
   UGN_CHECK(n % 4 == 0, "optimizer arena length must be a multiple of 4 (got %lld)", n);
   if (reg_out) UGN_CUDA(cudaMemsetAsync(reg_out, 0, sizeof(float), st));
   long long n4 = n / 4;
   int grid = (int)std::min<long long>((n4 + 255) / 256, (long long)ctx->sm_count * 8);
   grid = std::max(grid, 1);
-  if (opt == 0) optim_kernel<0><<<grid, 256, 0, st>>>(w, g, m, v, off, l2, S, n4, lr, b1, b2, eps, gscale, reg_out, lr_dev, pack, packP, f16);
-  else optim_kernel<1><<<grid, 256, 0, st>>>(w, g, m, v, off, l2, S, n4, lr, b1, b2, eps, gscale, reg_out, lr_dev, pack, packP, f16);
+  if (opt == 0) optim_kernel<0><<<grid, 256, 0, st>>>(w, g, m, v, off, l2, S, n4, lr, b1, b2, eps, gscale, reg_out, lr_dev, pack, packP, f16, vhat, wd);
+  else optim_kernel<1><<<grid, 256, 0, st>>>(w, g, m, v, off, l2, S, n4, lr, b1, b2, eps, gscale, reg_out, lr_dev, pack, packP, f16, nullptr, 0.f);
   UGN_LAUNCHED(ctx);
   return UGN_OK;
 }

@@ -48,7 +48,7 @@ class UGaitEngine:
     def __init__(self, cfg: NetConfig, device: Optional[int] = None, math_mode: str = "fp32",
                  seed: int = 232323, optimizer: str = "adam", lr: float = 1e-4, momentum: float = 0.9,
                  beta1: float = 0.9, beta2: float = 0.999, eps: float = 1e-7, process_group=None,
-                 use_graph: bool = False):
+                 use_graph: bool = False, lr_decay: float = 0.0, decoupled_weight_decay: float = 0.0):
         if not torch.cuda.is_available():
             raise RuntimeError("ugaitnet_b200 needs a CUDA device (no CPU fallback)")
         assert math_mode in MATH_MODES
@@ -61,6 +61,8 @@ class UGaitEngine:
         self.pad = 32 if self.P else 1
         self.optimizer, self.lr, self.momentum = optimizer.lower(), float(lr), momentum
         self.beta1, self.beta2, self.eps = beta1, beta2, eps
+        # optimizers.SGD(decay=...) -> lr / (1 + decay * iterations); tfa AdamW(weight_decay=...) -> decoupled decay
+        self.lr_decay, self.decoupled_wd = float(lr_decay), float(decoupled_weight_decay)
         self.pg = process_group
         self.world = torch.distributed.get_world_size(process_group) if process_group is not None else 1
         self.use_graph = use_graph
@@ -533,10 +535,15 @@ class UGaitEngine:
         h, st, R = self.ctx.h, stream_ptr(), self.R
         pk = R["pack_table"].ptr if self.pack_table is not None else None
         f16 = int(self.dt16 is torch.float16)
-        if self.optimizer == "adam":
-            check(lib.ugn_adam_step(h, R["w"].ptr, R["g"].ptr, R["m"].ptr, R["v"].ptr, R["seg_off"].ptr,
-                                    R["seg_l2"].ptr, 0.0, self.beta1, self.beta2, self.eps, gscale,
-                                    R["reg_out"].ptr, R["lr_dev"].ptr, pk, max(self.P, 1), f16, st))
+        if self.optimizer in ("adam", "amsgrad", "adamw"):
+            if self.optimizer == "amsgrad" and "vhat" not in R:
+                self.vhat = torch.zeros_like(self.v)
+                R["vhat"] = TRef(self.vhat)
+            check(lib.ugn_adam_step_ex(h, R["w"].ptr, R["g"].ptr, R["m"].ptr, R["v"].ptr,
+                                       R["vhat"].ptr if self.optimizer == "amsgrad" else None,
+                                       self.decoupled_wd if self.optimizer == "adamw" else 0.0, R["seg_off"].ptr,
+                                       R["seg_l2"].ptr, 0.0, self.beta1, self.beta2, self.eps, gscale,
+                                       R["reg_out"].ptr, R["lr_dev"].ptr, pk, max(self.P, 1), f16, st))
         elif self.optimizer == "sgd":
             check(lib.ugn_sgd_step(h, R["w"].ptr, R["g"].ptr, R["v"].ptr, R["seg_off"].ptr, R["seg_l2"].ptr, 0.0,
                                    self.momentum, gscale, R["reg_out"].ptr, R["lr_dev"].ptr, pk, max(self.P, 1),
@@ -561,10 +568,10 @@ class UGaitEngine:
 
     def _next_lr(self):
         self.t += 1
-        if self.optimizer == "adam":
+        if self.optimizer in ("adam", "amsgrad", "adamw"):
             lr_t = self.lr * math.sqrt(1.0 - self.beta2 ** self.t) / (1.0 - self.beta1 ** self.t)
         else:
-            lr_t = self.lr
+            lr_t = self.lr / (1.0 + self.lr_decay * (self.t - 1))      # Keras: iterations counts finished steps
         self._lr_host[0] = lr_t
         self.lr_dev.copy_(self._lr_host, non_blocking=True)
 
