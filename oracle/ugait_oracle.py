@@ -60,6 +60,8 @@ class NetConfig:
     #                           no fusion, NO l2_normalize on the signature.
     label_smoothing: float = 0.0   # smoothlabels: tf.losses.CategoricalCrossentropy(label_smoothing) (:1252-1262)
     normbfmerge: bool = False      # per-branch l2_normalize before the gate (:1167-1168)
+    aux_losses: bool = False       # classprob_{of,gray,depth} heads on the gated branch outputs (:1222-1251)
+    waux: float = 1.0              # loss_weights[-1] (:1264-1268)
 
     @property
     def nmods(self):
@@ -82,6 +84,7 @@ class NetConfig:
 
 
 BRANCH_NAMES = ("ofBranch", "grayBranch", "depthBranch")
+AUX_NAMES = ("classprob_of", "classprob_gray", "classprob_depth")
 
 
 def init_params(cfg: NetConfig, seed: int = 232323, dtype=torch.float32) -> Dict[str, torch.Tensor]:
@@ -114,6 +117,10 @@ def init_params(cfg: NetConfig, seed: int = 232323, dtype=torch.float32) -> Dict
     if cfg.nclasses > 0:
         P["classprob/w"] = uni((cfg.nclasses, feat), math.sqrt(6.0 / (feat + cfg.nclasses)))
         P["classprob/b"] = torch.zeros(cfg.nclasses, dtype=dtype)
+    if cfg.nclasses > 0 and getattr(cfg, "aux_losses", False):
+        for m in range(cfg.nmods):
+            P[f"{AUX_NAMES[m]}/w"] = uni((cfg.nclasses, cfg.nd), math.sqrt(6.0 / (cfg.nd + cfg.nclasses)))
+            P[f"{AUX_NAMES[m]}/b"] = torch.zeros(cfg.nclasses, dtype=dtype)
     return P
 
 
@@ -266,6 +273,8 @@ def model_forward(inputs, flags, P, cfg: NetConfig, drop_masks=None, code_drop_m
             if cfg.normbfmerge:
                 b = l2_normalize(b, 1)                                  # "nrmbfl2*" Lambda (:1167-1168)
             gated.append(b * flags[m])                                  # :51-54
+            if cfg.aux_losses and cfg.nclasses > 0:                     # classprob_{of,gray,depth} (:1222-1225)
+                outs[f"aux_logits{m}"] = F.linear(gated[-1], P[f"{AUX_NAMES[m]}/w"], P[f"{AUX_NAMES[m]}/b"])
     if cfg.single:
         sig = gated[0]                                                  # :904 (no normalise)
     else:
@@ -304,6 +313,14 @@ def total_loss(inputs, flags, labels, P, cfg: NetConfig, drop_masks=None, code_d
             ce, _ = softmax_ce(outs["logits"], onehot * (1.0 - cfg.label_smoothing) + cfg.label_smoothing / cfg.nclasses)
         res["ce"], res["acc"] = ce, acc
         loss = loss + cfg.wid * ce
+        if cfg.aux_losses:
+            # one more CE per head, all weighted by loss_weights[-1] (:1245-1251, :1264-1268)
+            res["aux_ce"] = []
+            for m in range(cfg.nmods):
+                tgt = onehot * (1.0 - cfg.label_smoothing) + cfg.label_smoothing / cfg.nclasses
+                ce_m, _ = softmax_ce(outs[f"aux_logits{m}"], tgt)
+                res["aux_ce"].append(ce_m)
+                loss = loss + cfg.waux * ce_m
     reg = torch.zeros((), dtype=trip.dtype)
     for m in range(cfg.nmods):
         bn = BRANCH_NAMES[m]
@@ -324,7 +341,8 @@ def loss_and_grads(inputs, flags, labels, P, cfg, drop_masks=None, code_drop_mas
     res = total_loss(inputs, flags, labels, Pg, cfg, drop_masks, code_drop_mask)
     res["loss"].backward()
     grads = {k: (v.grad if v.grad is not None else torch.zeros_like(v)) for k, v in Pg.items()}
-    return {k: (v.detach() if torch.is_tensor(v) else v) for k, v in res.items()}, grads
+    det = lambda v: v.detach() if torch.is_tensor(v) else ([x.detach() for x in v] if isinstance(v, list) else v)
+    return {k: det(v) for k, v in res.items()}, grads
 
 
 def adam_step(P, G, M, V, t, lr=1e-4, b1=0.9, b2=0.999, eps=1e-7, Vhat=None, weight_decay=0.0):

@@ -26,6 +26,14 @@ def make_case(name):
         oc = O.NetConfig(in_channels=(6, 4, 4), filters_numbers=(8, 8, 16, 16), nd=32, nclasses=10,
                          merge=O.MERGE_SIGNMAX, wver=1.0, wid=0.5, label_smoothing=0.1, normbfmerge=True)
         return oc, dict(base_rows=6, expand=4, kinds=("of", "gray", "depth")), None
+    if name == "3mod_aux":           # aux_losses: classprob_{of,gray,depth} heads, with normbfmerge underneath
+        oc = O.NetConfig(in_channels=(6, 4, 4), filters_numbers=(8, 8, 16, 16), nd=32, nclasses=10,
+                         merge=O.MERGE_SIGNMAX, wver=1.0, wid=0.3, aux_losses=True, waux=0.3, normbfmerge=True)
+        return oc, dict(base_rows=6, expand=4, kinds=("of", "gray", "depth")), None
+    if name == "2mod_aux":
+        oc = O.NetConfig(in_channels=(6, 4), filters_numbers=(8, 8, 16, 16), nd=32, nclasses=7, merge=O.MERGE_MAX,
+                         wver=1.0, wid=1.0, aux_losses=True, waux=1.0, label_smoothing=0.05)
+        return oc, dict(base_rows=8, expand=2, kinds=("of", "gray")), None
     if name == "2mod_max_leaky_code":  # FC1 "code" + LeakyReLU + dropout masks
         oc = O.NetConfig(in_channels=(6, 4), filters_numbers=(8, 8, 16, 16), nd=32, nc=8, nclasses=7,
                          merge=O.MERGE_MAX, act=O.ACT_LEAKY, wver=1.0, wid=1.0)
@@ -50,7 +58,8 @@ def to_engine_cfg(oc, dropout=0.0):
                      filters_size=tuple(oc.filters_size), nd=oc.nd, nc=oc.nc, nclasses=oc.nclasses,
                      weight_decay=oc.weight_decay, merge=oc.merge, act=oc.act, alpha=oc.alpha, margin=oc.margin,
                      wver=oc.wver, wid=oc.wid, hw=oc.hw, dropout=dropout, single=oc.single,
-                     label_smoothing=oc.label_smoothing, normbfmerge=oc.normbfmerge)
+                     label_smoothing=oc.label_smoothing, normbfmerge=oc.normbfmerge, aux_losses=oc.aux_losses,
+                     waux=oc.waux)
 
 
 def setup(name, math_mode="fp32", seed=11):
@@ -95,7 +104,7 @@ def reg_grad(oc, name, w):
 
 
 @pytest.mark.parametrize("name", ["3mod_signmax", "2mod_max_leaky_code", "3mod_avg", "1mod_gray", "real_shapes",
-                                  "3mod_norm_smooth"])
+                                  "3mod_norm_smooth", "3mod_aux", "2mod_aux"])
 def test_step_parity_fp32(name):
     oc, eng, P, xs, fl, lab, masks, cmask = setup(name)
     res, G = oracle_step(oc, P, xs, fl, lab, masks, cmask)
@@ -106,6 +115,8 @@ def test_step_parity_fp32(name):
     assert float(out["count"]) == float(res["count"].sum())
     assert float(out["ce"]) == pytest.approx(float(res["ce"]), rel=tol)
     assert float(out["acc"]) == pytest.approx(float(res["acc"]), abs=1e-6)
+    for m, v in enumerate(res.get("aux_ce", [])):
+        assert float(out["aux_ce"][m]) == pytest.approx(float(v), rel=tol)
     cos = torch.nn.functional.cosine_similarity(out["signature"].double().cpu(), res["signature"], dim=1)
     assert float(cos.min()) >= 0.99999
     assert rel(out["signature"], res["signature"]) < tol
@@ -299,13 +310,16 @@ def test_device_side_expansion_equals_host_expanded_batch():
             assert rel(outs[1][2][k], outs[0][2][k].double().cpu()) < 1e-5, k
 
 
-def test_segmented_graph_capture_equals_eager():
+@pytest.mark.parametrize("dp_reduce", ["single", "bucketed"])
+def test_segmented_graph_capture_equals_eager(dp_reduce):
     """The data-parallel step is replayed as CUDA-graph SEGMENTS cut at the all-reduce points (NCCL stays
-    outside the graphs).  Forced on one GPU here: the segmented replay must reproduce the eager step."""
+    outside the graphs): "single" = [forward + backward] | one all-reduce | [optimiser]; "bucketed" = a cut per
+    gradient bucket.  Forced on one GPU here: the segmented replay must reproduce the eager step."""
     from ugaitnet_b200.net import UGaitEngine
     oc, eng, P, xs, fl, lab, masks, cmask = setup("3mod_signmax")
     eng_s = UGaitEngine(to_engine_cfg(oc), math_mode="fp32", lr=1e-3, use_graph=True)
     eng_s.force_segments = True
+    eng_s.dp_reduce = dp_reduce
     eng_s.load_params(P)
     ins = engine_inputs(xs, fl, lab, masks, cmask)
     for _ in range(3):
@@ -314,7 +328,8 @@ def test_segmented_graph_capture_equals_eager():
         assert float(a["triplet"]) == pytest.approx(float(b["triplet"]), rel=1e-5)
         assert float(a["ce"]) == pytest.approx(float(b["ce"]), rel=1e-5)
     gr = next(iter(eng_s._graphs.values()))
-    assert isinstance(gr, list) and len(gr) == 1 + 2 * oc.nmods + 1      # heads | (fc, conv) per branch | optim
+    # bucketed: heads | (fc, conv) per branch | optim
+    assert isinstance(gr, list) and len(gr) == (2 if dp_reduce == "single" else 1 + 2 * oc.nmods + 1)
     Wa, Wb = eng.export_params(), eng_s.export_params()
     for k in Wa:
         assert rel(Wb[k], Wa[k].double().cpu()) < 1e-5, k

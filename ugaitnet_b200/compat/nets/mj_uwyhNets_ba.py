@@ -10,10 +10,11 @@ step runs on the B200 engine (ugaitnet_b200.net.UGaitEngine).
 branch type (build_gaitset_branch :420-484) on ugaitnet_b200.gaitset.GaitSetEngine: inputs
 [B,25,60,60,c], signature [62,B,256], descriptor layer "flatten" (typecode 3).
 
-``smoothlabels`` (label-smoothed cross-entropy, :1252-1262) and ``normbfmerge`` (per-branch l2_normalize
-before the gate, :1167-1168) are implemented.  Builder arguments that select graphs outside the hot path
-raise NotImplementedError: use3D, aux_losses, postriplet == 2, init_branches / initnet weight surgery from
-Keras .hdf5 files, tfa TripletHardLoss (compile_hard).
+``smoothlabels`` (label-smoothed cross-entropy, :1252-1262), ``normbfmerge`` (per-branch l2_normalize before
+the gate, :1167-1168) and ``aux_losses`` (classprob_{of,gray,depth} heads on the gated branch outputs,
+:1222-1251; stacked-CNN branches) are implemented.  Builder arguments that select graphs outside the hot path
+raise NotImplementedError: use3D, postriplet == 2, init_branches / initnet weight surgery from Keras .hdf5
+files, tfa TripletHardLoss (compile_hard), aux_losses together with gaitset.
 """
 from __future__ import annotations
 
@@ -120,6 +121,9 @@ class UGaitModel:
             if self.gaitset:
                 names.append(_LayerProxy(self, "flatten", units=62 * (cfg.nc or cfg.nd)))     # typecode 3 (:1213)
             names.append(_LayerProxy(self, "classprob", units=cfg.nclasses))
+            if getattr(cfg, "aux_losses", False):
+                names += [_LayerProxy(self, n, units=cfg.nclasses) for n in
+                          ("classprob_of", "classprob_gray", "classprob_depth")[:cfg.nmods]]
         self.layers = names
         self.input = [_Tag(self, n) for n in ("ofinput1", "ofuse1", "grayinput1", "grayuse1", "depthinput1",
                                               "depthuse1")[:2 * cfg.nmods]] if multimodal else _Tag(self, "ofinput1")
@@ -183,6 +187,10 @@ class UGaitModel:
             logs[prefix + "signature_loss"], logs[prefix + "classprob_loss"] = trip, ce
             logs[prefix + "classprob_acc"] = float(out["acc"])
             total += cfg.wid * ce
+            for m, v in enumerate(out.get("aux_ce", [])):           # classprob_{of,gray,depth} heads (:1222-1251)
+                name = ("classprob_of", "classprob_gray", "classprob_depth")[m]
+                logs[prefix + name + "_loss"], logs[prefix + name + "_acc"] = float(v), float(out["aux_acc"][m])
+                total += cfg.waux * float(v)
         if "reg" in out:
             total += float(out["reg"])
         logs[prefix + "loss"] = total
@@ -306,7 +314,7 @@ class UGaitModel:
 
 def _cfg_from_args(input_shapes, number_convolutional_layers, filters_size, filters_numbers, ndense_units,
                    weight_decay, dropout, margin, nclasses, loss_weights, fMerge, fActivation, alpha, single,
-                   smoothlabels=0, normbfmerge=False):
+                   smoothlabels=0, normbfmerge=False, aux_losses=False):
     fs = [k[0] if isinstance(k, (tuple, list)) else int(k) for k in filters_size][:number_convolutional_layers]
     fn = list(filters_numbers if filters_numbers is not None else [64, 128, 512, 512])[:number_convolutional_layers]
     if isinstance(ndense_units, (list, tuple)):
@@ -323,7 +331,9 @@ def _cfg_from_args(input_shapes, number_convolutional_layers, filters_size, filt
                      act=ACT_RELU if fActivation == "relu" else ACT_LEAKY, alpha=float(alpha), margin=float(margin),
                      wver=float(lw[0]) if nclasses > 0 else 1.0, wid=float(lw[1]) if nclasses > 0 and len(lw) > 1 else 0.0,
                      hw=int(shapes[0][1]), dropout=float(dropout) if dropout > 0.001 else 0.0, single=single,
-                     label_smoothing=float(smoothlabels), normbfmerge=bool(normbfmerge))
+                     label_smoothing=float(smoothlabels), normbfmerge=bool(normbfmerge),
+                     aux_losses=bool(aux_losses) and nclasses > 0 and not single,
+                     waux=float(lw[-1]))         # loss_weights padded with its last entry (:1264-1268)
 
 
 def _gs_cfg_from_args(input_shapes, ndense_units, dropout, margin, nclasses, loss_weights, fMerge, fActivation, alpha,
@@ -374,8 +384,8 @@ class UWYHSemiNet:
               ndense_units=512, weight_decay=1e-4, dropout=0.4, optimizer=None, margin=0.2,
               nclasses=0, loss_weights=[1.0, 1.0], use3D=False, smoothlabels=0, postriplet=1, init_branches=None,
               freeze_branches=False, aux_losses=False, fMerge=Maximum, fActivation='relu', alpha=0.3, gaitset=False):
-        _unsupported(use3D=use3D, postriplet_2=(postriplet == 2), aux_losses=aux_losses,
-                     freeze_branches=freeze_branches,
+        _unsupported(use3D=use3D, postriplet_2=(postriplet == 2), freeze_branches=freeze_branches,
+                     aux_losses_with_gaitset=(aux_losses and gaitset),
                      init_branches=bool(init_branches) and any(init_branches.values()))
         single = not isinstance(input_shapes, list)
         if gaitset:
@@ -386,7 +396,7 @@ class UWYHSemiNet:
             return UGaitModel(cfg, optimizer, losses, loss_weights if nclasses > 0 else 1.0, multimodal=True)
         cfg = _cfg_from_args(input_shapes, number_convolutional_layers, filters_size, filters_numbers, ndense_units,
                              weight_decay, dropout, margin, nclasses, loss_weights, fMerge, fActivation, alpha, single,
-                             smoothlabels=smoothlabels)
+                             smoothlabels=smoothlabels, aux_losses=aux_losses)
         losses = [triplet_loss(margin=margin), 'categorical_crossentropy'] if nclasses > 0 else triplet_loss(margin=margin)
         return UGaitModel(cfg, optimizer, losses, loss_weights if nclasses > 0 else 1.0, multimodal=not single)
 
@@ -479,7 +489,7 @@ class UWYHSemiNet3Mods(UWYHSemiNet):
               nclasses=0, loss_weights=[1.0, 1.0], use3D=False, smoothlabels=0,
               postriplet=1, init_branches=None, freeze_branches=False, aux_losses=False, fMerge=Maximum,
               normbfmerge=False, fActivation='relu', alpha=0.3, gaitset=False):
-        _unsupported(use3D=use3D, aux_losses=aux_losses, freeze_branches=freeze_branches,
+        _unsupported(use3D=use3D, aux_losses_with_gaitset=(aux_losses and gaitset), freeze_branches=freeze_branches,
                      init_branches=bool(init_branches) and any(init_branches.values()))
         if gaitset:
             cfg = _gs_cfg_from_args(input_shapes, ndense_units, dropout, margin, nclasses, loss_weights, fMerge,
@@ -488,7 +498,8 @@ class UWYHSemiNet3Mods(UWYHSemiNet):
             return UGaitModel(cfg, optimizer, losses, loss_weights if nclasses > 0 else 1.0, multimodal=True)
         cfg = _cfg_from_args(list(input_shapes), number_convolutional_layers, filters_size, filters_numbers,
                              ndense_units, weight_decay, dropout, margin, nclasses, loss_weights, fMerge, fActivation,
-                             alpha, single=False, smoothlabels=smoothlabels, normbfmerge=normbfmerge)
+                             alpha, single=False, smoothlabels=smoothlabels, normbfmerge=normbfmerge,
+                             aux_losses=aux_losses)
         losses = [triplet_loss(margin=margin), 'categorical_crossentropy'] if nclasses > 0 else triplet_loss(margin=margin)
         return UGaitModel(cfg, optimizer, losses, loss_weights if nclasses > 0 else 1.0, multimodal=True)
 

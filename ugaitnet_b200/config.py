@@ -8,6 +8,7 @@ MERGE_MAX, MERGE_AVG, MERGE_SIGNMAX = 0, 1, 2
 ACT_LINEAR, ACT_RELU, ACT_LEAKY = 0, 1, 2
 
 BRANCH_NAMES = ("ofBranch", "grayBranch", "depthBranch")
+AUX_NAMES = ("classprob_of", "classprob_gray", "classprob_depth")
 
 
 def round_up(x: int, m: int) -> int:
@@ -36,6 +37,8 @@ class NetConfig:
     single: bool = False           # 1-modality graph: no gate / fusion / l2_normalize (:900-915)
     label_smoothing: float = 0.0   # smoothlabels -> tf.losses.CategoricalCrossentropy(label_smoothing) (:1252-1262)
     normbfmerge: bool = False      # l2_normalize every branch output before its gate (:1167-1168)
+    aux_losses: bool = False       # extra Dense(nclasses, softmax) head + CE on every gated branch output (:1222-1251)
+    waux: float = 1.0              # their loss weight: loss_weights[-1] (:1264-1268)
 
     @property
     def nmods(self) -> int:

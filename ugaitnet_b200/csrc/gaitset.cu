@@ -47,7 +47,7 @@ __device__ __forceinline__ void gs_store(void* p, int mode, int f16, long long p
 // One thread = one output pixel x 32 channels; the 5x5 halo tile of the frame and the kernel live in smem.
 // ---------------------------------------------------------------------------------------------------
 template <int C>
-__global__ void __launch_bounds__(256) gs_conv1_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w,
+__global__ void __launch_bounds__(256, 2) gs_conv1_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w,
                                                            void* __restrict__ y, long long F, int H, int W, int S,
                                                            int mode, int f16, float alpha) {
   constexpr int K = 25 * C;
@@ -107,22 +107,22 @@ __global__ void __launch_bounds__(256) gs_conv1_fwd_kernel(const float* __restri
 #pragma unroll
         for (int o = 0; o < 8; ++o) d[o] = make_float4(acc[4 * o], acc[4 * o + 1], acc[4 * o + 2], acc[4 * o + 3]);
       } else {
-        uint32_t hw[16], lw[16];
+        // 8 channels (one 16-byte store per plane) at a time: keeps the live registers under the 128 that two
+        // resident blocks per SM allow
 #pragma unroll
-        for (int o = 0; o < 32; o += 2) {
-          u16 h0, l0, h1, l1;
-          ugn_split16(acc[o], f16, h0, l0);
-          ugn_split16(acc[o + 1], f16, h1, l1);
-          hw[o >> 1] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
-          lw[o >> 1] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
-        }
-        uint4* dh = reinterpret_cast<uint4*>(reinterpret_cast<u16*>(y) + o0);
+        for (int q = 0; q < 4; ++q) {
+          uint32_t hw[4], lw[4];
 #pragma unroll
-        for (int q = 0; q < 4; ++q) dh[q] = make_uint4(hw[4 * q], hw[4 * q + 1], hw[4 * q + 2], hw[4 * q + 3]);
-        if (mode == 2) {
-          uint4* dl = reinterpret_cast<uint4*>(reinterpret_cast<u16*>(y) + plane + o0);
-#pragma unroll
-          for (int q = 0; q < 4; ++q) dl[q] = make_uint4(lw[4 * q], lw[4 * q + 1], lw[4 * q + 2], lw[4 * q + 3]);
+          for (int o = 0; o < 8; o += 2) {
+            u16 h0, l0, h1, l1;
+            ugn_split16(acc[8 * q + o], f16, h0, l0);
+            ugn_split16(acc[8 * q + o + 1], f16, h1, l1);
+            hw[o >> 1] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
+            lw[o >> 1] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+          }
+          reinterpret_cast<uint4*>(reinterpret_cast<u16*>(y) + o0)[q] = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+          if (mode == 2)
+            reinterpret_cast<uint4*>(reinterpret_cast<u16*>(y) + plane + o0)[q] = make_uint4(lw[0], lw[1], lw[2], lw[3]);
         }
       }
     }
@@ -320,21 +320,18 @@ extern "C" int ugn_gs_conv1_wgrad(ugn_ctx* ctx, const ugn_tensor* x, const ugn_t
 // zero-bordered input is kept as S = 2 overlapping column halves, [N*S][H+2][W/S+2][C] (half h = padded
 // columns [h*W/S, h*W/S + W/S + 2)), and its valid-convolution output as [N*S][H][W/S][C].  pad / crop
 // convert between split and plain images: the split factor is the ratio of the leading dimensions.
-__global__ void __launch_bounds__(256) gs_pad_kernel(const uint4* __restrict__ src, uint4* __restrict__ dst, int P,
-                                                     long long Ns, int H, int Ws, int rowv, int p, int S) {
-  // src [P][Ns = N*S][H][Ws][rowv] -> dst [P][N][H+2p][Ws*S+2p][rowv]
+__global__ void __launch_bounds__(128) gs_pad_kernel(const uint4* __restrict__ src, uint4* __restrict__ dst, int H, int Ws,
+                                                     int rowv, int p, int S) {
+  // src [P][Ns = N*S][H][Ws][rowv] -> dst [P][N][H+2p][Ws*S+2p][rowv]; one block = one source pixel row
   const int Hd = H + 2 * p, Wd = Ws * S + 2 * p;
-  const long long per_plane = Ns * H * Ws * rowv, total = per_plane * P;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    int v = (int)(i % rowv);
-    long long pix = i / rowv;
-    int xx = (int)(pix % Ws);
-    int yy = (int)((pix / Ws) % H);
-    long long ns = pix / ((long long)Ws * H);         // plane-major split-image index (pl*Ns + n*S + h)
-    long long n = ns / S;
-    int h = (int)(ns - n * S);
-    dst[((n * Hd + yy + p) * Wd + h * Ws + xx + p) * rowv + v] = src[i];
-  }
+  const long long row = blockIdx.x;                 // (plane-major split image) * H + y
+  const long long ns = row / H;
+  const int yy = (int)(row - ns * H);
+  const long long n = ns / S;
+  const int h = (int)(ns - n * S);
+  const uint4* sp = src + row * Ws * rowv;
+  uint4* dp = dst + ((n * Hd + yy + p) * Wd + h * Ws + p) * rowv;
+  for (int i = threadIdx.x; i < Ws * rowv; i += blockDim.x) dp[i] = sp[i];
 }
 
 extern "C" int ugn_pad_hw(ugn_ctx* ctx, const ugn_tensor* src, ugn_tensor* dst, void* stream) {
@@ -354,32 +351,32 @@ extern "C" int ugn_pad_hw(ugn_ctx* ctx, const ugn_tensor* src, ugn_tensor* dst, 
   UGN_CHECK((a[3] * es) % 16 == 0, "pad_hw: channel row must be a multiple of 16 bytes");
   if (ugn_numel(src) == 0) return UGN_OK;
   int rowv = (int)(a[3] * es / 16), P = ms == 0 ? 1 : ms;
-  long long total = (long long)P * a[0] * a[1] * a[2] * rowv;
-  gs_pad_kernel<<<gs_grid(ctx, total, 256), 256, 0, (cudaStream_t)stream>>>(ugn_ptr<uint4>(src), ugn_ptr<uint4>(dst), P, a[0],
-                                                                          (int)a[1], (int)a[2], rowv, p, S);
+  long long rows = (long long)P * a[0] * a[1];
+  UGN_CHECK(rows < (1LL << 31), "pad_hw: too many rows");
+  gs_pad_kernel<<<(unsigned)rows, 128, 0, (cudaStream_t)stream>>>(ugn_ptr<uint4>(src), ugn_ptr<uint4>(dst), (int)a[1], (int)a[2],
+                                                                rowv, p, S);
   UGN_LAUNCHED(ctx);
   return UGN_OK;
 }
 
-__global__ void __launch_bounds__(256) gs_crop_kernel(const float4* __restrict__ src, float4* __restrict__ dst, long long Ns,
-                                                      int H, int Ws, int rowv, int p, int S, int accumulate) {
-  // src [N][H+2p][Ws*S+2p][rowv] -> dst [Ns = N*S][H][Ws][rowv]
+__global__ void __launch_bounds__(128) gs_crop_kernel(const float4* __restrict__ src, float4* __restrict__ dst, int H, int Ws,
+                                                      int rowv, int p, int S, int accumulate) {
+  // src [N][H+2p][Ws*S+2p][rowv] -> dst [Ns = N*S][H][Ws][rowv]; one block = one destination pixel row
   const int Hs = H + 2 * p, Wsrc = Ws * S + 2 * p;
-  const long long total = Ns * H * Ws * rowv;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    int v = (int)(i % rowv);
-    long long pix = i / rowv;
-    int xx = (int)(pix % Ws);
-    int yy = (int)((pix / Ws) % H);
-    long long ns = pix / ((long long)Ws * H);
-    long long n = ns / S;
-    int h = (int)(ns - n * S);
-    float4 s4 = src[((n * Hs + yy + p) * Wsrc + h * Ws + xx + p) * rowv + v];
+  const long long row = blockIdx.x;
+  const long long ns = row / H;
+  const int yy = (int)(row - ns * H);
+  const long long n = ns / S;
+  const int h = (int)(ns - n * S);
+  const float4* sp = src + ((n * Hs + yy + p) * Wsrc + h * Ws + p) * rowv;
+  float4* dp = dst + row * Ws * rowv;
+  for (int i = threadIdx.x; i < Ws * rowv; i += blockDim.x) {
+    float4 s4 = sp[i];
     if (accumulate) {
-      float4 d = dst[i];
+      const float4 d = dp[i];
       s4.x += d.x; s4.y += d.y; s4.z += d.z; s4.w += d.w;
     }
-    dst[i] = s4;
+    dp[i] = s4;
   }
 }
 
@@ -396,9 +393,10 @@ extern "C" int ugn_crop_hw(ugn_ctx* ctx, const ugn_tensor* src, ugn_tensor* dst,
             "crop_hw: src must be [N,H+2p,W*S+2p,C] for dst [N*S,H,W,C]");
   if (ugn_numel(dst) == 0) return UGN_OK;
   int rowv = (int)b[3] / 4;
-  long long total = b[0] * b[1] * b[2] * rowv;
-  gs_crop_kernel<<<gs_grid(ctx, total, 256), 256, 0, (cudaStream_t)stream>>>(ugn_ptr<float4>(src), ugn_ptr<float4>(dst), b[0],
-                                                                           (int)b[1], (int)b[2], rowv, p, S, accumulate);
+  long long rows = b[0] * b[1];
+  UGN_CHECK(rows < (1LL << 31), "crop_hw: too many rows");
+  gs_crop_kernel<<<(unsigned)rows, 128, 0, (cudaStream_t)stream>>>(ugn_ptr<float4>(src), ugn_ptr<float4>(dst), (int)b[1], (int)b[2],
+                                                                 rowv, p, S, accumulate);
   UGN_LAUNCHED(ctx);
   return UGN_OK;
 }
@@ -408,20 +406,64 @@ extern "C" int ugn_crop_hw(ugn_ctx* ctx, const ugn_tensor* src, ugn_tensor* dst,
 // the layers.Add() that follows it (:455,:466).  m = max_t a[b,t]; y = m + addend.
 // Backward: tf reduce_max splits the gradient evenly among the frames that attain the maximum.
 // ---------------------------------------------------------------------------------------------------
+// 8 consecutive elements (channels) per thread: 16-byte loads of each 16-bit plane / two float4 of an f32 tensor
+__device__ __forceinline__ void gs_load8(const void* p, int mode, int f16, long long plane, long long i, float v[8]) {
+  if (mode == 0) {
+    const float4 a = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p) + i);
+    const float4 b = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p) + i + 4);
+    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+    return;
+  }
+  const u16* q = reinterpret_cast<const u16*>(p);
+  union { uint4 u; u16 h[8]; } hi, lo;
+  hi.u = *reinterpret_cast<const uint4*>(q + i);
+#pragma unroll
+  for (int k = 0; k < 8; ++k) v[k] = ugn_f16to32(hi.h[k], f16);
+  if (mode == 2) {
+    lo.u = *reinterpret_cast<const uint4*>(q + plane + i);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) v[k] += ugn_f16to32(lo.h[k], f16);
+  }
+}
+__device__ __forceinline__ void gs_store8(void* p, int mode, int f16, long long plane, long long i, const float v[8]) {
+  if (mode == 0) {
+    *reinterpret_cast<float4*>(reinterpret_cast<float*>(p) + i) = make_float4(v[0], v[1], v[2], v[3]);
+    *reinterpret_cast<float4*>(reinterpret_cast<float*>(p) + i + 4) = make_float4(v[4], v[5], v[6], v[7]);
+    return;
+  }
+  u16* q = reinterpret_cast<u16*>(p);
+  union { uint4 u; u16 h[8]; } hi, lo;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    hi.h[k] = ugn_cvt16(v[k], f16);
+    lo.h[k] = ugn_cvt16(v[k] - ugn_f16to32(hi.h[k], f16), f16);
+  }
+  *reinterpret_cast<uint4*>(q + i) = hi.u;
+  if (mode == 2) *reinterpret_cast<uint4*>(q + plane + i) = lo.u;
+}
+
 __global__ void __launch_bounds__(256) gs_setmax_fwd_kernel(const void* __restrict__ a, int amode, long long aplane,
                                                             const void* __restrict__ addend, int dmode, long long dplane,
                                                             float* __restrict__ m, void* __restrict__ y, int ymode,
                                                             long long yplane, int B, int T, long long Q, int f16) {
-  const long long total = (long long)B * Q;
+  const long long Q8 = Q >> 3, total = (long long)B * Q8;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    long long b = i / Q, q = i - b * Q;
-    float best = gs_load(a, amode, f16, aplane, (b * T) * Q + q);
-    for (int t = 1; t < T; ++t) best = fmaxf(best, gs_load(a, amode, f16, aplane, (b * T + t) * Q + q));
-    if (m) m[i] = best;
+    const long long b = i / Q8, q = (i - b * Q8) << 3;
+    float best[8], v[8];
+    gs_load8(a, amode, f16, aplane, (b * T) * Q + q, best);
+    for (int t = 1; t < T; ++t) {
+      gs_load8(a, amode, f16, aplane, (b * T + t) * Q + q, v);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) best[k] = fmaxf(best[k], v[k]);
+    }
+    if (m) gs_store8(m, 0, 0, 0, b * Q + q, best);
     if (y) {
-      float v = best;
-      if (addend) v += gs_load(addend, dmode, f16, dplane, i);
-      gs_store(y, ymode, f16, yplane, i, v);
+      if (addend) {
+        gs_load8(addend, dmode, f16, dplane, b * Q + q, v);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) best[k] += v[k];
+      }
+      gs_store8(y, ymode, f16, yplane, b * Q + q, best);
     }
   }
 }
@@ -451,7 +493,8 @@ extern "C" int ugn_setmax_fwd(ugn_ctx* ctx, const ugn_tensor* a, int T, const ug
     if (ym) { UGN_CHECK((!am && !dm) || gs_f16(y) == f16, "setmax_fwd: 16-bit formats differ"); f16 = gs_f16(y); }
   }
   if (B == 0 || Q == 0) return UGN_OK;
-  gs_setmax_fwd_kernel<<<gs_grid(ctx, B * Q, 256), 256, 0, (cudaStream_t)stream>>>(
+  UGN_CHECK(s[3] % 8 == 0, "setmax_fwd: channel count must be a multiple of 8");
+  gs_setmax_fwd_kernel<<<gs_grid(ctx, B * Q / 8, 256), 256, 0, (cudaStream_t)stream>>>(
       ugn_ptr<void>(a), am, s[0] * Q, addend ? ugn_ptr<void>(addend) : nullptr, dm, B * Q, m ? ugn_ptr<float>(m) : nullptr,
       y ? ugn_ptr<void>(y) : nullptr, ym, B * Q, B, T, Q, f16);
   UGN_LAUNCHED(ctx);
@@ -462,17 +505,28 @@ __global__ void __launch_bounds__(256) gs_setmax_bwd_kernel(const float* __restr
                                                             int amode, long long aplane, const float* __restrict__ m,
                                                             float* __restrict__ da, int B, int T, long long Q, int f16,
                                                             int accumulate) {
-  const long long total = (long long)B * Q;
+  const long long Q8 = Q >> 3, total = (long long)B * Q8;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    long long b = i / Q, q = i - b * Q;
-    const float mx = m[i];
-    int cnt = 0;
-    for (int t = 0; t < T; ++t) cnt += gs_load(a, amode, f16, aplane, (b * T + t) * Q + q) == mx;
-    const float g = dm[i] / (float)max(cnt, 1);
+    const long long b = i / Q8, q = (i - b * Q8) << 3;
+    float mx[8], g[8], v[8];
+    gs_load8(m, 0, 0, 0, b * Q + q, mx);
+    gs_load8(dm, 0, 0, 0, b * Q + q, g);
+    int cnt[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     for (int t = 0; t < T; ++t) {
-      long long o = (b * T + t) * Q + q;
-      float v = gs_load(a, amode, f16, aplane, o) == mx ? g : 0.f;
-      da[o] = accumulate ? da[o] + v : v;
+      gs_load8(a, amode, f16, aplane, (b * T + t) * Q + q, v);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) cnt[k] += v[k] == mx[k];
+    }
+#pragma unroll
+    for (int k = 0; k < 8; ++k) g[k] /= (float)max(cnt[k], 1);
+    for (int t = 0; t < T; ++t) {
+      const long long o = (b * T + t) * Q + q;
+      gs_load8(a, amode, f16, aplane, o, v);
+      float out[8];
+      if (accumulate) gs_load8(da, 0, 0, 0, o, out);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) out[k] = (accumulate ? out[k] : 0.f) + (v[k] == mx[k] ? g[k] : 0.f);
+      gs_store8(da, 0, 0, 0, o, out);
     }
   }
 }
@@ -492,7 +546,8 @@ extern "C" int ugn_setmax_bwd(ugn_ctx* ctx, const ugn_tensor* dm, const ugn_tens
   long long Q = s[1] * s[2] * s[3];
   UGN_CHECK(ugn_numel(dm) == B * Q && ugn_numel(m) == B * Q && ugn_numel(da) == s[0] * Q, "setmax_bwd: shape mismatch");
   if (B == 0 || Q == 0) return UGN_OK;
-  gs_setmax_bwd_kernel<<<gs_grid(ctx, B * Q, 256), 256, 0, (cudaStream_t)stream>>>(
+  UGN_CHECK(s[3] % 8 == 0, "setmax_bwd: channel count must be a multiple of 8");
+  gs_setmax_bwd_kernel<<<gs_grid(ctx, B * Q / 8, 256), 256, 0, (cudaStream_t)stream>>>(
       ugn_ptr<float>(dm), ugn_ptr<void>(a), am, s[0] * Q, ugn_ptr<float>(m), ugn_ptr<float>(da), B, T, Q, gs_f16(a), accumulate);
   UGN_LAUNCHED(ctx);
   return UGN_OK;

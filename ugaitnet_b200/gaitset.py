@@ -339,7 +339,7 @@ class GaitSetEngine(UGaitEngine):
         check(lib.ugn_fuse3_bwd(h, cfg.nmods, p.R["dsig"].ptr, p.R["sig"].ptr, p.R["winner"].ptr, p.R["col_norm"].ptr,
                                 p.flag_ptrs, p.dbr_ptrs, cfg.merge, st))
         # MatMul + HPP backward stay in f32; the conv stacks below consume 16-bit gradient operands
-        streams = self._fork() if self.world == 1 and self._cap is None else None
+        streams = self._fork() if self._branches_concurrent() else None
         for m in range(cfg.nmods):
             with torch.cuda.stream(streams[m] if streams else torch.cuda.current_stream()):
                 self._backward_head(p, m)
@@ -354,7 +354,7 @@ class GaitSetEngine(UGaitEngine):
         elif getattr(self.ctx, "grad_scaled", False):
             check(lib.ugn_grad_scale_set(h, 1.0, st))
             self.ctx.grad_scaled = False
-        streams = self._fork() if self.world == 1 and self._cap is None else None
+        streams = self._fork() if self._branches_concurrent() else None
         for m in range(cfg.nmods):
             with torch.cuda.stream(streams[m] if streams else torch.cuda.current_stream()):
                 self._backward_branch(p, m)

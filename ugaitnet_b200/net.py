@@ -21,7 +21,7 @@ import torch
 
 from . import ops
 from ._ffi import TRef, check, lib, ptr_array, stream_ptr
-from .config import ACT_LEAKY, ACT_LINEAR, BRANCH_NAMES, MERGE_AVG, NetConfig, round_up
+from .config import ACT_LEAKY, ACT_LINEAR, AUX_NAMES, BRANCH_NAMES, MERGE_AVG, NetConfig, round_up
 from .expand import NOISE
 
 # math mode -> (forward planes, backward/gradient planes, 16-bit dtype)
@@ -71,6 +71,11 @@ class UGaitEngine:
         # data-parallel CUDA graphs: the step is captured as segments cut at the all-reduce points
         # (_capture_segments); NCCL itself is never captured (capturing the async work handles hung)
         self.dp_graph = os.environ.get("UGN_DP_GRAPH", "1") != "0"
+        # data-parallel exchange: "single" = forward + backward stay ONE graph segment with concurrent modality
+        # branches and the whole gradient arena is all-reduced in one NCCL call before the optimiser segment;
+        # "bucketed" = one all-reduce per finished bucket, overlapping the rest of the backward pass, which
+        # costs the branch concurrency (every bucket has to be issued from the stream NCCL orders against)
+        self.dp_reduce = os.environ.get("UGN_DP_REDUCE", "single")
         self.multistream = os.environ.get("UGN_MULTISTREAM", "1") != "0"   # concurrent modality branches
         self._bstreams = None
         self.force_segments = False     # tests: use the segmented capture on a single GPU too
@@ -113,6 +118,11 @@ class UGaitEngine:
         if cfg.nclasses > 0:
             add("classprob/w", (cfg.nclasses, feat))
             add("classprob/b", (cfg.nclasses,))
+        self.aux = bool(getattr(cfg, "aux_losses", False)) and cfg.nclasses > 0 and not cfg.single
+        if self.aux:       # classprob_{of,gray,depth}: Dense(nclasses, softmax) on every gated branch output (:1222-1229)
+            for m in range(cfg.nmods):
+                add(f"{AUX_NAMES[m]}/w", (cfg.nclasses, cfg.nd))
+                add(f"{AUX_NAMES[m]}/b", (cfg.nclasses,))
         self.segs = {s.name: s for s in segs}
         self.seg_list = segs
         self.n_arena = off
@@ -299,6 +309,16 @@ class UGaitEngine:
             check(lib.ugn_fuse_fwd(h, cfg.nmods, p.brn_ptrs if cfg.normbfmerge else p.br_ptrs, p.flag_ptrs,
                                    p.R["sig"].ptr, None, p.R["winner"].ptr, p.R["inv_norm"].ptr, cfg.merge, 1, st))
             sig = p.R["sig"]
+            if self.aux:
+                # auxiliary classifiers on the GATED branch outputs: gate = the fusion kernel on one modality without
+                # the normalisation (x * flag), then Dense(nclasses)
+                for m in range(cfg.nmods):
+                    b = p.br[m]
+                    check(lib.ugn_fuse_fwd(h, 1, b.gate_in, b.flag1, b.R["gated"].ptr, None, b.R["gwin"].ptr,
+                                           b.R["ginv"].ptr, 0, 0, st))
+                    check(lib.ugn_linear_fwd(h, b.R["gated"].ptr, self.Rw[f"{AUX_NAMES[m]}/w"].ptr,
+                                             self.Rw[f"{AUX_NAMES[m]}/b"].ptr, None, b.R["aux_logits"].ptr, None,
+                                             ACT_LINEAR, 0.0, st))
         feat = sig
         if cfg.nc > 0:
             cmask = p.R["cmask"].ptr if (train and cfg.dropout > 0.001) else None
@@ -384,6 +404,8 @@ class UGaitEngine:
     def _reduce_bucket(self, key):
         """Data-parallel gradient exchange, bucketed so that the all-reduce of a finished branch overlaps
         the backward pass of the next one (NCCL runs on its own stream)."""
+        if self.dp_reduce == "single":
+            return
         if (self.world > 1 or self._cap is not None) and self._dp_async and self.buckets.get(key) is not None:
             if self._cap is not None:          # capturing: close this graph segment, the all-reduce runs between
                 self._cut(key)                 # the replays of two segments
@@ -431,6 +453,10 @@ class UGaitEngine:
             g.replay()
             for key in keys:
                 if key == "wait":
+                    if self.dp_reduce == "single":
+                        if self.world > 1:
+                            torch.distributed.all_reduce(self.g, group=self.pg)
+                        continue
                     for w in self._works:
                         w.wait()
                 elif self.world > 1:
@@ -469,6 +495,16 @@ class UGaitEngine:
                 p.dsig.add_(p.dsig2)
             else:
                 p.dsig.add_(p.dfeat)
+        if self.aux:
+            for m in range(cfg.nmods):
+                b = p.br[m]
+                check(lib.ugn_softmax_ce_ls(h, b.R["aux_logits"].ptr, p.R["labels"].ptr, b.R["aux_ce"].ptr,
+                                            b.R["daux_logits"].ptr, cfg.waux, cfg.label_smoothing, st))
+                check(lib.ugn_linear_bwd(h, b.R["gated"].ptr, self.Rw[f"{AUX_NAMES[m]}/w"].ptr, b.R["daux_logits"].ptr,
+                                         b.R["dgated"].ptr, self.Rg[f"{AUX_NAMES[m]}/w"].ptr,
+                                         self.Rg[f"{AUX_NAMES[m]}/b"].ptr, st))
+                check(lib.ugn_fuse_bwd(h, 1, b.R["dgated"].ptr, b.R["gated"].ptr, b.R["gwin"].ptr, b.R["ginv"].ptr,
+                                       b.flag1, b.aux_dout, 0, 0, st))
         self._reduce_bucket("heads")
         if self.scaled:
             # fp16 gradient operands: pick this step's power-of-two scale from the signature gradient
@@ -484,6 +520,10 @@ class UGaitEngine:
             check(lib.ugn_fuse_bwd(h, cfg.nmods, p.R["dsig"].ptr, p.R["sig"].ptr, p.R["winner"].ptr,
                                    p.R["inv_norm"].ptr, p.flag_ptrs, p.dbrn_ptrs if cfg.normbfmerge else p.dbr_ptrs,
                                    cfg.merge, 1, st))
+            if self.aux:       # + the auxiliary heads' gradient wrt the (normalised) branch output
+                for m in range(cfg.nmods):
+                    b = p.br[m]
+                    (b.T["doutn"] if cfg.normbfmerge else b.dout).add_(b.T["daux"])
             if cfg.normbfmerge:
                 for m in range(cfg.nmods):
                     b = p.br[m]
@@ -491,11 +531,16 @@ class UGaitEngine:
                                            p.one_ptrs, b.nrm_dout, 0, 1, st))
         # per-branch backward on concurrent streams (single GPU; with data parallelism the branches stay in
         # sequence so that every all-reduce bucket is issued from the one stream NCCL orders against)
-        streams = self._fork() if self.world == 1 and self._cap is None else None
+        streams = self._fork() if self._branches_concurrent() else None
         for m in range(cfg.nmods):
             with torch.cuda.stream(streams[m] if streams else torch.cuda.current_stream()):
                 self._backward_branch(p, m)
         self._join(streams)
+
+    def _branches_concurrent(self) -> bool:
+        """Backward of the modality branches on concurrent streams: always on one GPU; with data parallelism
+        only when the gradients are exchanged in one call after the backward pass (dp_reduce == "single")."""
+        return (self.world == 1 and self._cap is None) or self.dp_reduce == "single"
 
     def _backward_branch(self, p: "_Plan", m: int):
         cfg, h, st = self.cfg, self.ctx.h, stream_ptr()
@@ -559,7 +604,7 @@ class UGaitEngine:
             if self._cap is not None:
                 self._cut("wait")
             elif self.world > 1:
-                if self._dp_async:
+                if self._dp_async and self.dp_reduce != "single":
                     for w in self._works:
                         w.wait()
                 else:
@@ -689,6 +734,10 @@ class UGaitEngine:
         if cfg.nclasses > 0:
             check(lib.ugn_softmax_ce_ls(h, p.R["logits"].ptr, p.R["labels"].ptr, p.R["ce_out"].ptr, None, 1.0,
                                         cfg.label_smoothing, st))
+            if getattr(self, "aux", False):
+                for b in p.br:
+                    check(lib.ugn_softmax_ce_ls(h, b.R["aux_logits"].ptr, p.R["labels"].ptr, b.R["aux_ce"].ptr, None, 1.0,
+                                                cfg.label_smoothing, st))
         return self._report(p)
 
     # ------------------------------------------------------------------ host -> device pipelining
@@ -733,6 +782,9 @@ class UGaitEngine:
         out = {"triplet": p.trip_out[0], "count": p.trip_out[1], "signature": p.br[0].out if self.cfg.single else p.sig}
         if self.cfg.nclasses > 0:
             out["ce"], out["acc"], out["logits"] = p.ce_out[0], p.ce_out[1], p.logits
+        if getattr(self, "aux", False) and p.train:
+            out["aux_ce"] = [b.T["aux_ce"][0] for b in p.br]
+            out["aux_acc"] = [b.T["aux_ce"][1] for b in p.br]
         if with_reg:
             out["reg"] = self.reg_out[0]
         return out
@@ -797,8 +849,24 @@ class _Plan:
                 T["ninv"] = torch.zeros(B, 2, **f32)
                 if train:
                     T["doutn"] = torch.zeros(B, cfg.nd, **f32)
+            if eng.aux:
+                T["gated"] = torch.zeros(B, cfg.nd, **f32)
+                T["gwin"] = torch.zeros(B, cfg.nd, device=d, dtype=torch.uint8)
+                T["ginv"] = torch.zeros(B, 2, **f32)
+                T["aux_logits"] = torch.zeros(B, cfg.nclasses, **f32)
+                if train:
+                    T["aux_ce"] = torch.zeros(2, **f32)
+                    T["daux_logits"] = torch.zeros(B, cfg.nclasses, **f32)
+                    T["dgated"] = torch.zeros(B, cfg.nd, **f32)
+                    T["daux"] = torch.zeros(B, cfg.nd, **f32)
             b.T = T
             b.R = {k: TRef(v) for k, v in T.items()}
+            if eng.aux:
+                b.gate_in = ptr_array([b.R["outn" if cfg.normbfmerge else "out"]])
+                b._flag1 = TRef(self.flags[m])
+                b.flag1 = ptr_array([b._flag1])
+                if train:
+                    b.aux_dout = ptr_array([b.R["daux"]])
             if cfg.normbfmerge and not cfg.single:
                 b.nrm_in = ptr_array([b.R["out"]])
                 if train:
