@@ -310,11 +310,12 @@ def test_device_side_expansion_equals_host_expanded_batch():
             assert rel(outs[1][2][k], outs[0][2][k].double().cpu()) < 1e-5, k
 
 
-@pytest.mark.parametrize("dp_reduce", ["single", "bucketed"])
+@pytest.mark.parametrize("dp_reduce", ["split", "single", "bucketed"])
 def test_segmented_graph_capture_equals_eager(dp_reduce):
     """The data-parallel step is replayed as CUDA-graph SEGMENTS cut at the all-reduce points (NCCL stays
-    outside the graphs): "single" = [forward + backward] | one all-reduce | [optimiser]; "bucketed" = a cut per
-    gradient bucket.  Forced on one GPU here: the segmented replay must reproduce the eager step."""
+    outside the graphs): "split" = [forward + dense backward] | dense all-reduces | [conv backward] | conv
+    all-reduces | [optimiser]; "single" = [forward + backward] | one all-reduce | [optimiser]; "bucketed" = a cut
+    per gradient bucket.  Forced on one GPU here: the segmented replay must reproduce the eager step."""
     from ugaitnet_b200.net import UGaitEngine
     oc, eng, P, xs, fl, lab, masks, cmask = setup("3mod_signmax")
     eng_s = UGaitEngine(to_engine_cfg(oc), math_mode="fp32", lr=1e-3, use_graph=True)
@@ -329,7 +330,7 @@ def test_segmented_graph_capture_equals_eager(dp_reduce):
         assert float(a["ce"]) == pytest.approx(float(b["ce"]), rel=1e-5)
     gr = next(iter(eng_s._graphs.values()))
     # bucketed: heads | (fc, conv) per branch | optim
-    assert isinstance(gr, list) and len(gr) == (2 if dp_reduce == "single" else 1 + 2 * oc.nmods + 1)
+    assert isinstance(gr, list) and len(gr) == {"split": 3, "single": 2, "bucketed": 1 + 2 * oc.nmods + 1}[dp_reduce]
     Wa, Wb = eng.export_params(), eng_s.export_params()
     for k in Wa:
         assert rel(Wb[k], Wa[k].double().cpu()) < 1e-5, k
