@@ -42,7 +42,9 @@ if os.environ.get("GS_LITE"):          # runs under ncu: one warm-up step, one m
     eng.multistream = False
     run(eng, 1)
     l0 = eng.ctx.launches
+    torch.cuda.profiler.start()
     ms, _ = run(eng, 1)
+    torch.cuda.profiler.stop()
     print(json.dumps({"lite": True, "B": B, "ms_per_step": ms, "launches_per_step": eng.ctx.launches - l0}), flush=True)
     sys.exit(0)
 run(eng, 2)
