@@ -334,3 +334,54 @@ def test_segmented_graph_capture_equals_eager(dp_reduce):
     Wa, Wb = eng.export_params(), eng_s.export_params()
     for k in Wa:
         assert rel(Wb[k], Wa[k].double().cpu()) < 1e-5, k
+
+
+# ---- BASELINE.json configs 3 and 4 at FULL size (CASIA-B shape bs = 40 x 3 = 120 rows with silhouettes, nclasses 74;
+# BL-all --nomissing bs = 512).  The fp64 oracle of the whole step takes minutes at these sizes, so parity is
+# asserted through size-independent properties plus the oracle on the parts that are cheap at any size:
+#   * descriptors are per-row functions of the inputs: the oracle forward of 6 sampled rows must match the rows of
+#     the full-batch signature (cosine >= 0.999, north_star);
+#   * the two losses, evaluated by the ORACLE on the engine's own signature / logits, must match the kernels' values;
+#   * a permutation of the batch rows leaves both losses and every weight gradient unchanged.
+@pytest.mark.parametrize("name", ["cfg3_casia_120", "cfg4_blall_512"])
+def test_full_size_configs_properties(name):
+    from ugaitnet_b200.net import UGaitEngine
+    if name == "cfg3_casia_120":
+        oc = O.NetConfig(in_channels=(50, 25, 25), nd=2048, nclasses=74, merge=O.MERGE_SIGNMAX, wver=1.0, wid=0.1)
+        xs, fl, lab = O.synth_batch(oc, base_rows=40, expand=3, seed=5, ids_per=10, kinds=("of", "gray", "sil"))
+    else:
+        oc = O.NetConfig(in_channels=(50, 25, 25), nd=2048, nclasses=150, merge=O.MERGE_SIGNMAX, wver=1.0, wid=0.1)
+        xs, fl, lab = O.synth_batch(oc, base_rows=512, expand=1, seed=6, ids_per=2)
+        lab = lab % 150
+    B = xs[0].shape[0]
+    assert B == (120 if name == "cfg3_casia_120" else 512)
+    P = O.init_params(oc, seed=4, dtype=torch.float32)
+    eng = UGaitEngine(to_engine_cfg(oc), math_mode="f16mix", lr=1e-4)
+    eng.load_params(P)
+    ins = engine_inputs(xs, fl, lab, None, None)
+    out = eng.loss_and_grad(*ins)
+    eng.ctx.check()
+    sig, logits = out["signature"].double().cpu(), out["logits"].double().cpu()
+    trip, ce, cnt = float(out["triplet"]), float(out["ce"]), float(out["count"])
+    g0 = {k: v.clone() for k, v in eng.export_grads().items()}
+    # (1) sampled rows against the oracle forward (fp32 CPU)
+    rows = [0, 1, B // 3, B // 2 + 1, B - 2, B - 1]
+    rs, _ = O.model_forward([torch.tensor(x[rows]) for x in xs], [torch.tensor(f[rows]) for f in fl], P, oc)
+    cos = torch.nn.functional.cosine_similarity(sig[rows], rs.double(), dim=1)
+    assert float(cos.min()) >= 0.999, cos
+    # (2) the loss kernels against the oracle on the same signature / logits
+    lt = torch.tensor(lab).reshape(-1).long()
+    rt, rc = O.triplet_loss_all(lt, sig, oc.margin)
+    assert trip == pytest.approx(float(rt), rel=1e-4) and cnt == float(rc.sum())
+    rce, racc = O.softmax_ce(logits, torch.nn.functional.one_hot(lt, oc.nclasses).double())
+    assert ce == pytest.approx(float(rce), rel=1e-5) and float(out["acc"]) == pytest.approx(float(racc), abs=1e-6)
+    assert torch.allclose(sig.norm(dim=1), torch.ones(B, dtype=torch.float64), atol=1e-5)
+    # (3) row permutation invariance of the losses and of every weight gradient
+    perm = torch.randperm(B, generator=torch.Generator().manual_seed(1))
+    pin = ([x[perm.cuda()] for x in ins[0]], [f[perm.cuda()] for f in ins[1]], ins[2][perm.cuda()], None, None)
+    out2 = eng.loss_and_grad(*pin)
+    assert float(out2["triplet"]) == pytest.approx(trip, rel=1e-4) and float(out2["ce"]) == pytest.approx(ce, rel=1e-5)
+    g1 = eng.export_grads()
+    for k in g0:
+        if float(g0[k].norm()) > 0:
+            assert rel(g1[k], g0[k].double().cpu()) < 2e-3, (k, rel(g1[k], g0[k].double().cpu()))
