@@ -18,13 +18,12 @@ from __future__ import annotations
 
 import math
 from dataclasses import dataclass
-from typing import Dict, List, Sequence
+from typing import Dict, Sequence
 
 import torch
 import torch.nn.functional as F
 
-from .ugait_oracle import (ACT_LEAKY, BRANCH_NAMES, MERGE_SIGNMAX, l2_normalize, merge_modalities, softmax_ce,
-                           triplet_loss_all)
+from .ugait_oracle import BRANCH_NAMES, MERGE_SIGNMAX, l2_normalize, merge_modalities, softmax_ce, triplet_loss_all
 
 # (name, cin, cout, k) of build_gaitset_branch, in graph order; cin None = per-frame input channels
 GS_CONVS = (("a1", None, 32, 5), ("a2", 32, 32, 3), ("b1", 32, 64, 3), ("b2", 64, 64, 3), ("a3", 32, 64, 3),

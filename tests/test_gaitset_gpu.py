@@ -1,6 +1,6 @@
 """GPU parity tests of the GaitSet branch type through the C ABI against the
 CPU oracle (oracle/gaitset_oracle.py) on the same seeded inputs.  fp32 validation mode: <= 1e-5 on losses /
-descriptors, <= 5e-5 on gradients; tensor-core modes: cosine >= 0.999, losses <= 1e-3, gradients <= 1e-2."""
+descriptors, <= 1e-4 on gradients; tensor-core modes: cosine >= 0.999, losses <= 1e-3, gradients <= 1e-2."""
 import numpy as np
 import pytest
 import torch

@@ -65,8 +65,8 @@ class NetConfig:
         return last["co"] * last["hp"] * last["hp"]
 
 
-# (name, cin, cout, k, input, pooled) of build_gaitset_branch, in graph order
-# (/root/reference/nets/mj_uwyhNets_ba.py:427-466); cin None = the im2col'd per-frame input
+# (name, cin, cout, k) of build_gaitset_branch, in graph order
+# (/root/reference/nets/mj_uwyhNets_ba.py:427-466); cin None = the per-frame input channels (1 | 2)
 GS_CONVS = (("a1", None, 32, 5), ("a2", 32, 32, 3), ("b1", 32, 64, 3), ("b2", 64, 64, 3), ("a3", 32, 64, 3),
             ("a4", 64, 64, 3), ("b3", 64, 128, 3), ("b4", 128, 128, 3), ("a5", 64, 128, 3), ("a6", 128, 128, 3))
 GS_PARTS = 62                      # 2 * (1 + 2 + 4 + 8 + 16) HPP strips (:468-479)

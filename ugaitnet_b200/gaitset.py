@@ -9,8 +9,9 @@ layout -- kept literally), FC1 "code", transpose + Flatten + FC2 "classprob", ba
 
 The engine reuses the conv / dense / loss / optimiser kernels of the stacked-CNN path through the same C
 ABI; ``padding='same'`` is realised with zero-bordered activation buffers (ugn_pad_hw / ugn_crop_hw), the
-first 5x5 convolution over 1 | 2 input channels is an im2col'd 1x1 convolution (ugn_gs_pack_input) so that
-its K is 32 | 64 instead of 25 taps x 32 padded channels.  PyTorch owns memory, streams and NCCL only.
+64-wide layers live in a 2-way column-split layout, and the first 5x5 convolution over 1 | 2 input channels
+(K = 25 | 50, far below a tensor-core tile) is a fused fp32 kernel of its own (ugn_gs_conv1_fwd / _wgrad).
+PyTorch owns memory, streams and NCCL only.
 """
 from __future__ import annotations
 
@@ -172,7 +173,7 @@ class GaitSetEngine(UGaitEngine):
             if len(s.shape) == 4:
                 v = v.permute(0, 2, 3, 1).contiguous()                 # [Cout,kh,kw,Cin]
                 if name.endswith("/a1/w"):
-                    v = v.reshape(v.shape[0], 1, 1, -1)               # tap-major (ky,kx,ci) == the im2col order
+                    v = v.reshape(v.shape[0], 1, 1, -1)               # tap-major (ky,kx,ci), the order ugn_gs_conv1_* read
                 self.pw[name].zero_()
                 self.pw[name][:v.shape[0]].copy_(v.to(self.dev))
             else:

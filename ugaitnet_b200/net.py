@@ -21,7 +21,7 @@ import torch
 
 from . import ops
 from ._ffi import TRef, check, lib, ptr_array, stream_ptr
-from .config import ACT_LEAKY, ACT_LINEAR, AUX_NAMES, BRANCH_NAMES, MERGE_AVG, NetConfig, round_up
+from .config import ACT_LEAKY, ACT_LINEAR, AUX_NAMES, BRANCH_NAMES, NetConfig, round_up
 from .expand import NOISE
 
 # math mode -> (forward planes, backward/gradient planes, 16-bit dtype)
