@@ -29,7 +29,10 @@ scfg = NetConfig(in_channels=(50, 25, 25), filters_numbers=(32, 64, 64, 64), nd=
                  wver=1.0, wid=0.1, weight_decay=0.0)
 sxs = [torch.randn(B, c, 60, 60, device="cuda", generator=g) * 0.3 for c in scfg.in_channels]
 res = {"world": world}
-cases = [("gaitset", GaitSetEngine, cfg, xs, "split")] + [("stacked", UGaitEngine, scfg, sxs, s) for s in ("split", "single", "bucketed")]
+cases = [("gaitset", GaitSetEngine, cfg, xs, s) for s in ("split", "fused")] + \
+        [("stacked", UGaitEngine, scfg, sxs, s) for s in ("fused", "split", "single", "bucketed")]
+if len(sys.argv) > 1:
+    cases = [c for c in cases if c[4] in sys.argv[1:]]
 for name, cls, c, x, sched in cases:
     for mode in ("fp32", "f16mix"):
         for graph in (False, True):
@@ -38,8 +41,8 @@ for name, cls, c, x, sched in cases:
             gmean = ref.g.clone()
             torch.distributed.all_reduce(gmean)
             gmean /= world
+            os.environ["UGN_DP_REDUCE"] = sched      # read at construction: "fused" allocates symmetric-memory arenas
             eng = cls(c, math_mode=mode, seed=5, optimizer="sgd", lr=1.0, momentum=0.0, process_group=pg, use_graph=graph)
-            eng.dp_reduce = sched
             w0 = eng.w.clone()
             for _ in range(2 if graph else 1):        # graph mode: the second call is the first pure replay
                 eng.w.copy_(w0)
@@ -59,6 +62,21 @@ for name, cls, c, x, sched in cases:
             res[f"{name}_{sched}_{mode}_{'graph' if graph else 'eager'}"] = {"rel_err_vs_mean_grad": err, "identical": same}
             assert err < (1e-5 if mode == "fp32" else 2e-2) and same, res
             del ref, eng
+# Adam: three steps with the fused exchange (sharded optimiser state) against the NCCL all-reduce schedule
+W = {}
+for sched in ("split", "fused"):
+    os.environ["UGN_DP_REDUCE"] = sched
+    eng = UGaitEngine(scfg, math_mode="fp32", seed=5, optimizer="adam", lr=1e-3, process_group=pg, use_graph=True)
+    assert eng.dp_reduce == sched
+    for _ in range(3):
+        out = eng.train_step(sxs, fl, lab)
+    torch.cuda.synchronize()
+    W[sched] = (eng.w.clone(), float(out["reg"]))
+    del eng
+d = (W["fused"][0] - W["split"][0]).norm() / (W["split"][0] - UGaitEngine(scfg, math_mode="fp32", seed=5).w).norm()
+res["adam_3steps_fused_vs_split_update_rel_diff"] = float(d)
+res["adam_reg_fused_vs_split"] = [W["fused"][1], W["split"][1]]
+assert float(d) < 2e-2 and abs(W["fused"][1] - W["split"][1]) <= 1e-4 * abs(W["split"][1]), res
 if rank == 0:
     print(json.dumps(res), flush=True)
 torch.distributed.destroy_process_group()

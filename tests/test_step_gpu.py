@@ -310,7 +310,7 @@ def test_device_side_expansion_equals_host_expanded_batch():
             assert rel(outs[1][2][k], outs[0][2][k].double().cpu()) < 1e-5, k
 
 
-@pytest.mark.parametrize("dp_reduce", ["split", "single", "bucketed"])
+@pytest.mark.parametrize("dp_reduce", ["split", "single", "bucketed", "fused"])
 def test_segmented_graph_capture_equals_eager(dp_reduce):
     """The data-parallel step is replayed as CUDA-graph SEGMENTS cut at the all-reduce points (NCCL stays
     outside the graphs): "split" = [forward + dense backward] | dense all-reduces | [conv backward] | conv
@@ -330,7 +330,7 @@ def test_segmented_graph_capture_equals_eager(dp_reduce):
         assert float(a["ce"]) == pytest.approx(float(b["ce"]), rel=1e-5)
     gr = next(iter(eng_s._graphs.values()))
     # bucketed: heads | (fc, conv) per branch | optim
-    assert isinstance(gr, list) and len(gr) == {"split": 3, "single": 2, "bucketed": 1 + 2 * oc.nmods + 1}[dp_reduce]
+    assert isinstance(gr, list) and len(gr) == {"split": 3, "single": 2, "fused": 2, "bucketed": 1 + 2 * oc.nmods + 1}[dp_reduce]
     Wa, Wb = eng.export_params(), eng_s.export_params()
     for k in Wa:
         assert rel(Wb[k], Wa[k].double().cpu()) < 1e-5, k

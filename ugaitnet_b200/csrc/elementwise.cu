@@ -578,6 +578,13 @@ __device__ __forceinline__ int seg_find(const long long* __restrict__ off, int S
   return lo;
 }
 
+// Arenas of the other ranks of a data-parallel group, mapped into this process (symmetric / peer memory).
+struct PeerArenas {
+  int n = 0;                 // 0: single-GPU step
+  const float* g[8] = {};    // gradient arena of every rank (own rank included)
+  float* w[8] = {};          // weight arena of every rank
+};
+
 template <int OPT>  // 0 adam, 1 sgd-momentum
 __global__ void __launch_bounds__(256) optim_kernel(float* __restrict__ w, const float* __restrict__ g,
                                                     float* __restrict__ m, float* __restrict__ v,
@@ -587,15 +594,29 @@ __global__ void __launch_bounds__(256) optim_kernel(float* __restrict__ w, const
                                                     float* __restrict__ reg_out,
                                                     const float* __restrict__ lr_dev,
                                                     const long long* __restrict__ pack, int packP, int f16,
-                                                    float* __restrict__ vhat, float wd) {
+                                                    float* __restrict__ vhat, float wd, PeerArenas peers,
+                                                    long long q0) {
   float reg = 0.f;
   if (lr_dev) lr = *lr_dev;  // CUDA-graph friendly: the step-dependent rate lives in device memory
-  for (long long q = blockIdx.x * (long long)blockDim.x + threadIdx.x; q < n4;
+  // n4 = end of this launch's range in float4 units, q0 = its start (0 and the arena length unless this rank owns
+  // one slice of a data-parallel arena, see ugn_dp_optim_step)
+  for (long long q = q0 + blockIdx.x * (long long)blockDim.x + threadIdx.x; q < n4;
        q += (long long)gridDim.x * blockDim.x) {
     int s = seg_find(off, S, q * 4);
     float c = l2[s];
     float4 wv = reinterpret_cast<float4*>(w)[q];
-    float4 gv = reinterpret_cast<const float4*>(g)[q];
+    float4 gv;
+    if (peers.n > 0) {
+      // fused reduce-scatter: this rank owns the slice, the gradient is the sum over the ranks' arenas read
+      // through NVLink peer memory (gscale carries the 1/N of the mean)
+      gv = reinterpret_cast<const float4*>(peers.g[0])[q];
+      for (int p = 1; p < peers.n; ++p) {
+        const float4 o = reinterpret_cast<const float4*>(peers.g[p])[q];
+        gv.x += o.x; gv.y += o.y; gv.z += o.z; gv.w += o.w;
+      }
+    } else {
+      gv = reinterpret_cast<const float4*>(g)[q];
+    }
     float ww[4] = {wv.x, wv.y, wv.z, wv.w}, gg[4] = {gv.x, gv.y, gv.z, gv.w};
     if (OPT == 0) {
       float4 mv = reinterpret_cast<float4*>(m)[q];
@@ -633,6 +654,9 @@ __global__ void __launch_bounds__(256) optim_kernel(float* __restrict__ w, const
       reinterpret_cast<float4*>(v)[q] = make_float4(v2[0], v2[1], v2[2], v2[3]);
     }
     reinterpret_cast<float4*>(w)[q] = make_float4(ww[0], ww[1], ww[2], ww[3]);
+    // fused all-gather: the owner stores the updated weights into every other rank's arena
+    for (int p = 0; p < peers.n; ++p)
+      if (peers.w[p] != w) reinterpret_cast<float4*>(peers.w[p])[q] = make_float4(ww[0], ww[1], ww[2], ww[3]);
     // fused refresh of the tensor-core compute copy of this segment ([P][numel] 16-bit planes): saves the
     // separate f32 re-read of ugn_pack_weight for the dense weights (92 % of the parameter bytes)
     if (pack && pack[2 * s]) {
@@ -668,14 +692,28 @@ __global__ void __launch_bounds__(256) optim_kernel(float* __restrict__ w, const
 int ew_optim(ugn_ctx* ctx, int opt, float* w, const float* g, float* m, float* v,
              const long long* off, const float* l2, int S, long long n, float lr, float b1,
              float b2, float eps, float gscale, float* reg_out, const float* lr_dev, const long long* pack,
-             int packP, int f16, float* vhat, float wd, cudaStream_t st) {
+             int packP, int f16, float* vhat, float wd, cudaStream_t st, int world, int rank,
+             const long long* g_peers, const long long* w_peers) {
   UGN_CHECK(n % 4 == 0, "optimizer arena length must be a multiple of 4 (got %lld)", n);
   if (reg_out) UGN_CUDA(cudaMemsetAsync(reg_out, 0, sizeof(float), st));
-  long long n4 = n / 4;
-  int grid = (int)std::min<long long>((n4 + 255) / 256, (long long)ctx->sm_count * 8);
+  long long n4 = n / 4, q0 = 0;
+  PeerArenas peers;
+  if (world > 1) {
+    UGN_CHECK(world <= 8 && rank >= 0 && rank < world && g_peers && w_peers, "dp optimizer: bad rank / world / peer tables");
+    peers.n = world;
+    for (int p = 0; p < world; ++p) {
+      peers.g[p] = reinterpret_cast<const float*>(g_peers[p]);
+      peers.w[p] = reinterpret_cast<float*>(w_peers[p]);
+    }
+    UGN_CHECK(peers.w[rank] == w, "dp optimizer: w_peers[rank] must be this rank's own arena");
+    const long long per = (n4 + world - 1) / world;           // this rank's slice, in float4 units
+    q0 = std::min(n4, per * rank);
+    n4 = std::min(n4, per * (rank + 1));
+  }
+  int grid = (int)std::min<long long>((n4 - q0 + 255) / 256, (long long)ctx->sm_count * 8);
   grid = std::max(grid, 1);
-  if (opt == 0) optim_kernel<0><<<grid, 256, 0, st>>>(w, g, m, v, off, l2, S, n4, lr, b1, b2, eps, gscale, reg_out, lr_dev, pack, packP, f16, vhat, wd);
-  else optim_kernel<1><<<grid, 256, 0, st>>>(w, g, m, v, off, l2, S, n4, lr, b1, b2, eps, gscale, reg_out, lr_dev, pack, packP, f16, nullptr, 0.f);
+  if (opt == 0) optim_kernel<0><<<grid, 256, 0, st>>>(w, g, m, v, off, l2, S, n4, lr, b1, b2, eps, gscale, reg_out, lr_dev, pack, packP, f16, vhat, wd, peers, q0);
+  else optim_kernel<1><<<grid, 256, 0, st>>>(w, g, m, v, off, l2, S, n4, lr, b1, b2, eps, gscale, reg_out, lr_dev, pack, packP, f16, nullptr, 0.f, peers, q0);
   UGN_LAUNCHED(ctx);
   return UGN_OK;
 }

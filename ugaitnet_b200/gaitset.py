@@ -91,8 +91,8 @@ class GaitSetEngine(UGaitEngine):
         heads = [s for s in segs if s.name.split("/")[0] in ("code", "classprob")]
         self.buckets["heads"] = (heads[0].off, off) if heads else None
         d = self.dev
-        self.w = torch.zeros(off, device=d)
-        self.g = torch.zeros(off, device=d)
+        self.w = self._new_arena(off, exchanged=True)
+        self.g = self._new_arena(off, exchanged=True)
         self.m = torch.zeros(off, device=d)
         self.v = torch.zeros(off, device=d)
         self.seg_off = torch.tensor([s.off for s in segs] + [off], dtype=torch.int64, device=d)

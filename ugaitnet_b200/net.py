@@ -71,12 +71,16 @@ class UGaitEngine:
         # data-parallel CUDA graphs: the step is captured as segments cut at the all-reduce points
         # (_capture_segments); NCCL itself is never captured (capturing the async work handles hung)
         self.dp_graph = os.environ.get("UGN_DP_GRAPH", "1") != "0"
-        # data-parallel exchange.  "split" (default): the backward pass runs in two phases with concurrent branches
+        # data-parallel exchange.  "fused" (default; falls back to "split" where symmetric memory cannot be mapped):
+        # see the end of this comment.  "split": the backward pass runs in two phases with concurrent branches
         # inside each -- dense layers first, then the convolution stacks -- and the all-reduce of the dense
         # gradients (92 % of the bytes) overlaps the second phase: 3 graph segments.  "single": forward + backward
         # are ONE segment, the whole arena is all-reduced in one call before the optimiser segment.  "bucketed":
-        # one all-reduce per finished bucket with the branches in sequence (8 segments)
-        self.dp_reduce = os.environ.get("UGN_DP_REDUCE", "split")
+        # one all-reduce per finished bucket with the branches in sequence (8 segments).  "fused": no all-reduce at
+        # all -- ugn_dp_optim_step reduce-scatters the gradients, updates this rank's slice with its slice of the
+        # optimiser state and all-gathers the weights in ONE kernel over NVLink peer memory
+        self.dp_reduce = os.environ.get("UGN_DP_REDUCE", "fused")
+        self._symm = []            # (tensor, symmetric-memory handle) of the exchanged arenas: [weights, gradients]
         self.multistream = os.environ.get("UGN_MULTISTREAM", "1") != "0"   # concurrent modality branches
         # dense-layer Adam issued right after the dense backward, on a side stream underneath the conv backward.
         # Opt-in: measured 3.79 ms vs 3.74 ms/step -- the persistent tcgen05 conv kernels own every SM (215 KB of
@@ -94,6 +98,29 @@ class UGaitEngine:
         self.init_weights(seed)
 
     # ------------------------------------------------------------------ parameters
+    def _new_arena(self, n: int, exchanged: bool = False) -> torch.Tensor:
+        """Flat f32 arena.  The weight and gradient arenas of a data-parallel engine with dp_reduce == "fused" live in
+        symmetric memory (torch.distributed._symmetric_memory: every rank maps every rank's buffer), which is what
+        ugn_dp_optim_step reads gradients from and writes weights to over NVLink."""
+        if exchanged and self.world > 1 and self.dp_reduce == "fused":
+            try:
+                import torch.distributed._symmetric_memory as symm_mem
+                t = symm_mem.empty(n, dtype=torch.float32, device=self.dev)
+                t.zero_()
+                hdl = symm_mem.rendezvous(t, self.pg)
+                ok = torch.ones(1, device=self.dev)
+            except Exception as e:                       # no peer mapping on this box (P2P disabled, old driver ...)
+                ok, err = torch.zeros(1, device=self.dev), e
+            torch.distributed.all_reduce(ok, op=torch.distributed.ReduceOp.MIN, group=self.pg)   # all ranks or none
+            if float(ok) == 1.0:
+                self._symm.append((t, hdl))
+                return t
+            import warnings
+            warnings.warn("ugaitnet_b200: symmetric memory unavailable, data-parallel exchange falls back to NCCL "
+                          f"all-reduce (UGN_DP_REDUCE=split): {locals().get('err', 'another rank failed')}")
+            self.dp_reduce, self._symm = "split", []
+        return torch.zeros(n, device=self.dev)
+
     def _build_arena(self):
         cfg = self.cfg
         segs: List[_Seg] = []
@@ -144,8 +171,8 @@ class UGaitEngine:
         heads = [s for s in segs if "/" in s.name and s.name.split("/")[0] in ("code", "classprob")]
         self.buckets["heads"] = (heads[0].off, off) if heads else None
         d = self.dev
-        self.w = torch.zeros(off, device=d)
-        self.g = torch.zeros(off, device=d)
+        self.w = self._new_arena(off, exchanged=True)
+        self.g = self._new_arena(off, exchanged=True)
         self.m = torch.zeros(off, device=d)
         self.v = torch.zeros(off, device=d)
         self.seg_off = torch.tensor([s.off for s in segs] + [off], dtype=torch.int64, device=d)
@@ -410,7 +437,7 @@ class UGaitEngine:
     def _reduce_bucket(self, key):
         """Data-parallel gradient exchange, bucketed so that the all-reduce of a finished branch overlaps
         the backward pass of the next one (NCCL runs on its own stream)."""
-        if self.dp_reduce == "single":
+        if self.dp_reduce in ("single", "fused"):
             return
         if (self.world > 1 or self._cap is not None) and self._dp_async and self.buckets.get(key) is not None:
             if self._cap is not None:          # capturing: close this graph segment, the all-reduce runs between
@@ -458,6 +485,9 @@ class UGaitEngine:
         for g, keys in segs:
             g.replay()
             for key in keys:
+                if key == "fused":
+                    self._dp_fused_exchange()
+                    continue
                 if key == "wait":
                     if self.dp_reduce == "single":
                         if self.world > 1:
@@ -570,7 +600,7 @@ class UGaitEngine:
     def _branches_concurrent(self) -> bool:
         """Branches on concurrent streams from start to end: always on one GPU; with data parallelism only when
         the gradients are exchanged in one call after the backward pass (dp_reduce == "single")."""
-        return (self.world == 1 and self._cap is None) or self.dp_reduce == "single"
+        return (self.world == 1 and self._cap is None) or self.dp_reduce in ("single", "fused")
 
     def _backward_branch(self, p: "_Plan", m: int):
         self._backward_branch_fc(p, m)
@@ -708,6 +738,14 @@ class UGaitEngine:
                                   and not self.cfg.single and type(self) is UGaitEngine)
         self._losses_and_backward(p, sig, feat)
         self._early_active = False
+        if do_optim and self.dp_reduce == "fused" and (self.world > 1 or self._cap is not None):
+            # gradient exchange fused into the optimiser: [forward + backward] | barrier, ONE kernel, barrier | [repack]
+            if self._cap is not None:
+                self._cut("fused")
+            else:
+                self._dp_fused_exchange()
+            self.repack_weights()
+            return
         if do_optim:
             if self._cap is not None:
                 self._cut("wait")
@@ -718,6 +756,38 @@ class UGaitEngine:
                 else:
                     torch.distributed.all_reduce(self.g, group=self.pg)
             self._optim(1.0 / self.world)
+
+    def _dp_fused_exchange(self):
+        """barrier | ugn_dp_optim_step (reduce-scatter + optimiser on this rank's slice + all-gather of the weights over
+        peer memory) | barrier.  On one GPU (tests of the segment machinery) it degenerates to the plain optimiser."""
+        if self.world == 1:
+            R = dict(self.R)
+            R.pop("pack_table", None)
+            self._optim_call(R, 1.0)
+            return
+        import ctypes
+        h, st, R = self.ctx.h, stream_ptr(), self.R
+        (_, hw), (_, hg) = self._symm
+        if not hasattr(self, "_peer_tabs"):
+            n = self.world
+            self._peer_tabs = ((ctypes.c_int64 * n)(*[int(p) for p in hg.buffer_ptrs]),
+                               (ctypes.c_int64 * n)(*[int(p) for p in hw.buffer_ptrs]))
+        gp, wp = self._peer_tabs
+        adam = self.optimizer in ("adam", "amsgrad", "adamw")
+        if self.optimizer == "amsgrad" and "vhat" not in R:
+            self.vhat = torch.zeros_like(self.v)
+            R["vhat"] = TRef(self.vhat)
+        if not adam and self.optimizer != "sgd":
+            raise ValueError(f"unknown optimizer {self.optimizer}")
+        hg.barrier(channel=0)                   # every rank's gradients are complete
+        check(lib.ugn_dp_optim_step(h, 0 if adam else 1, self.world, torch.distributed.get_rank(self.pg), gp, wp,
+                                    R["w"].ptr, R["g"].ptr, R["m"].ptr if adam else None, R["v"].ptr,
+                                    R["vhat"].ptr if self.optimizer == "amsgrad" else None,
+                                    self.decoupled_wd if self.optimizer == "adamw" else 0.0, R["seg_off"].ptr,
+                                    R["seg_l2"].ptr, self.beta1 if adam else self.momentum, self.beta2, self.eps,
+                                    R["reg_out"].ptr, R["lr_dev"].ptr, st))
+        hw.barrier(channel=0)                   # every rank's slice of the new weights has landed here
+        torch.distributed.all_reduce(self.reg_out, group=self.pg)      # regulariser value: sum of the slices (4 bytes)
 
     def _next_lr(self):
         self.t += 1
