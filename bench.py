@@ -347,11 +347,14 @@ def main():
     value = rows_total / (ms * 1e-3)
     e2e = rows_total / (ms_e2e * 1e-3)
 
+    cfg_line = workload_config(world)
+    if world > 1:
+        cfg_line["dp_exchange"] = eng.dp_reduce + (" (NVSwitch multimem)" if all(getattr(eng, "_mc", (0, 0))) else "")
     line = {"metric": "train rows/s (3-mod fwd+bwd+triplet+CE+Adam)", "value": value, "unit": "rows/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": DTYPE_NAMES[args.mode],
-            "data": "synthetic", "config": workload_config(world),
+            "data": "synthetic", "config": cfg_line,
             "literal_seq_per_s": value / EXPAND,
             "e2e": {"value": e2e, "unit": "rows/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 12,
                     "ms_per_step": ms_e2e, "api": "UGaitEngine.prefetch + train_step_staged (H2D of step i+1 "

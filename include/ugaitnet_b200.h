@@ -225,12 +225,15 @@ int ugn_adam_step_ex(ugn_ctx*, ugn_tensor* w, const ugn_tensor* g, ugn_tensor* m
  * and the optimiser's HBM traffic drops by 1/world), and stores the updated weights into every rank's weight arena
  * (all-gather).  g_peers / w_peers: HOST arrays [world] of device addresses of the ranks' gradient / weight arenas
  * mapped into this process (e.g. torch.distributed._symmetric_memory buffer_ptrs); w_peers[rank] must be `w`.
+ * g_multicast / w_multicast (0 = none): NVSwitch multicast addresses of the two arenas; when both are given the
+ * sum is formed inside the switch (multimem.ld_reduce) and the weights are broadcast by it (multimem.st), which
+ * halves the NVLink traffic of the unicast path.
  * The caller brackets the call with two group barriers (all gradients written before; all weights written after)
  * and refreshes its 16-bit compute copies afterwards (ugn_pack_weight).  opt: 0 Adam family (vhat / weight_decay as
  * ugn_adam_step_ex), 1 SGD with momentum (beta1 = momentum).  The mean (1/world) is applied inside; reg_out receives
  * this rank's slice of the regulariser value.  lr_dev (required): the step's learning rate in device memory. */
 int ugn_dp_optim_step(ugn_ctx*, int opt, int world, int rank, const int64_t* g_peers, const int64_t* w_peers,
-                      ugn_tensor* w, const ugn_tensor* g, ugn_tensor* m, ugn_tensor* v, ugn_tensor* vhat,
+                      int64_t g_multicast, int64_t w_multicast, ugn_tensor* w, const ugn_tensor* g, ugn_tensor* m, ugn_tensor* v, ugn_tensor* vhat,
                       float weight_decay, const ugn_tensor* seg_off, const ugn_tensor* seg_l2, float beta1,
                       float beta2, float eps, ugn_tensor* reg_out, const ugn_tensor* lr_dev, void* stream);
 /* SGD with momentum (optimizers.SGD(lr, momentum, decay), :245): v = mom*v - lr*g'; w += v.  Keras' `decay`

@@ -72,9 +72,12 @@ for sched in ("split", "fused"):
         out = eng.train_step(sxs, fl, lab)
     torch.cuda.synchronize()
     W[sched] = (eng.w.clone(), float(out["reg"]))
+    if sched == "fused":
+        res["multicast_ptrs_in_use"] = bool(all(getattr(eng, "_mc", (0, 0))))
     del eng
 d = (W["fused"][0] - W["split"][0]).norm() / (W["split"][0] - UGaitEngine(scfg, math_mode="fp32", seed=5).w).norm()
 res["adam_3steps_fused_vs_split_update_rel_diff"] = float(d)
+res["multicast"] = os.environ.get("UGN_DP_MULTIMEM", "1") != "0"
 res["adam_reg_fused_vs_split"] = [W["fused"][1], W["split"][1]]
 assert float(d) < 2e-2 and abs(W["fused"][1] - W["split"][1]) <= 1e-4 * abs(W["split"][1]), res
 if rank == 0:

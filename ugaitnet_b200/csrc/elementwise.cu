@@ -583,7 +583,20 @@ struct PeerArenas {
   int n = 0;                 // 0: single-GPU step
   const float* g[8] = {};    // gradient arena of every rank (own rank included)
   float* w[8] = {};          // weight arena of every rank
+  const float* mc_g = nullptr;   // NVSwitch multicast addresses of the two arenas (nullptr: unicast peer accesses):
+  float* mc_w = nullptr;         // multimem.ld_reduce sums in the switch, multimem.st broadcasts -- half the link traffic
 };
+
+__device__ __forceinline__ float4 multimem_ld_reduce_add(const float* addr) {
+  float4 r;
+  asm volatile("multimem.ld_reduce.relaxed.sys.global.add.v4.f32 {%0,%1,%2,%3}, [%4];"
+               : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(addr) : "memory");
+  return r;
+}
+__device__ __forceinline__ void multimem_st(float* addr, float4 v) {
+  asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1,%2,%3,%4};"
+               :: "l"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
 
 template <int OPT>  // 0 adam, 1 sgd-momentum
 __global__ void __launch_bounds__(256) optim_kernel(float* __restrict__ w, const float* __restrict__ g,
@@ -606,7 +619,9 @@ __global__ void __launch_bounds__(256) optim_kernel(float* __restrict__ w, const
     float c = l2[s];
     float4 wv = reinterpret_cast<float4*>(w)[q];
     float4 gv;
-    if (peers.n > 0) {
+    if (peers.mc_g) {
+      gv = multimem_ld_reduce_add(peers.mc_g + 4 * q);       // reduced inside the NVSwitch
+    } else if (peers.n > 0) {
       // fused reduce-scatter: this rank owns the slice, the gradient is the sum over the ranks' arenas read
       // through NVLink peer memory (gscale carries the 1/N of the mean)
       gv = reinterpret_cast<const float4*>(peers.g[0])[q];
@@ -655,8 +670,12 @@ __global__ void __launch_bounds__(256) optim_kernel(float* __restrict__ w, const
     }
     reinterpret_cast<float4*>(w)[q] = make_float4(ww[0], ww[1], ww[2], ww[3]);
     // fused all-gather: the owner stores the updated weights into every other rank's arena
-    for (int p = 0; p < peers.n; ++p)
-      if (peers.w[p] != w) reinterpret_cast<float4*>(peers.w[p])[q] = make_float4(ww[0], ww[1], ww[2], ww[3]);
+    if (peers.mc_w) {
+      multimem_st(peers.mc_w + 4 * q, make_float4(ww[0], ww[1], ww[2], ww[3]));
+    } else {
+      for (int p = 0; p < peers.n; ++p)
+        if (peers.w[p] != w) reinterpret_cast<float4*>(peers.w[p])[q] = make_float4(ww[0], ww[1], ww[2], ww[3]);
+    }
     // fused refresh of the tensor-core compute copy of this segment ([P][numel] 16-bit planes): saves the
     // separate f32 re-read of ugn_pack_weight for the dense weights (92 % of the parameter bytes)
     if (pack && pack[2 * s]) {
@@ -693,7 +712,7 @@ int ew_optim(ugn_ctx* ctx, int opt, float* w, const float* g, float* m, float* v
              const long long* off, const float* l2, int S, long long n, float lr, float b1,
              float b2, float eps, float gscale, float* reg_out, const float* lr_dev, const long long* pack,
              int packP, int f16, float* vhat, float wd, cudaStream_t st, int world, int rank,
-             const long long* g_peers, const long long* w_peers) {
+             const long long* g_peers, const long long* w_peers, long long g_mc, long long w_mc) {
   UGN_CHECK(n % 4 == 0, "optimizer arena length must be a multiple of 4 (got %lld)", n);
   if (reg_out) UGN_CUDA(cudaMemsetAsync(reg_out, 0, sizeof(float), st));
   long long n4 = n / 4, q0 = 0;
@@ -706,6 +725,10 @@ int ew_optim(ugn_ctx* ctx, int opt, float* w, const float* g, float* m, float* v
       peers.w[p] = reinterpret_cast<float*>(w_peers[p]);
     }
     UGN_CHECK(peers.w[rank] == w, "dp optimizer: w_peers[rank] must be this rank's own arena");
+    if (g_mc && w_mc) {
+      peers.mc_g = reinterpret_cast<const float*>(g_mc);
+      peers.mc_w = reinterpret_cast<float*>(w_mc);
+    }
     const long long per = (n4 + world - 1) / world;           // this rank's slice, in float4 units
     q0 = std::min(n4, per * rank);
     n4 = std::min(n4, per * (rank + 1));
