@@ -373,6 +373,9 @@ def main():
         if eager is not eng:
             eager.w.copy_(eng.w)
             eager.repack_weights()
+        # per-op timing needs the branches in sequence: with one stream per branch the CUDA-event interval of a call
+        # includes the time its kernels wait for SMs held by the other branches
+        eager.multistream = False
         for _ in range(2):
             eager.train_step(dx, df, dl) if world == 1 else None
         if world == 1:

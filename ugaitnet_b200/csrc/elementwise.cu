@@ -598,7 +598,9 @@ __device__ __forceinline__ void multimem_st(float* addr, float4 v) {
                :: "l"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
 }
 
-template <int OPT>  // 0 adam, 1 sgd-momentum
+// OPT: 0 adam, 1 sgd-momentum.  DP: the data-parallel instantiation (peer arenas); compile-time so that the
+// single-GPU kernel carries none of it (the dynamically indexed peer table costs it 25 % otherwise)
+template <int OPT, bool DP>
 __global__ void __launch_bounds__(256) optim_kernel(float* __restrict__ w, const float* __restrict__ g,
                                                     float* __restrict__ m, float* __restrict__ v,
                                                     const long long* __restrict__ off,
@@ -619,9 +621,9 @@ __global__ void __launch_bounds__(256) optim_kernel(float* __restrict__ w, const
     float c = l2[s];
     float4 wv = reinterpret_cast<float4*>(w)[q];
     float4 gv;
-    if (peers.mc_g) {
+    if (DP && peers.mc_g) {
       gv = multimem_ld_reduce_add(peers.mc_g + 4 * q);       // reduced inside the NVSwitch
-    } else if (peers.n > 0) {
+    } else if (DP && peers.n > 0) {
       // fused reduce-scatter: this rank owns the slice, the gradient is the sum over the ranks' arenas read
       // through NVLink peer memory (gscale carries the 1/N of the mean)
       gv = reinterpret_cast<const float4*>(peers.g[0])[q];
@@ -670,11 +672,13 @@ __global__ void __launch_bounds__(256) optim_kernel(float* __restrict__ w, const
     }
     reinterpret_cast<float4*>(w)[q] = make_float4(ww[0], ww[1], ww[2], ww[3]);
     // fused all-gather: the owner stores the updated weights into every other rank's arena
-    if (peers.mc_w) {
-      multimem_st(peers.mc_w + 4 * q, make_float4(ww[0], ww[1], ww[2], ww[3]));
-    } else {
-      for (int p = 0; p < peers.n; ++p)
-        if (peers.w[p] != w) reinterpret_cast<float4*>(peers.w[p])[q] = make_float4(ww[0], ww[1], ww[2], ww[3]);
+    if (DP) {
+      if (peers.mc_w) {
+        multimem_st(peers.mc_w + 4 * q, make_float4(ww[0], ww[1], ww[2], ww[3]));
+      } else {
+        for (int p = 0; p < peers.n; ++p)
+          if (peers.w[p] != w) reinterpret_cast<float4*>(peers.w[p])[q] = make_float4(ww[0], ww[1], ww[2], ww[3]);
+      }
     }
     // fused refresh of the tensor-core compute copy of this segment ([P][numel] 16-bit planes): saves the
     // separate f32 re-read of ugn_pack_weight for the dense weights (92 % of the parameter bytes)
@@ -735,8 +739,11 @@ int ew_optim(ugn_ctx* ctx, int opt, float* w, const float* g, float* m, float* v
   }
   int grid = (int)std::min<long long>((n4 - q0 + 255) / 256, (long long)ctx->sm_count * 8);
   grid = std::max(grid, 1);
-  if (opt == 0) optim_kernel<0><<<grid, 256, 0, st>>>(w, g, m, v, off, l2, S, n4, lr, b1, b2, eps, gscale, reg_out, lr_dev, pack, packP, f16, vhat, wd, peers, q0);
-  else optim_kernel<1><<<grid, 256, 0, st>>>(w, g, m, v, off, l2, S, n4, lr, b1, b2, eps, gscale, reg_out, lr_dev, pack, packP, f16, nullptr, 0.f, peers, q0);
+#define UGN_OPTIM(O, D, VH, WD) \
+  optim_kernel<O, D><<<grid, 256, 0, st>>>(w, g, m, v, off, l2, S, n4, lr, b1, b2, eps, gscale, reg_out, lr_dev, pack, packP, f16, VH, WD, peers, q0)
+  if (world > 1) { if (opt == 0) UGN_OPTIM(0, true, vhat, wd); else UGN_OPTIM(1, true, nullptr, 0.f); }
+  else { if (opt == 0) UGN_OPTIM(0, false, vhat, wd); else UGN_OPTIM(1, false, nullptr, 0.f); }
+#undef UGN_OPTIM
   UGN_LAUNCHED(ctx);
   return UGN_OK;
 }
