@@ -34,8 +34,32 @@ def _worker(rank, world, port, tmp):
     g = torch.full((130,), float(rank + 1))
     allreduce_mean_(g)
     ok_dp = torch.allclose(g, torch.full((130,), (world + 1) / 2.0))
+    # fused exchange contract (ugn_dp_optim_step): reduce-scatter to the slice owner -> Adam on the slice with the
+    # owner's slice of m / v -> all-gather of the weights  ==  all-reduce(mean) + full Adam on every rank
+    from ugaitnet_b200.dist import owner_slice
+    n = 4 * 37
+    gen = torch.Generator().manual_seed(7)
+    w0 = torch.randn(n, generator=gen, dtype=torch.float64)
+    w_ref, m_ref, v_ref = {"w": w0.clone()}, {"w": torch.zeros(n, dtype=torch.float64)}, {"w": torch.zeros(n, dtype=torch.float64)}
+    w, m, v = w0.clone(), torch.zeros(n, dtype=torch.float64), torch.zeros(n, dtype=torch.float64)
+    lo, hi = owner_slice(n, rank, world)
+    for t in range(1, 4):
+        g = torch.randn(n, generator=torch.Generator().manual_seed(100 * t + rank), dtype=torch.float64)
+        allg = [torch.empty_like(g) for _ in range(world)]
+        dist.all_gather(allg, g)                                   # the peers' gradient arenas
+        gm = torch.stack(allg).mean(0)
+        O.adam_step(w_ref, {"w": gm.clone()}, m_ref, v_ref, t, lr=1e-2)
+        sl = {"w": w[lo:hi]}                                       # views: the owner touches only its slice of m, v
+        O.adam_step(sl, {"w": gm[lo:hi].clone()}, {"w": m[lo:hi]}, {"w": v[lo:hi]}, t, lr=1e-2)
+        pad = max(owner_slice(n, r, world)[1] - owner_slice(n, r, world)[0] for r in range(world))
+        mine = torch.zeros(pad, dtype=torch.float64)
+        mine[:hi - lo] = w[lo:hi]
+        parts = [torch.empty(pad, dtype=torch.float64) for _ in range(world)]
+        dist.all_gather(parts, mine)                               # the owners' stores into every rank's arena
+        w = torch.cat([parts[r][:owner_slice(n, r, world)[1] - owner_slice(n, r, world)[0]] for r in range(world)])
+    ok_fused = torch.allclose(w, w_ref["w"], rtol=0, atol=1e-12) and float(m[:lo].abs().sum() + m[hi:].abs().sum()) == 0.0
     with open(os.path.join(tmp, f"r{rank}"), "w") as f:
-        f.write(f"{int(ok_knn)} {int(ok_dp)}")
+        f.write(f"{int(ok_knn)} {int(ok_dp)} {int(ok_fused)}")
     dist.destroy_process_group()
 
 
@@ -43,7 +67,16 @@ def test_sharded_knn_merge_and_dp_mean_gloo(tmp_path):
     port = 29500 + os.getpid() % 2000
     mp.spawn(_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
     for r in range(2):
-        assert open(tmp_path / f"r{r}").read() == "1 1"
+        assert open(tmp_path / f"r{r}").read() == "1 1 1"
+
+
+def test_owner_slices_cover_the_arena():
+    from ugaitnet_b200.dist import owner_slice
+    for n in (0, 4, 8, 4 * 37, 4 * 1001, 89_600_000):
+        for w in (2, 3, 4, 8):
+            b = [owner_slice(n, r, w) for r in range(w)]
+            assert b[0][0] == 0 and b[-1][1] == n and all(lo % 4 == 0 and hi % 4 == 0 for lo, hi in b)
+            assert all(b[i][1] == b[i + 1][0] for i in range(w - 1))
 
 
 def test_shard_bounds_cover_everything():

@@ -4,6 +4,9 @@
   (/root/reference/mains/mj_trainUWYHGaitNet_DataGen_CasiaB.py:342-349): every rank mines triplets on
   its own rows, gradients are summed by one all-reduce over the flat gradient arena and scaled by 1/G
   inside the fused optimiser kernel (ugn_adam_step gscale).
+  Default on NVLink boxes: the exchange is fused into the optimiser (ugn_dp_optim_step): rank r owns the r-th
+  slice of the arena (owner_slice), sums the ranks' gradients for it through peer memory, updates it with its slice
+  of the optimiser state and stores the new weights into every rank's arena.
 * The k-NN gallery is row-sharded; the only exchange is an all-gather of the per-rank
   (dist2, global idx, label)[Q,k] lists, merged with the (distance, index) order.
 """
@@ -20,6 +23,15 @@ def shard_bounds(n: int, rank: int, world: int) -> Tuple[int, int]:
     base, rem = divmod(n, world)
     lo = rank * base + min(rank, rem)
     return lo, lo + base + (1 if rank < rem else 0)
+
+
+def owner_slice(n: int, rank: int, world: int) -> Tuple[int, int]:
+    """Element range of the flat arena (length n, a multiple of 4) that `rank` owns in ugn_dp_optim_step: equal
+    slices of ceil(n/4 / world) float4 vectors, the last one(s) possibly shorter or empty (the twin of the slice
+    arithmetic in csrc/elementwise.cu: ew_optim)."""
+    n4 = n // 4
+    per = (n4 + world - 1) // world
+    return 4 * min(n4, per * rank), 4 * min(n4, per * (rank + 1))
 
 
 def allreduce_mean_(flat: torch.Tensor, group=None) -> torch.Tensor:
