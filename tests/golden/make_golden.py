@@ -10,7 +10,10 @@
 * triplet.npz  : the literal op-by-op fp64 restatement of nets/triplet_loss_all.py:33-61 (TensorFlow is
                  not installable here: "parity unpinned" for this file) on balanced batches with
                  near-margin and duplicate rows.
-* step_*.npz   : fp64 oracle (oracle/ugait_oracle.py) losses/gradient norms for tiny model configs.
+* step_*.npz   : fp64 oracle (oracle/ugait_oracle.py, oracle/gaitset_oracle.py) losses, descriptors and gradient
+                 norms of one training step of a tiny stacked-CNN and a tiny GaitSet model ("parity unpinned":
+                 TensorFlow is not installable; the fixtures pin the restatement against drift and give the GPU
+                 tests a committed target).   python tests/golden/make_golden.py steps   regenerates only these.
 """
 import os
 import sys
@@ -45,7 +48,58 @@ def knn_case(seed, N, D, Q, k, ncls, dup):
                 dist=dist)
 
 
+STEP_CASES = {
+    # name: (kind, config kwargs, batch kwargs, seed)
+    "step_stacked": ("stacked", dict(in_channels=(6, 4, 4), filters_numbers=(8, 8, 16, 16), nd=32, nc=8, nclasses=10, merge=2,
+                                     act=2, wver=1.0, wid=0.3, label_smoothing=0.1, normbfmerge=True, aux_losses=True,
+                                     waux=0.3), dict(base_rows=6, expand=4, kinds=("of", "gray", "depth")), 21),
+    # (seed: no max-pool / set-max / LeakyReLU-sign decision of this tiny net within fp32 rounding of its boundary)
+    "step_gaitset": ("gaitset", dict(in_channels=(2, 1), frames=4, hw=12, nc=16, nclasses=10, merge=0, wver=1.0, wid=1.0,
+                                     label_smoothing=0.1), dict(ids=3, per_id=2), 9),
+}
+
+
+def step_case(name):
+    """One fp64 oracle step; returns the fixture dict (everything needed to rebuild the inputs is the seed)."""
+    import torch
+    from oracle import gaitset_oracle as G
+    from oracle import ugait_oracle as O
+    kind, ckw, bkw, seed = STEP_CASES[name]
+    if kind == "stacked":
+        oc = O.NetConfig(**ckw)
+        xs, fl, lab = O.synth_batch(oc, seed=seed, **bkw)
+        lab = lab % oc.nclasses
+        P = O.init_params(oc, seed=seed, dtype=torch.float64)
+        g = torch.Generator().manual_seed(seed)
+        for k in P:
+            if k.endswith("/b"):
+                P[k] = torch.randn(P[k].shape, generator=g, dtype=torch.float64) * 0.05
+        res, grads = O.loss_and_grads([torch.tensor(x, dtype=torch.float64) for x in xs],
+                                      [torch.tensor(f, dtype=torch.float64) for f in fl], torch.tensor(lab), P, oc)
+        sig = res["signature"]
+    else:
+        oc = G.GaitSetConfig(**ckw)
+        xs, fl, lab = G.synth_batch(oc, seed=seed, dtype=torch.float64, **bkw)
+        P = G.init_params(oc, seed=seed, dtype=torch.float64)
+        res, grads = G.loss_and_grads(xs, fl, lab, P, oc)
+        sig = res["signature"][[0, 1, 2, 30, 61]]                 # five of the 62 parts
+    out = dict(triplet=float(res["triplet"]), ce=float(res["ce"]), count=float(res["count"].sum()), reg=float(res["reg"]),
+               loss=float(res["loss"]), signature=sig.numpy(), names=np.array(sorted(grads)),
+               grad_norms=np.array([float(grads[k].norm()) for k in sorted(grads)]))
+    if "aux_ce" in res:
+        out["aux_ce"] = np.array([float(v) for v in res["aux_ce"]])
+    return out
+
+
+def steps():
+    for name in STEP_CASES:
+        np.savez_compressed(os.path.join(HERE, name + ".npz"), **step_case(name))
+    print("step fixtures written to", HERE)
+
+
 def main():
+    if len(sys.argv) > 1 and sys.argv[1] == "steps":
+        return steps()
     import sklearn
     for name, args in {
         "knn_small": (1, 2000, 64, 96, 3, 20, 0),
@@ -86,6 +140,7 @@ def main():
         trip[f"lab{ci}"], trip[f"emb{ci}"], trip[f"margin{ci}"] = lab, e, margin
         trip[f"loss{ci}"], trip[f"cnt{ci}"] = loss, cnt
     np.savez_compressed(os.path.join(HERE, "triplet.npz"), n=4, **trip)
+    steps()
     print("golden vectors written to", HERE)
 
 

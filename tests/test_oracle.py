@@ -2,6 +2,7 @@
 reference can run here) and against itself (literal vs general triplet form)."""
 import ctypes
 import os
+import sys
 
 import numpy as np
 import pytest
@@ -197,3 +198,17 @@ def test_gaitset_hpp_layout_and_shapes():
     # axis=1 of [62,B,d] is the batch axis: every (part, feature) column of the signature has unit norm
     sig, _ = G.model_forward([x], [torch.ones(2, 1, dtype=torch.float64)], P, cfg)
     assert torch.allclose((sig ** 2).sum(1), torch.ones(62, 256, dtype=torch.float64))
+
+
+# ---- committed step fixtures: the restatement must not drift
+@pytest.mark.parametrize("name", ["step_stacked", "step_gaitset"])
+def test_oracle_reproduces_step_fixture(golden_dir, name):
+    sys.path.insert(0, golden_dir)
+    import make_golden
+    z = np.load(os.path.join(golden_dir, name + ".npz"))
+    got = make_golden.step_case(name)
+    for k in ("triplet", "ce", "count", "reg", "loss"):
+        assert float(got[k]) == pytest.approx(float(z[k]), rel=1e-12), k
+    assert np.allclose(got["signature"], z["signature"], rtol=0, atol=1e-12)
+    assert list(got["names"]) == list(z["names"])
+    assert np.allclose(got["grad_norms"], z["grad_norms"], rtol=1e-10)

@@ -385,3 +385,57 @@ def test_full_size_configs_properties(name):
     for k in g0:
         if float(g0[k].norm()) > 0:
             assert rel(g1[k], g0[k].double().cpu()) < 2e-3, (k, rel(g1[k], g0[k].double().cpu()))
+
+
+@pytest.mark.parametrize("name", ["step_stacked", "step_gaitset"])
+def test_engine_matches_committed_step_fixture(name):
+    """fp32 validation mode against tests/golden/step_*.npz (fp64 oracle outputs committed with their generator,
+    tests/golden/make_golden.py): losses, descriptors and the norm of every gradient tensor."""
+    import os
+    import sys
+    gdir = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    sys.path.insert(0, gdir)
+    import make_golden
+    from oracle import gaitset_oracle as GO
+    z = np.load(os.path.join(gdir, name + ".npz"))
+    kind, ckw, bkw, seed = make_golden.STEP_CASES[name]
+    if kind == "stacked":
+        from ugaitnet_b200.net import UGaitEngine
+        oc = O.NetConfig(**ckw)
+        xs, fl, lab = O.synth_batch(oc, seed=seed, **bkw)
+        lab = lab % oc.nclasses
+        P = O.init_params(oc, seed=seed, dtype=torch.float64)
+        g = torch.Generator().manual_seed(seed)
+        for k in P:
+            if k.endswith("/b"):
+                P[k] = torch.randn(P[k].shape, generator=g, dtype=torch.float64) * 0.05
+        eng = UGaitEngine(to_engine_cfg(oc), math_mode="fp32", lr=1e-3)
+        eng.load_params(P)
+        out = eng.loss_and_grad(*engine_inputs(xs, fl, lab, None, None))
+        sig = out["signature"]
+        regs = {k: reg_grad(oc, k, P[k]) for k in P}
+    else:
+        from ugaitnet_b200.config import GaitSetConfig
+        from ugaitnet_b200.gaitset import GaitSetEngine
+        oc = GO.GaitSetConfig(**ckw)
+        xs, fl, lab = GO.synth_batch(oc, seed=seed, dtype=torch.float64, **bkw)
+        P = GO.init_params(oc, seed=seed, dtype=torch.float64)
+        eng = GaitSetEngine(GaitSetConfig(**ckw), math_mode="fp32", lr=1e-3)
+        eng.load_params(P)
+        out = eng.loss_and_grad([x.float().cuda() for x in xs], [f.float().cuda() for f in fl], lab.cuda())
+        sig = out["signature"][[0, 1, 2, 30, 61]]
+        regs = {k: torch.zeros_like(v) for k, v in P.items()}
+    eng.ctx.check()
+    assert float(out["triplet"]) == pytest.approx(float(z["triplet"]), rel=1e-5)
+    assert float(out["ce"]) == pytest.approx(float(z["ce"]), rel=1e-5)
+    assert float(out["count"]) == float(z["count"])
+    assert rel(sig, torch.tensor(z["signature"])) < 1e-5
+    if "aux_ce" in z.files:
+        for m, v in enumerate(z["aux_ce"]):
+            assert float(out["aux_ce"][m]) == pytest.approx(float(v), rel=1e-5)
+    got = eng.export_grads()
+    for k, n in zip(z["names"], z["grad_norms"]):
+        k = str(k)
+        # the fixture holds gradients of the TOTAL loss; the engine applies the weight regulariser in the optimiser
+        mine = float((got[k].double().cpu() + regs[k]).norm())
+        assert mine == pytest.approx(float(n), rel=2e-4, abs=1e-9), k
