@@ -466,6 +466,12 @@ class UGaitEngine:
         side.wait_stream(cur)
         torch.cuda.synchronize()
         l0 = self.ctx.launches
+        # no garbage collection while a capture is open: the finaliser of an unrelated, dead CUDAGraph (a previous
+        # engine) calls cudaGraph reset, which is illegal during capture and invalidates it
+        import gc
+        gc.collect()
+        gc_on = gc.isenabled()
+        gc.disable()
         with torch.cuda.stream(side):
             g = torch.cuda.CUDAGraph()
             self._cap = {"cur": g, "segs": [], "pool": torch.cuda.graph_pool_handle(), "mark": self.ctx.launches}
@@ -476,6 +482,8 @@ class UGaitEngine:
                 self._cap["segs"].append((self._cap["cur"], []))
             finally:
                 segs, self._cap = self._cap["segs"], None
+                if gc_on:
+                    gc.enable()
         cur.wait_stream(side)
         self.graph_launches = self.ctx.launches - l0
         return segs
@@ -896,8 +904,15 @@ class UGaitEngine:
                 else:
                     gr = torch.cuda.CUDAGraph()
                     l0 = self.ctx.launches
-                    with torch.cuda.graph(gr):
-                        self._step_body(p, True, expanded)
+                    import gc
+                    gc_on = gc.isenabled()
+                    gc.disable()                     # (see _capture_segments)
+                    try:
+                        with torch.cuda.graph(gr):
+                            self._step_body(p, True, expanded)
+                    finally:
+                        if gc_on:
+                            gc.enable()
                     self.graph_launches = self.ctx.launches - l0   # kernels of ours inside one replay
                 self._graphs[gkey] = gr
                 # the capture itself did not execute: fall through to replay
