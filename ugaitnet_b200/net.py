@@ -369,30 +369,29 @@ class UGaitEngine:
 
     def _forward_branch(self, p: "_Plan", m: int, train: bool, expanded: bool):
         cfg, h, st = self.cfg, self.ctx.h, stream_ptr()
-        if True:   # (kept as a block: body of the former per-branch loop)
-            bn = BRANCH_NAMES[m]
-            b = p.br[m]
-            if expanded:
-                # device-side missing-modality expansion: row i reads base row src_row[i]; a cleared
-                # use-flag turns the row's volume into the reference's 1e-9 constant
-                check(lib.ugn_pack_input_expand(h, b.R["x_base"].ptr, p.R["src_row"].ptr,
-                                                None if cfg.single else p.R_flags[m].ptr,
-                                                p.R["mirror"].ptr if p.use_mirror else None, NOISE,
-                                                b.R["a0"].ptr, st))
-            else:
-                check(lib.ugn_pack_input(h, b.R["x_in"].ptr, b.R["a0"].ptr, st))
-            for li, L in enumerate(b.layers):
-                check(lib.ugn_conv2d_fwd(h, b.R[f"a{li}"].ptr, self.Rcw[f"{bn}/conv{li}/w"].ptr,
-                                         self.Rw[f"{bn}/conv{li}/b"].ptr, b.R[f"a{li + 1}"].ptr,
-                                         b.R[f"idx{li}"].ptr if L["pool"] else None, cfg.act, cfg.alpha,
-                                         int(L["pool"]), st))
-            nl = len(b.layers)
-            check(lib.ugn_flatten_chw(h, b.R[f"a{nl}"].ptr, b.R["flat"].ptr, st))
-            mask = b.R["mask"].ptr if (train and cfg.dropout > 0.001) else None
-            check(lib.ugn_linear_fwd(h, b.R["flat"].ptr, self.Rcw[f"{bn}/dense/w"].ptr, self.Rw[f"{bn}/dense/b"].ptr,
-                                     mask, b.R["h1"].ptr, b.R["h1_16"].ptr if self.P else None, ACT_LINEAR, 0.0, st))
-            check(lib.ugn_linear_fwd(h, (b.R["h1_16"] if self.P else b.R["h1"]).ptr, self.Rcw[f"{bn}/ofCode/w"].ptr,
-                                     self.Rw[f"{bn}/ofCode/b"].ptr, None, b.R["out"].ptr, None, ACT_LINEAR, 0.0, st))
+        bn = BRANCH_NAMES[m]
+        b = p.br[m]
+        if expanded:
+            # device-side missing-modality expansion: row i reads base row src_row[i]; a cleared
+            # use-flag turns the row's volume into the reference's 1e-9 constant
+            check(lib.ugn_pack_input_expand(h, b.R["x_base"].ptr, p.R["src_row"].ptr,
+                                            None if cfg.single else p.R_flags[m].ptr,
+                                            p.R["mirror"].ptr if p.use_mirror else None, NOISE,
+                                            b.R["a0"].ptr, st))
+        else:
+            check(lib.ugn_pack_input(h, b.R["x_in"].ptr, b.R["a0"].ptr, st))
+        for li, L in enumerate(b.layers):
+            check(lib.ugn_conv2d_fwd(h, b.R[f"a{li}"].ptr, self.Rcw[f"{bn}/conv{li}/w"].ptr,
+                                     self.Rw[f"{bn}/conv{li}/b"].ptr, b.R[f"a{li + 1}"].ptr,
+                                     b.R[f"idx{li}"].ptr if L["pool"] else None, cfg.act, cfg.alpha,
+                                     int(L["pool"]), st))
+        nl = len(b.layers)
+        check(lib.ugn_flatten_chw(h, b.R[f"a{nl}"].ptr, b.R["flat"].ptr, st))
+        mask = b.R["mask"].ptr if (train and cfg.dropout > 0.001) else None
+        check(lib.ugn_linear_fwd(h, b.R["flat"].ptr, self.Rcw[f"{bn}/dense/w"].ptr, self.Rw[f"{bn}/dense/b"].ptr,
+                                 mask, b.R["h1"].ptr, b.R["h1_16"].ptr if self.P else None, ACT_LINEAR, 0.0, st))
+        check(lib.ugn_linear_fwd(h, (b.R["h1_16"] if self.P else b.R["h1"]).ptr, self.Rcw[f"{bn}/ofCode/w"].ptr,
+                                 self.Rw[f"{bn}/ofCode/b"].ptr, None, b.R["out"].ptr, None, ACT_LINEAR, 0.0, st))
 
     def _set_inputs(self, p, inputs, flags, labels=None, drop_masks=None, code_drop_mask=None):
         cfg = self.cfg
