@@ -405,13 +405,16 @@ class UWYHSemiNet:
                       weight_decay=1e-4, dropout=0.4, optimizer=None, margin=0.2, nclasses=0,
                       loss_weights=[1.0, 1.0], initnet="", freeze_convs=False, use3D=False, smoothlabels=0,
                       freeze_all=False, postriplet=1, init_branches=None, freeze_branches=False, aux_losses=False,
-                      fMerge=Maximum, fActivation='relu', alpha=0.3, gaitset=False):
+                      fMerge=Maximum, fActivation='relu', gaitset=False):
+        # (the reference's 2-modality build_or_load has no `alpha` argument, :582-588: LeakyReLU keeps build()'s 0.3)
         _unsupported(freeze_convs=freeze_convs, freeze_all=freeze_all)
+        if gaitset:
+            fActivation = 'leaky'          # :588-589
         model = UWYHSemiNet.build(input_shapes, number_convolutional_layers, filters_size, filters_numbers,
                                   ndense_units, weight_decay, dropout, optimizer, margin, nclasses, loss_weights,
                                   use3D=use3D, smoothlabels=smoothlabels, postriplet=postriplet,
                                   init_branches=init_branches, freeze_branches=freeze_branches, aux_losses=aux_losses,
-                                  fMerge=fMerge, fActivation=fActivation, alpha=alpha, gaitset=gaitset)
+                                  fMerge=fMerge, fActivation=fActivation, gaitset=gaitset)
         if initnet != "":
             model.load_weights(UWYHSemiNet.get_weights_filename(initnet), by_name=True, skip_mismatch=True)
         return model
