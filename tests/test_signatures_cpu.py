@@ -42,6 +42,9 @@ _EQUIV = {"optimizers.SGD(0.001, 0.9)": "None"}
                                 "UWYHSemiNet.build", "UWYHSemiNet.build_or_load", "UWYHSemiNet.fit_generator",
                                 "UWYHSemiNet.encode", "UWYHSemiNet.loadnet", "mj_tensor_times_scalar"]),
     ("nets/triplet_loss_all.py", ["triplet_loss"]),
+    ("nets/mj_loss.py", ["mj_l2normalize", "mj_smoothL1", "mj_smoothL1bis", "PairLossLayer.pair_loss", "PairLossLayer.call",
+                         "VerifLossLayer.pair_loss", "VerifLossLayer.call", "TripletLossLayer.__init__",
+                         "TripletLossLayer.triplet_loss", "TripletLossLayer.call"]),
     ("nets/mj_metrics.py", ["mj_eerVerifDist"]),
 ])
 def test_entry_points_keep_reference_signatures(rel, names):
