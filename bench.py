@@ -6,7 +6,12 @@
 A "step" is one Keras train_function step of the 3-modality (OF+gray+depth) TUM-GAID-shaped model
 (nd=2048, 150 classes, sign_max fusion, dropout 0.4, Adam) on one batch of bs=24 literal sequences
 expanded x4 by the reference's missing-modality generator = 96 rows per GPU (weak scaling, batch
-data-parallel, gradient all-reduce over NCCL).  One JSON line is printed by rank 0.
+data-parallel; the gradient exchange is fused into the optimiser kernel over NVLink peer memory, NCCL
+all-reduce as the fallback -- `config.dp_exchange` says which ran).  One JSON line is printed by rank 0:
+the contract keys (value = device-resident rows/s, e2e = pinned-host inputs through the public API,
+roofline = the conv-forward kernel, cpu_baseline = the oracle port on the host cores, clocks,
+gpu_launches) plus two further legs: `knn` (open-world k = 3 search over a 1 M x 256 gallery, sharded over
+the ranks) and, at N = 1, `gaitset` (the same step with the GaitSet branch type).
 """
 from __future__ import annotations
 
