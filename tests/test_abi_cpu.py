@@ -51,3 +51,21 @@ def test_config_geometry_matches_reference_shapes():
     assert [(l["h"], l["ho"], l["hp"]) for l in L] == [(60, 54, 27), (27, 23, 11), (11, 9, 4), (4, 3, 3)]
     assert L[0]["cp"] == 64 and cfg.layers(1, 32)[0]["cp"] == 32
     assert cfg.flat == 4608
+
+
+def test_gaitset_input_layout_matches_generator_restating():
+    """to_gaitset_layout against the literal statements of the reference generator
+    (data/mj_dataGeneratorMMUWYHsingle_repetitions.py:426-434)."""
+    import numpy as np
+    from ugaitnet_b200.expand import to_gaitset_layout
+    rng = np.random.default_rng(0)
+    of = rng.normal(size=(50, 6, 5)).astype(np.float32)
+    x_new = np.zeros((25, of.shape[1], of.shape[2], 2), dtype=of.dtype)
+    x_new[:, :, :, 0] = of[::2, :, :]
+    x_new[:, :, :, 1] = of[1::2, :, :]
+    assert np.array_equal(to_gaitset_layout(of), x_new)
+    gray = rng.normal(size=(25, 6, 5)).astype(np.float32)
+    g_new = np.zeros((25, gray.shape[1], gray.shape[2], 1), dtype=gray.dtype)
+    g_new[:, :, :, 0] = gray
+    assert np.array_equal(to_gaitset_layout(gray), g_new)
+    assert to_gaitset_layout(np.stack([of, of])).shape == (2, 25, 6, 5, 2)

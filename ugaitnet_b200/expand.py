@@ -53,3 +53,19 @@ def mirror_sequence(sample: np.ndarray) -> np.ndarray:
     out = np.asarray(sample)[..., ::-1].copy()
     out[0::2] = -out[0::2]
     return out
+
+
+def to_gaitset_layout(sample: np.ndarray) -> np.ndarray:
+    """Stacked-frame sample [C,H,W] -> the gaitset=True input [25,H,W,c]
+    (data/mj_dataGeneratorMMUWYHsingle_repetitions.py:426-434): an optical-flow sample (C == 50, channels interleaved
+    x0,y0,x1,y1,...) becomes 25 frames of 2 channels (x = even, y = odd channels), any other sample [T,H,W] gets a
+    trailing channel axis of 1.  Accepts a leading batch axis as well."""
+    x = np.asarray(sample)
+    if x.ndim == 4:
+        return np.stack([to_gaitset_layout(s) for s in x])
+    if x.shape[0] == 50:
+        out = np.zeros((25, x.shape[1], x.shape[2], 2), dtype=x.dtype)
+        out[..., 0] = x[::2]
+        out[..., 1] = x[1::2]
+        return out
+    return x[..., None].copy()
