@@ -135,17 +135,60 @@ def _act(x, act, alpha):
     return x
 
 
-def branch_forward(x, P, bn, cfg: NetConfig, drop_mask=None, return_acts=False):
+def _windows2x2(h):
+    """[B,C,H,W] -> [B,C,H//2,W//2,4], window position = dy*2+dx (floor pooling: odd last row/column dropped)."""
+    B, C, H, W = h.shape
+    Hp, Wp = H // 2, W // 2
+    return h[:, :, :2 * Hp, :2 * Wp].reshape(B, C, Hp, 2, Wp, 2).permute(0, 1, 2, 4, 3, 5).reshape(B, C, Hp, Wp, 4)
+
+
+def branch_forward(x, P, bn, cfg: NetConfig, drop_mask=None, return_acts=False, decisions=None, record=None):
     """UWYHNet.buildBranch / buildBranchLReLU (nets/mj_uwyhNets_ba.py:67-107, :110-152).
-    x: [B,Cin,60,60] NCHW.  drop_mask: already-scaled inverted-dropout mask [B,2nd] or None."""
+    x: [B,Cin,60,60] NCHW.  drop_mask: already-scaled inverted-dropout mask [B,2nd] or None.
+
+    Discrete-decision bookkeeping for the gradient-parity tests (tests/test_decisions_gpu.py):
+      record    -- dict that receives, per conv layer li, the decisions this run takes: ``pool{li}`` arg-max position
+                   (dy*2+dx, first maximum wins) of every 2x2 window, ``gap{li}`` = best minus second best activated
+                   value of the window, ``act{li}`` = (selected pre-activation > 0), ``mag{li}`` = |selected pre-activation|;
+      decisions -- dict with ``pool{li}`` / ``act{li}`` taken by ANOTHER implementation: the forward pass then gathers
+                   exactly those window positions and applies exactly those activation branches, so that autograd
+                   routes the gradient the way that implementation did (the graph is linear once the decisions are fixed)."""
     acts = {}
     h = x
     nl = len(cfg.filters_numbers)
     for li in range(nl):
-        h = F.conv2d(h, P[f"{bn}/conv{li}/w"], P[f"{bn}/conv{li}/b"])      # valid, stride 1
-        h = _act(h, cfg.act, cfg.alpha)
-        if li != nl - 1:
-            h = F.max_pool2d(h, 2)                                         # floor pooling
+        z = F.conv2d(h, P[f"{bn}/conv{li}/w"], P[f"{bn}/conv{li}/b"])      # valid, stride 1
+        pooled = li != nl - 1
+        if decisions is None and record is None:
+            h = _act(z, cfg.act, cfg.alpha)
+            if pooled:
+                h = F.max_pool2d(h, 2)                                     # floor pooling
+        else:
+            if pooled:
+                win = _windows2x2(z)                                       # activation is monotonic: pool(act(z)) = act(pool(z))
+                if decisions is not None:
+                    idx = decisions[f"pool{li}"].long()
+                else:                                                      # first maximum of the ACTIVATED window (an all-<=0
+                    a = _act(win.detach(), cfg.act, cfg.alpha)             # ReLU window is a 4-way tie -> position 0)
+                    idx = (a == a.max(dim=4, keepdim=True).values).to(torch.uint8).argmax(dim=4)
+                sel = torch.gather(win, 4, idx.unsqueeze(4)).squeeze(4)
+                if record is not None:
+                    a = _act(win.detach(), cfg.act, cfg.alpha)
+                    top2 = a.topk(2, dim=4).values
+                    record[f"pool{li}"] = idx
+                    record[f"gap{li}"] = top2[..., 0] - top2[..., 1]
+            else:
+                sel = z
+            mask = decisions[f"act{li}"].bool() if decisions is not None else (sel.detach() > 0)
+            if record is not None:
+                record[f"act{li}"] = mask
+                record[f"mag{li}"] = sel.detach().abs()
+            if cfg.act == ACT_RELU:
+                h = torch.where(mask, sel, torch.zeros_like(sel))
+            elif cfg.act == ACT_LEAKY:
+                h = torch.where(mask, sel, cfg.alpha * sel)
+            else:
+                h = sel
         acts[f"conv{li}"] = h
     h = h.flatten(1)                                                       # (C,H,W) order
     h = F.linear(h, P[f"{bn}/dense/w"], P[f"{bn}/dense/b"])
@@ -163,20 +206,25 @@ def l2_normalize(x, axis=1, eps=1e-12):
     return x * torch.rsqrt(torch.clamp(ss, min=eps))
 
 
-def merge_modalities(gated: List[torch.Tensor], merge: int):
+def merge_modalities(gated: List[torch.Tensor], merge: int, winner=None, record=None):
     """fMerge(name="fusion") (nets/mj_uwyhNets_ba.py:1189).
     MAX:     keras Maximum = left fold of tf.maximum (ties -> gradient to the earlier input).
     AVG:     keras Average (gated zeros included in the mean).
     SIGNMAX: mains/mj_trainUWYHGaitNet_DataGen_CasiaB.py:169-178 -- argmax(|x|) over the
-             modality axis (ties -> lowest modality index), gather the signed value."""
+             modality axis (ties -> lowest modality index), gather the signed value.
+    winner: forced winner index [B,d] (another implementation's decision); record: receives ``winner`` and ``wgap``
+    (best minus second best score) of this run."""
     st = torch.stack(gated, 0)
     if merge == MERGE_AVG:
         return st.mean(0)
-    if merge == MERGE_MAX:
-        # explicit first-winner index so autograd routes ties to the earlier input
-        idx = _first_argmax(st)
-    else:
-        idx = _first_argmax(st.abs())
+    score = st if merge == MERGE_MAX else st.abs()
+    # explicit first-winner index so autograd routes ties to the earlier input
+    idx = _first_argmax(score.detach()) if winner is None else winner.long()
+    if record is not None:
+        record["winner"] = idx
+        if st.shape[0] > 1:
+            t2 = score.detach().topk(2, dim=0).values
+            record["wgap"] = t2[0] - t2[1]
     return torch.gather(st, 0, idx.unsqueeze(0)).squeeze(0)
 
 
@@ -258,14 +306,18 @@ def softmax_ce(logits, onehot):
 
 
 def model_forward(inputs, flags, P, cfg: NetConfig, drop_masks=None, code_drop_mask=None,
-                  return_all=False):
+                  return_all=False, decisions=None, record=None):
     """UWYHSemiNet3Mods.build graph (nets/mj_uwyhNets_ba.py:1163-1214) for 2-D CNN branches;
     with cfg.single the 1-modality graph of UWYHSemiNet.build (:900-915)."""
     outs = {}
     gated = []
     for m in range(cfg.nmods):
         dm = None if drop_masks is None else drop_masks[m]
-        b = branch_forward(inputs[m], P, BRANCH_NAMES[m], cfg, dm)
+        rec_m = None
+        if record is not None:
+            rec_m = record.setdefault(m, {})
+        b = branch_forward(inputs[m], P, BRANCH_NAMES[m], cfg, dm, decisions=None if decisions is None else decisions[m],
+                           record=rec_m)
         outs[f"branch{m}"] = b
         if cfg.single:
             gated.append(b)
@@ -278,7 +330,7 @@ def model_forward(inputs, flags, P, cfg: NetConfig, drop_masks=None, code_drop_m
     if cfg.single:
         sig = gated[0]                                                  # :904 (no normalise)
     else:
-        fused = merge_modalities(gated, cfg.merge)
+        fused = merge_modalities(gated, cfg.merge, None if decisions is None else decisions.get("winner"), record)
         outs["fusion"] = fused
         sig = l2_normalize(fused, 1)
     outs["signature"] = sig
@@ -296,11 +348,13 @@ def model_forward(inputs, flags, P, cfg: NetConfig, drop_masks=None, code_drop_m
     return outs if return_all else (outs["signature"], outs.get("logits"))
 
 
-def total_loss(inputs, flags, labels, P, cfg: NetConfig, drop_masks=None, code_drop_mask=None):
+def total_loss(inputs, flags, labels, P, cfg: NetConfig, drop_masks=None, code_drop_mask=None, decisions=None,
+               record=None):
     """model.compile(loss=[triplet, CE], loss_weights=[wver, wid]) + Keras regularisers
     (nets/mj_uwyhNets_ba.py:1297; :79,:104 kernel L2 = wd*sum(w^2) without 1/2; activity
     L2 on "code" = 1e-3*sum(code^2)/batch).  Returns dict of scalars."""
-    outs = model_forward(inputs, flags, P, cfg, drop_masks, code_drop_mask, return_all=True)
+    outs = model_forward(inputs, flags, P, cfg, drop_masks, code_drop_mask, return_all=True, decisions=decisions,
+                         record=record)
     res = {}
     trip, cnt = triplet_loss_all(labels, outs["signature"], cfg.margin)
     res["triplet"], res["count"] = trip, cnt
@@ -336,9 +390,11 @@ def total_loss(inputs, flags, labels, P, cfg: NetConfig, drop_masks=None, code_d
     return res
 
 
-def loss_and_grads(inputs, flags, labels, P, cfg, drop_masks=None, code_drop_mask=None):
+def loss_and_grads(inputs, flags, labels, P, cfg, drop_masks=None, code_drop_mask=None, decisions=None, record=None):
+    """Autograd gradients of the TOTAL loss (regularisers included) w.r.t. every parameter.  decisions / record: see
+    branch_forward -- run with another implementation's discrete decisions injected / export this run's."""
     Pg = {k: v.detach().clone().requires_grad_(True) for k, v in P.items()}
-    res = total_loss(inputs, flags, labels, Pg, cfg, drop_masks, code_drop_mask)
+    res = total_loss(inputs, flags, labels, Pg, cfg, drop_masks, code_drop_mask, decisions, record)
     res["loss"].backward()
     grads = {k: (v.grad if v.grad is not None else torch.zeros_like(v)) for k, v in Pg.items()}
     det = lambda v: v.detach() if torch.is_tensor(v) else ([x.detach() for x in v] if isinstance(v, list) else v)

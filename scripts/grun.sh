@@ -1,0 +1,10 @@
+#!/bin/bash
+# gpurun with retry on "no box free" (exit 3).  usage: scripts/grun.sh <timeout_s> '<command>'
+t=$1; shift
+for i in $(seq 1 30); do
+  /usr/local/graft/bin/gpurun --timeout "$t" -- "$@"
+  rc=$?
+  [ $rc -ne 3 ] && exit $rc
+  sleep 90
+done
+exit 3

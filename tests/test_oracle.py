@@ -212,3 +212,115 @@ def test_oracle_reproduces_step_fixture(golden_dir, name):
     assert np.allclose(got["signature"], z["signature"], rtol=0, atol=1e-12)
     assert list(got["names"]) == list(z["names"])
     assert np.allclose(got["grad_norms"], z["grad_norms"], rtol=1e-10)
+
+
+# ---- second, independent restatement (oracle/numpy_restatement.py): numpy, hand-derived backward -------------------
+def _np_case(name):
+    from oracle import numpy_restatement as NR
+    if name == "3mod_signmax":
+        oc = O.NetConfig(in_channels=(3, 2, 2), filters_numbers=(4, 4, 6, 6), nd=8, nclasses=5, merge=O.MERGE_SIGNMAX,
+                         wver=1.0, wid=0.1)
+        sb = dict(base_rows=4, expand=4)
+    elif name == "2mod_max_leaky_code":
+        oc = O.NetConfig(in_channels=(3, 2), filters_numbers=(4, 4, 6, 6), nd=8, nc=4, nclasses=5, merge=O.MERGE_MAX,
+                         act=O.ACT_LEAKY, wver=0.7, wid=1.0, label_smoothing=0.1)
+        sb = dict(base_rows=6, expand=2, kinds=("of", "gray"))
+    elif name == "3mod_avg_relu_code":
+        oc = O.NetConfig(in_channels=(2, 2, 2), filters_numbers=(4, 4, 6, 6), nd=8, nc=4, nclasses=4, merge=O.MERGE_AVG,
+                         wver=0.5, wid=0.5)
+        sb = dict(base_rows=4, expand=3, kinds=("of", "gray", "sil"))
+    else:
+        oc = O.NetConfig(in_channels=(3,), filters_numbers=(4, 4, 6, 6), nd=8, nclasses=6, single=True, wver=1.0, wid=0.1)
+        sb = dict(base_rows=8, expand=1, kinds=("gray",))
+    xs, fl, lab = O.synth_batch(oc, seed=21, dtype=np.float64, **sb)
+    lab = lab % oc.nclasses
+    P = O.init_params(oc, seed=21, dtype=torch.float64)
+    g = torch.Generator().manual_seed(3)
+    for k in P:
+        if k.endswith("/b"):
+            P[k] = torch.randn(P[k].shape, generator=g, dtype=torch.float64) * 0.05
+    B = xs[0].shape[0]
+    masks = [(torch.rand(B, 2 * oc.nd, generator=g) >= 0.3).double() / 0.7 for _ in range(oc.nmods)]
+    cmask = (torch.rand(B, oc.nc, generator=g) >= 0.3).double() / 0.7 if oc.nc else None
+    return NR, oc, xs, fl, lab, P, masks, cmask
+
+
+@pytest.mark.parametrize("name", ["3mod_signmax", "2mod_max_leaky_code", "3mod_avg_relu_code", "1mod_gray"])
+def test_torch_oracle_equals_independent_numpy_restatement(name):
+    """conv / pool / gate / fusion / l2_normalize / FC1 / FC2+CE / triplet / regularisers: the autograd oracle and the
+    hand-derived numpy restatement agree on every loss (1e-11) and every gradient tensor (1e-9)."""
+    NR, oc, xs, fl, lab, P, masks, cmask = _np_case(name)
+    res, G = O.loss_and_grads([torch.tensor(x) for x in xs], [torch.tensor(f) for f in fl], torch.tensor(lab), P, oc,
+                              masks, cmask)
+    Pn = {k: v.numpy() for k, v in P.items()}
+    rn, Gn = NR.step(xs, fl, lab, Pn, oc, [m.numpy() for m in masks], None if cmask is None else cmask.numpy())
+    # 1mod_gray: the signature is NOT normalised there (|x|^2 ~ 10), and batch_dist forms d^2 by cancellation
+    # (x2a + x2b - 2ab): two summation orders differ by ~1e-16 |x|^2 / d^2 -> 1e-9 relative
+    ltol, gtol = (5e-9, 1e-7) if oc.single else (1e-11, 1e-9)
+    for key in ("triplet", "ce", "reg", "loss", "acc"):
+        assert float(rn[key]) == pytest.approx(float(res[key]), rel=ltol, abs=1e-13), key
+    assert float(rn["count"]) == float(res["count"].sum())
+    assert np.allclose(rn["signature"], res["signature"].numpy(), rtol=1e-11, atol=1e-13)
+    assert set(Gn) == set(G)
+    for k in G:
+        ref = G[k].numpy()
+        assert np.abs(Gn[k] - ref).max() <= gtol * max(np.abs(ref).max(), 1e-6), k
+
+
+def test_numpy_restatement_gradients_match_finite_differences():
+    """The hand-derived backward against central differences of its own forward (a few coordinates per tensor)."""
+    NR, oc, xs, fl, lab, P, masks, cmask = _np_case("2mod_max_leaky_code")
+    Pn = {k: v.numpy().copy() for k, v in P.items()}
+    mk = [m.numpy() for m in masks]
+    _, Gn = NR.step(xs, fl, lab, Pn, oc, mk, cmask.numpy())
+    rng = np.random.default_rng(0)
+    h = 1e-7        # the graph is piecewise linear in places (LeakyReLU / pool / hinge kinks): a small step keeps both
+    for k in Pn:    # probes on one piece (measured: 1e-6 already straddles a kink for one conv0 weight); fp64 noise ~1e-9
+        flat = Pn[k].reshape(-1)
+        for j in rng.choice(flat.size, size=min(3, flat.size), replace=False):
+            w0 = flat[j]
+            flat[j] = w0 + h
+            lp = NR.step(xs, fl, lab, Pn, oc, mk, cmask.numpy(), want_grads=False)[0]["loss"]
+            flat[j] = w0 - h
+            lm = NR.step(xs, fl, lab, Pn, oc, mk, cmask.numpy(), want_grads=False)[0]["loss"]
+            flat[j] = w0
+            fd = (lp - lm) / (2 * h)
+            an = Gn[k].reshape(-1)[j]
+            assert abs(fd - an) <= 2e-6 * max(1.0, abs(an)) + 1e-8, (k, j, fd, an)
+
+
+def test_adam_update_equals_independent_numpy_restatement():
+    NR, oc, xs, fl, lab, P, masks, cmask = _np_case("3mod_signmax")
+    Pt = {k: v.clone() for k, v in P.items()}
+    Mt = {k: torch.zeros_like(v) for k, v in P.items()}
+    Vt = {k: torch.zeros_like(v) for k, v in P.items()}
+    Pn = {k: v.numpy().copy() for k, v in P.items()}
+    Mn = {k: np.zeros_like(v) for k, v in Pn.items()}
+    Vn = {k: np.zeros_like(v) for k, v in Pn.items()}
+    mk = [m.numpy() for m in masks]
+    for t in (1, 2, 3):
+        _, G = O.loss_and_grads([torch.tensor(x) for x in xs], [torch.tensor(f) for f in fl], torch.tensor(lab), Pt, oc, masks)
+        O.adam_step(Pt, G, Mt, Vt, t, lr=1e-3)
+        _, Gn = NR.step(xs, fl, lab, Pn, oc, mk)
+        NR.adam_update(Pn, Gn, Mn, Vn, t, lr=1e-3)
+    for k in Pn:
+        assert np.abs(Pn[k] - Pt[k].numpy()).max() <= 1e-9, k
+
+
+def test_decision_injection_reproduces_free_run():
+    """oracle.loss_and_grads(decisions=its own recorded decisions) == the free-running oracle (the machinery the GPU
+    gradient-parity tests rely on, tests/test_decisions_gpu.py)."""
+    NR, oc, xs, fl, lab, P, masks, cmask = _np_case("3mod_signmax")
+    args = ([torch.tensor(x) for x in xs], [torch.tensor(f) for f in fl], torch.tensor(lab), P, oc, masks)
+    rec = {}
+    r0, G0 = O.loss_and_grads(*args)
+    r1, G1 = O.loss_and_grads(*args, record=rec)
+    dec = {m: {k: v for k, v in rec[m].items() if k.startswith(("pool", "act"))} for m in range(oc.nmods)}
+    dec["winner"] = rec["winner"]
+    r2, G2 = O.loss_and_grads(*args, decisions=dec)
+    for k in G0:
+        assert torch.equal(G0[k], G1[k]) and torch.allclose(G0[k], G2[k], rtol=0, atol=1e-15), k
+    # a deliberately flipped arg-max reroutes the gradient of the tensors upstream of it
+    dec[0]["pool1"] = (dec[0]["pool1"] + 1) % 4
+    _, G3 = O.loss_and_grads(*args, decisions=dec)
+    assert not torch.allclose(G3["ofBranch/conv0/w"], G0["ofBranch/conv0/w"])

@@ -287,6 +287,27 @@ class UGaitEngine:
     def export_grads(self):
         return self._export(self.pg_)
 
+    def export_decisions(self, B: int, train: bool = True):
+        """The discrete decisions the last forward pass of batch size B took, in the oracle's layout: per modality m
+        ``{pool{li}: [B,C,Hp,Wp] arg-max position dy*2+dx, act{li}: [B,C,Hp,Wp] bool (selected pre-activation > 0)}``
+        and ``winner`` [B,nd] (max / sign_max fusion).  Read back from the buffers the backward pass itself routes
+        gradients with (pool arg-max bytes, stored activations, fusion winner bytes): parity tests inject them into the
+        CPU oracle so that gradients are compared on identical routing (tests/test_decisions_gpu.py)."""
+        p = self._plans[(B, train)]
+        dec = {}
+        for m, b in enumerate(p.br):
+            d = {}
+            for li, L in enumerate(b.layers):
+                a = b.T[f"a{li + 1}"]
+                a = a.float().sum(0) if self.P else a                       # 16-bit planes: value = hi + lo
+                d[f"act{li}"] = (a > 0).permute(0, 3, 1, 2).contiguous().cpu()
+                if L["pool"]:
+                    d[f"pool{li}"] = b.T[f"idx{li}"].permute(0, 3, 1, 2).contiguous().cpu()
+            dec[m] = d
+        if not self.cfg.single:
+            dec["winner"] = p.T["winner"].cpu()
+        return dec
+
     # ------------------------------------------------------------------ plans
     def plan(self, B: int, train: bool) -> "_Plan":
         key = (B, train)
