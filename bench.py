@@ -43,7 +43,14 @@ NCU_TRAFFIC = {"conv_fwd_bytes_per_step": 319.6e6}
 
 DTYPE_NAMES = {"fp32": "f32", "bf16": "bf16", "bf16x3": "bf16 (3-pass hi/lo split, fp32 accumulate)",
                "f16x3": "f16 (3-pass hi/lo split, fp32 accumulate)",
-               "f16mix": "f16 (forward: 3-pass hi/lo split; backward: 1 pass, scaled fp16 gradients; fp32 accumulate)"}
+               "f16mix": "f16 (forward: 3-pass hi/lo split; backward: 1 pass, scaled fp16 gradients; fp32 accumulate)",
+               "f16mix2": "f16 (forward: 2 passes, weights hi/lo split x activations hi; backward: 1 pass; fp32 accumulate)",
+               "f16mix1": "f16 (forward and backward: 1 pass on 11-bit operands; fp32 accumulate)"}
+
+
+# MMA passes issued per algorithmic product (forward, backward) in each math mode
+MMA_PASSES = {"fp32": (1, 1), "bf16": (1, 1), "bf16x3": (3, 3), "f16x3": (3, 3), "f16mix": (3, 1), "f16mix2": (2, 1),
+              "f16mix1": (1, 1)}
 
 
 def peaks():
@@ -403,7 +410,7 @@ def main():
             conv_fwd_row = 2.0214e9 + 2 * 1.3356e9
             conv_flops = (3 * conv_fwd_row - (1.3717e9 + 2 * 0.6858e9)) * B
             # MMA passes issued per algorithmic product (forward, backward)
-            pf, pb = {"fp32": (1, 1), "bf16": (1, 1), "bf16x3": (3, 3), "f16x3": (3, 3), "f16mix": (3, 1)}[args.mode]
+            pf, pb = MMA_PASSES[args.mode]
             fwd_flops = conv_fwd_row * B
             passes = (pf * fwd_flops + pb * (conv_flops - fwd_flops)) / conv_flops
             ach = conv_flops / (conv_ms * 1e-3) / 1e12
@@ -527,7 +534,7 @@ def gaitset_leg(pk, args):
     conv_ms = sum(agg.get(k, 0.0) for k in ("ugn_conv2d_fwd", "ugn_conv2d_dgrad", "ugn_conv2d_wgrad"))
     tc_flops = (train_row - 2 * sum(T * fr(64, c, 32, 5) for c in cfg.in_channels)) * B     # a1 runs on the FFMA pipe
     ach = tc_flops / (conv_ms * 1e-3) / 1e12 if conv_ms else 0.0
-    pf, pb = {"fp32": (1, 1), "bf16": (1, 1), "bf16x3": (3, 3), "f16x3": (3, 3), "f16mix": (3, 1)}[args.mode]
+    pf, pb = MMA_PASSES[args.mode]
     passes = (pf + 2 * pb) / 3.0
     out["roofline"] = {"bound": "tensor", "kernel": "tc_convp_kernel / tc_wgradv_kernel on the 3x3 'same' layers",
                        "achieved": ach, "peak": pk["tf_sust"], "unit": "TFLOP/s", "frac": ach / pk["tf_sust"],

@@ -372,6 +372,21 @@ int ugn_split_bf16(ugn_ctx*, const ugn_tensor* src_f32, ugn_tensor* dst_bf16, vo
 int ugn_grad_scale_update(ugn_ctx*, const ugn_tensor* ref, float target, void* stream);
 int ugn_grad_scale_set(ugn_ctx*, float scale, void* stream);
 
+/* out f32 [cols] = column sums of x f32 [rows, cols]: the bias gradient of a Dense layer taken from the f32 output
+ * gradient BEFORE it is rounded to a 16-bit GEMM operand.  Where the rows of dy cancel (sum_b dL/dsignature_b = 0 for the
+ * translation-invariant triplet loss on an un-normalised signature, nets/mj_uwyhNets_ba.py:900-915), the sum of the
+ * rounded operand carries the rounding noise of every row against a near-zero total. */
+int ugn_colsum(ugn_ctx*, const ugn_tensor* x, ugn_tensor* out, void* stream);
+
+/* MMA passes per product of the FORWARD convolution / dense layers when their operands are hi/lo split
+ * 16-bit planes (host-side ctx state, not stream-ordered; applies to ugn_conv2d_fwd / ugn_linear_fwd):
+ *   0 or 3: hi*hi + hi*lo + lo*hi (~fp32 products)      1: hi*hi only (11-bit operands, "TF32 class")
+ *   2: hi*hi + hi*lo(weights): activations at 11 bits, weights at 22 -- the activation lo plane is not even loaded
+ *   4: hi*hi + lo(activations)*hi: weights at 11 bits -- the weight lo plane is not loaded (weight-streaming dense layers)
+ * Replaces nothing in the reference (Keras computes in fp32, nets/mj_uwyhNets_ba.py:82-105); it is the precision knob
+ * of the tensor-core restatement, gated by tests/test_decisions_gpu.py. */
+int ugn_set_fwd_passes(ugn_ctx*, int conv_passes, int dense_passes);
+
 /* number of kernels this library has launched on this ctx since creation (bench.py's
  * gpu_launches claim is read from here). */
 int64_t ugn_launch_count(ugn_ctx*);

@@ -168,9 +168,11 @@ def branch_forward(x, P, bn, cfg: NetConfig, drop_mask=None, return_acts=False, 
                 win = _windows2x2(z)                                       # activation is monotonic: pool(act(z)) = act(pool(z))
                 if decisions is not None:
                     idx = decisions[f"pool{li}"].long()
-                else:                                                      # first maximum of the ACTIVATED window (an all-<=0
-                    a = _act(win.detach(), cfg.act, cfg.alpha)             # ReLU window is a 4-way tie -> position 0)
-                    idx = (a == a.max(dim=4, keepdim=True).values).to(torch.uint8).argmax(dim=4)
+                else:
+                    # first maximum of the window.  The activation is monotonic, so this is the arg-max of the activated
+                    # window wherever its maximum is positive; an all-<=0 ReLU window is a 4-way tie of zeros that routes
+                    # no gradient, and recording its largest pre-activation tells how far it is from switching on
+                    idx = win.detach().argmax(dim=4)
                 sel = torch.gather(win, 4, idx.unsqueeze(4)).squeeze(4)
                 if record is not None:
                     a = _act(win.detach(), cfg.act, cfg.alpha)

@@ -136,10 +136,11 @@ def test_step_parity_fp32(name):
     print(f"[{name}] worst gradient rel err {worst:.2e}")
 
 
-# Gradient tolerance: with ~16-bit (hi+lo) activations a few of the ~10^6 max-pool / ReLU decisions
-# land on the other side of their boundary than in fp64; each flip reroutes that window's gradient,
-# so tensors upstream of the pools (conv0 is the worst) show a few 1e-3 of norm-wise deviation even
-# though every GEMM is accurate to ~1e-5 (scripts/tc_check.py).  Losses and descriptors meet 1e-3.
+# FREE-RUNNING gradient comparison (engine decisions vs oracle decisions, no accounting): 9-12 of the 2.5 M max-pool /
+# ReLU decisions of this case are ties to within 1e-6 of the activation scale and fall on the other side than in
+# fp64; each flip reroutes that window's gradient, so the tensors upstream of it deviate by a few 1e-3 although the
+# arithmetic is accurate to ~1e-5.  The 1e-3 north_star gate is asserted, with every flip accounted for, in
+# tests/test_decisions_gpu.py; the bound here only catches gross errors of the free-running comparison.
 @pytest.mark.parametrize("mode,loss_tol,grad_tol", [("bf16x3", 1e-3, 1e-2), ("f16x3", 1e-3, 1e-2),
                                                     ("f16mix", 1e-3, 1e-2), ("bf16", 1e-1, 5e-1)])
 def test_step_parity_tensor_core(mode, loss_tol, grad_tol):

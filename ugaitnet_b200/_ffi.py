@@ -97,6 +97,8 @@ _PROTOS = {
     "ugn_gemm_bf16": (c_int, [c_void_p, _T, c_int, _T, c_int, _T, c_int, c_void_p]),
     "ugn_grad_scale_update": (c_int, [c_void_p, _T, c_float, c_void_p]),
     "ugn_grad_scale_set": (c_int, [c_void_p, c_float, c_void_p]),
+    "ugn_set_fwd_passes": (c_int, [c_void_p, c_int, c_int]),
+    "ugn_colsum": (c_int, [c_void_p, _T, _T, c_void_p]),
 }
 
 EXPORTED_SYMBOLS = tuple(_PROTOS)

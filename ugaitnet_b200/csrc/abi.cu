@@ -645,6 +645,26 @@ extern "C" int ugn_grad_scale_set(ugn_ctx* ctx, float scale, void* stream) {
   return ew_gscale_update(ctx, nullptr, 0, 1.f, scale, (cudaStream_t)stream);
 }
 
+// ---- f32 column sums (bias gradient of a Dense layer from the UNROUNDED f32 output gradient) ----
+extern "C" int ugn_colsum(ugn_ctx* ctx, const ugn_tensor* x, ugn_tensor* out, void* stream) {
+  UGN_CHECK(ctx && x && out, "ugn_colsum: null argument");
+  UGN_TENSOR(x, DT_F32, 2, 2);
+  UGN_TENSOR(out, DT_F32, 1, 1);
+  UGN_CHECK(out->shape[0] == x->shape[1], "ugn_colsum: out must be [cols]");
+  return simt_colsum(ctx, ugn_ptr<float>(x), x->shape[0], (int)x->shape[1], (int)x->shape[1], ugn_ptr<float>(out),
+                     (cudaStream_t)stream);
+}
+
+// ---- MMA passes of the forward tensor-core layers over hi/lo split operands --------------------
+extern "C" int ugn_set_fwd_passes(ugn_ctx* ctx, int conv_passes, int dense_passes) {
+  UGN_CHECK(ctx, "ugn_set_fwd_passes: null ctx");
+  UGN_CHECK((conv_passes >= 0 && conv_passes <= 4) && (dense_passes >= 0 && dense_passes <= 4),
+            "ugn_set_fwd_passes: pass codes are 0 (all three) | 1 | 2 | 3 | 4");
+  ctx->fwd_conv_pass = conv_passes;
+  ctx->fwd_dense_pass = dense_passes;
+  return UGN_OK;
+}
+
 // ---- a13: video-level pooling and vote --------------------------------------------------------
 int ew_segment_pool(ugn_ctx*, const float*, const int*, const int*, int, int, int, float*, cudaStream_t);
 int ew_segment_mode(ugn_ctx*, const int*, const int*, const int*, int, int, int*, cudaStream_t);

@@ -29,6 +29,10 @@ struct ugn_ctx {
   // and every kernel that consumes them multiplies its f32 output by 1/s (fp16 range management;
   // lives in device memory so that a captured CUDA graph picks up each step's value)
   float* gscale = nullptr;
+  // MMA passes per product of the FORWARD tensor-core layers over split (hi/lo) operands (ugn_set_fwd_passes;
+  // 0 = all three): 1 hi*hi, 2 hi*hi + hi*lo(weights), 4 hi*hi + lo(activations)*hi.  gemm_npass is the transient
+  // hand-over from tc_linear_fwd to tc_gemm_ex
+  int fwd_conv_pass = 0, fwd_dense_pass = 0, gemm_npass = 0;
   // grow-only device scratch (split-K partial sums of small convolutions); sized on first use, i.e. in
   // the warm-up step before any CUDA-graph capture
   // round-robin pool (the engine runs the modality branches on concurrent streams: consecutive calls

@@ -33,6 +33,11 @@ struct TcParams {
   int mode, epi;
   int M, N, block_n;
   int ksteps_total, ksplit, kslices, planes, stages;
+  // MMA passes per product over split (hi/lo) operands and the planes each operand actually loads:
+  //   1: hi*hi                     (pa = 1, pb = 1)     3: hi*hi + hi*lo + lo*hi (pa = 2, pb = 2)
+  //   2: hi*hi + hi*lo(B)          (pa = 1, pb = 2)     4: hi*hi + lo(A)*hi      (pa = 2, pb = 1)
+  // `planes` stays the plane count of the TENSORS (TMA map extent, epilogue output planes)
+  int npass, pa, pb;
   // conv
   int bw, bh, bn, ntx, nty, KW, ncc, sgn, Wout, Hout, Bn, Cout;
   int Hp, Wp;
@@ -282,11 +287,11 @@ __device__ __forceinline__ void convp_pool_epilogue(const TcParams& p, float* st
 
 // PL2 (split operands) and KSL (K slices per ring stage; 0 = run-time) are compile-time so that the MMA issue
 // sequence of a stage is straight-line code (see tc_convp_kernel).
-template <int MODE, bool PL2, int KSL>
+template <int MODE, int NPASS, int KSL>
 __global__ void __launch_bounds__(kThreads, 1) tc_kernel(const __grid_constant__ TcParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // carve: [stages x (A planes | B planes)] | barriers | tmem ptr
-  const uint32_t a_stage = p.planes * p.a.plane_bytes, b_stage = p.planes * p.b.plane_bytes;
+  const uint32_t a_stage = p.pa * p.a.plane_bytes, b_stage = p.pb * p.b.plane_bytes;
   const uint32_t stage_bytes = a_stage + b_stage;
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + (size_t)p.stages * stage_bytes);
@@ -338,7 +343,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_kernel(const __grid_constant__
       int remain = p.nch * p.ntaps - tile_n * p.b.nbox;
       nb_b = min(nb_b, remain);
     }
-    const uint32_t tx_bytes = p.planes * (p.a.nbox * p.a.box_bytes + nb_b * p.b.box_bytes);
+    const uint32_t tx_bytes = p.pa * p.a.nbox * p.a.box_bytes + p.pb * nb_b * p.b.box_bytes;
     // incremental K-step decode (no div/mod in the loop)
     int d0 = 0, d1 = 0, d2 = 0;   // CONV: cc, kw, kh ; WGRAD: bx, by, bb
     if (MODE == MODE_CONV) { d0 = ks_beg % p.ncc; int tap = ks_beg / p.ncc; d1 = tap % p.KW; d2 = tap / p.KW; }
@@ -350,30 +355,32 @@ __global__ void __launch_bounds__(kThreads, 1) tc_kernel(const __grid_constant__
       const int ks = ks_beg + it;
       uint8_t* sa = smem + (size_t)s * stage_bytes;
       uint8_t* sb = sa + a_stage;
-      for (int pl = 0; pl < p.planes; ++pl) {
+      const int plmax = p.pa > p.pb ? p.pa : p.pb;
+      for (int pl = 0; pl < plmax; ++pl) {
+        const bool la_ = pl < p.pa, lb_ = pl < p.pb;       // which operands load this plane
         if (MODE == MODE_GEMM) {
-          for (int j = 0; j < p.a.nbox; ++j) {
+          for (int j = 0; la_ && j < p.a.nbox; ++j) {
             if (p.a.major == 0) tma_load_5d(&p.a.map, &full[s], sa + pl * p.a.plane_bytes, ks * BK, m0, pl, 0, 0);
             else tma_load_5d(&p.a.map, &full[s], sa + pl * p.a.plane_bytes + j * p.a.box_bytes, m0 + j * cwA, ks * BK, pl, 0, 0);
           }
-          for (int j = 0; j < p.b.nbox; ++j) {
+          for (int j = 0; lb_ && j < p.b.nbox; ++j) {
             if (p.b.major == 0) tma_load_5d(&p.b.map, &full[s], sb + pl * p.b.plane_bytes, ks * BK, n0, pl, 0, 0);
             else tma_load_5d(&p.b.map, &full[s], sb + pl * p.b.plane_bytes + j * p.b.box_bytes, n0 + j * cwB, ks * BK, pl, 0, 0);
           }
         } else if (MODE == MODE_CONV) {
           const int cc = d0, kw = d1, kh = d2, tap = kh * p.KW + kw;
-          tma_load_5d(&p.a.map, &full[s], sa + pl * p.a.plane_bytes, cc * BK, x0 + p.sgn * kw, y0 + p.sgn * kh, nn0, pl);
-          for (int j = 0; j < p.b.nbox; ++j) {
+          if (la_) tma_load_5d(&p.a.map, &full[s], sa + pl * p.a.plane_bytes, cc * BK, x0 + p.sgn * kw, y0 + p.sgn * kh, nn0, pl);
+          for (int j = 0; lb_ && j < p.b.nbox; ++j) {
             if (p.b.major == 0) tma_load_5d(&p.b.map, &full[s], sb + pl * p.b.plane_bytes, cc * BK, tap, n0, pl, 0);
             else tma_load_5d(&p.b.map, &full[s], sb + pl * p.b.plane_bytes + j * p.b.box_bytes, n0 + j * cwB, tap, cc * BK, pl, 0);
           }
         } else {
           const int px = d0 * p.bw, py = d1 * p.bh, pn = d2 * p.bn;
-          for (int j = 0; j < p.a.nbox; ++j)
+          for (int j = 0; la_ && j < p.a.nbox; ++j)
             tma_load_5d(&p.a.map, &full[s], sa + pl * p.a.plane_bytes + j * p.a.box_bytes, m0 + j * cwA, px, py, pn, pl);
           int chunk = (tile_n * p.b.nbox) % p.nch, tap = (tile_n * p.b.nbox) / p.nch;
           int tkw = tap % p.KW, tkh = tap / p.KW;
-          for (int j = 0; j < nb_b; ++j) {
+          for (int j = 0; lb_ && j < nb_b; ++j) {
             tma_load_5d(&p.b.map, &full[s], sb + pl * p.b.plane_bytes + j * p.b.box_bytes, chunk * p.cw,
                               px + tkw, py + tkh, pn, pl);
             if (++chunk == p.nch) { chunk = 0; if (++tkw == p.KW) { tkw = 0; ++tkh; } }
@@ -408,10 +415,8 @@ __global__ void __launch_bounds__(kThreads, 1) tc_kernel(const __grid_constant__
         const uint64_t ak = a_hi + (uint64_t)(k * ka16), bk = b_hi + (uint64_t)(k * kb16);
         umma_f16(tmem_base, ak, bk, idesc, accum);
         accum = 1;
-        if (PL2) {
-          umma_f16(tmem_base, ak, bk + pb16, idesc, 1);
-          umma_f16(tmem_base, ak + pa16, bk, idesc, 1);
-        }
+        if (NPASS == 2 || NPASS == 3) umma_f16(tmem_base, ak, bk + pb16, idesc, 1);
+        if (NPASS == 3 || NPASS == 4) umma_f16(tmem_base, ak + pa16, bk, idesc, 1);
       }
       umma_commit(&empty[s]);  // frees the smem slot once these MMAs have read it
       if (++s == p.stages) { s = 0; ph ^= 1; }
@@ -506,15 +511,15 @@ __global__ void __launch_bounds__(kThreads, 1) tc_kernel(const __grid_constant__
 // TT (tiles per work item), KSL (K slices per ring stage) and PL2 (split operands) are compile-time too, so
 // that the MMA issue sequence of one ring stage is a straight line of UTCHMMAs with immediate descriptor
 // offsets.
-template <bool CONCAT, bool PROF, int TT, int KSL, bool PL2>
+template <bool CONCAT, bool PROF, int TT, int KSL, int NPASS>
 __global__ void __launch_bounds__(kConvpThreads, 1) tc_convp_kernel(const __grid_constant__ TcParams p) {
   // PERSISTENT: each CTA walks tiles blockIdx.x, +gridDim.x, ...; two TMEM accumulator sets so that the
   // epilogue of tile i (CUDA cores) overlaps the mainloop of tile i+1 (tensor pipe).
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   // patch slot = cps channel chunks x planes; nslots == 2 streams the chunks through a 2-deep ring
-  const uint32_t slot_bytes = p.planes * p.patch_plane_bytes;
-  const uint32_t b_stage = p.planes * p.b.plane_bytes;
+  const uint32_t slot_bytes = p.pa * p.patch_plane_bytes;
+  const uint32_t b_stage = p.pb * p.b.plane_bytes;
   uint8_t* stg = smem + p.nslots * slot_bytes;                 // epilogue staging, 128 x 33 floats (17 KB region)
   uint8_t* ring = stg + 17 * 1024;
   uint64_t* full = reinterpret_cast<uint64_t*>(ring + (size_t)p.stages * b_stage);
@@ -555,7 +560,7 @@ __global__ void __launch_bounds__(kConvpThreads, 1) tc_convp_kernel(const __grid
   if (warp == 0) {
    if (elect_one()) {
     // ---- producer ----
-    const uint32_t tx_bytes = p.planes * p.b.nbox * p.b.box_bytes;
+    const uint32_t tx_bytes = p.pb * p.b.nbox * p.b.box_bytes;
     int s = 0, ph = 0, li = 0;
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++li) {
       const int tile_n = tile / tiles_mn, rem = tile % tiles_mn;
@@ -568,7 +573,7 @@ __global__ void __launch_bounds__(kConvpThreads, 1) tc_convp_kernel(const __grid
         mbar_wait(&patch_empty[slot], sph ^ 1, p.err, 5);
         if (PROF) atomicAdd((unsigned long long*)p.dbg + 7, (unsigned long long)(clock64() - tw0));
         mbar_expect_tx(&patch_full[slot], slot_bytes);
-        for (int pl = 0; pl < p.planes; ++pl)
+        for (int pl = 0; pl < p.pa; ++pl)
           for (int c = 0; c < p.cps; ++c)
             tma_load_5d(&p.a.map, &patch_full[slot], pslot + pl * p.patch_plane_bytes + c * p.patch_chunk_bytes,
                         (g * p.cps + c) * (p.a.rowbytes >> 1), p.xorg, y0 + p.yorg, img, pl);
@@ -580,7 +585,7 @@ __global__ void __launch_bounds__(kConvpThreads, 1) tc_convp_kernel(const __grid
           if (PROF) atomicAdd((unsigned long long*)p.dbg + 6, (unsigned long long)(clock64() - tw1));
           mbar_expect_tx(&full[s], tx_bytes);
           uint8_t* sb = ring + (size_t)s * b_stage;
-          for (int pl = 0; pl < p.planes; ++pl)
+          for (int pl = 0; pl < p.pb; ++pl)
             for (int j = 0; j < p.b.nbox; ++j) {
               if (p.b.major == 0) tma_load_5d(&p.b.map, &full[s], sb + pl * p.b.plane_bytes, cc * BK, tap, n0, pl, 0);
               else tma_load_5d(&p.b.map, &full[s], sb + pl * p.b.plane_bytes + j * p.b.box_bytes, n0 + j * cwB, tap, cc * BK, pl, 0);
@@ -637,13 +642,11 @@ __global__ void __launch_bounds__(kConvpThreads, 1) tc_convp_kernel(const __grid
             const uint64_t b_hi = b_st + (uint64_t)(k * kb16);
             if (CONCAT) {
               umma_f16(td, a_hi, b_hi, idesc2, (k > 0) ? 1u : acc0);   // [hi*hi | hi*lo], N = 2*block_n
-              umma_f16(td, a_hi + pa16, b_hi, idesc, 1);               // lo*hi into the hi*hi columns
+              if (NPASS == 3) umma_f16(td, a_hi + pa16, b_hi, idesc, 1);   // lo*hi into the hi*hi columns
             } else {
               umma_f16(td, a_hi, b_hi, idesc, (k > 0) ? 1u : acc0);
-              if (PL2) {
-                umma_f16(td, a_hi, b_hi + pb16, idesc, 1);
-                umma_f16(td, a_hi + pa16, b_hi, idesc, 1);
-              }
+              if (NPASS == 2 || NPASS == 3) umma_f16(td, a_hi, b_hi + pb16, idesc, 1);
+              if (NPASS == 3 || NPASS == 4) umma_f16(td, a_hi + pa16, b_hi, idesc, 1);
             }
           }
         }
@@ -937,7 +940,8 @@ template <int MODE>
 static int launch(ugn_ctx* ctx, TcParams& p, dim3 grid, cudaStream_t st) {
   UGN_CHECK(ctx->cc_major == 10, "tensor-core path needs an sm_100 device (found sm_%d%d)", ctx->cc_major, ctx->cc_minor);
   UGN_CHECK(p.block_n % 16 == 0 && p.block_n >= 16 && p.block_n <= 256, "block_n=%d invalid", p.block_n);
-  size_t stage = (size_t)p.planes * (p.a.plane_bytes + p.b.plane_bytes);
+  if (p.npass == 0) { p.npass = p.planes == 2 ? 3 : 1; p.pa = p.pb = p.planes; }
+  size_t stage = (size_t)p.pa * p.a.plane_bytes + (size_t)p.pb * p.b.plane_bytes;
   int stages = (int)std::min<size_t>(8, (200 * 1024) / stage);
   UGN_CHECK(stages >= 2, "tensor-core tile does not fit shared memory (stage=%zu B)", stage);
   stages = std::min(stages, std::max(2, (p.ksteps_total + p.ksplit - 1) / p.ksplit));
@@ -949,16 +953,21 @@ static int launch(ugn_ctx* ctx, TcParams& p, dim3 grid, cudaStream_t st) {
     UGN_CUDA(cudaMemset(ctx->err_flag, 0, sizeof(int)));
   }
   p.err = ctx->err_flag;
-#define TC_LAUNCH(PL2, KSL)                                                                                     \
+#define TC_LAUNCH(NP, KSL)                                                                                      \
   do {                                                                                                         \
-    UGN_CUDA(cudaFuncSetAttribute(tc_kernel<MODE, PL2, KSL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-    tc_kernel<MODE, PL2, KSL><<<grid, kThreads, smem, st>>>(p);                                                \
+    UGN_CUDA(cudaFuncSetAttribute(tc_kernel<MODE, NP, KSL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+    tc_kernel<MODE, NP, KSL><<<grid, kThreads, smem, st>>>(p);                                                 \
   } while (0)
-  if (p.planes == 2) {
-    if (p.kslices == 4) TC_LAUNCH(true, 4); else if (p.kslices == 2) TC_LAUNCH(true, 2); else TC_LAUNCH(true, 0);
-  } else {
-    if (p.kslices == 4) TC_LAUNCH(false, 4); else if (p.kslices == 2) TC_LAUNCH(false, 2); else TC_LAUNCH(false, 0);
-  }
+#define TC_LAUNCH_K(NP)                                                                                         \
+  do {                                                                                                         \
+    if (p.kslices == 4) TC_LAUNCH(NP, 4); else if (p.kslices == 2) TC_LAUNCH(NP, 2); else TC_LAUNCH(NP, 0);    \
+  } while (0)
+  if (p.npass == 3) TC_LAUNCH_K(3);
+  else if (p.npass == 1) TC_LAUNCH_K(1);
+  else if (MODE != MODE_WGRAD && p.npass == 2) TC_LAUNCH_K(2);
+  else if (MODE != MODE_WGRAD && p.npass == 4) TC_LAUNCH_K(4);
+  else UGN_FAIL(UGN_ERR_UNSUPPORTED, "tc_kernel: npass=%d unsupported in mode %d", p.npass, MODE);
+#undef TC_LAUNCH_K
 #undef TC_LAUNCH
   UGN_LAUNCHED(ctx);
   return UGN_OK;
@@ -992,8 +1001,13 @@ int tc_gemm_ex(ugn_ctx* ctx, int P, int f16, int M, int N, int K, const __nv_bfl
   TcParams p{};
   p.mode = MODE_GEMM; p.f16 = f16; p.oscale = oscale;
   p.M = M; p.N = N; p.planes = P;
+  if (P == 2 && ctx->gemm_npass) {       // forward dense layers: reduced pass count (ugn_set_fwd_passes)
+    p.npass = ctx->gemm_npass;
+    p.pa = (p.npass == 3 || p.npass == 4) ? 2 : 1;
+    p.pb = (p.npass == 2 || p.npass == 3) ? 2 : 1;
+  }
   p.block_n = N > 128 ? 256 : (N > 64 ? 128 : 64);
-  if (P == 2 && p.block_n > 128) p.block_n = 128;
+  if (P == 2 && p.block_n > 128 && !(p.npass == 1 || p.npass == 4)) p.block_n = 128;
   p.kslices = 4;
   const int BK = 64;
   int rc;
@@ -1051,6 +1065,8 @@ static void conv_box(int Wn, int Hn, int Bn, int pool, int& bw, int& bh, int& bn
 // the geometry does not fit so that the caller falls back to the per-tap-box kernel.
 static int convp_launch(ugn_ctx* ctx, TcParams& p, const __nv_bfloat16* act, int P, int B, int H, int W, int C,
                         int KH, int KW, int Wneed, int Hneed, int pool, int sgn, cudaStream_t st) {
+  if (p.npass == 0) { p.npass = P == 2 ? 3 : 1; p.pa = p.pb = P; }
+  const int PA = p.pa, PB = p.pb;
   const int cbox = (C % 64 == 0) ? 64 : 32;
   const int rowbytes = cbox * 2;
   int SW = 16;
@@ -1061,11 +1077,11 @@ static int convp_launch(ugn_ctx* ctx, TcParams& p, const __nv_bfloat16* act, int
   p.ncc = C / cbox; p.KW = KW; p.KH = KH; p.sgn = sgn;
   p.kslices = cbox / 16;
   p.ksteps_total = KH * KW * p.ncc; p.ksplit = 1;
-  const size_t b_stage = (size_t)P * p.b.plane_bytes;
+  const size_t b_stage = (size_t)PB * p.b.plane_bytes;
   const size_t budget = 222 * 1024, fixed = 17 * 1024 + 2048;
   // accumulator columns per tile: block_n, or 2*block_n when hi*[hi|lo] is issued as one MMA (K-major
   // weight planes that are exactly adjacent in the ring stage)
-  p.concat = (P == 2 && sgn > 0 && p.b.major == 0 && p.block_n <= 128 && p.b.plane_bytes == p.block_n * rowbytes &&
+  p.concat = (PB == 2 && sgn > 0 && p.b.major == 0 && p.block_n <= 128 && p.b.plane_bytes == p.block_n * rowbytes &&
               !getenv("UGN_NO_CONCAT")) ? 1 : 0;
   p.acc_tile_cols = p.concat ? 2 * p.block_n : p.block_n;
   int T = 0;
@@ -1075,7 +1091,7 @@ static int convp_launch(ugn_ctx* ctx, TcParams& p, const __nv_bfloat16* act, int
     for (int cand : {2, 1}) {
       if (cand * p.acc_tile_cols > 512) continue;         // at least one accumulator set in the 512 TMEM columns
       if (cand > 1 && (cand - 1) * RH >= Hneed) continue;
-      size_t chunk = (size_t)P * (size_t)(cand * RH + KH - 1) * SW * rowbytes;
+      size_t chunk = (size_t)PA * (size_t)(cand * RH + KH - 1) * SW * rowbytes;
       size_t patch = ring ? 2 * chunk : p.ncc * chunk;
       if (patch + fixed + 2 * b_stage <= budget) { T = cand; p.cps = ring ? 1 : p.ncc; p.nslots = ring ? 2 : 1; break; }
     }
@@ -1103,7 +1119,7 @@ static int convp_launch(ugn_ctx* ctx, TcParams& p, const __nv_bfloat16* act, int
     int rc = make_map(ctx, &p.a.map, act, dims, str, box, rowbytes);
     if (rc != UGN_OK) return rc;
   }
-  size_t patch = (size_t)p.nslots * P * p.patch_plane_bytes;
+  size_t patch = (size_t)p.nslots * PA * p.patch_plane_bytes;
   int stages = (int)std::min<size_t>(8, (budget - fixed - patch) / b_stage);
   stages = std::max(2, stages);
   p.stages = stages;
@@ -1124,27 +1140,32 @@ static int convp_launch(ugn_ctx* ctx, TcParams& p, const __nv_bfloat16* act, int
     UGN_CUDA(cudaMemsetAsync(dbg_buf, 0, 8 * sizeof(long long), st));
     p.dbg = dbg_buf;
   }
-#define CONVP_LAUNCH(C, PR, TT, KSL, PL2)                                                                      \
+#define CONVP_LAUNCH(C, PR, TT, KSL, NP)                                                                       \
   do {                                                                                                         \
-    UGN_CUDA(cudaFuncSetAttribute(tc_convp_kernel<C, PR, TT, KSL, PL2>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+    UGN_CUDA(cudaFuncSetAttribute(tc_convp_kernel<C, PR, TT, KSL, NP>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
                                   (int)smem));                                                                 \
-    tc_convp_kernel<C, PR, TT, KSL, PL2><<<grid, kConvpThreads, smem, st>>>(p);                                \
+    tc_convp_kernel<C, PR, TT, KSL, NP><<<grid, kConvpThreads, smem, st>>>(p);                                 \
   } while (0)
-#define CONVP_T_K(C, PR, PL2)                                                          \
+#define CONVP_T_K(C, PR, NP)                                                           \
   do {                                                                                 \
-    if (p.T == 2 && p.kslices == 4) CONVP_LAUNCH(C, PR, 2, 4, PL2);                    \
-    else if (p.T == 2 && p.kslices == 2) CONVP_LAUNCH(C, PR, 2, 2, PL2);               \
-    else if (p.T == 1 && p.kslices == 4) CONVP_LAUNCH(C, PR, 1, 4, PL2);               \
-    else if (p.T == 1 && p.kslices == 2) CONVP_LAUNCH(C, PR, 1, 2, PL2);               \
+    if (p.T == 2 && p.kslices == 4) CONVP_LAUNCH(C, PR, 2, 4, NP);                     \
+    else if (p.T == 2 && p.kslices == 2) CONVP_LAUNCH(C, PR, 2, 2, NP);                \
+    else if (p.T == 1 && p.kslices == 4) CONVP_LAUNCH(C, PR, 1, 4, NP);                \
+    else if (p.T == 1 && p.kslices == 2) CONVP_LAUNCH(C, PR, 1, 2, NP);                \
     else UGN_FAIL(UGN_ERR_UNSUPPORTED, "convp: unsupported T=%d kslices=%d", p.T, p.kslices); \
   } while (0)
-  if (prof) {          // profiling build of the two shapes of interest only (code size)
-    if (p.concat) CONVP_T_K(true, true, true);
-    else if (P == 2) CONVP_T_K(false, true, true);
-    else CONVP_T_K(false, true, false);
-  } else if (p.concat) CONVP_T_K(true, false, true);
-  else if (P == 2) CONVP_T_K(false, false, true);
-  else CONVP_T_K(false, false, false);
+  if (prof) {          // profiling build of the shapes of interest only (code size)
+    if (p.concat && p.npass == 3) CONVP_T_K(true, true, 3);
+    else if (p.concat) CONVP_T_K(true, true, 2);
+    else if (p.npass == 3) CONVP_T_K(false, true, 3);
+    else if (p.npass == 2) CONVP_T_K(false, true, 2);
+    else CONVP_T_K(false, true, 1);
+  } else if (p.concat && p.npass == 3) CONVP_T_K(true, false, 3);
+  else if (p.concat) CONVP_T_K(true, false, 2);
+  else if (p.npass == 3) CONVP_T_K(false, false, 3);
+  else if (p.npass == 2) CONVP_T_K(false, false, 2);
+  else if (p.npass == 4) CONVP_T_K(false, false, 4);
+  else CONVP_T_K(false, false, 1);
 #undef CONVP_T_K
 #undef CONVP_LAUNCH
   UGN_LAUNCHED(ctx);
@@ -1171,6 +1192,11 @@ int tc_conv_fwd(ugn_ctx* ctx, const ConvGeom& g, int P, int f16, const __nv_bflo
   UGN_CHECK(g.Cp % 32 == 0 && g.Co % 16 == 0, "tensor-core conv needs Cin %% 32 == 0 and Cout %% 16 == 0");
   TcParams p{};
   p.mode = MODE_CONV; p.planes = P; p.sgn = 1; p.f16 = f16;
+  if (P == 2 && ctx->fwd_conv_pass) {    // reduced pass count of the forward convolutions (ugn_set_fwd_passes)
+    p.npass = ctx->fwd_conv_pass;
+    p.pa = (p.npass == 3 || p.npass == 4) ? 2 : 1;
+    p.pb = (p.npass == 2 || p.npass == 3) ? 2 : 1;
+  }
   const int cbox = (g.Cp % 64 == 0) ? 64 : 32;
   p.kslices = cbox / 16;
   p.ncc = g.Cp / cbox; p.KW = g.KW;
@@ -1182,7 +1208,7 @@ int tc_conv_fwd(ugn_ctx* ctx, const ConvGeom& g, int P, int f16, const __nv_bflo
   if (p.block_n > 256) p.block_n = 256;
   // split operands: N = 192 tiles run at the full tensor rate (96 clk per MMA), N <= 128 tiles cost 73 clk
   // each and are issued as hi*[hi|lo] pairs instead (convp_launch: concat)
-  if (P == 2 && p.block_n > 128)
+  if (P == 2 && p.block_n > 128 && p.npass != 1)
     p.block_n = (g.Co % 192 == 0 && !getenv("UGN_NO_N192")) ? 192 : (g.Co % 128 == 0) ? 128 : ((g.Co % 96 == 0) ? 96 : 64);
   int rc;
   {  // weights [P][Co][taps][Cp] K-major: dims (Cp, taps, Co, P, 1)
@@ -1422,13 +1448,18 @@ int tc_linear_fwd(ugn_ctx* ctx, int P, int f16, int B, int N, int K, const __nv_
   // Small batch: the layer is a weight-streaming (HBM-bound) GEMM with a single M tile, so spread K over
   // the SMs (split-K, red.add into zeroed y) and apply bias / activation / dropout mask in a tiny post pass.
   int tiles = ugn_cdiv(B, 128) * ugn_cdiv(N, P == 2 ? 128 : 256);
+  ctx->gemm_npass = ctx->fwd_dense_pass;
+  int rc;
   if (tiles * 2 <= ctx->sm_count && K >= 512) {
-    int rc = tc_gemm_ex(ctx, P, f16, B, N, K, x, 0, w, 0, y, N, 0, nullptr, nullptr, UGN_ACT_LINEAR, 0.f, nullptr, st);
+    rc = tc_gemm_ex(ctx, P, f16, B, N, K, x, 0, w, 0, y, N, 0, nullptr, nullptr, UGN_ACT_LINEAR, 0.f, nullptr, st);
+    ctx->gemm_npass = 0;
     if (rc != UGN_OK) return rc;
     if (bias || mask || act != UGN_ACT_LINEAR) return ew_bias_act_mask(ctx, y, bias, mask, B, N, act, alpha, st);
     return UGN_OK;
   }
-  return tc_gemm_ex(ctx, P, f16, B, N, K, x, 0, w, 0, y, N, 0, bias, mask, act, alpha, nullptr, st);
+  rc = tc_gemm_ex(ctx, P, f16, B, N, K, x, 0, w, 0, y, N, 0, bias, mask, act, alpha, nullptr, st);
+  ctx->gemm_npass = 0;
+  return rc;
 }
 
 int tc_linear_bwd(ugn_ctx* ctx, int P, int f16, int B, int N, int K, const __nv_bfloat16* x, const __nv_bfloat16* w,

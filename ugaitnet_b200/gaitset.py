@@ -266,6 +266,7 @@ class GaitSetEngine(UGaitEngine):
 
     def _forward(self, p, train: bool, expanded: bool = False):
         cfg, h = self.cfg, self.ctx.h
+        check(lib.ugn_set_fwd_passes(h, *self.fwd_passes))
         streams = self._fork()
         for m in range(cfg.nmods):
             with torch.cuda.stream(streams[m] if streams else torch.cuda.current_stream()):

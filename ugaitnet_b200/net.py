@@ -32,8 +32,15 @@ from .expand import NOISE
 #   f16mix  fp16 hi/lo split 3-pass FORWARD (every discrete decision -- ReLU, max-pool argmax, sign_max
 #           winner -- is taken at ~fp32 accuracy), single-pass fp16 BACKWARD on the hi planes with a
 #           device-side power-of-two gradient scale (linear maps of the gradient need 11 bits, not 22)
+#   f16mix2 as f16mix with TWO forward passes: convolutions hi*hi + hi*lo(weights) (activation lo plane not loaded, the
+#           pair issued as one N = 2*Cout MMA where Cout <= 128), dense layers hi*hi + lo(activations)*hi (the weight lo
+#           plane is not streamed)
+#   f16mix1 single-pass fp16 forward and backward (11-bit operands: the "TF32 class" north_star names)
 MATH_MODES = {"fp32": (0, 0, None), "bf16": (1, 1, torch.bfloat16), "bf16x3": (2, 2, torch.bfloat16),
-              "f16x3": (2, 2, torch.float16), "f16mix": (2, 1, torch.float16)}
+              "f16x3": (2, 2, torch.float16), "f16mix": (2, 1, torch.float16), "f16mix2": (2, 1, torch.float16),
+              "f16mix1": (2, 1, torch.float16)}
+# (conv, dense) pass codes of ugn_set_fwd_passes per math mode (default 0 = all three)
+FWD_PASSES = {"f16mix2": (2, 4), "f16mix1": (1, 1)}
 GRAD_SCALE_TARGET = 1024.0      # max|dL/dsignature| * s lands in [512, 1024]: 6 binades of headroom below 65504
 
 
@@ -57,6 +64,7 @@ class UGaitEngine:
         self.ctx = ops.get_ctx(self.dev.index)
         self.math_mode = math_mode
         self.P, self.PB, self.dt16 = MATH_MODES[math_mode]
+        self.fwd_passes = FWD_PASSES.get(math_mode, (0, 0))
         self.scaled = self.dt16 is torch.float16
         self.pad = 32 if self.P else 1
         self.optimizer, self.lr, self.momentum = optimizer.lower(), float(lr), momentum
@@ -344,6 +352,7 @@ class UGaitEngine:
 
     def _forward(self, p: "_Plan", train: bool, expanded: bool = False):
         cfg, h = self.cfg, self.ctx.h
+        check(lib.ugn_set_fwd_passes(h, *self.fwd_passes))      # ctx state (host side): engines share the ctx
         streams = self._fork()
         for m in range(cfg.nmods):
             with torch.cuda.stream(streams[m] if streams else torch.cuda.current_stream()):
@@ -643,9 +652,13 @@ class UGaitEngine:
         use_mask = cfg.dropout > 0.001
         if self.P:
             check(lib.ugn_act_mask_bwd(h, R["dout"].ptr, None, None, None, R["dout16"].ptr, ACT_LINEAR, 0.0, st))
+        # tensor-core mode: the bias gradient comes from the f32 dout, not from its rounded 16-bit copy (the rows of
+        # dL/dsignature cancel under the triplet loss: summing the rounded operand leaves mostly rounding noise)
         check(lib.ugn_linear_bwd(h, (R["h1_16"] if self.P else R["h1"]).ptr, self.Rcw[f"{bn}/ofCode/w"].ptr,
                                  (R["dout16"] if self.P else R["dout"]).ptr, R["dh1"].ptr,
-                                 self.Rg[f"{bn}/ofCode/w"].ptr, self.Rg[f"{bn}/ofCode/b"].ptr, st))
+                                 self.Rg[f"{bn}/ofCode/w"].ptr, None if self.P else self.Rg[f"{bn}/ofCode/b"].ptr, st))
+        if self.P:
+            check(lib.ugn_colsum(h, R["dout"].ptr, self.Rg[f"{bn}/ofCode/b"].ptr, st))
         check(lib.ugn_act_mask_bwd(h, R["dh1"].ptr, None, R["mask"].ptr if use_mask else None,
                                    None if self.P else R["dz1"].ptr, R["dz1_16"].ptr if self.P else None,
                                    ACT_LINEAR, 0.0, st))
