@@ -36,10 +36,18 @@ FLOP_FWD_ROW = {"of": 2.0214e9 + 0.0545e9, "c25": 1.3356e9 + 0.0545e9}   # BASEL
 TRAIN_FLOP_ROW = 11.83e9                                                  # 3-mod fwd+dgrad+wgrad
 
 
-# ncu-derived DRAM traffic of the dominant kernel (profiles/<round>_tc_convp_kernel.md), bytes per step
-# r01c: 12 forward launches of one step, sum of dram__bytes_read.sum + dram__bytes_write.sum = 319.6 MB
-# (activation planes in: 177 MB; the pooled outputs mostly stay in the 126 MB L2 until the next layer reads them)
-NCU_TRAFFIC = {"conv_fwd_bytes_per_step": 319.6e6}
+def ncu_traffic(key, mode):
+    """DRAM bytes per step of a kernel family from the LATEST committed ncu --set full capture
+    (profiles/traffic.json, written by scripts/summarise_profiles.py from dram__bytes_read.sum + dram__bytes_write.sum
+    of the launches of one step).  None when no capture of this math mode is recorded -- never a stale constant."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            t = json.load(f)
+        ent = t.get(mode, {}).get(key)
+        return None if ent is None else float(ent["bytes_per_step"])
+    except Exception:
+        return None
+
 
 DTYPE_NAMES = {"fp32": "f32", "bf16": "bf16", "bf16x3": "bf16 (3-pass hi/lo split, fp32 accumulate)",
                "f16x3": "f16 (3-pass hi/lo split, fp32 accumulate)",
@@ -116,7 +124,7 @@ def run_reference(args, rank, world):
     from oracle import ugait_oracle as O
     torch.set_num_threads(os.cpu_count() or 1)
     oc = O.NetConfig(in_channels=(50, 25, 25), nd=ND, nclasses=NCLASSES, merge=O.MERGE_SIGNMAX, wver=1.0, wid=0.1)
-    rows = 24          # bounded sample: 24 of the 96 rows of one step (6 sequences x 4 variants)
+    rows = BS_LITERAL * EXPAND      # the FULL 96-row step of the configuration (about 1.2 s per step on 16 cores)
     xs, fl, lab = O.synth_batch(oc, base_rows=rows // EXPAND, expand=EXPAND, seed=232323)
     xs = [torch.tensor(x) for x in xs]
     fl = [torch.tensor(f) for f in fl]
@@ -144,7 +152,8 @@ def run_reference(args, rank, world):
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "impl": "reference",
             "config": workload_config(world),
             "cpu_baseline": {"value": val, "unit": "rows/s", "cores": torch.get_num_threads(), "kind": "port",
-                             "sample": f"{rows} of the 96 rows of one cfg2 step per CPU step, {args.steps} steps"},
+                             "sample": f"all {rows} rows of one cfg2 step per CPU step (PyTorch-CPU fp32 restatement; TensorFlow is "
+                                       f"absent from the image: profiles/r02a_tf_probe.log), {args.steps} steps"},
             "e2e": {"value": val, "unit": "rows/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line), flush=True)
@@ -230,6 +239,7 @@ def main():
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-knn", action="store_true")
     ap.add_argument("--no-gaitset", action="store_true", help="skip the GaitSet-branch leg (SURVEY 8f-1)")
+    ap.add_argument("--no-configs", action="store_true", help="skip the cfg1 / cfg3 / cfg4 legs")
     ap.add_argument("--lite", action="store_true", help="timed steps only (for runs under ncu)")
     ap.add_argument("--knn-only", action="store_true", help="only the open-world k-NN leg (development aid)")
     args = ap.parse_args()
@@ -292,14 +302,14 @@ def main():
         return ms / steps
 
     step_dev = lambda: eng.train_step(dx, df, dl)
-    loss_host = torch.zeros(3).pin_memory()
+    loss_host = torch.zeros(8).pin_memory()
+
+    def read_losses(out):
+        loss_host.copy_(out["losses"], non_blocking=True)      # {triplet, count, ce, acc, reg}: ONE D2H read
+        torch.cuda.current_stream().synchronize()                # the user reads the loss every step
 
     def step_e2e():
-        out = eng.train_step(hx, hf, hl)          # H2D copies of this step's inputs happen inside
-        loss_host[0].copy_(out["triplet"], non_blocking=True)
-        loss_host[1].copy_(out["ce"], non_blocking=True)
-        loss_host[2].copy_(out["reg"], non_blocking=True)
-        torch.cuda.current_stream().synchronize()  # the user reads the loss every step
+        read_losses(eng.train_step(hx, hf, hl))                  # 7 H2D copies of this step's inputs happen inside
 
     for _ in range(args.warmup):
         step_dev()
@@ -320,47 +330,60 @@ def main():
         step_e2e()
     ms_e2e_serial = timed(step_e2e, args.steps)
 
-    # pipelined public API: the H2D copy of step i+1's pinned host batch is enqueued (side stream) before
-    # the host blocks on step i's loss, so it overlaps step i's kernels.  Every step still copies its own
-    # inputs from host memory and reads its loss back inside the timed region.
-    def step_e2e_pipelined():
-        out = eng.train_step_staged()
-        eng.prefetch(hx, hf, hl)
-        loss_host[0].copy_(out["triplet"], non_blocking=True)
-        loss_host[1].copy_(out["ce"], non_blocking=True)
-        loss_host[2].copy_(out["reg"], non_blocking=True)
-        torch.cuda.current_stream().synchronize()
+    # Single-copy public API: the loader fills a pinned HostBatch (byte image of the engine's input block) in place;
+    # prefetch_batch() moves it with ONE cudaMemcpyAsync on a copy stream while the previous step runs, and the step
+    # reads its losses back with ONE D2H copy.  Every step still copies its own inputs from host memory and reads its
+    # loss inside the timed region.
+    def fill(hb, base):
+        for m in range(3):
+            hb.inputs[m][...] = xs[m][::EXPAND] if base else xs[m]
+            hb.flags[m][...] = fl[m]
+        hb.labels[...] = lab.reshape(-1).astype(np.int32)
+        if base:
+            hb.src_row[...] = np.repeat(np.arange(BS_LITERAL, dtype=np.int32), EXPAND)
 
-    eng.prefetch(hx, hf, hl)
-    for _ in range(2):
-        step_e2e_pipelined()
-    ms_e2e = timed(step_e2e_pipelined, args.steps)
+    def pipelined(hbs):
+        k = [0]
 
-    # device-side expansion: only the 24 base sequences cross PCIe, the E-fold batch with its
-    # missing-modality pattern is built inside the input pack -- same step, a quarter of the H2D bytes
-    src_row = np.repeat(np.arange(BS_LITERAL, dtype=np.int32), EXPAND)
-    use = np.concatenate([f.reshape(-1, 1) for f in fl], axis=1).astype(np.float32)
-    hbase = [torch.from_numpy(np.ascontiguousarray(x[::EXPAND])).pin_memory() for x in xs]
-    hlab0 = torch.from_numpy(np.ascontiguousarray(lab.reshape(-1)[::EXPAND].astype(np.int32)))
-    h2d_exp = sum(t.numel() * t.element_size() for t in hbase) + use.nbytes + src_row.nbytes + hlab0.numel() * 4
+        def step():
+            out = eng.train_step_prefetched()
+            k[0] ^= 1
+            eng.prefetch_batch(hbs[k[0]])                        # H2D of step i+1 overlaps step i
+            read_losses(out)
+        eng.prefetch_batch(hbs[0])
+        for _ in range(3):
+            step()
+        return timed(step, args.steps)
 
-    def step_e2e_expanded():
-        out = eng.train_step_expanded(hbase, hlab0, src_row, use)
-        loss_host[0].copy_(out["triplet"], non_blocking=True)
-        loss_host[1].copy_(out["ce"], non_blocking=True)
-        loss_host[2].copy_(out["reg"], non_blocking=True)
-        torch.cuda.current_stream().synchronize()
-
-    for _ in range(3):
-        step_e2e_expanded()
-    ms_e2e_exp = timed(step_e2e_expanded, args.steps)
+    hb_full = [eng.host_batch(B), eng.host_batch(B)]
+    for h in hb_full:
+        fill(h, False)
+    ms_e2e_full = pipelined(hb_full)
+    # device-side expansion: only the 24 complete sequences + the expansion tables cross PCIe, the
+    # E-fold batch with its missing-modality pattern is built inside the input pack -- same step, a quarter of the bytes
+    hb_exp = [eng.host_batch(B, base_rows=BS_LITERAL), eng.host_batch(B, base_rows=BS_LITERAL)]
+    for h in hb_exp:
+        fill(h, True)
+    ms_e2e = pipelined(hb_exp)
+    h2d_exp, h2d_full = hb_exp[0].nbytes, hb_full[0].nbytes
     eng.ctx.check()
+    # data-parallel sanity inside the bench itself: finite losses and bit-identical weights on every rank after the run
+    assert bool(torch.isfinite(loss_host[[0, 2, 4]]).all()), f"non-finite loss on rank {rank}: {loss_host.tolist()}"
+    rank_check = None
+    if world > 1:
+        wsum = torch.stack([eng.w.double().sum(), eng.w.double().abs().sum()])
+        allw = [torch.zeros_like(wsum) for _ in range(world)]
+        torch.distributed.all_gather(allw, wsum)
+        rank_check = {"weights_identical_on_all_ranks": all(torch.equal(a, allw[0]) for a in allw),
+                      "loss_finite": True}
+        assert rank_check["weights_identical_on_all_ranks"], "ranks diverged"
     rows_total = B * world
     value = rows_total / (ms * 1e-3)
     e2e = rows_total / (ms_e2e * 1e-3)
 
     cfg_line = workload_config(world)
     if world > 1:
+        cfg_line["rank_check"] = rank_check
         cfg_line["dp_exchange"] = eng.dp_reduce + (" (NVSwitch multimem)" if all(getattr(eng, "_mc", (0, 0))) else "")
     line = {"metric": "train rows/s (3-mod fwd+bwd+triplet+CE+Adam)", "value": value, "unit": "rows/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
@@ -368,13 +391,17 @@ def main():
             "dtype": DTYPE_NAMES[args.mode],
             "data": "synthetic", "config": cfg_line,
             "literal_seq_per_s": value / EXPAND,
-            "e2e": {"value": e2e, "unit": "rows/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 12,
-                    "ms_per_step": ms_e2e, "api": "UGaitEngine.prefetch + train_step_staged (H2D of step i+1 "
-                    "overlaps step i)", "serial_ms_per_step": ms_e2e_serial,
-                    "serial_value": rows_total / (ms_e2e_serial * 1e-3),
-                    "device_expansion": {"value": rows_total / (ms_e2e_exp * 1e-3), "ms_per_step": ms_e2e_exp,
-                                         "h2d_bytes_per_step": int(h2d_exp),
-                                         "api": "UGaitEngine.train_step_expanded (base rows + pattern; serial)"}},
+            "e2e": {"value": e2e, "unit": "rows/s", "h2d_bytes_per_step": int(h2d_exp), "d2h_bytes_per_step": 32,
+                    "ms_per_step": ms_e2e, "copies_per_step": {"h2d": 1, "d2h": 1},
+                    "api": "UGaitEngine.host_batch(B, base_rows) + prefetch_batch + train_step_prefetched: the 24 complete "
+                           "sequences + expansion tables in ONE pinned block / ONE cudaMemcpyAsync (step i+1's copy overlaps "
+                           "step i), device-side missing-modality expansion, ONE packed loss D2H",
+                    "full_batch": {"value": rows_total / (ms_e2e_full * 1e-3), "ms_per_step": ms_e2e_full,
+                                   "h2d_bytes_per_step": int(h2d_full),
+                                   "api": "same, host-expanded 96-row batch (generator layout) in one pinned block"},
+                    "serial_7_copies": {"value": rows_total / (ms_e2e_serial * 1e-3), "ms_per_step": ms_e2e_serial,
+                                        "h2d_bytes_per_step": int(h2d),
+                                        "api": "UGaitEngine.train_step(pinned host tensors): 7 H2D copies, not overlapped"}},
             "gpu_launches": int(launches), "clocks": sampler.summary(),
             "model_tflops": TRAIN_FLOP_ROW * rows_total / (ms * 1e-3) / 1e12}
 
@@ -421,7 +448,7 @@ def main():
             ach_f = fwd_flops / (fwd_ms * 1e-3) / 1e12 if fwd_ms else 0.0
             line["roofline"] = {"bound": "tensor", "kernel": "tc_convp_kernel (conv forward, 12 launches/step)",
                                 "achieved": ach_f, "peak": pk["tf_sust"], "unit": "TFLOP/s", "frac": ach_f / pk["tf_sust"],
-                                "traffic": NCU_TRAFFIC.get("conv_fwd_bytes_per_step"),
+                                "traffic": ncu_traffic("conv_fwd", args.mode),
                                 "algorithmic_flop_per_step": fwd_flops, "launch_ms_per_step": fwd_ms,
                                 "share_of_step": fwd_ms / total if total else None,
                                 "mma_passes": pf, "issued_frac": ach_f * pf / pk["tf_sust"],
@@ -432,10 +459,16 @@ def main():
                                              "mma_passes": passes, "issued_frac": ach * passes / pk["tf_sust"],
                                              "share_of_step": conv_ms / total if total else None}}
             line["cpu_baseline"] = cpu_baseline_leg()
+        if not args.no_configs and world == 1:
+            del eager
+            torch.cuda.empty_cache()
+            line["configs"] = config_legs(pk, args)
+            eager = None
         if not args.no_knn and world == 1:
             line["knn"] = knn_leg(pk)
         if not args.no_gaitset and world == 1:
-            del eng, eager
+            del eng
+            eager = None
             torch.cuda.empty_cache()
             line["gaitset"] = gaitset_leg(pk, args)
     if world > 1 and not args.no_knn:
@@ -446,6 +479,55 @@ def main():
         print(json.dumps(line), flush=True)
     if world > 1:
         torch.distributed.destroy_process_group()
+
+
+def config_legs(pk, args):
+    """BASELINE.json configs 1, 3 and 4 (the other training configurations; cfg2 is the headline above): device-resident
+    CUDA-graph replay of the full step on one GPU, same engine and math mode.  Parity of exactly these configurations
+    against the fp64 oracle: tests/test_decisions_gpu.py::test_full_size_config_against_oracle."""
+    from oracle.ugait_oracle import NetConfig as OC, synth_batch
+    from ugaitnet_b200.config import MERGE_SIGNMAX, NetConfig
+    from ugaitnet_b200.net import UGaitEngine
+    legs = {
+        "cfg1": dict(desc="1-modality gray, casenet D, nclasses 150, bs 24 (no expansion)", inch=(25,), ncls=150,
+                     batch=dict(base_rows=24, expand=1, kinds=("gray",)), single=True, flop_row=3.48e9),
+        "cfg3": dict(desc="CASIA-B shape (gray+OF+silhouette), nclasses 74, bs 40 x expand 3 = 120 rows", inch=(50, 25, 25),
+                     ncls=74, batch=dict(base_rows=40, expand=3, ids_per=10, kinds=("of", "gray", "sil")), single=False,
+                     flop_row=TRAIN_FLOP_ROW),
+        "cfg4": dict(desc="early-fusion BL-all (--nomissing), bs 512, every modality present", inch=(50, 25, 25), ncls=150,
+                     batch=dict(base_rows=512, expand=1, ids_per=2), single=False, flop_row=TRAIN_FLOP_ROW),
+    }
+    out = {}
+    for name, c in legs.items():
+        oc = OC(in_channels=c["inch"], nd=ND, nclasses=c["ncls"], single=c["single"])
+        xs, fl, lab = synth_batch(oc, seed=232323, **c["batch"])
+        cfg = NetConfig(in_channels=c["inch"], nd=ND, nc=0, nclasses=c["ncls"], weight_decay=5e-5, merge=MERGE_SIGNMAX,
+                        margin=0.2, wver=1.0, wid=0.1, dropout=0.4, single=c["single"])
+        eng = UGaitEngine(cfg, math_mode=args.mode, lr=1e-4, use_graph=not args.no_graph)
+        dx = [torch.from_numpy(np.ascontiguousarray(x)).cuda() for x in xs]
+        df = [torch.from_numpy(np.ascontiguousarray(f)).cuda() for f in fl]
+        dl = torch.from_numpy(np.ascontiguousarray((lab % c["ncls"]).reshape(-1).astype(np.int32))).cuda()
+        B = dx[0].shape[0]
+        for _ in range(3):
+            o = eng.train_step(dx, df, dl)
+        steps = max(5, args.steps // 2)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            o = eng.train_step(dx, df, dl)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / steps
+        eng.ctx.check()
+        assert bool(torch.isfinite(o["losses"][[0, 2, 4]]).all())
+        tf = c["flop_row"] * B / (ms * 1e-3) / 1e12
+        out[name] = {"workload": c["desc"], "rows_per_step": B, "value": B / (ms * 1e-3), "unit": "rows/s",
+                     "ms_per_step": ms, "steps": steps, "model_tflops": tf, "frac_of_tensor_peak": tf / pk["tf_sust"],
+                     "gpu_launches_per_step": int(eng.graph_launches) if eng.use_graph else None}
+        del eng, dx, df, dl
+        torch.cuda.empty_cache()
+    return out
 
 
 def gaitset_leg(pk, args):

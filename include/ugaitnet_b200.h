@@ -231,11 +231,15 @@ int ugn_adam_step_ex(ugn_ctx*, ugn_tensor* w, const ugn_tensor* g, ugn_tensor* m
  * The caller brackets the call with two group barriers (all gradients written before; all weights written after)
  * and refreshes its 16-bit compute copies afterwards (ugn_pack_weight).  opt: 0 Adam family (vhat / weight_decay as
  * ugn_adam_step_ex), 1 SGD with momentum (beta1 = momentum).  The mean (1/world) is applied inside; reg_out receives
- * this rank's slice of the regulariser value.  lr_dev (required): the step's learning rate in device memory. */
+ * this rank's slice of the regulariser value -- or, when reg_peers (HOST array [world] of the device addresses of every
+ * rank's reg_out scalar, peer-mapped; nullable) is given, every rank's scalar receives the sum over all slices through
+ * system-scope atomic adds (no all-reduce on the step's critical path); the caller then zeroes its scalar BEFORE the
+ * first barrier.  lr_dev (required): the step's learning rate in device memory. */
 int ugn_dp_optim_step(ugn_ctx*, int opt, int world, int rank, const int64_t* g_peers, const int64_t* w_peers,
                       int64_t g_multicast, int64_t w_multicast, ugn_tensor* w, const ugn_tensor* g, ugn_tensor* m, ugn_tensor* v, ugn_tensor* vhat,
                       float weight_decay, const ugn_tensor* seg_off, const ugn_tensor* seg_l2, float beta1,
-                      float beta2, float eps, ugn_tensor* reg_out, const ugn_tensor* lr_dev, void* stream);
+                      float beta2, float eps, ugn_tensor* reg_out, const int64_t* reg_peers, const ugn_tensor* lr_dev,
+                      void* stream);
 /* SGD with momentum (optimizers.SGD(lr, momentum, decay), :245): v = mom*v - lr*g'; w += v.  Keras' `decay`
  * is a learning-rate schedule, lr / (1 + decay*iterations): the caller passes the scheduled rate. */
 int ugn_sgd_step(ugn_ctx*, ugn_tensor* w, const ugn_tensor* g, ugn_tensor* v,

@@ -96,8 +96,39 @@ def kernel(tag, name, src, dst):
     return rows
 
 
+def to_bytes(v, u):
+    v = float(str(v).replace(",", ""))
+    return v * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "B": 1, "KB": 1e3, "MB": 1e6, "GB": 1e9}.get(u, 1)
+
+
+def traffic(tag, mode, rows_by_kernel, dst):
+    """profiles/traffic.json: DRAM bytes per step of the kernel families bench.py quotes in `roofline.traffic`
+    (dram__bytes_read.sum + dram__bytes_write.sum summed over the launches of ONE step of this capture)."""
+    path = os.path.join(dst, "traffic.json")
+    t = json.load(open(path)) if os.path.exists(path) else {}
+    ent = t.setdefault(mode, {})
+
+    def total(rows):
+        tot = 0.0
+        for r in rows:
+            for key in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+                v, u = find(r, key)
+                tot += to_bytes(v, u) if v is not None else 0.0
+        return tot
+    if "tc_convp_kernel" in rows_by_kernel:      # launch order of one step: 12 forward launches, then 3 input gradients
+        rows = rows_by_kernel["tc_convp_kernel"]
+        ent["conv_fwd"] = {"bytes_per_step": total(rows[:12]), "launches": min(12, len(rows)), "capture": tag}
+    if "optim_kernel" in rows_by_kernel:
+        ent["optim"] = {"bytes_per_step": total(rows_by_kernel["optim_kernel"][:1]), "launches": 1, "capture": tag}
+    if "gs_convp" in rows_by_kernel:
+        ent["gaitset_convp_first_modality"] = {"bytes_per_step": total(rows_by_kernel["gs_convp"]),
+                                                "launches": len(rows_by_kernel["gs_convp"]), "capture": tag}
+    json.dump(t, open(path, "w"), indent=1, sort_keys=True)
+
+
 def main():
     tag = sys.argv[1]
+    mode = sys.argv[2] if len(sys.argv) > 2 else "f16mix"
     src = os.path.join(ROOT, "gpurun_out", tag)
     dst = os.path.join(ROOT, "profiles")
     os.makedirs(dst, exist_ok=True)
@@ -106,10 +137,12 @@ def main():
     if os.path.exists(os.path.join(src, "gs_launches.csv")):
         launches(tag, os.path.join(src, "gs_launches.csv"), os.path.join(dst, f"{tag}_gs_launches.md"),
                  "GaitSet branches, 3 modalities, 24 rows, `GS_LITE=1 scripts/gs_bench.py 24 f16mix 1`")
+    rows_by_kernel = {}
     for fn in sorted(os.listdir(src)):
         if fn.startswith("prof_") and fn.endswith("_raw.csv"):
             name = fn[len("prof_"):-len("_raw.csv")]
-            kernel(tag, name, os.path.join(src, fn), os.path.join(dst, f"{tag}_{name}.md"))
+            rows_by_kernel[name] = kernel(tag, name, os.path.join(src, fn), os.path.join(dst, f"{tag}_{name}.md"))
+    traffic(tag, mode, rows_by_kernel, dst)
     for fn in ("bench_n1.json", "pytest_gpu.log"):
         p = os.path.join(src, fn)
         if os.path.exists(p):

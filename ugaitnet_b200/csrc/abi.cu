@@ -131,7 +131,7 @@ int ew_fuse_bwd(ugn_ctx*, const FusePtrs&, int, int, int, const float*, const fl
 int ew_softmax_ce(ugn_ctx*, const float*, const int*, float*, float*, int, int, float, float, cudaStream_t);
 int ew_optim(ugn_ctx*, int, float*, const float*, float*, float*, const long long*, const float*, int,
              long long, float, float, float, float, float, float*, const float*, const long long*, int, int,
-             float*, float, cudaStream_t, int, int, const long long*, const long long*, long long, long long);
+             float*, float, cudaStream_t, int, int, const long long*, const long long*, long long, long long, const long long* = nullptr);
 int simt_conv_fwd(ugn_ctx*, const ConvGeom&, const float*, const float*, const float*, float*, uint8_t*,
                   int, float, int, cudaStream_t);
 int simt_conv_dgrad(ugn_ctx*, const ConvGeom&, const float*, const float*, float*, cudaStream_t);
@@ -551,7 +551,7 @@ static int optim_common(ugn_ctx* ctx, int opt, ugn_tensor* w, const ugn_tensor* 
                         float gscale, ugn_tensor* reg_out, const ugn_tensor* lr_dev, const ugn_tensor* pack_table,
                         int pack_planes, int pack_f16, void* stream, ugn_tensor* vhat = nullptr, float wd = 0.f,
                         int world = 1, int rank = 0, const int64_t* g_peers = nullptr, const int64_t* w_peers = nullptr,
-                        int64_t g_mc = 0, int64_t w_mc = 0) {
+                        int64_t g_mc = 0, int64_t w_mc = 0, const int64_t* reg_peers = nullptr) {
   UGN_CHECK(ctx && w && g && v && seg_off && seg_l2, "optimizer: null argument");
   if (vhat) { UGN_TENSOR(vhat, DT_F32, 1, 1); UGN_CHECK(vhat->shape[0] == w->shape[0], "optimizer: vhat arena length mismatch"); }
   UGN_CHECK(wd >= 0.f && wd < 1.f, "optimizer: decoupled weight decay must be in [0,1)");
@@ -579,7 +579,7 @@ static int optim_common(ugn_ctx* ctx, int opt, ugn_tensor* w, const ugn_tensor* 
                   pack_table ? ugn_ptr<long long>(pack_table) : nullptr, pack_planes, pack_f16,
                   vhat ? ugn_ptr<float>(vhat) : nullptr, wd, (cudaStream_t)stream, world, rank,
                   reinterpret_cast<const long long*>(g_peers), reinterpret_cast<const long long*>(w_peers), (long long)g_mc,
-                  (long long)w_mc);
+                  (long long)w_mc, reinterpret_cast<const long long*>(reg_peers));
 }
 
 extern "C" int ugn_adam_step(ugn_ctx* ctx, ugn_tensor* w, const ugn_tensor* g, ugn_tensor* m, ugn_tensor* v,
@@ -601,12 +601,13 @@ extern "C" int ugn_adam_step_ex(ugn_ctx* ctx, ugn_tensor* w, const ugn_tensor* g
 extern "C" int ugn_dp_optim_step(ugn_ctx* ctx, int opt, int world, int rank, const int64_t* g_peers, const int64_t* w_peers,
                                  int64_t g_multicast, int64_t w_multicast, ugn_tensor* w, const ugn_tensor* g, ugn_tensor* m, ugn_tensor* v, ugn_tensor* vhat,
                                  float weight_decay, const ugn_tensor* seg_off, const ugn_tensor* seg_l2, float beta1,
-                                 float beta2, float eps, ugn_tensor* reg_out, const ugn_tensor* lr_dev, void* stream) {
+                                 float beta2, float eps, ugn_tensor* reg_out, const int64_t* reg_peers, const ugn_tensor* lr_dev,
+                                 void* stream) {
   UGN_CHECK(opt == 0 || opt == 1, "ugn_dp_optim_step: opt must be 0 (Adam family) or 1 (SGD momentum)");
   UGN_CHECK(world >= 2 && world <= 8 && g_peers && w_peers && lr_dev, "ugn_dp_optim_step: world in [2,8], peer tables and lr_dev required");
   return optim_common(ctx, opt, w, g, opt == 0 ? m : nullptr, v, seg_off, seg_l2, 0.f, beta1, beta2, eps, 1.f / (float)world,
                       reg_out, lr_dev, nullptr, 1, 0, stream, opt == 0 ? vhat : nullptr, opt == 0 ? weight_decay : 0.f, world,
-                      rank, g_peers, w_peers, g_multicast, w_multicast);
+                      rank, g_peers, w_peers, g_multicast, w_multicast, reg_peers);
 }
 extern "C" int ugn_sgd_step(ugn_ctx* ctx, ugn_tensor* w, const ugn_tensor* g, ugn_tensor* v, const ugn_tensor* seg_off,
                             const ugn_tensor* seg_l2, float lr, float momentum, float gscale, ugn_tensor* reg_out,

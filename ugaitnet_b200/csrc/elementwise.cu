@@ -583,6 +583,7 @@ struct PeerArenas {
   int n = 0;                 // 0: single-GPU step
   const float* g[8] = {};    // gradient arena of every rank (own rank included)
   float* w[8] = {};          // weight arena of every rank
+  float* reg[8] = {};        // regulariser-value scalar of every rank (nullptr: only the local slice value is produced)
   const float* mc_g = nullptr;   // NVSwitch multicast addresses of the two arenas (nullptr: unicast peer accesses):
   float* mc_w = nullptr;         // multimem.ld_reduce sums in the switch, multimem.st broadcasts -- half the link traffic
 };
@@ -707,7 +708,15 @@ __global__ void __launch_bounds__(256) optim_kernel(float* __restrict__ w, const
     if (threadIdx.x < 32) {
       float r = threadIdx.x < 8 ? red[threadIdx.x] : 0.f;
       r = warp_sum(r);
-      if (threadIdx.x == 0) atomicAdd(reg_out, r);
+      if (threadIdx.x == 0) {
+        if (DP && peers.reg[0]) {
+          // every rank ends up with the sum over the slices: system-scope adds into all ranks' scalars (a few thousand
+          // 4-byte NVLink atomics) instead of a 4-byte all-reduce on the step's critical path
+          for (int p = 0; p < peers.n; ++p) atomicAdd_system(peers.reg[p], r);
+        } else {
+          atomicAdd(reg_out, r);
+        }
+      }
     }
   }
 }
@@ -716,9 +725,12 @@ int ew_optim(ugn_ctx* ctx, int opt, float* w, const float* g, float* m, float* v
              const long long* off, const float* l2, int S, long long n, float lr, float b1,
              float b2, float eps, float gscale, float* reg_out, const float* lr_dev, const long long* pack,
              int packP, int f16, float* vhat, float wd, cudaStream_t st, int world, int rank,
-             const long long* g_peers, const long long* w_peers, long long g_mc, long long w_mc) {
+             const long long* g_peers, const long long* w_peers, long long g_mc, long long w_mc,
+             const long long* reg_peers) {
   UGN_CHECK(n % 4 == 0, "optimizer arena length must be a multiple of 4 (got %lld)", n);
-  if (reg_out) UGN_CUDA(cudaMemsetAsync(reg_out, 0, sizeof(float), st));
+  // reg_peers: the caller zeroed every rank's scalar BEFORE the group barrier (a memset here would race with the adds
+  // of a faster peer)
+  if (reg_out && !(world > 1 && reg_peers)) UGN_CUDA(cudaMemsetAsync(reg_out, 0, sizeof(float), st));
   long long n4 = n / 4, q0 = 0;
   PeerArenas peers;
   if (world > 1) {
@@ -727,6 +739,7 @@ int ew_optim(ugn_ctx* ctx, int opt, float* w, const float* g, float* m, float* v
     for (int p = 0; p < world; ++p) {
       peers.g[p] = reinterpret_cast<const float*>(g_peers[p]);
       peers.w[p] = reinterpret_cast<float*>(w_peers[p]);
+      if (reg_peers) peers.reg[p] = reinterpret_cast<float*>(reg_peers[p]);
     }
     UGN_CHECK(peers.w[rank] == w, "dp optimizer: w_peers[rank] must be this rank's own arena");
     if (g_mc && w_mc) {

@@ -98,6 +98,10 @@ class GaitSetEngine(UGaitEngine):
         self.seg_off = torch.tensor([s.off for s in segs] + [off], dtype=torch.int64, device=d)
         self.seg_l2 = torch.tensor([s.l2 for s in segs], dtype=torch.float32, device=d)
         self.reg_out = torch.zeros(1, device=d)
+        if self._symm:                 # fused data-parallel exchange: summed over the ranks by peer atomics (net.py)
+            r = self._new_arena(64, exchanged=True)
+            if len(self._symm) > 2:
+                self.reg_out = r[:1]
         self.lr_dev = torch.zeros(1, device=d)
         self._lr_host = torch.zeros(1).pin_memory()
         self.R = {k: TRef(t) for k, t in dict(w=self.w, g=self.g, m=self.m, v=self.v, seg_off=self.seg_off,
@@ -414,7 +418,8 @@ class GaitSetEngine(UGaitEngine):
         if self.cfg.nclasses > 0:
             out["ce"], out["acc"], out["logits"] = p.ce_out[0], p.ce_out[1], p.logits
         if with_reg:
-            out["reg"] = self.reg_out[0]
+            out["reg"] = p.loss_pack[4]
+            out["losses"] = p.loss_pack
         return out
 
     def train_step_expanded(self, *a, **k):
@@ -449,14 +454,19 @@ class _GsPlan:
             return torch.zeros(tuple(shape), **f32)
 
         self.br: List[_Branch] = []
-        self.flags = [torch.ones(B, 1, **f32) for _ in range(cfg.nmods)]
+        from .net import IOBlock
+        self.io = IOBlock(d, B, [(T, cfg.hw, cfg.hw, c) for c in cfg.in_channels])     # one H2D copy per step
+        iov = self.io.views(self.io.dev_buf)
+        self.flags = iov["flags"]
+        for f in self.flags:
+            f.fill_(1.0)
         dhead = torch.zeros(cfg.nmods, 2, B, H2, H2, 128, **f32) if train else None
         # (name, N, H, C): activations in storage mode; "<name>p" = zero-bordered copy
         for m in range(cfg.nmods):
             b = _Branch()
             c = cfg.in_channels[m]
             Tn = {}
-            b.x_in = Tn["x_in"] = torch.zeros(B, T, cfg.hw, cfg.hw, c, **f32)
+            b.x_in = Tn["x_in"] = iov["x"][m]
             # name -> (N, H, W, C); "a1p" / "a2" / "g0" live in the S-way column-split layout
             geo = {"a2": (F * S, H1, H1 // S, c2), "a3": (F, H1, H1, 64), "a4": (F, H2, H2, 64), "a5": (F, H2, H2, 128),
                    "a6": (F, H2, H2, 128), "g0": (B * S, H1, H1 // S, c2), "b1": (B, H1, H1, 64), "b2": (B, H2, H2, 64),
@@ -514,13 +524,14 @@ class _GsPlan:
         if cfg.nclasses > 0:
             Tn["flat"] = torch.zeros(B, GS_PARTS * feat, **f32)
             self.logits = Tn["logits"] = torch.zeros(B, cfg.nclasses, **f32)
+        self.labels = Tn["labels"] = iov["labels"]
         if train:
-            self.labels = Tn["labels"] = torch.zeros(B, device=d, dtype=torch.int32)
-            self.trip_out = Tn["trip_out"] = torch.zeros(2, **f32)
+            self.loss_pack = Tn["loss_pack"] = torch.zeros(8, **f32)     # {triplet, count, ce, acc, reg}
+            self.trip_out = Tn["trip_out"] = self.loss_pack[0:2]
             self.dsig = Tn["dsig"] = torch.zeros(GS_PARTS, B, nd, **f32)
             Tn["trip_ws"] = torch.zeros(ops.triplet_workspace_bytes(GS_PARTS, B) // 4 + 16, **f32)
             if cfg.nclasses > 0:
-                self.ce_out = Tn["ce_out"] = torch.zeros(2, **f32)
+                self.ce_out = Tn["ce_out"] = self.loss_pack[2:4]
                 Tn["dlogits"] = torch.zeros(B, cfg.nclasses, **f32)
                 Tn["dflat"] = torch.zeros(B, GS_PARTS * feat, **f32)
                 Tn["dflat3d"] = Tn["dflat"].view(B, GS_PARTS, feat)

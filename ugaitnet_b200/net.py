@@ -44,6 +44,92 @@ FWD_PASSES = {"f16mix2": (2, 4), "f16mix1": (1, 1)}
 GRAD_SCALE_TARGET = 1024.0      # max|dL/dsignature| * s lands in [512, 1024]: 6 binades of headroom below 65504
 
 
+class IOBlock:
+    """Every per-step INPUT of one plan in ONE contiguous device block, mirrored byte for byte by pinned host blocks,
+    so that a step's inputs cross PCIe in a single cudaMemcpyAsync (one DMA descriptor instead of 2M+1 small copies).
+
+    Layout (256-byte aligned fields): flags[M] f32 [B,1] | labels i32 [B] | src_row i32 [B] | mirror u8 [B] | volumes.
+    The volume area is viewed in two ways that never coexist inside one step: ``x[m]`` = the full batch [B,...], and
+    ``xb(B0)[m]`` = the B0 base rows of the device-side expansion packed back to back right behind the header, so
+    the bytes a step has to copy are always one prefix ``[0, nbytes_full)`` / ``[0, nbytes_base(B0))`` of the block."""
+
+    ALIGN = 256
+
+    def __init__(self, dev, B: int, vol_shapes, has_flags: bool = True):
+        self.B, self.vol_shapes, self.M = B, [tuple(s) for s in vol_shapes], len(vol_shapes)
+        off = 0
+        self.f_off = []
+        for _ in range(self.M if has_flags else 0):
+            self.f_off.append(off)
+            off = round_up(off + 4 * B, self.ALIGN)
+        self.has_flags = has_flags
+        self.lab_off = off
+        off = round_up(off + 4 * B, self.ALIGN)
+        self.src_off = off
+        off = round_up(off + 4 * B, self.ALIGN)
+        self.mir_off = off
+        off = round_up(off + B, self.ALIGN)
+        self.header = off
+        self.row_bytes = [4 * int(torch.tensor(s).prod()) for s in self.vol_shapes]
+        self.x_off, o = [], off
+        for rb in self.row_bytes:
+            self.x_off.append(o)
+            o = round_up(o + rb * B, self.ALIGN)
+        self.nbytes_full = o
+        self.dev_buf = torch.zeros(o, dtype=torch.uint8, device=dev)
+        self._host = {}
+
+    def base_offsets(self, B0: int):
+        offs, o = [], self.header
+        for rb in self.row_bytes:
+            offs.append(o)
+            o = round_up(o + rb * B0, self.ALIGN)
+        return offs, o
+
+    def nbytes_base(self, B0: int) -> int:
+        return self.base_offsets(B0)[1]
+
+    @staticmethod
+    def _view(buf, off, shape, dtype):
+        n = 1
+        for s in shape:
+            n *= s
+        return buf[off:off + n * torch.empty(0, dtype=dtype).element_size()].view(dtype).view(tuple(shape))
+
+    def views(self, buf, B0: Optional[int] = None):
+        """Typed views of a buffer with this layout (device block, staging block or pinned host block)."""
+        B = self.B
+        v = {"flags": [self._view(buf, o, (B, 1), torch.float32) for o in self.f_off],
+             "labels": self._view(buf, self.lab_off, (B,), torch.int32),
+             "src_row": self._view(buf, self.src_off, (B,), torch.int32),
+             "mirror": self._view(buf, self.mir_off, (B,), torch.uint8)}
+        if B0 is None:
+            v["x"] = [self._view(buf, o, (B,) + s, torch.float32) for o, s in zip(self.x_off, self.vol_shapes)]
+        else:
+            offs, _ = self.base_offsets(B0)
+            v["x"] = [self._view(buf, o, (B0,) + s, torch.float32) for o, s in zip(offs, self.vol_shapes)]
+        return v
+
+
+class HostBatch:
+    """Pinned host mirror of a plan's IOBlock: the data loader fills ``inputs[m]`` / ``flags[m]`` / ``labels`` (and
+    ``src_row`` / ``mirror`` for the device-side expansion) IN PLACE (numpy views), ``UGaitEngine.prefetch_batch`` then
+    moves the whole batch with one cudaMemcpyAsync."""
+
+    def __init__(self, io: IOBlock, B0: Optional[int]):
+        self.io, self.B0 = io, B0
+        self.nbytes = io.nbytes_full if B0 is None else io.nbytes_base(B0)
+        self.buf = torch.zeros(self.nbytes, dtype=torch.uint8).pin_memory()
+        v = io.views(self.buf, B0)
+        self.t = v                                       # torch views
+        self.inputs = [x.numpy() for x in v["x"]]
+        self.flags = [f.numpy() for f in v["flags"]]
+        self.labels, self.src_row, self.mirror = v["labels"].numpy(), v["src_row"].numpy(), v["mirror"].numpy()
+        self.use_mirror = False
+        for f in self.flags:
+            f[...] = 1.0
+
+
 class _Seg:
     __slots__ = ("name", "shape", "off", "n", "l2")
 
@@ -88,6 +174,7 @@ class UGaitEngine:
         # all -- ugn_dp_optim_step reduce-scatters the gradients, updates this rank's slice with its slice of the
         # optimiser state and all-gathers the weights in ONE kernel over NVLink peer memory
         self.dp_reduce = os.environ.get("UGN_DP_REDUCE", "fused")
+        self.dp_onegraph = os.environ.get("UGN_DP_ONEGRAPH", "0") == "1"
         self._symm = []            # (tensor, symmetric-memory handle) of the exchanged arenas: [weights, gradients]
         self.multistream = os.environ.get("UGN_MULTISTREAM", "1") != "0"   # concurrent modality branches
         # dense-layer Adam issued right after the dense backward, on a side stream underneath the conv backward.
@@ -186,6 +273,10 @@ class UGaitEngine:
         self.seg_off = torch.tensor([s.off for s in segs] + [off], dtype=torch.int64, device=d)
         self.seg_l2 = torch.tensor([s.l2 for s in segs], dtype=torch.float32, device=d)
         self.reg_out = torch.zeros(1, device=d)
+        if self._symm:                 # fused data-parallel exchange: the scalar is summed over the ranks by peer atomics
+            r = self._new_arena(64, exchanged=True)
+            if len(self._symm) > 2:
+                self.reg_out = r[:1]
         self.lr_dev = torch.zeros(1, device=d)
         self._lr_host = torch.zeros(1).pin_memory()
         self.R = {k: TRef(t) for k, t in dict(w=self.w, g=self.g, m=self.m, v=self.v, seg_off=self.seg_off,
@@ -781,11 +872,14 @@ class UGaitEngine:
         self._early_active = False
         if do_optim and self.dp_reduce == "fused" and (self.world > 1 or self._cap is not None):
             # gradient exchange fused into the optimiser: [forward + backward] | barrier, ONE kernel, barrier | [repack]
-            if self._cap is not None:
+            # the two group barriers and the exchange kernel are plain stream-ordered kernels: with dp_onegraph they are
+            # captured too and the whole data-parallel step replays as ONE CUDA graph (no host work between segments)
+            if self._cap is not None and not self.dp_onegraph:
                 self._cut("fused")
             else:
                 self._dp_fused_exchange()
             self.repack_weights()
+            p.loss_pack[4:5].copy_(self.reg_out, non_blocking=True)
             return
         if do_optim:
             if self._cap is not None:
@@ -797,6 +891,7 @@ class UGaitEngine:
                 else:
                     torch.distributed.all_reduce(self.g, group=self.pg)
             self._optim(1.0 / self.world)
+            p.loss_pack[4:5].copy_(self.reg_out, non_blocking=True)
 
     def _dp_fused_exchange(self):
         """barrier | ugn_dp_optim_step (reduce-scatter + optimiser on this rank's slice + all-gather of the weights over
@@ -808,11 +903,16 @@ class UGaitEngine:
             return
         import ctypes
         h, st, R = self.ctx.h, stream_ptr(), self.R
-        (_, hw), (_, hg) = self._symm
+        (_, hw), (_, hg) = self._symm[:2]
         if not hasattr(self, "_peer_tabs"):
             n = self.world
             self._peer_tabs = ((ctypes.c_int64 * n)(*[int(p) for p in hg.buffer_ptrs]),
                                (ctypes.c_int64 * n)(*[int(p) for p in hw.buffer_ptrs]))
+            # regulariser value: every rank's scalar (symmetric memory) receives the sum of the slices by peer atomics
+            self._reg_tab = None
+            if len(self._symm) > 2:
+                hr = self._symm[2][1]
+                self._reg_tab = (ctypes.c_int64 * n)(*[int(p) for p in hr.buffer_ptrs])
             # NVSwitch multicast mappings (multimem.ld_reduce / multimem.st) when the fabric offers them
             # measured: N = 2 unicast 4.02 ms vs multicast 4.32 ms per step, N = 8 unicast 4.53 vs multicast 4.29 -- the
             # unicast path moves 2(N-1)/N arenas per GPU and direction, the multicast path (1 + 1/N): on from N = 4
@@ -831,15 +931,18 @@ class UGaitEngine:
             R["vhat"] = TRef(self.vhat)
         if not adam and self.optimizer != "sgd":
             raise ValueError(f"unknown optimizer {self.optimizer}")
+        if self._reg_tab is not None:
+            self.reg_out.zero_()                # before the barrier: peers add their slice values into it
         hg.barrier(channel=0)                   # every rank's gradients are complete
         check(lib.ugn_dp_optim_step(h, 0 if adam else 1, self.world, torch.distributed.get_rank(self.pg), gp, wp,
                                     self._mc[0], self._mc[1], R["w"].ptr, R["g"].ptr, R["m"].ptr if adam else None, R["v"].ptr,
                                     R["vhat"].ptr if self.optimizer == "amsgrad" else None,
                                     self.decoupled_wd if self.optimizer == "adamw" else 0.0, R["seg_off"].ptr,
                                     R["seg_l2"].ptr, self.beta1 if adam else self.momentum, self.beta2, self.eps,
-                                    R["reg_out"].ptr, R["lr_dev"].ptr, st))
-        hw.barrier(channel=0)                   # every rank's slice of the new weights has landed here
-        torch.distributed.all_reduce(self.reg_out, group=self.pg)      # regulariser value: sum of the slices (4 bytes)
+                                    R["reg_out"].ptr, self._reg_tab, R["lr_dev"].ptr, st))
+        hw.barrier(channel=0)                   # every rank's slice of the new weights (and of the regulariser sum) has landed
+        if self._reg_tab is None:
+            torch.distributed.all_reduce(self.reg_out, group=self.pg)  # fallback: sum of the slice values (4 bytes)
 
     def _next_lr(self):
         self.t += 1
@@ -919,7 +1022,7 @@ class UGaitEngine:
     def _run_train(self, p, B, expanded):
         self._next_lr()
         if self.use_graph and (self.world == 1 or self.dp_graph):
-            gkey = (B, expanded, p.use_mirror)
+            gkey = (B, expanded, p.use_mirror, getattr(p, "_B0", None) if expanded else None)
             gr = self._graphs.get(gkey)
             if gr is None:
                 # warm-up on a side stream (first-use allocations / attribute sets), then capture
@@ -1015,6 +1118,78 @@ class UGaitEngine:
         self._stage_free[k].record(torch.cuda.current_stream())
         return out
 
+    # ---- single-copy input path: the loader writes into a pinned HostBatch whose bytes mirror the plan's IOBlock
+    def host_batch(self, B: int, base_rows: Optional[int] = None, train: bool = True) -> HostBatch:
+        """A NEW pinned host batch for batch size B (base_rows = B0 selects the device-side-expansion layout: only the
+        B0 complete sequences + the expansion tables cross PCIe).  Allocate two and alternate them to overlap the
+        loader / the H2D copy of step i+1 with step i."""
+        return HostBatch(self.plan(B, train).io, base_rows)
+
+    def prefetch_batch(self, hb: HostBatch, train: bool = True):
+        """ONE cudaMemcpyAsync of the whole batch (flags, labels, expansion tables, volumes) on the copy stream into
+        the alternate device staging block; consume with train_step_prefetched() / predict_prefetched()."""
+        p = self.plan(hb.io.B, train)
+        if not hasattr(self, "_io_stage"):
+            self._io_copy_stream = torch.cuda.Stream(device=self.dev)
+            self._io_stage, self._io_k = {}, 0
+        key = (hb.io.B, train)
+        st = self._io_stage.get(key)
+        if st is None:
+            st = self._io_stage[key] = {"buf": [torch.empty(p.io.nbytes_full, dtype=torch.uint8, device=self.dev) for _ in range(2)],
+                                        "ready": [torch.cuda.Event(), torch.cuda.Event()],
+                                        "free": [torch.cuda.Event(), torch.cuda.Event()], "hb": [None, None]}
+        k = self._io_k ^ 1
+        with torch.cuda.stream(self._io_copy_stream):
+            self._io_copy_stream.wait_event(st["free"][k])           # the step that consumed this block is done
+            st["buf"][k][:hb.nbytes].copy_(hb.buf, non_blocking=True)
+            st["ready"][k].record(self._io_copy_stream)
+        st["hb"][k] = hb
+        self._io_k, self._io_key = k, key
+
+    def _consume_prefetched(self):
+        key, k = self._io_key, self._io_k
+        st = self._io_stage[key]
+        hb = st["hb"][k]
+        p = self.plan(*key)
+        cur = torch.cuda.current_stream()
+        cur.wait_event(st["ready"][k])
+        p.io.dev_buf[:hb.nbytes].copy_(st["buf"][k][:hb.nbytes], non_blocking=True)   # ONE device-to-device copy
+        st["free"][k].record(cur)
+        return p, hb
+
+    def _draw_dropout(self, p):
+        cfg = self.cfg
+        if p.train and cfg.dropout > 0.001:
+            keep = 1.0 - cfg.dropout
+            for b in p.br:
+                if hasattr(b, "mask"):
+                    b.mask.bernoulli_(keep).div_(keep)
+            if cfg.nc > 0:
+                p.cmask.bernoulli_(keep).div_(keep)
+
+    @torch.no_grad()
+    def train_step_prefetched(self) -> Dict[str, torch.Tensor]:
+        """train_step on the HostBatch most recently passed to prefetch_batch()."""
+        p, hb = self._consume_prefetched()
+        self._draw_dropout(p)
+        expanded = hb.B0 is not None
+        if expanded:
+            p.ensure_base(hb.B0)
+            p.use_mirror = bool(hb.use_mirror)
+        return self._run_train(p, p.B, expanded=expanded)
+
+    @torch.no_grad()
+    def predict_prefetched(self, layer: str = "signature") -> torch.Tensor:
+        p, hb = self._consume_prefetched()
+        expanded = hb.B0 is not None
+        if expanded:
+            p.ensure_base(hb.B0)
+            p.use_mirror = bool(hb.use_mirror)
+        self._forward(p, False, expanded)
+        if layer == "signature":
+            return (p.br[0].out if self.cfg.single else p.sig).clone()
+        return p.code.clone() if layer == "code" else p.logits.clone()
+
     def _report(self, p: "_Plan", with_reg: bool = False) -> Dict[str, torch.Tensor]:
         out = {"triplet": p.trip_out[0], "count": p.trip_out[1], "signature": p.br[0].out if self.cfg.single else p.sig}
         if self.cfg.nclasses > 0:
@@ -1023,7 +1198,8 @@ class UGaitEngine:
             out["aux_ce"] = [b.T["aux_ce"][0] for b in p.br]
             out["aux_acc"] = [b.T["aux_ce"][1] for b in p.br]
         if with_reg:
-            out["reg"] = self.reg_out[0]
+            out["reg"] = p.loss_pack[4]
+            out["losses"] = p.loss_pack          # [triplet, count, ce, acc, reg, -, -, -]: one D2H read
         return out
 
     def launches_per_step(self) -> int:
@@ -1050,13 +1226,19 @@ class _Plan:
         self.eng = eng
         self.use_mirror = False
         self.br: List[_Branch] = []
-        self.flags = [torch.ones(B, 1, **f32) for _ in range(cfg.nmods)]
+        # every per-step input lives in ONE device block (IOBlock): one H2D copy per step, see UGaitEngine.prefetch_batch
+        self.io = IOBlock(d, B, [(cfg.layers(m, eng.pad)[0]["cin"], cfg.hw, cfg.hw) for m in range(cfg.nmods)])
+        iov = self.io.views(self.io.dev_buf)
+        self.flags = iov["flags"]
+        for f in self.flags:
+            f.fill_(1.0)
+        self._base = {}
         for m in range(cfg.nmods):
             b = _Branch()
             b.layers = cfg.layers(m, eng.pad)
             T = {}
             L0 = b.layers[0]
-            b.x_in = T["x_in"] = torch.zeros(B, L0["cin"], cfg.hw, cfg.hw, **f32)
+            b.x_in = T["x_in"] = iov["x"][m]
             T["a0"] = act((B, L0["h"], L0["h"], L0["cp"]))
             for li, L in enumerate(b.layers):
                 T[f"a{li + 1}"] = act((B, L["hp"], L["hp"], L["co"]))
@@ -1121,13 +1303,17 @@ class _Plan:
             feat = cfg.nc
         if cfg.nclasses > 0:
             self.logits = T["logits"] = torch.zeros(B, cfg.nclasses, **f32)
+        self.labels = T["labels"] = iov["labels"]
+        self.src_row = T["src_row"] = iov["src_row"]
+        self.mirror = T["mirror"] = iov["mirror"]
         if train:
-            self.labels = T["labels"] = torch.zeros(B, device=d, dtype=torch.int32)
-            self.trip_out = T["trip_out"] = torch.zeros(2, **f32)
+            # {triplet, count, ce, acc, reg}: one buffer, one D2H read per step
+            self.loss_pack = T["loss_pack"] = torch.zeros(8, **f32)
+            self.trip_out = T["trip_out"] = self.loss_pack[0:2]
             self.dsig = T["dsig"] = torch.zeros(B, cfg.nd, **f32)
             T["trip_ws"] = torch.zeros(ops.triplet_workspace_bytes(1, B) // 4 + 16, **f32)
             if cfg.nclasses > 0:
-                self.ce_out = T["ce_out"] = torch.zeros(2, **f32)
+                self.ce_out = T["ce_out"] = self.loss_pack[2:4]
                 T["dlogits"] = torch.zeros(B, cfg.nclasses, **f32)
                 self.dfeat = T["dfeat"] = torch.zeros(B, feat, **f32)
             if cfg.nc > 0:
@@ -1150,14 +1336,14 @@ class _Plan:
                 self.dbrn_ptrs = ptr_array([b.R["doutn"] for b in self.br])
 
     def ensure_base(self, B0: int):
-        """Buffers of the device-side expansion: base rows per modality, source-row and mirror tables."""
-        if getattr(self, "_B0", None) == B0:
-            return
-        cfg, d = self.eng.cfg, self.eng.dev
-        for m, b in enumerate(self.br):
-            b.x_base = torch.zeros(B0, b.layers[0]["cin"], cfg.hw, cfg.hw, device=d)
-            b.R["x_base"] = TRef(b.x_base)
-        self.src_row = torch.zeros(self.B, dtype=torch.int32, device=d)
-        self.mirror = torch.zeros(self.B, dtype=torch.uint8, device=d)
-        self.R["src_row"], self.R["mirror"] = TRef(self.src_row), TRef(self.mirror)
+        """Views of the device-side expansion's base rows (B0 rows per modality, packed right behind the header of the
+        IO block).  Nothing is allocated or freed here: a CUDA graph captured for one B0 keeps reading valid memory
+        when another B0 is used in between (the graph key carries B0)."""
+        assert 0 < B0 <= self.B, "base rows must be in [1, B]"
+        ent = self._base.get(B0)
+        if ent is None:
+            xs = self.io.views(self.io.dev_buf, B0)["x"]
+            ent = self._base[B0] = (xs, [TRef(x) for x in xs])
+        for b, x, r in zip(self.br, ent[0], ent[1]):
+            b.x_base, b.R["x_base"] = x, r
         self._B0 = B0
