@@ -62,6 +62,8 @@ class NetConfig:
     normbfmerge: bool = False      # per-branch l2_normalize before the gate (:1167-1168)
     aux_losses: bool = False       # classprob_{of,gray,depth} heads on the gated branch outputs (:1222-1251)
     waux: float = 1.0              # loss_weights[-1] (:1264-1268)
+    postriplet: int = 1            # 2: fusion -> Dense "signature" (activity-regularised) -> l2_normalize "code" = the
+    #                                embedding of the triplet loss and of the classifier (:814-832, 2-modality builder)
 
     @property
     def nmods(self):
@@ -335,6 +337,17 @@ def model_forward(inputs, flags, P, cfg: NetConfig, drop_masks=None, code_drop_m
         fused = merge_modalities(gated, cfg.merge, None if decisions is None else decisions.get("winner"), record)
         outs["fusion"] = fused
         sig = l2_normalize(fused, 1)
+    if getattr(cfg, "postriplet", 1) == 2 and cfg.nc > 0 and not cfg.single:
+        # :819-832 -- no normalisation of the fusion; Dense(nc) named "signature" (+ LeakyReLU), its l2_normalize named
+        # "code" is `outsignature`; Dropout("dropcode") feeds the classifier
+        z = F.linear(fused, P["code/w"], P["code/b"])
+        outs["code_reg"] = F.relu(z) if cfg.act == ACT_RELU else z
+        x = l2_normalize(_act(z, cfg.act, cfg.alpha), 1)
+        outs["signature"] = outs["code"] = x
+        feat = x if code_drop_mask is None else x * code_drop_mask
+        if cfg.nclasses > 0:
+            outs["logits"] = F.linear(feat, P["classprob/w"], P["classprob/b"])
+        return outs if return_all else (outs["signature"], outs.get("logits"))
     outs["signature"] = sig
     feat = sig
     if cfg.nc > 0:

@@ -91,7 +91,18 @@ def test_reference_import_paths_and_training_protocol(compat_path, tmp_path):
     m2.load_weights(path, by_name=True, skip_mismatch=True)
     assert np.array_equal(m2.predict(X)[0], sig)
     w = model.get_layer("classprob").get_weights()
-    assert sorted(a.shape for a in w) == [(10,), (32, 10)]          # Keras (in,out) kernel + bias
+    assert [a.shape for a in w] == [(32, 10), (10,)]                # Keras order: (in,out) kernel, then bias
+    wb = model.get_layer("ofBranch").get_weights()                  # Sequential: kernel, bias of every sublayer in graph order
+    assert [a.shape for a in wb][:4] == [(7, 7, 6, 8), (8,), (5, 5, 8, 8), (8,)] and len(wb) == 12
+    # the file is a regular HDF5 file in Keras' save_weights layout
+    from ugaitnet_b200 import hdf5
+    assert hdf5.is_hdf5(path)
+    f = hdf5.File(path)
+    names = [n.decode() for n in f.attrs["layer_names"]]
+    assert names[:3] == ["ofBranch", "grayBranch", "depthBranch"] and names[-1] == "classprob"
+    wn = [n.decode() for n in f["grayBranch"].attrs["weight_names"]]
+    assert wn[0] == "conv2d_4/kernel:0" and wn[-1] == "ofCode/bias:0"
+    assert f["classprob/classprob/kernel:0"].value.shape == (32, 10)
     eer, thr = mj_eerVerifDist(np.array([1, 1, 1, 1, 1, 0, 0, 0, 0]),
                                np.array([0.01, 0.02, 0.015, 0.08, 0.05, 0.07, 0.2, 0.15, 0.18]))
     assert eer == pytest.approx(0.25) and thr == pytest.approx(0.07)   # the reference demo's known answer
@@ -168,3 +179,84 @@ def test_gaitset_builder_protocol(compat_path, tmp_path):
     assert np.array_equal(m2.predict(X)[0], model.predict(X)[0])
     w = model.get_layer("ofBranch").layers[0].get_weights()
     assert [a.shape for a in w] == [(5, 5, 2, 32)]                               # Keras (kh,kw,cin,cout) kernel
+
+
+def test_model_save_loadnet_initnet_freeze_and_init_branches(compat_path, tmp_path):
+    """model.save -> loadnet (:1008-1029), build_or_load(initnet=..., freeze_convs / freeze_all) (:1325-1391) with
+    classifier "surgery" (a different nclasses keeps every compatible layer), init_branches (:57-75) and the optimiser
+    state (m, v, AMSGrad vhat, iterations, lr) in the checkpoint."""
+    from nets.mj_uwyhNets_ba import UWYHSemiNet3Mods
+    from ugaitnet_b200.compat import optimizers, sign_max
+    import nets.mj_uwyhNets_ba as mod
+    mod.MATH_MODE = "fp32"
+    shp, fs, fn = [(6, 60, 60), (4, 60, 60), (4, 60, 60)], [(7, 7), (5, 5), (3, 3), (2, 2)], [8, 8, 16, 16]
+    model = UWYHSemiNet3Mods.build(shp, 4, fs, fn, [32, 16], 0.00005, 0.0, optimizer=optimizers.Adam(lr=1e-3, amsgrad=True),
+                                   nclasses=10, loss_weights=[1.0, 0.1], fMerge=sign_max)
+    oc = O.NetConfig(in_channels=(6, 4, 4), filters_numbers=(8, 8, 16, 16), nd=32, nc=16, nclasses=10)
+    gen = FakeGen(oc, n=2)
+    X, y = gen[0]
+    for _ in range(2):
+        model.train_on_batch(X, y)
+    model.optimizer.lr = 5e-4
+    path = str(tmp_path / "model-state-0002.hdf5")
+    model.save(path)
+    model.save_weights(UWYHSemiNet3Mods.get_weights_filename(path))
+    m2 = UWYHSemiNet3Mods.loadnet(path)
+    assert np.array_equal(m2.predict(X)[0], model.predict(X)[0])
+    e, e2 = model.engine, m2.engine
+    assert e2.t == e.t == 2 and e2.lr == pytest.approx(5e-4) and e2.optimizer == "amsgrad"
+    assert torch.equal(e2.m, e.m) and torch.equal(e2.v, e.v) and torch.equal(e2.vhat, e.vhat)
+    l1, l2 = model.train_on_batch(X, y), m2.train_on_batch(X, y)                 # resumed training continues identically
+    assert l2["loss"] == pytest.approx(l1["loss"], rel=1e-6)
+    # initnet with another classifier width + freeze_convs
+    m3 = UWYHSemiNet3Mods.build_or_load(shp, 4, fs, fn, [32, 16], 0.00005, 0.0, optimizer=optimizers.SGD(1e-2, 0.9),
+                                        nclasses=7, loss_weights=[1.0, 0.1], initnet=path, freeze_convs=True, fMerge=sign_max)
+    W, W3 = model.engine.export_params(), m3.engine.export_params()
+    assert torch.equal(W3["ofBranch/conv2/w"], W["ofBranch/conv2/w"]) and torch.equal(W3["code/w"], W["code/w"])
+    assert W3["classprob/w"].shape == (7, 16)                                     # skipped: built fresh
+    assert sorted(m3.engine.frozen()) == sorted(k for k in W3 if "/conv" in k)
+    assert m3.get_layer("ofBranch").layers[0].trainable is False and m3.get_layer("ofBranch").layers[5].trainable is True
+    gen7 = FakeGen(O.NetConfig(in_channels=(6, 4, 4), filters_numbers=(8, 8, 16, 16), nd=32, nc=16, nclasses=7), n=1)
+    m3.train_on_batch(*gen7[0])
+    W3b = m3.engine.export_params()
+    assert torch.equal(W3b["grayBranch/conv0/w"], W3["grayBranch/conv0/w"])       # frozen
+    assert not torch.equal(W3b["grayBranch/dense/w"], W3["grayBranch/dense/w"])   # trained
+    m4 = UWYHSemiNet3Mods.build_or_load(shp, 4, fs, fn, [32, 16], 0.00005, 0.0, optimizer=optimizers.SGD(1e-2, 0.9),
+                                        nclasses=10, loss_weights=[1.0, 0.1], initnet=path, freeze_all=True, fMerge=sign_max)
+    assert sorted(m4.engine.frozen()) == sorted(k for k in W if k.split("/")[0].endswith("Branch"))
+    # init_branches: a stand-alone branch file initialises the same-named branch
+    bpath = str(tmp_path / "gray_branch.hdf5")
+    model.save_branch(bpath, "grayBranch")
+    m5 = UWYHSemiNet3Mods.build(shp, 4, fs, fn, [32, 16], 0.00005, 0.0, optimizer=optimizers.SGD(1e-2, 0.9), nclasses=10,
+                                loss_weights=[1.0, 0.1], init_branches={"of": "", "gray": bpath, "depth": ""},
+                                freeze_branches=False, fMerge=sign_max)
+    W5 = m5.engine.export_params()
+    assert all(torch.equal(W5[k], W[k]) for k in W if k.startswith("grayBranch/"))
+    assert not torch.equal(W5["ofBranch/dense/w"], W["ofBranch/dense/w"])
+
+
+def test_postriplet2_builder(compat_path):
+    """UWYHSemiNet.build(..., postriplet=2) (2-modality builder, :819-832): 'signature' is the Dense layer, 'code' its
+    l2_normalize -- the embedding of the triplet loss."""
+    from nets.mj_uwyhNets_ba import UWYHSemiNet
+    from ugaitnet_b200.compat import Model, optimizers
+    import nets.mj_uwyhNets_ba as mod
+    mod.MATH_MODE = "fp32"
+    model = UWYHSemiNet.build([(6, 60, 60), (4, 60, 60)], 4, [(7, 7), (5, 5), (3, 3), (2, 2)], [8, 8, 16, 16], [32, 8],
+                              0.00005, 0.0, optimizer=optimizers.Adam(lr=1e-3), nclasses=7, loss_weights=[1.0, 0.5],
+                              postriplet=2)
+    oc = O.NetConfig(in_channels=(6, 4), filters_numbers=(8, 8, 16, 16), nd=32, nc=8, nclasses=7, merge=O.MERGE_MAX,
+                     wver=1.0, wid=0.5, postriplet=2)
+    gen = FakeGen(oc, n=1, base_rows=8, expand=2)
+    X, y = gen[0]
+    P = {k: v.double().cpu() for k, v in model.engine.export_params().items()}
+    outs = O.model_forward([torch.tensor(X[0]), torch.tensor(X[2])], [torch.tensor(X[1]), torch.tensor(X[3])], P, oc,
+                           return_all=True)
+    code = Model(model.input, model.get_layer("code").output).predict(X)
+    assert code.shape == (16, 8) and np.allclose(code, outs["code"].numpy(), atol=2e-5)
+    assert np.allclose(np.linalg.norm(code, axis=1), 1.0, atol=1e-5)
+    logs = model.train_on_batch(X, y)
+    res, _ = O.loss_and_grads([torch.tensor(X[0]), torch.tensor(X[2])], [torch.tensor(X[1]), torch.tensor(X[3])],
+                              torch.tensor(y[0]), P, oc)
+    assert logs["signature_loss"] == pytest.approx(float(res["triplet"]), rel=1e-5)
+    assert logs["loss"] == pytest.approx(float(res["loss"]), rel=1e-5)

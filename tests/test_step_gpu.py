@@ -38,6 +38,14 @@ def make_case(name):
         oc = O.NetConfig(in_channels=(6, 4), filters_numbers=(8, 8, 16, 16), nd=32, nc=8, nclasses=7,
                          merge=O.MERGE_MAX, act=O.ACT_LEAKY, wver=1.0, wid=1.0)
         return oc, dict(base_rows=8, expand=2, kinds=("of", "gray")), 0.3
+    if name == "2mod_postriplet2":     # postriplet == 2 (:819-832): Dense "signature" -> l2_normalize "code" = embedding
+        oc = O.NetConfig(in_channels=(6, 4), filters_numbers=(8, 8, 16, 16), nd=32, nc=8, nclasses=7,
+                         merge=O.MERGE_MAX, act=O.ACT_LEAKY, wver=1.0, wid=0.5, postriplet=2)
+        return oc, dict(base_rows=8, expand=2, kinds=("of", "gray")), 0.3
+    if name == "2mod_postriplet2_relu":
+        oc = O.NetConfig(in_channels=(6, 4), filters_numbers=(8, 8, 16, 16), nd=32, nc=8, nclasses=7,
+                         merge=O.MERGE_SIGNMAX, act=O.ACT_RELU, wver=1.0, wid=0.5, postriplet=2)
+        return oc, dict(base_rows=8, expand=2, kinds=("of", "gray")), None
     if name == "3mod_avg":
         oc = O.NetConfig(in_channels=(4, 4, 4), filters_numbers=(8, 8, 16, 16), nd=16, nclasses=6,
                          merge=O.MERGE_AVG, wver=0.5, wid=0.5)
@@ -59,7 +67,7 @@ def to_engine_cfg(oc, dropout=0.0):
                      weight_decay=oc.weight_decay, merge=oc.merge, act=oc.act, alpha=oc.alpha, margin=oc.margin,
                      wver=oc.wver, wid=oc.wid, hw=oc.hw, dropout=dropout, single=oc.single,
                      label_smoothing=oc.label_smoothing, normbfmerge=oc.normbfmerge, aux_losses=oc.aux_losses,
-                     waux=oc.waux)
+                     waux=oc.waux, postriplet=oc.postriplet)
 
 
 def setup(name, math_mode="fp32", seed=11):
@@ -104,7 +112,7 @@ def reg_grad(oc, name, w):
 
 
 @pytest.mark.parametrize("name", ["3mod_signmax", "2mod_max_leaky_code", "3mod_avg", "1mod_gray", "real_shapes",
-                                  "3mod_norm_smooth", "3mod_aux", "2mod_aux"])
+                                  "3mod_norm_smooth", "3mod_aux", "2mod_aux", "2mod_postriplet2", "2mod_postriplet2_relu"])
 def test_step_parity_fp32(name):
     oc, eng, P, xs, fl, lab, masks, cmask = setup(name)
     res, G = oracle_step(oc, P, xs, fl, lab, masks, cmask)
@@ -440,3 +448,42 @@ def test_engine_matches_committed_step_fixture(name):
         # the fixture holds gradients of the TOTAL loss; the engine applies the weight regulariser in the optimiser
         mine = float((got[k].double().cpu() + regs[k]).norm())
         assert mine == pytest.approx(float(n), rel=2e-4, abs=1e-9), k
+
+
+def test_frozen_layers_receive_no_update_but_keep_their_regulariser():
+    """layer.trainable = False (freeze_convs / freeze_all, nets/mj_uwyhNets_ba.py:1366-1391): the optimiser kernel skips
+    the frozen tensors (weights, m, v untouched), everything else moves exactly as without freezing, and the
+    regulariser value still counts the frozen kernels."""
+    from ugaitnet_b200.net import UGaitEngine
+    oc, eng, P, xs, fl, lab, masks, cmask = setup("3mod_signmax")
+    eng_f = UGaitEngine(to_engine_cfg(oc), math_mode="fp32", lr=1e-3)
+    eng_f.load_params(P)
+    for m in range(3):
+        for li in range(4):
+            eng_f.set_trainable(f"{O.BRANCH_NAMES[m]}/conv{li}", False)
+    assert len(eng_f.frozen()) == 24
+    ins = engine_inputs(xs, fl, lab, masks, cmask)
+    for _ in range(2):
+        a = eng.train_step(*ins)
+        b = eng_f.train_step(*ins)
+    W0, Wa, Wb = P, eng.export_params(), eng_f.export_params()
+    for k in Wa:
+        if "/conv" in k:
+            assert torch.equal(Wb[k].double().cpu(), W0[k].float().double()), k       # frozen: bit-identical to the start
+            assert not torch.equal(Wa[k].double().cpu(), W0[k].float().double()), k
+    # first step: identical forward -> identical regulariser value (frozen kernels included)
+    eng2 = UGaitEngine(to_engine_cfg(oc), math_mode="fp32", lr=1e-3)
+    eng2.load_params(P)
+    eng3 = UGaitEngine(to_engine_cfg(oc), math_mode="fp32", lr=1e-3)
+    eng3.load_params(P)
+    eng3.set_trainable("ofBranch", False)
+    r2, r3 = float(eng2.train_step(*ins)["reg"]), float(eng3.train_step(*ins)["reg"])
+    assert r3 == pytest.approx(r2, rel=1e-6)
+    W2, W3 = eng2.export_params(), eng3.export_params()
+    for k in W2:
+        if k.startswith("ofBranch/"):
+            assert torch.equal(W3[k].double().cpu(), P[k].float().double()), k
+        else:
+            assert torch.equal(W3[k], W2[k]), k           # unfrozen tensors: the same update as without freezing
+    eng3.set_trainable("ofBranch", True)
+    assert eng3.frozen() == []

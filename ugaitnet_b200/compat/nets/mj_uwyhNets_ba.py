@@ -11,10 +11,12 @@ branch type (build_gaitset_branch :420-484) on ugaitnet_b200.gaitset.GaitSetEngi
 [B,25,60,60,c], signature [62,B,256], descriptor layer "flatten" (typecode 3).
 
 ``smoothlabels`` (label-smoothed cross-entropy, :1252-1262), ``normbfmerge`` (per-branch l2_normalize before
-the gate, :1167-1168) and ``aux_losses`` (classprob_{of,gray,depth} heads on the gated branch outputs,
-:1222-1251; stacked-CNN branches) are implemented.  Builder arguments that select graphs outside the hot path
-raise NotImplementedError: use3D, postriplet == 2, init_branches / initnet weight surgery from Keras .hdf5
-files, tfa TripletHardLoss (compile_hard), aux_losses together with gaitset.
+the gate, :1167-1168), ``aux_losses`` (classprob_{of,gray,depth} heads on the gated branch outputs, :1222-1251;
+stacked-CNN branches), ``postriplet == 2`` (2-modality builder, :819-832), ``freeze_convs`` / ``freeze_all`` /
+``freeze_branches`` and ``layer.trainable`` (:193, :1366-1391), ``initnet`` / ``init_branches`` / ``loadnet`` from Keras
+HDF5 files (ugaitnet_b200.hdf5: pure-Python reader / writer, h5py is absent) are implemented.  Builder arguments that
+select graphs outside the hot path raise NotImplementedError: use3D (Conv3D branches), tfa TripletHardLoss
+(compile_hard), aux_losses together with gaitset.
 """
 from __future__ import annotations
 
@@ -32,7 +34,8 @@ from ugaitnet_b200.net import UGaitEngine
 from ugaitnet_b200.compat.keras_shim import Average, History, Maximum, _Tag, merge_id_of, optimizers  # noqa: F401
 from ugaitnet_b200.compat.nets.triplet_loss_all import triplet_loss
 
-MATH_MODE = os.environ.get("UGN_MATH_MODE", "bf16x3")
+# the benchmarked, parity-gated math mode (tests/test_decisions_gpu.py): fp16 hi/lo split, 3-pass forward, 1-pass backward
+MATH_MODE = os.environ.get("UGN_MATH_MODE", "f16mix")
 
 
 def mj_tensor_times_scalar(d):
@@ -47,9 +50,22 @@ def _unsupported(**flags):
 
 
 class _LayerProxy:
-    def __init__(self, model, name, units=None, sublayers=()):
-        self.model, self.name, self.units, self.trainable = model, name, units, True
+    def __init__(self, model, name, units=None, sublayers=(), kind="layer"):
+        self.model, self.name, self.units, self._trainable = model, name, units, True
         self.layers = list(sublayers)
+        self.kind = kind                 # "conv" | "dense" | "layer": freeze_convs freezes the Conv2D sublayers only
+
+    @property
+    def trainable(self):
+        return self._trainable
+
+    @trainable.setter
+    def trainable(self, flag):
+        """layer.trainable = False (:1366-1391): the optimiser stops updating the layer's tensors."""
+        self._trainable = bool(flag)
+        for sub in self.layers:
+            sub.trainable = flag
+        self.model._set_trainable(self.name, bool(flag))
 
     @property
     def output(self):
@@ -109,8 +125,9 @@ class UGaitModel:
                 sub = [_LayerProxy(self, f"{BRANCH_NAMES[m]}/{n[0]}") for n in GS_CONVS] + \
                       [_LayerProxy(self, f"{BRANCH_NAMES[m]}/matmul")]
             else:
-                sub = [_LayerProxy(self, f"{BRANCH_NAMES[m]}/{n}") for n in
-                       [f"conv{i}" for i in range(len(cfg.filters_numbers))] + ["ofFlat", "dense", "drop", "ofCode"]]
+                sub = [_LayerProxy(self, f"{BRANCH_NAMES[m]}/conv{i}", kind="conv") for i in range(len(cfg.filters_numbers))] + \
+                      [_LayerProxy(self, f"{BRANCH_NAMES[m]}/{n}", kind="dense" if n in ("dense", "ofCode") else "layer")
+                       for n in ["ofFlat", "dense", "drop", "ofCode"]]
             names.append(_LayerProxy(self, BRANCH_NAMES[m], units=cfg.nd, sublayers=sub))
         for n in ("gate_of1", "gate_gray1", "gate_depth1")[:cfg.nmods]:
             names.append(_LayerProxy(self, n))
@@ -210,10 +227,7 @@ class UGaitModel:
         callbacks = callbacks or []
         for cb in callbacks:
             if hasattr(cb, "set_model"):
-                try:
-                    cb.set_model(self)
-                except Exception:
-                    pass
+                cb.set_model(self)
         for epoch in range(initial_epoch, epochs):
             n = steps_per_epoch or len(gen)
             acc: Dict[str, float] = {}
@@ -238,24 +252,52 @@ class UGaitModel:
                 gen.on_epoch_end()
             for cb in callbacks:
                 if hasattr(cb, "on_epoch_end"):
-                    try:
-                        cb.on_epoch_end(epoch, logs)
-                    except Exception:
-                        pass
+                    cb.on_epoch_end(epoch, logs)      # a failing checkpoint / LR callback must surface, as in Keras
             if self.stop_training:
                 break
         return hist
 
     # -- weights: Keras names / layouts ((kh,kw,cin,cout) conv kernels, (in,out) dense kernels) -------
+    def _set_trainable(self, name, flag):
+        try:
+            self.engine.set_trainable(name, flag)
+        except KeyError:
+            pass                          # a layer without parameters (gates, fusion, dropout ...)
+
     @staticmethod
     def _keras_name(seg_name):
         base, kind = seg_name.rsplit("/", 1)
         return f"{base}/{'kernel' if kind == 'w' else 'bias'}"
 
+    def _keras_layout(self):
+        """[(keras layer name, [(keras weight name, engine tensor name), ...]), ...] in the order Keras lists
+        model.layers / layer.weights: a branch is ONE layer (a Sequential) whose weights are kernel, bias of every
+        sublayer in graph order; the Conv2D sublayers carry Keras' auto-generated names (conv2d, conv2d_1, ...)."""
+        e, out, conv_no = self.engine, [], 0
+        top: Dict[str, list] = {}
+        for sg in e.seg_list:
+            parts = sg.name.split("/")
+            kind = "kernel:0" if parts[-1] == "w" else "bias:0"
+            if len(parts) == 3:                        # <branch>/<sublayer>/<w|b>
+                sub = parts[1]
+                if sub.startswith("conv") and not self.gaitset:
+                    if parts[-1] == "w":
+                        conv_no += 1
+                    sub = "conv2d" if conv_no == 1 else f"conv2d_{conv_no - 1}"
+                top.setdefault(parts[0], []).append((f"{sub}/{kind}", sg.name))
+            else:                                      # code / classprob / classprob_of ...
+                top.setdefault(parts[0], []).append((f"{parts[0]}/{kind}", sg.name))
+        for l in self.layers:
+            out.append((l.name, top.get(l.name, [])))
+        return out
+
     def _layer_weights(self, name):
+        """layer.get_weights(): Keras order -- layers in graph order, kernel before bias
+        (consumers index it: nets/mj_utils.py:159-160 ``filters = w[0]``)."""
         P = self.engine.export_params()
         out = []
-        for k in sorted(P):
+        for sg in self.engine.seg_list:               # arena order = graph order, w before b
+            k = sg.name
             if k.startswith(name + "/") or k.rsplit("/", 1)[0] == name:
                 out.append(self._to_keras(k, P[k]).cpu().numpy())
         return out
@@ -270,26 +312,78 @@ class UGaitModel:
 
     @staticmethod
     def _from_keras(v):
-        v = torch.as_tensor(v)
+        v = torch.as_tensor(np.asarray(v))
         if v.dim() == 4:
             return v.permute(3, 2, 0, 1).contiguous()
         if v.dim() == 2:
             return v.t().contiguous()
         return v
 
-    def save_weights(self, path, **kw):
+    def _write_weight_groups(self, w, root: str):
+        """Keras' hdf5_format.save_weights_to_hdf5_group layout: attrs layer_names / backend / keras_version on the
+        group, one sub-group per layer with attr weight_names and one dataset per weight."""
         P = self.engine.export_params()
-        arrs = {self._keras_name(k): self._to_keras(k, v).cpu().numpy() for k, v in P.items()}
-        with open(path, "wb") as f:          # .hdf5 in the reference; h5py is unavailable -> npz container
-            np.savez(f, **arrs)
+        g = w.group(root)
+        layout = self._keras_layout()
+        g.attrs["layer_names"] = [n.encode("utf8") for n, _ in layout]
+        g.attrs["backend"] = b"tensorflow"
+        g.attrs["keras_version"] = b"2.4.0"
+        for lname, weights in layout:
+            lg = w.group(f"{root}/{lname}")
+            lg.attrs["weight_names"] = [wn.encode("utf8") for wn, _ in weights] if weights else np.zeros((0,), dtype="S1")
+            for wn, seg in weights:
+                w.dataset(f"{root}/{lname}/{wn}", self._to_keras(seg, P[seg]).cpu().numpy())
+
+    def save_weights(self, path, **kw):
+        """model.save_weights(path): a regular HDF5 file in Keras' layout (ugaitnet_b200.hdf5 writer)."""
+        from ugaitnet_b200 import hdf5
+        w = hdf5.Writer()
+        self._write_weight_groups(w, "/")
+        w.save(path)
 
     def save(self, path, **kw):
-        self.save_weights(path)
-        e = self.engine
-        with open(path + ".opt", "wb") as f:
-            np.savez(f, m=e.m.cpu().numpy(), v=e.v.cpu().numpy(), t=e.t, lr=e.lr)
+        """model.save(path): Keras full-model layout -- weights under /model_weights, the builder arguments as a JSON
+        attribute (what loadnet() rebuilds the graph from) and the optimiser state under /optimizer_weights."""
+        import json
+        from ugaitnet_b200 import hdf5
+        w, e = hdf5.Writer(), self.engine
+        self._write_weight_groups(w, "/model_weights")
+        w.root.attrs["backend"] = b"tensorflow"
+        w.root.attrs["keras_version"] = b"2.4.0"
+        w.root.attrs["ugn_builder_config"] = json.dumps(getattr(self, "builder_config", {})).encode("utf8")
+        og = w.group("/optimizer_weights")
+        og.attrs["optimizer"] = e.optimizer.encode("utf8")
+        og.attrs["iterations"] = np.int64(e.t)
+        og.attrs["lr"] = np.float64(e.lr)
+        w.dataset("/optimizer_weights/m", e.m.cpu().numpy())
+        w.dataset("/optimizer_weights/v", e.v.cpu().numpy())
+        if getattr(e, "vhat", None) is not None:
+            w.dataset("/optimizer_weights/vhat", e.vhat.cpu().numpy())
+        w.save(path)
 
-    def load_weights(self, path, by_name=True, skip_mismatch=False, **kw):
+    def load_branch(self, path, bname):
+        return _load_branch(self, path, bname)
+
+    def save_branch(self, path, bname):
+        """Stand-alone branch file in the layout of Keras' Sequential.save: one layer group per sublayer."""
+        from ugaitnet_b200 import hdf5
+        P = self.engine.export_params()
+        w = hdf5.Writer()
+        weights = dict(self._keras_layout())[bname]
+        subs = []
+        for wn, seg in weights:
+            sub = wn.split("/")[0]
+            if sub not in subs:
+                subs.append(sub)
+            w.dataset(f"/model_weights/{sub}/{wn}", self._to_keras(seg, P[seg]).cpu().numpy())
+        g = w.group("/model_weights")
+        g.attrs["layer_names"] = [s.encode("utf8") for s in subs]
+        for sub in subs:
+            w.group(f"/model_weights/{sub}").attrs["weight_names"] = [wn.encode("utf8") for wn, _ in weights
+                                                                      if wn.split("/")[0] == sub]
+        w.save(path)
+
+    def _load_npz(self, path, skip_mismatch):
         z = np.load(path)
         mine = {self._keras_name(k): k for k in self.engine.segs}
         upd = {}
@@ -298,23 +392,106 @@ class UGaitModel:
             if k is None:
                 continue
             v = self._from_keras(z[kn])
-            tshape = self.engine.oracle_shape(k)
-            if tuple(v.shape) != tuple(tshape):
+            if tuple(v.shape) != tuple(self.engine.oracle_shape(k)):
                 if skip_mismatch:
                     continue
-                raise ValueError(f"shape mismatch for {kn}: {tuple(v.shape)} vs {tuple(tshape)}")
+                raise ValueError(f"shape mismatch for {kn}: {tuple(v.shape)} vs {tuple(self.engine.oracle_shape(k))}")
             upd[k] = v
         self.engine.load_params(upd)
-        if osp.exists(path + ".opt"):
-            o = np.load(path + ".opt")
-            if o["m"].shape[0] == self.engine.m.shape[0]:
-                self.engine.m.copy_(torch.from_numpy(o["m"])); self.engine.v.copy_(torch.from_numpy(o["v"]))
-                self.engine.t = int(o["t"])
+
+    def load_weights(self, path, by_name=True, skip_mismatch=False, **kw):
+        """Keras load_weights on an HDF5 weights file (or the /model_weights group of a full-model file).
+        by_name=True: layers are matched by name and their weights by position inside the layer (Keras'
+        load_weights_from_hdf5_group_by_name); by_name=False: all weights in file order against all tensors in graph
+        order (topological loading).  skip_mismatch skips layers whose weight count or shapes differ."""
+        from ugaitnet_b200 import hdf5
+        if not hdf5.is_hdf5(path):
+            with open(path, "rb") as fh:
+                magic = fh.read(4)
+            if magic[:2] == b"PK":              # round-1 checkpoints: npz container under the .hdf5 name
+                return self._load_npz(path, skip_mismatch)
+            raise ValueError(f"{path}: neither an HDF5 file nor a ugaitnet_b200 npz checkpoint")
+        f = hdf5.File(path)
+        g = f["model_weights"] if "model_weights" in f.keys() else f
+        names = [n.decode("utf8") if isinstance(n, bytes) else str(n) for n in np.atleast_1d(g.attrs.get("layer_names", []))]
+        file_layers = []
+        for ln in names:
+            lg = g[ln]
+            wn = [n.decode("utf8") if isinstance(n, bytes) else str(n) for n in np.atleast_1d(lg.attrs.get("weight_names", []))]
+            file_layers.append((ln, [lg[n].value for n in wn if n]))
+        layout = dict(self._keras_layout())
+        upd = {}
+
+        def assign(segs, vals, what):
+            if len(segs) != len(vals):
+                if skip_mismatch:
+                    return
+                raise ValueError(f"layer {what}: {len(vals)} weights in the file, {len(segs)} in the model")
+            tmp = {}
+            for seg, v in zip(segs, vals):
+                t = self._from_keras(v)
+                if tuple(t.shape) != tuple(self.engine.oracle_shape(seg)):
+                    if skip_mismatch:
+                        return
+                    raise ValueError(f"shape mismatch for {seg}: {tuple(t.shape)} vs {tuple(self.engine.oracle_shape(seg))}")
+                tmp[seg] = t
+            upd.update(tmp)
+        if by_name:
+            for ln, vals in file_layers:
+                if ln in layout and (vals or layout[ln]):
+                    assign([s for _, s in layout[ln]], vals, ln)
+        else:
+            assign([s for _, ws in self._keras_layout() for _, s in ws], [v for _, vs in file_layers for v in vs], "(all)")
+        self.engine.load_params(upd)
+        if "optimizer_weights" in f.keys():
+            og, e = f["optimizer_weights"], self.engine
+            m = og["m"].value
+            if m.shape[0] == e.m.shape[0]:
+                e.m.copy_(torch.from_numpy(m))
+                e.v.copy_(torch.from_numpy(og["v"].value))
+                if "vhat" in og.keys():
+                    from ugaitnet_b200._ffi import TRef
+                    e.vhat = torch.from_numpy(og["vhat"].value).to(e.dev)
+                    e.R["vhat"] = TRef(e.vhat)
+                e.t = int(og.attrs.get("iterations", 0))
+                e.lr = float(og.attrs.get("lr", e.lr))
+        return self
+
+
+def _file_layers(g):
+    names = [n.decode("utf8") if isinstance(n, bytes) else str(n) for n in np.atleast_1d(g.attrs.get("layer_names", []))]
+    out = []
+    for ln in names:
+        lg = g[ln]
+        wn = [n.decode("utf8") if isinstance(n, bytes) else str(n) for n in np.atleast_1d(lg.attrs.get("weight_names", []))]
+        out.append((ln, [lg[n].value for n in wn if n]))
+    return out
+
+
+def _load_branch(model, path, bname):
+    """fc_loadBranch (:57-66): initialise branch `bname` from a saved model -- a stand-alone branch file (Keras
+    Sequential.save: its sublayers are the file's layers) or a full model that contains a layer of that name."""
+    from ugaitnet_b200 import hdf5
+    f = hdf5.File(path)
+    g = f["model_weights"] if "model_weights" in f.keys() else f
+    layers = _file_layers(g)
+    byname = dict(layers)
+    vals = byname[bname] if bname in byname and byname[bname] else [v for _, vs in layers for v in vs]
+    segs = [s for _, s in dict(model._keras_layout())[bname]]
+    if len(vals) != len(segs):
+        raise ValueError(f"{path}: {len(vals)} weights for branch {bname}, the graph has {len(segs)}")
+    upd = {}
+    for seg, v in zip(segs, vals):
+        t = model._from_keras(v)
+        if tuple(t.shape) != tuple(model.engine.oracle_shape(seg)):
+            raise ValueError(f"{path}: shape mismatch for {seg}: {tuple(t.shape)} vs {tuple(model.engine.oracle_shape(seg))}")
+        upd[seg] = t
+    model.engine.load_params(upd)
 
 
 def _cfg_from_args(input_shapes, number_convolutional_layers, filters_size, filters_numbers, ndense_units,
                    weight_decay, dropout, margin, nclasses, loss_weights, fMerge, fActivation, alpha, single,
-                   smoothlabels=0, normbfmerge=False, aux_losses=False):
+                   smoothlabels=0, normbfmerge=False, aux_losses=False, postriplet=1):
     fs = [k[0] if isinstance(k, (tuple, list)) else int(k) for k in filters_size][:number_convolutional_layers]
     fn = list(filters_numbers if filters_numbers is not None else [64, 128, 512, 512])[:number_convolutional_layers]
     if isinstance(ndense_units, (list, tuple)):
@@ -333,7 +510,8 @@ def _cfg_from_args(input_shapes, number_convolutional_layers, filters_size, filt
                      hw=int(shapes[0][1]), dropout=float(dropout) if dropout > 0.001 else 0.0, single=single,
                      label_smoothing=float(smoothlabels), normbfmerge=bool(normbfmerge),
                      aux_losses=bool(aux_losses) and nclasses > 0 and not single,
-                     waux=float(lw[-1]))         # loss_weights padded with its last entry (:1264-1268)
+                     waux=float(lw[-1]),         # loss_weights padded with its last entry (:1264-1268)
+                     postriplet=int(postriplet) if (nc and not single) else 1)
 
 
 def _gs_cfg_from_args(input_shapes, ndense_units, dropout, margin, nclasses, loss_weights, fMerge, fActivation, alpha,
@@ -354,6 +532,74 @@ def _gs_cfg_from_args(input_shapes, ndense_units, dropout, margin, nclasses, los
                          margin=float(margin), wver=float(lw[0]) if nclasses > 0 else 1.0,
                          wid=float(lw[1]) if nclasses > 0 and len(lw) > 1 else 0.0,
                          dropout=float(dropout) if (dropout > 0.001 and nc) else 0.0, label_smoothing=float(smoothlabels))
+
+
+def _jsonable(v):
+    if isinstance(v, (list, tuple)):
+        return [_jsonable(x) for x in v]
+    if isinstance(v, (np.integer,)):
+        return int(v)
+    if isinstance(v, (np.floating,)):
+        return float(v)
+    if callable(v) or hasattr(v, "merge_id"):
+        return {"__merge__": {0: "Maximum", 1: "Average", 2: "sign_max"}[merge_id_of(v)]}
+    if hasattr(v, "name") and hasattr(v, "kw"):          # optimizer stand-in
+        return {"__optimizer__": v.name, "lr": v.lr, "kw": {k: float(x) for k, x in v.kw.items()}}
+    return v
+
+
+def _unjson(v):
+    from ugaitnet_b200.compat.keras_shim import _Optimizer, sign_max
+    if isinstance(v, dict) and "__merge__" in v:
+        return {"Maximum": Maximum, "Average": Average, "sign_max": sign_max}[v["__merge__"]]
+    if isinstance(v, dict) and "__optimizer__" in v:
+        return _Optimizer(v["__optimizer__"], v["lr"], **v["kw"])
+    if isinstance(v, list):
+        return [_unjson(x) for x in v]
+    return v
+
+
+def _remember(model, cls_name, **kwargs):
+    """The builder call that made `model`, JSON-able: model.save() stores it, loadnet() rebuilds from it (the role of
+    Keras' model_config attribute / the reference's model-config.hdf5)."""
+    model.builder_config = {"class": cls_name, "kwargs": {k: _jsonable(v) for k, v in kwargs.items()}}
+    return model
+
+
+def _apply_init_branches(model, init_branches):
+    """init_branches = {'of': path, 'gray': path, 'depth': path} (:57-66 fc_loadBranch, :69-75): every given branch
+    is initialised from a saved model file -- here: the tensors of the same-named branch layer of that file."""
+    if not init_branches:
+        return
+    for key, bname in (("of", "ofBranch"), ("gray", "grayBranch"), ("depth", "depthBranch")):
+        path = init_branches.get(key, "")
+        if path:
+            model.load_branch(path, bname)
+
+
+def _freeze(model, freeze_convs=False, freeze_all=False, freeze_branches=False):
+    """:193 (freeze_branches: whole branches), :1366-1391 (freeze_convs: the Conv2D layers of every branch; freeze_all:
+    every layer of every branch -- with gaitset every model layer but the last)."""
+    if not (freeze_convs or freeze_all or freeze_branches):
+        return
+    if model.gaitset:
+        if freeze_all:
+            for l in model.layers[:-1]:
+                l.trainable = False
+        elif freeze_branches:
+            for l in model.layers:
+                if l.name in BRANCH_NAMES:
+                    l.trainable = False
+        return
+    for l in model.layers:
+        if l.name not in BRANCH_NAMES:
+            continue
+        if freeze_all or freeze_branches:
+            l.trainable = False
+        else:
+            for sub in l.layers:
+                if sub.kind == "conv":
+                    sub.trainable = False
 
 
 class UWYHNet:
@@ -384,21 +630,39 @@ class UWYHSemiNet:
               ndense_units=512, weight_decay=1e-4, dropout=0.4, optimizer=None, margin=0.2,
               nclasses=0, loss_weights=[1.0, 1.0], use3D=False, smoothlabels=0, postriplet=1, init_branches=None,
               freeze_branches=False, aux_losses=False, fMerge=Maximum, fActivation='relu', alpha=0.3, gaitset=False):
-        _unsupported(use3D=use3D, postriplet_2=(postriplet == 2), freeze_branches=freeze_branches,
-                     aux_losses_with_gaitset=(aux_losses and gaitset),
-                     init_branches=bool(init_branches) and any(init_branches.values()))
+        _unsupported(use3D=use3D, aux_losses_with_gaitset=(aux_losses and gaitset))
         single = not isinstance(input_shapes, list)
+        kwargs = dict(input_shapes=input_shapes, number_convolutional_layers=number_convolutional_layers,
+                      filters_size=filters_size, filters_numbers=filters_numbers, ndense_units=ndense_units,
+                      weight_decay=weight_decay, dropout=dropout, optimizer=optimizer, margin=margin, nclasses=nclasses,
+                      loss_weights=loss_weights, smoothlabels=smoothlabels, postriplet=postriplet, aux_losses=aux_losses,
+                      fMerge=fMerge, fActivation=fActivation, alpha=alpha, gaitset=gaitset)
+        losses = [triplet_loss(margin=margin), 'categorical_crossentropy'] if nclasses > 0 else triplet_loss(margin=margin)
         if gaitset:
-            _unsupported(gaitset_single_modality=single)
+            _unsupported(gaitset_single_modality=single, postriplet_2_with_gaitset=(postriplet == 2))
             cfg = _gs_cfg_from_args(input_shapes, ndense_units, dropout, margin, nclasses, loss_weights, fMerge,
                                     fActivation, alpha, smoothlabels)
-            losses = [triplet_loss(margin=margin), 'categorical_crossentropy'] if nclasses > 0 else triplet_loss(margin=margin)
-            return UGaitModel(cfg, optimizer, losses, loss_weights if nclasses > 0 else 1.0, multimodal=True)
-        cfg = _cfg_from_args(input_shapes, number_convolutional_layers, filters_size, filters_numbers, ndense_units,
-                             weight_decay, dropout, margin, nclasses, loss_weights, fMerge, fActivation, alpha, single,
-                             smoothlabels=smoothlabels, aux_losses=aux_losses)
-        losses = [triplet_loss(margin=margin), 'categorical_crossentropy'] if nclasses > 0 else triplet_loss(margin=margin)
-        return UGaitModel(cfg, optimizer, losses, loss_weights if nclasses > 0 else 1.0, multimodal=not single)
+            model = UGaitModel(cfg, optimizer, losses, loss_weights if nclasses > 0 else 1.0, multimodal=True)
+        else:
+            cfg = _cfg_from_args(input_shapes, number_convolutional_layers, filters_size, filters_numbers, ndense_units,
+                                 weight_decay, dropout, margin, nclasses, loss_weights, fMerge, fActivation, alpha, single,
+                                 smoothlabels=smoothlabels, aux_losses=aux_losses, postriplet=postriplet)
+            model = UGaitModel(cfg, optimizer, losses, loss_weights if nclasses > 0 else 1.0, multimodal=not single)
+        _apply_init_branches(model, init_branches)
+        _freeze(model, freeze_branches=freeze_branches)
+        return _remember(model, "UWYHSemiNet", **kwargs)
+
+    @staticmethod
+    def build_by_config(netconfig):
+        """:487-534 -- rebuild from the dict the mains store next to their checkpoints (model-config.hdf5)."""
+        g = netconfig.get
+        fn = netconfig["filters_numbers"]
+        return UWYHSemiNet.build(netconfig["input_shape"], len(fn), netconfig["filters_size"], fn,
+                                 netconfig["ndense_units"], netconfig["weight_decay"], netconfig["dropout"],
+                                 nclasses=g("nclasses", 150), loss_weights=g("loss_weights", [1.0, 0.1]),
+                                 optimizer=netconfig.get("optimizer"), margin=netconfig["margin"], use3D=g("use3D", False),
+                                 postriplet=g("postriplet", 1), fMerge=g("fMerge", Maximum),
+                                 fActivation=g("fActivation", "relu"))
 
     @staticmethod
     def build_or_load(input_shapes, number_convolutional_layers, filters_size, filters_numbers, ndense_units=512,
@@ -407,7 +671,6 @@ class UWYHSemiNet:
                       freeze_all=False, postriplet=1, init_branches=None, freeze_branches=False, aux_losses=False,
                       fMerge=Maximum, fActivation='relu', gaitset=False):
         # (the reference's 2-modality build_or_load has no `alpha` argument, :582-588: LeakyReLU keeps build()'s 0.3)
-        _unsupported(freeze_convs=freeze_convs, freeze_all=freeze_all)
         if gaitset:
             fActivation = 'leaky'          # :588-589
         model = UWYHSemiNet.build(input_shapes, number_convolutional_layers, filters_size, filters_numbers,
@@ -416,13 +679,18 @@ class UWYHSemiNet:
                                   init_branches=init_branches, freeze_branches=freeze_branches, aux_losses=aux_losses,
                                   fMerge=fMerge, fActivation=fActivation, gaitset=gaitset)
         if initnet != "":
-            model.load_weights(UWYHSemiNet.get_weights_filename(initnet), by_name=True, skip_mismatch=True)
+            # :598-664 -- the reference loads the saved model and, when the classifier width differs ("surgery"),
+            # rebuilds and loads the compatible weights by name; both paths end in exactly this state
+            model.load_weights(_weights_file_of(initnet), by_name=True, skip_mismatch=True)
+            _freeze(model, freeze_convs=freeze_convs, freeze_all=freeze_all)
         return model
 
     @staticmethod
     def loadnet(netpath: str):
-        raise NotImplementedError("loading Keras .hdf5 models needs h5py/TensorFlow; rebuild with build() and "
-                                  "model.load_weights(<npz written by save_weights>)")
+        """:554-579 / :1008-1029 -- load_model(netpath, compile=False): rebuild the graph from the builder arguments
+        stored in the file (this wrapper's model.save) or, for a checkpoint directory written by the reference's mains,
+        from `ugn_builder_config.json` next to it, then load the weights."""
+        return _loadnet(netpath)
 
     @staticmethod
     def fit_generator(model, epochs, callbacks, training_generator, validation_generator, current_step, steps_per_epoch,
@@ -492,19 +760,26 @@ class UWYHSemiNet3Mods(UWYHSemiNet):
               nclasses=0, loss_weights=[1.0, 1.0], use3D=False, smoothlabels=0,
               postriplet=1, init_branches=None, freeze_branches=False, aux_losses=False, fMerge=Maximum,
               normbfmerge=False, fActivation='relu', alpha=0.3, gaitset=False):
-        _unsupported(use3D=use3D, aux_losses_with_gaitset=(aux_losses and gaitset), freeze_branches=freeze_branches,
-                     init_branches=bool(init_branches) and any(init_branches.values()))
+        # (postriplet is accepted and ignored by the reference's 3-modality graph: "TODO implement use of 'postriplet'", :1054)
+        _unsupported(use3D=use3D, aux_losses_with_gaitset=(aux_losses and gaitset))
+        kwargs = dict(input_shapes=list(input_shapes), number_convolutional_layers=number_convolutional_layers,
+                      filters_size=filters_size, filters_numbers=filters_numbers, ndense_units=ndense_units,
+                      weight_decay=weight_decay, dropout=dropout, optimizer=optimizer, margin=margin, nclasses=nclasses,
+                      loss_weights=loss_weights, smoothlabels=smoothlabels, aux_losses=aux_losses, fMerge=fMerge,
+                      normbfmerge=normbfmerge, fActivation=fActivation, alpha=alpha, gaitset=gaitset)
+        losses = [triplet_loss(margin=margin), 'categorical_crossentropy'] if nclasses > 0 else triplet_loss(margin=margin)
         if gaitset:
             cfg = _gs_cfg_from_args(input_shapes, ndense_units, dropout, margin, nclasses, loss_weights, fMerge,
                                     fActivation, alpha, smoothlabels)       # (normbfmerge is ignored with gaitset, :1164)
-            losses = [triplet_loss(margin=margin), 'categorical_crossentropy'] if nclasses > 0 else triplet_loss(margin=margin)
-            return UGaitModel(cfg, optimizer, losses, loss_weights if nclasses > 0 else 1.0, multimodal=True)
-        cfg = _cfg_from_args(list(input_shapes), number_convolutional_layers, filters_size, filters_numbers,
-                             ndense_units, weight_decay, dropout, margin, nclasses, loss_weights, fMerge, fActivation,
-                             alpha, single=False, smoothlabels=smoothlabels, normbfmerge=normbfmerge,
-                             aux_losses=aux_losses)
-        losses = [triplet_loss(margin=margin), 'categorical_crossentropy'] if nclasses > 0 else triplet_loss(margin=margin)
-        return UGaitModel(cfg, optimizer, losses, loss_weights if nclasses > 0 else 1.0, multimodal=True)
+        else:
+            cfg = _cfg_from_args(list(input_shapes), number_convolutional_layers, filters_size, filters_numbers,
+                                 ndense_units, weight_decay, dropout, margin, nclasses, loss_weights, fMerge, fActivation,
+                                 alpha, single=False, smoothlabels=smoothlabels, normbfmerge=normbfmerge,
+                                 aux_losses=aux_losses)
+        model = UGaitModel(cfg, optimizer, losses, loss_weights if nclasses > 0 else 1.0, multimodal=True)
+        _apply_init_branches(model, init_branches)
+        _freeze(model, freeze_branches=freeze_branches)
+        return _remember(model, "UWYHSemiNet3Mods", **kwargs)
 
     @staticmethod
     def compile_hard(model, optimizer, loss_weights, margin):
@@ -516,7 +791,6 @@ class UWYHSemiNet3Mods(UWYHSemiNet):
                       loss_weights=[1.0, 1.0], initnet="", freeze_convs=False, use3D=False, smoothlabels=0,
                       freeze_all=False, postriplet=1, init_branches=None, freeze_branches=False, aux_losses=False,
                       fMerge=Maximum, normbfmerge=False, fActivation='relu', alpha=0.3, gaitset=False):
-        _unsupported(freeze_convs=freeze_convs, freeze_all=freeze_all)
         if gaitset:
             fActivation = 'leaky'
         model = UWYHSemiNet3Mods.build(input_shapes, number_convolutional_layers, filters_size, filters_numbers,
@@ -526,5 +800,43 @@ class UWYHSemiNet3Mods(UWYHSemiNet):
                                        aux_losses=aux_losses, fMerge=fMerge, normbfmerge=normbfmerge,
                                        fActivation=fActivation, alpha=alpha, gaitset=gaitset)
         if initnet != "":
-            model.load_weights(UWYHSemiNet.get_weights_filename(initnet), by_name=True, skip_mismatch=True)
+            # :1325-1391 -- load (with classifier "surgery" = by-name loading that skips the mismatching classprob), then
+            # freeze the convolutions / every branch layer
+            model.load_weights(_weights_file_of(initnet), by_name=True, skip_mismatch=True)
+            _freeze(model, freeze_convs=freeze_convs, freeze_all=freeze_all)
         return model
+
+
+def _weights_file_of(initnet: str) -> str:
+    """initnet names the full-model file; the mains keep the weights next to it as <name>_weights.hdf5
+    (:536-544).  Fall back to the model file itself (its /model_weights group) when only that exists."""
+    wf = UWYHSemiNet.get_weights_filename(initnet)
+    return wf if osp.exists(wf) else initnet
+
+
+def _loadnet(netpath: str):
+    import json
+    from ugaitnet_b200 import hdf5
+    conf = None
+    if osp.exists(netpath) and hdf5.is_hdf5(netpath):
+        f = hdf5.File(netpath)
+        raw = f.attrs.get("ugn_builder_config")
+        if raw is not None:
+            conf = json.loads(raw.decode("utf8") if isinstance(raw, bytes) else raw)
+    if conf is None:
+        side = osp.join(osp.dirname(netpath), "ugn_builder_config.json")
+        if osp.exists(side):
+            with open(side) as fh:
+                conf = json.load(fh)
+    if conf is None or "kwargs" not in conf:
+        raise ValueError(f"{netpath}: no builder configuration found (files written by tf.keras carry a Keras "
+                         "model_config; rebuild the graph with build() / build_by_config() and call "
+                         "model.load_weights(path, by_name=True), which reads Keras HDF5 weight files)")
+    cls = {"UWYHSemiNet": UWYHSemiNet, "UWYHSemiNet3Mods": UWYHSemiNet3Mods}[conf["class"]]
+    kw = {k: _unjson(v) for k, v in conf["kwargs"].items()}
+    shapes = kw.pop("input_shapes")
+    shapes = [tuple(s) for s in shapes] if isinstance(shapes[0], (list, tuple)) else tuple(shapes)
+    kw["filters_size"] = [tuple(k) if isinstance(k, list) else k for k in kw["filters_size"]]
+    model = cls.build(shapes, kw.pop("number_convolutional_layers"), kw.pop("filters_size"), kw.pop("filters_numbers"), **kw)
+    model.load_weights(netpath if "model_weights" in hdf5.File(netpath).keys() else _weights_file_of(netpath), by_name=True)
+    return model

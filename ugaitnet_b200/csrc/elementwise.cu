@@ -620,6 +620,17 @@ __global__ void __launch_bounds__(256) optim_kernel(float* __restrict__ w, const
        q += (long long)gridDim.x * blockDim.x) {
     int s = seg_find(off, S, q * 4);
     float c = l2[s];
+    // FROZEN segment (layer.trainable = False, nets/mj_uwyhNets_ba.py:1366-1391): the coefficient table stores
+    // -(c + 1); the regulariser value still counts (Keras keeps the losses of non-trainable layers), weights and
+    // optimiser state stay untouched, nothing is exchanged or re-split for it
+    if (c < 0.f) {
+      c = -c - 1.f;
+      if (c > 0.f) {
+        const float4 fw = reinterpret_cast<const float4*>(w)[q];
+        reg += c * (fw.x * fw.x + fw.y * fw.y + fw.z * fw.z + fw.w * fw.w);
+      }
+      continue;
+    }
     float4 wv = reinterpret_cast<float4*>(w)[q];
     float4 gv;
     if (DP && peers.mc_g) {

@@ -199,6 +199,13 @@ extern "C" int ugn_triplet_all(ugn_ctx* ctx, const ugn_tensor* emb, const ugn_te
   UGN_LAUNCHED(ctx);
   trip_dist_kernel<<<dim3(ugn_cdiv(B, 128), B, n), 128, 0, st>>>(D, x2, B);
   UGN_LAUNCHED(ctx);
+  if (2 * (size_t)B * sizeof(float) > 48 * 1024) {      // B > 6144: opt in to the large dynamic shared memory carve-out
+    static bool attr_set = false;
+    if (!attr_set) {
+      UGN_CUDA(cudaFuncSetAttribute(trip_hinge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 8192 * (int)sizeof(float)));
+      attr_set = true;
+    }
+  }
   trip_hinge_kernel<<<dim3(B, n), 128, 2 * B * sizeof(float), st>>>(D, ugn_ptr<int>(labels), Wc, acc, B, margin);
   UGN_LAUNCHED(ctx);
   trip_finalize_kernel<<<1, 32, 0, st>>>(acc, n, ugn_ptr<float>(out));

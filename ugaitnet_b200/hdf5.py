@@ -1,0 +1,584 @@
+"""Minimal pure-Python HDF5 reader / writer for the subset Keras' ``save_weights`` / ``model.save`` (h5py, default
+``libver='earliest'``) and the reference's ``.h5`` sample files use.  h5py is not part of this image, and the reference
+keeps its checkpoints in this format (/root/reference/nets/mj_uwyhNets_ba.py:554-579, :1008-1029 ``load_model`` /
+``load_weights``; mains/mj_trainUWYHGaitNet_DataGen_3mods.py:563-570 ``ModelCheckpoint``), so weight interchange needs it
+(SURVEY.md 8f-3).
+
+Supported (HDF5 File Format Specification 2.0/3.0):
+  * superblock versions 0/1 (symbol-table root) and 2/3 (root object header);
+  * object headers version 1 and version 2 ("OHDR"), continuation blocks;
+  * old-style groups (symbol table message -> v1 B-tree "TREE" + "SNOD" leaves + local "HEAP") and compact new-style
+    groups (link messages); dense link storage (fractal heaps) is NOT supported and raises;
+  * datasets: contiguous and compact layouts, and chunked layouts without filters (v1 chunk B-tree);
+    little-endian fixed-point / IEEE float / fixed-length string element types;
+  * attributes (message versions 1, 2, 3) with scalar / simple dataspaces of the same element types plus
+    variable-length strings (global heap "GCOL").
+The writer emits superblock 0, version-1 object headers, old-style groups, contiguous datasets and version-1
+attribute messages -- the layout h5py produces by default -- so a file written here is a regular HDF5 file.
+
+Parity status: no HDF5 implementation or file exists in the build image or on the GPU box to cross-check against;
+the module follows the published format specification and is round-trip tested (tests/test_hdf5_cpu.py: writer ->
+reader, plus structural checks of the emitted bytes against the specification's field offsets).
+"""
+from __future__ import annotations
+
+import struct
+from typing import Dict, List, Optional, Tuple
+
+import numpy as np
+
+SIGNATURE = b"\x89HDF\r\n\x1a\n"
+UNDEF = 0xFFFFFFFFFFFFFFFF
+
+
+class HDF5Error(ValueError):
+    pass
+
+
+# ======================================================================================== reader
+class _Type:
+    def __init__(self, kind, size, np_dtype=None, base=None, vlen_str=False):
+        self.kind, self.size, self.np_dtype, self.base, self.vlen_str = kind, size, np_dtype, base, vlen_str
+
+
+class Node:
+    """A group or dataset.  Groups: ``keys()`` / ``[name]`` (paths with '/' allowed); datasets: ``value`` (numpy)."""
+
+    def __init__(self, f: "File", addr: int, name: str = "/"):
+        self._f, self._addr, self.name = f, addr, name
+        self.attrs: Dict[str, object] = {}
+        self._links: Optional[Dict[str, int]] = None
+        self._dtype = self._shape = self._layout = None
+        self._parse()
+
+    # -- object header -------------------------------------------------------------------------
+    def _messages(self):
+        b, a = self._f.buf, self._addr
+        if b[a:a + 4] == b"OHDR":                        # version 2
+            flags = b[a + 5]
+            p = a + 6
+            if flags & 0x20:
+                p += 16
+            if flags & 0x10:
+                p += 4
+            szb = 1 << (flags & 3)
+            chunk0 = int.from_bytes(b[p:p + szb], "little")
+            p += szb
+            blocks = [(p, p + chunk0)]
+            track = bool(flags & 0x04)
+            while blocks:
+                p, end = blocks.pop(0)
+                while p + 4 <= end - 0:                   # (the last 4 bytes of a v2 chunk are its checksum)
+                    mtype, msize, mflags = b[p], struct.unpack_from("<H", b, p + 1)[0], b[p + 3]
+                    p += 4 + (2 if track else 0)
+                    if p + msize > end:
+                        break
+                    data = b[p:p + msize]
+                    p += msize
+                    if mtype == 0x10:
+                        off, ln = struct.unpack_from("<QQ", data)
+                        blocks.append((off + 4, off + ln - 4))     # "OCHK" signature in front, checksum behind
+                    else:
+                        yield mtype, data
+            return
+        if b[a] != 1:
+            raise HDF5Error(f"unsupported object header version {b[a]} at {a}")
+        nmsg = struct.unpack_from("<H", b, a + 2)[0]
+        hsize = struct.unpack_from("<I", b, a + 8)[0]
+        blocks = [(a + 16, a + 16 + hsize)]
+        seen = 0
+        while blocks and seen < nmsg:
+            p, end = blocks.pop(0)
+            while p + 8 <= end and seen < nmsg:
+                mtype, msize, _ = struct.unpack_from("<HHB", b, p)
+                data = b[p + 8:p + 8 + msize]
+                p += 8 + msize
+                seen += 1
+                if mtype == 0x10:
+                    off, ln = struct.unpack_from("<QQ", data)
+                    blocks.append((off, off + ln))
+                else:
+                    yield mtype, data
+
+    def _parse(self):
+        for mtype, data in self._messages():
+            if mtype == 0x01:
+                self._shape = _parse_dataspace(data)
+            elif mtype == 0x03:
+                self._dtype = _parse_datatype(data)[0]
+            elif mtype == 0x08:
+                self._layout = data
+            elif mtype == 0x0C:
+                k, v = self._parse_attribute(data)
+                self.attrs[k] = v
+            elif mtype == 0x11:
+                bt, heap = struct.unpack_from("<QQ", data)
+                self._links = self._f._read_symbol_table(bt, heap)
+            elif mtype == 0x06:
+                if self._links is None:
+                    self._links = {}
+                nm, addr = _parse_link(data)
+                if addr is not None:
+                    self._links[nm] = addr
+            elif mtype == 0x02:
+                # link info: a defined fractal-heap address means dense link storage
+                flags = data[1]
+                p = 2 + (8 if flags & 1 else 0)
+                fheap = struct.unpack_from("<Q", data, p)[0]
+                if fheap != UNDEF:
+                    raise HDF5Error("dense link storage (fractal heap) is not supported")
+                if self._links is None:
+                    self._links = {}
+            elif mtype == 0x15:
+                fheap = struct.unpack_from("<Q", data, 2 + (2 if data[1] & 1 else 0))[0]
+                if fheap != UNDEF:
+                    raise HDF5Error("dense attribute storage is not supported")
+
+    def _parse_attribute(self, d: bytes):
+        ver = d[0]
+        if ver == 1:
+            nsz, tsz, ssz = struct.unpack_from("<HHH", d, 2)
+            p = 8
+            pad = lambda n: (n + 7) & ~7
+            name = d[p:p + nsz].split(b"\0")[0].decode("utf8")
+            p += pad(nsz)
+            tp = _parse_datatype(d[p:p + tsz])[0]
+            p += pad(tsz)
+            shape = _parse_dataspace(d[p:p + ssz])
+            p += pad(ssz)
+        elif ver in (2, 3):
+            nsz, tsz, ssz = struct.unpack_from("<HHH", d, 2)
+            p = 8 + (1 if ver == 3 else 0)
+            name = d[p:p + nsz].split(b"\0")[0].decode("utf8")
+            p += nsz
+            tp = _parse_datatype(d[p:p + tsz])[0]
+            p += tsz
+            shape = _parse_dataspace(d[p:p + ssz])
+            p += ssz
+        else:
+            raise HDF5Error(f"attribute message version {ver}")
+        return name, self._f._decode(tp, shape, d[p:])
+
+    # -- public --------------------------------------------------------------------------------
+    @property
+    def is_group(self):
+        return self._links is not None
+
+    def keys(self) -> List[str]:
+        return list(self._links or {})
+
+    def __contains__(self, name):
+        try:
+            self[name]
+            return True
+        except KeyError:
+            return False
+
+    def __getitem__(self, path: str) -> "Node":
+        node = self
+        for part in [q for q in path.split("/") if q]:
+            if not node.is_group or part not in node._links:
+                raise KeyError(path)
+            node = Node(self._f, node._links[part], (node.name.rstrip("/") + "/" + part))
+        return node
+
+    @property
+    def shape(self):
+        return self._shape
+
+    @property
+    def value(self) -> np.ndarray:
+        if self._layout is None or self._dtype is None:
+            raise HDF5Error(f"{self.name} is not a dataset")
+        L, b = self._layout, self._f.buf
+        shape = self._shape or ()
+        n = int(np.prod(shape)) if shape else 1
+        nbytes = n * self._dtype.size
+        if L[0] == 3:
+            cls = L[1]
+            if cls == 0:
+                sz = struct.unpack_from("<H", L, 2)[0]
+                raw = L[4:4 + sz]
+            elif cls == 1:
+                addr, sz = struct.unpack_from("<QQ", L, 2)
+                raw = b"\0" * nbytes if addr == UNDEF else b[addr:addr + nbytes]
+            elif cls == 2:
+                rank = L[2]
+                bt = struct.unpack_from("<Q", L, 3)[0]
+                cdims = struct.unpack_from("<" + "I" * rank, L, 11)
+                raw = self._f._read_chunked(bt, shape, cdims[:-1], self._dtype.size)
+            else:
+                raise HDF5Error(f"layout class {cls}")
+        elif L[0] in (1, 2):
+            rank, cls = L[1], L[2]
+            p = 8
+            if cls != 1:
+                raise HDF5Error("only contiguous data in layout message versions 1/2")
+            addr = struct.unpack_from("<Q", L, p)[0]
+            raw = b[addr:addr + nbytes]
+        else:
+            raise HDF5Error(f"data layout message version {L[0]}")
+        return self._f._decode(self._dtype, shape, raw)
+
+    def visit(self, prefix=""):
+        """Yield (path, node) of every dataset below this group, depth first, in link-name order of each group."""
+        for k in self.keys():
+            child = self[k]
+            path = prefix + "/" + k if prefix else k
+            if child.is_group:
+                yield from child.visit(path)
+            else:
+                yield path, child
+
+
+def _parse_dataspace(d: bytes) -> Tuple[int, ...]:
+    ver, rank, flags = d[0], d[1], d[2]
+    if ver == 1:
+        p = 8
+    elif ver == 2:
+        if d[3] == 2:            # null dataspace
+            return (0,)
+        p = 4
+    else:
+        raise HDF5Error(f"dataspace version {ver}")
+    return tuple(struct.unpack_from("<" + "Q" * rank, d, p))
+
+
+def _parse_datatype(d: bytes):
+    cls, ver = d[0] & 0x0F, d[0] >> 4
+    bits = d[1] | (d[2] << 8) | (d[3] << 16)
+    size = struct.unpack_from("<I", d, 4)[0]
+    if cls == 0:
+        if bits & 1:
+            raise HDF5Error("big-endian integers are not supported")
+        signed = bool(bits & 0x08)
+        return _Type("int", size, np.dtype(f"<{'i' if signed else 'u'}{size}")), 8 + 4
+    if cls == 1:
+        if bits & 1:
+            raise HDF5Error("big-endian floats are not supported")
+        return _Type("float", size, np.dtype(f"<f{size}")), 8 + 12
+    if cls == 3:
+        return _Type("str", size, np.dtype(f"S{size}")), 8
+    if cls == 9:
+        base, used = _parse_datatype(d[8:])
+        is_str = (bits & 0x0F) == 1
+        return _Type("vlen", size, None, base, vlen_str=is_str), 8 + used
+    raise HDF5Error(f"datatype class {cls} is not supported")
+
+
+def _parse_link(d: bytes):
+    flags = d[1]
+    p = 2
+    ltype = 0
+    if flags & 0x08:
+        ltype = d[p]
+        p += 1
+    if flags & 0x04:
+        p += 8
+    if flags & 0x10:
+        p += 1
+    lsz = 1 << (flags & 3)
+    ln = int.from_bytes(d[p:p + lsz], "little")
+    p += lsz
+    name = d[p:p + ln].decode("utf8")
+    p += ln
+    if ltype != 0:
+        return name, None
+    return name, struct.unpack_from("<Q", d, p)[0]
+
+
+class File(Node):
+    def __init__(self, path_or_bytes):
+        if isinstance(path_or_bytes, (bytes, bytearray, memoryview)):
+            self.buf = bytes(path_or_bytes)
+        else:
+            with open(path_or_bytes, "rb") as fh:
+                self.buf = fh.read()
+        b = self.buf
+        base = next((o for o in (0, 512, 1024, 2048) if b[o:o + 8] == SIGNATURE), None)
+        if base is None:
+            raise HDF5Error("not an HDF5 file (signature missing)")
+        ver = b[base + 8]
+        if ver in (0, 1):
+            if b[base + 13] != 8 or b[base + 14] != 8:
+                raise HDF5Error("only 8-byte offsets / lengths are supported")
+            p = base + 24 + (4 if ver == 1 else 0)
+            p += 32                                        # base, free-space, eof, driver-info addresses
+            root = struct.unpack_from("<Q", b, p + 8)[0]   # symbol table entry: name offset, object header address
+        elif ver in (2, 3):
+            if b[base + 9] != 8 or b[base + 10] != 8:
+                raise HDF5Error("only 8-byte offsets / lengths are supported")
+            root = struct.unpack_from("<Q", b, base + 12 + 24)[0]
+        else:
+            raise HDF5Error(f"superblock version {ver}")
+        self._f = self
+        super().__init__(self, root, "/")
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        return False
+
+    # -- groups: v1 B-tree + symbol nodes + local heap --------------------------------------------
+    def _read_symbol_table(self, btree: int, heap: int) -> Dict[str, int]:
+        b = self.buf
+        if b[heap:heap + 4] != b"HEAP":
+            raise HDF5Error("local heap signature missing")
+        data_addr = struct.unpack_from("<Q", b, heap + 24)[0]
+        out: Dict[str, int] = {}
+
+        def name_at(off):
+            e = b.index(b"\0", data_addr + off)
+            return b[data_addr + off:e].decode("utf8")
+
+        def walk(addr):
+            if b[addr:addr + 4] == b"SNOD":
+                n = struct.unpack_from("<H", b, addr + 6)[0]
+                for i in range(n):
+                    e = addr + 8 + 40 * i
+                    noff, oaddr = struct.unpack_from("<QQ", b, e)
+                    out[name_at(noff)] = oaddr
+                return
+            if b[addr:addr + 4] != b"TREE":
+                raise HDF5Error("group B-tree signature missing")
+            used = struct.unpack_from("<H", b, addr + 6)[0]
+            p = addr + 24
+            for i in range(used):
+                child = struct.unpack_from("<Q", b, p + 8)[0]
+                walk(child)
+                p += 16
+        if btree != UNDEF:
+            walk(btree)
+        return out
+
+    # -- chunked datasets without filters: v1 chunk B-tree ---------------------------------------------
+    def _read_chunked(self, btree, shape, cdims, esize) -> bytes:
+        b = self.buf
+        rank = len(shape)
+        out = np.zeros(shape, dtype=np.uint8 if esize == 1 else f"V{esize}")
+
+        def walk(addr):
+            if b[addr:addr + 4] != b"TREE":
+                raise HDF5Error("chunk B-tree signature missing")
+            level, used = b[addr + 5], struct.unpack_from("<H", b, addr + 6)[0]
+            p = addr + 24
+            ksz = 8 + 8 * (rank + 1)
+            for i in range(used):
+                csize, fmask = struct.unpack_from("<II", b, p)
+                offs = struct.unpack_from("<" + "Q" * (rank + 1), b, p + 8)[:rank]
+                child = struct.unpack_from("<Q", b, p + ksz)[0]
+                if level > 0:
+                    walk(child)
+                else:
+                    if fmask != 0 and csize != int(np.prod(cdims)) * esize:
+                        raise HDF5Error("filtered (compressed) chunks are not supported")
+                    chunk = np.frombuffer(b, dtype=out.dtype, count=int(np.prod(cdims)), offset=child).reshape(cdims)
+                    sl = tuple(slice(o, min(o + c, s)) for o, c, s in zip(offs, cdims, shape))
+                    out[sl] = chunk[tuple(slice(0, s.stop - s.start) for s in sl)]
+                p += ksz + 8
+        if btree != UNDEF:
+            walk(btree)
+        return out.tobytes()
+
+    # -- element decoding -----------------------------------------------------------------------
+    def _decode(self, tp: _Type, shape, raw: bytes):
+        n = int(np.prod(shape)) if shape else 1
+        if tp.kind == "vlen":
+            b, vals = self.buf, []
+            for i in range(n):
+                ln, gaddr, gidx = struct.unpack_from("<IQI", raw, 16 * i)
+                vals.append(self._global_heap_object(gaddr, gidx)[:ln * (tp.base.size if not tp.vlen_str else 1)])
+            if tp.vlen_str:
+                vals = [v.decode("utf8") for v in vals]
+            else:
+                vals = [np.frombuffer(v, dtype=tp.base.np_dtype) for v in vals]
+            if not shape:
+                return vals[0]
+            arr = np.empty(n, dtype=object)
+            arr[:] = vals
+            return arr.reshape(shape)
+        arr = np.frombuffer(raw, dtype=tp.np_dtype, count=n).reshape(shape if shape else ())
+        if tp.kind == "str":
+            return arr.copy() if shape else bytes(arr.tobytes()).split(b"\0")[0]
+        return arr.copy() if shape else arr.reshape(()).copy()[()]
+
+    def _global_heap_object(self, addr, idx) -> bytes:
+        b = self.buf
+        if b[addr:addr + 4] != b"GCOL":
+            raise HDF5Error("global heap signature missing")
+        size = struct.unpack_from("<Q", b, addr + 8)[0]
+        p, end = addr + 16, addr + size
+        while p + 16 <= end:
+            oi, _, _, osz = struct.unpack_from("<HHIQ", b, p)
+            if oi == idx:
+                return b[p + 16:p + 16 + osz]
+            if oi == 0:
+                break
+            p += 16 + ((osz + 7) & ~7)
+        raise HDF5Error("global heap object not found")
+
+
+# ======================================================================================== writer
+def _pad8(b: bytes) -> bytes:
+    return b + b"\0" * (-len(b) % 8)
+
+
+def _dt_message(arr: np.ndarray) -> bytes:
+    dt = arr.dtype
+    if dt.kind == "f":
+        sz = dt.itemsize
+        exp, man, bias = {2: (5, 10, 15), 4: (8, 23, 127), 8: (11, 52, 1023)}[sz]
+        bits = 0x20 | ((sz * 8 - 1) << 8)            # little-endian, implied mantissa msb, sign bit location
+        head = struct.pack("<B3BI", 0x11, bits & 0xFF, (bits >> 8) & 0xFF, 0, sz)
+        return head + struct.pack("<HHBBBBI", 0, sz * 8, man, exp, 0, man, bias)
+    if dt.kind in "iu":
+        sz = dt.itemsize
+        head = struct.pack("<B3BI", 0x10, 0x08 if dt.kind == "i" else 0, 0, 0, sz)
+        return head + struct.pack("<HH", 0, sz * 8)
+    if dt.kind == "S":
+        return struct.pack("<B3BI", 0x13, 0x01, 0, 0, max(dt.itemsize, 1))       # null-padded ASCII (numpy 'S')
+    raise HDF5Error(f"cannot store dtype {dt}")
+
+
+def _ds_message(shape) -> bytes:
+    rank = len(shape)
+    return struct.pack("<BBBB4x", 1, rank, 0, 0) + b"".join(struct.pack("<Q", s) for s in shape)
+
+
+def _as_storable(v) -> np.ndarray:
+    if isinstance(v, str):
+        v = v.encode("utf8")
+    if isinstance(v, bytes):
+        return np.array(v if v else b"\0", dtype=f"S{max(len(v), 1)}")
+    if isinstance(v, (list, tuple)) and v and isinstance(v[0], (str, bytes)):
+        bs = [x.encode("utf8") if isinstance(x, str) else x for x in v]
+        return np.array(bs, dtype=f"S{max(max(len(x) for x in bs), 1)}")
+    a = np.asarray(v)
+    if a.dtype.kind == "U":
+        a = np.char.encode(a, "utf8")
+    if a.dtype.kind not in "fiuS":
+        raise HDF5Error(f"cannot store {a.dtype}")
+    return a.astype(a.dtype.newbyteorder("<")) if a.dtype.kind in "fiu" else a
+
+
+class Writer:
+    """Build a file in memory: ``w.group("/a/b").attrs[...] = ...``, ``w.dataset("/a/b/kernel:0", array)``, ``w.save(path)``."""
+
+    class _G:
+        def __init__(self):
+            self.attrs: Dict[str, object] = {}
+            self.children: Dict[str, object] = {}
+
+    class _D:
+        def __init__(self, arr):
+            self.attrs: Dict[str, object] = {}
+            self.arr = arr
+
+    def __init__(self):
+        self.root = Writer._G()
+
+    def group(self, path: str) -> "Writer._G":
+        g = self.root
+        for part in [q for q in path.split("/") if q]:
+            nxt = g.children.get(part)
+            if nxt is None:
+                nxt = g.children[part] = Writer._G()
+            if not isinstance(nxt, Writer._G):
+                raise HDF5Error(f"{part} is a dataset")
+            g = nxt
+        return g
+
+    def dataset(self, path: str, arr) -> "Writer._D":
+        parts = [q for q in path.split("/") if q]
+        g = self.group("/".join(parts[:-1]))
+        d = g.children[parts[-1]] = Writer._D(_as_storable(arr))
+        return d
+
+    # -- serialisation ---------------------------------------------------------------------------
+    def tobytes(self) -> bytes:
+        out = bytearray(96)                                  # superblock, filled in at the end
+
+        def alloc(data: bytes) -> int:
+            while len(out) % 8:
+                out.append(0)
+            addr = len(out)
+            out.extend(data)
+            return addr
+
+        def attr_msgs(attrs):
+            msgs = []
+            for k, v in attrs.items():
+                a = _as_storable(v)
+                name = k.encode("utf8") + b"\0"
+                dt, ds = _dt_message(a), _ds_message(a.shape)
+                body = struct.pack("<BBHHH", 1, 0, len(name), len(dt), len(ds)) + _pad8(name) + _pad8(dt) + _pad8(ds) + a.tobytes()
+                msgs.append((0x0C, body))
+            return msgs
+
+        def header(msgs) -> int:
+            blob = b"".join(struct.pack("<HHB3x", t, len(_pad8(d)), 0) + _pad8(d) for t, d in msgs)
+            return alloc(struct.pack("<BBHII4x", 1, 0, len(msgs), 1, len(blob)) + blob)
+
+        def write_dataset(d) -> int:
+            a = np.ascontiguousarray(d.arr)
+            raw = a.tobytes()
+            addr = alloc(raw) if raw else UNDEF
+            msgs = [(0x01, _ds_message(a.shape)), (0x03, _dt_message(a)),
+                    (0x05, struct.pack("<BBBB", 2, 2, 2, 0)),                       # fill value: late alloc, undefined
+                    (0x08, struct.pack("<BBQQ", 3, 1, addr, len(raw)))] + attr_msgs(d.attrs)
+            return header(msgs)
+
+        def write_group(g) -> int:
+            entries = []
+            for name in sorted(g.children):                  # symbol tables are ordered by name
+                c = g.children[name]
+                entries.append((name, write_group(c) if isinstance(c, Writer._G) else write_dataset(c)))
+            # local heap: offset 0 holds the empty string (the B-tree's left-most key)
+            heap = bytearray(b"\0" * 8)
+            offs = []
+            for name, _ in entries:
+                offs.append(len(heap))
+                heap.extend(name.encode("utf8") + b"\0")
+                while len(heap) % 8:
+                    heap.append(0)
+            free_off = len(heap)
+            heap.extend(struct.pack("<QQ", 1, 16))           # one free block: next = 1 (none), size 16
+            data_addr = alloc(bytes(heap))
+            heap_addr = alloc(b"HEAP" + struct.pack("<B3xQQQ", 0, len(heap), free_off, data_addr))
+            # symbol nodes of at most 2K = 8 entries, one B-tree node above them (up to 2K = 32 children)
+            leaves = []
+            for i in range(0, max(len(entries), 1), 8):
+                chunk = entries[i:i + 8]
+                body = b"SNOD" + struct.pack("<BBH", 1, 0, len(chunk))
+                for j, (name, oaddr) in enumerate(chunk):
+                    body += struct.pack("<QQII16x", offs[i + j], oaddr, 0, 0)
+                body += b"\0" * (40 * (8 - len(chunk)))
+                leaves.append((alloc(body), offs[i + len(chunk) - 1] if chunk else 0))
+            if len(leaves) > 32:
+                raise HDF5Error("more than 256 links in one group are not supported by this writer")
+            node = b"TREE" + struct.pack("<BBHQQ", 0, 0, len(leaves), UNDEF, UNDEF) + struct.pack("<Q", 0)
+            for addr, last_key in leaves:
+                node += struct.pack("<QQ", addr, last_key)
+            node += b"\0" * (16 * (32 - len(leaves)))
+            bt_addr = alloc(node)
+            return header([(0x11, struct.pack("<QQ", bt_addr, heap_addr))] + attr_msgs(g.attrs))
+
+        root = write_group(self.root)
+        while len(out) % 8:
+            out.append(0)
+        sb = SIGNATURE + struct.pack("<BBBBBBBBHHI", 0, 0, 0, 0, 0, 8, 8, 0, 4, 16, 0)
+        sb += struct.pack("<QQQQ", 0, UNDEF, len(out), UNDEF)
+        sb += struct.pack("<QQII16x", 0, root, 0, 0)
+        assert len(sb) == 96
+        out[:96] = sb
+        return bytes(out)
+
+    def save(self, path):
+        with open(path, "wb") as fh:
+            fh.write(self.tobytes())
+
+
+def is_hdf5(path) -> bool:
+    with open(path, "rb") as fh:
+        return fh.read(8) == SIGNATURE

@@ -247,6 +247,7 @@ class UGaitEngine:
             add("classprob/w", (cfg.nclasses, feat))
             add("classprob/b", (cfg.nclasses,))
         self.aux = bool(getattr(cfg, "aux_losses", False)) and cfg.nclasses > 0 and not cfg.single
+        self.post2 = getattr(cfg, "postriplet", 1) == 2 and cfg.nc > 0 and not cfg.single
         if self.aux:       # classprob_{of,gray,depth}: Dense(nclasses, softmax) on every gated branch output (:1222-1229)
             for m in range(cfg.nmods):
                 add(f"{AUX_NAMES[m]}/w", (cfg.nclasses, cfg.nd))
@@ -386,6 +387,29 @@ class UGaitEngine:
     def export_grads(self):
         return self._export(self.pg_)
 
+    def set_trainable(self, prefix: str, trainable: bool):
+        """layer.trainable of the Keras protocol (freeze_convs / freeze_all / freeze_branches, nets/mj_uwyhNets_ba.py:193,
+        :1366-1391): every parameter tensor whose name starts with `prefix` is (un)frozen.  Frozen tensors keep their
+        regulariser term in the loss value but receive no update (the optimiser kernel skips them)."""
+        hit = 0
+        l2 = self.seg_l2.cpu()
+        for i, s in enumerate(self.seg_list):
+            if s.name == prefix or s.name.startswith(prefix.rstrip("/") + "/"):
+                hit += 1
+                frozen = float(l2[i]) < 0
+                if trainable and frozen:
+                    l2[i] = -float(l2[i]) - 1.0
+                elif not trainable and not frozen:
+                    l2[i] = -(float(l2[i]) + 1.0)
+        if not hit:
+            raise KeyError(f"no parameter tensor under {prefix!r}")
+        self.seg_l2.copy_(l2)
+        self._opt_ranges = None          # per-range coefficient tables are rebuilt on demand
+        return hit
+
+    def frozen(self) -> List[str]:
+        return [s.name for s, c in zip(self.seg_list, self.seg_l2.cpu().tolist()) if c < 0]
+
     def export_decisions(self, B: int, train: bool = True):
         """The discrete decisions the last forward pass of batch size B took, in the oracle's layout: per modality m
         ``{pool{li}: [B,C,Hp,Wp] arg-max position dy*2+dx, act{li}: [B,C,Hp,Wp] bool (selected pre-activation > 0)}``
@@ -461,7 +485,8 @@ class UGaitEngine:
                     check(lib.ugn_fuse_fwd(h, 1, b.nrm_in, p.one_ptrs, b.R["outn"].ptr, None, b.R["nwin"].ptr,
                                            b.R["ninv"].ptr, 0, 1, st))
             check(lib.ugn_fuse_fwd(h, cfg.nmods, p.brn_ptrs if cfg.normbfmerge else p.br_ptrs, p.flag_ptrs,
-                                   p.R["sig"].ptr, None, p.R["winner"].ptr, p.R["inv_norm"].ptr, cfg.merge, 1, st))
+                                   p.R["sig"].ptr, None, p.R["winner"].ptr, p.R["inv_norm"].ptr, cfg.merge,
+                                   0 if self.post2 else 1, st))
             sig = p.R["sig"]
             if self.aux:
                 # auxiliary classifiers on the GATED branch outputs: gate = the fusion kernel on one modality without
@@ -478,11 +503,18 @@ class UGaitEngine:
             cmask = p.R["cmask"].ptr if (train and cfg.dropout > 0.001) else None
             check(lib.ugn_linear_fwd(h, sig.ptr, self.Rw["code/w"].ptr, self.Rw["code/b"].ptr, None, p.R["code"].ptr,
                                      None, cfg.act, cfg.alpha, st))
+            emb = p.code
+            if self.post2:
+                # postriplet == 2 (:819-832): the Dense above is the layer "signature"; its l2_normalize ("code") is the
+                # embedding of the triplet loss and the classifier input = the fusion kernel on ONE modality, unit flag
+                check(lib.ugn_fuse_fwd(h, 1, p.code_ptrs, p.one_ptrs, p.R["codeN"].ptr, None, p.R["cwin"].ptr,
+                                       p.R["cinv"].ptr, 0, 1, st))
+                emb, sig = p.codeN, p.R["codeN"]
             if cmask is not None:
-                torch.mul(p.code, p.cmask, out=p.dropcode)
+                torch.mul(emb, p.cmask, out=p.dropcode)
                 feat = p.R["dropcode"]
             else:
-                feat = p.R["code"]
+                feat = p.R["codeN"] if self.post2 else p.R["code"]
         if cfg.nclasses > 0:
             check(lib.ugn_linear_fwd(h, feat.ptr, self.Rw["classprob/w"].ptr, self.Rw["classprob/b"].ptr, None,
                                      p.R["logits"].ptr, None, ACT_LINEAR, 0.0, st))
@@ -545,6 +577,12 @@ class UGaitEngine:
         p = self.plan(B, False)
         self._set_inputs(p, inputs, flags)
         self._forward(p, False)
+        if self.post2:      # postriplet == 2: "signature" is the Dense layer (:821-826), "code" its l2_normalize (:828)
+            if layer == "signature":
+                y = p.code
+                return (y.clone() if self.cfg.act != ACT_LEAKY else torch.where(y > 0, y, y / self.cfg.alpha))
+            if layer == "code":
+                return p.codeN.clone()
         if layer == "signature":
             return (p.br[0].out if self.cfg.single else p.sig).clone()
         if layer == "code":
@@ -633,14 +671,18 @@ class UGaitEngine:
         self._works = []
         # triplet: demb = wver * dL/dsig
         check(lib.ugn_triplet_all(h, sig.ptr, p.R["labels"].ptr, cfg.margin, cfg.wver, p.R["trip_out"].ptr,
-                                  p.R["dsig"].ptr, p.R["trip_ws"].ptr, st))
+                                  (p.R["dcodeN"] if self.post2 else p.R["dsig"]).ptr, p.R["trip_ws"].ptr, st))
+        if self.post2 and cfg.nclasses == 0:
+            self._post2_backward(p, None)
         if cfg.nclasses > 0:
             check(lib.ugn_softmax_ce_ls(h, p.R["logits"].ptr, p.R["labels"].ptr, p.R["ce_out"].ptr, p.R["dlogits"].ptr,
                                         cfg.wid, cfg.label_smoothing, st))
             check(lib.ugn_linear_bwd(h, feat.ptr, self.Rw["classprob/w"].ptr, p.R["dlogits"].ptr, p.R["dfeat"].ptr,
                                      self.Rg["classprob/w"].ptr, self.Rg["classprob/b"].ptr, st))
             dfeat = p.R["dfeat"]
-            if cfg.nc > 0:
+            if self.post2:
+                self._post2_backward(p, dfeat)
+            elif cfg.nc > 0:
                 # activity regulariser l2(1e-3) on "code": + 1e-3*sum(code^2)/B  (:1196)
                 use_mask = cfg.dropout > 0.001
                 check(lib.ugn_act_mask_bwd(h, dfeat.ptr, None, p.R["cmask"].ptr if use_mask else None,
@@ -684,7 +726,7 @@ class UGaitEngine:
         else:
             check(lib.ugn_fuse_bwd(h, cfg.nmods, p.R["dsig"].ptr, p.R["sig"].ptr, p.R["winner"].ptr,
                                    p.R["inv_norm"].ptr, p.flag_ptrs, p.dbrn_ptrs if cfg.normbfmerge else p.dbr_ptrs,
-                                   cfg.merge, 1, st))
+                                   cfg.merge, 0 if self.post2 else 1, st))
             if self.aux:       # + the auxiliary heads' gradient wrt the (normalised) branch output
                 for m in range(cfg.nmods):
                     b = p.br[m]
@@ -697,6 +739,28 @@ class UGaitEngine:
         # per-branch backward on concurrent streams (single GPU; with data parallelism the branches stay in
         # sequence so that every all-reduce bucket is issued from the one stream NCCL orders against)
         self._run_branch_backward(p)
+
+    def _post2_backward(self, p, dfeat):
+        """postriplet == 2: gradient of [triplet(codeN) + CE(classprob(dropout(codeN)))] back to the un-normalised fusion:
+        dropout mask -> l2_normalize backward -> activity regulariser + activation -> Dense "signature" -> dsig."""
+        cfg, h, st, B = self.cfg, self.ctx.h, stream_ptr(), p.B
+        if dfeat is not None:
+            use_mask = cfg.dropout > 0.001
+            check(lib.ugn_act_mask_bwd(h, dfeat.ptr, None, p.R["cmask"].ptr if use_mask else None, p.R["dcode"].ptr,
+                                       None, ACT_LINEAR, 0.0, st))
+            p.dcodeN.add_(p.dcode)
+        check(lib.ugn_fuse_bwd(h, 1, p.R["dcodeN"].ptr, p.R["codeN"].ptr, p.R["cwin"].ptr, p.R["cinv"].ptr, p.one_ptrs,
+                               p.dcode_ptrs, 0, 1, st))                      # -> p.dcode = dL/d(activated Dense output)
+        relu = cfg.act != ACT_LEAKY
+        if relu:
+            p.dcode.add_(p.code, alpha=2e-3 / B)
+        check(lib.ugn_act_mask_bwd(h, p.R["dcode"].ptr, p.R["code"].ptr, None, p.R["dcode_z"].ptr, None, cfg.act,
+                                   cfg.alpha, st))
+        if not relu:
+            torch.where(p.code > 0, p.code, p.code / cfg.alpha, out=p.dsig2_code)
+            p.dcode_z.add_(p.dsig2_code, alpha=2e-3 / B)
+        check(lib.ugn_linear_bwd(h, p.R["sig"].ptr, self.Rw["code/w"].ptr, p.R["dcode_z"].ptr, p.R["dsig"].ptr,
+                                 self.Rg["code/w"].ptr, self.Rg["code/b"].ptr, st))
 
     def _run_branch_backward(self, p):
         """Per-branch backward.  One GPU: every branch on its own stream, start to end (the HBM-bound dense GEMMs
@@ -1191,7 +1255,8 @@ class UGaitEngine:
         return p.code.clone() if layer == "code" else p.logits.clone()
 
     def _report(self, p: "_Plan", with_reg: bool = False) -> Dict[str, torch.Tensor]:
-        out = {"triplet": p.trip_out[0], "count": p.trip_out[1], "signature": p.br[0].out if self.cfg.single else p.sig}
+        out = {"triplet": p.trip_out[0], "count": p.trip_out[1],
+               "signature": p.br[0].out if self.cfg.single else (p.codeN if self.post2 else p.sig)}
         if self.cfg.nclasses > 0:
             out["ce"], out["acc"], out["logits"] = p.ce_out[0], p.ce_out[1], p.logits
         if getattr(self, "aux", False) and p.train:
@@ -1301,6 +1366,12 @@ class _Plan:
             self.dropcode = T["dropcode"] = torch.zeros(B, cfg.nc, **f32)
             self.cmask = T["cmask"] = torch.ones(B, cfg.nc, **f32)
             feat = cfg.nc
+            if eng.post2:
+                self.codeN = T["codeN"] = torch.zeros(B, cfg.nc, **f32)
+                T["cwin"] = torch.zeros(B, cfg.nc, device=d, dtype=torch.uint8)
+                T["cinv"] = torch.zeros(B, 2, **f32)
+                if train:
+                    self.dcodeN = T["dcodeN"] = torch.zeros(B, cfg.nc, **f32)
         if cfg.nclasses > 0:
             self.logits = T["logits"] = torch.zeros(B, cfg.nclasses, **f32)
         self.labels = T["labels"] = iov["labels"]
@@ -1328,9 +1399,14 @@ class _Plan:
         self.flag_ptrs = ptr_array(self.R_flags)
         if train:
             self.dbr_ptrs = ptr_array([b.R["dout"] for b in self.br])
-        if cfg.normbfmerge and not cfg.single:
+        if eng.post2:
+            self.code_ptrs = ptr_array([self.R["code"]])
+            if train:
+                self.dcode_ptrs = ptr_array([self.R["dcode"]])
+        if (cfg.normbfmerge and not cfg.single) or eng.post2:
             self._ones = TRef(torch.ones(B, 1, **f32))
             self.one_ptrs = ptr_array([self._ones])
+        if cfg.normbfmerge and not cfg.single:
             self.brn_ptrs = ptr_array([b.R["outn"] for b in self.br])
             if train:
                 self.dbrn_ptrs = ptr_array([b.R["doutn"] for b in self.br])
