@@ -282,6 +282,11 @@ int ugn_knn_topk_tc(ugn_ctx*, const ugn_tensor* queries, const ugn_tensor* q16,
 int ugn_knn_merge_vote(ugn_ctx*, const ugn_tensor* d2, const ugn_tensor* idx,
                        const ugn_tensor* lab, int k, ugn_tensor* out_d2, ugn_tensor* out_idx,
                        ugn_tensor* out_lab, ugn_tensor* pred, void* stream);
+/* The same merge on the buffer ONE all-gather of the sharded search produces: packed u8 [G, row] (row >= 20*Q*k, a
+ * multiple of 8), row g = rank g's lists back to back: d2 f64 [Q,k] | idx i64 [Q,k] | lab i32 [Q,k]. */
+int ugn_knn_merge_vote_packed(ugn_ctx*, const ugn_tensor* packed, long long Q, int k, ugn_tensor* out_d2,
+                              ugn_tensor* out_idx, ugn_tensor* out_lab, ugn_tensor* pred, void* stream);
+
 
 /* ---- a13: video-level summaries of the open-world test -----------------------------------
  * (mains/mj_testUWYHGaitNet_open_tum.py:355-420).  Rows are grouped by video through a CSR built

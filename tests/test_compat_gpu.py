@@ -201,6 +201,7 @@ def test_model_save_loadnet_initnet_freeze_and_init_branches(compat_path, tmp_pa
     path = str(tmp_path / "model-state-0002.hdf5")
     model.save(path)
     model.save_weights(UWYHSemiNet3Mods.get_weights_filename(path))
+    W = model.engine.export_params()                                              # the state in the checkpoint
     m2 = UWYHSemiNet3Mods.loadnet(path)
     assert np.array_equal(m2.predict(X)[0], model.predict(X)[0])
     e, e2 = model.engine, m2.engine
@@ -211,7 +212,7 @@ def test_model_save_loadnet_initnet_freeze_and_init_branches(compat_path, tmp_pa
     # initnet with another classifier width + freeze_convs
     m3 = UWYHSemiNet3Mods.build_or_load(shp, 4, fs, fn, [32, 16], 0.00005, 0.0, optimizer=optimizers.SGD(1e-2, 0.9),
                                         nclasses=7, loss_weights=[1.0, 0.1], initnet=path, freeze_convs=True, fMerge=sign_max)
-    W, W3 = model.engine.export_params(), m3.engine.export_params()
+    W3 = m3.engine.export_params()
     assert torch.equal(W3["ofBranch/conv2/w"], W["ofBranch/conv2/w"]) and torch.equal(W3["code/w"], W["code/w"])
     assert W3["classprob/w"].shape == (7, 16)                                     # skipped: built fresh
     assert sorted(m3.engine.frozen()) == sorted(k for k in W3 if "/conv" in k)
@@ -227,6 +228,7 @@ def test_model_save_loadnet_initnet_freeze_and_init_branches(compat_path, tmp_pa
     # init_branches: a stand-alone branch file initialises the same-named branch
     bpath = str(tmp_path / "gray_branch.hdf5")
     model.save_branch(bpath, "grayBranch")
+    W = model.engine.export_params()                                              # (the model trained on after the checkpoint)
     m5 = UWYHSemiNet3Mods.build(shp, 4, fs, fn, [32, 16], 0.00005, 0.0, optimizer=optimizers.SGD(1e-2, 0.9), nclasses=10,
                                 loss_weights=[1.0, 0.1], init_branches={"of": "", "gray": bpath, "depth": ""},
                                 freeze_branches=False, fMerge=sign_max)

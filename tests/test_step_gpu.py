@@ -478,12 +478,13 @@ def test_frozen_layers_receive_no_update_but_keep_their_regulariser():
     eng3.load_params(P)
     eng3.set_trainable("ofBranch", False)
     r2, r3 = float(eng2.train_step(*ins)["reg"]), float(eng3.train_step(*ins)["reg"])
-    assert r3 == pytest.approx(r2, rel=1e-6)
+    assert r3 == pytest.approx(r2, rel=1e-4)        # (fp32 atomics: the summation order differs between launches)
     W2, W3 = eng2.export_params(), eng3.export_params()
     for k in W2:
         if k.startswith("ofBranch/"):
             assert torch.equal(W3[k].double().cpu(), P[k].float().double()), k
         else:
-            assert torch.equal(W3[k], W2[k]), k           # unfrozen tensors: the same update as without freezing
+            # unfrozen tensors: the same update as without freezing (split-K atomics reorder fp32 sums between runs)
+            assert rel(W3[k], W2[k].double().cpu()) < 1e-6, k
     eng3.set_trainable("ofBranch", True)
     assert eng3.frozen() == []

@@ -80,6 +80,7 @@ _PROTOS = {
     "ugn_knn_topk_tc": (c_int, [c_void_p, _T, _T, _T, _T, _T, _T, _T, c_int, c_int64, _T, _T, _T, _T, _T, c_void_p]),
     "ugn_knn_topk": (c_int, [c_void_p, _T, _T, _T, _T, c_int, c_int64, _T, _T, _T, _T, c_void_p]),
     "ugn_knn_merge_vote": (c_int, [c_void_p, _T, _T, _T, c_int, _T, _T, _T, _T, c_void_p]),
+    "ugn_knn_merge_vote_packed": (c_int, [c_void_p, _T, ctypes.c_longlong, c_int, _T, _T, _T, _T, c_void_p]),
     "ugn_segment_pool": (c_int, [c_void_p, _T, _T, _T, c_int, _T, c_void_p]),
     "ugn_segment_mode": (c_int, [c_void_p, _T, _T, _T, c_int, _T, c_void_p]),
     "ugn_gs_conv1_fwd": (c_int, [c_void_p, _T, _T, _T, c_float, c_void_p]),

@@ -210,6 +210,8 @@ class UGaitModel:
                 total += cfg.waux * float(v)
         if "reg" in out:
             total += float(out["reg"])
+        if "act_reg" in out:            # activity regulariser of "code" (:1196): part of Keras' total loss
+            total += float(out["act_reg"])
         logs[prefix + "loss"] = total
         return logs
 

@@ -265,8 +265,11 @@ __global__ void __launch_bounds__(256) knn_rerank_kernel(const float* __restrict
 }
 
 // merge G shards' [G,Q,k] lists by (d2, idx), emit the k best and the uniform vote.
+// sd / si / sl: element stride between two shards' lists (Q*k when the three arrays are separate and contiguous; the
+// packed all-gather buffer of the sharded search keeps {d2 | idx | lab} of one rank back to back)
 __global__ void knn_merge_vote_kernel(const double* __restrict__ d2, const long long* __restrict__ idx,
-                                      const int* __restrict__ lab, int G, int Q, int k,
+                                      const int* __restrict__ lab, long long sd, long long si, long long sl,
+                                      int G, int Q, int k,
                                       double* __restrict__ od2, long long* __restrict__ oidx,
                                       int* __restrict__ olab, int* __restrict__ pred) {
   int q = blockIdx.x * blockDim.x + threadIdx.x;
@@ -280,15 +283,15 @@ __global__ void knn_merge_vote_kernel(const double* __restrict__ d2, const long 
     long long bi = 0;
     for (int g = 0; g < G; ++g) {
       if (head[g] >= k) continue;
-      long long o = ((long long)g * Q + q) * k + head[g];
-      long long ii = idx[o];
+      const long long o = (long long)q * k + head[g];
+      long long ii = idx[g * si + o];
       if (ii < 0) continue;
-      double dd = d2[o];
+      double dd = d2[g * sd + o];
       if (bg < 0 || dd < bd || (dd == bd && ii < bi)) { bg = g; bd = dd; bi = ii; }
     }
     int lb = -1;
     if (bg >= 0) {
-      lb = lab[((long long)bg * Q + q) * k + head[bg]];
+      lb = lab[bg * sl + (long long)q * k + head[bg]];
       head[bg]++;
     } else {
       bd = DBL_MAX; bi = -1;
@@ -557,7 +560,33 @@ extern "C" int ugn_knn_merge_vote(ugn_ctx* ctx, const ugn_tensor* d2, const ugn_
   if (out_lab) UGN_TENSOR(out_lab, DT_I32, 2, 2);
   if (Q == 0) return UGN_OK;
   knn_merge_vote_kernel<<<ugn_cdiv(Q, 128), 128, 0, st>>>(
-      ugn_ptr<double>(d2), ugn_ptr<long long>(idx), ugn_ptr<int>(lab), G, (int)Q, k,
+      ugn_ptr<double>(d2), ugn_ptr<long long>(idx), ugn_ptr<int>(lab), Q * k, Q * k, Q * k, G, (int)Q, k,
+      out_d2 ? ugn_ptr<double>(out_d2) : nullptr, out_idx ? ugn_ptr<long long>(out_idx) : nullptr,
+      out_lab ? ugn_ptr<int>(out_lab) : nullptr, ugn_ptr<int>(pred));
+  UGN_LAUNCHED(ctx);
+  return UGN_OK;
+}
+
+// Sharded search: `packed` u8 [G, 20*Q*k (+pad)] is the all-gathered buffer whose row g holds rank g's lists back to
+// back: d2 f64 [Q,k] | idx i64 [Q,k] | lab i32 [Q,k] -- ONE collective instead of three.
+extern "C" int ugn_knn_merge_vote_packed(ugn_ctx* ctx, const ugn_tensor* packed, long long Q, int k, ugn_tensor* out_d2,
+                                         ugn_tensor* out_idx, ugn_tensor* out_lab, ugn_tensor* pred, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  UGN_CHECK(ctx && packed && pred, "ugn_knn_merge_vote_packed: null argument");
+  UGN_TENSOR(packed, DT_U8, 2, 2);
+  UGN_TENSOR(pred, DT_I32, 1, 1);
+  const int G = (int)packed->shape[0];
+  const long long row = packed->shape[1], n = Q * k;
+  UGN_CHECK(G >= 1 && G <= 16 && k >= 1 && k <= KNN_MAXKC, "1..16 shards, k <= %d", KNN_MAXKC);
+  UGN_CHECK(row >= 20 * n && row % 8 == 0 && pred->shape[0] == Q, "packed rows must hold 20*Q*k bytes and be 8-byte multiples");
+  if (out_d2) UGN_TENSOR(out_d2, DT_F64, 2, 2);
+  if (out_idx) UGN_TENSOR(out_idx, DT_I64, 2, 2);
+  if (out_lab) UGN_TENSOR(out_lab, DT_I32, 2, 2);
+  if (Q == 0) return UGN_OK;
+  const uint8_t* base = ugn_ptr<uint8_t>(packed);
+  knn_merge_vote_kernel<<<ugn_cdiv(Q, 128), 128, 0, st>>>(
+      reinterpret_cast<const double*>(base), reinterpret_cast<const long long*>(base + 8 * n),
+      reinterpret_cast<const int*>(base + 16 * n), row / 8, row / 8, row / 4, G, (int)Q, k,
       out_d2 ? ugn_ptr<double>(out_d2) : nullptr, out_idx ? ugn_ptr<long long>(out_idx) : nullptr,
       out_lab ? ugn_ptr<int>(out_lab) : nullptr, ugn_ptr<int>(pred));
   UGN_LAUNCHED(ctx);

@@ -46,6 +46,10 @@ class KNeighborsClassifier:
         # candidate scan on the tensor cores (tcgen05 distance GEMM + fused top-k) unless disabled
         self.use_tc = self.ctx.has_tcgen05 and not os.environ.get("UGN_KNN_SIMT")
         self.flagged = 0            # queries whose candidate-containment proof failed (recomputed exactly)
+        # replay the search of a query count as CUDA graphs from its second call on (the fixed per-call cost -- a dozen
+        # launches and their host work -- is what limits strong scaling once a shard's scan takes ~1 ms)
+        self.use_graph = os.environ.get("UGN_KNN_GRAPH", "1") == "1"
+        self._works = {}
 
     # ---- fit: keep (this rank's shard of) the gallery resident in HBM ------------------------
     def fit(self, X, y, idx_base: int = 0, sharded: bool = False):
@@ -70,50 +74,134 @@ class KNeighborsClassifier:
             self.G16 = torch.empty(2, self.kch, n, 64, dtype=torch.float16, device=self.dev)
             ops.knn_pack(self.ctx, self.G, self.G16)        # fp16 hi/lo planes, K-chunk major, zero padded
         self.classes_ = None
+        self._works = {}
+        if hasattr(self, "_RG"):
+            del self._RG
         return self
 
-    # ---- local shard search -------------------------------------------------------------------
-    def _local_topk(self, Q: torch.Tensor):
-        nq, k = Q.shape[0], self.k
-        d2 = torch.empty(nq, k, dtype=torch.float64, device=self.dev)
-        idx = torch.empty(nq, k, dtype=torch.int64, device=self.dev)
-        lab = torch.empty(nq, k, dtype=torch.int32, device=self.dev)
-        flags = torch.zeros(nq, dtype=torch.int32, device=self.dev) if self.use_tc else None
+    # ---- per-query-count workspace: every buffer of a search allocated once, DLPack handles cached -------------
+    def _work(self, nq: int):
+        w = self._works.get(nq)
+        if w is not None:
+            return w
+        from ._ffi import TRef
+        k, dev = self.k, self.dev
+        n = nq * k
+        world = torch.distributed.get_world_size(self.pg) if self.pg is not None else 1
+        row = (20 * n + 7) // 8 * 8
+        w = {"nq": nq, "row": row, "world": world}
+        # this rank's lists back to back in ONE byte buffer: d2 f64 | idx i64 | lab i32  (-> one all-gather)
+        w["pack"] = torch.zeros(row, dtype=torch.uint8, device=dev)
+        w["d2"] = w["pack"][:8 * n].view(torch.float64).view(nq, k)
+        w["idx"] = w["pack"][8 * n:16 * n].view(torch.int64).view(nq, k)
+        w["lab"] = w["pack"][16 * n:20 * n].view(torch.int32).view(nq, k)
+        w["gathered"] = torch.zeros(world, row, dtype=torch.uint8, device=dev) if world > 1 else w["pack"].view(1, row)
+        w["od2"] = torch.empty(nq, k, dtype=torch.float64, device=dev)
+        w["oidx"] = torch.empty(nq, k, dtype=torch.int64, device=dev)
+        w["olab"] = torch.empty(nq, k, dtype=torch.int32, device=dev)
+        w["pred"] = torch.empty(nq, dtype=torch.int32, device=dev)
+        w["q"] = torch.empty(nq, self.G.shape[1], device=dev)
+        blocks = []
         for s in range(0, nq, self.query_block):
             e = min(nq, s + self.query_block)
-            ws = torch.empty(max(ops.knn_workspace_bytes(e - s, self.G.shape[0], self.G.shape[1], k) // 4, 4),
-                             dtype=torch.float32, device=self.dev)
+            b = {"s": s, "e": e,
+                 "ws": torch.empty(max(ops.knn_workspace_bytes(e - s, self.G.shape[0], self.G.shape[1], k) // 4, 4),
+                                   dtype=torch.float32, device=dev)}
             if self.use_tc:
-                q16 = torch.empty(2, self.kch, e - s, 64, dtype=torch.float16, device=self.dev)
-                ops.knn_pack(self.ctx, Q[s:e], q16)
-                ops.knn_topk_tc(self.ctx, Q[s:e], q16, self.G, self.G16, self.g2, self.gmax2, self.labels, k,
-                                self.idx_base, d2[s:e], idx[s:e], lab[s:e], flags[s:e], ws)
+                b["q16"] = torch.empty(2, self.kch, e - s, 64, dtype=torch.float16, device=dev)
+            b["R"] = {n_: TRef(t) for n_, t in dict(q=w["q"][s:e], d2=w["d2"][s:e], idx=w["idx"][s:e], lab=w["lab"][s:e],
+                                                    ws=b["ws"], **({"q16": b["q16"]} if self.use_tc else {})).items()}
+            blocks.append(b)
+        w["blocks"] = blocks
+        w["flags"] = torch.zeros(nq, dtype=torch.int32, device=dev) if self.use_tc else None
+        if self.use_tc:
+            for b in blocks:
+                b["R"]["flags"] = TRef(w["flags"][b["s"]:b["e"]])
+        w["R"] = {n_: TRef(w[n_]) for n_ in ("gathered", "od2", "oidx", "olab", "pred")}
+        if not hasattr(self, "_RG"):
+            self._RG = {n_: TRef(t) for n_, t in dict(G=self.G, g2=self.g2, gmax2=self.gmax2, labels=self.labels,
+                                                      **({"G16": self.G16} if self.use_tc else {})).items()}
+        w["graph"] = None
+        self._works[nq] = w
+        return w
+
+    # ---- local shard search -------------------------------------------------------------------
+    def _local_topk_into(self, w):
+        """Candidate scan + exact re-rank of w["q"] into the packed list buffer (kernels only: capturable)."""
+        from ._ffi import check, lib, stream_ptr
+        h, st, G, k = self.ctx.h, stream_ptr(), self._RG, self.k
+        if w["flags"] is not None:
+            w["flags"].zero_()
+        for b in w["blocks"]:
+            R = b["R"]
+            if self.use_tc:
+                check(lib.ugn_knn_pack(h, R["q"].ptr, R["q16"].ptr, st))
+                check(lib.ugn_knn_topk_tc(h, R["q"].ptr, R["q16"].ptr, G["G"].ptr, G["G16"].ptr, G["g2"].ptr,
+                                          G["gmax2"].ptr, G["labels"].ptr, k, self.idx_base, R["d2"].ptr, R["idx"].ptr,
+                                          R["lab"].ptr, R["flags"].ptr, R["ws"].ptr, st))
             else:
-                ops.knn_topk(self.ctx, Q[s:e], self.G, self.g2, self.labels, k, self.idx_base, d2[s:e], idx[s:e],
-                             lab[s:e], ws)
-        self._flags = flags
-        return d2, idx, lab
+                check(lib.ugn_knn_topk(h, R["q"].ptr, G["G"].ptr, G["g2"].ptr, G["labels"].ptr, k, self.idx_base,
+                                       R["d2"].ptr, R["idx"].ptr, R["lab"].ptr, R["ws"].ptr, st))
+
+    def _local_topk(self, Q: torch.Tensor):
+        w = self._work(Q.shape[0])
+        w["q"].copy_(Q)
+        self._local_topk_into(w)
+        self._flags = w["flags"]
+        return w["d2"], w["idx"], w["lab"]
 
     def flagged_queries(self) -> int:
         """How many queries of the last search failed the containment proof and were recomputed exactly."""
         return 0 if getattr(self, "_flags", None) is None else int(self._flags.sum())
 
+    def _merge_into(self, w):
+        from ._ffi import check, lib, stream_ptr
+        R = w["R"]
+        check(lib.ugn_knn_merge_vote_packed(self.ctx.h, R["gathered"].ptr, w["nq"], self.k, R["od2"].ptr, R["oidx"].ptr,
+                                            R["olab"].ptr, R["pred"].ptr, stream_ptr()))
+
     def _search(self, Q):
-        Q = _as_cuda(Q, torch.float32, self.dev)
-        d2, idx, lab = self._local_topk(Q)
-        if self.pg is not None and torch.distributed.get_world_size(self.pg) > 1:
-            world = torch.distributed.get_world_size(self.pg)
-            D2 = torch.empty((world,) + d2.shape, dtype=d2.dtype, device=self.dev)
-            IX = torch.empty((world,) + idx.shape, dtype=idx.dtype, device=self.dev)
-            LB = torch.empty((world,) + lab.shape, dtype=lab.dtype, device=self.dev)
-            torch.distributed.all_gather_into_tensor(D2, d2, group=self.pg)
-            torch.distributed.all_gather_into_tensor(IX, idx, group=self.pg)
-            torch.distributed.all_gather_into_tensor(LB, lab, group=self.pg)
+        """Search of this rank's shard -> ONE all-gather of the packed (d2, idx, label) lists -> merge + vote.
+        The kernels of the two halves replay as CUDA graphs after the first call of a query count (use_graph)."""
+        nq = int(Q.shape[0])
+        w = self._work(nq)
+        if isinstance(Q, torch.Tensor) and Q.is_cuda and Q.dtype == torch.float32:
+            w["q"].copy_(Q, non_blocking=True)
         else:
-            D2, IX, LB = d2.unsqueeze(0), idx.unsqueeze(0), lab.unsqueeze(0)
-        return merge_vote(self.ctx, D2.contiguous(), IX.contiguous(), LB.contiguous(), self.k)
+            w["q"].copy_(_as_cuda(Q, torch.float32, self.dev), non_blocking=True)
+        self._flags = w["flags"]
+        world = w["world"]
+        if self.use_graph and w["graph"] is None and w.get("warm", 0) >= 1:
+            g1 = torch.cuda.CUDAGraph()
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                with torch.cuda.graph(g1, stream=side):
+                    self._local_topk_into(w)
+                    if world == 1:
+                        self._merge_into(w)
+                g2 = None
+                if world > 1:
+                    g2 = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(g2, stream=side):
+                        self._merge_into(w)
+            torch.cuda.current_stream().wait_stream(side)
+            w["graph"] = (g1, g2)
+        if w["graph"] is not None:
+            w["graph"][0].replay()
+            if world > 1:
+                torch.distributed.all_gather_into_tensor(w["gathered"].view(-1), w["pack"], group=self.pg)
+                w["graph"][1].replay()
+        else:
+            self._local_topk_into(w)
+            if world > 1:
+                torch.distributed.all_gather_into_tensor(w["gathered"].view(-1), w["pack"], group=self.pg)
+            self._merge_into(w)
+            w["warm"] = w.get("warm", 0) + 1
+        return w["od2"], w["oidx"], w["olab"], w["pred"]
 
     def predict_device(self, Q) -> torch.Tensor:
+        """Predicted labels i32 [Q] on the device (a view of the search workspace: valid until the next search)."""
         return self._search(Q)[3]
 
     def predict(self, Q) -> np.ndarray:
@@ -122,7 +210,7 @@ class KNeighborsClassifier:
     def kneighbors_exact(self, Q):
         """(squared fp64 distances [Q,k], global indices [Q,k]) ordered by (distance, index)."""
         d2, idx, _, _ = self._search(Q)
-        return d2.cpu().numpy(), idx.cpu().numpy()
+        return d2.cpu().numpy().copy(), idx.cpu().numpy().copy()
 
     def kneighbors(self, Q, return_distance=True):
         d2, idx = self.kneighbors_exact(Q)
@@ -147,7 +235,7 @@ def knn_sharded_local(G, y, Q, k, shards: int):
     for r in range(shards):
         lo, hi = shard_bounds(len(G), r, shards)
         clf = KNeighborsClassifier(n_neighbors=k).fit(G[lo:hi], y[lo:hi], idx_base=lo, sharded=True)
-        parts.append(clf._local_topk(_as_cuda(Q, torch.float32, clf.dev)))
+        parts.append(tuple(t.clone() for t in clf._local_topk(_as_cuda(Q, torch.float32, clf.dev))))
         ctx = clf.ctx
     D2 = torch.stack([p[0] for p in parts]).contiguous()
     IX = torch.stack([p[1] for p in parts]).contiguous()

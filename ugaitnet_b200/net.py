@@ -696,6 +696,7 @@ class UGaitEngine:
                     #             recovered from the activated one (z = y for y > 0, y / alpha otherwise)
                     torch.where(p.code > 0, p.code, p.code / cfg.alpha, out=p.dsig2_code)
                     p.dcode_z.add_(p.dsig2_code, alpha=2e-3 / B)
+                self._activity_reg_value(p, relu)
                 check(lib.ugn_linear_bwd(h, sig.ptr, self.Rw["code/w"].ptr, p.R["dcode_z"].ptr, p.R["dsig2"].ptr,
                                          self.Rg["code/w"].ptr, self.Rg["code/b"].ptr, st))
                 p.dsig.add_(p.dsig2)
@@ -740,6 +741,14 @@ class UGaitEngine:
         # sequence so that every all-reduce bucket is issued from the one stream NCCL orders against)
         self._run_branch_backward(p)
 
+    def _activity_reg_value(self, p, relu: bool):
+        """Value of Dense(..., activity_regularizer=l2(1e-3)) on "code": 1e-3 * sum(out^2) / batch -- part of the total
+        loss Keras reports (its gradient is folded into the backward pass above).  loss_pack[5]."""
+        src = p.code if relu else p.dsig2_code            # activated output (ReLU) | linear output (LeakyReLU path)
+        torch.mul(src, src, out=p.act_sq)
+        torch.sum(p.act_sq, dim=(0, 1), keepdim=False, out=p.loss_pack[5])
+        p.loss_pack[5:6].mul_(1e-3 / p.B)
+
     def _post2_backward(self, p, dfeat):
         """postriplet == 2: gradient of [triplet(codeN) + CE(classprob(dropout(codeN)))] back to the un-normalised fusion:
         dropout mask -> l2_normalize backward -> activity regulariser + activation -> Dense "signature" -> dsig."""
@@ -759,6 +768,7 @@ class UGaitEngine:
         if not relu:
             torch.where(p.code > 0, p.code, p.code / cfg.alpha, out=p.dsig2_code)
             p.dcode_z.add_(p.dsig2_code, alpha=2e-3 / B)
+        self._activity_reg_value(p, relu)
         check(lib.ugn_linear_bwd(h, p.R["sig"].ptr, self.Rw["code/w"].ptr, p.R["dcode_z"].ptr, p.R["dsig"].ptr,
                                  self.Rg["code/w"].ptr, self.Rg["code/b"].ptr, st))
 
@@ -1264,7 +1274,9 @@ class UGaitEngine:
             out["aux_acc"] = [b.T["aux_ce"][1] for b in p.br]
         if with_reg:
             out["reg"] = p.loss_pack[4]
-            out["losses"] = p.loss_pack          # [triplet, count, ce, acc, reg, -, -, -]: one D2H read
+            out["losses"] = p.loss_pack          # [triplet, count, ce, acc, reg, activity reg, -, -]: one D2H read
+            if self.cfg.nc > 0:
+                out["act_reg"] = p.loss_pack[5]
         return out
 
     def launches_per_step(self) -> int:
@@ -1391,6 +1403,7 @@ class _Plan:
                 self.dcode = T["dcode"] = torch.zeros(B, cfg.nc, **f32)
                 self.dcode_z = T["dcode_z"] = torch.zeros(B, cfg.nc, **f32)
                 self.dsig2_code = torch.zeros(B, cfg.nc, **f32)
+                self.act_sq = torch.zeros(B, cfg.nc, **f32)
                 self.dsig2 = T["dsig2"] = torch.zeros(B, cfg.nd, **f32)
         self.T = T
         self.R = {k: TRef(v) for k, v in T.items()}
