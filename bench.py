@@ -463,9 +463,14 @@ def main():
             del eager
             torch.cuda.empty_cache()
             line["configs"] = config_legs(pk, args)
+            line["e2e"]["compat_fit"] = compat_leg(args)
+            torch.cuda.empty_cache()
             eager = None
         if not args.no_knn and world == 1:
             line["knn"] = knn_leg(pk)
+            torch.cuda.empty_cache()
+            line["knn_d2048"] = knn_leg(pk, D=2048)
+            torch.cuda.empty_cache()
         if not args.no_gaitset and world == 1:
             del eng
             eager = None
@@ -473,12 +478,75 @@ def main():
             line["gaitset"] = gaitset_leg(pk, args)
     if world > 1 and not args.no_knn:
         kn = knn_leg(peaks(), rank, world, pg)          # collective: every rank searches its gallery shard
+        torch.cuda.empty_cache()
+        kn2 = knn_leg(peaks(), rank, world, pg, D=2048)
         if rank == 0:
-            line["knn"] = kn
+            line["knn"], line["knn_d2048"] = kn, kn2
     if rank == 0:
         print(json.dumps(line), flush=True)
     if world > 1:
         torch.distributed.destroy_process_group()
+
+
+def compat_leg(args):
+    """End to end through the DROP-IN API exactly as mains/mj_trainUWYHGaitNet_DataGen_3mods.py drives it: the model
+    from UWYHSemiNet3Mods.build_or_load (reference signature), model.fit on a generator that yields the reference
+    generator's batches -- float64 numpy volumes + flags, [labels, one-hot] (data/mj_dataGeneratorMMUWYHsingle.py:664-823)
+    -- and model.predict on the same.  Wall-clock with the f64 -> f32 cast, the H2D copies and the per-batch loss
+    read-back inside the timed region."""
+    from ugaitnet_b200.compat import optimizers, sign_max
+    import ugaitnet_b200.compat.nets.mj_uwyhNets_ba as nets
+    nets.MATH_MODE = args.mode
+    model = nets.UWYHSemiNet3Mods.build_or_load([(50, 60, 60), (25, 60, 60), (25, 60, 60)], 4,
+                                                [(7, 7), (5, 5), (3, 3), (2, 2)], [96, 192, 512, 512], ND, 0.00005, 0.4,
+                                                optimizer=optimizers.Adam(lr=1e-4), margin=0.2, nclasses=NCLASSES,
+                                                loss_weights=[1.0, 0.1], initnet="", fMerge=sign_max)
+
+    class Gen:
+        def __init__(self):
+            self.items = []
+            for i in range(2):
+                xs, fl, lab = make_batch(232323 + i)
+                X = []
+                for x, f in zip(xs, fl):
+                    X += [x.astype(np.float64), f.astype(np.float64)]
+                self.items.append((X, [lab.astype(np.float64), np.eye(NCLASSES)[lab.reshape(-1).astype(int) % NCLASSES]]))
+
+        def __len__(self):
+            return len(self.items)
+
+        def __getitem__(self, i):
+            return self.items[i]
+
+        def on_epoch_end(self):
+            pass
+
+    gen = Gen()
+    B = gen[0][0][0].shape[0]
+    f64_bytes = sum(a.nbytes for a in gen[0][0])
+    model.fit(gen, epochs=1, steps_per_epoch=4, verbose=0)           # warm-up: plans, graph capture, pinned blocks
+    torch.cuda.synchronize()
+    n = max(8, args.steps)
+    t0 = time.perf_counter()
+    hist = model.fit(gen, epochs=1, steps_per_epoch=n, verbose=0)
+    torch.cuda.synchronize()
+    dt = (time.perf_counter() - t0) / n
+    X = gen[0][0]
+    model.predict(X)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(5):
+        sig, prob = model.predict(X)
+    dtp = (time.perf_counter() - t0) / 5
+    assert np.isfinite(hist.history["loss"][-1])
+    return {"api": "compat UWYHSemiNet3Mods.build_or_load + model.fit(generator of float64 numpy batches) / model.predict",
+            "math_mode": model.engine.math_mode, "rows_per_step": B,
+            "fit": {"value": B / dt, "unit": "rows/s", "ms_per_step": dt * 1e3, "host_f64_bytes_per_step": int(f64_bytes),
+                    "h2d_bytes_per_step": int(f64_bytes // 2), "d2h_bytes_per_step": 32,
+                    "path": "f64 -> f32 cast across the host cores straight into the pinned input block, ONE H2D copy, "
+                            "cast + copy of batch i+1 overlapping step i, ONE packed loss read per batch"},
+            "predict": {"value": B / dtp, "unit": "rows/s", "ms_per_call": dtp * 1e3,
+                        "returns": "[signature [B,2048], classprob [B,150]] as numpy"}}
 
 
 def config_legs(pk, args):
@@ -641,23 +709,26 @@ def gaitset_leg(pk, args):
     return out
 
 
-def knn_leg(pk, rank=0, world=1, pg=None):
-    """Open-world test (BASELINE cfg5): k=3 queries/s over a synthetic 1 M x 256 gallery of L2-normalised
+def knn_leg(pk, rank=0, world=1, pg=None, D=256):
+    """Open-world test (BASELINE cfg5): k=3 queries/s over a synthetic 1 M x D gallery of L2-normalised
     descriptors clustered around 155 class centroids (0.1 % exact duplicate rows), row-sharded over the
-    ranks; Q = 4096 (tensor-bound) and Q = 64 (gallery-streaming, HBM-bound)."""
+    ranks; Q = 4096 (tensor-bound) and Q = 64 (gallery-streaming, HBM-bound).  D = 256: the FC1 "code" descriptor
+    (casenet C); D = 2048: the `signature` descriptor of the benchmarked model (nd = 2048, no FC1)."""
     from ugaitnet_b200.knn import KNeighborsClassifier, shard_bounds
-    N, D, k = 1_000_000, 256, 3
+    N, k = 1_000_000, 3
     lo, hi = shard_bounds(N, rank, world)
     g = torch.Generator(device="cuda").manual_seed(5)          # same stream on every rank -> same gallery
     cent = torch.randn(155, D, device="cuda", generator=g)
     lab_all = torch.randint(0, 155, (N,), device="cuda", generator=g, dtype=torch.int32)
     G = torch.empty(hi - lo, D, device="cuda")
-    for s in range(0, N, 125_000):                             # generate the full stream, keep this rank's rows
-        blk = cent[lab_all[s:s + 125_000].long()] + 0.35 * torch.randn(125_000, D, device="cuda", generator=g)
+    step = 125_000 if D <= 256 else 25_000
+    for s in range(0, N, step):                                # generate the full stream, keep this rank's rows
+        blk = cent[lab_all[s:s + step].long()] + 0.35 * torch.randn(step, D, device="cuda", generator=g)
         blk = blk / blk.norm(dim=1, keepdim=True)
-        a, b = max(s, lo), min(s + 125_000, hi)
+        a, b = max(s, lo), min(s + step, hi)
         if a < b:
             G[a - lo:b - lo] = blk[a - s:b - s]
+        del blk
     dup = torch.arange(0, hi - lo - 1, 1000, device="cuda")
     G[dup + 1] = G[dup]                                        # exact duplicates (distance ties)
     lab = lab_all[lo:hi].contiguous()
@@ -688,12 +759,14 @@ def knn_leg(pk, rank=0, world=1, pg=None):
 
     for Q in (4096, 64):
         qd = Qall[:Q].contiguous()
-        ms, pred = timed(lambda: clf.predict_device(qd), 5)
+        ms, pred = timed(lambda: clf.predict_device(qd), 5 if D <= 256 else 3)
         flops = 2.0 * Q * N * D
         gal_bytes = (hi - lo) * clf.dp * 4 if clf.use_tc else (hi - lo) * D * 4
         out[f"Q{Q}"] = {"queries_per_s": Q / (ms * 1e-3), "ms": ms, "flagged_exact_recompute": clf.flagged_queries(),
                         "algorithmic_tflops": flops / (ms * 1e-3) / 1e12,
-                        "tensor_frac_of_peak": flops / (ms * 1e-3) / 1e12 / pk["tf_sust"],
+                        # aggregate FLOP/s over `world` GPUs against world x one GPU's peak (x3: issued MMA passes)
+                        "tensor_frac_of_peak": flops / (ms * 1e-3) / 1e12 / (pk["tf_sust"] * world),
+                        "tensor_issued_frac_of_peak": 3 * flops / (ms * 1e-3) / 1e12 / (pk["tf_sust"] * world),
                         "gallery_GBps_per_gpu": gal_bytes / (ms * 1e-3) / 1e9, "hbm_frac_of_peak": gal_bytes / (ms * 1e-3) / 1e9 / pk["hbm"]}
     # end to end: pinned host queries -> labels on the host
     hq = Qall.cpu().pin_memory()
@@ -705,7 +778,7 @@ def knn_leg(pk, rank=0, world=1, pg=None):
     ms, _ = timed(e2e, 3)
     out["e2e_Q4096"] = {"queries_per_s": 4096 / (ms * 1e-3), "ms": ms, "h2d_bytes": 4096 * D * 4, "d2h_bytes": 4096 * 4}
     out["queries_per_s"] = out["Q4096"]["queries_per_s"]
-    if rank == 0 and world == 1:
+    if rank == 0 and world == 1 and D <= 256:
         try:   # the reference's exact call on the host cores, bounded sample of the same queries
             from sklearn.neighbors import KNeighborsClassifier as SK
             Gh, yh, Qh = G.cpu().numpy(), lab.cpu().numpy(), Qall[:128].cpu().numpy()

@@ -103,6 +103,16 @@ int ugn_pack_input(ugn_ctx*, const ugn_tensor* x_nchw, ugn_tensor* x_nhwc, void*
 int ugn_pack_input_expand(ugn_ctx*, const ugn_tensor* x_base, const ugn_tensor* src_row,
                           const ugn_tensor* enable, const ugn_tensor* mirror, float noise,
                           ugn_tensor* x_nhwc, void* stream);
+/* The same pack with the integer-exact rest of the generator's augmentation (data/mj_dataGeneratorMMUWYHsingle.py:718-746,
+ * data/mj_augmentation.py:35-50, __load_dd :318-321), each nullable:
+ *   shift i8 [B,2] = (tx, ty) of the random transform: out[y][x] = in[clamp(y+tx)][clamp(x+ty)] (ImageDataGenerator
+ *     .apply_transform with integer displacements, order-1 interpolation, fill_mode='nearest'), applied before the mirror;
+ *   clip u8 [B] != 0: the optical-flow magnitude clip, on decoded values: |v| > clip_hi or |v| < clip_lo -> clip_val
+ *     (raw thresholds 2300 / 50 and 1e-8 before the 1/compressFactor * 0.1 scaling: 2.3 / 0.05 / 1e-11). */
+int ugn_pack_input_augment(ugn_ctx*, const ugn_tensor* x_base, const ugn_tensor* src_row, const ugn_tensor* enable,
+                           const ugn_tensor* mirror, const ugn_tensor* shift, const ugn_tensor* clip, float clip_lo,
+                           float clip_hi, float clip_val, float noise, ugn_tensor* x_nhwc, void* stream);
+
 
 /* master f32 conv kernel [Cout][kh][kw][Cin] -> compute copy f32 [Cout][kh][kw][Cp] or
  * bf16 [P][Cout][kh][kw][Cp]; also used for dense weights with w viewed as [out][1][1][in]. */

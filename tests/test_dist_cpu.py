@@ -87,3 +87,24 @@ def test_shard_bounds_cover_everything():
             assert b[0][0] == 0 and b[-1][1] == n
             assert all(b[i][1] == b[i + 1][0] for i in range(w - 1))
             assert max(h - l for l, h in b) - min(h - l for l, h in b) <= 1
+
+
+def test_integer_shift_restatement_equals_scipy_affine_transform():
+    """expand.shift_sequence == what ImageDataGenerator.apply_transform does for a pure integer displacement
+    (keras_preprocessing apply_affine_transform: scipy.ndimage.affine_transform(channel, identity, offset=(tx, ty),
+    order=1, mode='nearest'); data/mj_augmentation.py:35-50,62-64), and the decoded-value clip == __load_dd's raw clip."""
+    import numpy as np
+    from scipy import ndimage
+    from ugaitnet_b200.expand import clip_flow, shift_sequence
+    rng = np.random.default_rng(0)
+    x = rng.normal(size=(6, 20, 20)).astype(np.float32)
+    for tx, ty in [(-5, 3), (0, 0), (5, 5), (3, -3), (-3, 0)]:
+        ref = np.stack([ndimage.affine_transform(x[i], np.eye(2), offset=(tx, ty), order=1, mode="nearest", cval=0.0)
+                        for i in range(x.shape[0])])
+        assert np.array_equal(shift_sequence(x, tx, ty), ref), (tx, ty)
+    raw = rng.integers(-3000, 3000, size=(50, 8, 8)).astype(np.float32)
+    lit = raw.copy()
+    lit[np.abs(lit) > 2300] = 1e-8
+    lit[np.abs(lit) < 50] = 1e-8
+    lit = lit / 100 * 0.1
+    assert np.allclose(clip_flow(raw / 100 * 0.1), lit, rtol=1e-6, atol=1e-12)

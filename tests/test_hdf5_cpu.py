@@ -109,3 +109,91 @@ def test_rejects_non_hdf5(tmp_path):
     assert not hdf5.is_hdf5(p)
     with pytest.raises(hdf5.HDF5Error):
         hdf5.File(str(p))
+
+
+def test_chunked_deflate_shuffle_dataset_is_read():
+    """A chunked dataset with the shuffle + deflate pipeline (pytables / deepdish compression='zlib'), assembled by hand
+    following the specification (layout class 2, filter pipeline message 0x000B version 1, v1 chunk B-tree)."""
+    import zlib
+    a = (np.arange(6 * 5, dtype=np.int16).reshape(6, 5) * 37 - 400)
+    cd = (4, 5)                                            # two chunks along axis 0, the second one partial
+    buf = bytearray(2048)
+
+    def put(off, b):
+        buf[off:off + len(b)] = b
+        return off
+    chunks = []
+    pos = 1024
+    for r0 in (0, 4):
+        c = np.zeros(cd, dtype=np.int16)
+        c[:min(4, 6 - r0)] = a[r0:r0 + 4]
+        raw = c.tobytes()
+        sh = np.frombuffer(raw, np.uint8).reshape(-1, 2).T.tobytes()          # shuffle
+        z = zlib.compress(sh)
+        put(pos, z)
+        chunks.append((pos, len(z), r0))
+        pos += (len(z) + 7) & ~7
+    bt = 512
+    node = b"TREE" + struct.pack("<BBHQQ", 1, 0, 2, hdf5.UNDEF, hdf5.UNDEF)
+    for addr, sz, r0 in chunks:
+        node += struct.pack("<IIQQQ", sz, 0, r0, 0, 0) + struct.pack("<Q", addr)
+    node += struct.pack("<IIQQQ", 0, 0, 8, 0, 0)
+    put(bt, node)
+    # dataset object header at 200
+    ds = struct.pack("<BBBB4x", 1, 2, 0, 0) + struct.pack("<QQ", 6, 5)
+    dt = struct.pack("<B3BI", 0x10, 0x08, 0, 0, 2) + struct.pack("<HH", 0, 16)
+    lay = struct.pack("<BBB", 3, 2, 3) + struct.pack("<Q", bt) + struct.pack("<III", 4, 5, 2)
+    flt = struct.pack("<BB6x", 1, 2)
+    flt += struct.pack("<HHHH", 2, 8, 0, 1) + b"shuffle\0" + struct.pack("<II", 2, 0)
+    flt += struct.pack("<HHHH", 1, 8, 0, 1) + b"deflate\0" + struct.pack("<II", 6, 0)
+    msgs = [(1, ds), (3, dt), (8, lay), (0x0B, flt)]
+    blob = b"".join(struct.pack("<HHB3x", t, len(hdf5._pad8(d)), 0) + hdf5._pad8(d) for t, d in msgs)
+    put(200, struct.pack("<BBHII4x", 1, 0, len(msgs), 1, len(blob)) + blob)
+    # wrap into a file: root group with one link "data" through the writer's machinery is simpler -> patch a Writer file
+    w = hdf5.Writer()
+    w.dataset("placeholder", np.zeros(1, np.uint8))
+    base = bytearray(w.tobytes())
+    shift = len(base)
+    # relocate: append our hand-made region and point the symbol table entry of "placeholder" at the new header
+    region = bytearray(buf)
+    # fix absolute addresses inside the region (B-tree address in the layout message, chunk addresses in the node)
+    off_lay = region.find(struct.pack("<BBB", 3, 2, 3) + struct.pack("<Q", bt))
+    region[off_lay + 3:off_lay + 11] = struct.pack("<Q", bt + shift)
+    p = bt + 24
+    for addr, sz, r0 in chunks:
+        region[p + 32:p + 40] = struct.pack("<Q", addr + shift)
+        p += 40
+    base += region
+    f0 = hdf5.File(bytes(base))
+    old_hdr = f0._links["placeholder"]
+    i = bytes(base).find(struct.pack("<Q", old_hdr), 96)
+    base[i:i + 8] = struct.pack("<Q", 200 + shift)
+    f = hdf5.File(bytes(base))
+    assert np.array_equal(f["placeholder"].value, a)
+
+
+def test_sample_files_round_trip_and_decode(tmp_path):
+    """data/generateOFData.py:136-148 layout -> ugaitnet_b200.samples.load_sample / decode_sample (= __load_dd)."""
+    from ugaitnet_b200 import samples
+    rng = np.random.default_rng(3)
+    of = rng.integers(-3000, 3000, size=(60, 60, 50)).astype(np.int16)
+    s = {"data": of, "label": np.uint16(17), "videoId": np.uint16(3), "gait": np.uint8(1),
+         "frames": np.arange(25, dtype=np.uint16), "compressFactor": np.uint8(100)}
+    p = tmp_path / "p017-n01-03.h5"
+    samples.save_sample(p, s)
+    got = samples.load_sample(p)
+    assert np.array_equal(got["data"], of) and int(got["label"]) == 17 and int(got["compressFactor"]) == 100
+    x = samples.decode_sample(got, ntype=2, clip_max=2300, clip_min=50)
+    # literal __load_dd statements (data/mj_dataGeneratorMMUWYHsingle.py:315-324) + moveaxis (:333)
+    ref = np.float32(of)
+    ref[np.abs(ref) > 2300] = 1e-8
+    ref[np.abs(ref) < 50] = 1e-8
+    ref = ref / 100
+    ref = ref * 0.1
+    assert x.shape == (50, 60, 60) and x.dtype == np.float32 and np.allclose(x, np.moveaxis(ref, 2, 0), rtol=1e-6, atol=0)
+    gray = rng.integers(0, 256, size=(60, 60, 25)).astype(np.uint8)
+    g = samples.decode_sample({"data": gray, "compressFactor": np.uint8(1)})
+    assert np.allclose(g, np.moveaxis(np.float32(gray) / 255.0 - 0.5, 2, 0))
+    sil = samples.decode_sample({"data": gray, "compressFactor": np.uint8(1)}, silhouette=True)
+    assert np.allclose(sil, np.moveaxis(np.float32(gray) / 255.0, 2, 0))
+    assert samples.decode_sample({"data": np.zeros((0,), np.uint8), "compressFactor": 1}) is None

@@ -419,3 +419,33 @@ def test_open_world_evaluation_end_to_end(ctx):
     assert np.array_equal(res["pred_vid_merged"].cpu().numpy(), pm)
     acc, acc_vid, score = res["summary"]
     assert acc > 0.9 and acc_vid >= acc - 0.05 and score > 0.9
+
+
+def test_device_side_augmentation_equals_host_restatement():
+    """ugn_pack_input_augment (integer shift of the random transform, optical-flow magnitude clip, mirror,
+    missing-modality expansion fused into the input pack) == the numpy restatement of the generator's statements
+    (data/mj_dataGeneratorMMUWYHsingle.py:718-746, data/mj_augmentation.py:12-50; the shift is pinned to
+    scipy.ndimage.affine_transform on CPU)."""
+    import random
+    from ugaitnet_b200._ffi import TRef, check, lib, stream_ptr
+    from ugaitnet_b200.expand import augment_on_host, expansion_pattern
+    from ugaitnet_b200.net import OF_CLIP_HI, OF_CLIP_LO, OF_CLIP_VAL
+    from ugaitnet_b200 import ops
+    ctx = ops.get_ctx()
+    rng = np.random.default_rng(2)
+    B0, E, C, H = 5, 4, 50, 60
+    base = np.clip(rng.normal(0, 0.8, size=(B0, C, H, H)), -3.3, 3.3).astype(np.float32)
+    src, use = expansion_pattern(B0, E, 3, random.Random(1))
+    B = len(src)
+    mirror = (rng.integers(0, 2, B)).astype(np.uint8)
+    shift = rng.choice([-5, -3, 0, 3, 5], size=(B, 2)).astype(np.int8)
+    clip = (rng.integers(0, 2, B)).astype(np.uint8)
+    ref = augment_on_host(base, src, use[:, 0], mirror, shift, clip)
+    out = torch.zeros(B, H, H, 64, device="cuda")
+    t = [torch.as_tensor(a).cuda() for a in (base, src.astype(np.int32), use[:, 0].astype(np.float32), mirror, shift, clip)]
+    R = [TRef(x) for x in t] + [TRef(out)]
+    check(lib.ugn_pack_input_augment(ctx.h, R[0].ptr, R[1].ptr, R[2].ptr, R[3].ptr, R[4].ptr, R[5].ptr, OF_CLIP_LO,
+                                     OF_CLIP_HI, OF_CLIP_VAL, 1e-9, R[6].ptr, stream_ptr()))
+    got = out[..., :C].permute(0, 3, 1, 2).cpu().numpy()
+    assert np.array_equal(got, ref)
+    assert float(out[..., C:].abs().max()) == 0.0

@@ -219,6 +219,60 @@ class UGaitModel:
         ins, fl = self._split_x(x)
         return self._logs(self.engine.train_step(ins, fl, self._labels(y)))
 
+    # -- pipelined input path of fit(): generator batch (float64 numpy, data/mj_dataGeneratorMMUWYHsingle.py:664-823)
+    #    -> multi-threaded cast straight into a pinned HostBatch -> ONE cudaMemcpyAsync -> step; the cast / copy of batch
+    #    i+1 runs while the GPU works on batch i
+    def _stage(self, X, y):
+        eng = self.engine
+        xs = [X[2 * m] for m in range(self.cfg.nmods)] if self.multimodal else [X[0] if isinstance(X, (list, tuple)) else X]
+        B = int(np.shape(xs[0])[0])
+        if not hasattr(self, "_hb"):
+            self._hb, self._hb_k = {}, 0
+        pair = self._hb.get(B)
+        if pair is None:
+            pair = self._hb[B] = [eng.host_batch(B), eng.host_batch(B)]
+        self._hb_k ^= 1
+        hb = pair[self._hb_k]
+        for m, x in enumerate(xs):
+            src = x if torch.is_tensor(x) else torch.from_numpy(np.ascontiguousarray(x))
+            hb.t["x"][m].copy_(src.reshape(hb.t["x"][m].shape))          # f64 -> f32 cast across the host cores
+            if self.multimodal:
+                f = X[2 * m + 1]
+                hb.flags[m][...] = np.asarray(f, dtype=np.float32).reshape(-1, 1)
+        lab = y[0] if isinstance(y, (list, tuple)) else y
+        hb.labels[...] = np.asarray(lab).reshape(-1).astype(np.int32)
+        eng.prefetch_batch(hb)
+
+    def _fit_epoch(self, gen, n):
+        """One epoch through the single-copy path; returns the per-batch logs (each read back with ONE D2H copy)."""
+        eng, logs = self.engine, []
+        ln = len(gen)
+        X, y = gen[0][:2]
+        self._stage(X, y)
+        pend = None
+        for i in range(n):
+            out = eng.train_step_prefetched()
+            if i + 1 < n:
+                X, y = gen[(i + 1) % ln][:2]
+                self._stage(X, y)                        # overlaps the step that was just launched
+            logs.append(self._logs_from_pack(out["losses"].cpu(), out))
+        return logs
+
+    def _logs_from_pack(self, pack, out):
+        """The same dictionary as _logs, from the packed loss buffer [triplet, count, ce, acc, reg, act_reg]."""
+        cfg = self.cfg
+        trip, ce, acc, reg, areg = float(pack[0]), float(pack[2]), float(pack[3]), float(pack[4]), float(pack[5])
+        logs, total = {}, cfg.wver * trip
+        if cfg.nclasses > 0:
+            logs["signature_loss"], logs["classprob_loss"], logs["classprob_acc"] = trip, ce, acc
+            total += cfg.wid * ce
+            for m, v in enumerate(out.get("aux_ce", [])):
+                name = ("classprob_of", "classprob_gray", "classprob_depth")[m]
+                logs[name + "_loss"], logs[name + "_acc"] = float(v), float(out["aux_acc"][m])
+                total += cfg.waux * float(v)
+        logs["loss"] = total + reg + (areg if cfg.nc > 0 else 0.0)
+        return logs
+
     def test_on_batch(self, x, y, **kw):
         ins, fl = self._split_x(x)
         return self._logs(self.engine.eval_losses(ins, fl, self._labels(y)))
@@ -233,9 +287,8 @@ class UGaitModel:
         for epoch in range(initial_epoch, epochs):
             n = steps_per_epoch or len(gen)
             acc: Dict[str, float] = {}
-            for i in range(n):
-                X, y = gen[i % len(gen)][:2]
-                for k, v in self.train_on_batch(X, y).items():
+            for step_logs in self._fit_epoch(gen, n):
+                for k, v in step_logs.items():
                     acc[k] = acc.get(k, 0.0) + v
             logs = {k: v / n for k, v in acc.items()}
             if validation_data is not None:

@@ -113,7 +113,7 @@ extern "C" int64_t ugn_launch_count(ugn_ctx* ctx) { return ctx ? ctx->launches :
 
 // ---- implementations living in other translation units --------------------------------
 int ew_pack_input(ugn_ctx*, const float*, void*, int, int, int, int, int, int, int, const int*, const float*,
-                  const uint8_t*, float, cudaStream_t);
+                  const uint8_t*, float, cudaStream_t, const int8_t* = nullptr, const uint8_t* = nullptr, float = 0.f, float = 0.f, float = 0.f);
 int ew_pack_weight(ugn_ctx*, const float*, void*, int, int, long long, int, int, cudaStream_t);
 int ew_split(ugn_ctx*, const float*, __nv_bfloat16*, int, int, long long, cudaStream_t);
 int ew_bwd_act(ugn_ctx*, const float*, const void*, int, const uint8_t*, void*, float*, int*, int, int, int, int,
@@ -159,7 +159,8 @@ static inline const int64_t* lshape(const ugn_tensor* t, int rank) { return t->s
 
 static int pack_input_common(ugn_ctx* ctx, const ugn_tensor* x_nchw, const ugn_tensor* src_row,
                              const ugn_tensor* enable, const ugn_tensor* mirror, float noise, ugn_tensor* x_nhwc,
-                             void* stream) {
+                             void* stream, const ugn_tensor* shift = nullptr, const ugn_tensor* clip = nullptr,
+                             float clip_lo = 0.f, float clip_hi = 0.f, float clip_val = 0.f) {
   UGN_CHECK(ctx && x_nchw && x_nhwc, "ugn_pack_input: null argument");
   UGN_TENSOR(x_nchw, DT_F32, 4, 4);
   UGN_TENSOR(x_nhwc, DT_BAD, 4, 5);
@@ -174,10 +175,21 @@ static int pack_input_common(ugn_ctx* ctx, const ugn_tensor* x_nchw, const ugn_t
   if (src_row) { UGN_TENSOR(src_row, DT_I32, 1, 1); UGN_CHECK(src_row->shape[0] == B, "pack_input: src_row must be i32 [B]"); }
   if (enable) { UGN_TENSOR(enable, DT_F32, 1, 2); UGN_CHECK(ugn_numel(enable) == B, "pack_input: enable must be f32 [B]"); }
   if (mirror) { UGN_TENSOR(mirror, DT_U8, 1, 1); UGN_CHECK(mirror->shape[0] == B, "pack_input: mirror must be u8 [B]"); }
+  if (shift) { UGN_TENSOR(shift, DT_I8, 2, 2); UGN_CHECK(shift->shape[0] == B && shift->shape[1] == 2, "pack_input: shift must be i8 [B,2]"); }
+  if (clip) { UGN_TENSOR(clip, DT_U8, 1, 1); UGN_CHECK(clip->shape[0] == B && clip_hi > clip_lo, "pack_input: clip must be u8 [B], clip_hi > clip_lo"); }
   if (B == 0) return UGN_OK;
   return ew_pack_input(ctx, ugn_ptr<float>(x_nchw), ugn_ptr<void>(x_nhwc), mode, is_f16(x_nhwc), B, C, H, W, (int)s[3],
                        src_row ? ugn_ptr<int>(src_row) : nullptr, enable ? ugn_ptr<float>(enable) : nullptr,
-                       mirror ? ugn_ptr<uint8_t>(mirror) : nullptr, noise, (cudaStream_t)stream);
+                       mirror ? ugn_ptr<uint8_t>(mirror) : nullptr, noise, (cudaStream_t)stream,
+                       shift ? ugn_ptr<int8_t>(shift) : nullptr, clip ? ugn_ptr<uint8_t>(clip) : nullptr, clip_lo, clip_hi,
+                       clip_val);
+}
+extern "C" int ugn_pack_input_augment(ugn_ctx* ctx, const ugn_tensor* x_base, const ugn_tensor* src_row,
+                                      const ugn_tensor* enable, const ugn_tensor* mirror, const ugn_tensor* shift,
+                                      const ugn_tensor* clip, float clip_lo, float clip_hi, float clip_val, float noise,
+                                      ugn_tensor* x_nhwc, void* stream) {
+  return pack_input_common(ctx, x_base, src_row, enable, mirror, noise, x_nhwc, stream, shift, clip, clip_lo, clip_hi,
+                           clip_val);
 }
 extern "C" int ugn_pack_input(ugn_ctx* ctx, const ugn_tensor* x_nchw, ugn_tensor* x_nhwc, void* stream) {
   return pack_input_common(ctx, x_nchw, nullptr, nullptr, nullptr, 0.f, x_nhwc, stream);

@@ -19,21 +19,33 @@ template <int MODE>  // 0 f32, 1 16-bit P=1, 2 16-bit P=2
 // data/mj_augmentation.py:12-32): output row b reads base row src_row[b]; enable[b] == 0 -> the whole volume
 // is the constant `noise` (1e-9, :102); mirror[b] != 0 -> every channel flipped left-right and, literally as
 // mj_mirrorsequence does for EVERY modality, even channels negated.
+// The rest of the generator's augmentation that is exact on integers (:718-746): shift[b] = (tx, ty) of the random
+// transform -- ImageDataGenerator.apply_transform with integer displacements, order-1 interpolation and
+// fill_mode='nearest' is out[y][x] = in[clamp(y + tx)][clamp(x + ty)], applied BEFORE the mirror -- and, on rows with
+// clip[b] != 0, the optical-flow magnitude clip of __load_dd (:318-321: |raw| > 2300 or < 50 -> 1e-8 before the
+// 1/compressFactor * 0.1 scaling), expressed on the decoded values: |v| > clip_hi or < clip_lo -> clip_val.
 __global__ void pack_input_kernel(const float* __restrict__ x, void* __restrict__ out, int B, int C,
                                   int H, int W, int Cp, long long plane, int f16,
                                   const int* __restrict__ src_row, const float* __restrict__ enable,
-                                  const uint8_t* __restrict__ mirror, float noise) {
+                                  const uint8_t* __restrict__ mirror, float noise,
+                                  const int8_t* __restrict__ shift, const uint8_t* __restrict__ clip,
+                                  float clip_lo, float clip_hi, float clip_val) {
   extern __shared__ float sm[];  // [C][W+1]
   int by = blockIdx.x;
   int b = by / H, y = by % H;
   const int sb = src_row ? src_row[b] : b;
   const bool on = !enable || enable[b] != 0.f;
   const bool mir = mirror && mirror[b];
+  const int sy = shift ? shift[2 * b] : 0, sx = shift ? shift[2 * b + 1] : 0;
+  const bool clp = clip && clip[b];
+  const int ys = min(max(y + sy, 0), H - 1);
   for (int e = threadIdx.x; e < C * W; e += blockDim.x) {
     int c = e / W, xx = e % W;
     float v = noise;
     if (on) {
-      v = x[(((long long)sb * C + c) * H + y) * W + (mir ? W - 1 - xx : xx)];
+      const int xs = min(max((mir ? W - 1 - xx : xx) + sx, 0), W - 1);
+      v = x[(((long long)sb * C + c) * H + ys) * W + xs];
+      if (clp) { const float a = fabsf(v); if (a > clip_hi || a < clip_lo) v = clip_val; }
       if (mir && !(c & 1)) v = -v;
     }
     sm[c * (W + 1) + xx] = v;
@@ -74,12 +86,15 @@ __global__ void pack_input_kernel(const float* __restrict__ x, void* __restrict_
 
 int ew_pack_input(ugn_ctx* ctx, const float* x, void* out, int mode, int f16, int B, int C, int H, int W,
                   int Cp, const int* src_row, const float* enable, const uint8_t* mirror, float noise,
-                  cudaStream_t st) {
+                  cudaStream_t st, const int8_t* shift, const uint8_t* clip, float clip_lo, float clip_hi,
+                  float clip_val) {
   size_t smem = sizeof(float) * C * (W + 1);
   long long plane = (long long)B * H * W * Cp;
-  if (mode == 0) pack_input_kernel<0><<<B * H, 256, smem, st>>>(x, out, B, C, H, W, Cp, plane, f16, src_row, enable, mirror, noise);
-  else if (mode == 1) pack_input_kernel<1><<<B * H, 256, smem, st>>>(x, out, B, C, H, W, Cp, plane, f16, src_row, enable, mirror, noise);
-  else pack_input_kernel<2><<<B * H, 256, smem, st>>>(x, out, B, C, H, W, Cp, plane, f16, src_row, enable, mirror, noise);
+#define UGN_PACK_ARGS x, out, B, C, H, W, Cp, plane, f16, src_row, enable, mirror, noise, shift, clip, clip_lo, clip_hi, clip_val
+  if (mode == 0) pack_input_kernel<0><<<B * H, 256, smem, st>>>(UGN_PACK_ARGS);
+  else if (mode == 1) pack_input_kernel<1><<<B * H, 256, smem, st>>>(UGN_PACK_ARGS);
+  else pack_input_kernel<2><<<B * H, 256, smem, st>>>(UGN_PACK_ARGS);
+#undef UGN_PACK_ARGS
   UGN_LAUNCHED(ctx);
   return UGN_OK;
 }

@@ -69,3 +69,40 @@ def to_gaitset_layout(sample: np.ndarray) -> np.ndarray:
         out[..., 1] = x[1::2]
         return out
     return x[..., None].copy()
+
+
+def shift_sequence(sample: np.ndarray, tx: int, ty: int) -> np.ndarray:
+    """mj_transformsequence (data/mj_augmentation.py:35-50) for a transform that is a pure integer displacement
+    {tx, ty} (ImageDataGenerator width/height_shift_range = [-5,-3,0,3,5], :62-64): every frame goes through
+    scipy.ndimage.affine_transform(frame, identity, offset=(tx, ty), order=1, mode='nearest'), i.e.
+    out[y, x] = in[clamp(y + tx), clamp(x + ty)] (pinned against scipy in tests/test_dist_cpu.py).  sample [C,H,W]."""
+    x = np.asarray(sample)
+    H, W = x.shape[-2:]
+    ys = np.clip(np.arange(H) + int(tx), 0, H - 1)
+    xs = np.clip(np.arange(W) + int(ty), 0, W - 1)
+    return x[..., ys[:, None], xs[None, :]].copy()
+
+
+def clip_flow(sample: np.ndarray, lo: float = 0.05, hi: float = 2.3, val: float = 1e-11) -> np.ndarray:
+    """The optical-flow magnitude clip of __load_dd (data/mj_dataGeneratorMMUWYHsingle.py:318-324) on DECODED values:
+    raw |v| > 2300 or < 50 -> 1e-8, then / compressFactor (100) * 0.1."""
+    x = np.asarray(sample).copy()
+    a = np.abs(x)
+    x[(a > hi) | (a < lo)] = val
+    return x
+
+
+def augment_on_host(base, src, use_col, mirror=None, shift=None, clip=None, noise: float = NOISE):
+    """numpy restatement of ugn_pack_input_augment for one modality: clip -> integer shift -> mirror -> expansion."""
+    base = np.asarray(base)
+    out = np.empty((len(src),) + base.shape[1:], dtype=base.dtype)
+    for i, s in enumerate(src):
+        v = base[s]
+        if clip is not None and clip[i]:
+            v = clip_flow(v)
+        if shift is not None:
+            v = shift_sequence(v, int(shift[i][0]), int(shift[i][1]))
+        if mirror is not None and mirror[i]:
+            v = mirror_sequence(v)
+        out[i] = v if use_col[i] != 0 else noise
+    return out

@@ -9,7 +9,8 @@ Supported (HDF5 File Format Specification 2.0/3.0):
   * object headers version 1 and version 2 ("OHDR"), continuation blocks;
   * old-style groups (symbol table message -> v1 B-tree "TREE" + "SNOD" leaves + local "HEAP") and compact new-style
     groups (link messages); dense link storage (fractal heaps) is NOT supported and raises;
-  * datasets: contiguous and compact layouts, and chunked layouts without filters (v1 chunk B-tree);
+  * datasets: contiguous and compact layouts, and chunked layouts (v1 chunk B-tree) without filters or with the
+    deflate / shuffle / fletcher32 filters (blosc -- deepdish's default -- is not available here and raises);
     little-endian fixed-point / IEEE float / fixed-length string element types;
   * attributes (message versions 1, 2, 3) with scalar / simple dataspaces of the same element types plus
     variable-length strings (global heap "GCOL").
@@ -49,6 +50,7 @@ class Node:
         self.attrs: Dict[str, object] = {}
         self._links: Optional[Dict[str, int]] = None
         self._dtype = self._shape = self._layout = None
+        self._filters: List[Tuple[int, Tuple[int, ...]]] = []
         self._parse()
 
     # -- object header -------------------------------------------------------------------------
@@ -108,6 +110,8 @@ class Node:
                 self._dtype = _parse_datatype(data)[0]
             elif mtype == 0x08:
                 self._layout = data
+            elif mtype == 0x0B:
+                self._filters = _parse_filters(data)
             elif mtype == 0x0C:
                 k, v = self._parse_attribute(data)
                 self.attrs[k] = v
@@ -206,7 +210,7 @@ class Node:
                 rank = L[2]
                 bt = struct.unpack_from("<Q", L, 3)[0]
                 cdims = struct.unpack_from("<" + "I" * rank, L, 11)
-                raw = self._f._read_chunked(bt, shape, cdims[:-1], self._dtype.size)
+                raw = self._f._read_chunked(bt, shape, cdims[:-1], self._dtype.size, self._filters)
             else:
                 raise HDF5Error(f"layout class {cls}")
         elif L[0] in (1, 2):
@@ -264,6 +268,51 @@ def _parse_datatype(d: bytes):
         is_str = (bits & 0x0F) == 1
         return _Type("vlen", size, None, base, vlen_str=is_str), 8 + used
     raise HDF5Error(f"datatype class {cls} is not supported")
+
+
+def _parse_filters(d: bytes):
+    """Filter pipeline message (0x000B), versions 1 and 2 -> [(filter id, client values)] in application order."""
+    ver, n = d[0], d[1]
+    p = 8 if ver == 1 else 2
+    out = []
+    for _ in range(n):
+        fid = struct.unpack_from("<H", d, p)[0]
+        p += 2
+        nlen = 0
+        if ver == 1 or fid >= 256:
+            nlen = struct.unpack_from("<H", d, p)[0]
+            p += 2
+        _flags, ncv = struct.unpack_from("<HH", d, p)
+        p += 4
+        p += ((nlen + 7) & ~7) if ver == 1 else nlen
+        cv = struct.unpack_from("<" + "I" * ncv, d, p)
+        p += 4 * ncv
+        if ver == 1 and ncv % 2:
+            p += 4
+        out.append((fid, cv))
+    return out
+
+
+def _unfilter(chunk: bytes, filters, mask: int, esize: int) -> bytes:
+    """Undo the pipeline of one chunk (reverse order): 1 = deflate (zlib), 2 = shuffle, 3 = fletcher32."""
+    import zlib
+    for i in reversed(range(len(filters))):
+        if mask & (1 << i):
+            continue
+        fid, cv = filters[i]
+        if fid == 1:
+            chunk = zlib.decompress(chunk)
+        elif fid == 2:
+            es = cv[0] if cv else esize
+            n = len(chunk) // es
+            a = np.frombuffer(chunk, dtype=np.uint8, count=n * es).reshape(es, n)
+            chunk = a.T.tobytes() + chunk[n * es:]
+        elif fid == 3:
+            chunk = chunk[:-4]
+        else:
+            raise HDF5Error(f"filter {fid} is not supported (32001 = blosc, deepdish's default: re-save the samples with "
+                            "compression=None or 'zlib')")
+    return chunk
 
 
 def _parse_link(d: bytes):
@@ -353,7 +402,7 @@ class File(Node):
         return out
 
     # -- chunked datasets without filters: v1 chunk B-tree ---------------------------------------------
-    def _read_chunked(self, btree, shape, cdims, esize) -> bytes:
+    def _read_chunked(self, btree, shape, cdims, esize, filters=()) -> bytes:
         b = self.buf
         rank = len(shape)
         out = np.zeros(shape, dtype=np.uint8 if esize == 1 else f"V{esize}")
@@ -371,9 +420,10 @@ class File(Node):
                 if level > 0:
                     walk(child)
                 else:
-                    if fmask != 0 and csize != int(np.prod(cdims)) * esize:
-                        raise HDF5Error("filtered (compressed) chunks are not supported")
-                    chunk = np.frombuffer(b, dtype=out.dtype, count=int(np.prod(cdims)), offset=child).reshape(cdims)
+                    rawc = b[child:child + csize]
+                    if filters:
+                        rawc = _unfilter(rawc, filters, fmask, esize)
+                    chunk = np.frombuffer(rawc, dtype=out.dtype, count=int(np.prod(cdims))).reshape(cdims)
                     sl = tuple(slice(o, min(o + c, s)) for o, c, s in zip(offs, cdims, shape))
                     out[sl] = chunk[tuple(slice(0, s.stop - s.start) for s in sl)]
                 p += ksz + 8
@@ -521,7 +571,7 @@ class Writer:
             return alloc(struct.pack("<BBHII4x", 1, 0, len(msgs), 1, len(blob)) + blob)
 
         def write_dataset(d) -> int:
-            a = np.ascontiguousarray(d.arr)
+            a = np.asarray(d.arr, order="C")           # (ascontiguousarray would turn a 0-d scalar into shape (1,))
             raw = a.tobytes()
             addr = alloc(raw) if raw else UNDEF
             msgs = [(0x01, _ds_message(a.shape)), (0x03, _dt_message(a)),

@@ -41,6 +41,9 @@ MATH_MODES = {"fp32": (0, 0, None), "bf16": (1, 1, torch.bfloat16), "bf16x3": (2
               "f16mix1": (2, 1, torch.float16)}
 # (conv, dense) pass codes of ugn_set_fwd_passes per math mode (default 0 = all three)
 FWD_PASSES = {"f16mix2": (2, 4), "f16mix1": (1, 1)}
+# optical-flow magnitude clip of the generator (__load_dd, data/mj_dataGeneratorMMUWYHsingle.py:318-324), on decoded
+# values: raw int16 / compressFactor (100) * 0.1 -> thresholds 2300 / 50 become 2.3 / 0.05, the fill 1e-8 becomes 1e-11
+OF_CLIP_LO, OF_CLIP_HI, OF_CLIP_VAL = 0.05, 2.3, 1e-11
 GRAD_SCALE_TARGET = 1024.0      # max|dL/dsignature| * s lands in [512, 1024]: 6 binades of headroom below 65504
 
 
@@ -68,6 +71,10 @@ class IOBlock:
         self.src_off = off
         off = round_up(off + 4 * B, self.ALIGN)
         self.mir_off = off
+        off = round_up(off + B, self.ALIGN)
+        self.shift_off = off                      # (tx, ty) i8 per row, OF-clip flag u8 per row: device-side augmentation
+        off = round_up(off + 2 * B, self.ALIGN)
+        self.clip_off = off
         off = round_up(off + B, self.ALIGN)
         self.header = off
         self.row_bytes = [4 * int(torch.tensor(s).prod()) for s in self.vol_shapes]
@@ -102,7 +109,9 @@ class IOBlock:
         v = {"flags": [self._view(buf, o, (B, 1), torch.float32) for o in self.f_off],
              "labels": self._view(buf, self.lab_off, (B,), torch.int32),
              "src_row": self._view(buf, self.src_off, (B,), torch.int32),
-             "mirror": self._view(buf, self.mir_off, (B,), torch.uint8)}
+             "mirror": self._view(buf, self.mir_off, (B,), torch.uint8),
+             "shift": self._view(buf, self.shift_off, (B, 2), torch.int8),
+             "clip": self._view(buf, self.clip_off, (B,), torch.uint8)}
         if B0 is None:
             v["x"] = [self._view(buf, o, (B,) + s, torch.float32) for o, s in zip(self.x_off, self.vol_shapes)]
         else:
@@ -125,7 +134,9 @@ class HostBatch:
         self.inputs = [x.numpy() for x in v["x"]]
         self.flags = [f.numpy() for f in v["flags"]]
         self.labels, self.src_row, self.mirror = v["labels"].numpy(), v["src_row"].numpy(), v["mirror"].numpy()
+        self.shift, self.clip = v["shift"].numpy(), v["clip"].numpy()
         self.use_mirror = False
+        self.use_augment = False          # True: shift / clip tables are applied (ugn_pack_input_augment)
         for f in self.flags:
             f[...] = 1.0
 
@@ -524,7 +535,14 @@ class UGaitEngine:
         cfg, h, st = self.cfg, self.ctx.h, stream_ptr()
         bn = BRANCH_NAMES[m]
         b = p.br[m]
-        if expanded:
+        if expanded and getattr(p, "use_augment", False):
+            # + integer shifts of the random transform on every modality, magnitude clip on the optical flow (modality 0)
+            check(lib.ugn_pack_input_augment(h, b.R["x_base"].ptr, p.R["src_row"].ptr,
+                                             None if cfg.single else p.R_flags[m].ptr,
+                                             p.R["mirror"].ptr if p.use_mirror else None, p.R["shift"].ptr,
+                                             p.R["clip"].ptr if (m == 0 and cfg.in_channels[0] == 50) else None,
+                                             OF_CLIP_LO, OF_CLIP_HI, OF_CLIP_VAL, NOISE, b.R["a0"].ptr, st))
+        elif expanded:
             # device-side missing-modality expansion: row i reads base row src_row[i]; a cleared
             # use-flag turns the row's volume into the reference's 1e-9 constant
             check(lib.ugn_pack_input_expand(h, b.R["x_base"].ptr, p.R["src_row"].ptr,
@@ -1038,7 +1056,7 @@ class UGaitEngine:
         self._step_body(p, False)
         return self._report(p)
 
-    def _set_base_inputs(self, p, base_inputs, src_row, use, labels, mirror=None):
+    def _set_base_inputs(self, p, base_inputs, src_row, use, labels, mirror=None, shift=None, clip=None):
         """Stage the BASE rows (+ the expansion pattern) of train_step_expanded / predict_expanded."""
         cfg = self.cfg
         B0 = int(base_inputs[0].shape[0])
@@ -1057,6 +1075,11 @@ class UGaitEngine:
         p.use_mirror = mirror is not None
         if mirror is not None:
             p.mirror.copy_(torch.as_tensor(mirror, dtype=torch.uint8), non_blocking=True)
+        p.use_augment = shift is not None or clip is not None
+        if p.use_augment:
+            B = p.B
+            p.shift.copy_(torch.as_tensor(shift if shift is not None else torch.zeros(B, 2), dtype=torch.int8), non_blocking=True)
+            p.clip.copy_(torch.as_tensor(clip if clip is not None else torch.zeros(B), dtype=torch.uint8), non_blocking=True)
         if labels is not None:
             lab = torch.as_tensor(labels).reshape(-1).to(torch.int32)
             if lab.numel() == B0:        # one label per base row: replicate along the expansion
@@ -1064,14 +1087,15 @@ class UGaitEngine:
             p.labels.copy_(lab, non_blocking=True)
 
     @torch.no_grad()
-    def train_step_expanded(self, base_inputs, base_labels, src_row, use, mirror=None) -> Dict[str, torch.Tensor]:
+    def train_step_expanded(self, base_inputs, base_labels, src_row, use, mirror=None, shift=None,
+                            clip=None) -> Dict[str, torch.Tensor]:
         """train_step on the reference generator's E-fold batch WITHOUT materialising it: base_inputs are
         the B0 sequences that have every modality ([B0,C,60,60] per modality), (src_row, use) is the
         expansion pattern (ugaitnet_b200.expand.expansion_pattern) and the volumes are expanded while
         they are packed on the device -- only the base rows cross PCIe."""
         B = int(len(src_row))
         p = self.plan(B, True)
-        self._set_base_inputs(p, base_inputs, src_row, use, base_labels, mirror)
+        self._set_base_inputs(p, base_inputs, src_row, use, base_labels, mirror, shift, clip)
         return self._run_train(p, B, expanded=True)
 
     @torch.no_grad()
@@ -1096,7 +1120,8 @@ class UGaitEngine:
     def _run_train(self, p, B, expanded):
         self._next_lr()
         if self.use_graph and (self.world == 1 or self.dp_graph):
-            gkey = (B, expanded, p.use_mirror, getattr(p, "_B0", None) if expanded else None)
+            gkey = (B, expanded, p.use_mirror, getattr(p, "_B0", None) if expanded else None,
+                    bool(getattr(p, "use_augment", False)) if expanded else False)
             gr = self._graphs.get(gkey)
             if gr is None:
                 # warm-up on a side stream (first-use allocations / attribute sets), then capture
@@ -1249,7 +1274,7 @@ class UGaitEngine:
         expanded = hb.B0 is not None
         if expanded:
             p.ensure_base(hb.B0)
-            p.use_mirror = bool(hb.use_mirror)
+            p.use_mirror, p.use_augment = bool(hb.use_mirror), bool(hb.use_augment)
         return self._run_train(p, p.B, expanded=expanded)
 
     @torch.no_grad()
@@ -1389,6 +1414,9 @@ class _Plan:
         self.labels = T["labels"] = iov["labels"]
         self.src_row = T["src_row"] = iov["src_row"]
         self.mirror = T["mirror"] = iov["mirror"]
+        self.shift, self.clip = iov["shift"], iov["clip"]
+        T["shift"], T["clip"] = self.shift, self.clip
+        self.use_augment = False
         if train:
             # {triplet, count, ce, acc, reg}: one buffer, one D2H read per step
             self.loss_pack = T["loss_pack"] = torch.zeros(8, **f32)
