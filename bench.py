@@ -172,7 +172,7 @@ def cpu_baseline_leg():
     from oracle import ugait_oracle as O
     torch.set_num_threads(os.cpu_count() or 1)
     oc = O.NetConfig(in_channels=(50, 25, 25), nd=ND, nclasses=NCLASSES, merge=O.MERGE_SIGNMAX, wver=1.0, wid=0.1)
-    rows = 24
+    rows = BS_LITERAL * EXPAND
     xs, fl, lab = O.synth_batch(oc, base_rows=rows // EXPAND, expand=EXPAND, seed=232323)
     xs = [torch.tensor(x) for x in xs]
     fl = [torch.tensor(f) for f in fl]
@@ -188,7 +188,8 @@ def cpu_baseline_leg():
         times.append(time.perf_counter() - t0)
     dt = min(times[1:])
     return {"value": rows / dt, "unit": "rows/s", "cores": torch.get_num_threads(), "kind": "port",
-            "sample": f"PyTorch-CPU fp32 restatement (TensorFlow unavailable), {rows} of 96 rows/step, best of 2 after 1 warm-up"}
+            "sample": f"PyTorch-CPU fp32 restatement (TensorFlow absent: profiles/r02a_tf_probe.log), the full {rows}-row "
+                      "cfg2 step incl. Adam, best of 2 after 1 warm-up"}
 
 
 class OpTimer:
@@ -371,7 +372,9 @@ def main():
     assert bool(torch.isfinite(loss_host[[0, 2, 4]]).all()), f"non-finite loss on rank {rank}: {loss_host.tolist()}"
     rank_check = None
     if world > 1:
-        wsum = torch.stack([eng.w.double().sum(), eng.w.double().abs().sum()])
+        eng.sync_master_weights()      # (owners hold the f32 masters of their arena slices; compute copies are exchanged)
+        csum = torch.stack([t.float().double().sum() for t in eng.cw.values()]).sum()
+        wsum = torch.stack([eng.w.double().sum(), eng.w.double().abs().sum(), csum])
         allw = [torch.zeros_like(wsum) for _ in range(world)]
         torch.distributed.all_gather(allw, wsum)
         rank_check = {"weights_identical_on_all_ranks": all(torch.equal(a, allw[0]) for a in allw),
@@ -384,6 +387,8 @@ def main():
     cfg_line = workload_config(world)
     if world > 1:
         cfg_line["rank_check"] = rank_check
+        if eng.dp_timing_summary() is not None:
+            cfg_line["dp_timing"] = eng.dp_timing_summary()
         cfg_line["dp_exchange"] = eng.dp_reduce + (" (NVSwitch multimem)" if all(getattr(eng, "_mc", (0, 0))) else "")
     line = {"metric": "train rows/s (3-mod fwd+bwd+triplet+CE+Adam)", "value": value, "unit": "rows/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
@@ -740,7 +745,8 @@ def knn_leg(pk, rank=0, world=1, pg=None, D=256):
            if clf.use_tc else "simt fp32"}
 
     def timed(fn, reps):
-        fn()
+        for _ in range(3):            # first call: workspaces; second: CUDA-graph capture of the search; third: a replay
+            fn()
         if world > 1:
             torch.distributed.barrier()
         torch.cuda.synchronize()

@@ -165,6 +165,16 @@ int ugn_act_mask_bwd(ugn_ctx*, const ugn_tensor* dy, const ugn_tensor* y, const 
  * Outputs (each nullable): dx f32 [B,K], dw f32 [N,K] (overwritten), db f32 [N]. */
 int ugn_linear_bwd(ugn_ctx*, const ugn_tensor* x, const ugn_tensor* w, const ugn_tensor* dz,
                    ugn_tensor* dx, ugn_tensor* dw, ugn_tensor* db, void* stream);
+/* ugn_linear_bwd with a FUSED input-gradient epilogue (tensor-core storage mode, B <= 128): the dx GEMM multiplies its
+ * result by dx_mask f32 [B,K] (the inverted-dropout mask of the layer below, nullable), writes dx16 [P,B,K] = the 16-bit
+ * gradient operand of that layer (still scaled by the ctx's gradient scale, so it feeds the next ugn_linear_bwd
+ * directly) and dbx f32 [K] = its bias gradient (column sums of the masked, unscaled dx).  dx f32 [B,K] receives the UNMASKED
+ * gradient (it doubles as the landing buffer of the split-K partial sums, so it is required).
+ * Replaces dx GEMM + ugn_act_mask_bwd + the bias column-sum pass of nets/mj_uwyhNets_ba.py:97-105's backward. */
+int ugn_linear_bwd_ex(ugn_ctx*, const ugn_tensor* x, const ugn_tensor* w, const ugn_tensor* dz, ugn_tensor* dx,
+                      const ugn_tensor* dx_mask, ugn_tensor* dx16, ugn_tensor* dbx, ugn_tensor* dw, ugn_tensor* db,
+                      void* stream);
+
 
 /* ---- a2+a3+a4: gate x use-flag, fusion, l2_normalize ---------------------------------
  * replaces mj_tensor_times_scalar (:51-54), fMerge(name="fusion") (:1189; sign_max at
@@ -244,12 +254,23 @@ int ugn_adam_step_ex(ugn_ctx*, ugn_tensor* w, const ugn_tensor* g, ugn_tensor* m
  * this rank's slice of the regulariser value -- or, when reg_peers (HOST array [world] of the device addresses of every
  * rank's reg_out scalar, peer-mapped; nullable) is given, every rank's scalar receives the sum over all slices through
  * system-scope atomic adds (no all-reduce on the step's critical path); the caller then zeroes its scalar BEFORE the
- * first barrier.  lr_dev (required): the step's learning rate in device memory. */
+ * first barrier.  lr_dev (required): the step's learning rate in device memory.
+ * stage (f32 [world * ceil(n/4/world)*4], nullable) + staged_ranges (HOST array of n_ranges <= 4 element ranges [lo, hi),
+ * multiples of 4): gradients of those arena ranges were PUSHED beforehand -- every rank p copied its part of this rank's
+ * slice to stage[p * slice_len + (e - slice_start)] (copy engines over NVLink, overlapped with the rest of the backward
+ * pass) -- so the kernel sums them from local memory instead of pulling them from the peers.
+ * pack_table (as ugn_adam_step, nullable) + cw_peers (HOST array [world] of the base addresses of every rank's
+ * symmetric arena of 16-bit compute copies; the table's addresses point into this rank's arena) [+ cw_multicast]:
+ * for the segments in the table the owner writes the hi / lo planes of its updated weights into EVERY rank's compute
+ * copy and skips the f32 broadcast -- the caller needs no re-split pass afterwards, and the other ranks' f32 masters
+ * of those segments are stale until refreshed (UGaitEngine.sync_master_weights). */
 int ugn_dp_optim_step(ugn_ctx*, int opt, int world, int rank, const int64_t* g_peers, const int64_t* w_peers,
                       int64_t g_multicast, int64_t w_multicast, ugn_tensor* w, const ugn_tensor* g, ugn_tensor* m, ugn_tensor* v, ugn_tensor* vhat,
                       float weight_decay, const ugn_tensor* seg_off, const ugn_tensor* seg_l2, float beta1,
                       float beta2, float eps, ugn_tensor* reg_out, const int64_t* reg_peers, const ugn_tensor* lr_dev,
-                      void* stream);
+                      const ugn_tensor* stage, const int64_t* staged_ranges, int n_ranges,
+                      const ugn_tensor* pack_table, int pack_planes, int pack_f16, const int64_t* cw_peers,
+                      int64_t cw_multicast, void* stream);
 /* SGD with momentum (optimizers.SGD(lr, momentum, decay), :245): v = mom*v - lr*g'; w += v.  Keras' `decay`
  * is a learning-rate schedule, lr / (1 + decay*iterations): the caller passes the scheduled rate. */
 int ugn_sgd_step(ugn_ctx*, ugn_tensor* w, const ugn_tensor* g, ugn_tensor* v,

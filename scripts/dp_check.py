@@ -49,6 +49,7 @@ for name, cls, c, x, sched in cases:
                 eng.repack_weights()
                 eng.train_step(x, fl, lab)
             torch.cuda.synchronize()
+            eng.sync_master_weights()
             delta = eng.w - w0
             l2 = torch.zeros_like(w0)                       # Keras L2 regulariser gradient 2*l2*w, applied in the optimiser
             for sg in eng.seg_list:
@@ -71,6 +72,7 @@ for sched in ("split", "fused"):
     for _ in range(3):
         out = eng.train_step(sxs, fl, lab)
     torch.cuda.synchronize()
+    eng.sync_master_weights()
     W[sched] = (eng.w.clone(), float(out["reg"]))
     if sched == "fused":
         res["multicast_ptrs_in_use"] = bool(all(getattr(eng, "_mc", (0, 0))))

@@ -72,7 +72,8 @@ _PROTOS = {
                                  c_float, _T, _T, _T, c_int, c_int, c_void_p]),
     "ugn_dp_optim_step": (c_int, [c_void_p, c_int, c_int, c_int, POINTER(c_int64), POINTER(c_int64), c_int64, c_int64,
                                   _T, _T, _T, _T, _T,
-                                  c_float, _T, _T, c_float, c_float, c_float, _T, POINTER(c_int64), _T, c_void_p]),
+                                  c_float, _T, _T, c_float, c_float, c_float, _T, POINTER(c_int64), _T,
+                                  _T, POINTER(c_int64), c_int, _T, c_int, c_int, POINTER(c_int64), c_int64, c_void_p]),
     "ugn_sgd_step": (c_int, [c_void_p, _T, _T, _T, _T, _T, c_float, c_float, c_float, _T, _T, _T, c_int, c_int,
                              c_void_p]),
     "ugn_knn_workspace_bytes": (c_int64, [c_int64, c_int64, c_int64, c_int]),
@@ -101,6 +102,7 @@ _PROTOS = {
     "ugn_grad_scale_set": (c_int, [c_void_p, c_float, c_void_p]),
     "ugn_set_fwd_passes": (c_int, [c_void_p, c_int, c_int]),
     "ugn_colsum": (c_int, [c_void_p, _T, _T, c_void_p]),
+    "ugn_linear_bwd_ex": (c_int, [c_void_p, _T, _T, _T, _T, _T, _T, _T, _T, _T, c_void_p]),
 }
 
 EXPORTED_SYMBOLS = tuple(_PROTOS)

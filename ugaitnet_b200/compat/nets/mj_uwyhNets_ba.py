@@ -189,10 +189,27 @@ class UGaitModel:
         return out.cpu().numpy()
 
     def predict(self, x, batch_size=None, verbose=0):
-        sig = self._predict_layer(x, "signature")
+        """model.predict(list): [signature, classprob] from ONE forward pass (single-copy input path)."""
+        eng = self.engine
+        xs = [x[2 * m] for m in range(self.cfg.nmods)] if self.multimodal else [x[0] if isinstance(x, (list, tuple)) else x]
+        B = int(np.shape(xs[0])[0])
+        if not hasattr(self, "_hbp"):
+            self._hbp = {}
+        hb = self._hbp.get(B)
+        if hb is None:
+            hb = self._hbp[B] = eng.host_batch(B, train=False)
+        for m, a in enumerate(xs):
+            src = a if torch.is_tensor(a) else torch.from_numpy(np.ascontiguousarray(a))
+            hb.t["x"][m].copy_(src.reshape(hb.t["x"][m].shape))
+            if self.multimodal:
+                hb.flags[m][...] = np.asarray(x[2 * m + 1], dtype=np.float32).reshape(-1, 1)
+        eng.prefetch_batch(hb, train=False)
+        sig = eng.predict_prefetched("signature")
         if self.cfg.nclasses > 0:
-            return [sig, self._predict_layer(x, "classprob")]
-        return sig
+            p = eng.plan(B, False)
+            prob = torch.softmax(p.logits, dim=1)
+            return [sig.cpu().numpy(), prob.cpu().numpy()]
+        return sig.cpu().numpy()
 
     def _logs(self, out, prefix=""):
         cfg = self.cfg

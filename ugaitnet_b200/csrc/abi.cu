@@ -131,7 +131,7 @@ int ew_fuse_bwd(ugn_ctx*, const FusePtrs&, int, int, int, const float*, const fl
 int ew_softmax_ce(ugn_ctx*, const float*, const int*, float*, float*, int, int, float, float, cudaStream_t);
 int ew_optim(ugn_ctx*, int, float*, const float*, float*, float*, const long long*, const float*, int,
              long long, float, float, float, float, float, float*, const float*, const long long*, int, int,
-             float*, float, cudaStream_t, int, int, const long long*, const long long*, long long, long long, const long long* = nullptr);
+             float*, float, cudaStream_t, int, int, const long long*, const long long*, long long, long long, const long long* = nullptr, const float* = nullptr, const long long* = nullptr, int = 0, const long long* = nullptr, long long = 0);
 int simt_conv_fwd(ugn_ctx*, const ConvGeom&, const float*, const float*, const float*, float*, uint8_t*,
                   int, float, int, cudaStream_t);
 int simt_conv_dgrad(ugn_ctx*, const ConvGeom&, const float*, const float*, float*, cudaStream_t);
@@ -414,9 +414,10 @@ extern "C" int ugn_linear_fwd(ugn_ctx* ctx, const ugn_tensor* x, const ugn_tenso
     rc = simt_linear_fwd(ctx, B, N, K, ugn_ptr<float>(x), ugn_ptr<float>(w), bias ? ugn_ptr<float>(bias) : nullptr,
                          drop_mask ? ugn_ptr<float>(drop_mask) : nullptr, ugn_ptr<float>(y), act, alpha, st);
   } else {
-    rc = tc_linear_fwd(ctx, mx, is_f16(x), B, N, K, ugn_ptr<__nv_bfloat16>(x), ugn_ptr<__nv_bfloat16>(w),
-                       bias ? ugn_ptr<float>(bias) : nullptr, drop_mask ? ugn_ptr<float>(drop_mask) : nullptr,
-                       ugn_ptr<float>(y), act, alpha, st);
+    if (y16) UGN_SAME_FMT(x, y16, "linear_fwd");
+    return tc_linear_fwd(ctx, mx, is_f16(x), B, N, K, ugn_ptr<__nv_bfloat16>(x), ugn_ptr<__nv_bfloat16>(w),
+                         bias ? ugn_ptr<float>(bias) : nullptr, drop_mask ? ugn_ptr<float>(drop_mask) : nullptr,
+                         ugn_ptr<float>(y), act, alpha, st, y16 ? ugn_ptr<__nv_bfloat16>(y16) : nullptr, P16);
   }
   if (rc != UGN_OK) return rc;
   if (y16) return ew_split(ctx, ugn_ptr<float>(y), ugn_ptr<__nv_bfloat16>(y16), P16, is_f16(y16), (long long)B * N, st);
@@ -445,8 +446,9 @@ extern "C" int ugn_act_mask_bwd(ugn_ctx* ctx, const ugn_tensor* dy, const ugn_te
                          (cudaStream_t)stream);
 }
 
-extern "C" int ugn_linear_bwd(ugn_ctx* ctx, const ugn_tensor* x, const ugn_tensor* w, const ugn_tensor* dz,
-                              ugn_tensor* dx, ugn_tensor* dw, ugn_tensor* db, void* stream) {
+static int linear_bwd_common(ugn_ctx* ctx, const ugn_tensor* x, const ugn_tensor* w, const ugn_tensor* dz,
+                             ugn_tensor* dx, ugn_tensor* dw, ugn_tensor* db, void* stream, const ugn_tensor* dx_mask,
+                             ugn_tensor* dx16, ugn_tensor* dbx) {
   UGN_CHECK(ctx && x && w && dz, "ugn_linear_bwd: null argument");
   UGN_TENSOR(x, DT_BAD, 2, 3);
   UGN_TENSOR(w, DT_BAD, 2, 3);
@@ -467,13 +469,35 @@ extern "C" int ugn_linear_bwd(ugn_ctx* ctx, const ugn_tensor* x, const ugn_tenso
   if (db) { UGN_TENSOR(db, DT_F32, 1, 1); UGN_CHECK(db->shape[0] == N, "linear_bwd: db must be [N]"); }
   if (dw) UGN_CHECK(dw->shape[1] == K, "linear_bwd: dw inner dim must equal K (dense weights are never padded)");
   cudaStream_t st = (cudaStream_t)stream;
+  int P16 = 0;
+  if (dx_mask) { UGN_TENSOR(dx_mask, DT_F32, 2, 2); UGN_CHECK(dx_mask->shape[0] == B && dx_mask->shape[1] == K, "linear_bwd: dx_mask must be [B,K]"); }
+  if (dx16) {
+    UGN_TENSOR(dx16, DT_BAD, 3, 3);
+    UGN_CHECK(is_16(dx16) && mx > 0, "linear_bwd: dx16 needs 16-bit operands");
+    UGN_SAME_FMT(x, dx16, "linear_bwd");
+    P16 = (int)dx16->shape[0];
+    UGN_CHECK((P16 == 1 || P16 == 2) && dx16->shape[1] == B && dx16->shape[2] == K, "linear_bwd: dx16 must be [P,B,K]");
+  }
+  if (dbx) { UGN_TENSOR(dbx, DT_F32, 1, 1); UGN_CHECK(dbx->shape[0] == K, "linear_bwd: dbx must be [K]"); }
+  UGN_CHECK(mx > 0 || (!dx_mask && !dx16 && !dbx), "linear_bwd: the fused input-gradient outputs need the tensor-core storage mode");
   if (mx == 0)
     return simt_linear_bwd(ctx, B, N, K, ugn_ptr<float>(x), ugn_ptr<float>(w), ugn_ptr<float>(dz),
                            dx ? ugn_ptr<float>(dx) : nullptr, dw ? ugn_ptr<float>(dw) : nullptr,
                            db ? ugn_ptr<float>(db) : nullptr, st);
   return tc_linear_bwd(ctx, mp, is_f16(x), B, N, K, ugn_ptr<__nv_bfloat16>(x), ugn_ptr<__nv_bfloat16>(w),
                        ugn_ptr<__nv_bfloat16>(dz), dx ? ugn_ptr<float>(dx) : nullptr,
-                       dw ? ugn_ptr<float>(dw) : nullptr, db ? ugn_ptr<float>(db) : nullptr, st);
+                       dw ? ugn_ptr<float>(dw) : nullptr, db ? ugn_ptr<float>(db) : nullptr, st,
+                       dx_mask ? ugn_ptr<float>(dx_mask) : nullptr, dx16 ? ugn_ptr<__nv_bfloat16>(dx16) : nullptr, P16,
+                       dbx ? ugn_ptr<float>(dbx) : nullptr);
+}
+extern "C" int ugn_linear_bwd(ugn_ctx* ctx, const ugn_tensor* x, const ugn_tensor* w, const ugn_tensor* dz,
+                              ugn_tensor* dx, ugn_tensor* dw, ugn_tensor* db, void* stream) {
+  return linear_bwd_common(ctx, x, w, dz, dx, dw, db, stream, nullptr, nullptr, nullptr);
+}
+extern "C" int ugn_linear_bwd_ex(ugn_ctx* ctx, const ugn_tensor* x, const ugn_tensor* w, const ugn_tensor* dz,
+                                 ugn_tensor* dx, const ugn_tensor* dx_mask, ugn_tensor* dx16, ugn_tensor* dbx,
+                                 ugn_tensor* dw, ugn_tensor* db, void* stream) {
+  return linear_bwd_common(ctx, x, w, dz, dx, dw, db, stream, dx_mask, dx16, dbx);
 }
 
 static int fuse_common(ugn_ctx* ctx, int nmods, const ugn_tensor* const* br, const ugn_tensor* const* flags,
@@ -563,7 +587,9 @@ static int optim_common(ugn_ctx* ctx, int opt, ugn_tensor* w, const ugn_tensor* 
                         float gscale, ugn_tensor* reg_out, const ugn_tensor* lr_dev, const ugn_tensor* pack_table,
                         int pack_planes, int pack_f16, void* stream, ugn_tensor* vhat = nullptr, float wd = 0.f,
                         int world = 1, int rank = 0, const int64_t* g_peers = nullptr, const int64_t* w_peers = nullptr,
-                        int64_t g_mc = 0, int64_t w_mc = 0, const int64_t* reg_peers = nullptr) {
+                        int64_t g_mc = 0, int64_t w_mc = 0, const int64_t* reg_peers = nullptr,
+                        const ugn_tensor* stage = nullptr, const int64_t* staged_ranges = nullptr, int n_ranges = 0,
+                        const int64_t* cw_peers = nullptr, int64_t cw_mc = 0) {
   UGN_CHECK(ctx && w && g && v && seg_off && seg_l2, "optimizer: null argument");
   if (vhat) { UGN_TENSOR(vhat, DT_F32, 1, 1); UGN_CHECK(vhat->shape[0] == w->shape[0], "optimizer: vhat arena length mismatch"); }
   UGN_CHECK(wd >= 0.f && wd < 1.f, "optimizer: decoupled weight decay must be in [0,1)");
@@ -591,7 +617,9 @@ static int optim_common(ugn_ctx* ctx, int opt, ugn_tensor* w, const ugn_tensor* 
                   pack_table ? ugn_ptr<long long>(pack_table) : nullptr, pack_planes, pack_f16,
                   vhat ? ugn_ptr<float>(vhat) : nullptr, wd, (cudaStream_t)stream, world, rank,
                   reinterpret_cast<const long long*>(g_peers), reinterpret_cast<const long long*>(w_peers), (long long)g_mc,
-                  (long long)w_mc, reinterpret_cast<const long long*>(reg_peers));
+                  (long long)w_mc, reinterpret_cast<const long long*>(reg_peers), stage ? ugn_ptr<float>(stage) : nullptr,
+                  reinterpret_cast<const long long*>(staged_ranges), n_ranges,
+                  reinterpret_cast<const long long*>(cw_peers), (long long)cw_mc);
 }
 
 extern "C" int ugn_adam_step(ugn_ctx* ctx, ugn_tensor* w, const ugn_tensor* g, ugn_tensor* m, ugn_tensor* v,
@@ -614,12 +642,15 @@ extern "C" int ugn_dp_optim_step(ugn_ctx* ctx, int opt, int world, int rank, con
                                  int64_t g_multicast, int64_t w_multicast, ugn_tensor* w, const ugn_tensor* g, ugn_tensor* m, ugn_tensor* v, ugn_tensor* vhat,
                                  float weight_decay, const ugn_tensor* seg_off, const ugn_tensor* seg_l2, float beta1,
                                  float beta2, float eps, ugn_tensor* reg_out, const int64_t* reg_peers, const ugn_tensor* lr_dev,
-                                 void* stream) {
+                                 const ugn_tensor* stage, const int64_t* staged_ranges, int n_ranges,
+                                 const ugn_tensor* pack_table, int pack_planes, int pack_f16, const int64_t* cw_peers,
+                                 int64_t cw_multicast, void* stream) {
   UGN_CHECK(opt == 0 || opt == 1, "ugn_dp_optim_step: opt must be 0 (Adam family) or 1 (SGD momentum)");
   UGN_CHECK(world >= 2 && world <= 8 && g_peers && w_peers && lr_dev, "ugn_dp_optim_step: world in [2,8], peer tables and lr_dev required");
   return optim_common(ctx, opt, w, g, opt == 0 ? m : nullptr, v, seg_off, seg_l2, 0.f, beta1, beta2, eps, 1.f / (float)world,
-                      reg_out, lr_dev, nullptr, 1, 0, stream, opt == 0 ? vhat : nullptr, opt == 0 ? weight_decay : 0.f, world,
-                      rank, g_peers, w_peers, g_multicast, w_multicast, reg_peers);
+                      reg_out, lr_dev, pack_table, pack_table ? pack_planes : 1, pack_f16, stream, opt == 0 ? vhat : nullptr,
+                      opt == 0 ? weight_decay : 0.f, world, rank, g_peers, w_peers, g_multicast, w_multicast, reg_peers,
+                      stage, staged_ranges, n_ranges, cw_peers, cw_multicast);
 }
 extern "C" int ugn_sgd_step(ugn_ctx* ctx, ugn_tensor* w, const ugn_tensor* g, ugn_tensor* v, const ugn_tensor* seg_off,
                             const ugn_tensor* seg_l2, float lr, float momentum, float gscale, ugn_tensor* reg_out,

@@ -599,6 +599,20 @@ struct PeerArenas {
   const float* g[8] = {};    // gradient arena of every rank (own rank included)
   float* w[8] = {};          // weight arena of every rank
   float* reg[8] = {};        // regulariser-value scalar of every rank (nullptr: only the local slice value is produced)
+  // PUSHED gradients: for arena ranges whose gradients are final early in the backward pass (the dense layers, 92 % of
+  // the bytes) every rank copies its part of the owner's slice into slot `rank` of the owner's staging buffer with the
+  // copy engines WHILE the convolution backward still runs; the owner then sums local memory instead of pulling over
+  // NVLink inside this kernel.  stage: [n][slice4] float4 slots of THIS rank, srange: staged [lo, hi) in float4 units
+  const float4* stage = nullptr;
+  long long slice4 = 0;
+  int rank = 0, nsr = 0;
+  long long srange[8] = {};
+  // 16-bit compute copies of the dense weights live in ONE symmetric arena per rank: the owner of a slice writes the
+  // hi / lo planes of its updated weights straight into every rank's copy (same 4 B / parameter on NVLink as the f32
+  // all-gather it replaces; the non-owners' f32 masters of those segments are refreshed on demand only) -- no local
+  // re-split pass after the exchange.  cw[p]: base of rank p's arena, cw_mc: its multicast address
+  unsigned char* cw[8] = {};
+  unsigned char* cw_mc = nullptr;
   const float* mc_g = nullptr;   // NVSwitch multicast addresses of the two arenas (nullptr: unicast peer accesses):
   float* mc_w = nullptr;         // multimem.ld_reduce sums in the switch, multimem.st broadcasts -- half the link traffic
 };
@@ -608,6 +622,10 @@ __device__ __forceinline__ float4 multimem_ld_reduce_add(const float* addr) {
   asm volatile("multimem.ld_reduce.relaxed.sys.global.add.v4.f32 {%0,%1,%2,%3}, [%4];"
                : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(addr) : "memory");
   return r;
+}
+__device__ __forceinline__ void multimem_st8(void* addr, uint2 v) {
+  asm volatile("multimem.st.relaxed.sys.global.v2.f32 [%0], {%1,%2};"
+               :: "l"(addr), "f"(__uint_as_float(v.x)), "f"(__uint_as_float(v.y)) : "memory");
 }
 __device__ __forceinline__ void multimem_st(float* addr, float4 v) {
   asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1,%2,%3,%4};"
@@ -648,7 +666,19 @@ __global__ void __launch_bounds__(256) optim_kernel(float* __restrict__ w, const
     }
     float4 wv = reinterpret_cast<float4*>(w)[q];
     float4 gv;
-    if (DP && peers.mc_g) {
+    bool staged = false;
+    if (DP && peers.nsr) {
+#pragma unroll 4
+      for (int r = 0; r < peers.nsr; ++r) staged = staged || (q >= peers.srange[2 * r] && q < peers.srange[2 * r + 1]);
+    }
+    if (DP && staged) {
+      gv = reinterpret_cast<const float4*>(g)[q];
+      for (int p = 0; p < peers.n; ++p) {
+        if (p == peers.rank) continue;
+        const float4 o = peers.stage[p * peers.slice4 + (q - q0)];
+        gv.x += o.x; gv.y += o.y; gv.z += o.z; gv.w += o.w;
+      }
+    } else if (DP && peers.mc_g) {
       gv = multimem_ld_reduce_add(peers.mc_g + 4 * q);       // reduced inside the NVSwitch
     } else if (DP && peers.n > 0) {
       // fused reduce-scatter: this rank owns the slice, the gradient is the sum over the ranks' arenas read
@@ -698,8 +728,10 @@ __global__ void __launch_bounds__(256) optim_kernel(float* __restrict__ w, const
       reinterpret_cast<float4*>(v)[q] = make_float4(v2[0], v2[1], v2[2], v2[3]);
     }
     reinterpret_cast<float4*>(w)[q] = make_float4(ww[0], ww[1], ww[2], ww[3]);
-    // fused all-gather: the owner stores the updated weights into every other rank's arena
-    if (DP) {
+    // fused all-gather: the owner stores the updated weights into every other rank's arena (segments whose 16-bit
+    // compute copies are exchanged instead skip the f32 broadcast)
+    const bool packed_x = DP && pack && pack[2 * s] && peers.cw[0];
+    if (DP && !packed_x) {
       if (peers.mc_w) {
         multimem_st(peers.mc_w + 4 * q, make_float4(ww[0], ww[1], ww[2], ww[3]));
       } else {
@@ -718,6 +750,19 @@ __global__ void __launch_bounds__(256) optim_kernel(float* __restrict__ w, const
       if (li + 4 <= numel) {
         *reinterpret_cast<uint2*>(dst + li) = *reinterpret_cast<const uint2*>(hi);
         if (packP == 2) *reinterpret_cast<uint2*>(dst + numel + li) = *reinterpret_cast<const uint2*>(lo);
+        if (packed_x) {
+          const long long ob = reinterpret_cast<unsigned char*>(dst + li) - peers.cw[peers.rank];   // byte offset in the arena
+          if (peers.cw_mc) {
+            multimem_st8(peers.cw_mc + ob, *reinterpret_cast<const uint2*>(hi));
+            if (packP == 2) multimem_st8(peers.cw_mc + ob + 2 * numel, *reinterpret_cast<const uint2*>(lo));
+          } else {
+            for (int p = 0; p < peers.n; ++p) {
+              if (p == peers.rank) continue;
+              *reinterpret_cast<uint2*>(peers.cw[p] + ob) = *reinterpret_cast<const uint2*>(hi);
+              if (packP == 2) *reinterpret_cast<uint2*>(peers.cw[p] + ob + 2 * numel) = *reinterpret_cast<const uint2*>(lo);
+            }
+          }
+        }
       } else {
         for (int i = 0; i < 4 && li + i < numel; ++i) {
           dst[li + i] = hi[i];
@@ -752,7 +797,8 @@ int ew_optim(ugn_ctx* ctx, int opt, float* w, const float* g, float* m, float* v
              float b2, float eps, float gscale, float* reg_out, const float* lr_dev, const long long* pack,
              int packP, int f16, float* vhat, float wd, cudaStream_t st, int world, int rank,
              const long long* g_peers, const long long* w_peers, long long g_mc, long long w_mc,
-             const long long* reg_peers) {
+             const long long* reg_peers, const float* stage, const long long* staged_ranges, int n_ranges,
+             const long long* cw_peers, long long cw_mc) {
   UGN_CHECK(n % 4 == 0, "optimizer arena length must be a multiple of 4 (got %lld)", n);
   // reg_peers: the caller zeroed every rank's scalar BEFORE the group barrier (a memset here would race with the adds
   // of a faster peer)
@@ -775,6 +821,21 @@ int ew_optim(ugn_ctx* ctx, int opt, float* w, const float* g, float* m, float* v
     const long long per = (n4 + world - 1) / world;           // this rank's slice, in float4 units
     q0 = std::min(n4, per * rank);
     n4 = std::min(n4, per * (rank + 1));
+    peers.rank = rank;
+    if (cw_peers && pack) {
+      for (int p = 0; p < world; ++p) peers.cw[p] = reinterpret_cast<unsigned char*>(cw_peers[p]);
+      peers.cw_mc = reinterpret_cast<unsigned char*>(cw_mc);
+    }
+    if (stage && n_ranges > 0) {
+      UGN_CHECK(n_ranges <= 4 && staged_ranges, "dp optimizer: at most 4 staged ranges");
+      peers.stage = reinterpret_cast<const float4*>(stage);
+      peers.slice4 = per; peers.rank = rank; peers.nsr = n_ranges;
+      for (int r = 0; r < n_ranges; ++r) {
+        UGN_CHECK(staged_ranges[2 * r] % 4 == 0 && staged_ranges[2 * r + 1] % 4 == 0, "staged ranges must be multiples of 4 elements");
+        peers.srange[2 * r] = staged_ranges[2 * r] / 4;
+        peers.srange[2 * r + 1] = staged_ranges[2 * r + 1] / 4;
+      }
+    }
   }
   int grid = (int)std::min<long long>((n4 - q0 + 255) / 256, (long long)ctx->sm_count * 8);
   grid = std::max(grid, 1);
@@ -801,6 +862,61 @@ int ew_bias_act_mask(ugn_ctx* ctx, float* y, const float* bias, const float* mas
                      int act, float alpha, cudaStream_t st) {
   long long n = rows * cols;
   bias_act_mask_kernel<<<grid_for(ctx, n, 256), 256, 0, st>>>(y, bias, mask, n, cols, act, alpha);
+  UGN_LAUNCHED(ctx);
+  return UGN_OK;
+}
+
+// ONE post pass of a split-K dense GEMM (forward: bias + activation + dropout mask -> f32 result + its 16-bit planes;
+// backward: dropout mask of the layer below -> that layer's scaled 16-bit gradient operand + its bias gradient).
+// Block = 32 columns x 8 row lanes over ALL rows, so the column sums need no atomics.
+template <int P16>
+__global__ void __launch_bounds__(256) dense_post_kernel(float* __restrict__ y, const float* __restrict__ bias,
+                                                         const float* __restrict__ mask, u16* __restrict__ out16,
+                                                         long long plane, int rows, int cols, int act, float alpha,
+                                                         int f16, const float* __restrict__ scale16,
+                                                         float* __restrict__ colsum, int write_f32) {
+  __shared__ float sm[8][33];
+  const int j = blockIdx.x * 32 + threadIdx.x;
+  const float s16 = scale16 ? *scale16 : 1.f;
+  float acc = 0.f;
+  if (j < cols) {
+    const float bj = bias ? bias[j] : 0.f;
+    for (int r = threadIdx.y; r < rows; r += 8) {
+      const long long e = (long long)r * cols + j;
+      float v = ugn_act_fwd(y[e] + bj, act, alpha);
+      if (mask) v *= mask[e];
+      if (write_f32) y[e] = v;
+      if (P16 > 0) {
+        u16 hi, lo;
+        ugn_split16(v * s16, f16, hi, lo);
+        out16[e] = hi;
+        if (P16 == 2) out16[plane + e] = lo;
+      }
+      acc += v;
+    }
+  }
+  if (colsum) {
+    sm[threadIdx.y][threadIdx.x] = acc;
+    __syncthreads();
+    if (threadIdx.y == 0 && j < cols) {
+      float t = 0.f;
+#pragma unroll
+      for (int q = 0; q < 8; ++q) t += sm[q][threadIdx.x];
+      colsum[j] = t;
+    }
+  }
+}
+int ew_dense_post(ugn_ctx* ctx, float* y, const float* bias, const float* mask, __nv_bfloat16* out16, int P16, int f16,
+                  const float* scale16, float* colsum, int write_f32, long long rows, int cols, int act, float alpha,
+                  cudaStream_t st) {
+  dim3 grid(ugn_cdiv(cols, 32)), block(32, 8);
+  const long long plane = rows * cols;
+  u16* o = reinterpret_cast<u16*>(out16);
+#define UGN_DP_ARGS y, bias, mask, o, plane, (int)rows, cols, act, alpha, f16, scale16, colsum, write_f32
+  if (!out16 || P16 == 0) dense_post_kernel<0><<<grid, block, 0, st>>>(UGN_DP_ARGS);
+  else if (P16 == 1) dense_post_kernel<1><<<grid, block, 0, st>>>(UGN_DP_ARGS);
+  else dense_post_kernel<2><<<grid, block, 0, st>>>(UGN_DP_ARGS);
+#undef UGN_DP_ARGS
   UGN_LAUNCHED(ctx);
   return UGN_OK;
 }

@@ -55,6 +55,14 @@ struct TcParams {
   int* err;
   int f16;                 // 16-bit operand format: 0 bf16, 1 fp16
   const float* oscale;     // device scalar multiplied into f32 outputs (1/grad-scale for backward ops), nullable
+  // fused GEMM epilogue extras (narrow-tile dense layers): 16-bit planes of the result for the next tensor-core
+  // consumer (out16: [planes][M][ldc]; the value converted is acc * o16scale, o16scale nullable = oscale-independent
+  // scaling of gradient operands), and per-column sums of the f32 result (bias gradient) by warp reduction + atomics
+  u16* out16;
+  long long out16_plane;
+  int out16_planes;
+  int out16_raw;           // 1: convert the RAW accumulator (x mask), not the oscale'd value (gradient operands stay scaled)
+  float* colsum;
   // patch-resident conv (tc_convp_kernel)
   int T, SW, RH, PR, KH, xorg, yorg, tiles_y, tmem_cols;
   int patch_chunk_bytes, patch_plane_bytes;
@@ -436,8 +444,59 @@ __global__ void __launch_bounds__(kThreads, 1) tc_kernel(const __grid_constant__
     if (MODE == MODE_GEMM) {
       const int m = m0 + r;
       const bool vec = (p.ldc & 3) == 0 && p.epi == EPI_F32 && !p.mask;
+      const bool fused = p.out16 != nullptr || p.colsum != nullptr;
       for (int c0 = 0; c0 < p.block_n; c0 += 16) {
         tmem_ld16(trow + c0, v);
+        if (fused) {
+          // narrow-tile dense layer: bias / activation / mask, f32 store (nullable), 16-bit planes, column sums.
+          // No early exit: the column sums are reduced across the warp.
+          const bool rv = ok && m < p.M;
+          float z[16];
+          __align__(16) u16 hi[16], lo[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const int n = n0 + c0 + i;
+            const long long o = (long long)m * p.ldc + n;
+            const bool cv = rv && n < p.N;
+            const float mk = (cv && p.mask) ? p.mask[o] : 1.f;
+            float zz = ugn_act_fwd(v[i] * os + ((p.bias && cv) ? p.bias[n] : 0.f), p.act, p.alpha) * mk;
+            z[i] = cv ? zz : 0.f;
+            if (p.out16) ugn_split16(p.out16_raw ? (cv ? v[i] * mk : 0.f) : z[i], p.f16, hi[i], lo[i]);
+          }
+          if (rv && n0 + c0 + 16 <= p.N && (p.ldc & 7) == 0) {
+            const long long o = (long long)m * p.ldc + n0 + c0;
+            if (p.out_f32) {
+#pragma unroll
+              for (int i = 0; i < 16; i += 4) *reinterpret_cast<float4*>(p.out_f32 + o + i) = make_float4(z[i], z[i + 1], z[i + 2], z[i + 3]);
+            }
+            if (p.out16) {
+              *reinterpret_cast<uint4*>(p.out16 + o) = *reinterpret_cast<const uint4*>(hi);
+              *reinterpret_cast<uint4*>(p.out16 + o + 8) = *reinterpret_cast<const uint4*>(hi + 8);
+              if (p.out16_planes == 2) {
+                *reinterpret_cast<uint4*>(p.out16 + p.out16_plane + o) = *reinterpret_cast<const uint4*>(lo);
+                *reinterpret_cast<uint4*>(p.out16 + p.out16_plane + o + 8) = *reinterpret_cast<const uint4*>(lo + 8);
+              }
+            }
+          } else if (rv) {
+            for (int i = 0; i < 16; ++i) {
+              const int n = n0 + c0 + i;
+              if (n >= p.N) break;
+              const long long o = (long long)m * p.ldc + n;
+              if (p.out_f32) p.out_f32[o] = z[i];
+              if (p.out16) { p.out16[o] = hi[i]; if (p.out16_planes == 2) p.out16[p.out16_plane + o] = lo[i]; }
+            }
+          }
+          if (p.colsum) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              float sacc = z[i];
+#pragma unroll
+              for (int d = 16; d > 0; d >>= 1) sacc += __shfl_xor_sync(0xffffffffu, sacc, d);
+              if (lane == 0 && n0 + c0 + i < p.N) atomicAdd(p.colsum + n0 + c0 + i, sacc);
+            }
+          }
+          continue;
+        }
         if (!ok || m >= p.M) continue;
         if (p.epi == EPI_F32_ATOMIC) {
           red_add_16(p.out_f32 + (long long)m * p.ldc + n0 + c0, v, os, p.N - (n0 + c0));
@@ -987,20 +1046,35 @@ static int gemm_operand(ugn_ctx* ctx, TcOp& op, const __nv_bfloat16* base, int P
     finish_op(op, 0, 128, 1, tile_rows, tile_rows);
   } else {          // [P][K][rows]
     UGN_CHECK(rows % 8 == 0, "MN-major operand needs its contiguous extent %% 8 == 0 (got %d)", rows);
+    UGN_CHECK(tile_rows >= 32, "MN-major operand tile must span >= 32 contiguous elements (64-byte swizzle rows)");
+    const int cw = tile_rows >= 64 ? 64 : 32;     // narrow tiles (dense layers at small batch): 64-byte swizzle rows
     dims[0] = rows; dims[1] = K; dims[2] = P; dims[3] = 1; dims[4] = 1;
     str[0] = (uint64_t)rows * 2; str[1] = (uint64_t)rows * K * 2; str[2] = str[1] * P; str[3] = str[2];
-    box[0] = 64; box[1] = BK;
-    finish_op(op, 1, 128, tile_rows / 64, BK, 0);
+    box[0] = cw; box[1] = BK;
+    finish_op(op, 1, cw * 2, tile_rows / cw, BK, 0);
+    return make_map(ctx, &op.map, base, dims, str, box, cw * 2);
   }
   return make_map(ctx, &op.map, base, dims, str, box, 128);
 }
 
+// Fused-epilogue request of a dense layer at small batch (M <= 128): NARROW output tiles (16 / 32 / 64 columns) give
+// ~sm_count tiles without split-K, so the result goes straight from TMEM through bias / activation / mask into its f32
+// and 16-bit destinations (no zero-fill, no red.add partial sums, no post pass), optionally with column sums.
+struct GemmFuse {
+  __nv_bfloat16* out16 = nullptr;   // [planes][M][ldc]
+  int out16_planes = 0;
+  int out16_raw = 0;                // convert acc * mask (scaled gradient operand) instead of the f32 result
+  float* colsum = nullptr;          // [N], zeroed here
+};
+
 int tc_gemm_ex(ugn_ctx* ctx, int P, int f16, int M, int N, int K, const __nv_bfloat16* A, int a_mn,
                const __nv_bfloat16* B, int b_mn, float* C, int ldc, int accumulate, const float* bias,
-               const float* mask, int act, float alpha, const float* oscale, cudaStream_t st) {
+               const float* mask, int act, float alpha, const float* oscale, cudaStream_t st,
+               const GemmFuse* fz = nullptr) {
   TcParams p{};
   p.mode = MODE_GEMM; p.f16 = f16; p.oscale = oscale;
   p.M = M; p.N = N; p.planes = P;
+  const bool narrow = fz != nullptr && M <= 128 && !accumulate && !getenv("UGN_NO_NARROW");
   if (P == 2 && ctx->gemm_npass) {       // forward dense layers: reduced pass count (ugn_set_fwd_passes)
     p.npass = ctx->gemm_npass;
     p.pa = (p.npass == 3 || p.npass == 4) ? 2 : 1;
@@ -1008,6 +1082,11 @@ int tc_gemm_ex(ugn_ctx* ctx, int P, int f16, int M, int N, int K, const __nv_bfl
   }
   p.block_n = N > 128 ? 256 : (N > 64 ? 128 : 64);
   if (P == 2 && p.block_n > 128 && !(p.npass == 1 || p.npass == 4)) p.block_n = 128;
+  if (narrow) {
+    // widest tile that still gives ~ one tile per SM; an MN-major B tile needs >= 32 contiguous columns
+    p.block_n = b_mn ? 32 : 16;
+    for (int bn : {64, 32}) if (ugn_cdiv(N, bn) * 10 >= ctx->sm_count * 8) { p.block_n = bn; break; }
+  }
   p.kslices = 4;
   const int BK = 64;
   int rc;
@@ -1016,9 +1095,17 @@ int tc_gemm_ex(ugn_ctx* ctx, int P, int f16, int M, int N, int K, const __nv_bfl
   p.ksteps_total = (K + BK - 1) / BK;
   int tiles = ugn_cdiv(M, 128) * ugn_cdiv(N, p.block_n);
   int split = 1;
-  if (!bias && !mask && act == UGN_ACT_LINEAR) {
+  if (!bias && !mask && act == UGN_ACT_LINEAR && !narrow) {
     split = std::max(1, std::min(ctx->sm_count / std::max(tiles, 1), p.ksteps_total / 4));
     split = std::min(split, 32);
+  }
+  if (fz) {
+    UGN_CHECK(narrow, "fused dense epilogue needs M <= 128 (got %d) and no accumulation", M);
+    p.out16 = reinterpret_cast<u16*>(fz->out16); p.out16_planes = fz->out16_planes; p.out16_raw = fz->out16_raw;
+    p.out16_plane = (long long)M * ldc;
+    p.colsum = fz->colsum;
+    if (p.colsum) UGN_CUDA(cudaMemsetAsync(p.colsum, 0, sizeof(float) * (size_t)N, st));
+    UGN_CHECK(p.out16 || p.colsum || C, "fused dense epilogue without any output");
   }
   p.ksplit = split;
   p.epi = (split > 1 || accumulate) ? EPI_F32_ATOMIC : EPI_F32;
@@ -1442,32 +1529,63 @@ int tc_conv_wgrad(ugn_ctx* ctx, const ConvGeom& g, int P, int f16, const __nv_bf
 // ---- dense ------------------------------------------------------------------------------
 int ew_bias_act_mask(ugn_ctx* ctx, float* y, const float* bias, const float* mask, long long rows, int cols,
                      int act, float alpha, cudaStream_t st);
+int ew_split(ugn_ctx*, const float*, __nv_bfloat16*, int, int, long long, cudaStream_t);
+int ew_dense_post(ugn_ctx* ctx, float* y, const float* bias, const float* mask, __nv_bfloat16* out16, int P16, int f16,
+                  const float* scale16, float* colsum, int write_f32, long long rows, int cols, int act, float alpha,
+                  cudaStream_t st);
 
 int tc_linear_fwd(ugn_ctx* ctx, int P, int f16, int B, int N, int K, const __nv_bfloat16* x, const __nv_bfloat16* w,
-                  const float* bias, const float* mask, float* y, int act, float alpha, cudaStream_t st) {
-  // Small batch: the layer is a weight-streaming (HBM-bound) GEMM with a single M tile, so spread K over
-  // the SMs (split-K, red.add into zeroed y) and apply bias / activation / dropout mask in a tiny post pass.
-  int tiles = ugn_cdiv(B, 128) * ugn_cdiv(N, P == 2 ? 128 : 256);
-  ctx->gemm_npass = ctx->fwd_dense_pass;
+                  const float* bias, const float* mask, float* y, int act, float alpha, cudaStream_t st,
+                  __nv_bfloat16* y16, int P16) {
   int rc;
+  ctx->gemm_npass = ctx->fwd_dense_pass;
+  if (B <= 128 && N % 16 == 0 && getenv("UGN_NARROW")) {
+    // EXPERIMENT (opt-in, measured slower: 0.36 vs 0.23 ms/step of dense forward at B = 96): narrow N tiles spread the
+    // weight stream over the SMs WITHOUT split-K and the whole epilogue leaves the accumulator in one pass -- but every
+    // CTA then re-reads the full 128-row activation tile per K step (32 KB next to 8 KB of weights), and the per-SM TMA
+    // ingest, not HBM, bounds the kernel.  Default below: 128-wide tiles + split-K + ONE fused post pass.
+    GemmFuse fz;
+    fz.out16 = y16; fz.out16_planes = P16;
+    rc = tc_gemm_ex(ctx, P, f16, B, N, K, x, 0, w, 0, y, N, 0, bias, mask, act, alpha, nullptr, st, &fz);
+    ctx->gemm_npass = 0;
+    return rc;
+  }
+  int tiles = ugn_cdiv(B, 128) * ugn_cdiv(N, P == 2 ? 128 : 256);
   if (tiles * 2 <= ctx->sm_count && K >= 512) {
     rc = tc_gemm_ex(ctx, P, f16, B, N, K, x, 0, w, 0, y, N, 0, nullptr, nullptr, UGN_ACT_LINEAR, 0.f, nullptr, st);
     ctx->gemm_npass = 0;
     if (rc != UGN_OK) return rc;
-    if (bias || mask || act != UGN_ACT_LINEAR) return ew_bias_act_mask(ctx, y, bias, mask, B, N, act, alpha, st);
+    // split-K partial sums -> ONE post pass: bias + activation + dropout mask + f32 result + its 16-bit planes
+    if (bias || mask || act != UGN_ACT_LINEAR || y16)
+      return ew_dense_post(ctx, y, bias, mask, y16, P16, f16, nullptr, nullptr, 1, B, N, act, alpha, st);
     return UGN_OK;
+  } else {
+    rc = tc_gemm_ex(ctx, P, f16, B, N, K, x, 0, w, 0, y, N, 0, bias, mask, act, alpha, nullptr, st);
+    ctx->gemm_npass = 0;
   }
-  rc = tc_gemm_ex(ctx, P, f16, B, N, K, x, 0, w, 0, y, N, 0, bias, mask, act, alpha, nullptr, st);
-  ctx->gemm_npass = 0;
-  return rc;
+  if (rc != UGN_OK || !y16) return rc;
+  return ew_split(ctx, y, y16, P16, f16, (long long)B * N, st);
 }
 
 int tc_linear_bwd(ugn_ctx* ctx, int P, int f16, int B, int N, int K, const __nv_bfloat16* x, const __nv_bfloat16* w,
-                  const __nv_bfloat16* dz, float* dx, float* dw, float* db, cudaStream_t st) {
+                  const __nv_bfloat16* dz, float* dx, float* dw, float* db, cudaStream_t st, const float* dx_mask,
+                  __nv_bfloat16* dx16, int P16, float* dbx) {
   int rc;
   const float* os = ctx->gscale ? ctx->gscale + 1 : nullptr;   // dz is a scaled gradient operand
+  const bool want_dx = dx || dx16 || dbx;
   // dx[B,K] = dz[B,N] . w[N,K]      : A = dz K-major (K'=N), B = w as MN-major [K'=N rows][K contiguous]
-  if (dx && (rc = tc_gemm_ex(ctx, P, f16, B, K, N, dz, 0, w, 1, dx, K, 0, nullptr, nullptr, 0, 0.f, os, st)) != UGN_OK) return rc;
+  if (want_dx && B <= 128 && K % 32 == 0 && getenv("UGN_NARROW")) {      // (experiment, see tc_linear_fwd)
+    GemmFuse fz;
+    fz.out16 = dx16; fz.out16_planes = P16; fz.out16_raw = 1; fz.colsum = dbx;
+    if ((rc = tc_gemm_ex(ctx, P, f16, B, K, N, dz, 0, w, 1, dx, K, 0, nullptr, dx_mask, 0, 0.f, os, st, &fz)) != UGN_OK) return rc;
+  } else if (want_dx) {
+    UGN_CHECK(dx, "linear_bwd: dx (f32 [B,K], may be scratch) is required: the split-K partial sums land there");
+    if ((rc = tc_gemm_ex(ctx, P, f16, B, K, N, dz, 0, w, 1, dx, K, 0, nullptr, nullptr, 0, 0.f, os, st)) != UGN_OK) return rc;
+    // ONE post pass over dx: x dropout mask of the layer below -> its 16-bit gradient operand (re-scaled by the
+    // gradient scale) + its bias gradient; dx itself stays the unmasked f32 gradient
+    if (dx_mask || dx16 || dbx)
+      if ((rc = ew_dense_post(ctx, dx, nullptr, dx_mask, dx16, P16, f16, ctx->gscale, dbx, 0, B, K, UGN_ACT_LINEAR, 0.f, st)) != UGN_OK) return rc;
+  }
   // dw[N,K] = dz^T . x             : A = dz MN-major [K'=B rows][N contiguous], B = x MN-major [B rows][K contiguous]
   if (dw && (rc = tc_gemm_ex(ctx, P, f16, N, K, B, dz, 1, x, 1, dw, K, 0, nullptr, nullptr, 0, 0.f, os, st)) != UGN_OK) return rc;
   if (db) return simt_colsum_bf16(ctx, dz, P, f16, B, N, db, st);

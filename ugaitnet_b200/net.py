@@ -285,10 +285,17 @@ class UGaitEngine:
         self.seg_off = torch.tensor([s.off for s in segs] + [off], dtype=torch.int64, device=d)
         self.seg_l2 = torch.tensor([s.l2 for s in segs], dtype=torch.float32, device=d)
         self.reg_out = torch.zeros(1, device=d)
+        self.gstage = None
         if self._symm:                 # fused data-parallel exchange: the scalar is summed over the ranks by peer atomics
             r = self._new_arena(64, exchanged=True)
             if len(self._symm) > 2:
                 self.reg_out = r[:1]
+            # staging buffer of PUSHED dense-layer gradients: slot p = rank p's part of this rank's arena slice
+            self.slice_len = ((off // 4 + self.world - 1) // self.world) * 4
+            if os.environ.get("UGN_DP_PUSH", "1") == "1" and len(self._symm) > 2:
+                gs = self._new_arena(self.world * self.slice_len, exchanged=True)
+                if len(self._symm) > 3:
+                    self.gstage = gs
         self.lr_dev = torch.zeros(1, device=d)
         self._lr_host = torch.zeros(1).pin_memory()
         self.R = {k: TRef(t) for k, t in dict(w=self.w, g=self.g, m=self.m, v=self.v, seg_off=self.seg_off,
@@ -311,7 +318,7 @@ class UGaitEngine:
                 name = f"{bn}/conv{li}/w"
                 shape = (L["co"], L["k"], L["k"], L["cp"])
                 if self.P:
-                    self.cw[name] = torch.zeros((self.P,) + shape, dtype=self.dt16, device=d)
+                    self.cw[name] = shape         # allocated below (one arena for every 16-bit compute copy)
                 elif L["cp"] != L["cin"]:
                     self.cw[name] = torch.zeros(shape, device=d)
                 else:
@@ -319,9 +326,33 @@ class UGaitEngine:
             for nm in ("dense", "ofCode"):
                 name = f"{bn}/{nm}/w"
                 if self.P:
-                    self.cw[name] = torch.zeros((self.P,) + self.segs[name].shape, dtype=self.dt16, device=d)
+                    self.cw[name] = self.segs[name].shape
                 else:
                     self.cw[name] = self.pw[name]
+        self.cw_arena = None
+        if self.P:
+            numel = lambda shp: int(torch.tensor(shp).prod())
+            dense_names = [k for k, t in self.cw.items() if isinstance(t, tuple)]
+            sizes = {k: round_up(self.P * numel(self.cw[k]), 64) for k in dense_names}
+            total = sum(sizes.values())
+            esz = 2
+            arena = None
+            if self._symm and os.environ.get("UGN_DP_CW16", "1") == "1":
+                # fused data-parallel exchange: the owner of an arena slice writes the 16-bit planes of its updated dense
+                # weights into every rank's compute copies (ugn_dp_optim_step: cw_peers) -- they must be peer-mapped
+                nsym = len(self._symm)
+                a32 = self._new_arena((total * esz + 3) // 4, exchanged=True)
+                if len(self._symm) > nsym:
+                    arena = a32.view(self.dt16)
+                    self.cw_arena = arena
+                    self._cw_symm = self._symm[-1][1]
+            if arena is None:
+                arena = torch.zeros(total, dtype=self.dt16, device=d)
+            o = 0
+            for k in dense_names:
+                shp = self.cw[k]
+                self.cw[k] = arena[o:o + self.P * numel(shp)].view((self.P,) + tuple(shp))
+                o += sizes[k]
         for k, t in self.cw.items():
             self.Rcw[k] = TRef(t)
         # optimiser-fused refresh of the unpadded (dense) compute copies: {address, numel} per segment
@@ -341,9 +372,24 @@ class UGaitEngine:
     def segs_off(segs, name):
         return next(s.off for s in segs if s.name == name)
 
+    def sync_master_weights(self):
+        """Fused data-parallel exchange with exchanged 16-bit copies: only the OWNER of an arena slice holds the current
+        f32 master of the dense weights in it.  Before anything reads the f32 arena as a whole (export / save /
+        re-pack / checks) every slice is broadcast from its owner."""
+        if not getattr(self, "_w_stale", False):
+            return
+        sl = self.slice_len
+        for r in range(self.world):
+            a, b = r * sl, min((r + 1) * sl, self.n_arena)
+            if a < b:
+                torch.distributed.broadcast(self.w[a:b], src=torch.distributed.get_global_rank(self.pg, r), group=self.pg)
+        self._w_stale = False
+
     def repack_weights(self, after_optim: bool = False):
         """master f32 -> padded / 16-bit compute copies.  After an optimiser step only the padded (conv)
         copies are left to do: the dense ones were re-split inside the optimiser kernel."""
+        if not after_optim:
+            self.sync_master_weights()
         for name, t in self.cw.items():
             if after_optim and name in self._fused_pack:
                 continue
@@ -393,6 +439,7 @@ class UGaitEngine:
         return out
 
     def export_params(self):
+        self.sync_master_weights()
         return self._export(self.pw)
 
     def export_grads(self):
@@ -666,11 +713,21 @@ class UGaitEngine:
 
     def _replay_segments(self, segs):
         self._works = []
-        for g, keys in segs:
+        timing = getattr(self, "_dp_timing", None)
+        if timing is None and os.environ.get("UGN_DP_TIMING"):
+            timing = self._dp_timing = []
+        if timing is not None:
+            evs = [torch.cuda.Event(enable_timing=True) for _ in range(2 * len(segs) + 2)]
+            evs[0].record()
+        for si, (g, keys) in enumerate(segs):
             g.replay()
+            if timing is not None:
+                evs[2 * si + 1].record()
             for key in keys:
                 if key == "fused":
                     self._dp_fused_exchange()
+                    if timing is not None:
+                        evs[2 * si + 2].record()
                     continue
                 if key == "wait":
                     if self.dp_reduce == "single":
@@ -682,6 +739,26 @@ class UGaitEngine:
                 elif self.world > 1:
                     lo, hi = self.buckets[key]
                     self._works.append(torch.distributed.all_reduce(self.g[lo:hi], group=self.pg, async_op=True))
+        if timing is not None:
+            evs[-1].record()
+            timing.append(evs)
+
+    def dp_timing_summary(self):
+        """Development aid (UGN_DP_TIMING=1): mean ms of [segment 1 | exchange | segment 2] over the recorded steps."""
+        t = getattr(self, "_dp_timing", None)
+        if not t:
+            return None
+        torch.cuda.synchronize()
+        rows = []
+        for evs in t[5:]:
+            try:
+                rows.append([evs[0].elapsed_time(evs[1]), evs[1].elapsed_time(evs[2]), evs[2].elapsed_time(evs[3])])
+            except Exception:
+                pass
+        if not rows:
+            return None
+        m = torch.tensor(rows).mean(0).tolist()
+        return {"fwd_bwd_ms": m[0], "exchange_ms": m[1], "repack_ms": m[2], "steps": len(rows)}
 
     def _losses_and_backward(self, p: "_Plan", sig: TRef, feat: TRef):
         cfg, h, st = self.cfg, self.ctx.h, stream_ptr()
@@ -809,13 +886,43 @@ class UGaitEngine:
                     self._reduce_bucket(key)
             return
         streams = self._fork() if self._branches_concurrent() else None
+        push = dp and self.dp_reduce == "fused" and self.gstage is not None and self.world > 1
         for m in range(cfg.nmods):
             with torch.cuda.stream(streams[m] if streams else torch.cuda.current_stream()):
                 self._backward_branch_fc(p, m)
                 if self._early_active:
                     self._optim_early(m, torch.cuda.current_stream())
+                if push:
+                    self._push_dense_grads(m, torch.cuda.current_stream())
                 self._backward_branch_conv(p, m)
         self._join(streams)
+        if push:                           # the pushes must have left before this rank enters the exchange barrier
+            ev = torch.cuda.Event()
+            ev.record(self._push_stream)
+            torch.cuda.current_stream().wait_event(ev)
+
+    def _push_dense_grads(self, m: int, branch_stream):
+        """Copy-engine push of branch m's dense-layer gradients (complete right after its two dense backward GEMMs) to
+        the ranks that own those arena slices, on a side stream underneath the convolution backward: 92 % of the
+        reduce-scatter bytes leave the critical path (the exchange kernel then sums them from its own HBM)."""
+        if getattr(self, "_push_stream", None) is None:
+            self._push_stream = torch.cuda.Stream(device=self.dev)
+            hs = self._symm[3][1]
+            n = self.world * self.slice_len
+            self._stage_peers = [hs.get_buffer(r, (n,), torch.float32) for r in range(self.world)]
+        rank, sl = torch.distributed.get_rank(self.pg), self.slice_len
+        lo, hi = self.buckets[(m, "fc")]
+        ev = torch.cuda.Event()
+        ev.record(branch_stream)
+        self._push_stream.wait_event(ev)
+        with torch.cuda.stream(self._push_stream):
+            for r in range(self.world):
+                if r == rank:
+                    continue
+                a, b = max(lo, r * sl), min(hi, (r + 1) * sl, self.n_arena)
+                if a < b:
+                    dst = self._stage_peers[r][rank * sl + (a - r * sl): rank * sl + (b - r * sl)]
+                    dst.copy_(self.g[a:b], non_blocking=True)
 
     def _branches_concurrent(self) -> bool:
         """Branches on concurrent streams from start to end: always on one GPU; with data parallelism only when
@@ -837,6 +944,18 @@ class UGaitEngine:
             check(lib.ugn_act_mask_bwd(h, R["dout"].ptr, None, None, None, R["dout16"].ptr, ACT_LINEAR, 0.0, st))
         # tensor-core mode: the bias gradient comes from the f32 dout, not from its rounded 16-bit copy (the rows of
         # dL/dsignature cancel under the triplet loss: summing the rounded operand leaves mostly rounding noise)
+        if self.P and p.B <= 128:
+            # ofCode backward with the fused input-gradient post pass: ONE kernel applies the dropout mask to the split-K
+            # sums, writes the dense layer's 16-bit gradient operand and its bias gradient (was: mask/convert + column sums)
+            check(lib.ugn_linear_bwd_ex(h, R["h1_16"].ptr, self.Rcw[f"{bn}/ofCode/w"].ptr, R["dout16"].ptr, R["dh1"].ptr,
+                                        R["mask"].ptr if use_mask else None, R["dz1_16"].ptr,
+                                        self.Rg[f"{bn}/dense/b"].ptr, self.Rg[f"{bn}/ofCode/w"].ptr, None, st))
+            check(lib.ugn_colsum(h, R["dout"].ptr, self.Rg[f"{bn}/ofCode/b"].ptr, st))
+            check(lib.ugn_linear_bwd(h, R["flat"].ptr, self.Rcw[f"{bn}/dense/w"].ptr, R["dz1_16"].ptr, R["dflat"].ptr,
+                                     self.Rg[f"{bn}/dense/w"].ptr, None, st))
+            if self.dp_reduce == "bucketed":
+                self._reduce_bucket((m, "fc"))
+            return
         check(lib.ugn_linear_bwd(h, (R["h1_16"] if self.P else R["h1"]).ptr, self.Rcw[f"{bn}/ofCode/w"].ptr,
                                  (R["dout16"] if self.P else R["dout"]).ptr, R["dh1"].ptr,
                                  self.Rg[f"{bn}/ofCode/w"].ptr, None if self.P else self.Rg[f"{bn}/ofCode/b"].ptr, st))
@@ -970,7 +1089,8 @@ class UGaitEngine:
                 self._cut("fused")
             else:
                 self._dp_fused_exchange()
-            self.repack_weights()
+            # exchanged 16-bit copies: only the padded conv copies are left to re-pack locally
+            self.repack_weights(after_optim=getattr(self, "_cw_exchange", False) and self.world > 1)
             p.loss_pack[4:5].copy_(self.reg_out, non_blocking=True)
             return
         if do_optim:
@@ -1005,6 +1125,12 @@ class UGaitEngine:
             if len(self._symm) > 2:
                 hr = self._symm[2][1]
                 self._reg_tab = (ctypes.c_int64 * n)(*[int(p) for p in hr.buffer_ptrs])
+            self._staged_ranges, self._n_staged = None, 0
+            if self.gstage is not None:
+                self.R["gstage"] = TRef(self.gstage)
+                rng = [self.buckets[(m, "fc")] for m in range(self.cfg.nmods)]
+                flat = [int(x) for ab in rng for x in ab]
+                self._staged_ranges, self._n_staged = (ctypes.c_int64 * len(flat))(*flat), len(rng)
             # NVSwitch multicast mappings (multimem.ld_reduce / multimem.st) when the fabric offers them
             # measured: N = 2 unicast 4.02 ms vs multicast 4.32 ms per step, N = 8 unicast 4.53 vs multicast 4.29 -- the
             # unicast path moves 2(N-1)/N arenas per GPU and direction, the multicast path (1 + 1/N): on from N = 4
@@ -1016,6 +1142,19 @@ class UGaitEngine:
                 except Exception:
                     mc = (0, 0)
             self._mc = mc if all(mc) else (0, 0)
+            self._cw_tab, self._cw_mc = None, 0
+            if getattr(self, "cw_arena", None) is not None:
+                self._cw_tab = (ctypes.c_int64 * n)(*[int(p) for p in self._cw_symm.buffer_ptrs])
+                if all(self._mc):
+                    try:
+                        self._cw_mc = int(self._cw_symm.multicast_ptr or 0)
+                    except Exception:
+                        self._cw_mc = 0
+                    if not self._cw_mc:
+                        self._cw_tab = None          # multicast arenas but no multicast copy arena: keep the f32 path
+            self._cw_exchange = self._cw_tab is not None and getattr(self, "pack_table", None) is not None
+            if not self._cw_exchange:
+                self._cw_tab = None
         gp, wp = self._peer_tabs
         adam = self.optimizer in ("adam", "amsgrad", "adamw")
         if self.optimizer == "amsgrad" and "vhat" not in R:
@@ -1031,7 +1170,13 @@ class UGaitEngine:
                                     R["vhat"].ptr if self.optimizer == "amsgrad" else None,
                                     self.decoupled_wd if self.optimizer == "adamw" else 0.0, R["seg_off"].ptr,
                                     R["seg_l2"].ptr, self.beta1 if adam else self.momentum, self.beta2, self.eps,
-                                    R["reg_out"].ptr, self._reg_tab, R["lr_dev"].ptr, st))
+                                    R["reg_out"].ptr, self._reg_tab, R["lr_dev"].ptr,
+                                    self.R["gstage"].ptr if self.gstage is not None else None,
+                                    self._staged_ranges, self._n_staged,
+                                    R["pack_table"].ptr if self._cw_tab is not None else None, max(self.P, 1),
+                                    int(self.dt16 is torch.float16), self._cw_tab, self._cw_mc, st))
+        if self._cw_tab is not None:
+            self._w_stale = True
         hw.barrier(channel=0)                   # every rank's slice of the new weights (and of the regulariser sum) has landed
         if self._reg_tab is None:
             torch.distributed.all_reduce(self.reg_out, group=self.pg)  # fallback: sum of the slice values (4 bytes)
