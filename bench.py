@@ -243,6 +243,7 @@ def main():
     ap.add_argument("--no-configs", action="store_true", help="skip the cfg1 / cfg3 / cfg4 legs")
     ap.add_argument("--lite", action="store_true", help="timed steps only (for runs under ncu)")
     ap.add_argument("--knn-only", action="store_true", help="only the open-world k-NN leg (development aid)")
+    ap.add_argument("--knn-d", type=int, default=256, help="descriptor width of the --knn-only leg")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
 
@@ -261,7 +262,7 @@ def main():
         pg = torch.distributed.group.WORLD
 
     if args.knn_only:
-        kn = knn_leg(peaks(), rank, world, pg)
+        kn = knn_leg(peaks(), rank, world, pg, D=args.knn_d)
         if rank == 0:
             print(json.dumps({"knn": kn}), flush=True)
         if world > 1:

@@ -152,7 +152,7 @@ class KNeighborsClassifier:
 
     def flagged_queries(self) -> int:
         """How many queries of the last search failed the containment proof and were recomputed exactly."""
-        return 0 if getattr(self, "_flags", None) is None else int(self._flags.sum())
+        return 0 if getattr(self, "_flags", None) is None else int((self._flags != 0).sum())
 
     def _merge_into(self, w):
         from ._ffi import check, lib, stream_ptr
