@@ -210,6 +210,13 @@ int64_t ugn_triplet_workspace_bytes(int n, int B);
 int ugn_triplet_all(ugn_ctx*, const ugn_tensor* emb, const ugn_tensor* labels, float margin,
                     float scale, ugn_tensor* out, ugn_tensor* demb, ugn_tensor* workspace,
                     void* stream);
+/* The same with the B x B Gram matrix as a tensor-core GEMM (north_star; nets/triplet_loss_all.py:70-77): emb16 = the
+ * 16-bit hi/lo planes [2,B,d] of emb (ugn_fuse_fwd writes them next to the f32 signature; d % 64 == 0, one part).
+ * tcgen05, three passes (~fp32 products), fp32 accumulation, no split-K: one accumulation order per element, identical
+ * rows keep an exactly zero distance.  Hinge, count and the analytic backward are shared with ugn_triplet_all. */
+int ugn_triplet_all_tc(ugn_ctx*, const ugn_tensor* emb, const ugn_tensor* emb16, const ugn_tensor* labels, float margin,
+                       float scale, ugn_tensor* out, ugn_tensor* demb, ugn_tensor* workspace, void* stream);
+
 
 /* ---- a8/a9: regulariser + optimiser --------------------------------------------------
  * One fused multi-tensor step over a FLAT parameter arena: for segment s covering

@@ -449,3 +449,42 @@ def test_device_side_augmentation_equals_host_restatement():
     got = out[..., :C].permute(0, 3, 1, 2).cpu().numpy()
     assert np.array_equal(got, ref)
     assert float(out[..., C:].abs().max()) == 0.0
+
+
+@pytest.mark.parametrize("B,d,dt", [(96, 2048, torch.float16), (120, 256, torch.bfloat16), (512, 2048, torch.float16)])
+def test_triplet_gram_on_tensor_cores(ctx, B, d, dt):
+    """ugn_triplet_all_tc (north_star: the B x B pairwise-distance matrix as a tensor-core GEMM): loss, active count and
+    gradient against the fp64 oracle, with duplicated rows (an expanded batch repeats sequences) that must keep an
+    exactly zero distance, and against the FFMA-Gram kernel."""
+    from ugaitnet_b200 import ops
+    from ugaitnet_b200._ffi import TRef, check, lib, stream_ptr
+    rng = np.random.default_rng(B)
+    per = 4 if B != 512 else 2
+    lab = np.repeat(np.arange(B // per), per).astype(np.int32)
+    e = rng.normal(size=(B, d)).astype(np.float32)
+    e[1] = e[0]                                            # identical rows with the same label
+    e[5] = e[4] + 1e-4 * rng.normal(size=d)                # and a near-duplicate
+    e /= np.linalg.norm(e, axis=1, keepdims=True)
+    x = torch.tensor(e).cuda()
+    hi = x.to(dt)
+    x16 = torch.stack([hi, (x - hi.float()).to(dt)]).contiguous()
+    out, de = torch.zeros(2, device="cuda"), torch.zeros(B, d, device="cuda")
+    ws = torch.zeros(ops.triplet_workspace_bytes(1, B) // 4 + 16, device="cuda")
+    R = [TRef(t) for t in (x, x16, torch.tensor(lab).cuda(), out, de, ws)]
+    check(lib.ugn_triplet_all_tc(ctx.h, R[0].ptr, R[1].ptr, R[2].ptr, 0.2, 1.0, R[3].ptr, R[4].ptr, R[5].ptr, stream_ptr()))
+    ctx.check()
+    e64 = torch.tensor(e, dtype=torch.float64, requires_grad=True)
+    loss, cnt = O.triplet_loss_all(torch.tensor(lab), e64, 0.2)
+    loss.backward()
+    assert float(out[0]) == pytest.approx(float(loss), rel=1e-4 if dt is torch.float16 else 1e-3)
+    assert abs(float(out[1]) - float(cnt.sum())) <= max(2, 1e-4 * float(cnt.sum()))
+    assert rel(de, e64.grad) < (2e-3 if dt is torch.float16 else 1e-2)
+    out2, de2 = _run_triplet(ctx, lab.astype(np.float32), e, 0.2)          # FFMA Gram
+    assert float(out[0]) == pytest.approx(float(out2[0]), rel=1e-4 if dt is torch.float16 else 1e-3)
+    # no split-K: one accumulation order per element, so identical rows are at distance EXACTLY 0 (no gradient flows
+    # between rows 0 and 1) and the diagonal is exactly 0; (a,b) and (b,a) add the hi*lo and lo*hi passes in swapped
+    # order and agree to fp32 rounding
+    accb, x2b = 256, (B * 4 + 255) // 256 * 256
+    D = ws[(accb + x2b) // 4:(accb + x2b) // 4 + B * B].view(B, B)
+    assert float(D[0, 1]) == 0.0 and float(D[1, 0]) == 0.0 and float(D.diagonal().abs().max()) == 0.0
+    assert float((D - D.t()).abs().max()) <= 1e-5

@@ -1095,7 +1095,7 @@ int tc_gemm_ex(ugn_ctx* ctx, int P, int f16, int M, int N, int K, const __nv_bfl
   p.ksteps_total = (K + BK - 1) / BK;
   int tiles = ugn_cdiv(M, 128) * ugn_cdiv(N, p.block_n);
   int split = 1;
-  if (!bias && !mask && act == UGN_ACT_LINEAR && !narrow) {
+  if (!bias && !mask && act == UGN_ACT_LINEAR && !narrow && !ctx->gemm_nosplit) {
     split = std::max(1, std::min(ctx->sm_count / std::max(tiles, 1), p.ksteps_total / 4));
     split = std::min(split, 32);
   }
@@ -1113,6 +1113,15 @@ int tc_gemm_ex(ugn_ctx* ctx, int P, int f16, int M, int N, int K, const __nv_bfl
   if (split > 1 && !accumulate) UGN_CUDA(cudaMemsetAsync(C, 0, sizeof(float) * (size_t)M * ldc, st));
   dim3 grid(ugn_cdiv(M, 128), ugn_cdiv(N, p.block_n), split);
   return launch<MODE_GEMM>(ctx, p, grid, st);
+}
+
+// G[B,B] = X X^T from the hi/lo planes X16 [2][B][d]: three-pass split GEMM, fp32 accumulation in TMEM, NO split-K (one
+// deterministic accumulation order per output element: the diagonal is consistent with the matrix)
+int tc_gram(ugn_ctx* ctx, int f16, int B, int d, const __nv_bfloat16* X16, float* G, cudaStream_t st) {
+  ctx->gemm_nosplit = 1;
+  int rc = tc_gemm_ex(ctx, 2, f16, B, B, d, X16, 0, X16, 0, G, B, 0, nullptr, nullptr, UGN_ACT_LINEAR, 0.f, nullptr, st);
+  ctx->gemm_nosplit = 0;
+  return rc;
 }
 
 int tc_gemm(ugn_ctx* ctx, int P, int f16, int M, int N, int K, const __nv_bfloat16* A, int a_mn,

@@ -149,9 +149,31 @@ extern "C" int64_t ugn_triplet_workspace_bytes(int n, int B) {
   return accb + x2b + 2 * (int64_t)n * B * B * 4;
 }
 
+int tc_gram(ugn_ctx* ctx, int f16, int B, int d, const __nv_bfloat16* X16, float* G, cudaStream_t st);
+
+static int triplet_common(ugn_ctx* ctx, const ugn_tensor* emb, const ugn_tensor* emb16, const ugn_tensor* labels,
+                          float margin, float scale, ugn_tensor* out, ugn_tensor* demb, ugn_tensor* workspace,
+                          void* stream);
 extern "C" int ugn_triplet_all(ugn_ctx* ctx, const ugn_tensor* emb, const ugn_tensor* labels,
                                float margin, float scale, ugn_tensor* out, ugn_tensor* demb,
                                ugn_tensor* workspace, void* stream) {
+  return triplet_common(ctx, emb, nullptr, labels, margin, scale, out, demb, workspace, stream);
+}
+// The same loss with the B x B Gram matrix on the tensor cores: emb16 = fp16 | bf16 hi/lo planes [2,B,d] of emb (written by
+// ugn_fuse_fwd next to the f32 signature), one tcgen05 GEMM with three passes (hi*hi + hi*lo + lo*hi, ~fp32 products,
+// fp32 accumulation in TMEM) and NO split-K, so that every element has ONE accumulation order: the diagonal
+// the squared norms are read from is consistent with the matrix and identical rows give an exactly zero distance, as in
+// the FFMA path.
+extern "C" int ugn_triplet_all_tc(ugn_ctx* ctx, const ugn_tensor* emb, const ugn_tensor* emb16, const ugn_tensor* labels,
+                                  float margin, float scale, ugn_tensor* out, ugn_tensor* demb, ugn_tensor* workspace,
+                                  void* stream) {
+  UGN_CHECK(emb16, "ugn_triplet_all_tc: emb16 required");
+  return triplet_common(ctx, emb, emb16, labels, margin, scale, out, demb, workspace, stream);
+}
+
+static int triplet_common(ugn_ctx* ctx, const ugn_tensor* emb, const ugn_tensor* emb16, const ugn_tensor* labels,
+                          float margin, float scale, ugn_tensor* out, ugn_tensor* demb, ugn_tensor* workspace,
+                          void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
   UGN_CHECK(ctx && emb && labels && out && workspace, "ugn_triplet_all: null argument");
   UGN_TENSOR(emb, DT_F32, 2, 3);
@@ -193,7 +215,16 @@ extern "C" int ugn_triplet_all(ugn_ctx* ctx, const ugn_tensor* emb, const ugn_te
     p.epi = EPI_ATOMIC;
     UGN_CUDA(cudaMemsetAsync(D, 0, sizeof(float) * (size_t)B * B, st));
   }
-  int rc = simt_gemm_launch(ctx, p, st);
+  int rc;
+  if (emb16) {
+    UGN_TENSOR(emb16, DT_BAD, 3, 3);
+    UGN_CHECK(n == 1 && emb16->shape[0] == 2 && emb16->shape[1] == B && emb16->shape[2] == d && d % 64 == 0,
+              "triplet_all_tc: emb16 must be 16-bit [2,B,d] of a single-part embedding with d %% 64 == 0");
+    UGN_CHECK(ugn_dtype(emb16) == DT_F16 || ugn_dtype(emb16) == DT_BF16, "triplet_all_tc: emb16 must be f16 or bf16");
+    rc = tc_gram(ctx, ugn_dtype(emb16) == DT_F16, B, d, ugn_ptr<__nv_bfloat16>(emb16), D, st);
+  } else {
+    rc = simt_gemm_launch(ctx, p, st);
+  }
   if (rc != UGN_OK) return rc;
   trip_diag_kernel<<<dim3(ugn_cdiv(B, 128), n), 128, 0, st>>>(D, x2, B);
   UGN_LAUNCHED(ctx);

@@ -543,8 +543,8 @@ class UGaitEngine:
                     check(lib.ugn_fuse_fwd(h, 1, b.nrm_in, p.one_ptrs, b.R["outn"].ptr, None, b.R["nwin"].ptr,
                                            b.R["ninv"].ptr, 0, 1, st))
             check(lib.ugn_fuse_fwd(h, cfg.nmods, p.brn_ptrs if cfg.normbfmerge else p.br_ptrs, p.flag_ptrs,
-                                   p.R["sig"].ptr, None, p.R["winner"].ptr, p.R["inv_norm"].ptr, cfg.merge,
-                                   0 if self.post2 else 1, st))
+                                   p.R["sig"].ptr, p.R["sig16"].ptr if p.tc_gram else None, p.R["winner"].ptr,
+                                   p.R["inv_norm"].ptr, cfg.merge, 0 if self.post2 else 1, st))
             sig = p.R["sig"]
             if self.aux:
                 # auxiliary classifiers on the GATED branch outputs: gate = the fusion kernel on one modality without
@@ -765,8 +765,12 @@ class UGaitEngine:
         B = p.B
         self._works = []
         # triplet: demb = wver * dL/dsig
-        check(lib.ugn_triplet_all(h, sig.ptr, p.R["labels"].ptr, cfg.margin, cfg.wver, p.R["trip_out"].ptr,
-                                  (p.R["dcodeN"] if self.post2 else p.R["dsig"]).ptr, p.R["trip_ws"].ptr, st))
+        if p.tc_gram:      # B x B Gram matrix on the tensor cores from the hi/lo planes the fusion kernel wrote (north_star)
+            check(lib.ugn_triplet_all_tc(h, sig.ptr, p.R["sig16"].ptr, p.R["labels"].ptr, cfg.margin, cfg.wver,
+                                         p.R["trip_out"].ptr, p.R["dsig"].ptr, p.R["trip_ws"].ptr, st))
+        else:
+            check(lib.ugn_triplet_all(h, sig.ptr, p.R["labels"].ptr, cfg.margin, cfg.wver, p.R["trip_out"].ptr,
+                                      (p.R["dcodeN"] if self.post2 else p.R["dsig"]).ptr, p.R["trip_ws"].ptr, st))
         if self.post2 and cfg.nclasses == 0:
             self._post2_backward(p, None)
         if cfg.nclasses > 0:
@@ -1540,6 +1544,11 @@ class _Plan:
             self.br.append(b)
         T = {}
         self.sig = T["sig"] = torch.zeros(B, cfg.nd, **f32)
+        # tensor-core modes: the fusion kernel also writes the signature's hi/lo planes, the triplet's Gram GEMM reads them
+        self.tc_gram = bool(P) and not cfg.single and not eng.post2 and cfg.nd % 64 == 0 and \
+            os.environ.get("UGN_TC_GRAM", "1") == "1"
+        if self.tc_gram:
+            T["sig16"] = torch.zeros(2, B, cfg.nd, device=d, dtype=dt16)
         T["winner"] = torch.zeros(B, cfg.nd, device=d, dtype=torch.uint8)
         T["inv_norm"] = torch.zeros(B, 2, **f32)
         feat = cfg.nd
