@@ -175,6 +175,23 @@ int ugn_linear_bwd_ex(ugn_ctx*, const ugn_tensor* x, const ugn_tensor* w, const 
                       const ugn_tensor* dx_mask, ugn_tensor* dx16, ugn_tensor* dbx, ugn_tensor* dw, ugn_tensor* db,
                       void* stream);
 
+/* ---- Dropout without mask tensors (north_star: "the dropout mask fused into the epilogue"; Keras Dropout,
+ * nets/mj_uwyhNets_ba.py:100) -- a counter-based generator (Philox4x32-10) keyed by rng i64 [2] = {seed, step} (device
+ * memory), the layer id and the element index: keep with probability `keep`, scaled 1/keep (inverted dropout).  The
+ * forward and backward passes regenerate the same bits; ugn_dropout_advance (rng[1] += 1, a kernel: CUDA-graph replays
+ * draw fresh masks) is called once per step; ugn_dropout_mask materialises the mask of a layer (tests, layers that want a
+ * tensor).  *_philox: ugn_linear_fwd / ugn_linear_bwd_ex with the mask generated in the dense post pass (tensor-core
+ * storage mode; in ugn_linear_bwd_philox the mask is that of the layer BELOW, applied to dx16 / dbx). */
+int ugn_dropout_advance(ugn_ctx*, ugn_tensor* rng, void* stream);
+int ugn_dropout_mask(ugn_ctx*, const ugn_tensor* rng, int layer, float keep, ugn_tensor* out, void* stream);
+int ugn_linear_fwd_philox(ugn_ctx*, const ugn_tensor* x, const ugn_tensor* w, const ugn_tensor* bias,
+                          const ugn_tensor* rng, int layer, float keep, ugn_tensor* y, ugn_tensor* y16, int act,
+                          float alpha, void* stream);
+int ugn_linear_bwd_philox(ugn_ctx*, const ugn_tensor* x, const ugn_tensor* w, const ugn_tensor* dz, ugn_tensor* dx,
+                          const ugn_tensor* rng, int layer, float keep, ugn_tensor* dx16, ugn_tensor* dbx,
+                          ugn_tensor* dw, ugn_tensor* db, void* stream);
+
+
 
 /* ---- a2+a3+a4: gate x use-flag, fusion, l2_normalize ---------------------------------
  * replaces mj_tensor_times_scalar (:51-54), fMerge(name="fusion") (:1189; sign_max at

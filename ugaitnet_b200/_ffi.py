@@ -104,6 +104,10 @@ _PROTOS = {
     "ugn_set_fwd_passes": (c_int, [c_void_p, c_int, c_int]),
     "ugn_colsum": (c_int, [c_void_p, _T, _T, c_void_p]),
     "ugn_linear_bwd_ex": (c_int, [c_void_p, _T, _T, _T, _T, _T, _T, _T, _T, _T, c_void_p]),
+    "ugn_dropout_advance": (c_int, [c_void_p, _T, c_void_p]),
+    "ugn_dropout_mask": (c_int, [c_void_p, _T, c_int, c_float, _T, c_void_p]),
+    "ugn_linear_fwd_philox": (c_int, [c_void_p, _T, _T, _T, _T, c_int, c_float, _T, _T, c_int, c_float, c_void_p]),
+    "ugn_linear_bwd_philox": (c_int, [c_void_p, _T, _T, _T, _T, _T, c_int, c_float, _T, _T, _T, _T, c_void_p]),
 }
 
 EXPORTED_SYMBOLS = tuple(_PROTOS)

@@ -500,6 +500,54 @@ extern "C" int ugn_linear_bwd_ex(ugn_ctx* ctx, const ugn_tensor* x, const ugn_te
   return linear_bwd_common(ctx, x, w, dz, dx, dw, db, stream, dx_mask, dx16, dbx);
 }
 
+// ---- dropout from a counter-based generator (no mask tensors) -----------------------------------
+int ew_dropout_advance(ugn_ctx*, unsigned long long*, cudaStream_t);
+int ew_dropout_mask(ugn_ctx*, const unsigned long long*, int, float, float*, long long, cudaStream_t);
+static int rng_check(ugn_ctx* ctx, const ugn_tensor* rng, float keep) {
+  UGN_CHECK(rng, "dropout: rng state required");
+  UGN_TENSOR(rng, DT_I64, 1, 1);
+  UGN_CHECK(rng->shape[0] >= 2 && keep > 0.f && keep <= 1.f, "dropout: rng must be i64 [2] = {seed, step}, keep in (0, 1]");
+  return UGN_OK;
+}
+extern "C" int ugn_dropout_advance(ugn_ctx* ctx, ugn_tensor* rng, void* stream) {
+  UGN_CHECK(ctx, "ugn_dropout_advance: null ctx");
+  int rc = rng_check(ctx, rng, 1.f);
+  if (rc != UGN_OK) return rc;
+  return ew_dropout_advance(ctx, ugn_ptr<unsigned long long>(rng), (cudaStream_t)stream);
+}
+extern "C" int ugn_dropout_mask(ugn_ctx* ctx, const ugn_tensor* rng, int layer, float keep, ugn_tensor* out, void* stream) {
+  UGN_CHECK(ctx && out, "ugn_dropout_mask: null argument");
+  int rc = rng_check(ctx, rng, keep);
+  if (rc != UGN_OK) return rc;
+  UGN_TENSOR(out, DT_F32, 1, 4);
+  return ew_dropout_mask(ctx, ugn_ptr<unsigned long long>(rng), layer, keep, ugn_ptr<float>(out), ugn_numel(out),
+                         (cudaStream_t)stream);
+}
+extern "C" int ugn_linear_fwd_philox(ugn_ctx* ctx, const ugn_tensor* x, const ugn_tensor* w, const ugn_tensor* bias,
+                                     const ugn_tensor* rng, int layer, float keep, ugn_tensor* y, ugn_tensor* y16, int act,
+                                     float alpha, void* stream) {
+  UGN_CHECK(ctx && x, "ugn_linear_fwd_philox: null argument");
+  int rc = rng_check(ctx, rng, keep);
+  if (rc != UGN_OK) return rc;
+  UGN_CHECK(is_16(x), "ugn_linear_fwd_philox: tensor-core storage mode only (fp32 validation mode takes mask tensors)");
+  ctx->drop_rng = ugn_ptr<unsigned long long>(rng); ctx->drop_layer = layer; ctx->drop_keep = keep;
+  rc = ugn_linear_fwd(ctx, x, w, bias, nullptr, y, y16, act, alpha, stream);
+  ctx->drop_rng = nullptr;
+  return rc;
+}
+extern "C" int ugn_linear_bwd_philox(ugn_ctx* ctx, const ugn_tensor* x, const ugn_tensor* w, const ugn_tensor* dz,
+                                     ugn_tensor* dx, const ugn_tensor* rng, int layer, float keep, ugn_tensor* dx16,
+                                     ugn_tensor* dbx, ugn_tensor* dw, ugn_tensor* db, void* stream) {
+  UGN_CHECK(ctx && x && dx, "ugn_linear_bwd_philox: null argument (dx is required)");
+  int rc = rng_check(ctx, rng, keep);
+  if (rc != UGN_OK) return rc;
+  UGN_CHECK(is_16(x), "ugn_linear_bwd_philox: tensor-core storage mode only");
+  ctx->drop_rng = ugn_ptr<unsigned long long>(rng); ctx->drop_layer = layer; ctx->drop_keep = keep;
+  rc = linear_bwd_common(ctx, x, w, dz, dx, dw, db, stream, nullptr, dx16, dbx);
+  ctx->drop_rng = nullptr;
+  return rc;
+}
+
 static int fuse_common(ugn_ctx* ctx, int nmods, const ugn_tensor* const* br, const ugn_tensor* const* flags,
                        int& B, int& d) {
   UGN_CHECK(nmods >= 1 && nmods <= 4, "fuse: 1..4 modalities supported");

@@ -33,6 +33,10 @@ struct ugn_ctx {
   // 0 = all three): 1 hi*hi, 2 hi*hi + hi*lo(weights), 4 hi*hi + lo(activations)*hi.  gemm_npass is the transient
   // hand-over from tc_linear_fwd to tc_gemm_ex
   int fwd_conv_pass = 0, fwd_dense_pass = 0, gemm_npass = 0;
+  // transient (set by the *_philox entry points around one call): Philox dropout source of the dense post pass
+  const unsigned long long* drop_rng = nullptr;
+  int drop_layer = 0;
+  float drop_keep = 1.f;
   int gemm_nosplit = 0;        // transient: tc_gemm_ex without split-K (deterministic accumulation order: triplet Gram)
   // grow-only device scratch (split-K partial sums of small convolutions); sized on first use, i.e. in
   // the warm-up step before any CUDA-graph capture

@@ -866,6 +866,50 @@ int ew_bias_act_mask(ugn_ctx* ctx, float* y, const float* bias, const float* mas
   return UGN_OK;
 }
 
+// ---------------------------------------------------------------------------------------
+// Dropout masks from a counter-based generator (Philox4x32-10, Salmon et al. 2011) instead of mask tensors: element e of
+// layer `layer` at step rng[1] with seed rng[0] -> keep (scaled 1/keep, Keras inverted dropout, nets/mj_uwyhNets_ba.py:100)
+// or 0.  Forward and backward post passes regenerate the same bits, so no mask tensor exists; the step counter lives in
+// device memory and is advanced by a kernel, so a captured CUDA graph draws fresh masks on every replay.
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ void philox_round(unsigned& c0, unsigned& c1, unsigned& c2, unsigned& c3, unsigned k0, unsigned k1) {
+  const unsigned long long p0 = 0xD2511F53ull * c0, p1 = 0xCD9E8D57ull * c2;
+  const unsigned n0 = (unsigned)(p1 >> 32) ^ c1 ^ k0, n2 = (unsigned)(p0 >> 32) ^ c3 ^ k1;
+  c1 = (unsigned)p1; c3 = (unsigned)p0; c0 = n0; c2 = n2;
+}
+__device__ __forceinline__ float philox_keep(const unsigned long long* __restrict__ rng, int layer, long long e, float keep) {
+  const unsigned long long seed = rng[0], step = rng[1];
+  unsigned c0 = (unsigned)(e >> 2), c1 = (unsigned)((e >> 34) | ((unsigned long long)layer << 16)), c2 = (unsigned)step,
+           c3 = (unsigned)(step >> 32);
+  unsigned k0 = (unsigned)seed, k1 = (unsigned)(seed >> 32);
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    philox_round(c0, c1, c2, c3, k0, k1);
+    k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+  }
+  const unsigned lane = (unsigned)(e & 3);
+  const unsigned x = lane == 0 ? c0 : (lane == 1 ? c1 : (lane == 2 ? c2 : c3));
+  const float u = (float)(x >> 8) * 5.9604644775390625e-08f;        // [0, 1)
+  return u < keep ? 1.f / keep : 0.f;
+}
+__global__ void dropout_advance_kernel(unsigned long long* rng) { rng[1] += 1ull; }
+__global__ void dropout_mask_kernel(const unsigned long long* __restrict__ rng, int layer, float keep, float* __restrict__ out,
+                                    long long n) {
+  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < n; e += (long long)gridDim.x * blockDim.x)
+    out[e] = philox_keep(rng, layer, e, keep);
+}
+int ew_dropout_advance(ugn_ctx* ctx, unsigned long long* rng, cudaStream_t st) {
+  dropout_advance_kernel<<<1, 1, 0, st>>>(rng);
+  UGN_LAUNCHED(ctx);
+  return UGN_OK;
+}
+int ew_dropout_mask(ugn_ctx* ctx, const unsigned long long* rng, int layer, float keep, float* out, long long n,
+                    cudaStream_t st) {
+  dropout_mask_kernel<<<grid_for(ctx, n, 256), 256, 0, st>>>(rng, layer, keep, out, n);
+  UGN_LAUNCHED(ctx);
+  return UGN_OK;
+}
+
 // ONE post pass of a split-K dense GEMM (forward: bias + activation + dropout mask -> f32 result + its 16-bit planes;
 // backward: dropout mask of the layer below -> that layer's scaled 16-bit gradient operand + its bias gradient).
 // Block = 32 columns x 8 row lanes over ALL rows, so the column sums need no atomics.
@@ -874,7 +918,9 @@ __global__ void __launch_bounds__(256) dense_post_kernel(float* __restrict__ y, 
                                                          const float* __restrict__ mask, u16* __restrict__ out16,
                                                          long long plane, int rows, int cols, int act, float alpha,
                                                          int f16, const float* __restrict__ scale16,
-                                                         float* __restrict__ colsum, int write_f32) {
+                                                         float* __restrict__ colsum, int write_f32,
+                                                         const unsigned long long* __restrict__ rng, int layer,
+                                                         float keep) {
   __shared__ float sm[8][33];
   const int j = blockIdx.x * 32 + threadIdx.x;
   const float s16 = scale16 ? *scale16 : 1.f;
@@ -884,7 +930,8 @@ __global__ void __launch_bounds__(256) dense_post_kernel(float* __restrict__ y, 
     for (int r = threadIdx.y; r < rows; r += 8) {
       const long long e = (long long)r * cols + j;
       float v = ugn_act_fwd(y[e] + bj, act, alpha);
-      if (mask) v *= mask[e];
+      if (rng) v *= philox_keep(rng, layer, e, keep);
+      else if (mask) v *= mask[e];
       if (write_f32) y[e] = v;
       if (P16 > 0) {
         u16 hi, lo;
@@ -908,11 +955,11 @@ __global__ void __launch_bounds__(256) dense_post_kernel(float* __restrict__ y, 
 }
 int ew_dense_post(ugn_ctx* ctx, float* y, const float* bias, const float* mask, __nv_bfloat16* out16, int P16, int f16,
                   const float* scale16, float* colsum, int write_f32, long long rows, int cols, int act, float alpha,
-                  cudaStream_t st) {
+                  cudaStream_t st, const unsigned long long* rng, int layer, float keep) {
   dim3 grid(ugn_cdiv(cols, 32)), block(32, 8);
   const long long plane = rows * cols;
   u16* o = reinterpret_cast<u16*>(out16);
-#define UGN_DP_ARGS y, bias, mask, o, plane, (int)rows, cols, act, alpha, f16, scale16, colsum, write_f32
+#define UGN_DP_ARGS y, bias, mask, o, plane, (int)rows, cols, act, alpha, f16, scale16, colsum, write_f32, rng, layer, keep
   if (!out16 || P16 == 0) dense_post_kernel<0><<<grid, block, 0, st>>>(UGN_DP_ARGS);
   else if (P16 == 1) dense_post_kernel<1><<<grid, block, 0, st>>>(UGN_DP_ARGS);
   else dense_post_kernel<2><<<grid, block, 0, st>>>(UGN_DP_ARGS);

@@ -1541,7 +1541,9 @@ int ew_bias_act_mask(ugn_ctx* ctx, float* y, const float* bias, const float* mas
 int ew_split(ugn_ctx*, const float*, __nv_bfloat16*, int, int, long long, cudaStream_t);
 int ew_dense_post(ugn_ctx* ctx, float* y, const float* bias, const float* mask, __nv_bfloat16* out16, int P16, int f16,
                   const float* scale16, float* colsum, int write_f32, long long rows, int cols, int act, float alpha,
-                  cudaStream_t st);
+                  cudaStream_t st, const unsigned long long* rng = nullptr, int layer = 0, float keep = 1.f);
+int ew_dropout_mask(ugn_ctx* ctx, const unsigned long long* rng, int layer, float keep, float* out, long long n,
+                    cudaStream_t st);
 
 int tc_linear_fwd(ugn_ctx* ctx, int P, int f16, int B, int N, int K, const __nv_bfloat16* x, const __nv_bfloat16* w,
                   const float* bias, const float* mask, float* y, int act, float alpha, cudaStream_t st,
@@ -1560,13 +1562,25 @@ int tc_linear_fwd(ugn_ctx* ctx, int P, int f16, int B, int N, int K, const __nv_
     return rc;
   }
   int tiles = ugn_cdiv(B, 128) * ugn_cdiv(N, P == 2 ? 128 : 256);
-  if (tiles * 2 <= ctx->sm_count && K >= 512) {
+  const bool post_route = tiles * 2 <= ctx->sm_count && K >= 512;
+  if (ctx->drop_rng && !post_route) {
+    // large batch: the GEMM epilogue applies the mask itself -> materialise the Philox mask once (same bits as the
+    // backward pass regenerates)
+    void* scr = nullptr;
+    if ((rc = ugn_scratch(ctx, sizeof(float) * (size_t)B * N, &scr)) != UGN_OK) return rc;
+    if ((rc = ew_dropout_mask(ctx, ctx->drop_rng, ctx->drop_layer, ctx->drop_keep, reinterpret_cast<float*>(scr),
+                              (long long)B * N, st)) != UGN_OK) return rc;
+    mask = reinterpret_cast<const float*>(scr);
+    ctx->drop_rng = nullptr;
+  }
+  if (post_route) {
     rc = tc_gemm_ex(ctx, P, f16, B, N, K, x, 0, w, 0, y, N, 0, nullptr, nullptr, UGN_ACT_LINEAR, 0.f, nullptr, st);
     ctx->gemm_npass = 0;
     if (rc != UGN_OK) return rc;
-    // split-K partial sums -> ONE post pass: bias + activation + dropout mask + f32 result + its 16-bit planes
-    if (bias || mask || act != UGN_ACT_LINEAR || y16)
-      return ew_dense_post(ctx, y, bias, mask, y16, P16, f16, nullptr, nullptr, 1, B, N, act, alpha, st);
+    // split-K partial sums -> ONE post pass: bias + activation + dropout (mask tensor | Philox) + f32 result + 16-bit planes
+    if (bias || mask || act != UGN_ACT_LINEAR || y16 || ctx->drop_rng)
+      return ew_dense_post(ctx, y, bias, mask, y16, P16, f16, nullptr, nullptr, 1, B, N, act, alpha, st, ctx->drop_rng,
+                           ctx->drop_layer, ctx->drop_keep);
     return UGN_OK;
   } else {
     rc = tc_gemm_ex(ctx, P, f16, B, N, K, x, 0, w, 0, y, N, 0, bias, mask, act, alpha, nullptr, st);
@@ -1592,8 +1606,9 @@ int tc_linear_bwd(ugn_ctx* ctx, int P, int f16, int B, int N, int K, const __nv_
     if ((rc = tc_gemm_ex(ctx, P, f16, B, K, N, dz, 0, w, 1, dx, K, 0, nullptr, nullptr, 0, 0.f, os, st)) != UGN_OK) return rc;
     // ONE post pass over dx: x dropout mask of the layer below -> its 16-bit gradient operand (re-scaled by the
     // gradient scale) + its bias gradient; dx itself stays the unmasked f32 gradient
-    if (dx_mask || dx16 || dbx)
-      if ((rc = ew_dense_post(ctx, dx, nullptr, dx_mask, dx16, P16, f16, ctx->gscale, dbx, 0, B, K, UGN_ACT_LINEAR, 0.f, st)) != UGN_OK) return rc;
+    if (dx_mask || dx16 || dbx || ctx->drop_rng)
+      if ((rc = ew_dense_post(ctx, dx, nullptr, dx_mask, dx16, P16, f16, ctx->gscale, dbx, 0, B, K, UGN_ACT_LINEAR, 0.f, st,
+                              ctx->drop_rng, ctx->drop_layer, ctx->drop_keep)) != UGN_OK) return rc;
   }
   // dw[N,K] = dz^T . x             : A = dz MN-major [K'=B rows][N contiguous], B = x MN-major [B rows][K contiguous]
   if (dw && (rc = tc_gemm_ex(ctx, P, f16, N, K, B, dz, 1, x, 1, dw, K, 0, nullptr, nullptr, 0, 0.f, os, st)) != UGN_OK) return rc;

@@ -98,6 +98,7 @@ class GaitSetEngine(UGaitEngine):
         self.seg_off = torch.tensor([s.off for s in segs] + [off], dtype=torch.int64, device=d)
         self.seg_l2 = torch.tensor([s.l2 for s in segs], dtype=torch.float32, device=d)
         self.reg_out = torch.zeros(1, device=d)
+        self.philox = False            # (the only dropout of this graph is "dropcode" after FC1: a mask tensor)
         self.gstage = None             # (no early-final gradient ranges worth pushing: 3 M parameters)
         self.cw_arena = None           # (compute copies stay local: re-packed after the f32 all-gather)
         if self._symm:                 # fused data-parallel exchange: summed over the ranks by peer atomics (net.py)

@@ -200,6 +200,12 @@ class UGaitEngine:
         self.graph_launches = 0
         self._plans: Dict[tuple, "_Plan"] = {}
         self._graphs = {}
+        # dropout masks from a counter-based generator inside the dense post passes (tensor-core modes): no mask tensors,
+        # no torch RNG kernels in the step.  rng = {seed, step}; the step is advanced by a kernel at the start of every
+        # training step (a captured CUDA graph therefore draws fresh masks on every replay)
+        self.philox = bool(self.P) and os.environ.get("UGN_PHILOX", "1") == "1"
+        self.rng_state = torch.tensor([int(seed) * 0x9E3779B97F4A7C15 % (1 << 62), 0], dtype=torch.int64, device=self.dev)
+        self._R_rng = TRef(self.rng_state)
         self._build_arena()
         self.init_weights(seed)
 
@@ -605,9 +611,15 @@ class UGaitEngine:
                                      int(L["pool"]), st))
         nl = len(b.layers)
         check(lib.ugn_flatten_chw(h, b.R[f"a{nl}"].ptr, b.R["flat"].ptr, st))
-        mask = b.R["mask"].ptr if (train and cfg.dropout > 0.001) else None
-        check(lib.ugn_linear_fwd(h, b.R["flat"].ptr, self.Rcw[f"{bn}/dense/w"].ptr, self.Rw[f"{bn}/dense/b"].ptr,
-                                 mask, b.R["h1"].ptr, b.R["h1_16"].ptr if self.P else None, ACT_LINEAR, 0.0, st))
+        drop = train and cfg.dropout > 0.001
+        if drop and p.use_philox:
+            check(lib.ugn_linear_fwd_philox(h, b.R["flat"].ptr, self.Rcw[f"{bn}/dense/w"].ptr, self.Rw[f"{bn}/dense/b"].ptr,
+                                            self._R_rng.ptr, m, 1.0 - cfg.dropout, b.R["h1"].ptr, b.R["h1_16"].ptr,
+                                            ACT_LINEAR, 0.0, st))
+        else:
+            mask = b.R["mask"].ptr if drop else None
+            check(lib.ugn_linear_fwd(h, b.R["flat"].ptr, self.Rcw[f"{bn}/dense/w"].ptr, self.Rw[f"{bn}/dense/b"].ptr,
+                                     mask, b.R["h1"].ptr, b.R["h1_16"].ptr if self.P else None, ACT_LINEAR, 0.0, st))
         check(lib.ugn_linear_fwd(h, (b.R["h1_16"] if self.P else b.R["h1"]).ptr, self.Rcw[f"{bn}/ofCode/w"].ptr,
                                  self.Rw[f"{bn}/ofCode/b"].ptr, None, b.R["out"].ptr, None, ACT_LINEAR, 0.0, st))
 
@@ -620,15 +632,17 @@ class UGaitEngine:
             if p.train and cfg.dropout > 0.001:
                 if drop_masks is not None:
                     p.br[m].mask.copy_(drop_masks[m])
-                else:
+                elif not self.philox:
                     keep = 1.0 - cfg.dropout
                     p.br[m].mask.bernoulli_(keep).div_(keep)
+        p.use_philox = self.philox and drop_masks is None and p.train and cfg.dropout > 0.001
         if p.train and cfg.dropout > 0.001 and cfg.nc > 0:
             if code_drop_mask is not None:
                 p.cmask.copy_(code_drop_mask)
-            else:
+            elif not self.philox:
                 keep = 1.0 - cfg.dropout
                 p.cmask.bernoulli_(keep).div_(keep)
+        p.philox_code = self.philox and code_drop_mask is None and p.train and cfg.dropout > 0.001 and cfg.nc > 0
         if labels is not None:
             p.labels.copy_(labels.reshape(-1).to(torch.int32), non_blocking=True)
 
@@ -948,6 +962,17 @@ class UGaitEngine:
             check(lib.ugn_act_mask_bwd(h, R["dout"].ptr, None, None, None, R["dout16"].ptr, ACT_LINEAR, 0.0, st))
         # tensor-core mode: the bias gradient comes from the f32 dout, not from its rounded 16-bit copy (the rows of
         # dL/dsignature cancel under the triplet loss: summing the rounded operand leaves mostly rounding noise)
+        if self.P and getattr(p, "use_philox", False):
+            # the same with the dropout mask REGENERATED inside the post pass (no mask tensor)
+            check(lib.ugn_linear_bwd_philox(h, R["h1_16"].ptr, self.Rcw[f"{bn}/ofCode/w"].ptr, R["dout16"].ptr, R["dh1"].ptr,
+                                            self._R_rng.ptr, m, 1.0 - cfg.dropout, R["dz1_16"].ptr,
+                                            self.Rg[f"{bn}/dense/b"].ptr, self.Rg[f"{bn}/ofCode/w"].ptr, None, st))
+            check(lib.ugn_colsum(h, R["dout"].ptr, self.Rg[f"{bn}/ofCode/b"].ptr, st))
+            check(lib.ugn_linear_bwd(h, R["flat"].ptr, self.Rcw[f"{bn}/dense/w"].ptr, R["dz1_16"].ptr, R["dflat"].ptr,
+                                     self.Rg[f"{bn}/dense/w"].ptr, None, st))
+            if self.dp_reduce == "bucketed":
+                self._reduce_bucket((m, "fc"))
+            return
         if self.P and p.B <= 128:
             # ofCode backward with the fused input-gradient post pass: ONE kernel applies the dropout mask to the split-K
             # sums, writes the dense layer's 16-bit gradient operand and its bias gradient (was: mask/convert + column sums)
@@ -1079,6 +1104,11 @@ class UGaitEngine:
         self.repack_weights(after_optim=True)
 
     def _step_body(self, p: "_Plan", do_optim: bool, expanded: bool = False):
+        if getattr(p, "use_philox", False) or getattr(p, "philox_code", False):
+            h, st = self.ctx.h, stream_ptr()
+            check(lib.ugn_dropout_advance(h, self._R_rng.ptr, st))
+            if getattr(p, "philox_code", False):      # Dropout("dropcode") after FC1: its mask as a tensor (layer id 8)
+                check(lib.ugn_dropout_mask(h, self._R_rng.ptr, 8, 1.0 - self.cfg.dropout, p.R["cmask"].ptr, st))
         sig, feat = self._forward(p, True, expanded)
         # early optimiser (one GPU): the dense ranges are updated inside the backward pass
         self._early_active = bool(do_optim and self.early_optim and self.world == 1 and self._cap is None
@@ -1214,12 +1244,7 @@ class UGaitEngine:
             p.br[m].x_base.copy_(base_inputs[m], non_blocking=True)
             if not cfg.single:
                 p.flags[m].copy_(torch.as_tensor(use[:, m]).reshape(-1, 1), non_blocking=True)
-            if p.train and cfg.dropout > 0.001:
-                keep = 1.0 - cfg.dropout
-                p.br[m].mask.bernoulli_(keep).div_(keep)
-        if p.train and cfg.dropout > 0.001 and cfg.nc > 0:
-            keep = 1.0 - cfg.dropout
-            p.cmask.bernoulli_(keep).div_(keep)
+        self._draw_dropout(p)
         p.src_row.copy_(torch.as_tensor(src_row, dtype=torch.int32), non_blocking=True)
         p.use_mirror = mirror is not None
         if mirror is not None:
@@ -1270,7 +1295,8 @@ class UGaitEngine:
         self._next_lr()
         if self.use_graph and (self.world == 1 or self.dp_graph):
             gkey = (B, expanded, p.use_mirror, getattr(p, "_B0", None) if expanded else None,
-                    bool(getattr(p, "use_augment", False)) if expanded else False)
+                    bool(getattr(p, "use_augment", False)) if expanded else False,
+                    bool(getattr(p, "use_philox", False)), bool(getattr(p, "philox_code", False)))
             gr = self._graphs.get(gkey)
             if gr is None:
                 # warm-up on a side stream (first-use allocations / attribute sets), then capture
@@ -1407,6 +1433,10 @@ class UGaitEngine:
 
     def _draw_dropout(self, p):
         cfg = self.cfg
+        p.use_philox = self.philox and p.train and cfg.dropout > 0.001 and any(hasattr(b, "mask") for b in p.br)
+        p.philox_code = self.philox and p.train and cfg.dropout > 0.001 and cfg.nc > 0
+        if self.philox:
+            return
         if p.train and cfg.dropout > 0.001:
             keep = 1.0 - cfg.dropout
             for b in p.br:
@@ -1476,6 +1506,7 @@ class _Plan:
 
         self.eng = eng
         self.use_mirror = False
+        self.use_philox = self.philox_code = False
         self.br: List[_Branch] = []
         # every per-step input lives in ONE device block (IOBlock): one H2D copy per step, see UGaitEngine.prefetch_batch
         self.io = IOBlock(d, B, [(cfg.layers(m, eng.pad)[0]["cin"], cfg.hw, cfg.hw) for m in range(cfg.nmods)])
