@@ -36,7 +36,9 @@ def triplet_loss(margin=1.0):
 
 
 def batch_dist(x):
-    """nets/triplet_loss_all.py:70-77 on a [n,m,d] tensor (host-side helper, torch)."""
+    """nets/triplet_loss_all.py:70-77 on a [n,m,d] tensor.  A stand-alone helper of the reference that its loss calls
+    internally; here the loss (above) computes its distances inside ugn_triplet_all{,_tc}, and this function only
+    restates the same formula with torch operators for callers that want the matrix itself (not on the step's path)."""
     x = torch.as_tensor(x)
     x2 = (x * x).sum(2)
     d = x2.unsqueeze(2) + x2.unsqueeze(1) - 2.0 * torch.matmul(x, x.transpose(1, 2))

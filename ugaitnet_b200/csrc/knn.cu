@@ -614,7 +614,9 @@ extern "C" int ugn_knn_topk_tc(ugn_ctx* ctx, const ugn_tensor* queries, const ug
   long long maxc = std::max<long long>(1, std::min<long long>(N / 2048, 512));
   long long best_cost = -1, rows = 0;
   int chunks = 1;
-  for (long long c = 1; c <= maxc; ++c) {
+  long long cmin = 1;
+  if (const char* e = getenv("UGN_KNN_CHUNKS")) { cmin = std::max(1LL, std::min<long long>(atoll(e), maxc)); maxc = cmin; }   // (experiments)
+  for (long long c = cmin; c <= maxc; ++c) {
     long long r = ((N + c - 1) / c + 255) / 256 * 256;
     long long cc = (N + r - 1) / r;
     long long waves = (qt * cc + ctx->sm_count - 1) / ctx->sm_count;
