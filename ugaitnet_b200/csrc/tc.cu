@@ -72,6 +72,9 @@ struct TcParams {
   // N <= 128 MMA costs 73 clk whatever N is, N = 192 costs 96: profiles/r01_umma_rate.txt), the hi*lo
   // partial sums live in columns [block_n, 2*block_n) of the tile and are added in the epilogue
   int nbuf, concat, acc_tile_cols;
+  // thread-block cluster of `cluster` (1 | 2) CTAs that work on tiles with the SAME weights: every CTA loads 1/cluster of
+  // each weight tile and TMA-multicasts it to all of them (b_half_rows / b_half_bytes: its share of a K-major tile)
+  int cluster, b_half_rows, b_half_bytes;
   long long* dbg;   // optional [8] cycle counters (UGN_CONVP_PROF): where each role of tc_convp_kernel waits
 };
 
@@ -570,7 +573,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_kernel(const __grid_constant__
 // TT (tiles per work item), KSL (K slices per ring stage) and PL2 (split operands) are compile-time too, so
 // that the MMA issue sequence of one ring stage is a straight line of UTCHMMAs with immediate descriptor
 // offsets.
-template <bool CONCAT, bool PROF, int TT, int KSL, int NPASS>
+template <bool CONCAT, bool PROF, int TT, int KSL, int NPASS, int CL>
 __global__ void __launch_bounds__(kConvpThreads, 1) tc_convp_kernel(const __grid_constant__ TcParams p) {
   // PERSISTENT: each CTA walks tiles blockIdx.x, +gridDim.x, ...; two TMEM accumulator sets so that the
   // epilogue of tile i (CUDA cores) overlaps the mainloop of tile i+1 (tensor pipe).
@@ -595,7 +598,9 @@ __global__ void __launch_bounds__(kConvpThreads, 1) tc_convp_kernel(const __grid
   const int tiles_mn = p.N;        // images * tiles_y
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < p.stages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    // a ring stage is refilled by EVERY CTA of the cluster (multicast halves), so it is free only when every CTA's MMA
+    // issuer has released it: CL arrivals
+    for (int s = 0; s < p.stages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], CL); }
     for (int b = 0; b < 2; ++b) {
       mbar_init(&patch_full[b], 1); mbar_init(&patch_empty[b], 1);
       mbar_init(&tmem_full[b], 1); mbar_init(&tmem_empty[b], 256);
@@ -610,11 +615,14 @@ __global__ void __launch_bounds__(kConvpThreads, 1) tc_convp_kernel(const __grid
   }
   fence_before_sync();
   __syncthreads();
+  if (CL > 1) cluster_sync();          // every CTA's barriers exist before a peer multicasts into / arrives on them
   fence_after_sync();
   const uint32_t tmem_base = *tmem_ptr;
   const int BK = p.kslices * 16;
   const int cwB = p.b.rowbytes >> 1;
   const uint32_t acc_cols = (uint32_t)(p.T * p.acc_tile_cols);
+  const uint32_t crank = CL > 1 ? cluster_ctarank() : 0u;
+  constexpr uint16_t kMask = (uint16_t)((1u << CL) - 1u);
 
   if (warp == 0) {
    if (elect_one()) {
@@ -644,11 +652,25 @@ __global__ void __launch_bounds__(kConvpThreads, 1) tc_convp_kernel(const __grid
           if (PROF) atomicAdd((unsigned long long*)p.dbg + 6, (unsigned long long)(clock64() - tw1));
           mbar_expect_tx(&full[s], tx_bytes);
           uint8_t* sb = ring + (size_t)s * b_stage;
-          for (int pl = 0; pl < p.pb; ++pl)
-            for (int j = 0; j < p.b.nbox; ++j) {
-              if (p.b.major == 0) tma_load_5d(&p.b.map, &full[s], sb + pl * p.b.plane_bytes, cc * BK, tap, n0, pl, 0);
-              else tma_load_5d(&p.b.map, &full[s], sb + pl * p.b.plane_bytes + j * p.b.box_bytes, n0 + j * cwB, tap, cc * BK, pl, 0);
+          if (CL == 1) {
+            for (int pl = 0; pl < p.pb; ++pl)
+              for (int j = 0; j < p.b.nbox; ++j) {
+                if (p.b.major == 0) tma_load_5d(&p.b.map, &full[s], sb + pl * p.b.plane_bytes, cc * BK, tap, n0, pl, 0);
+                else tma_load_5d(&p.b.map, &full[s], sb + pl * p.b.plane_bytes + j * p.b.box_bytes, n0 + j * cwB, tap, cc * BK, pl, 0);
+              }
+          } else {
+            // this CTA's share of the stage, delivered to every CTA of the cluster (the peers deliver the rest)
+            for (int pl = 0; pl < p.pb; ++pl) {
+              if (p.b.major == 0) {
+                tma_load_5d_mc(&p.b.map, &full[s], sb + pl * p.b.plane_bytes + crank * p.b_half_bytes, cc * BK, tap,
+                               n0 + (int)crank * p.b_half_rows, pl, 0, kMask);
+              } else {
+                for (int j = (int)crank; j < p.b.nbox; j += CL)
+                  tma_load_5d_mc(&p.b.map, &full[s], sb + pl * p.b.plane_bytes + j * p.b.box_bytes, n0 + j * cwB, tap,
+                                 cc * BK, pl, 0, kMask);
+              }
             }
+          }
           if (++c == p.cps) { c = 0; ++tap; }
           if (++s == p.stages) { s = 0; ph ^= 1; }
         }
@@ -709,7 +731,8 @@ __global__ void __launch_bounds__(kConvpThreads, 1) tc_convp_kernel(const __grid
             }
           }
         }
-        umma_commit(&empty[s]);
+        if (CL == 1) umma_commit(&empty[s]);
+        else umma_commit_mc(&empty[s], kMask);      // releases the stage in every CTA of the cluster
         if (++cc == p.cps) { cc = 0; if (++kw == p.KW) { kw = 0; ++kh; } }
         if (++s == p.stages) { s = 0; ph ^= 1; }
       }
@@ -750,6 +773,7 @@ __global__ void __launch_bounds__(kConvpThreads, 1) tc_convp_kernel(const __grid
     }
   }
   __syncthreads();
+  if (CL > 1) cluster_sync();          // no CTA leaves while a peer may still multicast into it or arrive on its barriers
   if (warp == 1) {
     __syncwarp();
     fence_after_sync();
@@ -1159,8 +1183,46 @@ static void conv_box(int Wn, int Hn, int Bn, int pool, int& bw, int& bh, int& bn
 
 // patch-resident launch (forward with sgn=+1, input gradient with sgn=-1); returns UGN_ERR_UNSUPPORTED when
 // the geometry does not fit so that the caller falls back to the per-tap-box kernel.
+// one launch of the patch-resident conv kernel; the 2-CTA cluster (multicast weights) variant exists for the pass counts
+// the training step uses (3-pass forward, 1-pass input gradient) and is only instantiated for them
+template <bool C, bool PR, int TT, int KSL, int NP>
+static int convp_do_launch(TcParams& p, dim3 grid, size_t smem, cudaStream_t st) {
+  if constexpr (!PR && (NP == 3 || NP == 1)) {
+    if (p.cluster == 2) {
+      auto kfn = tc_convp_kernel<C, false, TT, KSL, NP, 2>;
+      UGN_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      cudaLaunchConfig_t lc = {};
+      lc.gridDim = grid; lc.blockDim = dim3(kConvpThreads); lc.dynamicSmemBytes = smem; lc.stream = st;
+      cudaLaunchAttribute at[1];
+      at[0].id = cudaLaunchAttributeClusterDimension;
+      at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+      lc.attrs = at; lc.numAttrs = 1;
+      int ncl = 0;
+      if (cudaOccupancyMaxActiveClusters(&ncl, kfn, &lc) == cudaSuccess && ncl > 0 && 2 * ncl < (int)lc.gridDim.x)
+        lc.gridDim.x = 2 * ncl;      // persistent kernel: only as many clusters as are co-resident (GPC pairing)
+      UGN_CUDA(cudaLaunchKernelEx(&lc, kfn, p));
+      return UGN_OK;
+    }
+  }
+  p.cluster = 1;
+  UGN_CUDA(cudaFuncSetAttribute(tc_convp_kernel<C, PR, TT, KSL, NP, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  tc_convp_kernel<C, PR, TT, KSL, NP, 1><<<grid, kConvpThreads, smem, st>>>(p);
+  return UGN_OK;
+}
+
+// description of the weight tensor map, so that convp_launch can re-encode it with a per-CTA share of the box when it
+// decides to run thread-block clusters with multicast weight loads
+struct WMapSpec {
+  const void* base;
+  uint64_t dims[5];
+  uint64_t str[4];
+  uint32_t box[5];
+  int rowbytes;
+};
+
 static int convp_launch(ugn_ctx* ctx, TcParams& p, const __nv_bfloat16* act, int P, int B, int H, int W, int C,
-                        int KH, int KW, int Wneed, int Hneed, int pool, int sgn, cudaStream_t st) {
+                        int KH, int KW, int Wneed, int Hneed, int pool, int sgn, cudaStream_t st,
+                        const WMapSpec* wspec = nullptr) {
   if (p.npass == 0) { p.npass = P == 2 ? 3 : 1; p.pa = p.pb = P; }
   const int PA = p.pa, PB = p.pb;
   const int cbox = (C % 64 == 0) ? 64 : 32;
@@ -1184,7 +1246,9 @@ static int convp_launch(ugn_ctx* ctx, TcParams& p, const __nv_bfloat16* act, int
   p.cps = p.ncc; p.nslots = 1;
   for (int ring = 0; ring < 2 && !T; ++ring) {           // ring: stream one channel chunk at a time (2 slots)
     if (ring && p.ncc == 1) break;
+    const int tforce = getenv("UGN_CONVP_T") ? atoi(getenv("UGN_CONVP_T")) : 0;     // (experiments)
     for (int cand : {2, 1}) {
+      if (tforce && cand != tforce) continue;
       if (cand * p.acc_tile_cols > 512) continue;         // at least one accumulator set in the 512 TMEM columns
       if (cand > 1 && (cand - 1) * RH >= Hneed) continue;
       size_t chunk = (size_t)PA * (size_t)(cand * RH + KH - 1) * SW * rowbytes;
@@ -1229,6 +1293,36 @@ static int convp_launch(ugn_ctx* ctx, TcParams& p, const __nv_bfloat16* act, int
   p.N = tiles_mn;
   p.M = tiles_mn * tiles_n;
   dim3 grid(std::min(p.M, ctx->sm_count), 1, 1);
+  // ---- thread-block clusters of 2 with TMA-multicast weight tiles (OPT-IN, UGN_CONV_CLUSTER=1): two CTAs that work on
+  // neighbouring tiles (same weights) each load half of every weight tile and multicast it to both -- half the L2 reads.
+  // MEASURED (round 2, B = 96): no gain (conv1-OF 394 vs 394 us, conv1-gray 238 vs 237, conv3 60.8 vs 60.8).  The "wait B"
+  // time of the MMA issuer in the role profile (UGN_CONVP_PROF: conv1-OF 216 of 644 kclk) is back-pressure, not
+  // starvation: the issuer runs a 2-3 stage ring ahead of the tensor pipe and then waits for it to drain; per stage the
+  // pipe is busy 676 of 751 clk.  The layer sits at 90 % of its MMA-issue bound (169 clk per K slice: the N = 96 floor).
+  p.cluster = 1;
+  const bool prof_ = getenv("UGN_CONVP_PROF") != nullptr;
+  if (wspec && !prof_ && (p.npass == 3 || p.npass == 1) && getenv("UGN_CONV_CLUSTER") && tiles_mn % 2 == 0 &&
+      p.M >= 2 * ctx->sm_count) {
+    bool ok = false;
+    if (p.b.major == 0) {
+      const int half = p.block_n / 2;
+      ok = p.block_n % 2 == 0 && (half * rowbytes) % 1024 == 0 && p.b.nbox == 1;
+      if (ok) { p.b_half_rows = half; p.b_half_bytes = half * rowbytes; }
+    } else {
+      ok = p.b.nbox % 2 == 0;
+    }
+    if (ok) p.cluster = 2;
+  }
+  if (p.cluster == 2) {
+    if (p.b.major == 0) {          // re-encode the weight map with this CTA's share of the box (half the rows)
+      uint32_t box[5];
+      for (int i = 0; i < 5; ++i) box[i] = wspec->box[i];
+      box[2] = (uint32_t)p.b_half_rows;
+      int rc = make_map(ctx, &p.b.map, wspec->base, wspec->dims, wspec->str, box, wspec->rowbytes);
+      if (rc != UGN_OK) return rc;
+    }
+    grid.x = (unsigned)std::min<long long>(p.M, (ctx->sm_count / 2) * 2);
+  }
   static long long* dbg_buf = nullptr;
   const bool prof = getenv("UGN_CONVP_PROF") != nullptr;
   if (prof) {
@@ -1238,9 +1332,8 @@ static int convp_launch(ugn_ctx* ctx, TcParams& p, const __nv_bfloat16* act, int
   }
 #define CONVP_LAUNCH(C, PR, TT, KSL, NP)                                                                       \
   do {                                                                                                         \
-    UGN_CUDA(cudaFuncSetAttribute(tc_convp_kernel<C, PR, TT, KSL, NP>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
-                                  (int)smem));                                                                 \
-    tc_convp_kernel<C, PR, TT, KSL, NP><<<grid, kConvpThreads, smem, st>>>(p);                                 \
+    int rcl = convp_do_launch<C, PR, TT, KSL, NP>(p, grid, smem, st);                                          \
+    if (rcl != UGN_OK) return rcl;                                                                             \
   } while (0)
 #define CONVP_T_K(C, PR, NP)                                                           \
   do {                                                                                 \
@@ -1307,6 +1400,7 @@ int tc_conv_fwd(ugn_ctx* ctx, const ConvGeom& g, int P, int f16, const __nv_bflo
   if (P == 2 && p.block_n > 128 && p.npass != 1)
     p.block_n = (g.Co % 192 == 0 && !getenv("UGN_NO_N192")) ? 192 : (g.Co % 128 == 0) ? 128 : ((g.Co % 96 == 0) ? 96 : 64);
   int rc;
+  WMapSpec wspec{};
   {  // weights [P][Co][taps][Cp] K-major: dims (Cp, taps, Co, P, 1)
     const int taps = g.KH * g.KW;
     uint64_t dims[5] = {(uint64_t)g.Cp, (uint64_t)taps, (uint64_t)g.Co, (uint64_t)P, 1};
@@ -1315,12 +1409,15 @@ int tc_conv_fwd(ugn_ctx* ctx, const ConvGeom& g, int P, int f16, const __nv_bflo
     uint32_t box[5] = {(uint32_t)cbox, 1, (uint32_t)p.block_n, 1, 1};
     finish_op(p.b, 0, cbox * 2, 1, p.block_n, p.block_n);
     if ((rc = make_map(ctx, &p.b.map, w, dims, str, box, cbox * 2)) != UGN_OK) return rc;
+    wspec.base = w; wspec.rowbytes = cbox * 2;
+    for (int i = 0; i < 5; ++i) { wspec.dims[i] = dims[i]; wspec.box[i] = box[i]; }
+    for (int i = 0; i < 4; ++i) wspec.str[i] = str[i];
   }
   p.epi = pool ? EPI_BF16_POOL : EPI_BF16_ACT;
   p.out_bf16 = y; p.out_plane = (long long)g.B * g.Hp * g.Wp * g.Co;
   p.pool_idx = idx; p.bias = bias; p.act = act; p.alpha = alpha;
   if (!getenv("UGN_NO_CONVP") && g.H * g.W > 16) {
-    rc = convp_launch(ctx, p, x, P, g.B, g.H, g.W, g.Cp, g.KH, g.KW, Wn, Hn, pool, +1, st);
+    rc = convp_launch(ctx, p, x, P, g.B, g.H, g.W, g.Cp, g.KH, g.KW, Wn, Hn, pool, +1, st, &wspec);
     if (rc != UGN_ERR_UNSUPPORTED) return rc;
   }
   conv_box(Wn, Hn, g.B, pool, p.bw, p.bh, p.bn);
