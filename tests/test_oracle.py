@@ -324,3 +324,47 @@ def test_decision_injection_reproduces_free_run():
     dec[0]["pool1"] = (dec[0]["pool1"] + 1) % 4
     _, G3 = O.loss_and_grads(*args, decisions=dec)
     assert not torch.allclose(G3["ofBranch/conv0/w"], G0["ofBranch/conv0/w"])
+
+
+def test_oracle_primitives_against_scipy_and_sklearn():
+    """Third-party pins of the restated primitives (TensorFlow itself is unavailable): valid cross-correlation against
+    scipy.signal.correlate, 2x2/2 max-pooling against scipy.ndimage.maximum_filter, categorical cross-entropy against
+    sklearn.metrics.log_loss, l2_normalize against sklearn.preprocessing.normalize, batch_dist against
+    scipy.spatial.distance.cdist, Adam against a scalar closed form of Kingma & Ba's update as Keras implements it."""
+    import math
+    import torch.nn.functional as F
+    from scipy import ndimage, signal
+    from scipy.spatial.distance import cdist
+    from sklearn.metrics import log_loss
+    from sklearn.preprocessing import normalize
+    rng = np.random.default_rng(5)
+    x = rng.normal(size=(2, 3, 12, 12))
+    w = rng.normal(size=(4, 3, 5, 5))
+    b = rng.normal(size=4)
+    y = F.conv2d(torch.tensor(x), torch.tensor(w), torch.tensor(b)).numpy()
+    ref = np.stack([np.stack([sum(signal.correlate(x[n, c], w[o, c], mode="valid") for c in range(3)) + b[o]
+                              for o in range(4)]) for n in range(2)])
+    assert np.allclose(y, ref, rtol=1e-12, atol=1e-12)
+    a = rng.normal(size=(2, 3, 9, 9))                        # odd size: the trailing row / column is dropped
+    pooled = F.max_pool2d(torch.tensor(a), 2).numpy()
+    mf = ndimage.maximum_filter(a, size=(1, 1, 2, 2), origin=(0, 0, -1, -1))[:, :, 0:8:2, 0:8:2]
+    assert np.array_equal(pooled, mf)
+    logits = rng.normal(size=(11, 7))
+    lab = rng.integers(0, 7, 11)
+    ce, _ = O.softmax_ce(torch.tensor(logits), F.one_hot(torch.tensor(lab), 7).double())
+    p = np.exp(logits) / np.exp(logits).sum(1, keepdims=True)
+    assert float(ce) == pytest.approx(log_loss(lab, p, labels=list(range(7))), rel=1e-12)
+    v = rng.normal(size=(6, 10))
+    assert np.allclose(O.l2_normalize(torch.tensor(v), 1).numpy(), normalize(v, norm="l2", axis=1), rtol=1e-12)
+    e = rng.normal(size=(1, 9, 5))
+    assert np.allclose(O.batch_dist(torch.tensor(e))[0].numpy(), cdist(e[0], e[0]) * (1 - np.eye(9)), atol=1e-7)
+    # Adam, three steps on one scalar with a constant gradient g: m_t = (1-b1^t) g, v_t = (1-b2^t) g^2 ->
+    # every update is -lr * g / (|g| + eps * sqrt(1-b2^t)) exactly (Keras folds the bias correction into lr_t)
+    P, G = {"w": torch.tensor([1.0], dtype=torch.float64)}, {"w": torch.tensor([0.3], dtype=torch.float64)}
+    M, V = {"w": torch.zeros(1, dtype=torch.float64)}, {"w": torch.zeros(1, dtype=torch.float64)}
+    wref = 1.0
+    for t in (1, 2, 3):
+        O.adam_step(P, G, M, V, t, lr=1e-2)
+        mt, vt = (1 - 0.9 ** t) * 0.3, (1 - 0.999 ** t) * 0.09
+        wref -= 1e-2 * math.sqrt(1 - 0.999 ** t) / (1 - 0.9 ** t) * mt / (math.sqrt(vt) + 1e-7)
+        assert float(P["w"]) == pytest.approx(wref, rel=1e-12)
