@@ -287,7 +287,11 @@ int ugn_adam_step_ex(ugn_ctx*, ugn_tensor* w, const ugn_tensor* g, ugn_tensor* m
  * symmetric arena of 16-bit compute copies; the table's addresses point into this rank's arena) [+ cw_multicast]:
  * for the segments in the table the owner writes the hi / lo planes of its updated weights into EVERY rank's compute
  * copy and skips the f32 broadcast -- the caller needs no re-split pass afterwards, and the other ranks' f32 masters
- * of those segments are stale until refreshed (UGaitEngine.sync_master_weights). */
+ * of those segments are stale until refreshed (UGaitEngine.sync_master_weights).
+ * cw_multicast == UGN_CW_DEFERRED: the kernel refreshes only THIS rank's copies of its slice; the caller sends those
+ * plane ranges to the peers itself (copy engines, on a side stream underneath the next step's convolution forward) and
+ * orders the next reader of the copies behind that transfer. */
+#define UGN_CW_DEFERRED ((int64_t)-1)
 int ugn_dp_optim_step(ugn_ctx*, int opt, int world, int rank, const int64_t* g_peers, const int64_t* w_peers,
                       int64_t g_multicast, int64_t w_multicast, ugn_tensor* w, const ugn_tensor* g, ugn_tensor* m, ugn_tensor* v, ugn_tensor* vhat,
                       float weight_decay, const ugn_tensor* seg_off, const ugn_tensor* seg_l2, float beta1,

@@ -613,6 +613,9 @@ struct PeerArenas {
   // re-split pass after the exchange.  cw[p]: base of rank p's arena, cw_mc: its multicast address
   unsigned char* cw[8] = {};
   unsigned char* cw_mc = nullptr;
+  // cw_defer: the kernel refreshes THIS rank's copies only; the caller then sends its slice of the planes to the peers
+  // with the copy engines underneath the next step's convolution forward (the all-gather leaves the critical path)
+  bool cw_defer = false;
   const float* mc_g = nullptr;   // NVSwitch multicast addresses of the two arenas (nullptr: unicast peer accesses):
   float* mc_w = nullptr;         // multimem.ld_reduce sums in the switch, multimem.st broadcasts -- half the link traffic
 };
@@ -750,7 +753,7 @@ __global__ void __launch_bounds__(256) optim_kernel(float* __restrict__ w, const
       if (li + 4 <= numel) {
         *reinterpret_cast<uint2*>(dst + li) = *reinterpret_cast<const uint2*>(hi);
         if (packP == 2) *reinterpret_cast<uint2*>(dst + numel + li) = *reinterpret_cast<const uint2*>(lo);
-        if (packed_x) {
+        if (packed_x && !peers.cw_defer) {
           const long long ob = reinterpret_cast<unsigned char*>(dst + li) - peers.cw[peers.rank];   // byte offset in the arena
           if (peers.cw_mc) {
             multimem_st8(peers.cw_mc + ob, *reinterpret_cast<const uint2*>(hi));
@@ -824,7 +827,8 @@ int ew_optim(ugn_ctx* ctx, int opt, float* w, const float* g, float* m, float* v
     peers.rank = rank;
     if (cw_peers && pack) {
       for (int p = 0; p < world; ++p) peers.cw[p] = reinterpret_cast<unsigned char*>(cw_peers[p]);
-      peers.cw_mc = reinterpret_cast<unsigned char*>(cw_mc);
+      peers.cw_defer = cw_mc == -1;          // UGN_CW_DEFERRED
+      peers.cw_mc = peers.cw_defer ? nullptr : reinterpret_cast<unsigned char*>(cw_mc);
     }
     if (stage && n_ranges > 0) {
       UGN_CHECK(n_ranges <= 4 && staged_ranges, "dp optimizer: at most 4 staged ranges");

@@ -373,10 +373,23 @@ class UGaitEngine:
                     self._fused_pack.add(sg.name)
             self.pack_table = tab.to(d)
             self.R["pack_table"] = TRef(self.pack_table)
+        # deferred weight all-gather: the exchange kernel refreshes this rank's slice of the 16-bit copies only; the copy
+        # engines send it to the peers on a side stream while the next step's convolution forward runs, and the first
+        # dense GEMM of that step waits on this (externally recorded, graph-capturable) event
+        self._cw_event = None
+        if (self.cw_arena is not None and self.pack_table is not None and not self.dp_onegraph
+                and os.environ.get("UGN_DP_DEFER", "1") == "1"):
+            self._cw_event = torch.cuda.Event(external=True)
+            self._cw_stream = torch.cuda.Stream(device=d)
 
     @staticmethod
     def segs_off(segs, name):
         return next(s.off for s in segs if s.name == name)
+
+    def _cw_wait(self):
+        """Order the current stream behind the deferred peer copies of the 16-bit dense weights (no-op otherwise)."""
+        if getattr(self, "_cw_event", None) is not None:
+            torch.cuda.current_stream().wait_event(self._cw_event)
 
     def sync_master_weights(self):
         """Fused data-parallel exchange with exchanged 16-bit copies: only the OWNER of an arena slice holds the current
@@ -395,6 +408,7 @@ class UGaitEngine:
         """master f32 -> padded / 16-bit compute copies.  After an optimiser step only the padded (conv)
         copies are left to do: the dense ones were re-split inside the optimiser kernel."""
         if not after_optim:
+            self._cw_wait()
             self.sync_master_weights()
         for name, t in self.cw.items():
             if after_optim and name in self._fused_pack:
@@ -612,6 +626,7 @@ class UGaitEngine:
         nl = len(b.layers)
         check(lib.ugn_flatten_chw(h, b.R[f"a{nl}"].ptr, b.R["flat"].ptr, st))
         drop = train and cfg.dropout > 0.001
+        self._cw_wait()        # data parallel: the peers' slices of the dense weights land underneath the convolutions
         if drop and p.use_philox:
             check(lib.ugn_linear_fwd_philox(h, b.R["flat"].ptr, self.Rcw[f"{bn}/dense/w"].ptr, self.Rw[f"{bn}/dense/b"].ptr,
                                             self._R_rng.ptr, m, 1.0 - cfg.dropout, b.R["h1"].ptr, b.R["h1_16"].ptr,
@@ -1179,7 +1194,10 @@ class UGaitEngine:
             self._cw_tab, self._cw_mc = None, 0
             if getattr(self, "cw_arena", None) is not None:
                 self._cw_tab = (ctypes.c_int64 * n)(*[int(p) for p in self._cw_symm.buffer_ptrs])
-                if all(self._mc):
+                if self._cw_event is not None:
+                    self._cw_mc = -1                 # UGN_CW_DEFERRED
+                    self._cw_deferred_setup()
+                elif all(self._mc):
                     try:
                         self._cw_mc = int(self._cw_symm.multicast_ptr or 0)
                     except Exception:
@@ -1211,9 +1229,46 @@ class UGaitEngine:
                                     int(self.dt16 is torch.float16), self._cw_tab, self._cw_mc, st))
         if self._cw_tab is not None:
             self._w_stale = True
+        if self._cw_mc == -1:
+            self._cw_send()
         hw.barrier(channel=0)                   # every rank's slice of the new weights (and of the regulariser sum) has landed
         if self._reg_tab is None:
             torch.distributed.all_reduce(self.reg_out, group=self.pg)  # fallback: sum of the slice values (4 bytes)
+
+    def _cw_deferred_setup(self):
+        """(destination view in a peer's arena, local source view) for every plane range of the exchanged 16-bit copies
+        that lies in this rank's arena slice."""
+        rank, sl = torch.distributed.get_rank(self.pg), self.slice_len
+        q0, q1 = rank * sl, min((rank + 1) * sl, self.n_arena)
+        arena = self.cw_arena
+        peers = [self._cw_symm.get_buffer(r, (arena.numel(),), self.dt16) for r in range(self.world)]
+        self._cw_pairs = []
+        for sg in self.seg_list:
+            if sg.name not in self._fused_pack:
+                continue
+            a, b = max(sg.off, q0), min(sg.off + sg.n, q1)
+            if a >= b:
+                continue
+            planes = self.cw[sg.name].view(self.P, -1)
+            for pl in range(self.P):
+                src = planes[pl, a - sg.off:b - sg.off]
+                e0 = (src.data_ptr() - arena.data_ptr()) // 2
+                for r in range(self.world):
+                    if r != rank:
+                        self._cw_pairs.append((peers[r][e0:e0 + (b - a)], src))
+
+    def _cw_send(self):
+        """After the exchange kernel: this rank's slice of the updated 16-bit planes goes to every peer by the copy
+        engines on the side stream; a group barrier there, then the event the next reader of the copies waits on."""
+        cur, side = torch.cuda.current_stream(), self._cw_stream
+        ev = torch.cuda.Event()
+        ev.record(cur)
+        side.wait_event(ev)
+        with torch.cuda.stream(side):
+            for dst, src in self._cw_pairs:
+                dst.copy_(src, non_blocking=True)
+            self._cw_symm.barrier(channel=1)     # every rank's copies INTO this rank have landed
+            self._cw_event.record(side)
 
     def _next_lr(self):
         self.t += 1
