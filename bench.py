@@ -390,7 +390,8 @@ def main():
         cfg_line["rank_check"] = rank_check
         if eng.dp_timing_summary() is not None:
             cfg_line["dp_timing"] = eng.dp_timing_summary()
-        cfg_line["dp_exchange"] = eng.dp_reduce + (" (NVSwitch multimem)" if all(getattr(eng, "_mc", (0, 0))) else "")
+        cfg_line["dp_exchange"] = eng.dp_reduce + (" (NVSwitch multimem)" if all(getattr(eng, "_mc", (0, 0))) else "") + (
+            " + deferred copy-engine weight all-gather" if getattr(eng, "_cw_mc", 0) == -1 else "")
     line = {"metric": "train rows/s (3-mod fwd+bwd+triplet+CE+Adam)", "value": value, "unit": "rows/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None,

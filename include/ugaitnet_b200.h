@@ -233,6 +233,14 @@ int ugn_triplet_all(ugn_ctx*, const ugn_tensor* emb, const ugn_tensor* labels, f
  * rows keep an exactly zero distance.  Hinge, count and the analytic backward are shared with ugn_triplet_all. */
 int ugn_triplet_all_tc(ugn_ctx*, const ugn_tensor* emb, const ugn_tensor* emb16, const ugn_tensor* labels, float margin,
                        float scale, ugn_tensor* out, ugn_tensor* demb, ugn_tensor* workspace, void* stream);
+/* Batch-HARD triplet loss: tfa.losses.TripletHardLoss(margin) as compiled by UWYHSemiNet3Mods.compile_hard
+ * (nets/mj_uwyhNets_ba.py:1302-1306; soft = False, L2 distances): mean over the anchors of
+ * max(farthest positive - nearest negative + margin, 0), tfa's masked_maximum / masked_minimum semantics (anchor without
+ * positives: 0; without negatives: the row maximum), gradient split evenly among tied entries.  emb f32 [B,d] (tfa takes
+ * rank-2 embeddings), emb16 nullable (given: tensor-core Gram as ugn_triplet_all_tc).  out f32 [2] = {loss, anchors
+ * with a positive term}; demb, workspace as ugn_triplet_all (n = 1). */
+int ugn_triplet_hard(ugn_ctx*, const ugn_tensor* emb, const ugn_tensor* emb16, const ugn_tensor* labels, float margin,
+                     float scale, ugn_tensor* out, ugn_tensor* demb, ugn_tensor* workspace, void* stream);
 
 
 /* ---- a8/a9: regulariser + optimiser --------------------------------------------------

@@ -62,6 +62,7 @@ class NetConfig:
     normbfmerge: bool = False      # per-branch l2_normalize before the gate (:1167-1168)
     aux_losses: bool = False       # classprob_{of,gray,depth} heads on the gated branch outputs (:1222-1251)
     waux: float = 1.0              # loss_weights[-1] (:1264-1268)
+    triplet_hard: bool = False     # compile_hard: tfa.losses.TripletHardLoss instead of the batch-all loss (:1302-1306)
     postriplet: int = 1            # 2: fusion -> Dense "signature" (activity-regularised) -> l2_normalize "code" = the
     #                                embedding of the triplet loss and of the classifier (:814-832, 2-modality builder)
 
@@ -273,6 +274,33 @@ def triplet_loss_all(labels, emb, margin):
     return mean.mean(0), cnt
 
 
+def triplet_hard_loss(labels, emb, margin):
+    """`tfa.losses.TripletHardLoss(margin)` as compiled by UWYHSemiNet3Mods.compile_hard
+    (nets/mj_uwyhNets_ba.py:1302-1306): soft=False, distance_metric="L2".  tensorflow_addons is an un-vendored,
+    unpinned dependency (absent here): this restates its published algorithm (tfa/losses/triplet.py `triplet_hard_loss`,
+    tfa/losses/metric_learning.py `pairwise_distance`), op by op:
+      pdist   = sqrt(max(|a|^2 + |b|^2 - 2ab, 0)), entries <= 0 forced to 0 with zero gradient, diagonal zeroed
+      hard_n  = masked_minimum(pdist, labels differ) = min_j((pdist - rowmax) * mask) + rowmax
+      hard_p  = masked_maximum(pdist, labels equal minus the diagonal) = max_j((pdist - rowmin) * mask) + rowmin
+      loss    = mean_a max(hard_p - hard_n + margin, 0)
+    reduce_max / reduce_min split the gradient evenly among tied entries (torch amax / amin do the same).
+    emb [m,d] (tfa accepts rank-2 embeddings only).  Returns (loss, number of anchors with a positive term)."""
+    lab = labels.reshape(-1, 1)
+    m = emb.shape[0]
+    pd = batch_dist(emb.unsqueeze(0))[0]
+    eye = torch.eye(m, dtype=emb.dtype)
+    pd = pd * (1.0 - eye)
+    adj = lab == lab.t()
+    adj_not = (~adj).to(emb.dtype)
+    rowmax = pd.amax(dim=1, keepdim=True)
+    hard_n = ((pd - rowmax) * adj_not).amin(dim=1, keepdim=True) + rowmax
+    mask_p = adj.to(emb.dtype) - eye
+    rowmin = pd.amin(dim=1, keepdim=True)
+    hard_p = ((pd - rowmin) * mask_p).amax(dim=1, keepdim=True) + rowmin
+    t = torch.clamp(hard_p - hard_n + margin, min=0.0)
+    return t.mean(), (t > 0).sum().to(emb.dtype)
+
+
 def triplet_loss_all_literal_np(labels, emb, margin):
     """Op-by-op numpy restatement of nets/triplet_loss_all.py:33-61 (boolean_mask + reshape,
     which REQUIRES equal #positives / #negatives per anchor).  fp64.  Used to pin the
@@ -371,7 +399,10 @@ def total_loss(inputs, flags, labels, P, cfg: NetConfig, drop_masks=None, code_d
     outs = model_forward(inputs, flags, P, cfg, drop_masks, code_drop_mask, return_all=True, decisions=decisions,
                          record=record)
     res = {}
-    trip, cnt = triplet_loss_all(labels, outs["signature"], cfg.margin)
+    if getattr(cfg, "triplet_hard", False):      # compile_hard (:1302-1306)
+        trip, cnt = triplet_hard_loss(labels, outs["signature"], cfg.margin)
+    else:
+        trip, cnt = triplet_loss_all(labels, outs["signature"], cfg.margin)
     res["triplet"], res["count"] = trip, cnt
     loss = cfg.wver * trip
     if cfg.nclasses > 0:

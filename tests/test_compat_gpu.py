@@ -262,3 +262,42 @@ def test_postriplet2_builder(compat_path):
                               torch.tensor(y[0]), P, oc)
     assert logs["signature_loss"] == pytest.approx(float(res["triplet"]), rel=1e-5)
     assert logs["loss"] == pytest.approx(float(res["loss"]), rel=1e-5)
+
+
+def test_compile_hard(compat_path):
+    """UWYHSemiNet3Mods.compile_hard(model, optimizer, loss_weights, margin) (:1302-1306): the compiled model switches to
+    tfa's TripletHardLoss (ugn_triplet_hard), keeps its CE loss and weights, and starts a fresh optimiser."""
+    from nets.mj_uwyhNets_ba import UWYHSemiNet3Mods, TripletHardLoss
+    from ugaitnet_b200.compat import optimizers
+    import nets.mj_uwyhNets_ba as mod
+    mod.MATH_MODE = "fp32"
+    shapes = [(6, 60, 60), (4, 60, 60), (4, 60, 60)]
+    model = UWYHSemiNet3Mods.build(shapes, 4, [(7, 7), (5, 5), (3, 3), (2, 2)], [8, 8, 16, 16], 32, 0.00005, 0.0,
+                                   optimizer=optimizers.Adam(lr=1e-3), nclasses=10, loss_weights=[1.0, 0.1])
+    oc = O.NetConfig(in_channels=(6, 4, 4), filters_numbers=(8, 8, 16, 16), nd=32, nclasses=10, merge=O.MERGE_MAX,
+                     wver=0.8, wid=0.3, margin=0.3, triplet_hard=True)
+    gen = FakeGen(oc, n=1, base_rows=6, expand=4)
+    X, y = gen[0]
+    model.train_on_batch(X, y)                                    # one batch-all step first: optimiser state exists
+    W = {k: v.clone() for k, v in model.engine.export_params().items()}
+    ret = UWYHSemiNet3Mods.compile_hard(model, optimizers.SGD(0.01, 0.9), [0.8, 0.3], 0.3)
+    assert ret is model and isinstance(model.loss[0], TripletHardLoss) and model.loss[0].margin == 0.3
+    assert model.engine.t == 0 and float(model.engine.m.abs().max()) == 0.0 and float(model.engine.v.abs().max()) == 0.0
+    assert all(torch.equal(W[k], v) for k, v in model.engine.export_params().items())
+    P = {k: v.double().cpu() for k, v in W.items()}
+    xs = [torch.tensor(X[0]), torch.tensor(X[2]), torch.tensor(X[4])]
+    fl = [torch.tensor(X[1]), torch.tensor(X[3]), torch.tensor(X[5])]
+    res, G = O.loss_and_grads(xs, fl, torch.tensor(y[0]), P, oc)
+    logs = model.train_on_batch(X, y)
+    assert logs["signature_loss"] == pytest.approx(float(res["triplet"]), rel=1e-5)
+    assert logs["loss"] == pytest.approx(float(res["loss"]), rel=1e-5)
+    # SGD(0.01, momentum 0.9), first step: w -= lr * g
+    W2 = model.engine.export_params()
+    k = "ofBranch/dense/w"
+    step = (W[k].double().cpu() - W2[k].double().cpu()) / 0.01
+    assert float((step - G[k]).norm() / G[k].norm()) < 1e-4
+    # the loss object itself is callable like the Keras one
+    sig = model.predict(X)[0]
+    v = model.loss[0](y[0], sig)
+    want, _ = O.triplet_hard_loss(torch.tensor(y[0]).reshape(-1), torch.tensor(np.asarray(sig), dtype=torch.float64), 0.3)
+    assert float(v) == pytest.approx(float(want), rel=1e-4)

@@ -214,6 +214,43 @@ def test_triplet_no_active_triplets_is_zero(ctx):
     assert float(out[0]) == 0.0 and float(out[1]) == 0.0 and float(de.abs().max()) == 0.0
 
 
+@pytest.mark.parametrize("case", ["balanced", "ragged", "one_class", "tc_gram"])
+def test_triplet_hard_vs_oracle(ctx, case):
+    """ugn_triplet_hard (compile_hard: tfa TripletHardLoss, nets/mj_uwyhNets_ba.py:1302-1306) against the fp64 restatement of
+    the tfa algorithm: loss, active anchors and gradient; an anchor without positives, a batch without negatives,
+    duplicated rows, and the tensor-core Gram variant."""
+    from ugaitnet_b200 import ops
+    rng = np.random.default_rng(5)
+    if case == "balanced":
+        lab, d, margin = np.repeat(np.arange(24), 4), 128, 0.2
+    elif case == "ragged":
+        lab, d, margin = np.array([0, 0, 0, 1, 2, 2, 3, 3, 3, 3, 4]), 32, 1.0
+    elif case == "one_class":
+        lab, d, margin = np.zeros(6, dtype=np.int64), 16, 0.5
+    else:
+        lab, d, margin = np.repeat(np.arange(64), 2), 256, 0.2
+    B = len(lab)
+    e = rng.normal(size=(B, d)).astype(np.float32)
+    e[1] = e[0]                                   # identical rows: zero distance, zero gradient between them
+    e /= np.linalg.norm(e, axis=1, keepdims=True)
+    x = torch.tensor(e).cuda()
+    x16 = None
+    if case == "tc_gram":
+        hi = x.half()
+        x16 = torch.stack([hi, (x - hi.float()).half()]).contiguous()
+    out, de = torch.zeros(2, device="cuda"), torch.zeros(B, d, device="cuda")
+    ws = torch.zeros(ops.triplet_workspace_bytes(1, B) // 4 + 16, device="cuda")
+    ops.triplet_hard(ctx, x, torch.tensor(lab).int().cuda(), margin, 0.5, out, de, ws, emb16=x16)
+    ctx.check()
+    e64 = torch.tensor(e, dtype=torch.float64, requires_grad=True)
+    loss, act = O.triplet_hard_loss(torch.tensor(lab), e64, margin)
+    (0.5 * loss).backward()
+    tol = 1e-4 if case == "tc_gram" else 1e-5
+    assert float(out[0]) == pytest.approx(float(loss), rel=tol)
+    assert float(out[1]) == float(act)
+    assert rel(de, e64.grad) < (2e-3 if case == "tc_gram" else 1e-4)
+
+
 def test_adam_and_sgd_step(ctx):
     from ugaitnet_b200 import ops
     n = 64 * 5

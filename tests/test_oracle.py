@@ -368,3 +368,48 @@ def test_oracle_primitives_against_scipy_and_sklearn():
         mt, vt = (1 - 0.9 ** t) * 0.3, (1 - 0.999 ** t) * 0.09
         wref -= 1e-2 * math.sqrt(1 - 0.999 ** t) / (1 - 0.9 ** t) * mt / (math.sqrt(vt) + 1e-7)
         assert float(P["w"]) == pytest.approx(wref, rel=1e-12)
+
+
+def _hard_triplet_plain(lab, e, margin):
+    """Batch-hard loss written directly from its definition (loops, fp64): farthest positive, nearest negative."""
+    B = len(lab)
+    d = np.sqrt(np.maximum(((e[:, None, :] - e[None, :, :]) ** 2).sum(2), 0.0))
+    tot, act = 0.0, 0
+    for a in range(B):
+        pos = [d[a, b] for b in range(B) if b != a and lab[b] == lab[a]]
+        neg = [d[a, b] for b in range(B) if lab[b] != lab[a]]
+        hp = max(pos) if pos else 0.0
+        hn = min(neg) if neg else d[a].max()          # masked_minimum without negatives leaves the row maximum
+        t = hp - hn + margin
+        if t > 0:
+            tot += t
+            act += 1
+    return tot / B, act
+
+
+def test_triplet_hard_oracle_against_plain_definition_and_fd():
+    """compile_hard's tfa TripletHardLoss (restated masked_maximum / masked_minimum form) against the loss written from
+    its definition, incl. an anchor without positives, a batch without negatives, duplicated rows; gradient by finite
+    differences."""
+    rng = np.random.default_rng(11)
+    for lab, B in ((np.repeat(np.arange(6), 4), 24), (np.array([0, 0, 0, 1, 2, 2, 3]), 7), (np.zeros(5, dtype=int), 5)):
+        e = rng.normal(size=(B, 16))
+        e[1] = e[0]
+        e /= np.linalg.norm(e, axis=1, keepdims=True)
+        for margin in (0.2, 1.0):
+            loss, act = O.triplet_hard_loss(torch.tensor(lab), torch.tensor(e), margin)
+            want, wact = _hard_triplet_plain(lab, e, margin)
+            assert float(loss) == pytest.approx(want, rel=1e-12, abs=1e-15)
+            assert int(act) == wact
+    lab = np.repeat(np.arange(4), 3)
+    e = rng.normal(size=(12, 8))
+    e64 = torch.tensor(e, requires_grad=True)
+    loss, _ = O.triplet_hard_loss(torch.tensor(lab), e64, 0.5)
+    loss.backward()
+    h = 1e-6
+    for (i, j) in ((0, 0), (3, 5), (11, 7)):
+        ep, em = e.copy(), e.copy()
+        ep[i, j] += h
+        em[i, j] -= h
+        fd = (_hard_triplet_plain(lab, ep, 0.5)[0] - _hard_triplet_plain(lab, em, 0.5)[0]) / (2 * h)
+        assert float(e64.grad[i, j]) == pytest.approx(fd, rel=1e-5, abs=1e-9)

@@ -22,6 +22,14 @@ def make_case(name):
         oc = O.NetConfig(in_channels=(6, 4, 4), filters_numbers=(8, 8, 16, 16), nd=32, nclasses=10,
                          merge=O.MERGE_SIGNMAX, wver=1.0, wid=0.1)
         return oc, dict(base_rows=6, expand=4, kinds=("of", "gray", "depth")), None
+    if name == "3mod_hard":          # compile_hard (:1302-1306): tfa TripletHardLoss instead of the batch-all loss
+        oc = O.NetConfig(in_channels=(6, 4, 4), filters_numbers=(8, 8, 16, 16), nd=32, nclasses=10,
+                         merge=O.MERGE_SIGNMAX, wver=1.0, wid=0.1, triplet_hard=True, margin=0.2)
+        return oc, dict(base_rows=6, expand=4, kinds=("of", "gray", "depth")), None
+    if name == "1mod_hard":
+        oc = O.NetConfig(in_channels=(5,), filters_numbers=(8, 8, 16, 16), nd=16, nclasses=9, single=True,
+                         wver=0.7, wid=0.1, triplet_hard=True, margin=1.0)
+        return oc, dict(base_rows=12, expand=1, kinds=("gray",)), None
     if name == "3mod_norm_smooth":   # normbfmerge + smoothlabels builder options (a17)
         oc = O.NetConfig(in_channels=(6, 4, 4), filters_numbers=(8, 8, 16, 16), nd=32, nclasses=10,
                          merge=O.MERGE_SIGNMAX, wver=1.0, wid=0.5, label_smoothing=0.1, normbfmerge=True)
@@ -67,7 +75,7 @@ def to_engine_cfg(oc, dropout=0.0):
                      weight_decay=oc.weight_decay, merge=oc.merge, act=oc.act, alpha=oc.alpha, margin=oc.margin,
                      wver=oc.wver, wid=oc.wid, hw=oc.hw, dropout=dropout, single=oc.single,
                      label_smoothing=oc.label_smoothing, normbfmerge=oc.normbfmerge, aux_losses=oc.aux_losses,
-                     waux=oc.waux, postriplet=oc.postriplet)
+                     waux=oc.waux, postriplet=oc.postriplet, triplet_hard=oc.triplet_hard)
 
 
 def setup(name, math_mode="fp32", seed=11):
@@ -112,7 +120,8 @@ def reg_grad(oc, name, w):
 
 
 @pytest.mark.parametrize("name", ["3mod_signmax", "2mod_max_leaky_code", "3mod_avg", "1mod_gray", "real_shapes",
-                                  "3mod_norm_smooth", "3mod_aux", "2mod_aux", "2mod_postriplet2", "2mod_postriplet2_relu"])
+                                  "3mod_norm_smooth", "3mod_aux", "2mod_aux", "2mod_postriplet2", "2mod_postriplet2_relu",
+                                  "3mod_hard", "1mod_hard"])
 def test_step_parity_fp32(name):
     oc, eng, P, xs, fl, lab, masks, cmask = setup(name)
     res, G = oracle_step(oc, P, xs, fl, lab, masks, cmask)

@@ -15,8 +15,8 @@ the gate, :1167-1168), ``aux_losses`` (classprob_{of,gray,depth} heads on the ga
 stacked-CNN branches), ``postriplet == 2`` (2-modality builder, :819-832), ``freeze_convs`` / ``freeze_all`` /
 ``freeze_branches`` and ``layer.trainable`` (:193, :1366-1391), ``initnet`` / ``init_branches`` / ``loadnet`` from Keras
 HDF5 files (ugaitnet_b200.hdf5: pure-Python reader / writer, h5py is absent) are implemented.  Builder arguments that
-select graphs outside the hot path raise NotImplementedError: use3D (Conv3D branches), tfa TripletHardLoss
-(compile_hard), aux_losses together with gaitset.
+select graphs outside the hot path raise NotImplementedError: use3D (Conv3D branches), aux_losses together with
+gaitset.  compile_hard (tfa TripletHardLoss) re-compiles a stacked-frame CNN model onto ugn_triplet_hard.
 """
 from __future__ import annotations
 
@@ -36,6 +36,28 @@ from ugaitnet_b200.compat.nets.triplet_loss_all import triplet_loss
 
 # the benchmarked, parity-gated math mode (tests/test_decisions_gpu.py): fp16 hi/lo split, 3-pass forward, 1-pass backward
 MATH_MODE = os.environ.get("UGN_MATH_MODE", "f16mix")
+
+
+class TripletHardLoss:
+    """Stand-in for `tfa.losses.TripletHardLoss(margin)` in model.loss after compile_hard (:1303); callable on
+    (y_true [m,1], y_pred [m,d]) like the Keras loss object, computed by ugn_triplet_hard."""
+    name = "triplet_hard_loss"
+
+    def __init__(self, margin=1.0, soft=False, distance_metric="L2", **kw):
+        if soft or distance_metric != "L2":
+            raise NotImplementedError("TripletHardLoss: only soft=False, distance_metric='L2' (what compile_hard uses)")
+        self.margin = margin
+
+    def __call__(self, y_true, y_pred):
+        dev = torch.device("cuda", torch.cuda.current_device())
+        emb = torch.as_tensor(np.asarray(y_pred) if not torch.is_tensor(y_pred) else y_pred,
+                              dtype=torch.float32).to(dev).contiguous()
+        lab = torch.as_tensor(np.asarray(y_true) if not torch.is_tensor(y_true) else y_true).to(dev)
+        lab = lab.reshape(-1).to(torch.int32).contiguous()
+        out = torch.zeros(2, device=dev)
+        ws = torch.zeros(ops.triplet_workspace_bytes(1, emb.shape[0]) // 4 + 8, device=dev)
+        ops.triplet_hard(ops.get_ctx(dev.index), emb, lab, float(self.margin), 1.0, out, None, ws)
+        return out[0]
 
 
 def mj_tensor_times_scalar(d):
@@ -855,7 +877,24 @@ class UWYHSemiNet3Mods(UWYHSemiNet):
 
     @staticmethod
     def compile_hard(model, optimizer, loss_weights, margin):
-        raise NotImplementedError("tfa.losses.TripletHardLoss is outside the B200 hot path")
+        """:1302-1306 -- re-compile with `tfa.losses.TripletHardLoss(margin)` (batch-hard: farthest positive, nearest
+        negative per anchor; CUDA: ugn_triplet_hard) in place of the batch-all loss; the CE loss, the weights of the net
+        and the metrics stay, the optimiser starts afresh as under model.compile."""
+        if model.gaitset:
+            raise NotImplementedError("tfa.losses.TripletHardLoss takes rank-2 embeddings; the GaitSet signature is "
+                                      "[62, B, 256] (the reference would fail inside tfa as well)")
+        opt = optimizer if optimizer is not None else optimizers.SGD(0.001, 0.9)
+        kw = dict(getattr(opt, "kw", {}))
+        lw = list(loss_weights) if loss_weights is not None else [1.0, 1.0]
+        model.engine.recompile(optimizer=getattr(opt, "name", "sgd"), lr=getattr(opt, "lr", 0.001), margin=float(margin),
+                               wver=float(lw[0]), wid=float(lw[1]) if len(lw) > 1 else None, triplet_hard=True,
+                               momentum=kw.get("momentum"), beta1=kw.get("beta1"), beta2=kw.get("beta2"),
+                               eps=kw.get("eps"), lr_decay=kw.get("decay"),
+                               decoupled_weight_decay=kw.get("weight_decay"))
+        model.cfg = model.engine.cfg
+        model.loss = [TripletHardLoss(margin=margin)] + list(model.loss[1:])
+        model.loss_weights = lw
+        return model
 
     @staticmethod
     def build_or_load(input_shapes, number_convolutional_layers, filters_size, filters_numbers, ndense_units=512,

@@ -176,6 +176,9 @@ def install(reference_root=None):
     for k in [k for k in sys.modules if k == "nets" or k.startswith("nets.")]:
         del sys.modules[k]
     nets = importlib.import_module("nets")
+    tfa_losses = sys.modules.get("tensorflow_addons.losses")
+    if tfa_losses is not None and not hasattr(tfa_losses, "TripletHardLoss"):
+        tfa_losses.TripletHardLoss = importlib.import_module("nets.mj_uwyhNets_ba").TripletHardLoss
     if reference_root:
         ref_nets = os.path.join(reference_root, "nets")
         if os.path.isdir(ref_nets) and ref_nets not in nets.__path__:

@@ -39,6 +39,7 @@ class NetConfig:
     normbfmerge: bool = False      # l2_normalize every branch output before its gate (:1167-1168)
     aux_losses: bool = False       # extra Dense(nclasses, softmax) head + CE on every gated branch output (:1222-1251)
     waux: float = 1.0              # their loss weight: loss_weights[-1] (:1264-1268)
+    triplet_hard: bool = False     # compile_hard (:1302-1306): tfa TripletHardLoss (batch-hard) instead of batch-all
     postriplet: int = 1            # 2 (needs nc > 0; 2-modality builder, :814-832): the fusion is NOT normalised, FC1 is the
     #                                layer "signature", its l2_normalize ("code") is what the triplet loss and the classifier see
 

@@ -11,11 +11,13 @@
 // Backward (the active count is a constant under autodiff):
 //   dL/dd_ab = (+#{q active} if same(a,b) else -#{p active}) / (n_parts * c_n)
 //   dd_ab/dx_a = (x_a - x_b)/d_ab,  dd_ab/dx_b = -(x_a - x_b)/d_ab, both 0 where d_ab == 0.
+#include <cfloat>
 #include "simt.cuh"
 
 struct TripAcc {
   double sum;
   unsigned long long cnt;
+  unsigned long long act;   // batch-hard loss: anchors with a positive term (cnt is the batch size there)
 };
 
 __global__ void trip_diag_kernel(const float* __restrict__ G, float* __restrict__ x2, int B) {
@@ -94,12 +96,107 @@ __global__ void __launch_bounds__(128) trip_hinge_kernel(const float* __restrict
   }
 }
 
-__global__ void trip_finalize_kernel(const TripAcc* __restrict__ acc, int nparts, float* __restrict__ out) {
+// Batch-HARD triplet loss: tfa.losses.TripletHardLoss(margin) as compiled by UWYHSemiNet3Mods.compile_hard
+// (nets/mj_uwyhNets_ba.py:1302-1306; soft = False, distance_metric = "L2"; tensorflow_addons is not vendored, the
+// published algorithm of tfa/losses/triplet.py is followed):
+//   hard_p(a) = masked_maximum(pdist, same label minus the diagonal) = the farthest positive (0 without positives)
+//   hard_n(a) = masked_minimum(pdist, other label) = min_j((d_aj - M_a) * mask) + M_a, M_a = max_j d_aj: the nearest
+//               negative; M_a itself when the anchor has no negative
+//   loss = mean_a max(hard_p - hard_n + margin, 0)
+// One block per anchor.  Wc receives dLoss/dd_ab * B (trip_bwd_kernel divides by acc.cnt = B); reduce_max / reduce_min
+// split the gradient evenly among tied entries, and the masked_minimum form also routes gradient through M_a when the
+// selected entry ties with the masked zeros -- both are kept literally.
+__global__ void __launch_bounds__(128) trip_hard_kernel(const float* __restrict__ D, const int* __restrict__ labels,
+                                                        float* __restrict__ Wc, TripAcc* __restrict__ acc, int B,
+                                                        float margin) {
+  extern __shared__ float sm[];  // drow[B] | lab[B]
+  float* drow = sm;
+  int* lab = reinterpret_cast<int*>(sm + B);
+  __shared__ float r_hp[4], r_hn[4], r_M[4];
+  __shared__ int r_c[4][4];
+  const int a = blockIdx.x;
+  for (int b = threadIdx.x; b < B; b += blockDim.x) {
+    drow[b] = b == a ? 0.f : D[(long long)a * B + b];      // pairwise_distance zeroes the diagonal
+    lab[b] = labels[b];
+  }
+  __syncthreads();
+  const int la = lab[a];
+  float hp = -1.f, hn = FLT_MAX, M = 0.f;
+  for (int b = threadIdx.x; b < B; b += blockDim.x) {
+    const float db = drow[b];
+    M = fmaxf(M, db);
+    if (b == a) continue;
+    if (lab[b] == la) hp = fmaxf(hp, db); else hn = fminf(hn, db);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    hp = fmaxf(hp, __shfl_xor_sync(0xffffffffu, hp, o));
+    hn = fminf(hn, __shfl_xor_sync(0xffffffffu, hn, o));
+    M = fmaxf(M, __shfl_xor_sync(0xffffffffu, M, o));
+  }
+  if ((threadIdx.x & 31) == 0) { r_hp[threadIdx.x >> 5] = hp; r_hn[threadIdx.x >> 5] = hn; r_M[threadIdx.x >> 5] = M; }
+  __syncthreads();
+  hp = fmaxf(fmaxf(r_hp[0], r_hp[1]), fmaxf(r_hp[2], r_hp[3]));
+  hn = fminf(fminf(r_hn[0], r_hn[1]), fminf(r_hn[2], r_hn[3]));
+  M = fmaxf(fmaxf(r_M[0], r_M[1]), fmaxf(r_M[2], r_M[3]));
+  const bool has_pos = hp >= 0.f, has_neg = hn < FLT_MAX;
+  // tie counts: positives at hp, negatives at hn, entries at M, masked (non-negative) entries
+  int np = 0, nn = 0, nM = 0, nmask = 0;
+  for (int b = threadIdx.x; b < B; b += blockDim.x) {
+    const float db = drow[b];
+    const bool same = lab[b] == la;
+    nM += db == M;
+    nmask += same;                       // the diagonal is a masked entry of adjacency_not too
+    if (b == a) continue;
+    np += same && db == hp;
+    nn += !same && db == hn;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    np += __shfl_xor_sync(0xffffffffu, np, o);
+    nn += __shfl_xor_sync(0xffffffffu, nn, o);
+    nM += __shfl_xor_sync(0xffffffffu, nM, o);
+    nmask += __shfl_xor_sync(0xffffffffu, nmask, o);
+  }
+  if ((threadIdx.x & 31) == 0) { int w = threadIdx.x >> 5; r_c[w][0] = np; r_c[w][1] = nn; r_c[w][2] = nM; r_c[w][3] = nmask; }
+  __syncthreads();
+  np = r_c[0][0] + r_c[1][0] + r_c[2][0] + r_c[3][0];
+  nn = r_c[0][1] + r_c[1][1] + r_c[2][1] + r_c[3][1];
+  nM = r_c[0][2] + r_c[1][2] + r_c[2][2] + r_c[3][2];
+  nmask = r_c[0][3] + r_c[1][3] + r_c[2][3] + r_c[3][3];
+  const float hp_v = (has_pos && hp > 0.f) ? hp : 0.f;            // max over (d * mask): never below the masked zeros
+  const float hn_v = has_neg ? hn : M;
+  const float t = hp_v - hn_v + margin;
+  const bool active = t > 0.f;
+  // masked_minimum: the selected set is {negatives at hn} when hn < M, else those AND every masked entry (all tie at 0)
+  const bool tie0 = !has_neg || hn == M;
+  const float sel = tie0 ? (float)((has_neg ? nn : 0) + nmask) : (float)nn;
+  const float w_neg = (has_neg && active) ? 1.f / sel : 0.f;                                  // direct part
+  const float w_M = (active && tie0) ? (1.f - (has_neg ? (float)nn : 0.f) / sel) / (float)nM : 0.f;   // through M_a
+  const float w_pos = (active && hp_v > 0.f) ? 1.f / (float)np : 0.f;
+  for (int b = threadIdx.x; b < B; b += blockDim.x) {
+    const float db = drow[b];
+    float w = 0.f;
+    if (b != a) {
+      const bool same = lab[b] == la;
+      if (same && db == hp) w += w_pos;
+      if (!same && db == hn) w -= w_neg;
+      if (db == M) w -= w_M;
+    }
+    Wc[(long long)a * B + b] = w;
+  }
+  if (threadIdx.x == 0) {
+    if (active) { atomicAdd(&acc[0].sum, (double)t); atomicAdd(&acc[0].act, 1ull); }
+    atomicAdd(&acc[0].cnt, 1ull);
+  }
+}
+
+__global__ void trip_finalize_kernel(const TripAcc* __restrict__ acc, int nparts, float* __restrict__ out, int hard) {
   if (threadIdx.x == 0 && blockIdx.x == 0) {
     double loss = 0.0, total = 0.0;
     for (int n = 0; n < nparts; ++n) {
       if (acc[n].cnt) loss += (double)((float)acc[n].sum / (float)acc[n].cnt);
-      total += (double)acc[n].cnt;
+      total += (double)(hard ? acc[n].act : acc[n].cnt);
     }
     out[0] = (float)(loss / nparts);
     out[1] = (float)total;
@@ -153,7 +250,14 @@ int tc_gram(ugn_ctx* ctx, int f16, int B, int d, const __nv_bfloat16* X16, float
 
 static int triplet_common(ugn_ctx* ctx, const ugn_tensor* emb, const ugn_tensor* emb16, const ugn_tensor* labels,
                           float margin, float scale, ugn_tensor* out, ugn_tensor* demb, ugn_tensor* workspace,
-                          void* stream);
+                          void* stream, int hard = 0);
+// tfa.losses.TripletHardLoss (compile_hard): emb [B,d] (tfa takes rank-2 embeddings), emb16 nullable (tensor-core Gram)
+extern "C" int ugn_triplet_hard(ugn_ctx* ctx, const ugn_tensor* emb, const ugn_tensor* emb16, const ugn_tensor* labels,
+                                float margin, float scale, ugn_tensor* out, ugn_tensor* demb, ugn_tensor* workspace,
+                                void* stream) {
+  UGN_CHECK(emb && emb->ndim == 2, "ugn_triplet_hard: embeddings must be [B,d]");
+  return triplet_common(ctx, emb, emb16, labels, margin, scale, out, demb, workspace, stream, 1);
+}
 extern "C" int ugn_triplet_all(ugn_ctx* ctx, const ugn_tensor* emb, const ugn_tensor* labels,
                                float margin, float scale, ugn_tensor* out, ugn_tensor* demb,
                                ugn_tensor* workspace, void* stream) {
@@ -173,7 +277,7 @@ extern "C" int ugn_triplet_all_tc(ugn_ctx* ctx, const ugn_tensor* emb, const ugn
 
 static int triplet_common(ugn_ctx* ctx, const ugn_tensor* emb, const ugn_tensor* emb16, const ugn_tensor* labels,
                           float margin, float scale, ugn_tensor* out, ugn_tensor* demb, ugn_tensor* workspace,
-                          void* stream) {
+                          void* stream, int hard) {
   cudaStream_t st = (cudaStream_t)stream;
   UGN_CHECK(ctx && emb && labels && out && workspace, "ugn_triplet_all: null argument");
   UGN_TENSOR(emb, DT_F32, 2, 3);
@@ -234,12 +338,16 @@ static int triplet_common(ugn_ctx* ctx, const ugn_tensor* emb, const ugn_tensor*
     static bool attr_set = false;
     if (!attr_set) {
       UGN_CUDA(cudaFuncSetAttribute(trip_hinge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 8192 * (int)sizeof(float)));
+      UGN_CUDA(cudaFuncSetAttribute(trip_hard_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 8192 * (int)sizeof(float)));
       attr_set = true;
     }
   }
-  trip_hinge_kernel<<<dim3(B, n), 128, 2 * B * sizeof(float), st>>>(D, ugn_ptr<int>(labels), Wc, acc, B, margin);
+  if (hard)
+    trip_hard_kernel<<<B, 128, 2 * B * sizeof(float), st>>>(D, ugn_ptr<int>(labels), Wc, acc, B, margin);
+  else
+    trip_hinge_kernel<<<dim3(B, n), 128, 2 * B * sizeof(float), st>>>(D, ugn_ptr<int>(labels), Wc, acc, B, margin);
   UGN_LAUNCHED(ctx);
-  trip_finalize_kernel<<<1, 32, 0, st>>>(acc, n, ugn_ptr<float>(out));
+  trip_finalize_kernel<<<1, 32, 0, st>>>(acc, n, ugn_ptr<float>(out), hard);
   UGN_LAUNCHED(ctx);
   if (demb) {
     trip_bwd_kernel<<<dim3(B, n, ugn_cdiv(d, 256)), 256, B * sizeof(float), st>>>(X, D, Wc, acc, ugn_ptr<float>(demb), n, B, d, scale);

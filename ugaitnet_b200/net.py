@@ -794,7 +794,11 @@ class UGaitEngine:
         B = p.B
         self._works = []
         # triplet: demb = wver * dL/dsig
-        if p.tc_gram:      # B x B Gram matrix on the tensor cores from the hi/lo planes the fusion kernel wrote (north_star)
+        if getattr(cfg, "triplet_hard", False):      # compile_hard: tfa TripletHardLoss (nets/mj_uwyhNets_ba.py:1302-1306)
+            check(lib.ugn_triplet_hard(h, sig.ptr, p.R["sig16"].ptr if p.tc_gram else None, p.R["labels"].ptr,
+                                       cfg.margin, cfg.wver, p.R["trip_out"].ptr,
+                                       (p.R["dcodeN"] if self.post2 else p.R["dsig"]).ptr, p.R["trip_ws"].ptr, st))
+        elif p.tc_gram:      # B x B Gram matrix on the tensor cores from the hi/lo planes the fusion kernel wrote (north_star)
             check(lib.ugn_triplet_all_tc(h, sig.ptr, p.R["sig16"].ptr, p.R["labels"].ptr, cfg.margin, cfg.wver,
                                          p.R["trip_out"].ptr, p.R["dsig"].ptr, p.R["trip_ws"].ptr, st))
         else:
@@ -1270,6 +1274,30 @@ class UGaitEngine:
             self._cw_symm.barrier(channel=1)     # every rank's copies INTO this rank have landed
             self._cw_event.record(side)
 
+    def recompile(self, optimizer=None, lr=None, margin=None, wver=None, wid=None, triplet_hard=None, **opt_kw):
+        """model.compile(...) on an existing model: new loss constants and a FRESH optimiser (Keras creates new slot
+        variables and restarts `iterations`); the weights stay.  Captured step graphs bake the constants in: dropped."""
+        import dataclasses
+        ch = {k: v for k, v in dict(margin=margin, wver=wver, wid=wid, triplet_hard=triplet_hard).items() if v is not None}
+        if ch:
+            self.cfg = dataclasses.replace(self.cfg, **ch)
+        if optimizer is not None:
+            self.optimizer = optimizer
+        if lr is not None:
+            self.lr = float(lr)
+        for k in ("momentum", "beta1", "beta2", "eps", "lr_decay"):
+            if k in opt_kw and opt_kw[k] is not None:
+                setattr(self, k, float(opt_kw[k]))
+        if opt_kw.get("decoupled_weight_decay") is not None:
+            self.decoupled_wd = float(opt_kw["decoupled_weight_decay"])
+        torch.cuda.synchronize(self.dev)
+        self.m.zero_()
+        self.v.zero_()
+        if getattr(self, "vhat", None) is not None:
+            self.vhat.zero_()
+        self.t = 0
+        self._graphs.clear()
+
     def _next_lr(self):
         self.t += 1
         if self.optimizer in ("adam", "amsgrad", "adamw"):
@@ -1398,8 +1426,12 @@ class UGaitEngine:
         self._set_inputs(p, inputs, flags, labels)
         sig, _ = self._forward(p, False)
         st = stream_ptr()
-        check(lib.ugn_triplet_all(h, sig.ptr, p.R["labels"].ptr, cfg.margin, 1.0, p.R["trip_out"].ptr, None,
-                                  p.R["trip_ws"].ptr, st))
+        if getattr(cfg, "triplet_hard", False):
+            check(lib.ugn_triplet_hard(h, sig.ptr, None, p.R["labels"].ptr, cfg.margin, 1.0, p.R["trip_out"].ptr, None,
+                                       p.R["trip_ws"].ptr, st))
+        else:
+            check(lib.ugn_triplet_all(h, sig.ptr, p.R["labels"].ptr, cfg.margin, 1.0, p.R["trip_out"].ptr, None,
+                                      p.R["trip_ws"].ptr, st))
         if cfg.nclasses > 0:
             check(lib.ugn_softmax_ce_ls(h, p.R["logits"].ptr, p.R["labels"].ptr, p.R["ce_out"].ptr, None, 1.0,
                                         cfg.label_smoothing, st))

@@ -136,6 +136,14 @@ def triplet_all(ctx, emb, labels, margin, scale, out, demb, workspace):
                               stream_ptr()))
 
 
+def triplet_hard(ctx, emb, labels, margin, scale, out, demb, workspace, emb16=None):
+    """tfa.losses.TripletHardLoss (compile_hard, nets/mj_uwyhNets_ba.py:1302-1306); emb [B,d]."""
+    rs = [_r(t) for t in (emb, emb16, labels)]
+    ro = [_r(t) for t in (out, demb, workspace)]
+    check(lib.ugn_triplet_hard(ctx.h, rs[0].ptr, _p(rs[1]), rs[2].ptr, float(margin), float(scale),
+                               *[_p(r) for r in ro], stream_ptr()))
+
+
 def adam_step(ctx, w, g, m, v, seg_off, seg_l2, lr_t, beta1=0.9, beta2=0.999, eps=1e-7, gscale=1.0,
               reg_out=None, lr_dev=None, pack_table=None, pack_planes=0, pack_f16=0):
     rs = [_r(t) for t in (w, g, m, v, seg_off, seg_l2)]
