@@ -65,6 +65,11 @@ def mj_tensor_times_scalar(d):
 
 
 def _unsupported(**flags):
+    if flags.get("aux_losses_with_gaitset"):
+        # :1222-1229 puts Dense(nclasses) on the GATED branch outputs, which are [62, B, 256] under gaitset (:1162): the
+        # heads emit [62, B, nclasses] against one-hot targets [B, nclasses] -- Keras rejects the shapes at fit time
+        raise NotImplementedError("aux_losses with gaitset: the reference graph itself is ill-formed (auxiliary heads on "
+                                  "[62, B, 256] gated outputs vs [B, nclasses] targets, nets/mj_uwyhNets_ba.py:1222-1229)")
     bad = [k for k, v in flags.items() if v]
     if bad:
         raise NotImplementedError(f"builder options outside the B200 hot path: {', '.join(bad)} "
