@@ -121,7 +121,7 @@ def test_triplet_loss_closure_and_unsupported_options(compat_path):
     assert got == pytest.approx(ref, rel=1e-5)
     with pytest.raises(ValueError, match="gaitset"):        # the reference builds GaitSet branches in its LeakyReLU path only
         UWYHSemiNet3Mods.build([(25, 60, 60, 1)] * 3, 4, [7, 5, 3, 2], [96, 192, 512, 512], gaitset=True)
-    with pytest.raises(NotImplementedError, match="aux_losses_with_gaitset"):
+    with pytest.raises(NotImplementedError, match="aux_losses with gaitset"):
         UWYHSemiNet3Mods.build([(25, 60, 60, 1)] * 3, 4, [7, 5, 3, 2], [96, 192, 512, 512], gaitset=True,
                                fActivation='lrelu', aux_losses=True, nclasses=5)
     with pytest.raises(NotImplementedError, match="use3D"):

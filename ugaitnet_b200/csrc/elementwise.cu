@@ -558,15 +558,19 @@ __global__ void softmax_ce_kernel(const float* __restrict__ logits, const int* _
   // label smoothing (tf.losses.CategoricalCrossentropy(label_smoothing=e), nets/mj_uwyhNets_ba.py:1252-1262):
   // y_s = y*(1-e) + e/C;  loss = -sum_j y_s[j] log p[j] = lse - (1-e) z[lab] - (e/C) sum_j z[j]
   const float uni = smooth / (float)C;
+  // an id outside [0, C) has an all-zero one-hot row (tf.one_hot semantics): its target mass is `smooth` only, and
+  // nothing is read outside the row
+  const bool valid = lab >= 0 && lab < C;
+  const float hot = valid ? 1.f - smooth : 0.f, mass = hot + smooth;
   if (lane == 0) {
-    atomicAdd(loss_acc, (lse - (1.f - smooth) * row[lab] - uni * sz) / (float)B);
-    atomicAdd(loss_acc + 1, (amax == lab ? 1.f : 0.f) / (float)B);
+    atomicAdd(loss_acc, (mass * lse - (valid ? hot * row[lab] : 0.f) - uni * sz) / (float)B);
+    atomicAdd(loss_acc + 1, (valid && amax == lab ? 1.f : 0.f) / (float)B);
   }
   if (dlogits) {
     float s = scale / (float)B;
     for (int j = lane; j < C; j += 32) {
       float p = expf(row[j] - lse);
-      dlogits[(long long)warp * C + j] = s * (p - (j == lab ? 1.f - smooth : 0.f) - uni);
+      dlogits[(long long)warp * C + j] = s * (mass * p - (j == lab ? hot : 0.f) - uni);
     }
   }
 }

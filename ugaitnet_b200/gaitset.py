@@ -209,6 +209,7 @@ class GaitSetEngine(UGaitEngine):
         return 2 if (self.P and Hs + 2 > 64 and Hs % 4 == 0) else 1
 
     def plan(self, B: int, train: bool) -> "_GsPlan":
+        self._check_batch(B)
         key = (B, train)
         p = self._plans.get(key)
         if p is None:
@@ -216,6 +217,7 @@ class GaitSetEngine(UGaitEngine):
         return p
 
     def _set_inputs(self, p, inputs, flags, labels=None, drop_masks=None, code_drop_mask=None):
+        self._check_shapes(p, inputs, flags)
         for m in range(self.cfg.nmods):
             p.br[m].x_in.copy_(inputs[m], non_blocking=True)
             if flags is not None:

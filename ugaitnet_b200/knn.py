@@ -56,6 +56,15 @@ class KNeighborsClassifier:
         """X [N,D] float, y [N] int labels.  With a process group and ``sharded=False`` the full
         gallery is given on every rank and this rank keeps rows shard_bounds(N, rank, world);
         with ``sharded=True`` X/y already are this rank's shard and idx_base its global offset."""
+        # input validation with scikit-learn's exceptions and wording (check_X_y / check_array of KNeighborsClassifier.fit)
+        if len(np.shape(X)) != 2:
+            raise ValueError(f"Expected 2D array, got {len(np.shape(X))}D array instead")
+        if np.shape(X)[0] != np.shape(y)[0]:
+            raise ValueError(f"Found input variables with inconsistent numbers of samples: [{np.shape(X)[0]}, {np.shape(y)[0]}]")
+        if np.shape(X)[0] == 0:
+            raise ValueError(f"Found array with 0 sample(s) (shape={tuple(np.shape(X))}) while a minimum of 1 is required "
+                             "by KNeighborsClassifier.")
+        self.n_total = int(np.shape(X)[0])
         if self.pg is not None and not sharded:
             rank, world = torch.distributed.get_rank(self.pg), torch.distributed.get_world_size(self.pg)
             lo, hi = shard_bounds(len(X), rank, world)
@@ -63,6 +72,15 @@ class KNeighborsClassifier:
         self.G = _as_cuda(X, torch.float32, self.dev)
         self.labels = _as_cuda(y, torch.int32, self.dev)
         self.idx_base = int(idx_base)
+        if self.pg is not None and sharded:
+            tot = torch.tensor([self.G.shape[0]], dtype=torch.int64, device=self.dev)
+            torch.distributed.all_reduce(tot, group=self.pg)
+            self.n_total = int(tot)
+        if not bool(torch.isfinite(self.G).all()):
+            raise ValueError("Input X contains NaN." if bool(torch.isnan(self.G).any()) else
+                             "Input X contains infinity or a value too large for dtype('float32').")
+        if self.G.shape[0] < self.k and self.n_total >= self.k:
+            raise ValueError(f"gallery shard of {self.G.shape[0]} rows is smaller than n_neighbors = {self.k}: use fewer ranks")
         n, d = self.G.shape
         npad = (n + 255) // 256 * 256
         self.g2 = torch.empty(npad, device=self.dev)
@@ -201,15 +219,42 @@ class KNeighborsClassifier:
         return w["od2"], w["oidx"], w["olab"], w["pred"]
 
     def predict_device(self, Q) -> torch.Tensor:
-        """Predicted labels i32 [Q] on the device (a view of the search workspace: valid until the next search)."""
+        """Predicted labels i32 [Q] on the device (a view of the search workspace: valid until the next search).
+        Device-side entry: shapes are validated, the values are not (no host synchronisation)."""
+        self._validate(Q)
         return self._search(Q)[3]
 
+    def _validate(self, Q):
+        """scikit-learn's exceptions and wording for the same mistakes (KNeighborsClassifier.predict / kneighbors)."""
+        shp = tuple(np.shape(Q))
+        if len(shp) != 2:
+            raise ValueError(f"Expected 2D array, got {len(shp)}D array instead")
+        if shp[0] == 0:
+            raise ValueError(f"Found array with 0 sample(s) (shape={shp}) while a minimum of 1 is required by "
+                             "KNeighborsClassifier.")
+        if shp[1] != self.G.shape[1]:
+            raise ValueError(f"X has {shp[1]} features, but KNeighborsClassifier is expecting {self.G.shape[1]} features "
+                             "as input.")
+        if self.k > self.n_total:
+            raise ValueError(f"Expected n_neighbors <= n_samples_fit, but n_neighbors = {self.k}, n_samples_fit = "
+                             f"{self.n_total}, n_samples = {shp[0]}")
+
+    def _finite_or_raise(self, nq):
+        q = self._works[nq]["q"]
+        if not bool(torch.isfinite(q).all()):
+            raise ValueError("Input X contains NaN." if bool(torch.isnan(q).any()) else
+                             "Input X contains infinity or a value too large for dtype('float32').")
+
     def predict(self, Q) -> np.ndarray:
-        return self.predict_device(Q).cpu().numpy()
+        pred = self.predict_device(Q)
+        self._finite_or_raise(int(np.shape(Q)[0]))
+        return pred.cpu().numpy()
 
     def kneighbors_exact(self, Q):
         """(squared fp64 distances [Q,k], global indices [Q,k]) ordered by (distance, index)."""
+        self._validate(Q)
         d2, idx, _, _ = self._search(Q)
+        self._finite_or_raise(int(np.shape(Q)[0]))
         return d2.cpu().numpy().copy(), idx.cpu().numpy().copy()
 
     def kneighbors(self, Q, return_distance=True):

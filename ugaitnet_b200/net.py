@@ -164,6 +164,11 @@ class UGaitEngine:
         self.fwd_passes = FWD_PASSES.get(math_mode, (0, 0))
         self.scaled = self.dt16 is torch.float16
         self.pad = 32 if self.P else 1
+        if self.P and type(cfg) is NetConfig:
+            bad = [c for c in cfg.filters_numbers if c % 32]
+            if bad:     # the activation of layer i is the (unpadded) K operand of layer i + 1
+                raise ValueError(f"math_mode={math_mode!r} (tensor cores) needs filter counts that are multiples of 32, got "
+                                 f"{list(cfg.filters_numbers)}; use math_mode='fp32' for such a net")
         self.optimizer, self.lr, self.momentum = optimizer.lower(), float(lr), momentum
         self.beta1, self.beta2, self.eps = beta1, beta2, eps
         # optimizers.SGD(decay=...) -> lr / (1 + decay * iterations); tfa AdamW(weight_decay=...) -> decoupled decay
@@ -510,7 +515,23 @@ class UGaitEngine:
         return dec
 
     # ------------------------------------------------------------------ plans
+    @staticmethod
+    def _check_batch(B: int):
+        if B <= 0:      # Keras: model.predict / fit on zero samples
+            raise ValueError("Expect x to be a non-empty array or dataset.")
+
+    def _check_shapes(self, p, inputs, flags):
+        """Keras' complaint for a mis-shaped input, before any copy is enqueued."""
+        for m in range(self.cfg.nmods):
+            want, got = tuple(p.br[m].x_in.shape), tuple(inputs[m].shape)
+            if got != want:
+                raise ValueError(f"Input {m} is incompatible with the model: expected shape=(None, "
+                                 f"{', '.join(str(v) for v in want[1:])}), found shape={got}")
+            if flags is not None and math.prod(tuple(flags[m].shape)) != want[0]:
+                raise ValueError(f"use-flag {m}: expected shape=(None, 1) with {want[0]} rows, found shape={tuple(flags[m].shape)}")
+
     def plan(self, B: int, train: bool) -> "_Plan":
+        self._check_batch(B)
         key = (B, train)
         p = self._plans.get(key)
         if p is None:
@@ -640,6 +661,7 @@ class UGaitEngine:
 
     def _set_inputs(self, p, inputs, flags, labels=None, drop_masks=None, code_drop_mask=None):
         cfg = self.cfg
+        self._check_shapes(p, inputs, None if cfg.single else flags)
         for m in range(cfg.nmods):
             p.br[m].x_in.copy_(inputs[m], non_blocking=True)
             if not cfg.single:
