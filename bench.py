@@ -241,6 +241,7 @@ def main():
     ap.add_argument("--no-knn", action="store_true")
     ap.add_argument("--no-gaitset", action="store_true", help="skip the GaitSet-branch leg (SURVEY 8f-1)")
     ap.add_argument("--no-configs", action="store_true", help="skip the cfg1 / cfg3 / cfg4 legs")
+    ap.add_argument("--no-extract", action="store_true", help="skip the descriptor-extraction leg")
     ap.add_argument("--lite", action="store_true", help="timed steps only (for runs under ncu)")
     ap.add_argument("--knn-only", action="store_true", help="only the open-world k-NN leg (development aid)")
     ap.add_argument("--knn-d", type=int, default=256, help="descriptor width of the --knn-only leg")
@@ -369,6 +370,45 @@ def main():
     ms_e2e = pipelined(hb_exp)
     h2d_exp, h2d_full = hb_exp[0].nbytes, hb_full[0].nbytes
     eng.ctx.check()
+
+    # descriptor extraction (model_code.predict in batches of --bs 64,
+    # mains/mj_testUWYHGaitNet_open_tum.py:139-148): forward to "signature" only; every rank extracts its own clips
+    extract = {}
+    if not args.no_extract:
+        desc_host = {}
+        for Bx in (64, 512):
+            reps = (Bx + B - 1) // B
+            ex = [torch.cat([t] * reps)[:Bx].contiguous() for t in dx]
+            ef = [torch.cat([t] * reps)[:Bx].contiguous() for t in df]
+            for _ in range(3):
+                eng.predict(ex, ef)
+            ms_x = timed(lambda: eng.predict(ex, ef), 10)
+            hbx = [eng.host_batch(Bx, train=False), eng.host_batch(Bx, train=False)]
+            for h in hbx:
+                for m in range(3):
+                    h.inputs[m][...] = ex[m].cpu().numpy()
+                    h.flags[m][...] = ef[m].cpu().numpy()
+            desc_host[Bx] = torch.zeros(Bx, 2048).pin_memory()
+            kx = [0]
+
+            def step_x():
+                sig = eng.predict_prefetched("signature")
+                kx[0] ^= 1
+                eng.prefetch_batch(hbx[kx[0]], train=False)          # next batch's H2D overlaps this forward pass
+                desc_host[Bx].copy_(sig, non_blocking=True)          # the descriptors are what the caller keeps
+                torch.cuda.current_stream().synchronize()
+            eng.prefetch_batch(hbx[0], train=False)
+            for _ in range(3):
+                step_x()
+            ms_xe = timed(step_x, 10)
+            extract[f"B{Bx}"] = {"value": Bx * world / (ms_x * 1e-3), "unit": "rows/s", "ms_per_batch": ms_x,
+                                 "model_tflops": 4.857e9 * Bx * world / (ms_x * 1e-3) / 1e12,
+                                 "e2e": {"value": Bx * world / (ms_xe * 1e-3), "ms_per_batch": ms_xe,
+                                         "h2d_bytes_per_batch": int(hbx[0].nbytes), "d2h_bytes_per_batch": Bx * 2048 * 4}}
+            del ex, ef, hbx
+        extract["api"] = ("UGaitEngine.predict(device tensors) | host_batch(train=False) + prefetch_batch + "
+                          "predict_prefetched + D2H of the [B, 2048] descriptors; every rank extracts its own clips")
+        torch.cuda.empty_cache()
     # data-parallel sanity inside the bench itself: finite losses and bit-identical weights on every rank after the run
     assert bool(torch.isfinite(loss_host[[0, 2, 4]]).all()), f"non-finite loss on rank {rank}: {loss_host.tolist()}"
     rank_check = None
@@ -411,6 +451,8 @@ def main():
                                         "api": "UGaitEngine.train_step(pinned host tensors): 7 H2D copies, not overlapped"}},
             "gpu_launches": int(launches), "clocks": sampler.summary(),
             "model_tflops": TRAIN_FLOP_ROW * rows_total / (ms * 1e-3) / 1e12}
+    if extract:
+        line["extract"] = extract
 
     if rank == 0:
         # ---- per-op profile pass (eager, CUDA events on the launch stream) -> dominant kernel roofline
