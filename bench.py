@@ -401,13 +401,34 @@ def main():
             for _ in range(3):
                 step_x()
             ms_xe = timed(step_x, 10)
+            # the same from the STORED sample integers (int16 flow / 100 * 0.1, uint8 gray & depth / 255 - 0.5,
+            # data/mj_dataGeneratorMMUWYHsingle.py:313-329), decoded on the device: 0.375 of the bytes cross PCIe
+            from ugaitnet_b200 import samples
+            nb_f32 = int(hbx[0].nbytes)
+            del hbx
+            hbx = [eng.host_batch(Bx, train=False, raw=[samples.RAW_FLOW, samples.RAW_GRAY, samples.RAW_GRAY])
+                   for _ in range(2)]
+            for h in hbx:
+                h.inputs[0][...] = np.clip(np.rint(ex[0].cpu().numpy() * 1000.0), -32768, 32767).astype(np.int16)
+                for m in (1, 2):
+                    h.inputs[m][...] = np.clip(np.rint((ex[m].cpu().numpy() + 0.5) * 255.0), 0, 255).astype(np.uint8)
+                    h.flags[m][...] = ef[m].cpu().numpy()
+                h.flags[0][...] = ef[0].cpu().numpy()
+            eng.prefetch_batch(hbx[0], train=False)
+            for _ in range(3):
+                step_x()
+            ms_xr = timed(step_x, 10)
             extract[f"B{Bx}"] = {"value": Bx * world / (ms_x * 1e-3), "unit": "rows/s", "ms_per_batch": ms_x,
                                  "model_tflops": 4.857e9 * Bx * world / (ms_x * 1e-3) / 1e12,
                                  "e2e": {"value": Bx * world / (ms_xe * 1e-3), "ms_per_batch": ms_xe,
-                                         "h2d_bytes_per_batch": int(hbx[0].nbytes), "d2h_bytes_per_batch": Bx * 2048 * 4}}
+                                         "h2d_bytes_per_batch": nb_f32, "d2h_bytes_per_batch": Bx * 2048 * 4},
+                                 "e2e_raw_samples": {"value": Bx * world / (ms_xr * 1e-3), "ms_per_batch": ms_xr,
+                                                     "h2d_bytes_per_batch": int(hbx[0].nbytes),
+                                                     "d2h_bytes_per_batch": Bx * 2048 * 4}}
             del ex, ef, hbx
-        extract["api"] = ("UGaitEngine.predict(device tensors) | host_batch(train=False) + prefetch_batch + "
-                          "predict_prefetched + D2H of the [B, 2048] descriptors; every rank extracts its own clips")
+        extract["api"] = ("UGaitEngine.predict(device tensors) | host_batch(train=False[, raw=stored int16 / uint8 samples, "
+                          "decoded on the device]) + prefetch_batch + predict_prefetched + D2H of the [B, 2048] "
+                          "descriptors; every rank extracts its own clips")
         torch.cuda.empty_cache()
     # data-parallel sanity inside the bench itself: finite losses and bit-identical weights on every rank after the run
     assert bool(torch.isfinite(loss_host[[0, 2, 4]]).all()), f"non-finite loss on rank {rank}: {loss_host.tolist()}"

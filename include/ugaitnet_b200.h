@@ -114,6 +114,13 @@ int ugn_pack_input_augment(ugn_ctx*, const ugn_tensor* x_base, const ugn_tensor*
                            float clip_hi, float clip_val, float noise, ugn_tensor* x_nhwc, void* stream);
 
 
+/* On-disk sample values -> the f32 volume of the generator (`__load_dd`, data/mj_dataGeneratorMMUWYHsingle.py:313-329),
+ * on the device: raw int16 (optical flow, compressFactor 100) or uint8 (gray / depth / silhouette), any shape; out f32 with
+ * the same number of elements.  x = float(raw); |x| > clip_max or |x| < clip_min (each when > 0) -> 1e-8; then
+ * x / divisor, * mul, - sub, each one IEEE f32 operation (bit-identical to the numpy statements): optical flow
+ * (divisor 100, mul 0.1, sub 0), gray / depth (255, 1, 0.5), silhouette (255, 1, 0).  Only the stored integers cross PCIe. */
+int ugn_decode_samples(ugn_ctx*, const ugn_tensor* raw, float divisor, float mul, float sub, float clip_min,
+                       float clip_max, ugn_tensor* out, void* stream);
 /* master f32 conv kernel [Cout][kh][kw][Cin] -> compute copy f32 [Cout][kh][kw][Cp] or
  * bf16 [P][Cout][kh][kw][Cp]; also used for dense weights with w viewed as [out][1][1][in]. */
 int ugn_pack_weight(ugn_ctx*, const ugn_tensor* w_master, ugn_tensor* w_packed, void* stream);

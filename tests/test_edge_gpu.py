@@ -105,3 +105,76 @@ def test_engine_rejects_empty_and_misshaped_inputs(mode):
     if mode != "fp32":      # the activation of layer i is the K operand of layer i + 1: multiples of 32 on the tensor cores
         with pytest.raises(ValueError, match="multiples of 32"):
             UGaitEngine(NetConfig(in_channels=(6, 4), filters_numbers=(16, 16, 32, 32), nd=64, nclasses=10), math_mode=mode)
+
+
+def test_decode_samples_bit_exact_vs_generator_arithmetic():
+    """ugn_decode_samples against samples.decode_sample (= __load_dd, data/mj_dataGeneratorMMUWYHsingle.py:313-329):
+    every int16 value with and without the raw-magnitude clip, every uint8 value for gray and silhouette."""
+    from ugaitnet_b200 import ops, samples
+    from ugaitnet_b200._ffi import TRef, check, lib, stream_ptr
+    ctx = ops.get_ctx(0)
+    i16 = np.arange(-32768, 32768, dtype=np.int16).reshape(64, 64, 16)
+    u8 = np.arange(256, dtype=np.uint8).repeat(5)[:1279].reshape(1, 1279, 1)          # odd length: scalar tail
+    for data, cf, sil, spec, clip in ((i16, 100, False, samples.RAW_FLOW, (0.0, 0.0)),
+                                      (i16, 100, False, samples.RAW_FLOW, (50.0, 2300.0)),
+                                      (u8, 1, False, samples.RAW_GRAY, (0.0, 0.0)),
+                                      (u8, 1, True, samples.RAW_SILHOUETTE, (0.0, 0.0))):
+        want = samples.decode_sample({"data": data, "compressFactor": cf}, silhouette=sil, ntype=2, clip_min=clip[0],
+                                     clip_max=clip[1])
+        raw = torch.tensor(np.ascontiguousarray(np.moveaxis(data, 2, 0))).cuda()
+        out = torch.empty(raw.shape, device="cuda")
+        a, b = TRef(raw), TRef(out)
+        check(lib.ugn_decode_samples(ctx.h, a.ptr, spec[1], spec[2], spec[3], clip[0], clip[1], b.ptr, stream_ptr()))
+        assert np.array_equal(out.cpu().numpy().view(np.uint32), want.view(np.uint32))
+
+
+@pytest.mark.parametrize("mode", ["fp32", "f16mix"])
+def test_raw_sample_batches_equal_decoded_batches(mode):
+    """HostBatch(raw=...): stored int16 / uint8 volumes cross PCIe and are decoded on the device -- descriptors and step
+    losses are bit-identical to feeding the host-decoded f32 volumes, plain and with the device-side expansion."""
+    from ugaitnet_b200 import samples
+    from ugaitnet_b200.config import NetConfig
+    from ugaitnet_b200.net import UGaitEngine
+    cfg = NetConfig(in_channels=(50, 25, 25), filters_numbers=(32, 32, 32, 64), nd=64, nclasses=10, merge=O.MERGE_SIGNMAX)
+    eng = UGaitEngine(cfg, math_mode=mode, use_graph=False)
+    rng = np.random.default_rng(4)
+    B, B0 = 8, 4
+    specs = [samples.RAW_FLOW, samples.RAW_GRAY, samples.RAW_SILHOUETTE]
+    raws = [rng.integers(-3000, 3000, size=(B, 50, 60, 60)).astype(np.int16),
+            rng.integers(0, 256, size=(B, 25, 60, 60)).astype(np.uint8),
+            (rng.random((B, 25, 60, 60)) > 0.7).astype(np.uint8) * 255]
+    dec = [(np.float32(r) / np.float32(s[1]) * np.float32(s[2]) - np.float32(s[3])).astype(np.float32)
+           for r, s in zip(raws, specs)]
+    assert int(raws[0].nbytes + raws[1].nbytes + raws[2].nbytes) * 8 == int(sum(d.nbytes for d in dec)) * 3
+    # descriptor extraction
+    hr, hf = eng.host_batch(B, train=False, raw=specs), eng.host_batch(B, train=False)
+    assert hr.nbytes < 0.4 * hf.nbytes and hr.inputs[0].dtype == np.int16 and hr.inputs[1].dtype == np.uint8
+    for m in range(3):
+        hr.inputs[m][...] = raws[m]
+        hf.inputs[m][...] = dec[m]
+        hr.flags[m][...] = hf.flags[m][...] = (rng.random((B, 1)) > 0.3)
+        hf.flags[m][...] = hr.flags[m]
+    eng.prefetch_batch(hf, train=False)
+    sig_f = eng.predict_prefetched("signature")
+    eng.prefetch_batch(hr, train=False)
+    sig_r = eng.predict_prefetched("signature")
+    for m in range(3):      # the decoded volumes in the plan's input block are the generator's f32 values, bit for bit
+        assert np.array_equal(eng.plan(B, False).br[m].x_in.cpu().numpy().view(np.uint32), dec[m].view(np.uint32))
+    # (two runs of the fp32 validation kernels differ by their atomic accumulation order)
+    assert float((sig_f - sig_r).norm() / sig_f.norm()) < 1e-6
+    # training step on base rows expanded on the device
+    lab = np.repeat(np.arange(B0 // 2), 2).astype(np.int32)
+    losses = []
+    for raw in (None, specs):
+        eng2 = UGaitEngine(cfg, math_mode=mode, use_graph=False, seed=3)
+        hb = eng2.host_batch(B, base_rows=B0, raw=raw)
+        for m in range(3):
+            hb.inputs[m][...] = (raws if raw else dec)[m][:B0]
+            hb.flags[m][...] = 1.0
+            hb.flags[m][1::2] = float(m == 1)
+        hb.labels[...] = np.repeat(lab, B // B0)
+        hb.src_row[...] = np.repeat(np.arange(B0, dtype=np.int32), B // B0)
+        eng2.prefetch_batch(hb)
+        out = eng2.train_step_prefetched()
+        losses.append(out["losses"].cpu().clone())
+    assert torch.allclose(losses[0][:4], losses[1][:4], rtol=1e-5, atol=1e-7) and float(losses[0][0]) > 0

@@ -121,6 +121,7 @@ int ew_bwd_act(ugn_ctx*, const float*, const void*, int, const uint8_t*, void*, 
 int simt_colsum(ugn_ctx*, const float*, long long, int, int, float*, cudaStream_t);
 int simt_colsum_bf16(ugn_ctx*, const __nv_bfloat16*, int, int, long long, int, float*, cudaStream_t);
 int ew_flatten(ugn_ctx*, const void*, void*, int, int, int, int, int, int, cudaStream_t);
+int ew_decode_samples(ugn_ctx*, const void*, int, float*, long long, float, float, float, float, float, cudaStream_t);
 int ew_act_mask_bwd(ugn_ctx*, const float*, const float*, const float*, float*, __nv_bfloat16*, int, int,
                     long long, int, float, cudaStream_t);
 int ew_fuse_fwd(ugn_ctx*, const FusePtrs&, int, int, int, float*, __nv_bfloat16*, int, int, uint8_t*, float*,
@@ -198,6 +199,19 @@ extern "C" int ugn_pack_input_expand(ugn_ctx* ctx, const ugn_tensor* x_base, con
                                      const ugn_tensor* enable, const ugn_tensor* mirror, float noise,
                                      ugn_tensor* x_nhwc, void* stream) {
   return pack_input_common(ctx, x_base, src_row, enable, mirror, noise, x_nhwc, stream);
+}
+
+extern "C" int ugn_decode_samples(ugn_ctx* ctx, const ugn_tensor* raw, float divisor, float mul, float sub, float clip_min,
+                                  float clip_max, ugn_tensor* out, void* stream) {
+  UGN_CHECK(ctx && raw && out, "ugn_decode_samples: null argument");
+  UGN_TENSOR(raw, DT_BAD, 1, 6);
+  UGN_TENSOR(out, DT_F32, 1, 6);
+  const UgnDType dt = ugn_dtype(raw);
+  UGN_CHECK(dt == DT_I16 || dt == DT_U8, "ugn_decode_samples: raw must be int16 or uint8");
+  UGN_CHECK(ugn_numel(raw) == ugn_numel(out), "ugn_decode_samples: raw and out must have the same number of elements");
+  UGN_CHECK(divisor != 0.f, "ugn_decode_samples: divisor must be non-zero");
+  return ew_decode_samples(ctx, ugn_ptr<void>(raw), dt == DT_I16, ugn_ptr<float>(out), ugn_numel(raw), divisor, mul, sub,
+                           clip_min, clip_max, (cudaStream_t)stream);
 }
 
 extern "C" int ugn_pack_weight(ugn_ctx* ctx, const ugn_tensor* w_master, ugn_tensor* w_packed, void* stream) {

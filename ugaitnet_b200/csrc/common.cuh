@@ -84,7 +84,7 @@ void ugn_set_error(const char* fmt, ...);
     (ctx)->launches++;                                                             \
   } while (0)
 
-enum UgnDType { DT_F32, DT_BF16, DT_I32, DT_I64, DT_U8, DT_F64, DT_F16, DT_I8, DT_BAD };
+enum UgnDType { DT_F32, DT_BF16, DT_I32, DT_I64, DT_U8, DT_F64, DT_F16, DT_I8, DT_I16, DT_BAD };
 
 static inline UgnDType ugn_dtype(const ugn_tensor* t) {
   if (t->dtype_lanes != 1) return DT_BAD;
@@ -96,6 +96,7 @@ static inline UgnDType ugn_dtype(const ugn_tensor* t) {
   if (t->dtype_code == UGN_DL_INT && t->dtype_bits == 64) return DT_I64;
   if (t->dtype_code == UGN_DL_UINT && t->dtype_bits == 8) return DT_U8;
   if (t->dtype_code == UGN_DL_INT && t->dtype_bits == 8) return DT_I8;
+  if (t->dtype_code == UGN_DL_INT && t->dtype_bits == 16) return DT_I16;
   return DT_BAD;
 }
 

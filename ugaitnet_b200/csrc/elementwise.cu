@@ -99,6 +99,46 @@ int ew_pack_input(ugn_ctx* ctx, const float* x, void* out, int mode, int f16, in
   return UGN_OK;
 }
 
+// On-disk sample values -> the f32 volume the generator would hand to Keras (__load_dd,
+// data/mj_dataGeneratorMMUWYHsingle.py:313-329), computed on the DEVICE so that only the stored integers cross PCIe
+// (int16 optical flow: 2 of 4 bytes per value; uint8 gray / depth / silhouette: 1 of 4):
+//   x = float(raw); |x| > clip_max or |x| < clip_min (when > 0) -> 1e-8; x = x / divisor; x = x * mul; x = x - sub
+// every step one IEEE f32 operation with its own rounding, as numpy evaluates the statements (no FMA contraction).
+template <typename T>
+__global__ void decode_samples_kernel(const T* __restrict__ raw, float* __restrict__ out, long long n, float divisor,
+                                      float mul, float sub, float clip_min, float clip_max) {
+  for (long long e = (blockIdx.x * (long long)blockDim.x + threadIdx.x) * 4; e < n;
+       e += (long long)gridDim.x * blockDim.x * 4) {
+    float v[4];
+    const int m = (int)min(4ll, n - e);
+    for (int i = 0; i < m; ++i) {
+      float x = (float)raw[e + i];
+      if (clip_max > 0.f && fabsf(x) > clip_max) x = 1e-8f;
+      if (clip_min > 0.f && fabsf(x) < clip_min) x = 1e-8f;
+      x = __fdiv_rn(x, divisor);
+      x = __fmul_rn(x, mul);
+      v[i] = __fsub_rn(x, sub);
+    }
+    if (m == 4 && (reinterpret_cast<uintptr_t>(out + e) & 15) == 0) {
+      *reinterpret_cast<float4*>(out + e) = make_float4(v[0], v[1], v[2], v[3]);
+    } else {
+      for (int i = 0; i < m; ++i) out[e + i] = v[i];
+    }
+  }
+}
+
+int ew_decode_samples(ugn_ctx* ctx, const void* raw, int is_i16, float* out, long long n, float divisor, float mul,
+                      float sub, float clip_min, float clip_max, cudaStream_t st) {
+  if (n == 0) return UGN_OK;
+  int grid = (int)std::min<long long>((n / 4 + 255) / 256 + 1, (long long)ctx->sm_count * 16);
+  if (is_i16)
+    decode_samples_kernel<short><<<grid, 256, 0, st>>>(reinterpret_cast<const short*>(raw), out, n, divisor, mul, sub, clip_min, clip_max);
+  else
+    decode_samples_kernel<unsigned char><<<grid, 256, 0, st>>>(reinterpret_cast<const unsigned char*>(raw), out, n, divisor, mul, sub, clip_min, clip_max);
+  UGN_LAUNCHED(ctx);
+  return UGN_OK;
+}
+
 // master [R][Cin] -> packed [P][R][Cp]   (R = Cout*kh*kw, or out-features for dense)
 template <int MODE>
 __global__ void pack_weight_kernel(const float* __restrict__ w, void* __restrict__ out, long long R,

@@ -96,6 +96,14 @@ class IOBlock:
     def nbytes_base(self, B0: int) -> int:
         return self.base_offsets(B0)[1]
 
+    def raw_offsets(self, rows: int, itemsizes):
+        """Volume offsets of a RAW block (stored integers instead of f32: HostBatch(raw=...)), `rows` rows per modality."""
+        offs, o = [], self.header
+        for rb, isz in zip(self.row_bytes, itemsizes):
+            offs.append(o)
+            o = round_up(o + rb // 4 * isz * rows, self.ALIGN)
+        return offs, o
+
     @staticmethod
     def _view(buf, off, shape, dtype):
         n = 1
@@ -103,8 +111,9 @@ class IOBlock:
             n *= s
         return buf[off:off + n * torch.empty(0, dtype=dtype).element_size()].view(dtype).view(tuple(shape))
 
-    def views(self, buf, B0: Optional[int] = None):
-        """Typed views of a buffer with this layout (device block, staging block or pinned host block)."""
+    def views(self, buf, B0: Optional[int] = None, raw=None):
+        """Typed views of a buffer with this layout (device block, staging block or pinned host block).  raw: the
+        volumes are stored integers (see HostBatch)."""
         B = self.B
         v = {"flags": [self._view(buf, o, (B, 1), torch.float32) for o in self.f_off],
              "labels": self._view(buf, self.lab_off, (B,), torch.int32),
@@ -112,7 +121,11 @@ class IOBlock:
              "mirror": self._view(buf, self.mir_off, (B,), torch.uint8),
              "shift": self._view(buf, self.shift_off, (B, 2), torch.int8),
              "clip": self._view(buf, self.clip_off, (B,), torch.uint8)}
-        if B0 is None:
+        if raw is not None:
+            rows = B if B0 is None else B0
+            offs, _ = self.raw_offsets(rows, [2 if r[0] is torch.int16 else 1 for r in raw])
+            v["x"] = [self._view(buf, o, (rows,) + s, r[0]) for o, s, r in zip(offs, self.vol_shapes, raw)]
+        elif B0 is None:
             v["x"] = [self._view(buf, o, (B,) + s, torch.float32) for o, s in zip(self.x_off, self.vol_shapes)]
         else:
             offs, _ = self.base_offsets(B0)
@@ -125,11 +138,22 @@ class HostBatch:
     ``src_row`` / ``mirror`` for the device-side expansion) IN PLACE (numpy views), ``UGaitEngine.prefetch_batch`` then
     moves the whole batch with one cudaMemcpyAsync."""
 
-    def __init__(self, io: IOBlock, B0: Optional[int]):
-        self.io, self.B0 = io, B0
-        self.nbytes = io.nbytes_full if B0 is None else io.nbytes_base(B0)
-        self.buf = torch.zeros(self.nbytes, dtype=torch.uint8).pin_memory()
-        v = io.views(self.buf, B0)
+    def __init__(self, io: IOBlock, B0: Optional[int], raw=None):
+        """raw: per modality (dtype "int16" | "uint8", divisor, mul, sub[, clip_min, clip_max]) -- the volumes are the
+        STORED sample integers (ugaitnet_b200.samples.RAW_FLOW / RAW_GRAY / RAW_SILHOUETTE) and are decoded on the device
+        (ugn_decode_samples) when the batch is consumed: a quarter / half of the f32 bytes cross PCIe."""
+        self.io, self.B0, self.raw = io, B0, None
+        if raw is not None:
+            self.raw = [(torch.int16 if r[0] == "int16" else torch.uint8,) + tuple(float(v) for v in r[1:]) +
+                        (0.0,) * (6 - len(r)) for r in raw]
+            assert len(self.raw) == io.M and all(r[0] in ("int16", "uint8") for r in raw)
+            rows = io.B if B0 is None else B0
+            self.raw_off, self.nbytes = io.raw_offsets(rows, [2 if r[0] is torch.int16 else 1 for r in self.raw])
+            self.buf = torch.zeros(self.nbytes, dtype=torch.uint8).pin_memory()
+        else:
+            self.nbytes = io.nbytes_full if B0 is None else io.nbytes_base(B0)
+            self.buf = torch.zeros(self.nbytes, dtype=torch.uint8).pin_memory()
+        v = io.views(self.buf, B0, raw=self.raw)
         self.t = v                                       # torch views
         self.inputs = [x.numpy() for x in v["x"]]
         self.flags = [f.numpy() for f in v["flags"]]
@@ -1502,11 +1526,12 @@ class UGaitEngine:
         return out
 
     # ---- single-copy input path: the loader writes into a pinned HostBatch whose bytes mirror the plan's IOBlock
-    def host_batch(self, B: int, base_rows: Optional[int] = None, train: bool = True) -> HostBatch:
+    def host_batch(self, B: int, base_rows: Optional[int] = None, train: bool = True, raw=None) -> HostBatch:
         """A NEW pinned host batch for batch size B (base_rows = B0 selects the device-side-expansion layout: only the
         B0 complete sequences + the expansion tables cross PCIe).  Allocate two and alternate them to overlap the
-        loader / the H2D copy of step i+1 with step i."""
-        return HostBatch(self.plan(B, train).io, base_rows)
+        loader / the H2D copy of step i+1 with step i.  raw: the volumes hold the STORED sample integers (one spec per
+        modality, ugaitnet_b200.samples.RAW_*) and are decoded on the device -- see HostBatch."""
+        return HostBatch(self.plan(B, train).io, base_rows, raw)
 
     def prefetch_batch(self, hb: HostBatch, train: bool = True):
         """ONE cudaMemcpyAsync of the whole batch (flags, labels, expansion tables, volumes) on the copy stream into
@@ -1536,7 +1561,22 @@ class UGaitEngine:
         p = self.plan(*key)
         cur = torch.cuda.current_stream()
         cur.wait_event(st["ready"][k])
-        p.io.dev_buf[:hb.nbytes].copy_(st["buf"][k][:hb.nbytes], non_blocking=True)   # ONE device-to-device copy
+        if hb.raw is not None:
+            # stored integers: the header moves as bytes, the volumes are DECODED into the plan's f32 block
+            # (ugn_decode_samples: the generator's __load_dd arithmetic, bit for bit) instead of copied
+            p.io.dev_buf[:p.io.header].copy_(st["buf"][k][:p.io.header], non_blocking=True)
+            src = p.io.views(st["buf"][k], hb.B0, raw=hb.raw)["x"]
+            dst = p.io.views(p.io.dev_buf, hb.B0)["x"]
+            h, sp = self.ctx.h, stream_ptr()
+            cache = st.setdefault("raw_refs", {})
+            ck = (k, hb.B0, tuple(r[0] for r in hb.raw))
+            refs = cache.get(ck)
+            if refs is None:        # DLPack handles of the (fixed) staging / plan views, created once
+                refs = cache[ck] = [(TRef(a), TRef(b)) for a, b in zip(src, dst)]
+            for (ra, rb), r in zip(refs, hb.raw):
+                check(lib.ugn_decode_samples(h, ra.ptr, r[1], r[2], r[3], r[4], r[5], rb.ptr, sp))
+        else:
+            p.io.dev_buf[:hb.nbytes].copy_(st["buf"][k][:hb.nbytes], non_blocking=True)   # ONE device-to-device copy
         st["free"][k].record(cur)
         return p, hb
 

@@ -16,6 +16,14 @@ import numpy as np
 from . import hdf5
 
 
+# HostBatch(raw=...) specs of the stored sample types: (dtype, divisor, mul, sub) of __load_dd (:313-329), applied on the
+# device by ugn_decode_samples -- optical flow int16 / compressFactor(100) * 0.1, gray / depth uint8 / 255 - 0.5,
+# silhouette uint8 / 255.  Append (clip_min, clip_max) for the raw-magnitude clip of the optical flow (:318-321).
+RAW_FLOW = ("int16", 100.0, 0.1, 0.0)
+RAW_GRAY = ("uint8", 255.0, 1.0, 0.5)
+RAW_SILHOUETTE = ("uint8", 255.0, 1.0, 0.0)
+
+
 def load_sample(path) -> Dict[str, object]:
     f = hdf5.File(path)
     out: Dict[str, object] = {}
