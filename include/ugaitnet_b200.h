@@ -248,6 +248,13 @@ int ugn_triplet_all_tc(ugn_ctx*, const ugn_tensor* emb, const ugn_tensor* emb16,
  * with a positive term}; demb, workspace as ugn_triplet_all (n = 1). */
 int ugn_triplet_hard(ugn_ctx*, const ugn_tensor* emb, const ugn_tensor* emb16, const ugn_tensor* labels, float margin,
                      float scale, ugn_tensor* out, ugn_tensor* demb, ugn_tensor* workspace, void* stream);
+/* Pair verification loss of the Siamese builder UWYHNet.build (nets/mj_uwyhNets_ba.py:154-245 -> VerifLossLayer,
+ * nets/mj_loss.py:65-95): emb f32 [2B,d] (rows [0,B) = first element of every pair, [B,2B) = second), labels i32 [>= B]
+ * (1 = same identity, 0 = different; other values: pair ignored).  loss = 0.5 * sum_{pos} (a-b)^2 + 0.5 * max(0, margin -
+ * sqrt(sum over ALL negative rows of (a-b)^2))^2.  out f32 [2] = {loss, 1 if the negative hinge is active}; demb f32
+ * [2B,d] (nullable) = scale * dLoss/dEmb; workspace >= 16 bytes (8-byte aligned). */
+int ugn_pair_verif_loss(ugn_ctx*, const ugn_tensor* emb, const ugn_tensor* labels, float margin, float scale,
+                        ugn_tensor* out, ugn_tensor* demb, ugn_tensor* workspace, void* stream);
 
 
 /* ---- a8/a9: regulariser + optimiser --------------------------------------------------

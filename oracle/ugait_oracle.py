@@ -63,6 +63,7 @@ class NetConfig:
     aux_losses: bool = False       # classprob_{of,gray,depth} heads on the gated branch outputs (:1222-1251)
     waux: float = 1.0              # loss_weights[-1] (:1264-1268)
     triplet_hard: bool = False     # compile_hard: tfa.losses.TripletHardLoss instead of the batch-all loss (:1302-1306)
+    pair_loss: bool = False        # UWYHNet.build (:154-245): rows [0,B) / [B,2B) are the two sides of B pairs, VerifLossLayer
     postriplet: int = 1            # 2: fusion -> Dense "signature" (activity-regularised) -> l2_normalize "code" = the
     #                                embedding of the triplet loss and of the classifier (:814-832, 2-modality builder)
 
@@ -274,6 +275,18 @@ def triplet_loss_all(labels, emb, margin):
     return mean.mean(0), cnt
 
 
+def pair_verif_loss(labels, emb, margin):
+    """VerifLossLayer(margin) of the Siamese builder UWYHNet.build (nets/mj_uwyhNets_ba.py:230-231 ->
+    nets/mj_loss.py:71-91): emb [2B,d] = the two signatures stacked (first elements, then second elements), labels [B]
+    (1 same / 0 different):  0.5 * sum_{pos rows} (a-b)^2 + 0.5 * max(0, m - sqrt(sum_{neg rows} (a-b)^2))^2."""
+    B = emb.shape[0] // 2
+    res2 = (emb[:B] - emb[B:]) ** 2
+    lab = labels.reshape(-1)[:B]
+    xpos = 0.5 * res2[lab == 1].sum()
+    xneg = 0.5 * torch.clamp(margin - torch.sqrt(res2[lab == 0].sum()), min=0.0) ** 2
+    return xpos + xneg
+
+
 def triplet_hard_loss(labels, emb, margin):
     """`tfa.losses.TripletHardLoss(margin)` as compiled by UWYHSemiNet3Mods.compile_hard
     (nets/mj_uwyhNets_ba.py:1302-1306): soft=False, distance_metric="L2".  tensorflow_addons is an un-vendored,
@@ -399,7 +412,9 @@ def total_loss(inputs, flags, labels, P, cfg: NetConfig, drop_masks=None, code_d
     outs = model_forward(inputs, flags, P, cfg, drop_masks, code_drop_mask, return_all=True, decisions=decisions,
                          record=record)
     res = {}
-    if getattr(cfg, "triplet_hard", False):      # compile_hard (:1302-1306)
+    if getattr(cfg, "pair_loss", False):         # UWYHNet.build (:154-245): the loss layer IS the model output
+        trip, cnt = pair_verif_loss(labels, outs["signature"], cfg.margin), torch.zeros(())
+    elif getattr(cfg, "triplet_hard", False):      # compile_hard (:1302-1306)
         trip, cnt = triplet_hard_loss(labels, outs["signature"], cfg.margin)
     else:
         trip, cnt = triplet_loss_all(labels, outs["signature"], cfg.margin)

@@ -301,3 +301,34 @@ def test_compile_hard(compat_path):
     v = model.loss[0](y[0], sig)
     want, _ = O.triplet_hard_loss(torch.tensor(y[0]).reshape(-1), torch.tensor(np.asarray(sig), dtype=torch.float64), 0.3)
     assert float(v) == pytest.approx(float(want), rel=1e-4)
+
+
+def test_pair_network_builder(compat_path):
+    """UWYHNet.build (:154-245): nine inputs, the output is VerifLossLayer's value; a training step moves it down."""
+    from nets.mj_uwyhNets_ba import UWYHNet
+    from ugaitnet_b200.compat import optimizers
+    import nets.mj_uwyhNets_ba as mod
+    mod.MATH_MODE = "fp32"
+    model = UWYHNet.build([(6, 60, 60), (4, 60, 60)], 4, [(7, 7), (5, 5), (3, 3), (2, 2)], [8, 8, 16, 16], 32, 0.00005, 0.0,
+                          optimizer=optimizers.SGD(0.05, 0.9), margin=0.9)
+    oc = O.NetConfig(in_channels=(6, 4), filters_numbers=(8, 8, 16, 16), nd=32, nclasses=0, merge=O.MERGE_MAX, margin=0.9,
+                     pair_loss=True)
+    rng = np.random.default_rng(2)
+    B = 5
+    X = [rng.normal(size=(B, 6, 60, 60)) * 0.3, np.ones((B, 1)), rng.uniform(-0.5, 0.5, size=(B, 4, 60, 60)), np.ones((B, 1)),
+         rng.normal(size=(B, 6, 60, 60)) * 0.3, np.ones((B, 1)), rng.uniform(-0.5, 0.5, size=(B, 4, 60, 60)),
+         np.array([1, 1, 0, 1, 1.0]).reshape(B, 1), np.array([1, 0, 1, 0, 0]).reshape(B, 1)]
+    P = {k: v.double().cpu() for k, v in model.engine.export_params().items()}
+    xs = [torch.tensor(np.concatenate([X[0], X[4]])), torch.tensor(np.concatenate([X[2], X[6]]))]
+    fl = [torch.tensor(np.concatenate([X[1], X[5]])), torch.tensor(np.concatenate([X[3], X[7]]))]
+    outs = O.model_forward(xs, fl, P, oc, return_all=True)
+    want = float(O.pair_verif_loss(torch.tensor(X[8]), outs["signature"], 0.9))
+    assert float(model.predict(X)) == pytest.approx(want, rel=1e-5)
+    e1 = model.embed(X[:4])
+    assert np.allclose(e1, outs["signature"][:B].numpy(), atol=2e-6)
+    l0 = model.train_on_batch(X)
+    for _ in range(5):
+        l1 = model.train_on_batch(X)
+    assert l1 < l0
+    with pytest.raises(ValueError, match="9 inputs"):
+        model.train_on_batch(X[:8])

@@ -525,3 +525,40 @@ def test_triplet_gram_on_tensor_cores(ctx, B, d, dt):
     D = ws[(accb + x2b) // 4:(accb + x2b) // 4 + B * B].view(B, B)
     assert float(D[0, 1]) == 0.0 and float(D[1, 0]) == 0.0 and float(D.diagonal().abs().max()) == 0.0
     assert float((D - D.t()).abs().max()) <= 1e-5
+
+
+@pytest.mark.parametrize("case", ["mixed", "all_pos", "far_negatives", "ignored"])
+def test_pair_verif_loss_vs_oracle(ctx, case):
+    """ugn_pair_verif_loss (UWYHNet.build's VerifLossLayer, nets/mj_loss.py:65-95) against the fp64 restatement: value
+    and gradient; only positives (sqrt of an empty sum), negatives beyond the margin (inactive hinge), labels that are
+    neither 0 nor 1 (the reference's tf.where(equal(labels, 1|0)) ignores them)."""
+    from ugaitnet_b200._ffi import TRef, check, lib, stream_ptr
+    rng = np.random.default_rng(9)
+    B, d = 12, 48
+    e = rng.normal(size=(2 * B, d)).astype(np.float32)
+    e /= np.linalg.norm(e, axis=1, keepdims=True)
+    lab = rng.integers(0, 2, B)
+    margin = 6.0
+    if case == "all_pos":
+        lab[:] = 1
+    elif case == "far_negatives":
+        margin = 0.5
+    elif case == "ignored":
+        lab[::3] = 7
+    x = torch.tensor(e).cuda()
+    out, de = torch.zeros(2, device="cuda"), torch.full((2 * B, d), 9.0, device="cuda")
+    ws = torch.zeros(8, device="cuda")
+    R = [TRef(t) for t in (x, torch.tensor(lab).int().cuda(), out, de, ws)]
+    check(lib.ugn_pair_verif_loss(ctx.h, R[0].ptr, R[1].ptr, margin, 0.5, R[2].ptr, R[3].ptr, R[4].ptr, stream_ptr()))
+    ctx.check()
+    e64 = torch.tensor(e, dtype=torch.float64, requires_grad=True)
+    loss = O.pair_verif_loss(torch.tensor(lab), e64, margin)
+    (0.5 * loss).backward()
+    assert float(out[0]) == pytest.approx(float(loss.detach()), rel=1e-5, abs=1e-7)
+    g = e64.grad
+    if float(g.norm()) == 0.0:
+        assert float(de.abs().max()) == 0.0
+    else:
+        assert rel(de, g) < 1e-5
+    if case == "far_negatives":
+        assert float(out[1]) == 0.0

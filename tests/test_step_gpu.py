@@ -75,7 +75,7 @@ def to_engine_cfg(oc, dropout=0.0):
                      weight_decay=oc.weight_decay, merge=oc.merge, act=oc.act, alpha=oc.alpha, margin=oc.margin,
                      wver=oc.wver, wid=oc.wid, hw=oc.hw, dropout=dropout, single=oc.single,
                      label_smoothing=oc.label_smoothing, normbfmerge=oc.normbfmerge, aux_losses=oc.aux_losses,
-                     waux=oc.waux, postriplet=oc.postriplet, triplet_hard=oc.triplet_hard)
+                     waux=oc.waux, postriplet=oc.postriplet, triplet_hard=oc.triplet_hard, pair_loss=oc.pair_loss)
 
 
 def setup(name, math_mode="fp32", seed=11):
@@ -550,3 +550,36 @@ def test_philox_dropout_masks_and_step_parity():
         seen.append(mk.clone())
     assert not torch.equal(seen[0], seen[1]) and not torch.equal(seen[1], seen[2])
     assert int(eng_g.rng_state[1]) >= 3
+
+
+def test_pair_network_step_parity_fp32():
+    """UWYHNet.build's graph (nets/mj_uwyhNets_ba.py:154-245): two weight-sharing (of, gray) towers on the two sides of B
+    pairs, VerifLossLayer on the normalised signatures.  Loss and every gradient against the fp64 oracle."""
+    from ugaitnet_b200.net import UGaitEngine
+    oc = O.NetConfig(in_channels=(6, 4), filters_numbers=(8, 8, 16, 16), nd=32, nclasses=0, merge=O.MERGE_MAX,
+                     margin=0.9, pair_loss=True)
+    xs, fl, _ = O.synth_batch(O.NetConfig(in_channels=(6, 4), filters_numbers=(8, 8, 16, 16), nd=32, nclasses=5),
+                              base_rows=6, expand=2, seed=5, kinds=("of", "gray"))
+    B2 = xs[0].shape[0]
+    pair_lab = np.array([1, 0, 1, 0, 0, 1][:B2 // 2])
+    P = O.init_params(oc, seed=5, dtype=torch.float64)
+    g = torch.Generator().manual_seed(5)
+    for k in P:
+        if k.endswith("/b"):
+            P[k] = torch.randn(P[k].shape, generator=g, dtype=torch.float64) * 0.05
+    eng = UGaitEngine(to_engine_cfg(oc), math_mode="fp32", lr=1e-3)
+    eng.load_params(P)
+    res, G = oracle_step(oc, P, xs, fl, pair_lab, None, None)
+    ins, fls, lab, _, _ = engine_inputs(xs, fl, pair_lab, None, None)
+    out = eng.loss_and_grad(ins, fls, lab)
+    torch.cuda.synchronize()
+    assert float(res["triplet"]) > 0.05
+    assert float(out["triplet"]) == pytest.approx(float(res["triplet"]), rel=1e-5)
+    grads = eng.export_grads()
+    for k, gk in G.items():
+        ref = gk - reg_grad(oc, k, P[k])
+        if float(ref.norm()) < 1e-12:
+            continue
+        assert rel(grads[k], ref) < 2e-5, k
+    ev = eng.eval_losses(ins, fls, lab)
+    assert float(ev["triplet"]) == pytest.approx(float(res["triplet"]), rel=1e-5)

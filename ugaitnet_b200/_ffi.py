@@ -69,6 +69,7 @@ _PROTOS = {
     "ugn_triplet_all": (c_int, [c_void_p, _T, _T, c_float, c_float, _T, _T, _T, c_void_p]),
     "ugn_triplet_all_tc": (c_int, [c_void_p, _T, _T, _T, c_float, c_float, _T, _T, _T, c_void_p]),
     "ugn_triplet_hard": (c_int, [c_void_p, _T, _T, _T, c_float, c_float, _T, _T, _T, c_void_p]),
+    "ugn_pair_verif_loss": (c_int, [c_void_p, _T, _T, c_float, c_float, _T, _T, _T, c_void_p]),
     "ugn_adam_step": (c_int, [c_void_p, _T, _T, _T, _T, _T, _T, c_float, c_float, c_float, c_float,
                               c_float, _T, _T, _T, c_int, c_int, c_void_p]),
     "ugn_adam_step_ex": (c_int, [c_void_p, _T, _T, _T, _T, _T, c_float, _T, _T, c_float, c_float, c_float, c_float,

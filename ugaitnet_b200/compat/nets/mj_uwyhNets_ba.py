@@ -557,6 +557,77 @@ class UGaitModel:
         return self
 
 
+class PairModel(UGaitModel):
+    """Model object of UWYHNet.build (:154-245): nine inputs, one output (the verification loss)."""
+    dtype = "float32"
+
+    def __init__(self, cfg, optimizer):
+        opt = optimizer if optimizer is not None else optimizers.SGD(0.001, 0.9)
+        kw = dict(getattr(opt, "kw", {}))
+        self.cfg, self.multimodal, self.gaitset = cfg, True, False
+        self.engine = UGaitEngine(cfg, math_mode=MATH_MODE, optimizer=getattr(opt, "name", "sgd"),
+                                  lr=getattr(opt, "lr", 0.001), momentum=kw.get("momentum", 0.9),
+                                  beta1=kw.get("beta1", 0.9), beta2=kw.get("beta2", 0.999), eps=kw.get("eps", 1e-7),
+                                  lr_decay=kw.get("decay", 0.0), decoupled_weight_decay=kw.get("weight_decay", 0.0),
+                                  use_graph=os.environ.get("UGN_GRAPH", "1") == "1")
+        self.optimizer = _OptimizerView(self)
+        self.loss, self.loss_weights, self.stop_training = None, [1.0], False
+        sub = lambda bn: [_LayerProxy(self, f"{bn}/conv{i}", kind="conv") for i in range(len(cfg.filters_numbers))] + \
+                         [_LayerProxy(self, f"{bn}/{n}", kind="dense" if n in ("dense", "ofCode") else "layer")
+                          for n in ["ofFlat", "dense", "drop", "ofCode"]]
+        self.layers = [_LayerProxy(self, BRANCH_NAMES[m], units=cfg.nd, sublayers=sub(BRANCH_NAMES[m])) for m in range(2)]
+        self.layers += [_LayerProxy(self, n) for n in ("gate_of1", "gate_gray1", "agg1", "embedL2_1", "gate_of2",
+                                                       "gate_gray2", "agg2", "embedL2_2", "loss_pair")]
+        self.input = [_Tag(self, n) for n in ("ofinput1", "ofuse1", "grayinput1", "grayuse1", "ofinput2", "ofuse2",
+                                              "grayinput2", "grayuse2", "label")]
+
+    def _stack(self, x):
+        cu = lambda a: torch.as_tensor(np.asarray(a), dtype=torch.float32).cuda(non_blocking=True)
+        if len(x) != 9:
+            raise ValueError(f"the pair network takes 9 inputs (:232), got {len(x)}")
+        ins = [torch.cat([cu(x[0]), cu(x[4])]), torch.cat([cu(x[2]), cu(x[6])])]
+        fl = [torch.cat([cu(x[1]).reshape(-1, 1), cu(x[5]).reshape(-1, 1)]),
+              torch.cat([cu(x[3]).reshape(-1, 1), cu(x[7]).reshape(-1, 1)])]
+        lab = torch.as_tensor(np.asarray(x[8])).reshape(-1).to(torch.int32).cuda()
+        return ins, fl, lab
+
+    def train_on_batch(self, x, y=None, **kw):
+        out = self.engine.train_step(*self._stack(x))
+        return float(out["triplet"]) * self.cfg.wver + float(out["reg"])
+
+    def test_on_batch(self, x, y=None, **kw):
+        out = self.engine.eval_losses(*self._stack(x))
+        return float(out["triplet"])
+
+    def predict(self, x, batch_size=None, verbose=0):
+        """The model's output tensor is the pair loss of the batch (:230-235)."""
+        return np.float32(self.test_on_batch(x))
+
+    def embed(self, x4):
+        """Normalised signature of ONE side ([of, ofuse, gray, grayuse]) -- the `embedL2_1` layer."""
+        cu = lambda a: torch.as_tensor(np.asarray(a), dtype=torch.float32).cuda()
+        return self.engine.predict([cu(x4[0]), cu(x4[2])], [cu(x4[1]).reshape(-1, 1), cu(x4[3]).reshape(-1, 1)]).cpu().numpy()
+
+    def fit(self, x=None, epochs=1, steps_per_epoch=None, callbacks=None, initial_epoch=0, verbose=2, **kw):
+        hist = History()
+        for epoch in range(initial_epoch, epochs):
+            n = steps_per_epoch or len(x)
+            tot = 0.0
+            for i in range(n):
+                item = x[i % len(x)]
+                tot += self.train_on_batch(item[0] if isinstance(item, tuple) else item)
+            hist.epoch.append(epoch)
+            hist.history.setdefault("loss", []).append(tot / n)
+            hist.history.setdefault("lr", []).append(float(self.engine.lr))
+            if hasattr(x, "on_epoch_end"):
+                x.on_epoch_end()
+        return hist
+
+    def summary(self):
+        print(f"UWYHNet pair network (B200 engine, math={self.engine.math_mode}): 2 shared branches, nd={self.cfg.nd}")
+
+
+
 def _file_layers(g):
     names = [n.decode("utf8") if isinstance(n, bytes) else str(n) for n in np.atleast_1d(g.attrs.get("layer_names", []))]
     out = []
@@ -709,6 +780,25 @@ class UWYHNet:
                                   "inside UWYHSemiNet{,3Mods}.build")
 
     buildBranchLReLU = buildBranch
+
+    @staticmethod
+    def build(input_shapes, number_convolutional_layers, filters_size, filters_numbers, ndense_units=512,
+              weight_decay=1e-4, dropout=0.4, optimizer=None, margin=0.2, init_branches=None, freeze_branches=False,
+              activation_fn='relu', alpha=0.3):
+        """:154-245 -- the Siamese PAIR network: two weight-sharing (of, gray) towers, gated, Maximum-merged and
+        l2-normalised, joined by VerifLossLayer(margin) on the pair label; the model's output IS the loss
+        (model.compile(optimizer) only).  Inputs [ofinput1, ofuse1, grayinput1, grayuse1, ofinput2, ofuse2, grayinput2,
+        grayuse2, label].  Here: both sides run as ONE 2B-row batch through the 2-modality engine
+        (NetConfig.pair_loss -> ugn_pair_verif_loss)."""
+        import dataclasses
+        cfg = _cfg_from_args(list(input_shapes)[:2], number_convolutional_layers, filters_size, filters_numbers,
+                             ndense_units, weight_decay, dropout, margin, 0, [1.0, 1.0], Maximum, activation_fn, alpha,
+                             single=False)
+        cfg = dataclasses.replace(cfg, pair_loss=True, nc=0)
+        model = PairModel(cfg, optimizer)
+        _apply_init_branches(model, init_branches)
+        _freeze(model, freeze_branches=freeze_branches)
+        return model
 
 
 class UWYHSemiNet:

@@ -40,6 +40,8 @@ class NetConfig:
     aux_losses: bool = False       # extra Dense(nclasses, softmax) head + CE on every gated branch output (:1222-1251)
     waux: float = 1.0              # their loss weight: loss_weights[-1] (:1264-1268)
     triplet_hard: bool = False     # compile_hard (:1302-1306): tfa TripletHardLoss (batch-hard) instead of batch-all
+    pair_loss: bool = False        # UWYHNet.build (:154-245): rows [0,B) / [B,2B) = the two sides of B pairs, labels [B] in
+    #                                {0,1}, VerifLossLayer (nets/mj_loss.py:65-95) instead of the triplet loss; nclasses == 0
     postriplet: int = 1            # 2 (needs nc > 0; 2-modality builder, :814-832): the fusion is NOT normalised, FC1 is the
     #                                layer "signature", its l2_normalize ("code") is what the triplet loss and the classifier see
 

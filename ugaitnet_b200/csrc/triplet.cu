@@ -240,6 +240,90 @@ __global__ void __launch_bounds__(256) trip_bwd_kernel(const float* __restrict__
   demb[((long long)n * B + a) * d + j] = s * ((g0 + g1) + (g2 + g3));
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Pair verification loss of the Siamese builder UWYHNet.build (nets/mj_uwyhNets_ba.py:154-245): VerifLossLayer
+// (nets/mj_loss.py:65-95) on the two normalised signatures a = emb[:B], b = emb[B:] and the pair labels:
+//   loss = 0.5 * sum_{label == 1} (a - b)^2  +  0.5 * max(0, m - sqrt(sum_{label == 0} (a - b)^2))^2
+// (the negative term takes the square root of the sum over ALL negative rows, as the reference does).
+// acc[0] = positive sum, acc[1] = negative sum S.  Backward: d/da = (a - b) on positive rows, -(m - sqrt S)/sqrt S (a - b)
+// on negative rows while m > sqrt S > 0; d/db = -d/da.
+__global__ void __launch_bounds__(256) pair_sums_kernel(const float* __restrict__ emb, const int* __restrict__ labels,
+                                                        double* __restrict__ acc, int B, int d) {
+  const int r = blockIdx.x;
+  const int lab = labels[r];
+  if (lab != 0 && lab != 1) return;
+  const float* a = emb + (long long)r * d;
+  const float* b = emb + (long long)(r + B) * d;
+  double s = 0.0;
+  for (int j = threadIdx.x; j < d; j += blockDim.x) {
+    const float df = a[j] - b[j];
+    s += (double)(df * df);
+  }
+  __shared__ double red[8];
+  s = warp_sum_d(s);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += red[w];
+    atomicAdd(&acc[lab == 1 ? 0 : 1], t);
+  }
+}
+
+__global__ void __launch_bounds__(256) pair_finish_kernel(const float* __restrict__ emb, const int* __restrict__ labels,
+                                                          const double* __restrict__ acc, float* __restrict__ out,
+                                                          float* __restrict__ demb, int B, int d, float margin,
+                                                          float scale) {
+  const float S = (float)acc[1];
+  const float rs = sqrtf(S);
+  const float gap = fmaxf(margin - rs, 0.f);
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    out[0] = 0.5f * (float)acc[0] + 0.5f * gap * gap;
+    out[1] = gap > 0.f ? 1.f : 0.f;
+  }
+  if (!demb) return;
+  const int r = blockIdx.x;
+  const int lab = labels[r];
+  float c = 0.f;
+  if (lab == 1) c = 1.f;
+  else if (lab == 0 && gap > 0.f && rs > 0.f) c = -gap / rs;
+  const float* a = emb + (long long)r * d;
+  const float* b = emb + (long long)(r + B) * d;
+  for (int j = threadIdx.x; j < d; j += blockDim.x) {
+    const float g = scale * c * (a[j] - b[j]);
+    demb[(long long)r * d + j] = g;
+    demb[(long long)(r + B) * d + j] = -g;
+  }
+}
+
+// emb f32 [2B,d] (rows [0,B) = first element of every pair, [B,2B) = second), labels i32 [>= B] (1 same / 0 different;
+// anything else: the pair is ignored), out f32 [2] = {loss, 1 if the negative hinge is active}, demb [2B,d] nullable,
+// workspace >= 16 bytes
+extern "C" int ugn_pair_verif_loss(ugn_ctx* ctx, const ugn_tensor* emb, const ugn_tensor* labels, float margin, float scale,
+                                   ugn_tensor* out, ugn_tensor* demb, ugn_tensor* workspace, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  UGN_CHECK(ctx && emb && labels && out && workspace, "ugn_pair_verif_loss: null argument");
+  UGN_TENSOR(emb, DT_F32, 2, 2);
+  UGN_TENSOR(labels, DT_I32, 1, 2);
+  UGN_TENSOR(out, DT_F32, 1, 1);
+  UGN_TENSOR(workspace, DT_BAD, 1, 8);
+  UGN_CHECK(emb->shape[0] % 2 == 0, "ugn_pair_verif_loss: emb must hold 2B rows");
+  const int B = (int)(emb->shape[0] / 2), d = (int)emb->shape[1];
+  UGN_CHECK(ugn_numel(labels) >= B && out->shape[0] >= 2, "ugn_pair_verif_loss: labels [>=B], out [2] expected");
+  UGN_CHECK(ugn_numel(workspace) * (workspace->dtype_bits / 8) >= 16, "ugn_pair_verif_loss: workspace too small");
+  if (demb) { UGN_TENSOR(demb, DT_F32, 2, 2); UGN_CHECK(ugn_numel(demb) == ugn_numel(emb), "demb shape mismatch"); }
+  double* acc = ugn_ptr<double>(workspace);
+  UGN_CUDA(cudaMemsetAsync(acc, 0, 16, st));
+  if (B > 0) {
+    pair_sums_kernel<<<B, 256, 0, st>>>(ugn_ptr<float>(emb), ugn_ptr<int>(labels), acc, B, d);
+    UGN_LAUNCHED(ctx);
+  }
+  pair_finish_kernel<<<std::max(B, 1), 256, 0, st>>>(ugn_ptr<float>(emb), ugn_ptr<int>(labels), acc, ugn_ptr<float>(out),
+                                                     (demb && B > 0) ? ugn_ptr<float>(demb) : nullptr, B, d, margin, scale);
+  UGN_LAUNCHED(ctx);
+  return UGN_OK;
+}
+
 extern "C" int64_t ugn_triplet_workspace_bytes(int n, int B) {
   int64_t accb = ((int64_t)n * sizeof(TripAcc) + 255) / 256 * 256;
   int64_t x2b = ((int64_t)n * B * 4 + 255) / 256 * 256;

@@ -705,7 +705,13 @@ class UGaitEngine:
                 p.cmask.bernoulli_(keep).div_(keep)
         p.philox_code = self.philox and code_drop_mask is None and p.train and cfg.dropout > 0.001 and cfg.nc > 0
         if labels is not None:
-            p.labels.copy_(labels.reshape(-1).to(torch.int32), non_blocking=True)
+            lab = labels.reshape(-1).to(torch.int32)
+            if getattr(cfg, "pair_loss", False):      # B pair labels for 2B rows
+                if lab.numel() * 2 != p.B:
+                    raise ValueError(f"pair labels: expected {p.B // 2} entries for {p.B} rows, found {lab.numel()}")
+                p.labels[:lab.numel()].copy_(lab, non_blocking=True)
+            else:
+                p.labels.copy_(lab, non_blocking=True)
 
     @torch.no_grad()
     def predict(self, inputs: Sequence[torch.Tensor], flags: Optional[Sequence[torch.Tensor]] = None,
@@ -840,7 +846,10 @@ class UGaitEngine:
         B = p.B
         self._works = []
         # triplet: demb = wver * dL/dsig
-        if getattr(cfg, "triplet_hard", False):      # compile_hard: tfa TripletHardLoss (nets/mj_uwyhNets_ba.py:1302-1306)
+        if getattr(cfg, "pair_loss", False):         # UWYHNet.build: VerifLossLayer on the two halves of the batch
+            check(lib.ugn_pair_verif_loss(h, sig.ptr, p.R["labels"].ptr, cfg.margin, cfg.wver, p.R["trip_out"].ptr,
+                                          p.R["dsig"].ptr, p.R["trip_ws"].ptr, st))
+        elif getattr(cfg, "triplet_hard", False):      # compile_hard: tfa TripletHardLoss (nets/mj_uwyhNets_ba.py:1302-1306)
             check(lib.ugn_triplet_hard(h, sig.ptr, p.R["sig16"].ptr if p.tc_gram else None, p.R["labels"].ptr,
                                        cfg.margin, cfg.wver, p.R["trip_out"].ptr,
                                        (p.R["dcodeN"] if self.post2 else p.R["dsig"]).ptr, p.R["trip_ws"].ptr, st))
@@ -1472,7 +1481,10 @@ class UGaitEngine:
         self._set_inputs(p, inputs, flags, labels)
         sig, _ = self._forward(p, False)
         st = stream_ptr()
-        if getattr(cfg, "triplet_hard", False):
+        if getattr(cfg, "pair_loss", False):
+            check(lib.ugn_pair_verif_loss(h, sig.ptr, p.R["labels"].ptr, cfg.margin, 1.0, p.R["trip_out"].ptr, None,
+                                          p.R["trip_ws"].ptr, st))
+        elif getattr(cfg, "triplet_hard", False):
             check(lib.ugn_triplet_hard(h, sig.ptr, None, p.R["labels"].ptr, cfg.margin, 1.0, p.R["trip_out"].ptr, None,
                                        p.R["trip_ws"].ptr, st))
         else:
