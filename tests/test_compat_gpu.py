@@ -332,3 +332,24 @@ def test_pair_network_builder(compat_path):
     assert l1 < l0
     with pytest.raises(ValueError, match="9 inputs"):
         model.train_on_batch(X[:8])
+
+
+def test_stand_alone_branch_builders(compat_path, tmp_path):
+    """UWYHNet.buildBranch / buildBranchLReLU (:67-152): one branch as a model of its own; init_branch loads a saved one."""
+    from nets.mj_uwyhNets_ba import UWYHNet
+    import nets.mj_uwyhNets_ba as mod
+    mod.MATH_MODE = "fp32"
+    rng = np.random.default_rng(1)
+    x = rng.uniform(-0.5, 0.5, size=(3, 5, 60, 60))
+    for builder, act in ((UWYHNet.buildBranch, O.ACT_RELU), (UWYHNet.buildBranchLReLU, O.ACT_LEAKY)):
+        br = builder("grayBranch", (5, 60, 60), 4, [(7, 7), (5, 5), (3, 3), (2, 2)], [8, 8, 16, 16], 16, 0.00005, 0.0, "")
+        oc = O.NetConfig(in_channels=(5,), filters_numbers=(8, 8, 16, 16), nd=16, nclasses=0, single=True, act=act)
+        P = {k: v.double().cpu() for k, v in br.engine.export_params().items()}
+        want = O.branch_forward(torch.tensor(x), P, "ofBranch", oc)
+        got = br.predict(x)
+        assert got.shape == (3, 16) and np.allclose(got, want.numpy(), atol=2e-6)
+    path = str(tmp_path / "branch.hdf5")
+    br.save_branch(path, "ofBranch")
+    br2 = UWYHNet.buildBranchLReLU("ofBranch", (5, 60, 60), 4, [(7, 7), (5, 5), (3, 3), (2, 2)], [8, 8, 16, 16], 16, 0.00005,
+                                   0.0, init_branch=path)
+    assert np.array_equal(br2.predict(x), br.predict(x))

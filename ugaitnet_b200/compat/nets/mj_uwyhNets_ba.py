@@ -775,11 +775,28 @@ def _freeze(model, freeze_convs=False, freeze_all=False, freeze_branches=False):
 class UWYHNet:
     @staticmethod
     def buildBranch(name, input_shape=(50, 60, 60), number_convolutional_layers=4, filters_size=None,
-                    filters_numbers=None, ndense_units=512, weight_decay=1e-4, dropout=0.4, init_branch=None):
-        raise NotImplementedError("stand-alone Keras Sequential branches are not exposed; branches are built "
-                                  "inside UWYHSemiNet{,3Mods}.build")
+                    filters_numbers=None, ndense_units=512, weight_decay=1e-4, dropout=0.4, init_branch=None,
+                    _activation='relu', alpha=0.3):
+        """:67-107 -- ONE stand-alone branch (the Keras Sequential conv stack -> ofFlat -> dense [-> drop] -> ofCode):
+        a single-modality model without heads whose predict() is the branch output [B, ndense_units].  init_branch:
+        a saved branch / model file to initialise from (fc_loadBranch, :57-66)."""
+        if filters_size is None:
+            filters_size = [(7, 7), (5, 5), (3, 3), (2, 2)]
+        cfg = _cfg_from_args(tuple(input_shape), number_convolutional_layers, filters_size, filters_numbers, ndense_units,
+                             weight_decay, dropout, 0.2, 0, [1.0, 1.0], Maximum, _activation, alpha, single=True)
+        model = UGaitModel(cfg, None, triplet_loss(margin=0.2), 1.0, multimodal=False)
+        model.name = name
+        if init_branch:
+            _load_branch(model, init_branch, BRANCH_NAMES[0])
+        return model
 
-    buildBranchLReLU = buildBranch
+    @staticmethod
+    def buildBranchLReLU(name, input_shape=(50, 60, 60), number_convolutional_layers=4, filters_size=None,
+                         filters_numbers=None, ndense_units=512, weight_decay=1e-4, dropout=0.4, init_branch=None,
+                         alpha=0.3):
+        """:110-152 -- the same stack with LeakyReLU(alpha) after every convolution."""
+        return UWYHNet.buildBranch(name, input_shape, number_convolutional_layers, filters_size, filters_numbers,
+                                   ndense_units, weight_decay, dropout, init_branch, _activation='leaky', alpha=alpha)
 
     @staticmethod
     def build(input_shapes, number_convolutional_layers, filters_size, filters_numbers, ndense_units=512,
