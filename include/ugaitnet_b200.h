@@ -114,6 +114,17 @@ int ugn_pack_input_augment(ugn_ctx*, const ugn_tensor* x_base, const ugn_tensor*
                            float clip_hi, float clip_val, float noise, ugn_tensor* x_nhwc, void* stream);
 
 
+/* ---- a17 use3D: Conv3D branches (UWYHSemiNet.build_3Dbranch{,LReLU}, nets/mj_uwyhNets_ba.py:336-417) --------------
+ * Strided 'valid' channels-last 3-D convolution, f32 only (fp32 validation engine: the option is outside the
+ * benchmarked configurations).  x [B,T,H,W,C], w [Cout,kt,kh,kw,C], bias [Cout] (nullable), y / dz
+ * [B,To,Ho,Wo,Cout] with To = (T-kt)/st+1 ...; act / alpha as ugn_conv2d_fwd (applied after the bias).
+ * wgrad: dw like w (overwritten), db [Cout] nullable = column sums of dz.  dgrad: dx like x (overwritten). */
+int ugn_conv3d_fwd(ugn_ctx*, const ugn_tensor* x, const ugn_tensor* w, const ugn_tensor* bias, ugn_tensor* y,
+                   int stride_t, int stride_h, int stride_w, int act, float alpha, void* stream);
+int ugn_conv3d_wgrad(ugn_ctx*, const ugn_tensor* x, const ugn_tensor* dz, ugn_tensor* dw, ugn_tensor* db,
+                     int stride_t, int stride_h, int stride_w, void* stream);
+int ugn_conv3d_dgrad(ugn_ctx*, const ugn_tensor* dz, const ugn_tensor* w, ugn_tensor* dx,
+                     int stride_t, int stride_h, int stride_w, void* stream);
 /* On-disk sample values -> the f32 volume of the generator (`__load_dd`, data/mj_dataGeneratorMMUWYHsingle.py:313-329),
  * on the device: raw int16 (optical flow, compressFactor 100) or uint8 (gray / depth / silhouette), any shape; out f32 with
  * the same number of elements.  x = float(raw); |x| > clip_max or |x| < clip_min (each when > 0) -> 1e-8; then

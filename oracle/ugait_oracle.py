@@ -63,6 +63,8 @@ class NetConfig:
     aux_losses: bool = False       # classprob_{of,gray,depth} heads on the gated branch outputs (:1222-1251)
     waux: float = 1.0              # loss_weights[-1] (:1264-1268)
     triplet_hard: bool = False     # compile_hard: tfa.losses.TripletHardLoss instead of the batch-all loss (:1302-1306)
+    branch3d: tuple = ()           # use3D: per modality True -> Conv3D branch (build_3Dbranch{,LReLU}, :336-417) on [B,25,60,60,1]
+    filters3d: tuple = (64, 128, 256, 512, 512, 512)   # its six activated Conv3D layers (geometry fixed, LAYERS3D below)
     pair_loss: bool = False        # UWYHNet.build (:154-245): rows [0,B) / [B,2B) are the two sides of B pairs, VerifLossLayer
     postriplet: int = 1            # 2: fusion -> Dense "signature" (activity-regularised) -> l2_normalize "code" = the
     #                                embedding of the triplet loss and of the classifier (:814-832, 2-modality builder)
@@ -88,6 +90,14 @@ class NetConfig:
 
 
 BRANCH_NAMES = ("ofBranch", "grayBranch", "depthBranch")
+# build_3Dbranch (:346-363): (kernel (kt,kh,kw), strides) of the six activated Conv3D layers, 'valid', channels_last;
+# then Conv3D(ndense_units, (1,1,1)) "grayCode" (linear, he_uniform, L2 1e-3) and Flatten.  [25,60,60,1] ends at 1x1x1.
+LAYERS3D = (((3, 5, 5), (1, 2, 2)), ((3, 3, 3), (1, 2, 2)), ((3, 3, 3), (2, 2, 2)), ((3, 3, 3), (2, 2, 2)),
+            ((3, 2, 2), (1, 1, 1)), ((2, 1, 1), (1, 1, 1)))
+
+
+def is3d(cfg, m):
+    return bool(len(getattr(cfg, "branch3d", ())) > m and cfg.branch3d[m])
 AUX_NAMES = ("classprob_of", "classprob_gray", "classprob_depth")
 
 
@@ -104,6 +114,16 @@ def init_params(cfg: NetConfig, seed: int = 232323, dtype=torch.float32) -> Dict
     for m in range(cfg.nmods):
         bn = BRANCH_NAMES[m]
         cin = cfg.in_channels[m]
+        if is3d(cfg, m):          # Keras defaults: glorot_uniform Conv3D kernels, zero biases; grayCode he_uniform
+            cin = 1
+            for li, (co, (k, _)) in enumerate(zip(cfg.filters3d, LAYERS3D)):
+                rf = k[0] * k[1] * k[2]
+                P[f"{bn}/conv{li}/w"] = uni((co, cin) + tuple(k), math.sqrt(6.0 / (cin * rf + co * rf)))
+                P[f"{bn}/conv{li}/b"] = torch.zeros(co, dtype=dtype)
+                cin = co
+            P[f"{bn}/ofCode/w"] = uni((cfg.nd, cin), math.sqrt(6.0 / cin))
+            P[f"{bn}/ofCode/b"] = torch.zeros(cfg.nd, dtype=dtype)
+            continue
         for li, (co, k) in enumerate(zip(cfg.filters_numbers, cfg.filters_size)):
             fan_in, fan_out = cin * k * k, co * k * k
             P[f"{bn}/conv{li}/w"] = uni((co, cin, k, k), math.sqrt(6.0 / (fan_in + fan_out)))
@@ -144,6 +164,17 @@ def _windows2x2(h):
     B, C, H, W = h.shape
     Hp, Wp = H // 2, W // 2
     return h[:, :, :2 * Hp, :2 * Wp].reshape(B, C, Hp, 2, Wp, 2).permute(0, 1, 2, 4, 3, 5).reshape(B, C, Hp, Wp, 4)
+
+
+def branch3d_forward(x, P, bn, cfg: NetConfig):
+    """UWYHSemiNet.build_3Dbranch / build_3DbranchLReLU (nets/mj_uwyhNets_ba.py:336-417): x [B,25,60,60,1] (the
+    generator's np.expand_dims(x, 3), data/mj_dataGeneratorMMUWYHsingle.py:431-432) -> six strided 'valid' Conv3D with
+    ReLU / LeakyReLU(alpha) -> Conv3D(nd, 1x1x1) "grayCode" (linear) -> Flatten."""
+    h = x.reshape(x.shape[0], 1, x.shape[1], x.shape[2], x.shape[3])          # channels_last C = 1 -> NCDHW
+    for li, (_, st) in enumerate(LAYERS3D):
+        h = _act(F.conv3d(h, P[f"{bn}/conv{li}/w"], P[f"{bn}/conv{li}/b"], stride=st), cfg.act, cfg.alpha)
+    assert tuple(h.shape[2:]) == (1, 1, 1), "build_3Dbranch expects the [25,60,60,1] volume"
+    return F.linear(h.flatten(1), P[f"{bn}/ofCode/w"], P[f"{bn}/ofCode/b"])
 
 
 def branch_forward(x, P, bn, cfg: NetConfig, drop_mask=None, return_acts=False, decisions=None, record=None):
@@ -361,8 +392,11 @@ def model_forward(inputs, flags, P, cfg: NetConfig, drop_masks=None, code_drop_m
         rec_m = None
         if record is not None:
             rec_m = record.setdefault(m, {})
-        b = branch_forward(inputs[m], P, BRANCH_NAMES[m], cfg, dm, decisions=None if decisions is None else decisions[m],
-                           record=rec_m)
+        if is3d(cfg, m):
+            b = branch3d_forward(inputs[m], P, BRANCH_NAMES[m], cfg)
+        else:
+            b = branch_forward(inputs[m], P, BRANCH_NAMES[m], cfg, dm, decisions=None if decisions is None else decisions[m],
+                               record=rec_m)
         outs[f"branch{m}"] = b
         if cfg.single:
             gated.append(b)
@@ -439,8 +473,9 @@ def total_loss(inputs, flags, labels, P, cfg: NetConfig, drop_masks=None, code_d
     reg = torch.zeros((), dtype=trip.dtype)
     for m in range(cfg.nmods):
         bn = BRANCH_NAMES[m]
-        for li in range(len(cfg.filters_numbers)):
-            reg = reg + cfg.weight_decay * (P[f"{bn}/conv{li}/w"] ** 2).sum()
+        if not is3d(cfg, m):        # the Conv3D layers carry no kernel regulariser (:346-363), only "grayCode" does
+            for li in range(len(cfg.filters_numbers)):
+                reg = reg + cfg.weight_decay * (P[f"{bn}/conv{li}/w"] ** 2).sum()
         reg = reg + 1e-3 * (P[f"{bn}/ofCode/w"] ** 2).sum()
     if cfg.nc > 0:
         reg = reg + 1e-3 * (outs["code_reg"] ** 2).sum() / outs["code_reg"].shape[0]

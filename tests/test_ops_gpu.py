@@ -562,3 +562,39 @@ def test_pair_verif_loss_vs_oracle(ctx, case):
         assert rel(de, g) < 1e-5
     if case == "far_negatives":
         assert float(out[1]) == 0.0
+
+
+@pytest.mark.parametrize("geom", [((2, 9, 20, 21, 1), 6, (3, 5, 5), (1, 2, 2)), ((3, 8, 9, 10, 8), 12, (3, 3, 3), (2, 2, 2)),
+                                  ((2, 5, 6, 6, 70), 66, (3, 2, 2), (1, 1, 1)), ((4, 2, 1, 1, 16), 8, (2, 1, 1), (1, 1, 1))])
+def test_conv3d_ops_vs_torch(ctx, geom):
+    """ugn_conv3d_{fwd,wgrad,dgrad} (use3D branches, nets/mj_uwyhNets_ba.py:346-363: strided 'valid' channels-last Conv3D)
+    against torch.nn.functional.conv3d and its autograd in fp64."""
+    import torch.nn.functional as F
+    from ugaitnet_b200._ffi import TRef, check, lib, stream_ptr
+    (B, T, H, W, C), Co, k, s = geom
+    g = torch.Generator().manual_seed(B * 7 + C)
+    x = torch.randn(B, T, H, W, C, generator=g)
+    w = torch.randn(Co, k[0], k[1], k[2], C, generator=g) * 0.2
+    bias = torch.randn(Co, generator=g) * 0.1
+    x64 = x.double().permute(0, 4, 1, 2, 3).requires_grad_(True)
+    w64 = w.double().permute(0, 4, 1, 2, 3).requires_grad_(True)
+    b64 = bias.double().requires_grad_(True)
+    z = F.conv3d(x64, w64, b64, stride=s)
+    y64 = F.leaky_relu(z, 0.3)
+    dy = torch.randn(y64.shape, generator=g, dtype=torch.float64)
+    z.backward(dy)                                                  # gradients w.r.t. the pre-activation dz = dy
+    To, Ho, Wo = y64.shape[2:]
+    xd, wd, bd = x.cuda(), w.cuda(), bias.cuda()
+    y = torch.empty(B, To, Ho, Wo, Co, device="cuda")
+    R = [TRef(t) for t in (xd, wd, bd, y)]
+    check(lib.ugn_conv3d_fwd(ctx.h, R[0].ptr, R[1].ptr, R[2].ptr, R[3].ptr, s[0], s[1], s[2], 2, 0.3, stream_ptr()))
+    assert rel(y.permute(0, 4, 1, 2, 3), y64.detach()) < 1e-5
+    dz = dy.permute(0, 2, 3, 4, 1).contiguous().float().cuda()
+    dw, db, dx = torch.full_like(wd, 7.0), torch.full_like(bd, 7.0), torch.full_like(xd, 7.0)
+    R2 = [TRef(t) for t in (dz, dw, db, dx)]
+    check(lib.ugn_conv3d_wgrad(ctx.h, R[0].ptr, R2[0].ptr, R2[1].ptr, R2[2].ptr, s[0], s[1], s[2], stream_ptr()))
+    check(lib.ugn_conv3d_dgrad(ctx.h, R2[0].ptr, R[1].ptr, R2[3].ptr, s[0], s[1], s[2], stream_ptr()))
+    ctx.check()
+    assert rel(dw.permute(0, 4, 1, 2, 3), w64.grad) < 1e-5
+    assert rel(db, b64.grad) < 1e-5
+    assert rel(dx.permute(0, 4, 1, 2, 3), x64.grad) < 1e-5

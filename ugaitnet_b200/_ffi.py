@@ -47,6 +47,9 @@ _PROTOS = {
     "ugn_pack_input": (c_int, [c_void_p, _T, _T, c_void_p]),
     "ugn_pack_input_expand": (c_int, [c_void_p, _T, _T, _T, _T, c_float, _T, c_void_p]),
     "ugn_pack_input_augment": (c_int, [c_void_p, _T, _T, _T, _T, _T, _T, c_float, c_float, c_float, c_float, _T, c_void_p]),
+    "ugn_conv3d_fwd": (c_int, [c_void_p, _T, _T, _T, _T, c_int, c_int, c_int, c_int, c_float, c_void_p]),
+    "ugn_conv3d_wgrad": (c_int, [c_void_p, _T, _T, _T, _T, c_int, c_int, c_int, c_void_p]),
+    "ugn_conv3d_dgrad": (c_int, [c_void_p, _T, _T, _T, c_int, c_int, c_int, c_void_p]),
     "ugn_decode_samples": (c_int, [c_void_p, _T, c_float, c_float, c_float, c_float, c_float, _T, c_void_p]),
     "ugn_pack_weight": (c_int, [c_void_p, _T, _T, c_void_p]),
     "ugn_split_bf16": (c_int, [c_void_p, _T, _T, c_void_p]),

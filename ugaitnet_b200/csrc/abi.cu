@@ -348,6 +348,63 @@ extern "C" int ugn_conv2d_dgrad(ugn_ctx* ctx, const ugn_tensor* dz, const ugn_te
                        (cudaStream_t)stream);
 }
 
+// ---- Conv3D branches (use3D, nets/mj_uwyhNets_ba.py:336-417): fp32 validation engine ----
+int simt_conv3d_fwd(ugn_ctx*, const Conv3Geom&, const float*, const float*, const float*, float*, int, float, cudaStream_t);
+int simt_conv3d_wgrad(ugn_ctx*, const Conv3Geom&, const float*, const float*, float*, float*, cudaStream_t);
+int simt_conv3d_dgrad(ugn_ctx*, const Conv3Geom&, const float*, const float*, float*, cudaStream_t);
+
+static int conv3_geom(ugn_ctx* ctx, const ugn_tensor* x, const ugn_tensor* w, const ugn_tensor* y, int st, int sh, int sw, Conv3Geom& g) {
+  UGN_TENSOR(x, DT_F32, 5, 5);
+  UGN_TENSOR(w, DT_F32, 5, 5);
+  UGN_TENSOR(y, DT_F32, 5, 5);
+  UGN_CHECK(st >= 1 && sh >= 1 && sw >= 1, "conv3d: strides must be >= 1");
+  g.B = (int)x->shape[0]; g.T = (int)x->shape[1]; g.H = (int)x->shape[2]; g.W = (int)x->shape[3]; g.C = (int)x->shape[4];
+  g.Co = (int)w->shape[0]; g.KT = (int)w->shape[1]; g.KH = (int)w->shape[2]; g.KW = (int)w->shape[3];
+  g.ST = st; g.SH = sh; g.SW = sw;
+  UGN_CHECK(w->shape[4] == g.C, "conv3d: weight inner dim %lld != input channels %d", (long long)w->shape[4], g.C);
+  UGN_CHECK(g.T >= g.KT && g.H >= g.KH && g.W >= g.KW, "conv3d: kernel larger than the input volume");
+  g.To = (g.T - g.KT) / st + 1; g.Ho = (g.H - g.KH) / sh + 1; g.Wo = (g.W - g.KW) / sw + 1;
+  UGN_CHECK(y->shape[0] == g.B && y->shape[1] == g.To && y->shape[2] == g.Ho && y->shape[3] == g.Wo && y->shape[4] == g.Co,
+            "conv3d: output must be [%d,%d,%d,%d,%d]", g.B, g.To, g.Ho, g.Wo, g.Co);
+  UGN_CHECK((long long)g.B * g.T * g.H * g.W * g.C < 0x7fffffffLL && (long long)g.B * g.To * g.Ho * g.Wo * g.Co < 0x7fffffffLL,
+            "conv3d: tensor too large for 32-bit offsets");
+  return UGN_OK;
+}
+
+extern "C" int ugn_conv3d_fwd(ugn_ctx* ctx, const ugn_tensor* x, const ugn_tensor* w, const ugn_tensor* bias, ugn_tensor* y,
+                              int st, int sh, int sw, int act, float alpha, void* stream) {
+  UGN_CHECK(ctx && x && w && y, "ugn_conv3d_fwd: null argument");
+  Conv3Geom g;
+  int rc = conv3_geom(ctx, x, w, y, st, sh, sw, g);
+  if (rc != UGN_OK) return rc;
+  if (bias) { UGN_TENSOR(bias, DT_F32, 1, 1); UGN_CHECK(bias->shape[0] == g.Co, "conv3d: bias must be f32 [Cout]"); }
+  if (g.B == 0) return UGN_OK;
+  return simt_conv3d_fwd(ctx, g, ugn_ptr<float>(x), ugn_ptr<float>(w), bias ? ugn_ptr<float>(bias) : nullptr, ugn_ptr<float>(y),
+                         act, alpha, (cudaStream_t)stream);
+}
+
+extern "C" int ugn_conv3d_wgrad(ugn_ctx* ctx, const ugn_tensor* x, const ugn_tensor* dz, ugn_tensor* dw, ugn_tensor* db,
+                                int st, int sh, int sw, void* stream) {
+  UGN_CHECK(ctx && x && dz && dw, "ugn_conv3d_wgrad: null argument");
+  Conv3Geom g;
+  int rc = conv3_geom(ctx, x, dw, dz, st, sh, sw, g);
+  if (rc != UGN_OK) return rc;
+  if (db) { UGN_TENSOR(db, DT_F32, 1, 1); UGN_CHECK(db->shape[0] == g.Co, "conv3d: db must be f32 [Cout]"); }
+  if (g.B == 0) return UGN_OK;
+  return simt_conv3d_wgrad(ctx, g, ugn_ptr<float>(x), ugn_ptr<float>(dz), ugn_ptr<float>(dw), db ? ugn_ptr<float>(db) : nullptr,
+                           (cudaStream_t)stream);
+}
+
+extern "C" int ugn_conv3d_dgrad(ugn_ctx* ctx, const ugn_tensor* dz, const ugn_tensor* w, ugn_tensor* dx, int st, int sh, int sw,
+                                void* stream) {
+  UGN_CHECK(ctx && dz && w && dx, "ugn_conv3d_dgrad: null argument");
+  Conv3Geom g;
+  int rc = conv3_geom(ctx, dx, w, dz, st, sh, sw, g);
+  if (rc != UGN_OK) return rc;
+  if (g.B == 0) return UGN_OK;
+  return simt_conv3d_dgrad(ctx, g, ugn_ptr<float>(dz), ugn_ptr<float>(w), ugn_ptr<float>(dx), (cudaStream_t)stream);
+}
+
 extern "C" int ugn_conv2d_wgrad(ugn_ctx* ctx, const ugn_tensor* x, const ugn_tensor* dz, ugn_tensor* dw,
                                 ugn_tensor* db, void* stream) {
   UGN_CHECK(ctx && x && dz && dw, "ugn_conv2d_wgrad: null argument");

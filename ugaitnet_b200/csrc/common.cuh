@@ -185,6 +185,13 @@ struct ConvGeom {
   int Cin;              // unpadded input channels (master weight layout)
 };
 
+struct Conv3Geom {        // strided 'valid' channels-last Conv3D (use3D branches)
+  int B, T, H, W, C;      // input
+  int Co, KT, KH, KW;     // filter
+  int ST, SH, SW;         // strides
+  int To, Ho, Wo;         // output
+};
+
 struct FusePtrs {
   const float* br[4];
   const float* flag[4];

@@ -332,3 +332,146 @@ int simt_colsum_bf16(ugn_ctx* ctx, const __nv_bfloat16* X, int P, int f16, long 
   UGN_LAUNCHED(ctx);
   return UGN_OK;
 }
+
+// ---------------------------------------------------------------------------------------
+// Conv3D branches (use3D: UWYHSemiNet.build_3Dbranch{,LReLU}, nets/mj_uwyhNets_ba.py:336-417): strided 'valid'
+// channels-last 3-D convolutions.  fp32 validation engine only (the builder option is outside the benchmarked
+// configurations): forward and kernel gradient are the generic mixed-radix GEMM with one more digit, the input gradient
+// is a gather with stride-divisibility tests in a kernel of its own.
+//   x [B,T,H,W,C], w [Co,KT,KH,KW,C], y / dz [B,To,Ho,Wo,Co]
+// ---------------------------------------------------------------------------------------
+static Radix radix4(int r0, int s0, int r1, int s1, int r2, int s2, int s3) {
+  Radix R;
+  R.n = 4;
+  R.r[0] = r0; R.r[1] = r1; R.r[2] = r2;
+  R.s[0] = s0; R.s[1] = s1; R.s[2] = s2; R.s[3] = s3;
+  return R;
+}
+
+int simt_conv3d_fwd(ugn_ctx* ctx, const Conv3Geom& g, const float* x, const float* w, const float* bias, float* y,
+                    int act, float alpha, cudaStream_t st) {
+  SGemm p;
+  p.A = x; p.B = w; p.C = y;
+  p.M = g.B * g.To * g.Ho * g.Wo; p.N = g.Co; p.K = g.KT * g.KH * g.KW * g.C;
+  p.ar = radix4(g.Wo, g.SW * g.C, g.Ho, g.SH * g.W * g.C, g.To, g.ST * g.H * g.W * g.C, g.T * g.H * g.W * g.C);
+  p.ak = radix4(g.C, 1, g.KW, g.C, g.KH, g.W * g.C, g.H * g.W * g.C);
+  p.br = radix1(p.K);
+  p.bk = radix1(1);
+  p.bias = bias; p.act = act; p.alpha = alpha; p.ldc = g.Co;
+  return simt_gemm_launch(ctx, p, st);
+}
+
+int simt_conv3d_wgrad(ugn_ctx* ctx, const Conv3Geom& g, const float* x, const float* dz, float* dw, float* db,
+                      cudaStream_t st) {
+  SGemm p;
+  p.A = dz; p.B = x; p.C = dw;
+  p.M = g.Co; p.N = g.KT * g.KH * g.KW * g.C; p.K = g.B * g.To * g.Ho * g.Wo;
+  p.ar = radix1(1);
+  p.ak = radix1(g.Co);
+  p.br = radix4(g.C, 1, g.KW, g.C, g.KH, g.W * g.C, g.H * g.W * g.C);
+  p.bk = radix4(g.Wo, g.SW * g.C, g.Ho, g.SH * g.W * g.C, g.To, g.ST * g.H * g.W * g.C, g.T * g.H * g.W * g.C);
+  p.ldc = p.N;
+  int blocks = ugn_cdiv(p.M, TBM) * ugn_cdiv(p.N, TBN);
+  int want = ugn_cdiv(4 * ctx->sm_count, blocks);
+  int maxs = std::max(1, p.K / 128);
+  p.ksplit = std::max(1, std::min(want, maxs));
+  p.epi = EPI_ATOMIC;
+  UGN_CUDA(cudaMemsetAsync(dw, 0, sizeof(float) * (size_t)p.M * p.N, st));
+  int rc = simt_gemm_launch(ctx, p, st);
+  if (rc != UGN_OK) return rc;
+  if (db) return simt_colsum(ctx, dz, (long long)p.K, g.Co, g.Co, db, st);
+  return UGN_OK;
+}
+
+// dx[b,t,y,x,c] = sum_{kt,ky,kx,co} dz[b,(t-kt)/ST,(y-ky)/SH,(x-kx)/SW,co] * w[co,kt,ky,kx,c] over the taps whose
+// differences are non-negative multiples of the strides and land inside the output volume.
+// GEMM view: M = B*T*H*W rows, N = C, K = (co fastest, kx, ky, kt).  64 x 64 x 16 tiles as simt_gemm_kernel.
+__global__ void __launch_bounds__(256) conv3d_dgrad_kernel(const float* __restrict__ dz, const float* __restrict__ w,
+                                                           float* __restrict__ dx, const Conv3Geom g) {
+  __shared__ __align__(16) float As[TBK][TBM + 4];
+  __shared__ __align__(16) float Bs[TBK][TBN + 4];
+  __shared__ int r_t[TBM], r_y[TBM], r_x[TBM], r_b[TBM];
+  const int t = threadIdx.x;
+  const int i0 = blockIdx.x * TBM, j0 = blockIdx.y * TBN;
+  const int M = g.B * g.T * g.H * g.W, K3 = g.KT * g.KH * g.KW * g.C, K = g.KT * g.KH * g.KW * g.Co;
+  if (t < TBM) {
+    int i = i0 + t;
+    if (i < M) {
+      r_x[t] = i % g.W; i /= g.W;
+      r_y[t] = i % g.H; i /= g.H;
+      r_t[t] = i % g.T; r_b[t] = i / g.T;
+    } else {
+      r_x[t] = r_y[t] = r_t[t] = 0; r_b[t] = -1;
+    }
+  }
+  __syncthreads();
+  float acc[4][4];
+#pragma unroll
+  for (int a = 0; a < 4; ++a)
+#pragma unroll
+    for (int b = 0; b < 4; ++b) acc[a][b] = 0.f;
+  const int kk = t & 15, r = t >> 4;
+  const int ty = t >> 4, tx = t & 15;
+  for (int k0 = 0; k0 < K; k0 += TBK) {
+    const int k = k0 + kk;
+    const bool kv = k < K;
+    int co = 0, kx = 0, ky = 0, kt = 0;
+    if (kv) {
+      int q = k;
+      co = q % g.Co; q /= g.Co;
+      kx = q % g.KW; q /= g.KW;
+      ky = q % g.KH; kt = q / g.KH;
+    }
+    const long long wk = (long long)co * K3 + ((long long)(kt * g.KH + ky) * g.KW + kx) * g.C;
+#pragma unroll
+    for (int jj = 0; jj < 4; ++jj) {
+      const int row = r + 16 * jj;
+      float av = 0.f;
+      if (kv && r_b[row] >= 0) {
+        const int dt = r_t[row] - kt, dy = r_y[row] - ky, dxx = r_x[row] - kx;
+        if (dt >= 0 && dy >= 0 && dxx >= 0 && dt % g.ST == 0 && dy % g.SH == 0 && dxx % g.SW == 0) {
+          const int to = dt / g.ST, yo = dy / g.SH, xo = dxx / g.SW;
+          if (to < g.To && yo < g.Ho && xo < g.Wo)
+            av = __ldg(dz + ((((long long)r_b[row] * g.To + to) * g.Ho + yo) * g.Wo + xo) * g.Co + co);
+        }
+      }
+      As[kk][row] = av;
+      const int j = j0 + row;
+      Bs[kk][row] = (kv && j < g.C) ? __ldg(w + wk + j) : 0.f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int q = 0; q < TBK; ++q) {
+      float4 a4v = *reinterpret_cast<const float4*>(&As[q][ty * 4]);
+      float4 b4v = *reinterpret_cast<const float4*>(&Bs[q][tx * 4]);
+      float a4[4] = {a4v.x, a4v.y, a4v.z, a4v.w};
+      float b4[4] = {b4v.x, b4v.y, b4v.z, b4v.w};
+#pragma unroll
+      for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int b = 0; b < 4; ++b) acc[a][b] = fmaf(a4[a], b4[b], acc[a][b]);
+    }
+    __syncthreads();
+  }
+  const int ib = i0 + ty * 4, jb = j0 + tx * 4;
+#pragma unroll
+  for (int a = 0; a < 4; ++a) {
+    const int i = ib + a;
+    if (i >= M) continue;
+#pragma unroll
+    for (int b = 0; b < 4; ++b) {
+      const int j = jb + b;
+      if (j < g.C) dx[(long long)i * g.C + j] = acc[a][b];
+    }
+  }
+}
+
+int simt_conv3d_dgrad(ugn_ctx* ctx, const Conv3Geom& g, const float* dz, const float* w, float* dx, cudaStream_t st) {
+  const int M = g.B * g.T * g.H * g.W;
+  if (M <= 0) return UGN_OK;
+  dim3 grid(ugn_cdiv(M, TBM), ugn_cdiv(g.C, TBN));
+  UGN_CHECK(grid.y <= 65535, "conv3d dgrad: too many input channels");
+  conv3d_dgrad_kernel<<<grid, 256, 0, st>>>(dz, w, dx, g);
+  UGN_LAUNCHED(ctx);
+  return UGN_OK;
+}

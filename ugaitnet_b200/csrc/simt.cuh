@@ -53,3 +53,10 @@ static inline Radix radix3(int r0, int s0, int r1, int s1, int s2, int cy = -1, 
   R.cy = cy; R.cx = cx;
   return R;
 }
+
+// Conv3D (use3D branches), fp32 validation engine
+int simt_conv3d_fwd(ugn_ctx* ctx, const Conv3Geom& g, const float* x, const float* w, const float* bias, float* y,
+                    int act, float alpha, cudaStream_t st);
+int simt_conv3d_wgrad(ugn_ctx* ctx, const Conv3Geom& g, const float* x, const float* dz, float* dw, float* db,
+                      cudaStream_t st);
+int simt_conv3d_dgrad(ugn_ctx* ctx, const Conv3Geom& g, const float* dz, const float* w, float* dx, cudaStream_t st);
