@@ -30,6 +30,19 @@ def make_case(name):
         oc = O.NetConfig(in_channels=(5,), filters_numbers=(8, 8, 16, 16), nd=16, nclasses=9, single=True,
                          wver=0.7, wid=0.1, triplet_hard=True, margin=1.0)
         return oc, dict(base_rows=12, expand=1, kinds=("gray",)), None
+    if name == "2mod_3d":            # use3D (:1077-1099): the optical-flow branch stays 2-D, gray becomes a Conv3D branch
+        oc = O.NetConfig(in_channels=(6, 25), filters_numbers=(8, 8, 16, 16), nd=32, nclasses=10, merge=O.MERGE_SIGNMAX,
+                         wver=1.0, wid=0.1, branch3d=(False, True), filters3d=(4, 8, 8, 16, 16, 16))
+        return oc, dict(base_rows=4, expand=2, kinds=("of", "gray")), None
+    if name == "3mod_3d_leaky":      # build_3DbranchLReLU on gray and depth
+        oc = O.NetConfig(in_channels=(6, 25, 25), filters_numbers=(8, 8, 16, 16), nd=32, nc=8, nclasses=10,
+                         merge=O.MERGE_MAX, act=O.ACT_LEAKY, wver=1.0, wid=0.5, branch3d=(False, True, True),
+                         filters3d=(4, 8, 8, 16, 16, 16))
+        return oc, dict(base_rows=4, expand=2, kinds=("of", "gray", "depth")), None
+    if name == "1mod_3d":            # UWYHSemiNet.build, one non-OF modality with use3D (:738-745)
+        oc = O.NetConfig(in_channels=(25,), filters_numbers=(8, 8, 16, 16), nd=16, nclasses=9, single=True, wver=1.0,
+                         wid=0.1, branch3d=(True,), filters3d=(4, 8, 8, 16, 16, 16))
+        return oc, dict(base_rows=6, expand=1, kinds=("gray",)), None
     if name == "3mod_norm_smooth":   # normbfmerge + smoothlabels builder options (a17)
         oc = O.NetConfig(in_channels=(6, 4, 4), filters_numbers=(8, 8, 16, 16), nd=32, nclasses=10,
                          merge=O.MERGE_SIGNMAX, wver=1.0, wid=0.5, label_smoothing=0.1, normbfmerge=True)
@@ -75,7 +88,8 @@ def to_engine_cfg(oc, dropout=0.0):
                      weight_decay=oc.weight_decay, merge=oc.merge, act=oc.act, alpha=oc.alpha, margin=oc.margin,
                      wver=oc.wver, wid=oc.wid, hw=oc.hw, dropout=dropout, single=oc.single,
                      label_smoothing=oc.label_smoothing, normbfmerge=oc.normbfmerge, aux_losses=oc.aux_losses,
-                     waux=oc.waux, postriplet=oc.postriplet, triplet_hard=oc.triplet_hard, pair_loss=oc.pair_loss)
+                     waux=oc.waux, postriplet=oc.postriplet, triplet_hard=oc.triplet_hard, pair_loss=oc.pair_loss,
+                     branch3d=tuple(oc.branch3d), filters3d=tuple(oc.filters3d))
 
 
 def setup(name, math_mode="fp32", seed=11):
@@ -112,6 +126,8 @@ def engine_inputs(xs, fl, lab, masks, cmask):
 
 
 def reg_grad(oc, name, w):
+    if "/conv" in name and name.endswith("/w") and w.dim() == 5:
+        return torch.zeros_like(w)          # build_3Dbranch: no kernel regulariser on the Conv3D layers (:346-363)
     if "/conv" in name and name.endswith("/w"):
         return 2 * oc.weight_decay * w
     if name.endswith("ofCode/w"):
@@ -121,7 +137,7 @@ def reg_grad(oc, name, w):
 
 @pytest.mark.parametrize("name", ["3mod_signmax", "2mod_max_leaky_code", "3mod_avg", "1mod_gray", "real_shapes",
                                   "3mod_norm_smooth", "3mod_aux", "2mod_aux", "2mod_postriplet2", "2mod_postriplet2_relu",
-                                  "3mod_hard", "1mod_hard"])
+                                  "3mod_hard", "1mod_hard", "2mod_3d", "3mod_3d_leaky", "1mod_3d"])
 def test_step_parity_fp32(name):
     oc, eng, P, xs, fl, lab, masks, cmask = setup(name)
     res, G = oracle_step(oc, P, xs, fl, lab, masks, cmask)

@@ -15,6 +15,11 @@ def round_up(x: int, m: int) -> int:
     return (x + m - 1) // m * m
 
 
+# build_3Dbranch (nets/mj_uwyhNets_ba.py:346-363): (kernel (kt,kh,kw), strides) of the six activated Conv3D layers
+LAYERS3D = (((3, 5, 5), (1, 2, 2)), ((3, 3, 3), (1, 2, 2)), ((3, 3, 3), (2, 2, 2)), ((3, 3, 3), (2, 2, 2)),
+            ((3, 2, 2), (1, 1, 1)), ((2, 1, 1), (1, 1, 1)))
+
+
 @dataclass
 class NetConfig:
     """Arguments of UWYHSemiNet3Mods.build / UWYHSemiNet.build that shape the graph
@@ -40,6 +45,9 @@ class NetConfig:
     aux_losses: bool = False       # extra Dense(nclasses, softmax) head + CE on every gated branch output (:1222-1251)
     waux: float = 1.0              # their loss weight: loss_weights[-1] (:1264-1268)
     triplet_hard: bool = False     # compile_hard (:1302-1306): tfa TripletHardLoss (batch-hard) instead of batch-all
+    branch3d: Sequence[bool] = ()  # use3D (:336-417, :1077-1099): per modality True -> Conv3D branch on [B,25,60,60,1] (frames =
+    #                                in_channels[m]); fp32 validation engine only
+    filters3d: Sequence[int] = (64, 128, 256, 512, 512, 512)    # its six activated Conv3D layers (geometry: LAYERS3D)
     pair_loss: bool = False        # UWYHNet.build (:154-245): rows [0,B) / [B,2B) = the two sides of B pairs, labels [B] in
     #                                {0,1}, VerifLossLayer (nets/mj_loss.py:65-95) instead of the triplet loss; nclasses == 0
     postriplet: int = 1            # 2 (needs nc > 0; 2-modality builder, :814-832): the fusion is NOT normalised, FC1 is the
@@ -62,6 +70,22 @@ class NetConfig:
             out.append(dict(cin=cin, cp=round_up(cin, pad) if pad > 1 else cin, h=s, k=k, co=co, ho=ho,
                             hp=hp, pool=pool))
             s, cin = hp, co
+        return out
+
+    def is3d(self, m: int) -> bool:
+        return bool(len(self.branch3d) > m and self.branch3d[m])
+
+    def layers3d(self, m: int) -> List[dict]:
+        """Geometry of the Conv3D stack of modality m (build_3Dbranch, nets/mj_uwyhNets_ba.py:346-363): strided 'valid'
+        channels-last convolutions that take the [25,60,60,1] volume down to 1x1x1."""
+        out = []
+        t, h, cin = self.in_channels[m], self.hw, 1
+        for co, (k, s) in zip(self.filters3d, LAYERS3D):
+            to, ho = (t - k[0]) // s[0] + 1, (h - k[1]) // s[1] + 1
+            out.append(dict(cin=cin, co=co, k=k, s=s, t=t, h=h, to=to, ho=ho))
+            t, h, cin = to, ho, co
+        if (t, h) != (1, 1):
+            raise ValueError(f"use3D expects {self.in_channels[m]} x {self.hw} x {self.hw} volumes that end at 1x1x1, got {t}x{h}x{h}")
         return out
 
     @property

@@ -275,8 +275,17 @@ class UGaitEngine:
             segs.append(_Seg(name, tuple(shape), off, n, l2))
             off += round_up(n, 64)
 
+        if any(cfg.is3d(m) for m in range(cfg.nmods)) and self.P:
+            raise ValueError("use3D (Conv3D branches) runs on the fp32 validation engine only: math_mode='fp32'")
         for m in range(cfg.nmods):
             bn = BRANCH_NAMES[m]
+            if cfg.is3d(m):     # build_3Dbranch (:346-363): no kernel regulariser on the Conv3D layers, L2 1e-3 on "grayCode"
+                for li, L in enumerate(cfg.layers3d(m)):
+                    add(f"{bn}/conv{li}/w", (L["co"],) + tuple(L["k"]) + (L["cin"],))
+                    add(f"{bn}/conv{li}/b", (L["co"],))
+                add(f"{bn}/ofCode/w", (cfg.nd, cfg.filters3d[-1]), 1e-3)
+                add(f"{bn}/ofCode/b", (cfg.nd,))
+                continue
             for li, L in enumerate(cfg.layers(m, 1)):
                 add(f"{bn}/conv{li}/w", (L["co"], L["k"], L["k"], L["cin"]), cfg.weight_decay)
                 add(f"{bn}/conv{li}/b", (L["co"],))
@@ -307,7 +316,7 @@ class UGaitEngine:
         self.buckets = {}
         for m in range(cfg.nmods):
             mine = [s for s in segs if s.name.startswith(BRANCH_NAMES[m] + "/")]
-            dense0 = self.segs_off(segs, f"{BRANCH_NAMES[m]}/dense/w")
+            dense0 = self.segs_off(segs, f"{BRANCH_NAMES[m]}/{'ofCode' if cfg.is3d(m) else 'dense'}/w")
             self.buckets[m] = (mine[0].off, dense0)
             self.buckets[(m, "fc")] = (dense0, round_up(mine[-1].off + mine[-1].n, 64))
         heads = [s for s in segs if "/" in s.name and s.name.split("/")[0] in ("code", "classprob")]
@@ -349,6 +358,11 @@ class UGaitEngine:
         self.Rcw: Dict[str, TRef] = {}
         for m in range(cfg.nmods):
             bn = BRANCH_NAMES[m]
+            if cfg.is3d(m):      # fp32 engine: the masters are the operands
+                for s3 in segs:
+                    if s3.name.startswith(bn + "/") and s3.name.endswith("/w"):
+                        self.cw[s3.name] = self.pw[s3.name]
+                continue
             for li, L in enumerate(cfg.layers(m, self.pad)):
                 name = f"{bn}/conv{li}/w"
                 shape = (L["co"], L["k"], L["k"], L["cp"])
@@ -456,6 +470,9 @@ class UGaitEngine:
             if len(s.shape) == 4:
                 co, kh, kw, cin = s.shape
                 fan_in, fan_out = cin * kh * kw, co * kh * kw
+            elif len(s.shape) == 5:
+                co, kt, kh, kw, cin = s.shape
+                fan_in, fan_out = cin * kt * kh * kw, co * kt * kh * kw
             else:
                 fan_out, fan_in = s.shape
             limit = math.sqrt(6.0 / fan_in) if s.name.endswith("ofCode/w") else math.sqrt(6.0 / (fan_in + fan_out))
@@ -470,12 +487,16 @@ class UGaitEngine:
             v = val.detach().to(torch.float32)
             if len(s.shape) == 4:
                 v = v.permute(0, 2, 3, 1)
+            elif len(s.shape) == 5:          # Conv3D: oracle [Cout,Cin,kt,kh,kw] -> [Cout,kt,kh,kw,Cin]
+                v = v.permute(0, 2, 3, 4, 1)
             self.pw[name].copy_(v.contiguous().to(self.dev))
         self.repack_weights()
 
     def oracle_shape(self, name):
         """Shape of a parameter in the oracle / PyTorch layout (conv [Cout,Cin,kh,kw], dense [out,in])."""
         s = self.segs[name].shape
+        if len(s) == 5:
+            return (s[0], s[4], s[1], s[2], s[3])
         return (s[0], s[3], s[1], s[2]) if len(s) == 4 else tuple(s)
 
     def _export(self, views) -> Dict[str, torch.Tensor]:
@@ -484,6 +505,8 @@ class UGaitEngine:
             v = views[s.name].detach().clone()
             if len(s.shape) == 4:
                 v = v.permute(0, 3, 1, 2).contiguous()
+            elif len(s.shape) == 5:
+                v = v.permute(0, 4, 1, 2, 3).contiguous()
             out[s.name] = v
         return out
 
@@ -548,7 +571,7 @@ class UGaitEngine:
         """Keras' complaint for a mis-shaped input, before any copy is enqueued."""
         for m in range(self.cfg.nmods):
             want, got = tuple(p.br[m].x_in.shape), tuple(inputs[m].shape)
-            if got != want:
+            if got != want and not (getattr(self.cfg, "is3d", None) and self.cfg.is3d(m) and got == want + (1,)):
                 raise ValueError(f"Input {m} is incompatible with the model: expected shape=(None, "
                                  f"{', '.join(str(v) for v in want[1:])}), found shape={got}")
             if flags is not None and math.prod(tuple(flags[m].shape)) != want[0]:
@@ -647,6 +670,8 @@ class UGaitEngine:
         cfg, h, st = self.cfg, self.ctx.h, stream_ptr()
         bn = BRANCH_NAMES[m]
         b = p.br[m]
+        if cfg.is3d(m):
+            return self._forward_branch3d(p, m, expanded)
         if expanded and getattr(p, "use_augment", False):
             # + integer shifts of the random transform on every modality, magnitude clip on the optical flow (modality 0)
             check(lib.ugn_pack_input_augment(h, b.R["x_base"].ptr, p.R["src_row"].ptr,
@@ -687,10 +712,10 @@ class UGaitEngine:
         cfg = self.cfg
         self._check_shapes(p, inputs, None if cfg.single else flags)
         for m in range(cfg.nmods):
-            p.br[m].x_in.copy_(inputs[m], non_blocking=True)
+            p.br[m].x_in.copy_(inputs[m].reshape(p.br[m].x_in.shape) if cfg.is3d(m) else inputs[m], non_blocking=True)
             if not cfg.single:
                 p.flags[m].copy_(flags[m].reshape(-1, 1), non_blocking=True)
-            if p.train and cfg.dropout > 0.001:
+            if p.train and cfg.dropout > 0.001 and hasattr(p.br[m], "mask"):
                 if drop_masks is not None:
                     p.br[m].mask.copy_(drop_masks[m])
                 elif not self.philox:
@@ -1025,9 +1050,48 @@ class UGaitEngine:
         self._backward_branch_fc(p, m)
         self._backward_branch_conv(p, m)
 
+    # ---- use3D: Conv3D branch (build_3Dbranch{,LReLU}, nets/mj_uwyhNets_ba.py:336-417) on the fp32 validation engine
+    def _forward_branch3d(self, p: "_Plan", m: int, expanded: bool):
+        cfg, h, st = self.cfg, self.ctx.h, stream_ptr()
+        if expanded:
+            raise NotImplementedError("device-side expansion is not wired for use3D branches: feed the expanded batch")
+        bn, b = BRANCH_NAMES[m], p.br[m]
+        for li, L in enumerate(b.layers3d):
+            s3 = L["s"]
+            check(lib.ugn_conv3d_fwd(h, b.R[f"a{li}"].ptr, self.Rw[f"{bn}/conv{li}/w"].ptr, self.Rw[f"{bn}/conv{li}/b"].ptr,
+                                     b.R[f"a{li + 1}"].ptr, s3[0], s3[1], s3[2], cfg.act, cfg.alpha, st))
+        # Conv3D(nd, 1x1x1) "grayCode" on the 1x1x1 volume + Flatten == a Dense layer
+        check(lib.ugn_linear_fwd(h, b.R["flat"].ptr, self.Rw[f"{bn}/ofCode/w"].ptr, self.Rw[f"{bn}/ofCode/b"].ptr, None,
+                                 b.R["out"].ptr, None, ACT_LINEAR, 0.0, st))
+
+    def _backward_branch3d_fc(self, p: "_Plan", m: int):
+        h, st = self.ctx.h, stream_ptr()
+        bn, R = BRANCH_NAMES[m], p.br[m].R
+        check(lib.ugn_linear_bwd(h, R["flat"].ptr, self.Rw[f"{bn}/ofCode/w"].ptr, R["dout"].ptr, R["dflat"].ptr,
+                                 self.Rg[f"{bn}/ofCode/w"].ptr, self.Rg[f"{bn}/ofCode/b"].ptr, st))
+
+    def _backward_branch3d_conv(self, p: "_Plan", m: int):
+        cfg, h, st = self.cfg, self.ctx.h, stream_ptr()
+        bn, b = BRANCH_NAMES[m], p.br[m]
+        R = b.R
+        for li in range(len(b.layers3d) - 1, -1, -1):
+            s3 = b.layers3d[li]["s"]
+            # dz = da * act'(a) on the flattened [rows, Cout] views, then kernel / bias / input gradients
+            check(lib.ugn_act_mask_bwd(h, R[f"da{li + 1}f"].ptr, R[f"a{li + 1}f"].ptr, None, R[f"dz{li}f"].ptr, None,
+                                       cfg.act, cfg.alpha, st))
+            check(lib.ugn_conv3d_wgrad(h, R[f"a{li}"].ptr, R[f"dz{li}"].ptr, self.Rg[f"{bn}/conv{li}/w"].ptr,
+                                       self.Rg[f"{bn}/conv{li}/b"].ptr, s3[0], s3[1], s3[2], st))
+            if li > 0:
+                check(lib.ugn_conv3d_dgrad(h, R[f"dz{li}"].ptr, self.Rw[f"{bn}/conv{li}/w"].ptr, R[f"da{li}"].ptr,
+                                           s3[0], s3[1], s3[2], st))
+        if self.dp_reduce == "bucketed":
+            self._reduce_bucket(m)
+
     def _backward_branch_fc(self, p: "_Plan", m: int):
         """ofCode + dense (+dropout) backward of one branch: 92 % of the branch's gradient bytes."""
         cfg, h, st = self.cfg, self.ctx.h, stream_ptr()
+        if cfg.is3d(m):
+            return self._backward_branch3d_fc(p, m)
         bn = BRANCH_NAMES[m]
         b = p.br[m]
         R = b.R
@@ -1075,6 +1139,8 @@ class UGaitEngine:
 
     def _backward_branch_conv(self, p: "_Plan", m: int):
         cfg, h, st = self.cfg, self.ctx.h, stream_ptr()
+        if cfg.is3d(m):
+            return self._backward_branch3d_conv(p, m)
         bn = BRANCH_NAMES[m]
         b = p.br[m]
         R = b.R
@@ -1670,7 +1736,7 @@ class _Plan:
         self.use_philox = self.philox_code = False
         self.br: List[_Branch] = []
         # every per-step input lives in ONE device block (IOBlock): one H2D copy per step, see UGaitEngine.prefetch_batch
-        self.io = IOBlock(d, B, [(cfg.layers(m, eng.pad)[0]["cin"], cfg.hw, cfg.hw) for m in range(cfg.nmods)])
+        self.io = IOBlock(d, B, [(cfg.in_channels[m], cfg.hw, cfg.hw) for m in range(cfg.nmods)])
         iov = self.io.views(self.io.dev_buf)
         self.flags = iov["flags"]
         for f in self.flags:
@@ -1678,6 +1744,9 @@ class _Plan:
         self._base = {}
         for m in range(cfg.nmods):
             b = _Branch()
+            if cfg.is3d(m):
+                self.br.append(self._branch3d(eng, b, m, iov["x"][m], train))
+                continue
             b.layers = cfg.layers(m, eng.pad)
             T = {}
             L0 = b.layers[0]
@@ -1797,6 +1866,35 @@ class _Plan:
             self.brn_ptrs = ptr_array([b.R["outn"] for b in self.br])
             if train:
                 self.dbrn_ptrs = ptr_array([b.R["doutn"] for b in self.br])
+
+    def _branch3d(self, eng, b, m, x_in, train):
+        """Buffers of a Conv3D branch (use3D): activations [B,T,H,W,C] f32, the gradient of every pre-activation, flat views."""
+        cfg, B = eng.cfg, self.B
+        f32 = dict(device=eng.dev, dtype=torch.float32)
+        b.layers, b.layers3d = [], cfg.layers3d(m)
+        T = {}
+        b.x_in = T["x_in"] = x_in                                        # [B,25,60,60] == channels-last [B,25,60,60,1]
+        T["a0"] = x_in.view(B, cfg.in_channels[m], cfg.hw, cfg.hw, 1)
+        for li, L in enumerate(b.layers3d):
+            shp = (B, L["to"], L["ho"], L["ho"], L["co"])
+            T[f"a{li + 1}"] = torch.zeros(shp, **f32)
+            T[f"a{li + 1}f"] = T[f"a{li + 1}"].view(-1, L["co"])
+            if train:
+                T[f"dz{li}"] = torch.zeros(shp, **f32)
+                T[f"dz{li}f"] = T[f"dz{li}"].view(-1, L["co"])
+                T[f"da{li + 1}"] = torch.zeros(shp, **f32)
+                T[f"da{li + 1}f"] = T[f"da{li + 1}"].view(-1, L["co"])
+        nl = len(b.layers3d)
+        T["flat"] = T[f"a{nl}"].view(B, -1)
+        b.out = T["out"] = torch.zeros(B, cfg.nd, **f32)
+        if train:
+            b.dout = T["dout"] = torch.zeros(B, cfg.nd, **f32)
+            T["dflat"] = T[f"da{nl}"].view(B, -1)
+        if (cfg.normbfmerge and not cfg.single) or eng.aux:
+            raise NotImplementedError("use3D together with normbfmerge / aux_losses")
+        b.T = T
+        b.R = {k: TRef(v) for k, v in T.items()}
+        return b
 
     def ensure_base(self, B0: int):
         """Views of the device-side expansion's base rows (B0 rows per modality, packed right behind the header of the
