@@ -124,8 +124,9 @@ def test_triplet_loss_closure_and_unsupported_options(compat_path):
     with pytest.raises(NotImplementedError, match="aux_losses with gaitset"):
         UWYHSemiNet3Mods.build([(25, 60, 60, 1)] * 3, 4, [7, 5, 3, 2], [96, 192, 512, 512], gaitset=True,
                                fActivation='lrelu', aux_losses=True, nclasses=5)
-    with pytest.raises(NotImplementedError, match="use3D"):
-        UWYHSemiNet3Mods.build([(50, 60, 60)] * 3, 4, [7, 5, 3, 2], [96, 192, 512, 512], use3D=True)
+    with pytest.raises(NotImplementedError, match="use3D_with_gaitset"):
+        UWYHSemiNet3Mods.build([(25, 60, 60, 1)] * 3, 4, [7, 5, 3, 2], [96, 192, 512, 512], gaitset=True,
+                               fActivation='lrelu', use3D=True)
 
 
 def test_gaitset_builder_protocol(compat_path, tmp_path):
@@ -353,3 +354,56 @@ def test_stand_alone_branch_builders(compat_path, tmp_path):
     br2 = UWYHNet.buildBranchLReLU("ofBranch", (5, 60, 60), 4, [(7, 7), (5, 5), (3, 3), (2, 2)], [8, 8, 16, 16], 16, 0.00005,
                                    0.0, init_branch=path)
     assert np.array_equal(br2.predict(x), br.predict(x))
+
+
+def test_use3d_builders(compat_path, tmp_path):
+    """use3D (:336-417, :721-745, :1077-1099): Conv3D branches for every modality but the 50-channel optical flow, on
+    [B,25,60,60,1] inputs; forward against the oracle, a training step, Keras-layout weight round trip (conv3d_N,
+    grayCode)."""
+    from nets.mj_uwyhNets_ba import UWYHSemiNet, UWYHSemiNet3Mods
+    from ugaitnet_b200.compat import Model, optimizers
+    from ugaitnet_b200 import hdf5
+    import nets.mj_uwyhNets_ba as mod
+    mod.MATH_MODE = "f16mix"                 # the builder itself falls back to the fp32 engine for use3D
+    rng = np.random.default_rng(3)
+    model = UWYHSemiNet3Mods.build([(50, 60, 60), (25, 60, 60, 1), (25, 60, 60, 1)], 4, [(7, 7), (5, 5), (3, 3), (2, 2)],
+                                   [32, 32, 32, 64], 32, 0.00005, 0.0, optimizer=optimizers.Adam(lr=1e-3), nclasses=6,
+                                   loss_weights=[1.0, 0.1], use3D=True)
+    assert model.engine.math_mode == "fp32" and tuple(model.cfg.branch3d) == (False, True, True)
+    B = 4
+    X = [rng.normal(size=(B, 50, 60, 60)) * 0.3, np.ones((B, 1)), rng.uniform(-0.5, 0.5, size=(B, 25, 60, 60, 1)),
+         np.array([1, 0, 1, 1.0]).reshape(B, 1), rng.uniform(-0.5, 0.5, size=(B, 25, 60, 60, 1)), np.ones((B, 1))]
+    lab = np.array([0, 0, 1, 1])
+    y = [lab.reshape(B, 1), np.eye(6)[lab]]
+    oc = O.NetConfig(in_channels=(50, 25, 25), filters_numbers=(32, 32, 32, 64), nd=32, nclasses=6, merge=O.MERGE_MAX,
+                     wver=1.0, wid=0.1, branch3d=(False, True, True))
+    P = {k: v.double().cpu() for k, v in model.engine.export_params().items()}
+    assert tuple(P["grayBranch/conv0/w"].shape) == (64, 1, 3, 5, 5) and tuple(P["depthBranch/ofCode/w"].shape) == (32, 512)
+    outs = O.model_forward([torch.tensor(X[0]), torch.tensor(X[2]), torch.tensor(X[4])],
+                           [torch.tensor(X[1]), torch.tensor(X[3]), torch.tensor(X[5])], P, oc, return_all=True)
+    sig = Model(model.input, model.get_layer("signature").output).predict(X)
+    assert np.allclose(sig, outs["signature"].numpy(), atol=2e-5)
+    l0 = model.train_on_batch(X, y)["loss"]
+    for _ in range(4):
+        l1 = model.train_on_batch(X, y)["loss"]
+    assert np.isfinite(l1) and l1 < l0
+    path = str(tmp_path / "w3d.hdf5")
+    model.save_weights(path)
+    f = hdf5.File(path)
+    names = [n.decode() for n in f["grayBranch"].attrs["weight_names"]]
+    assert names[0] == "conv3d/kernel:0" and names[-2:] == ["grayCode/kernel:0", "grayCode/bias:0"]
+    assert tuple(f["grayBranch"]["conv3d"]["kernel:0"].value.shape) == (3, 5, 5, 1, 64)
+    assert tuple(f["depthBranch"]["grayCode"]["kernel:0"].value.shape) == (1, 1, 1, 512, 32)
+    W = {k: v.clone() for k, v in model.engine.export_params().items()}
+    model.train_on_batch(X, y)
+    model.load_weights(path)
+    assert all(torch.equal(W[k], v) for k, v in model.engine.export_params().items())
+    # one modality: a non-optical-flow input with use3D gets the Conv3D branch, no fusion / normalisation (:738-745)
+    single = UWYHSemiNet.build((25, 60, 60, 1), 4, [(7, 7), (5, 5), (3, 3), (2, 2)], [32, 32, 32, 64], 16, 0.00005, 0.0,
+                               optimizer=optimizers.SGD(0.01, 0.9), nclasses=6, loss_weights=[1.0, 0.1], use3D=True)
+    assert tuple(single.cfg.branch3d) == (True,)
+    oc1 = O.NetConfig(in_channels=(25,), nd=16, nclasses=6, single=True, branch3d=(True,))
+    P1 = {k: v.double().cpu() for k, v in single.engine.export_params().items()}
+    want = O.branch3d_forward(torch.tensor(X[2]), P1, "ofBranch", oc1)
+    got = single.predict(X[2])[0]
+    assert np.allclose(got, want.numpy(), atol=2e-5)

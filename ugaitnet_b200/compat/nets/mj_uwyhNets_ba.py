@@ -15,8 +15,8 @@ the gate, :1167-1168), ``aux_losses`` (classprob_{of,gray,depth} heads on the ga
 stacked-CNN branches), ``postriplet == 2`` (2-modality builder, :819-832), ``freeze_convs`` / ``freeze_all`` /
 ``freeze_branches`` and ``layer.trainable`` (:193, :1366-1391), ``initnet`` / ``init_branches`` / ``loadnet`` from Keras
 HDF5 files (ugaitnet_b200.hdf5: pure-Python reader / writer, h5py is absent) are implemented.  Builder arguments that
-select graphs outside the hot path raise NotImplementedError: use3D (Conv3D branches), aux_losses together with
-gaitset.  compile_hard (tfa TripletHardLoss) re-compiles a stacked-frame CNN model onto ugn_triplet_hard.
+select ill-formed graphs raise NotImplementedError: aux_losses together with gaitset.  use3D builds the Conv3D branches
+(:336-417) for every modality but a 50-channel optical flow; they run on the fp32 validation engine.  compile_hard (tfa TripletHardLoss) re-compiles a stacked-frame CNN model onto ugn_triplet_hard.
 """
 from __future__ import annotations
 
@@ -138,7 +138,8 @@ class UGaitModel:
         kw = dict(getattr(opt, "kw", {}))
         self.gaitset = isinstance(cfg, GaitSetConfig)
         engine_cls = GaitSetEngine if self.gaitset else UGaitEngine
-        self.engine = engine_cls(cfg, math_mode=MATH_MODE, optimizer=getattr(opt, "name", "sgd"),
+        has3d = bool(getattr(cfg, "branch3d", ()))       # use3D: Conv3D branches run on the fp32 validation engine
+        self.engine = engine_cls(cfg, math_mode="fp32" if has3d else MATH_MODE, optimizer=getattr(opt, "name", "sgd"),
                                   lr=getattr(opt, "lr", 0.001), momentum=kw.get("momentum", 0.9),
                                   beta1=kw.get("beta1", 0.9), beta2=kw.get("beta2", 0.999), eps=kw.get("eps", 1e-7),
                                   lr_decay=kw.get("decay", 0.0), decoupled_weight_decay=kw.get("weight_decay", 0.0),
@@ -151,6 +152,9 @@ class UGaitModel:
             if self.gaitset:
                 sub = [_LayerProxy(self, f"{BRANCH_NAMES[m]}/{n[0]}") for n in GS_CONVS] + \
                       [_LayerProxy(self, f"{BRANCH_NAMES[m]}/matmul")]
+            elif cfg.is3d(m):
+                sub = [_LayerProxy(self, f"{BRANCH_NAMES[m]}/conv{i}", kind="conv") for i in range(len(cfg.filters3d))] + \
+                      [_LayerProxy(self, f"{BRANCH_NAMES[m]}/ofCode", kind="dense")]
             else:
                 sub = [_LayerProxy(self, f"{BRANCH_NAMES[m]}/conv{i}", kind="conv") for i in range(len(cfg.filters_numbers))] + \
                       [_LayerProxy(self, f"{BRANCH_NAMES[m]}/{n}", kind="dense" if n in ("dense", "ofCode") else "layer")
@@ -372,14 +376,19 @@ class UGaitModel:
         """[(keras layer name, [(keras weight name, engine tensor name), ...]), ...] in the order Keras lists
         model.layers / layer.weights: a branch is ONE layer (a Sequential) whose weights are kernel, bias of every
         sublayer in graph order; the Conv2D sublayers carry Keras' auto-generated names (conv2d, conv2d_1, ...)."""
-        e, out, conv_no = self.engine, [], 0
+        e, out, conv_no, conv3_no = self.engine, [], 0, 0
         top: Dict[str, list] = {}
+        b3 = {BRANCH_NAMES[m] for m in range(self.cfg.nmods) if getattr(self.cfg, "is3d", None) and self.cfg.is3d(m)}
         for sg in e.seg_list:
             parts = sg.name.split("/")
             kind = "kernel:0" if parts[-1] == "w" else "bias:0"
             if len(parts) == 3:                        # <branch>/<sublayer>/<w|b>
                 sub = parts[1]
-                if sub.startswith("conv") and not self.gaitset:
+                if parts[0] in b3:                     # Conv3D branch (:346-363): conv3d, conv3d_1, ..., then "grayCode"
+                    if parts[-1] == "w":
+                        conv3_no += 1
+                    sub = "grayCode" if sub == "ofCode" else ("conv3d" if conv3_no == 1 else f"conv3d_{conv3_no - 1}")
+                elif sub.startswith("conv") and not self.gaitset:
                     if parts[-1] == "w":
                         conv_no += 1
                     sub = "conv2d" if conv_no == 1 else f"conv2d_{conv_no - 1}"
@@ -403,6 +412,8 @@ class UGaitModel:
 
     @staticmethod
     def _to_keras(k, v):
+        if v.dim() == 5:
+            return v.permute(2, 3, 4, 1, 0).contiguous()   # Conv3D [Cout,Cin,kt,kh,kw] -> (kt,kh,kw,cin,cout)
         if v.dim() == 4:
             return v.permute(2, 3, 1, 0).contiguous()      # [Cout,Cin,kh,kw] -> (kh,kw,cin,cout)
         if v.dim() == 2:
@@ -412,6 +423,10 @@ class UGaitModel:
     @staticmethod
     def _from_keras(v):
         v = torch.as_tensor(np.asarray(v))
+        if v.dim() == 5 and tuple(v.shape[:3]) == (1, 1, 1):
+            return v.reshape(v.shape[3], v.shape[4]).t().contiguous()     # "grayCode": Conv3D 1x1x1 == Dense
+        if v.dim() == 5:
+            return v.permute(4, 3, 0, 1, 2).contiguous()
         if v.dim() == 4:
             return v.permute(3, 2, 0, 1).contiguous()
         if v.dim() == 2:
@@ -431,7 +446,10 @@ class UGaitModel:
             lg = w.group(f"{root}/{lname}")
             lg.attrs["weight_names"] = [wn.encode("utf8") for wn, _ in weights] if weights else np.zeros((0,), dtype="S1")
             for wn, seg in weights:
-                w.dataset(f"{root}/{lname}/{wn}", self._to_keras(seg, P[seg]).cpu().numpy())
+                arr = self._to_keras(seg, P[seg]).cpu().numpy()
+                if wn == "grayCode/kernel:0":            # Conv3D(nd, (1,1,1)) of a use3D branch: (1,1,1,in,out)
+                    arr = arr.reshape((1, 1, 1) + arr.shape)
+                w.dataset(f"{root}/{lname}/{wn}", arr)
 
     def save_weights(self, path, **kw):
         """model.save_weights(path): a regular HDF5 file in Keras' layout (ugaitnet_b200.hdf5 writer)."""
@@ -661,7 +679,7 @@ def _load_branch(model, path, bname):
 
 def _cfg_from_args(input_shapes, number_convolutional_layers, filters_size, filters_numbers, ndense_units,
                    weight_decay, dropout, margin, nclasses, loss_weights, fMerge, fActivation, alpha, single,
-                   smoothlabels=0, normbfmerge=False, aux_losses=False, postriplet=1):
+                   smoothlabels=0, normbfmerge=False, aux_losses=False, postriplet=1, use3D=False):
     fs = [k[0] if isinstance(k, (tuple, list)) else int(k) for k in filters_size][:number_convolutional_layers]
     fn = list(filters_numbers if filters_numbers is not None else [64, 128, 512, 512])[:number_convolutional_layers]
     if isinstance(ndense_units, (list, tuple)):
@@ -672,7 +690,11 @@ def _cfg_from_args(input_shapes, number_convolutional_layers, filters_size, filt
         dropout = dropout[0]
     shapes = [input_shapes] if single else list(input_shapes)
     lw = list(loss_weights) if isinstance(loss_weights, (list, tuple)) else [loss_weights, loss_weights]
-    return NetConfig(in_channels=tuple(int(s[0]) for s in shapes), filters_numbers=tuple(fn), filters_size=tuple(fs),
+    # use3D (:721-745, :1077-1099): every modality but a 50-channel optical flow gets a Conv3D branch on [25,60,60,1]
+    b3 = tuple(bool(use3D) and int(s[0]) != 50 for s in shapes)
+    if any(b3) and (normbfmerge or aux_losses):
+        _unsupported(use3D_with_normbfmerge_or_aux_losses=True)
+    return NetConfig(branch3d=b3 if any(b3) else (), in_channels=tuple(int(s[0]) for s in shapes), filters_numbers=tuple(fn), filters_size=tuple(fs),
                      nd=int(nd), nc=int(nc) if not single else 0, nclasses=int(nclasses), weight_decay=float(weight_decay),
                      merge=merge_id_of(fMerge) if not single else MERGE_MAX,
                      act=ACT_RELU if fActivation == "relu" else ACT_LEAKY, alpha=float(alpha), margin=float(margin),
@@ -836,13 +858,13 @@ class UWYHSemiNet:
               ndense_units=512, weight_decay=1e-4, dropout=0.4, optimizer=None, margin=0.2,
               nclasses=0, loss_weights=[1.0, 1.0], use3D=False, smoothlabels=0, postriplet=1, init_branches=None,
               freeze_branches=False, aux_losses=False, fMerge=Maximum, fActivation='relu', alpha=0.3, gaitset=False):
-        _unsupported(use3D=use3D, aux_losses_with_gaitset=(aux_losses and gaitset))
+        _unsupported(use3D_with_gaitset=(use3D and gaitset), aux_losses_with_gaitset=(aux_losses and gaitset))
         single = not isinstance(input_shapes, list)
         kwargs = dict(input_shapes=input_shapes, number_convolutional_layers=number_convolutional_layers,
                       filters_size=filters_size, filters_numbers=filters_numbers, ndense_units=ndense_units,
                       weight_decay=weight_decay, dropout=dropout, optimizer=optimizer, margin=margin, nclasses=nclasses,
                       loss_weights=loss_weights, smoothlabels=smoothlabels, postriplet=postriplet, aux_losses=aux_losses,
-                      fMerge=fMerge, fActivation=fActivation, alpha=alpha, gaitset=gaitset)
+                      fMerge=fMerge, fActivation=fActivation, alpha=alpha, gaitset=gaitset, use3D=use3D)
         losses = [triplet_loss(margin=margin), 'categorical_crossentropy'] if nclasses > 0 else triplet_loss(margin=margin)
         if gaitset:
             _unsupported(gaitset_single_modality=single, postriplet_2_with_gaitset=(postriplet == 2))
@@ -852,7 +874,7 @@ class UWYHSemiNet:
         else:
             cfg = _cfg_from_args(input_shapes, number_convolutional_layers, filters_size, filters_numbers, ndense_units,
                                  weight_decay, dropout, margin, nclasses, loss_weights, fMerge, fActivation, alpha, single,
-                                 smoothlabels=smoothlabels, aux_losses=aux_losses, postriplet=postriplet)
+                                 smoothlabels=smoothlabels, aux_losses=aux_losses, postriplet=postriplet, use3D=use3D)
             model = UGaitModel(cfg, optimizer, losses, loss_weights if nclasses > 0 else 1.0, multimodal=not single)
         _apply_init_branches(model, init_branches)
         _freeze(model, freeze_branches=freeze_branches)
@@ -967,12 +989,12 @@ class UWYHSemiNet3Mods(UWYHSemiNet):
               postriplet=1, init_branches=None, freeze_branches=False, aux_losses=False, fMerge=Maximum,
               normbfmerge=False, fActivation='relu', alpha=0.3, gaitset=False):
         # (postriplet is accepted and ignored by the reference's 3-modality graph: "TODO implement use of 'postriplet'", :1054)
-        _unsupported(use3D=use3D, aux_losses_with_gaitset=(aux_losses and gaitset))
+        _unsupported(use3D_with_gaitset=(use3D and gaitset), aux_losses_with_gaitset=(aux_losses and gaitset))
         kwargs = dict(input_shapes=list(input_shapes), number_convolutional_layers=number_convolutional_layers,
                       filters_size=filters_size, filters_numbers=filters_numbers, ndense_units=ndense_units,
                       weight_decay=weight_decay, dropout=dropout, optimizer=optimizer, margin=margin, nclasses=nclasses,
                       loss_weights=loss_weights, smoothlabels=smoothlabels, aux_losses=aux_losses, fMerge=fMerge,
-                      normbfmerge=normbfmerge, fActivation=fActivation, alpha=alpha, gaitset=gaitset)
+                      normbfmerge=normbfmerge, fActivation=fActivation, alpha=alpha, gaitset=gaitset, use3D=use3D)
         losses = [triplet_loss(margin=margin), 'categorical_crossentropy'] if nclasses > 0 else triplet_loss(margin=margin)
         if gaitset:
             cfg = _gs_cfg_from_args(input_shapes, ndense_units, dropout, margin, nclasses, loss_weights, fMerge,
@@ -981,7 +1003,7 @@ class UWYHSemiNet3Mods(UWYHSemiNet):
             cfg = _cfg_from_args(list(input_shapes), number_convolutional_layers, filters_size, filters_numbers,
                                  ndense_units, weight_decay, dropout, margin, nclasses, loss_weights, fMerge, fActivation,
                                  alpha, single=False, smoothlabels=smoothlabels, normbfmerge=normbfmerge,
-                                 aux_losses=aux_losses)
+                                 aux_losses=aux_losses, use3D=use3D)
         model = UGaitModel(cfg, optimizer, losses, loss_weights if nclasses > 0 else 1.0, multimodal=True)
         _apply_init_branches(model, init_branches)
         _freeze(model, freeze_branches=freeze_branches)
