@@ -220,6 +220,15 @@ int ugn_linear_bwd_philox(ugn_ctx*, const ugn_tensor* x, const ugn_tensor* w, co
 int ugn_fuse_fwd(ugn_ctx*, int nmods, const ugn_tensor* const* br, const ugn_tensor* const* flags,
                  ugn_tensor* sig, ugn_tensor* sig16, ugn_tensor* winner, ugn_tensor* inv_norm,
                  int merge, int normalize, void* stream);
+/* a2+a3+a4+a5 in ONE kernel (north_star: "gated sign_max fusion plus FC1 is a single kernel"): ugn_fuse_fwd followed by
+ * the FC1 layer "code" = act(sig . code_w^T + code_b) (nets/mj_uwyhNets_ba.py:1194-1203) computed from the normalised
+ * row while it is still in shared memory, and dropcode = code * drop_mask (Dropout "dropcode", mask already scaled by
+ * 1/(1-p); drop_mask nullable: dropcode = code; dropcode nullable).  code_w f32 [nc,d], code_b f32 [nc] (nullable),
+ * code / dropcode / drop_mask f32 [B,nc]; d % 4 == 0.  A modality whose use-flag is 0 is not read. */
+int ugn_fuse_fc1_fwd(ugn_ctx*, int nmods, const ugn_tensor* const* br, const ugn_tensor* const* flags,
+                     ugn_tensor* sig, ugn_tensor* sig16, ugn_tensor* winner, ugn_tensor* inv_norm, int merge,
+                     int normalize, const ugn_tensor* code_w, const ugn_tensor* code_b, ugn_tensor* code,
+                     const ugn_tensor* drop_mask, ugn_tensor* dropcode, int act, float alpha, void* stream);
 /* dsig f32 [B,d] -> dbr[m] f32 [B,d] (gradient wrt each branch output, gate applied). */
 int ugn_fuse_bwd(ugn_ctx*, int nmods, const ugn_tensor* dsig, const ugn_tensor* sig,
                  const ugn_tensor* winner, const ugn_tensor* inv_norm,

@@ -598,3 +598,54 @@ def test_conv3d_ops_vs_torch(ctx, geom):
     assert rel(dw.permute(0, 4, 1, 2, 3), w64.grad) < 1e-5
     assert rel(db, b64.grad) < 1e-5
     assert rel(dx.permute(0, 4, 1, 2, 3), x64.grad) < 1e-5
+
+
+@pytest.mark.parametrize("merge", [0, 1, 2])
+@pytest.mark.parametrize("cfg", [(3, 200, 37, 1, 2, True), (2, 2048, 256, 2, 0, False), (1, 64, 5, 0, 1, True)])
+def test_fusion_plus_fc1_single_kernel(ctx, merge, cfg):
+    """ugn_fuse_fc1_fwd (north_star: gated fusion + l2_normalize + FC1 "code" in ONE kernel, nets/mj_uwyhNets_ba.py:1163-1203)
+    against the oracle pieces and against the two-kernel path: signature, winners, 16-bit planes, code, dropped code; rows
+    with every modality missing, exact |x| ties, odd nc, with and without normalisation / dropout mask."""
+    from ugaitnet_b200 import ops
+    from ugaitnet_b200._ffi import TRef, check, lib, ptr_array, stream_ptr
+    nmods, d, nc, act, P, normalize = cfg
+    B = 11
+    g = torch.Generator().manual_seed(merge * 7 + d)
+    br = [torch.randn(B, d, generator=g) for _ in range(nmods)]
+    if nmods > 1:
+        br[1][:, :20] = br[0][:, :20]
+        br[1][:, 20:30] = -br[0][:, 20:30]
+    fl = [(torch.rand(B, 1, generator=g) > 0.3).float() for _ in range(nmods)]
+    for f in fl:
+        f[0] = 0.0
+    fl[0][1] = 1.0
+    W = torch.randn(nc, d, generator=g) / d ** 0.5
+    bias = torch.randn(nc, generator=g) * 0.1
+    cm = (torch.rand(B, nc, generator=g) > 0.4).float() / 0.6
+    dev = lambda t: t.cuda()
+    sig, win, inv = torch.zeros(B, d, device="cuda"), torch.zeros(B, d, dtype=torch.uint8, device="cuda"), torch.zeros(B, 2, device="cuda")
+    sig16 = torch.zeros(P, B, d, dtype=torch.float16, device="cuda") if P else None
+    code, dropc = torch.zeros(B, nc, device="cuda"), torch.zeros(B, nc, device="cuda")
+    rb, rf = [TRef(dev(t)) for t in br], [TRef(dev(f)) for f in fl]
+    R = [TRef(t) if t is not None else None for t in (sig, sig16, win, inv, dev(W), dev(bias), code, dev(cm), dropc)]
+    pp = lambda r: None if r is None else r.ptr
+    check(lib.ugn_fuse_fc1_fwd(ctx.h, nmods, ptr_array(rb), ptr_array(rf), pp(R[0]), pp(R[1]), pp(R[2]), pp(R[3]), merge,
+                               int(normalize), pp(R[4]), pp(R[5]), pp(R[6]), pp(R[7]), pp(R[8]), act, 0.3, stream_ptr()))
+    ctx.check()
+    b64 = [t.double() for t in br]
+    ref = O.merge_modalities([t * f.double() for t, f in zip(b64, fl)], merge)
+    if normalize:
+        ref = O.l2_normalize(ref, 1)
+    assert torch.allclose(sig.cpu().double(), ref, atol=2e-6, rtol=1e-5)
+    assert float(sig[0].abs().max()) == 0.0
+    z = ref @ W.double().t() + bias.double()
+    want = O._act(z, act, 0.3)
+    assert rel(code, want) < 1e-5
+    assert rel(dropc, want * cm.double()) < 1e-5
+    # the two-kernel path gives the same signature, winners and planes
+    sig2, win2, inv2 = torch.zeros_like(sig), torch.zeros_like(win), torch.zeros_like(inv)
+    sig16b = torch.zeros_like(sig16) if P else None
+    ops.fuse_fwd(ctx, [dev(t) for t in br], [dev(f) for f in fl], sig2, sig16b, win2, inv2, merge, normalize)
+    assert torch.equal(win, win2) and torch.allclose(sig, sig2, atol=1e-7) and torch.allclose(inv, inv2, rtol=1e-6)
+    if P:
+        assert torch.allclose(sig16.float(), sig16b.float(), atol=1e-6)

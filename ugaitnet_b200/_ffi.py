@@ -62,6 +62,8 @@ _PROTOS = {
     "ugn_linear_fwd": (c_int, [c_void_p, _T, _T, _T, _T, _T, _T, c_int, c_float, c_void_p]),
     "ugn_act_mask_bwd": (c_int, [c_void_p, _T, _T, _T, _T, _T, c_int, c_float, c_void_p]),
     "ugn_linear_bwd": (c_int, [c_void_p, _T, _T, _T, _T, _T, _T, c_void_p]),
+    "ugn_fuse_fc1_fwd": (c_int, [c_void_p, c_int, POINTER(c_void_p), POINTER(c_void_p), _T, _T, _T, _T, c_int, c_int,
+                                 _T, _T, _T, _T, _T, c_int, c_float, c_void_p]),
     "ugn_fuse_fwd": (c_int, [c_void_p, c_int, POINTER(c_void_p), POINTER(c_void_p), _T, _T, _T, _T,
                              c_int, c_int, c_void_p]),
     "ugn_fuse_bwd": (c_int, [c_void_p, c_int, _T, _T, _T, _T, POINTER(c_void_p), POINTER(c_void_p),

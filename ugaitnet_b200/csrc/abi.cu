@@ -660,6 +660,49 @@ extern "C" int ugn_fuse_fwd(ugn_ctx* ctx, int nmods, const ugn_tensor* const* br
                      merge, normalize, (cudaStream_t)stream);
 }
 
+int ew_fuse_fc1_fwd(ugn_ctx*, const FusePtrs&, int, int, int, float*, __nv_bfloat16*, int, int, uint8_t*, float*, int, int,
+                    const float*, const float*, int, float*, const float*, float*, int, float, cudaStream_t);
+
+extern "C" int ugn_fuse_fc1_fwd(ugn_ctx* ctx, int nmods, const ugn_tensor* const* br, const ugn_tensor* const* flags,
+                                ugn_tensor* sig, ugn_tensor* sig16, ugn_tensor* winner, ugn_tensor* inv_norm, int merge,
+                                int normalize, const ugn_tensor* code_w, const ugn_tensor* code_b, ugn_tensor* code,
+                                const ugn_tensor* drop_mask, ugn_tensor* dropcode, int act, float alpha, void* stream) {
+  UGN_CHECK(ctx && br && flags && sig && code_w && code, "ugn_fuse_fc1_fwd: null argument");
+  int B = 0, d = 0;
+  int rc = fuse_common(ctx, nmods, br, flags, B, d);
+  if (rc != UGN_OK) return rc;
+  UGN_CHECK(d % 4 == 0 && (size_t)d * 4 <= 48 * 1024, "fuse_fc1_fwd: signature width must be a multiple of 4 and <= 12288");
+  UGN_TENSOR(sig, DT_F32, 2, 2);
+  UGN_CHECK(sig->shape[0] == B && sig->shape[1] == d, "fuse_fc1_fwd: sig must be [B,d]");
+  int P = 0;
+  if (sig16) {
+    UGN_TENSOR(sig16, DT_BAD, 3, 3);
+    UGN_CHECK(is_16(sig16), "fuse_fc1_fwd: sig16 must be bf16 or f16");
+    P = (int)sig16->shape[0];
+    UGN_CHECK((P == 1 || P == 2) && sig16->shape[1] == B && sig16->shape[2] == d, "fuse_fc1_fwd: sig16 must be [P,B,d]");
+  }
+  if (winner) { UGN_TENSOR(winner, DT_U8, 2, 2); UGN_CHECK(ugn_numel(winner) == (int64_t)B * d, "fuse_fc1_fwd: winner must be [B,d]"); }
+  if (inv_norm) { UGN_TENSOR(inv_norm, DT_F32, 2, 2); UGN_CHECK(inv_norm->shape[0] == B && inv_norm->shape[1] == 2, "fuse_fc1_fwd: inv_norm must be [B,2]"); }
+  UGN_CHECK(merge >= 0 && merge <= 2, "fuse_fc1_fwd: unknown merge mode %d", merge);
+  UGN_TENSOR(code_w, DT_F32, 2, 2);
+  const int nc = (int)code_w->shape[0];
+  UGN_CHECK(code_w->shape[1] == d, "fuse_fc1_fwd: code_w must be f32 [nc,d]");
+  if (code_b) { UGN_TENSOR(code_b, DT_F32, 1, 1); UGN_CHECK(code_b->shape[0] == nc, "fuse_fc1_fwd: code_b must be f32 [nc]"); }
+  UGN_TENSOR(code, DT_F32, 2, 2);
+  UGN_CHECK(code->shape[0] == B && code->shape[1] == nc, "fuse_fc1_fwd: code must be f32 [B,nc]");
+  if (drop_mask) { UGN_TENSOR(drop_mask, DT_F32, 2, 2); UGN_CHECK(ugn_numel(drop_mask) == (int64_t)B * nc && dropcode, "fuse_fc1_fwd: drop_mask [B,nc] needs dropcode"); }
+  if (dropcode) { UGN_TENSOR(dropcode, DT_F32, 2, 2); UGN_CHECK(ugn_numel(dropcode) == (int64_t)B * nc, "fuse_fc1_fwd: dropcode must be f32 [B,nc]"); }
+  if (B == 0) return UGN_OK;
+  FusePtrs p{};
+  for (int m = 0; m < nmods; ++m) { p.br[m] = ugn_ptr<float>(br[m]); p.flag[m] = ugn_ptr<float>(flags[m]); }
+  return ew_fuse_fc1_fwd(ctx, p, nmods, B, d, ugn_ptr<float>(sig), sig16 ? ugn_ptr<__nv_bfloat16>(sig16) : nullptr, P,
+                         sig16 ? is_f16(sig16) : 0, winner ? ugn_ptr<uint8_t>(winner) : nullptr,
+                         inv_norm ? ugn_ptr<float>(inv_norm) : nullptr, merge, normalize, ugn_ptr<float>(code_w),
+                         code_b ? ugn_ptr<float>(code_b) : nullptr, nc, ugn_ptr<float>(code),
+                         drop_mask ? ugn_ptr<float>(drop_mask) : nullptr, dropcode ? ugn_ptr<float>(dropcode) : nullptr,
+                         act, alpha, (cudaStream_t)stream);
+}
+
 extern "C" int ugn_fuse_bwd(ugn_ctx* ctx, int nmods, const ugn_tensor* dsig, const ugn_tensor* sig,
                             const ugn_tensor* winner, const ugn_tensor* inv_norm, const ugn_tensor* const* flags,
                             ugn_tensor* const* dbr, int merge, int normalize, void* stream) {

@@ -514,6 +514,134 @@ int ew_fuse_fwd(ugn_ctx* ctx, const FusePtrs& ptrs, int nmods, int B, int d, flo
   return UGN_OK;
 }
 
+// ---------------------------------------------------------------------------------------
+// a2+a3+a4+a5 in ONE kernel (north_star): gate x flag -> merge -> l2_normalize -> FC1 "code" = act(sig . Wc^T + b)
+// [-> dropcode = code * dropout mask] (nets/mj_uwyhNets_ba.py:1163-1203).  One CTA per row:
+//   phase 1  float4 loads of every AVAILABLE modality's branch output (the use-flag is uniform over the row: a missing
+//            modality -- flag 0, gated value 0 -- is not read at all), merge, winner as uchar4, sum(x^2) by warp
+//            shuffles + smem
+//   phase 2  normalise; the row stays in shared memory, sig (f32, and its 16-bit planes for the tensor-core Gram) is
+//            written once
+//   phase 3  FC1 from shared memory: a warp per output feature pair, float4 loads of the weight rows (L2-resident:
+//            every CTA reads the same nc x d matrix), warp-shuffle reduction, bias + activation + dropout mask
+// ---------------------------------------------------------------------------------------
+template <int P>
+__global__ void __launch_bounds__(256) fuse_fc1_fwd_kernel(FusePtrs ptrs, int nmods, int d, float* __restrict__ sig,
+                                                           __nv_bfloat16* __restrict__ sig16,
+                                                           uint8_t* __restrict__ winner, float* __restrict__ inv_norm,
+                                                           int merge, int normalize, long long plane, int f16,
+                                                           const float* __restrict__ Wc, const float* __restrict__ bc,
+                                                           int nc, float* __restrict__ code,
+                                                           const float* __restrict__ cmask, float* __restrict__ dropcode,
+                                                           int act, float alpha) {
+  extern __shared__ __align__(16) float row[];  // [d] fused values
+  __shared__ float red[8];
+  const int b = blockIdx.x, d4 = d >> 2;
+  float fl[4];
+  for (int m = 0; m < nmods; ++m) fl[m] = ptrs.flag[m][b];
+  float ss = 0.f;
+  for (int q = threadIdx.x; q < d4; q += blockDim.x) {
+    float best[4] = {0.f, 0.f, 0.f, 0.f}, key[4];
+    int win[4] = {0, 0, 0, 0};
+    if (fl[0] != 0.f) {
+      const float4 v = *reinterpret_cast<const float4*>(ptrs.br[0] + (long long)b * d + 4 * q);
+      best[0] = v.x * fl[0]; best[1] = v.y * fl[0]; best[2] = v.z * fl[0]; best[3] = v.w * fl[0];
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) key[i] = merge == UGN_MERGE_SIGNMAX ? fabsf(best[i]) : best[i];
+    for (int m = 1; m < nmods; ++m) {
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (fl[m] != 0.f) v = *reinterpret_cast<const float4*>(ptrs.br[m] + (long long)b * d + 4 * q);
+      const float vv[4] = {v.x * fl[m], v.y * fl[m], v.z * fl[m], v.w * fl[m]};
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        if (merge == UGN_MERGE_AVG) {
+          best[i] += vv[i];
+        } else {
+          const float kv = merge == UGN_MERGE_SIGNMAX ? fabsf(vv[i]) : vv[i];
+          if (kv > key[i]) { key[i] = kv; best[i] = vv[i]; win[i] = m; }   // strict: ties -> earlier modality
+        }
+      }
+    }
+    if (merge == UGN_MERGE_AVG) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) best[i] = best[i] / (float)nmods;
+    }
+    *reinterpret_cast<float4*>(row + 4 * q) = make_float4(best[0], best[1], best[2], best[3]);
+    if (winner)
+      *reinterpret_cast<uchar4*>(winner + (long long)b * d + 4 * q) = make_uchar4((unsigned char)win[0], (unsigned char)win[1],
+                                                                                 (unsigned char)win[2], (unsigned char)win[3]);
+    ss += best[0] * best[0] + best[1] * best[1] + best[2] * best[2] + best[3] * best[3];
+  }
+  ss = warp_sum(ss);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = ss;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    float v = threadIdx.x < (blockDim.x >> 5) ? red[threadIdx.x] : 0.f;
+    v = warp_sum(v);
+    if (threadIdx.x == 0) red[0] = v;
+  }
+  __syncthreads();
+  ss = red[0];
+  const float inv = normalize ? rsqrtf(fmaxf(ss, 1e-12f)) : 1.f;
+  if (threadIdx.x == 0 && inv_norm) {
+    inv_norm[2 * b] = inv;
+    inv_norm[2 * b + 1] = ss;
+  }
+  for (int q = threadIdx.x; q < d4; q += blockDim.x) {
+    float4 v = *reinterpret_cast<float4*>(row + 4 * q);
+    v.x *= inv; v.y *= inv; v.z *= inv; v.w *= inv;
+    *reinterpret_cast<float4*>(row + 4 * q) = v;
+    *reinterpret_cast<float4*>(sig + (long long)b * d + 4 * q) = v;
+    if (P > 0) {
+      const float vv[4] = {v.x, v.y, v.z, v.w};
+      __align__(8) u16 hi[4], lo[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) ugn_split16(vv[i], f16, hi[i], lo[i]);
+      *reinterpret_cast<uint2*>(sig16 + (long long)b * d + 4 * q) = *reinterpret_cast<const uint2*>(hi);
+      if (P == 2) *reinterpret_cast<uint2*>(sig16 + plane + (long long)b * d + 4 * q) = *reinterpret_cast<const uint2*>(lo);
+    }
+  }
+  __syncthreads();
+  // FC1: two output features per warp iteration (two independent weight streams in flight)
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+  for (int j = 2 * warp; j < nc; j += 2 * nw) {
+    const bool two = j + 1 < nc;
+    const float4* w0 = reinterpret_cast<const float4*>(Wc + (long long)j * d);
+    const float4* w1 = reinterpret_cast<const float4*>(Wc + (long long)(two ? j + 1 : j) * d);
+    float a0 = 0.f, a1 = 0.f;
+    for (int q = lane; q < d4; q += 32) {
+      const float4 s4 = *reinterpret_cast<const float4*>(row + 4 * q);
+      const float4 x0 = __ldg(w0 + q), x1 = __ldg(w1 + q);
+      a0 = fmaf(x0.x, s4.x, fmaf(x0.y, s4.y, fmaf(x0.z, s4.z, fmaf(x0.w, s4.w, a0))));
+      a1 = fmaf(x1.x, s4.x, fmaf(x1.y, s4.y, fmaf(x1.z, s4.z, fmaf(x1.w, s4.w, a1))));
+    }
+    a0 = warp_sum(a0);
+    a1 = warp_sum(a1);
+    if (lane < (two ? 2 : 1)) {
+      const int jj = j + lane;
+      const float y = ugn_act_fwd((lane ? a1 : a0) + (bc ? bc[jj] : 0.f), act, alpha);
+      const long long o = (long long)b * nc + jj;
+      code[o] = y;
+      if (dropcode) dropcode[o] = cmask ? y * cmask[o] : y;
+    }
+  }
+}
+
+int ew_fuse_fc1_fwd(ugn_ctx* ctx, const FusePtrs& ptrs, int nmods, int B, int d, float* sig, __nv_bfloat16* sig16, int P,
+                    int f16, uint8_t* winner, float* inv_norm, int merge, int normalize, const float* Wc, const float* bc,
+                    int nc, float* code, const float* cmask, float* dropcode, int act, float alpha, cudaStream_t st) {
+  size_t smem = sizeof(float) * d;
+  long long plane = (long long)B * d;
+#define UGN_FF_ARGS ptrs, nmods, d, sig, sig16, winner, inv_norm, merge, normalize, plane, f16, Wc, bc, nc, code, cmask, dropcode, act, alpha
+  if (P == 0) fuse_fc1_fwd_kernel<0><<<B, 256, smem, st>>>(UGN_FF_ARGS);
+  else if (P == 1) fuse_fc1_fwd_kernel<1><<<B, 256, smem, st>>>(UGN_FF_ARGS);
+  else fuse_fc1_fwd_kernel<2><<<B, 256, smem, st>>>(UGN_FF_ARGS);
+#undef UGN_FF_ARGS
+  UGN_LAUNCHED(ctx);
+  return UGN_OK;
+}
+
 // backward: y = x*inv, inv = rsqrt(max(ss,eps)).  ss > eps: dx = inv*(dy - y*sum(dy*y));
 // clamped (ss <= eps): inv is a constant, dx = dy*inv.  Then route dx to the winning modality
 // (max / sign_max) or spread it (avg), times the gate flag.

@@ -630,9 +630,21 @@ class UGaitEngine:
                     b = p.br[m]
                     check(lib.ugn_fuse_fwd(h, 1, b.nrm_in, p.one_ptrs, b.R["outn"].ptr, None, b.R["nwin"].ptr,
                                            b.R["ninv"].ptr, 0, 1, st))
-            check(lib.ugn_fuse_fwd(h, cfg.nmods, p.brn_ptrs if cfg.normbfmerge else p.br_ptrs, p.flag_ptrs,
-                                   p.R["sig"].ptr, p.R["sig16"].ptr if p.tc_gram else None, p.R["winner"].ptr,
-                                   p.R["inv_norm"].ptr, cfg.merge, 0 if self.post2 else 1, st))
+            # north_star: gate + fusion + l2_normalize + FC1 ("code") [+ its dropout] as ONE kernel when the graph has an FC1
+            fused_fc1 = cfg.nc > 0 and cfg.nd % 4 == 0 and cfg.nd <= 12288 and os.environ.get("UGN_FUSE_FC1", "1") == "1"
+            drop_code = train and cfg.dropout > 0.001 and cfg.nc > 0
+            if fused_fc1:
+                fuse_drop = drop_code and not self.post2         # postriplet 2 drops the NORMALISED code further down
+                check(lib.ugn_fuse_fc1_fwd(h, cfg.nmods, p.brn_ptrs if cfg.normbfmerge else p.br_ptrs, p.flag_ptrs,
+                                           p.R["sig"].ptr, p.R["sig16"].ptr if p.tc_gram else None, p.R["winner"].ptr,
+                                           p.R["inv_norm"].ptr, cfg.merge, 0 if self.post2 else 1, self.Rw["code/w"].ptr,
+                                           self.Rw["code/b"].ptr, p.R["code"].ptr,
+                                           p.R["cmask"].ptr if fuse_drop else None,
+                                           p.R["dropcode"].ptr if fuse_drop else None, cfg.act, cfg.alpha, st))
+            else:
+                check(lib.ugn_fuse_fwd(h, cfg.nmods, p.brn_ptrs if cfg.normbfmerge else p.br_ptrs, p.flag_ptrs,
+                                       p.R["sig"].ptr, p.R["sig16"].ptr if p.tc_gram else None, p.R["winner"].ptr,
+                                       p.R["inv_norm"].ptr, cfg.merge, 0 if self.post2 else 1, st))
             sig = p.R["sig"]
             if self.aux:
                 # auxiliary classifiers on the GATED branch outputs: gate = the fusion kernel on one modality without
@@ -647,8 +659,10 @@ class UGaitEngine:
         feat = sig
         if cfg.nc > 0:
             cmask = p.R["cmask"].ptr if (train and cfg.dropout > 0.001) else None
-            check(lib.ugn_linear_fwd(h, sig.ptr, self.Rw["code/w"].ptr, self.Rw["code/b"].ptr, None, p.R["code"].ptr,
-                                     None, cfg.act, cfg.alpha, st))
+            fused = (not cfg.single) and fused_fc1
+            if not fused:
+                check(lib.ugn_linear_fwd(h, sig.ptr, self.Rw["code/w"].ptr, self.Rw["code/b"].ptr, None, p.R["code"].ptr,
+                                         None, cfg.act, cfg.alpha, st))
             emb = p.code
             if self.post2:
                 # postriplet == 2 (:819-832): the Dense above is the layer "signature"; its l2_normalize ("code") is the
@@ -657,7 +671,8 @@ class UGaitEngine:
                                        p.R["cinv"].ptr, 0, 1, st))
                 emb, sig = p.codeN, p.R["codeN"]
             if cmask is not None:
-                torch.mul(emb, p.cmask, out=p.dropcode)
+                if not (fused and not self.post2):           # (the fused kernel wrote dropcode = code * mask already)
+                    torch.mul(emb, p.cmask, out=p.dropcode)
                 feat = p.R["dropcode"]
             else:
                 feat = p.R["codeN"] if self.post2 else p.R["code"]
