@@ -502,9 +502,18 @@ __global__ void __launch_bounds__(256) fuse_fwd_kernel(FusePtrs ptrs, int nmods,
   }
 }
 
+int ew_fuse_fc1_fwd(ugn_ctx* ctx, const FusePtrs& ptrs, int nmods, int B, int d, float* sig, __nv_bfloat16* sig16, int P,
+                    int f16, uint8_t* winner, float* inv_norm, int merge, int normalize, const float* Wc, const float* bc,
+                    int nc, float* code, const float* cmask, float* dropcode, int act, float alpha, cudaStream_t st);
+
 int ew_fuse_fwd(ugn_ctx* ctx, const FusePtrs& ptrs, int nmods, int B, int d, float* sig,
                 __nv_bfloat16* sig16, int P, int f16, uint8_t* winner, float* inv_norm, int merge,
                 int normalize, cudaStream_t st) {
+  // vectorised kernel (float4 loads, missing modalities skipped) whenever the row width allows: the FC1-fused kernel
+  // with no FC1 behind it
+  if (d % 4 == 0 && (size_t)d * 4 <= 48 * 1024)
+    return ew_fuse_fc1_fwd(ctx, ptrs, nmods, B, d, sig, sig16, P, f16, winner, inv_norm, merge, normalize, nullptr, nullptr,
+                           0, nullptr, nullptr, nullptr, 0, 0.f, st);
   size_t smem = sizeof(float) * d;
   long long plane = (long long)B * d;
   if (P == 0) fuse_fwd_kernel<0><<<B, 256, smem, st>>>(ptrs, nmods, d, sig, sig16, winner, inv_norm, merge, normalize, plane, f16);
