@@ -108,3 +108,26 @@ def test_integer_shift_restatement_equals_scipy_affine_transform():
     lit[np.abs(lit) < 50] = 1e-8
     lit = lit / 100 * 0.1
     assert np.allclose(clip_flow(raw / 100 * 0.1), lit, rtol=1e-6, atol=1e-12)
+
+
+def test_owned_segment_ranges_partition_every_segment():
+    """Deferred weight all-gather: the plane ranges each rank sends (its arena slice cut by the exchanged segments) tile
+    every exchanged segment exactly once, for any world size, and agree with the slice arithmetic of ugn_dp_optim_step."""
+    from ugaitnet_b200.dist import owned_segment_ranges, owner_slice
+    rng = np.random.default_rng(5)
+    for world in (1, 2, 3, 4, 8):
+        off, segs = 0, []
+        for i in range(9):
+            n = int(rng.integers(1, 40)) * 4
+            if i % 3 != 1:                       # some segments are not exchanged (conv weights, biases)
+                segs.append((f"s{i}", off, n))
+            off += (n + 63) // 64 * 64           # arena offsets are rounded up to 64 elements
+        n_arena = off
+        cover = {name: np.zeros(n, dtype=np.int32) for name, _, n in segs}
+        for rank in range(world):
+            q0, q1 = owner_slice(n_arena, rank, world)
+            for name, lo, hi in owned_segment_ranges(segs, rank, world, n_arena):
+                so = next(o for nm, o, _ in segs if nm == name)
+                assert 0 <= lo < hi <= len(cover[name]) and q0 <= so + lo and so + hi <= q1
+                cover[name][lo:hi] += 1
+        assert all((c == 1).all() for c in cover.values())

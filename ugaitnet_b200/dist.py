@@ -34,6 +34,19 @@ def owner_slice(n: int, rank: int, world: int) -> Tuple[int, int]:
     return 4 * min(n4, per * rank), 4 * min(n4, per * (rank + 1))
 
 
+def owned_segment_ranges(segments, rank: int, world: int, n_arena: int):
+    """For the deferred weight all-gather: the parts of the given arena segments ``(name, offset, numel)`` that lie inside
+    the slice `rank` owns -> [(name, lo, hi)] with lo / hi relative to the segment start.  Over all ranks every element
+    of every segment is covered exactly once."""
+    q0, q1 = owner_slice(n_arena, rank, world)
+    out = []
+    for name, off, n in segments:
+        a, b = max(off, q0), min(off + n, q1)
+        if a < b:
+            out.append((name, a - off, b - off))
+    return out
+
+
 def allreduce_mean_(flat: torch.Tensor, group=None) -> torch.Tensor:
     """In-place mean over ranks of a flat gradient arena (CPU/gloo test helper; on the GPU the 1/G
     factor is folded into the optimiser kernel instead of a separate pass)."""

@@ -1378,24 +1378,20 @@ class UGaitEngine:
     def _cw_deferred_setup(self):
         """(destination view in a peer's arena, local source view) for every plane range of the exchanged 16-bit copies
         that lies in this rank's arena slice."""
-        rank, sl = torch.distributed.get_rank(self.pg), self.slice_len
-        q0, q1 = rank * sl, min((rank + 1) * sl, self.n_arena)
+        from .dist import owned_segment_ranges
+        rank = torch.distributed.get_rank(self.pg)
         arena = self.cw_arena
         peers = [self._cw_symm.get_buffer(r, (arena.numel(),), self.dt16) for r in range(self.world)]
         self._cw_pairs = []
-        for sg in self.seg_list:
-            if sg.name not in self._fused_pack:
-                continue
-            a, b = max(sg.off, q0), min(sg.off + sg.n, q1)
-            if a >= b:
-                continue
-            planes = self.cw[sg.name].view(self.P, -1)
+        segs = [(sg.name, sg.off, sg.n) for sg in self.seg_list if sg.name in self._fused_pack]
+        for name, lo, hi in owned_segment_ranges(segs, rank, self.world, self.n_arena):
+            planes = self.cw[name].view(self.P, -1)
             for pl in range(self.P):
-                src = planes[pl, a - sg.off:b - sg.off]
+                src = planes[pl, lo:hi]
                 e0 = (src.data_ptr() - arena.data_ptr()) // 2
                 for r in range(self.world):
                     if r != rank:
-                        self._cw_pairs.append((peers[r][e0:e0 + (b - a)], src))
+                        self._cw_pairs.append((peers[r][e0:e0 + (hi - lo)], src))
 
     def _cw_send(self):
         """After the exchange kernel: this rank's slice of the updated 16-bit planes goes to every peer by the copy
