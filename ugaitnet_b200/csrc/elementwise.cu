@@ -546,8 +546,12 @@ __global__ void __launch_bounds__(256) fuse_fc1_fwd_kernel(FusePtrs ptrs, int nm
   extern __shared__ __align__(16) float row[];  // [d] fused values
   __shared__ float red[8];
   const int b = blockIdx.x, d4 = d >> 2;
-  float fl[4];
-  for (int m = 0; m < nmods; ++m) fl[m] = ptrs.flag[m][b];
+  // (fully unrolled over the <= 4 modalities with constant indices: the pointer table stays in the parameter bank and
+  // the flags in registers -- no local-memory copies)
+  float fl[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+  for (int m = 0; m < 4; ++m)
+    if (m < nmods) fl[m] = ptrs.flag[m][b];
   float ss = 0.f;
   for (int q = threadIdx.x; q < d4; q += blockDim.x) {
     float best[4] = {0.f, 0.f, 0.f, 0.f}, key[4];
@@ -558,7 +562,9 @@ __global__ void __launch_bounds__(256) fuse_fc1_fwd_kernel(FusePtrs ptrs, int nm
     }
 #pragma unroll
     for (int i = 0; i < 4; ++i) key[i] = merge == UGN_MERGE_SIGNMAX ? fabsf(best[i]) : best[i];
-    for (int m = 1; m < nmods; ++m) {
+#pragma unroll
+    for (int m = 1; m < 4; ++m) {
+      if (m >= nmods) break;
       float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
       if (fl[m] != 0.f) v = *reinterpret_cast<const float4*>(ptrs.br[m] + (long long)b * d + 4 * q);
       const float vv[4] = {v.x * fl[m], v.y * fl[m], v.z * fl[m], v.w * fl[m]};
