@@ -688,17 +688,19 @@ __global__ void __launch_bounds__(256) fuse_bwd_kernel(FusePtrs ptrs, int nmods,
       dot = red[0];
     }
   }
-  float fl[4];
-  for (int m = 0; m < nmods; ++m) fl[m] = ptrs.flag[m][b];
+  float fl[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+  for (int m = 0; m < 4; ++m)          // constant indices: pointer table and flags never go through local memory
+    if (m < nmods) fl[m] = ptrs.flag[m][b];
   for (int j = threadIdx.x; j < d; j += blockDim.x) {
     long long o = (long long)b * d + j;
     float g = dsig[o];
     if (normalize) g = clamped ? g * inv : inv * (g - sig[o] * dot);
-    if (merge == UGN_MERGE_AVG) {
-      for (int m = 0; m < nmods; ++m) ptrs.dbr[m][o] = g * fl[m] / (float)nmods;
-    } else {
-      int w = winner[o];
-      for (int m = 0; m < nmods; ++m) ptrs.dbr[m][o] = (m == w) ? g * fl[m] : 0.f;
+    const int w = merge == UGN_MERGE_AVG ? -1 : (int)winner[o];
+#pragma unroll
+    for (int m = 0; m < 4; ++m) {
+      if (m >= nmods) break;
+      ptrs.dbr[m][o] = merge == UGN_MERGE_AVG ? g * fl[m] / (float)nmods : ((m == w) ? g * fl[m] : 0.f);
     }
   }
 }
