@@ -144,9 +144,11 @@ class HostBatch:
         (ugn_decode_samples) when the batch is consumed: a quarter / half of the f32 bytes cross PCIe."""
         self.io, self.B0, self.raw = io, B0, None
         if raw is not None:
+            if len(raw) != io.M or any(r[0] not in ("int16", "uint8") or not 4 <= len(r) <= 6 for r in raw):
+                raise ValueError(f"raw: one (\"int16\" | \"uint8\", divisor, mul, sub[, clip_min, clip_max]) per modality "
+                                 f"({io.M}) expected, got {raw!r}")
             self.raw = [(torch.int16 if r[0] == "int16" else torch.uint8,) + tuple(float(v) for v in r[1:]) +
                         (0.0,) * (6 - len(r)) for r in raw]
-            assert len(self.raw) == io.M and all(r[0] in ("int16", "uint8") for r in raw)
             rows = io.B if B0 is None else B0
             self.raw_off, self.nbytes = io.raw_offsets(rows, [2 if r[0] is torch.int16 else 1 for r in self.raw])
             self.buf = torch.zeros(self.nbytes, dtype=torch.uint8).pin_memory()
