@@ -69,3 +69,29 @@ def test_gaitset_input_layout_matches_generator_restating():
     g_new[:, :, :, 0] = gray
     assert np.array_equal(to_gaitset_layout(gray), g_new)
     assert to_gaitset_layout(np.stack([of, of])).shape == (2, 25, 6, 5, 2)
+
+
+def test_product_package_never_touches_the_oracle():
+    """The oracle is test infrastructure: nothing under ugaitnet_b200/ may import, load or execute anything from
+    oracle/ (only tests/, __graft_entry__.smoke() and bench.py's CPU legs do)."""
+    import pathlib
+    import re
+    root = pathlib.Path(__file__).resolve().parents[1] / "ugaitnet_b200"
+    pat = re.compile(r"^\s*(from|import)\s+oracle\b|importlib\.import_module\(\s*['\"]oracle|oracle/_ref|liboracle", re.M)
+    offenders = [str(p) for p in root.rglob("*.py") if pat.search(p.read_text())]
+    inc = re.compile(r'#\s*include\s*[<"][^>"]*oracle')
+    offenders += [str(p) for p in list(root.rglob("*.cu")) + list(root.rglob("*.cuh")) if inc.search(p.read_text())]
+    assert offenders == []
+
+
+def test_conv3d_branch_geometry_matches_reference_chain():
+    # build_3Dbranch (nets/mj_uwyhNets_ba.py:346-363) on [25,60,60,1]: (23,28,28,64) (21,13,13,128) (10,6,6,256)
+    # (4,2,2,512) (2,1,1,512) (1,1,1,512), then the 1x1x1 "grayCode"
+    from ugaitnet_b200.config import NetConfig
+    cfg = NetConfig(in_channels=(50, 25, 25), branch3d=(False, True, True))
+    L = cfg.layers3d(1)
+    assert [(l["to"], l["ho"], l["co"]) for l in L] == [(23, 28, 64), (21, 13, 128), (10, 6, 256), (4, 2, 512), (2, 1, 512),
+                                                        (1, 1, 512)]
+    assert [l["cin"] for l in L] == [1, 64, 128, 256, 512, 512] and cfg.is3d(1) and not cfg.is3d(0)
+    with pytest.raises(ValueError, match="1x1x1"):
+        NetConfig(in_channels=(30,), branch3d=(True,)).layers3d(0)
