@@ -178,3 +178,38 @@ def test_raw_sample_batches_equal_decoded_batches(mode):
         out = eng2.train_step_prefetched()
         losses.append(out["losses"].cpu().clone())
     assert torch.allclose(losses[0][:4], losses[1][:4], rtol=1e-5, atol=1e-7) and float(losses[0][0]) > 0
+
+
+def test_resident_input_buffers_equal_train_step():
+    """input_buffers() + train_step_resident() / predict_resident(): the same step as train_step(tensors), with the batch
+    written straight into the engine's input block."""
+    from ugaitnet_b200.config import NetConfig
+    from ugaitnet_b200.net import UGaitEngine
+    cfg = NetConfig(in_channels=(6, 4, 4), filters_numbers=(8, 8, 16, 16), nd=32, nclasses=10, merge=O.MERGE_SIGNMAX)
+    g = torch.Generator().manual_seed(1)
+    B = 6
+    xs = [torch.randn(B, c, 60, 60, generator=g).cuda() for c in cfg.in_channels]
+    fl = [(torch.rand(B, 1, generator=g) > 0.2).float().cuda() for _ in cfg.in_channels]
+    lab = torch.tensor([0, 0, 1, 1, 2, 2]).cuda()
+    outs = []
+    for resident in (False, True):
+        eng = UGaitEngine(cfg, math_mode="fp32", lr=1e-3, seed=5, use_graph=False)
+        if resident:
+            xi, fi, li = eng.input_buffers(B)
+            for m in range(3):
+                xi[m].copy_(xs[m])
+                fi[m].copy_(fl[m])
+            li.copy_(lab.to(torch.int32))
+            o = eng.train_step_resident(B)
+            xp, fp, _ = eng.input_buffers(B, train=False)
+            for m in range(3):
+                xp[m].copy_(xs[m])
+                fp[m].copy_(fl[m])
+            sig = eng.predict_resident(B)
+        else:
+            o = eng.train_step(xs, fl, lab)
+            sig = eng.predict(xs, fl)
+        outs.append((o["losses"][:5].cpu().clone(), sig.cpu().clone(), eng.export_params()["ofBranch/dense/w"].cpu()))
+    assert torch.allclose(outs[0][0], outs[1][0], rtol=1e-5, atol=1e-7)
+    assert torch.allclose(outs[0][1], outs[1][1], rtol=1e-5, atol=1e-6)
+    assert torch.allclose(outs[0][2], outs[1][2], rtol=1e-5, atol=1e-7)

@@ -1508,6 +1508,28 @@ class UGaitEngine:
         self._set_inputs(p, inputs, flags, labels, drop_masks, code_drop_mask)
         return self._run_train(p, B, expanded=False)
 
+    def input_buffers(self, B: int, train: bool = True):
+        """(volumes [B,C,60,60] per modality, use-flags [B,1] per modality, labels i32 [B]): the plan's OWN input block as
+        device tensors.  A producer that already runs on the GPU (a device-side loader, a previous kernel) writes the
+        batch here and calls train_step_resident() / predict_resident(): no per-step input copy at all."""
+        p = self.plan(B, train)
+        return [b.x_in for b in p.br], list(p.flags), p.labels
+
+    @torch.no_grad()
+    def train_step_resident(self, B: int) -> Dict[str, torch.Tensor]:
+        """train_step on whatever input_buffers(B) currently hold."""
+        p = self.plan(B, True)
+        self._draw_dropout(p)
+        return self._run_train(p, B, expanded=False)
+
+    @torch.no_grad()
+    def predict_resident(self, B: int, layer: str = "signature") -> torch.Tensor:
+        p = self.plan(B, False)
+        self._forward(p, False)
+        if layer == "signature":
+            return (p.br[0].out if self.cfg.single else (p.codeN if self.post2 else p.sig)).clone()
+        return p.code.clone() if layer == "code" else p.logits.clone()
+
     def _run_train(self, p, B, expanded):
         self._next_lr()
         if self.use_graph and (self.world == 1 or self.dp_graph):
