@@ -353,6 +353,74 @@ __global__ void __launch_bounds__(256) bwd_act_vec8_kernel(const float* __restri
   }
 }
 
+// POOLED layers, input-driven: a thread owns one pooled element group (8 channels) -- dy / y / idx are loaded ONCE
+// (the output-driven kernel above reads them from each of the four window positions) -- and writes the four
+// pre-pool pixels of its 2x2 window (the selected position gets dy * act'(y), the others zero).  Odd Ho / Wo leave a
+// last row / column outside every window: the work items of the fringe (yp == Hp or xp == Wp) zero-fill it.
+template <int P>
+__global__ void __launch_bounds__(256) bwd_act_pool_vec8_kernel(const float* __restrict__ dy,
+                                                                const __nv_bfloat16* __restrict__ y,
+                                                                const uint8_t* __restrict__ idx,
+                                                                __nv_bfloat16* __restrict__ dz, float* __restrict__ db,
+                                                                int B, int Ho, int Wo, int Hp, int Wp, int C8, int act,
+                                                                float alpha, int f16, const float* __restrict__ gs) {
+  __shared__ float red[256 * 8];
+  const float scale = gs ? gs[0] : 1.f;
+  const int He = (Ho + 1) >> 1, We = (Wo + 1) >> 1;            // window grid incl. the fringe
+  const unsigned nwin = (unsigned)B * He * We;
+  const long long plane = (long long)B * Ho * Wo * C8 * 8;
+  const unsigned lanes = 256u / C8, c8 = threadIdx.x % C8, lane = threadIdx.x / C8;
+  float acc[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+  if (lane < lanes) {
+    for (unsigned wdx = blockIdx.x * lanes + lane; wdx < nwin; wdx += gridDim.x * lanes) {
+      const unsigned xp = wdx % We, t2 = wdx / We, yp = t2 % He, b = t2 / He;
+      const bool live = yp < (unsigned)Hp && xp < (unsigned)Wp;
+      float g[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+      unsigned long long ib = 0;
+      if (live) {
+        const long long o = ((((long long)b * Hp + yp) * Wp + xp) * C8 + c8) * 8;
+        const float4 d0 = *reinterpret_cast<const float4*>(dy + o), d1 = *reinterpret_cast<const float4*>(dy + o + 4);
+        const uint4 yr = *reinterpret_cast<const uint4*>(y + o);
+        const __nv_bfloat16* yh = reinterpret_cast<const __nv_bfloat16*>(&yr);
+        ib = *reinterpret_cast<const unsigned long long*>(idx + o);
+        const float dd[8] = {d0.x, d0.y, d0.z, d0.w, d1.x, d1.y, d1.z, d1.w};
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          g[i] = dd[i] * ugn_act_bwd(ugn_f16to32(yh[i], f16), act, alpha);
+          acc[i] += g[i];
+        }
+      }
+#pragma unroll
+      for (int pos = 0; pos < 4; ++pos) {
+        const unsigned yo = 2 * yp + (pos >> 1), xo = 2 * xp + (pos & 1);
+        if (yo >= (unsigned)Ho || xo >= (unsigned)Wo) continue;
+        __align__(16) u16 hi[8], lo[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float v = (live && (int)((ib >> (8 * i)) & 0xff) == pos) ? g[i] * scale : 0.f;
+          ugn_split16(v, f16, hi[i], lo[i]);
+        }
+        const long long e = ((((long long)b * Ho + yo) * Wo + xo) * C8 + c8) * 8;
+        *reinterpret_cast<uint4*>(dz + e) = *reinterpret_cast<const uint4*>(hi);
+        if (P == 2) *reinterpret_cast<uint4*>(dz + plane + e) = *reinterpret_cast<const uint4*>(lo);
+      }
+    }
+  }
+  if (db) {
+    const int C = C8 * 8;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) red[threadIdx.x * 8 + i] = acc[i];
+    __syncthreads();
+    for (int c = threadIdx.x; c < C; c += 256) {
+      float sacc = 0.f;
+      for (unsigned l = 0; l < lanes; ++l) sacc += red[l * C + c];
+      atomicAdd(db + c, sacc);
+    }
+  }
+}
+
 int ew_bwd_act(ugn_ctx* ctx, const float* dy, const void* y, int y_bf16, const uint8_t* idx,
                void* dz, float* db, int* db_done, int mode, int f16, int B, int Ho, int Wo, int Hp, int Wp, int C,
                int act, float alpha, int pool, cudaStream_t st) {
@@ -363,6 +431,17 @@ int ew_bwd_act(ugn_ctx* ctx, const float* dy, const void* y, int y_bf16, const u
     if (db) {
       UGN_CUDA(cudaMemsetAsync(db, 0, sizeof(float) * C, st));
       *db_done = 1;
+    }
+    static const bool pool_in = !(getenv("UGN_BWDACT_OUT") && atoi(getenv("UGN_BWDACT_OUT")));
+    if (pool && pool_in) {
+      const long long nwin = (long long)B * ((Ho + 1) / 2) * ((Wo + 1) / 2) * (C / 8);
+      const int gp = grid_for(ctx, nwin, 256);
+      if (mode == 1)
+        bwd_act_pool_vec8_kernel<1><<<gp, 256, 0, st>>>(dy, (const __nv_bfloat16*)y, idx, (__nv_bfloat16*)dz, db, B, Ho, Wo, Hp, Wp, C / 8, act, alpha, f16, gs);
+      else
+        bwd_act_pool_vec8_kernel<2><<<gp, 256, 0, st>>>(dy, (const __nv_bfloat16*)y, idx, (__nv_bfloat16*)dz, db, B, Ho, Wo, Hp, Wp, C / 8, act, alpha, f16, gs);
+      UGN_LAUNCHED(ctx);
+      return UGN_OK;
     }
     if (mode == 1)
       bwd_act_vec8_kernel<1><<<g8, 256, 0, st>>>(dy, (const __nv_bfloat16*)y, idx, (__nv_bfloat16*)dz, db, B, Ho, Wo, Hp, Wp, C / 8, act, alpha, pool, f16, gs);
