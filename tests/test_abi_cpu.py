@@ -95,3 +95,33 @@ def test_conv3d_branch_geometry_matches_reference_chain():
     assert [l["cin"] for l in L] == [1, 64, 128, 256, 512, 512] and cfg.is3d(1) and not cfg.is3d(0)
     with pytest.raises(ValueError, match="1x1x1"):
         NetConfig(in_channels=(30,), branch3d=(True,)).layers3d(0)
+
+
+def test_io_block_layouts_are_aligned_and_disjoint():
+    """IOBlock (the single-copy input block): every field 256-byte aligned, fields disjoint, the base-row and raw-sample
+    layouts are prefixes that never exceed the full block; raw int16 / uint8 volumes take 0.375 of the f32 bytes."""
+    from ugaitnet_b200.net import IOBlock
+    B, B0 = 96, 24
+    io = IOBlock(torch.device("cpu"), B, [(50, 60, 60), (25, 60, 60), (25, 60, 60)])
+    v = io.views(io.dev_buf)
+    spans = []
+    for name in ("labels", "src_row", "mirror", "shift", "clip"):
+        t = v[name]
+        spans.append((t.data_ptr() - io.dev_buf.data_ptr(), t.numel() * t.element_size()))
+    for t in v["flags"] + v["x"]:
+        spans.append((t.data_ptr() - io.dev_buf.data_ptr(), t.numel() * t.element_size()))
+    spans.sort()
+    assert all(o % IOBlock.ALIGN == 0 for o, _ in spans)
+    assert all(a + n <= b for (a, n), (b, _) in zip(spans, spans[1:])) and spans[-1][0] + spans[-1][1] <= io.nbytes_full
+    assert [tuple(t.shape) for t in v["x"]] == [(B, 50, 60, 60), (B, 25, 60, 60), (B, 25, 60, 60)]
+    vb = io.views(io.dev_buf, B0)
+    assert [tuple(t.shape) for t in vb["x"]] == [(B0, 50, 60, 60), (B0, 25, 60, 60), (B0, 25, 60, 60)]
+    assert io.header < io.nbytes_base(B0) < io.nbytes_full
+    raw = [(torch.int16, 100.0, 0.1, 0.0, 0.0, 0.0), (torch.uint8, 255.0, 1.0, 0.5, 0.0, 0.0), (torch.uint8, 255.0, 1.0, 0.5, 0.0, 0.0)]
+    vr = io.views(io.dev_buf, None, raw=raw)
+    assert [t.dtype for t in vr["x"]] == [torch.int16, torch.uint8, torch.uint8]
+    _, nraw = io.raw_offsets(B, [2, 1, 1])
+    vol_f32 = io.nbytes_full - io.header
+    assert abs((nraw - io.header) / vol_f32 - 0.375) < 1e-3
+    last = vr["x"][-1]
+    assert last.data_ptr() - io.dev_buf.data_ptr() + last.numel() <= nraw <= io.nbytes_full
