@@ -213,3 +213,42 @@ def test_resident_input_buffers_equal_train_step():
     assert torch.allclose(outs[0][0], outs[1][0], rtol=1e-5, atol=1e-7)
     assert torch.allclose(outs[0][1], outs[1][1], rtol=1e-5, atol=1e-6)
     assert torch.allclose(outs[0][2], outs[1][2], rtol=1e-5, atol=1e-7)
+
+
+def test_piecewise_prefetch_delivers_the_bytes_of_the_single_copy():
+    """prefetch_open / prefetch_upto / prefetch_close (the loader's cast of volume m + 1 overlaps the H2D copy of volume
+    m): the staging block ends up byte-identical to the one prefetch_batch fills, for any cut points, and the step /
+    the descriptors computed from it are those of the single copy."""
+    from ugaitnet_b200.config import NetConfig
+    from ugaitnet_b200.net import UGaitEngine
+    cfg = NetConfig(in_channels=(6, 4, 4), filters_numbers=(8, 8, 16, 16), nd=32, nclasses=10, merge=O.MERGE_SIGNMAX)
+    rng = np.random.default_rng(9)
+    B = 6
+    res = []
+    for piecewise in (False, True):
+        eng = UGaitEngine(cfg, math_mode="fp32", lr=1e-3, seed=5, use_graph=False)
+        rng = np.random.default_rng(9)
+        for train in (True, False):
+            hb = eng.host_batch(B, train=train)
+            for m in range(3):
+                hb.inputs[m][...] = rng.standard_normal(hb.inputs[m].shape)
+                hb.flags[m][...] = rng.random((B, 1)) > 0.2
+            hb.labels[...] = [0, 0, 1, 1, 2, 2]
+            if piecewise:
+                eng.prefetch_open(hb, train)
+                eng.prefetch_upto(100)                       # inside the header
+                eng.prefetch_upto(hb.io.x_off[1])
+                eng.prefetch_upto(hb.io.x_off[1])            # nothing new: no-op
+                eng.prefetch_upto(hb.io.x_off[2] + 12345)    # mid-volume cut
+                eng.prefetch_close()
+            else:
+                eng.prefetch_batch(hb, train)
+            torch.cuda.synchronize()
+            st = eng._io_stage[(B, train)]
+            assert torch.equal(st["buf"][eng._io_k][:hb.nbytes].cpu(), hb.buf)
+            if train:
+                res.append(eng.train_step_prefetched()["losses"][:5].cpu().clone())
+            else:
+                res.append(eng.predict_prefetched("signature").cpu().clone())
+    assert torch.allclose(res[0], res[2], rtol=1e-5, atol=1e-7) and float(res[0][0]) > 0
+    assert torch.allclose(res[1], res[3], rtol=1e-5, atol=1e-6)

@@ -229,12 +229,7 @@ class UGaitModel:
         hb = self._hbp.get(B)
         if hb is None:
             hb = self._hbp[B] = eng.host_batch(B, train=False)
-        for m, a in enumerate(xs):
-            src = a if torch.is_tensor(a) else torch.from_numpy(np.ascontiguousarray(a))
-            hb.t["x"][m].copy_(src.reshape(hb.t["x"][m].shape))
-            if self.multimodal:
-                hb.flags[m][...] = np.asarray(x[2 * m + 1], dtype=np.float32).reshape(-1, 1)
-        eng.prefetch_batch(hb, train=False)
+        self._fill_and_send(hb, xs, x, train=False)
         sig = eng.predict_prefetched("signature")
         if self.cfg.nclasses > 0:
             p = eng.plan(B, False)
@@ -281,15 +276,24 @@ class UGaitModel:
             pair = self._hb[B] = [eng.host_batch(B), eng.host_batch(B)]
         self._hb_k ^= 1
         hb = pair[self._hb_k]
+        lab = y[0] if isinstance(y, (list, tuple)) else y
+        hb.labels[...] = np.asarray(lab).reshape(-1).astype(np.int32)
+        self._fill_and_send(hb, xs, X, train=True)
+
+    def _fill_and_send(self, hb, xs, X, train):
+        """Header (flags; the caller has written the labels) first, then volume after volume: the H2D copy of modality m
+        (UGaitEngine.prefetch_upto, a prefix of the ONE pinned block) runs underneath the f64 -> f32 cast of modality
+        m + 1, so a batch is on the device one last-volume copy after the loader has finished with it."""
+        eng, io = self.engine, hb.io
+        if self.multimodal:
+            for m in range(len(xs)):
+                hb.flags[m][...] = np.asarray(X[2 * m + 1], dtype=np.float32).reshape(-1, 1)
+        eng.prefetch_open(hb, train)
         for m, x in enumerate(xs):
             src = x if torch.is_tensor(x) else torch.from_numpy(np.ascontiguousarray(x))
             hb.t["x"][m].copy_(src.reshape(hb.t["x"][m].shape))          # f64 -> f32 cast across the host cores
-            if self.multimodal:
-                f = X[2 * m + 1]
-                hb.flags[m][...] = np.asarray(f, dtype=np.float32).reshape(-1, 1)
-        lab = y[0] if isinstance(y, (list, tuple)) else y
-        hb.labels[...] = np.asarray(lab).reshape(-1).astype(np.int32)
-        eng.prefetch_batch(hb)
+            eng.prefetch_upto(io.x_off[m + 1] if m + 1 < len(xs) else hb.nbytes)
+        eng.prefetch_close()
 
     def _fit_epoch(self, gen, n):
         """One epoch through the single-copy path; returns the per-batch logs (each read back with ONE D2H copy)."""

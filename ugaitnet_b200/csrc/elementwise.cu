@@ -613,6 +613,7 @@ int ew_fuse_fwd(ugn_ctx* ctx, const FusePtrs& ptrs, int nmods, int B, int d, flo
     return ew_fuse_fc1_fwd(ctx, ptrs, nmods, B, d, sig, sig16, P, f16, winner, inv_norm, merge, normalize, nullptr, nullptr,
                            0, nullptr, nullptr, nullptr, 0, 0.f, st);
   size_t smem = sizeof(float) * d;
+  UGN_CHECK(smem <= 48 * 1024, "fuse_fwd: signature width %d exceeds the 12288 floats one shared-memory row holds", d);
   long long plane = (long long)B * d;
   if (P == 0) fuse_fwd_kernel<0><<<B, 256, smem, st>>>(ptrs, nmods, d, sig, sig16, winner, inv_norm, merge, normalize, plane, f16);
   else if (P == 1) fuse_fwd_kernel<1><<<B, 256, smem, st>>>(ptrs, nmods, d, sig, sig16, winner, inv_norm, merge, normalize, plane, f16);

@@ -156,6 +156,7 @@ extern "C" int ugn_gs_conv1_fwd(ugn_ctx* ctx, const ugn_tensor* x, const ugn_ten
   const int Ws = W + 4, rows = std::max(1, 256 / Ws);
   const long long ntiles = F * ugn_cdiv(H + 4, rows);
   size_t smem = sizeof(float) * (25 * c * 32 + (size_t)(rows + 4) * (Ws + 4) * c);
+  UGN_CHECK(smem <= 48 * 1024, "gs_conv1_fwd: frame too wide");
   int grid = (int)std::min<long long>(ntiles, (long long)ctx->sm_count * 8);
   if (c == 1)
     gs_conv1_fwd_kernel<1><<<grid, 256, smem, (cudaStream_t)stream>>>(ugn_ptr<float>(x), ugn_ptr<float>(w), ugn_ptr<void>(yp), F, H, W, S,

@@ -1667,6 +1667,42 @@ class UGaitEngine:
         st["hb"][k] = hb
         self._io_k, self._io_key = k, key
 
+    # The same copy in PREFIX pieces, for a loader that fills the block front to back (header, then one volume after the
+    # other): prefetch_open(hb); fill header + volume 0; prefetch_upto(io.x_off[1]); fill volume 1; ...; prefetch_close().
+    # Each piece is a cudaMemcpyAsync that runs while the host produces the next one (the compat model's f64 -> f32 cast
+    # of modality m+1 overlaps the H2D copy of modality m).  The bytes that arrive are those of prefetch_batch(hb).
+    def prefetch_open(self, hb: HostBatch, train: bool = True):
+        p = self.plan(hb.io.B, train)
+        if not hasattr(self, "_io_stage"):
+            self._io_copy_stream = torch.cuda.Stream(device=self.dev)
+            self._io_stage, self._io_k = {}, 0
+        key = (hb.io.B, train)
+        st = self._io_stage.get(key)
+        if st is None:
+            st = self._io_stage[key] = {"buf": [torch.empty(p.io.nbytes_full, dtype=torch.uint8, device=self.dev) for _ in range(2)],
+                                        "ready": [torch.cuda.Event(), torch.cuda.Event()],
+                                        "free": [torch.cuda.Event(), torch.cuda.Event()], "hb": [None, None]}
+        k = self._io_k ^ 1
+        self._io_copy_stream.wait_event(st["free"][k])               # the step that consumed this block is done
+        self._io_open = [st, k, hb, key, 0]
+
+    def prefetch_upto(self, end: int):
+        """Copy the not yet copied bytes below `end` of the HostBatch given to prefetch_open (asynchronous)."""
+        st, k, hb, _, done = self._io_open
+        end = min(int(end), hb.nbytes)
+        if end > done:
+            with torch.cuda.stream(self._io_copy_stream):
+                st["buf"][k][done:end].copy_(hb.buf[done:end], non_blocking=True)
+            self._io_open[4] = end
+
+    def prefetch_close(self):
+        st, k, hb, key, _ = self._io_open
+        self.prefetch_upto(hb.nbytes)
+        st["ready"][k].record(self._io_copy_stream)
+        st["hb"][k] = hb
+        self._io_k, self._io_key = k, key
+        self._io_open = None
+
     def _consume_prefetched(self):
         key, k = self._io_key, self._io_k
         st = self._io_stage[key]
