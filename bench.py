@@ -479,7 +479,8 @@ def main():
                     "serial_7_copies": {"value": rows_total / (ms_e2e_serial * 1e-3), "ms_per_step": ms_e2e_serial,
                                         "h2d_bytes_per_step": int(h2d),
                                         "api": "UGaitEngine.train_step(pinned host tensors): 7 H2D copies, not overlapped"}},
-            "gpu_launches": int(launches), "clocks": sampler.summary(),
+            "gpu_launches": int(launches), "gpu_launches_per_step": int(launches) // max(1, args.steps),
+            "clocks": sampler.summary(),
             "model_tflops": TRAIN_FLOP_ROW * rows_total / (ms * 1e-3) / 1e12}
     if extract:
         line["extract"] = extract
@@ -624,7 +625,8 @@ def compat_leg(args):
             "math_mode": model.engine.math_mode, "rows_per_step": B,
             "fit": {"value": B / dt, "unit": "rows/s", "ms_per_step": dt * 1e3, "host_f64_bytes_per_step": int(f64_bytes),
                     "h2d_bytes_per_step": int(f64_bytes // 2), "d2h_bytes_per_step": 32,
-                    "path": "f64 -> f32 cast across the host cores straight into the pinned input block, ONE H2D copy, "
+                    "path": "f64 -> f32 cast across the host cores straight into ONE pinned input block whose prefix "
+                            "pieces are copied as they are produced (the H2D of modality m under the cast of m+1), "
                             "cast + copy of batch i+1 overlapping step i, ONE packed loss read per batch"},
             "predict": {"value": B / dtp, "unit": "rows/s", "ms_per_call": dtp * 1e3,
                         "ms_calls": [round(c * 1e3, 2) for c in calls],
@@ -752,7 +754,8 @@ def gaitset_leg(pk, args):
            "value": B / (ms * 1e-3), "unit": "rows/s", "ms_per_step": ms, "steps": steps,
            "e2e": {"value": B / (ms_e2e * 1e-3), "unit": "rows/s", "ms_per_step": ms_e2e, "h2d_bytes_per_step": h2d,
                    "d2h_bytes_per_step": 8, "api": "GaitSetEngine.train_step (pinned host inputs, serial)"},
-           "gpu_launches": int(launches), "model_tflops": train_row * B / (ms * 1e-3) / 1e12,
+           "gpu_launches": int(launches), "gpu_launches_per_step": int(launches) // steps,
+           "model_tflops": train_row * B / (ms * 1e-3) / 1e12,
            "train_gflop_per_row": train_row / 1e9}
     # per-op pass (eager, branches in sequence) -> share of the conv kernels and their tensor roofline
     eager = GaitSetEngine(cfg, math_mode=args.mode, lr=1e-4, use_graph=False) if eng.use_graph else eng
