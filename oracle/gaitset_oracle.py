@@ -48,6 +48,8 @@ class GaitSetConfig:
     wver: float = 1.0
     wid: float = 0.1
     label_smoothing: float = 0.0                 # smoothlabels (:1252-1262)
+    single: bool = False                         # UWYHSemiNet.build on ONE input shape (:890-905): the branch output IS
+    #                                              the signature -- no use-flag gate, no fusion, no l2_normalize, no FC1
 
     @property
     def nmods(self):
@@ -131,8 +133,16 @@ def gaitset_branch_forward(x, P, bn, cfg: GaitSetConfig, return_acts: bool = Fal
 
 
 def model_forward(inputs, flags, P, cfg: GaitSetConfig, return_all: bool = False):
-    """UWYHSemiNet3Mods.build with gaitset=True (:1163-1214)."""
+    """UWYHSemiNet3Mods.build with gaitset=True (:1163-1214); cfg.single: the 1-modality graph of UWYHSemiNet.build
+    (:890-905: ``ofout1 = ofBranch; outsignature = ofout1``, then transpose + Flatten + "classprob")."""
     outs = {}
+    if cfg.single:
+        assert cfg.nmods == 1 and cfg.nc == 0
+        sig = gaitset_branch_forward(inputs[0], P, BRANCH_NAMES[0], cfg)
+        outs["branch0"] = outs["signature"] = sig
+        if cfg.nclasses > 0:
+            outs["logits"] = F.linear(sig.permute(1, 0, 2).flatten(1), P["classprob/w"], P["classprob/b"])
+        return outs if return_all else (outs["signature"], outs.get("logits"))
     gated = []
     for m in range(cfg.nmods):
         b = gaitset_branch_forward(inputs[m], P, BRANCH_NAMES[m], cfg)

@@ -182,6 +182,55 @@ def test_gaitset_builder_protocol(compat_path, tmp_path):
     assert [a.shape for a in w] == [(5, 5, 2, 32)]                               # Keras (kh,kw,cin,cout) kernel
 
 
+def test_gaitset_single_modality_builder(compat_path, tmp_path):
+    """The README "blsingle" recipe: mains/mj_trainUWYHGaitNet_DataGen_CasiaB_1mod.py:329-333 calls
+    UWYHSemiNet.build_or_load(ONE shape (25,60,60,1), ..., [dropout0, dropout], ..., postriplet, gaitset=True); build_or_load
+    switches to the LeakyReLU path (:588-589) and build() makes the 1-modality GaitSet graph (:776-777, :890-905): the
+    branch output [62,B,256] is the signature, no gate / fusion / normalisation, "classprob" on transpose + Flatten."""
+    from nets.mj_uwyhNets_ba import UWYHSemiNet
+    from ugaitnet_b200.compat import Model, optimizers
+    from oracle import gaitset_oracle as G
+    import nets.mj_uwyhNets_ba as mod
+    mod.MATH_MODE = "fp32"
+    model = UWYHSemiNet.build_or_load((3, 12, 12, 1), 4, [(7, 7), (5, 5), (3, 3), (2, 2)], [96, 192, 512, 512], [256],
+                                      0.00005, [0.0, 0.4], optimizer=optimizers.Adam(lr=1e-3), margin=0.2, nclasses=12,
+                                      loss_weights=[1.0, 0.1], initnet="", freeze_convs=False, use3D=False,
+                                      smoothlabels=0, freeze_all=False, postriplet=1, gaitset=True)
+    assert model.gaitset and not model.multimodal and model.cfg.single and model.cfg.nmods == 1
+    oc = G.GaitSetConfig(in_channels=(1,), frames=3, hw=12, nc=0, nclasses=12, wver=1.0, wid=0.1, single=True)
+    xs, fl, lab = G.synth_batch(oc, 3, 2, seed=5)
+
+    class Gen:
+        def __len__(self):
+            return 2
+
+        def __getitem__(self, i):       # the 1-modality generator yields the volume alone (no use-flags)
+            return xs[0].numpy(), [lab.numpy().reshape(-1, 1).astype(np.float32), np.eye(12, dtype=np.float32)[lab.numpy()]]
+
+        def on_epoch_end(self):
+            pass
+
+    gen = Gen()
+    X, _ = gen[0]
+    P = {k: v.double().cpu() for k, v in model.engine.export_params().items()}
+    outs = G.model_forward([xs[0].double()], None, P, oc, return_all=True)
+    sig, prob = model.predict(X)
+    assert sig.shape == (62, 6, 256) and np.allclose(sig, outs["signature"].numpy(), atol=2e-5)
+    assert np.allclose(prob, torch.softmax(outs["logits"], 1).numpy(), atol=2e-5)
+    flat = Model(model.input, model.get_layer("flatten").output).predict(X)       # typecode 3 descriptor
+    assert flat.shape == (6, 62 * 256) and np.allclose(flat, outs["signature"].permute(1, 0, 2).flatten(1).numpy(), atol=2e-5)
+    logs = model.train_on_batch(X, gen[0][1])
+    assert np.isfinite(logs["loss"]) and "classprob_acc" in logs
+    model, hist = UWYHSemiNet.fit_generator(model, 3, [], gen, None, 0, len(gen), 1)
+    assert min(hist.history["loss"][1:]) < hist.history["loss"][0]
+    path = str(tmp_path / "gs1_weights.hdf5")
+    model.save_weights(path)
+    m2 = UWYHSemiNet.build((3, 12, 12, 1), 4, [7, 5, 3, 2], [96, 192, 512, 512], [256], nclasses=12,
+                           loss_weights=[1.0, 0.1], fActivation='lrelu', gaitset=True)
+    m2.load_weights(path, by_name=True)
+    assert np.array_equal(m2.predict(X)[0], model.predict(X)[0])
+
+
 def test_model_save_loadnet_initnet_freeze_and_init_branches(compat_path, tmp_path):
     """model.save -> loadnet (:1008-1029), build_or_load(initnet=..., freeze_convs / freeze_all) (:1325-1391) with
     classifier "surgery" (a different nclasses keeps every compatible layer), init_branches (:57-75) and the optimiser

@@ -200,6 +200,36 @@ def test_gaitset_hpp_layout_and_shapes():
     assert torch.allclose((sig ** 2).sum(1), torch.ones(62, 256, dtype=torch.float64))
 
 
+def test_gaitset_single_modality_graph_is_the_bare_branch():
+    """UWYHSemiNet.build on ONE input shape with gaitset (nets/mj_uwyhNets_ba.py:890-905): ``ofout1 = ofBranch;
+    outsignature = ofout1`` -- no use-flag gate, no fusion, no l2_normalize; "classprob" on transpose([1,0,2]) + Flatten;
+    losses = [triplet over the 62 parts, plain categorical cross-entropy].  Gradients against central differences."""
+    from oracle import gaitset_oracle as G
+    cfg = G.GaitSetConfig(in_channels=(1,), frames=2, hw=12, nc=0, nclasses=5, wver=1.0, wid=0.1, single=True)
+    P = G.init_params(cfg, seed=3, dtype=torch.float64)
+    xs, fl, lab = G.synth_batch(cfg, ids=2, per_id=2, seed=3, dtype=torch.float64)
+    sig, logits = G.model_forward(xs, None, P, cfg)
+    branch = G.gaitset_branch_forward(xs[0], P, "ofBranch", cfg)
+    assert torch.equal(sig, branch) and sig.shape == (62, 4, 256)
+    assert not torch.allclose((sig ** 2).sum(1), torch.ones(62, 256, dtype=torch.float64))      # NOT normalised
+    lit = torch.tensor(np.transpose(sig.numpy(), (1, 0, 2)).reshape(4, -1)) @ P["classprob/w"].t() + P["classprob/b"]
+    assert torch.allclose(logits, lit, rtol=0, atol=1e-12)
+    res, grads = G.loss_and_grads(xs, fl, lab, P, cfg)
+    trip, cnt = O.triplet_loss_all(lab, sig, cfg.margin)
+    ce = -torch.log_softmax(logits, 1)[torch.arange(4), lab].mean()
+    assert abs(float(res["loss"]) - float(trip + 0.1 * ce)) < 1e-12 and float(res["reg"]) == 0.0
+    # central differences on a few coordinates of the classifier and the per-part MatMul (smooth everywhere); the conv
+    # kernels are checked through a directional derivative of the triplet + CE loss
+    for name in ("classprob/w", "ofBranch/matmul/w", "ofBranch/a6/w", "ofBranch/a1/w"):
+        d = grads[name] / grads[name].norm()            # steepest direction: the derivative is |grad|, not ~0
+        eps = 1e-5      # the a == p diagonal distances are sqrt(rounding residue) ~ 1e-8: a noise floor of ~3e-11 on the loss
+        Pp, Pm = dict(P), dict(P)
+        Pp[name], Pm[name] = P[name] + eps * d, P[name] - eps * d
+        fd = (float(G.total_loss(xs, fl, lab, Pp, cfg)["loss"]) - float(G.total_loss(xs, fl, lab, Pm, cfg)["loss"])) / (2 * eps)
+        an = float((grads[name] * d).sum())
+        assert an > 0 and abs(fd - an) <= 1e-3 * an, (name, fd, an)
+
+
 # ---- committed step fixtures: the restatement must not drift
 @pytest.mark.parametrize("name", ["step_stacked", "step_gaitset"])
 def test_oracle_reproduces_step_fixture(golden_dir, name):

@@ -711,18 +711,25 @@ def _cfg_from_args(input_shapes, number_convolutional_layers, filters_size, filt
 
 
 def _gs_cfg_from_args(input_shapes, ndense_units, dropout, margin, nclasses, loss_weights, fMerge, fActivation, alpha,
-                      smoothlabels=0):
-    """gaitset=True: input_shapes [(25,60,60,2), (25,60,60,1), ...] (mains/mj_trainUWYHGaitNet_DataGen_CasiaB.py:212-213)."""
+                      smoothlabels=0, single=False):
+    """gaitset=True: input_shapes [(25,60,60,2), (25,60,60,1), ...] (mains/mj_trainUWYHGaitNet_DataGen_CasiaB.py:212-213);
+    single: ONE shape (25,60,60,c) -> the 1-modality graph (UWYHSemiNet.build :776-777, :890-905: the branch output is the
+    signature; no gate / fusion / l2_normalize, no FC1 (`if False and add_extra_dense`), plain cross-entropy)."""
     if fActivation == 'relu':
         raise ValueError("gaitset=True needs a non-'relu' fActivation: the reference only builds the GaitSet "
                          "branches in its LeakyReLU path (nets/mj_uwyhNets_ba.py:1101-1113)")
-    shapes = list(input_shapes)
+    shapes = [tuple(input_shapes)] if single else list(input_shapes)
     if any(len(s) != 4 for s in shapes):
         raise ValueError("gaitset=True expects input shapes (frames, H, W, channels)")
     nc = ndense_units[1] if isinstance(ndense_units, (list, tuple)) and len(ndense_units) > 1 else 0
     if isinstance(dropout, (list, tuple)):
         dropout = dropout[-1]
     lw = list(loss_weights) if isinstance(loss_weights, (list, tuple)) else [loss_weights, loss_weights]
+    if single:
+        return GaitSetConfig(in_channels=(int(shapes[0][3]),), frames=int(shapes[0][0]), hw=int(shapes[0][1]), nc=0,
+                             nclasses=int(nclasses), alpha=float(alpha), margin=float(margin),
+                             wver=float(lw[0]) if nclasses > 0 else 1.0,
+                             wid=float(lw[1]) if nclasses > 0 and len(lw) > 1 else 0.0, dropout=0.0, single=True)
     return GaitSetConfig(in_channels=tuple(int(s[3]) for s in shapes), frames=int(shapes[0][0]), hw=int(shapes[0][1]),
                          nc=int(nc), nclasses=int(nclasses), merge=merge_id_of(fMerge), alpha=float(alpha),
                          margin=float(margin), wver=float(lw[0]) if nclasses > 0 else 1.0,
@@ -871,10 +878,10 @@ class UWYHSemiNet:
                       fMerge=fMerge, fActivation=fActivation, alpha=alpha, gaitset=gaitset, use3D=use3D)
         losses = [triplet_loss(margin=margin), 'categorical_crossentropy'] if nclasses > 0 else triplet_loss(margin=margin)
         if gaitset:
-            _unsupported(gaitset_single_modality=single, postriplet_2_with_gaitset=(postriplet == 2))
+            _unsupported(postriplet_2_with_gaitset=(postriplet == 2 and not single))
             cfg = _gs_cfg_from_args(input_shapes, ndense_units, dropout, margin, nclasses, loss_weights, fMerge,
-                                    fActivation, alpha, smoothlabels)
-            model = UGaitModel(cfg, optimizer, losses, loss_weights if nclasses > 0 else 1.0, multimodal=True)
+                                    fActivation, alpha, smoothlabels, single=single)
+            model = UGaitModel(cfg, optimizer, losses, loss_weights if nclasses > 0 else 1.0, multimodal=not single)
         else:
             cfg = _cfg_from_args(input_shapes, number_convolutional_layers, filters_size, filters_numbers, ndense_units,
                                  weight_decay, dropout, margin, nclasses, loss_weights, fMerge, fActivation, alpha, single,

@@ -36,6 +36,9 @@ class GaitSetEngine(UGaitEngine):
 
     def __init__(self, cfg: GaitSetConfig, force_split: Optional[int] = None, **kw):
         self.force_split = force_split       # tests: exercise the split layout on small frames / in fp32 mode
+        if cfg.single and (cfg.nmods != 1 or cfg.nc > 0):
+            raise ValueError("GaitSetConfig.single: the 1-modality graph has one branch and no FC1 "
+                             "(nets/mj_uwyhNets_ba.py:890-911)")
         super().__init__(cfg, **kw)
 
     # ------------------------------------------------------------------ parameters
@@ -282,8 +285,9 @@ class GaitSetEngine(UGaitEngine):
                 self._forward_branch(p, m, train, expanded)
         self._join(streams)
         st = stream_ptr()
-        check(lib.ugn_fuse3_fwd(h, cfg.nmods, p.br_ptrs, p.flag_ptrs, p.R["sig"].ptr, p.R["winner"].ptr,
-                                p.R["col_norm"].ptr, cfg.merge, st))
+        if not cfg.single:      # 1-modality graph (UWYHSemiNet.build, :890-905): the branch output IS the signature
+            check(lib.ugn_fuse3_fwd(h, cfg.nmods, p.br_ptrs, p.flag_ptrs, p.R["sig"].ptr, p.R["winner"].ptr,
+                                    p.R["col_norm"].ptr, cfg.merge, st))
         sig = p.R["sig"]
         feat = p.R["sig2d"]
         if cfg.nc > 0:
@@ -347,8 +351,9 @@ class GaitSetEngine(UGaitEngine):
             else:
                 p.dsig.add_(p.dfeat)
         self._reduce_bucket("heads")
-        check(lib.ugn_fuse3_bwd(h, cfg.nmods, p.R["dsig"].ptr, p.R["sig"].ptr, p.R["winner"].ptr, p.R["col_norm"].ptr,
-                                p.flag_ptrs, p.dbr_ptrs, cfg.merge, st))
+        if not cfg.single:      # (1-modality graph: dsig is the branch's output gradient buffer itself)
+            check(lib.ugn_fuse3_bwd(h, cfg.nmods, p.R["dsig"].ptr, p.R["sig"].ptr, p.R["winner"].ptr, p.R["col_norm"].ptr,
+                                    p.flag_ptrs, p.dbr_ptrs, cfg.merge, st))
         # MatMul + HPP backward stay in f32; the conv stacks below consume 16-bit gradient operands
         streams = self._fork() if self._branches_concurrent() else None
         for m in range(cfg.nmods):
@@ -515,7 +520,9 @@ class _GsPlan:
             self.br.append(b)
         Tn = {}
         nd = cfg.hidden
-        self.sig = Tn["sig"] = torch.zeros(GS_PARTS, B, nd, **f32)
+        # 1-modality graph (cfg.single): no gate / fusion / l2_normalize -- the signature and its gradient are the
+        # branch's own output / output-gradient buffers
+        self.sig = Tn["sig"] = self.br[0].out if cfg.single else torch.zeros(GS_PARTS, B, nd, **f32)
         Tn["sig2d"] = self.sig.view(GS_PARTS * B, nd)
         Tn["winner"] = torch.zeros(GS_PARTS, B, nd, device=d, dtype=torch.uint8)
         Tn["col_norm"] = torch.zeros(GS_PARTS, nd, 2, **f32)
@@ -533,7 +540,7 @@ class _GsPlan:
         if train:
             self.loss_pack = Tn["loss_pack"] = torch.zeros(8, **f32)     # {triplet, count, ce, acc, reg}
             self.trip_out = Tn["trip_out"] = self.loss_pack[0:2]
-            self.dsig = Tn["dsig"] = torch.zeros(GS_PARTS, B, nd, **f32)
+            self.dsig = Tn["dsig"] = self.br[0].dout if cfg.single else torch.zeros(GS_PARTS, B, nd, **f32)
             Tn["trip_ws"] = torch.zeros(ops.triplet_workspace_bytes(GS_PARTS, B) // 4 + 16, **f32)
             if cfg.nclasses > 0:
                 self.ce_out = Tn["ce_out"] = self.loss_pack[2:4]
