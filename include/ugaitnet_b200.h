@@ -80,6 +80,9 @@ typedef struct ugn_ctx ugn_ctx;
 
 enum { UGN_ACT_LINEAR = 0, UGN_ACT_RELU = 1, UGN_ACT_LEAKY = 2 };
 enum { UGN_MERGE_MAX = 0, UGN_MERGE_AVG = 1, UGN_MERGE_SIGNMAX = 2 };
+/* OR-ed into the `merge` argument of ugn_fuse3_fwd / ugn_fuse3_bwd: gate + fusion only, no l2_normalize -- the
+ * postriplet == 2 graph normalises AFTER the Dense layer "signature" (nets/mj_uwyhNets_ba.py:814-832). */
+enum { UGN_FUSE3_NO_NORM = 0x100 };
 
 int ugn_abi_version(void);
 const char* ugn_last_error(void);
@@ -455,7 +458,8 @@ int ugn_bmm_f32(ugn_ctx*, const ugn_tensor* A, int a_t, const ugn_tensor* B, int
 /* Gate x use-flag (:51-54), fusion (:1189) and tf.math.l2_normalize(axis=1) (:1191) on the GaitSet
  * layout: br[m] f32 [n,B,d], flags[m] f32 [B,1].  axis 1 of [n,B,d] is the BATCH axis: every
  * (part, feature) column is normalised over the rows of the batch -- the reference's literal
- * behaviour.  sig f32 [n,B,d], winner u8 [n,B,d], col_norm f32 [n,d,2] = {1/norm, sum x^2}. */
+ * behaviour.  sig f32 [n,B,d], winner u8 [n,B,d], col_norm f32 [n,d,2] = {1/norm, sum x^2}.
+ * merge = UGN_MERGE_* [| UGN_FUSE3_NO_NORM: sig is the un-normalised fusion, col_norm = {1, sum x^2}]. */
 int ugn_fuse3_fwd(ugn_ctx*, int nmods, const ugn_tensor* const* br, const ugn_tensor* const* flags,
                   ugn_tensor* sig, ugn_tensor* winner, ugn_tensor* col_norm, int merge, void* stream);
 int ugn_fuse3_bwd(ugn_ctx*, int nmods, const ugn_tensor* dsig, const ugn_tensor* sig,

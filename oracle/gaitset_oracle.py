@@ -48,6 +48,9 @@ class GaitSetConfig:
     wver: float = 1.0
     wid: float = 0.1
     label_smoothing: float = 0.0                 # smoothlabels (:1252-1262)
+    postriplet: int = 1                          # 2 (with nc > 0; 2-modality builder :814-832): the fusion is NOT normalised,
+    #                                              FC1 is the layer "signature", its l2_normalize(axis=1) "code" is the
+    #                                              embedding the triplet loss and the classifier see
     single: bool = False                         # UWYHSemiNet.build on ONE input shape (:890-905): the branch output IS
     #                                              the signature -- no use-flag gate, no fusion, no l2_normalize, no FC1
 
@@ -150,6 +153,14 @@ def model_forward(inputs, flags, P, cfg: GaitSetConfig, return_all: bool = False
         gated.append(b * flags[m].reshape(1, -1, 1))                # mj_tensor_times_scalar broadcast (:51-54)
     fused = merge_modalities(gated, cfg.merge)
     outs["fusion"] = fused
+    if cfg.postriplet == 2 and cfg.nc > 0:                          # :819-832 (LeakyReLU path :825-827)
+        lin = F.linear(fused, P["code/w"], P["code/b"])             # Dense(nc, activation=None, activity_regularizer, name="signature")
+        outs["code_lin"] = outs["signature_layer"] = lin
+        sig = l2_normalize(F.leaky_relu(lin, cfg.alpha), 1)         # Lambda(l2_normalize(axis=1), name="code") = outsignature
+        outs["signature"] = outs["code"] = sig
+        if cfg.nclasses > 0:                                        # Dropout("dropcode") -> transpose + Flatten -> "classprob"
+            outs["logits"] = F.linear(sig.permute(1, 0, 2).flatten(1), P["classprob/w"], P["classprob/b"])
+        return outs if return_all else (outs["signature"], outs.get("logits"))
     sig = l2_normalize(fused, 1)                                    # axis=1 == the batch axis here (:1191)
     outs["signature"] = sig
     feat = sig

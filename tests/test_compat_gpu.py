@@ -307,11 +307,44 @@ def test_postriplet2_builder(compat_path):
     code = Model(model.input, model.get_layer("code").output).predict(X)
     assert code.shape == (16, 8) and np.allclose(code, outs["code"].numpy(), atol=2e-5)
     assert np.allclose(np.linalg.norm(code, axis=1), 1.0, atol=1e-5)
+    sig, prob = model.predict(X)                 # output 0 of the postriplet-2 model is the normalised code (:829)
+    assert sig.shape == (16, 8) and np.allclose(sig, outs["code"].numpy(), atol=2e-5)
+    assert np.allclose(prob, torch.softmax(outs["logits"], 1).numpy(), atol=2e-5)
     logs = model.train_on_batch(X, y)
     res, _ = O.loss_and_grads([torch.tensor(X[0]), torch.tensor(X[2])], [torch.tensor(X[1]), torch.tensor(X[3])],
                               torch.tensor(y[0]), P, oc)
     assert logs["signature_loss"] == pytest.approx(float(res["triplet"]), rel=1e-5)
     assert logs["loss"] == pytest.approx(float(res["loss"]), rel=1e-5)
+
+
+def test_postriplet2_gaitset_builder(compat_path):
+    """UWYHSemiNet.build(two shapes, [nd, nc], postriplet=2, gaitset=True) (:748-765 + :814-832): output 0 is the
+    normalised code [62, B, nc]; losses against the oracle restatement."""
+    from nets.mj_uwyhNets_ba import UWYHSemiNet
+    from ugaitnet_b200.compat import Model, optimizers, sign_max
+    from oracle import gaitset_oracle as G
+    import nets.mj_uwyhNets_ba as mod
+    mod.MATH_MODE = "fp32"
+    model = UWYHSemiNet.build([(3, 12, 12, 2), (3, 12, 12, 1)], 4, [(7, 7), (5, 5), (3, 3), (2, 2)], [96, 192, 512, 512],
+                              [256, 16], 0.00005, 0.0, optimizer=optimizers.Adam(lr=1e-3), margin=0.2, nclasses=10,
+                              loss_weights=[1.0, 0.5], postriplet=2, fMerge=sign_max, fActivation='lrelu', gaitset=True)
+    assert model.engine.post2 and model.cfg.postriplet == 2
+    oc = G.GaitSetConfig(in_channels=(2, 1), frames=3, hw=12, nc=16, nclasses=10, merge=O.MERGE_SIGNMAX, wver=1.0, wid=0.5,
+                         postriplet=2)
+    xs, fl, lab = G.synth_batch(oc, 3, 2, seed=5)
+    X = [xs[0].numpy(), fl[0].numpy(), xs[1].numpy(), fl[1].numpy()]
+    y = [lab.numpy().reshape(-1, 1).astype(np.float32), np.eye(10, dtype=np.float32)[lab.numpy()]]
+    P = {k: v.double().cpu() for k, v in model.engine.export_params().items()}
+    outs = G.model_forward([x.double() for x in xs], [f.double() for f in fl], P, oc, return_all=True)
+    sig, prob = model.predict(X)
+    assert sig.shape == (62, 6, 16) and np.allclose(sig, outs["code"].numpy(), atol=2e-5)
+    assert np.allclose(prob, torch.softmax(outs["logits"], 1).numpy(), atol=2e-5)
+    dense = Model(model.input, model.get_layer("signature").output).predict(X)    # the Dense layer named "signature"
+    assert dense.shape == (62, 6, 16) and np.allclose(dense, outs["signature_layer"].numpy(), atol=2e-5)
+    res, _ = G.loss_and_grads([x.double() for x in xs], [f.double() for f in fl], lab, P, oc)
+    logs = model.train_on_batch(X, y)
+    assert logs["signature_loss"] == pytest.approx(float(res["triplet"]), rel=1e-5)
+    assert logs["classprob_loss"] == pytest.approx(float(res["ce"]), rel=1e-5)
 
 
 def test_compile_hard(compat_path):

@@ -226,6 +226,9 @@ def make_case(name):
     if name == "small_1mod_single":    # UWYHSemiNet.build on ONE shape (README recipe "blsingle": CasiaB_1mod --gaitset)
         return G.GaitSetConfig(in_channels=(1,), frames=3, hw=12, nc=0, nclasses=12, wver=1.0, wid=0.1,
                                single=True), dict(ids=3, per_id=2)
+    if name == "small_2mod_post2":     # UWYHSemiNet.build(two shapes, ndense_units=[nd, nc], postriplet=2, gaitset=True) (:814-832)
+        return G.GaitSetConfig(in_channels=(2, 1), frames=3, hw=12, nc=16, nclasses=10, merge=O.MERGE_SIGNMAX,
+                               wver=1.0, wid=0.5, postriplet=2), dict(ids=3, per_id=2)
     if name == "real_shapes":       # 25 x 60 x 60 clips, the reference's branch at full size, tiny batch
         return G.GaitSetConfig(in_channels=(2, 1), frames=25, hw=60, nc=0, nclasses=20, merge=O.MERGE_SIGNMAX,
                                wver=1.0, wid=0.1), dict(ids=2, per_id=2)
@@ -236,7 +239,8 @@ def to_engine_cfg(oc):
     from ugaitnet_b200.config import GaitSetConfig
     return GaitSetConfig(in_channels=tuple(oc.in_channels), frames=oc.frames, hw=oc.hw, hidden=oc.hidden, nc=oc.nc,
                          nclasses=oc.nclasses, merge=oc.merge, alpha=oc.alpha, margin=oc.margin, wver=oc.wver,
-                         wid=oc.wid, label_smoothing=oc.label_smoothing, single=getattr(oc, "single", False))
+                         wid=oc.wid, label_smoothing=oc.label_smoothing, single=getattr(oc, "single", False),
+                         postriplet=getattr(oc, "postriplet", 1))
 
 
 def setup(name, math_mode="fp32", seed=7, dtype=torch.float64, split=None):
@@ -305,6 +309,37 @@ def test_gaitset_single_modality_graph_fp32():
     for _ in range(4):
         o = eng.train_step(cu(xs), None, lab.cuda())
         tot.append(float(o["triplet"]) + 0.1 * float(o["ce"]))
+    assert min(tot[1:]) < tot[0], tot
+
+
+def test_gaitset_postriplet2_graph_fp32():
+    """postriplet == 2 with GaitSet branches (nets/mj_uwyhNets_ba.py:814-832): gate + fusion WITHOUT l2_normalize
+    (UGN_FUSE3_NO_NORM), Dense "signature" (linear, activity-regularised), LeakyReLU, l2_normalize(axis=1) "code" = the
+    embedding of the triplet loss and the input of the classifier.  Seeds as in the 1-modality test."""
+    worst = []
+    for seed in (7, 9, 11):
+        oc, eng, P, xs, fl, lab = setup("small_2mod_post2", seed=seed)
+        res, grads = G.loss_and_grads(xs, fl, lab, P, oc)
+        outs = G.model_forward(xs, fl, P, oc, return_all=True)
+        out = eng.loss_and_grad(cu(xs), cu(fl), lab.cuda())
+        eng.ctx.check()
+        assert out["signature"].shape == (62, 6, 16) and rel(out["signature"], res["signature"]) < 1e-5
+        assert abs(float(out["triplet"]) - float(res["triplet"])) <= 1e-5 * abs(float(res["triplet"]))
+        assert abs(float(out["ce"]) - float(res["ce"])) <= 1e-5 * abs(float(res["ce"]))
+        assert float(out["count"]) == float(res["count"].sum())
+        got = eng.export_grads()
+        assert set(got) == set(grads)
+        worst.append(max(rel(got[k], g) for k, g in grads.items()))
+        assert worst[-1] < 2e-2, worst
+        assert rel(eng.predict(cu(xs), cu(fl), "signature"), outs["signature_layer"]) < 1e-5     # the Dense layer
+        assert rel(eng.predict(cu(xs), cu(fl), "code"), outs["code"]) < 1e-5                     # its normalised LeakyReLU
+        assert rel(eng.predict(cu(xs), cu(fl), "flatten"), outs["code"].permute(1, 0, 2).flatten(1)) < 1e-5
+        assert rel(eng.predict(cu(xs), cu(fl), "classprob"), outs["logits"]) < 1e-5
+    assert sorted(worst)[1] < 1e-4, worst
+    tot = []
+    for _ in range(4):
+        o = eng.train_step(cu(xs), cu(fl), lab.cuda())
+        tot.append(float(o["triplet"]) + 0.5 * float(o["ce"]))
     assert min(tot[1:]) < tot[0], tot
 
 

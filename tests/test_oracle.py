@@ -230,6 +230,41 @@ def test_gaitset_single_modality_graph_is_the_bare_branch():
         assert an > 0 and abs(fd - an) <= 1e-3 * an, (name, fd, an)
 
 
+def test_gaitset_postriplet2_graph_literal():
+    """postriplet == 2 with GaitSet branches (nets/mj_uwyhNets_ba.py:814-832, LeakyReLU path): fusion NOT normalised ->
+    Dense(nc, None, activity_regularizer l2(1e-3)) "signature" -> LeakyReLU -> l2_normalize(axis=1) "code" (outsignature) ->
+    transpose + Flatten -> "classprob"; against the literal numpy statements."""
+    from oracle import gaitset_oracle as G
+    cfg = G.GaitSetConfig(in_channels=(2, 1), frames=2, hw=12, nc=8, nclasses=5, merge=O.MERGE_SIGNMAX, wver=1.0, wid=0.5,
+                          postriplet=2)
+    P = G.init_params(cfg, seed=4, dtype=torch.float64)
+    xs, fl, lab = G.synth_batch(cfg, ids=2, per_id=2, seed=4, dtype=torch.float64)
+    outs = G.model_forward(xs, fl, P, cfg, return_all=True)
+    fus = outs["fusion"].numpy()                                                     # [62, B, 256], un-normalised
+    assert not np.allclose((fus ** 2).sum(1), 1.0)
+    lin = fus @ P["code/w"].numpy().T + P["code/b"].numpy()
+    act = np.where(lin > 0, lin, cfg.alpha * lin)
+    code = act / np.sqrt(np.maximum((act ** 2).sum(1, keepdims=True), 1e-12))        # axis 1 = the batch axis of [62, B, nc]
+    assert np.allclose(outs["signature_layer"].numpy(), lin, rtol=0, atol=1e-12)
+    assert np.allclose(outs["signature"].numpy(), code, rtol=0, atol=1e-12) and outs["code"] is outs["signature"]
+    logits = np.transpose(code, (1, 0, 2)).reshape(4, -1) @ P["classprob/w"].numpy().T + P["classprob/b"].numpy()
+    assert np.allclose(outs["logits"].numpy(), logits, rtol=0, atol=1e-12)
+    res, grads = G.loss_and_grads(xs, fl, lab, P, cfg)
+    trip, _ = O.triplet_loss_all(lab, torch.tensor(code), cfg.margin)
+    ce = -torch.log_softmax(torch.tensor(logits), 1)[torch.arange(4), lab].mean()
+    reg = 1e-3 * (lin ** 2).sum() / 62                                               # Keras: / shape(output)[0]
+    assert abs(float(res["loss"]) - float(trip + 0.5 * ce + reg)) < 1e-9 and abs(float(res["reg"]) - reg) < 1e-15   # (a == p distances: sqrt of rounding residue)
+    # (not code/b: lin ~ 1e-4 sits on the LeakyReLU kink; not the conv kernels: sign_max winners flip -- a discontinuity)
+    for name in ("code/w", "classprob/w", "ofBranch/matmul/w"):
+        d = grads[name] / grads[name].norm()
+        eps = 1e-5
+        Pp, Pm = dict(P), dict(P)
+        Pp[name], Pm[name] = P[name] + eps * d, P[name] - eps * d
+        fd = (float(G.total_loss(xs, fl, lab, Pp, cfg)["loss"]) - float(G.total_loss(xs, fl, lab, Pm, cfg)["loss"])) / (2 * eps)
+        an = float((grads[name] * d).sum())
+        assert an > 0 and abs(fd - an) <= 1e-3 * an, (name, fd, an)
+
+
 # ---- committed step fixtures: the restatement must not drift
 @pytest.mark.parametrize("name", ["step_stacked", "step_gaitset"])
 def test_oracle_reproduces_step_fixture(golden_dir, name):

@@ -230,7 +230,7 @@ class UGaitModel:
         if hb is None:
             hb = self._hbp[B] = eng.host_batch(B, train=False)
         self._fill_and_send(hb, xs, x, train=False)
-        sig = eng.predict_prefetched("signature")
+        sig = eng.predict_prefetched("embedding")      # the model's output 0 (postriplet == 2: the normalised "code")
         if self.cfg.nclasses > 0:
             p = eng.plan(B, False)
             prob = torch.softmax(p.logits, dim=1)
@@ -711,7 +711,7 @@ def _cfg_from_args(input_shapes, number_convolutional_layers, filters_size, filt
 
 
 def _gs_cfg_from_args(input_shapes, ndense_units, dropout, margin, nclasses, loss_weights, fMerge, fActivation, alpha,
-                      smoothlabels=0, single=False):
+                      smoothlabels=0, single=False, postriplet=1):
     """gaitset=True: input_shapes [(25,60,60,2), (25,60,60,1), ...] (mains/mj_trainUWYHGaitNet_DataGen_CasiaB.py:212-213);
     single: ONE shape (25,60,60,c) -> the 1-modality graph (UWYHSemiNet.build :776-777, :890-905: the branch output is the
     signature; no gate / fusion / l2_normalize, no FC1 (`if False and add_extra_dense`), plain cross-entropy)."""
@@ -734,7 +734,8 @@ def _gs_cfg_from_args(input_shapes, ndense_units, dropout, margin, nclasses, los
                          nc=int(nc), nclasses=int(nclasses), merge=merge_id_of(fMerge), alpha=float(alpha),
                          margin=float(margin), wver=float(lw[0]) if nclasses > 0 else 1.0,
                          wid=float(lw[1]) if nclasses > 0 and len(lw) > 1 else 0.0,
-                         dropout=float(dropout) if (dropout > 0.001 and nc) else 0.0, label_smoothing=float(smoothlabels))
+                         dropout=float(dropout) if (dropout > 0.001 and nc) else 0.0, label_smoothing=float(smoothlabels),
+                         postriplet=int(postriplet) if nc else 1)
 
 
 def _jsonable(v):
@@ -869,8 +870,10 @@ class UWYHSemiNet:
               ndense_units=512, weight_decay=1e-4, dropout=0.4, optimizer=None, margin=0.2,
               nclasses=0, loss_weights=[1.0, 1.0], use3D=False, smoothlabels=0, postriplet=1, init_branches=None,
               freeze_branches=False, aux_losses=False, fMerge=Maximum, fActivation='relu', alpha=0.3, gaitset=False):
-        _unsupported(use3D_with_gaitset=(use3D and gaitset), aux_losses_with_gaitset=(aux_losses and gaitset))
         single = not isinstance(input_shapes, list)
+        # use3D + gaitset: the 1-modality builder takes the GaitSet branch whatever use3D says (:776-784); with two
+        # modalities the graph would fuse a [62,B,256] GaitSet output with a [B,nd] Conv3D output (:764-773) -- ill-formed
+        _unsupported(use3D_with_gaitset=(use3D and gaitset and not single), aux_losses_with_gaitset=(aux_losses and gaitset))
         kwargs = dict(input_shapes=input_shapes, number_convolutional_layers=number_convolutional_layers,
                       filters_size=filters_size, filters_numbers=filters_numbers, ndense_units=ndense_units,
                       weight_decay=weight_decay, dropout=dropout, optimizer=optimizer, margin=margin, nclasses=nclasses,
@@ -878,9 +881,8 @@ class UWYHSemiNet:
                       fMerge=fMerge, fActivation=fActivation, alpha=alpha, gaitset=gaitset, use3D=use3D)
         losses = [triplet_loss(margin=margin), 'categorical_crossentropy'] if nclasses > 0 else triplet_loss(margin=margin)
         if gaitset:
-            _unsupported(postriplet_2_with_gaitset=(postriplet == 2 and not single))
             cfg = _gs_cfg_from_args(input_shapes, ndense_units, dropout, margin, nclasses, loss_weights, fMerge,
-                                    fActivation, alpha, smoothlabels, single=single)
+                                    fActivation, alpha, smoothlabels, single=single, postriplet=postriplet)
             model = UGaitModel(cfg, optimizer, losses, loss_weights if nclasses > 0 else 1.0, multimodal=not single)
         else:
             cfg = _cfg_from_args(input_shapes, number_convolutional_layers, filters_size, filters_numbers, ndense_units,

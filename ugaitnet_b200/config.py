@@ -5,6 +5,7 @@ from dataclasses import dataclass, field
 from typing import List, Sequence, Tuple
 
 MERGE_MAX, MERGE_AVG, MERGE_SIGNMAX = 0, 1, 2
+FUSE3_NO_NORM = 0x100            # include/ugaitnet_b200.h: UGN_FUSE3_NO_NORM (gate + fusion without l2_normalize)
 ACT_LINEAR, ACT_RELU, ACT_LEAKY = 0, 1, 2
 
 BRANCH_NAMES = ("ofBranch", "grayBranch", "depthBranch")
@@ -118,8 +119,10 @@ class GaitSetConfig:
     wver: float = 1.0
     wid: float = 1.0
     dropout: float = 0.0           # Dropout(name="dropcode") after FC1 (:1203); the branches have none
-    single: bool = False
+    single: bool = False           # UWYHSemiNet.build on ONE shape (:890-905): the branch output is the signature
     label_smoothing: float = 0.0   # smoothlabels (:1252-1262)
+    postriplet: int = 1            # 2 (needs nc > 0; 2-modality builder :814-832): un-normalised fusion -> Dense "signature"
+    #                                -> LeakyReLU -> l2_normalize(axis=1) "code" = the embedding of the triplet loss / classifier
 
     @property
     def nmods(self) -> int:

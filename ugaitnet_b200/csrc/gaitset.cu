@@ -727,6 +727,8 @@ __global__ void __launch_bounds__(128) gs_fuse3_fwd_kernel(FusePtrs ptrs, int nm
                                                            float* __restrict__ col, int merge) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n * d) return;
+  const bool no_norm = (merge & UGN_FUSE3_NO_NORM) != 0;      // postriplet == 2 (:814-816): the fusion stays un-normalised
+  merge &= 0xff;
   const int part = i / d, j = i - part * d;
   float ss = 0.f;
   for (int b = 0; b < B; ++b) {
@@ -748,9 +750,10 @@ __global__ void __launch_bounds__(128) gs_fuse3_fwd_kernel(FusePtrs ptrs, int nm
     winner[o] = (uint8_t)win;
     ss += best * best;
   }
-  const float inv = rsqrtf(fmaxf(ss, 1e-12f));
+  const float inv = no_norm ? 1.f : rsqrtf(fmaxf(ss, 1e-12f));
   col[2 * i] = inv;
   col[2 * i + 1] = ss;
+  if (no_norm) return;
   for (int b = 0; b < B; ++b) {
     const long long o = ((long long)part * B + b) * d + j;
     sig[o] *= inv;
@@ -763,9 +766,11 @@ __global__ void __launch_bounds__(128) gs_fuse3_bwd_kernel(FusePtrs ptrs, int nm
                                                            const float* __restrict__ col, int merge) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n * d) return;
+  const bool no_norm = (merge & UGN_FUSE3_NO_NORM) != 0;      // g passes through unchanged (inv = 1, no projection)
+  merge &= 0xff;
   const int part = i / d, j = i - part * d;
-  const float inv = col[2 * i];
-  const bool clamped = !(col[2 * i + 1] > 1e-12f);
+  const float inv = no_norm ? 1.f : col[2 * i];
+  const bool clamped = no_norm || !(col[2 * i + 1] > 1e-12f);
   float dot = 0.f;
   if (!clamped)
     for (int b = 0; b < B; ++b) {

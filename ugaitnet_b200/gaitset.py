@@ -22,7 +22,8 @@ import torch
 
 from . import ops
 from ._ffi import TRef, check, lib, ptr_array, stream_ptr
-from .config import ACT_LEAKY, ACT_LINEAR, BRANCH_NAMES, GS_ALPHA, GS_CONVS, GS_PARTS, GaitSetConfig, round_up
+from .config import (ACT_LEAKY, ACT_LINEAR, BRANCH_NAMES, FUSE3_NO_NORM, GS_ALPHA, GS_CONVS, GS_PARTS, MERGE_MAX, GaitSetConfig,
+                     round_up)
 from .net import GRAD_SCALE_TARGET, UGaitEngine, _Seg
 
 # conv name -> (input buffer, output buffer, pooled)
@@ -287,9 +288,25 @@ class GaitSetEngine(UGaitEngine):
         st = stream_ptr()
         if not cfg.single:      # 1-modality graph (UWYHSemiNet.build, :890-905): the branch output IS the signature
             check(lib.ugn_fuse3_fwd(h, cfg.nmods, p.br_ptrs, p.flag_ptrs, p.R["sig"].ptr, p.R["winner"].ptr,
-                                    p.R["col_norm"].ptr, cfg.merge, st))
+                                    p.R["col_norm"].ptr, cfg.merge | (FUSE3_NO_NORM if self.post2 else 0), st))
         sig = p.R["sig"]
         feat = p.R["sig2d"]
+        if self.post2:
+            # postriplet == 2 (:819-832): un-normalised fusion -> Dense(nc, activation=None, activity_regularizer)
+            # "signature" -> LeakyReLU -> l2_normalize(axis=1) "code" (= the embedding) -> Dropout "dropcode" -> classifier
+            check(lib.ugn_linear_fwd(h, p.R["sig2d"].ptr, self.Rw["code/w"].ptr, self.Rw["code/b"].ptr, None,
+                                     p.R["code_lin"].ptr, None, ACT_LINEAR, 0.0, st))
+            check(lib.ugn_linear_fwd(h, p.R["sig2d"].ptr, self.Rw["code/w"].ptr, self.Rw["code/b"].ptr, None,
+                                     p.R["code"].ptr, None, ACT_LEAKY, cfg.alpha, st))
+            check(lib.ugn_fuse3_fwd(h, 1, p.code_ptrs, p.one_ptrs, p.R["codeN"].ptr, p.R["cwin"].ptr, p.R["ccol"].ptr,
+                                    MERGE_MAX, st))
+            if p.dropN is not p.codeN:
+                torch.mul(p.codeN, p.cmask.view_as(p.codeN), out=p.dropN)
+            if cfg.nclasses > 0:
+                check(lib.ugn_permute102(h, p.R["dropN"].ptr, p.R["flat"].ptr, st))
+                check(lib.ugn_linear_fwd(h, p.R["flat"].ptr, self.Rw["classprob/w"].ptr, self.Rw["classprob/b"].ptr, None,
+                                         p.R["logits"].ptr, None, ACT_LINEAR, 0.0, st))
+            return p.R["codeN"], p.R["dropN"]
         if cfg.nc > 0:
             # Dense(activation=None, activity_regularizer) -> LeakyReLU(alpha) -> Dropout (:1199-1203): the linear
             # output is kept for the regulariser, the activated (and, in training, dropped) one feeds FC2
@@ -315,7 +332,18 @@ class GaitSetEngine(UGaitEngine):
         p = self.plan(B, False)
         self._set_inputs(p, inputs, flags)
         self._forward(p, False)
-        if layer == "signature":
+        return self._layer_output(p, layer)
+
+    def _layer_output(self, p, layer: str) -> torch.Tensor:
+        B = p.B
+        if self.post2:          # "signature" is the (linear) Dense layer, "code" its normalised LeakyReLU: the model's output 0
+            if layer == "signature":
+                return p.code_lin.view(GS_PARTS, B, -1).clone()
+            if layer in ("code", "embedding"):
+                return p.codeN.clone()
+            if layer == "flatten":
+                return p.codeN.permute(1, 0, 2).reshape(B, -1).clone()
+        if layer in ("signature", "embedding"):
             return p.sig.clone()
         if layer == "flatten":
             return (p.code3d if self.cfg.nc > 0 else p.sig).permute(1, 0, 2).reshape(B, -1).clone()
@@ -325,11 +353,53 @@ class GaitSetEngine(UGaitEngine):
             return p.logits.clone()
         raise KeyError(layer)
 
+    @torch.no_grad()
+    def predict_prefetched(self, layer: str = "signature") -> torch.Tensor:
+        p, hb = self._consume_prefetched()
+        self._forward(p, False)
+        return self._layer_output(p, layer)
+
     # ------------------------------------------------------------------ backward
     def _losses_and_backward(self, p, sig: TRef, feat: TRef):
         cfg, h, st = self.cfg, self.ctx.h, stream_ptr()
         B = p.B
         self._works = []
+        if self.post2:
+            self._post2_losses_and_head_backward(p)
+        else:
+            self._losses_and_head_backward(p, sig)
+        self._reduce_bucket("heads")
+        if not cfg.single:      # (1-modality graph: dsig is the branch's output gradient buffer itself)
+            check(lib.ugn_fuse3_bwd(h, cfg.nmods, p.R["dsig"].ptr, p.R["sig"].ptr, p.R["winner"].ptr, p.R["col_norm"].ptr,
+                                    p.flag_ptrs, p.dbr_ptrs, cfg.merge | (FUSE3_NO_NORM if self.post2 else 0), st))
+        self._backward_branches(p)
+
+    def _post2_losses_and_head_backward(self, p):
+        """postriplet == 2: triplet + CE on the normalised code, back through Dropout, l2_normalize(axis=1), LeakyReLU, the
+        activity regulariser of the linear Dense output (divided by shape(output)[0] = 62) and the Dense layer, into dsig =
+        the gradient of the un-normalised fusion."""
+        cfg, h, st = self.cfg, self.ctx.h, stream_ptr()
+        check(lib.ugn_triplet_all(h, p.R["codeN"].ptr, p.R["labels"].ptr, cfg.margin, cfg.wver, p.R["trip_out"].ptr,
+                                  p.R["dcodeN"].ptr, p.R["trip_ws"].ptr, st))
+        if cfg.nclasses > 0:
+            check(lib.ugn_softmax_ce_ls(h, p.R["logits"].ptr, p.R["labels"].ptr, p.R["ce_out"].ptr, p.R["dlogits"].ptr,
+                                        cfg.wid, cfg.label_smoothing, st))
+            check(lib.ugn_linear_bwd(h, p.R["flat"].ptr, self.Rw["classprob/w"].ptr, p.R["dlogits"].ptr,
+                                     p.R["dflat"].ptr, self.Rg["classprob/w"].ptr, self.Rg["classprob/b"].ptr, st))
+            check(lib.ugn_permute102(h, p.R["dflat3d"].ptr, p.R["dfeat"].ptr, st))        # [B,62,nc] -> [62,B,nc]
+            if p.dropN is not p.codeN:
+                p.dfeat.mul_(p.cmask.view_as(p.dfeat))
+            p.dcodeN.add_(p.dfeat)
+        check(lib.ugn_fuse3_bwd(h, 1, p.R["dcodeN"].ptr, p.R["codeN"].ptr, p.R["cwin"].ptr, p.R["ccol"].ptr, p.one_ptrs,
+                                p.dcode_ptrs, MERGE_MAX, st))
+        check(lib.ugn_act_mask_bwd(h, p.R["dcode"].ptr, p.R["code"].ptr, None, p.R["dcode_z"].ptr, None, ACT_LEAKY,
+                                   cfg.alpha, st))
+        p.dcode_z.add_(p.code_lin, alpha=2e-3 / GS_PARTS)
+        check(lib.ugn_linear_bwd(h, p.R["sig2d"].ptr, self.Rw["code/w"].ptr, p.R["dcode_z"].ptr, p.R["dsig2d"].ptr,
+                                 self.Rg["code/w"].ptr, self.Rg["code/b"].ptr, st))
+
+    def _losses_and_head_backward(self, p, sig: TRef):
+        cfg, h, st = self.cfg, self.ctx.h, stream_ptr()
         check(lib.ugn_triplet_all(h, sig.ptr, p.R["labels"].ptr, cfg.margin, cfg.wver, p.R["trip_out"].ptr,
                                   p.R["dsig"].ptr, p.R["trip_ws"].ptr, st))
         if cfg.nclasses > 0:
@@ -350,10 +420,9 @@ class GaitSetEngine(UGaitEngine):
                 p.dsig.add_(p.dsig2.view_as(p.dsig))
             else:
                 p.dsig.add_(p.dfeat)
-        self._reduce_bucket("heads")
-        if not cfg.single:      # (1-modality graph: dsig is the branch's output gradient buffer itself)
-            check(lib.ugn_fuse3_bwd(h, cfg.nmods, p.R["dsig"].ptr, p.R["sig"].ptr, p.R["winner"].ptr, p.R["col_norm"].ptr,
-                                    p.flag_ptrs, p.dbr_ptrs, cfg.merge, st))
+
+    def _backward_branches(self, p):
+        cfg, h, st = self.cfg, self.ctx.h, stream_ptr()
         # MatMul + HPP backward stay in f32; the conv stacks below consume 16-bit gradient operands
         streams = self._fork() if self._branches_concurrent() else None
         for m in range(cfg.nmods):
@@ -424,7 +493,7 @@ class GaitSetEngine(UGaitEngine):
         self._reduce_bucket(m)
 
     def _report(self, p, with_reg: bool = False) -> Dict[str, torch.Tensor]:
-        out = {"triplet": p.trip_out[0], "count": p.trip_out[1], "signature": p.sig}
+        out = {"triplet": p.trip_out[0], "count": p.trip_out[1], "signature": p.codeN if self.post2 else p.sig}
         if self.cfg.nclasses > 0:
             out["ce"], out["acc"], out["logits"] = p.ce_out[0], p.ce_out[1], p.logits
         if with_reg:
@@ -533,6 +602,13 @@ class _GsPlan:
             self.code3d = Tn["code3d"] = Tn["code"].view(GS_PARTS, B, cfg.nc)
             self.cmask = Tn["cmask"] = torch.ones(GS_PARTS * B, cfg.nc, **f32)
             feat = cfg.nc
+        if eng.post2:           # postriplet == 2: the normalised code [62,B,nc] is the embedding (see GaitSetEngine._forward)
+            self.codeN = Tn["codeN"] = torch.zeros(GS_PARTS, B, cfg.nc, **f32)
+            Tn["cwin"] = torch.zeros(GS_PARTS, B, cfg.nc, device=d, dtype=torch.uint8)
+            Tn["ccol"] = torch.zeros(GS_PARTS, cfg.nc, 2, **f32)
+            drop = train and cfg.dropout > 0.001
+            self.dropN = Tn["dropN"] = torch.zeros(GS_PARTS, B, cfg.nc, **f32) if drop else self.codeN
+            self.ones = Tn["ones"] = torch.ones(B, 1, **f32)
         if cfg.nclasses > 0:
             Tn["flat"] = torch.zeros(B, GS_PARTS * feat, **f32)
             self.logits = Tn["logits"] = torch.zeros(B, cfg.nclasses, **f32)
@@ -552,6 +628,13 @@ class _GsPlan:
             if cfg.nc > 0:
                 self.dcode_z = Tn["dcode_z"] = torch.zeros(GS_PARTS * B, cfg.nc, **f32)
                 self.dsig2 = Tn["dsig2"] = torch.zeros(GS_PARTS * B, nd, **f32)
+            if eng.post2:
+                self.dcodeN = Tn["dcodeN"] = torch.zeros(GS_PARTS, B, cfg.nc, **f32)
+                Tn["dcode3d"] = torch.zeros(GS_PARTS, B, cfg.nc, **f32)
+                Tn["dcode"] = Tn["dcode3d"].view(GS_PARTS * B, cfg.nc)
+                Tn["dsig2d"] = self.dsig.view(GS_PARTS * B, nd)
+                if cfg.nclasses == 0:
+                    self.dfeat = None
         if train:
             Tn["dhead"] = dhead.view(-1)
         self.T = Tn
@@ -561,6 +644,10 @@ class _GsPlan:
         self.flag_ptrs = ptr_array(self.R_flags)
         if train:
             self.dbr_ptrs = ptr_array([b.R["dout"] for b in self.br])
+        if eng.post2:
+            self.code_ptrs, self.one_ptrs = ptr_array([self.R["code3d"]]), ptr_array([self.R["ones"]])
+            if train:
+                self.dcode_ptrs = ptr_array([self.R["dcode3d"]])
 
 
 # conv outputs that have a pre-activation gradient buffer: name -> spatial factor (2 = the layer is pooled,

@@ -765,13 +765,17 @@ class UGaitEngine:
         p = self.plan(B, False)
         self._set_inputs(p, inputs, flags)
         self._forward(p, False)
+        return self._layer_output(p, layer)
+
+    def _layer_output(self, p, layer: str) -> torch.Tensor:
+        """A named layer of the graph after a forward pass; "embedding" = the model's output 0 (what the triplet loss sees)."""
         if self.post2:      # postriplet == 2: "signature" is the Dense layer (:821-826), "code" its l2_normalize (:828)
             if layer == "signature":
                 y = p.code
                 return (y.clone() if self.cfg.act != ACT_LEAKY else torch.where(y > 0, y, y / self.cfg.alpha))
-            if layer == "code":
+            if layer in ("code", "embedding"):
                 return p.codeN.clone()
-        if layer == "signature":
+        if layer in ("signature", "embedding"):
             return (p.br[0].out if self.cfg.single else p.sig).clone()
         if layer == "code":
             return p.code.clone()
@@ -1497,8 +1501,7 @@ class UGaitEngine:
         p = self.plan(B, False)
         self._set_base_inputs(p, base_inputs, src_row, use, None, mirror)
         self._forward(p, False, expanded=True)
-        return (p.br[0].out if self.cfg.single else p.sig).clone() if layer == "signature" else \
-            (p.code.clone() if layer == "code" else p.logits.clone())
+        return self._layer_output(p, layer)
 
     @torch.no_grad()
     def train_step(self, inputs, flags, labels, drop_masks=None, code_drop_mask=None) -> Dict[str, torch.Tensor]:
@@ -1526,9 +1529,7 @@ class UGaitEngine:
     def predict_resident(self, B: int, layer: str = "signature") -> torch.Tensor:
         p = self.plan(B, False)
         self._forward(p, False)
-        if layer == "signature":
-            return (p.br[0].out if self.cfg.single else (p.codeN if self.post2 else p.sig)).clone()
-        return p.code.clone() if layer == "code" else p.logits.clone()
+        return self._layer_output(p, layer)
 
     def _run_train(self, p, B, expanded):
         self._next_lr()
@@ -1762,9 +1763,7 @@ class UGaitEngine:
             p.ensure_base(hb.B0)
             p.use_mirror = bool(hb.use_mirror)
         self._forward(p, False, expanded)
-        if layer == "signature":
-            return (p.br[0].out if self.cfg.single else p.sig).clone()
-        return p.code.clone() if layer == "code" else p.logits.clone()
+        return self._layer_output(p, layer)
 
     def _report(self, p: "_Plan", with_reg: bool = False) -> Dict[str, torch.Tensor]:
         out = {"triplet": p.trip_out[0], "count": p.trip_out[1],
