@@ -40,6 +40,9 @@ class GaitSetEngine(UGaitEngine):
         if cfg.single and (cfg.nmods != 1 or cfg.nc > 0):
             raise ValueError("GaitSetConfig.single: the 1-modality graph has one branch and no FC1 "
                              "(nets/mj_uwyhNets_ba.py:890-911)")
+        # (UGaitEngine sets these in ITS _build_arena, which this class overrides)
+        self.aux = False
+        self.post2 = getattr(cfg, "postriplet", 1) == 2 and cfg.nc > 0 and not cfg.single
         super().__init__(cfg, **kw)
 
     # ------------------------------------------------------------------ parameters
