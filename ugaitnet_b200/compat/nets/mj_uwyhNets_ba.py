@@ -8,14 +8,17 @@ step runs on the B200 engine (ugaitnet_b200.net.UGaitEngine).
 
 ``gaitset=True`` (with a non-'relu' fActivation, as the reference requires, :1101) builds the GaitSet
 branch type (build_gaitset_branch :420-484) on ugaitnet_b200.gaitset.GaitSetEngine: inputs
-[B,25,60,60,c], signature [62,B,256], descriptor layer "flatten" (typecode 3).
+[B,25,60,60,c], signature [62,B,256], descriptor layer "flatten" (typecode 3); on three, two or ONE input shape
+(UWYHSemiNet.build_or_load(one shape, gaitset=True), :588-589 + :776-777 + :890-905: the branch output is the
+signature -- what mains/mj_trainUWYHGaitNet_DataGen_CasiaB_1mod.py:329-333 builds) and with postriplet == 2 (:814-832).
 
 ``smoothlabels`` (label-smoothed cross-entropy, :1252-1262), ``normbfmerge`` (per-branch l2_normalize before
 the gate, :1167-1168), ``aux_losses`` (classprob_{of,gray,depth} heads on the gated branch outputs, :1222-1251;
 stacked-CNN branches), ``postriplet == 2`` (2-modality builder, :819-832), ``freeze_convs`` / ``freeze_all`` /
 ``freeze_branches`` and ``layer.trainable`` (:193, :1366-1391), ``initnet`` / ``init_branches`` / ``loadnet`` from Keras
 HDF5 files (ugaitnet_b200.hdf5: pure-Python reader / writer, h5py is absent) are implemented.  Builder arguments that
-select ill-formed graphs raise NotImplementedError: aux_losses together with gaitset.  use3D builds the Conv3D branches
+select graphs that are ill-formed in the reference itself raise NotImplementedError: aux_losses together with gaitset,
+use3D with a multi-modal gaitset graph, compile_hard with gaitset.  use3D builds the Conv3D branches
 (:336-417) for every modality but a 50-channel optical flow; they run on the fp32 validation engine.  compile_hard (tfa TripletHardLoss) re-compiles a stacked-frame CNN model onto ugn_triplet_hard.
 """
 from __future__ import annotations
