@@ -347,6 +347,61 @@ def test_postriplet2_gaitset_builder(compat_path):
     assert logs["classprob_loss"] == pytest.approx(float(res["ce"]), rel=1e-5)
 
 
+def test_standalone_branch_builders_and_small_entry_points(compat_path, tmp_path):
+    """UWYHSemiNet.build_gaitset_branch / build_3Dbranch{,LReLU} (:336-484) as stand-alone branch models, fc_loadBranch
+    (:57-62), mj_buildnet_by_config (:299-330), MatMul (:23-48), UWYHNet.encode / fit_generator (:248-295)."""
+    from nets.mj_uwyhNets_ba import MatMul, UWYHNet, UWYHSemiNet, UWYHSemiNet3Mods, fc_loadBranch, mj_buildnet_by_config
+    from ugaitnet_b200.compat import optimizers
+    from oracle import gaitset_oracle as G
+    import nets.mj_uwyhNets_ba as mod
+    mod.MATH_MODE = "fp32"
+    # GaitSet branch alone: predict() is the [62, B, 256] branch output
+    gb = UWYHSemiNet.build_gaitset_branch("ofBranch", None, input_shape=(3, 12, 12, 2))
+    oc = G.GaitSetConfig(in_channels=(2,), frames=3, hw=12, nc=0, nclasses=0, single=True)
+    xs, _, _ = G.synth_batch(oc, 2, 2, seed=3)
+    P = {k: v.double().cpu() for k, v in gb.engine.export_params().items()}
+    ref = G.gaitset_branch_forward(xs[0].double(), P, "ofBranch", oc)
+    out = gb.predict(xs[0].numpy())
+    assert out.shape == (62, 4, 256) and np.allclose(out, ref.numpy(), atol=2e-5)
+    # the MatMul stand-in reproduces the last layer of that branch on the host
+    mm = MatMul(bin_num=31, hidden_dim=256).set_kernel(P["ofBranch/matmul/w"].numpy())
+    assert mm.get_config()["bin_num"] == 31 and mm(np.zeros((62, 4, 128), np.float32)).shape == (62, 4, 256)
+    # Conv3D branches alone
+    for b3 in (UWYHSemiNet.build_3Dbranch("grayBranch", ndense_units=32),
+               UWYHSemiNet.build_3DbranchLReLU("grayBranch", ndense_units=32, alpha=0.2)):
+        y = b3.predict(np.random.default_rng(0).random((2, 25, 60, 60, 1), dtype=np.float32) - 0.5)
+        assert y.shape == (2, 32) and np.isfinite(y).all() and b3.cfg.is3d(0)
+    # fc_loadBranch: the first branch of a saved model, stand-alone, with the saved tensors
+    shapes, fs, fn = [(6, 60, 60), (4, 60, 60), (4, 60, 60)], [(7, 7), (5, 5), (3, 3), (2, 2)], [8, 8, 16, 16]
+    model = UWYHSemiNet3Mods.build(shapes, 4, fs, fn, 32, 0.00005, 0.0, optimizer=optimizers.Adam(lr=1e-3), nclasses=10,
+                                   loss_weights=[1.0, 0.1])
+    path = str(tmp_path / "model-final.hdf5")
+    model.save(path)
+    br = fc_loadBranch(path)
+    Pm, Pb = model.engine.export_params(), br.engine.export_params()
+    assert set(Pb) == {k for k in Pm if k.startswith("ofBranch/")} and all(torch.equal(Pb[k], Pm[k]) for k in Pb)
+    x = np.random.default_rng(1).random((3, 6, 60, 60), dtype=np.float32) - 0.5
+    yb = br.predict(x)
+    ob = O.NetConfig(in_channels=(6,), filters_numbers=(8, 8, 16, 16), nd=32, nclasses=0, single=True)
+    yr, _ = O.model_forward([torch.tensor(x).double()], None, {k: v.double().cpu() for k, v in Pb.items()}, ob)
+    assert yb.shape == (3, 32) and np.allclose(yb, yr.numpy(), atol=2e-5)
+    # mj_buildnet_by_config through any builder
+    nc = dict(filters_size=fs, filters_numbers=fn, input_shape=shapes, ndense_units=32, weight_decay=0.00005, dropout=0.0,
+              nclasses=10, optimizer=optimizers.Adam(lr=1e-3), margin=0.2, loss_weights=[1.0, 0.1])
+    m2 = mj_buildnet_by_config(nc, UWYHSemiNet3Mods.build)
+    assert m2.cfg.nmods == 3 and m2.cfg.nd == 32 and m2.cfg.nclasses == 10
+    # UWYHNet.encode == UWYHSemiNet.encode on a 2-modality model
+    m3 = UWYHSemiNet.build(shapes[:2], 4, fs, fn, 32, 0.00005, 0.0, optimizer=optimizers.Adam(lr=1e-3), nclasses=10,
+                           loss_weights=[1.0, 0.1])
+    rng = np.random.default_rng(2)
+    bd = [rng.random((4, 6, 60, 60), dtype=np.float32) - 0.5, rng.random((4, 4, 60, 60), dtype=np.float32) - 0.5]
+    ud = [np.ones((4, 1), np.float32), np.array([[1], [0], [1], [0]], np.float32)]
+    e1, e2 = UWYHNet.encode(m3, list(bd), list(ud)), UWYHSemiNet.encode(m3, list(bd), list(ud))
+    assert e1.shape == (4, 32) and np.allclose(e1, e2, rtol=1e-5, atol=1e-6)     # (fp32 kernels accumulate with atomics)
+    assert np.allclose(np.linalg.norm(e1, axis=1), 1.0, atol=1e-5)
+    assert UWYHSemiNet.get_weights_filename("/a/b/model-final.hdf5") == "/a/b/model-final_weights.hdf5"
+
+
 def test_compile_hard(compat_path):
     """UWYHSemiNet3Mods.compile_hard(model, optimizer, loss_weights, margin) (:1302-1306): the compiled model switches to
     tfa's TripletHardLoss (ugn_triplet_hard), keeps its CE loss and weights, and starts a fresh optimiser."""

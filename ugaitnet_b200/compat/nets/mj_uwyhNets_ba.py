@@ -809,6 +809,70 @@ def _freeze(model, freeze_convs=False, freeze_all=False, freeze_branches=False):
                     sub.trainable = False
 
 
+class MatMul:
+    """Stand-in for the Keras layer of the GaitSet branch (:23-48): out[n] = x[n] . kernel[n] over the 2 * bin_num = 62
+    parts, kernel [62, 128, hidden_dim].  The arithmetic lives in the engine (ugn_bmm_f32, tensor "<branch>/matmul/w");
+    this class keeps the constructor / get_config protocol (it is named in custom_objects dictionaries, :58) and can
+    multiply host arrays for inspection."""
+
+    def __init__(self, bin_num=31, hidden_dim=256, **kwargs):
+        self.bin_num, self.hidden_dim = bin_num, hidden_dim
+        self.name = kwargs.get("name", "mat_mul")
+        self.kernel = None                      # set_kernel(): e.g. model.get_layer("ofBranch").layers[-1].get_weights()[0]
+
+    def set_kernel(self, kernel):
+        k = np.asarray(kernel, dtype=np.float32)
+        if k.shape != (2 * self.bin_num, 128, self.hidden_dim):
+            raise ValueError(f"MatMul kernel must be {(2 * self.bin_num, 128, self.hidden_dim)}, got {k.shape}")
+        self.kernel = k
+        return self
+
+    def call(self, x):
+        if self.kernel is None:
+            raise ValueError("MatMul: no kernel set (set_kernel)")
+        return np.matmul(np.asarray(x, dtype=np.float32), self.kernel)
+
+    __call__ = call
+
+    def get_config(self):
+        return {"name": self.name, "bin_num": self.bin_num, "hidden_dim": self.hidden_dim}
+
+
+def fc_loadBranch(init_branch):
+    """:57-62 -- the branch of a saved model as a stand-alone branch model: the saved file names its builder arguments
+    (model.save of this package); the first branch of that graph is rebuilt alone and initialised from the file."""
+    saved = _loadnet(init_branch)
+    bname = BRANCH_NAMES[0]
+    if saved.gaitset:
+        import dataclasses
+        cfg = dataclasses.replace(saved.cfg, in_channels=saved.cfg.in_channels[:1], nc=0, nclasses=0, single=True, postriplet=1)
+        branch = UGaitModel(cfg, None, triplet_loss(margin=cfg.margin), 1.0, multimodal=False)
+    else:
+        c = saved.cfg
+        act = "relu" if c.act == ACT_RELU else "leaky"
+        if c.is3d(0):
+            branch = UWYHSemiNet._branch3d(bname, (c.in_channels[0], c.hw, c.hw, 1), c.nd, "", act, c.alpha)
+        else:
+            branch = UWYHNet.buildBranch(bname, (c.in_channels[0], c.hw, c.hw), len(c.filters_numbers),
+                                         [(k, k) for k in c.filters_size], list(c.filters_numbers), c.nd, c.weight_decay,
+                                         c.dropout, None, _activation=act, alpha=c.alpha)
+    P = saved.engine.export_params()
+    branch.engine.load_params({k: v for k, v in P.items() if k.startswith(bname + "/")})
+    branch.name = bname
+    return branch
+
+
+def mj_buildnet_by_config(netconfig, buildfun):
+    """:299-330 -- rebuild a network from the dictionary the mains store next to their checkpoints, through ANY of the
+    builders (`buildfun(input_shape, nlayers, filters_size, filters_numbers, ndense_units, weight_decay, dropout, ...)`)."""
+    g = netconfig.get
+    fn = netconfig["filters_numbers"]
+    return buildfun(netconfig["input_shape"], len(fn), netconfig["filters_size"], fn, netconfig["ndense_units"],
+                    netconfig["weight_decay"], netconfig["dropout"], nclasses=g("nclasses", 150),
+                    loss_weights=g("loss_weights", [1.0, 0.1]), optimizer=netconfig["optimizer"],
+                    margin=netconfig["margin"], use3D=g("use3D", False))
+
+
 class UWYHNet:
     @staticmethod
     def buildBranch(name, input_shape=(50, 60, 60), number_convolutional_layers=4, filters_size=None,
@@ -854,19 +918,65 @@ class UWYHNet:
         _freeze(model, freeze_branches=freeze_branches)
         return model
 
+    @staticmethod
+    def fit_generator(model, epochs, callbacks, training_generator, validation_generator, current_step, steps_per_epoch,
+                      validation_steps, nworkers=0, new_lr=None):
+        """:248-272 -- the same driver as UWYHSemiNet.fit_generator."""
+        return UWYHSemiNet.fit_generator(model, epochs, callbacks, training_generator, validation_generator, current_step,
+                                         steps_per_epoch, validation_steps, nworkers, new_lr)
+
+    @staticmethod
+    def encode(model, batch_data, use_data):
+        """:275-295 -- gated, Maximum-merged, l2-normalised (of, gray) codes of a batch as numpy [B, nd]."""
+        return UWYHSemiNet.encode(model, batch_data, use_data)
+
 
 class UWYHSemiNet:
     def __init__(self):
         self.model = None
 
     @staticmethod
-    def get_weights_filename(netpath):
-        base, ext = osp.splitext(netpath)
-        return base + "_weights" + ext
+    def _branch3d(name, input_shape, ndense_units, init_branch, activation, alpha):
+        cfg = _cfg_from_args(tuple(input_shape), 4, [(7, 7), (5, 5), (3, 3), (2, 2)], None, ndense_units, 0.0, 0.0, 0.2, 0,
+                             [1.0, 1.0], Maximum, activation, alpha, single=True, use3D=True)
+        model = UGaitModel(cfg, None, triplet_loss(margin=0.2), 1.0, multimodal=False)
+        model.name = name
+        if init_branch:
+            _load_branch(model, init_branch, BRANCH_NAMES[0])
+        return model
 
     @staticmethod
-    def get_netconfig_filename(netpath):
-        return osp.join(osp.dirname(netpath), "model-config.hdf5")
+    def build_3Dbranch(name, input_shape=(25, 60, 60, 1), ndense_units=512, init_branch=""):
+        """:336-372 -- ONE stand-alone Conv3D branch (six strided 'valid' Conv3D + ReLU, Conv3D(ndense_units, 1x1x1)
+        "grayCode", Flatten) as a single-modality model whose predict() is the branch output [B, ndense_units]."""
+        return UWYHSemiNet._branch3d(name, input_shape, ndense_units, init_branch, 'relu', 0.3)
+
+    @staticmethod
+    def build_3DbranchLReLU(name, input_shape=(25, 60, 60, 1), ndense_units=512, init_branch="", alpha=0.3):
+        """:375-417 -- the same stack with LeakyReLU(alpha) after every convolution."""
+        return UWYHSemiNet._branch3d(name, input_shape, ndense_units, init_branch, 'leaky', alpha)
+
+    @staticmethod
+    def build_gaitset_branch(name, input_layer, input_shape=(25, 60, 60, 1), ndense_units=512, init_branch="", norm=True):
+        """:420-484 -- ONE stand-alone GaitSet branch: predict() is its [62, B, 256] output.  The reference applies the
+        branch to `input_layer` (a Keras tensor) and returns the output tensor; here the handle is the model itself
+        (`input_layer`, `ndense_units` and `norm` do not shape the branch in the reference either, :427-482)."""
+        cfg = GaitSetConfig(in_channels=(int(input_shape[3]),), frames=int(input_shape[0]), hw=int(input_shape[1]), nc=0,
+                            nclasses=0, single=True)
+        model = UGaitModel(cfg, None, triplet_loss(margin=cfg.margin), 1.0, multimodal=False)
+        model.name = name
+        if init_branch:
+            _load_branch(model, init_branch, BRANCH_NAMES[0])
+        return model
+
+    @staticmethod
+    def get_weights_filename(modelpath):
+        """:537-545 -- <dir>/<basename without extension>_weights.hdf5"""
+        return osp.join(osp.dirname(modelpath), osp.splitext(osp.basename(modelpath))[0] + "_weights.hdf5")
+
+    @staticmethod
+    def get_netconfig_filename(modelpath):
+        return osp.join(osp.dirname(modelpath), "model-config.hdf5")
 
     @staticmethod
     def build(input_shapes, number_convolutional_layers, filters_size, filters_numbers,
@@ -1024,6 +1134,11 @@ class UWYHSemiNet3Mods(UWYHSemiNet):
         _apply_init_branches(model, init_branches)
         _freeze(model, freeze_branches=freeze_branches)
         return _remember(model, "UWYHSemiNet3Mods", **kwargs)
+
+    @staticmethod
+    def loadnet(netpath: str):
+        """:1008-1029 -- as UWYHSemiNet.loadnet (the file names the builder that made it)."""
+        return _loadnet(netpath)
 
     @staticmethod
     def compile_hard(model, optimizer, loss_weights, margin):
