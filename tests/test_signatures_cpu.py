@@ -40,7 +40,13 @@ _EQUIV = {"optimizers.SGD(0.001, 0.9)": "None"}
 @pytest.mark.parametrize("rel,names", [
     ("nets/mj_uwyhNets_ba.py", ["UWYHSemiNet3Mods.build", "UWYHSemiNet3Mods.build_or_load", "UWYHSemiNet3Mods.compile_hard",
                                 "UWYHSemiNet.build", "UWYHSemiNet.build_or_load", "UWYHSemiNet.fit_generator",
-                                "UWYHSemiNet.encode", "UWYHSemiNet.loadnet", "mj_tensor_times_scalar"]),
+                                "UWYHSemiNet.encode", "UWYHSemiNet.loadnet", "mj_tensor_times_scalar",
+                                "UWYHSemiNet3Mods.loadnet", "UWYHSemiNet.build_by_config", "UWYHSemiNet.get_weights_filename",
+                                "UWYHSemiNet.get_netconfig_filename", "UWYHSemiNet.build_3Dbranch",
+                                "UWYHSemiNet.build_3DbranchLReLU", "UWYHSemiNet.build_gaitset_branch",
+                                "UWYHNet.buildBranchLReLU", "UWYHNet.build", "UWYHNet.fit_generator", "UWYHNet.encode",
+                                "fc_loadBranch", "mj_buildnet_by_config", "MatMul.__init__", "MatMul.call",
+                                "MatMul.get_config"]),
     ("nets/triplet_loss_all.py", ["triplet_loss"]),
     ("nets/mj_loss.py", ["mj_l2normalize", "mj_smoothL1", "mj_smoothL1bis", "PairLossLayer.pair_loss", "PairLossLayer.call",
                          "VerifLossLayer.pair_loss", "VerifLossLayer.call", "TripletLossLayer.__init__",
