@@ -56,6 +56,12 @@ STEP_CASES = {
     # (seed: no max-pool / set-max / LeakyReLU-sign decision of this tiny net within fp32 rounding of its boundary)
     "step_gaitset": ("gaitset", dict(in_channels=(2, 1), frames=4, hw=12, nc=16, nclasses=10, merge=0, wver=1.0, wid=1.0,
                                      label_smoothing=0.1), dict(ids=3, per_id=2), 9),
+    # the two GaitSet graphs added last: ONE modality (branch output = signature) and postriplet == 2 (CPU pin of the
+    # restatement; the engine is compared with the live oracle in tests/test_gaitset_gpu.py)
+    "step_gaitset_single": ("gaitset", dict(in_channels=(1,), frames=3, hw=12, nc=0, nclasses=12, wver=1.0, wid=0.1,
+                                            single=True), dict(ids=3, per_id=2), 7),
+    "step_gaitset_post2": ("gaitset", dict(in_channels=(2, 1), frames=3, hw=12, nc=16, nclasses=10, merge=2, wver=1.0,
+                                           wid=0.5, postriplet=2), dict(ids=3, per_id=2), 9),
 }
 
 

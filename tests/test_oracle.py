@@ -266,7 +266,7 @@ def test_gaitset_postriplet2_graph_literal():
 
 
 # ---- committed step fixtures: the restatement must not drift
-@pytest.mark.parametrize("name", ["step_stacked", "step_gaitset"])
+@pytest.mark.parametrize("name", ["step_stacked", "step_gaitset", "step_gaitset_single", "step_gaitset_post2"])
 def test_oracle_reproduces_step_fixture(golden_dir, name):
     sys.path.insert(0, golden_dir)
     import make_golden
