@@ -84,3 +84,46 @@ def test_unmodified_reference_main_imports_and_runs_its_metric_loop(shim, monkey
     np.random.seed(0)
     d2, eer2, _, _ = main.mj_computeDistMetrics(object(), Gen(), True, None)
     assert eer2 == eer and np.array_equal(d2, distances)
+
+
+@pytest.mark.parametrize("main", ["mj_trainUWYHGaitNet_DataGen_3mods", "mj_trainUWYHGaitNet_DataGen_CasiaB",
+                                  "mj_trainUWYHGaitNet_DataGen_CasiaB_1mod", "mj_trainUWYHGaitNet_DataGen_1mod",
+                                  "mj_testUWYHGaitNet_open_tum", "mj_testUWYHGaitNet_open_casiab"])
+def test_every_in_scope_main_imports_through_the_shim(shim, main):
+    """Every training / open-world test main of the reference (the both-datasets fork is out of scope) resolves its
+    imports -- tensorflow, tensorflow_addons, deepdish, tensorboard, nets.* -- and binds the drop-in builders."""
+    import warnings
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")              # (the reference's own "\\d" escape warnings)
+        mod = importlib.import_module("mains." + main)
+    import ugaitnet_b200.compat.nets.mj_uwyhNets_ba as drop_in
+    nets_ba = importlib.import_module("nets.mj_uwyhNets_ba")      # (the test mains import it under __main__ only)
+    assert os.path.samefile(nets_ba.__file__, drop_in.__file__)
+    if hasattr(mod, "UWYHSemiNet"):
+        assert mod.UWYHSemiNet is nets_ba.UWYHSemiNet
+
+
+def test_shim_routes_sklearn_knn_to_the_gpu_search_on_request():
+    """The open-world test mains import KNeighborsClassifier from sklearn.neighbors inside evalUWYHNet
+    (mains/mj_testUWYHGaitNet_open_tum.py:331): install(gpu_knn=True) makes that import yield the B200 classifier."""
+    import sklearn.neighbors
+    from ugaitnet_b200.compat import tf_shim
+    from ugaitnet_b200.knn import KNeighborsClassifier as GpuKNN
+    saved = dict(sys.modules)
+    saved_path = list(sys.path)
+    orig = sklearn.neighbors.KNeighborsClassifier
+    try:
+        tf_shim.install(REF, gpu_knn=True)
+        from sklearn.neighbors import KNeighborsClassifier as K1
+        assert K1 is GpuKNN
+        for name in ("fit", "predict", "kneighbors"):
+            assert callable(getattr(K1, name))
+        tf_shim.install(REF)
+        from sklearn.neighbors import KNeighborsClassifier as K2
+        assert K2 is orig
+    finally:
+        sklearn.neighbors.KNeighborsClassifier = orig
+        for k in list(sys.modules):
+            if k not in saved:
+                del sys.modules[k]
+        sys.path[:] = saved_path

@@ -131,11 +131,23 @@ def _mod(name, cls=_StubModule, **attrs):
     return m
 
 
-def install(reference_root=None):
+def install(reference_root=None, gpu_knn=False):
     """Register the stand-in modules (idempotent).  reference_root: the checkout whose mains/ will be imported; its
-    directory goes on sys.path (as the mains themselves do) and its nets/ becomes the fallback of the `nets` package."""
+    directory goes on sys.path (as the mains themselves do) and its nets/ becomes the fallback of the `nets` package.
+    gpu_knn: `from sklearn.neighbors import KNeighborsClassifier` -- what the open-world test mains do INSIDE their
+    evaluation functions (mains/mj_testUWYHGaitNet_open_tum.py:331, mj_testUWYHGaitNet_open_casiab.py) -- then yields
+    ugaitnet_b200.knn.KNeighborsClassifier (same fit / predict / kneighbors, B200 search); install(gpu_knn=False)
+    puts scikit-learn's class back."""
     from ugaitnet_b200.compat import keras_shim as ks
     here = os.path.dirname(os.path.abspath(__file__))
+    import sklearn.neighbors as skn
+    if not hasattr(skn, "_ugn_sklearn_knn"):
+        skn._ugn_sklearn_knn = skn.KNeighborsClassifier
+    if gpu_knn:
+        from ugaitnet_b200.knn import KNeighborsClassifier as GpuKNN
+        skn.KNeighborsClassifier = GpuKNN
+    else:
+        skn.KNeighborsClassifier = skn._ugn_sklearn_knn
     if "tensorflow" not in sys.modules or not isinstance(sys.modules["tensorflow"], _StubModule):
         tf = _mod("tensorflow", __version__="2.3.0-ugaitnet_b200-shim")
         tf.executing_eagerly = lambda: True
