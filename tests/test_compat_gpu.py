@@ -544,3 +544,36 @@ def test_use3d_builders(compat_path, tmp_path):
     want = O.branch3d_forward(torch.tensor(X[2]), P1, "ofBranch", oc1)
     got = single.predict(X[2])[0]
     assert np.allclose(got, want.numpy(), atol=2e-5)
+
+
+def test_shim_gpu_knn_is_what_the_test_mains_import():
+    """tf_shim.install(gpu_knn=True): `from sklearn.neighbors import KNeighborsClassifier`, the statement INSIDE evalUWYHNet
+    (mains/mj_testUWYHGaitNet_open_tum.py:331-341), binds the B200 classifier; fit / predict on numpy arrays as the main
+    calls them, labels equal to scikit-learn's own class on tie-free data."""
+    import sys
+    import sklearn.neighbors as skn
+    from ugaitnet_b200.compat import tf_shim
+    saved, saved_path = dict(sys.modules), list(sys.path)
+    real = getattr(skn, "_ugn_sklearn_knn", skn.KNeighborsClassifier)
+    rng = np.random.default_rng(12)
+    cent = rng.standard_normal((12, 32))
+    y = rng.integers(0, 12, 600)
+    G = (cent[y] + 0.4 * rng.standard_normal((600, 32))).astype(np.float32)
+    yq = rng.integers(0, 12, 50)
+    Q = (cent[yq] + 0.4 * rng.standard_normal((50, 32))).astype(np.float32)
+    ref = real(n_neighbors=3).fit(G, y).predict(Q)
+    try:
+        tf_shim.install(None, gpu_knn=True)
+        from sklearn.neighbors import KNeighborsClassifier
+        from ugaitnet_b200.knn import KNeighborsClassifier as GpuKNN
+        assert KNeighborsClassifier is GpuKNN
+        clf = KNeighborsClassifier(n_neighbors=3)
+        clf.fit(G, y)
+        pred = clf.predict(Q)
+        assert isinstance(pred, np.ndarray) and np.array_equal(pred.astype(np.int64), ref.astype(np.int64))
+    finally:
+        skn.KNeighborsClassifier = real
+        for k in list(sys.modules):
+            if k not in saved:
+                del sys.modules[k]
+        sys.path[:] = saved_path
