@@ -12,7 +12,9 @@ TensorFlow cannot be installed here and the reference holds no test or golden ve
 restatement follows the call sites cited per function and documented Keras/TF semantics
 (``padding='same'`` zero padding, ``LeakyReLU()`` alpha 0.3, ``reduce_max`` gradient split evenly among
 ties, ``MaxPooling2D`` gradient to the first maximum, GlorotUniform fans of a rank-3 kernel,
-activity regulariser divided by ``shape(output)[0]``).
+activity regulariser divided by ``shape(output)[0]``).  The ARITHMETIC of the restated graph is pinned by a second,
+independent restatement (tests/test_oracle.py: layer-by-layer channels-last numpy, forward to 1e-12, gradients against
+central differences of that forward); what stays unpinned is whether the graph is the one TF 2.3 builds.
 """
 from __future__ import annotations
 

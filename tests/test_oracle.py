@@ -200,6 +200,81 @@ def test_gaitset_hpp_layout_and_shapes():
     assert torch.allclose((sig ** 2).sum(1), torch.ones(62, 256, dtype=torch.float64))
 
 
+def _gs_branch_literal_np(x, P, bn, alpha=0.3):
+    """build_gaitset_branch (nets/mj_uwyhNets_ba.py:427-482) layer by layer in numpy, CHANNELS-LAST as Keras runs it, with no
+    operator shared with the torch oracle: ZeroPadding2D(2), Conv2D(k, 'same', no bias) as a sum over sliding windows with
+    the kernel in Keras' (kh, kw, cin, cout) layout, LeakyReLU(), MaxPooling2D(2), reduce_max over the frame axis, Add,
+    the five Reshape((num_bin, -1, c)) + mean + max strips of both maps, Concatenate(axis=1), transpose([1,0,2]), MatMul."""
+    from numpy.lib.stride_tricks import sliding_window_view
+
+    def conv_same(a, w):                                   # a [n,h,w,c]; w oracle layout [cout,cin,kh,kw] -> Keras (kh,kw,cin,cout)
+        k = np.transpose(w, (2, 3, 1, 0))
+        ph = k.shape[0] // 2
+        ap = np.pad(a, ((0, 0), (ph, ph), (ph, ph), (0, 0)))
+        win = sliding_window_view(ap, (k.shape[0], k.shape[1]), axis=(1, 2))       # [n,h,w,c,kh,kw]
+        return np.einsum("nhwcij,ijco->nhwo", win, k)
+
+    def lrelu(a):
+        return np.where(a > 0, a, alpha * a)
+
+    def pool(a):
+        n, h, w, c = a.shape
+        return a.reshape(n, h // 2, 2, w // 2, 2, c).max((2, 4))
+
+    W = {k.split("/")[1]: v.numpy() for k, v in P.items() if k.startswith(bn + "/")}
+    B, T = x.shape[:2]
+    a = np.pad(x, ((0, 0), (0, 0), (2, 2), (2, 2), (0, 0))).reshape((B * T,) + (x.shape[2] + 4, x.shape[3] + 4, x.shape[4]))
+    td_max = lambda t: t.reshape((B, T) + t.shape[1:]).max(1)                      # Lambda(reduce_max(axis=1))
+    a = lrelu(conv_same(a, W["a1"]))
+    a = pool(lrelu(conv_same(a, W["a2"])))
+    b = td_max(a)
+    b = lrelu(conv_same(b, W["b1"]))
+    b = pool(lrelu(conv_same(b, W["b2"])))
+    a = lrelu(conv_same(a, W["a3"]))
+    a = pool(lrelu(conv_same(a, W["a4"])))
+    b = b + td_max(a)
+    b = lrelu(conv_same(b, W["b3"]))
+    b = lrelu(conv_same(b, W["b4"]))
+    a = lrelu(conv_same(a, W["a5"]))
+    a = lrelu(conv_same(a, W["a6"]))
+    a = td_max(a)
+    b = b + a
+    feats = []
+    for nb in (1, 2, 4, 8, 16):
+        for m in (a, b):
+            r = m.reshape(m.shape[0], nb, -1, m.shape[-1])
+            feats.append(r.mean(2) + r.max(2))
+    f = np.transpose(np.concatenate(feats, 1), (1, 0, 2))                         # [62, B, 128]
+    return np.matmul(f, W["matmul"])
+
+
+def test_gaitset_branch_against_literal_channels_last_numpy():
+    """The whole GaitSet branch of the torch oracle == the layer-by-layer channels-last numpy restatement (fp64)."""
+    from oracle import gaitset_oracle as G
+    for c, seed in ((1, 2), (2, 5)):
+        cfg = G.GaitSetConfig(in_channels=(c,), frames=3, hw=12, nclasses=0)
+        P = G.init_params(cfg, seed=seed, dtype=torch.float64)
+        xs, _, _ = G.synth_batch(cfg, ids=2, per_id=1, seed=seed, dtype=torch.float64)
+        got = G.gaitset_branch_forward(xs[0], P, "ofBranch", cfg).numpy()
+        lit = _gs_branch_literal_np(xs[0].numpy(), P, "ofBranch")
+        assert got.shape == lit.shape == (62, 2, 256)
+        assert np.abs(got - lit).max() <= 1e-12 * max(1.0, np.abs(lit).max())
+        # gradients: torch autograd of the oracle == central differences of the NUMPY forward (a linear functional of the
+        # branch output, so the only non-smooth points are LeakyReLU / max kinks, measure-zero for a 1e-6 step)
+        R = torch.randn(got.shape, generator=torch.Generator().manual_seed(seed), dtype=torch.float64)
+        Pg = {k: v.clone().requires_grad_(True) for k, v in P.items()}
+        (G.gaitset_branch_forward(xs[0], Pg, "ofBranch", cfg) * R).sum().backward()
+        for name in ("ofBranch/a1/w", "ofBranch/b3/w", "ofBranch/a6/w", "ofBranch/matmul/w"):
+            g = Pg[name].grad
+            d = g / g.norm()
+            eps = 1e-6
+            Pp, Pm = dict(P), dict(P)
+            Pp[name], Pm[name] = P[name] + eps * d, P[name] - eps * d
+            fd = float(((_gs_branch_literal_np(xs[0].numpy(), Pp, "ofBranch") - _gs_branch_literal_np(xs[0].numpy(), Pm, "ofBranch"))
+                        * R.numpy()).sum()) / (2 * eps)
+            assert abs(fd - float(g.norm())) <= 1e-6 * float(g.norm()), (name, fd, float(g.norm()))
+
+
 def test_gaitset_single_modality_graph_is_the_bare_branch():
     """UWYHSemiNet.build on ONE input shape with gaitset (nets/mj_uwyhNets_ba.py:890-905): ``ofout1 = ofBranch;
     outsignature = ofout1`` -- no use-flag gate, no fusion, no l2_normalize; "classprob" on transpose([1,0,2]) + Flatten;
