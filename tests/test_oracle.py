@@ -200,6 +200,35 @@ def test_gaitset_hpp_layout_and_shapes():
     assert torch.allclose((sig ** 2).sum(1), torch.ones(62, 256, dtype=torch.float64))
 
 
+def test_conv3d_branch_against_literal_channels_last_numpy():
+    """build_3Dbranch / build_3DbranchLReLU (nets/mj_uwyhNets_ba.py:346-372, :385-417) restated in channels-last numpy:
+    six strided 'valid' Conv3D as sums over strided sliding windows with Keras' (kt,kh,kw,cin,cout) kernels, ReLU |
+    LeakyReLU(alpha), Conv3D(nd, (1,1,1)) "grayCode", Flatten -- equal to the torch oracle's branch3d_forward."""
+    from numpy.lib.stride_tricks import sliding_window_view
+    layers = (((3, 5, 5), (1, 2, 2)), ((3, 3, 3), (1, 2, 2)), ((3, 3, 3), (2, 2, 2)), ((3, 3, 3), (2, 2, 2)),
+              ((3, 2, 2), (1, 1, 1)), ((2, 1, 1), (1, 1, 1)))                       # the literal kernel / stride list
+    for act, alpha in ((O.ACT_RELU, 0.0), (O.ACT_LEAKY, 0.2)):
+        cfg = O.NetConfig(in_channels=(25,), nd=6, nclasses=0, single=True, act=act, alpha=alpha, branch3d=(True,),
+                          filters3d=(3, 4, 5, 6, 6, 7))
+        P = O.init_params(cfg, seed=8, dtype=torch.float64)
+        g = torch.Generator().manual_seed(8)
+        for k in P:
+            if k.endswith("/b"):
+                P[k] = torch.randn(P[k].shape, generator=g, dtype=torch.float64) * 0.1
+        x = torch.rand(2, 25, 60, 60, 1, generator=g, dtype=torch.float64) - 0.5
+        got = O.branch3d_forward(x, P, "ofBranch", cfg).numpy()
+        a = x.numpy()                                                                # [B, T, H, W, C] channels-last
+        for li, (ks, st) in enumerate(layers):
+            k = np.transpose(P[f"ofBranch/conv{li}/w"].numpy(), (2, 3, 4, 1, 0))     # [cout,cin,kt,kh,kw] -> (kt,kh,kw,cin,cout)
+            assert k.shape[:3] == ks
+            win = sliding_window_view(a, ks, axis=(1, 2, 3))[:, ::st[0], ::st[1], ::st[2]]   # [B,t,h,w,C,kt,kh,kw]
+            z = np.einsum("bthwcijk,ijkco->bthwo", win, k) + P[f"ofBranch/conv{li}/b"].numpy()
+            a = np.maximum(z, 0) if act == O.ACT_RELU else np.where(z > 0, z, alpha * z)
+        assert a.shape[1:4] == (1, 1, 1)
+        lit = a.reshape(2, -1) @ P["ofBranch/ofCode/w"].numpy().T + P["ofBranch/ofCode/b"].numpy()
+        assert got.shape == lit.shape == (2, 6) and np.abs(got - lit).max() <= 1e-12 * max(1.0, np.abs(lit).max())
+
+
 def _gs_branch_literal_np(x, P, bn, alpha=0.3):
     """build_gaitset_branch (nets/mj_uwyhNets_ba.py:427-482) layer by layer in numpy, CHANNELS-LAST as Keras runs it, with no
     operator shared with the torch oracle: ZeroPadding2D(2), Conv2D(k, 'same', no bias) as a sum over sliding windows with
