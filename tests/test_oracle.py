@@ -200,6 +200,57 @@ def test_gaitset_hpp_layout_and_shapes():
     assert torch.allclose((sig ** 2).sum(1), torch.ones(62, 256, dtype=torch.float64))
 
 
+def test_optimizer_variants_against_torch_optim():
+    """Adam, AMSGrad, decoupled weight decay (tfa AdamW) and SGD with momentum of the oracle against torch.optim -- an
+    implementation the restatement shares no code with.  torch places epsilon after the bias correction of sqrt(v)
+    (Kingma & Ba, algorithm 1) where Keras uses the "epsilon hat" form (the note before their section 2.1): with
+    |g| = O(1) and eps = 1e-7 the two differ by O(eps / sqrt(v)), the tolerance below."""
+    g = torch.Generator().manual_seed(17)
+    w0 = torch.randn(50, generator=g, dtype=torch.float64)
+    grads = []
+    for i in range(6):          # |g| >= 0.5: the eps-placement difference is lr * eps / sqrt(v) <= 1e-2 * 1e-7 / (0.03 * 0.5) per step
+        r = torch.randn(50, generator=g, dtype=torch.float64) * (1.0 + 0.5 * (5 - i))    # shrinking: v decays, vhat holds
+        grads.append(torch.sign(r) * (0.5 + r.abs()))
+    lr, wd = 1e-2, 1e-3
+
+    def run_torch(opt_cls, **kw):
+        p = torch.nn.Parameter(w0.clone())
+        opt = opt_cls([p], **kw)
+        for gr in grads:
+            p.grad = gr.clone()
+            opt.step()
+        return p.detach()
+
+    def run_oracle(amsgrad=False, weight_decay=0.0, b2=0.999):
+        P, G = {"w": w0.clone()}, None
+        M, V = {"w": torch.zeros_like(w0)}, {"w": torch.zeros_like(w0)}
+        Vh = {"w": torch.zeros_like(w0)} if amsgrad else None
+        for t, gr in enumerate(grads, 1):
+            O.adam_step(P, {"w": gr}, M, V, t, lr=lr, b2=b2, eps=1e-7, Vhat=Vh, weight_decay=weight_decay)
+        return P["w"]
+    tol = dict(rtol=0, atol=1e-6)
+    assert torch.allclose(run_oracle(), run_torch(torch.optim.Adam, lr=lr, eps=1e-7), **tol)
+    # (beta_2 = 0.5: with 0.999 v only grows over six steps and vhat never differs from it)
+    assert torch.allclose(run_oracle(amsgrad=True, b2=0.5),
+                          run_torch(torch.optim.Adam, lr=lr, betas=(0.9, 0.5), eps=1e-7, amsgrad=True), **tol)
+    assert torch.allclose(run_oracle(b2=0.5), run_torch(torch.optim.Adam, lr=lr, betas=(0.9, 0.5), eps=1e-7), **tol)
+    # tfa AdamW subtracts weight_decay * var (NOT scaled by lr); torch scales its coefficient by lr
+    assert torch.allclose(run_oracle(weight_decay=wd), run_torch(torch.optim.AdamW, lr=lr, eps=1e-7, weight_decay=wd / lr), **tol)
+    assert not torch.allclose(run_oracle(b2=0.5), run_oracle(amsgrad=True, b2=0.5), rtol=0, atol=1e-5)   # (the variants do differ)
+    # SGD(momentum): Keras keeps v = mu v - lr g, torch v = mu v + g and steps by -lr v: identical for a constant lr
+    P, V = {"w": w0.clone()}, {"w": torch.zeros_like(w0)}
+    for t, gr in enumerate(grads, 1):
+        O.sgd_step(P, {"w": gr}, V, t, lr=lr, momentum=0.9)
+    assert torch.allclose(P["w"], run_torch(torch.optim.SGD, lr=lr, momentum=0.9), rtol=0, atol=1e-14)
+    # ... and Keras' `decay`: lr_t = lr / (1 + decay * iterations), baked into the velocity at the step it is applied
+    P, V, wn, vn = {"w": w0.clone()}, {"w": torch.zeros_like(w0)}, w0.numpy().copy(), np.zeros(50)
+    for t, gr in enumerate(grads, 1):
+        O.sgd_step(P, {"w": gr}, V, t, lr=lr, momentum=0.9, decay=0.1)
+        vn = 0.9 * vn - lr / (1 + 0.1 * (t - 1)) * gr.numpy()
+        wn = wn + vn
+    assert np.allclose(P["w"].numpy(), wn, rtol=0, atol=1e-14)
+
+
 def test_conv3d_branch_against_literal_channels_last_numpy():
     """build_3Dbranch / build_3DbranchLReLU (nets/mj_uwyhNets_ba.py:346-372, :385-417) restated in channels-last numpy:
     six strided 'valid' Conv3D as sums over strided sliding windows with Keras' (kt,kh,kw,cin,cout) kernels, ReLU |
