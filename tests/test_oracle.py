@@ -574,6 +574,12 @@ def test_oracle_primitives_against_scipy_and_sklearn():
     ce, _ = O.softmax_ce(torch.tensor(logits), F.one_hot(torch.tensor(lab), 7).double())
     p = np.exp(logits) / np.exp(logits).sum(1, keepdims=True)
     assert float(ce) == pytest.approx(log_loss(lab, p, labels=list(range(7))), rel=1e-12)
+    # smoothlabels (:1252-1262): tf.losses.CategoricalCrossentropy(label_smoothing=e) = targets y (1-e) + e/C -- the
+    # definition torch's cross_entropy(label_smoothing=e) implements
+    oh = F.one_hot(torch.tensor(lab), 7).double()
+    ce_s, _ = O.softmax_ce(torch.tensor(logits), oh * 0.9 + 0.1 / 7)
+    assert float(ce_s) == pytest.approx(float(F.cross_entropy(torch.tensor(logits), torch.tensor(lab), label_smoothing=0.1)),
+                                        rel=1e-12)
     v = rng.normal(size=(6, 10))
     assert np.allclose(O.l2_normalize(torch.tensor(v), 1).numpy(), normalize(v, norm="l2", axis=1), rtol=1e-12)
     e = rng.normal(size=(1, 9, 5))
