@@ -576,4 +576,5 @@ def test_shim_gpu_knn_is_what_the_test_mains_import():
         for k in list(sys.modules):
             if k not in saved:
                 del sys.modules[k]
+        sys.modules.update(saved)            # (install() re-imports `nets.*`: put the module objects of this session back)
         sys.path[:] = saved_path
